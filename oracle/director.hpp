@@ -1,0 +1,655 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see score.hpp header).
+//
+// CPU restatement of the reference's score director, moves, candidate order and the
+// local-search candidate loop around it.
+//   ScoreDirector            solverforge-scoring/src/director/score_director/incremental.rs:141-224
+//   ChangeMove               solverforge-solver/src/heuristic/move/change.rs:125-175
+//   SwapMove                 heuristic/move/swap.rs:140-215
+//   CompoundScalarMove       heuristic/move/compound_scalar.rs:245-319,397-406
+//   ListChangeMove           heuristic/move/list_kernel/change.rs:23-153
+//   ListSwapMove             heuristic/move/list_kernel/swap.rs:31-110
+//   evaluate_candidate       phase/localsearch/evaluation.rs:20-115
+//   MoveStreamContext        heuristic/selector/move_selector/iter.rs:14-207
+//   ChangeMove order         heuristic/selector/move_selector/change.rs:66-104,246-307
+//   nearby list change order heuristic/selector/list_kernel/nearby_change.rs:102-232,
+//                            heuristic/selector/nearby_list_support.rs:3-34
+//   foragers                 phase/localsearch/forager.rs:70-425, forager/improving.rs
+//   acceptors                phase/localsearch/acceptor/{hill_climbing,late_acceptance,simulated_annealing}.rs
+//   candidate loop           phase/localsearch/phase/candidates.rs:47-285
+#pragma once
+#include <cmath>
+#include <functional>
+#include <limits>
+
+#include "constraints.hpp"
+
+namespace sfo {
+
+using OptVal = std::optional<size_t>;
+
+// Accessors a model provides (the reference generates these with macros).
+template <class S>
+struct Access {
+  OptVal (*get)(const S&, size_t desc, size_t entity) = nullptr;
+  void (*set)(S&, size_t desc, size_t entity, OptVal v) = nullptr;
+  std::vector<size_t>& (*list)(S&, size_t desc, size_t entity) = nullptr;
+  size_t (*entity_count)(const S&, size_t desc) = nullptr;
+  void (*update_entity_shadows)(S&, size_t desc, size_t entity) = nullptr;  // domain/traits.rs:61-68
+};
+
+template <class S, class Sc>
+struct ScoreDirector {
+  S working;
+  ConstraintSet<S, Sc> constraints;
+  Access<S> access;
+  Sc cached = Sc::zero();
+  bool initialized = false;
+  uint64_t score_calculations = 0;
+
+  Sc calculate_score() {
+    if (!initialized) {
+      cached = constraints.initialize_all(working);
+      initialized = true;
+    }
+    return cached;
+  }
+  Sc fresh_score() const { return constraints.evaluate_all(working); }
+  void before_variable_changed(size_t desc, size_t entity) {
+    if (!initialized) return;
+    cached = cached + constraints.on_retract_all(working, entity, desc);
+  }
+  void after_variable_changed(size_t desc, size_t entity) {
+    if (!initialized) return;
+    if (access.update_entity_shadows) access.update_entity_shadows(working, desc, entity);
+    cached = cached + constraints.on_insert_all(working, entity, desc);
+  }
+  struct ScoreState {
+    Sc committed;
+    bool initialized;
+  };
+  ScoreState snapshot_score_state() const { return {cached, initialized}; }
+  void restore_score_state(ScoreState st) {
+    if (st.initialized) {
+      cached = st.committed;
+      initialized = true;
+    } else {
+      constraints.reset_all();
+      cached = Sc::zero();
+      initialized = false;
+    }
+  }
+  void reset() {
+    constraints.reset_all();
+    initialized = false;
+    cached = Sc::zero();
+  }
+};
+
+struct ScalarEdit {  // planning/scalar/candidate.rs:6-12
+  size_t descriptor_index, entity_index;
+  OptVal to_value;
+};
+
+struct Move {
+  enum Kind { Change, Swap, Compound, ListChange, ListSwap } kind = Change;
+  size_t desc = 0;
+  size_t a = 0, b = 0, c = 0, d = 0;  // Change: a=entity; Swap: a,b; List*: a=src_e b=src_p c=dst_e d=dst_p
+  OptVal to;
+  std::vector<ScalarEdit> edits;
+  bool requires_hard_improvement = false;
+  bool requires_score_improvement = false;
+
+  static Move change(size_t desc, size_t e, OptVal to) { Move m; m.kind = Change; m.desc = desc; m.a = e; m.to = to; return m; }
+  static Move swap(size_t desc, size_t l, size_t r) { Move m; m.kind = Swap; m.desc = desc; m.a = l; m.b = r; return m; }
+  static Move compound(std::vector<ScalarEdit> e) { Move m; m.kind = Compound; m.edits = std::move(e); return m; }
+  static Move list_change(size_t desc, size_t se, size_t sp, size_t de, size_t dp) {
+    Move m; m.kind = ListChange; m.desc = desc; m.a = se; m.b = sp; m.c = de; m.d = dp; return m;
+  }
+  static Move list_swap(size_t desc, size_t e1, size_t p1, size_t e2, size_t p2) {
+    Move m; m.kind = ListSwap; m.desc = desc; m.a = e1; m.b = p1; m.c = e2; m.d = p2; return m;
+  }
+};
+
+struct Undo {
+  OptVal v0, v1;
+  std::vector<OptVal> many;
+};
+
+inline size_t adjusted_destination(const Move& m) {  // list_kernel/change.rs:28-34
+  return (m.a == m.c && m.d > m.b) ? m.d - 1 : m.d;
+}
+
+template <class S, class Sc>
+bool is_doable(const Move& m, ScoreDirector<S, Sc>& dir) {
+  S& s = dir.working;
+  auto& ac = dir.access;
+  switch (m.kind) {
+    case Move::Change: {
+      OptVal cur = ac.get(s, m.desc, m.a);
+      if (!cur && !m.to) return false;
+      if (cur && m.to) return *cur != *m.to;
+      return true;
+    }
+    case Move::Swap: return ac.get(s, m.desc, m.a) != ac.get(s, m.desc, m.b);
+    case Move::Compound: {
+      if (m.edits.empty()) return false;
+      bool changes = false;
+      for (auto& e : m.edits) changes |= ac.get(s, e.descriptor_index, e.entity_index) != e.to_value;
+      return changes;
+    }
+    case Move::ListChange: {
+      size_t src_len = ac.list(s, m.desc, m.a).size();
+      if (m.b >= src_len) return false;
+      size_t dst_len = ac.list(s, m.desc, m.c).size();
+      size_t max_dst = m.a == m.c ? src_len : dst_len;
+      if (m.d > max_dst) return false;
+      return m.a != m.c || (m.b != m.d && m.d != m.b + 1);
+    }
+    case Move::ListSwap: {
+      auto& l1 = ac.list(s, m.desc, m.a);
+      auto& l2 = ac.list(s, m.desc, m.c);
+      if (m.b >= l1.size() || m.d >= l2.size() || (m.a == m.c && m.b == m.d)) return false;
+      return l1[m.b] != l2[m.d];
+    }
+  }
+  return false;
+}
+
+inline std::vector<std::pair<size_t, size_t>> unique_affected(const std::vector<ScalarEdit>& edits) {
+  std::vector<std::pair<size_t, size_t>> out;
+  for (auto& e : edits) {
+    auto p = std::make_pair(e.descriptor_index, e.entity_index);
+    if (std::find(out.begin(), out.end(), p) == out.end()) out.push_back(p);
+  }
+  return out;
+}
+
+template <class S, class Sc>
+Undo do_move(const Move& m, ScoreDirector<S, Sc>& dir) {
+  S& s = dir.working;
+  auto& ac = dir.access;
+  Undo u;
+  switch (m.kind) {
+    case Move::Change:
+      u.v0 = ac.get(s, m.desc, m.a);
+      dir.before_variable_changed(m.desc, m.a);
+      ac.set(s, m.desc, m.a, m.to);
+      dir.after_variable_changed(m.desc, m.a);
+      break;
+    case Move::Swap:
+      u.v0 = ac.get(s, m.desc, m.a);
+      u.v1 = ac.get(s, m.desc, m.b);
+      dir.before_variable_changed(m.desc, m.a);
+      dir.before_variable_changed(m.desc, m.b);
+      ac.set(s, m.desc, m.a, u.v1);
+      ac.set(s, m.desc, m.b, u.v0);
+      dir.after_variable_changed(m.desc, m.a);
+      dir.after_variable_changed(m.desc, m.b);
+      break;
+    case Move::Compound: {
+      auto affected = unique_affected(m.edits);
+      for (auto& e : m.edits) u.many.push_back(ac.get(s, e.descriptor_index, e.entity_index));
+      for (auto& p : affected) dir.before_variable_changed(p.first, p.second);
+      for (auto& e : m.edits) ac.set(s, e.descriptor_index, e.entity_index, e.to_value);
+      for (auto it = affected.rbegin(); it != affected.rend(); ++it) dir.after_variable_changed(it->first, it->second);
+      break;
+    }
+    case Move::ListChange: {
+      bool intra = m.a == m.c;
+      dir.before_variable_changed(m.desc, m.a);
+      if (!intra) dir.before_variable_changed(m.desc, m.c);
+      auto& src = ac.list(s, m.desc, m.a);
+      size_t value = src[m.b];
+      src.erase(src.begin() + (ptrdiff_t)m.b);
+      auto& dst = ac.list(s, m.desc, m.c);
+      dst.insert(dst.begin() + (ptrdiff_t)adjusted_destination(m), value);
+      dir.after_variable_changed(m.desc, m.a);
+      if (!intra) dir.after_variable_changed(m.desc, m.c);
+      break;
+    }
+    case Move::ListSwap: {
+      bool intra = m.a == m.c;
+      size_t v1 = ac.list(s, m.desc, m.a)[m.b];
+      size_t v2 = ac.list(s, m.desc, m.c)[m.d];
+      dir.before_variable_changed(m.desc, m.a);
+      if (!intra) dir.before_variable_changed(m.desc, m.c);
+      ac.list(s, m.desc, m.a)[m.b] = v2;
+      ac.list(s, m.desc, m.c)[m.d] = v1;
+      dir.after_variable_changed(m.desc, m.a);
+      if (!intra) dir.after_variable_changed(m.desc, m.c);
+      break;
+    }
+  }
+  return u;
+}
+
+template <class S, class Sc>
+void undo_move(const Move& m, ScoreDirector<S, Sc>& dir, const Undo& u) {
+  S& s = dir.working;
+  auto& ac = dir.access;
+  switch (m.kind) {
+    case Move::Change:
+      dir.before_variable_changed(m.desc, m.a);
+      ac.set(s, m.desc, m.a, u.v0);
+      dir.after_variable_changed(m.desc, m.a);
+      break;
+    case Move::Swap:
+      dir.before_variable_changed(m.desc, m.a);
+      dir.before_variable_changed(m.desc, m.b);
+      ac.set(s, m.desc, m.a, u.v0);
+      ac.set(s, m.desc, m.b, u.v1);
+      dir.after_variable_changed(m.desc, m.a);
+      dir.after_variable_changed(m.desc, m.b);
+      break;
+    case Move::Compound: {
+      auto affected = unique_affected(m.edits);
+      for (auto& p : affected) dir.before_variable_changed(p.first, p.second);
+      for (size_t i = 0; i < m.edits.size(); ++i)
+        ac.set(s, m.edits[i].descriptor_index, m.edits[i].entity_index, u.many[i]);
+      for (auto it = affected.rbegin(); it != affected.rend(); ++it) dir.after_variable_changed(it->first, it->second);
+      break;
+    }
+    case Move::ListChange: {  // list_kernel/change.rs:122-153 — destination notified first
+      bool intra = m.a == m.c;
+      dir.before_variable_changed(m.desc, m.c);
+      if (!intra) dir.before_variable_changed(m.desc, m.a);
+      auto& dst = ac.list(s, m.desc, m.c);
+      size_t adj = adjusted_destination(m);
+      size_t value = dst[adj];
+      dst.erase(dst.begin() + (ptrdiff_t)adj);
+      auto& src = ac.list(s, m.desc, m.a);
+      src.insert(src.begin() + (ptrdiff_t)m.b, value);
+      dir.after_variable_changed(m.desc, m.c);
+      if (!intra) dir.after_variable_changed(m.desc, m.a);
+      break;
+    }
+    case Move::ListSwap: {  // a swap is its own inverse
+      do_move(m, dir);
+      break;
+    }
+  }
+}
+
+// evaluation.rs:20-115
+enum class EvalKind { Scored, NotDoable, RejectedByHardImprovement, RejectedByScoreImprovement };
+template <class Sc>
+struct CandidateEvaluation {
+  EvalKind kind;
+  Sc score;
+};
+
+template <class S, class Sc>
+CandidateEvaluation<Sc> evaluate_candidate(const Move& m, ScoreDirector<S, Sc>& dir, Sc reference_score) {
+  if (!is_doable(m, dir)) return {EvalKind::NotDoable, Sc::zero()};
+  auto state = dir.snapshot_score_state();
+  Undo u = do_move(m, dir);
+  Sc move_score = dir.calculate_score();
+  undo_move(m, dir, u);
+  dir.restore_score_state(state);
+  dir.score_calculations += 1;
+  HardDelta hd = hard_score_delta(reference_score, move_score);
+  if (m.requires_hard_improvement && hd != HardDelta::Improving) return {EvalKind::RejectedByHardImprovement, move_score};
+  if (m.requires_score_improvement && move_score <= reference_score) return {EvalKind::RejectedByScoreImprovement, move_score};
+  return {EvalKind::Scored, move_score};
+}
+
+// ---------------------------------------------------------------------------------------------
+inline uint64_t splitmix64(uint64_t v) {  // iter.rs:193-198
+  v += 0x9E3779B97F4A7C15ull;
+  v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull;
+  v = (v ^ (v >> 27)) * 0x94D049BB133111EBull;
+  return v ^ (v >> 31);
+}
+inline size_t gcd_sz(size_t l, size_t r) {
+  while (r != 0) {
+    size_t t = l % r;
+    l = r;
+    r = t;
+  }
+  return l;
+}
+
+enum class SelectionOrder { Original, Sorted, Probabilistic, Random, Shuffled };
+
+struct MoveStreamContext {  // iter.rs:14-184
+  uint64_t step_index = 0, step_seed = 0;
+  SelectionOrder order = SelectionOrder::Original;
+  bool is_canonical() const {
+    return order == SelectionOrder::Original || order == SelectionOrder::Sorted || order == SelectionOrder::Probabilistic;
+  }
+  uint64_t mixed_seed(uint64_t salt) const {
+    return splitmix64(step_seed ^ (step_index * 0x9E3779B97F4A7C15ull) ^ salt);
+  }
+  size_t random_index(size_t len, uint64_t salt) const { return len <= 1 ? 0 : (size_t)(mixed_seed(salt) % len); }
+  size_t random_stride(size_t len, uint64_t salt) const {
+    if (len <= 1) return 1;
+    size_t stride = (size_t)(mixed_seed(salt) % (len - 1)) + 1;
+    while (gcd_sz(stride, len) != 1) stride = stride == len - 1 ? 1 : stride + 1;
+    return stride;
+  }
+  size_t selection_index(size_t offset, size_t len, uint64_t salt) const {
+    switch (order) {
+      case SelectionOrder::Random:
+        return random_index(len, salt ^ ((uint64_t)offset * 0xD1B54A32D192ED03ull));
+      case SelectionOrder::Shuffled: {
+        size_t start = random_index(len, salt);
+        size_t stride = random_stride(len, salt ^ 0xA24BAED4963EE407ull);
+        return (start + offset * stride) % len;
+      }
+      default: return offset;
+    }
+  }
+};
+
+// move_selector/change.rs:66-104,246-307 — values in order, then the to-None move when
+// allows_unassigned and the entity is currently assigned.
+template <class S>
+std::vector<Move> enumerate_change_moves(const S& s, const Access<S>& ac, size_t desc, size_t variable_index,
+                                         size_t n_values, bool allows_unassigned, MoveStreamContext ctx) {
+  std::vector<Move> out;
+  size_t n = ac.entity_count(s, desc);
+  uint64_t entity_salt = 0xC4A46E0000000001ull ^ ((uint64_t)desc << 32) ^ (uint64_t)variable_index;
+  for (size_t eo = 0; eo < n; ++eo) {
+    size_t e = ctx.selection_index(eo, n, entity_salt);
+    bool assigned = ac.get(s, desc, e).has_value();
+    uint64_t value_salt = 0xC4A46E0000000000ull ^ (uint64_t)e ^ ((uint64_t)desc << 32) ^ (uint64_t)variable_index;
+    for (size_t vo = 0; vo < n_values; ++vo) {
+      size_t v = ctx.is_canonical() ? vo : ctx.selection_index(vo, n_values, value_salt);
+      out.push_back(Move::change(desc, e, OptVal(v)));
+    }
+    if (allows_unassigned && assigned) out.push_back(Move::change(desc, e, std::nullopt));
+  }
+  return out;
+}
+
+// nearby_list_support.rs:3-34 — stable bounded insertion sort on the f64 distance.
+struct NearbyCandidate {
+  size_t entity, position;
+  double distance;
+};
+inline void sort_and_limit_nearby_candidates(std::vector<NearbyCandidate>& c, size_t max_nearby) {
+  if (max_nearby == 0) {
+    c.clear();
+    return;
+  }
+  size_t retained = 0;
+  for (size_t read = 0; read < c.size(); ++read) {
+    NearbyCandidate cand = c[read];
+    // partition_point(existing.distance <= cand.distance), NaN compares Equal.
+    size_t lo = 0, hi = retained;
+    while (lo < hi) {
+      size_t mid = lo + (hi - lo) / 2;
+      bool greater = c[mid].distance > cand.distance;
+      if (!greater) lo = mid + 1; else hi = mid;
+    }
+    size_t insertion = lo;
+    if (insertion >= max_nearby) continue;
+    size_t next_retained = std::min(retained + 1, max_nearby);
+    for (size_t i = next_retained - 1; i > insertion; --i) c[i] = c[i - 1];
+    c[insertion] = cand;
+    retained = next_retained;
+  }
+  c.resize(retained);
+}
+
+// list_kernel/nearby_change.rs:102-232 (no owner restriction, no precedence graph).
+// distance(src_e, src_p, dst_e, ref_p) is the CrossEntityDistanceMeter.
+template <class S, class Dist>
+std::vector<Move> enumerate_nearby_list_change_moves(S& s, const Access<S>& ac, size_t desc, size_t max_nearby,
+                                                     MoveStreamContext ctx, Dist distance) {
+  constexpr uint64_t ENTITY_SALT = 0xA1EA2B17C4A40001ull, SOURCE_SALT = 0xA1EA2B17C4A40002ull;
+  size_t n = ac.entity_count(s, desc);
+  std::vector<size_t> entities(n), lens(n);
+  for (size_t o = 0; o < n; ++o) {
+    size_t e = n <= 1 ? o : ctx.selection_index(o, n, ENTITY_SALT ^ (uint64_t)desc);
+    entities[o] = e;
+    lens[o] = ac.list(s, desc, e).size();
+  }
+  std::vector<Move> out;
+  std::vector<NearbyCandidate> cand;
+  for (size_t si = 0; si < n; ++si) {
+    size_t se = entities[si], slen = lens[si];
+    for (size_t po = 0; po < slen; ++po) {
+      size_t sp = ctx.selection_index(po, slen, SOURCE_SALT ^ (uint64_t)se ^ (uint64_t)desc);
+      cand.clear();
+      for (size_t dp = 0; dp <= slen; ++dp) {
+        if (dp == sp || dp == sp + 1) continue;
+        double dist = distance(s, se, sp, se, std::min(dp, slen > 0 ? slen - 1 : 0));
+        if (std::isfinite(dist)) cand.push_back({se, dp, dist});
+      }
+      for (size_t di = 0; di < n; ++di) {
+        if (di == si) continue;
+        size_t de = entities[di], dlen = lens[di];
+        for (size_t dp = 0; dp <= dlen; ++dp) {
+          double dist = distance(s, se, sp, de, std::min(dp, dlen > 0 ? dlen - 1 : 0));
+          if (std::isfinite(dist)) cand.push_back({de, dp, dist});
+        }
+      }
+      sort_and_limit_nearby_candidates(cand, max_nearby);
+      for (auto& c : cand) out.push_back(Move::list_change(desc, se, sp, c.entity, c.position));
+    }
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Foragers (forager.rs). CandidateId = pull index.
+inline bool reservoir_pick(uint64_t step_seed, uint64_t equal_count) {  // forager.rs:143-148
+  uint64_t mixed = splitmix64(step_seed ^ (equal_count * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
+  return mixed % equal_count == 0;
+}
+
+template <class Sc>
+struct BestCandidate {  // forager.rs:70-141
+  bool has = false;
+  size_t index = 0;
+  Sc score = Sc::zero();
+  uint64_t equal_count = 0, step_seed = 0;
+  bool random_ties = true;
+  void reset(uint64_t seed) {
+    has = false;
+    equal_count = 0;
+    step_seed = seed;
+  }
+  void consider(size_t idx, Sc sc) {
+    if (!has) {
+      has = true;
+      index = idx;
+      score = sc;
+      equal_count = 1;
+      return;
+    }
+    if (sc < score) return;
+    if (sc > score) {
+      index = idx;
+      score = sc;
+      equal_count = 1;
+      return;
+    }
+    equal_count += 1;
+    if (random_ties && reservoir_pick(step_seed, equal_count)) {
+      index = idx;
+      score = sc;
+    }
+  }
+};
+
+enum class ForagerKind { AcceptedCount, FirstAccepted, BestScore, FirstBestScoreImproving, FirstLastStepScoreImproving };
+
+template <class Sc>
+struct Forager {  // forager.rs:167-425, forager/improving.rs:17-227
+  ForagerKind kind = ForagerKind::BestScore;
+  size_t accepted_count_limit = 1;
+  size_t accepted_count = 0;
+  BestCandidate<Sc> best;
+  Sc best_score = Sc::zero(), last_step_score = Sc::zero();
+  bool found_improving = false;
+  bool has_improving_limit = false;  // FirstLastStepScoreImproving::with_accepted_count_limit
+  void step_started(Sc best_sc, Sc last_sc, uint64_t step_seed) {
+    accepted_count = 0;
+    best.reset(step_seed);
+    best_score = best_sc;
+    last_step_score = last_sc;
+    found_improving = false;
+  }
+  void add_move_index(size_t idx, Sc sc) {
+    switch (kind) {
+      case ForagerKind::AcceptedCount:
+        if (accepted_count >= accepted_count_limit) return;
+        accepted_count += 1;
+        best.consider(idx, sc);
+        return;
+      case ForagerKind::FirstAccepted:
+        if (!best.has) {
+          best.has = true;
+          best.index = idx;
+          best.score = sc;
+        }
+        return;
+      case ForagerKind::BestScore: best.consider(idx, sc); return;
+      case ForagerKind::FirstBestScoreImproving:  // improving.rs:86-95
+        if (sc > best_score) {
+          found_improving = true;
+          best.has = true;
+          best.index = idx;
+          best.score = sc;
+          best.equal_count = 1;
+          return;
+        }
+        if (found_improving) return;
+        best.consider(idx, sc);
+        return;
+      case ForagerKind::FirstLastStepScoreImproving:  // improving.rs:197-211
+        if (found_improving || (has_improving_limit && accepted_count >= accepted_count_limit)) return;
+        accepted_count += 1;
+        if (sc > last_step_score) {
+          found_improving = true;
+          best.has = true;
+          best.index = idx;
+          best.score = sc;
+          best.equal_count = 1;
+          return;
+        }
+        best.consider(idx, sc);
+        return;
+    }
+  }
+  bool is_quit_early() const {
+    switch (kind) {
+      case ForagerKind::AcceptedCount: return accepted_count >= accepted_count_limit;
+      case ForagerKind::FirstAccepted: return best.has;
+      case ForagerKind::BestScore: return false;
+      case ForagerKind::FirstBestScoreImproving: return found_improving;
+      default: return found_improving || (has_improving_limit && accepted_count >= accepted_count_limit);
+    }
+  }
+};
+
+enum class AcceptorKind { HillClimbing, LateAcceptance, SimulatedAnnealing, AcceptAll };
+
+template <class Sc>
+struct Acceptor {
+  AcceptorKind kind = AcceptorKind::HillClimbing;
+  // LateAcceptance (late_acceptance.rs:89-126)
+  std::vector<Sc> history;
+  size_t history_idx = 0;
+  // SimulatedAnnealing (simulated_annealing.rs): the uniform stream is injected by the caller
+  // because the reference draws from rand::SmallRng (third party, unpinned — SURVEY §8c).
+  std::function<double()> uniform;
+  double decay = 0.999985, hill_climbing_temperature = 1e-9, fallback_temperature = 1.0;
+  size_t calibration_samples = 128;
+  double target_acceptance = 0.80;
+  std::vector<double> level_temperature, sample_sum;
+  std::vector<size_t> sample_count;
+  bool calibrated = false;
+  bool never_accept_hard_regression = false;
+
+  void phase_started(Sc initial, size_t late_size = 400) {
+    if (kind == AcceptorKind::LateAcceptance) {
+      history.assign(late_size, initial);
+      history_idx = 0;
+    }
+    if (kind == AcceptorKind::SimulatedAnnealing) {
+      level_temperature.assign(Sc::levels, 0.0);
+      sample_sum.assign(Sc::levels, 0.0);
+      sample_count.assign(Sc::levels, 0);
+      calibrated = false;
+    }
+  }
+  bool is_accepted(Sc last, Sc mv) {
+    switch (kind) {
+      case AcceptorKind::AcceptAll: return true;
+      case AcceptorKind::HillClimbing: return mv > last;  // hill_climbing.rs:33-42
+      case AcceptorKind::LateAcceptance: return mv >= last || mv >= history[history_idx];
+      case AcceptorKind::SimulatedAnnealing: {
+        if (mv >= last) return true;
+        int lvl = 0;
+        for (; lvl < Sc::levels; ++lvl)
+          if (mv.level(lvl) != last.level(lvl)) break;
+        double delta = (double)(mv.level(lvl) - last.level(lvl));  // < 0
+        if (never_accept_hard_regression && Sc::level_is_hard(lvl)) return false;  // :353-357
+        if (!calibrated) {  // CalibrationState::record / temperatures, :57-88,359-366
+          sample_sum[lvl] += std::fabs(delta);
+          sample_count[lvl] += 1;
+          size_t total = 0;
+          for (auto c : sample_count) total += c;
+          if (total < calibration_samples) return false;
+          for (int l = 0; l < Sc::levels; ++l) {
+            double t = sample_count[l] ? (sample_sum[l] / (double)sample_count[l]) / -std::log(target_acceptance)
+                                       : fallback_temperature;
+            level_temperature[l] = std::max(t, fallback_temperature);
+          }
+          calibrated = true;
+        }
+        double T = level_temperature[lvl];
+        if (T <= hill_climbing_temperature) return false;
+        return uniform() < std::exp(delta / T);
+      }
+    }
+    return false;
+  }
+  void step_ended(Sc step_score) {
+    if (kind == AcceptorKind::LateAcceptance) {
+      history[history_idx] = step_score;
+      history_idx = (history_idx + 1) % history.size();
+    }
+    if (kind == AcceptorKind::SimulatedAnnealing && calibrated)
+      for (auto& t : level_temperature) t = std::max(t * decay, hill_climbing_temperature);
+  }
+};
+
+// Replay of phase/candidates.rs:66-282 given per-candidate (doable, score) in pull order.
+template <class Sc>
+struct StepOutcome {
+  bool has_winner = false;
+  size_t winner = 0;
+  Sc winner_score = Sc::zero();
+  uint64_t moves_evaluated = 0, score_calculations = 0, moves_accepted = 0;
+};
+
+template <class Sc, class GetEval>
+StepOutcome<Sc> replay_step(size_t n_candidates, GetEval eval, Sc best_score, Sc last_step_score,
+                            uint64_t step_seed, Forager<Sc>& forager, Acceptor<Sc>& acceptor) {
+  StepOutcome<Sc> out;
+  forager.step_started(best_score, last_step_score, step_seed);
+  for (size_t i = 0; i < n_candidates; ++i) {
+    if (forager.is_quit_early()) break;
+    CandidateEvaluation<Sc> ev = eval(i);
+    out.moves_evaluated += 1;
+    if (ev.kind == EvalKind::NotDoable) continue;
+    out.score_calculations += 1;
+    if (ev.kind != EvalKind::Scored) continue;
+    if (acceptor.is_accepted(last_step_score, ev.score)) {
+      out.moves_accepted += 1;
+      forager.add_move_index(i, ev.score);
+    }
+  }
+  if (forager.best.has) {
+    out.has_winner = true;
+    out.winner = forager.best.index;
+    out.winner_score = forager.best.score;
+  }
+  return out;
+}
+
+}  // namespace sfo

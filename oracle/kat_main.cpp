@@ -1,0 +1,608 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see score.hpp header).
+//
+// Pins the oracle against the reference's own known-answer tests. Every block re-encodes one
+// reference test (fixture + asserted numbers), cited as file:line under /root/reference/crates.
+// Exit code 0 and a final "KAT OK n" line mean every vector matched.
+#include <cstdio>
+#include <cstdlib>
+
+#include "models.hpp"
+
+using namespace sfo;
+
+static int g_checks = 0, g_fail = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    ++g_checks;                                                            \
+    if (!(cond)) {                                                         \
+      ++g_fail;                                                            \
+      std::fprintf(stderr, "KAT FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); \
+    }                                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------- scores
+static void kat_scores() {
+  // solverforge-core/src/score/tests/hard_soft_score.rs:3-57
+  auto s = HardSoftScore::of(-2, -100);
+  CHECK(s.hard == -2 && s.soft == -100);
+  CHECK(HardSoftScore::of(0, -1000).is_feasible());
+  CHECK(HardSoftScore::of(10, -50).is_feasible());
+  CHECK(!HardSoftScore::of(-1, 0).is_feasible());
+  CHECK(HardSoftScore::of(0, -1000) > HardSoftScore::of(-1, 0));
+  CHECK(HardSoftScore::of(0, -50) > HardSoftScore::of(0, -100));
+  CHECK(HardSoftScore::of(-1, -1000) > HardSoftScore::of(-2, 0));
+  auto s1 = HardSoftScore::of(-1, -100), s2 = HardSoftScore::of(-1, -50);
+  CHECK(s1 + s2 == HardSoftScore::of(-2, -150));
+  CHECK(s1 - s2 == HardSoftScore::of(0, -50));
+  CHECK(-s1 == HardSoftScore::of(1, 100));
+  CHECK(s1.str() == "-1hard/-100soft");
+  // solverforge-core/src/score/tests/hard_soft_decimal_score.rs:3-60
+  auto d = HardSoftDecimalScore::of(-2, -100);
+  CHECK(d.hard == -200000 && d.soft == -10000000);
+  auto ds = HardSoftDecimalScore::of_scaled(-30500, -208250);
+  CHECK(ds.hard == -30500 && ds.soft == -208250);
+  CHECK(!HardSoftDecimalScore::of_scaled(-1, 0).is_feasible());
+  CHECK(HardSoftDecimalScore::of(0, -1000) > HardSoftDecimalScore::of(-1, 0));
+  auto d1 = HardSoftDecimalScore::of(-1, -100), d2 = HardSoftDecimalScore::of(-1, -50);
+  CHECK(d1 + d2 == HardSoftDecimalScore::of(-2, -150));
+  CHECK(d1 - d2 == HardSoftDecimalScore::of(0, -50));
+  // solverforge-solver/src/phase/hard_delta.rs:11-35
+  CHECK(hard_score_delta(HardSoftScore::of(-2, 0), HardSoftScore::of(-1, -9)) == HardDelta::Improving);
+  CHECK(hard_score_delta(HardSoftScore::of(-2, 0), HardSoftScore::of(-2, 5)) == HardDelta::Neutral);
+  CHECK(hard_score_delta(HardSoftScore::of(-2, 0), HardSoftScore::of(-3, 5)) == HardDelta::Worse);
+  CHECK(hard_score_delta(SoftScore::of(1), SoftScore::of(2)) == HardDelta::None);
+}
+
+// ---------------------------------------------------------------- uni + director
+struct TestSolution {
+  std::vector<OptVal> values;
+};
+static const std::vector<OptVal>& ts_values(const TestSolution& s) { return s.values; }
+
+static void kat_director() {
+  // solverforge-scoring/src/director/tests/score_director.rs:63-115
+  auto make = [](std::vector<OptVal> v) {
+    auto d = std::make_unique<ScoreDirector<TestSolution, SoftScore>>();
+    d->working.values = std::move(v);
+    auto f = [](const TestSolution&, const OptVal& v) { return !v.has_value(); };
+    auto w = [](const OptVal&) { return SoftScore::of(1); };
+    d->constraints.add(std::make_unique<UniConstraint<TestSolution, OptVal, SoftScore, decltype(f), decltype(w)>>(
+        "Unassigned", Impact::Penalty, Source<TestSolution, OptVal>{ts_values, ChangeSource::Desc(0)}, f, w, false));
+    return d;
+  };
+  {
+    auto d = make({OptVal(1), std::nullopt, std::nullopt, OptVal(2)});
+    CHECK(!d->initialized);
+    CHECK(d->calculate_score() == SoftScore::of(-2));
+    CHECK(d->initialized);
+  }
+  {
+    auto d = make({OptVal(1), std::nullopt});
+    CHECK(d->calculate_score() == SoftScore::of(-1));
+    CHECK(d->calculate_score() == SoftScore::of(-1));
+  }
+  {
+    auto d = make({OptVal(1), std::nullopt, OptVal(2)});
+    CHECK(d->calculate_score() == SoftScore::of(-1));
+    d->before_variable_changed(0, 1);
+    d->working.values[1] = OptVal(3);
+    d->after_variable_changed(0, 1);
+    CHECK(d->calculate_score() == SoftScore::of(0));
+    CHECK(d->fresh_score() == SoftScore::of(0));
+    // out-of-range entity => zero delta (constraint/incremental.rs:128-130)
+    d->before_variable_changed(0, 99);
+    d->after_variable_changed(0, 99);
+    CHECK(d->calculate_score() == SoftScore::of(0));
+    // foreign descriptor => ignored (collection_extract.rs:83-93)
+    d->before_variable_changed(7, 0);
+    d->after_variable_changed(7, 0);
+    CHECK(d->calculate_score() == SoftScore::of(0));
+  }
+}
+
+// ---------------------------------------------------------------- cross-bi
+struct Shift {
+  OptVal employee_id;
+  int day;
+};
+struct Employee {
+  size_t id;
+  std::vector<int> unavailable_days;
+};
+struct Schedule {
+  std::vector<Shift> shifts;
+  std::vector<Employee> employees;
+};
+static const std::vector<Shift>& sch_shifts(const Schedule& s) { return s.shifts; }
+static const std::vector<Employee>& sch_employees(const Schedule& s) { return s.employees; }
+struct OptKeyHash {
+  size_t operator()(const OptVal& v) const { return v ? *v + 1 : 0; }
+};
+
+static void kat_cross_bi() {
+  // solverforge-scoring/src/constraint/tests/cross_bi_incr.rs:122-165 fixtures
+  auto sample = [] {
+    return Schedule{{{OptVal(0), 5}, {OptVal(0), 6}}, {{0, {5}}}};
+  };
+  auto two_emp = [] {
+    return Schedule{{{OptVal(0), 5}, {OptVal(0), 6}}, {{0, {}}, {1, {}}}};
+  };
+  Source<Schedule, Shift> ss{sch_shifts, ChangeSource::Desc(0)};
+  Source<Schedule, Employee> se{sch_employees, ChangeSource::Desc(1)};
+  auto ka = [](const Shift& s) { return s.employee_id; };
+  auto kb = [](const Employee& e) { return OptVal(e.id); };
+  auto f = [](const Schedule&, const Shift& s, const Employee& e, size_t, size_t) {
+    return s.employee_id.has_value() &&
+           std::find(e.unavailable_days.begin(), e.unavailable_days.end(), s.day) != e.unavailable_days.end();
+  };
+  auto w = [](const Schedule&, const Shift&, const Employee&, size_t, size_t) { return SoftScore::of(1); };
+  using C = CrossBiConstraint<Schedule, Shift, Employee, OptVal, SoftScore, decltype(ka), decltype(kb), decltype(f),
+                              decltype(w), OptKeyHash>;
+  {
+    // :193-201 evaluate without initialize == -1; match_count 1 (:205-217)
+    C c("Unavailable employee", Impact::Penalty, ss, se, ka, kb, f, w, false);
+    auto sc = sample();
+    CHECK(c.evaluate(sc) == SoftScore::of(-1));
+    CHECK(c.match_count(sc) == 1);
+  }
+  {
+    // :252-264 incremental retract/insert: -1, +1, -1; :167-191 unrelated descriptor => zero
+    C c("Unavailable employee", Impact::Penalty, ss, se, ka, kb, f, w, false);
+    auto sc = sample();
+    CHECK(c.initialize(sc) == SoftScore::of(-1));
+    CHECK(c.on_insert(sc, 0, 2) == SoftScore::zero());
+    CHECK(c.on_retract(sc, 0, 0) == SoftScore::of(1));
+    CHECK(c.on_insert(sc, 0, 0) == SoftScore::of(-1));
+  }
+  {
+    // :267-279 B-side retract / mutate / insert
+    C c("Unavailable employee", Impact::Penalty, ss, se, ka, kb, f, w, false);
+    auto sc = sample();
+    SoftScore total = c.initialize(sc);
+    CHECK(total == SoftScore::of(-1));
+    total = total + c.on_retract(sc, 0, 1);
+    sc.employees[0].unavailable_days = {6};
+    total = total + c.on_insert(sc, 0, 1);
+    CHECK(total == SoftScore::of(-1));
+    CHECK(total == c.evaluate(sc));
+  }
+  {
+    // :308-341 index-aware filter: shift_idx == 1 && employee_idx == 0, weight = shift.day => -6
+    auto fi = [](const Schedule&, const Shift&, const Employee&, size_t si, size_t ei) { return si == 1 && ei == 0; };
+    auto wi = [](const Schedule&, const Shift& s, const Employee&, size_t, size_t) { return SoftScore::of(s.day); };
+    CrossBiConstraint<Schedule, Shift, Employee, OptVal, SoftScore, decltype(ka), decltype(kb), decltype(fi),
+                      decltype(wi), OptKeyHash>
+        c("indexed cross path", Impact::Penalty, ss, se, ka, kb, fi, wi, false);
+    auto sc = two_emp();
+    CHECK(c.match_count(sc) == 1);
+    CHECK(c.evaluate(sc) == SoftScore::of(-6));
+  }
+  {
+    // :283-304 cross group_by (sum of 1 per pair, penalise count^2): -4 -> -2 after moving shift 1
+    auto tf = [](const Schedule&, const Shift&, const Employee&, size_t, size_t) { return true; };
+    auto gk = [](const Shift&, const Employee& e) { return e.id; };
+    auto vf = [](const Shift&, const Employee&) { return (int64_t)1; };
+    auto kt = [](const Employee& e) { return e.id; };
+    auto df = [](const Employee&) { return (int64_t)0; };
+    auto gw = [](const size_t&, const int64_t& c) { return SoftScore::of(c * c); };
+    CrossComplementedGroupedConstraint<Schedule, Shift, Employee, Employee, OptVal, size_t, SoftScore, SumAcc,
+                                       decltype(ka), decltype(kb), decltype(tf), decltype(gk), decltype(vf),
+                                       decltype(kt), decltype(df), decltype(gw), OptKeyHash>
+        c("grouped assigned shift count", Impact::Penalty, ss, se, se, ka, kb, tf, gk, vf, kt, df, gw, false,
+          /*with_complement=*/false);
+    auto sc = two_emp();
+    CHECK(c.match_count(sc) == 1);
+    CHECK(c.evaluate(sc) == SoftScore::of(-4));
+    SoftScore total = c.initialize(sc);
+    CHECK(total == SoftScore::of(-4));
+    total = total + c.on_retract(sc, 1, 0);
+    sc.shifts[1].employee_id = OptVal(1);
+    total = total + c.on_insert(sc, 1, 0);
+    CHECK(total == SoftScore::of(-2));
+    CHECK(total == c.evaluate(sc));
+  }
+}
+
+// ---------------------------------------------------------------- self-join bi
+struct BQueen {
+  int64_t row, col;
+};
+struct BSolution {
+  std::vector<BQueen> queens;
+};
+static const std::vector<BQueen>& bq(const BSolution& s) { return s.queens; }
+static void kat_self_join() {
+  // solverforge-scoring/src/constraint/tests/bi_incr.rs:21-200
+  Source<BSolution, BQueen> src{bq, ChangeSource::Desc(0)};
+  auto key = [](const BQueen& q) { return q.row; };
+  auto f = [](const BSolution&, const BQueen& a, const BQueen& b, size_t, size_t) { return a.col < b.col; };
+  auto w = [](const BSolution&, const BQueen&, const BQueen&) { return SoftScore::of(1); };
+  using C = SelfJoinBiConstraint<BSolution, BQueen, int64_t, SoftScore, decltype(key), decltype(f), decltype(w)>;
+  {
+    C c("Row conflict", Impact::Penalty, src, key, f, w, false);
+    BSolution s{{{0, 0}, {1, 1}, {2, 2}}};
+    CHECK(c.evaluate(s) == SoftScore::of(0));
+    CHECK(c.match_count(s) == 0);
+  }
+  {
+    C c("Row conflict", Impact::Penalty, src, key, f, w, false);
+    BSolution s{{{0, 0}, {0, 1}, {2, 2}}};
+    CHECK(c.evaluate(s) == SoftScore::of(-1));
+    CHECK(c.match_count(s) == 1);
+    c.initialize(s);
+    c.reset();
+    CHECK(c.on_insert(s, 0, 0) == SoftScore::of(0));
+    CHECK(c.on_insert(s, 1, 0) == SoftScore::of(-1));
+    CHECK(c.on_insert(s, 2, 0) == SoftScore::of(0));
+    CHECK(c.on_retract(s, 0, 0) == SoftScore::of(1));
+  }
+  {
+    // :172-200 dynamic weight |b.col - a.col| => -3
+    auto wd = [](const BSolution&, const BQueen& a, const BQueen& b) { return SoftScore::of(std::llabs(b.col - a.col)); };
+    SelfJoinBiConstraint<BSolution, BQueen, int64_t, SoftScore, decltype(key), decltype(f), decltype(wd)> c(
+        "Column distance", Impact::Penalty, src, key, f, wd, false);
+    BSolution s{{{0, 0}, {0, 3}}};
+    CHECK(c.evaluate(s) == SoftScore::of(-3));
+  }
+  {
+    // :143-170 reward, adjacent columns => +2
+    auto fr = [](const BSolution&, const BQueen& a, const BQueen& b, size_t, size_t) {
+      return a.col < b.col && std::llabs(a.col - b.col) == 1;
+    };
+    auto w2 = [](const BSolution&, const BQueen&, const BQueen&) { return SoftScore::of(2); };
+    SelfJoinBiConstraint<BSolution, BQueen, int64_t, SoftScore, decltype(key), decltype(fr), decltype(w2)> c(
+        "Adjacent queens", Impact::Reward, src, key, fr, w2, false);
+    BSolution s{{{0, 0}, {0, 1}}};
+    CHECK(c.evaluate(s) == SoftScore::of(2));
+  }
+}
+
+// ---------------------------------------------------------------- exists
+struct Task {
+  OptVal assignee;
+};
+struct Worker {
+  size_t id;
+  bool available;
+};
+struct TaskSchedule {
+  std::vector<Task> tasks;
+  std::vector<Worker> workers;
+};
+static const std::vector<Task>& tsk(const TaskSchedule& s) { return s.tasks; }
+static const std::vector<Worker>& wrk(const TaskSchedule& s) { return s.workers; }
+struct CustomerState {
+  std::vector<size_t> customers;
+  std::vector<std::vector<size_t>> routes;
+};
+static const std::vector<size_t>& cs_c(const CustomerState& s) { return s.customers; }
+static const std::vector<std::vector<size_t>>& cs_r(const CustomerState& s) { return s.routes; }
+struct TaggedItem {
+  size_t key;
+  bool enabled;
+};
+struct TaggedItems {
+  std::vector<TaggedItem> items;
+};
+static const std::vector<TaggedItem>& ti(const TaggedItems& s) { return s.items; }
+
+static void kat_exists() {
+  {
+    // solverforge-scoring/src/constraint/tests/exists.rs:34-84: 0 -> -2 after worker 0 becomes unavailable
+    auto ka = [](const Task& t) { return t.assignee; };
+    auto kb = [](const Worker& w) { return OptVal(w.id); };
+    auto fa = [](const TaskSchedule&, const Task& t) { return t.assignee.has_value(); };
+    auto fp = [](const TaskSchedule&, const Worker& w) { return !w.available; };
+    auto fl = [](const Worker& w) { return std::vector<Worker>{w}; };
+    auto w1 = [](const Task&) { return SoftScore::of(1); };
+    ExistsConstraint<TaskSchedule, Task, Worker, Worker, OptVal, SoftScore, decltype(ka), decltype(kb), decltype(fa),
+                     decltype(fp), decltype(fl), decltype(w1), OptKeyHash>
+        c("unavailable worker", Impact::Penalty, ExistenceMode::Exists, {tsk, ChangeSource::Stat()},
+          {wrk, ChangeSource::Desc(0)}, ka, kb, fa, fp, fl, w1, false);
+    TaskSchedule s{{{OptVal(0)}, {OptVal(0)}, {OptVal(1)}}, {{0, true}, {1, true}}};
+    SoftScore total = c.initialize(s);
+    CHECK(total == SoftScore::of(0));
+    total = total + c.on_retract(s, 0, 0);
+    s.workers[0].available = false;
+    total = total + c.on_insert(s, 0, 0);
+    CHECK(total == c.evaluate(s));
+    CHECK(total == SoftScore::of(-2));
+  }
+  {
+    // exists.rs:100-135 flattened not-exists: -3 -> 0 after route gets [1,2,3]
+    auto ka = [](const size_t& c) { return c; };
+    auto kb = [](const size_t& a) { return a; };
+    auto fa = [](const CustomerState&, const size_t&) { return true; };
+    auto fp = [](const CustomerState&, const std::vector<size_t>&) { return true; };
+    auto fl = [](const std::vector<size_t>& r) -> const std::vector<size_t>& { return r; };
+    auto w1 = [](const size_t&) { return SoftScore::of(1); };
+    ExistsConstraint<CustomerState, size_t, std::vector<size_t>, size_t, size_t, SoftScore, decltype(ka), decltype(kb),
+                     decltype(fa), decltype(fp), decltype(fl), decltype(w1)>
+        c("missing assignment", Impact::Penalty, ExistenceMode::NotExists, {cs_c, ChangeSource::Stat()},
+          {cs_r, ChangeSource::Desc(0)}, ka, kb, fa, fp, fl, w1, false);
+    CustomerState s{{1, 2, 3}, {{}}};
+    SoftScore total = c.initialize(s);
+    CHECK(total == SoftScore::of(-3));
+    total = total + c.on_retract(s, 0, 0);
+    s.routes[0] = {1, 2, 3};
+    total = total + c.on_insert(s, 0, 0);
+    CHECK(total == c.evaluate(s));
+    CHECK(total == SoftScore::of(0));
+  }
+  {
+    // exists.rs:150-190 same-source exists: -2 -> 0
+    auto ka = [](const TaggedItem& i) { return i.key; };
+    auto kb = [](const TaggedItem& i) { return i.key; };
+    auto fa = [](const TaggedItems&, const TaggedItem&) { return true; };
+    auto fp = [](const TaggedItems&, const TaggedItem& i) { return i.enabled; };
+    auto fl = [](const TaggedItem& i) { return std::vector<TaggedItem>{i}; };
+    auto w1 = [](const TaggedItem&) { return SoftScore::of(1); };
+    ExistsConstraint<TaggedItems, TaggedItem, TaggedItem, TaggedItem, size_t, SoftScore, decltype(ka), decltype(kb),
+                     decltype(fa), decltype(fp), decltype(fl), decltype(w1)>
+        c("key has enabled peer", Impact::Penalty, ExistenceMode::Exists, {ti, ChangeSource::Desc(0)},
+          {ti, ChangeSource::Desc(0)}, ka, kb, fa, fp, fl, w1, false);
+    TaggedItems s{{{1, false}, {1, true}}};
+    SoftScore total = c.initialize(s);
+    CHECK(total == SoftScore::of(-2));
+    total = total + c.on_retract(s, 1, 0);
+    s.items[1].enabled = false;
+    total = total + c.on_insert(s, 1, 0);
+    CHECK(total == c.evaluate(s));
+    CHECK(total == SoftScore::of(0));
+  }
+}
+
+// ---------------------------------------------------------------- grouped
+struct GShift {
+  size_t employee_id;
+};
+struct GSolution {
+  std::vector<GShift> shifts;
+};
+static const std::vector<GShift>& gs(const GSolution& s) { return s.shifts; }
+static void kat_grouped() {
+  // solverforge-scoring/src/constraint/tests/grouped.rs:26-150
+  Source<GSolution, GShift> src{gs, ChangeSource::Desc(0)};
+  auto tf = [](const GSolution&, const GShift&) { return true; };
+  auto key = [](const GShift& s) { return s.employee_id; };
+  auto val = [](const GShift&) { return (char)0; };
+  {
+    auto w = [](const size_t&, const size_t& c) { return SoftScore::of((int64_t)(c * c)); };
+    GroupedConstraint<GSolution, GShift, size_t, SoftScore, CountAcc, decltype(tf), decltype(key), decltype(val),
+                      decltype(w)>
+        c("Workload", Impact::Penalty, src, tf, key, val, w, false);
+    GSolution s{{{1}, {1}, {1}, {2}}};
+    CHECK(c.evaluate(s) == SoftScore::of(-10));
+  }
+  {
+    auto w = [](const size_t&, const size_t& c) { return SoftScore::of((int64_t)c); };
+    GroupedConstraint<GSolution, GShift, size_t, SoftScore, CountAcc, decltype(tf), decltype(key), decltype(val),
+                      decltype(w)>
+        c("Workload", Impact::Penalty, src, tf, key, val, w, false);
+    GSolution s{{{1}, {1}, {2}}};
+    CHECK(c.initialize(s) == SoftScore::of(-3));
+    CHECK(c.on_retract(s, 0, 0) == SoftScore::of(1));
+    CHECK(c.on_insert(s, 0, 0) == SoftScore::of(-1));
+    GroupedConstraint<GSolution, GShift, size_t, SoftScore, CountAcc, decltype(tf), decltype(key), decltype(val),
+                      decltype(w)>
+        r("Collaboration", Impact::Reward, src, tf, key, val, w, false);
+    GSolution s2{{{1}, {1}}};
+    CHECK(r.evaluate(s2) == SoftScore::of(2));
+  }
+  {
+    // solverforge-scoring/src/stream/collector/load_balance.rs:38-55: loads 2,1 => unfairness 1
+    LoadBalanceAcc acc;
+    acc.accumulate({0, 1});
+    acc.accumulate({0, 1});
+    acc.accumulate({1, 1});
+    CHECK(acc.result() == 1);
+    auto r = acc.accumulate({1, 1});  // 2,2 => 0
+    CHECK(acc.result() == 0);
+    acc.retract(r);
+    CHECK(acc.result() == 1);
+    // count.rs:85-98 / sum.rs:176-191 round trips
+    CountAcc ca;
+    ca.accumulate(0);
+    ca.accumulate(0);
+    CHECK(ca.result() == 2);
+    ca.retract(0);
+    CHECK(ca.result() == 1);
+    SumAcc sa;
+    auto r1 = sa.accumulate(5);
+    sa.accumulate(7);
+    CHECK(sa.result() == 12);
+    sa.retract(r1);
+    CHECK(sa.result() == 7);
+  }
+}
+
+// ---------------------------------------------------------------- cross complemented grouped
+struct CEmployee {
+  size_t id;
+};
+struct CShift {
+  OptVal employee_id;
+};
+struct CTarget {
+  size_t employee_id;
+};
+struct CSchedule {
+  std::vector<CShift> shifts;
+  std::vector<CEmployee> employees;
+  std::vector<CTarget> targets;
+};
+static const std::vector<CShift>& c_sh(const CSchedule& s) { return s.shifts; }
+static const std::vector<CEmployee>& c_em(const CSchedule& s) { return s.employees; }
+static const std::vector<CTarget>& c_tg(const CSchedule& s) { return s.targets; }
+
+static void kat_cross_complemented() {
+  // solverforge-scoring/src/constraint/tests/cross_complemented_grouped.rs:58-215
+  auto ka = [](const CShift& s) { return s.employee_id; };
+  auto kb = [](const CEmployee& e) { return OptVal(e.id); };
+  auto tf = [](const CSchedule&, const CShift&, const CEmployee&, size_t, size_t) { return true; };
+  auto gk = [](const CShift&, const CEmployee& e) { return e.id; };
+  auto vf = [](const CShift&, const CEmployee&) { return (int64_t)1; };
+  auto kt = [](const CTarget& t) { return t.employee_id; };
+  auto df = [](const CTarget&) { return (int64_t)5; };
+  auto gw = [](const size_t&, const int64_t& c) { return SoftScore::of(c); };
+  using C = CrossComplementedGroupedConstraint<CSchedule, CShift, CEmployee, CTarget, OptVal, size_t, SoftScore, SumAcc,
+                                               decltype(ka), decltype(kb), decltype(tf), decltype(gk), decltype(vf),
+                                               decltype(kt), decltype(df), decltype(gw), OptKeyHash>;
+  Source<CSchedule, CShift> ss{c_sh, ChangeSource::Desc(0)};
+  Source<CSchedule, CEmployee> se{c_em, ChangeSource::Desc(1)};
+  Source<CSchedule, CTarget> st{c_tg, ChangeSource::Desc(2)};
+  auto two = [] { return CSchedule{{{OptVal(0)}, {OptVal(0)}}, {{0}, {1}}, {{0}, {1}}}; };
+  {
+    C c("complemented", Impact::Penalty, ss, se, st, ka, kb, tf, gk, vf, kt, df, gw, false);
+    auto s = two();
+    CHECK(c.match_count(s) == 2);
+    CHECK(c.evaluate(s) == SoftScore::of(-7));
+  }
+  {
+    C c("complemented", Impact::Penalty, ss, se, st, ka, kb, tf, gk, vf, kt, df, gw, false);
+    auto s = two();
+    SoftScore total = c.initialize(s);
+    CHECK(total == SoftScore::of(-7));
+    total = total + c.on_retract(s, 1, 0);
+    s.shifts[1].employee_id = OptVal(1);
+    total = total + c.on_insert(s, 1, 0);
+    CHECK(total == SoftScore::of(-2));
+    CHECK(total == c.evaluate(s));
+  }
+  {
+    C c("complemented", Impact::Penalty, ss, se, st, ka, kb, tf, gk, vf, kt, df, gw, false);
+    auto s = two();
+    SoftScore total = c.initialize(s);
+    total = total + c.on_retract(s, 0, 1);
+    s.employees[0].id = 2;
+    total = total + c.on_insert(s, 0, 1);
+    CHECK(total == SoftScore::of(-10));
+    CHECK(total == c.evaluate(s));
+  }
+  {
+    C c("complemented", Impact::Penalty, ss, se, st, ka, kb, tf, gk, vf, kt, df, gw, false);
+    auto s = two();
+    SoftScore total = c.initialize(s);
+    s.targets.push_back({2});
+    total = total + c.on_insert(s, 2, 2);
+    CHECK(total == SoftScore::of(-12));
+    CHECK(total == c.evaluate(s));
+  }
+  {
+    // :191-215 filtered join + filtered complement sources: -6 -> -10
+    Source<CSchedule, CEmployee> sef{c_em, ChangeSource::Desc(1),
+                                     [](const CSchedule&, const CEmployee& e) { return e.id != 0; }};
+    Source<CSchedule, CTarget> stf{c_tg, ChangeSource::Desc(2),
+                                   [](const CSchedule&, const CTarget& t) { return t.employee_id != 2; }};
+    C c("filtered complemented", Impact::Penalty, ss, sef, stf, ka, kb, tf, gk, vf, kt, df, gw, false);
+    CSchedule s{{{OptVal(0)}, {OptVal(1)}}, {{0}, {1}}, {{0}, {1}, {2}}};
+    CHECK(c.match_count(s) == 2);
+    CHECK(c.evaluate(s) == SoftScore::of(-6));
+    SoftScore total = c.initialize(s);
+    CHECK(total == SoftScore::of(-6));
+    total = total + c.on_retract(s, 1, 1);
+    s.employees[1].id = 0;
+    total = total + c.on_insert(s, 1, 1);
+    CHECK(total == SoftScore::of(-10));
+    CHECK(total == c.evaluate(s));
+  }
+}
+
+// ---------------------------------------------------------------- selectors / foragers
+static void kat_nearby_sort() {
+  // solverforge-solver/src/heuristic/selector/nearby_list_support.rs:51-73
+  for (size_t len = 0; len < 96; ++len) {
+    uint32_t state = 0x9E3779B9u ^ (uint32_t)len;
+    std::vector<NearbyCandidate> cands;
+    for (size_t i = 0; i < len; ++i) {
+      state = state * 1664525u + 1013904223u;
+      double dist = i % 17 == 0 ? -0.0 : (double)(state % 11);
+      cands.push_back({i / 7, i, dist});
+    }
+    for (size_t k = 0; k <= len + 2; ++k) {
+      auto expected = cands;
+      std::stable_sort(expected.begin(), expected.end(),
+                       [](const NearbyCandidate& l, const NearbyCandidate& r) { return l.distance < r.distance; });
+      if (expected.size() > k) expected.resize(k);
+      auto actual = cands;
+      sort_and_limit_nearby_candidates(actual, k);
+      bool same = actual.size() == expected.size();
+      for (size_t i = 0; same && i < actual.size(); ++i)
+        same = actual[i].entity == expected[i].entity && actual[i].position == expected[i].position;
+      CHECK(same);
+    }
+  }
+}
+
+static void kat_moves_and_loop() {
+  // list_kernel/change.rs:46-75 doability + do/undo round trip on a tiny CVRP (score invariant
+  // incremental == evaluate_all, scope/solver/scope_core.rs:642-653).
+  auto pd = std::make_shared<ProblemData>();
+  pd->capacity = 3;
+  pd->depot = 0;
+  pd->demands = {0, 1, 2, 3, 1};
+  pd->distance_matrix = {{0, 2, 3, 4, 5}, {2, 0, 6, 7, 8}, {3, 6, 0, 9, 1}, {4, 7, 9, 0, 2}, {5, 8, 1, 2, 0}};
+  CvrpPlan plan;
+  plan.shared = pd;
+  for (size_t i = 1; i <= 4; ++i) plan.customers.push_back({i});
+  plan.routes = {{0, {1, 2}, pd.get()}, {1, {3}, pd.get()}, {2, {}, pd.get()}};
+  CvrpModel m(plan);
+  // customer 4 unassigned: -1 hard; route 1 load 3 (ok), route 0 load 3 (ok); distance 2+6+3 + 4+4 = 19
+  CHECK(m.calculate_score() == Sc::of(-1, -19));
+  CHECK(m.fresh_score() == Sc::of(-1, -19));
+  CHECK(!is_doable(Move::list_change(0, 0, 0, 0, 0), m.dir));
+  CHECK(!is_doable(Move::list_change(0, 0, 0, 0, 1), m.dir));
+  CHECK(is_doable(Move::list_change(0, 0, 0, 0, 2), m.dir));
+  CHECK(!is_doable(Move::list_change(0, 0, 2, 1, 0), m.dir));
+  CHECK(!is_doable(Move::list_change(0, 0, 0, 1, 2), m.dir));
+  CHECK(is_doable(Move::list_change(0, 0, 0, 2, 0), m.dir));
+  auto ev = m.evaluate(Move::list_change(0, 0, 1, 1, 1));  // move customer 2 after 3: load 5 > 3 => -2 hard
+  CHECK(ev.kind == EvalKind::Scored);
+  CHECK(ev.score == Sc::of(-1 - 2, -(2 + 2 + 4 + 9 + 3)));
+  CHECK(m.calculate_score() == Sc::of(-1, -19));
+  m.apply(Move::list_change(0, 0, 1, 1, 1));
+  CHECK(m.calculate_score() == m.fresh_score());
+  CHECK(m.calculate_score() == Sc::of(-3, -20));
+  // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
+  BestCandidate<Sc> bc;
+  bc.reset(42);
+  bc.consider(0, Sc::of(0, -5));
+  bc.consider(1, Sc::of(0, -7));
+  CHECK(bc.index == 0);
+  bc.consider(2, Sc::of(0, -3));
+  CHECK(bc.index == 2 && bc.equal_count == 1);
+  bc.random_ties = false;
+  bc.consider(3, Sc::of(0, -3));
+  CHECK(bc.index == 2 && bc.equal_count == 2);
+  // phase/localsearch/phase/tests/foraging.rs: accepted-count horizon stops evaluation
+  Forager<Sc> fg;
+  fg.kind = ForagerKind::AcceptedCount;
+  fg.accepted_count_limit = 2;
+  Acceptor<Sc> acc;
+  acc.kind = AcceptorKind::HillClimbing;
+  std::vector<Sc> scores = {Sc::of(0, -12), Sc::of(0, -8), Sc::of(0, -9), Sc::of(0, -1)};
+  auto out = replay_step<Sc>(
+      scores.size(), [&](size_t i) { return CandidateEvaluation<Sc>{EvalKind::Scored, scores[i]}; }, Sc::of(0, -10),
+      Sc::of(0, -10), 7, fg, acc);
+  CHECK(out.moves_evaluated == 3);
+  CHECK(out.moves_accepted == 2);
+  CHECK(out.has_winner && out.winner == 1);
+}
+
+int main() {
+  kat_scores();
+  kat_director();
+  kat_cross_bi();
+  kat_self_join();
+  kat_exists();
+  kat_grouped();
+  kat_cross_complemented();
+  kat_nearby_sort();
+  kat_moves_and_loop();
+  if (g_fail) {
+    std::printf("KAT FAILED %d of %d\n", g_fail, g_checks);
+    return 1;
+  }
+  std::printf("KAT OK %d\n", g_checks);
+  return 0;
+}

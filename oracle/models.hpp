@@ -1,0 +1,312 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see score.hpp header).
+//
+// The four BASELINE.json config models, authored against the oracle's restatement of the
+// reference ConstraintStream API, closure for closure:
+//   C1 n-queens        examples/nqueens/src/domain/board.rs:21-47
+//   C2 graph colouring examples/scalar-graph-coloring/src/domain/graph_coloring.rs:21-44
+//   C3 CVRP            constraint (i) verbatim from crates/solverforge/tests/list_clarke_wright_publication/
+//                      domain/publication_plan.rs:51-65; (ii) capacity and (iii) distance are authored by us
+//                      (the reference ships no CVRP constraints — SURVEY §0.1-5) over
+//                      crates/solverforge-cvrp/src/problem_data.rs:14-47 semantics (distance_cost)
+//   C4 mixed job-shop  examples/mixed-job-shop/src/domain/job_shop_plan.rs:28-69 plus one authored
+//                      grouped-complement constraint
+#pragma once
+#include <memory>
+
+#include "director.hpp"
+
+namespace sfo {
+
+using Sc = HardSoftScore;
+
+// Type-erased handle used by the C API.
+struct OracleModel {
+  virtual ~OracleModel() = default;
+  virtual Sc calculate_score() = 0;
+  virtual Sc fresh_score() = 0;
+  virtual CandidateEvaluation<Sc> evaluate(const Move& m) = 0;
+  virtual void apply(const Move& m) = 0;
+  virtual std::vector<Move> enumerate_scalar(MoveStreamContext ctx) { return {}; }
+  virtual std::vector<Move> enumerate_list(size_t max_nearby, MoveStreamContext ctx) { return {}; }
+  virtual size_t scalar_desc() const { return 0; }
+  virtual size_t list_desc() const { return 0; }
+  virtual uint64_t score_calculations() const = 0;
+};
+
+template <class S>
+struct ModelImpl : OracleModel {
+  ScoreDirector<S, Sc> dir;
+  Sc calculate_score() override { return dir.calculate_score(); }
+  Sc fresh_score() override { return dir.fresh_score(); }
+  CandidateEvaluation<Sc> evaluate(const Move& m) override {
+    return evaluate_candidate(m, dir, dir.calculate_score());
+  }
+  void apply(const Move& m) override {
+    dir.calculate_score();
+    do_move(m, dir);
+  }
+  uint64_t score_calculations() const override { return dir.score_calculations; }
+};
+
+struct ConstKey {
+  uint8_t operator()(...) const { return 0; }
+};
+
+// ------------------------------------------------------------------------------------------- C2
+struct GcNode {
+  size_t id;
+  std::vector<size_t> neighbors;
+  OptVal color_idx;
+};
+struct GraphColoring {
+  std::vector<GcNode> nodes;
+  size_t n_colors = 0;
+};
+inline const std::vector<GcNode>& gc_nodes(const GraphColoring& s) { return s.nodes; }
+
+struct GraphColoringModel final : ModelImpl<GraphColoring> {
+  GraphColoringModel(GraphColoring sol) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const GraphColoring& s, size_t, size_t e) { return s.nodes[e].color_idx; };
+    dir.access.set = [](GraphColoring& s, size_t, size_t e, OptVal v) { s.nodes[e].color_idx = v; };
+    dir.access.entity_count = [](const GraphColoring& s, size_t) { return s.nodes.size(); };
+    Source<GraphColoring, GcNode> src{gc_nodes, ChangeSource::Desc(0)};
+    auto uf = [](const GraphColoring&, const GcNode& n) { return !n.color_idx.has_value(); };
+    auto uw = [](const GcNode&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<GraphColoring, GcNode, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned color", Impact::Penalty, src, uf, uw, true));
+    auto pf = [](const GraphColoring&, const GcNode& l, const GcNode& r, size_t, size_t) {
+      return l.id < r.id && std::find(l.neighbors.begin(), l.neighbors.end(), r.id) != l.neighbors.end() &&
+             l.color_idx.has_value() && l.color_idx == r.color_idx;
+    };
+    auto pw = [](const GraphColoring&, const GcNode&, const GcNode&, size_t, size_t) { return Sc::ONE_HARD(); };
+    dir.constraints.add(
+        std::make_unique<CrossBiConstraint<GraphColoring, GcNode, GcNode, uint8_t, Sc, ConstKey, ConstKey,
+                                           decltype(pf), decltype(pw)>>(
+            "Adjacent color conflict", Impact::Penalty, src, src, ConstKey{}, ConstKey{}, pf, pw, true));
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.n_colors, true, ctx);
+  }
+};
+
+// ------------------------------------------------------------------------------------------- C1
+struct Queen {
+  size_t id, column;
+  OptVal row_idx;
+};
+struct Board {
+  std::vector<Queen> queens;
+  size_t n_rows = 0;
+};
+inline const std::vector<Queen>& board_queens(const Board& s) { return s.queens; }
+
+struct NQueensModel final : ModelImpl<Board> {
+  NQueensModel(Board sol) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const Board& s, size_t, size_t e) { return s.queens[e].row_idx; };
+    dir.access.set = [](Board& s, size_t, size_t e, OptVal v) { s.queens[e].row_idx = v; };
+    dir.access.entity_count = [](const Board& s, size_t) { return s.queens.size(); };
+    Source<Board, Queen> src{board_queens, ChangeSource::Desc(0)};
+    auto uf = [](const Board&, const Queen& q) { return !q.row_idx.has_value(); };
+    auto uw = [](const Queen&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<Board, Queen, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned queen", Impact::Penalty, src, uf, uw, true));
+    auto pf = [](const Board&, const Queen& l, const Queen& r, size_t, size_t) {
+      if (l.column >= r.column) return false;
+      if (!l.row_idx || !r.row_idx) return false;
+      size_t lr = *l.row_idx, rr = *r.row_idx;
+      size_t dr = lr > rr ? lr - rr : rr - lr;
+      size_t dc = l.column > r.column ? l.column - r.column : r.column - l.column;
+      return lr == rr || dr == dc;
+    };
+    auto pw = [](const Board&, const Queen&, const Queen&, size_t, size_t) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<CrossBiConstraint<Board, Queen, Queen, uint8_t, Sc, ConstKey, ConstKey,
+                                                           decltype(pf), decltype(pw)>>(
+        "Queen conflict", Impact::Penalty, src, src, ConstKey{}, ConstKey{}, pf, pw, true));
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.n_rows, true, ctx);
+  }
+};
+
+// ------------------------------------------------------------------------------------------- C3
+// crates/solverforge-cvrp/src/problem_data.rs:6-47
+constexpr int64_t UNREACHABLE = std::numeric_limits<int64_t>::max();
+constexpr int64_t MAX_SAFE_LEG_COST = std::numeric_limits<int64_t>::max() / 4;
+struct ProblemData {
+  int64_t capacity = 0;
+  size_t depot = 0;
+  std::vector<int32_t> demands;
+  std::vector<std::vector<int64_t>> distance_matrix;
+  std::optional<int64_t> finite_distance(size_t from, size_t to) const {
+    if (from >= distance_matrix.size() || to >= distance_matrix[from].size()) return std::nullopt;
+    int64_t v = distance_matrix[from][to];
+    if (v >= 0 && v != UNREACHABLE) return v;
+    return std::nullopt;
+  }
+  int64_t distance_cost(size_t from, size_t to) const { return finite_distance(from, to).value_or(MAX_SAFE_LEG_COST); }
+};
+struct Customer {
+  size_t id;
+};
+struct Route {
+  size_t id;
+  std::vector<size_t> visits;
+  const ProblemData* data;
+};
+struct CvrpPlan {
+  std::vector<Customer> customers;
+  std::vector<Route> routes;
+  std::shared_ptr<ProblemData> shared;
+};
+inline const std::vector<Customer>& cvrp_customers(const CvrpPlan& s) { return s.customers; }
+inline const std::vector<Route>& cvrp_routes(const CvrpPlan& s) { return s.routes; }
+
+struct CvrpModel final : ModelImpl<CvrpPlan> {
+  CvrpModel(CvrpPlan sol) {
+    dir.working = std::move(sol);
+    dir.access.list = [](CvrpPlan& s, size_t, size_t e) -> std::vector<size_t>& { return s.routes[e].visits; };
+    dir.access.entity_count = [](const CvrpPlan& s, size_t) { return s.routes.size(); };
+    Source<CvrpPlan, Customer> cust{cvrp_customers, ChangeSource::Stat()};
+    Source<CvrpPlan, Route> routes{cvrp_routes, ChangeSource::Desc(0)};
+    // (i) all_customers_assigned — publication_plan.rs:51-65
+    auto ka = [](const Customer& c) { return c.id; };
+    auto kb = [](const size_t& assigned) { return assigned; };
+    auto fa = [](const CvrpPlan&, const Customer&) { return true; };
+    auto fp = [](const CvrpPlan&, const Route&) { return true; };
+    auto fl = [](const Route& r) -> const std::vector<size_t>& { return r.visits; };
+    auto w1 = [](const Customer&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<ExistsConstraint<CvrpPlan, Customer, Route, size_t, size_t, Sc, decltype(ka),
+                                                          decltype(kb), decltype(fa), decltype(fp), decltype(fl),
+                                                          decltype(w1)>>(
+        "all_customers_assigned", Impact::Penalty, ExistenceMode::NotExists, cust, routes, ka, kb, fa, fp, fl, w1,
+        true));
+    // (ii) capacity: of_hard(max(0, load - capacity))
+    auto always = [](const CvrpPlan&, const Route&) { return true; };
+    auto wcap = [](const Route& r) {
+      int64_t load = 0;
+      for (size_t v : r.visits) load += r.data->demands[v];
+      return Sc::of_hard(std::max<int64_t>(0, load - r.data->capacity));
+    };
+    dir.constraints.add(std::make_unique<UniConstraint<CvrpPlan, Route, Sc, decltype(always), decltype(wcap)>>(
+        "vehicle_capacity", Impact::Penalty, routes, always, wcap, true));
+    // (iii) distance: depot -> visits... -> depot via distance_cost; empty route costs 0
+    auto wdist = [](const Route& r) {
+      if (r.visits.empty()) return Sc::zero();
+      int64_t total = 0;
+      size_t prev = r.data->depot;
+      for (size_t v : r.visits) {
+        total = wadd(total, r.data->distance_cost(prev, v));
+        prev = v;
+      }
+      total = wadd(total, r.data->distance_cost(prev, r.data->depot));
+      return Sc::of_soft(total);
+    };
+    dir.constraints.add(std::make_unique<UniConstraint<CvrpPlan, Route, Sc, decltype(always), decltype(wdist)>>(
+        "total_distance", Impact::Penalty, routes, always, wdist, false));
+  }
+  // crates/solverforge-cvrp/src/meters.rs:10-28 (MatrixDistanceMeter)
+  static double meter(CvrpPlan& s, size_t se, size_t sp, size_t de, size_t dp) {
+    auto& sv = s.routes[se].visits;
+    auto& dv = s.routes[de].visits;
+    if (sp >= sv.size() || dp >= dv.size()) return std::numeric_limits<double>::infinity();
+    auto d = s.shared->finite_distance(sv[sp], dv[dp]);
+    return d ? (double)*d : std::numeric_limits<double>::infinity();
+  }
+  std::vector<Move> enumerate_list(size_t max_nearby, MoveStreamContext ctx) override {
+    return enumerate_nearby_list_change_moves(dir.working, dir.access, 0, max_nearby, ctx, meter);
+  }
+};
+
+// ------------------------------------------------------------------------------------------- C4
+struct Operation {
+  size_t id, job, step;
+  OptVal machine_idx;
+};
+struct Machine {
+  size_t id;
+};
+struct MachineSequence {
+  size_t id;
+  std::vector<size_t> operations;
+};
+struct JobShopPlan {
+  std::vector<Machine> machines;
+  std::vector<Operation> operations;
+  std::vector<MachineSequence> machine_sequences;
+};
+inline const std::vector<Machine>& js_machines(const JobShopPlan& s) { return s.machines; }
+inline const std::vector<Operation>& js_operations(const JobShopPlan& s) { return s.operations; }
+inline const std::vector<MachineSequence>& js_sequences(const JobShopPlan& s) { return s.machine_sequences; }
+
+struct OptHash {
+  size_t operator()(const OptVal& v) const { return v ? std::hash<size_t>()(*v) + 1 : 0; }
+};
+
+struct JobShopModel final : ModelImpl<JobShopPlan> {
+  // descriptor indices = declaration order of entity collections (job_shop_plan.rs:15-22):
+  // operations = 0, machine_sequences = 1.
+  explicit JobShopModel(JobShopPlan sol, bool with_grouped_complement = true) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const JobShopPlan& s, size_t, size_t e) { return s.operations[e].machine_idx; };
+    dir.access.set = [](JobShopPlan& s, size_t, size_t e, OptVal v) { s.operations[e].machine_idx = v; };
+    dir.access.list = [](JobShopPlan& s, size_t, size_t e) -> std::vector<size_t>& {
+      return s.machine_sequences[e].operations;
+    };
+    dir.access.entity_count = [](const JobShopPlan& s, size_t d) {
+      return d == 0 ? s.operations.size() : s.machine_sequences.size();
+    };
+    Source<JobShopPlan, Operation> ops{js_operations, ChangeSource::Desc(0)};
+    Source<JobShopPlan, MachineSequence> seqs{js_sequences, ChangeSource::Desc(1)};
+    Source<JobShopPlan, Machine> machines{js_machines, ChangeSource::Stat()};
+    auto uf = [](const JobShopPlan&, const Operation& o) { return !o.machine_idx.has_value(); };
+    auto uw = [](const Operation&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<JobShopPlan, Operation, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned operation machine", Impact::Penalty, ops, uf, uw, true));
+    auto ka = [](const Operation& o) { return o.id; };
+    auto kb = [](const size_t& assigned) { return assigned; };
+    auto fa = [](const JobShopPlan&, const Operation&) { return true; };
+    auto fp = [](const JobShopPlan&, const MachineSequence&) { return true; };
+    auto fl = [](const MachineSequence& m) -> const std::vector<size_t>& { return m.operations; };
+    auto w1 = [](const Operation&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(
+        std::make_unique<ExistsConstraint<JobShopPlan, Operation, MachineSequence, size_t, size_t, Sc, decltype(ka),
+                                          decltype(kb), decltype(fa), decltype(fp), decltype(fl), decltype(w1)>>(
+            "Unscheduled operation", Impact::Penalty, ExistenceMode::NotExists, ops, seqs, ka, kb, fa, fp, fl, w1,
+            true));
+    auto pf = [](const JobShopPlan&, const Operation& l, const Operation& r, size_t, size_t) {
+      return l.id < r.id && l.job == r.job && l.machine_idx.has_value() && l.machine_idx == r.machine_idx;
+    };
+    auto pw = [](const JobShopPlan&, const Operation&, const Operation&, size_t, size_t) { return Sc::ONE_SOFT(); };
+    dir.constraints.add(
+        std::make_unique<CrossBiConstraint<JobShopPlan, Operation, Operation, uint8_t, Sc, ConstKey, ConstKey,
+                                           decltype(pf), decltype(pw)>>(
+            "Same job machine reuse", Impact::Penalty, ops, ops, ConstKey{}, ConstKey{}, pf, pw, false));
+    if (with_grouped_complement) {
+      // for_each(operations).join((machines, equal_bi(op.machine_idx, Some(m.id))))
+      //   .group_by(|_, m| m.id, count()).complement(machines, |m| m.id, |_| 0usize)
+      //   .penalize(|_, load| of_soft(load^2))
+      auto jka = [](const Operation& o) { return o.machine_idx; };
+      auto jkb = [](const Machine& m) { return OptVal(m.id); };
+      auto jf = [](const JobShopPlan&, const Operation&, const Machine&, size_t, size_t) { return true; };
+      auto gk = [](const Operation&, const Machine& m) { return m.id; };
+      auto vf = [](const Operation&, const Machine&) { return (char)0; };
+      auto kt = [](const Machine& m) { return m.id; };
+      auto df = [](const Machine&) { return (size_t)0; };
+      auto gw = [](const size_t&, const size_t& load) { return Sc::of_soft((int64_t)(load * load)); };
+      dir.constraints.add(
+          std::make_unique<CrossComplementedGroupedConstraint<
+              JobShopPlan, Operation, Machine, Machine, OptVal, size_t, Sc, CountAcc, decltype(jka), decltype(jkb),
+              decltype(jf), decltype(gk), decltype(vf), decltype(kt), decltype(df), decltype(gw), OptHash>>(
+              "Machine load balance", Impact::Penalty, ops, machines, machines, jka, jkb, jf, gk, vf, kt, df, gw,
+              false));
+    }
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.machines.size(), true, ctx);
+  }
+  size_t list_desc() const override { return 1; }
+};
+
+}  // namespace sfo

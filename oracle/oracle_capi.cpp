@@ -1,0 +1,228 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see score.hpp header).
+//
+// C ABI over the oracle so tests/ and bench.py's cpu_baseline / --impl reference legs can drive
+// it through ctypes. Each score call performs exactly the reference's evaluate_candidate
+// (phase/localsearch/evaluation.rs:20-115): is_doable -> snapshot -> do_move -> calculate_score
+// -> undo_move -> restore, through the retained incremental constraint state.
+#include <cstring>
+
+#include "models.hpp"
+
+using namespace sfo;
+
+namespace {
+inline OptVal opt(int32_t v) { return v < 0 ? std::nullopt : OptVal((size_t)v); }
+
+template <class MakeMove>
+int score_batch(void* h, uint64_t n, MakeMove mk, int64_t* hard, int64_t* soft, uint8_t* doable) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->calculate_score();
+  for (uint64_t i = 0; i < n; ++i) {
+    auto ev = m->evaluate(mk(i));
+    bool ok = ev.kind != EvalKind::NotDoable;
+    if (doable) doable[i] = ok ? 1 : 0;
+    hard[i] = ok ? ev.score.hard : 0;
+    soft[i] = ok ? ev.score.soft : 0;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+void* sfo_gc_create(uint32_t n, uint32_t k, const uint32_t* row_ptr, const uint32_t* col, const int32_t* color) {
+  GraphColoring g;
+  g.n_colors = k;
+  g.nodes.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    g.nodes[i].id = i;
+    g.nodes[i].color_idx = opt(color[i]);
+    for (uint32_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j) g.nodes[i].neighbors.push_back(col[j]);
+  }
+  return new GraphColoringModel(std::move(g));
+}
+
+void* sfo_nq_create(uint32_t n, const int32_t* row) {
+  Board b;
+  b.n_rows = n;
+  for (uint32_t i = 0; i < n; ++i) b.queens.push_back({i, i, opt(row[i])});
+  return new NQueensModel(std::move(b));
+}
+
+void* sfo_cvrp_create(uint32_t dim, uint32_t n_routes, int64_t capacity, uint32_t depot, const int32_t* demands,
+                      const int64_t* matrix, const uint32_t* offsets, const uint32_t* elems) {
+  auto pd = std::make_shared<ProblemData>();
+  pd->capacity = capacity;
+  pd->depot = depot;
+  pd->demands.assign(demands, demands + dim);
+  pd->distance_matrix.resize(dim);
+  for (uint32_t i = 0; i < dim; ++i) pd->distance_matrix[i].assign(matrix + (size_t)i * dim, matrix + (size_t)(i + 1) * dim);
+  CvrpPlan p;
+  p.shared = pd;
+  for (uint32_t i = 0; i < dim; ++i)
+    if (i != depot) p.customers.push_back({i});
+  for (uint32_t r = 0; r < n_routes; ++r) {
+    Route rt{r, {}, pd.get()};
+    for (uint32_t j = offsets[r]; j < offsets[r + 1]; ++j) rt.visits.push_back(elems[j]);
+    p.routes.push_back(std::move(rt));
+  }
+  return new CvrpModel(std::move(p));
+}
+
+void* sfo_js_create(uint32_t n_ops, uint32_t n_machines, const uint32_t* job, const uint32_t* step,
+                    const int32_t* machine_idx, const uint32_t* seq_offsets, const uint32_t* seq_elems,
+                    int with_complement) {
+  JobShopPlan p;
+  for (uint32_t m = 0; m < n_machines; ++m) p.machines.push_back({m});
+  for (uint32_t i = 0; i < n_ops; ++i) p.operations.push_back({i, job[i], step[i], opt(machine_idx[i])});
+  for (uint32_t m = 0; m < n_machines; ++m) {
+    MachineSequence s{m, {}};
+    for (uint32_t j = seq_offsets[m]; j < seq_offsets[m + 1]; ++j) s.operations.push_back(seq_elems[j]);
+    p.machine_sequences.push_back(std::move(s));
+  }
+  return new JobShopModel(std::move(p), with_complement != 0);
+}
+
+void sfo_destroy(void* h) { delete static_cast<OracleModel*>(h); }
+
+int sfo_committed_score(void* h, int64_t out[2]) {
+  Sc s = static_cast<OracleModel*>(h)->calculate_score();
+  out[0] = s.hard;
+  out[1] = s.soft;
+  return 0;
+}
+int sfo_evaluate_all(void* h, int64_t out[2]) {
+  Sc s = static_cast<OracleModel*>(h)->fresh_score();
+  out[0] = s.hard;
+  out[1] = s.soft;
+  return 0;
+}
+uint64_t sfo_score_calculations(void* h) { return static_cast<OracleModel*>(h)->score_calculations(); }
+
+int sfo_score_change(void* h, uint64_t n, const uint32_t* e, const int32_t* v, int64_t* hard, int64_t* soft,
+                     uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->scalar_desc();
+  return score_batch(h, n, [&](uint64_t i) { return Move::change(d, e[i], opt(v[i])); }, hard, soft, doable);
+}
+int sfo_score_swap(void* h, uint64_t n, const uint32_t* l, const uint32_t* r, int64_t* hard, int64_t* soft,
+                   uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->scalar_desc();
+  return score_batch(h, n, [&](uint64_t i) { return Move::swap(d, l[i], r[i]); }, hard, soft, doable);
+}
+int sfo_score_compound(void* h, uint64_t n, const uint32_t* offs, const uint32_t* e, const int32_t* v, int64_t* hard,
+                       int64_t* soft, uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->scalar_desc();
+  return score_batch(
+      h, n,
+      [&](uint64_t i) {
+        std::vector<ScalarEdit> edits;
+        for (uint32_t j = offs[i]; j < offs[i + 1]; ++j) edits.push_back({d, e[j], opt(v[j])});
+        return Move::compound(std::move(edits));
+      },
+      hard, soft, doable);
+}
+int sfo_score_list_change(void* h, uint64_t n, const uint32_t* se, const uint32_t* sp, const uint32_t* de,
+                          const uint32_t* dp, int64_t* hard, int64_t* soft, uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->list_desc();
+  return score_batch(h, n, [&](uint64_t i) { return Move::list_change(d, se[i], sp[i], de[i], dp[i]); }, hard, soft,
+                     doable);
+}
+int sfo_score_list_swap(void* h, uint64_t n, const uint32_t* e1, const uint32_t* p1, const uint32_t* e2,
+                        const uint32_t* p2, int64_t* hard, int64_t* soft, uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->list_desc();
+  return score_batch(h, n, [&](uint64_t i) { return Move::list_swap(d, e1[i], p1[i], e2[i], p2[i]); }, hard, soft,
+                     doable);
+}
+
+int sfo_apply_change(void* h, uint32_t e, int32_t v) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(Move::change(m->scalar_desc(), e, opt(v)));
+  return 0;
+}
+int sfo_apply_swap(void* h, uint32_t l, uint32_t r) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(Move::swap(m->scalar_desc(), l, r));
+  return 0;
+}
+int sfo_apply_compound(void* h, uint32_t n_edits, const uint32_t* e, const int32_t* v) {
+  auto* m = static_cast<OracleModel*>(h);
+  std::vector<ScalarEdit> edits;
+  for (uint32_t j = 0; j < n_edits; ++j) edits.push_back({m->scalar_desc(), e[j], opt(v[j])});
+  m->apply(Move::compound(std::move(edits)));
+  return 0;
+}
+int sfo_apply_list_change(void* h, uint32_t se, uint32_t sp, uint32_t de, uint32_t dp) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(Move::list_change(m->list_desc(), se, sp, de, dp));
+  return 0;
+}
+int sfo_apply_list_swap(void* h, uint32_t e1, uint32_t p1, uint32_t e2, uint32_t p2) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(Move::list_swap(m->list_desc(), e1, p1, e2, p2));
+  return 0;
+}
+
+static MoveStreamContext make_ctx(uint64_t step_index, uint64_t step_seed, int order) {
+  MoveStreamContext c;
+  c.step_index = step_index;
+  c.step_seed = step_seed;
+  c.order = order == 1 ? SelectionOrder::Random : order == 2 ? SelectionOrder::Shuffled : SelectionOrder::Original;
+  return c;
+}
+
+// Returns the number of candidates (may exceed cap; only the first cap are written).
+int64_t sfo_enumerate_change(void* h, uint64_t step_index, uint64_t step_seed, int order, uint64_t cap, uint32_t* e,
+                             int32_t* v) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_scalar(make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    e[i] = (uint32_t)moves[i].a;
+    v[i] = moves[i].to ? (int32_t)*moves[i].to : -1;
+  }
+  return (int64_t)moves.size();
+}
+int64_t sfo_enumerate_nearby_list_change(void* h, uint32_t max_nearby, uint64_t step_index, uint64_t step_seed,
+                                         int order, uint64_t cap, uint32_t* se, uint32_t* sp, uint32_t* de,
+                                         uint32_t* dp) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_list(max_nearby, make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    se[i] = (uint32_t)moves[i].a;
+    sp[i] = (uint32_t)moves[i].b;
+    de[i] = (uint32_t)moves[i].c;
+    dp[i] = (uint32_t)moves[i].d;
+  }
+  return (int64_t)moves.size();
+}
+
+// Replay of the candidate loop (phase/candidates.rs:66-282) over precomputed evaluations.
+// forager: 0 AcceptedCount(limit) 1 FirstAccepted 2 BestScore 3 FirstBestScoreImproving
+//          4 FirstLastStepScoreImproving; acceptor: 0 HillClimbing 1 LateAcceptance(late_score) 3 AcceptAll.
+// out[0]=has_winner out[1]=winner out[2]=moves_evaluated out[3]=score_calculations out[4]=moves_accepted
+int sfo_replay_step(uint64_t n, const int64_t* hard, const int64_t* soft, const uint8_t* doable,
+                    const int64_t best_score[2], const int64_t last_step_score[2], const int64_t late_score[2],
+                    uint64_t step_seed, int forager_kind, uint64_t accepted_limit, int random_ties, int acceptor_kind,
+                    uint64_t out[5]) {
+  Forager<Sc> fg;
+  fg.kind = (ForagerKind)forager_kind;
+  fg.accepted_count_limit = accepted_limit;
+  fg.best.random_ties = random_ties != 0;
+  Acceptor<Sc> ac;
+  ac.kind = (AcceptorKind)acceptor_kind;
+  if (ac.kind == AcceptorKind::LateAcceptance) {
+    ac.history.assign(1, Sc::of(late_score[0], late_score[1]));
+    ac.history_idx = 0;
+  }
+  auto o = replay_step<Sc>(
+      n,
+      [&](size_t i) {
+        return CandidateEvaluation<Sc>{doable[i] ? EvalKind::Scored : EvalKind::NotDoable, Sc::of(hard[i], soft[i])};
+      },
+      Sc::of(best_score[0], best_score[1]), Sc::of(last_step_score[0], last_step_score[1]), step_seed, fg, ac);
+  out[0] = o.has_winner;
+  out[1] = o.winner;
+  out[2] = o.moves_evaluated;
+  out[3] = o.score_calculations;
+  out[4] = o.moves_accepted;
+  return 0;
+}
+
+}  // extern "C"
