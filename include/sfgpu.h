@@ -1,0 +1,253 @@
+/*
+ * sfgpu.h — C ABI of libsfgpu: batched, read-only re-scoring of local-search candidate moves
+ * on B200 (sm_100a). This is the drop-in boundary for SolverForge's incremental
+ * ConstraintStream scoring path; a Rust `solverforge-gpu-sys` crate (or cgo/ctypes) binds
+ * exactly these symbols (INTEGRATION.md shows the Rust side).
+ *
+ * Reference interfaces this replaces (paths under the reference's crates/):
+ *   ScoreDirector::with_descriptor / calculate_score / before|after_variable_changed
+ *       solverforge-scoring/src/director/score_director/incremental.rs:64-82,141-224
+ *   ConstraintSet::{initialize_all,evaluate_all,on_insert_all,on_retract_all}
+ *       solverforge-scoring/src/api/constraint_set/incremental.rs:152-212
+ *   evaluate_candidate (do -> score -> undo per candidate)
+ *       solverforge-solver/src/phase/localsearch/evaluation.rs:20-115
+ *   BestCandidate::consider / reservoir_pick (forager tie rule)
+ *       solverforge-solver/src/phase/localsearch/forager.rs:99-155
+ *
+ * Conventions
+ *   - every function returns int32: 0 = OK, <0 = SFGPU_E_*; message via sfgpu_last_error().
+ *   - nothing unwinds across the boundary; there is NO CPU fallback: without a CUDA device
+ *     every compute entry point fails with SFGPU_E_CUDA.
+ *   - the caller owns host pointers for the duration of the call only; the library owns all
+ *     device memory it allocates. With SFGPU_DEVICE_IO the data pointers of a call are DEVICE
+ *     pointers owned by the caller (already resident in HBM) and the call is asynchronous on
+ *     the context's stream.
+ *   - one context per solve; a context is not thread-safe but may move between threads
+ *     (reference: Director: Send, not Sync — solverforge-scoring/src/director/traits.rs:27).
+ *   - a context holds R independent replicas (seeded restarts) of the planning state; static
+ *     facts (adjacency, matrices, columns) are shared by all replicas.
+ *   - scores are (hard, soft) int64 pairs, HardSoftScore / HardSoftDecimalScore layout
+ *       solverforge-core/src/score/hard_soft.rs:35-38, hard_soft_decimal.rs:45-48.
+ */
+#ifndef SFGPU_H
+#define SFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFGPU_ABI_VERSION 1
+
+#define SFGPU_OK 0
+#define SFGPU_E_INVALID (-1)     /* bad argument / out of range */
+#define SFGPU_E_UNSUPPORTED (-2) /* model shape not expressible on device (never a silent fallback) */
+#define SFGPU_E_CUDA (-3)
+#define SFGPU_E_NCCL (-4)
+#define SFGPU_E_OOM (-5)
+#define SFGPU_E_STATE (-6)       /* call order violated (e.g. score before commit) */
+
+/* call flags */
+#define SFGPU_DEVICE_IO 1u /* data pointers are device pointers; call is stream-asynchronous */
+
+typedef struct sfgpu_ctx sfgpu_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create
+ * a private non-blocking stream. */
+int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgpu_ctx** out);
+int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx);
+const char* sfgpu_last_error(const sfgpu_ctx* ctx);
+int32_t sfgpu_abi_version(void);
+int32_t sfgpu_synchronize(sfgpu_ctx* ctx);
+
+/* ---- model ---------------------------------------------------------------------------- */
+/* descriptor_index: declaration order of the #[planning_entity_collection]
+ * (solverforge-macros/src/planning_model/metadata.rs:9-44); -1 = problem fact (ChangeSource::Static). */
+int32_t sfgpu_model_begin(sfgpu_ctx* ctx, uint32_t n_replicas);
+int32_t sfgpu_add_collection(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, int32_t descriptor_index,
+                             uint32_t* out_collection);
+/* static int64 fact column of a collection (n_rows values), shared by all replicas */
+int32_t sfgpu_add_column_i64(sfgpu_ctx* ctx, uint32_t collection, const char* name, const int64_t* values,
+                             uint32_t* out_column);
+/* scalar planning variable: value in [0, n_values) or -1 (None)
+ * (#[planning_variable(allows_unassigned)], examples/scalar-graph-coloring/src/domain/node.rs) */
+int32_t sfgpu_add_scalar_variable(sfgpu_ctx* ctx, uint32_t collection, const char* name, uint32_t n_values,
+                                  int32_t allows_unassigned, uint32_t* out_variable);
+/* list planning variable: each owner row holds an ordered list of element row indices
+ * (#[planning_list_variable], crates/solverforge-cvrp/src/solution.rs:11-16) */
+int32_t sfgpu_add_list_variable(sfgpu_ctx* ctx, uint32_t owner_collection, uint32_t element_collection,
+                                const char* name, uint32_t* out_variable);
+/* CSR adjacency over one collection (Node::neighbors) */
+int32_t sfgpu_add_csr(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, const uint32_t* row_ptr,
+                      const uint32_t* col_idx, uint32_t* out_csr);
+/* dense int64 matrix. cost_semantics 1 applies ProblemData::distance_cost at upload: a cell v is
+ * kept when 0 <= v != INT64_MAX, else replaced by INT64_MAX/4
+ * (crates/solverforge-cvrp/src/problem_data.rs:6-12,28-47). */
+int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, uint32_t cols,
+                             const int64_t* values, int32_t cost_semantics, uint32_t* out_matrix);
+
+/* weight(x) on one score level */
+#define SFGPU_W_CONST 0  /* a */
+#define SFGPU_W_LINEAR 1 /* a*x + b */
+#define SFGPU_W_SQUARE 2 /* a*x*x + b */
+#define SFGPU_W_EXCESS 3 /* a*max(0, x - b) */
+typedef struct sfgpu_weight {
+  int32_t fn;
+  int32_t level; /* 0 = hard, 1 = soft */
+  int64_t a, b;
+} sfgpu_weight;
+
+#define SFGPU_PENALTY 0
+#define SFGPU_REWARD 1
+
+/* constraint kinds — each is one ConstraintStream shape of the reference */
+/* for_each(E)[.unassigned()|.filter(assigned)].penalize(w(x)); x = const | entity column | value column
+ *   solverforge-scoring/src/constraint/incremental.rs:97-156
+ *   p0: filter 0 = unassigned, 1 = assigned, 2 = always; aux0: column id or UINT32_MAX (x = 0);
+ *   p1: 0 = column indexed by entity row, 1 = column indexed by assigned value */
+#define SFGPU_K_UNI 1
+/* for_each(E).join(E, |l,r| l.id < r.id && l.neighbors.contains(r.id) && l.var.is_some() && l.var == r.var)
+ *   predicate cross-bi, solverforge-scoring/src/constraint/cross_bi_incremental/, stream/join_target.rs:83-110
+ *   aux0: csr id; weight must be CONST */
+#define SFGPU_K_PAIR_CSR_EQUAL 2
+/* for_each(E).join(E, equal(key)).filter(l.id < r.id && var.is_some()); key(e) = column[e]*p0 + var[e]*p1
+ *   keyed self-join, constraint/nary_incremental/bi.rs:78-206 (and the keyed form of predicate joins)
+ *   aux0: key column id or UINT32_MAX (column = 0); weight must be CONST */
+#define SFGPU_K_PAIR_KEY_EQUAL 3
+/* for_each(A).if_exists|if_not_exists(for_each(owners).flattened(list), equal(a.row, element))
+ *   constraint/exists.rs:126-417; p0: 0 = exists, 1 = not exists; weight must be CONST */
+#define SFGPU_K_EXISTS_FLAT 4
+/* for_each(E).join(values, equal(var, Some(v.row))).group_by(v.row, count()|sum(column))
+ *   [.complement(values, default p1)].penalize(w(result))
+ *   constraint/grouped/, cross_grouped/, cross_complemented_grouped/
+ *   aux0: summed entity column id or UINT32_MAX (count); p0: 1 = complemented; p1: default result */
+#define SFGPU_K_GROUP 5
+/* for_each(owners).penalize(w(sum of matrix legs depot -> list... -> depot)); empty list = 0
+ *   uni constraint whose weight walks the route; aux0: matrix id; p0: depot row */
+#define SFGPU_K_LIST_PATH_COST 6
+/* for_each(owners).penalize(w(sum of column[element])) (C3-ii: EXCESS weight with b = capacity)
+ *   aux0: element column id */
+#define SFGPU_K_LIST_SUM 7
+/* for_each(E).group_by((), load_balance(var, metric column|1)).penalize(w(unfairness))
+ *   stream/collector/load_balance.rs:104-240; aux0: metric column id or UINT32_MAX (metric = 1) */
+#define SFGPU_K_LOAD_BALANCE 8
+
+typedef struct sfgpu_constraint_desc {
+  int32_t kind;
+  int32_t impact;      /* SFGPU_PENALTY / SFGPU_REWARD (constraint/incremental.rs:70-76) */
+  sfgpu_weight weight;
+  uint32_t collection; /* source collection (A side) */
+  uint32_t variable;   /* scalar or list variable the constraint reads */
+  uint32_t aux0;
+  uint32_t aux1;
+  int64_t p0, p1;
+  const char* name;
+} sfgpu_constraint_desc;
+
+int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, uint32_t* out_constraint);
+
+/* planning state upload. per_replica 0: one copy broadcast to every replica; 1: [R] copies.
+ * scalar: int32 values[n_rows]; list: offsets[n_owners+1] + elems[offsets[n_owners]] per copy
+ * (per_replica 1: offsets is [R][n_owners+1], elems is the concatenation of the R copies). */
+int32_t sfgpu_set_scalar_state(sfgpu_ctx* ctx, uint32_t variable, const int32_t* values, int32_t per_replica);
+int32_t sfgpu_set_list_state(sfgpu_ctx* ctx, uint32_t variable, const uint32_t* offsets, const uint32_t* elems,
+                             int32_t per_replica);
+/* freezes the model, lays out HBM, runs initialize_all on every replica
+ * (ScoreDirector::calculate_score first call, incremental.rs:141-149); out_scores [R][2] or NULL */
+int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores);
+
+/* ---- candidate batches ---------------------------------------------------------------- */
+/* A batch holds the candidates of all R replicas back to back; replica r owns rows
+ * [cand_offsets[r], cand_offsets[r+1]); n_candidates == cand_offsets[R] (passed separately so the
+ * device-pointer path never reads an offset back). Rows are packed so one candidate is one aligned vector
+ * load. Outputs: out_scores[n][2] = score of the working solution AFTER the move (what
+ * evaluate_candidate returns); out_doable[n] = Move::is_doable. Not-doable rows get score (0,0).
+ *
+ * scalar rows: {uint32 entity, int32 to_value(-1 = None)}  == ScalarEdit
+ *   (solverforge-solver/src/planning/scalar/candidate.rs:6-12); ChangeMove semantics change.rs:125-175 */
+int32_t sfgpu_score_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                           int64_t* out_scores, uint8_t* out_doable);
+/* swap rows: {uint32 left_entity, uint32 right_entity} (heuristic/move/swap.rs:140-215) */
+int32_t sfgpu_score_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                         int64_t* out_scores, uint8_t* out_doable);
+/* compound: candidate i owns ScalarEdit rows [edit_offsets[i], edit_offsets[i+1])
+ * (CompoundScalarMove, heuristic/move/compound_scalar.rs:245-319); at most SFGPU_MAX_EDITS per candidate */
+#define SFGPU_MAX_EDITS 8
+int32_t sfgpu_score_compound(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                             const uint64_t* edit_offsets, const uint32_t* edit_rows, int64_t* out_scores,
+                             uint8_t* out_doable);
+/* list change rows: {src_entity, src_position, dst_entity, dst_position} uint32 x4
+ * (ListChangeMove, heuristic/move/list_kernel/change.rs:15-153) */
+int32_t sfgpu_score_list_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                                const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
+/* list swap rows: {first_entity, first_position, second_entity, second_position}
+ * (ListSwapMove, heuristic/move/list_kernel/swap.rs:16-110) */
+int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                              int64_t* out_scores, uint8_t* out_doable);
+
+/* ---- winner selection on device ------------------------------------------------------- */
+/* Per replica: replay of acceptor + forager over the scored rows in pull order
+ * (phase/candidates.rs:66-282 with BestCandidate::consider, forager.rs:99-155).
+ * acceptor: 0 = accept every doable candidate, 1 = HillClimbing (score > last_step_score),
+ *           2 = LateAcceptance (score >= last_step_score || score >= late_score)
+ * forager : accepted_limit 0 = BestScore (never quits early); N > 0 = AcceptedCount(N)
+ * tie_mode: 0 = ScoreTieBreak::First, 1 = reservoir (random_ties)
+ * ref_scores[R][2][2] = {last_step_score, late_score}; step_seeds[R].
+ * out_index[R] = winning pull index inside the replica's range, or UINT32_MAX when none accepted;
+ * out_best[R][2] its score; out_evaluated[R] = moves_evaluated (pulls up to the quit point). */
+typedef struct sfgpu_forage_params {
+  int32_t acceptor;
+  int32_t tie_mode;
+  uint32_t accepted_limit;
+  uint32_t reserved;
+} sfgpu_forage_params;
+int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                      const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
+                      const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
+                      int64_t* out_best, uint32_t* out_evaluated);
+
+/* ---- committing the winner ------------------------------------------------------------ */
+/* One row per replica (same packing as the score calls); mask[r] == 0 skips replica r
+ * (mask may be NULL). Updates the replica's planning state, its retained aggregates and its
+ * committed score (Move::do_move on the committed director, phase/step.rs:140-142). */
+int32_t sfgpu_apply_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+/* apply the winner found by sfgpu_argbest straight from the batch, no host round trip:
+ * row = batch_rows[cand_offsets[r] + index[r]]; replicas with index == UINT32_MAX are skipped.
+ * move_kind: 0 change, 1 swap, 2 list change, 3 list swap. All pointers are device pointers. */
+int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
+                            const uint32_t* batch_rows, const uint32_t* index);
+
+/* ---- reading state back --------------------------------------------------------------- */
+int32_t sfgpu_committed_scores(sfgpu_ctx* ctx, int64_t* out_scores /* [R][2] host */);
+/* stateless full recompute on a scratch copy (ConstraintSet::evaluate_all; FullAssert invariant
+ * cached == fresh, solverforge-solver/src/scope/solver/scope_core.rs:642-653) */
+int32_t sfgpu_evaluate_all(sfgpu_ctx* ctx, int64_t* out_scores /* [R][2] host */);
+int32_t sfgpu_get_scalar_state(sfgpu_ctx* ctx, uint32_t variable, int32_t* out_values /* [R][n_rows] host */);
+int32_t sfgpu_get_list_state(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_offsets /* [R][n_owners+1] */,
+                             uint32_t* out_elems /* [R][n_elements_capacity] */);
+int32_t sfgpu_list_capacity(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_capacity);
+
+/* ---- replicas across GPUs -------------------------------------------------------------- */
+/* Order-preserving packed key of each replica's committed score for a MAX all-reduce:
+ * key = ((hard + 2^23) << 40) | (soft + 2^39), valid for hard in [-2^23, 2^23), soft in [-2^39, 2^39)
+ * (out-of-range levels saturate). out_keys is a DEVICE pointer to R int64 (e.g. a torch tensor the
+ * caller then passes to torch.distributed.all_reduce(MAX) / ncclAllReduce). */
+int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys);
+
+/* ---- timing ----------------------------------------------------------------------------- */
+/* device time of the most recent scoring kernel launch of this context (CUDA events recorded on
+ * the launching stream around the kernel), in nanoseconds; synchronizes the stream. */
+int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns);
+/* number of kernels this context has launched since creation */
+int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFGPU_H */

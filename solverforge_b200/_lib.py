@@ -1,0 +1,117 @@
+"""ctypes binding of libsfgpu.so (the C ABI in include/sfgpu.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C solverforge_b200/csrc``).
+There is no CPU fallback: a missing library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfgpu.so")
+
+OK = 0
+E_INVALID, E_UNSUPPORTED, E_CUDA, E_NCCL, E_OOM, E_STATE = -1, -2, -3, -4, -5, -6
+DEVICE_IO = 1
+
+W_CONST, W_LINEAR, W_SQUARE, W_EXCESS = 0, 1, 2, 3
+PENALTY, REWARD = 0, 1
+K_UNI, K_PAIR_CSR_EQUAL, K_PAIR_KEY_EQUAL, K_EXISTS_FLAT, K_GROUP = 1, 2, 3, 4, 5
+K_LIST_PATH_COST, K_LIST_SUM, K_LOAD_BALANCE = 6, 7, 8
+NO_COLUMN = 0xFFFFFFFF
+LIST_VAR = 0x80000000
+MAX_EDITS = 8
+
+
+class Weight(C.Structure):
+    _fields_ = [("fn", C.c_int32), ("level", C.c_int32), ("a", C.c_int64), ("b", C.c_int64)]
+
+
+class ConstraintDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("impact", C.c_int32),
+        ("weight", Weight),
+        ("collection", C.c_uint32),
+        ("variable", C.c_uint32),
+        ("aux0", C.c_uint32),
+        ("aux1", C.c_uint32),
+        ("p0", C.c_int64),
+        ("p1", C.c_int64),
+        ("name", C.c_char_p),
+    ]
+
+
+class ForageParams(C.Structure):
+    _fields_ = [("acceptor", C.c_int32), ("tie_mode", C.c_int32), ("accepted_limit", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+# every symbol include/sfgpu.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "sfgpu_ctx_create": (C.c_int32, [C.c_int32, C.c_uint64, _P, C.POINTER(_P)]),
+    "sfgpu_ctx_destroy": (C.c_int32, [_P]),
+    "sfgpu_last_error": (C.c_char_p, [_P]),
+    "sfgpu_abi_version": (C.c_int32, []),
+    "sfgpu_synchronize": (C.c_int32, [_P]),
+    "sfgpu_model_begin": (C.c_int32, [_P, C.c_uint32]),
+    "sfgpu_add_collection": (C.c_int32, [_P, C.c_char_p, C.c_uint32, C.c_int32, C.POINTER(C.c_uint32)]),
+    "sfgpu_add_column_i64": (C.c_int32, [_P, C.c_uint32, C.c_char_p, _P, C.POINTER(C.c_uint32)]),
+    "sfgpu_add_scalar_variable": (C.c_int32, [_P, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int32,
+                                              C.POINTER(C.c_uint32)]),
+    "sfgpu_add_list_variable": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32)]),
+    "sfgpu_add_csr": (C.c_int32, [_P, C.c_char_p, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
+    "sfgpu_add_matrix_i64": (C.c_int32, [_P, C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_int32,
+                                         C.POINTER(C.c_uint32)]),
+    "sfgpu_add_constraint": (C.c_int32, [_P, C.POINTER(ConstraintDesc), C.POINTER(C.c_uint32)]),
+    "sfgpu_set_scalar_state": (C.c_int32, [_P, C.c_uint32, _P, C.c_int32]),
+    "sfgpu_set_list_state": (C.c_int32, [_P, C.c_uint32, _P, _P, C.c_int32]),
+    "sfgpu_model_commit": (C.c_int32, [_P, _P]),
+    "sfgpu_score_change": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
+    "sfgpu_score_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
+    "sfgpu_score_compound": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P, _P]),
+    "sfgpu_score_list_change": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
+    "sfgpu_score_list_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
+    "sfgpu_argbest": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sfgpu_apply_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_apply_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_apply_list_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_apply_list_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_apply_winners": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
+    "sfgpu_committed_scores": (C.c_int32, [_P, _P]),
+    "sfgpu_evaluate_all": (C.c_int32, [_P, _P]),
+    "sfgpu_get_scalar_state": (C.c_int32, [_P, C.c_uint32, _P]),
+    "sfgpu_get_list_state": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_list_capacity": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "sfgpu_pack_best_keys": (C.c_int32, [_P, _P]),
+    "sfgpu_last_kernel_ns": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "sfgpu_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+}
+
+_lib = None
+
+
+class SfgpuError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libsfgpu error {code}: {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Loads libsfgpu.so and binds every declared symbol; raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

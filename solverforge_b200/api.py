@@ -1,0 +1,541 @@
+"""Host-side mirror of the reference's scoring interface above the C ABI.
+
+The reference plugs its scorer in as ``ScoreDirector::with_descriptor(solution, constraints, ..)``
+(solverforge-solver/src/run.rs:552-557) and authors constraints with the fluent
+``ConstraintFactory::new().for_each(..)...penalize(..).named(..)`` builder
+(solverforge-scoring/src/stream/factory.rs:43-73). This module keeps those names and shapes;
+closures become column expressions that lower to ``sfgpu_constraint_desc`` rows.
+
+All compute happens in libsfgpu (CUDA); nothing here scores anything on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass(frozen=True, order=True)
+class HardSoftScore:
+    """solverforge-core/src/score/hard_soft.rs:35-153 — ordering is hard, then soft."""
+    hard: int = 0
+    soft: int = 0
+
+    @staticmethod
+    def of(hard: int, soft: int) -> "HardSoftScore":
+        return HardSoftScore(hard, soft)
+
+    @staticmethod
+    def of_hard(h: int) -> "HardSoftScore":
+        return HardSoftScore(h, 0)
+
+    @staticmethod
+    def of_soft(s: int) -> "HardSoftScore":
+        return HardSoftScore(0, s)
+
+    def is_feasible(self) -> bool:
+        return self.hard >= 0
+
+    def __add__(self, o):
+        return HardSoftScore(self.hard + o.hard, self.soft + o.soft)
+
+    def __sub__(self, o):
+        return HardSoftScore(self.hard - o.hard, self.soft - o.soft)
+
+    def __neg__(self):
+        return HardSoftScore(-self.hard, -self.soft)
+
+    def __str__(self):
+        return f"{self.hard}hard/{self.soft}soft"
+
+
+HardSoftScore.ZERO = HardSoftScore(0, 0)
+HardSoftScore.ONE_HARD = HardSoftScore(1, 0)
+HardSoftScore.ONE_SOFT = HardSoftScore(0, 1)
+
+
+class HardSoftDecimalScore(HardSoftScore):
+    """Same layout, levels pre-scaled by 100000 (hard_soft_decimal.rs:14,45-48)."""
+    SCALE = 100000
+
+    @staticmethod
+    def of(hard: int, soft: int) -> "HardSoftDecimalScore":
+        return HardSoftDecimalScore(hard * 100000, soft * 100000)
+
+    @staticmethod
+    def of_scaled(hard: int, soft: int) -> "HardSoftDecimalScore":
+        return HardSoftDecimalScore(hard, soft)
+
+
+@dataclass(frozen=True)
+class WeightFn:
+    """weight(x) on one score level: the device form of a ``penalize(|..| Score)`` closure."""
+    fn: int
+    level: int
+    a: int
+    b: int = 0
+
+
+def _const_weight(score: HardSoftScore) -> WeightFn:
+    if score.hard != 0 and score.soft != 0:
+        raise L.SfgpuError(L.E_UNSUPPORTED, "a constant weight must sit on one level")
+    return WeightFn(L.W_CONST, 0 if score.hard != 0 else 1, score.hard if score.hard != 0 else score.soft)
+
+
+def hard(fn: int = L.W_LINEAR, a: int = 1, b: int = 0) -> WeightFn:
+    return WeightFn(fn, 0, a, b)
+
+
+def soft(fn: int = L.W_LINEAR, a: int = 1, b: int = 0) -> WeightFn:
+    return WeightFn(fn, 1, a, b)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GpuScoreDirector:
+    """Owns one ``sfgpu_ctx``: R replicas of the planning state + the constraint program.
+
+    Reference counterpart: ``ScoreDirector<S, C>`` (director/score_director/incremental.rs:64-224)
+    and, for the batch seam the reference lacks, ``evaluate_candidate`` (evaluation.rs:20-115)
+    applied to a whole neighbourhood at once.
+    """
+
+    def __init__(self, n_replicas: int = 1, device: int = 0, stream: Optional[int] = None):
+        self.lib = L.load()
+        self.R = int(n_replicas)
+        h = C.c_void_p()
+        rc = self.lib.sfgpu_ctx_create(device, 0, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != L.OK:
+            raise L.SfgpuError(rc, self.lib.sfgpu_last_error(None).decode())
+        self.h = h
+        self._check(self.lib.sfgpu_model_begin(self.h, self.R))
+        self.coll_rows: dict[int, int] = {}
+        self.scalar_var: Optional[int] = None
+        self.list_var: Optional[int] = None
+        self.n_owners = 0
+        self.n_entities = 0
+        self._keep = []
+
+    # ---- plumbing -------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != L.OK:
+            raise L.SfgpuError(rc, self.lib.sfgpu_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- model ----------------------------------------------------------------------
+    def add_collection(self, name: str, n_rows: int, descriptor_index: int = -1) -> int:
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_collection(self.h, name.encode(), n_rows, descriptor_index, C.byref(out)))
+        self.coll_rows[out.value] = n_rows
+        return out.value
+
+    def add_column(self, collection: int, name: str, values) -> int:
+        v = np.ascontiguousarray(values, dtype=np.int64)
+        if v.shape != (self.coll_rows[collection],):
+            raise L.SfgpuError(L.E_INVALID, "column length != collection rows")
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_column_i64(self.h, collection, name.encode(), _ptr(v), C.byref(out)))
+        return out.value
+
+    def add_scalar_variable(self, collection: int, name: str, n_values: int, allows_unassigned: bool = True) -> int:
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_scalar_variable(self.h, collection, name.encode(), n_values,
+                                                       1 if allows_unassigned else 0, C.byref(out)))
+        self.scalar_var = out.value
+        self.n_entities = self.coll_rows[collection]
+        return out.value
+
+    def add_list_variable(self, owner_collection: int, element_collection: int, name: str) -> int:
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_list_variable(self.h, owner_collection, element_collection, name.encode(),
+                                                     C.byref(out)))
+        self.list_var = out.value
+        self.n_owners = self.coll_rows[owner_collection]
+        return out.value
+
+    def add_csr(self, name: str, row_ptr, col_idx) -> int:
+        rp = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_csr(self.h, name.encode(), len(rp) - 1, _ptr(rp), _ptr(ci), C.byref(out)))
+        return out.value
+
+    def add_matrix(self, name: str, values, cost_semantics: bool = False) -> int:
+        m = np.ascontiguousarray(values, dtype=np.int64)
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_matrix_i64(self.h, name.encode(), m.shape[0], m.shape[1], _ptr(m),
+                                                  1 if cost_semantics else 0, C.byref(out)))
+        return out.value
+
+    def add_constraint(self, kind: int, impact: int, weight: WeightFn, collection: int = 0, variable: int = 0,
+                       aux0: int = L.NO_COLUMN, aux1: int = 0, p0: int = 0, p1: int = 0, name: str = "") -> int:
+        d = L.ConstraintDesc(kind, impact, L.Weight(weight.fn, weight.level, weight.a, weight.b), collection,
+                             variable, aux0, aux1, p0, p1, name.encode())
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_constraint(self.h, C.byref(d), C.byref(out)))
+        return out.value
+
+    def set_scalar_state(self, values):
+        v = np.ascontiguousarray(values, dtype=np.int32)
+        per = 1 if v.ndim == 2 else 0
+        self._check(self.lib.sfgpu_set_scalar_state(self.h, self.scalar_var, _ptr(v), per))
+
+    def set_list_state(self, offsets, elems):
+        """offsets: [n_owners+1] (broadcast) or [R][n_owners+1]; elems: concatenated copies."""
+        o = np.ascontiguousarray(offsets, dtype=np.uint32)
+        e = np.ascontiguousarray(elems, dtype=np.uint32)
+        per = 1 if o.ndim == 2 else 0
+        self._check(self.lib.sfgpu_set_list_state(self.h, self.list_var, _ptr(o), _ptr(e), per))
+
+    def commit(self) -> np.ndarray:
+        """Freezes the model and runs initialize_all; returns committed scores [R, 2]."""
+        out = np.zeros((self.R, 2), dtype=np.int64)
+        self._check(self.lib.sfgpu_model_commit(self.h, _ptr(out)))
+        return out
+
+    # ---- Director surface --------------------------------------------------------------
+    def calculate_score(self) -> np.ndarray:
+        """Committed (cached) score of every replica — Director::calculate_score."""
+        out = np.zeros((self.R, 2), dtype=np.int64)
+        self._check(self.lib.sfgpu_committed_scores(self.h, _ptr(out)))
+        return out
+
+    def fresh_score(self) -> np.ndarray:
+        """Stateless full recompute — Director::fresh_score / ConstraintSet::evaluate_all."""
+        out = np.zeros((self.R, 2), dtype=np.int64)
+        self._check(self.lib.sfgpu_evaluate_all(self.h, _ptr(out)))
+        return out
+
+    # ---- batched candidate scoring (host buffers) ---------------------------------------
+    def _offsets(self, cand_offsets, n: int) -> np.ndarray:
+        if cand_offsets is None:
+            if self.R != 1:
+                raise L.SfgpuError(L.E_INVALID, "cand_offsets is required when R > 1")
+            return np.array([0, n], dtype=np.uint64)
+        o = np.ascontiguousarray(cand_offsets, dtype=np.uint64)
+        if o.shape != (self.R + 1,):
+            raise L.SfgpuError(L.E_INVALID, "cand_offsets must have R+1 entries")
+        return o
+
+    def _score(self, fn, rows: np.ndarray, words: int, cand_offsets):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1, words)
+        n = rows.shape[0]
+        offs = self._offsets(cand_offsets, n)
+        scores = np.zeros((n, 2), dtype=np.int64)
+        doable = np.zeros(n, dtype=np.uint8)
+        self._check(fn(self.h, 0, n, _ptr(offs), _ptr(rows), _ptr(scores), _ptr(doable)))
+        return scores, doable
+
+    def score_change(self, rows, cand_offsets=None):
+        """rows[n][2] = (entity, to_value) with -1 (0xFFFFFFFF) for None."""
+        return self._score(self.lib.sfgpu_score_change, np.asarray(rows).astype(np.int64).astype(np.uint32), 2,
+                           cand_offsets)
+
+    def score_swap(self, rows, cand_offsets=None):
+        return self._score(self.lib.sfgpu_score_swap, rows, 2, cand_offsets)
+
+    def score_list_change(self, rows, cand_offsets=None):
+        return self._score(self.lib.sfgpu_score_list_change, rows, 4, cand_offsets)
+
+    def score_list_swap(self, rows, cand_offsets=None):
+        return self._score(self.lib.sfgpu_score_list_swap, rows, 4, cand_offsets)
+
+    def score_compound(self, edit_offsets, edit_rows, cand_offsets=None):
+        eo = np.ascontiguousarray(edit_offsets, dtype=np.uint64)
+        rows = np.ascontiguousarray(np.asarray(edit_rows).astype(np.int64).astype(np.uint32)).reshape(-1, 2)
+        n = len(eo) - 1
+        offs = self._offsets(cand_offsets, n)
+        scores = np.zeros((n, 2), dtype=np.int64)
+        doable = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.sfgpu_score_compound(self.h, 0, n, _ptr(offs), _ptr(eo), _ptr(rows), _ptr(scores),
+                                                  _ptr(doable)))
+        return scores, doable
+
+    # ---- device-pointer variants (torch tensors / raw pointers, asynchronous) ------------
+    def score_device(self, kind: str, n: int, offsets_ptr: int, rows_ptr: int, scores_ptr: int, doable_ptr: int):
+        fn = getattr(self.lib, f"sfgpu_score_{kind}")
+        self._check(fn(self.h, L.DEVICE_IO, n, C.c_void_p(offsets_ptr), C.c_void_p(rows_ptr), C.c_void_p(scores_ptr),
+                       C.c_void_p(doable_ptr)))
+
+    def argbest_device(self, params: "ForageParams", offsets_ptr, scores_ptr, doable_ptr, seeds_ptr, ref_ptr,
+                       index_ptr, best_ptr, evaluated_ptr):
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        v = lambda p: C.c_void_p(p) if p else None
+        self._check(self.lib.sfgpu_argbest(self.h, L.DEVICE_IO, C.byref(fp), v(offsets_ptr), v(scores_ptr),
+                                           v(doable_ptr), v(seeds_ptr), v(ref_ptr), v(index_ptr), v(best_ptr),
+                                           v(evaluated_ptr)))
+
+    def apply_winners_device(self, move_kind: int, offsets_ptr: int, rows_ptr: int, index_ptr: int):
+        self._check(self.lib.sfgpu_apply_winners(self.h, move_kind, C.c_void_p(offsets_ptr), C.c_void_p(rows_ptr),
+                                                 C.c_void_p(index_ptr)))
+
+    def pack_best_keys_device(self, keys_ptr: int):
+        self._check(self.lib.sfgpu_pack_best_keys(self.h, C.c_void_p(keys_ptr)))
+
+    # ---- forager / acceptor replay on device ------------------------------------------
+    def argbest(self, scores, doable, cand_offsets=None, params: "ForageParams" = None, step_seeds=None,
+                ref_scores=None):
+        params = params or ForageParams()
+        scores = np.ascontiguousarray(scores, dtype=np.int64).reshape(-1, 2)
+        doable = np.ascontiguousarray(doable, dtype=np.uint8)
+        offs = self._offsets(cand_offsets, scores.shape[0])
+        seeds = None if step_seeds is None else np.ascontiguousarray(step_seeds, dtype=np.uint64)
+        ref = None if ref_scores is None else np.ascontiguousarray(ref_scores, dtype=np.int64).reshape(self.R, 4)
+        idx = np.zeros(self.R, dtype=np.uint32)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint32)
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        self._check(self.lib.sfgpu_argbest(self.h, 0, C.byref(fp), _ptr(offs), _ptr(scores), _ptr(doable),
+                                           _ptr(seeds), _ptr(ref), _ptr(idx), _ptr(best), _ptr(ev)))
+        return idx, best, ev
+
+    # ---- committing moves ---------------------------------------------------------------
+    def _apply(self, fn, rows, words, mask):
+        rows = np.ascontiguousarray(np.asarray(rows).astype(np.int64).astype(np.uint32)).reshape(self.R, words)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._check(fn(self.h, 0, _ptr(rows), _ptr(m)))
+
+    def apply_change(self, rows, mask=None):
+        self._apply(self.lib.sfgpu_apply_change, rows, 2, mask)
+
+    def apply_swap(self, rows, mask=None):
+        self._apply(self.lib.sfgpu_apply_swap, rows, 2, mask)
+
+    def apply_list_change(self, rows, mask=None):
+        self._apply(self.lib.sfgpu_apply_list_change, rows, 4, mask)
+
+    def apply_list_swap(self, rows, mask=None):
+        self._apply(self.lib.sfgpu_apply_list_swap, rows, 4, mask)
+
+    # ---- state read-back ------------------------------------------------------------------
+    def scalar_state(self) -> np.ndarray:
+        out = np.zeros((self.R, self.n_entities), dtype=np.int32)
+        self._check(self.lib.sfgpu_get_scalar_state(self.h, self.scalar_var, _ptr(out)))
+        return out
+
+    def list_state(self):
+        cap = C.c_uint32()
+        self._check(self.lib.sfgpu_list_capacity(self.h, self.list_var, C.byref(cap)))
+        offs = np.zeros((self.R, self.n_owners + 1), dtype=np.uint32)
+        elems = np.zeros((self.R, cap.value), dtype=np.uint32)
+        self._check(self.lib.sfgpu_get_list_state(self.h, self.list_var, _ptr(offs), _ptr(elems)))
+        return offs, elems
+
+    def last_kernel_ns(self) -> int:
+        out = C.c_uint64()
+        self._check(self.lib.sfgpu_last_kernel_ns(self.h, C.byref(out)))
+        return out.value
+
+    def launch_count(self) -> int:
+        out = C.c_uint64()
+        self._check(self.lib.sfgpu_launch_count(self.h, C.byref(out)))
+        return out.value
+
+    def synchronize(self):
+        self._check(self.lib.sfgpu_synchronize(self.h))
+
+
+@dataclass
+class ForageParams:
+    """acceptor: 0 accept-all, 1 HillClimbing, 2 LateAcceptance; accepted_limit 0 = BestScore forager,
+    N = AcceptedCount(N); tie_mode 1 = reservoir ties (forager.rs:99-155)."""
+    acceptor: int = 0
+    tie_mode: int = 1
+    accepted_limit: int = 0
+
+
+# ---------------------------------------------------------------------------------------------
+# Fluent ConstraintFactory (stream/factory.rs:43-73, uni_stream/, cross_bi_stream/, grouped.rs)
+# ---------------------------------------------------------------------------------------------
+class ConstraintFactory:
+    def __init__(self, director: GpuScoreDirector):
+        self.d = director
+
+    def for_each(self, collection: int) -> "UniStream":
+        return UniStream(self.d, collection)
+
+
+@dataclass
+class AdjacentEqual:
+    """|l, r| l.id < r.id && l.neighbors.contains(r.id) && l.var.is_some() && l.var == r.var"""
+    csr: int
+
+
+@dataclass
+class EqualKey:
+    """equal(key) joiner with key(e) = column[e]*col_mul + var[e]*var_mul, plus l.id < r.id && var.is_some()"""
+    column: int = L.NO_COLUMN
+    col_mul: int = 0
+    var_mul: int = 1
+
+
+@dataclass
+class EqualVarToRow:
+    """equal_bi(|e| e.var, |v| Some(v.row)) — joins an entity with the value row it is assigned to."""
+    pass
+
+
+@dataclass
+class EqualId:
+    """equal_bi(|a| a.id, |element| *element); id column or the row index."""
+    column: int = L.NO_COLUMN
+
+
+@dataclass
+class PathCost:
+    matrix: int
+    depot: int
+
+
+@dataclass
+class ListSum:
+    column: int
+
+
+@dataclass
+class Count:
+    pass
+
+
+@dataclass
+class Sum:
+    column: int
+
+
+@dataclass
+class LoadBalance:
+    metric_column: int = L.NO_COLUMN
+
+
+class _Terminal:
+    def __init__(self, d: GpuScoreDirector, **kw):
+        self.d, self.kw = d, kw
+
+    def named(self, name: str) -> int:
+        return self.d.add_constraint(name=name, **self.kw)
+
+
+class UniStream:
+    def __init__(self, d: GpuScoreDirector, collection: int, filt: int = 2):
+        self.d, self.collection, self.filt = d, collection, filt
+
+    def unassigned(self) -> "UniStream":
+        return UniStream(self.d, self.collection, 0)
+
+    def assigned(self) -> "UniStream":
+        return UniStream(self.d, self.collection, 1)
+
+    def flattened(self) -> "UniStream":
+        s = UniStream(self.d, self.collection, self.filt)
+        s._flattened = True
+        return s
+
+    def _impact(self, impact: int, weight, x=None, by_value: bool = False) -> _Terminal:
+        if isinstance(x, PathCost):
+            return _Terminal(self.d, kind=L.K_LIST_PATH_COST, impact=impact, weight=weight, collection=self.collection,
+                             variable=L.LIST_VAR, aux0=x.matrix, p0=x.depot)
+        if isinstance(x, ListSum):
+            return _Terminal(self.d, kind=L.K_LIST_SUM, impact=impact, weight=weight, collection=self.collection,
+                             variable=L.LIST_VAR, aux0=x.column)
+        w = _const_weight(weight) if isinstance(weight, HardSoftScore) else weight
+        return _Terminal(self.d, kind=L.K_UNI, impact=impact, weight=w, collection=self.collection,
+                         aux0=L.NO_COLUMN if x is None else x, p0=self.filt, p1=1 if by_value else 0)
+
+    def penalize(self, weight, x=None, by_value: bool = False) -> _Terminal:
+        return self._impact(L.PENALTY, weight, x, by_value)
+
+    def reward(self, weight, x=None, by_value: bool = False) -> _Terminal:
+        return self._impact(L.REWARD, weight, x, by_value)
+
+    def join(self, other, joiner) -> "BiStream":
+        return BiStream(self.d, self.collection, other, joiner)
+
+    def if_exists(self, flattened_owners: "UniStream", joiner: EqualId) -> "ExistsStream":
+        return ExistsStream(self.d, self.collection, joiner, 0)
+
+    def if_not_exists(self, flattened_owners: "UniStream", joiner: EqualId) -> "ExistsStream":
+        return ExistsStream(self.d, self.collection, joiner, 1)
+
+    def group_by(self, collector) -> "GroupedStream":
+        # for_each(E).group_by(|e| e.var, collector) over assigned entities
+        return GroupedStream(self.d, self.collection, collector)
+
+
+class ExistsStream:
+    def __init__(self, d, collection, joiner: EqualId, mode: int):
+        self.d, self.collection, self.joiner, self.mode = d, collection, joiner, mode
+
+    def penalize(self, weight: HardSoftScore) -> _Terminal:
+        return _Terminal(self.d, kind=L.K_EXISTS_FLAT, impact=L.PENALTY, weight=_const_weight(weight),
+                         collection=self.collection, variable=L.LIST_VAR, aux0=self.joiner.column, p0=self.mode)
+
+    def reward(self, weight: HardSoftScore) -> _Terminal:
+        return _Terminal(self.d, kind=L.K_EXISTS_FLAT, impact=L.REWARD, weight=_const_weight(weight),
+                         collection=self.collection, variable=L.LIST_VAR, aux0=self.joiner.column, p0=self.mode)
+
+
+class BiStream:
+    def __init__(self, d, collection, other, joiner):
+        self.d, self.collection, self.other, self.joiner = d, collection, other, joiner
+
+    def _impact(self, impact, weight: HardSoftScore) -> _Terminal:
+        w = _const_weight(weight)
+        j = self.joiner
+        if isinstance(j, AdjacentEqual):
+            return _Terminal(self.d, kind=L.K_PAIR_CSR_EQUAL, impact=impact, weight=w, collection=self.collection,
+                             aux0=j.csr)
+        if isinstance(j, EqualKey):
+            return _Terminal(self.d, kind=L.K_PAIR_KEY_EQUAL, impact=impact, weight=w, collection=self.collection,
+                             aux0=j.column, p0=j.col_mul, p1=j.var_mul)
+        raise L.SfgpuError(L.E_UNSUPPORTED, f"joiner {type(j).__name__} is not expressible on device")
+
+    def penalize(self, weight) -> _Terminal:
+        return self._impact(L.PENALTY, weight)
+
+    def reward(self, weight) -> _Terminal:
+        return self._impact(L.REWARD, weight)
+
+    def group_by(self, collector) -> "GroupedStream":
+        if not isinstance(self.joiner, EqualVarToRow):
+            raise L.SfgpuError(L.E_UNSUPPORTED, "group_by over a join needs the var -> value-row joiner")
+        return GroupedStream(self.d, self.collection, collector)
+
+
+class GroupedStream:
+    def __init__(self, d, collection, collector, complemented: bool = False, default: int = 0):
+        self.d, self.collection, self.collector = d, collection, collector
+        self.complemented, self.default = complemented, default
+
+    def complement(self, targets: int, default: int = 0) -> "GroupedStream":
+        return GroupedStream(self.d, self.collection, self.collector, True, default)
+
+    def _impact(self, impact, weight: WeightFn) -> _Terminal:
+        c = self.collector
+        if isinstance(c, LoadBalance):
+            return _Terminal(self.d, kind=L.K_LOAD_BALANCE, impact=impact, weight=weight, collection=self.collection,
+                             aux0=c.metric_column)
+        col = L.NO_COLUMN if isinstance(c, Count) else c.column
+        return _Terminal(self.d, kind=L.K_GROUP, impact=impact, weight=weight, collection=self.collection, aux0=col,
+                         p0=1 if self.complemented else 0, p1=self.default)
+
+    def penalize(self, weight: WeightFn) -> _Terminal:
+        return self._impact(L.PENALTY, weight)
+
+    def reward(self, weight: WeightFn) -> _Terminal:
+        return self._impact(L.REWARD, weight)

@@ -1,0 +1,993 @@
+// libsfgpu — host side of the C ABI declared in include/sfgpu.h: context, model lowering,
+// HBM layout, kernel launches. No CPU scoring path exists in this file: every compute entry
+// point launches a CUDA kernel or fails with SFGPU_E_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "sfgpu_kernels.cuh"
+
+namespace {
+
+struct Collection {
+  std::string name;
+  uint32_t n_rows;
+  int32_t descriptor;
+};
+struct Column {
+  uint32_t coll;
+  std::vector<int64_t> host;
+  int64_t* dev = nullptr;
+};
+struct Csr {
+  uint32_t n_rows;
+  std::vector<uint32_t> row_ptr, col;
+};
+struct Matrix {
+  uint32_t rows, cols;
+  std::vector<int64_t> host;
+  void* dev = nullptr;
+  bool i32 = false;
+};
+struct ScalarVar {
+  uint32_t coll, n_values;
+  int allows_unassigned;
+  std::vector<int32_t> init;  // [n] or [R][n]
+  bool per_replica = false;
+};
+struct ListVar {
+  uint32_t owner_coll, elem_coll;
+  std::vector<uint32_t> offsets, elems;
+  bool per_replica = false;
+};
+struct ConsHost {
+  sfgpu_constraint_desc d;
+  std::string name;
+};
+
+}  // namespace
+
+struct sfgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  // model under construction
+  bool building = false, committed = false;
+  uint32_t R = 0;
+  std::vector<Collection> colls;
+  std::vector<Column> cols;
+  std::vector<Csr> csrs;
+  std::vector<Matrix> mats;
+  std::vector<ScalarVar> svars;
+  std::vector<ListVar> lvars;
+  std::vector<ConsHost> cons;
+  // device
+  DevModel dm{};
+  char* scratch_state = nullptr;
+  std::vector<void*> dev_allocs;
+  int max_smem_optin = 0;
+  int sm_count = 0;
+  bool staged = false;
+  bool has_load_balance = false;
+  // staging for host-pointer calls
+  void* pin = nullptr;
+  size_t pin_bytes = 0;
+  void* dscr = nullptr;
+  size_t dscr_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_noctx_err;
+
+int fail(sfgpu_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_noctx_err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? SFGPU_E_OOM : SFGPU_E_CUDA,               \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+  } while (0)
+
+template <class T>
+int dev_upload(sfgpu_ctx* ctx, const T* host, size_t n, T** out) {
+  void* p = nullptr;
+  CU(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+  ctx->dev_allocs.push_back(p);
+  if (n) CU(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = (T*)p;
+  return SFGPU_OK;
+}
+
+uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+int ensure_staging(sfgpu_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
+  if (pin_bytes > ctx->pin_bytes) {
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr;
+    ctx->pin_bytes = 0;
+    CU(cudaMallocHost(&ctx->pin, pin_bytes));
+    ctx->pin_bytes = pin_bytes;
+  }
+  if (dev_bytes > ctx->dscr_bytes) {
+    if (ctx->dscr) cudaFree(ctx->dscr);
+    ctx->dscr = nullptr;
+    ctx->dscr_bytes = 0;
+    CU(cudaMalloc(&ctx->dscr, dev_bytes));
+    ctx->dscr_bytes = dev_bytes;
+  }
+  return SFGPU_OK;
+}
+
+int check_committed(sfgpu_ctx* ctx) {
+  if (!ctx) return SFGPU_E_INVALID;
+  if (!ctx->committed) return fail(ctx, SFGPU_E_STATE, "model not committed");
+  return SFGPU_OK;
+}
+
+// chunks per replica so that the grid covers the machine a few times over
+uint32_t chunks_for(const sfgpu_ctx* ctx, uint64_t n_total, uint32_t R, uint32_t threads) {
+  uint64_t per_replica = (n_total + R - 1) / std::max<uint32_t>(R, 1);
+  uint64_t max_chunks = std::max<uint64_t>(1, (per_replica + threads - 1) / threads);
+  uint64_t target_ctas = (uint64_t)ctx->sm_count * 8;
+  uint64_t want = std::max<uint64_t>(1, (target_ctas + R - 1) / R);
+  // amortise the block staging: at least 4 candidates per thread when there is enough work
+  uint64_t amort = std::max<uint64_t>(1, per_replica / (threads * 4ull));
+  uint64_t chunks = std::min(max_chunks, std::max(want, std::min<uint64_t>(amort, want * 4)));
+  return (uint32_t)std::min<uint64_t>(chunks, 65535);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sfgpu_abi_version(void) { return SFGPU_ABI_VERSION; }
+
+const char* sfgpu_last_error(const sfgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
+
+int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgpu_ctx** out) {
+  (void)flags;
+  if (!out) return SFGPU_E_INVALID;
+  *out = nullptr;
+  sfgpu_ctx* ctx = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, SFGPU_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                           " (libsfgpu has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, SFGPU_E_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  ctx = new sfgpu_ctx();
+  ctx->device = device;
+  if (cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return fail(nullptr, SFGPU_E_CUDA, cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  *out = ctx;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
+  if (!ctx) return SFGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->dev_allocs) cudaFree(p);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  if (ctx->dscr) cudaFree(ctx->dscr);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_synchronize(sfgpu_ctx* ctx) {
+  if (!ctx) return SFGPU_E_INVALID;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_model_begin(sfgpu_ctx* ctx, uint32_t n_replicas) {
+  if (!ctx) return SFGPU_E_INVALID;
+  if (ctx->committed || ctx->building) return fail(ctx, SFGPU_E_STATE, "model already begun");
+  if (n_replicas == 0 || n_replicas > 65535) return fail(ctx, SFGPU_E_INVALID, "n_replicas must be in [1, 65535]");
+  ctx->building = true;
+  ctx->R = n_replicas;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_collection(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, int32_t descriptor_index,
+                             uint32_t* out_collection) {
+  if (!ctx || !out_collection) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  ctx->colls.push_back({name ? name : "", n_rows, descriptor_index});
+  *out_collection = (uint32_t)ctx->colls.size() - 1;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_column_i64(sfgpu_ctx* ctx, uint32_t collection, const char* name, const int64_t* values,
+                             uint32_t* out_column) {
+  (void)name;
+  if (!ctx || !values || !out_column) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  if (collection >= ctx->colls.size()) return fail(ctx, SFGPU_E_INVALID, "unknown collection");
+  Column c;
+  c.coll = collection;
+  c.host.assign(values, values + ctx->colls[collection].n_rows);
+  ctx->cols.push_back(std::move(c));
+  *out_column = (uint32_t)ctx->cols.size() - 1;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_scalar_variable(sfgpu_ctx* ctx, uint32_t collection, const char* name, uint32_t n_values,
+                                  int32_t allows_unassigned, uint32_t* out_variable) {
+  (void)name;
+  if (!ctx || !out_variable) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  if (collection >= ctx->colls.size()) return fail(ctx, SFGPU_E_INVALID, "unknown collection");
+  if (!ctx->svars.empty()) return fail(ctx, SFGPU_E_UNSUPPORTED, "one scalar planning variable per model");
+  if (n_values == 0 || n_values > 0x7FFFFFFFu) return fail(ctx, SFGPU_E_INVALID, "n_values out of range");
+  ctx->svars.push_back({collection, n_values, allows_unassigned, {}, false});
+  *out_variable = 0;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_list_variable(sfgpu_ctx* ctx, uint32_t owner_collection, uint32_t element_collection,
+                                const char* name, uint32_t* out_variable) {
+  (void)name;
+  if (!ctx || !out_variable) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  if (owner_collection >= ctx->colls.size() || element_collection >= ctx->colls.size())
+    return fail(ctx, SFGPU_E_INVALID, "unknown collection");
+  if (!ctx->lvars.empty()) return fail(ctx, SFGPU_E_UNSUPPORTED, "one list planning variable per model");
+  ctx->lvars.push_back({owner_collection, element_collection, {}, {}, false});
+  *out_variable = 0x80000000u;  // list variables live in their own id space
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_csr(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, const uint32_t* row_ptr,
+                      const uint32_t* col_idx, uint32_t* out_csr) {
+  (void)name;
+  if (!ctx || !row_ptr || !out_csr) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  Csr c;
+  c.n_rows = n_rows;
+  c.row_ptr.assign(row_ptr, row_ptr + n_rows + 1);
+  uint32_t nnz = row_ptr[n_rows];
+  if (nnz && !col_idx) return SFGPU_E_INVALID;
+  c.col.assign(col_idx, col_idx + nnz);
+  for (uint32_t v : c.col)
+    if (v >= n_rows) return fail(ctx, SFGPU_E_INVALID, "csr column index out of range");
+  ctx->csrs.push_back(std::move(c));
+  *out_csr = (uint32_t)ctx->csrs.size() - 1;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, uint32_t cols,
+                             const int64_t* values, int32_t cost_semantics, uint32_t* out_matrix) {
+  (void)name;
+  if (!ctx || !values || !out_matrix) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  Matrix m;
+  m.rows = rows;
+  m.cols = cols;
+  m.host.assign(values, values + (size_t)rows * cols);
+  if (cost_semantics == 1) {
+    // ProblemData::distance_cost (problem_data.rs:28-47)
+    const int64_t UNREACH = std::numeric_limits<int64_t>::max();
+    for (auto& v : m.host)
+      if (!(v >= 0 && v != UNREACH)) v = UNREACH / 4;
+  }
+  ctx->mats.push_back(std::move(m));
+  *out_matrix = (uint32_t)ctx->mats.size() - 1;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, uint32_t* out_constraint) {
+  if (!ctx || !desc) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
+  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_LOAD_BALANCE)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
+  if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_EXCESS || desc->weight.level < 0 ||
+      desc->weight.level > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad weight");
+  bool needs_const = desc->kind == SFGPU_K_PAIR_CSR_EQUAL || desc->kind == SFGPU_K_PAIR_KEY_EQUAL ||
+                     desc->kind == SFGPU_K_EXISTS_FLAT;
+  if (needs_const && desc->weight.fn != SFGPU_W_CONST)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "pair/exists constraints take a constant weight");
+  ConsHost c;
+  c.d = *desc;
+  c.name = desc->name ? desc->name : "";
+  c.d.name = nullptr;
+  ctx->cons.push_back(std::move(c));
+  if (out_constraint) *out_constraint = (uint32_t)ctx->cons.size() - 1;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_set_scalar_state(sfgpu_ctx* ctx, uint32_t variable, const int32_t* values, int32_t per_replica) {
+  if (!ctx || !values) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "state is uploaded before sfgpu_model_commit");
+  if (variable != 0 || ctx->svars.empty()) return fail(ctx, SFGPU_E_INVALID, "unknown scalar variable");
+  ScalarVar& v = ctx->svars[0];
+  size_t n = ctx->colls[v.coll].n_rows;
+  size_t total = per_replica ? n * ctx->R : n;
+  for (size_t i = 0; i < total; ++i)
+    if (values[i] >= (int32_t)v.n_values) return fail(ctx, SFGPU_E_INVALID, "scalar value out of range");
+  v.init.assign(values, values + total);
+  for (auto& x : v.init)
+    if (x < 0) x = SFGPU_NONE;
+  v.per_replica = per_replica != 0;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_set_list_state(sfgpu_ctx* ctx, uint32_t variable, const uint32_t* offsets, const uint32_t* elems,
+                             int32_t per_replica) {
+  if (!ctx || !offsets) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "state is uploaded before sfgpu_model_commit");
+  if (variable != 0x80000000u || ctx->lvars.empty()) return fail(ctx, SFGPU_E_INVALID, "unknown list variable");
+  ListVar& v = ctx->lvars[0];
+  uint32_t no = ctx->colls[v.owner_coll].n_rows, ne = ctx->colls[v.elem_coll].n_rows;
+  uint32_t copies = per_replica ? ctx->R : 1;
+  v.offsets.assign(offsets, offsets + (size_t)copies * (no + 1));
+  size_t total = 0;
+  for (uint32_t c = 0; c < copies; ++c) {
+    const uint32_t* o = offsets + (size_t)c * (no + 1);
+    if (o[0] != 0) return fail(ctx, SFGPU_E_INVALID, "list offsets must start at 0");
+    for (uint32_t i = 0; i < no; ++i)
+      if (o[i + 1] < o[i]) return fail(ctx, SFGPU_E_INVALID, "list offsets must be non-decreasing");
+    total += o[no];
+  }
+  if (total && !elems) return SFGPU_E_INVALID;
+  v.elems.assign(elems, elems + total);
+  for (uint32_t e : v.elems)
+    if (e >= ne) return fail(ctx, SFGPU_E_INVALID, "list element out of range");
+  v.per_replica = per_replica != 0;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
+  if (!ctx) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  CU(cudaSetDevice(ctx->device));
+  DevModel& dm = ctx->dm;
+  memset(&dm, 0, sizeof(dm));
+  dm.R = ctx->R;
+  // upload shared static data
+  for (auto& c : ctx->cols) {
+    int rc = dev_upload(ctx, c.host.data(), c.host.size(), &c.dev);
+    if (rc) return rc;
+  }
+  for (auto& m : ctx->mats) {
+    bool fits = true;
+    for (int64_t v : m.host)
+      if (v < 0 || v > 0x7FFFFFFF) {
+        fits = false;
+        break;
+      }
+    m.i32 = fits;
+    if (fits) {
+      std::vector<int32_t> narrow(m.host.begin(), m.host.end());
+      int32_t* p = nullptr;
+      int rc = dev_upload(ctx, narrow.data(), narrow.size(), &p);
+      if (rc) return rc;
+      m.dev = p;
+    } else {
+      int64_t* p = nullptr;
+      int rc = dev_upload(ctx, m.host.data(), m.host.size(), &p);
+      if (rc) return rc;
+      m.dev = p;
+    }
+  }
+  // block layout: [score][scalar var][list offsets][list elems][staged retained][unstaged retained]
+  uint32_t off = 0;
+  dm.off_score = off;
+  off += 16;
+  if (!ctx->svars.empty()) {
+    ScalarVar& v = ctx->svars[0];
+    dm.has_scalar = 1;
+    dm.n_entities = ctx->colls[v.coll].n_rows;
+    dm.n_values = v.n_values;
+    dm.allows_unassigned = v.allows_unassigned;
+    dm.off_var = off;
+    off = align_up(off + dm.n_entities * 4, 16);
+    if (v.init.empty()) v.init.assign(dm.n_entities, SFGPU_NONE);
+  }
+  if (!ctx->lvars.empty()) {
+    ListVar& v = ctx->lvars[0];
+    dm.has_list = 1;
+    dm.n_owners = ctx->colls[v.owner_coll].n_rows;
+    dm.n_elem_rows = ctx->colls[v.elem_coll].n_rows;
+    if (v.offsets.empty()) v.offsets.assign(dm.n_owners + 1, 0);
+    uint32_t copies = v.per_replica ? ctx->R : 1;
+    uint32_t cap = 0;
+    for (uint32_t c = 0; c < copies; ++c) cap = std::max(cap, v.offsets[(size_t)c * (dm.n_owners + 1) + dm.n_owners]);
+    dm.elem_cap = std::max(cap, 1u);  // relocations and swaps keep the element count
+    dm.off_offsets = off;
+    off = align_up(off + (dm.n_owners + 1) * 4, 16);
+    dm.off_elems = off;
+    off = align_up(off + dm.elem_cap * 4, 16);
+  }
+  // constraints: staged sections first
+  dm.n_cons = (uint32_t)ctx->cons.size();
+  std::vector<uint32_t> unstaged_bytes(dm.n_cons, 0);
+  for (uint32_t k = 0; k < dm.n_cons; ++k) {
+    const sfgpu_constraint_desc& d = ctx->cons[k].d;
+    ConsDev& c = dm.cons[k];
+    c.kind = d.kind;
+    c.sign = d.impact == SFGPU_REWARD ? 1 : -1;
+    c.w = WeightDev{d.weight.fn, d.weight.level, d.weight.a, d.weight.b};
+    auto column = [&](uint32_t id, uint32_t want_rows, const int64_t** out) -> int {
+      *out = nullptr;
+      if (id == 0xFFFFFFFFu) return SFGPU_OK;
+      if (id >= ctx->cols.size()) return fail(ctx, SFGPU_E_INVALID, "unknown column in constraint " + ctx->cons[k].name);
+      if (ctx->colls[ctx->cols[id].coll].n_rows != want_rows)
+        return fail(ctx, SFGPU_E_INVALID, "column row count mismatch in constraint " + ctx->cons[k].name);
+      *out = ctx->cols[id].dev;
+      return SFGPU_OK;
+    };
+    bool scalar_kind = d.kind == SFGPU_K_UNI || d.kind == SFGPU_K_PAIR_CSR_EQUAL || d.kind == SFGPU_K_PAIR_KEY_EQUAL ||
+                       d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE;
+    if (scalar_kind && !dm.has_scalar) return fail(ctx, SFGPU_E_INVALID, "constraint needs a scalar variable");
+    if (!scalar_kind && !dm.has_list) return fail(ctx, SFGPU_E_INVALID, "constraint needs a list variable");
+    switch (d.kind) {
+      case SFGPU_K_UNI: {
+        c.p0 = d.p0;
+        const int64_t* col = nullptr;
+        bool by_value = d.p1 == 1;
+        uint32_t want = dm.n_entities;
+        if (by_value && d.aux0 != 0xFFFFFFFFu && d.aux0 < ctx->cols.size())
+          want = ctx->colls[ctx->cols[d.aux0].coll].n_rows;
+        int rc = column(d.aux0, want, &col);
+        if (rc) return rc;
+        if (by_value && col && want < dm.n_values) return fail(ctx, SFGPU_E_INVALID, "value column too short");
+        c.g0 = col;
+        if (by_value) c.flags |= SFGPU_CF_COL_BY_VALUE;
+        break;
+      }
+      case SFGPU_K_PAIR_CSR_EQUAL: {
+        if (d.aux0 >= ctx->csrs.size()) return fail(ctx, SFGPU_E_INVALID, "unknown csr");
+        const Csr& g = ctx->csrs[d.aux0];
+        if (g.n_rows != dm.n_entities) return fail(ctx, SFGPU_E_INVALID, "csr row count != entity count");
+        // partner lists: b is a partner of e iff the ordered pair (min,max) passes
+        // `left.id < right.id && left.neighbors.contains(right.id)` (row index == id).
+        std::vector<std::vector<uint32_t>> partners(g.n_rows);
+        for (uint32_t a = 0; a < g.n_rows; ++a)
+          for (uint32_t j = g.row_ptr[a]; j < g.row_ptr[a + 1]; ++j) {
+            uint32_t b = g.col[j];
+            if (a < b) {
+              partners[a].push_back(b);
+              partners[b].push_back(a);
+            }
+          }
+        std::vector<uint32_t> rp(g.n_rows + 1, 0), ci;
+        for (uint32_t a = 0; a < g.n_rows; ++a) {
+          auto& p = partners[a];
+          std::sort(p.begin(), p.end());
+          p.erase(std::unique(p.begin(), p.end()), p.end());
+          rp[a + 1] = rp[a] + (uint32_t)p.size();
+          ci.insert(ci.end(), p.begin(), p.end());
+        }
+        uint32_t *drp = nullptr, *dci = nullptr;
+        int rc = dev_upload(ctx, rp.data(), rp.size(), &drp);
+        if (rc) return rc;
+        rc = dev_upload(ctx, ci.data(), ci.size(), &dci);
+        if (rc) return rc;
+        c.g0 = drp;
+        c.g1 = dci;
+        break;
+      }
+      case SFGPU_K_PAIR_KEY_EQUAL: {
+        const int64_t* col = nullptr;
+        int rc = column(d.aux0, dm.n_entities, &col);
+        if (rc) return rc;
+        c.g0 = col;
+        c.p0 = d.p0;
+        c.p1 = d.p1;
+        if (d.p1 == 0) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EQUAL needs p1 != 0 (the variable must enter the key)");
+        // key range over every (entity, value)
+        int64_t kmin = std::numeric_limits<int64_t>::max(), kmax = std::numeric_limits<int64_t>::min();
+        for (uint32_t e = 0; e < dm.n_entities; ++e) {
+          int64_t base = (col ? ctx->cols[d.aux0].host[e] : 0) * d.p0;
+          int64_t k0 = base, k1 = base + (int64_t)(dm.n_values - 1) * d.p1;
+          kmin = std::min(kmin, std::min(k0, k1));
+          kmax = std::max(kmax, std::max(k0, k1));
+        }
+        if (dm.n_entities == 0) kmin = kmax = 0;
+        if (kmax - kmin + 1 > (1 << 24)) return fail(ctx, SFGPU_E_UNSUPPORTED, "join key range too wide for a dense table");
+        c.p2 = kmin;
+        c.n0 = (uint32_t)(kmax - kmin + 1);
+        c.off0 = off;
+        off = align_up(off + c.n0 * 4, 16);
+        break;
+      }
+      case SFGPU_K_GROUP: {
+        const int64_t* col = nullptr;
+        int rc = column(d.aux0, dm.n_entities, &col);
+        if (rc) return rc;
+        c.g0 = col;
+        if (d.p0 == 1) c.flags |= SFGPU_CF_COMPLEMENT;
+        c.p1 = d.p1;
+        c.off0 = off;
+        off = align_up(off + dm.n_values * 4, 16);
+        c.off1 = off;
+        off = align_up(off + dm.n_values * 8, 16);
+        break;
+      }
+      case SFGPU_K_LOAD_BALANCE: {
+        const int64_t* col = nullptr;
+        int rc = column(d.aux0, dm.n_entities, &col);
+        if (rc) return rc;
+        c.g0 = col;
+        c.off0 = off;
+        off = align_up(off + dm.n_values * 8, 16);
+        c.off1 = off;
+        off = align_up(off + dm.n_values * 4, 16);
+        c.off2 = off;
+        off = align_up(off + 24, 16);
+        ctx->has_load_balance = true;
+        break;
+      }
+      case SFGPU_K_EXISTS_FLAT: {
+        if (d.collection >= ctx->colls.size()) return fail(ctx, SFGPU_E_INVALID, "unknown collection");
+        const int64_t* col = nullptr;
+        int rc = column(d.aux0, ctx->colls[d.collection].n_rows, &col);
+        if (rc) return rc;
+        c.g0 = col;
+        c.n0 = ctx->colls[d.collection].n_rows;
+        c.p0 = d.p0;
+        unstaged_bytes[k] = align_up(dm.n_elem_rows * 4, 16);
+        break;
+      }
+      case SFGPU_K_LIST_PATH_COST: {
+        if (d.aux0 >= ctx->mats.size()) return fail(ctx, SFGPU_E_INVALID, "unknown matrix");
+        const Matrix& mt = ctx->mats[d.aux0];
+        if (mt.rows < dm.n_elem_rows || mt.cols < dm.n_elem_rows)
+          return fail(ctx, SFGPU_E_INVALID, "matrix smaller than the element collection");
+        if (d.p0 < 0 || d.p0 >= (int64_t)mt.rows) return fail(ctx, SFGPU_E_INVALID, "depot out of range");
+        c.g0 = mt.dev;
+        c.n0 = mt.cols;
+        if (mt.i32) c.flags |= SFGPU_CF_MATRIX_I32;
+        c.p0 = d.p0;
+        c.off0 = off;
+        off = align_up(off + dm.n_owners * 8, 16);
+        break;
+      }
+      case SFGPU_K_LIST_SUM: {
+        const int64_t* col = nullptr;
+        int rc = column(d.aux0, dm.n_elem_rows, &col);
+        if (rc) return rc;
+        if (!col) return fail(ctx, SFGPU_E_INVALID, "LIST_SUM needs an element column");
+        c.g0 = col;
+        c.off0 = off;
+        off = align_up(off + dm.n_owners * 8, 16);
+        break;
+      }
+    }
+  }
+  dm.stage_bytes = align_up(off, 16);
+  for (uint32_t k = 0; k < dm.n_cons; ++k)
+    if (unstaged_bytes[k]) {
+      dm.cons[k].off0 = off;
+      off += unstaged_bytes[k];
+    }
+  dm.block_bytes = align_up(off, 128);
+  size_t total = (size_t)dm.block_bytes * dm.R;
+  CU(cudaMalloc((void**)&dm.state, total));
+  ctx->dev_allocs.push_back(dm.state);
+  CU(cudaMalloc((void**)&ctx->scratch_state, total));
+  ctx->dev_allocs.push_back(ctx->scratch_state);
+  // host image of the planning state
+  {
+    std::vector<char> img(total, 0);
+    for (uint32_t r = 0; r < dm.R; ++r) {
+      char* b = img.data() + (size_t)r * dm.block_bytes;
+      if (dm.has_scalar) {
+        const ScalarVar& v = ctx->svars[0];
+        const int32_t* src = v.init.data() + (v.per_replica ? (size_t)r * dm.n_entities : 0);
+        memcpy(b + dm.off_var, src, (size_t)dm.n_entities * 4);
+      }
+      if (dm.has_list) {
+        const ListVar& v = ctx->lvars[0];
+        size_t oc = v.per_replica ? (size_t)r * (dm.n_owners + 1) : 0;
+        const uint32_t* o = v.offsets.data() + oc;
+        size_t ebase = 0;
+        if (v.per_replica)
+          for (uint32_t q = 0; q < r; ++q) ebase += v.offsets[(size_t)q * (dm.n_owners + 1) + dm.n_owners];
+        memcpy(b + dm.off_offsets, o, (size_t)(dm.n_owners + 1) * 4);
+        if (o[dm.n_owners]) memcpy(b + dm.off_elems, v.elems.data() + ebase, (size_t)o[dm.n_owners] * 4);
+      }
+    }
+    CU(cudaMemcpyAsync(dm.state, img.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  // shared-memory staging of the replica block (TMA bulk copy) when it fits
+  ctx->staged = dm.stage_bytes + 1024 <= (uint32_t)ctx->max_smem_optin;
+  if (ctx->staged) {
+    int bytes = (int)dm.stage_bytes;
+    CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
+  if (dm.has_list) {
+    int bytes = (int)dm.elem_cap * 4;
+    if (bytes > ctx->max_smem_optin) return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the apply kernel");
+    CU(cudaFuncSetAttribute(apply_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
+  // initialize_all
+  init_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, dm.state);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->building = false;
+  ctx->committed = true;
+  if (out_scores) return sfgpu_committed_scores(ctx, out_scores);
+  return SFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scoring
+// ------------------------------------------------------------------------------------------
+namespace {
+
+enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP };
+
+int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
+                 const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable) {
+  const DevModel& dm = ctx->dm;
+  const uint32_t threads = 256;
+  dim3 grid(chunks_for(ctx, n_total, dm.R, threads), dm.R);
+  size_t smem = ctx->staged ? dm.stage_bytes : 0;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+#define LAUNCH_SCALAR(MODE)                                                                                    \
+  if (ctx->staged)                                                                                             \
+    score_scalar_kernel<MODE, true><<<grid, threads, smem, ctx->stream>>>(dm, d_offs, d_rows, d_edit_offs,    \
+                                                                          d_scores, d_doable);                 \
+  else                                                                                                         \
+    score_scalar_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(dm, d_offs, d_rows, d_edit_offs,      \
+                                                                        d_scores, d_doable)
+#define LAUNCH_LIST(MODE)                                                                                      \
+  if (ctx->staged)                                                                                             \
+    score_list_kernel<MODE, true><<<grid, threads, smem, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); \
+  else                                                                                                         \
+    score_list_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable)
+  switch (kind) {
+    case SK_CHANGE: LAUNCH_SCALAR(MODE_CHANGE); break;
+    case SK_SWAP: LAUNCH_SCALAR(MODE_SWAP); break;
+    case SK_COMPOUND: LAUNCH_SCALAR(MODE_COMPOUND); break;
+    case SK_LIST_CHANGE: LAUNCH_LIST(LMODE_CHANGE); break;
+    case SK_LIST_SWAP: LAUNCH_LIST(LMODE_SWAP); break;
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  ctx->ev_valid = true;
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
+// Host-pointer path: stage through pinned memory, H2D, kernel, D2H, synchronize.
+int score_entry(sfgpu_ctx* ctx, ScoreKind kind, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                const uint64_t* edit_offsets, int64_t* out_scores, uint8_t* out_doable) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!cand_offsets || !out_scores || !out_doable) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  const DevModel& dm = ctx->dm;
+  bool scalar = kind == SK_CHANGE || kind == SK_SWAP || kind == SK_COMPOUND;
+  if (scalar && !dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
+  if (!scalar && !dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
+  if (kind == SK_COMPOUND && ctx->has_load_balance)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "compound moves over a load_balance constraint");
+  if (kind == SK_SWAP && ctx->has_load_balance)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "swap moves over a load_balance constraint");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t row_words = scalar ? 2 : 4;
+  if (flags & SFGPU_DEVICE_IO) {
+    const uint64_t n_total = n_candidates;
+    if (n_total == 0) return SFGPU_OK;
+    if (!rows) return fail(ctx, SFGPU_E_INVALID, "null rows");
+    return launch_score(ctx, kind, n_total, cand_offsets, rows, edit_offsets, out_scores, out_doable);
+  }
+  if (cand_offsets[0] != 0) return fail(ctx, SFGPU_E_INVALID, "cand_offsets[0] must be 0");
+  for (uint32_t r = 0; r < dm.R; ++r)
+    if (cand_offsets[r + 1] < cand_offsets[r]) return fail(ctx, SFGPU_E_INVALID, "cand_offsets must be non-decreasing");
+  const uint64_t n = cand_offsets[dm.R];
+  if (n != n_candidates) return fail(ctx, SFGPU_E_INVALID, "n_candidates != cand_offsets[R]");
+  if (n == 0) return SFGPU_OK;
+  if (!rows) return fail(ctx, SFGPU_E_INVALID, "null rows");
+  uint64_t n_rows = n;
+  if (kind == SK_COMPOUND) {
+    if (!edit_offsets) return fail(ctx, SFGPU_E_INVALID, "null edit_offsets");
+    n_rows = edit_offsets[n];
+  }
+  // layout of both staging areas: [offsets (R+1) u64][edit offsets (n+1) u64][rows][scores][doable]
+  size_t o_off = 0;
+  size_t o_eoff = o_off + (dm.R + 1) * 8;
+  size_t o_rows = o_eoff + (kind == SK_COMPOUND ? (n + 1) * 8 : 0);
+  size_t o_scores = (o_rows + n_rows * row_words * 4 + 15) / 16 * 16;
+  size_t o_doable = o_scores + n * 16;
+  size_t total = o_doable + (n + 15) / 16 * 16;
+  rc = ensure_staging(ctx, total, total);
+  if (rc) return rc;
+  char* pin = (char*)ctx->pin;
+  char* dv = (char*)ctx->dscr;
+  memcpy(pin + o_off, cand_offsets, (dm.R + 1) * 8);
+  if (kind == SK_COMPOUND) memcpy(pin + o_eoff, edit_offsets, (n + 1) * 8);
+  memcpy(pin + o_rows, rows, n_rows * row_words * 4);
+  CU(cudaMemcpyAsync(dv, pin, o_scores, cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_score(ctx, kind, n, (const uint64_t*)(dv + o_off), (const uint32_t*)(dv + o_rows),
+                    kind == SK_COMPOUND ? (const uint64_t*)(dv + o_eoff) : nullptr, (int64_t*)(dv + o_scores),
+                    (uint8_t*)(dv + o_doable));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(pin + o_scores, dv + o_scores, total - o_scores, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_scores, pin + o_scores, n * 16);
+  memcpy(out_doable, pin + o_doable, n);
+  return SFGPU_OK;
+}
+
+}  // namespace
+
+int32_t sfgpu_score_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                           int64_t* out_scores, uint8_t* out_doable) {
+  return score_entry(ctx, SK_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+}
+int32_t sfgpu_score_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                         int64_t* out_scores, uint8_t* out_doable) {
+  return score_entry(ctx, SK_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+}
+int32_t sfgpu_score_compound(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                             const uint64_t* edit_offsets, const uint32_t* edit_rows, int64_t* out_scores,
+                             uint8_t* out_doable) {
+  return score_entry(ctx, SK_COMPOUND, flags, n_candidates, cand_offsets, edit_rows, edit_offsets, out_scores, out_doable);
+}
+int32_t sfgpu_score_list_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                                const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
+  return score_entry(ctx, SK_LIST_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+}
+int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                              int64_t* out_scores, uint8_t* out_doable) {
+  return score_entry(ctx, SK_LIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+}
+
+// ------------------------------------------------------------------------------------------
+int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                      const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
+                      const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
+                      int64_t* out_best, uint32_t* out_evaluated) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!params || !cand_offsets || !scores || !doable || !out_index || !out_best)
+    return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = ctx->dm.R;
+  ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit};
+  if (flags & SFGPU_DEVICE_IO) {
+    argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, cand_offsets, scores, doable, step_seeds, ref_scores, out_index,
+                                                out_best, out_evaluated);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SFGPU_OK;
+  }
+  const uint64_t n = cand_offsets[R];
+  size_t o_off = 0, o_seed = o_off + (R + 1) * 8, o_ref = o_seed + R * 8, o_scores = o_ref + R * 32;
+  size_t o_doable = o_scores + n * 16;
+  size_t o_idx = (o_doable + n + 15) / 16 * 16, o_best = o_idx + (R * 4 + 15) / 16 * 16, o_eval = o_best + R * 16;
+  size_t total = o_eval + (R * 4 + 15) / 16 * 16;
+  rc = ensure_staging(ctx, total, total);
+  if (rc) return rc;
+  char* pin = (char*)ctx->pin;
+  char* dv = (char*)ctx->dscr;
+  memcpy(pin + o_off, cand_offsets, (R + 1) * 8);
+  if (step_seeds) memcpy(pin + o_seed, step_seeds, R * 8); else memset(pin + o_seed, 0, R * 8);
+  if (ref_scores) memcpy(pin + o_ref, ref_scores, R * 32); else memset(pin + o_ref, 0, R * 32);
+  memcpy(pin + o_scores, scores, n * 16);
+  memcpy(pin + o_doable, doable, n);
+  CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
+  argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, (const uint64_t*)(dv + o_off), (const int64_t*)(dv + o_scores),
+                                              (const uint8_t*)(dv + o_doable), (const uint64_t*)(dv + o_seed),
+                                              (const int64_t*)(dv + o_ref), (uint32_t*)(dv + o_idx),
+                                              (int64_t*)(dv + o_best), (uint32_t*)(dv + o_eval));
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, total - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_index, pin + o_idx, R * 4);
+  memcpy(out_best, pin + o_best, R * 16);
+  if (out_evaluated) memcpy(out_evaluated, pin + o_eval, R * 4);
+  return SFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+int apply_entry(sfgpu_ctx* ctx, int kind, uint32_t flags, const uint32_t* rows, const uint8_t* mask,
+                const uint64_t* d_offsets, const uint32_t* d_index) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!rows) return fail(ctx, SFGPU_E_INVALID, "null rows");
+  const DevModel& dm = ctx->dm;
+  bool scalar = kind < 2;
+  if (scalar && !dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
+  if (!scalar && !dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
+  if (kind == 1 && ctx->has_load_balance)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "swap moves over a load_balance constraint");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R;
+  const uint32_t* d_rows = rows;
+  const uint8_t* d_mask = mask;
+  if (!(flags & SFGPU_DEVICE_IO)) {
+    size_t row_bytes = (size_t)R * (scalar ? 8 : 16);
+    size_t total = row_bytes + (R + 15) / 16 * 16;
+    rc = ensure_staging(ctx, total, total);
+    if (rc) return rc;
+    memcpy(ctx->pin, rows, row_bytes);
+    if (mask) memcpy((char*)ctx->pin + row_bytes, mask, R);
+    CU(cudaMemcpyAsync(ctx->dscr, ctx->pin, total, cudaMemcpyHostToDevice, ctx->stream));
+    d_rows = (const uint32_t*)ctx->dscr;
+    d_mask = mask ? (const uint8_t*)ctx->dscr + row_bytes : nullptr;
+  }
+  if (scalar)
+    apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  else
+    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  if (!(flags & SFGPU_DEVICE_IO)) CU(cudaStreamSynchronize(ctx->stream));
+  return SFGPU_OK;
+}
+}  // namespace
+
+int32_t sfgpu_apply_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+  return apply_entry(ctx, 0, flags, rows, mask, nullptr, nullptr);
+}
+int32_t sfgpu_apply_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+  return apply_entry(ctx, 1, flags, rows, mask, nullptr, nullptr);
+}
+int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+  return apply_entry(ctx, 2, flags, rows, mask, nullptr, nullptr);
+}
+int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+  return apply_entry(ctx, 3, flags, rows, mask, nullptr, nullptr);
+}
+int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
+                            const uint32_t* batch_rows, const uint32_t* index) {
+  if (move_kind < 0 || move_kind > 3) return fail(ctx, SFGPU_E_INVALID, "bad move kind");
+  if (!cand_offsets || !index) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  return apply_entry(ctx, move_kind, SFGPU_DEVICE_IO, batch_rows, nullptr, cand_offsets, index);
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void gather_scores_kernel(const __grid_constant__ DevModel m, const char* __restrict__ state,
+                                     int64_t* __restrict__ out) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m.R) return;
+  const int64_t* cs = (const int64_t*)(state + (size_t)r * m.block_bytes + m.off_score);
+  out[r * 2] = cs[0];
+  out[r * 2 + 1] = cs[1];
+}
+
+int read_scores(sfgpu_ctx* ctx, const char* state, int64_t* out) {
+  const uint32_t R = ctx->dm.R;
+  int rc = ensure_staging(ctx, (size_t)R * 16, (size_t)R * 16);
+  if (rc) return rc;
+  gather_scores_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(ctx->dm, state, (int64_t*)ctx->dscr);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->pin, ctx->dscr, (size_t)R * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->pin, (size_t)R * 16);
+  return SFGPU_OK;
+}
+}  // namespace
+
+int32_t sfgpu_committed_scores(sfgpu_ctx* ctx, int64_t* out_scores) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!out_scores) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  CU(cudaSetDevice(ctx->device));
+  return read_scores(ctx, ctx->dm.state, out_scores);
+}
+
+int32_t sfgpu_evaluate_all(sfgpu_ctx* ctx, int64_t* out_scores) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!out_scores) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  CU(cudaSetDevice(ctx->device));
+  const DevModel& dm = ctx->dm;
+  CU(cudaMemcpyAsync(ctx->scratch_state, dm.state, (size_t)dm.block_bytes * dm.R, cudaMemcpyDeviceToDevice,
+                     ctx->stream));
+  init_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, ctx->scratch_state);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return read_scores(ctx, ctx->scratch_state, out_scores);
+}
+
+int32_t sfgpu_get_scalar_state(sfgpu_ctx* ctx, uint32_t variable, int32_t* out_values) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  const DevModel& dm = ctx->dm;
+  if (variable != 0 || !dm.has_scalar || !out_values) return fail(ctx, SFGPU_E_INVALID, "unknown scalar variable");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy2D(out_values, (size_t)dm.n_entities * 4, dm.state + dm.off_var, dm.block_bytes,
+                  (size_t)dm.n_entities * 4, dm.R, cudaMemcpyDeviceToHost));
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_list_capacity(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_capacity) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (variable != 0x80000000u || !ctx->dm.has_list || !out_capacity) return fail(ctx, SFGPU_E_INVALID, "unknown list variable");
+  *out_capacity = ctx->dm.elem_cap;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_get_list_state(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_offsets, uint32_t* out_elems) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  const DevModel& dm = ctx->dm;
+  if (variable != 0x80000000u || !dm.has_list || !out_offsets || !out_elems)
+    return fail(ctx, SFGPU_E_INVALID, "unknown list variable");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy2D(out_offsets, (size_t)(dm.n_owners + 1) * 4, dm.state + dm.off_offsets, dm.block_bytes,
+                  (size_t)(dm.n_owners + 1) * 4, dm.R, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy2D(out_elems, (size_t)dm.elem_cap * 4, dm.state + dm.off_elems, dm.block_bytes,
+                  (size_t)dm.elem_cap * 4, dm.R, cudaMemcpyDeviceToHost));
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!out_keys) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  CU(cudaSetDevice(ctx->device));
+  pack_keys_kernel<<<(ctx->dm.R + 127) / 128, 128, 0, ctx->stream>>>(ctx->dm, out_keys);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns) {
+  if (!ctx || !out_ns) return SFGPU_E_INVALID;
+  if (!ctx->ev_valid) return fail(ctx, SFGPU_E_STATE, "no scoring kernel launched yet");
+  CU(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *out_ns = (uint64_t)((double)ms * 1e6);
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count) {
+  if (!ctx || !out_count) return SFGPU_E_INVALID;
+  *out_count = ctx->launches;
+  return SFGPU_OK;
+}
+
+}  // extern "C"

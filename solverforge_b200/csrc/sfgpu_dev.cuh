@@ -1,0 +1,128 @@
+// Device-side model description and small device helpers shared by every kernel of libsfgpu.
+// HBM layout: one contiguous "replica block" per replica holding the planning
+// state and the retained aggregates of that replica; static facts are shared by all replicas.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sfgpu.h"
+
+#define SFGPU_MAX_CONS 16
+#define SFGPU_NONE (-1)
+
+struct WeightDev {
+  int32_t fn, level;
+  int64_t a, b;
+};
+
+struct ConsDev {
+  int32_t kind;
+  int32_t sign;  // -1 penalty, +1 reward (constraint/incremental.rs:70-76)
+  WeightDev w;
+  uint32_t off0, off1, off2;  // byte offsets of this constraint's retained sections in the replica block
+  uint32_t n0;                // table length / stride
+  const void* g0;             // shared static arrays (CSR row_ptr, column, matrix ...)
+  const void* g1;
+  int64_t p0, p1, p2;
+  uint32_t flags;
+  uint32_t pad;
+};
+#define SFGPU_CF_MATRIX_I32 1u   // g0 is int32 cells (cooked costs all fit in 31 bits)
+#define SFGPU_CF_COMPLEMENT 2u
+#define SFGPU_CF_COL_BY_VALUE 4u
+
+struct DevModel {
+  char* state;  // [R][block_bytes]
+  uint32_t block_bytes;
+  uint32_t stage_bytes;  // prefix of a block the scoring kernels stage into shared memory
+  uint32_t R;
+  uint32_t n_cons;
+  uint32_t off_score;
+  // scalar variable
+  uint32_t has_scalar, n_entities, n_values, allows_unassigned, off_var;
+  // list variable
+  uint32_t has_list, n_owners, n_elem_rows, elem_cap, off_offsets, off_elems;
+  uint32_t pad;
+  ConsDev cons[SFGPU_MAX_CONS];
+};
+
+struct Score2 {
+  int64_t hard, soft;
+};
+
+__device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
+  switch (w.fn) {
+    case SFGPU_W_CONST: return w.a;
+    case SFGPU_W_LINEAR: return w.a * x + w.b;
+    case SFGPU_W_SQUARE: return w.a * x * x + w.b;
+    default: {
+      int64_t d = x - w.b;
+      return d > 0 ? w.a * d : 0;
+    }
+  }
+}
+
+// adds sign * v to the constraint's level
+__device__ __forceinline__ void add_level(Score2& s, const ConsDev& c, int64_t v) {
+  int64_t sv = c.sign < 0 ? -v : v;
+  if (c.w.level == 0) s.hard += sv; else s.soft += sv;
+}
+
+__device__ __forceinline__ bool score_less(int64_t h1, int64_t s1, int64_t h2, int64_t s2) {
+  return h1 != h2 ? h1 < h2 : s1 < s2;
+}
+
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t v) {
+  v += 0x9E3779B97F4A7C15ull;
+  v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull;
+  v = (v ^ (v >> 27)) * 0x94D049BB133111EBull;
+  return v ^ (v >> 31);
+}
+
+// ---- TMA (bulk async copy) staging of a replica block into shared memory ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Stage `bytes` (multiple of 16, 16 B aligned both sides) of global memory into shared memory
+// with TMA bulk copies; every thread of the CTA must call this. `bar` is a shared mbarrier slot.
+__device__ __forceinline__ void stage_block(char* smem_dst, const char* gmem_src, uint32_t bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes);
+    const uint32_t piece = 32768;
+    for (uint32_t o = 0; o < bytes; o += piece) {
+      uint32_t n = bytes - o < piece ? bytes - o : piece;
+      tma_bulk_g2s(smem_dst + o, gmem_src + o, n, bar);
+    }
+  }
+  mbar_wait(bar, 0);
+}

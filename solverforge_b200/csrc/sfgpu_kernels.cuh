@@ -1,0 +1,951 @@
+// CUDA kernels of libsfgpu (sm_100a). All integer/index work, HBM/L2-bound; no tensor cores.
+//
+// Key idea: the GPU never replays do/undo. For a candidate m against the
+// immutable committed state S of its replica it computes
+//     score(m) = committed + sum_k [ contrib_k(S (+) m, touched) - contrib_k(S, touched) ]
+// read-only, so every candidate is independent. The retained aggregates of the reference
+// (per-key counts, per-group accumulators, per-route sums) live in the replica block and are
+// only updated when the winning move is applied.
+#pragma once
+#include "sfgpu_dev.cuh"
+
+// =============================================================================================
+// scalar edits (ChangeMove / SwapMove / CompoundScalarMove)
+// =============================================================================================
+struct EditDev {
+  uint32_t e;
+  int32_t old_v, new_v;
+};
+
+__device__ __forceinline__ int32_t var_at(const int32_t* var, const EditDev* prev, int n_prev, uint32_t x) {
+  int32_t v = var[x];
+  for (int i = 0; i < n_prev; ++i)
+    if (prev[i].e == x) v = prev[i].new_v;
+  return v;
+}
+
+__device__ __forceinline__ int64_t col_at(const void* col, uint32_t i) {
+  return col ? ((const int64_t*)col)[i] : 0;
+}
+
+// key(e, v) of a PAIR_KEY_EQUAL constraint, relative to the table origin p2
+__device__ __forceinline__ int64_t pair_key(const ConsDev& c, uint32_t e, int32_t v) {
+  return col_at(c.g0, e) * c.p0 + (int64_t)v * c.p1 - c.p2;
+}
+
+__device__ __forceinline__ int64_t uni_x(const ConsDev& c, uint32_t e, int32_t v) {
+  if (!c.g0) return 0;
+  if (c.flags & SFGPU_CF_COL_BY_VALUE) return v >= 0 ? ((const int64_t*)c.g0)[v] : 0;
+  return ((const int64_t*)c.g0)[e];
+}
+__device__ __forceinline__ int64_t uni_contrib(const ConsDev& c, uint32_t e, int32_t v) {
+  bool pass = c.p0 == 0 ? v < 0 : (c.p0 == 1 ? v >= 0 : true);
+  return pass ? weight_eval(c.w, uni_x(c, e, v)) : 0;
+}
+
+// score of a group with `count` rows and accumulated `sum` (count() result == count)
+__device__ __forceinline__ int64_t group_score(const ConsDev& c, int64_t count, int64_t sum) {
+  bool counting = c.g0 == nullptr;
+  if (count > 0) return weight_eval(c.w, counting ? count : sum);
+  if (c.flags & SFGPU_CF_COMPLEMENT) return weight_eval(c.w, c.p1);
+  return 0;
+}
+
+// load_balance.rs:165-183
+__device__ __forceinline__ int64_t lb_unfairness(int64_t n, int64_t sum, int64_t sumsq) {
+  if (n == 0) return 0;
+  double frac = (double)(-(sum * sum));
+  double tmp = n == 1 ? frac + (double)sumsq : frac / (double)n + (double)sumsq;
+  return (int64_t)round(sqrt(tmp));
+}
+
+// Delta of ONE edit (e: old -> new) against the replica state `st` overlaid with the edits
+// prev[0..n_prev) that were already applied by the same candidate.
+__device__ void scalar_edit_delta(const DevModel& m, const char* st, const EditDev* prev, int n_prev, EditDev cur,
+                                  Score2& d) {
+  if (cur.old_v == cur.new_v) return;
+  const int32_t* var = (const int32_t*)(st + m.off_var);
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    switch (c.kind) {
+      case SFGPU_K_UNI: {
+        add_level(d, c, uni_contrib(c, cur.e, cur.new_v) - uni_contrib(c, cur.e, cur.old_v));
+        break;
+      }
+      case SFGPU_K_PAIR_CSR_EQUAL: {
+        // g0 = partner row_ptr, g1 = partner ids (symmetrised, deduplicated at commit)
+        const uint32_t* rp = (const uint32_t*)c.g0;
+        const uint32_t* ci = (const uint32_t*)c.g1;
+        uint32_t lo = rp[cur.e], hi = rp[cur.e + 1];
+        int64_t cnt = 0;
+        for (uint32_t j = lo; j < hi; ++j) {
+          int32_t vp = var_at(var, prev, n_prev, ci[j]);
+          cnt += (cur.new_v >= 0 && vp == cur.new_v) ? 1 : 0;
+          cnt -= (cur.old_v >= 0 && vp == cur.old_v) ? 1 : 0;
+        }
+        add_level(d, c, cnt * c.w.a);
+        break;
+      }
+      case SFGPU_K_PAIR_KEY_EQUAL: {
+        const int32_t* tab = (const int32_t*)(st + c.off0);
+        int64_t cnt = 0;
+        if (cur.new_v >= 0) {
+          int64_t key = pair_key(c, cur.e, cur.new_v);
+          int64_t n = tab[key];
+          for (int i = 0; i < n_prev; ++i) {
+            n += (prev[i].new_v >= 0 && pair_key(c, prev[i].e, prev[i].new_v) == key) ? 1 : 0;
+            n -= (prev[i].old_v >= 0 && pair_key(c, prev[i].e, prev[i].old_v) == key) ? 1 : 0;
+          }
+          cnt += n;
+        }
+        if (cur.old_v >= 0) {
+          int64_t key = pair_key(c, cur.e, cur.old_v);
+          int64_t n = tab[key];
+          for (int i = 0; i < n_prev; ++i) {
+            n += (prev[i].new_v >= 0 && pair_key(c, prev[i].e, prev[i].new_v) == key) ? 1 : 0;
+            n -= (prev[i].old_v >= 0 && pair_key(c, prev[i].e, prev[i].old_v) == key) ? 1 : 0;
+          }
+          cnt -= n - 1;
+        }
+        add_level(d, c, cnt * c.w.a);
+        break;
+      }
+      case SFGPU_K_GROUP: {
+        const int32_t* gc = (const int32_t*)(st + c.off0);
+        const int64_t* gs = (const int64_t*)(st + c.off1);
+        int64_t x = c.g0 ? ((const int64_t*)c.g0)[cur.e] : 1;
+        int64_t delta = 0;
+        for (int side = 0; side < 2; ++side) {
+          int32_t v = side == 0 ? cur.old_v : cur.new_v;
+          if (v < 0) continue;
+          int64_t cn = gc[v], sm = gs[v];
+          for (int i = 0; i < n_prev; ++i) {
+            int64_t xi = c.g0 ? ((const int64_t*)c.g0)[prev[i].e] : 1;
+            if (prev[i].new_v == v) { cn += 1; sm += xi; }
+            if (prev[i].old_v == v) { cn -= 1; sm -= xi; }
+          }
+          int64_t before = group_score(c, cn, sm);
+          int64_t after = side == 0 ? group_score(c, cn - 1, sm - x) : group_score(c, cn + 1, sm + x);
+          delta += after - before;
+        }
+        add_level(d, c, delta);
+        break;
+      }
+      case SFGPU_K_LOAD_BALANCE: {
+        // single group; balanced key = assigned value; metric x (zero metrics are skipped,
+        // load_balance.rs:196-200). Overlay-free: compound candidates touching a load-balance
+        // constraint are rejected at the API (SFGPU_E_UNSUPPORTED) unless n_prev == 0.
+        const int64_t* loads = (const int64_t*)(st + c.off0);
+        const int32_t* icnt = (const int32_t*)(st + c.off1);
+        const int64_t* agg = (const int64_t*)(st + c.off2);  // {sum, sumsq, nkeys}
+        int64_t x = c.g0 ? ((const int64_t*)c.g0)[cur.e] : 1;
+        if (x == 0) break;
+        int64_t sum = agg[0], sumsq = agg[1], nk = agg[2];
+        int64_t before = weight_eval(c.w, lb_unfairness(nk, sum, sumsq));
+        if (cur.old_v >= 0) {
+          int64_t l = loads[cur.old_v];
+          int64_t nl = icnt[cur.old_v] == 1 ? 0 : l - x;
+          if (icnt[cur.old_v] == 1) nk -= 1;
+          sumsq += nl * nl - l * l;
+          sum += nl - l;
+        }
+        if (cur.new_v >= 0) {
+          int64_t l = loads[cur.new_v];  // 0 when the key has no items
+          if (icnt[cur.new_v] == 0) nk += 1;
+          int64_t nl = l + x;
+          sumsq += nl * nl - l * l;
+          sum += x;
+        }
+        add_level(d, c, weight_eval(c.w, lb_unfairness(nk, sum, sumsq)) - before);
+        break;
+      }
+      default: break;  // list-only kinds do not react to scalar edits (ChangeSource routing)
+    }
+  }
+}
+
+enum { MODE_CHANGE = 0, MODE_SWAP = 1, MODE_COMPOUND = 2 };
+
+// one thread = one candidate. Returns doable; d = score delta.
+template <int MODE>
+__device__ __forceinline__ bool score_scalar_candidate(const DevModel& m, const char* st, const uint32_t* rows,
+                                                       const uint64_t* edit_offsets, uint64_t i, Score2& d) {
+  const int32_t* var = (const int32_t*)(st + m.off_var);
+  d.hard = 0;
+  d.soft = 0;
+  if (MODE == MODE_CHANGE) {
+    uint2 row = ((const uint2*)rows)[i];
+    uint32_t e = row.x;
+    int32_t nv = (int32_t)row.y;
+    if (e >= m.n_entities || nv >= (int32_t)m.n_values) return false;
+    if (nv < 0) nv = SFGPU_NONE;
+    int32_t ov = var[e];
+    if (ov == nv) return false;  // change.rs:125-139
+    scalar_edit_delta(m, st, nullptr, 0, EditDev{e, ov, nv}, d);
+    return true;
+  } else if (MODE == MODE_SWAP) {
+    uint2 row = ((const uint2*)rows)[i];
+    if (row.x >= m.n_entities || row.y >= m.n_entities) return false;
+    int32_t lv = var[row.x], rv = var[row.y];
+    if (lv == rv) return false;  // swap.rs:140-157
+    EditDev e0{row.x, lv, rv};
+    scalar_edit_delta(m, st, nullptr, 0, e0, d);
+    scalar_edit_delta(m, st, &e0, 1, EditDev{row.y, rv, lv}, d);
+    return true;
+  } else {
+    uint64_t lo = edit_offsets[i], hi = edit_offsets[i + 1];
+    int n = (int)(hi - lo);
+    if (n <= 0 || n > SFGPU_MAX_EDITS) return false;
+    EditDev ed[SFGPU_MAX_EDITS];
+    bool changes = false;
+    for (int j = 0; j < n; ++j) {
+      uint2 row = ((const uint2*)rows)[lo + j];
+      if (row.x >= m.n_entities || (int32_t)row.y >= (int32_t)m.n_values) return false;
+      int32_t nv = (int32_t)row.y < 0 ? SFGPU_NONE : (int32_t)row.y;
+      changes |= var[row.x] != nv;  // compound_scalar.rs:245-261 (against the unmodified solution)
+      ed[j].e = row.x;
+      ed[j].new_v = nv;
+      ed[j].old_v = var_at(var, ed, j, row.x);
+    }
+    if (!changes) return false;
+    for (int j = 0; j < n; ++j) scalar_edit_delta(m, st, ed, j, ed[j], d);
+    return true;
+  }
+}
+
+// grid = (chunks, R). Each CTA stages its replica block (TMA bulk copy) and scores a strided
+// share of the replica's candidate range.
+template <int MODE, bool STAGED>
+__global__ void __launch_bounds__(256) score_scalar_kernel(const __grid_constant__ DevModel m,
+                                                           const uint64_t* __restrict__ cand_offsets,
+                                                           const uint32_t* __restrict__ rows,
+                                                           const uint64_t* __restrict__ edit_offsets,
+                                                           int64_t* __restrict__ out_scores,
+                                                           uint8_t* __restrict__ out_doable) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  const uint32_t r = blockIdx.y;
+  const char* gblock = m.state + (size_t)r * m.block_bytes;
+  const char* st = gblock;
+  if (STAGED) {
+    stage_block(smem, gblock, m.stage_bytes, &bar);
+    st = smem;
+  }
+  const int64_t* cs = (const int64_t*)(st + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    Score2 d;
+    bool ok = score_scalar_candidate<MODE>(m, st, rows, edit_offsets, i, d);
+    longlong2 o;
+    o.x = ok ? ch + d.hard : 0;
+    o.y = ok ? csf + d.soft : 0;
+    ((longlong2*)out_scores)[i] = o;
+    out_doable[i] = ok ? 1 : 0;
+  }
+}
+
+// =============================================================================================
+// list moves (ListChangeMove / ListSwapMove)
+// =============================================================================================
+__device__ __forceinline__ int64_t mat_at(const ConsDev& c, uint32_t from, uint32_t to) {
+  size_t idx = (size_t)from * c.n0 + to;
+  if (c.flags & SFGPU_CF_MATRIX_I32) return ((const int32_t*)c.g0)[idx];
+  return ((const int64_t*)c.g0)[idx];
+}
+
+// ListChange delta. Returns doable (list_kernel/change.rs:46-75).
+__device__ __forceinline__ bool list_change_delta(const DevModel& m, const char* st, uint4 row, Score2& d) {
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  d.hard = 0;
+  d.soft = 0;
+  const uint32_t se = row.x, sp = row.y, de = row.z, dp = row.w;
+  if (se >= m.n_owners || de >= m.n_owners) return false;
+  const uint32_t sb = off[se], slen = off[se + 1] - sb;
+  if (sp >= slen) return false;
+  const bool intra = se == de;
+  const uint32_t db = off[de], dlen = off[de + 1] - db;
+  if (dp > (intra ? slen : dlen)) return false;
+  if (intra && (dp == sp || dp == sp + 1)) return false;
+  const uint32_t x = el[sb + sp];
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind == SFGPU_K_LIST_PATH_COST) {
+      const uint32_t depot = (uint32_t)c.p0;
+      const uint32_t prev = sp > 0 ? el[sb + sp - 1] : depot;
+      const uint32_t next = sp + 1 < slen ? el[sb + sp + 1] : depot;
+      const uint32_t a = dp > 0 ? el[db + dp - 1] : depot;
+      const uint32_t b = dp < dlen ? el[db + dp] : depot;
+      // removal; an emptied route costs 0 (no depot->depot leg)
+      int64_t rem = -mat_at(c, prev, x) - mat_at(c, x, next) + (slen > 1 ? mat_at(c, prev, next) : 0);
+      // insertion; inserting into an empty route has no old leg to remove
+      int64_t ins = mat_at(c, a, x) + mat_at(c, x, b) - ((intra || dlen > 0) ? mat_at(c, a, b) : 0);
+      const int64_t* rcost = (const int64_t*)(st + c.off0);
+      if (intra) {
+        int64_t old_c = rcost[se];
+        add_level(d, c, weight_eval(c.w, old_c + rem + ins) - weight_eval(c.w, old_c));
+      } else {
+        int64_t os = rcost[se], od = rcost[de];
+        add_level(d, c, weight_eval(c.w, os + rem) - weight_eval(c.w, os) + weight_eval(c.w, od + ins) -
+                            weight_eval(c.w, od));
+      }
+    } else if (c.kind == SFGPU_K_LIST_SUM) {
+      if (!intra) {
+        const int64_t* rsum = (const int64_t*)(st + c.off0);
+        int64_t v = ((const int64_t*)c.g0)[x];
+        int64_t ss = rsum[se], ds = rsum[de];
+        add_level(d, c, weight_eval(c.w, ss - v) - weight_eval(c.w, ss) + weight_eval(c.w, ds + v) -
+                            weight_eval(c.w, ds));
+      }
+    }
+    // EXISTS_FLAT: a relocation keeps the multiset of flattened keys => per-key counts unchanged => 0.
+  }
+  return true;
+}
+
+// ListSwap delta (list_kernel/swap.rs:31-57 doability).
+__device__ __forceinline__ bool list_swap_delta(const DevModel& m, const char* st, uint4 row, Score2& d) {
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  d.hard = 0;
+  d.soft = 0;
+  const uint32_t e1 = row.x, p1 = row.y, e2 = row.z, p2 = row.w;
+  if (e1 >= m.n_owners || e2 >= m.n_owners) return false;
+  const uint32_t b1 = off[e1], len1 = off[e1 + 1] - b1;
+  const uint32_t b2 = off[e2], len2 = off[e2 + 1] - b2;
+  if (p1 >= len1 || p2 >= len2) return false;
+  const bool intra = e1 == e2;
+  if (intra && p1 == p2) return false;
+  const uint32_t x1 = el[b1 + p1], x2 = el[b2 + p2];
+  if (x1 == x2) return false;
+  const uint32_t f1 = b1 + p1, f2 = b2 + p2;  // flat positions
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind == SFGPU_K_LIST_PATH_COST) {
+      const uint32_t depot = (uint32_t)c.p0;
+      // legs touched: (e1,p1) (e1,p1+1) (e2,p2) (e2,p2+1); leg (e,i) joins position i-1 and i
+      // (position -1 and len are the depot). Patched accessor sees the swapped values.
+      int64_t delta1 = 0, delta2 = 0;
+      for (int t = 0; t < 4; ++t) {
+        const bool first = t < 2;
+        const uint32_t base = first ? b1 : b2, len = first ? len1 : len2;
+        const uint32_t leg = (first ? p1 : p2) + (t & 1);
+        if (!first && intra && (leg == p1 || leg == p1 + 1)) continue;  // already counted
+        const uint32_t fa = base + leg - 1, fb = base + leg;
+        const uint32_t oa = leg > 0 ? el[fa] : depot;
+        const uint32_t ob = leg < len ? el[fb] : depot;
+        const uint32_t na = leg > 0 ? (fa == f1 ? x2 : (fa == f2 ? x1 : oa)) : depot;
+        const uint32_t nb = leg < len ? (fb == f1 ? x2 : (fb == f2 ? x1 : ob)) : depot;
+        int64_t dl = mat_at(c, na, nb) - mat_at(c, oa, ob);
+        if (first) delta1 += dl; else delta2 += dl;
+      }
+      const int64_t* rcost = (const int64_t*)(st + c.off0);
+      if (intra) {
+        int64_t oc = rcost[e1];
+        add_level(d, c, weight_eval(c.w, oc + delta1 + delta2) - weight_eval(c.w, oc));
+      } else {
+        int64_t o1 = rcost[e1], o2 = rcost[e2];
+        add_level(d, c, weight_eval(c.w, o1 + delta1) - weight_eval(c.w, o1) + weight_eval(c.w, o2 + delta2) -
+                            weight_eval(c.w, o2));
+      }
+    } else if (c.kind == SFGPU_K_LIST_SUM) {
+      if (!intra) {
+        const int64_t* rsum = (const int64_t*)(st + c.off0);
+        int64_t v1 = ((const int64_t*)c.g0)[x1], v2 = ((const int64_t*)c.g0)[x2];
+        int64_t s1 = rsum[e1], s2 = rsum[e2];
+        add_level(d, c, weight_eval(c.w, s1 - v1 + v2) - weight_eval(c.w, s1) + weight_eval(c.w, s2 - v2 + v1) -
+                            weight_eval(c.w, s2));
+      }
+    }
+  }
+  return true;
+}
+
+enum { LMODE_CHANGE = 0, LMODE_SWAP = 1 };
+
+template <int LMODE, bool STAGED>
+__global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__ DevModel m,
+                                                         const uint64_t* __restrict__ cand_offsets,
+                                                         const uint32_t* __restrict__ rows,
+                                                         int64_t* __restrict__ out_scores,
+                                                         uint8_t* __restrict__ out_doable) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  const uint32_t r = blockIdx.y;
+  const char* gblock = m.state + (size_t)r * m.block_bytes;
+  const char* st = gblock;
+  if (STAGED) {
+    stage_block(smem, gblock, m.stage_bytes, &bar);
+    st = smem;
+  }
+  const int64_t* cs = (const int64_t*)(st + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint4 row = ((const uint4*)rows)[i];  // one 128-bit load per candidate
+    Score2 d;
+    bool ok = LMODE == LMODE_CHANGE ? list_change_delta(m, st, row, d) : list_swap_delta(m, st, row, d);
+    longlong2 o;
+    o.x = ok ? ch + d.hard : 0;
+    o.y = ok ? csf + d.soft : 0;
+    ((longlong2*)out_scores)[i] = o;
+    out_doable[i] = ok ? 1 : 0;
+  }
+}
+
+// =============================================================================================
+// block reductions
+// =============================================================================================
+__device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t* scratch /* >= 32 */) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = threadIdx.x < nw ? scratch[threadIdx.x] : 0;
+  if (warp == 0)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (threadIdx.x == 0) scratch[0] = v;
+  __syncthreads();
+  v = scratch[0];
+  __syncthreads();
+  return v;
+}
+
+// =============================================================================================
+// initialize_all / evaluate_all: one CTA per replica, full recompute + (re)build of the retained
+// aggregates inside the block it is pointed at (the live state at commit, a scratch copy for
+// sfgpu_evaluate_all).  Reference: IncrementalConstraint::evaluate of every constraint kind.
+// =============================================================================================
+__global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevModel m, char* __restrict__ state) {
+  __shared__ int64_t scratch[32];
+  const uint32_t r = blockIdx.x;
+  char* st = state + (size_t)r * m.block_bytes;
+  const int32_t* var = (const int32_t*)(st + m.off_var);
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  int64_t hard = 0, soft = 0;
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    int64_t local = 0;
+    switch (c.kind) {
+      case SFGPU_K_UNI:
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) local += uni_contrib(c, e, var[e]);
+        break;
+      case SFGPU_K_PAIR_CSR_EQUAL: {
+        const uint32_t* rp = (const uint32_t*)c.g0;
+        const uint32_t* ci = (const uint32_t*)c.g1;
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) {
+          int32_t v = var[e];
+          if (v < 0) continue;
+          for (uint32_t j = rp[e]; j < rp[e + 1]; ++j)
+            if (ci[j] > e && var[ci[j]] == v) local += c.w.a;
+        }
+        break;
+      }
+      case SFGPU_K_PAIR_KEY_EQUAL: {
+        int32_t* tab = (int32_t*)(st + c.off0);
+        for (uint32_t i = threadIdx.x; i < c.n0; i += blockDim.x) tab[i] = 0;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x)
+          if (var[e] >= 0) atomicAdd(&tab[pair_key(c, e, var[e])], 1);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < c.n0; i += blockDim.x) {
+          int64_t n = tab[i];
+          local += n * (n - 1) / 2 * c.w.a;
+        }
+        break;
+      }
+      case SFGPU_K_GROUP: {
+        int32_t* gc = (int32_t*)(st + c.off0);
+        unsigned long long* gs = (unsigned long long*)(st + c.off1);
+        for (uint32_t i = threadIdx.x; i < m.n_values; i += blockDim.x) {
+          gc[i] = 0;
+          gs[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x)
+          if (var[e] >= 0) {
+            atomicAdd(&gc[var[e]], 1);
+            atomicAdd(&gs[var[e]], (unsigned long long)(c.g0 ? ((const int64_t*)c.g0)[e] : 1));
+          }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < m.n_values; i += blockDim.x)
+          local += group_score(c, gc[i], (int64_t)gs[i]);
+        break;
+      }
+      case SFGPU_K_LOAD_BALANCE: {
+        unsigned long long* loads = (unsigned long long*)(st + c.off0);
+        int32_t* icnt = (int32_t*)(st + c.off1);
+        int64_t* agg = (int64_t*)(st + c.off2);
+        for (uint32_t i = threadIdx.x; i < m.n_values; i += blockDim.x) {
+          loads[i] = 0;
+          icnt[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) {
+          int64_t x = c.g0 ? ((const int64_t*)c.g0)[e] : 1;
+          if (var[e] >= 0 && x != 0) {
+            atomicAdd(&icnt[var[e]], 1);
+            atomicAdd(&loads[var[e]], (unsigned long long)x);
+          }
+        }
+        __syncthreads();
+        int64_t s = 0, sq = 0, nk = 0;
+        for (uint32_t i = threadIdx.x; i < m.n_values; i += blockDim.x) {
+          int64_t l = (int64_t)loads[i];
+          s += l;
+          sq += l * l;
+          nk += icnt[i] > 0 ? 1 : 0;
+        }
+        s = block_sum_i64(s, scratch);
+        sq = block_sum_i64(sq, scratch);
+        nk = block_sum_i64(nk, scratch);
+        if (threadIdx.x == 0) {
+          agg[0] = s;
+          agg[1] = sq;
+          agg[2] = nk;
+          local = weight_eval(c.w, lb_unfairness(nk, s, sq));
+        }
+        break;
+      }
+      case SFGPU_K_EXISTS_FLAT: {
+        int32_t* bc = (int32_t*)(st + c.off0);
+        for (uint32_t i = threadIdx.x; i < m.n_elem_rows; i += blockDim.x) bc[i] = 0;
+        __syncthreads();
+        const uint32_t total = off[m.n_owners];
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x)
+          if (el[i] < m.n_elem_rows) atomicAdd(&bc[el[i]], 1);
+        __syncthreads();
+        // A rows: key_a = key column (g0) or the row index; n0 = |A|
+        for (uint32_t a = threadIdx.x; a < c.n0; a += blockDim.x) {
+          int64_t key = c.g0 ? ((const int64_t*)c.g0)[a] : (int64_t)a;
+          int32_t n = (key >= 0 && key < (int64_t)m.n_elem_rows) ? bc[key] : 0;
+          bool match = c.p0 == 0 ? n > 0 : n == 0;
+          if (match) local += c.w.a;
+        }
+        break;
+      }
+      case SFGPU_K_LIST_PATH_COST: {
+        int64_t* rcost = (int64_t*)(st + c.off0);
+        const uint32_t depot = (uint32_t)c.p0;
+        for (uint32_t o = threadIdx.x; o < m.n_owners; o += blockDim.x) {
+          int64_t cost = 0;
+          uint32_t b = off[o], e = off[o + 1];
+          if (e > b) {
+            uint32_t prev = depot;
+            for (uint32_t i = b; i < e; ++i) {
+              cost += mat_at(c, prev, el[i]);
+              prev = el[i];
+            }
+            cost += mat_at(c, prev, depot);
+          }
+          rcost[o] = cost;
+          local += weight_eval(c.w, cost);
+        }
+        break;
+      }
+      case SFGPU_K_LIST_SUM: {
+        int64_t* rsum = (int64_t*)(st + c.off0);
+        for (uint32_t o = threadIdx.x; o < m.n_owners; o += blockDim.x) {
+          int64_t s = 0;
+          for (uint32_t i = off[o]; i < off[o + 1]; ++i) s += ((const int64_t*)c.g0)[el[i]];
+          rsum[o] = s;
+          local += weight_eval(c.w, s);
+        }
+        break;
+      }
+      default: break;
+    }
+    int64_t tot = block_sum_i64(local, scratch);
+    tot = c.sign < 0 ? -tot : tot;
+    if (c.w.level == 0) hard += tot; else soft += tot;
+  }
+  if (threadIdx.x == 0) {
+    int64_t* cs = (int64_t*)(st + m.off_score);
+    cs[0] = hard;
+    cs[1] = soft;
+  }
+}
+
+// =============================================================================================
+// apply: one CTA per replica commits one move (Move::do_move on the committed director).
+// =============================================================================================
+__device__ void apply_scalar_edit(const DevModel& m, char* st, EditDev cur) {
+  // thread 0 only; the retained tables move with the variable
+  int32_t* var = (int32_t*)(st + m.off_var);
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind == SFGPU_K_PAIR_KEY_EQUAL) {
+      int32_t* tab = (int32_t*)(st + c.off0);
+      if (cur.old_v >= 0) tab[pair_key(c, cur.e, cur.old_v)] -= 1;
+      if (cur.new_v >= 0) tab[pair_key(c, cur.e, cur.new_v)] += 1;
+    } else if (c.kind == SFGPU_K_GROUP) {
+      int32_t* gc = (int32_t*)(st + c.off0);
+      int64_t* gs = (int64_t*)(st + c.off1);
+      int64_t x = c.g0 ? ((const int64_t*)c.g0)[cur.e] : 1;
+      if (cur.old_v >= 0) { gc[cur.old_v] -= 1; gs[cur.old_v] -= x; }
+      if (cur.new_v >= 0) { gc[cur.new_v] += 1; gs[cur.new_v] += x; }
+    } else if (c.kind == SFGPU_K_LOAD_BALANCE) {
+      int64_t* loads = (int64_t*)(st + c.off0);
+      int32_t* icnt = (int32_t*)(st + c.off1);
+      int64_t* agg = (int64_t*)(st + c.off2);
+      int64_t x = c.g0 ? ((const int64_t*)c.g0)[cur.e] : 1;
+      if (x == 0) continue;
+      if (cur.old_v >= 0) {
+        int64_t l = loads[cur.old_v];
+        icnt[cur.old_v] -= 1;
+        int64_t nl = icnt[cur.old_v] == 0 ? 0 : l - x;
+        if (icnt[cur.old_v] == 0) agg[2] -= 1;
+        agg[1] += nl * nl - l * l;
+        agg[0] += nl - l;
+        loads[cur.old_v] = nl;
+      }
+      if (cur.new_v >= 0) {
+        int64_t l = loads[cur.new_v];
+        if (icnt[cur.new_v] == 0) agg[2] += 1;
+        icnt[cur.new_v] += 1;
+        int64_t nl = l + x;
+        agg[1] += nl * nl - l * l;
+        agg[0] += x;
+        loads[cur.new_v] = nl;
+      }
+    }
+  }
+  var[cur.e] = cur.new_v;
+}
+
+// rows: one per replica (mask / index select). kind 0 change, 1 swap.
+__global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind, const uint32_t* __restrict__ rows,
+                                    const uint8_t* __restrict__ mask, const uint64_t* __restrict__ cand_offsets,
+                                    const uint32_t* __restrict__ index) {
+  const uint32_t r = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  if (mask && !mask[r]) return;
+  uint64_t ri = r;
+  if (index) {
+    if (index[r] == 0xFFFFFFFFu) return;
+    ri = cand_offsets[r] + index[r];
+  }
+  char* st = m.state + (size_t)r * m.block_bytes;
+  int64_t* cs = (int64_t*)(st + m.off_score);
+  Score2 d;
+  bool ok = kind == 0 ? score_scalar_candidate<MODE_CHANGE>(m, st, rows, nullptr, ri, d)
+                      : score_scalar_candidate<MODE_SWAP>(m, st, rows, nullptr, ri, d);
+  if (!ok) return;
+  const int32_t* var = (const int32_t*)(st + m.off_var);
+  uint2 row = ((const uint2*)rows)[ri];
+  if (kind == 0) {
+    int32_t nv = (int32_t)row.y < 0 ? SFGPU_NONE : (int32_t)row.y;
+    apply_scalar_edit(m, st, EditDev{row.x, var[row.x], nv});
+  } else {
+    int32_t lv = var[row.x], rv = var[row.y];
+    apply_scalar_edit(m, st, EditDev{row.x, lv, rv});
+    apply_scalar_edit(m, st, EditDev{row.y, rv, lv});
+  }
+  cs[0] += d.hard;
+  cs[1] += d.soft;
+}
+
+// kind 2 list change, 3 list swap. Dynamic smem: elem_cap uint32 (old element copy).
+__global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__ DevModel m, int kind,
+                                                         const uint32_t* __restrict__ rows,
+                                                         const uint8_t* __restrict__ mask,
+                                                         const uint64_t* __restrict__ cand_offsets,
+                                                         const uint32_t* __restrict__ index) {
+  extern __shared__ __align__(16) uint32_t old_el[];
+  __shared__ int s_ok;
+  const uint32_t r = blockIdx.x;
+  if (mask && !mask[r]) return;
+  uint64_t ri = r;
+  if (index) {
+    if (index[r] == 0xFFFFFFFFu) return;
+    ri = cand_offsets[r] + index[r];
+  }
+  char* st = m.state + (size_t)r * m.block_bytes;
+  uint32_t* off = (uint32_t*)(st + m.off_offsets);
+  uint32_t* el = (uint32_t*)(st + m.off_elems);
+  const uint4 row = ((const uint4*)rows)[ri];
+  const uint32_t total = off[m.n_owners];
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) old_el[i] = el[i];
+  if (threadIdx.x == 0) {
+    Score2 d;
+    bool ok = kind == 2 ? list_change_delta(m, st, row, d) : list_swap_delta(m, st, row, d);
+    s_ok = ok ? 1 : 0;
+    if (ok) {
+      // retained per-route aggregates
+      const uint32_t e1 = row.x, p1 = row.y, e2 = row.z, p2 = row.w;
+      const uint32_t x1 = el[off[e1] + p1];
+      for (uint32_t k = 0; k < m.n_cons; ++k) {
+        const ConsDev& c = m.cons[k];
+        if (c.kind == SFGPU_K_LIST_SUM && e1 != e2) {
+          int64_t* rsum = (int64_t*)(st + c.off0);
+          int64_t v1 = ((const int64_t*)c.g0)[x1];
+          if (kind == 2) {
+            rsum[e1] -= v1;
+            rsum[e2] += v1;
+          } else {
+            int64_t v2 = ((const int64_t*)c.g0)[el[off[e2] + p2]];
+            rsum[e1] += v2 - v1;
+            rsum[e2] += v1 - v2;
+          }
+        }
+      }
+      int64_t* cs = (int64_t*)(st + m.off_score);
+      cs[0] += d.hard;
+      cs[1] += d.soft;
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  if (kind == 3) {
+    if (threadIdx.x == 0) {
+      uint32_t f1 = off[row.x] + row.y, f2 = off[row.z] + row.w;
+      el[f1] = old_el[f2];
+      el[f2] = old_el[f1];
+    }
+  } else {
+    const uint32_t se = row.x, sp = row.y, de = row.z, dp = row.w;
+    const uint32_t S = off[se] + sp;
+    const uint32_t adj = (se == de && dp > sp) ? dp - 1 : dp;
+    const uint32_t T = off[de] - (de > se ? 1 : 0) + adj;  // insertion index in the post-removal array
+    const uint32_t x = old_el[S];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+      uint32_t v;
+      if (i == T) v = x;
+      else {
+        uint32_t j = i > T ? i - 1 : i;      // index in post-removal array
+        v = old_el[j < S ? j : j + 1];
+      }
+      el[i] = v;
+    }
+    __syncthreads();
+    for (uint32_t o = threadIdx.x; o <= m.n_owners; o += blockDim.x) {
+      uint32_t v = off[o];
+      v = v - (o > se ? 1 : 0) + (o > de ? 1 : 0);
+      // all reads of off[] above happened before this barrier-separated write phase
+      off[o] = v;
+    }
+  }
+  __syncthreads();
+  // per-route path costs are recomputed for the (at most two) touched routes
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind != SFGPU_K_LIST_PATH_COST) continue;
+    int64_t* rcost = (int64_t*)(st + c.off0);
+    const uint32_t depot = (uint32_t)c.p0;
+    if (threadIdx.x < 2) {
+      uint32_t o = threadIdx.x == 0 ? row.x : row.z;
+      if (!(threadIdx.x == 1 && row.x == row.z)) {
+        int64_t cost = 0;
+        uint32_t b = off[o], e = off[o + 1];
+        if (e > b) {
+          uint32_t prev = depot;
+          for (uint32_t i = b; i < e; ++i) {
+            cost += mat_at(c, prev, el[i]);
+            prev = el[i];
+          }
+          cost += mat_at(c, prev, depot);
+        }
+        rcost[o] = cost;
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// argbest: one CTA per replica replays acceptor + forager over the scored rows in pull order.
+// =============================================================================================
+struct ForageDev {
+  int32_t acceptor, tie_mode;
+  uint32_t accepted_limit;
+};
+
+__device__ __forceinline__ bool accepted_at(const ForageDev& f, const int64_t* scores, const uint8_t* doable,
+                                            uint64_t i, int64_t lh, int64_t ls, int64_t th, int64_t ts) {
+  if (!doable[i]) return false;
+  if (f.acceptor == 0) return true;
+  longlong2 s = ((const longlong2*)scores)[i];
+  if (f.acceptor == 1) return score_less(lh, ls, s.x, s.y);                          // move > last
+  return !score_less(s.x, s.y, lh, ls) || !score_less(s.x, s.y, th, ts);             // >= last || >= late
+}
+
+// inclusive block scan of a 32-bit count; returns this thread's inclusive prefix, total in *total
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t* scratch /* >= 33 */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[warp] = x;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (warp == 0) {
+    uint32_t w = lane < nw ? scratch[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    scratch[lane] = w;
+  }
+  __syncthreads();
+  uint32_t base = warp > 0 ? scratch[warp - 1] : 0;
+  *total = scratch[nw - 1];
+  __syncthreads();
+  return x + base;
+}
+
+__global__ void __launch_bounds__(1024) argbest_kernel(ForageDev f, const uint64_t* __restrict__ cand_offsets,
+                                                       const int64_t* __restrict__ scores,
+                                                       const uint8_t* __restrict__ doable,
+                                                       const uint64_t* __restrict__ step_seeds,
+                                                       const int64_t* __restrict__ ref_scores,
+                                                       uint32_t* __restrict__ out_index,
+                                                       int64_t* __restrict__ out_best,
+                                                       uint32_t* __restrict__ out_evaluated) {
+  __shared__ uint32_t scratch[33];
+  __shared__ int64_t s_h[32], s_s[32];
+  __shared__ uint64_t s_end;
+  __shared__ uint32_t s_pick;
+  const uint32_t r = blockIdx.x;
+  const uint64_t lo = cand_offsets[r], hi0 = cand_offsets[r + 1];
+  const int64_t lh = ref_scores ? ref_scores[r * 4 + 0] : 0, ls = ref_scores ? ref_scores[r * 4 + 1] : 0;
+  const int64_t th = ref_scores ? ref_scores[r * 4 + 2] : 0, ts = ref_scores ? ref_scores[r * 4 + 3] : 0;
+  const uint64_t seed = step_seeds ? step_seeds[r] : 0;
+  uint64_t hi = hi0;
+  // pass 0 (AcceptedCount(N) only): the step stops right after the N-th accepted pull
+  if (f.accepted_limit > 0) {
+    if (threadIdx.x == 0) s_end = hi0;
+    __syncthreads();
+    uint32_t seen = 0;
+    for (uint64_t base = lo; base < hi0; base += blockDim.x) {
+      uint64_t i = base + threadIdx.x;
+      uint32_t a = (i < hi0 && accepted_at(f, scores, doable, i, lh, ls, th, ts)) ? 1 : 0;
+      uint32_t tot;
+      uint32_t incl = block_scan_u32(a, scratch, &tot);
+      if (a && seen + incl == f.accepted_limit) s_end = i + 1;
+      seen += tot;
+      __syncthreads();
+      if (seen >= f.accepted_limit) break;
+    }
+    __syncthreads();
+    hi = s_end;
+  }
+  // pass 1: best accepted score
+  int64_t bh = INT64_MIN, bs = INT64_MIN;
+  uint32_t cnt = 0;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (!accepted_at(f, scores, doable, i, lh, ls, th, ts)) continue;
+    longlong2 s = ((const longlong2*)scores)[i];
+    if (cnt == 0 || score_less(bh, bs, s.x, s.y)) {
+      bh = s.x;
+      bs = s.y;
+    }
+    cnt = 1;
+  }
+  // warp + block lexicographic max (threads without a candidate carry INT64_MIN pairs)
+  for (int o = 16; o > 0; o >>= 1) {
+    int64_t oh = __shfl_down_sync(0xffffffffu, bh, o), os = __shfl_down_sync(0xffffffffu, bs, o);
+    uint32_t oc = __shfl_down_sync(0xffffffffu, cnt, o);
+    if (oc && (!cnt || score_less(bh, bs, oh, os))) {
+      bh = oh;
+      bs = os;
+    }
+    cnt |= oc;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_h[warp] = bh;
+    s_s[warp] = bs;
+    scratch[warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    int64_t h = 0, s = 0;
+    uint32_t any = 0;
+    for (int w = 0; w < nw; ++w)
+      if (scratch[w] && (!any || score_less(h, s, s_h[w], s_s[w]))) {
+        h = s_h[w];
+        s = s_s[w];
+        any = 1;
+      }
+    s_h[0] = h;
+    s_s[0] = s;
+    s_pick = any;
+  }
+  __syncthreads();
+  const int64_t mh = s_h[0], ms = s_s[0];
+  const uint32_t any = s_pick;
+  __syncthreads();
+  if (out_evaluated && threadIdx.x == 0) out_evaluated[r] = (uint32_t)(hi - lo);
+  if (!any) {
+    if (threadIdx.x == 0) {
+      out_index[r] = 0xFFFFFFFFu;
+      out_best[r * 2] = 0;
+      out_best[r * 2 + 1] = 0;
+    }
+    return;
+  }
+  // pass 2: number of accepted rows equal to the best score
+  uint32_t eq = 0;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (!accepted_at(f, scores, doable, i, lh, ls, th, ts)) continue;
+    longlong2 s = ((const longlong2*)scores)[i];
+    eq += (s.x == mh && s.y == ms) ? 1 : 0;
+  }
+  uint32_t m_total;
+  block_scan_u32(eq, scratch, &m_total);
+  // which occurrence wins: First => 1; reservoir => the largest k in [1, m] with pick(seed, k)
+  // (BestCandidate::consider replaces the selection at every k whose reservoir_pick fires)
+  if (threadIdx.x == 0) s_pick = 1;
+  __syncthreads();
+  if (f.tie_mode == 1) {
+    uint32_t best_k = 1;
+    for (uint32_t k = 2 + threadIdx.x; k <= m_total; k += blockDim.x) {
+      uint64_t mixed = splitmix64_dev(seed ^ ((uint64_t)k * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
+      if (mixed % k == 0) best_k = k;
+    }
+    atomicMax(&s_pick, best_k);
+    __syncthreads();
+  }
+  const uint32_t want = s_pick;
+  __syncthreads();
+  // pass 3: locate the want-th occurrence in pull order
+  uint32_t seen = 0;
+  for (uint64_t base = lo; base < hi; base += blockDim.x) {
+    uint64_t i = base + threadIdx.x;
+    uint32_t a = 0;
+    if (i < hi && accepted_at(f, scores, doable, i, lh, ls, th, ts)) {
+      longlong2 s = ((const longlong2*)scores)[i];
+      a = (s.x == mh && s.y == ms) ? 1 : 0;
+    }
+    uint32_t tot;
+    uint32_t incl = block_scan_u32(a, scratch, &tot);
+    if (a && seen + incl == want) {
+      out_index[r] = (uint32_t)(i - lo);
+      out_best[r * 2] = mh;
+      out_best[r * 2 + 1] = ms;
+    }
+    seen += tot;
+    if (seen >= want) break;
+  }
+}
+
+__global__ void pack_keys_kernel(const __grid_constant__ DevModel m, int64_t* __restrict__ out_keys) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m.R) return;
+  const int64_t* cs = (const int64_t*)(m.state + (size_t)r * m.block_bytes + m.off_score);
+  int64_t h = cs[0], s = cs[1];
+  const int64_t HB = (int64_t)1 << 23, SB = (int64_t)1 << 39;
+  h = h < -HB ? -HB : (h >= HB ? HB - 1 : h);
+  s = s < -SB ? -SB : (s >= SB ? SB - 1 : s);
+  out_keys[r] = (int64_t)(((uint64_t)(h + HB) << 40) | (uint64_t)(s + SB));
+}

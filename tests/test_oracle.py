@@ -1,0 +1,126 @@
+"""CPU tests of the oracle: pinned against the reference's known-answer vectors (oracle/kat_main.cpp)
+and against its own FullAssert invariant (incremental == evaluate_all,
+solverforge-solver/src/scope/solver/scope_core.rs:642-653) on the config models."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from solverforge_b200 import instances
+from tests import oracle_lib
+from tests.oracle_lib import Oracle
+
+
+def test_reference_known_answer_vectors():
+    oracle_lib.lib()
+    out = subprocess.run([oracle_lib.KAT], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("KAT OK")
+
+
+def test_nqueens_64_full_neighbourhood():
+    # config C1: 64 x (64 values + None) = 4160 pulls, 64 not doable
+    q = instances.nqueens(64)
+    o = Oracle.nqueens(q)
+    assert np.array_equal(o.committed_score(), o.evaluate_all())
+    rows = o.enumerate_change()
+    assert len(rows) == 4160
+    assert np.array_equal(rows, instances.change_neighbourhood(q.row, q.n))
+    scores, doable = o.score_change(rows)
+    assert int((doable == 0).sum()) == 64
+    # brute force (test_utils.rs:110-131 calculate_conflicts) on a few candidates
+    def conflicts(row):
+        c = 0
+        for i in range(len(row)):
+            for j in range(i + 1, len(row)):
+                if row[i] >= 0 and row[j] >= 0 and (row[i] == row[j] or abs(row[i] - row[j]) == j - i):
+                    c += 1
+        return c
+    for i in (0, 65, 1234, 4159):
+        e, v = rows[i]
+        r = q.row.copy()
+        r[e] = v
+        if doable[i]:
+            assert scores[i][0] == -(conflicts(r) + int((r < 0).sum()))
+    assert np.array_equal(o.committed_score(), o.evaluate_all())
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_graph_coloring_incremental_equals_full(seed):
+    g = instances.graph_coloring(300, 1200, 4, seed_edges=seed, seed_colors=seed + 10, unassigned_permille=50)
+    o = Oracle.graph_coloring(g)
+    rows = instances.change_neighbourhood(g.color, g.k)
+    scores, doable = o.score_change(rows)
+    color = g.color.copy()
+    pick = instances.splitmix64_stream(seed, 40) % np.uint64(len(rows))
+    for i in pick:
+        e, v = rows[int(i)]
+        cur = o.score_change(np.array([[e, v]]))
+        if not cur[1][0]:
+            continue
+        o.apply_change(e, v)
+        color[e] = v
+        assert np.array_equal(o.committed_score(), cur[0][0])
+        assert np.array_equal(o.committed_score(), o.evaluate_all())
+    fresh = Oracle.graph_coloring(g, color)
+    assert np.array_equal(fresh.committed_score(), o.committed_score())
+
+
+def test_cvrp_moves_round_trip():
+    c = instances.cvrp(60, 6, seed=3)
+    o = Oracle.cvrp(c)
+    base = o.committed_score().copy()
+    rows = o.enumerate_nearby_list_change(8)
+    assert len(rows) == 60 * 8
+    scores, doable = o.score_list_change(rows)
+    assert doable.all()
+    assert np.array_equal(o.committed_score(), base)  # do/undo restores the committed score
+    for i in (0, 17, 300, 479):
+        o.apply_list_change(*rows[i])
+        assert np.array_equal(o.committed_score(), o.evaluate_all())
+        rows2 = o.enumerate_nearby_list_change(8)
+        s2, d2 = o.score_list_change(rows2[:50])
+        assert np.array_equal(o.committed_score(), o.evaluate_all())
+    # list swaps, including adjacent / same-route / cross-route
+    swaps = np.array([[0, 0, 0, 1], [0, 0, 0, 3], [0, 1, 2, 0], [1, 2, 1, 2], [5, 0, 4, 99]])
+    s, d = o.score_list_swap(swaps)
+    assert list(d) == [1, 1, 1, 0, 0]
+    o.apply_list_swap(*swaps[0])
+    assert np.array_equal(o.committed_score(), s[0])
+    assert np.array_equal(o.committed_score(), o.evaluate_all())
+
+
+def test_job_shop_grouped_complement():
+    j = instances.job_shop(12, 5, 4, seed=5, unassigned_permille=100)
+    o = Oracle.job_shop(j)
+    assert np.array_equal(o.committed_score(), o.evaluate_all())
+    # soft = -(same job+machine pairs) - sum(load^2)
+    m = j.machine_idx
+    loads = np.bincount(m[m >= 0], minlength=j.n_machines)
+    pairs = 0
+    for a in range(j.n_ops):
+        for b in range(a + 1, j.n_ops):
+            if j.job[a] == j.job[b] and m[a] >= 0 and m[a] == m[b]:
+                pairs += 1
+    sc = o.committed_score()
+    assert sc[1] == -(pairs + int((loads ** 2).sum()))
+    assert sc[0] == -2 * int((m < 0).sum())  # unassigned operations are also unscheduled (not in any sequence)
+    rows = instances.change_neighbourhood(m, j.n_machines)
+    scores, doable = o.score_change(rows)
+    for i in (0, 7, 33):
+        if doable[i]:
+            o.apply_change(*rows[i])
+            assert np.array_equal(o.committed_score(), scores[i])
+            assert np.array_equal(o.committed_score(), o.evaluate_all())
+            scores, doable = o.score_change(rows)
+
+
+def test_replay_matches_reference_forager_rules():
+    # AcceptedCount(2) + HillClimbing: stops after the 2nd accepted pull (forager.rs:240-250)
+    scores = np.array([[0, -12], [0, -8], [0, -9], [0, -1]])
+    out = oracle_lib.replay_step(scores, [1, 1, 1, 1], [0, -10], [0, -10], [0, -10], 7, 0, 2, True, 0)
+    assert out == (1, 1, 3, 3, 2)
+    # BestScore + accept-all, First tie break
+    scores = np.array([[0, -5], [0, -3], [0, -3], [0, -9]])
+    out = oracle_lib.replay_step(scores, [1, 1, 1, 0], [0, 0], [0, 0], [0, 0], 1, 2, 0, False, 3)
+    assert out[:3] == (1, 1, 4) and out[3] == 3
