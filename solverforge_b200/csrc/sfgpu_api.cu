@@ -724,8 +724,8 @@ int score_entry(sfgpu_ctx* ctx, ScoreKind kind, uint32_t flags, uint64_t n_candi
   }
   // layout of both staging areas: [offsets (R+1) u64][edit offsets (n+1) u64][rows][scores][doable]
   size_t o_off = 0;
-  size_t o_eoff = o_off + (dm.R + 1) * 8;
-  size_t o_rows = o_eoff + (kind == SK_COMPOUND ? (n + 1) * 8 : 0);
+  size_t o_eoff = (o_off + (dm.R + 1) * 8 + 15) / 16 * 16;
+  size_t o_rows = (o_eoff + (kind == SK_COMPOUND ? (n + 1) * 8 : 0) + 15) / 16 * 16;
   size_t o_scores = (o_rows + n_rows * row_words * 4 + 15) / 16 * 16;
   size_t o_doable = o_scores + n * 16;
   size_t total = o_doable + (n + 15) / 16 * 16;
@@ -795,7 +795,8 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
     return SFGPU_OK;
   }
   const uint64_t n = cand_offsets[R];
-  size_t o_off = 0, o_seed = o_off + (R + 1) * 8, o_ref = o_seed + R * 8, o_scores = o_ref + R * 32;
+  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t o_off = 0, o_seed = a16(o_off + (R + 1) * 8), o_ref = a16(o_seed + R * 8), o_scores = a16(o_ref + R * 32);
   size_t o_doable = o_scores + n * 16;
   size_t o_idx = (o_doable + n + 15) / 16 * 16, o_best = o_idx + (R * 4 + 15) / 16 * 16, o_eval = o_best + R * 16;
   size_t total = o_eval + (R * 4 + 15) / 16 * 16;
