@@ -56,7 +56,10 @@ typedef struct sfgpu_ctx sfgpu_ctx;
 
 /* ---- context -------------------------------------------------------------------------- */
 /* cuda_stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create
- * a private non-blocking stream. */
+ * a private non-blocking stream (NULL + SFGPU_CTX_LEGACY_DEFAULT_STREAM = the legacy stream 0). */
+#define SFGPU_CTX_LEGACY_DEFAULT_STREAM 1ull
+/* always use the generic constraint-interpreting kernels (parity testing of the fast paths) */
+#define SFGPU_CTX_GENERIC_KERNELS 2ull
 int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgpu_ctx** out);
 int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx);
 const char* sfgpu_last_error(const sfgpu_ctx* ctx);

@@ -106,11 +106,11 @@ class GpuScoreDirector:
     applied to a whole neighbourhood at once.
     """
 
-    def __init__(self, n_replicas: int = 1, device: int = 0, stream: Optional[int] = None):
+    def __init__(self, n_replicas: int = 1, device: int = 0, stream: Optional[int] = None, flags: int = 0):
         self.lib = L.load()
         self.R = int(n_replicas)
         h = C.c_void_p()
-        rc = self.lib.sfgpu_ctx_create(device, 0, C.c_void_p(stream) if stream else None, C.byref(h))
+        rc = self.lib.sfgpu_ctx_create(device, flags, C.c_void_p(stream) if stream else None, C.byref(h))
         if rc != L.OK:
             raise L.SfgpuError(rc, self.lib.sfgpu_last_error(None).decode())
         self.h = h

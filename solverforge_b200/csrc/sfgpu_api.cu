@@ -73,6 +73,7 @@ struct sfgpu_ctx {
   int sm_count = 0;
   bool staged = false;
   bool has_load_balance = false;
+  bool force_generic = false;  // SFGPU_CTX_GENERIC_KERNELS: never take a specialised fast path (testing)
   // staging for host-pointer calls
   void* pin = nullptr;
   size_t pin_bytes = 0;
@@ -157,7 +158,6 @@ int32_t sfgpu_abi_version(void) { return SFGPU_ABI_VERSION; }
 const char* sfgpu_last_error(const sfgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 
 int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgpu_ctx** out) {
-  (void)flags;
   if (!out) return SFGPU_E_INVALID;
   *out = nullptr;
   sfgpu_ctx* ctx = nullptr;
@@ -170,8 +170,9 @@ int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgp
   CU(cudaSetDevice(device));
   ctx = new sfgpu_ctx();
   ctx->device = device;
-  if (cuda_stream) {
-    ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->force_generic = (flags & SFGPU_CTX_GENERIC_KERNELS) != 0;
+  if (cuda_stream || (flags & SFGPU_CTX_LEGACY_DEFAULT_STREAM)) {
+    ctx->stream = (cudaStream_t)cuda_stream;  // NULL + flag = the legacy default stream
   } else {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -414,6 +415,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     off = align_up(off + dm.n_entities * 4, 16);
     if (v.init.empty()) v.init.assign(dm.n_entities, SFGPU_NONE);
   }
+  dm.fast_pc = dm.fast_ls = -1;
   if (!ctx->lvars.empty()) {
     ListVar& v = ctx->lvars[0];
     dm.has_list = 1;
@@ -424,6 +426,36 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     uint32_t cap = 0;
     for (uint32_t c = 0; c < copies; ++c) cap = std::max(cap, v.offsets[(size_t)c * (dm.n_owners + 1) + dm.n_owners]);
     dm.elem_cap = std::max(cap, 1u);  // relocations and swaps keep the element count
+    // fast list path eligibility (see score_list_change_fast_kernel)
+    bool fast = true;
+    for (uint32_t k = 0; k < ctx->cons.size() && fast; ++k) {
+      const sfgpu_constraint_desc& d = ctx->cons[k].d;
+      if (d.kind == SFGPU_K_LIST_PATH_COST) {
+        if (dm.fast_pc >= 0 || d.weight.fn != SFGPU_W_LINEAR || d.aux0 >= ctx->mats.size()) { fast = false; break; }
+        const Matrix& mt = ctx->mats[d.aux0];
+        int64_t mx = 0;
+        for (int64_t c : mt.host) mx = std::max(mx, c);
+        if (!mt.i32 || mx >= (1 << 28) || (uint64_t)mt.rows * mt.cols >= (1ull << 31)) { fast = false; break; }
+        dm.fast_pc = (int32_t)k;
+      } else if (d.kind == SFGPU_K_LIST_SUM) {
+        if (dm.fast_ls >= 0 || d.aux0 >= ctx->cols.size()) { fast = false; break; }
+        for (int64_t c : ctx->cols[d.aux0].host)
+          if (c < -(1ll << 30) || c > (1ll << 30)) fast = false;
+        dm.fast_ls = (int32_t)k;
+      }
+    }
+    if (fast && (dm.fast_pc >= 0 || dm.fast_ls >= 0)) {
+      dm.fast_list = 1;
+      dm.off_route_rec = off;
+      off += dm.n_owners * 16;
+      dm.off_pos_rec = off;
+      off += dm.elem_cap * 16;
+      dm.off_slot_rec = off;
+      off += (dm.elem_cap + dm.n_owners) * 16;
+      dm.fast_stage_bytes = off;
+    } else {
+      dm.fast_pc = dm.fast_ls = -1;
+    }
     dm.off_offsets = off;
     off = align_up(off + (dm.n_owners + 1) * 4, 16);
     dm.off_elems = off;
@@ -632,6 +664,18 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
+  if (dm.fast_list) {
+    if (dm.fast_stage_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
+      dm.fast_list = 0;
+    } else {
+      int bytes = (int)dm.fast_stage_bytes;
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
+  }
   if (dm.has_list) {
     int bytes = (int)dm.elem_cap * 4;
     if (bytes > ctx->max_smem_optin) return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the apply kernel");
@@ -678,7 +722,26 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
     case SK_CHANGE: LAUNCH_SCALAR(MODE_CHANGE); break;
     case SK_SWAP: LAUNCH_SCALAR(MODE_SWAP); break;
     case SK_COMPOUND: LAUNCH_SCALAR(MODE_COMPOUND); break;
-    case SK_LIST_CHANGE: LAUNCH_LIST(LMODE_CHANGE); break;
+    case SK_LIST_CHANGE:
+      if (dm.fast_list && !ctx->force_generic) {
+        // contiguous chunk per CTA; fewer, fatter CTAs amortise the 16 B/record staging
+        uint64_t per_replica = (n_total + dm.R - 1) / dm.R;
+        uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 4095) / 4096, 64));
+        while ((uint64_t)chunks * dm.R < (uint64_t)ctx->sm_count * 4 && (uint64_t)chunks * 512 < per_replica) chunks *= 2;
+        dim3 fgrid(chunks, dm.R);
+        size_t fsm = dm.fast_stage_bytes;
+        int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
+        switch (fn) {
+          case -1: score_list_change_fast_kernel<-1><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
+          case SFGPU_W_CONST: score_list_change_fast_kernel<SFGPU_W_CONST><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
+          case SFGPU_W_LINEAR: score_list_change_fast_kernel<SFGPU_W_LINEAR><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
+          case SFGPU_W_SQUARE: score_list_change_fast_kernel<SFGPU_W_SQUARE><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
+          default: score_list_change_fast_kernel<SFGPU_W_EXCESS><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
+        }
+      } else {
+        LAUNCH_LIST(LMODE_CHANGE);
+      }
+      break;
     case SK_LIST_SWAP: LAUNCH_LIST(LMODE_SWAP); break;
   }
   cudaEventRecord(ctx->ev1, ctx->stream);
@@ -686,6 +749,15 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
 }
 
 // Host-pointer path: stage through pinned memory, H2D, kernel, D2H, synchronize.
@@ -729,22 +801,37 @@ int score_entry(sfgpu_ctx* ctx, ScoreKind kind, uint32_t flags, uint64_t n_candi
   size_t o_scores = (o_rows + n_rows * row_words * 4 + 15) / 16 * 16;
   size_t o_doable = o_scores + n * 16;
   size_t total = o_doable + (n + 15) / 16 * 16;
-  rc = ensure_staging(ctx, total, total);
+  // page-locked caller buffers are copied directly; pageable ones go through the pinned staging area
+  const bool in_pinned = is_pinned(rows), out_pinned = is_pinned(out_scores) && is_pinned(out_doable);
+  const size_t pin_need = (in_pinned ? o_rows : o_scores) + (out_pinned ? 0 : total - o_scores);
+  rc = ensure_staging(ctx, std::max<size_t>(pin_need, 64), total);
   if (rc) return rc;
   char* pin = (char*)ctx->pin;
   char* dv = (char*)ctx->dscr;
   memcpy(pin + o_off, cand_offsets, (dm.R + 1) * 8);
   if (kind == SK_COMPOUND) memcpy(pin + o_eoff, edit_offsets, (n + 1) * 8);
-  memcpy(pin + o_rows, rows, n_rows * row_words * 4);
-  CU(cudaMemcpyAsync(dv, pin, o_scores, cudaMemcpyHostToDevice, ctx->stream));
+  if (in_pinned) {
+    CU(cudaMemcpyAsync(dv, pin, o_rows, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dv + o_rows, rows, n_rows * row_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    memcpy(pin + o_rows, rows, n_rows * row_words * 4);
+    CU(cudaMemcpyAsync(dv, pin, o_scores, cudaMemcpyHostToDevice, ctx->stream));
+  }
   rc = launch_score(ctx, kind, n, (const uint64_t*)(dv + o_off), (const uint32_t*)(dv + o_rows),
                     kind == SK_COMPOUND ? (const uint64_t*)(dv + o_eoff) : nullptr, (int64_t*)(dv + o_scores),
                     (uint8_t*)(dv + o_doable));
   if (rc) return rc;
-  CU(cudaMemcpyAsync(pin + o_scores, dv + o_scores, total - o_scores, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  memcpy(out_scores, pin + o_scores, n * 16);
-  memcpy(out_doable, pin + o_doable, n);
+  if (out_pinned) {
+    CU(cudaMemcpyAsync(out_scores, dv + o_scores, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_doable, dv + o_doable, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  } else {
+    char* stage = pin + (in_pinned ? o_rows : o_scores);
+    CU(cudaMemcpyAsync(stage, dv + o_scores, total - o_scores, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_scores, stage, n * 16);
+    memcpy(out_doable, stage + (o_doable - o_scores), n);
+  }
   return SFGPU_OK;
 }
 

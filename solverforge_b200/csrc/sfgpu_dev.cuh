@@ -42,8 +42,30 @@ struct DevModel {
   uint32_t has_scalar, n_entities, n_values, allows_unassigned, off_var;
   // list variable
   uint32_t has_list, n_owners, n_elem_rows, elem_cap, off_offsets, off_elems;
+  // fast list path: packed per-route / per-position / per-slot records
+  uint32_t fast_list;       // 1 when the constraint program fits the specialised list-change kernel
+  uint32_t fast_stage_bytes;
+  uint32_t off_route_rec, off_pos_rec, off_slot_rec;
+  int32_t fast_pc, fast_ls;  // constraint indices of the path-cost / list-sum constraint, or -1
   uint32_t pad;
   ConsDev cons[SFGPU_MAX_CONS];
+};
+
+// 16-byte records so one candidate needs four 128-bit shared-memory loads
+struct RouteRec {   // per owner
+  uint32_t base, len;
+  int64_t sum;      // retained LIST_SUM aggregate (0 without a LIST_SUM constraint)
+};
+struct PosRec {     // per flat element position
+  uint32_t elem;
+  int32_t rem;      // path-cost delta of removing this element from its route
+  int32_t val;      // LIST_SUM column value of the element
+  uint32_t pad;
+};
+struct SlotRec {    // per insertion slot (owner e, position p in 0..=len), index = base + e + p
+  uint32_t a, b;    // neighbours of the slot (depot at the ends)
+  int32_t gap;      // cost of the existing leg a -> b (0 for an empty route)
+  uint32_t pad;
 };
 
 struct Score2 {

@@ -396,6 +396,170 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast list-change path. Preconditions (checked at commit, DevModel::fast_list): at most one
+// LIST_PATH_COST constraint with a LINEAR weight over an int32 matrix whose cells are < 2^28, at
+// most one LIST_SUM constraint whose column fits int32, any number of EXISTS_FLAT constraints
+// (relocations never change their score). The replica block then carries packed records that
+// are rebuilt whenever a move is committed, and one candidate costs four 128-bit LDS, two matrix
+// gathers, one 128-bit LDG and one 128-bit STG.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) {
+  // block-parallel over owners; reads offsets/elems, writes the three record arrays
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  RouteRec* rr = (RouteRec*)(st + m.off_route_rec);
+  PosRec* pr = (PosRec*)(st + m.off_pos_rec);
+  SlotRec* sr = (SlotRec*)(st + m.off_slot_rec);
+  const ConsDev* pc = m.fast_pc >= 0 ? &m.cons[m.fast_pc] : nullptr;
+  const ConsDev* ls = m.fast_ls >= 0 ? &m.cons[m.fast_ls] : nullptr;
+  const int32_t* mat = pc ? (const int32_t*)pc->g0 : nullptr;
+  const uint32_t dim = pc ? pc->n0 : 0;
+  const uint32_t depot = pc ? (uint32_t)pc->p0 : 0;
+  for (uint32_t o = threadIdx.x; o < m.n_owners; o += blockDim.x) {
+    const uint32_t b = off[o], len = off[o + 1] - b;
+    int64_t sum = 0;
+    for (uint32_t p = 0; p <= len; ++p) {
+      const uint32_t a_el = p > 0 ? el[b + p - 1] : depot;
+      const uint32_t b_el = p < len ? el[b + p] : depot;
+      SlotRec s;
+      s.a = a_el;
+      s.b = b_el;
+      s.gap = (pc && len > 0) ? mat[a_el * dim + b_el] : 0;
+      s.pad = 0;
+      sr[b + o + p] = s;
+      if (p < len) {
+        const uint32_t x = b_el;
+        const uint32_t nx = p + 1 < len ? el[b + p + 1] : depot;
+        PosRec q;
+        q.elem = x;
+        q.rem = pc ? (-mat[a_el * dim + x] - mat[x * dim + nx] + (len > 1 ? mat[a_el * dim + nx] : 0)) : 0;
+        q.val = ls ? (int32_t)((const int64_t*)ls->g0)[x] : 0;
+        q.pad = 0;
+        pr[b + p] = q;
+        sum += q.val;
+      }
+    }
+    RouteRec r;
+    r.base = b;
+    r.len = len;
+    r.sum = sum;
+    rr[o] = r;
+  }
+}
+
+template <int SUM_FN /* -1: no LIST_SUM constraint */>
+__global__ void __launch_bounds__(256) score_list_change_fast_kernel(const __grid_constant__ DevModel m,
+                                                                     const uint64_t* __restrict__ cand_offsets,
+                                                                     const uint32_t* __restrict__ rows,
+                                                                     int64_t* __restrict__ out_scores,
+                                                                     uint8_t* __restrict__ out_doable) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  const uint32_t r = blockIdx.y;
+  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
+  const int64_t* cs = (const int64_t*)(smem + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const uint4* rr = (const uint4*)(smem + m.off_route_rec);
+  const uint4* pr = (const uint4*)(smem + m.off_pos_rec);
+  const uint4* sr = (const uint4*)(smem + m.off_slot_rec);
+  const uint32_t n_owners = m.n_owners;
+  // path cost: LINEAR weight => weight(old + d) - weight(old) = a * d
+  const bool has_pc = m.fast_pc >= 0;
+  const ConsDev& pc = m.cons[has_pc ? m.fast_pc : 0];
+  const int32_t* __restrict__ mat = (const int32_t*)pc.g0;
+  const uint32_t dim = pc.n0;
+  const int64_t pc_a = has_pc ? (pc.sign < 0 ? -pc.w.a : pc.w.a) : 0;
+  const bool pc_hard = pc.w.level == 0;
+  const ConsDev& ls = m.cons[SUM_FN >= 0 ? m.fast_ls : 0];
+  const int64_t ls_a = ls.sign < 0 ? -ls.w.a : ls.w.a, ls_b = ls.w.b;
+  const bool ls_hard = ls.w.level == 0;
+  // contiguous chunk per CTA (keeps pull order inside a chunk for the fused forager partials)
+  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  const uint64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  const uint64_t c_lo = lo + per * blockIdx.x;
+  const uint64_t c_hi = c_lo + per < hi ? c_lo + per : hi;
+  // U candidates per thread per trip with the next trip's rows prefetched into registers: the
+  // DRAM latency of the streamed rows is hidden by 2*U independent 128-bit loads per thread.
+  constexpr int U = 4;
+  const uint4* __restrict__ rows4 = (const uint4*)rows;
+  const uint64_t stride = (uint64_t)blockDim.x * U;
+  uint4 nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint64_t i = c_lo + threadIdx.x + (uint64_t)u * blockDim.x;
+    nxt[u] = i < c_hi ? __ldcs(rows4 + i) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+  }
+  for (uint64_t base = c_lo + threadIdx.x; base < c_hi; base += stride) {
+    uint4 cur[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      cur[u] = nxt[u];
+      const uint64_t i = base + stride + (uint64_t)u * blockDim.x;
+      nxt[u] = i < c_hi ? __ldcs(rows4 + i) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+    }
+    // phase 1: route records + doability
+    bool ok[U];
+    uint32_t pidx[U], sidx[U];
+    int64_t sums[U], sumd[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t se = cur[u].x, sp = cur[u].y, de = cur[u].z, dp = cur[u].w;
+      ok[u] = se < n_owners && de < n_owners;
+      const uint4 rs = rr[ok[u] ? se : 0], rd = rr[ok[u] ? de : 0];
+      ok[u] = ok[u] && sp < rs.y && dp <= rd.y && !(se == de && (dp == sp || dp == sp + 1));
+      pidx[u] = ok[u] ? rs.x + sp : 0;
+      sidx[u] = ok[u] ? rd.x + de + dp : 0;
+      if (SUM_FN >= 0) {
+        sums[u] = (int64_t)(((uint64_t)rs.w << 32) | rs.z);
+        sumd[u] = (int64_t)(((uint64_t)rd.w << 32) | rd.z);
+      }
+    }
+    // phase 2: position / slot records, then the two matrix gathers
+    uint4 p[U], sl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      p[u] = pr[pidx[u]];
+      sl[u] = sr[sidx[u]];
+    }
+    int32_t m0[U], m1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      m0[u] = has_pc ? __ldg(mat + sl[u].x * dim + p[u].x) : 0;
+      m1[u] = has_pc ? __ldg(mat + p[u].x * dim + sl[u].y) : 0;
+    }
+    // phase 3: deltas + stores
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = base + (uint64_t)u * blockDim.x;
+      if (i >= c_hi) continue;
+      int64_t dh = 0, ds = 0;
+      if (has_pc) {
+        const int64_t d = pc_a * (int64_t)((int32_t)p[u].y + m0[u] + m1[u] - (int32_t)sl[u].z);
+        if (pc_hard) dh += d; else ds += d;
+      }
+      if (SUM_FN >= 0 && cur[u].x != cur[u].z) {
+        const int64_t v = (int32_t)p[u].z;
+        int64_t d = 0;
+        if (SUM_FN == SFGPU_W_EXCESS) {
+          const int64_t e0 = sums[u] - ls_b, e1 = sumd[u] - ls_b;
+          d = (max(e0 - v, (int64_t)0) - max(e0, (int64_t)0)) + (max(e1 + v, (int64_t)0) - max(e1, (int64_t)0));
+          d *= ls_a;
+        } else if (SUM_FN == SFGPU_W_SQUARE) {
+          const int64_t ss = sums[u], sd = sumd[u];
+          d = ls_a * (((ss - v) * (ss - v) - ss * ss) + ((sd + v) * (sd + v) - sd * sd));
+        }  // LINEAR: -a*v + a*v = 0; CONST: the number of routes is unchanged
+        if (ls_hard) dh += d; else ds += d;
+      }
+      longlong2 o;
+      o.x = ok[u] ? ch + dh : 0;
+      o.y = ok[u] ? csf + ds : 0;
+      __stcs((longlong2*)out_scores + i, o);
+      out_doable[i] = ok[u] ? 1 : 0;
+    }
+  }
+}
+
 // =============================================================================================
 // block reductions
 // =============================================================================================
@@ -569,6 +733,10 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
     int64_t* cs = (int64_t*)(st + m.off_score);
     cs[0] = hard;
     cs[1] = soft;
+  }
+  if (m.fast_list) {
+    __syncthreads();
+    build_fast_records(m, st);
   }
 }
 
@@ -755,6 +923,10 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
         rcost[o] = cost;
       }
     }
+  }
+  if (m.fast_list) {
+    __syncthreads();
+    build_fast_records(m, st);
   }
 }
 

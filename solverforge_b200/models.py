@@ -19,8 +19,8 @@ from .instances import CvrpInstance, GraphColoringInstance, JobShopInstance, NQu
 
 
 def graph_coloring_director(inst: GraphColoringInstance, n_replicas: int = 1, colors=None, device: int = 0,
-                            stream=None) -> GpuScoreDirector:
-    d = GpuScoreDirector(n_replicas, device, stream)
+                            stream=None, flags: int = 0) -> GpuScoreDirector:
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
     d.add_collection("colors", inst.k, -1)
     nodes = d.add_collection("nodes", inst.n, 0)
     d.add_scalar_variable(nodes, "color_idx", inst.k, allows_unassigned=True)
@@ -35,10 +35,10 @@ def graph_coloring_director(inst: GraphColoringInstance, n_replicas: int = 1, co
 
 
 def nqueens_director(inst: NQueensInstance, n_replicas: int = 1, rows=None, device: int = 0,
-                     stream=None) -> GpuScoreDirector:
+                     stream=None, flags: int = 0) -> GpuScoreDirector:
     """`left.column < right.column && (same row || same diagonal)` is the disjoint union of three
     equal-key joins: row, row + column, row - column."""
-    d = GpuScoreDirector(n_replicas, device, stream)
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
     d.add_collection("rows", inst.n, -1)
     queens = d.add_collection("queens", inst.n, 0)
     d.add_scalar_variable(queens, "row_idx", inst.n, allows_unassigned=True)
@@ -54,8 +54,8 @@ def nqueens_director(inst: NQueensInstance, n_replicas: int = 1, rows=None, devi
 
 
 def cvrp_director(inst: CvrpInstance, n_replicas: int = 1, offsets=None, elems=None, device: int = 0,
-                  stream=None) -> GpuScoreDirector:
-    d = GpuScoreDirector(n_replicas, device, stream)
+                  stream=None, flags: int = 0) -> GpuScoreDirector:
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
     locations = d.add_collection("locations", inst.dim, -1)       # matrix rows: depot + customers
     customers = d.add_collection("customers", inst.dim - 1, -1)   # problem facts, id = 1..n
     routes = d.add_collection("routes", inst.n_routes, 0)
@@ -74,8 +74,8 @@ def cvrp_director(inst: CvrpInstance, n_replicas: int = 1, offsets=None, elems=N
 
 
 def job_shop_director(inst: JobShopInstance, n_replicas: int = 1, machine_idx=None, with_complement: bool = True,
-                      device: int = 0, stream=None) -> GpuScoreDirector:
-    d = GpuScoreDirector(n_replicas, device, stream)
+                      device: int = 0, stream=None, flags: int = 0) -> GpuScoreDirector:
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
     machines = d.add_collection("machines", inst.n_machines, -1)
     ops = d.add_collection("operations", inst.n_ops, 0)
     seqs = d.add_collection("machine_sequences", inst.n_machines, 1)

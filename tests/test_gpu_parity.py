@@ -275,6 +275,35 @@ def test_cvrp_empty_routes_and_unreachable_cells():
         _eq(d.fresh_score()[0], o.evaluate_all())
 
 
+def test_fast_list_kernel_equals_generic_kernel():
+    c = instances.cvrp(300, 20, seed=4)
+    offs, el = instances.perturb_routes(c, 9, 200)
+    o = Oracle.cvrp(c, offs, el)
+    rows = o.enumerate_nearby_list_change(20)
+    r = instances.splitmix64_stream(8, 8000)
+    rnd = np.stack([r[:2000] % np.uint64(20), r[2000:4000] % np.uint64(40), r[4000:6000] % np.uint64(20),
+                    r[6000:] % np.uint64(40)], axis=1).astype(np.uint32)      # many not-doable / out-of-range rows
+    rows = np.concatenate([rows, rnd])
+    fast = models.cvrp_director(c, offsets=offs, elems=el)
+    gen = models.cvrp_director(c, offsets=offs, elems=el, flags=L.CTX_GENERIC_KERNELS)
+    sf, okf = fast.score_list_change(rows)
+    sg, okg = gen.score_list_change(rows)
+    so, oko = o.score_list_change(rows)
+    _eq(okf, okg, "fast vs generic doable")
+    _eq(sf, sg, "fast vs generic scores")
+    _eq(okf, oko)
+    _eq(sf, so, "fast vs oracle")
+    for i in np.flatnonzero(okf)[[5, 900, 4000]]:
+        fast.apply_list_change(rows[i][None, :])
+        gen.apply_list_change(rows[i][None, :])
+        o.apply_list_change(*rows[i])
+        sf, okf = fast.score_list_change(rows)
+        so, oko = o.score_list_change(rows)
+        _eq(sf, so, "fast after apply")
+        _eq(okf, oko)
+    _eq(fast.calculate_score(), gen.calculate_score())
+
+
 def test_replicas_are_independent():
     c = instances.cvrp(120, 8, seed=7)
     R = 5
