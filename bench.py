@@ -271,7 +271,7 @@ def run_ours(args):
                          t_idx.data_ptr(), t_best.data_ptr(), t_eval.data_ptr())
         if world > 1 and (i + 1) % args.sync_every == 0:
             # best packed score over this rank's replicas, then one 8-byte MAX all-reduce (NCCL)
-            best = (((t_best[:, 0] + (1 << 23)) << 40) | (t_best[:, 1] + (1 << 39))).max().reshape(1)
+            best = (((t_best[:, 0] + (1 << 22)) << 40) | (t_best[:, 1] + (1 << 39))).max().reshape(1)
             dist.all_reduce(best, op=dist.ReduceOp.MAX)
 
     # cpu_baseline leg (rank 0): the oracle scores replica 0's batch on one host core; its output

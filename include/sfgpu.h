@@ -238,7 +238,7 @@ int32_t sfgpu_list_capacity(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_cap
 
 /* ---- replicas across GPUs -------------------------------------------------------------- */
 /* Order-preserving packed key of each replica's committed score for a MAX all-reduce:
- * key = ((hard + 2^23) << 40) | (soft + 2^39), valid for hard in [-2^23, 2^23), soft in [-2^39, 2^39)
+ * key = ((hard + 2^22) << 40) | (soft + 2^39), valid for hard in [-2^22, 2^22), soft in [-2^39, 2^39)
  * (out-of-range levels saturate). out_keys is a DEVICE pointer to R int64 (e.g. a torch tensor the
  * caller then passes to torch.distributed.all_reduce(MAX) / ncclAllReduce). */
 int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys);

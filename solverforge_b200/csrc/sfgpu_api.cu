@@ -669,11 +669,11 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       dm.fast_list = 0;
     } else {
       int bytes = (int)dm.fast_stage_bytes;
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
   }
   if (dm.has_list) {
@@ -726,17 +726,19 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
       if (dm.fast_list && !ctx->force_generic) {
         // contiguous chunk per CTA; fewer, fatter CTAs amortise the 16 B/record staging
         uint64_t per_replica = (n_total + dm.R - 1) / dm.R;
-        uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 4095) / 4096, 64));
+        uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 6143) / 6144, 64));
         while ((uint64_t)chunks * dm.R < (uint64_t)ctx->sm_count * 4 && (uint64_t)chunks * 512 < per_replica) chunks *= 2;
         dim3 fgrid(chunks, dm.R);
         size_t fsm = dm.fast_stage_bytes;
         int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
+        if (getenv("SFGPU_FAST_CHUNKS")) fgrid.x = atoi(getenv("SFGPU_FAST_CHUNKS"));  // tuning knob
+#define FASTK(FN) score_list_change_fast_kernel<FN, 2, 3><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable)
         switch (fn) {
-          case -1: score_list_change_fast_kernel<-1><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
-          case SFGPU_W_CONST: score_list_change_fast_kernel<SFGPU_W_CONST><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
-          case SFGPU_W_LINEAR: score_list_change_fast_kernel<SFGPU_W_LINEAR><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
-          case SFGPU_W_SQUARE: score_list_change_fast_kernel<SFGPU_W_SQUARE><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
-          default: score_list_change_fast_kernel<SFGPU_W_EXCESS><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); break;
+          case -1: FASTK(-1); break;
+          case SFGPU_W_CONST: FASTK(SFGPU_W_CONST); break;
+          case SFGPU_W_LINEAR: FASTK(SFGPU_W_LINEAR); break;
+          case SFGPU_W_SQUARE: FASTK(SFGPU_W_SQUARE); break;
+          default: FASTK(SFGPU_W_EXCESS); break;
         }
       } else {
         LAUNCH_LIST(LMODE_CHANGE);

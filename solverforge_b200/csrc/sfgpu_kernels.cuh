@@ -448,8 +448,8 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   }
 }
 
-template <int SUM_FN /* -1: no LIST_SUM constraint */>
-__global__ void __launch_bounds__(256) score_list_change_fast_kernel(const __grid_constant__ DevModel m,
+template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3>
+__global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const __grid_constant__ DevModel m,
                                                                      const uint64_t* __restrict__ cand_offsets,
                                                                      const uint32_t* __restrict__ rows,
                                                                      int64_t* __restrict__ out_scores,
@@ -481,7 +481,6 @@ __global__ void __launch_bounds__(256) score_list_change_fast_kernel(const __gri
   const uint64_t c_hi = c_lo + per < hi ? c_lo + per : hi;
   // U candidates per thread per trip with the next trip's rows prefetched into registers: the
   // DRAM latency of the streamed rows is hidden by 2*U independent 128-bit loads per thread.
-  constexpr int U = 4;
   const uint4* __restrict__ rows4 = (const uint4*)rows;
   const uint64_t stride = (uint64_t)blockDim.x * U;
   uint4 nxt[U];
@@ -1116,7 +1115,7 @@ __global__ void pack_keys_kernel(const __grid_constant__ DevModel m, int64_t* __
   if (r >= m.R) return;
   const int64_t* cs = (const int64_t*)(m.state + (size_t)r * m.block_bytes + m.off_score);
   int64_t h = cs[0], s = cs[1];
-  const int64_t HB = (int64_t)1 << 23, SB = (int64_t)1 << 39;
+  const int64_t HB = (int64_t)1 << 22, SB = (int64_t)1 << 39;  // 23 + 40 = 63 bits: stays positive in int64
   h = h < -HB ? -HB : (h >= HB ? HB - 1 : h);
   s = s < -SB ? -SB : (s >= SB ? SB - 1 : s);
   out_keys[r] = (int64_t)(((uint64_t)(h + HB) << 40) | (uint64_t)(s + SB));

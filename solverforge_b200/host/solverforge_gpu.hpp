@@ -1,0 +1,454 @@
+// solverforge_gpu.hpp — C++ host-side mirror of the reference's scoring interface, above the C ABI.
+//
+// The reference is Rust; this image has no Rust toolchain, so the host layer a Rust
+// `solverforge-gpu` crate would provide is written in C++17 with the same names, argument
+// meaning and error behaviour (INTEGRATION.md shows the Rust binding):
+//
+//   HardSoftScore / HardSoftDecimalScore   solverforge-core/src/score/hard_soft.rs:35-153, hard_soft_decimal.rs:14-221
+//   ConstraintFactory .for_each(..)...     solverforge-scoring/src/stream/factory.rs:43-73
+//   Director surface (calculate_score, fresh_score, ...)   solverforge-scoring/src/director/traits.rs:27-95
+//   ScalarEdit                             solverforge-solver/src/planning/scalar/candidate.rs:6-12
+//   Acceptor / LocalSearchForager replay   solverforge-solver/src/phase/localsearch/{acceptor/*,forager.rs,phase/candidates.rs:66-282}
+//
+// Everything that touches scores runs in libsfgpu (CUDA). Errors surface as sf::GpuError; there is no
+// CPU scoring fallback (north_star). The host replay below only *orders* already-computed scores, which
+// is what the reference's acceptor/forager do.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sfgpu.h"
+
+namespace sf {
+
+struct GpuError : std::runtime_error {
+  int code;
+  GpuError(int c, const std::string& m) : std::runtime_error("libsfgpu error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+struct HardSoftScore {
+  int64_t hard = 0, soft = 0;
+  static constexpr HardSoftScore of(int64_t h, int64_t s) { return {h, s}; }
+  static constexpr HardSoftScore of_hard(int64_t h) { return {h, 0}; }
+  static constexpr HardSoftScore of_soft(int64_t s) { return {0, s}; }
+  static constexpr HardSoftScore ZERO() { return {0, 0}; }
+  static constexpr HardSoftScore ONE_HARD() { return {1, 0}; }
+  static constexpr HardSoftScore ONE_SOFT() { return {0, 1}; }
+  bool is_feasible() const { return hard >= 0; }
+  HardSoftScore operator+(HardSoftScore o) const { return {hard + o.hard, soft + o.soft}; }
+  HardSoftScore operator-(HardSoftScore o) const { return {hard - o.hard, soft - o.soft}; }
+  HardSoftScore operator-() const { return {-hard, -soft}; }
+  bool operator==(HardSoftScore o) const { return hard == o.hard && soft == o.soft; }
+  bool operator!=(HardSoftScore o) const { return !(*this == o); }
+  bool operator<(HardSoftScore o) const { return hard != o.hard ? hard < o.hard : soft < o.soft; }
+  bool operator>(HardSoftScore o) const { return o < *this; }
+  bool operator<=(HardSoftScore o) const { return !(o < *this); }
+  bool operator>=(HardSoftScore o) const { return !(*this < o); }
+  int64_t level(int l) const { return l == 0 ? hard : soft; }
+};
+// HardSoftDecimalScore shares the layout with levels pre-scaled by 100000.
+struct HardSoftDecimalScore : HardSoftScore {
+  static constexpr int64_t SCALE = 100000;
+  static constexpr HardSoftScore of(int64_t h, int64_t s) { return {h * SCALE, s * SCALE}; }
+  static constexpr HardSoftScore of_scaled(int64_t h, int64_t s) { return {h, s}; }
+};
+
+struct ScalarEdit {  // planning/scalar/candidate.rs:6-12 (descriptor + variable are fixed per model here)
+  uint32_t entity_index;
+  int32_t to_value;  // -1 = None
+};
+struct ListChange {  // heuristic/move/list_kernel/change.rs:15-21
+  uint32_t source_entity, source_position, destination_entity, destination_position;
+};
+
+struct Weight {
+  sfgpu_weight w;
+  static Weight constant(HardSoftScore s) {
+    if (s.hard != 0 && s.soft != 0) throw GpuError(SFGPU_E_UNSUPPORTED, "a constant weight must sit on one level");
+    return {{SFGPU_W_CONST, s.hard != 0 ? 0 : 1, s.hard != 0 ? s.hard : s.soft, 0}};
+  }
+  static Weight hard(int fn, int64_t a = 1, int64_t b = 0) { return {{fn, 0, a, b}}; }
+  static Weight soft(int fn, int64_t a = 1, int64_t b = 0) { return {{fn, 1, a, b}}; }
+};
+
+class GpuScoreDirector;
+
+// joiners / collectors (device forms of the reference closures)
+struct AdjacentEqual { uint32_t csr; };
+struct EqualKey { uint32_t column = UINT32_MAX; int64_t col_mul = 0, var_mul = 1; };
+struct EqualVarToRow {};
+struct EqualId { uint32_t column = UINT32_MAX; };
+struct PathCost { uint32_t matrix; uint32_t depot; };
+struct ListSum { uint32_t column; };
+struct Count {};
+struct Sum { uint32_t column; };
+struct LoadBalance { uint32_t metric_column = UINT32_MAX; };
+
+struct Terminal {
+  GpuScoreDirector* d;
+  sfgpu_constraint_desc desc;
+  uint32_t named(const std::string& name);
+};
+
+struct GroupedStream {
+  GpuScoreDirector* d;
+  uint32_t collection, column;
+  bool load_balance, complemented = false;
+  int64_t default_result = 0;
+  GroupedStream complement(uint32_t /*targets*/, int64_t def) const {
+    GroupedStream g = *this;
+    g.complemented = true;
+    g.default_result = def;
+    return g;
+  }
+  Terminal impact(int imp, Weight w) const {
+    sfgpu_constraint_desc c{};
+    c.kind = load_balance ? SFGPU_K_LOAD_BALANCE : SFGPU_K_GROUP;
+    c.impact = imp;
+    c.weight = w.w;
+    c.collection = collection;
+    c.aux0 = column;
+    c.p0 = complemented ? 1 : 0;
+    c.p1 = default_result;
+    return {d, c};
+  }
+  Terminal penalize(Weight w) const { return impact(SFGPU_PENALTY, w); }
+  Terminal reward(Weight w) const { return impact(SFGPU_REWARD, w); }
+};
+
+struct BiStream {
+  GpuScoreDirector* d;
+  uint32_t collection;
+  int joiner_kind;  // 0 adjacent, 1 key, 2 var->row
+  AdjacentEqual adj{};
+  EqualKey key{};
+  Terminal impact(int imp, HardSoftScore w) const {
+    sfgpu_constraint_desc c{};
+    c.impact = imp;
+    c.weight = Weight::constant(w).w;
+    c.collection = collection;
+    if (joiner_kind == 0) {
+      c.kind = SFGPU_K_PAIR_CSR_EQUAL;
+      c.aux0 = adj.csr;
+    } else if (joiner_kind == 1) {
+      c.kind = SFGPU_K_PAIR_KEY_EQUAL;
+      c.aux0 = key.column;
+      c.p0 = key.col_mul;
+      c.p1 = key.var_mul;
+    } else {
+      throw GpuError(SFGPU_E_UNSUPPORTED, "joiner is not expressible on device without group_by");
+    }
+    return {d, c};
+  }
+  Terminal penalize(HardSoftScore w) const { return impact(SFGPU_PENALTY, w); }
+  Terminal reward(HardSoftScore w) const { return impact(SFGPU_REWARD, w); }
+  GroupedStream group_by(Count) const { return {d, collection, UINT32_MAX, false}; }
+  GroupedStream group_by(Sum s) const { return {d, collection, s.column, false}; }
+};
+
+struct ExistsStream {
+  GpuScoreDirector* d;
+  uint32_t collection, column;
+  int mode;
+  Terminal impact(int imp, HardSoftScore w) const {
+    sfgpu_constraint_desc c{};
+    c.kind = SFGPU_K_EXISTS_FLAT;
+    c.impact = imp;
+    c.weight = Weight::constant(w).w;
+    c.collection = collection;
+    c.variable = 0x80000000u;
+    c.aux0 = column;
+    c.p0 = mode;
+    return {d, c};
+  }
+  Terminal penalize(HardSoftScore w) const { return impact(SFGPU_PENALTY, w); }
+  Terminal reward(HardSoftScore w) const { return impact(SFGPU_REWARD, w); }
+};
+
+struct UniStream {
+  GpuScoreDirector* d;
+  uint32_t collection;
+  int filter = 2;  // 0 unassigned, 1 assigned, 2 always
+  UniStream unassigned() const { return {d, collection, 0}; }
+  UniStream assigned() const { return {d, collection, 1}; }
+  UniStream flattened() const { return *this; }
+  Terminal uni(int imp, Weight w, uint32_t column, bool by_value) const {
+    sfgpu_constraint_desc c{};
+    c.kind = SFGPU_K_UNI;
+    c.impact = imp;
+    c.weight = w.w;
+    c.collection = collection;
+    c.aux0 = column;
+    c.p0 = filter;
+    c.p1 = by_value ? 1 : 0;
+    return {d, c};
+  }
+  Terminal penalize(HardSoftScore w) const { return uni(SFGPU_PENALTY, Weight::constant(w), UINT32_MAX, false); }
+  Terminal reward(HardSoftScore w) const { return uni(SFGPU_REWARD, Weight::constant(w), UINT32_MAX, false); }
+  Terminal penalize(Weight w, uint32_t column, bool by_value = false) const { return uni(SFGPU_PENALTY, w, column, by_value); }
+  Terminal penalize(Weight w, PathCost pc) const {
+    sfgpu_constraint_desc c{};
+    c.kind = SFGPU_K_LIST_PATH_COST;
+    c.impact = SFGPU_PENALTY;
+    c.weight = w.w;
+    c.collection = collection;
+    c.variable = 0x80000000u;
+    c.aux0 = pc.matrix;
+    c.p0 = pc.depot;
+    return {d, c};
+  }
+  Terminal penalize(Weight w, ListSum ls) const {
+    sfgpu_constraint_desc c{};
+    c.kind = SFGPU_K_LIST_SUM;
+    c.impact = SFGPU_PENALTY;
+    c.weight = w.w;
+    c.collection = collection;
+    c.variable = 0x80000000u;
+    c.aux0 = ls.column;
+    return {d, c};
+  }
+  BiStream join(const UniStream&, AdjacentEqual j) const { return {d, collection, 0, j, {}}; }
+  BiStream join(const UniStream&, EqualKey j) const { return {d, collection, 1, {}, j}; }
+  BiStream join(uint32_t /*values*/, EqualVarToRow) const { return {d, collection, 2, {}, {}}; }
+  ExistsStream if_exists(const UniStream&, EqualId j) const { return {d, collection, j.column, 0}; }
+  ExistsStream if_not_exists(const UniStream&, EqualId j) const { return {d, collection, j.column, 1}; }
+  GroupedStream group_by(Count) const { return {d, collection, UINT32_MAX, false}; }
+  GroupedStream group_by(Sum s) const { return {d, collection, s.column, false}; }
+  GroupedStream group_by(LoadBalance lb) const { return {d, collection, lb.metric_column, true}; }
+};
+
+struct ConstraintFactory {
+  GpuScoreDirector* d;
+  explicit ConstraintFactory(GpuScoreDirector& dir) : d(&dir) {}
+  UniStream for_each(uint32_t collection) const { return {d, collection, 2}; }
+};
+
+// RAII owner of one sfgpu_ctx — the Director of R replicas.
+class GpuScoreDirector {
+ public:
+  explicit GpuScoreDirector(uint32_t n_replicas = 1, int device = 0, void* stream = nullptr, uint64_t flags = 0)
+      : R_(n_replicas) {
+    int rc = sfgpu_ctx_create(device, flags, stream, &ctx_);
+    if (rc != SFGPU_OK) throw GpuError(rc, sfgpu_last_error(nullptr));
+    check(sfgpu_model_begin(ctx_, n_replicas));
+  }
+  ~GpuScoreDirector() {
+    if (ctx_) sfgpu_ctx_destroy(ctx_);
+  }
+  GpuScoreDirector(const GpuScoreDirector&) = delete;
+  GpuScoreDirector& operator=(const GpuScoreDirector&) = delete;
+
+  uint32_t replicas() const { return R_; }
+  sfgpu_ctx* raw() const { return ctx_; }
+  void check(int rc) const {
+    if (rc != SFGPU_OK) throw GpuError(rc, sfgpu_last_error(ctx_));
+  }
+
+  uint32_t add_collection(const std::string& name, uint32_t n_rows, int32_t descriptor_index = -1) {
+    uint32_t id;
+    check(sfgpu_add_collection(ctx_, name.c_str(), n_rows, descriptor_index, &id));
+    return id;
+  }
+  uint32_t add_column(uint32_t coll, const std::string& name, const std::vector<int64_t>& v) {
+    uint32_t id;
+    check(sfgpu_add_column_i64(ctx_, coll, name.c_str(), v.data(), &id));
+    return id;
+  }
+  uint32_t add_scalar_variable(uint32_t coll, const std::string& name, uint32_t n_values, bool allows_unassigned) {
+    uint32_t id;
+    check(sfgpu_add_scalar_variable(ctx_, coll, name.c_str(), n_values, allows_unassigned ? 1 : 0, &id));
+    return id;
+  }
+  uint32_t add_list_variable(uint32_t owners, uint32_t elements, const std::string& name) {
+    uint32_t id;
+    check(sfgpu_add_list_variable(ctx_, owners, elements, name.c_str(), &id));
+    return id;
+  }
+  uint32_t add_csr(const std::string& name, const std::vector<uint32_t>& row_ptr, const std::vector<uint32_t>& col) {
+    uint32_t id;
+    check(sfgpu_add_csr(ctx_, name.c_str(), (uint32_t)row_ptr.size() - 1, row_ptr.data(), col.data(), &id));
+    return id;
+  }
+  uint32_t add_matrix(const std::string& name, uint32_t rows, uint32_t cols, const std::vector<int64_t>& v,
+                      bool cost_semantics) {
+    uint32_t id;
+    check(sfgpu_add_matrix_i64(ctx_, name.c_str(), rows, cols, v.data(), cost_semantics ? 1 : 0, &id));
+    return id;
+  }
+  void set_scalar_state(const std::vector<int32_t>& values, bool per_replica = false) {
+    check(sfgpu_set_scalar_state(ctx_, 0, values.data(), per_replica ? 1 : 0));
+  }
+  void set_list_state(const std::vector<uint32_t>& offsets, const std::vector<uint32_t>& elems, bool per_replica = false) {
+    check(sfgpu_set_list_state(ctx_, 0x80000000u, offsets.data(), elems.data(), per_replica ? 1 : 0));
+  }
+  std::vector<HardSoftScore> commit() {
+    std::vector<HardSoftScore> s(R_);
+    check(sfgpu_model_commit(ctx_, reinterpret_cast<int64_t*>(s.data())));
+    return s;
+  }
+  // Director::calculate_score / fresh_score
+  std::vector<HardSoftScore> calculate_score() {
+    std::vector<HardSoftScore> s(R_);
+    check(sfgpu_committed_scores(ctx_, reinterpret_cast<int64_t*>(s.data())));
+    return s;
+  }
+  std::vector<HardSoftScore> fresh_score() {
+    std::vector<HardSoftScore> s(R_);
+    check(sfgpu_evaluate_all(ctx_, reinterpret_cast<int64_t*>(s.data())));
+    return s;
+  }
+  // the batch seam: scores of a whole neighbourhood (evaluate_candidate for every pull)
+  void score_candidates(const std::vector<ScalarEdit>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_change(ctx_, 0, batch.size(), cand_offsets.data(), reinterpret_cast<const uint32_t*>(batch.data()),
+                             reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void score_candidates(const std::vector<ListChange>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_list_change(ctx_, 0, batch.size(), cand_offsets.data(),
+                                  reinterpret_cast<const uint32_t*>(batch.data()),
+                                  reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void apply(const std::vector<ScalarEdit>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_change(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
+  }
+  void apply(const std::vector<ListChange>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_list_change(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
+  }
+
+ private:
+  sfgpu_ctx* ctx_ = nullptr;
+  uint32_t R_;
+};
+
+inline uint32_t Terminal::named(const std::string& name) {
+  desc.name = name.c_str();
+  uint32_t id;
+  d->check(sfgpu_add_constraint(d->raw(), &desc, &id));
+  return id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Acceptor / forager replay over batched scores, in pull order (phase/candidates.rs:66-282).
+// ---------------------------------------------------------------------------------------------
+inline uint64_t splitmix64(uint64_t v) {
+  v += 0x9E3779B97F4A7C15ull;
+  v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull;
+  v = (v ^ (v >> 27)) * 0x94D049BB133111EBull;
+  return v ^ (v >> 31);
+}
+inline bool reservoir_pick(uint64_t step_seed, uint64_t equal_count) {  // forager.rs:143-148
+  return splitmix64(step_seed ^ (equal_count * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull) % equal_count == 0;
+}
+
+struct Acceptor {  // acceptor/traits.rs:13-43
+  virtual ~Acceptor() = default;
+  virtual void phase_started(HardSoftScore) {}
+  virtual bool is_accepted(HardSoftScore last_step, HardSoftScore move) = 0;
+  virtual void step_ended(HardSoftScore) {}
+};
+struct HillClimbingAcceptor : Acceptor {  // hill_climbing.rs:33-42
+  bool is_accepted(HardSoftScore last, HardSoftScore mv) override { return mv > last; }
+};
+struct LateAcceptanceAcceptor : Acceptor {  // late_acceptance.rs:89-126
+  size_t size;
+  std::vector<HardSoftScore> history;
+  size_t idx = 0;
+  explicit LateAcceptanceAcceptor(size_t n = 400) : size(n) {}
+  void phase_started(HardSoftScore initial) override {
+    history.assign(size, initial);
+    idx = 0;
+  }
+  bool is_accepted(HardSoftScore last, HardSoftScore mv) override { return mv >= last || mv >= history[idx]; }
+  void step_ended(HardSoftScore step) override {
+    history[idx] = step;
+    idx = (idx + 1) % size;
+  }
+};
+struct SimulatedAnnealingAcceptor : Acceptor {  // simulated_annealing.rs:338-431 (uniform stream injected)
+  std::function<double()> uniform;
+  double decay = 0.999985, hill_climbing_temperature = 1e-9, fallback = 1.0, target = 0.80;
+  size_t calibration_samples = 128, seen = 0;
+  double sum[2] = {0, 0}, temperature[2] = {0, 0};
+  size_t count[2] = {0, 0};
+  bool calibrated = false;
+  explicit SimulatedAnnealingAcceptor(std::function<double()> u) : uniform(std::move(u)) {}
+  bool is_accepted(HardSoftScore last, HardSoftScore mv) override {
+    if (mv >= last) return true;
+    int lvl = mv.hard != last.hard ? 0 : 1;
+    double delta = (double)(mv.level(lvl) - last.level(lvl));
+    if (!calibrated) {
+      sum[lvl] += std::fabs(delta);
+      count[lvl]++;
+      if (++seen < calibration_samples) return false;
+      for (int l = 0; l < 2; ++l)
+        temperature[l] = count[l] ? std::max((sum[l] / (double)count[l]) / -std::log(target), fallback) : fallback;
+      calibrated = true;
+    }
+    if (temperature[lvl] <= hill_climbing_temperature) return false;
+    return uniform() < std::exp(delta / temperature[lvl]);
+  }
+  void step_ended(HardSoftScore) override {
+    if (calibrated)
+      for (double& t : temperature) t = std::max(t * decay, hill_climbing_temperature);
+  }
+};
+
+struct ForagerConfig {
+  enum Kind { AcceptedCount, FirstAccepted, BestScore } kind = BestScore;
+  size_t accepted_count_limit = 1;
+  bool random_ties = true;
+};
+struct StepOutcome {
+  bool has_winner = false;
+  size_t winner = 0;  // CandidateId == pull index (move_selector/borrowed.rs:396-430)
+  HardSoftScore score;
+  uint64_t moves_evaluated = 0, score_calculations = 0, moves_accepted = 0;
+};
+
+inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doable, size_t n, HardSoftScore last_step,
+                               uint64_t step_seed, const ForagerConfig& fc, Acceptor& acceptor) {
+  StepOutcome out;
+  uint64_t equal_count = 0;
+  size_t accepted = 0;
+  for (size_t i = 0; i < n; ++i) {
+    bool quit = fc.kind == ForagerConfig::BestScore ? false
+              : fc.kind == ForagerConfig::FirstAccepted ? out.has_winner
+                                                        : accepted >= fc.accepted_count_limit;
+    if (quit) break;
+    out.moves_evaluated++;
+    if (!doable[i]) continue;
+    out.score_calculations++;
+    if (!acceptor.is_accepted(last_step, scores[i])) continue;
+    out.moves_accepted++;
+    accepted++;
+    if (fc.kind == ForagerConfig::FirstAccepted) {
+      if (!out.has_winner) {
+        out.has_winner = true;
+        out.winner = i;
+        out.score = scores[i];
+      }
+      continue;
+    }
+    if (!out.has_winner || scores[i] > out.score) {  // BestCandidate::consider, forager.rs:99-141
+      out.has_winner = true;
+      out.winner = i;
+      out.score = scores[i];
+      equal_count = 1;
+    } else if (scores[i] == out.score) {
+      equal_count++;
+      if (fc.random_ties && reservoir_pick(step_seed, equal_count)) out.winner = i;
+    }
+  }
+  return out;
+}
+
+}  // namespace sf
