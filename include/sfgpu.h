@@ -97,6 +97,7 @@ int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, ui
 #define SFGPU_W_LINEAR 1 /* a*x + b */
 #define SFGPU_W_SQUARE 2 /* a*x*x + b */
 #define SFGPU_W_EXCESS 3 /* a*max(0, x - b) */
+#define SFGPU_W_ABSDIFF 4 /* a*|x - b| */
 typedef struct sfgpu_weight {
   int32_t fn;
   int32_t level; /* 0 = hard, 1 = soft */
@@ -110,7 +111,8 @@ typedef struct sfgpu_weight {
 /* for_each(E)[.unassigned()|.filter(assigned)].penalize(w(x)); x = const | entity column | value column
  *   solverforge-scoring/src/constraint/incremental.rs:97-156
  *   p0: filter 0 = unassigned, 1 = assigned, 2 = always; aux0: column id or UINT32_MAX (x = 0);
- *   p1: 0 = column indexed by entity row, 1 = column indexed by assigned value */
+ *   p1: 0 = column indexed by entity row, 1 = column indexed by assigned value;
+ *   aux1: entity mask column id or UINT32_MAX — `.filter(|e| e.flag)`: rows whose mask is 0 never match */
 #define SFGPU_K_UNI 1
 /* for_each(E).join(E, |l,r| l.id < r.id && l.neighbors.contains(r.id) && l.var.is_some() && l.var == r.var)
  *   predicate cross-bi, solverforge-scoring/src/constraint/cross_bi_incremental/, stream/join_target.rs:83-110
@@ -211,6 +213,15 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
                       const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
                       const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
                       int64_t* out_best, uint32_t* out_evaluated);
+
+/* Fused step for list-change batches (DEVICE pointers, stream-asynchronous): scores every candidate and
+ * replays acceptor + forager in the same pass — evaluate_candidates (phase/candidates.rs:47-285) for a
+ * whole neighbourhood. out_scores / out_doable may both be NULL: then per-candidate scores are never
+ * written to HBM (only the winner leaves the kernel). Same outputs as sfgpu_argbest. */
+int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint64_t* cand_offsets,
+                               const uint32_t* rows, const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                               const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
+                               uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated);
 
 /* ---- committing the winner ------------------------------------------------------------ */
 /* One row per replica (same packing as the score calls); mask[r] == 0 skips replica r

@@ -309,4 +309,78 @@ struct JobShopModel final : ModelImpl<JobShopPlan> {
   size_t list_desc() const override { return 1; }
 };
 
+// ------------------------------------------------------------------------------ shift scheduling
+// examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 — constraints 1, 2 and 4 verbatim
+// ("Long work streaks" uses the consecutive_runs collector, out of scope per SURVEY §2 row 10), plus
+// one authored load_balance constraint over stream/collector/load_balance.rs (metric = `hours`).
+struct SNurse {
+  size_t id;
+};
+struct SShift {
+  size_t id;
+  int64_t day;
+  size_t slot;
+  bool required;
+  int64_t hours;
+  OptVal nurse_idx;
+};
+struct ShiftSchedule {
+  std::vector<SNurse> nurses;
+  std::vector<SShift> shifts;
+};
+inline const std::vector<SNurse>& ss_nurses(const ShiftSchedule& s) { return s.nurses; }
+inline const std::vector<SShift>& ss_shifts(const ShiftSchedule& s) { return s.shifts; }
+
+struct ShiftModel final : ModelImpl<ShiftSchedule> {
+  explicit ShiftModel(ShiftSchedule sol, int64_t target = 4) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const ShiftSchedule& s, size_t, size_t e) { return s.shifts[e].nurse_idx; };
+    dir.access.set = [](ShiftSchedule& s, size_t, size_t e, OptVal v) { s.shifts[e].nurse_idx = v; };
+    dir.access.entity_count = [](const ShiftSchedule& s, size_t) { return s.shifts.size(); };
+    Source<ShiftSchedule, SShift> shifts{ss_shifts, ChangeSource::Desc(0)};
+    Source<ShiftSchedule, SNurse> nurses{ss_nurses, ChangeSource::Stat()};
+    auto uf = [](const ShiftSchedule&, const SShift& s) { return s.required && !s.nurse_idx.has_value(); };
+    auto uw = [](const SShift&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<ShiftSchedule, SShift, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned required shift", Impact::Penalty, shifts, uf, uw, true));
+    auto pf = [](const ShiftSchedule&, const SShift& l, const SShift& r, size_t, size_t) {
+      return l.id < r.id && l.day == r.day && l.nurse_idx.has_value() && l.nurse_idx == r.nurse_idx;
+    };
+    auto pw = [](const ShiftSchedule&, const SShift&, const SShift&, size_t, size_t) { return Sc::ONE_HARD(); };
+    dir.constraints.add(
+        std::make_unique<CrossBiConstraint<ShiftSchedule, SShift, SShift, uint8_t, Sc, ConstKey, ConstKey,
+                                           decltype(pf), decltype(pw)>>(
+            "One shift per nurse day", Impact::Penalty, shifts, shifts, ConstKey{}, ConstKey{}, pf, pw, true));
+    // Balanced workload: group_by(nurse, count()).complement(nurses, id, 0).penalize(|count - target|)
+    auto jka = [](const SShift& s) { return s.nurse_idx; };
+    auto jkb = [](const SNurse& n) { return OptVal(n.id); };
+    auto jf = [](const ShiftSchedule&, const SShift&, const SNurse&, size_t, size_t) { return true; };
+    auto gk = [](const SShift&, const SNurse& n) { return n.id; };
+    auto vf = [](const SShift&, const SNurse&) { return (char)0; };
+    auto kt = [](const SNurse& n) { return n.id; };
+    auto df = [](const SNurse&) { return (size_t)0; };
+    auto gw = [target](const size_t&, const size_t& count) {
+      int64_t d = (int64_t)count - target;
+      return Sc::of_soft(d < 0 ? -d : d);
+    };
+    dir.constraints.add(
+        std::make_unique<CrossComplementedGroupedConstraint<
+            ShiftSchedule, SShift, SNurse, SNurse, OptVal, size_t, Sc, CountAcc, decltype(jka), decltype(jkb),
+            decltype(jf), decltype(gk), decltype(vf), decltype(kt), decltype(df), decltype(gw), OptHash>>(
+            "Balanced workload", Impact::Penalty, shifts, nurses, nurses, jka, jkb, jf, gk, vf, kt, df, gw, false));
+    // authored: group_by(|_| (), load_balance(|s| nurse, |s| hours)).penalize(|_, lb| of_soft(lb.unfairness()))
+    auto lf = [](const ShiftSchedule&, const SShift& s) { return s.nurse_idx.has_value(); };
+    auto lk = [](const SShift&) { return (char)0; };
+    auto lv = [](const SShift& s) { return std::make_pair((int64_t)*s.nurse_idx, s.hours); };
+    auto lw = [](const char&, const int64_t& unfairness) { return Sc::of_soft(unfairness); };
+    dir.constraints.add(
+        std::make_unique<GroupedConstraint<ShiftSchedule, SShift, char, Sc, LoadBalanceAcc, decltype(lf), decltype(lk),
+                                           decltype(lv), decltype(lw)>>("Fair hours", Impact::Penalty, shifts, lf, lk,
+                                                                        lv, lw, false));
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.nurses.size(), true, ctx);
+  }
+};
+
 }  // namespace sfo

@@ -83,6 +83,15 @@ void* sfo_js_create(uint32_t n_ops, uint32_t n_machines, const uint32_t* job, co
   return new JobShopModel(std::move(p), with_complement != 0);
 }
 
+void* sfo_shift_create(uint32_t n_shifts, uint32_t n_nurses, const int64_t* day, const uint32_t* slot,
+                       const uint8_t* required, const int64_t* hours, const int32_t* nurse_idx, int64_t target) {
+  ShiftSchedule s;
+  for (uint32_t i = 0; i < n_nurses; ++i) s.nurses.push_back({i});
+  for (uint32_t i = 0; i < n_shifts; ++i)
+    s.shifts.push_back({i, day[i], slot[i], required[i] != 0, hours[i], opt(nurse_idx[i])});
+  return new ShiftModel(std::move(s), target);
+}
+
 void sfo_destroy(void* h) { delete static_cast<OracleModel*>(h); }
 
 int sfo_committed_score(void* h, int64_t out[2]) {

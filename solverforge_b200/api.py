@@ -184,7 +184,7 @@ class GpuScoreDirector:
         return out.value
 
     def add_constraint(self, kind: int, impact: int, weight: WeightFn, collection: int = 0, variable: int = 0,
-                       aux0: int = L.NO_COLUMN, aux1: int = 0, p0: int = 0, p1: int = 0, name: str = "") -> int:
+                       aux0: int = L.NO_COLUMN, aux1: int = L.NO_COLUMN, p0: int = 0, p1: int = 0, name: str = "") -> int:
         d = L.ConstraintDesc(kind, impact, L.Weight(weight.fn, weight.level, weight.a, weight.b), collection,
                              variable, aux0, aux1, p0, p1, name.encode())
         out = C.c_uint32()
@@ -280,6 +280,16 @@ class GpuScoreDirector:
         self._check(self.lib.sfgpu_argbest(self.h, L.DEVICE_IO, C.byref(fp), v(offsets_ptr), v(scores_ptr),
                                            v(doable_ptr), v(seeds_ptr), v(ref_ptr), v(index_ptr), v(best_ptr),
                                            v(evaluated_ptr)))
+
+    def step_list_change_device(self, n: int, offsets_ptr: int, rows_ptr: int, params: "ForageParams", seeds_ptr: int,
+                                ref_ptr: int, scores_ptr: int, doable_ptr: int, index_ptr: int, best_ptr: int,
+                                evaluated_ptr: int):
+        """Fused score + acceptor/forager replay (sfgpu_step_list_change); scores_ptr/doable_ptr may be 0."""
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        v = lambda p: C.c_void_p(p) if p else None
+        self._check(self.lib.sfgpu_step_list_change(self.h, n, v(offsets_ptr), v(rows_ptr), C.byref(fp), v(seeds_ptr),
+                                                    v(ref_ptr), v(scores_ptr), v(doable_ptr), v(index_ptr),
+                                                    v(best_ptr), v(evaluated_ptr)))
 
     def apply_winners_device(self, move_kind: int, offsets_ptr: int, rows_ptr: int, index_ptr: int):
         self._check(self.lib.sfgpu_apply_winners(self.h, move_kind, C.c_void_p(offsets_ptr), C.c_void_p(rows_ptr),
@@ -432,19 +442,21 @@ class _Terminal:
 
 
 class UniStream:
-    def __init__(self, d: GpuScoreDirector, collection: int, filt: int = 2):
-        self.d, self.collection, self.filt = d, collection, filt
+    def __init__(self, d: GpuScoreDirector, collection: int, filt: int = 2, mask: int = L.NO_COLUMN):
+        self.d, self.collection, self.filt, self.mask = d, collection, filt, mask
 
     def unassigned(self) -> "UniStream":
-        return UniStream(self.d, self.collection, 0)
+        return UniStream(self.d, self.collection, 0, self.mask)
 
     def assigned(self) -> "UniStream":
-        return UniStream(self.d, self.collection, 1)
+        return UniStream(self.d, self.collection, 1, self.mask)
+
+    def filter(self, mask_column: int) -> "UniStream":
+        """`.filter(|e| e.flag)` over a static 0/1 fact column."""
+        return UniStream(self.d, self.collection, self.filt, mask_column)
 
     def flattened(self) -> "UniStream":
-        s = UniStream(self.d, self.collection, self.filt)
-        s._flattened = True
-        return s
+        return UniStream(self.d, self.collection, self.filt, self.mask)
 
     def _impact(self, impact: int, weight, x=None, by_value: bool = False) -> _Terminal:
         if isinstance(x, PathCost):
@@ -455,7 +467,7 @@ class UniStream:
                              variable=L.LIST_VAR, aux0=x.column)
         w = _const_weight(weight) if isinstance(weight, HardSoftScore) else weight
         return _Terminal(self.d, kind=L.K_UNI, impact=impact, weight=w, collection=self.collection,
-                         aux0=L.NO_COLUMN if x is None else x, p0=self.filt, p1=1 if by_value else 0)
+                         aux0=L.NO_COLUMN if x is None else x, aux1=self.mask, p0=self.filt, p1=1 if by_value else 0)
 
     def penalize(self, weight, x=None, by_value: bool = False) -> _Terminal:
         return self._impact(L.PENALTY, weight, x, by_value)

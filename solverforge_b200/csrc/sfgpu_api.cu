@@ -79,6 +79,8 @@ struct sfgpu_ctx {
   size_t pin_bytes = 0;
   void* dscr = nullptr;
   size_t dscr_bytes = 0;
+  void* partials = nullptr;  // fused forager chunk partials
+  size_t partials_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   uint64_t launches = 0;
@@ -196,6 +198,7 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
   for (void* p : ctx->dev_allocs) cudaFree(p);
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->dscr) cudaFree(ctx->dscr);
+  if (ctx->partials) cudaFree(ctx->partials);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -311,7 +314,7 @@ int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, 
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
   if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_LOAD_BALANCE)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
-  if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_EXCESS || desc->weight.level < 0 ||
+  if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_ABSDIFF || desc->weight.level < 0 ||
       desc->weight.level > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad weight");
   bool needs_const = desc->kind == SFGPU_K_PAIR_CSR_EQUAL || desc->kind == SFGPU_K_PAIR_KEY_EQUAL ||
@@ -438,7 +441,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         if (!mt.i32 || mx >= (1 << 28) || (uint64_t)mt.rows * mt.cols >= (1ull << 31)) { fast = false; break; }
         dm.fast_pc = (int32_t)k;
       } else if (d.kind == SFGPU_K_LIST_SUM) {
-        if (dm.fast_ls >= 0 || d.aux0 >= ctx->cols.size()) { fast = false; break; }
+        if (dm.fast_ls >= 0 || d.aux0 >= ctx->cols.size() || d.weight.fn == SFGPU_W_ABSDIFF) { fast = false; break; }
         for (int64_t c : ctx->cols[d.aux0].host)
           if (c < -(1ll << 30) || c > (1ll << 30)) fast = false;
         dm.fast_ls = (int32_t)k;
@@ -496,6 +499,10 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         if (by_value && col && want < dm.n_values) return fail(ctx, SFGPU_E_INVALID, "value column too short");
         c.g0 = col;
         if (by_value) c.flags |= SFGPU_CF_COL_BY_VALUE;
+        const int64_t* mask = nullptr;
+        rc = column(d.aux1, dm.n_entities, &mask);
+        if (rc) return rc;
+        c.g1 = mask;
         break;
       }
       case SFGPU_K_PAIR_CSR_EQUAL: {
@@ -669,11 +676,16 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       dm.fast_list = 0;
     } else {
       int bytes = (int)dm.fast_stage_bytes;
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
   }
   if (dm.has_list) {
@@ -699,8 +711,11 @@ namespace {
 
 enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP };
 
+// forage != nullptr (fast list path only): the kernel also emits per-chunk forager partials into
+// forage->partials and *out_chunks receives the chunk count the finishing kernel needs.
 int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
-                 const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable) {
+                 const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable, ForageArgs* forage = nullptr,
+                 uint32_t* out_chunks = nullptr) {
   const DevModel& dm = ctx->dm;
   const uint32_t threads = 256;
   dim3 grid(chunks_for(ctx, n_total, dm.R, threads), dm.R);
@@ -729,10 +744,27 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
         uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 6143) / 6144, 64));
         while ((uint64_t)chunks * dm.R < (uint64_t)ctx->sm_count * 4 && (uint64_t)chunks * 512 < per_replica) chunks *= 2;
         dim3 fgrid(chunks, dm.R);
+        if (forage) {
+          size_t need = (size_t)chunks * dm.R * sizeof(ChunkPartial);
+          if (need > ctx->partials_bytes) {
+            if (ctx->partials) cudaFree(ctx->partials);
+            ctx->partials = nullptr;
+            ctx->partials_bytes = 0;
+            CU(cudaMalloc(&ctx->partials, need));
+            ctx->partials_bytes = need;
+          }
+          forage->partials = (ChunkPartial*)ctx->partials;
+          if (out_chunks) *out_chunks = chunks;
+        }
         size_t fsm = dm.fast_stage_bytes;
         int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
-        if (getenv("SFGPU_FAST_CHUNKS")) fgrid.x = atoi(getenv("SFGPU_FAST_CHUNKS"));  // tuning knob
-#define FASTK(FN) score_list_change_fast_kernel<FN, 2, 3><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable)
+#define FASTK(FN)                                                                                              \
+  if (forage)                                                                                                  \
+    score_list_change_fast_kernel<FN, 2, 3, true><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows,   \
+                                                                                        d_scores, d_doable, *forage); \
+  else                                                                                                         \
+    score_list_change_fast_kernel<FN, 2, 3, false><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows,  \
+                                                                                         d_scores, d_doable, ForageArgs{})
         switch (fn) {
           case -1: FASTK(-1); break;
           case SFGPU_W_CONST: FASTK(SFGPU_W_CONST); break;
@@ -859,6 +891,59 @@ int32_t sfgpu_score_list_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candi
 int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
                               int64_t* out_scores, uint8_t* out_doable) {
   return score_entry(ctx, SK_LIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused step: score every candidate and replay acceptor + forager in one call. Device pointers only.
+int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint64_t* cand_offsets,
+                               const uint32_t* rows, const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                               const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
+                               uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!cand_offsets || !rows || !params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if ((out_scores == nullptr) != (out_doable == nullptr))
+    return fail(ctx, SFGPU_E_INVALID, "out_scores and out_doable are given together or not at all");
+  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  const DevModel& dm = ctx->dm;
+  if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
+  CU(cudaSetDevice(ctx->device));
+  if (n_candidates == 0) return fail(ctx, SFGPU_E_INVALID, "empty batch");
+  const bool fused = dm.fast_list && !ctx->force_generic && params->accepted_limit == 0;
+  if (fused) {
+    ForageArgs fa{};
+    fa.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
+    fa.ref_scores = ref_scores;
+    uint32_t chunks = 0;
+    rc = launch_score(ctx, SK_LIST_CHANGE, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable, &fa,
+                      &chunks);
+    if (rc) return rc;
+    forage_finish_kernel<<<dm.R, 32, 0, ctx->stream>>>(dm, fa, chunks, cand_offsets, rows, out_scores, out_doable,
+                                                       step_seeds, out_index, out_best, out_evaluated);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SFGPU_OK;
+  }
+  // unfused: materialise scores (caller's buffers or internal scratch), then the ordered replay kernel
+  int64_t* d_scores = out_scores;
+  uint8_t* d_doable = out_doable;
+  if (!d_scores) {
+    size_t need = n_candidates * 16 + (n_candidates + 15) / 16 * 16;
+    rc = ensure_staging(ctx, 64, need);
+    if (rc) return rc;
+    d_scores = (int64_t*)ctx->dscr;
+    d_doable = (uint8_t*)ctx->dscr + n_candidates * 16;
+  }
+  rc = launch_score(ctx, SK_LIST_CHANGE, n_candidates, cand_offsets, rows, nullptr, d_scores, d_doable);
+  if (rc) return rc;
+  ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit};
+  argbest_kernel<<<dm.R, 1024, 0, ctx->stream>>>(f, cand_offsets, d_scores, d_doable, step_seeds, ref_scores, out_index,
+                                                 out_best, out_evaluated);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -72,11 +72,30 @@ struct Score2 {
   int64_t hard, soft;
 };
 
+// acceptor + forager parameters of one step (sfgpu_forage_params)
+struct ForageDev {
+  int32_t acceptor, tie_mode;
+  uint32_t accepted_limit;
+};
+
+// Per (replica, chunk) partial of the fused score+forage path: best accepted score of the chunk,
+// how many accepted rows equal it, the first such row (pull index inside the replica) and the
+// number of accepted rows.
+struct ChunkPartial {
+  int64_t best_h, best_s;
+  uint32_t n_best, n_accepted;
+  uint32_t first_idx, pad;
+};
+
 __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
   switch (w.fn) {
     case SFGPU_W_CONST: return w.a;
     case SFGPU_W_LINEAR: return w.a * x + w.b;
     case SFGPU_W_SQUARE: return w.a * x * x + w.b;
+    case SFGPU_W_ABSDIFF: {
+      int64_t d = x - w.b;
+      return w.a * (d < 0 ? -d : d);
+    }
     default: {
       int64_t d = x - w.b;
       return d > 0 ? w.a * d : 0;

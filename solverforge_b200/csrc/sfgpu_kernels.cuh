@@ -40,6 +40,7 @@ __device__ __forceinline__ int64_t uni_x(const ConsDev& c, uint32_t e, int32_t v
 }
 __device__ __forceinline__ int64_t uni_contrib(const ConsDev& c, uint32_t e, int32_t v) {
   bool pass = c.p0 == 0 ? v < 0 : (c.p0 == 1 ? v >= 0 : true);
+  if (c.g1 && ((const int64_t*)c.g1)[e] == 0) pass = false;  // entity mask column
   return pass ? weight_eval(c.w, uni_x(c, e, v)) : 0;
 }
 
@@ -448,15 +449,39 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   }
 }
 
-template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3>
+// acceptor predicate on a score (HillClimbing: move > last; LateAcceptance: >= last || >= late)
+__device__ __forceinline__ bool accept_score(int acceptor, int64_t h, int64_t s, int64_t lh, int64_t ls, int64_t th,
+                                             int64_t ts) {
+  if (acceptor == 0) return true;
+  if (acceptor == 1) return score_less(lh, ls, h, s);
+  return !score_less(h, s, lh, ls) || !score_less(h, s, th, ts);
+}
+
+struct ForageArgs {
+  ForageDev f;
+  const int64_t* ref_scores;  // [R][4] = {last_step, late} or null
+  ChunkPartial* partials;     // [R][gridDim.x]
+};
+
+template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3, bool FORAGE = false>
 __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const __grid_constant__ DevModel m,
                                                                      const uint64_t* __restrict__ cand_offsets,
                                                                      const uint32_t* __restrict__ rows,
                                                                      int64_t* __restrict__ out_scores,
-                                                                     uint8_t* __restrict__ out_doable) {
+                                                                     uint8_t* __restrict__ out_doable,
+                                                                     const ForageArgs fa) {
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   const uint32_t r = blockIdx.y;
+  // fused forager partial (FORAGE): this thread's best accepted score, multiplicity, first row
+  int64_t tb_h = 0, tb_s = 0, f_lh = 0, f_ls = 0, f_th = 0, f_ts = 0;
+  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
+  if (FORAGE && fa.ref_scores) {
+    f_lh = fa.ref_scores[r * 4 + 0];
+    f_ls = fa.ref_scores[r * 4 + 1];
+    f_th = fa.ref_scores[r * 4 + 2];
+    f_ts = fa.ref_scores[r * 4 + 3];
+  }
   stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
   const int64_t* cs = (const int64_t*)(smem + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
@@ -553,9 +578,180 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
       longlong2 o;
       o.x = ok[u] ? ch + dh : 0;
       o.y = ok[u] ? csf + ds : 0;
-      __stcs((longlong2*)out_scores + i, o);
-      out_doable[i] = ok[u] ? 1 : 0;
+      if (!FORAGE || out_scores) {
+        __stcs((longlong2*)out_scores + i, o);
+        out_doable[i] = ok[u] ? 1 : 0;
+      }
+      if (FORAGE && ok[u] && accept_score(fa.f.acceptor, o.x, o.y, f_lh, f_ls, f_th, f_ts)) {
+        t_acc++;
+        if (tb_n == 0 || score_less(tb_h, tb_s, o.x, o.y)) {
+          tb_h = o.x;
+          tb_s = o.y;
+          tb_n = 1;
+          tb_first = (uint32_t)(i - lo);
+        } else if (tb_h == o.x && tb_s == o.y) {
+          tb_n++;  // rows of one thread are visited in increasing pull order: tb_first stays the minimum
+        }
+      }
     }
+  }
+  if (FORAGE) {
+    // merge: better score wins; equal scores add multiplicities and keep the earliest row
+    __shared__ int64_t sh_h[8], sh_s[8];
+    __shared__ uint32_t sh_n[8], sh_f[8], sh_a[8];
+    for (int o = 16; o > 0; o >>= 1) {
+      const int64_t oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+      const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
+      t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
+      if (on && (!tb_n || score_less(tb_h, tb_s, oh, os))) {
+        tb_h = oh; tb_s = os; tb_n = on; tb_first = of;
+      } else if (on && tb_n && oh == tb_h && os == tb_s) {
+        tb_n += on;
+        tb_first = min(tb_first, of);
+      }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+      sh_h[warp] = tb_h; sh_s[warp] = tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first; sh_a[warp] = t_acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ChunkPartial cp{0, 0, 0, 0, 0xFFFFFFFFu, 0};
+      for (int w = 0; w < 8; ++w) {
+        cp.n_accepted += sh_a[w];
+        if (!sh_n[w]) continue;
+        if (!cp.n_best || score_less(cp.best_h, cp.best_s, sh_h[w], sh_s[w])) {
+          cp.best_h = sh_h[w]; cp.best_s = sh_s[w]; cp.n_best = sh_n[w]; cp.first_idx = sh_f[w];
+        } else if (sh_h[w] == cp.best_h && sh_s[w] == cp.best_s) {
+          cp.n_best += sh_n[w];
+          cp.first_idx = min(cp.first_idx, sh_f[w]);
+        }
+      }
+      fa.partials[(size_t)r * gridDim.x + blockIdx.x] = cp;
+    }
+  }
+}
+
+// Finishes the fused forager: one warp per replica combines the chunk partials, applies the tie
+// rule (largest firing k <= m, BestCandidate::consider) and, only when the winner is not the first
+// best row of its chunk, rescans that chunk in pull order (scores re-derived with the generic
+// per-candidate function, or read back when they were materialised).
+__global__ void __launch_bounds__(32) forage_finish_kernel(const __grid_constant__ DevModel m, ForageArgs fa,
+                                                           uint32_t n_chunks,
+                                                           const uint64_t* __restrict__ cand_offsets,
+                                                           const uint32_t* __restrict__ rows,
+                                                           const int64_t* __restrict__ scores,
+                                                           const uint8_t* __restrict__ doable,
+                                                           const uint64_t* __restrict__ step_seeds,
+                                                           uint32_t* __restrict__ out_index,
+                                                           int64_t* __restrict__ out_best,
+                                                           uint32_t* __restrict__ out_evaluated) {
+  const uint32_t r = blockIdx.x, lane = threadIdx.x;
+  const ChunkPartial* cp = fa.partials + (size_t)r * n_chunks;
+  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  // global best over chunks
+  int64_t bh = 0, bs = 0;
+  uint32_t any = 0;
+  for (uint32_t c = lane; c < n_chunks; c += 32) {
+    if (!cp[c].n_best) continue;
+    if (!any || score_less(bh, bs, cp[c].best_h, cp[c].best_s)) {
+      bh = cp[c].best_h;
+      bs = cp[c].best_s;
+    }
+    any = 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t oh = __shfl_xor_sync(0xffffffffu, bh, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const uint32_t oa = __shfl_xor_sync(0xffffffffu, any, o);
+    if (oa && (!any || score_less(bh, bs, oh, os))) {
+      bh = oh;
+      bs = os;
+    }
+    any |= oa;
+  }
+  if (out_evaluated && lane == 0) out_evaluated[r] = (uint32_t)(hi - lo);
+  if (!any) {
+    if (lane == 0) {
+      out_index[r] = 0xFFFFFFFFu;
+      out_best[r * 2] = 0;
+      out_best[r * 2 + 1] = 0;
+    }
+    return;
+  }
+  uint32_t mtot = 0;
+  for (uint32_t c = lane; c < n_chunks; c += 32)
+    if (cp[c].n_best && cp[c].best_h == bh && cp[c].best_s == bs) mtot += cp[c].n_best;
+  for (int o = 16; o > 0; o >>= 1) mtot += __shfl_xor_sync(0xffffffffu, mtot, o);
+  uint32_t want = 1;
+  if (fa.f.tie_mode == 1) {
+    const uint64_t seed = step_seeds ? step_seeds[r] : 0;
+    for (uint32_t k = 2 + lane; k <= mtot; k += 32) {
+      const uint64_t mixed = splitmix64_dev(seed ^ ((uint64_t)k * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
+      if (mixed % k == 0) want = k;
+    }
+    for (int o = 16; o > 0; o >>= 1) want = max(want, __shfl_xor_sync(0xffffffffu, want, o));
+  }
+  // chunk holding the want-th occurrence (chunks are contiguous and in pull order)
+  uint32_t c_star = 0, before = 0;
+  for (uint32_t c = 0; c < n_chunks; ++c) {
+    const uint32_t nb = (cp[c].n_best && cp[c].best_h == bh && cp[c].best_s == bs) ? cp[c].n_best : 0;
+    if (before + nb >= want) {
+      c_star = c;
+      break;
+    }
+    before += nb;
+  }
+  const uint32_t j = want - before;  // 1-based rank inside the chunk
+  uint32_t winner = cp[c_star].first_idx;
+  if (j > 1) {
+    const uint64_t per = (hi - lo + n_chunks - 1) / n_chunks;
+    const uint64_t c_lo = lo + per * c_star;
+    const uint64_t c_hi = c_lo + per < hi ? c_lo + per : hi;
+    const char* st = m.state + (size_t)r * m.block_bytes;
+    const int64_t* cs = (const int64_t*)(st + m.off_score);
+    int64_t lh = 0, ls = 0, th = 0, ts = 0;
+    if (fa.ref_scores) {
+      lh = fa.ref_scores[r * 4 + 0];
+      ls = fa.ref_scores[r * 4 + 1];
+      th = fa.ref_scores[r * 4 + 2];
+      ts = fa.ref_scores[r * 4 + 3];
+    }
+    uint32_t seen = 0;
+    for (uint64_t base = c_lo; base < c_hi; base += 32) {
+      const uint64_t i = base + lane;
+      bool hit = false;
+      if (i < c_hi) {
+        int64_t h, s2;
+        bool ok;
+        if (scores) {
+          const longlong2 v = ((const longlong2*)scores)[i];
+          h = v.x;
+          s2 = v.y;
+          ok = doable[i] != 0;
+        } else {
+          Score2 d;
+          ok = list_change_delta(m, st, ((const uint4*)rows)[i], d);
+          h = cs[0] + d.hard;
+          s2 = cs[1] + d.soft;
+        }
+        hit = ok && h == bh && s2 == bs && accept_score(fa.f.acceptor, h, s2, lh, ls, th, ts);
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      const uint32_t cnt = __popc(mask);
+      if (seen + cnt >= j) {
+        // the (j - seen)-th set bit
+        uint32_t mm = mask;
+        for (uint32_t t = 1; t < j - seen; ++t) mm &= mm - 1;
+        winner = (uint32_t)(base + (__ffs(mm) - 1) - lo);
+        break;
+      }
+      seen += cnt;
+    }
+  }
+  if (lane == 0) {
+    out_index[r] = winner;
+    out_best[r * 2] = bh;
+    out_best[r * 2 + 1] = bs;
   }
 }
 
@@ -932,11 +1128,6 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
 // =============================================================================================
 // argbest: one CTA per replica replays acceptor + forager over the scored rows in pull order.
 // =============================================================================================
-struct ForageDev {
-  int32_t acceptor, tie_mode;
-  uint32_t accepted_limit;
-};
-
 __device__ __forceinline__ bool accepted_at(const ForageDev& f, const int64_t* scores, const uint8_t* doable,
                                             uint64_t i, int64_t lh, int64_t ls, int64_t th, int64_t ts) {
   if (!doable[i]) return false;

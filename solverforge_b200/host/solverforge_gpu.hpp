@@ -173,8 +173,10 @@ struct UniStream {
   GpuScoreDirector* d;
   uint32_t collection;
   int filter = 2;  // 0 unassigned, 1 assigned, 2 always
-  UniStream unassigned() const { return {d, collection, 0}; }
-  UniStream assigned() const { return {d, collection, 1}; }
+  uint32_t mask = UINT32_MAX;  // `.filter(|e| e.flag)` over a static 0/1 column
+  UniStream unassigned() const { return {d, collection, 0, mask}; }
+  UniStream assigned() const { return {d, collection, 1, mask}; }
+  UniStream filtered(uint32_t mask_column) const { return {d, collection, filter, mask_column}; }
   UniStream flattened() const { return *this; }
   Terminal uni(int imp, Weight w, uint32_t column, bool by_value) const {
     sfgpu_constraint_desc c{};
@@ -183,6 +185,7 @@ struct UniStream {
     c.weight = w.w;
     c.collection = collection;
     c.aux0 = column;
+    c.aux1 = mask;
     c.p0 = filter;
     c.p1 = by_value ? 1 : 0;
     return {d, c};
@@ -224,7 +227,7 @@ struct UniStream {
 struct ConstraintFactory {
   GpuScoreDirector* d;
   explicit ConstraintFactory(GpuScoreDirector& dir) : d(&dir) {}
-  UniStream for_each(uint32_t collection) const { return {d, collection, 2}; }
+  UniStream for_each(uint32_t collection) const { return {d, collection, 2, UINT32_MAX}; }
 };
 
 // RAII owner of one sfgpu_ctx — the Director of R replicas.

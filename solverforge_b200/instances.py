@@ -167,3 +167,29 @@ def change_neighbourhood(values: np.ndarray, n_values: int, allows_unassigned: b
     else:
         keep[val == -1] = False
     return np.stack([ent[keep], val[keep]], axis=1)
+
+
+@dataclass
+class ShiftInstance:
+    n_shifts: int
+    n_nurses: int
+    day: np.ndarray        # int64
+    slot: np.ndarray       # uint32
+    required: np.ndarray   # uint8
+    hours: np.ndarray      # int64 (0 hours exercises load_balance's zero-metric skip)
+    nurse_idx: np.ndarray  # int32, -1 = unassigned
+    target: int = 4
+
+
+def shift_scheduling(n_days: int = 14, slots_per_day: int = 3, n_nurses: int = 6, seed: int = 21,
+                     unassigned_permille: int = 150) -> ShiftInstance:
+    """examples/minimal-shift-scheduling scaled up: shift id = day*slots + slot."""
+    n = n_days * slots_per_day
+    ids = np.arange(n)
+    s = splitmix64_stream(seed, 4 * n)
+    nurse = (s[:n] % np.uint64(n_nurses)).astype(np.int32)
+    nurse[(s[n:2 * n] % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    required = ((s[2 * n:3 * n] % np.uint64(4)) != 0).astype(np.uint8)
+    hours = (s[3 * n:4 * n] % np.uint64(4)).astype(np.int64) * 4   # 0, 4, 8, 12
+    return ShiftInstance(n, n_nurses, (ids // slots_per_day).astype(np.int64), (ids % slots_per_day).astype(np.uint32),
+                         required, hours, nurse)

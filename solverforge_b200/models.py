@@ -95,3 +95,27 @@ def job_shop_director(inst: JobShopInstance, n_replicas: int = 1, machine_idx=No
     d.set_list_state(inst.seq_offsets, inst.seq_elems)
     d.commit()
     return d
+
+
+def shift_scheduling_director(inst, n_replicas: int = 1, nurse_idx=None, device: int = 0, stream=None,
+                              flags: int = 0) -> GpuScoreDirector:
+    """examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 (constraints 1, 2, 4) + an authored
+    load_balance constraint; "Long work streaks" (consecutive_runs collector) is out of scope."""
+    from .api import LoadBalance
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
+    nurses = d.add_collection("nurses", inst.n_nurses, -1)
+    shifts = d.add_collection("shifts", inst.n_shifts, 0)
+    d.add_scalar_variable(shifts, "nurse_idx", inst.n_nurses, allows_unassigned=True)
+    day = d.add_column(shifts, "day", inst.day)
+    required = d.add_column(shifts, "required", inst.required)
+    hours = d.add_column(shifts, "hours", inst.hours)
+    f = ConstraintFactory(d)
+    f.for_each(shifts).filter(required).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned required shift")
+    f.for_each(shifts).join(f.for_each(shifts), EqualKey(day, inst.n_nurses, 1)).penalize(
+        HardSoftScore.ONE_HARD).named("One shift per nurse day")
+    f.for_each(shifts).assigned().group_by(Count()).complement(nurses, 0).penalize(
+        soft(L.W_ABSDIFF, 1, inst.target)).named("Balanced workload")
+    f.for_each(shifts).assigned().group_by(LoadBalance(hours)).penalize(soft(L.W_LINEAR, 1, 0)).named("Fair hours")
+    d.set_scalar_state(inst.nurse_idx if nurse_idx is None else nurse_idx)
+    d.commit()
+    return d

@@ -30,12 +30,13 @@ def lib() -> C.CDLL:
         if not os.path.exists(LIB):
             build()
         l = C.CDLL(LIB)
-        for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create"):
+        for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create", "sfo_shift_create"):
             getattr(l, name).restype = _P
         l.sfo_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
         l.sfo_nq_create.argtypes = [C.c_uint32, _P]
         l.sfo_cvrp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, _P, _P, _P, _P]
         l.sfo_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int]
+        l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64]
         l.sfo_destroy.argtypes = [_P]
         l.sfo_committed_score.argtypes = [_P, _P]
         l.sfo_evaluate_all.argtypes = [_P, _P]
@@ -106,6 +107,13 @@ class Oracle:
         return Oracle(lib().sfo_js_create(inst.n_ops, inst.n_machines, _p(_u32(inst.job)), _p(_u32(inst.step)), _p(m),
                                           _p(_u32(inst.seq_offsets)), _p(_u32(inst.seq_elems)),
                                           1 if with_complement else 0))
+
+    @staticmethod
+    def shift_scheduling(inst, nurse_idx=None) -> "Oracle":
+        n = np.ascontiguousarray(inst.nurse_idx if nurse_idx is None else nurse_idx, dtype=np.int32)
+        return Oracle(lib().sfo_shift_create(inst.n_shifts, inst.n_nurses, _p(np.ascontiguousarray(inst.day, np.int64)),
+                                             _p(_u32(inst.slot)), _p(np.ascontiguousarray(inst.required, np.uint8)),
+                                             _p(np.ascontiguousarray(inst.hours, np.int64)), _p(n), inst.target))
 
     # ---- scores -------------------------------------------------------------------------
     def committed_score(self) -> np.ndarray:

@@ -205,6 +205,30 @@ def test_job_shop_matches_oracle():
         _eq(s3, so3, "list change on job shop")
 
 
+def test_shift_scheduling_load_balance_and_masked_uni_match_oracle():
+    # examples/minimal-shift-scheduling + load_balance: unfairness = round(sqrt(f64)) must be bit-identical
+    for seed in (21, 22, 23):
+        inst = instances.shift_scheduling(seed=seed)
+        o = Oracle.shift_scheduling(inst)
+        d = models.shift_scheduling_director(inst)
+        _eq(d.calculate_score()[0], o.committed_score(), "initial")
+        for step in range(8):
+            rows = o.enumerate_change()
+            s, ok = d.score_change(rows)
+            so, oko = o.score_change(rows)
+            _eq(ok, oko, "doable")
+            _eq(s, so, f"scores step {step}")
+            idx, best, _ = d.argbest(s, ok, params=ForageParams(0, 1, 0), step_seeds=[seed * 100 + step])
+            w = int(idx[0])
+            d.apply_change(rows[w][None, :])
+            o.apply_change(*rows[w])
+            _eq(d.calculate_score()[0], o.committed_score(), "committed")
+            _eq(d.fresh_score()[0], o.evaluate_all(), "fresh")
+        with pytest.raises(L.SfgpuError) as e:
+            d.score_swap(np.array([[0, 1]]))
+        assert e.value.code == L.E_UNSUPPORTED
+
+
 def test_cvrp_matches_oracle_lists_swaps_and_apply():
     c = instances.cvrp(200, 12, seed=7)
     o = Oracle.cvrp(c)
@@ -302,6 +326,73 @@ def test_fast_list_kernel_equals_generic_kernel():
         _eq(sf, so, "fast after apply")
         _eq(okf, oko)
     _eq(fast.calculate_score(), gen.calculate_score())
+
+
+def test_fused_step_matches_unfused_and_oracle_replay():
+    import torch
+    c = instances.cvrp(150, 10, seed=5)
+    c.matrix = (c.matrix // 40) * 40          # coarse distances => many equal scores => tie rule matters
+    R = 4
+    starts = [instances.perturb_routes(c, 50 + r, 40) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    batches = [oracles[r].enumerate_nearby_list_change(12) for r in range(R)]
+    co = np.concatenate([[0], np.cumsum([len(b) for b in batches])]).astype(np.uint64)
+    rows = np.concatenate(batches).astype(np.uint32)
+    n = len(rows)
+    dev = torch.device("cuda")
+    t_off = torch.from_numpy(co.view(np.int64)).to(dev)
+    t_rows = torch.from_numpy(rows.view(np.int32)).to(dev)
+    t_scores = torch.zeros((n, 2), dtype=torch.int64, device=dev)
+    t_doable = torch.zeros(n, dtype=torch.uint8, device=dev)
+    t_idx = torch.zeros(R, dtype=torch.int32, device=dev)
+    t_best = torch.zeros((R, 2), dtype=torch.int64, device=dev)
+    t_ev = torch.zeros(R, dtype=torch.int32, device=dev)
+    so = [oracles[r].score_list_change(batches[r]) for r in range(R)]
+    base = d.calculate_score()
+    for seed in (3, 4):
+        for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+            for ties in (0, 1):
+                for limit in (0, 5):
+                    for materialise in (True, False):
+                        # reference scores: last step = committed score + a little slack, late = worse
+                        ref = np.stack([np.concatenate([base[r] + [0, -30], base[r] + [0, -60]]) for r in range(R)])
+                        t_ref = torch.from_numpy(ref).to(dev)
+                        t_seed = torch.full((R,), seed, dtype=torch.int64, device=dev)
+                        t_idx.fill_(-7)
+                        d.step_list_change_device(n, t_off.data_ptr(), t_rows.data_ptr(),
+                                                  ForageParams(acceptor, ties, limit), t_seed.data_ptr(),
+                                                  t_ref.data_ptr(), t_scores.data_ptr() if materialise else 0,
+                                                  t_doable.data_ptr() if materialise else 0, t_idx.data_ptr(),
+                                                  t_best.data_ptr(), t_ev.data_ptr())
+                        d.synchronize()
+                        idx = t_idx.cpu().numpy().view(np.uint32)
+                        best = t_best.cpu().numpy()
+                        for r in range(R):
+                            out = oracle_lib.replay_step(so[r][0], so[r][1], [0, 0], ref[r][:2], ref[r][2:], seed,
+                                                         0 if limit else 2, max(limit, 1), bool(ties), okind)
+                            what = f"seed={seed} acc={acceptor} ties={ties} limit={limit} mat={materialise} r={r}"
+                            if out[0]:
+                                assert int(idx[r]) == out[1], what
+                                assert best[r].tolist() == so[r][0][out[1]].tolist(), what
+                            else:
+                                assert idx[r] == 0xFFFFFFFF, what
+                            assert int(t_ev.cpu()[r]) == out[2], what
+                        if materialise:
+                            sc = t_scores.cpu().numpy()
+                            for r in range(R):
+                                _eq(sc[int(co[r]):int(co[r + 1])], so[r][0], "materialised scores")
+    # winners applied straight from the batch on device
+    d.step_list_change_device(n, t_off.data_ptr(), t_rows.data_ptr(), ForageParams(0, 0, 0), 0, 0, 0, 0,
+                              t_idx.data_ptr(), t_best.data_ptr(), t_ev.data_ptr())
+    d.apply_winners_device(2, t_off.data_ptr(), t_rows.data_ptr(), t_idx.data_ptr())
+    d.synchronize()
+    idx = t_idx.cpu().numpy().view(np.uint32)
+    after = d.calculate_score()
+    for r in range(R):
+        oracles[r].apply_list_change(*batches[r][int(idx[r])])
+        _eq(after[r], oracles[r].committed_score(), "apply_winners")
+    _eq(d.fresh_score(), after)
 
 
 def test_replicas_are_independent():

@@ -124,3 +124,36 @@ def test_replay_matches_reference_forager_rules():
     scores = np.array([[0, -5], [0, -3], [0, -3], [0, -9]])
     out = oracle_lib.replay_step(scores, [1, 1, 1, 0], [0, 0], [0, 0], [0, 0], 1, 2, 0, False, 3)
     assert out[:3] == (1, 1, 4) and out[3] == 3
+
+
+def test_shift_scheduling_invariant_and_unfairness():
+    inst = instances.shift_scheduling(seed=21)
+    o = Oracle.shift_scheduling(inst)
+    assert np.array_equal(o.committed_score(), o.evaluate_all())
+    # independent recompute of every constraint
+    m = inst.nurse_idx
+    hard = -int(((m < 0) & (inst.required != 0)).sum())
+    for a in range(inst.n_shifts):
+        for b in range(a + 1, inst.n_shifts):
+            if inst.day[a] == inst.day[b] and m[a] >= 0 and m[a] == m[b]:
+                hard -= 1
+    counts = np.bincount(m[m >= 0], minlength=inst.n_nurses)
+    soft = -int(np.abs(counts - inst.target).sum())
+    loads = {}
+    for i in range(inst.n_shifts):
+        if m[i] >= 0 and inst.hours[i] != 0:
+            loads[int(m[i])] = loads.get(int(m[i]), 0) + int(inst.hours[i])
+    if loads:
+        v = np.array(list(loads.values()), dtype=np.float64)
+        n = len(v)
+        tmp = float(-(int(v.sum()) ** 2)) / n + float(int((v * v).sum())) if n > 1 else float(-(int(v.sum()) ** 2)) + float(int((v * v).sum()))
+        import math
+        unf = int(math.floor(math.sqrt(tmp) + 0.5))
+        soft -= unf
+    assert o.committed_score().tolist() == [hard, soft]
+    rows = o.enumerate_change()
+    s, ok = o.score_change(rows)
+    for i in (0, 5, 50, 100):
+        if ok[i]:
+            o.apply_change(*rows[i])
+            assert np.array_equal(o.committed_score(), o.evaluate_all())
