@@ -920,7 +920,7 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
     rc = launch_score(ctx, SK_LIST_CHANGE, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable, &fa,
                       &chunks);
     if (rc) return rc;
-    forage_finish_kernel<<<dm.R, 32, 0, ctx->stream>>>(dm, fa, chunks, cand_offsets, rows, out_scores, out_doable,
+    forage_finish_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, fa, chunks, cand_offsets, rows, out_scores, out_doable,
                                                        step_seeds, out_index, out_best, out_evaluated);
     ctx->launches++;
     CU(cudaGetLastError());

@@ -636,76 +636,84 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
 // rule (largest firing k <= m, BestCandidate::consider) and, only when the winner is not the first
 // best row of its chunk, rescans that chunk in pull order (scores re-derived with the generic
 // per-candidate function, or read back when they were materialised).
-__global__ void __launch_bounds__(32) forage_finish_kernel(const __grid_constant__ DevModel m, ForageArgs fa,
-                                                           uint32_t n_chunks,
-                                                           const uint64_t* __restrict__ cand_offsets,
-                                                           const uint32_t* __restrict__ rows,
-                                                           const int64_t* __restrict__ scores,
-                                                           const uint8_t* __restrict__ doable,
-                                                           const uint64_t* __restrict__ step_seeds,
-                                                           uint32_t* __restrict__ out_index,
-                                                           int64_t* __restrict__ out_best,
-                                                           uint32_t* __restrict__ out_evaluated) {
-  const uint32_t r = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(256) forage_finish_kernel(const __grid_constant__ DevModel m, ForageArgs fa,
+                                                            uint32_t n_chunks,
+                                                            const uint64_t* __restrict__ cand_offsets,
+                                                            const uint32_t* __restrict__ rows,
+                                                            const int64_t* __restrict__ scores,
+                                                            const uint8_t* __restrict__ doable,
+                                                            const uint64_t* __restrict__ step_seeds,
+                                                            uint32_t* __restrict__ out_index,
+                                                            int64_t* __restrict__ out_best,
+                                                            uint32_t* __restrict__ out_evaluated) {
+  __shared__ int64_t s_bh, s_bs;
+  __shared__ uint32_t s_any, s_cstar, s_j, s_winner, s_warp_cnt[8];
+  const uint32_t r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const ChunkPartial* cp = fa.partials + (size_t)r * n_chunks;
   const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
-  // global best over chunks
-  int64_t bh = 0, bs = 0;
-  uint32_t any = 0;
-  for (uint32_t c = lane; c < n_chunks; c += 32) {
-    if (!cp[c].n_best) continue;
-    if (!any || score_less(bh, bs, cp[c].best_h, cp[c].best_s)) {
-      bh = cp[c].best_h;
-      bs = cp[c].best_s;
+  if (warp == 0) {
+    // global best over chunks
+    int64_t bh = 0, bs = 0;
+    uint32_t any = 0;
+    for (uint32_t c = lane; c < n_chunks; c += 32) {
+      if (!cp[c].n_best) continue;
+      if (!any || score_less(bh, bs, cp[c].best_h, cp[c].best_s)) {
+        bh = cp[c].best_h;
+        bs = cp[c].best_s;
+      }
+      any = 1;
     }
-    any = 1;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const int64_t oh = __shfl_xor_sync(0xffffffffu, bh, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
-    const uint32_t oa = __shfl_xor_sync(0xffffffffu, any, o);
-    if (oa && (!any || score_less(bh, bs, oh, os))) {
-      bh = oh;
-      bs = os;
+    for (int o = 16; o > 0; o >>= 1) {
+      const int64_t oh = __shfl_xor_sync(0xffffffffu, bh, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const uint32_t oa = __shfl_xor_sync(0xffffffffu, any, o);
+      if (oa && (!any || score_less(bh, bs, oh, os))) {
+        bh = oh;
+        bs = os;
+      }
+      any |= oa;
     }
-    any |= oa;
-  }
-  if (out_evaluated && lane == 0) out_evaluated[r] = (uint32_t)(hi - lo);
-  if (!any) {
+    uint32_t mtot = 0;
+    for (uint32_t c = lane; c < n_chunks; c += 32)
+      if (any && cp[c].n_best && cp[c].best_h == bh && cp[c].best_s == bs) mtot += cp[c].n_best;
+    for (int o = 16; o > 0; o >>= 1) mtot += __shfl_xor_sync(0xffffffffu, mtot, o);
+    // BestCandidate::consider: the winner is the occurrence with the largest firing k <= m
+    uint32_t want = 1;
+    if (fa.f.tie_mode == 1) {
+      const uint64_t seed = step_seeds ? step_seeds[r] : 0;
+      for (uint32_t k = 2 + lane; k <= mtot; k += 32) {
+        const uint64_t mixed = splitmix64_dev(seed ^ ((uint64_t)k * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
+        if (mixed % k == 0) want = k;
+      }
+      for (int o = 16; o > 0; o >>= 1) want = max(want, __shfl_xor_sync(0xffffffffu, want, o));
+    }
     if (lane == 0) {
-      out_index[r] = 0xFFFFFFFFu;
-      out_best[r * 2] = 0;
-      out_best[r * 2 + 1] = 0;
+      // chunk holding the want-th occurrence (chunks are contiguous and in pull order)
+      uint32_t c_star = 0, before = 0;
+      for (uint32_t c = 0; any && c < n_chunks; ++c) {
+        const uint32_t nb = (cp[c].n_best && cp[c].best_h == bh && cp[c].best_s == bs) ? cp[c].n_best : 0;
+        if (before + nb >= want) {
+          c_star = c;
+          break;
+        }
+        before += nb;
+      }
+      s_bh = bh;
+      s_bs = bs;
+      s_any = any;
+      s_cstar = c_star;
+      s_j = want - before;  // 1-based rank inside the chunk
+      s_winner = any ? cp[c_star].first_idx : 0xFFFFFFFFu;
+      if (out_evaluated) out_evaluated[r] = (uint32_t)(hi - lo);
     }
-    return;
   }
-  uint32_t mtot = 0;
-  for (uint32_t c = lane; c < n_chunks; c += 32)
-    if (cp[c].n_best && cp[c].best_h == bh && cp[c].best_s == bs) mtot += cp[c].n_best;
-  for (int o = 16; o > 0; o >>= 1) mtot += __shfl_xor_sync(0xffffffffu, mtot, o);
-  uint32_t want = 1;
-  if (fa.f.tie_mode == 1) {
-    const uint64_t seed = step_seeds ? step_seeds[r] : 0;
-    for (uint32_t k = 2 + lane; k <= mtot; k += 32) {
-      const uint64_t mixed = splitmix64_dev(seed ^ ((uint64_t)k * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
-      if (mixed % k == 0) want = k;
-    }
-    for (int o = 16; o > 0; o >>= 1) want = max(want, __shfl_xor_sync(0xffffffffu, want, o));
-  }
-  // chunk holding the want-th occurrence (chunks are contiguous and in pull order)
-  uint32_t c_star = 0, before = 0;
-  for (uint32_t c = 0; c < n_chunks; ++c) {
-    const uint32_t nb = (cp[c].n_best && cp[c].best_h == bh && cp[c].best_s == bs) ? cp[c].n_best : 0;
-    if (before + nb >= want) {
-      c_star = c;
-      break;
-    }
-    before += nb;
-  }
-  const uint32_t j = want - before;  // 1-based rank inside the chunk
-  uint32_t winner = cp[c_star].first_idx;
-  if (j > 1) {
+  __syncthreads();
+  const int64_t bh = s_bh, bs = s_bs;
+  const uint32_t j = s_j;
+  if (s_any && j > 1) {
+    // the winner is not the chunk's first best row: ordered rescan of that chunk, 4 consecutive
+    // rows per thread so the loads are independent and the pull order is thread order
     const uint64_t per = (hi - lo + n_chunks - 1) / n_chunks;
-    const uint64_t c_lo = lo + per * c_star;
+    const uint64_t c_lo = lo + per * s_cstar;
     const uint64_t c_hi = c_lo + per < hi ? c_lo + per : hi;
     const char* st = m.state + (size_t)r * m.block_bytes;
     const int64_t* cs = (const int64_t*)(st + m.off_score);
@@ -717,10 +725,12 @@ __global__ void __launch_bounds__(32) forage_finish_kernel(const __grid_constant
       ts = fa.ref_scores[r * 4 + 3];
     }
     uint32_t seen = 0;
-    for (uint64_t base = c_lo; base < c_hi; base += 32) {
-      const uint64_t i = base + lane;
-      bool hit = false;
-      if (i < c_hi) {
+    for (uint64_t base = c_lo; base < c_hi; base += 1024) {
+      uint32_t hits = 0;  // bit q set: row base + 4*tid + q is an accepted best row
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint64_t i = base + (uint64_t)threadIdx.x * 4 + q;
+        if (i >= c_hi) continue;
         int64_t h, s2;
         bool ok;
         if (scores) {
@@ -734,24 +744,38 @@ __global__ void __launch_bounds__(32) forage_finish_kernel(const __grid_constant
           h = cs[0] + d.hard;
           s2 = cs[1] + d.soft;
         }
-        hit = ok && h == bh && s2 == bs && accept_score(fa.f.acceptor, h, s2, lh, ls, th, ts);
+        if (ok && h == bh && s2 == bs && accept_score(fa.f.acceptor, h, s2, lh, ls, th, ts)) hits |= 1u << q;
       }
-      const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-      const uint32_t cnt = __popc(mask);
-      if (seen + cnt >= j) {
-        // the (j - seen)-th set bit
-        uint32_t mm = mask;
-        for (uint32_t t = 1; t < j - seen; ++t) mm &= mm - 1;
-        winner = (uint32_t)(base + (__ffs(mm) - 1) - lo);
-        break;
+      const uint32_t mine = __popc(hits);
+      // inclusive scan over the 256 threads (thread order == pull order)
+      uint32_t incl = mine;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
       }
-      seen += cnt;
+      if (lane == 31) s_warp_cnt[warp] = incl;
+      __syncthreads();
+      uint32_t warp_base = 0, total = 0;
+      for (uint32_t w = 0; w < 8; ++w) {
+        if (w < warp) warp_base += s_warp_cnt[w];
+        total += s_warp_cnt[w];
+      }
+      const uint32_t excl = seen + warp_base + incl - mine;
+      if (mine && excl < j && j <= excl + mine) {
+        uint32_t mm = hits;
+        for (uint32_t t = 1; t < j - excl; ++t) mm &= mm - 1;
+        s_winner = (uint32_t)(base + (uint64_t)threadIdx.x * 4 + (__ffs(mm) - 1) - lo);
+      }
+      seen += total;
+      __syncthreads();
+      if (seen >= j) break;
     }
   }
-  if (lane == 0) {
-    out_index[r] = winner;
-    out_best[r * 2] = bh;
-    out_best[r * 2 + 1] = bs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out_index[r] = s_winner;
+    out_best[r * 2] = s_any ? bh : 0;
+    out_best[r * 2 + 1] = s_any ? bs : 0;
   }
 }
 
