@@ -223,6 +223,26 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
                                const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
                                uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated);
 
+/* Whole local-search step on device: generates the nearby list-change neighbourhood of every replica
+ * (NearbyListChangeMoveSelector, heuristic/selector/list_kernel/nearby_change.rs:102-232 with the matrix
+ * distance meter crates/solverforge-cvrp/src/meters.rs:10-28; canonical SelectionOrder::Original), scores
+ * it, replays acceptor + forager and optionally commits the winners — evaluate_candidates + pick + apply
+ * (phase/step.rs:30-225) without the neighbourhood ever crossing PCIe.
+ *   flags & SFGPU_DEVICE_IO selects where the small per-replica arrays live (step_seeds, ref_scores,
+ *   out_index, out_best, out_evaluated, out_winner_rows); without it they are HOST pointers.
+ *   out_cand_offsets / out_rows / out_scores / out_doable are optional DEVICE buffers that receive the
+ *   generated batch: replica r owns rows [r*S, (r+1)*S), S = list_capacity * max_nearby, source position f
+ *   owns rows f*max_nearby .. +max_nearby in pull order; rows that do not exist are not-doable sentinels.
+ *   out_index is the reference pull index (CandidateId): source_position * candidates_per_source + rank.
+ *   out_winner_rows[R][4] = the winning ListChangeMove of each replica (sentinel 0xFFFFFFFF when none).
+ * Requires the fast list program (SFGPU_E_UNSUPPORTED otherwise) and max_nearby <= 32. */
+int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
+                                      const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                      const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
+                                      int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
+                                      int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                                      int32_t apply_winners);
+
 /* ---- committing the winner ------------------------------------------------------------ */
 /* One row per replica (same packing as the score calls); mask[r] == 0 skips replica r
  * (mask may be NULL). Updates the replica's planning state, its retained aggregates and its

@@ -78,6 +78,8 @@ SYMBOLS = {
     "sfgpu_argbest": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     "sfgpu_step_list_change": (C.c_int32, [_P, C.c_uint64, _P, _P, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P,
                                            _P]),
+    "sfgpu_step_nearby_list_change": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P,
+                                                  _P, _P, _P, _P, _P, _P, C.c_int32]),
     "sfgpu_apply_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_list_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),

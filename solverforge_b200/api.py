@@ -291,6 +291,36 @@ class GpuScoreDirector:
                                                     v(ref_ptr), v(scores_ptr), v(doable_ptr), v(index_ptr),
                                                     v(best_ptr), v(evaluated_ptr)))
 
+    def step_nearby_list_change(self, max_nearby: int = 20, params: "ForageParams" = None, step_seeds=None,
+                                ref_scores=None, apply: bool = False, out_rows_ptr: int = 0, out_scores_ptr: int = 0,
+                                out_doable_ptr: int = 0, out_offsets_ptr: int = 0):
+        """One whole local-search step on device (sfgpu_step_nearby_list_change) with HOST per-replica
+        arrays: returns (index[R], best[R,2], moves_evaluated[R], winner_rows[R,4])."""
+        params = params or ForageParams()
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        seeds = None if step_seeds is None else np.ascontiguousarray(step_seeds, dtype=np.uint64)
+        ref = None if ref_scores is None else np.ascontiguousarray(ref_scores, dtype=np.int64).reshape(self.R, 4)
+        idx = np.zeros(self.R, dtype=np.uint32)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint32)
+        win = np.zeros((self.R, 4), dtype=np.uint32)
+        v = lambda p: C.c_void_p(p) if p else None
+        self._check(self.lib.sfgpu_step_nearby_list_change(
+            self.h, 0, max_nearby, C.byref(fp), _ptr(seeds), _ptr(ref), v(out_offsets_ptr), v(out_rows_ptr),
+            v(out_scores_ptr), v(out_doable_ptr), _ptr(idx), _ptr(best), _ptr(ev), _ptr(win), 1 if apply else 0))
+        return idx, best, ev, win
+
+    def step_nearby_list_change_device(self, max_nearby: int, params: "ForageParams", seeds_ptr: int, ref_ptr: int,
+                                       index_ptr: int, best_ptr: int, evaluated_ptr: int, winner_rows_ptr: int,
+                                       apply: bool = False, out_offsets_ptr: int = 0, out_rows_ptr: int = 0,
+                                       out_scores_ptr: int = 0, out_doable_ptr: int = 0):
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        v = lambda p: C.c_void_p(p) if p else None
+        self._check(self.lib.sfgpu_step_nearby_list_change(
+            self.h, L.DEVICE_IO, max_nearby, C.byref(fp), v(seeds_ptr), v(ref_ptr), v(out_offsets_ptr),
+            v(out_rows_ptr), v(out_scores_ptr), v(out_doable_ptr), v(index_ptr), v(best_ptr), v(evaluated_ptr),
+            v(winner_rows_ptr), 1 if apply else 0))
+
     def apply_winners_device(self, move_kind: int, offsets_ptr: int, rows_ptr: int, index_ptr: int):
         self._check(self.lib.sfgpu_apply_winners(self.h, move_kind, C.c_void_p(offsets_ptr), C.c_void_p(rows_ptr),
                                                  C.c_void_p(index_ptr)))

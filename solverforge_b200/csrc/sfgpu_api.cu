@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "sfgpu_kernels.cuh"
+#include "sfgpu_nearby.cuh"
 
 namespace {
 
@@ -80,6 +80,9 @@ struct sfgpu_ctx {
   void* dscr = nullptr;
   size_t dscr_bytes = 0;
   void* partials = nullptr;  // fused forager chunk partials
+  void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
+  void* small_dev = nullptr;
+  size_t small_bytes = 0;
   size_t partials_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
@@ -199,6 +202,8 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->dscr) cudaFree(ctx->dscr);
   if (ctx->partials) cudaFree(ctx->partials);
+  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+  if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -455,6 +460,13 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       off += dm.elem_cap * 16;
       dm.off_slot_rec = off;
       off += (dm.elem_cap + dm.n_owners) * 16;
+      // device-side nearby neighbourhood: needs the path-cost matrix as the distance meter, every
+      // cell finite (guaranteed by the < 2^28 test above) and 16-bit owner / position fields
+      if (dm.fast_pc >= 0 && dm.n_owners < 65536 && dm.elem_cap < 65536) {
+        dm.nearby_ok = 1;
+        dm.off_pos_of = off;
+        off = align_up(off + dm.n_elem_rows * 4, 16);
+      }
       dm.fast_stage_bytes = off;
     } else {
       dm.fast_pc = dm.fast_ls = -1;
@@ -671,10 +683,40 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
+  if (dm.fast_list && dm.fast_stage_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
+    dm.fast_list = 0;
+    dm.nearby_ok = 0;
+  }
+  if (dm.nearby_ok) {
+    // static neighbour lists: for every element row, the other rows by (distance, row) ascending
+    const Matrix& mt = ctx->mats[ctx->cons[dm.fast_pc].d.aux0];
+    const uint32_t nrow = dm.n_elem_rows;
+    dm.nbr_stride = nrow > 0 ? nrow - 1 : 0;
+    std::vector<uint32_t> nbr((size_t)nrow * dm.nbr_stride);
+    std::vector<uint32_t> order(dm.nbr_stride);
+    for (uint32_t x = 0; x < nrow; ++x) {
+      uint32_t k = 0;
+      for (uint32_t y = 0; y < nrow; ++y)
+        if (y != x) order[k++] = y;
+      const int64_t* row = mt.host.data() + (size_t)x * mt.cols;
+      std::sort(order.begin(), order.end(), [row](uint32_t l, uint32_t r) {
+        return row[l] != row[r] ? row[l] < row[r] : l < r;
+      });
+      std::copy(order.begin(), order.end(), nbr.begin() + (size_t)x * dm.nbr_stride);
+    }
+    uint32_t* dn = nullptr;
+    int rc = dev_upload(ctx, nbr.data(), nbr.size(), &dn);
+    if (rc) return rc;
+    dm.nbr = dn;
+    int bytes = (int)dm.fast_stage_bytes;
+    CU(cudaFuncSetAttribute(nearby_step_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_EXCESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
   if (dm.fast_list) {
-    if (dm.fast_stage_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
-      dm.fast_list = 0;
-    } else {
+    {
       int bytes = (int)dm.fast_stage_bytes;
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -748,6 +790,8 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
           size_t need = (size_t)chunks * dm.R * sizeof(ChunkPartial);
           if (need > ctx->partials_bytes) {
             if (ctx->partials) cudaFree(ctx->partials);
+  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+  if (ctx->small_dev) cudaFree(ctx->small_dev);
             ctx->partials = nullptr;
             ctx->partials_bytes = 0;
             CU(cudaMalloc(&ctx->partials, need));
@@ -943,6 +987,122 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
                                                  out_best, out_evaluated);
   ctx->launches++;
   CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole local-search step on device: nearby list-change neighbourhood generation + scoring + forager.
+int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
+                                      const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                      const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
+                                      int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
+                                      int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                                      int32_t apply_winners) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  const DevModel& dm = ctx->dm;
+  if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if (!dm.nearby_ok || ctx->force_generic)
+    return fail(ctx, SFGPU_E_UNSUPPORTED,
+                "device-side nearby neighbourhood needs the fast list program (int32 path-cost matrix as the "
+                "distance meter, every cell finite); enumerate on the host and call sfgpu_step_list_change");
+  if (max_nearby == 0 || max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  if (out_scores && (!out_rows || !out_doable)) return fail(ctx, SFGPU_E_INVALID, "out_scores needs out_rows and out_doable");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R;
+  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
+  // per-source partials
+  size_t need = (size_t)R * dm.elem_cap * sizeof(SrcPartial);
+  if (need > ctx->partials_bytes) {
+    if (ctx->partials) cudaFree(ctx->partials);
+  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+  if (ctx->small_dev) cudaFree(ctx->small_dev);
+    ctx->partials = nullptr;
+    ctx->partials_bytes = 0;
+    CU(cudaMalloc(&ctx->partials, need));
+    ctx->partials_bytes = need;
+  }
+  // small per-replica arrays: host pointers are staged through pinned memory
+  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
+  size_t o_eval = a16(o_best + (size_t)R * 16), o_win = a16(o_eval + (size_t)R * 4), small = a16(o_win + (size_t)R * 16);
+  const uint64_t* d_seeds = step_seeds;
+  const int64_t* d_ref = ref_scores;
+  uint32_t *d_idx = out_index, *d_eval = out_evaluated, *d_win = out_winner_rows;
+  int64_t* d_best = out_best;
+  if (!dev_io) {
+    if (small > ctx->small_bytes) {
+      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+      if (ctx->small_dev) cudaFree(ctx->small_dev);
+      ctx->small_pin = ctx->small_dev = nullptr;
+      ctx->small_bytes = 0;
+      CU(cudaMallocHost(&ctx->small_pin, small));
+      CU(cudaMalloc(&ctx->small_dev, small));
+      ctx->small_bytes = small;
+    }
+    char* pin = (char*)ctx->small_pin;
+    char* dv = (char*)ctx->small_dev;
+    if (step_seeds) memcpy(pin + o_seed, step_seeds, (size_t)R * 8);
+    if (ref_scores) memcpy(pin + o_ref, ref_scores, (size_t)R * 32);
+    if (step_seeds || ref_scores) CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
+    d_seeds = step_seeds ? (const uint64_t*)(dv + o_seed) : nullptr;
+    d_ref = ref_scores ? (const int64_t*)(dv + o_ref) : nullptr;
+    d_idx = (uint32_t*)(dv + o_idx);
+    d_best = (int64_t*)(dv + o_best);
+    d_eval = (uint32_t*)(dv + o_eval);
+    d_win = (uint32_t*)(dv + o_win);
+  } else if (apply_winners && !d_win) {
+    return fail(ctx, SFGPU_E_INVALID, "apply_winners needs out_winner_rows on the device path");
+  }
+  NearbyArgs a{};
+  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
+  a.max_nearby = max_nearby;
+  a.step_seeds = d_seeds;
+  a.ref_scores = d_ref;
+  a.partials = (SrcPartial*)ctx->partials;
+  a.out_rows = out_rows;
+  a.out_scores = out_scores;
+  a.out_doable = out_doable;
+  a.out_offsets = out_cand_offsets;
+  // sources per CTA: 8 warps, >= 24 sources each when there is enough work
+  uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((dm.elem_cap + 255) / 256, 64));
+  dim3 grid(chunks, R);
+  size_t smem = dm.fast_stage_bytes;
+  int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+#define NEARBYK(FN)                                                                         \
+  nearby_step_kernel<FN><<<grid, 256, smem, ctx->stream>>>(dm, a);                          \
+  nearby_finish_kernel<FN><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win)
+  switch (fn) {
+    case -1: NEARBYK(-1); break;
+    case SFGPU_W_CONST: NEARBYK(SFGPU_W_CONST); break;
+    case SFGPU_W_LINEAR: NEARBYK(SFGPU_W_LINEAR); break;
+    case SFGPU_W_SQUARE: NEARBYK(SFGPU_W_SQUARE); break;
+    default: NEARBYK(SFGPU_W_EXCESS); break;
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  ctx->ev_valid = true;
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  if (apply_winners) {
+    // a replica without a winner carries the sentinel row (owner 0xFFFFFFFF): not doable, skipped
+    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, d_win, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  if (!dev_io) {
+    char* pin = (char*)ctx->small_pin;
+    char* dv = (char*)ctx->small_dev;
+    CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, small - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_index, pin + o_idx, (size_t)R * 4);
+    memcpy(out_best, pin + o_best, (size_t)R * 16);
+    if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
+    if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
+  }
   return SFGPU_OK;
 }
 

@@ -47,7 +47,11 @@ struct DevModel {
   uint32_t fast_stage_bytes;
   uint32_t off_route_rec, off_pos_rec, off_slot_rec;
   int32_t fast_pc, fast_ls;  // constraint indices of the path-cost / list-sum constraint, or -1
-  uint32_t pad;
+  // device-side nearby neighbourhood
+  uint32_t nearby_ok;        // 1 when the fused generate+score+forage kernel can run on this model
+  uint32_t off_pos_of;       // uint32[n_elem_rows]: (owner << 16 | position) of each element, or 0xFFFFFFFF
+  uint32_t nbr_stride;       // entries per row of `nbr`
+  const uint32_t* nbr;       // static: for every element row, the other rows sorted by (distance, row)
   ConsDev cons[SFGPU_MAX_CONS];
 };
 
@@ -60,12 +64,19 @@ struct PosRec {     // per flat element position
   uint32_t elem;
   int32_t rem;      // path-cost delta of removing this element from its route
   int32_t val;      // LIST_SUM column value of the element
-  uint32_t pad;
+  uint32_t owner;   // owner (route) index of this position
 };
 struct SlotRec {    // per insertion slot (owner e, position p in 0..=len), index = base + e + p
   uint32_t a, b;    // neighbours of the slot (depot at the ends)
   int32_t gap;      // cost of the existing leg a -> b (0 for an empty route)
-  uint32_t pad;
+  uint32_t where;   // (owner << 16) | position of the slot
+};
+
+// Per (replica, source position) partial of the fused nearby step.
+struct SrcPartial {
+  int64_t best_h, best_s;
+  uint32_t n_best, n_accepted;
+  uint32_t first_lane, pad;
 };
 
 struct Score2 {

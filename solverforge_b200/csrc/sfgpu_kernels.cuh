@@ -417,6 +417,11 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   const int32_t* mat = pc ? (const int32_t*)pc->g0 : nullptr;
   const uint32_t dim = pc ? pc->n0 : 0;
   const uint32_t depot = pc ? (uint32_t)pc->p0 : 0;
+  uint32_t* pos_of = m.nearby_ok ? (uint32_t*)(st + m.off_pos_of) : nullptr;
+  if (pos_of) {
+    for (uint32_t i = threadIdx.x; i < m.n_elem_rows; i += blockDim.x) pos_of[i] = 0xFFFFFFFFu;
+    __syncthreads();
+  }
   for (uint32_t o = threadIdx.x; o < m.n_owners; o += blockDim.x) {
     const uint32_t b = off[o], len = off[o + 1] - b;
     int64_t sum = 0;
@@ -427,7 +432,7 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
       s.a = a_el;
       s.b = b_el;
       s.gap = (pc && len > 0) ? mat[a_el * dim + b_el] : 0;
-      s.pad = 0;
+      s.where = (o << 16) | p;
       sr[b + o + p] = s;
       if (p < len) {
         const uint32_t x = b_el;
@@ -436,8 +441,9 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
         q.elem = x;
         q.rem = pc ? (-mat[a_el * dim + x] - mat[x * dim + nx] + (len > 1 ? mat[a_el * dim + nx] : 0)) : 0;
         q.val = ls ? (int32_t)((const int64_t*)ls->g0)[x] : 0;
-        q.pad = 0;
+        q.owner = o;
         pr[b + p] = q;
+        if (pos_of) pos_of[x] = (o << 16) | p;
         sum += q.val;
       }
     }

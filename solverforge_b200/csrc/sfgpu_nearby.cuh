@@ -1,0 +1,506 @@
+// Device-side nearby list-change neighbourhood, fused with scoring and the forager replay.
+//
+// Reference: NearbyListChangeMoveSelector — solverforge-solver/src/heuristic/selector/
+//   list_kernel/nearby_change.rs:102-232 (scan order, skip rules, min(dp, len-1) reference element),
+//   nearby_list_support.rs:3-34 (stable bounded top-k: ties keep scan order),
+//   crates/solverforge-cvrp/src/meters.rs:10-28 (MatrixDistanceMeter: finite cell as f64).
+//
+// The reference scans ~n slots per source element. Here the distance from source x to a slot depends
+// only on the slot's reference element y, and every routed element y is the reference of slot
+// (route(y), pos(y)) plus, when it is last in its route, of the append slot (route(y), len). So walking
+// the STATIC list of x's neighbours in increasing distance (built once at commit) and mapping each
+// neighbour through the per-replica inverse index pos_of[] enumerates slots in increasing distance;
+// the walk stops as soon as max_nearby slots are held and the next neighbour is strictly farther than
+// the current max_nearby-th. Ties are ordered by the slot's scan index, exactly like the reference's
+// stable insertion sort. One warp handles one source; its first `count` lanes then score one
+// candidate each (same record math as score_list_change_fast_kernel) and feed the forager partial.
+//
+// Canonical order only (SelectionOrder::Original): pull index = source_flat_position * count + lane.
+#pragma once
+#include "sfgpu_kernels.cuh"
+
+#define NB_MAXKEY 0xFFFFFFFFFFFFFFFFull
+#define NB_SCAN_BITS 24
+
+struct NearbyArgs {
+  ForageDev f;
+  uint32_t max_nearby;           // <= 32
+  const uint64_t* step_seeds;    // [R] or null
+  const int64_t* ref_scores;     // [R][4] or null
+  SrcPartial* partials;          // [R][elem_cap]
+  uint32_t* out_rows;            // [R][elem_cap * max_nearby][4] or null
+  int64_t* out_scores;           // [R][elem_cap * max_nearby][2] or null
+  uint8_t* out_doable;           // or null
+  uint64_t* out_offsets;         // [R+1] or null: candidate offsets of the materialised batch
+};
+
+// bitonic sort of 64 keys held as (k0 = index lane, k1 = index lane + 32), ascending
+__device__ __forceinline__ void warp_sort64(uint64_t& k0, uint64_t& k1, const uint32_t lane) {
+#pragma unroll
+  for (uint32_t size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 32) {
+        if (k0 > k1) {
+          const uint64_t t = k0;
+          k0 = k1;
+          k1 = t;
+        }
+      } else {
+        const uint64_t p0 = __shfl_xor_sync(0xffffffffu, k0, stride), p1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+        const bool up0 = (lane & size) == 0, up1 = ((lane + 32) & size) == 0;
+        const bool lower = (lane & stride) == 0;
+        k0 = (lower == up0) ? (k0 < p0 ? k0 : p0) : (k0 > p0 ? k0 : p0);
+        k1 = (lower == up1) ? (k1 < p1 ? k1 : p1) : (k1 > p1 ? k1 : p1);
+      }
+    }
+  }
+}
+
+// merges the 32 smallest keys of a freshly sorted batch (k0, ascending) into the kept list L
+__device__ __forceinline__ uint64_t warp_merge32(uint64_t L, uint64_t k0, const uint32_t lane) {
+  const uint64_t rev = __shfl_sync(0xffffffffu, k0, 31 - lane);
+  uint64_t v = L < rev ? L : rev;  // bitonic sequence holding the 32 smallest of the union
+#pragma unroll
+  for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+    const uint64_t p = __shfl_xor_sync(0xffffffffu, v, stride);
+    const bool lower = (lane & stride) == 0;
+    v = lower ? (v < p ? v : p) : (v > p ? v : p);
+  }
+  return v;
+}
+
+struct NearbyView {  // pointers into the (staged or global) fast section of one replica block
+  const uint4* rr;
+  const uint4* pr;
+  const uint4* sr;
+  const uint32_t* pos_of;
+};
+
+// Returns, in lane l, the l-th nearest destination slot key of source flat position f
+// (key = distance << 24 | scan index; NB_MAXKEY when fewer than l+1 exist). All 32 lanes participate.
+__device__ __forceinline__ uint64_t nearby_gen_source(const DevModel& m, const NearbyView& v,
+                                                      const int32_t* __restrict__ mat, const uint32_t dim,
+                                                      const uint32_t f, const uint32_t K, const uint32_t lane,
+                                                      uint32_t& x, uint32_t& se, uint32_t& sp, uint4& prec,
+                                                      uint4& rsrc) {
+  prec = v.pr[f];
+  x = prec.x;
+  se = prec.w;
+  rsrc = v.rr[se];
+  sp = f - rsrc.x;
+  const uint32_t slen = rsrc.y;
+  const uint32_t g_own = rsrc.x + se;  // first slot index of the source's own route
+  const uint32_t* __restrict__ nb = m.nbr + (size_t)x * m.nbr_stride;
+  const int32_t* __restrict__ mrow = mat + (size_t)x * dim;
+  uint64_t L = NB_MAXKEY;
+  for (uint32_t start = 0; start < m.nbr_stride; start += 32) {
+    if (start > 0) {
+      const uint64_t kth = __shfl_sync(0xffffffffu, L, K - 1);
+      if (kth != NB_MAXKEY) {
+        const uint32_t d_next = (uint32_t)__ldg(mrow + __ldg(nb + start));
+        if ((uint64_t)d_next > (kth >> NB_SCAN_BITS)) break;  // strictly farther: cannot enter the top K
+      }
+    }
+    uint64_t k0 = NB_MAXKEY, k1 = NB_MAXKEY;
+    const uint32_t idx = start + lane;
+    if (idx < m.nbr_stride) {
+      const uint32_t y = __ldg(nb + idx);
+      const uint32_t where = v.pos_of[y];
+      if (where != 0xFFFFFFFFu) {
+        const uint32_t e = where >> 16, py = where & 0xFFFFu;
+        const uint64_t dy = (uint64_t)(uint32_t)__ldg(mrow + y);
+        const uint4 re = v.rr[e];
+        const uint32_t g = re.x + e + py;
+        const bool own = e == se;
+        // slot (e, py): the element at py is its reference
+        if (!(own && (py == sp || py == sp + 1))) {
+          const uint32_t scan = own ? py : (g < g_own ? g + slen + 1 : g);
+          k0 = (dy << NB_SCAN_BITS) | scan;
+        }
+        // append slot (e, len): its reference is the last element
+        if (py + 1 == re.y) {
+          const uint32_t dp = re.y;
+          if (!(own && (dp == sp || dp == sp + 1))) {
+            const uint32_t scan = own ? dp : (g + 1 < g_own ? g + 1 + slen + 1 : g + 1);
+            k1 = (dy << NB_SCAN_BITS) | scan;
+          }
+        }
+      }
+    }
+    warp_sort64(k0, k1, lane);
+    L = warp_merge32(L, k0, lane);
+  }
+  return lane < K ? L : NB_MAXKEY;
+}
+
+// score of candidate (source f -> slot of `key`) with the fast-path record math; returns the
+// destination (e, dp) too. Identical arithmetic to score_list_change_fast_kernel.
+template <int SUM_FN>
+__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyView& v, const int32_t* __restrict__ mat,
+                                             const uint32_t dim, const uint64_t key, const uint32_t x,
+                                             const uint32_t se, const uint4 prec, const uint4 rsrc, int64_t ch,
+                                             int64_t csf, int64_t& oh, int64_t& os, uint32_t& de, uint32_t& dp) {
+  const uint32_t scan = (uint32_t)(key & ((1u << NB_SCAN_BITS) - 1));
+  const uint32_t slen = rsrc.y, g_own = rsrc.x + se;
+  const uint32_t g = scan <= slen ? g_own + scan : (scan - (slen + 1) < g_own ? scan - (slen + 1) : scan);
+  const uint4 s = v.sr[g];
+  de = s.w >> 16;
+  dp = s.w & 0xFFFFu;
+  const uint4 rd = v.rr[de];
+  int64_t dh = 0, ds = 0;
+  if (m.fast_pc >= 0) {
+    const ConsDev& pc = m.cons[m.fast_pc];
+    const int64_t pc_a = pc.sign < 0 ? -pc.w.a : pc.w.a;
+    const int32_t ins = __ldg(mat + s.x * dim + x) + __ldg(mat + x * dim + s.y) - (int32_t)s.z;
+    const int64_t d = pc_a * (int64_t)((int32_t)prec.y + ins);
+    if (pc.w.level == 0) dh += d; else ds += d;
+  }
+  if (SUM_FN >= 0 && se != de) {
+    const ConsDev& ls = m.cons[m.fast_ls];
+    const int64_t ls_a = ls.sign < 0 ? -ls.w.a : ls.w.a, ls_b = ls.w.b;
+    const int64_t val = (int32_t)prec.z;
+    const int64_t ss = (int64_t)(((uint64_t)rsrc.w << 32) | rsrc.z), sd = (int64_t)(((uint64_t)rd.w << 32) | rd.z);
+    int64_t d = 0;
+    if (SUM_FN == SFGPU_W_EXCESS) {
+      const int64_t e0 = ss - ls_b, e1 = sd - ls_b;
+      d = (max(e0 - val, (int64_t)0) - max(e0, (int64_t)0)) + (max(e1 + val, (int64_t)0) - max(e1, (int64_t)0));
+      d *= ls_a;
+    } else if (SUM_FN == SFGPU_W_SQUARE) {
+      d = ls_a * (((ss - val) * (ss - val) - ss * ss) + ((sd + val) * (sd + val) - sd * sd));
+    }
+    if (ls.w.level == 0) dh += d; else ds += d;
+  }
+  oh = ch + dh;
+  os = csf + ds;
+}
+
+// number of candidates every source yields: min(K, slots of non-empty routes - 2)
+__device__ __forceinline__ uint32_t nearby_count(const DevModel& m, const uint4* rr, uint32_t K) {
+  uint32_t slots = 0;
+  for (uint32_t o = 0; o < m.n_owners; ++o) {
+    const uint32_t len = rr[o].y;
+    slots += len ? len + 1 : 0;
+  }
+  const uint32_t valid = slots >= 2 ? slots - 2 : 0;
+  return valid < K ? valid : K;
+}
+
+// grid = (chunks, R), 256 threads. Warp w of chunk c handles sources c_lo + w, c_lo + w + 8, ...
+template <int SUM_FN>
+__global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant__ DevModel m, const NearbyArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_count;
+  const uint32_t r = blockIdx.y;
+  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
+  NearbyView v;
+  v.rr = (const uint4*)(smem + m.off_route_rec);
+  v.pr = (const uint4*)(smem + m.off_pos_rec);
+  v.sr = (const uint4*)(smem + m.off_slot_rec);
+  v.pos_of = (const uint32_t*)(smem + m.off_pos_of);
+  const int64_t* cs = (const int64_t*)(smem + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  if (threadIdx.x == 0) s_count = nearby_count(m, v.rr, a.max_nearby);
+  __syncthreads();
+  const uint32_t count = s_count;
+  const ConsDev& pc = m.cons[m.fast_pc];
+  const int32_t* __restrict__ mat = (const int32_t*)pc.g0;
+  const uint32_t dim = pc.n0;
+  const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;  // routed elements
+  int64_t lh = 0, ls = 0, th = 0, ts = 0;
+  if (a.ref_scores) {
+    lh = a.ref_scores[r * 4 + 0];
+    ls = a.ref_scores[r * 4 + 1];
+    th = a.ref_scores[r * 4 + 2];
+    ts = a.ref_scores[r * 4 + 3];
+  }
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+  const uint32_t c_lo = per * blockIdx.x, c_hi = min(c_lo + per, total);
+  const size_t out_base = (size_t)r * m.elem_cap * a.max_nearby;
+  if (a.out_offsets && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.out_offsets[r] = out_base;
+    if (r == m.R - 1) a.out_offsets[m.R] = out_base + (size_t)m.elem_cap * a.max_nearby;
+  }
+  if (a.out_rows && blockIdx.x == 0) {
+    // padding of the materialised batch: unrouted capacity [total, elem_cap) holds not-doable rows
+    for (size_t q = (size_t)total * a.max_nearby + threadIdx.x; q < (size_t)m.elem_cap * a.max_nearby; q += blockDim.x) {
+      ((uint4*)a.out_rows)[out_base + q] = make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+      if (a.out_scores) {
+        ((longlong2*)a.out_scores)[out_base + q] = make_longlong2(0, 0);
+        a.out_doable[out_base + q] = 0;
+      }
+    }
+  }
+  for (uint32_t f = c_lo + warp; f < c_hi; f += 8) {
+    uint32_t x, se, sp;
+    uint4 prec, rsrc;
+    const uint64_t key = nearby_gen_source(m, v, mat, dim, f, a.max_nearby, lane, x, se, sp, prec, rsrc);
+    const bool have = lane < count && key != NB_MAXKEY;
+    int64_t oh = 0, os = 0;
+    uint32_t de = 0, dp = 0;
+    if (have) nearby_score<SUM_FN>(m, v, mat, dim, key, x, se, prec, rsrc, ch, csf, oh, os, de, dp);
+    const bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+    // warp-level forager partial: best accepted score, multiplicity, first lane
+    int64_t bh = oh, bs = os;
+    uint32_t any = acc ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      const int64_t ph = __shfl_xor_sync(0xffffffffu, bh, o), ps = __shfl_xor_sync(0xffffffffu, bs, o);
+      const uint32_t pa = __shfl_xor_sync(0xffffffffu, any, o);
+      if (pa && (!any || score_less(bh, bs, ph, ps))) {
+        bh = ph;
+        bs = ps;
+      }
+      any |= pa;
+    }
+    const uint32_t eq = __ballot_sync(0xffffffffu, acc && oh == bh && os == bs);
+    const uint32_t accm = __ballot_sync(0xffffffffu, acc);
+    if (lane == 0) {
+      SrcPartial p;
+      p.best_h = any ? bh : 0;
+      p.best_s = any ? bs : 0;
+      p.n_best = __popc(eq);
+      p.n_accepted = __popc(accm);
+      p.first_lane = eq ? __ffs(eq) - 1 : 0;
+      p.pad = 0;
+      a.partials[(size_t)r * m.elem_cap + f] = p;
+    }
+    if (a.out_rows && lane < a.max_nearby) {
+      // materialised batch: fixed stride of max_nearby rows per source; missing rows are not doable
+      const size_t q = out_base + (size_t)f * a.max_nearby + lane;
+      ((uint4*)a.out_rows)[q] = have ? make_uint4(se, sp, de, dp) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+      if (a.out_scores) {
+        longlong2 o2;
+        o2.x = have ? oh : 0;
+        o2.y = have ? os : 0;
+        ((longlong2*)a.out_scores)[q] = o2;
+        a.out_doable[q] = have ? 1 : 0;
+      }
+    }
+  }
+}
+
+// One CTA per replica: ordered replay over the per-source partials (AcceptedCount cut, best, tie
+// rule), regeneration of the one or two sources whose lanes matter, winner row out.
+template <int SUM_FN>
+__global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constant__ DevModel m, const NearbyArgs a,
+                                                            uint32_t* __restrict__ out_index,
+                                                            int64_t* __restrict__ out_best,
+                                                            uint32_t* __restrict__ out_evaluated,
+                                                            uint32_t* __restrict__ out_winner_rows) {
+  __shared__ uint32_t scratch[33];
+  __shared__ int64_t s_h[8], s_s[8];
+  __shared__ uint32_t s_flag[8];
+  __shared__ uint32_t s_fcut, s_lcut, s_evaluated, s_any, s_fstar, s_jstar, s_count;
+  __shared__ int64_t s_bh, s_bs;
+  __shared__ SrcPartial s_cutp;  // truncated partial of the cut source
+  const uint32_t r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const char* st = m.state + (size_t)r * m.block_bytes;
+  NearbyView v;
+  v.rr = (const uint4*)(st + m.off_route_rec);
+  v.pr = (const uint4*)(st + m.off_pos_rec);
+  v.sr = (const uint4*)(st + m.off_slot_rec);
+  v.pos_of = (const uint32_t*)(st + m.off_pos_of);
+  const int64_t* cs = (const int64_t*)(st + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const ConsDev& pc = m.cons[m.fast_pc];
+  const int32_t* __restrict__ mat = (const int32_t*)pc.g0;
+  const uint32_t dim = pc.n0;
+  const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;
+  const SrcPartial* P = a.partials + (size_t)r * m.elem_cap;
+  int64_t lh = 0, ls = 0, th = 0, ts = 0;
+  if (a.ref_scores) {
+    lh = a.ref_scores[r * 4 + 0];
+    ls = a.ref_scores[r * 4 + 1];
+    th = a.ref_scores[r * 4 + 2];
+    ts = a.ref_scores[r * 4 + 3];
+  }
+  if (threadIdx.x == 0) {
+    s_count = nearby_count(m, v.rr, a.max_nearby);
+    s_fcut = total;       // sources [0, s_fcut) count fully; source s_fcut only up to lane s_lcut
+    s_lcut = 0;
+    s_cutp.n_best = 0;
+    s_cutp.n_accepted = 0;
+  }
+  __syncthreads();
+  const uint32_t count = s_count;
+  // ---- AcceptedCount(N): the step ends right after the N-th accepted pull -------------------
+  if (a.f.accepted_limit > 0) {
+    uint32_t seen = 0;
+    bool found = false;
+    for (uint32_t base = 0; base < total && !found; base += blockDim.x) {
+      const uint32_t f = base + threadIdx.x;
+      const uint32_t na = f < total ? P[f].n_accepted : 0;
+      uint32_t tot;
+      const uint32_t incl = block_scan_u32(na, scratch, &tot);
+      if (na && seen + incl - na < a.f.accepted_limit && a.f.accepted_limit <= seen + incl) {
+        s_fcut = f;
+        s_lcut = a.f.accepted_limit - (seen + incl - na);  // rank (1-based) of the cutting accepted lane
+      }
+      seen += tot;
+      __syncthreads();
+      found = seen >= a.f.accepted_limit;
+    }
+    __syncthreads();
+    if (s_fcut < total && warp == 0) {
+      // regenerate the cut source; keep lanes up to the s_lcut-th accepted one
+      uint32_t x, se, sp;
+      uint4 prec, rsrc;
+      const uint64_t key = nearby_gen_source(m, v, mat, dim, s_fcut, a.max_nearby, lane, x, se, sp, prec, rsrc);
+      const bool have = lane < count && key != NB_MAXKEY;
+      int64_t oh = 0, os = 0;
+      uint32_t de = 0, dp = 0;
+      if (have) nearby_score<SUM_FN>(m, v, mat, dim, key, x, se, prec, rsrc, ch, csf, oh, os, de, dp);
+      bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+      const uint32_t accm = __ballot_sync(0xffffffffu, acc);
+      uint32_t mm = accm;
+      for (uint32_t t = 1; t < s_lcut; ++t) mm &= mm - 1;
+      const uint32_t cut_lane = __ffs(mm) - 1;
+      acc = acc && lane <= cut_lane;
+      int64_t bh = oh, bs = os;
+      uint32_t any = acc ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) {
+        const int64_t ph = __shfl_xor_sync(0xffffffffu, bh, o), ps = __shfl_xor_sync(0xffffffffu, bs, o);
+        const uint32_t pa = __shfl_xor_sync(0xffffffffu, any, o);
+        if (pa && (!any || score_less(bh, bs, ph, ps))) {
+          bh = ph;
+          bs = ps;
+        }
+        any |= pa;
+      }
+      const uint32_t eq = __ballot_sync(0xffffffffu, acc && oh == bh && os == bs);
+      if (lane == 0) {
+        s_cutp.best_h = bh;
+        s_cutp.best_s = bs;
+        s_cutp.n_best = __popc(eq);
+        s_cutp.n_accepted = s_lcut;
+        s_cutp.first_lane = eq ? __ffs(eq) - 1 : 0;
+        s_lcut = cut_lane;  // from here on: last counted lane of the cut source
+      }
+    }
+    __syncthreads();
+  }
+  const uint32_t fcut = s_fcut;
+  const uint32_t n_src = fcut < total ? fcut + 1 : total;  // sources that contribute
+  // ---- best accepted score ---------------------------------------------------------------------
+  int64_t bh = 0, bs = 0;
+  uint32_t any = 0;
+  for (uint32_t f = threadIdx.x; f < n_src; f += blockDim.x) {
+    const SrcPartial p = (f == fcut) ? s_cutp : P[f];
+    if (!p.n_best) continue;
+    if (!any || score_less(bh, bs, p.best_h, p.best_s)) {
+      bh = p.best_h;
+      bs = p.best_s;
+    }
+    any = 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t ph = __shfl_xor_sync(0xffffffffu, bh, o), ps = __shfl_xor_sync(0xffffffffu, bs, o);
+    const uint32_t pa = __shfl_xor_sync(0xffffffffu, any, o);
+    if (pa && (!any || score_less(bh, bs, ph, ps))) {
+      bh = ph;
+      bs = ps;
+    }
+    any |= pa;
+  }
+  if (lane == 0) {
+    s_h[warp] = bh;
+    s_s[warp] = bs;
+    s_flag[warp] = any;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t h = 0, s2 = 0;
+    uint32_t an = 0;
+    for (int w = 0; w < 8; ++w)
+      if (s_flag[w] && (!an || score_less(h, s2, s_h[w], s_s[w]))) {
+        h = s_h[w];
+        s2 = s_s[w];
+        an = 1;
+      }
+    s_bh = h;
+    s_bs = s2;
+    s_any = an;
+    s_evaluated = fcut < total ? fcut * count + s_lcut + 1 : total * count;
+  }
+  __syncthreads();
+  bh = s_bh;
+  bs = s_bs;
+  if (!s_any) {
+    if (threadIdx.x == 0) {
+      out_index[r] = 0xFFFFFFFFu;
+      out_best[r * 2] = 0;
+      out_best[r * 2 + 1] = 0;
+      if (out_evaluated) out_evaluated[r] = s_evaluated;
+      if (out_winner_rows) ((uint4*)out_winner_rows)[r] = make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+    }
+    return;
+  }
+  // ---- multiplicity of the best and the tie rule -----------------------------------------------
+  uint32_t mloc = 0;
+  for (uint32_t f = threadIdx.x; f < n_src; f += blockDim.x) {
+    const SrcPartial p = (f == fcut) ? s_cutp : P[f];
+    if (p.n_best && p.best_h == bh && p.best_s == bs) mloc += p.n_best;
+  }
+  uint32_t mtot;
+  block_scan_u32(mloc, scratch, &mtot);
+  if (threadIdx.x == 0) s_jstar = 1;
+  __syncthreads();
+  if (a.f.tie_mode == 1) {
+    const uint64_t seed = a.step_seeds ? a.step_seeds[r] : 0;
+    uint32_t best_k = 1;
+    for (uint32_t k = 2 + threadIdx.x; k <= mtot; k += blockDim.x) {
+      const uint64_t mixed = splitmix64_dev(seed ^ ((uint64_t)k * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
+      if (mixed % k == 0) best_k = k;
+    }
+    atomicMax(&s_jstar, best_k);
+    __syncthreads();
+  }
+  const uint32_t want = s_jstar;
+  __syncthreads();
+  // ---- source holding the want-th best occurrence (sources are in pull order) -------------------
+  {
+    uint32_t seen = 0;
+    bool found = false;
+    for (uint32_t base = 0; base < n_src && !found; base += blockDim.x) {
+      const uint32_t f = base + threadIdx.x;
+      uint32_t nb = 0;
+      if (f < n_src) {
+        const SrcPartial p = (f == fcut) ? s_cutp : P[f];
+        nb = (p.n_best && p.best_h == bh && p.best_s == bs) ? p.n_best : 0;
+      }
+      uint32_t tot;
+      const uint32_t incl = block_scan_u32(nb, scratch, &tot);
+      if (nb && seen + incl - nb < want && want <= seen + incl) {
+        s_fstar = f;
+        s_jstar = want - (seen + incl - nb);  // rank inside the source
+      }
+      seen += tot;
+      __syncthreads();
+      found = seen >= want;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t fstar = s_fstar, j = s_jstar;
+    uint32_t x, se, sp;
+    uint4 prec, rsrc;
+    const uint64_t key = nearby_gen_source(m, v, mat, dim, fstar, a.max_nearby, lane, x, se, sp, prec, rsrc);
+    const bool have = lane < count && key != NB_MAXKEY && !(fstar == fcut && lane > s_lcut);
+    int64_t oh = 0, os = 0;
+    uint32_t de = 0, dp = 0;
+    if (have) nearby_score<SUM_FN>(m, v, mat, dim, key, x, se, prec, rsrc, ch, csf, oh, os, de, dp);
+    const bool hit = have && oh == bh && os == bs && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+    uint32_t mm = __ballot_sync(0xffffffffu, hit);
+    for (uint32_t t = 1; t < j; ++t) mm &= mm - 1;
+    const uint32_t wl = __ffs(mm) - 1;
+    if (lane == wl) {
+      out_index[r] = fstar * count + wl;
+      out_best[r * 2] = bh;
+      out_best[r * 2 + 1] = bs;
+      if (out_evaluated) out_evaluated[r] = s_evaluated;
+      if (out_winner_rows) ((uint4*)out_winner_rows)[r] = make_uint4(se, sp, de, dp);
+    }
+  }
+}

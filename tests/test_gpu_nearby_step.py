@@ -1,0 +1,142 @@
+"""GPU parity of the device-side nearby neighbourhood + fused step (sfgpu_step_nearby_list_change):
+generated rows, their order (CandidateId), scores, acceptor/forager replay and committed winners
+against the oracle's NearbyListChangeMoveSelector + candidate loop restatement. Bit-exact."""
+import numpy as np
+import pytest
+
+from solverforge_b200 import ForageParams, instances, models
+from solverforge_b200 import _lib as L
+from tests import oracle_lib
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _materialise(d, R, cap, K):
+    import torch
+    dev = torch.device("cuda")
+    S = cap * K
+    return (torch.zeros(R + 1, dtype=torch.int64, device=dev), torch.zeros((R * S, 4), dtype=torch.int32, device=dev),
+            torch.zeros((R * S, 2), dtype=torch.int64, device=dev), torch.zeros(R * S, dtype=torch.uint8, device=dev))
+
+
+def _check_generated(t_off, t_rows, t_scores, t_doable, R, cap, K, oracles):
+    rows = t_rows.cpu().numpy().view(np.uint32)
+    scores = t_scores.cpu().numpy()
+    doable = t_doable.cpu().numpy()
+    off = t_off.cpu().numpy()
+    S = cap * K
+    assert off.tolist() == [r * S for r in range(R + 1)]
+    out = []
+    for r in range(R):
+        want = oracles[r].enumerate_nearby_list_change(K)
+        blk = slice(r * S, (r + 1) * S)
+        ok = doable[blk] == 1
+        got = rows[blk][ok]
+        assert got.shape == want.shape, f"replica {r}: {got.shape} vs {want.shape}"
+        assert np.array_equal(got, want), f"replica {r}: generated rows differ from the reference selector order"
+        so, oko = oracles[r].score_list_change(want)
+        assert oko.all()
+        assert np.array_equal(scores[blk][ok], so), f"replica {r}: scores differ"
+        # sentinels everywhere else
+        assert (rows[blk][~ok][:, 0] == 0xFFFFFFFF).all()
+        out.append((want, so))
+    return out
+
+
+@pytest.mark.parametrize("coarse", [1, 40])
+def test_generated_neighbourhood_and_step_match_oracle(coarse):
+    c = instances.cvrp(180, 11, seed=13)
+    c.matrix = (c.matrix // coarse) * coarse       # coarse => many equal distances => tie order matters
+    R, K = 3, 20
+    starts = [instances.perturb_routes(c, 70 + r, 60) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    cap = 180
+    bufs = _materialise(d, R, cap, K)
+    base = d.calculate_score()
+    idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(0, 1, 0), step_seeds=[5, 6, 7],
+                                                   out_offsets_ptr=bufs[0].data_ptr(), out_rows_ptr=bufs[1].data_ptr(),
+                                                   out_scores_ptr=bufs[2].data_ptr(), out_doable_ptr=bufs[3].data_ptr())
+    gen = _check_generated(*bufs, R, cap, K, oracles)
+    for seed in (5, 9):
+        for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+            for ties in (0, 1):
+                for limit in (0, 1, 37, 256, 100000):
+                    ref = np.stack([np.concatenate([base[r] + [0, -20], base[r] + [0, -45]]) for r in range(R)])
+                    idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(acceptor, ties, limit),
+                                                                   step_seeds=[seed] * R, ref_scores=ref)
+                    for r in range(R):
+                        rows, so = gen[r]
+                        out = oracle_lib.replay_step(so, np.ones(len(so), np.uint8), [0, 0], ref[r][:2], ref[r][2:],
+                                                     seed, 0 if limit else 2, max(limit, 1), bool(ties), okind)
+                        what = f"coarse={coarse} seed={seed} acc={acceptor} ties={ties} limit={limit} r={r}"
+                        assert int(ev[r]) == out[2], what + " moves_evaluated"
+                        if out[0]:
+                            assert int(idx[r]) == out[1], what
+                            assert best[r].tolist() == so[out[1]].tolist(), what
+                            assert win[r].tolist() == rows[out[1]].tolist(), what + " winner row"
+                        else:
+                            assert idx[r] == 0xFFFFFFFF, what
+
+
+def test_step_loop_on_device_tracks_oracle_for_many_steps():
+    c = instances.cvrp(120, 9, seed=3)
+    R, K = 2, 12
+    starts = [instances.perturb_routes(c, 30 + r, 25) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    for step in range(25):
+        last = d.calculate_score()
+        ref = np.concatenate([last, last], axis=1)
+        # hill climbing + best score: commit the winner on device in the same call
+        idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(1, 1, 0), step_seeds=[100 + step] * R,
+                                                       ref_scores=ref, apply=True)
+        after = d.calculate_score()
+        for r in range(R):
+            rows = oracles[r].enumerate_nearby_list_change(K)
+            so, oko = oracles[r].score_list_change(rows)
+            out = oracle_lib.replay_step(so, oko, [0, 0], last[r], last[r], 100 + step, 2, 1, True, 0)
+            if out[0]:
+                assert int(idx[r]) == out[1], f"step {step} replica {r}"
+                oracles[r].apply_list_change(*rows[out[1]])
+            else:
+                assert idx[r] == 0xFFFFFFFF
+            assert after[r].tolist() == oracles[r].committed_score().tolist(), f"step {step} replica {r}"
+        assert np.array_equal(d.fresh_score(), after)
+
+
+def test_full_size_cvrp_1000_generation_matches_oracle():
+    c = instances.cvrp()
+    R, K = 2, 20
+    starts = [(c.offsets, c.elems), instances.perturb_routes(c, 77, 300)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    bufs = _materialise(d, R, 1000, K)
+    idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(0, 1, 0), step_seeds=[1, 2],
+                                                   out_offsets_ptr=bufs[0].data_ptr(), out_rows_ptr=bufs[1].data_ptr(),
+                                                   out_scores_ptr=bufs[2].data_ptr(), out_doable_ptr=bufs[3].data_ptr())
+    gen = _check_generated(*bufs, R, 1000, K, oracles)
+    for r in range(R):
+        rows, so = gen[r]
+        out = oracle_lib.replay_step(so, np.ones(len(so), np.uint8), [0, 0], [0, 0], [0, 0], r + 1, 2, 1, True, 3)
+        assert int(idx[r]) == out[1] and int(ev[r]) == 20000
+        assert win[r].tolist() == rows[out[1]].tolist()
+
+
+def test_unsupported_models_are_rejected_not_emulated():
+    g = instances.graph_coloring(50, 100, 3)
+    d = models.graph_coloring_director(g)
+    with pytest.raises(L.SfgpuError) as e:
+        d.step_nearby_list_change(20)
+    assert e.value.code == L.E_UNSUPPORTED
+    c = instances.cvrp(30, 4, seed=2)
+    c.matrix = c.matrix.copy()
+    c.matrix[3, 7] = -1            # non-finite cell: the fast program (and device generation) is refused
+    d2 = models.cvrp_director(c)
+    with pytest.raises(L.SfgpuError) as e:
+        d2.step_nearby_list_change(20)
+    assert e.value.code == L.E_UNSUPPORTED
+    d3 = models.cvrp_director(instances.cvrp(30, 4, seed=2))
+    with pytest.raises(L.SfgpuError):
+        d3.step_nearby_list_change(33)
