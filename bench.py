@@ -326,21 +326,40 @@ def run_ours(args):
     launches = d.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # e2e: the same step through the host-buffer C-ABI call (pinned host rows -> H2D -> kernel ->
-    # D2H of every score), then the device argbest on the returned scores' device copy is replaced
-    # by a host-visible winner read: timed with the host clock around the blocking calls.
-    scores_host = torch.empty((n, 2), dtype=torch.int64).pin_memory()
-    doable_host = torch.empty(n, dtype=torch.uint8).pin_memory()
-    fn = getattr(d.lib, f"sfgpu_score_{kind}")
+    # e2e: the same metric through the reference-facing call with HOST buffers, copies inside the timed
+    # region. CVRP: the whole step runs on device (sfgpu_step_nearby_list_change generates the nearby
+    # neighbourhood, scores it, replays the forager) so only the per-replica step seeds go in (pinned
+    # H2D) and the winners come back (D2H). Other workloads: sfgpu_score_* with pinned host rows in and
+    # every score out.
     import ctypes as C
-    off_np = offsets
+    if name == "cvrp":
+        seeds_host = np.arange(R, dtype=np.uint64)
+        e2e_api = "sfgpu_step_nearby_list_change (device-side neighbourhood + score + forager; host seeds in, winners out)"
+        h2d, d2h = R * 8, R * (4 + 16 + 4 + 16)
 
-    def e2e_step():
-        d._check(fn(d.h, 0, n, off_np.ctypes.data_as(C.c_void_p), C.c_void_p(rows_host.data_ptr()),
-                    C.c_void_p(scores_host.data_ptr()), C.c_void_p(doable_host.data_ptr())))
+        def e2e_step():
+            return d.step_nearby_list_change(20, fp, step_seeds=seeds_host)
 
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+        idx_e2e, best_e2e, ev_e2e, win_e2e = e2e_step()
+        # same winners as the rows-resident path (replica starts, seeds and forager are identical)
+        if not (np.array_equal(idx_e2e, t_idx.cpu().numpy().view(np.uint32)) and
+                np.array_equal(best_e2e, t_best.cpu().numpy()) and int(ev_e2e.sum()) == n):
+            raise SystemExit("bench.py: device-generated step disagrees with the rows-resident step")
+        e2e_steps = max(5, min(args.steps, 50))
+    else:
+        scores_host = torch.empty((n, 2), dtype=torch.int64).pin_memory()
+        doable_host = torch.empty(n, dtype=torch.uint8).pin_memory()
+        fn = getattr(d.lib, f"sfgpu_score_{kind}")
+        off_np = offsets
+        e2e_api = f"sfgpu_score_{kind} with pinned host buffers"
+        h2d, d2h = n * ROW_BYTES[name] + (R + 1) * 8, n * OUT_BYTES
+
+        def e2e_step():
+            d._check(fn(d.h, 0, n, off_np.ctypes.data_as(C.c_void_p), C.c_void_p(rows_host.data_ptr()),
+                        C.c_void_p(scores_host.data_ptr()), C.c_void_p(doable_host.data_ptr())))
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -378,8 +397,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample},
             "e2e": {"value": total_cands / (e2e_ms / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": n * ROW_BYTES[name] + (R + 1) * 8, "d2h_bytes_per_step": n * OUT_BYTES,
-                    "ms_per_step": e2e_ms, "api": f"sfgpu_score_{kind} with pinned host buffers"},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": e2e_api},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
