@@ -454,6 +454,18 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     }
     if (fast && (dm.fast_pc >= 0 || dm.fast_ls >= 0)) {
       dm.fast_list = 1;
+      // 32-bit delta form: multipliers fit int32, sums / values / offsets stay below 2^29
+      bool narrow = true;
+      auto fits31 = [](int64_t v) { return v > -(1ll << 31) && v < (1ll << 31); };
+      if (dm.fast_pc >= 0 && !fits31(ctx->cons[dm.fast_pc].d.weight.a)) narrow = false;
+      if (dm.fast_ls >= 0) {
+        const sfgpu_constraint_desc& d = ctx->cons[dm.fast_ls].d;
+        int64_t tot = 0;
+        for (int64_t c : ctx->cols[d.aux0].host) tot += c < 0 ? -c : c;
+        if (!fits31(d.weight.a) || tot >= (1ll << 29) || d.weight.b <= -(1ll << 29) || d.weight.b >= (1ll << 29))
+          narrow = false;
+      }
+      dm.fast_narrow = narrow ? 1 : 0;
       dm.off_route_rec = off;
       off += dm.n_owners * 16;
       dm.off_pos_rec = off;
@@ -687,6 +699,55 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     dm.fast_list = 0;
     dm.nearby_ok = 0;
   }
+  if (dm.fast_list && dm.fast_pc >= 0) {
+    // gather-friendly copies of the path-cost matrix for the fast kernel: narrowest cell type that
+    // holds every cost, plus the transpose (shared when the matrix is symmetric)
+    const Matrix& mt = ctx->mats[ctx->cons[dm.fast_pc].d.aux0];
+    int64_t mx = 0;
+    bool sym = mt.rows == mt.cols;
+    for (int64_t c : mt.host) mx = std::max(mx, c);
+    for (uint32_t i = 0; sym && i < mt.rows; ++i)
+      for (uint32_t j = i + 1; j < mt.cols; ++j)
+        if (mt.host[(size_t)i * mt.cols + j] != mt.host[(size_t)j * mt.cols + i]) { sym = false; break; }
+    dm.fm_u16 = mx < 65536 && mt.rows == mt.cols ? 1 : 0;
+    if (mt.rows != mt.cols) {
+      dm.fm_row = mt.dev;  // rectangular: no transpose trick, plain int32 gathers
+      dm.fm_col = nullptr;
+    } else if (dm.fm_u16) {
+      std::vector<uint16_t> a(mt.host.size()), t(mt.host.size());
+      for (uint32_t i = 0; i < mt.rows; ++i)
+        for (uint32_t j = 0; j < mt.cols; ++j) {
+          a[(size_t)i * mt.cols + j] = (uint16_t)mt.host[(size_t)i * mt.cols + j];
+          t[(size_t)j * mt.cols + i] = (uint16_t)mt.host[(size_t)i * mt.cols + j];
+        }
+      uint16_t *da = nullptr, *dt = nullptr;
+      int rc = dev_upload(ctx, a.data(), a.size(), &da);
+      if (rc) return rc;
+      dm.fm_row = da;
+      dm.fm_col = da;
+      if (!sym) {
+        rc = dev_upload(ctx, t.data(), t.size(), &dt);
+        if (rc) return rc;
+        dm.fm_col = dt;
+      }
+    } else {
+      dm.fm_row = mt.dev;
+      dm.fm_col = mt.dev;
+      if (!sym) {
+        std::vector<int32_t> t(mt.host.size());
+        for (uint32_t i = 0; i < mt.rows; ++i)
+          for (uint32_t j = 0; j < mt.cols; ++j) t[(size_t)j * mt.cols + i] = (int32_t)mt.host[(size_t)i * mt.cols + j];
+        int32_t* dt = nullptr;
+        int rc = dev_upload(ctx, t.data(), t.size(), &dt);
+        if (rc) return rc;
+        dm.fm_col = dt;
+      }
+    }
+    if (!dm.fm_col) {  // rectangular matrix: keep the generic kernel
+      dm.fast_list = 0;
+      dm.nearby_ok = 0;
+    }
+  }
   if (dm.nearby_ok) {
     // static neighbour lists: for every element row, the other rows by (distance, row) ascending
     const Matrix& mt = ctx->mats[ctx->cons[dm.fast_pc].d.aux0];
@@ -718,16 +779,26 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
   if (dm.fast_list) {
     {
       int bytes = (int)dm.fast_stage_bytes;
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
   }
   if (dm.has_list) {
@@ -804,11 +875,11 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
         int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
 #define FASTK(FN)                                                                                              \
   if (forage)                                                                                                  \
-    score_list_change_fast_kernel<FN, 2, 3, true><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows,   \
-                                                                                        d_scores, d_doable, *forage); \
+    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 3, true, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
+    else score_list_change_fast_kernel<FN, 2, 3, true, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
   else                                                                                                         \
-    score_list_change_fast_kernel<FN, 2, 3, false><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows,  \
-                                                                                         d_scores, d_doable, ForageArgs{})
+    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 3, false, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
+    else score_list_change_fast_kernel<FN, 2, 3, false, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{})
         switch (fn) {
           case -1: FASTK(-1); break;
           case SFGPU_W_CONST: FASTK(SFGPU_W_CONST); break;

@@ -49,6 +49,10 @@ struct DevModel {
   int32_t fast_pc, fast_ls;  // constraint indices of the path-cost / list-sum constraint, or -1
   // device-side nearby neighbourhood
   uint32_t nearby_ok;        // 1 when the fused generate+score+forage kernel can run on this model
+  uint32_t fast_narrow;      // 1 when every fast-path delta fits int32 (multipliers, sums, offsets < 2^29)
+  uint32_t fm_u16;           // 1: fm_row / fm_col hold uint16 cells (every cost < 65536), else int32
+  const void* fm_row;        // path-cost matrix, row-major: d(x, .) is row x
+  const void* fm_col;        // its transpose: d(., x) is row x (same array when the matrix is symmetric)
   uint32_t off_pos_of;       // uint32[n_elem_rows]: (owner << 16 | position) of each element, or 0xFFFFFFFF
   uint32_t nbr_stride;       // entries per row of `nbr`
   const uint32_t* nbr;       // static: for every element row, the other rows sorted by (distance, row)

@@ -469,7 +469,7 @@ struct ForageArgs {
   ChunkPartial* partials;     // [R][gridDim.x]
 };
 
-template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3, bool FORAGE = false>
+template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3, bool FORAGE = false, typename CELL = int32_t>
 __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const __grid_constant__ DevModel m,
                                                                      const uint64_t* __restrict__ cand_offsets,
                                                                      const uint32_t* __restrict__ rows,
@@ -498,7 +498,8 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
   // path cost: LINEAR weight => weight(old + d) - weight(old) = a * d
   const bool has_pc = m.fast_pc >= 0;
   const ConsDev& pc = m.cons[has_pc ? m.fast_pc : 0];
-  const int32_t* __restrict__ mat = (const int32_t*)pc.g0;
+  const CELL* __restrict__ mrow = (const CELL*)m.fm_row;
+  const CELL* __restrict__ mcol = (const CELL*)m.fm_col;
   const uint32_t dim = pc.n0;
   const int64_t pc_a = has_pc ? (pc.sign < 0 ? -pc.w.a : pc.w.a) : 0;
   const bool pc_hard = pc.w.level == 0;
@@ -555,8 +556,10 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     int32_t m0[U], m1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      m0[u] = has_pc ? __ldg(mat + sl[u].x * dim + p[u].x) : 0;
-      m1[u] = has_pc ? __ldg(mat + p[u].x * dim + sl[u].y) : 0;
+      // both gathers address row x (of the transpose and of the matrix): the candidates of one
+      // source share two short rows, so a warp's gathers fall into few 128 B lines
+      m0[u] = has_pc ? (int32_t)__ldg(mcol + p[u].x * dim + sl[u].x) : 0;
+      m1[u] = has_pc ? (int32_t)__ldg(mrow + p[u].x * dim + sl[u].y) : 0;
     }
     // phase 3: deltas + stores
 #pragma unroll
