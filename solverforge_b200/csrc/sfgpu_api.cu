@@ -3,6 +3,7 @@
 // point launches a CUDA kernel or fails with SFGPU_E_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -73,6 +74,8 @@ struct sfgpu_ctx {
   int sm_count = 0;
   bool staged = false;
   bool has_load_balance = false;
+  bool nb_key32 = false;      // nearby keys fit 32 bits
+  uint32_t nb_scan_bits = 24;
   bool force_generic = false;  // SFGPU_CTX_GENERIC_KERNELS: never take a specialised fast path (testing)
   // staging for host-pointer calls
   void* pin = nullptr;
@@ -454,17 +457,24 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     }
     if (fast && (dm.fast_pc >= 0 || dm.fast_ls >= 0)) {
       dm.fast_list = 1;
-      // 32-bit delta form: multipliers fit int32, sums / values / offsets stay below 2^29
+      // narrow model: every fast-path score delta provably fits int32 (lets the fused kernels
+      // reduce deltas with 32-bit REDUX instead of 64-bit shuffles)
       bool narrow = true;
-      auto fits31 = [](int64_t v) { return v > -(1ll << 31) && v < (1ll << 31); };
-      if (dm.fast_pc >= 0 && !fits31(ctx->cons[dm.fast_pc].d.weight.a)) narrow = false;
+      double bound = 0;
+      if (dm.fast_pc >= 0) {
+        const sfgpu_constraint_desc& d = ctx->cons[dm.fast_pc].d;
+        int64_t mx = 0;
+        for (int64_t c : ctx->mats[d.aux0].host) mx = std::max(mx, c);
+        bound += std::fabs((double)d.weight.a) * 4.0 * (double)mx;
+      }
       if (dm.fast_ls >= 0) {
         const sfgpu_constraint_desc& d = ctx->cons[dm.fast_ls].d;
-        int64_t tot = 0;
-        for (int64_t c : ctx->cols[d.aux0].host) tot += c < 0 ? -c : c;
-        if (!fits31(d.weight.a) || tot >= (1ll << 29) || d.weight.b <= -(1ll << 29) || d.weight.b >= (1ll << 29))
-          narrow = false;
+        double tot = 0;
+        for (int64_t c : ctx->cols[d.aux0].host) tot += std::fabs((double)c);
+        if (d.weight.fn == SFGPU_W_EXCESS) bound += std::fabs((double)d.weight.a) * 2.0 * tot;
+        else if (d.weight.fn == SFGPU_W_SQUARE) bound += std::fabs((double)d.weight.a) * 4.0 * tot * tot;
       }
+      if (bound >= 2147483647.0) narrow = false;
       dm.fast_narrow = narrow ? 1 : 0;
       dm.off_route_rec = off;
       off += dm.n_owners * 16;
@@ -770,11 +780,22 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     if (rc) return rc;
     dm.nbr = dn;
     int bytes = (int)dm.fast_stage_bytes;
-    CU(cudaFuncSetAttribute(nearby_step_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(nearby_step_kernel<SFGPU_W_EXCESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define NB_ATTR(FN, KEY, CELL) CU(cudaFuncSetAttribute(nearby_step_kernel<FN, KEY, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+#define NB_ATTR4(FN) NB_ATTR(FN, uint32_t, uint16_t); NB_ATTR(FN, uint32_t, int32_t); NB_ATTR(FN, uint64_t, uint16_t); NB_ATTR(FN, uint64_t, int32_t)
+    NB_ATTR4(-1);
+    NB_ATTR4(SFGPU_W_SQUARE);
+    NB_ATTR4(SFGPU_W_EXCESS);
+    // key layout: distance bits above scan-index bits; 32-bit keys when both fit in 31 bits
+    {
+      const Matrix& mt2 = ctx->mats[ctx->cons[dm.fast_pc].d.aux0];
+      int64_t mx = 0;
+      for (int64_t c : mt2.host) mx = std::max(mx, c);
+      uint32_t dbits = 1, sbits = 1;
+      while ((1ll << dbits) <= mx) ++dbits;
+      while ((1u << sbits) <= dm.elem_cap + dm.n_owners + 1) ++sbits;
+      ctx->nb_key32 = dbits + sbits <= 31;
+      ctx->nb_scan_bits = ctx->nb_key32 ? sbits : 24;
+    }
   }
   if (dm.fast_list) {
     {
@@ -1144,16 +1165,19 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   size_t smem = dm.fast_stage_bytes;
   int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
   cudaEventRecord(ctx->ev0, ctx->stream);
-#define NEARBYK(FN)                                                                         \
-  nearby_step_kernel<FN><<<grid, 256, smem, ctx->stream>>>(dm, a);                          \
-  nearby_finish_kernel<FN><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win)
-  switch (fn) {
-    case -1: NEARBYK(-1); break;
-    case SFGPU_W_CONST: NEARBYK(SFGPU_W_CONST); break;
-    case SFGPU_W_LINEAR: NEARBYK(SFGPU_W_LINEAR); break;
-    case SFGPU_W_SQUARE: NEARBYK(SFGPU_W_SQUARE); break;
-    default: NEARBYK(SFGPU_W_EXCESS); break;
+#define NEARBYK(FN, KEY, CELL)                                                                       \
+  nearby_step_kernel<FN, KEY, CELL><<<grid, 256, smem, ctx->stream>>>(dm, a);                         \
+  nearby_finish_kernel<FN, KEY, CELL><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win)
+#define NEARBYK4(FN)                                                                                 \
+  if (ctx->nb_key32) {                                                                               \
+    if (dm.fm_u16) { NEARBYK(FN, uint32_t, uint16_t); } else { NEARBYK(FN, uint32_t, int32_t); }     \
+  } else {                                                                                           \
+    if (dm.fm_u16) { NEARBYK(FN, uint64_t, uint16_t); } else { NEARBYK(FN, uint64_t, int32_t); }     \
   }
+  a.scan_bits = ctx->nb_scan_bits;
+  if (fn == SFGPU_W_EXCESS) { NEARBYK4(SFGPU_W_EXCESS) }
+  else if (fn == SFGPU_W_SQUARE) { NEARBYK4(SFGPU_W_SQUARE) }
+  else { NEARBYK4(-1) }  // no LIST_SUM, or a LINEAR / CONST weight whose relocation delta is 0
   cudaEventRecord(ctx->ev1, ctx->stream);
   ctx->ev_valid = true;
   ctx->launches += 2;

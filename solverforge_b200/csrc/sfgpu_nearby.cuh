@@ -12,19 +12,21 @@
 // neighbour through the per-replica inverse index pos_of[] enumerates slots in increasing distance;
 // the walk stops as soon as max_nearby slots are held and the next neighbour is strictly farther than
 // the current max_nearby-th. Ties are ordered by the slot's scan index, exactly like the reference's
-// stable insertion sort. One warp handles one source; its first `count` lanes then score one
+// stable insertion sort. One warp handles one source: NB_BATCH neighbours per trip are expanded to
+// slot keys (distance << scan_bits | scan index), compacted through shared memory, sorted with a
+// 32-lane bitonic network and merged into the kept top-32. The first `count` lanes then score one
 // candidate each (same record math as score_list_change_fast_kernel) and feed the forager partial.
 //
 // Canonical order only (SelectionOrder::Original): pull index = source_flat_position * count + lane.
 #pragma once
 #include "sfgpu_kernels.cuh"
 
-#define NB_MAXKEY 0xFFFFFFFFFFFFFFFFull
-#define NB_SCAN_BITS 24
+#define NB_BATCH 28  // neighbours expanded per trip: 28 + their append slots rarely exceed 32 keys
 
 struct NearbyArgs {
   ForageDev f;
   uint32_t max_nearby;           // <= 32
+  uint32_t scan_bits;            // low bits of a key that hold the scan index
   const uint64_t* step_seeds;    // [R] or null
   const int64_t* ref_scores;     // [R][4] or null
   SrcPartial* partials;          // [R][elem_cap]
@@ -34,36 +36,41 @@ struct NearbyArgs {
   uint64_t* out_offsets;         // [R+1] or null: candidate offsets of the materialised batch
 };
 
-// bitonic sort of 64 keys held as (k0 = index lane, k1 = index lane + 32), ascending
-__device__ __forceinline__ void warp_sort64(uint64_t& k0, uint64_t& k1, const uint32_t lane) {
+template <typename KEY>
+struct KeyTraits;
+template <>
+struct KeyTraits<uint32_t> {
+  static __device__ __forceinline__ uint32_t maxkey() { return 0xFFFFFFFFu; }
+};
+template <>
+struct KeyTraits<uint64_t> {
+  static __device__ __forceinline__ uint64_t maxkey() { return 0xFFFFFFFFFFFFFFFFull; }
+};
+
+// bitonic sort of 32 keys, one per lane, ascending by lane
+template <typename KEY>
+__device__ __forceinline__ KEY warp_sort32(KEY k, const uint32_t lane) {
 #pragma unroll
-  for (uint32_t size = 2; size <= 64; size <<= 1) {
+  for (uint32_t size = 2; size <= 32; size <<= 1) {
 #pragma unroll
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride == 32) {
-        if (k0 > k1) {
-          const uint64_t t = k0;
-          k0 = k1;
-          k1 = t;
-        }
-      } else {
-        const uint64_t p0 = __shfl_xor_sync(0xffffffffu, k0, stride), p1 = __shfl_xor_sync(0xffffffffu, k1, stride);
-        const bool up0 = (lane & size) == 0, up1 = ((lane + 32) & size) == 0;
-        const bool lower = (lane & stride) == 0;
-        k0 = (lower == up0) ? (k0 < p0 ? k0 : p0) : (k0 > p0 ? k0 : p0);
-        k1 = (lower == up1) ? (k1 < p1 ? k1 : p1) : (k1 > p1 ? k1 : p1);
-      }
+      const KEY p = __shfl_xor_sync(0xffffffffu, k, stride);
+      const bool up = (lane & size) == 0 || size == 32;
+      const bool lower = (lane & stride) == 0;
+      k = (lower == up) ? (k < p ? k : p) : (k > p ? k : p);
     }
   }
+  return k;
 }
 
-// merges the 32 smallest keys of a freshly sorted batch (k0, ascending) into the kept list L
-__device__ __forceinline__ uint64_t warp_merge32(uint64_t L, uint64_t k0, const uint32_t lane) {
-  const uint64_t rev = __shfl_sync(0xffffffffu, k0, 31 - lane);
-  uint64_t v = L < rev ? L : rev;  // bitonic sequence holding the 32 smallest of the union
+// merges a sorted batch b into the kept sorted list L: the 32 smallest of the union, ascending
+template <typename KEY>
+__device__ __forceinline__ KEY warp_merge32(KEY L, KEY b, const uint32_t lane) {
+  const KEY rev = __shfl_sync(0xffffffffu, b, 31 - lane);
+  KEY v = L < rev ? L : rev;  // bitonic sequence holding the 32 smallest of the union
 #pragma unroll
   for (uint32_t stride = 16; stride > 0; stride >>= 1) {
-    const uint64_t p = __shfl_xor_sync(0xffffffffu, v, stride);
+    const KEY p = __shfl_xor_sync(0xffffffffu, v, stride);
     const bool lower = (lane & stride) == 0;
     v = lower ? (v < p ? v : p) : (v > p ? v : p);
   }
@@ -78,12 +85,13 @@ struct NearbyView {  // pointers into the (staged or global) fast section of one
 };
 
 // Returns, in lane l, the l-th nearest destination slot key of source flat position f
-// (key = distance << 24 | scan index; NB_MAXKEY when fewer than l+1 exist). All 32 lanes participate.
-__device__ __forceinline__ uint64_t nearby_gen_source(const DevModel& m, const NearbyView& v,
-                                                      const int32_t* __restrict__ mat, const uint32_t dim,
-                                                      const uint32_t f, const uint32_t K, const uint32_t lane,
-                                                      uint32_t& x, uint32_t& se, uint32_t& sp, uint4& prec,
-                                                      uint4& rsrc) {
+// (maxkey when fewer than l+1 exist). All 32 lanes participate. `buf` = 64 KEY slots of this warp.
+template <typename KEY, typename CELL>
+__device__ __forceinline__ KEY nearby_gen_source(const DevModel& m, const NearbyView& v, const uint32_t scan_bits,
+                                                 const uint32_t f, const uint32_t K, const uint32_t lane,
+                                                 KEY* __restrict__ buf, uint32_t& x, uint32_t& se, uint32_t& sp,
+                                                 uint4& prec, uint4& rsrc) {
+  const KEY MAXK = KeyTraits<KEY>::maxkey();
   prec = v.pr[f];
   x = prec.x;
   se = prec.w;
@@ -92,68 +100,88 @@ __device__ __forceinline__ uint64_t nearby_gen_source(const DevModel& m, const N
   const uint32_t slen = rsrc.y;
   const uint32_t g_own = rsrc.x + se;  // first slot index of the source's own route
   const uint32_t* __restrict__ nb = m.nbr + (size_t)x * m.nbr_stride;
-  const int32_t* __restrict__ mrow = mat + (size_t)x * dim;
-  uint64_t L = NB_MAXKEY;
-  for (uint32_t start = 0; start < m.nbr_stride; start += 32) {
+  const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * m.cons[m.fast_pc].n0;
+  KEY L = MAXK;
+  for (uint32_t start = 0; start < m.nbr_stride; start += NB_BATCH) {
     if (start > 0) {
-      const uint64_t kth = __shfl_sync(0xffffffffu, L, K - 1);
-      if (kth != NB_MAXKEY) {
+      const KEY kth = __shfl_sync(0xffffffffu, L, K - 1);
+      if (kth != MAXK) {
         const uint32_t d_next = (uint32_t)__ldg(mrow + __ldg(nb + start));
-        if ((uint64_t)d_next > (kth >> NB_SCAN_BITS)) break;  // strictly farther: cannot enter the top K
+        if ((KEY)d_next > (kth >> scan_bits)) break;  // strictly farther: cannot enter the top K
       }
     }
-    uint64_t k0 = NB_MAXKEY, k1 = NB_MAXKEY;
+    KEY k0 = MAXK, k1 = MAXK;
     const uint32_t idx = start + lane;
-    if (idx < m.nbr_stride) {
+    if (lane < NB_BATCH && idx < m.nbr_stride) {
       const uint32_t y = __ldg(nb + idx);
       const uint32_t where = v.pos_of[y];
       if (where != 0xFFFFFFFFu) {
         const uint32_t e = where >> 16, py = where & 0xFFFFu;
-        const uint64_t dy = (uint64_t)(uint32_t)__ldg(mrow + y);
+        const KEY dy = (KEY)(uint32_t)__ldg(mrow + y);
         const uint4 re = v.rr[e];
         const uint32_t g = re.x + e + py;
         const bool own = e == se;
         // slot (e, py): the element at py is its reference
         if (!(own && (py == sp || py == sp + 1))) {
           const uint32_t scan = own ? py : (g < g_own ? g + slen + 1 : g);
-          k0 = (dy << NB_SCAN_BITS) | scan;
+          k0 = (dy << scan_bits) | scan;
         }
         // append slot (e, len): its reference is the last element
         if (py + 1 == re.y) {
           const uint32_t dp = re.y;
           if (!(own && (dp == sp || dp == sp + 1))) {
             const uint32_t scan = own ? dp : (g + 1 < g_own ? g + 1 + slen + 1 : g + 1);
-            k1 = (dy << NB_SCAN_BITS) | scan;
+            k1 = (dy << scan_bits) | scan;
           }
         }
       }
     }
-    warp_sort64(k0, k1, lane);
-    L = warp_merge32(L, k0, lane);
+    // compaction: all k0 keys first, then the append-slot keys
+    const uint32_t m0 = __ballot_sync(0xffffffffu, k0 != MAXK), m1 = __ballot_sync(0xffffffffu, k1 != MAXK);
+    const uint32_t n0 = __popc(m0), total = n0 + __popc(m1);
+    const uint32_t lt = (1u << lane) - 1;
+    buf[lane] = MAXK;
+    buf[lane + 32] = MAXK;
+    __syncwarp();
+    if (k0 != MAXK) buf[__popc(m0 & lt)] = k0;
+    if (k1 != MAXK) buf[n0 + __popc(m1 & lt)] = k1;
+    __syncwarp();
+    KEY b = warp_sort32(buf[lane], lane);
+    L = (start == 0) ? b : warp_merge32(L, b, lane);
+    if (total > 32) {  // rare: more than 32 slots from one batch
+      b = warp_sort32(buf[lane + 32], lane);
+      L = warp_merge32(L, b, lane);
+    }
+    __syncwarp();
   }
-  return lane < K ? L : NB_MAXKEY;
+  return lane < K ? L : MAXK;
 }
 
 // score of candidate (source f -> slot of `key`) with the fast-path record math; returns the
 // destination (e, dp) too. Identical arithmetic to score_list_change_fast_kernel.
-template <int SUM_FN>
-__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyView& v, const int32_t* __restrict__ mat,
-                                             const uint32_t dim, const uint64_t key, const uint32_t x,
-                                             const uint32_t se, const uint4 prec, const uint4 rsrc, int64_t ch,
-                                             int64_t csf, int64_t& oh, int64_t& os, uint32_t& de, uint32_t& dp) {
-  const uint32_t scan = (uint32_t)(key & ((1u << NB_SCAN_BITS) - 1));
+template <int SUM_FN, typename KEY, typename CELL>
+__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyView& v, const uint32_t scan_bits,
+                                             const KEY key, const uint32_t x, const uint32_t se, const uint4 prec,
+                                             const uint4 rsrc, int64_t& dh, int64_t& ds, uint32_t& de, uint32_t& dp) {
+  const uint32_t scan = (uint32_t)(key & (((KEY)1 << scan_bits) - 1));
   const uint32_t slen = rsrc.y, g_own = rsrc.x + se;
   const uint32_t g = scan <= slen ? g_own + scan : (scan - (slen + 1) < g_own ? scan - (slen + 1) : scan);
   const uint4 s = v.sr[g];
   de = s.w >> 16;
   dp = s.w & 0xFFFFu;
   const uint4 rd = v.rr[de];
-  int64_t dh = 0, ds = 0;
-  if (m.fast_pc >= 0) {
+  dh = 0;
+  ds = 0;
+  {
     const ConsDev& pc = m.cons[m.fast_pc];
+    const uint32_t dim = pc.n0;
     const int64_t pc_a = pc.sign < 0 ? -pc.w.a : pc.w.a;
-    const int32_t ins = __ldg(mat + s.x * dim + x) + __ldg(mat + x * dim + s.y) - (int32_t)s.z;
-    const int64_t d = pc_a * (int64_t)((int32_t)prec.y + ins);
+    const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * dim;
+    const CELL* __restrict__ mcol = (const CELL*)m.fm_col + (size_t)x * dim;
+    // d(x, b): for a non-append slot b is the slot's reference element, whose distance is in the key
+    const int32_t xb = dp < rd.y ? (int32_t)(uint32_t)(key >> scan_bits) : (int32_t)__ldg(mrow + s.y);
+    const int32_t ax = (int32_t)__ldg(mcol + s.x);
+    const int64_t d = pc_a * (int64_t)((int32_t)prec.y + ax + xb - (int32_t)s.z);
     if (pc.w.level == 0) dh += d; else ds += d;
   }
   if (SUM_FN >= 0 && se != de) {
@@ -171,8 +199,33 @@ __device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyView
     }
     if (ls.w.level == 0) dh += d; else ds += d;
   }
-  oh = ch + dh;
-  os = csf + ds;
+}
+
+// warp-level lexicographic max of (dh, ds) over the lanes with `acc`: returns the multiplicity
+// mask of the best; `any` = at least one accepted lane. Narrow models use two REDUX instructions.
+__device__ __forceinline__ uint32_t warp_best_mask(const DevModel& m, bool acc, int64_t dh, int64_t ds, uint32_t& accm) {
+  accm = __ballot_sync(0xffffffffu, acc);
+  if (!accm) return 0;
+  if (m.fast_narrow) {
+    const int32_t h32 = acc ? (int32_t)dh : INT32_MIN;
+    const int32_t bh = __reduce_max_sync(0xffffffffu, h32);
+    const bool top = acc && (int32_t)dh == bh;
+    const int32_t s32 = top ? (int32_t)ds : INT32_MIN;
+    const int32_t bs = __reduce_max_sync(0xffffffffu, s32);
+    return __ballot_sync(0xffffffffu, top && (int32_t)ds == bs);
+  }
+  int64_t bh = dh, bs = ds;
+  uint32_t any = acc ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t ph = __shfl_xor_sync(0xffffffffu, bh, o), ps = __shfl_xor_sync(0xffffffffu, bs, o);
+    const uint32_t pa = __shfl_xor_sync(0xffffffffu, any, o);
+    if (pa && (!any || score_less(bh, bs, ph, ps))) {
+      bh = ph;
+      bs = ps;
+    }
+    any |= pa;
+  }
+  return __ballot_sync(0xffffffffu, acc && dh == bh && ds == bs);
 }
 
 // number of candidates every source yields: min(K, slots of non-empty routes - 2)
@@ -187,11 +240,12 @@ __device__ __forceinline__ uint32_t nearby_count(const DevModel& m, const uint4*
 }
 
 // grid = (chunks, R), 256 threads. Warp w of chunk c handles sources c_lo + w, c_lo + w + 8, ...
-template <int SUM_FN>
+template <int SUM_FN, typename KEY, typename CELL>
 __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant__ DevModel m, const NearbyArgs a) {
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t s_count;
+  __shared__ KEY s_buf[8][64];
   const uint32_t r = blockIdx.y;
   stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
   NearbyView v;
@@ -204,9 +258,6 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
   if (threadIdx.x == 0) s_count = nearby_count(m, v.rr, a.max_nearby);
   __syncthreads();
   const uint32_t count = s_count;
-  const ConsDev& pc = m.cons[m.fast_pc];
-  const int32_t* __restrict__ mat = (const int32_t*)pc.g0;
-  const uint32_t dim = pc.n0;
   const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;  // routed elements
   int64_t lh = 0, ls = 0, th = 0, ts = 0;
   if (a.ref_scores) {
@@ -236,30 +287,20 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
   for (uint32_t f = c_lo + warp; f < c_hi; f += 8) {
     uint32_t x, se, sp;
     uint4 prec, rsrc;
-    const uint64_t key = nearby_gen_source(m, v, mat, dim, f, a.max_nearby, lane, x, se, sp, prec, rsrc);
-    const bool have = lane < count && key != NB_MAXKEY;
-    int64_t oh = 0, os = 0;
+    const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, a.max_nearby, lane, s_buf[warp], x, se, sp,
+                                                 prec, rsrc);
+    const bool have = lane < count && key != KeyTraits<KEY>::maxkey();
+    int64_t dh = 0, ds = 0;
     uint32_t de = 0, dp = 0;
-    if (have) nearby_score<SUM_FN>(m, v, mat, dim, key, x, se, prec, rsrc, ch, csf, oh, os, de, dp);
+    if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    const int64_t oh = ch + dh, os = csf + ds;
     const bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
-    // warp-level forager partial: best accepted score, multiplicity, first lane
-    int64_t bh = oh, bs = os;
-    uint32_t any = acc ? 1 : 0;
-    for (int o = 16; o > 0; o >>= 1) {
-      const int64_t ph = __shfl_xor_sync(0xffffffffu, bh, o), ps = __shfl_xor_sync(0xffffffffu, bs, o);
-      const uint32_t pa = __shfl_xor_sync(0xffffffffu, any, o);
-      if (pa && (!any || score_less(bh, bs, ph, ps))) {
-        bh = ph;
-        bs = ps;
-      }
-      any |= pa;
-    }
-    const uint32_t eq = __ballot_sync(0xffffffffu, acc && oh == bh && os == bs);
-    const uint32_t accm = __ballot_sync(0xffffffffu, acc);
-    if (lane == 0) {
+    uint32_t accm;
+    const uint32_t eq = warp_best_mask(m, acc, dh, ds, accm);
+    if (lane == (eq ? __ffs(eq) - 1 : 0)) {
       SrcPartial p;
-      p.best_h = any ? bh : 0;
-      p.best_s = any ? bs : 0;
+      p.best_h = eq ? oh : 0;
+      p.best_s = eq ? os : 0;
       p.n_best = __popc(eq);
       p.n_accepted = __popc(accm);
       p.first_lane = eq ? __ffs(eq) - 1 : 0;
@@ -283,7 +324,7 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
 
 // One CTA per replica: ordered replay over the per-source partials (AcceptedCount cut, best, tie
 // rule), regeneration of the one or two sources whose lanes matter, winner row out.
-template <int SUM_FN>
+template <int SUM_FN, typename KEY, typename CELL>
 __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constant__ DevModel m, const NearbyArgs a,
                                                             uint32_t* __restrict__ out_index,
                                                             int64_t* __restrict__ out_best,
@@ -295,6 +336,7 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
   __shared__ uint32_t s_fcut, s_lcut, s_evaluated, s_any, s_fstar, s_jstar, s_count;
   __shared__ int64_t s_bh, s_bs;
   __shared__ SrcPartial s_cutp;  // truncated partial of the cut source
+  __shared__ KEY s_buf[64];
   const uint32_t r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const char* st = m.state + (size_t)r * m.block_bytes;
   NearbyView v;
@@ -304,9 +346,6 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
   v.pos_of = (const uint32_t*)(st + m.off_pos_of);
   const int64_t* cs = (const int64_t*)(st + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
-  const ConsDev& pc = m.cons[m.fast_pc];
-  const int32_t* __restrict__ mat = (const int32_t*)pc.g0;
-  const uint32_t dim = pc.n0;
   const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;
   const SrcPartial* P = a.partials + (size_t)r * m.elem_cap;
   int64_t lh = 0, ls = 0, th = 0, ts = 0;
@@ -347,32 +386,23 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
       // regenerate the cut source; keep lanes up to the s_lcut-th accepted one
       uint32_t x, se, sp;
       uint4 prec, rsrc;
-      const uint64_t key = nearby_gen_source(m, v, mat, dim, s_fcut, a.max_nearby, lane, x, se, sp, prec, rsrc);
-      const bool have = lane < count && key != NB_MAXKEY;
-      int64_t oh = 0, os = 0;
+      const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, lane, s_buf, x, se, sp,
+                                                   prec, rsrc);
+      const bool have = lane < count && key != KeyTraits<KEY>::maxkey();
+      int64_t dh = 0, ds = 0;
       uint32_t de = 0, dp = 0;
-      if (have) nearby_score<SUM_FN>(m, v, mat, dim, key, x, se, prec, rsrc, ch, csf, oh, os, de, dp);
+      if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+      const int64_t oh = ch + dh, os = csf + ds;
       bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
-      const uint32_t accm = __ballot_sync(0xffffffffu, acc);
-      uint32_t mm = accm;
+      uint32_t mm = __ballot_sync(0xffffffffu, acc);
       for (uint32_t t = 1; t < s_lcut; ++t) mm &= mm - 1;
       const uint32_t cut_lane = __ffs(mm) - 1;
       acc = acc && lane <= cut_lane;
-      int64_t bh = oh, bs = os;
-      uint32_t any = acc ? 1 : 0;
-      for (int o = 16; o > 0; o >>= 1) {
-        const int64_t ph = __shfl_xor_sync(0xffffffffu, bh, o), ps = __shfl_xor_sync(0xffffffffu, bs, o);
-        const uint32_t pa = __shfl_xor_sync(0xffffffffu, any, o);
-        if (pa && (!any || score_less(bh, bs, ph, ps))) {
-          bh = ph;
-          bs = ps;
-        }
-        any |= pa;
-      }
-      const uint32_t eq = __ballot_sync(0xffffffffu, acc && oh == bh && os == bs);
-      if (lane == 0) {
-        s_cutp.best_h = bh;
-        s_cutp.best_s = bs;
+      uint32_t accm;
+      const uint32_t eq = warp_best_mask(m, acc, dh, ds, accm);
+      if (lane == (eq ? __ffs(eq) - 1 : 0)) {
+        s_cutp.best_h = oh;
+        s_cutp.best_s = os;
         s_cutp.n_best = __popc(eq);
         s_cutp.n_accepted = s_lcut;
         s_cutp.first_lane = eq ? __ffs(eq) - 1 : 0;
@@ -486,11 +516,13 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     const uint32_t fstar = s_fstar, j = s_jstar;
     uint32_t x, se, sp;
     uint4 prec, rsrc;
-    const uint64_t key = nearby_gen_source(m, v, mat, dim, fstar, a.max_nearby, lane, x, se, sp, prec, rsrc);
-    const bool have = lane < count && key != NB_MAXKEY && !(fstar == fcut && lane > s_lcut);
-    int64_t oh = 0, os = 0;
+    const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, lane, s_buf, x, se, sp, prec,
+                                                 rsrc);
+    const bool have = lane < count && key != KeyTraits<KEY>::maxkey() && !(fstar == fcut && lane > s_lcut);
+    int64_t dh = 0, ds = 0;
     uint32_t de = 0, dp = 0;
-    if (have) nearby_score<SUM_FN>(m, v, mat, dim, key, x, se, prec, rsrc, ch, csf, oh, os, de, dp);
+    if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    const int64_t oh = ch + dh, os = csf + ds;
     const bool hit = have && oh == bh && os == bs && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
     uint32_t mm = __ballot_sync(0xffffffffu, hit);
     for (uint32_t t = 1; t < j; ++t) mm &= mm - 1;
