@@ -391,7 +391,7 @@ def run_ours(args):
                        "sync_every": args.sync_every if world > 1 else None,
                        "parity_gate": "replica 0 bit-identical to the oracle before timing"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(name, R), "peak_source": peak_src,
                          "kernel": "score_list_change_fast_kernel (+ forage_finish_kernel, ~2 us)" if use_fused
                          else f"score_{kind}_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
@@ -404,6 +404,16 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_traffic(name, R):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None
+    when no capture exists for this workload / replica count."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(f"{name}:{R}")
+        return t["dram_bytes_read"] + t["dram_bytes_write"] if t else None
+    except Exception:
+        return None
 
 
 def d_state_bytes(name, inst) -> int:
