@@ -1,55 +1,137 @@
 """Host-side candidate enumeration in the reference's pull order (the SoA rows the score kernels
-consume). Mirrors, for SelectionOrder::Original:
+consume). Mirrors:
 
-  ChangeMoveSelector            solverforge-solver/src/heuristic/selector/move_selector/change.rs:66-104,246-307
+  MoveStreamContext             solverforge-solver/src/heuristic/selector/move_selector/iter.rs:14-207
+  ChangeMoveSelector            heuristic/selector/move_selector/change.rs:66-104,246-307
   NearbyListChangeMoveSelector  heuristic/selector/list_kernel/nearby_change.rs:102-232
   bounded stable top-k          heuristic/selector/nearby_list_support.rs:3-34
   MatrixDistanceMeter           crates/solverforge-cvrp/src/meters.rs:10-28
 
-CandidateId == row index (move_selector/borrowed.rs:396-430).
+CandidateId == row index (move_selector/borrowed.rs:396-430). Pure integer arithmetic on splitmix64,
+so the order is reproducible bit for bit. (The device-side generator, sfgpu_step_nearby_list_change,
+covers the canonical order; seeded orders are enumerated here and scored with sfgpu_step_list_change.)
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+from math import gcd
+
 import numpy as np
 
-from .instances import change_neighbourhood  # noqa: F401  (ChangeMove order)
+from .instances import change_neighbourhood  # noqa: F401  (canonical ChangeMove order, vectorised)
 
 _I64_MAX = np.iinfo(np.int64).max
+_M64 = (1 << 64) - 1
+ORIGINAL, RANDOM, SHUFFLED = 0, 1, 2
 
 
-def nearby_list_change_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.ndarray, max_nearby: int = 20
-                            ) -> np.ndarray:
-    """rows[n][4] = (src_entity, src_position, dst_entity, dst_position) uint32 in canonical order.
+def splitmix64(v: int) -> int:
+    v = (v + 0x9E3779B97F4A7C15) & _M64
+    v = ((v ^ (v >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    v = ((v ^ (v >> 27)) * 0x94D049BB133111EB) & _M64
+    return v ^ (v >> 31)
 
-    For every source (entity, position) in order: scan the intra-list destinations 0..=len (skipping
-    position and position+1), then every other entity's 0..=len, measure
-    distance(src element, element at min(dst_position, len-1)) — infinite (dropped) when that list is
-    empty or the cell is negative / UNREACHABLE — and keep the max_nearby smallest, ties in scan order.
+
+@dataclass(frozen=True)
+class MoveStreamContext:
+    """iter.rs:14-184 — seeded, stateless index maps for every selector leaf."""
+    step_index: int = 0
+    step_seed: int = 0
+    selection_order: int = ORIGINAL
+
+    def is_canonical(self) -> bool:
+        return self.selection_order == ORIGINAL
+
+    def mixed_seed(self, salt: int) -> int:
+        return splitmix64(self.step_seed ^ ((self.step_index * 0x9E3779B97F4A7C15) & _M64) ^ salt)
+
+    def random_index(self, length: int, salt: int) -> int:
+        return 0 if length <= 1 else self.mixed_seed(salt) % length
+
+    def random_stride(self, length: int, salt: int) -> int:
+        if length <= 1:
+            return 1
+        stride = self.mixed_seed(salt) % (length - 1) + 1
+        while gcd(stride, length) != 1:
+            stride = 1 if stride == length - 1 else stride + 1
+        return stride
+
+    def selection_index(self, offset: int, length: int, salt: int) -> int:
+        if self.selection_order == RANDOM:
+            return self.random_index(length, salt ^ ((offset * 0xD1B54A32D192ED03) & _M64))
+        if self.selection_order == SHUFFLED:
+            start = self.random_index(length, salt)
+            stride = self.random_stride(length, salt ^ 0xA24BAED4963EE407)
+            return (start + offset * stride) % length
+        return offset
+
+
+def change_move_rows(values: np.ndarray, n_values: int, allows_unassigned: bool = True,
+                     ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0,
+                     variable_index: int = 0) -> np.ndarray:
+    """rows[n][2] int64 = (entity, to_value | -1). change.rs:66-104: per (permuted) entity its
+    (permuted) values, then the to-None move when the entity is currently assigned."""
+    if ctx.is_canonical():
+        return change_neighbourhood(np.asarray(values), n_values, allows_unassigned)
+    n = len(values)
+    entity_salt = 0xC4A46E0000000001 ^ (descriptor_index << 32) ^ variable_index
+    out = []
+    for eo in range(n):
+        e = ctx.selection_index(eo, n, entity_salt)
+        value_salt = 0xC4A46E0000000000 ^ e ^ (descriptor_index << 32) ^ variable_index
+        for vo in range(n_values):
+            out.append((e, ctx.selection_index(vo, n_values, value_salt)))
+        if allows_unassigned and values[e] >= 0:
+            out.append((e, -1))
+    return np.array(out, dtype=np.int64).reshape(-1, 2)
+
+
+def nearby_list_change_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.ndarray, max_nearby: int = 20,
+                            ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0) -> np.ndarray:
+    """rows[n][4] = (src_entity, src_position, dst_entity, dst_position) uint32 in pull order.
+
+    For every source (entity, position) in (permuted) order: scan the intra-list destinations 0..=len
+    (skipping position and position+1), then every other entity's 0..=len in the (permuted) entity
+    order, measure distance(src element, element at min(dst_position, len-1)) — infinite (dropped)
+    when that list is empty or the cell is negative / UNREACHABLE — and keep the max_nearby smallest,
+    ties in scan order.
     """
     offsets = np.asarray(offsets, dtype=np.int64)
     elems = np.asarray(elems, dtype=np.int64)
     n_owners = len(offsets) - 1
     lens = np.diff(offsets)
-    # every destination slot (entity, position 0..=len) with its reference element, in entity order
-    slot_e = np.repeat(np.arange(n_owners), lens + 1)
-    slot_first = np.concatenate([[0], np.cumsum(lens + 1)])[:-1]
-    slot_p = np.arange(len(slot_e)) - np.repeat(slot_first, lens + 1)
+    entity_salt = 0xA1EA2B17C4A40001 ^ descriptor_index
+    if n_owners <= 1 or ctx.is_canonical():
+        entities = np.arange(n_owners)
+    else:
+        entities = np.array([ctx.selection_index(o, n_owners, entity_salt) for o in range(n_owners)])
+    # destination slots (entity, position 0..=len) with their reference element, in entity scan order
+    e_lens = lens[entities]
+    slot_rank = np.repeat(np.arange(n_owners), e_lens + 1)      # index into `entities`
+    slot_e = entities[slot_rank]
+    slot_first = np.concatenate([[0], np.cumsum(e_lens + 1)])[:-1]
+    slot_p = np.arange(len(slot_e)) - np.repeat(slot_first, e_lens + 1)
     slot_len = lens[slot_e]
     has_ref = slot_len > 0
     ref_pos = np.minimum(slot_p, np.maximum(slot_len - 1, 0))
-    ref_elem = np.where(has_ref, elems[np.minimum(offsets[slot_e] + ref_pos, max(len(elems) - 1, 0))]
-                        if len(elems) else 0, 0)
+    if len(elems):
+        ref_elem = np.where(has_ref, elems[np.minimum(offsets[slot_e] + ref_pos, len(elems) - 1)], 0)
+    else:
+        ref_elem = np.zeros(len(slot_e), dtype=np.int64)
     out = []
-    for se in range(n_owners):
+    for si in range(n_owners):
+        se = int(entities[si])
         slen = int(lens[se])
         if slen == 0:
             continue
-        intra = np.flatnonzero(slot_e == se)
-        inter = np.flatnonzero(slot_e != se)
+        intra = np.flatnonzero(slot_rank == si)
+        inter = np.flatnonzero(slot_rank != si)
         order = np.concatenate([intra, inter])            # scan order: own list first
         o_e, o_p, o_ref, o_has = slot_e[order], slot_p[order], ref_elem[order], has_ref[order]
         own = np.arange(len(order)) < len(intra)
-        for sp in range(slen):
+        source_salt = 0xA1EA2B17C4A40002 ^ se ^ descriptor_index
+        for po in range(slen):
+            sp = ctx.selection_index(po, slen, source_salt)
             x = elems[offsets[se] + sp]
             cell = matrix[x, o_ref]
             finite = o_has & (cell >= 0) & (cell != _I64_MAX)

@@ -1,0 +1,43 @@
+"""CPU tests: the product's host-side selectors reproduce the reference pull order (oracle
+restatement of MoveStreamContext / ChangeMoveSelector / NearbyListChangeMoveSelector) for every
+selection order."""
+import numpy as np
+import pytest
+
+from solverforge_b200 import instances, selectors
+from solverforge_b200.selectors import MoveStreamContext
+from tests.oracle_lib import Oracle
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_change_move_order_matches_reference(order):
+    g = instances.graph_coloring(97, 300, 5, seed_edges=3, seed_colors=4, unassigned_permille=100)
+    o = Oracle.graph_coloring(g)
+    for step_index, seed in ((0, 0), (3, 12345), (17, 0xDEADBEEFCAFE)):
+        want = o.enumerate_change(step_index, seed, order)
+        got = selectors.change_move_rows(g.color, g.k, True, MoveStreamContext(step_index, seed, order))
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_nearby_list_change_order_matches_reference(order):
+    c = instances.cvrp(70, 7, seed=5)
+    c.matrix = (c.matrix // 30) * 30                   # ties exercise the stable top-k
+    offs, el = instances.perturb_routes(c, 4, 40)
+    o = Oracle.cvrp(c, offs, el)
+    for step_index, seed in ((0, 0), (5, 987654321), (40, 0xABCDEF0123456789)):
+        want = o.enumerate_nearby_list_change(9, step_index, seed, order)
+        got = selectors.nearby_list_change_rows(offs, el, c.matrix, 9, MoveStreamContext(step_index, seed, order))
+        assert np.array_equal(got, want), f"order={order} step={step_index}"
+
+
+def test_nearby_handles_empty_routes_and_unreachable_cells():
+    c = instances.cvrp(20, 5, seed=2)
+    c.matrix = c.matrix.copy()
+    c.matrix[3, 7] = np.iinfo(np.int64).max
+    c.matrix[5, :] = -1
+    routes = [[1, 2, 3, 7, 9], [], [4, 5, 10], [], list(range(11, 21)) + [6, 8]]
+    offs = np.cumsum([0] + [len(r) for r in routes]).astype(np.uint32)
+    el = np.array([x for r in routes for x in r], dtype=np.uint32)
+    o = Oracle.cvrp(c, offs, el)
+    assert np.array_equal(selectors.nearby_list_change_rows(offs, el, c.matrix, 6), o.enumerate_nearby_list_change(6))
