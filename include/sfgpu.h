@@ -243,6 +243,30 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
                                       int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
                                       int32_t apply_winners);
 
+/* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
+ * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA
+ * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.
+ * acceptor: 1 HillClimbing, 2 LateAcceptance(late_size). The reference draws step seeds from
+ * rand::StdRng (unpinned third-party stream); here step t of replica r uses
+ * splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t), so a trajectory is reproducible and each of its
+ * steps can be checked against the oracle, but it is not the reference's trajectory.
+ * Host outputs (may be NULL): best score per replica, moves_evaluated and committed steps per replica.
+ * restore_best != 0 makes the best solution of each replica its working solution at the end
+ * (read it with sfgpu_get_list_state). */
+typedef struct sfgpu_solve_params {
+  uint32_t max_nearby;
+  uint32_t n_steps;
+  int32_t acceptor;
+  uint32_t late_size;
+  int32_t tie_mode;
+  uint32_t accepted_limit;
+  uint64_t seed_base;
+  int32_t restore_best;
+  int32_t reserved;
+} sfgpu_solve_params;
+int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* params, int64_t* out_best_scores,
+                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps);
+
 /* ---- committing the winner ------------------------------------------------------------ */
 /* One row per replica (same packing as the score calls); mask[r] == 0 skips replica r
  * (mask may be NULL). Updates the replica's planning state, its retained aggregates and its

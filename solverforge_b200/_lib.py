@@ -44,6 +44,12 @@ class ConstraintDesc(C.Structure):
     ]
 
 
+class SolveParams(C.Structure):
+    _fields_ = [("max_nearby", C.c_uint32), ("n_steps", C.c_uint32), ("acceptor", C.c_int32),
+                ("late_size", C.c_uint32), ("tie_mode", C.c_int32), ("accepted_limit", C.c_uint32),
+                ("seed_base", C.c_uint64), ("restore_best", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ForageParams(C.Structure):
     _fields_ = [("acceptor", C.c_int32), ("tie_mode", C.c_int32), ("accepted_limit", C.c_uint32),
                 ("reserved", C.c_uint32)]
@@ -80,6 +86,7 @@ SYMBOLS = {
                                            _P]),
     "sfgpu_step_nearby_list_change": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P,
                                                   _P, _P, _P, _P, _P, _P, C.c_int32]),
+    "sfgpu_solve_nearby_list_change": (C.c_int32, [_P, C.POINTER(SolveParams), _P, _P, _P]),
     "sfgpu_apply_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_list_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),

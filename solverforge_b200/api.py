@@ -321,6 +321,19 @@ class GpuScoreDirector:
             v(out_rows_ptr), v(out_scores_ptr), v(out_doable_ptr), v(index_ptr), v(best_ptr), v(evaluated_ptr),
             v(winner_rows_ptr), 1 if apply else 0))
 
+    def solve_nearby_list_change(self, n_steps: int, max_nearby: int = 20, acceptor: int = 2, late_size: int = 400,
+                                 tie_mode: int = 1, accepted_limit: int = 0, seed_base: int = 0,
+                                 restore_best: bool = False):
+        """Device-resident local-search loop (sfgpu_solve_nearby_list_change): returns
+        (best_scores[R,2], moves_evaluated[R], committed_steps[R])."""
+        p = L.SolveParams(max_nearby, n_steps, acceptor, late_size, tie_mode, accepted_limit, seed_base,
+                          1 if restore_best else 0, 0)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint64)
+        acc = np.zeros(self.R, dtype=np.uint64)
+        self._check(self.lib.sfgpu_solve_nearby_list_change(self.h, C.byref(p), _ptr(best), _ptr(ev), _ptr(acc)))
+        return best, ev, acc
+
     def apply_winners_device(self, move_kind: int, offsets_ptr: int, rows_ptr: int, index_ptr: int):
         self._check(self.lib.sfgpu_apply_winners(self.h, move_kind, C.c_void_p(offsets_ptr), C.c_void_p(rows_ptr),
                                                  C.c_void_p(index_ptr)))

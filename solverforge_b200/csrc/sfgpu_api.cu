@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "sfgpu_nearby.cuh"
+#include "sfgpu_solve.cuh"
 
 namespace {
 
@@ -83,6 +83,8 @@ struct sfgpu_ctx {
   void* dscr = nullptr;
   size_t dscr_bytes = 0;
   void* partials = nullptr;  // fused forager chunk partials
+  void* solve_buf = nullptr;  // device-resident loop state
+  size_t solve_bytes = 0;
   void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
   void* small_dev = nullptr;
   size_t small_bytes = 0;
@@ -205,6 +207,7 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->dscr) cudaFree(ctx->dscr);
   if (ctx->partials) cudaFree(ctx->partials);
+  if (ctx->solve_buf) cudaFree(ctx->solve_buf);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -882,6 +885,7 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
           size_t need = (size_t)chunks * dm.R * sizeof(ChunkPartial);
           if (need > ctx->partials_bytes) {
             if (ctx->partials) cudaFree(ctx->partials);
+  if (ctx->solve_buf) cudaFree(ctx->solve_buf);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
             ctx->partials = nullptr;
@@ -1082,6 +1086,45 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
   return SFGPU_OK;
 }
 
+namespace {
+// generate + score + forage (two kernels) on the context's stream
+int launch_nearby_kernels(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t* d_best, uint32_t* d_eval,
+                          uint32_t* d_win) {
+  const DevModel& dm = ctx->dm;
+  const uint32_t R = dm.R;
+  // sources per CTA: 8 warps, >= 24 sources each when there is enough work
+  uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((dm.elem_cap + 255) / 256, 64));
+  dim3 grid(chunks, R);
+  size_t smem = dm.fast_stage_bytes;
+  int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
+#define NEARBYK(FN, KEY, CELL)                                                                       \
+  nearby_step_kernel<FN, KEY, CELL><<<grid, 256, smem, ctx->stream>>>(dm, a);                         \
+  nearby_finish_kernel<FN, KEY, CELL><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win)
+#define NEARBYK4(FN)                                                                                 \
+  if (ctx->nb_key32) {                                                                               \
+    if (dm.fm_u16) { NEARBYK(FN, uint32_t, uint16_t); } else { NEARBYK(FN, uint32_t, int32_t); }     \
+  } else {                                                                                           \
+    if (dm.fm_u16) { NEARBYK(FN, uint64_t, uint16_t); } else { NEARBYK(FN, uint64_t, int32_t); }     \
+  }
+  a.scan_bits = ctx->nb_scan_bits;
+  if (fn == SFGPU_W_EXCESS) { NEARBYK4(SFGPU_W_EXCESS) }
+  else if (fn == SFGPU_W_SQUARE) { NEARBYK4(SFGPU_W_SQUARE) }
+  else { NEARBYK4(-1) }  // no LIST_SUM, or a LINEAR / CONST weight whose relocation delta is 0
+  return SFGPU_OK;
+}
+
+int ensure_partials(sfgpu_ctx* ctx, size_t need) {
+  if (need > ctx->partials_bytes) {
+    if (ctx->partials) cudaFree(ctx->partials);
+    ctx->partials = nullptr;
+    ctx->partials_bytes = 0;
+    CU(cudaMalloc(&ctx->partials, need));
+    ctx->partials_bytes = need;
+  }
+  return SFGPU_OK;
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------------
 // Whole local-search step on device: nearby list-change neighbourhood generation + scoring + forager.
 int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
@@ -1106,17 +1149,8 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   CU(cudaSetDevice(ctx->device));
   const uint32_t R = dm.R;
   const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
-  // per-source partials
-  size_t need = (size_t)R * dm.elem_cap * sizeof(SrcPartial);
-  if (need > ctx->partials_bytes) {
-    if (ctx->partials) cudaFree(ctx->partials);
-  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
-  if (ctx->small_dev) cudaFree(ctx->small_dev);
-    ctx->partials = nullptr;
-    ctx->partials_bytes = 0;
-    CU(cudaMalloc(&ctx->partials, need));
-    ctx->partials_bytes = need;
-  }
+  rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
+  if (rc) return rc;
   // small per-replica arrays: host pointers are staged through pinned memory
   auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
   size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
@@ -1127,7 +1161,8 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   int64_t* d_best = out_best;
   if (!dev_io) {
     if (small > ctx->small_bytes) {
-      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+      if (ctx->solve_buf) cudaFree(ctx->solve_buf);
+  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
       if (ctx->small_dev) cudaFree(ctx->small_dev);
       ctx->small_pin = ctx->small_dev = nullptr;
       ctx->small_bytes = 0;
@@ -1159,25 +1194,9 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   a.out_scores = out_scores;
   a.out_doable = out_doable;
   a.out_offsets = out_cand_offsets;
-  // sources per CTA: 8 warps, >= 24 sources each when there is enough work
-  uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((dm.elem_cap + 255) / 256, 64));
-  dim3 grid(chunks, R);
-  size_t smem = dm.fast_stage_bytes;
-  int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
   cudaEventRecord(ctx->ev0, ctx->stream);
-#define NEARBYK(FN, KEY, CELL)                                                                       \
-  nearby_step_kernel<FN, KEY, CELL><<<grid, 256, smem, ctx->stream>>>(dm, a);                         \
-  nearby_finish_kernel<FN, KEY, CELL><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win)
-#define NEARBYK4(FN)                                                                                 \
-  if (ctx->nb_key32) {                                                                               \
-    if (dm.fm_u16) { NEARBYK(FN, uint32_t, uint16_t); } else { NEARBYK(FN, uint32_t, int32_t); }     \
-  } else {                                                                                           \
-    if (dm.fm_u16) { NEARBYK(FN, uint64_t, uint16_t); } else { NEARBYK(FN, uint64_t, int32_t); }     \
-  }
-  a.scan_bits = ctx->nb_scan_bits;
-  if (fn == SFGPU_W_EXCESS) { NEARBYK4(SFGPU_W_EXCESS) }
-  else if (fn == SFGPU_W_SQUARE) { NEARBYK4(SFGPU_W_SQUARE) }
-  else { NEARBYK4(-1) }  // no LIST_SUM, or a LINEAR / CONST weight whose relocation delta is 0
+  rc = launch_nearby_kernels(ctx, a, d_idx, d_best, d_eval, d_win);
+  if (rc) return rc;
   cudaEventRecord(ctx->ev1, ctx->stream);
   ctx->ev_valid = true;
   ctx->launches += 2;
@@ -1198,6 +1217,113 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
     if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
     if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
   }
+  return SFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-resident local-search loop (sfgpu_solve.cuh).
+int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
+                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
+  const DevModel& dm = ctx->dm;
+  if (!dm.nearby_ok || ctx->force_generic)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
+  if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+  if (p->acceptor < 1 || p->acceptor > 2) return fail(ctx, SFGPU_E_INVALID, "acceptor: 1 HillClimbing, 2 LateAcceptance");
+  if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R;
+  const uint32_t late = std::max<uint32_t>(p->late_size, 1);
+  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = a16(o + bytes); return at; };
+  const size_t o_cnt = take(8), o_seed = take((size_t)R * 8), o_ref = take((size_t)R * 32);
+  const size_t o_hist = take((size_t)R * late * 16), o_hidx = take((size_t)R * 4), o_bests = take((size_t)R * 16);
+  const size_t o_eval = take((size_t)R * 8), o_acc = take((size_t)R * 8), o_idx = take((size_t)R * 4);
+  const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
+  const size_t o_snap = take((size_t)R * dm.block_bytes);
+  if (o > ctx->solve_bytes) {
+    if (ctx->solve_buf) cudaFree(ctx->solve_buf);
+    ctx->solve_buf = nullptr;
+    ctx->solve_bytes = 0;
+    CU(cudaMalloc(&ctx->solve_buf, o));
+    ctx->solve_bytes = o;
+  }
+  char* b = (char*)ctx->solve_buf;
+  SolveState s{};
+  s.step_counter = (uint64_t*)(b + o_cnt);
+  s.step_seeds = (uint64_t*)(b + o_seed);
+  s.ref_scores = (int64_t*)(b + o_ref);
+  s.history = (int64_t*)(b + o_hist);
+  s.hist_idx = (uint32_t*)(b + o_hidx);
+  s.best_scores = (int64_t*)(b + o_bests);
+  s.evaluated = (uint64_t*)(b + o_eval);
+  s.accepted_steps = (uint64_t*)(b + o_acc);
+  s.out_index = (uint32_t*)(b + o_idx);
+  s.out_best = (int64_t*)(b + o_ob);
+  s.out_evaluated = (uint32_t*)(b + o_oe);
+  s.winner_rows = (uint32_t*)(b + o_win);
+  s.best_state = b + o_snap;
+  s.seed_base = p->seed_base;
+  s.late_size = late;
+  s.acceptor = p->acceptor;
+  rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
+  if (rc) return rc;
+  NearbyArgs a{};
+  a.f = ForageDev{p->acceptor, p->tie_mode, p->accepted_limit};
+  a.max_nearby = p->max_nearby;
+  a.step_seeds = s.step_seeds;
+  a.ref_scores = s.ref_scores;
+  a.partials = (SrcPartial*)ctx->partials;
+  solve_init_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  auto one_step = [&]() -> int {
+    solve_prep_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s);
+    int rc2 = launch_nearby_kernels(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
+    if (rc2) return rc2;
+    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, s.winner_rows, nullptr, nullptr, nullptr);
+    solve_post_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
+    return SFGPU_OK;
+  };
+  // steps are captured once into a CUDA graph of `per_graph` steps and replayed
+  const uint32_t per_graph = std::min<uint32_t>(p->n_steps, 16);
+  uint32_t done = 0;
+  if (per_graph >= 2) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc2 = SFGPU_OK;
+    for (uint32_t i = 0; i < per_graph && rc2 == SFGPU_OK; ++i) rc2 = one_step();
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc2 != SFGPU_OK || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return fail(ctx, SFGPU_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    }
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    for (; done + per_graph <= p->n_steps; done += per_graph) {
+      CU(cudaGraphLaunch(exec, ctx->stream));
+      ctx->launches += 5ull * per_graph;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+  }
+  for (; done < p->n_steps; ++done) {
+    rc = one_step();
+    if (rc) return rc;
+    ctx->launches += 5;
+  }
+  if (p->restore_best) {
+    solve_restore_best_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (out_best_scores) CU(cudaMemcpy(out_best_scores, s.best_scores, (size_t)R * 16, cudaMemcpyDeviceToHost));
+  if (out_moves_evaluated) CU(cudaMemcpy(out_moves_evaluated, s.evaluated, (size_t)R * 8, cudaMemcpyDeviceToHost));
+  if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
   return SFGPU_OK;
 }
 

@@ -406,8 +406,10 @@ struct SimulatedAnnealingAcceptor : Acceptor {  // simulated_annealing.rs:338-43
 };
 
 struct ForagerConfig {
-  enum Kind { AcceptedCount, FirstAccepted, BestScore } kind = BestScore;
-  size_t accepted_count_limit = 1;
+  // forager.rs:167-425 + forager/improving.rs:17-227
+  enum Kind { AcceptedCount, FirstAccepted, BestScore, FirstBestScoreImproving, FirstLastStepScoreImproving } kind = BestScore;
+  size_t accepted_count_limit = 1;  // AcceptedCount(N); optional horizon of FirstLastStepScoreImproving
+  bool has_improving_limit = false;
   bool random_ties = true;
 };
 struct StepOutcome {
@@ -417,31 +419,16 @@ struct StepOutcome {
   uint64_t moves_evaluated = 0, score_calculations = 0, moves_accepted = 0;
 };
 
-inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doable, size_t n, HardSoftScore last_step,
-                               uint64_t step_seed, const ForagerConfig& fc, Acceptor& acceptor) {
+// Replays phase/candidates.rs:66-282 over batched scores: pull order, quit-early, acceptor, forager.
+inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doable, size_t n, HardSoftScore best_score,
+                               HardSoftScore last_step, uint64_t step_seed, const ForagerConfig& fc,
+                               Acceptor& acceptor) {
   StepOutcome out;
   uint64_t equal_count = 0;
   size_t accepted = 0;
-  for (size_t i = 0; i < n; ++i) {
-    bool quit = fc.kind == ForagerConfig::BestScore ? false
-              : fc.kind == ForagerConfig::FirstAccepted ? out.has_winner
-                                                        : accepted >= fc.accepted_count_limit;
-    if (quit) break;
-    out.moves_evaluated++;
-    if (!doable[i]) continue;
-    out.score_calculations++;
-    if (!acceptor.is_accepted(last_step, scores[i])) continue;
-    out.moves_accepted++;
-    accepted++;
-    if (fc.kind == ForagerConfig::FirstAccepted) {
-      if (!out.has_winner) {
-        out.has_winner = true;
-        out.winner = i;
-        out.score = scores[i];
-      }
-      continue;
-    }
-    if (!out.has_winner || scores[i] > out.score) {  // BestCandidate::consider, forager.rs:99-141
+  bool found_improving = false;
+  auto consider = [&](size_t i) {  // BestCandidate::consider, forager.rs:99-141
+    if (!out.has_winner || scores[i] > out.score) {
       out.has_winner = true;
       out.winner = i;
       out.score = scores[i];
@@ -449,6 +436,57 @@ inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doabl
     } else if (scores[i] == out.score) {
       equal_count++;
       if (fc.random_ties && reservoir_pick(step_seed, equal_count)) out.winner = i;
+    }
+  };
+  auto replace = [&](size_t i) {
+    out.has_winner = true;
+    out.winner = i;
+    out.score = scores[i];
+    equal_count = 1;
+  };
+  for (size_t i = 0; i < n; ++i) {
+    bool quit = false;
+    switch (fc.kind) {
+      case ForagerConfig::BestScore: quit = false; break;
+      case ForagerConfig::FirstAccepted: quit = out.has_winner; break;
+      case ForagerConfig::AcceptedCount: quit = accepted >= fc.accepted_count_limit; break;
+      case ForagerConfig::FirstBestScoreImproving: quit = found_improving; break;
+      case ForagerConfig::FirstLastStepScoreImproving:
+        quit = found_improving || (fc.has_improving_limit && accepted >= fc.accepted_count_limit);
+        break;
+    }
+    if (quit) break;
+    out.moves_evaluated++;
+    if (!doable[i]) continue;
+    out.score_calculations++;
+    if (!acceptor.is_accepted(last_step, scores[i])) continue;
+    out.moves_accepted++;
+    switch (fc.kind) {
+      case ForagerConfig::FirstAccepted:
+        if (!out.has_winner) replace(i);
+        break;
+      case ForagerConfig::AcceptedCount:
+        accepted++;
+        consider(i);
+        break;
+      case ForagerConfig::BestScore: consider(i); break;
+      case ForagerConfig::FirstBestScoreImproving:  // improving.rs:86-95
+        if (scores[i] > best_score) {
+          found_improving = true;
+          replace(i);
+        } else {
+          consider(i);
+        }
+        break;
+      case ForagerConfig::FirstLastStepScoreImproving:  // improving.rs:197-211
+        accepted++;
+        if (scores[i] > last_step) {
+          found_improving = true;
+          replace(i);
+        } else {
+          consider(i);
+        }
+        break;
     }
   }
   return out;

@@ -29,20 +29,23 @@ static int test_replay() {
     }
     sf::HardSoftScore last{-1, -3};
     uint64_t seed = sfo::splitmix64(s++);
-    for (int fk = 0; fk < 3; ++fk)
+    for (int fk = 0; fk < 5; ++fk)
       for (int ak = 0; ak < 2; ++ak)
         for (int ties = 0; ties < 2; ++ties) {
           sf::ForagerConfig fc;
-          fc.kind = fk == 0 ? sf::ForagerConfig::AcceptedCount : fk == 1 ? sf::ForagerConfig::FirstAccepted : sf::ForagerConfig::BestScore;
+          fc.kind = fk == 0 ? sf::ForagerConfig::AcceptedCount : fk == 1 ? sf::ForagerConfig::FirstAccepted : fk == 2 ? sf::ForagerConfig::BestScore : fk == 3 ? sf::ForagerConfig::FirstBestScoreImproving : sf::ForagerConfig::FirstLastStepScoreImproving;
+          fc.has_improving_limit = (trial % 2) == 1;
           fc.accepted_count_limit = 1 + trial % 9;
           fc.random_ties = ties;
           sf::HillClimbingAcceptor hc;
           sf::LateAcceptanceAcceptor la(4);
           la.phase_started({-1, -5});
           sf::Acceptor& acc = ak == 0 ? (sf::Acceptor&)hc : (sf::Acceptor&)la;
-          auto got = sf::replay_step(scores.data(), doable.data(), n, last, seed, fc, acc);
+          const sf::HardSoftScore best_so_far{-1, -2};
+          auto got = sf::replay_step(scores.data(), doable.data(), n, best_so_far, last, seed, fc, acc);
           sfo::Forager<sfo::Sc> of;
-          of.kind = fk == 0 ? sfo::ForagerKind::AcceptedCount : fk == 1 ? sfo::ForagerKind::FirstAccepted : sfo::ForagerKind::BestScore;
+          of.kind = fk == 0 ? sfo::ForagerKind::AcceptedCount : fk == 1 ? sfo::ForagerKind::FirstAccepted : fk == 2 ? sfo::ForagerKind::BestScore : fk == 3 ? sfo::ForagerKind::FirstBestScoreImproving : sfo::ForagerKind::FirstLastStepScoreImproving;
+          of.has_improving_limit = fc.has_improving_limit;
           of.accepted_count_limit = fc.accepted_count_limit;
           of.best.random_ties = ties;
           sfo::Acceptor<sfo::Sc> oa;
@@ -57,7 +60,7 @@ static int test_replay() {
                 return sfo::CandidateEvaluation<sfo::Sc>{doable[i] ? sfo::EvalKind::Scored : sfo::EvalKind::NotDoable,
                                                          sfo::Sc::of(scores[i].hard, scores[i].soft)};
               },
-              sfo::Sc::of(0, 0), sfo::Sc::of(last.hard, last.soft), seed, of, oa);
+              sfo::Sc::of(best_so_far.hard, best_so_far.soft), sfo::Sc::of(last.hard, last.soft), seed, of, oa);
           CHECK(got.has_winner == want.has_winner);
           if (want.has_winner) CHECK(got.winner == want.winner);
           CHECK(got.moves_evaluated == want.moves_evaluated);
@@ -120,7 +123,7 @@ static int test_gpu() {
   }
   sf::HillClimbingAcceptor hc;
   sf::ForagerConfig fc;
-  auto out = sf::replay_step(scores.data(), doable.data(), scores.size(), init[0], 99, fc, hc);
+  auto out = sf::replay_step(scores.data(), doable.data(), scores.size(), init[0], init[0], 99, fc, hc);
   if (out.has_winner) {
     d.apply(std::vector<sf::ScalarEdit>{batch[out.winner]});
     oracle.apply(moves[out.winner]);

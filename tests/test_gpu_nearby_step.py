@@ -140,3 +140,75 @@ def test_unsupported_models_are_rejected_not_emulated():
     d3 = models.cvrp_director(instances.cvrp(30, 4, seed=2))
     with pytest.raises(L.SfgpuError):
         d3.step_nearby_list_change(33)
+
+
+def _solve_seed(seed_base, r, t):
+    from solverforge_b200.selectors import splitmix64
+    return splitmix64(seed_base ^ ((r * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) ^ t)
+
+
+@pytest.mark.parametrize("acceptor,limit", [(1, 0), (2, 0), (2, 40)])
+def test_device_resident_loop_equals_step_by_step_and_oracle(acceptor, limit):
+    c = instances.cvrp(100, 8, seed=9)
+    R, K, steps, late = 3, 10, 37, 5
+    starts = [instances.perturb_routes(c, 11 + r, 30) for r in range(R)]
+    offs = np.stack([s[0] for s in starts])
+    elems = np.concatenate([s[1] for s in starts])
+    loop = models.cvrp_director(c, R, offsets=offs, elems=elems)
+    ref = models.cvrp_director(c, R, offsets=offs, elems=elems)
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    seed_base = 0xC0FFEE
+    best, evaluated, committed = loop.solve_nearby_list_change(steps, K, acceptor, late, 1, limit, seed_base)
+    # the same loop driven one step at a time through sfgpu_step_nearby_list_change (already pinned to the
+    # oracle above) with the acceptor state kept on the host
+    init = ref.calculate_score()
+    history = [[init[r].copy() for _ in range(late)] for r in range(R)]
+    hidx = [0] * R
+    best_h = init.copy()
+    ev_h = np.zeros(R, dtype=np.uint64)
+    acc_h = np.zeros(R, dtype=np.uint64)
+    for t in range(steps):
+        last = ref.calculate_score()
+        refs = np.stack([np.concatenate([last[r], history[r][hidx[r]]]) for r in range(R)])
+        seeds = [_solve_seed(seed_base, r, t) for r in range(R)]
+        idx, b, ev, win = ref.step_nearby_list_change(K, ForageParams(acceptor, 1, limit), step_seeds=seeds,
+                                                      ref_scores=refs, apply=True)
+        after = ref.calculate_score()
+        for r in range(R):
+            if t < 6:   # oracle cross-check of the first steps
+                rows = oracles[r].enumerate_nearby_list_change(K)
+                so, oko = oracles[r].score_list_change(rows)
+                out = oracle_lib.replay_step(so, oko, [0, 0], last[r], history[r][hidx[r]], seeds[r],
+                                             0 if limit else 2, max(limit, 1), True, 0 if acceptor == 1 else 1)
+                if out[0]:
+                    assert int(idx[r]) == out[1]
+                    oracles[r].apply_list_change(*rows[out[1]])
+                assert after[r].tolist() == oracles[r].committed_score().tolist()
+            history[r][hidx[r]] = after[r].copy()
+            hidx[r] = (hidx[r] + 1) % late
+            ev_h[r] += ev[r]
+            acc_h[r] += 1 if idx[r] != 0xFFFFFFFF else 0
+            if (after[r][0], after[r][1]) > (best_h[r][0], best_h[r][1]):
+                best_h[r] = after[r]
+    assert np.array_equal(loop.calculate_score(), ref.calculate_score()), "final committed scores differ"
+    lo, le = loop.list_state()
+    ro, re_ = ref.list_state()
+    assert np.array_equal(lo, ro) and np.array_equal(le, re_), "final solutions differ"
+    assert np.array_equal(best, best_h)
+    assert np.array_equal(evaluated, ev_h) and np.array_equal(committed, acc_h)
+    assert np.array_equal(loop.fresh_score(), loop.calculate_score())
+    assert (best[:, 0] >= init[:, 0]).all()
+
+
+def test_device_loop_restore_best_and_improves():
+    c = instances.cvrp(200, 12, seed=7)
+    d = models.cvrp_director(c, 2)
+    init = d.calculate_score()
+    best, ev, acc = d.solve_nearby_list_change(300, 20, 2, 50, 1, 64, seed_base=5, restore_best=True)
+    now = d.calculate_score()
+    assert np.array_equal(now, best)                 # working solution := best solution
+    assert np.array_equal(d.fresh_score(), best)     # and it is a consistent state
+    for r in range(2):
+        assert (best[r][0], best[r][1]) > (init[r][0], init[r][1])
+    offs, el = d.list_state()
+    assert sorted(el[0][:200].tolist()) == list(range(1, 201))
