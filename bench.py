@@ -369,6 +369,19 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
 
+    # informational: the device-resident loop (reference defaults for list models: LateAcceptance(400) +
+    # AcceptedCount(256), default_local_search/policy.rs:18-82) — whole steps incl. commit, no host round trip
+    device_loop = None
+    if name == "cvrp" and args.loop_steps > 0:
+        d.synchronize()
+        t0 = time.perf_counter()
+        best_l, ev_l, acc_l = d.solve_nearby_list_change(args.loop_steps, 20, 2, 400, 1, 256, seed_base=1000)
+        dt = time.perf_counter() - t0
+        device_loop = {"steps": args.loop_steps, "replicas": R, "ms_per_step": dt * 1e3 / args.loop_steps,
+                       "moves_evaluated_per_s": float(ev_l.sum()) / dt, "committed_steps": int(acc_l.sum()),
+                       "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
+                       "best_score_replica0": [int(best_l[0][0]), int(best_l[0][1])]}
+
     t = torch.tensor([elapsed_ms, kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,6 +413,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": e2e_api},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "device_loop": device_loop,
         }
         print(json.dumps(line))
     if world > 1:
@@ -441,6 +455,7 @@ def main():
     ap.add_argument("--workload", default="cvrp", choices=["cvrp", "graph_coloring", "job_shop"])
     ap.add_argument("--replicas", type=int, default=1024, help="independent seeded replicas per GPU per launch")
     ap.add_argument("--distinct", type=int, default=16, help="distinct replica starts (tiled over the replicas)")
+    ap.add_argument("--loop-steps", type=int, default=64, help="steps of the device-resident loop demo (0 = skip)")
     ap.add_argument("--sync-every", type=int, default=4, help="steps between NCCL best-score syncs (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
