@@ -302,6 +302,10 @@ int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys);
 /* device time of the most recent scoring kernel launch of this context (CUDA events recorded on
  * the launching stream around the kernel), in nanoseconds; synchronizes the stream. */
 int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns);
+/* device times (ns) of the most recent <= max_n scoring-kernel launches, oldest first: every score /
+ * step call records a CUDA event pair on the launching stream around its dominant kernel only
+ * (ring of 512), so a benchmark can read per-kernel durations of its timed region afterwards. */
+int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, uint32_t* out_n);
 /* number of kernels this context has launched since creation */
 int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count);
 

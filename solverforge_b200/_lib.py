@@ -99,6 +99,7 @@ SYMBOLS = {
     "sfgpu_list_capacity": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "sfgpu_pack_best_keys": (C.c_int32, [_P, _P]),
     "sfgpu_last_kernel_ns": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "sfgpu_kernel_times_ns": (C.c_int32, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
     "sfgpu_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
 }
 

@@ -395,6 +395,13 @@ class GpuScoreDirector:
         self._check(self.lib.sfgpu_last_kernel_ns(self.h, C.byref(out)))
         return out.value
 
+    def kernel_times_ns(self, max_n: int = 512) -> np.ndarray:
+        """Device durations of the most recent scoring-kernel launches (oldest first)."""
+        out = np.zeros(max_n, dtype=np.uint64)
+        n = C.c_uint32()
+        self._check(self.lib.sfgpu_kernel_times_ns(self.h, max_n, _ptr(out), C.byref(n)))
+        return out[:n.value]
+
     def launch_count(self) -> int:
         out = C.c_uint64()
         self._check(self.lib.sfgpu_launch_count(self.h, C.byref(out)))

@@ -89,8 +89,10 @@ struct sfgpu_ctx {
   void* small_dev = nullptr;
   size_t small_bytes = 0;
   size_t partials_bytes = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ev_valid = false;
+  // ring of CUDA event pairs around the dominant (scoring) kernel of each call
+  static constexpr uint32_t EV_RING = 512;
+  std::vector<cudaEvent_t> ev_a, ev_b;
+  uint64_t ev_count = 0;  // scoring launches recorded so far
   uint64_t launches = 0;
 };
 
@@ -139,6 +141,22 @@ int ensure_staging(sfgpu_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
     ctx->dscr_bytes = dev_bytes;
   }
   return SFGPU_OK;
+}
+
+void ev_begin(sfgpu_ctx* ctx) {
+  if (ctx->ev_a.empty()) {
+    ctx->ev_a.resize(sfgpu_ctx::EV_RING);
+    ctx->ev_b.resize(sfgpu_ctx::EV_RING);
+    for (uint32_t i = 0; i < sfgpu_ctx::EV_RING; ++i) {
+      cudaEventCreate(&ctx->ev_a[i]);
+      cudaEventCreate(&ctx->ev_b[i]);
+    }
+  }
+  cudaEventRecord(ctx->ev_a[ctx->ev_count % sfgpu_ctx::EV_RING], ctx->stream);
+}
+void ev_end(sfgpu_ctx* ctx) {
+  cudaEventRecord(ctx->ev_b[ctx->ev_count % sfgpu_ctx::EV_RING], ctx->stream);
+  ctx->ev_count++;
 }
 
 int check_committed(sfgpu_ctx* ctx) {
@@ -193,8 +211,6 @@ int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgp
   }
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  cudaEventCreate(&ctx->ev0);
-  cudaEventCreate(&ctx->ev1);
   *out = ctx;
   return SFGPU_OK;
 }
@@ -210,8 +226,8 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
   if (ctx->solve_buf) cudaFree(ctx->solve_buf);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (auto e : ctx->ev_a) cudaEventDestroy(e);
+  for (auto e : ctx->ev_b) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SFGPU_OK;
@@ -857,7 +873,7 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
   const uint32_t threads = 256;
   dim3 grid(chunks_for(ctx, n_total, dm.R, threads), dm.R);
   size_t smem = ctx->staged ? dm.stage_bytes : 0;
-  cudaEventRecord(ctx->ev0, ctx->stream);
+  ev_begin(ctx);
 #define LAUNCH_SCALAR(MODE)                                                                                    \
   if (ctx->staged)                                                                                             \
     score_scalar_kernel<MODE, true><<<grid, threads, smem, ctx->stream>>>(dm, d_offs, d_rows, d_edit_offs,    \
@@ -918,8 +934,7 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
       break;
     case SK_LIST_SWAP: LAUNCH_LIST(LMODE_SWAP); break;
   }
-  cudaEventRecord(ctx->ev1, ctx->stream);
-  ctx->ev_valid = true;
+  ev_end(ctx);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;
@@ -1093,7 +1108,11 @@ int launch_nearby_kernels(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_
   const DevModel& dm = ctx->dm;
   const uint32_t R = dm.R;
   // sources per CTA: 8 warps, >= 24 sources each when there is enough work
+  // few fat CTAs when there are many replicas (amortises the record staging); with few replicas
+  // spread the sources over the machine: down to one source per warp
   uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((dm.elem_cap + 255) / 256, 64));
+  const uint32_t max_chunks = std::max<uint32_t>(1, (dm.elem_cap + 7) / 8);
+  while ((uint64_t)chunks * R < (uint64_t)ctx->sm_count * 2 && chunks * 2 <= max_chunks) chunks *= 2;
   dim3 grid(chunks, R);
   size_t smem = dm.fast_stage_bytes;
   int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
@@ -1194,11 +1213,10 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   a.out_scores = out_scores;
   a.out_doable = out_doable;
   a.out_offsets = out_cand_offsets;
-  cudaEventRecord(ctx->ev0, ctx->stream);
+  ev_begin(ctx);
   rc = launch_nearby_kernels(ctx, a, d_idx, d_best, d_eval, d_win);
   if (rc) return rc;
-  cudaEventRecord(ctx->ev1, ctx->stream);
-  ctx->ev_valid = true;
+  ev_end(ctx);
   ctx->launches += 2;
   CU(cudaGetLastError());
   if (apply_winners) {
@@ -1531,12 +1549,23 @@ int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys) {
 }
 
 int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns) {
-  if (!ctx || !out_ns) return SFGPU_E_INVALID;
-  if (!ctx->ev_valid) return fail(ctx, SFGPU_E_STATE, "no scoring kernel launched yet");
-  CU(cudaEventSynchronize(ctx->ev1));
-  float ms = 0;
-  CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  *out_ns = (uint64_t)((double)ms * 1e6);
+  uint32_t n = 0;
+  return sfgpu_kernel_times_ns(ctx, 1, out_ns, &n);
+}
+
+int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, uint32_t* out_n) {
+  if (!ctx || !out_ns || !out_n) return SFGPU_E_INVALID;
+  if (ctx->ev_count == 0) return fail(ctx, SFGPU_E_STATE, "no scoring kernel launched yet");
+  const uint64_t avail = std::min<uint64_t>(ctx->ev_count, sfgpu_ctx::EV_RING);
+  const uint32_t n = (uint32_t)std::min<uint64_t>(avail, max_n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint64_t slot = (ctx->ev_count - n + i) % sfgpu_ctx::EV_RING;
+    CU(cudaEventSynchronize(ctx->ev_b[slot]));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_a[slot], ctx->ev_b[slot]));
+    out_ns[i] = (uint64_t)((double)ms * 1e6);
+  }
+  *out_n = n;
   return SFGPU_OK;
 }
 
