@@ -44,7 +44,8 @@ struct DevModel {
   uint32_t has_list, n_owners, n_elem_rows, elem_cap, off_offsets, off_elems;
   // fast list path: packed per-route / per-position / per-slot records
   uint32_t fast_list;       // 1 when the constraint program fits the specialised list-change kernel
-  uint32_t fast_stage_bytes;
+  uint32_t fast_stage_bytes;  // records + pos_of (nearby kernels)
+  uint32_t fast_score_bytes;  // records only (score kernels)
   uint32_t off_route_rec, off_pos_rec, off_slot_rec;
   int32_t fast_pc, fast_ls;  // constraint indices of the path-cost / list-sum constraint, or -1
   // device-side nearby neighbourhood

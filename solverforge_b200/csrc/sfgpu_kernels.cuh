@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     f_th = fa.ref_scores[r * 4 + 2];
     f_ts = fa.ref_scores[r * 4 + 3];
   }
-  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
+  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_score_bytes, &bar);
   const int64_t* cs = (const int64_t*)(smem + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
   const uint4* rr = (const uint4*)(smem + m.off_route_rec);
