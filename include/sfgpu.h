@@ -243,6 +243,19 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
                                       int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
                                       int32_t apply_winners);
 
+/* The same whole step for scalar models: generates the full ChangeMove neighbourhood of every replica in
+ * the canonical order of ChangeMoveSelector (heuristic/selector/move_selector/change.rs:66-104,246-307:
+ * entities in order, per entity every value then the to-None move when it is assigned), scores it with
+ * every scalar constraint kind, replays acceptor + forager, optionally commits the winners. Pointer
+ * conventions as sfgpu_step_nearby_list_change; the materialised batch gives replica r the rows
+ * [r*S, (r+1)*S), S = n_entities * (n_values + 1), in pull order, padded with not-doable sentinels;
+ * out_winner_rows[R][2] = the winning ScalarEdit {entity, to_value} (entity 0xFFFFFFFF when none). */
+int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                          const uint64_t* step_seeds, const int64_t* ref_scores, uint64_t* out_cand_offsets,
+                          uint32_t* out_rows, int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
+                          int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                          int32_t apply_winners);
+
 /* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
  * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.

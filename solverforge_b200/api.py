@@ -321,6 +321,24 @@ class GpuScoreDirector:
             v(out_rows_ptr), v(out_scores_ptr), v(out_doable_ptr), v(index_ptr), v(best_ptr), v(evaluated_ptr),
             v(winner_rows_ptr), 1 if apply else 0))
 
+    def step_change(self, params: "ForageParams" = None, step_seeds=None, ref_scores=None, apply: bool = False,
+                    out_rows_ptr: int = 0, out_scores_ptr: int = 0, out_doable_ptr: int = 0, out_offsets_ptr: int = 0):
+        """One whole step of a scalar model on device (sfgpu_step_change): full ChangeMove neighbourhood +
+        scoring + forager. Returns (index[R], best[R,2], moves_evaluated[R], winner_rows[R,2])."""
+        params = params or ForageParams()
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        seeds = None if step_seeds is None else np.ascontiguousarray(step_seeds, dtype=np.uint64)
+        ref = None if ref_scores is None else np.ascontiguousarray(ref_scores, dtype=np.int64).reshape(self.R, 4)
+        idx = np.zeros(self.R, dtype=np.uint32)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint32)
+        win = np.zeros((self.R, 2), dtype=np.uint32)
+        v = lambda p: C.c_void_p(p) if p else None
+        self._check(self.lib.sfgpu_step_change(self.h, 0, C.byref(fp), _ptr(seeds), _ptr(ref), v(out_offsets_ptr),
+                                               v(out_rows_ptr), v(out_scores_ptr), v(out_doable_ptr), _ptr(idx),
+                                               _ptr(best), _ptr(ev), _ptr(win), 1 if apply else 0))
+        return idx, best, ev, win.view(np.int32)
+
     def solve_nearby_list_change(self, n_steps: int, max_nearby: int = 20, acceptor: int = 2, late_size: int = 400,
                                  tie_mode: int = 1, accepted_limit: int = 0, seed_base: int = 0,
                                  restore_best: bool = False):

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "sfgpu_change_step.cuh"
 #include "sfgpu_solve.cuh"
 
 namespace {
@@ -721,6 +722,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
   if (ctx->staged) {
     int bytes = (int)dm.stage_bytes;
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(change_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1347,6 +1349,102 @@ int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params*
   if (out_best_scores) CU(cudaMemcpy(out_best_scores, s.best_scores, (size_t)R * 16, cudaMemcpyDeviceToHost));
   if (out_moves_evaluated) CU(cudaMemcpy(out_moves_evaluated, s.evaluated, (size_t)R * 8, cudaMemcpyDeviceToHost));
   if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
+  return SFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole step for scalar models: ChangeMove neighbourhood generation + scoring + forager on device.
+int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                          const uint64_t* step_seeds, const int64_t* ref_scores, uint64_t* out_cand_offsets,
+                          uint32_t* out_rows, int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
+                          int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                          int32_t apply_winners) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  const DevModel& dm = ctx->dm;
+  if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
+  if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
+  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  if (out_scores && (!out_rows || !out_doable)) return fail(ctx, SFGPU_E_INVALID, "out_scores needs out_rows and out_doable");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R;
+  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
+  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
+  size_t o_eval = a16(o_best + (size_t)R * 16), o_win = a16(o_eval + (size_t)R * 4), small = a16(o_win + (size_t)R * 8);
+  const uint64_t* d_seeds = step_seeds;
+  const int64_t* d_ref = ref_scores;
+  uint32_t *d_idx = out_index, *d_eval = out_evaluated, *d_win = out_winner_rows;
+  int64_t* d_best = out_best;
+  if (!dev_io) {
+    if (small > ctx->small_bytes) {
+      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+      if (ctx->small_dev) cudaFree(ctx->small_dev);
+      ctx->small_pin = ctx->small_dev = nullptr;
+      ctx->small_bytes = 0;
+      CU(cudaMallocHost(&ctx->small_pin, small));
+      CU(cudaMalloc(&ctx->small_dev, small));
+      ctx->small_bytes = small;
+    }
+    char* pin = (char*)ctx->small_pin;
+    char* dv = (char*)ctx->small_dev;
+    if (step_seeds) memcpy(pin + o_seed, step_seeds, (size_t)R * 8);
+    if (ref_scores) memcpy(pin + o_ref, ref_scores, (size_t)R * 32);
+    if (step_seeds || ref_scores) CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
+    d_seeds = step_seeds ? (const uint64_t*)(dv + o_seed) : nullptr;
+    d_ref = ref_scores ? (const int64_t*)(dv + o_ref) : nullptr;
+    d_idx = (uint32_t*)(dv + o_idx);
+    d_best = (int64_t*)(dv + o_best);
+    d_eval = (uint32_t*)(dv + o_eval);
+    d_win = (uint32_t*)(dv + o_win);
+  } else if (apply_winners && !d_win) {
+    return fail(ctx, SFGPU_E_INVALID, "apply_winners needs out_winner_rows on the device path");
+  }
+  ChangeStepArgs a{};
+  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
+  a.step_seeds = d_seeds;
+  a.ref_scores = d_ref;
+  a.out_rows = out_rows;
+  a.out_scores = out_scores;
+  a.out_doable = out_doable;
+  a.out_offsets = out_cand_offsets;
+  // entities per CTA: amortise the state staging, but cover the machine when replicas are few
+  uint32_t per = 2048;
+  while (per > 256 && (uint64_t)((dm.n_entities + per - 1) / per) * R < (uint64_t)ctx->sm_count * 4) per /= 2;
+  a.ents_per_cta = per;
+  const uint32_t chunks = (dm.n_entities + per - 1) / per;
+  rc = ensure_partials(ctx, (size_t)R * chunks * sizeof(ChunkPartial));
+  if (rc) return rc;
+  a.partials = (ChunkPartial*)ctx->partials;
+  dim3 grid(chunks, R);
+  ev_begin(ctx);
+  if (ctx->staged)
+    change_step_kernel<true><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a);
+  else
+    change_step_kernel<false><<<grid, 256, 0, ctx->stream>>>(dm, a);
+  ev_end(ctx);
+  change_finish_kernel<<<R, 256, 0, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  if (apply_winners) {
+    apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, 0, d_win, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  if (!dev_io) {
+    char* pin = (char*)ctx->small_pin;
+    char* dv = (char*)ctx->small_dev;
+    CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, small - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_index, pin + o_idx, (size_t)R * 4);
+    memcpy(out_best, pin + o_best, (size_t)R * 16);
+    if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
+    if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 8);
+  }
   return SFGPU_OK;
 }
 

@@ -1,0 +1,90 @@
+"""GPU parity of the device-side ChangeMove neighbourhood + fused step (sfgpu_step_change) against the
+oracle's ChangeMoveSelector order, scores and candidate-loop replay. Bit-exact."""
+import numpy as np
+import pytest
+
+from solverforge_b200 import ForageParams, instances, models
+from tests import oracle_lib
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_and_check(d, oracle, n_entities, k, seeds=(3, 11), limits=(0, 1, 9, 300, 10 ** 6)):
+    import torch
+    dev = torch.device("cuda")
+    S = n_entities * (k + 1)
+    t_off = torch.zeros(2, dtype=torch.int64, device=dev)
+    t_rows = torch.zeros((S, 2), dtype=torch.int32, device=dev)
+    t_scores = torch.zeros((S, 2), dtype=torch.int64, device=dev)
+    t_doable = torch.full((S,), 7, dtype=torch.uint8, device=dev)
+    d.step_change(ForageParams(0, 1, 0), step_seeds=[1], out_offsets_ptr=t_off.data_ptr(),
+                  out_rows_ptr=t_rows.data_ptr(), out_scores_ptr=t_scores.data_ptr(), out_doable_ptr=t_doable.data_ptr())
+    want = oracle.enumerate_change()
+    so, oko = oracle.score_change(want)
+    n = len(want)
+    rows = t_rows.cpu().numpy()
+    assert t_off.cpu().tolist() == [0, S]
+    assert np.array_equal(rows[:n], want.astype(np.int32)), "generated ChangeMove order differs from the reference"
+    assert np.array_equal(t_doable.cpu().numpy()[:n], oko)
+    assert np.array_equal(t_scores.cpu().numpy()[:n], so)
+    assert (t_doable.cpu().numpy()[n:] == 0).all() and (rows[n:, 0] == -1).all()
+    base = d.calculate_score()[0]
+    for seed in seeds:
+        for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+            for ties in (0, 1):
+                for limit in limits:
+                    ref = np.concatenate([base + [0, -1], base + [-1, 0]])[None, :]
+                    idx, best, ev, win = d.step_change(ForageParams(acceptor, ties, limit), step_seeds=[seed],
+                                                       ref_scores=ref)
+                    out = oracle_lib.replay_step(so, oko, [0, 0], ref[0][:2], ref[0][2:], seed, 0 if limit else 2,
+                                                 max(limit, 1), bool(ties), okind)
+                    what = f"seed={seed} acc={acceptor} ties={ties} limit={limit}"
+                    assert int(ev[0]) == out[2], what + " moves_evaluated"
+                    if out[0]:
+                        assert int(idx[0]) == out[1], what
+                        assert best[0].tolist() == so[out[1]].tolist(), what
+                        assert win[0].tolist() == want[out[1]].tolist(), what
+                    else:
+                        assert idx[0] == 0xFFFFFFFF, what
+
+
+def test_graph_coloring_change_step():
+    g = instances.graph_coloring(700, 3000, 5, seed_edges=3, seed_colors=4, unassigned_permille=80)
+    _run_and_check(models.graph_coloring_director(g), Oracle.graph_coloring(g), g.n, g.k)
+
+
+def test_job_shop_change_step():
+    j = instances.job_shop(30, 8, 5, seed=3, unassigned_permille=60)
+    _run_and_check(models.job_shop_director(j), Oracle.job_shop(j), j.n_ops, j.n_machines, seeds=(5,))
+
+
+def test_shift_and_nqueens_change_step():
+    s = instances.shift_scheduling(seed=25)
+    _run_and_check(models.shift_scheduling_director(s), Oracle.shift_scheduling(s), s.n_shifts, s.n_nurses, seeds=(2,))
+    q = instances.nqueens(24, seed=5)
+    _run_and_check(models.nqueens_director(q), Oracle.nqueens(q), q.n, q.n, seeds=(9,), limits=(0, 50))
+
+
+def test_change_step_loop_with_apply_tracks_oracle():
+    g = instances.graph_coloring(400, 1600, 4, seed_edges=8, seed_colors=9, unassigned_permille=100)
+    R = 3
+    colors = np.stack([instances.graph_coloring(400, 1600, 4, seed_edges=8, seed_colors=20 + r).color for r in range(R)])
+    d = models.graph_coloring_director(g, R, colors=colors)
+    oracles = [Oracle.graph_coloring(g, colors[r]) for r in range(R)]
+    for step in range(12):
+        last = d.calculate_score()
+        ref = np.concatenate([last, last], axis=1)
+        idx, best, ev, win = d.step_change(ForageParams(1, 1, 0), step_seeds=[40 + step] * R, ref_scores=ref, apply=True)
+        after = d.calculate_score()
+        for r in range(R):
+            rows = oracles[r].enumerate_change()
+            so, oko = oracles[r].score_change(rows)
+            out = oracle_lib.replay_step(so, oko, [0, 0], last[r], last[r], 40 + step, 2, 1, True, 0)
+            if out[0]:
+                assert int(idx[r]) == out[1], f"step {step} replica {r}"
+                oracles[r].apply_change(*rows[out[1]])
+            else:
+                assert idx[r] == 0xFFFFFFFF
+            assert after[r].tolist() == oracles[r].committed_score().tolist()
+        assert np.array_equal(d.fresh_score(), after)
