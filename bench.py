@@ -351,19 +351,18 @@ def run_ours(args):
             raise SystemExit("bench.py: device-generated step disagrees with the rows-resident step")
         e2e_steps = max(5, min(args.steps, 50))
     else:
-        scores_host = torch.empty((n, 2), dtype=torch.int64).pin_memory()
-        doable_host = torch.empty(n, dtype=torch.uint8).pin_memory()
-        fn = getattr(d.lib, f"sfgpu_score_{kind}")
-        off_np = offsets
-        e2e_api = f"sfgpu_score_{kind} with pinned host buffers"
-        h2d, d2h = n * ROW_BYTES[name] + (R + 1) * 8, n * OUT_BYTES
+        seeds_host = np.arange(R, dtype=np.uint64)
+        e2e_api = "sfgpu_step_change (device-side ChangeMove neighbourhood + score + forager; host seeds in, winners out)"
+        h2d, d2h = R * 8, R * (4 + 16 + 4 + 8)
 
         def e2e_step():
-            d._check(fn(d.h, 0, n, off_np.ctypes.data_as(C.c_void_p), C.c_void_p(rows_host.data_ptr()),
-                        C.c_void_p(scores_host.data_ptr()), C.c_void_p(doable_host.data_ptr())))
+            return d.step_change(fp, step_seeds=seeds_host)
 
-        e2e_steps = max(2, min(args.steps, 5))
-        e2e_step()
+        idx_e2e, best_e2e, ev_e2e, win_e2e = e2e_step()
+        if not (np.array_equal(idx_e2e, t_idx.cpu().numpy().view(np.uint32)) and
+                np.array_equal(best_e2e, t_best.cpu().numpy()) and int(ev_e2e.sum()) == n):
+            raise SystemExit("bench.py: device-generated step disagrees with the rows-resident step")
+        e2e_steps = max(5, min(args.steps, 50))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -128,7 +128,10 @@ typedef struct sfgpu_weight {
 /* for_each(E).join(values, equal(var, Some(v.row))).group_by(v.row, count()|sum(column))
  *   [.complement(values, default p1)].penalize(w(result))
  *   constraint/grouped/, cross_grouped/, cross_complemented_grouped/
- *   aux0: summed entity column id or UINT32_MAX (count); p0: 1 = complemented; p1: default result */
+ *   aux0: summed entity column id or UINT32_MAX (count); p0: 1 = complemented; p1: default result;
+ *   aux1: per-value column that replaces the weight offset b for that key, or UINT32_MAX — key-dependent
+ *   weights |key, result| (e.g. max(0, result - capacity[key])). A single-emit `.project(..)` row keyed by
+ *   the planning variable (stream/projected_stream/source.rs:13-24) lowers to this kind as well. */
 #define SFGPU_K_GROUP 5
 /* for_each(owners).penalize(w(sum of matrix legs depot -> list... -> depot)); empty list = 0
  *   uni constraint whose weight walks the route; aux0: matrix id; p0: depot row */
@@ -279,6 +282,9 @@ typedef struct sfgpu_solve_params {
 } sfgpu_solve_params;
 int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* params, int64_t* out_best_scores,
                                        uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps);
+/* the same loop over the full ChangeMove neighbourhood of a scalar model (max_nearby is ignored) */
+int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* params, int64_t* out_best_scores,
+                           uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps);
 
 /* ---- committing the winner ------------------------------------------------------------ */
 /* One row per replica (same packing as the score calls); mask[r] == 0 skips replica r

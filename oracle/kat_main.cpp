@@ -508,6 +508,50 @@ static void kat_cross_complemented() {
   }
 }
 
+// ---------------------------------------------------------------- projected rows (single emit)
+struct PWork {
+  size_t bucket;
+  int64_t demand;
+};
+struct PCapacity {
+  size_t bucket;
+};
+struct PPlan {
+  std::vector<PWork> work;
+  std::vector<PCapacity> capacity;
+};
+static const std::vector<PWork>& pp_work(const PPlan& s) { return s.work; }
+static const std::vector<PCapacity>& pp_cap(const PPlan& s) { return s.capacity; }
+static void kat_projected() {
+  // solverforge-scoring/src/constraint/tests/projected/updates.rs:196-278: Work -> Entry{bucket, delta}
+  // (MAX_EMITS = 1), group_by(bucket, sum(delta)).complement(capacity buckets, default 3)
+  // .penalize(bucket*10 + demand). A single-emit projection is a per-row map, so the grouped join over
+  // (work, capacity bucket) with a key-dependent weight restates it.
+  auto ka = [](const PWork& w) { return w.bucket; };
+  auto kb = [](const PCapacity& c) { return c.bucket; };
+  auto tf = [](const PPlan&, const PWork&, const PCapacity&, size_t, size_t) { return true; };
+  auto gk = [](const PWork&, const PCapacity& c) { return c.bucket; };
+  auto vf = [](const PWork& w, const PCapacity&) { return w.demand; };
+  auto kt = [](const PCapacity& c) { return c.bucket; };
+  auto df = [](const PCapacity&) { return (int64_t)3; };
+  auto gw = [](const size_t& bucket, const int64_t& demand) { return SoftScore::of((int64_t)bucket * 10 + demand); };
+  CrossComplementedGroupedConstraint<PPlan, PWork, PCapacity, PCapacity, size_t, size_t, SoftScore, SumAcc, decltype(ka),
+                                     decltype(kb), decltype(tf), decltype(gk), decltype(vf), decltype(kt), decltype(df),
+                                     decltype(gw)>
+      c("projected demand by capacity bucket", Impact::Penalty, {pp_work, ChangeSource::Desc(0)},
+        {pp_cap, ChangeSource::Desc(1)}, {pp_cap, ChangeSource::Desc(1)}, ka, kb, tf, gk, vf, kt, df, gw, false);
+  PPlan plan{{{0, 5}}, {{0}, {1}}};
+  CHECK(c.match_count(plan) == 2);
+  CHECK(c.evaluate(plan) == SoftScore::of(-18));
+  SoftScore total = c.initialize(plan);
+  CHECK(total == SoftScore::of(-18));
+  total = total + c.on_retract(plan, 0, 0);
+  plan.work[0].demand = 7;
+  total = total + c.on_insert(plan, 0, 0);
+  CHECK(total == SoftScore::of(-20));
+  CHECK(total == c.evaluate(plan));
+}
+
 // ---------------------------------------------------------------- selectors / foragers
 static void kat_nearby_sort() {
   // solverforge-solver/src/heuristic/selector/nearby_list_support.rs:51-73
@@ -597,6 +641,7 @@ int main() {
   kat_exists();
   kat_grouped();
   kat_cross_complemented();
+  kat_projected();
   kat_nearby_sort();
   kat_moves_and_loop();
   if (g_fail) {

@@ -352,6 +352,17 @@ class GpuScoreDirector:
         self._check(self.lib.sfgpu_solve_nearby_list_change(self.h, C.byref(p), _ptr(best), _ptr(ev), _ptr(acc)))
         return best, ev, acc
 
+    def solve_change(self, n_steps: int, acceptor: int = 2, late_size: int = 400, tie_mode: int = 1,
+                     accepted_limit: int = 0, seed_base: int = 0, restore_best: bool = False):
+        """Device-resident loop over the full ChangeMove neighbourhood (sfgpu_solve_change)."""
+        p = L.SolveParams(0, n_steps, acceptor, late_size, tie_mode, accepted_limit, seed_base,
+                          1 if restore_best else 0, 0)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint64)
+        acc = np.zeros(self.R, dtype=np.uint64)
+        self._check(self.lib.sfgpu_solve_change(self.h, C.byref(p), _ptr(best), _ptr(ev), _ptr(acc)))
+        return best, ev, acc
+
     def apply_winners_device(self, move_kind: int, offsets_ptr: int, rows_ptr: int, index_ptr: int):
         self._check(self.lib.sfgpu_apply_winners(self.h, move_kind, C.c_void_p(offsets_ptr), C.c_void_p(rows_ptr),
                                                  C.c_void_p(index_ptr)))
@@ -605,17 +616,18 @@ class GroupedStream:
     def complement(self, targets: int, default: int = 0) -> "GroupedStream":
         return GroupedStream(self.d, self.collection, self.collector, True, default)
 
-    def _impact(self, impact, weight: WeightFn) -> _Terminal:
+    def _impact(self, impact, weight: WeightFn, key_offset_column: int = L.NO_COLUMN) -> _Terminal:
         c = self.collector
         if isinstance(c, LoadBalance):
             return _Terminal(self.d, kind=L.K_LOAD_BALANCE, impact=impact, weight=weight, collection=self.collection,
                              aux0=c.metric_column)
         col = L.NO_COLUMN if isinstance(c, Count) else c.column
         return _Terminal(self.d, kind=L.K_GROUP, impact=impact, weight=weight, collection=self.collection, aux0=col,
-                         p0=1 if self.complemented else 0, p1=self.default)
+                         aux1=key_offset_column, p0=1 if self.complemented else 0, p1=self.default)
 
-    def penalize(self, weight: WeightFn) -> _Terminal:
-        return self._impact(L.PENALTY, weight)
+    def penalize(self, weight: WeightFn, key_offset_column: int = L.NO_COLUMN) -> _Terminal:
+        """key_offset_column: per-value column replacing the weight's b for that key (|key, result| weights)."""
+        return self._impact(L.PENALTY, weight, key_offset_column)
 
-    def reward(self, weight: WeightFn) -> _Terminal:
-        return self._impact(L.REWARD, weight)
+    def reward(self, weight: WeightFn, key_offset_column: int = L.NO_COLUMN) -> _Terminal:
+        return self._impact(L.REWARD, weight, key_offset_column)

@@ -624,6 +624,11 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         c.g0 = col;
         if (d.p0 == 1) c.flags |= SFGPU_CF_COMPLEMENT;
         c.p1 = d.p1;
+        if (d.aux1 != 0xFFFFFFFFu) {  // per-value weight offset column (key-dependent weight)
+          if (d.aux1 >= ctx->cols.size() || ctx->colls[ctx->cols[d.aux1].coll].n_rows < dm.n_values)
+            return fail(ctx, SFGPU_E_INVALID, "GROUP: aux1 must be a column with one row per value");
+          c.g1 = ctx->cols[d.aux1].dev;
+        }
         c.off0 = off;
         off = align_up(off + dm.n_values * 4, 16);
         c.off1 = off;
@@ -1247,15 +1252,22 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
 
 // ------------------------------------------------------------------------------------------
 // Device-resident local-search loop (sfgpu_solve.cuh).
-int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
-                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+namespace {
+int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t* out_best_scores,
+               uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
   const DevModel& dm = ctx->dm;
-  if (!dm.nearby_ok || ctx->force_generic)
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
-  if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+  if (scalar) {
+    if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
+    if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
+      return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
+  } else {
+    if (!dm.nearby_ok || ctx->force_generic)
+      return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
+    if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+  }
   if (p->acceptor < 1 || p->acceptor > 2) return fail(ctx, SFGPU_E_INVALID, "acceptor: 1 HillClimbing, 2 LateAcceptance");
   if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
   CU(cudaSetDevice(ctx->device));
@@ -1294,22 +1306,48 @@ int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params*
   s.seed_base = p->seed_base;
   s.late_size = late;
   s.acceptor = p->acceptor;
-  rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
-  if (rc) return rc;
   NearbyArgs a{};
-  a.f = ForageDev{p->acceptor, p->tie_mode, p->accepted_limit};
-  a.max_nearby = p->max_nearby;
-  a.step_seeds = s.step_seeds;
-  a.ref_scores = s.ref_scores;
-  a.partials = (SrcPartial*)ctx->partials;
+  ChangeStepArgs ca{};
+  uint32_t c_chunks = 0;
+  if (scalar) {
+    uint32_t per = 2048;
+    while (per > 256 && (uint64_t)((dm.n_entities + per - 1) / per) * R < (uint64_t)ctx->sm_count * 4) per /= 2;
+    c_chunks = (dm.n_entities + per - 1) / per;
+    rc = ensure_partials(ctx, (size_t)R * c_chunks * sizeof(ChunkPartial));
+    if (rc) return rc;
+    ca.f = ForageDev{p->acceptor, p->tie_mode, p->accepted_limit};
+    ca.ents_per_cta = per;
+    ca.step_seeds = s.step_seeds;
+    ca.ref_scores = s.ref_scores;
+    ca.partials = (ChunkPartial*)ctx->partials;
+  } else {
+    rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
+    if (rc) return rc;
+    a.f = ForageDev{p->acceptor, p->tie_mode, p->accepted_limit};
+    a.max_nearby = p->max_nearby;
+    a.step_seeds = s.step_seeds;
+    a.ref_scores = s.ref_scores;
+    a.partials = (SrcPartial*)ctx->partials;
+  }
   solve_init_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
   ctx->launches++;
   CU(cudaGetLastError());
   auto one_step = [&]() -> int {
     solve_prep_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s);
-    int rc2 = launch_nearby_kernels(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
-    if (rc2) return rc2;
-    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, s.winner_rows, nullptr, nullptr, nullptr);
+    if (scalar) {
+      dim3 grid(c_chunks, R);
+      if (ctx->staged)
+        change_step_kernel<true><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, ca);
+      else
+        change_step_kernel<false><<<grid, 256, 0, ctx->stream>>>(dm, ca);
+      change_finish_kernel<<<R, 256, 0, ctx->stream>>>(dm, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated,
+                                                      s.winner_rows);
+      apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, 0, s.winner_rows, nullptr, nullptr, nullptr);
+    } else {
+      int rc2 = launch_nearby_kernels(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
+      if (rc2) return rc2;
+      apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, s.winner_rows, nullptr, nullptr, nullptr);
+    }
     solve_post_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
     return SFGPU_OK;
   };
@@ -1351,6 +1389,8 @@ int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params*
   if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
   return SFGPU_OK;
 }
+
+}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // Whole step for scalar models: ChangeMove neighbourhood generation + scoring + forager on device.
@@ -1446,6 +1486,16 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
     if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 8);
   }
   return SFGPU_OK;
+}
+
+int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
+                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+  return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps);
+}
+
+int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
+                           uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+  return solve_impl(ctx, p, true, out_best_scores, out_moves_evaluated, out_accepted_steps);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -45,10 +45,14 @@ __device__ __forceinline__ int64_t uni_contrib(const ConsDev& c, uint32_t e, int
 }
 
 // score of a group with `count` rows and accumulated `sum` (count() result == count)
-__device__ __forceinline__ int64_t group_score(const ConsDev& c, int64_t count, int64_t sum) {
+// `key` = the group's value row; a per-value column (g1) may replace the weight offset b, which is
+// how key-dependent weights such as max(0, demand - capacity[key]) or key*10 + demand are expressed
+__device__ __forceinline__ int64_t group_score(const ConsDev& c, uint32_t key, int64_t count, int64_t sum) {
   bool counting = c.g0 == nullptr;
-  if (count > 0) return weight_eval(c.w, counting ? count : sum);
-  if (c.flags & SFGPU_CF_COMPLEMENT) return weight_eval(c.w, c.p1);
+  WeightDev w = c.w;
+  if (c.g1) w.b = ((const int64_t*)c.g1)[key];
+  if (count > 0) return weight_eval(w, counting ? count : sum);
+  if (c.flags & SFGPU_CF_COMPLEMENT) return weight_eval(w, c.p1);
   return 0;
 }
 
@@ -125,8 +129,8 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const EditD
             if (prev[i].new_v == v) { cn += 1; sm += xi; }
             if (prev[i].old_v == v) { cn -= 1; sm -= xi; }
           }
-          int64_t before = group_score(c, cn, sm);
-          int64_t after = side == 0 ? group_score(c, cn - 1, sm - x) : group_score(c, cn + 1, sm + x);
+          int64_t before = group_score(c, (uint32_t)v, cn, sm);
+          int64_t after = side == 0 ? group_score(c, (uint32_t)v, cn - 1, sm - x) : group_score(c, (uint32_t)v, cn + 1, sm + x);
           delta += after - before;
         }
         add_level(d, c, delta);
@@ -867,7 +871,7 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
           }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < m.n_values; i += blockDim.x)
-          local += group_score(c, gc[i], (int64_t)gs[i]);
+          local += group_score(c, i, gc[i], (int64_t)gs[i]);
         break;
       }
       case SFGPU_K_LOAD_BALANCE: {

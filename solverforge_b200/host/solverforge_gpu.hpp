@@ -105,19 +105,25 @@ struct GroupedStream {
     g.default_result = def;
     return g;
   }
-  Terminal impact(int imp, Weight w) const {
+  Terminal impact(int imp, Weight w, uint32_t key_offset_column = UINT32_MAX) const {
     sfgpu_constraint_desc c{};
     c.kind = load_balance ? SFGPU_K_LOAD_BALANCE : SFGPU_K_GROUP;
     c.impact = imp;
     c.weight = w.w;
     c.collection = collection;
     c.aux0 = column;
+    c.aux1 = key_offset_column;
     c.p0 = complemented ? 1 : 0;
     c.p1 = default_result;
     return {d, c};
   }
-  Terminal penalize(Weight w) const { return impact(SFGPU_PENALTY, w); }
-  Terminal reward(Weight w) const { return impact(SFGPU_REWARD, w); }
+  // key_offset_column: per-value column replacing the weight's b for that key (|key, result| weights)
+  Terminal penalize(Weight w, uint32_t key_offset_column = UINT32_MAX) const {
+    return impact(SFGPU_PENALTY, w, key_offset_column);
+  }
+  Terminal reward(Weight w, uint32_t key_offset_column = UINT32_MAX) const {
+    return impact(SFGPU_REWARD, w, key_offset_column);
+  }
 };
 
 struct BiStream {

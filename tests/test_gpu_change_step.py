@@ -88,3 +88,37 @@ def test_change_step_loop_with_apply_tracks_oracle():
                 assert idx[r] == 0xFFFFFFFF
             assert after[r].tolist() == oracles[r].committed_score().tolist()
         assert np.array_equal(d.fresh_score(), after)
+
+
+def test_device_resident_change_loop_equals_step_by_step():
+    from solverforge_b200.selectors import splitmix64
+    g = instances.graph_coloring(300, 1200, 4, seed_edges=2, seed_colors=3, unassigned_permille=150)
+    R, steps, late = 2, 40, 7
+    colors = np.stack([instances.graph_coloring(300, 1200, 4, seed_edges=2, seed_colors=30 + r, unassigned_permille=150).color
+                       for r in range(R)])
+    loop = models.graph_coloring_director(g, R, colors=colors)
+    ref = models.graph_coloring_director(g, R, colors=colors)
+    seed_base = 77
+    best, evaluated, committed = loop.solve_change(steps, 2, late, 1, 25, seed_base)
+    init = ref.calculate_score()
+    history = [[init[r].copy() for _ in range(late)] for r in range(R)]
+    hidx = [0] * R
+    best_h = init.copy()
+    ev_h = np.zeros(R, dtype=np.uint64)
+    for t in range(steps):
+        last = ref.calculate_score()
+        refs = np.stack([np.concatenate([last[r], history[r][hidx[r]]]) for r in range(R)])
+        seeds = [splitmix64(seed_base ^ ((r * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) ^ t) for r in range(R)]
+        idx, b, ev, win = ref.step_change(ForageParams(2, 1, 25), step_seeds=seeds, ref_scores=refs, apply=True)
+        after = ref.calculate_score()
+        for r in range(R):
+            history[r][hidx[r]] = after[r].copy()
+            hidx[r] = (hidx[r] + 1) % late
+            ev_h[r] += ev[r]
+            if (after[r][0], after[r][1]) > (best_h[r][0], best_h[r][1]):
+                best_h[r] = after[r]
+    assert np.array_equal(loop.calculate_score(), ref.calculate_score())
+    assert np.array_equal(loop.scalar_state(), ref.scalar_state())
+    assert np.array_equal(best, best_h) and np.array_equal(evaluated, ev_h)
+    assert np.array_equal(loop.fresh_score(), loop.calculate_score())
+    assert (best[:, 0] > init[:, 0]).all()      # hard score improved (conflicts / unassigned removed)

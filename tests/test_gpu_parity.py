@@ -78,6 +78,28 @@ def test_reference_kats_grouped():
         assert d.fresh_score()[0].tolist() == [0, v["soft_after"]]
 
 
+def test_reference_kats_projected_grouped_complement():
+    # a single-emit projection keyed by the planning variable lowers to GROUP with a per-key weight offset
+    for v in GOLDEN["projected_grouped_complement"]:
+        for demand, want in ((v["demand"], v["soft"]), (v["demand_after"], v["soft_after"])):
+            d = GpuScoreDirector(1)
+            buckets = d.add_collection("capacity", v["n_values"], -1)
+            work = d.add_collection("work", len(v["bucket"]), 0)
+            d.add_scalar_variable(work, "bucket", v["n_values"], True)
+            dem = d.add_column(work, "demand", demand)
+            off = d.add_column(buckets, "bucket_x10", v["key_offset"])
+            ConstraintFactory(d).for_each(work).join(buckets, EqualVarToRow()).group_by(Sum(dem)).complement(
+                buckets, v["default"]).penalize(soft(L.W_LINEAR, 1, 0), key_offset_column=off).named(
+                "projected demand by capacity bucket")
+            d.set_scalar_state(v["bucket"])
+            assert d.commit()[0].tolist() == [0, want], v["cite"]
+        # moving the only work row to bucket 1: bucket 0 falls back to its default
+        s, ok = d.score_change(np.array([[0, 1]]))
+        assert ok[0] == 1 and s[0].tolist() == [0, -(0 + 3) - (10 + 7)]
+        d.apply_change(np.array([[0, 1]]))
+        assert d.fresh_score()[0].tolist() == [0, -20]
+
+
 def test_reference_kats_exists_and_self_join():
     for v in GOLDEN["exists_flattened"]:
         for routes, want in ((v["routes_before"], v["soft_before"]), (v["routes_after"], v["soft_after"])):
