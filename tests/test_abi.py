@@ -66,3 +66,10 @@ def test_product_never_imports_oracle():
                     if re.search(r"oracle_lib|liboracle|oracle/|import oracle|from oracle|sfo_", src):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """bindings/rust/solverforge-gpu-sys cannot be compiled here (no cargo); keep its symbol list in sync."""
+    src = open(os.path.join(ROOT, "bindings", "rust", "solverforge-gpu-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (sfgpu_[a-z0-9_]+)\(", src))
+    assert declared == set(_declared_symbols())

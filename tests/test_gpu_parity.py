@@ -321,6 +321,32 @@ def test_cvrp_empty_routes_and_unreachable_cells():
         _eq(d.fresh_score()[0], o.evaluate_all())
 
 
+def test_hard_soft_decimal_score_is_exact_on_device():
+    # HardSoftDecimalScore = the same int64 pair pre-scaled by 100000 (hard_soft_decimal.rs:14,45-48):
+    # authoring the weights scaled must give exactly 100000 x the HardSoftScore result, candidate by candidate
+    from solverforge_b200 import HardSoftDecimalScore
+    g = instances.graph_coloring(500, 2200, 5, seed_edges=12, seed_colors=13, unassigned_permille=60)
+    plain = models.graph_coloring_director(g)
+    dec = GpuScoreDirector(1)
+    dec.add_collection("colors", g.k, -1)
+    nodes = dec.add_collection("nodes", g.n, 0)
+    dec.add_scalar_variable(nodes, "color_idx", g.k, True)
+    adj = dec.add_csr("neighbors", g.row_ptr, g.col)
+    from solverforge_b200 import AdjacentEqual
+    f = ConstraintFactory(dec)
+    one_hard = HardSoftDecimalScore.of(1, 0)
+    assert (one_hard.hard, one_hard.soft) == (100000, 0)
+    f.for_each(nodes).unassigned().penalize(one_hard).named("Unassigned color")
+    f.for_each(nodes).join(f.for_each(nodes), AdjacentEqual(adj)).penalize(one_hard).named("Adjacent color conflict")
+    dec.set_scalar_state(g.color)
+    assert np.array_equal(dec.commit()[0], plain.calculate_score()[0] * 100000)
+    rows = instances.change_neighbourhood(g.color, g.k)
+    sp, okp = plain.score_change(rows)
+    sd, okd = dec.score_change(rows)
+    _eq(okd, okp)
+    _eq(sd, sp * 100000, "decimal scores")
+
+
 def test_fast_list_kernel_equals_generic_kernel():
     c = instances.cvrp(300, 20, seed=4)
     offs, el = instances.perturb_routes(c, 9, 200)
