@@ -907,7 +907,8 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
         // 10 000 beat 4 x 5 000 by 7 %); with few replicas split further until the machine is covered
         uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 10239) / 10240, 64));
         while ((uint64_t)chunks * dm.R < (uint64_t)ctx->sm_count * 6 && (uint64_t)chunks * 512 < per_replica) chunks *= 2;
-        if (const char* ev = getenv("SFGPU_FAST_CHUNKS")) chunks = (uint32_t)std::max(1, atoi(ev));  // tuning knob
+        static const int chunk_override = getenv("SFGPU_FAST_CHUNKS") ? atoi(getenv("SFGPU_FAST_CHUNKS")) : 0;  // tuning knob
+        if (chunk_override > 0) chunks = (uint32_t)chunk_override;
         dim3 fgrid(chunks, dm.R);
         if (forage) {
           size_t need = (size_t)chunks * dm.R * sizeof(ChunkPartial);
