@@ -289,13 +289,22 @@ def run_ours(args):
     # doubles as the parity gate — an incorrect kernel is never timed.
     step(0)
     torch.cuda.synchronize()
-    cpu_v = cpu_sample = None
+    cpu_v = cpu_sample = cpu_o1 = None
     if rank == 0:
         cap = 600 if name != "cvrp" else None
         cpu_v, cpu_sample, so, oko = cpu_reference_pass(name, inst, starts[0], 1, 12.0, cap, want_scores=True)
         r0 = slice(0, len(so))
         if not (np.array_equal(t_scores[r0].cpu().numpy(), so) and np.array_equal(t_doable[r0].cpu().numpy(), oko)):
             raise SystemExit("bench.py: GPU scores differ from the oracle — refusing to time an incorrect kernel")
+        if name == "cvrp":
+            # a second, STRONGER CPU figure so the GPU/CPU ratio is not read off the reference's O(route)
+            # closures alone: the same read-only O(1) delta as the GPU fast path, plain C++ (oracle/fast_cpu.cpp)
+            from tests.oracle_lib import FastCvrp
+            fc = FastCvrp(inst, *starts[0][0])
+            cores = os.cpu_count() or 1
+            cpu_o1 = {"one_thread": fc.bench(starts[0][1], 1, 2.0), "all_threads": fc.bench(starts[0][1], cores, 3.0),
+                      "cores": cores, "unit": UNIT,
+                      "what": "O(1)-delta list-change scorer (GPU fast-path algorithm) in C++, one solver per thread"}
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -412,6 +421,7 @@ def run_ours(args):
                          else f"score_{kind}_kernel", "kernel_ms": kernel_ms, "call_ms": call_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample},
+            "cpu_baseline_o1_delta": cpu_o1,
             "e2e": {"value": total_cands / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": e2e_api},
             "gpu_launches": int(launches),

@@ -213,3 +213,55 @@ def replay_step(scores, doable, best_score, last_step_score, late_score, step_se
     lib().sfo_replay_step(len(h), _p(h), _p(s), _p(d), _p(b), _p(l_), _p(t), step_seed, forager_kind, accepted_limit,
                           1 if random_ties else 0, acceptor_kind, _p(out))
     return tuple(int(x) for x in out)
+
+
+# ---- the stronger O(1)-delta CPU baseline (oracle/fast_cpu.cpp) ---------------------------------
+FAST_LIB = os.path.join(ORACLE_DIR, "_build", "libfastcpu.so")
+_fast = None
+
+
+def fast_lib() -> C.CDLL:
+    global _fast
+    if _fast is None:
+        if not os.path.exists(FAST_LIB):
+            build()
+        l = C.CDLL(FAST_LIB)
+        l.sfo_fast_cvrp_create.restype = _P
+        l.sfo_fast_cvrp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, _P, _P, _P, _P]
+        l.sfo_fast_cvrp_destroy.argtypes = [_P]
+        l.sfo_fast_cvrp_score.argtypes = [_P, C.c_uint64, _P, _P, _P]
+        l.sfo_fast_cvrp_bench.restype = C.c_double
+        l.sfo_fast_cvrp_bench.argtypes = [_P, C.c_uint64, _P, C.c_uint32, C.c_double]
+        _fast = l
+    return _fast
+
+
+class FastCvrp:
+    """Read-only O(1)-delta CPU scorer for CVRP list-change batches (same algorithm as the GPU fast path)."""
+
+    def __init__(self, inst, offsets=None, elems=None):
+        self.l = fast_lib()
+        o = _u32(inst.offsets if offsets is None else offsets)
+        e = _u32(inst.elems if elems is None else elems)
+        dm = np.ascontiguousarray(inst.demands, dtype=np.int32)
+        mx = np.ascontiguousarray(inst.matrix, dtype=np.int64)
+        self.h = self.l.sfo_fast_cvrp_create(inst.dim, inst.n_routes, inst.capacity, inst.depot, _p(dm), _p(mx), _p(o),
+                                             _p(e))
+        if not self.h:
+            raise ValueError("matrix does not fit the int32 fast path")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.sfo_fast_cvrp_destroy(self.h)
+            self.h = None
+
+    def score(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1, 4)
+        sc = np.zeros((len(rows), 2), dtype=np.int64)
+        ok = np.zeros(len(rows), dtype=np.uint8)
+        self.l.sfo_fast_cvrp_score(self.h, len(rows), _p(rows), _p(sc), _p(ok))
+        return sc, ok
+
+    def bench(self, rows, n_threads: int, seconds: float) -> float:
+        rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1, 4)
+        return float(self.l.sfo_fast_cvrp_bench(self.h, len(rows), _p(rows), n_threads, seconds))

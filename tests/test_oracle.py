@@ -157,3 +157,18 @@ def test_shift_scheduling_invariant_and_unfairness():
         if ok[i]:
             o.apply_change(*rows[i])
             assert np.array_equal(o.committed_score(), o.evaluate_all())
+
+
+def test_fast_cpu_baseline_matches_the_oracle():
+    from tests.oracle_lib import FastCvrp
+    c = instances.cvrp(150, 9, seed=4)
+    offs, el = instances.perturb_routes(c, 3, 80)
+    o = Oracle.cvrp(c, offs, el)
+    f = FastCvrp(c, offs, el)
+    rows = o.enumerate_nearby_list_change(15)
+    extra = np.array([[0, 0, 0, 0], [0, 0, 0, 1], [0, 99, 1, 0], [1, 0, 2, 99], [3, 1, 3, 0]], dtype=np.uint32)
+    rows = np.concatenate([rows, extra])
+    so, oko = o.score_list_change(rows)
+    sf, okf = f.score(rows)
+    assert np.array_equal(okf, oko) and np.array_equal(sf, so)
+    assert f.bench(rows, 2, 0.2) > 0
