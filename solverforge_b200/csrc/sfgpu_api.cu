@@ -504,7 +504,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       off += (dm.elem_cap + dm.n_owners) * 16;
       // device-side nearby neighbourhood: needs the path-cost matrix as the distance meter, every
       // cell finite (guaranteed by the < 2^28 test above) and 16-bit owner / position fields
-      if (dm.fast_pc >= 0 && dm.n_owners < 65536 && dm.elem_cap < 65536) {
+      if (dm.fast_pc >= 0 && dm.n_owners >= 1 && dm.n_owners < 65536 && dm.elem_cap < 65536) {
         dm.fast_score_bytes = off;  // the score kernels do not need pos_of
         dm.nearby_ok = 1;
         dm.off_pos_of = off;
@@ -1078,7 +1078,6 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
   const DevModel& dm = ctx->dm;
   if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
   CU(cudaSetDevice(ctx->device));
-  if (n_candidates == 0) return fail(ctx, SFGPU_E_INVALID, "empty batch");
   const bool fused = dm.fast_list && !ctx->force_generic && params->accepted_limit == 0;
   if (fused) {
     ForageArgs fa{};

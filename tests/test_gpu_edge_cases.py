@@ -1,0 +1,119 @@
+"""GPU edge cases the reference's tests also poke at: empty and ragged batches, tiny models where the
+neighbourhood is smaller than max_nearby, single-value ranges, everything unassigned. Oracle parity."""
+import numpy as np
+import pytest
+
+from solverforge_b200 import ForageParams, instances, models
+from solverforge_b200.instances import CvrpInstance
+from tests import oracle_lib
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_cvrp(routes, dim, seed=1):
+    s = instances.splitmix64_stream(seed, dim * dim + dim)
+    m = (s[:dim * dim] % np.uint64(50)).astype(np.int64).reshape(dim, dim) + 1   # asymmetric on purpose
+    np.fill_diagonal(m, 0)
+    demands = (s[dim * dim:] % np.uint64(5)).astype(np.int32) + 1
+    demands[0] = 0
+    offs = np.cumsum([0] + [len(r) for r in routes]).astype(np.uint32)
+    el = np.array([x for r in routes for x in r], dtype=np.uint32)
+    return CvrpInstance(dim, len(routes), 6, 0, demands, m, offs, el)
+
+
+@pytest.mark.parametrize("routes", [
+    [[1, 2], [3]],                      # 5 slots - 2 = 3 candidates per source < max_nearby
+    [[1], [], [2, 3, 4], []],           # empty routes, single-element route
+    [[1, 2, 3, 4, 5, 6]],               # one route only: intra moves only
+    [[1], [2]],
+])
+def test_tiny_neighbourhoods_match_oracle(routes):
+    import torch
+    dim = 1 + sum(len(r) for r in routes)
+    c = _tiny_cvrp(routes, dim)
+    o = Oracle.cvrp(c)
+    d = models.cvrp_director(c)
+    assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+    K = 20
+    cap = dim - 1
+    dev = torch.device("cuda")
+    t_rows = torch.zeros((cap * K, 4), dtype=torch.int32, device=dev)
+    t_scores = torch.zeros((cap * K, 2), dtype=torch.int64, device=dev)
+    t_doable = torch.zeros(cap * K, dtype=torch.uint8, device=dev)
+    t_off = torch.zeros(2, dtype=torch.int64, device=dev)
+    idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(0, 0, 0), out_offsets_ptr=t_off.data_ptr(),
+                                                   out_rows_ptr=t_rows.data_ptr(), out_scores_ptr=t_scores.data_ptr(),
+                                                   out_doable_ptr=t_doable.data_ptr())
+    want = o.enumerate_nearby_list_change(K)
+    ok = t_doable.cpu().numpy() == 1
+    got = t_rows.cpu().numpy().view(np.uint32)[ok]
+    assert np.array_equal(got, want), (got.tolist(), want.tolist())
+    so, oko = o.score_list_change(want) if len(want) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+    assert np.array_equal(t_scores.cpu().numpy()[ok], so)
+    assert int(ev[0]) == len(want)
+    if len(want):
+        out = oracle_lib.replay_step(so, oko, [0, 0], [0, 0], [0, 0], 0, 2, 1, False, 3)
+        assert int(idx[0]) == out[1] and win[0].tolist() == want[out[1]].tolist()
+    else:
+        assert idx[0] == 0xFFFFFFFF
+    # the generic scoring path agrees too, including out-of-range rows
+    rows = np.concatenate([want.reshape(-1, 4), np.array([[0, 0, 0, 0], [9, 0, 0, 0], [0, 7, 0, 0]], dtype=np.uint32)])
+    s, okk = d.score_list_change(rows)
+    assert okk[-3:].tolist() == [0, 0, 0]
+
+
+def test_empty_and_ragged_batches():
+    import torch
+    c = instances.cvrp(40, 4, seed=3)
+    R = 3
+    d = models.cvrp_director(c, R)
+    o = Oracle.cvrp(c)
+    rows = o.enumerate_nearby_list_change(5)
+    # replica 1 gets no candidates at all
+    co = np.array([0, len(rows), len(rows), 2 * len(rows)], dtype=np.uint64)
+    batch = np.concatenate([rows, rows])
+    s, ok = d.score_list_change(batch, co)
+    so, oko = o.score_list_change(rows)
+    assert np.array_equal(s[:len(rows)], so) and np.array_equal(s[len(rows):], so)
+    idx, best, ev = d.argbest(s, ok, co, ForageParams(0, 0, 0))
+    assert idx[1] == 0xFFFFFFFF and ev[1] == 0 and idx[0] == idx[2]
+    dev = torch.device("cuda")
+    t_off = torch.from_numpy(co.view(np.int64)).to(dev)
+    t_rows = torch.from_numpy(batch.view(np.int32)).to(dev)
+    t_idx = torch.zeros(R, dtype=torch.int32, device=dev)
+    t_best = torch.zeros((R, 2), dtype=torch.int64, device=dev)
+    t_ev = torch.zeros(R, dtype=torch.int32, device=dev)
+    d.step_list_change_device(len(batch), t_off.data_ptr(), t_rows.data_ptr(), ForageParams(0, 0, 0), 0, 0, 0, 0,
+                              t_idx.data_ptr(), t_best.data_ptr(), t_ev.data_ptr())
+    d.synchronize()
+    assert t_idx.cpu().numpy().view(np.uint32).tolist() == idx.tolist()
+    # a completely empty batch is a step with no winner, not an error
+    empty = np.zeros(R + 1, dtype=np.uint64)
+    t_off0 = torch.from_numpy(empty.view(np.int64)).to(dev)
+    d.step_list_change_device(0, t_off0.data_ptr(), t_rows.data_ptr(), ForageParams(0, 0, 0), 0, 0, 0, 0,
+                              t_idx.data_ptr(), t_best.data_ptr(), t_ev.data_ptr())
+    d.synchronize()
+    assert (t_idx.cpu().numpy().view(np.uint32) == 0xFFFFFFFF).all()
+    s0, ok0 = d.score_list_change(np.zeros((0, 4), dtype=np.uint32), empty)
+    assert s0.shape == (0, 2)
+
+
+def test_scalar_extremes():
+    # one value only; everything unassigned; fewer entities than a warp
+    g = instances.graph_coloring(7, 9, 1, seed_edges=2, seed_colors=3)
+    for colors in (np.full(7, -1, np.int32), np.zeros(7, np.int32), np.array([0, -1, 0, -1, 0, 0, -1], np.int32)):
+        o = Oracle.graph_coloring(g, colors)
+        d = models.graph_coloring_director(g, colors=colors)
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        rows = o.enumerate_change()
+        so, oko = o.score_change(rows)
+        s, ok = d.score_change(rows)
+        assert np.array_equal(ok, oko) and np.array_equal(s, so)
+        idx, best, ev, win = d.step_change(ForageParams(0, 0, 0))
+        assert int(ev[0]) == len(rows)
+        out = oracle_lib.replay_step(so, oko, [0, 0], [0, 0], [0, 0], 0, 2, 1, False, 3)
+        if out[0]:
+            assert int(idx[0]) == out[1]
+        else:
+            assert idx[0] == 0xFFFFFFFF
