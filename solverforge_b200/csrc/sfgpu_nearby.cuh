@@ -394,8 +394,10 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
       if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
       const int64_t oh = ch + dh, os = csf + ds;
       bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+      const uint32_t cut_rank = s_lcut;  // read by every lane before one lane overwrites it below
+      __syncwarp();
       uint32_t mm = __ballot_sync(0xffffffffu, acc);
-      for (uint32_t t = 1; t < s_lcut; ++t) mm &= mm - 1;
+      for (uint32_t t = 1; t < cut_rank; ++t) mm &= mm - 1;
       const uint32_t cut_lane = __ffs(mm) - 1;
       acc = acc && lane <= cut_lane;
       uint32_t accm;
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
         s_cutp.best_h = oh;
         s_cutp.best_s = os;
         s_cutp.n_best = __popc(eq);
-        s_cutp.n_accepted = s_lcut;
+        s_cutp.n_accepted = cut_rank;
         s_cutp.first_lane = eq ? __ffs(eq) - 1 : 0;
         s_lcut = cut_lane;  // from here on: last counted lane of the cut source
       }

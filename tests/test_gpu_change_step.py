@@ -18,6 +18,7 @@ def _run_and_check(d, oracle, n_entities, k, seeds=(3, 11), limits=(0, 1, 9, 300
     t_rows = torch.zeros((S, 2), dtype=torch.int32, device=dev)
     t_scores = torch.zeros((S, 2), dtype=torch.int64, device=dev)
     t_doable = torch.full((S,), 7, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()  # the director launches on its own stream: order after torch's fills
     d.step_change(ForageParams(0, 1, 0), step_seeds=[1], out_offsets_ptr=t_off.data_ptr(),
                   out_rows_ptr=t_rows.data_ptr(), out_scores_ptr=t_scores.data_ptr(), out_doable_ptr=t_doable.data_ptr())
     want = oracle.enumerate_change()

@@ -42,6 +42,7 @@ def test_tiny_neighbourhoods_match_oracle(routes):
     t_scores = torch.zeros((cap * K, 2), dtype=torch.int64, device=dev)
     t_doable = torch.zeros(cap * K, dtype=torch.uint8, device=dev)
     t_off = torch.zeros(2, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()  # the director launches on its own stream: order after torch's fills
     idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(0, 0, 0), out_offsets_ptr=t_off.data_ptr(),
                                                    out_rows_ptr=t_rows.data_ptr(), out_scores_ptr=t_scores.data_ptr(),
                                                    out_doable_ptr=t_doable.data_ptr())
@@ -84,6 +85,7 @@ def test_empty_and_ragged_batches():
     t_idx = torch.zeros(R, dtype=torch.int32, device=dev)
     t_best = torch.zeros((R, 2), dtype=torch.int64, device=dev)
     t_ev = torch.zeros(R, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # the director launches on its own stream: order after torch's copies
     d.step_list_change_device(len(batch), t_off.data_ptr(), t_rows.data_ptr(), ForageParams(0, 0, 0), 0, 0, 0, 0,
                               t_idx.data_ptr(), t_best.data_ptr(), t_ev.data_ptr())
     d.synchronize()
@@ -91,6 +93,7 @@ def test_empty_and_ragged_batches():
     # a completely empty batch is a step with no winner, not an error
     empty = np.zeros(R + 1, dtype=np.uint64)
     t_off0 = torch.from_numpy(empty.view(np.int64)).to(dev)
+    torch.cuda.synchronize()
     d.step_list_change_device(0, t_off0.data_ptr(), t_rows.data_ptr(), ForageParams(0, 0, 0), 0, 0, 0, 0,
                               t_idx.data_ptr(), t_best.data_ptr(), t_ev.data_ptr())
     d.synchronize()

@@ -16,8 +16,10 @@ def _materialise(d, R, cap, K):
     import torch
     dev = torch.device("cuda")
     S = cap * K
-    return (torch.zeros(R + 1, dtype=torch.int64, device=dev), torch.zeros((R * S, 4), dtype=torch.int32, device=dev),
+    bufs = (torch.zeros(R + 1, dtype=torch.int64, device=dev), torch.zeros((R * S, 4), dtype=torch.int32, device=dev),
             torch.zeros((R * S, 2), dtype=torch.int64, device=dev), torch.zeros(R * S, dtype=torch.uint8, device=dev))
+    torch.cuda.synchronize()  # the director launches on its own stream: order after torch's fills
+    return bufs
 
 
 def _check_generated(t_off, t_rows, t_scores, t_doable, R, cap, K, oracles):

@@ -396,6 +396,7 @@ def test_fused_step_matches_unfused_and_oracle_replay():
     t_idx = torch.zeros(R, dtype=torch.int32, device=dev)
     t_best = torch.zeros((R, 2), dtype=torch.int64, device=dev)
     t_ev = torch.zeros(R, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # the director launches on its own stream: order after torch's copies
     so = [oracles[r].score_list_change(batches[r]) for r in range(R)]
     base = d.calculate_score()
     for seed in (3, 4):
@@ -408,6 +409,7 @@ def test_fused_step_matches_unfused_and_oracle_replay():
                         t_ref = torch.from_numpy(ref).to(dev)
                         t_seed = torch.full((R,), seed, dtype=torch.int64, device=dev)
                         t_idx.fill_(-7)
+                        torch.cuda.synchronize()
                         d.step_list_change_device(n, t_off.data_ptr(), t_rows.data_ptr(),
                                                   ForageParams(acceptor, ties, limit), t_seed.data_ptr(),
                                                   t_ref.data_ptr(), t_scores.data_ptr() if materialise else 0,
