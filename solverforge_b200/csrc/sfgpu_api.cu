@@ -166,13 +166,13 @@ int check_committed(sfgpu_ctx* ctx) {
   return SFGPU_OK;
 }
 
-// chunks per replica so that the grid covers the machine a few times over
+// chunks per replica so that the grid covers the machine a few times over (measured on C2: more, smaller
+// CTAs beat fewer fat ones for the generic kernels even though each stages the replica block again)
 uint32_t chunks_for(const sfgpu_ctx* ctx, uint64_t n_total, uint32_t R, uint32_t threads) {
   uint64_t per_replica = (n_total + R - 1) / std::max<uint32_t>(R, 1);
   uint64_t max_chunks = std::max<uint64_t>(1, (per_replica + threads - 1) / threads);
   uint64_t target_ctas = (uint64_t)ctx->sm_count * 8;
   uint64_t want = std::max<uint64_t>(1, (target_ctas + R - 1) / R);
-  // amortise the block staging: at least 4 candidates per thread when there is enough work
   uint64_t amort = std::max<uint64_t>(1, per_replica / (threads * 4ull));
   uint64_t chunks = std::min(max_chunks, std::max(want, std::min<uint64_t>(amort, want * 4)));
   return (uint32_t)std::min<uint64_t>(chunks, 65535);
@@ -591,6 +591,13 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         if (rc) return rc;
         c.g0 = drp;
         c.g1 = dci;
+        // retained partner-value counts (uint16 [n_entities][n_values], unstaged): only when the table is
+        // small enough and no entity has more than 65535 partners
+        uint32_t maxdeg = 0;
+        for (uint32_t a2 = 0; a2 < g.n_rows; ++a2) maxdeg = std::max(maxdeg, rp[a2 + 1] - rp[a2]);
+        c.off0 = 0xFFFFFFFFu;
+        if ((uint64_t)dm.n_entities * dm.n_values <= (1ull << 24) && maxdeg <= 65535)
+          unstaged_bytes[k] = align_up(dm.n_entities * dm.n_values * 2, 16);
         break;
       }
       case SFGPU_K_PAIR_KEY_EQUAL: {

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
       const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
       const bool ok = nv != old;
       Score2 d{0, 0};
-      if (ok) scalar_edit_delta(m, st, nullptr, 0, EditDev{e, old, nv}, d);
+      if (ok) scalar_edit_delta(m, st, gblock, nullptr, 0, EditDev{e, old, nv}, d);
       const int64_t oh = ok ? ch + d.hard : 0, os = ok ? csf + d.soft : 0;
       if (a.out_rows) {
         const size_t q = (size_t)r * stride + base + v;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, co
       const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
       if (nv == old) continue;
       Score2 d{0, 0};
-      scalar_edit_delta(m, st, nullptr, 0, EditDev{e, old, nv}, d);
+      scalar_edit_delta(m, st, st, nullptr, 0, EditDev{e, old, nv}, d);
       const int64_t oh = ch + d.hard, os = csf + d.soft;
       if (accept_score(f.acceptor, oh, os, lh, ls, th, ts) && (mode == 0 || (oh == bh && os == bs))) mine++;
     }
@@ -191,7 +191,7 @@ __device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, co
         const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
         if (nv == old) continue;
         Score2 d{0, 0};
-        scalar_edit_delta(m, st, nullptr, 0, EditDev{e, old, nv}, d);
+        scalar_edit_delta(m, st, st, nullptr, 0, EditDev{e, old, nv}, d);
         const int64_t oh = ch + d.hard, os = csf + d.soft;
         if (accept_score(f.acceptor, oh, os, lh, ls, th, ts) && (mode == 0 || (oh == bh && os == bs))) {
           if (++hit == want - excl) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) change_finish_kernel(const __grid_constan
             const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
             if (nv == old) continue;
             Score2 d{0, 0};
-            scalar_edit_delta(m, st, nullptr, 0, EditDev{e, old, nv}, d);
+            scalar_edit_delta(m, st, st, nullptr, 0, EditDev{e, old, nv}, d);
             const int64_t oh = ch + d.hard, os = csf + d.soft;
             if (!accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) continue;
             if (tb_n == 0 || score_less(tb_h, tb_s, oh, os)) {

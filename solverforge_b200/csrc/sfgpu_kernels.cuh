@@ -66,7 +66,9 @@ __device__ __forceinline__ int64_t lb_unfairness(int64_t n, int64_t sum, int64_t
 
 // Delta of ONE edit (e: old -> new) against the replica state `st` overlaid with the edits
 // prev[0..n_prev) that were already applied by the same candidate.
-__device__ void scalar_edit_delta(const DevModel& m, const char* st, const EditDev* prev, int n_prev, EditDev cur,
+// `st` = the replica block as the kernel sees it (possibly the staged shared-memory prefix); `gst` = the
+// same block in global memory, for retained sections too large to stage (CSR partner-value counts).
+__device__ void scalar_edit_delta(const DevModel& m, const char* st, const char* gst, const EditDev* prev, int n_prev, EditDev cur,
                                   Score2& d) {
   if (cur.old_v == cur.new_v) return;
   const int32_t* var = (const int32_t*)(st + m.off_var);
@@ -81,12 +83,19 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const EditD
         // g0 = partner row_ptr, g1 = partner ids (symmetrised, deduplicated at commit)
         const uint32_t* rp = (const uint32_t*)c.g0;
         const uint32_t* ci = (const uint32_t*)c.g1;
-        uint32_t lo = rp[cur.e], hi = rp[cur.e + 1];
         int64_t cnt = 0;
-        for (uint32_t j = lo; j < hi; ++j) {
-          int32_t vp = var_at(var, prev, n_prev, ci[j]);
-          cnt += (cur.new_v >= 0 && vp == cur.new_v) ? 1 : 0;
-          cnt -= (cur.old_v >= 0 && vp == cur.old_v) ? 1 : 0;
+        if (c.off0 != 0xFFFFFFFFu && n_prev == 0) {
+          // retained partner-value counts cc[e][v] (the analogue of the reference's retained match rows):
+          // O(1) instead of a walk over the partners
+          const uint16_t* cc = (const uint16_t*)(gst + c.off0) + (size_t)cur.e * m.n_values;
+          cnt = (cur.new_v >= 0 ? (int64_t)cc[cur.new_v] : 0) - (cur.old_v >= 0 ? (int64_t)cc[cur.old_v] : 0);
+        } else {
+          uint32_t lo = rp[cur.e], hi = rp[cur.e + 1];
+          for (uint32_t j = lo; j < hi; ++j) {
+            int32_t vp = var_at(var, prev, n_prev, ci[j]);
+            cnt += (cur.new_v >= 0 && vp == cur.new_v) ? 1 : 0;
+            cnt -= (cur.old_v >= 0 && vp == cur.old_v) ? 1 : 0;
+          }
         }
         add_level(d, c, cnt * c.w.a);
         break;
@@ -171,31 +180,39 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const EditD
 
 enum { MODE_CHANGE = 0, MODE_SWAP = 1, MODE_COMPOUND = 2 };
 
+// ChangeMove {entity, to_value}: doable iff the target differs from the current value (change.rs:125-139)
+__device__ __forceinline__ bool score_change_row(const DevModel& m, const char* st, const char* gst, uint2 row,
+                                                 Score2& d) {
+  const int32_t* var = (const int32_t*)(st + m.off_var);
+  d.hard = 0;
+  d.soft = 0;
+  uint32_t e = row.x;
+  int32_t nv = (int32_t)row.y;
+  if (e >= m.n_entities || nv >= (int32_t)m.n_values) return false;
+  if (nv < 0) nv = SFGPU_NONE;
+  int32_t ov = var[e];
+  if (ov == nv) return false;
+  scalar_edit_delta(m, st, gst, nullptr, 0, EditDev{e, ov, nv}, d);
+  return true;
+}
+
 // one thread = one candidate. Returns doable; d = score delta.
 template <int MODE>
-__device__ __forceinline__ bool score_scalar_candidate(const DevModel& m, const char* st, const uint32_t* rows,
+__device__ __forceinline__ bool score_scalar_candidate(const DevModel& m, const char* st, const char* gst, const uint32_t* rows,
                                                        const uint64_t* edit_offsets, uint64_t i, Score2& d) {
   const int32_t* var = (const int32_t*)(st + m.off_var);
   d.hard = 0;
   d.soft = 0;
   if (MODE == MODE_CHANGE) {
-    uint2 row = ((const uint2*)rows)[i];
-    uint32_t e = row.x;
-    int32_t nv = (int32_t)row.y;
-    if (e >= m.n_entities || nv >= (int32_t)m.n_values) return false;
-    if (nv < 0) nv = SFGPU_NONE;
-    int32_t ov = var[e];
-    if (ov == nv) return false;  // change.rs:125-139
-    scalar_edit_delta(m, st, nullptr, 0, EditDev{e, ov, nv}, d);
-    return true;
+    return score_change_row(m, st, gst, ((const uint2*)rows)[i], d);
   } else if (MODE == MODE_SWAP) {
     uint2 row = ((const uint2*)rows)[i];
     if (row.x >= m.n_entities || row.y >= m.n_entities) return false;
     int32_t lv = var[row.x], rv = var[row.y];
     if (lv == rv) return false;  // swap.rs:140-157
     EditDev e0{row.x, lv, rv};
-    scalar_edit_delta(m, st, nullptr, 0, e0, d);
-    scalar_edit_delta(m, st, &e0, 1, EditDev{row.y, rv, lv}, d);
+    scalar_edit_delta(m, st, gst, nullptr, 0, e0, d);
+    scalar_edit_delta(m, st, gst, &e0, 1, EditDev{row.y, rv, lv}, d);
     return true;
   } else {
     uint64_t lo = edit_offsets[i], hi = edit_offsets[i + 1];
@@ -213,7 +230,7 @@ __device__ __forceinline__ bool score_scalar_candidate(const DevModel& m, const 
       ed[j].old_v = var_at(var, ed, j, row.x);
     }
     if (!changes) return false;
-    for (int j = 0; j < n; ++j) scalar_edit_delta(m, st, ed, j, ed[j], d);
+    for (int j = 0; j < n; ++j) scalar_edit_delta(m, st, gst, ed, j, ed[j], d);
     return true;
   }
 }
@@ -239,10 +256,37 @@ __global__ void __launch_bounds__(256) score_scalar_kernel(const __grid_constant
   const int64_t* cs = (const int64_t*)(st + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
   const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  if (MODE == MODE_CHANGE) {
+    // four rows per thread per trip, loaded before any is scored: four independent 64-bit loads in
+    // flight hide the DRAM latency of the streamed batch
+    constexpr int U = 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < hi; base += stride * U) {
+      uint2 row[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t i = base + u * stride;
+        row[u] = i < hi ? __ldcs((const uint2*)rows + i) : make_uint2(0xFFFFFFFFu, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t i = base + u * stride;
+        if (i >= hi) break;
+        Score2 d;
+        const bool ok = score_change_row(m, st, gblock, row[u], d);
+        longlong2 o;
+        o.x = ok ? ch + d.hard : 0;
+        o.y = ok ? csf + d.soft : 0;
+        __stcs((longlong2*)out_scores + i, o);
+        out_doable[i] = ok ? 1 : 0;
+      }
+    }
+    return;
+  }
   for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
        i += (uint64_t)gridDim.x * blockDim.x) {
     Score2 d;
-    bool ok = score_scalar_candidate<MODE>(m, st, rows, edit_offsets, i, d);
+    bool ok = score_scalar_candidate<MODE>(m, st, gblock, rows, edit_offsets, i, d);
     longlong2 o;
     o.x = ok ? ch + d.hard : 0;
     o.y = ok ? csf + d.soft : 0;
@@ -835,8 +879,17 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
       case SFGPU_K_PAIR_CSR_EQUAL: {
         const uint32_t* rp = (const uint32_t*)c.g0;
         const uint32_t* ci = (const uint32_t*)c.g1;
+        uint16_t* cc = c.off0 != 0xFFFFFFFFu ? (uint16_t*)(st + c.off0) : nullptr;
         for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) {
           int32_t v = var[e];
+          if (cc) {
+            uint16_t* row = cc + (size_t)e * m.n_values;
+            for (uint32_t q = 0; q < m.n_values; ++q) row[q] = 0;
+            for (uint32_t j = rp[e]; j < rp[e + 1]; ++j) {
+              int32_t vp = var[ci[j]];
+              if (vp >= 0) row[vp] += 1;
+            }
+          }
           if (v < 0) continue;
           for (uint32_t j = rp[e]; j < rp[e + 1]; ++j)
             if (ci[j] > e && var[ci[j]] == v) local += c.w.a;
@@ -980,7 +1033,16 @@ __device__ void apply_scalar_edit(const DevModel& m, char* st, EditDev cur) {
   int32_t* var = (int32_t*)(st + m.off_var);
   for (uint32_t k = 0; k < m.n_cons; ++k) {
     const ConsDev& c = m.cons[k];
-    if (c.kind == SFGPU_K_PAIR_KEY_EQUAL) {
+    if (c.kind == SFGPU_K_PAIR_CSR_EQUAL && c.off0 != 0xFFFFFFFFu) {
+      uint16_t* cc = (uint16_t*)(st + c.off0);
+      const uint32_t* rp = (const uint32_t*)c.g0;
+      const uint32_t* ci = (const uint32_t*)c.g1;
+      for (uint32_t j = rp[cur.e]; j < rp[cur.e + 1]; ++j) {
+        uint16_t* row = cc + (size_t)ci[j] * m.n_values;
+        if (cur.old_v >= 0) row[cur.old_v] -= 1;
+        if (cur.new_v >= 0) row[cur.new_v] += 1;
+      }
+    } else if (c.kind == SFGPU_K_PAIR_KEY_EQUAL) {
       int32_t* tab = (int32_t*)(st + c.off0);
       if (cur.old_v >= 0) tab[pair_key(c, cur.e, cur.old_v)] -= 1;
       if (cur.new_v >= 0) tab[pair_key(c, cur.e, cur.new_v)] += 1;
@@ -1034,8 +1096,8 @@ __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind
   char* st = m.state + (size_t)r * m.block_bytes;
   int64_t* cs = (int64_t*)(st + m.off_score);
   Score2 d;
-  bool ok = kind == 0 ? score_scalar_candidate<MODE_CHANGE>(m, st, rows, nullptr, ri, d)
-                      : score_scalar_candidate<MODE_SWAP>(m, st, rows, nullptr, ri, d);
+  bool ok = kind == 0 ? score_scalar_candidate<MODE_CHANGE>(m, st, st, rows, nullptr, ri, d)
+                      : score_scalar_candidate<MODE_SWAP>(m, st, st, rows, nullptr, ri, d);
   if (!ok) return;
   const int32_t* var = (const int32_t*)(st + m.off_var);
   uint2 row = ((const uint2*)rows)[ri];
