@@ -754,7 +754,8 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     for (uint32_t i = 0; sym && i < mt.rows; ++i)
       for (uint32_t j = i + 1; j < mt.cols; ++j)
         if (mt.host[(size_t)i * mt.cols + j] != mt.host[(size_t)j * mt.cols + i]) { sym = false; break; }
-    dm.fm_u16 = mx < 65536 && mt.rows == mt.cols ? 1 : 0;
+    // uint16 cells select the 32-bit arithmetic of the fast kernels (FastArith): narrow models only
+    dm.fm_u16 = mx < 65536 && mt.rows == mt.cols && dm.fast_narrow ? 1 : 0;
     if (mt.rows != mt.cols) {
       dm.fm_row = mt.dev;  // rectangular: no transpose trick, plain int32 gathers
       dm.fm_col = nullptr;
@@ -836,25 +837,25 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     {
       int bytes = (int)dm.fast_stage_bytes;
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
   }
   if (dm.has_list) {
@@ -936,10 +937,10 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
         int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
 #define FASTK(FN)                                                                                              \
   if (forage)                                                                                                  \
-    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 3, true, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
+    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 4, true, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
     else score_list_change_fast_kernel<FN, 2, 3, true, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
   else                                                                                                         \
-    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 3, false, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
+    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 4, false, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
     else score_list_change_fast_kernel<FN, 2, 3, false, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{})
         switch (fn) {
           case -1: FASTK(-1); break;

@@ -281,17 +281,17 @@ __global__ void __launch_bounds__(256) score_scalar_kernel(const __grid_constant
         out_doable[i] = ok ? 1 : 0;
       }
     }
-    return;
-  }
-  for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    Score2 d;
-    bool ok = score_scalar_candidate<MODE>(m, st, gblock, rows, edit_offsets, i, d);
-    longlong2 o;
-    o.x = ok ? ch + d.hard : 0;
-    o.y = ok ? csf + d.soft : 0;
-    ((longlong2*)out_scores)[i] = o;
-    out_doable[i] = ok ? 1 : 0;
+  } else {
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+      Score2 d;
+      bool ok = score_scalar_candidate<MODE>(m, st, gblock, rows, edit_offsets, i, d);
+      longlong2 o;
+      o.x = ok ? ch + d.hard : 0;
+      o.y = ok ? csf + d.soft : 0;
+      ((longlong2*)out_scores)[i] = o;
+      out_doable[i] = ok ? 1 : 0;
+    }
   }
 }
 
@@ -511,6 +511,58 @@ __device__ __forceinline__ bool accept_score(int acceptor, int64_t h, int64_t s,
   return !score_less(h, s, lh, ls) || !score_less(h, s, th, ts);
 }
 
+// Arithmetic width of the fast list kernels. uint16 cells are only selected for narrow models (every
+// fast-path delta provably inside int32, sfgpu_api.cu commit), so those kernels run the whole delta,
+// the acceptor test and the running best on 32-bit registers; wider models keep int64. Products and
+// sums go through the unsigned type (two's-complement wrap, exact whenever the result fits).
+template <typename CELL>
+struct FastArith {
+  typedef int64_t S;
+  typedef uint64_t US;
+};
+template <>
+struct FastArith<uint16_t> {
+  typedef int32_t S;
+  typedef uint32_t US;
+};
+template <typename S>
+__device__ __forceinline__ S clamp_to(int64_t v, int64_t lim) {
+  return (S)(v < -lim ? -lim : (v > lim ? lim : v));
+}
+// 32-bit threshold of an acceptor reference score relative to the committed score: deltas are
+// strictly inside (INT32_MIN, INT32_MAX), so a clamped threshold compares like the exact one
+__device__ __forceinline__ void rel_threshold(int64_t ref, int64_t committed, int32_t& out) {
+  const int64_t d = ref - committed;
+  out = d < (int64_t)INT32_MIN ? INT32_MIN : (d > (int64_t)INT32_MAX ? INT32_MAX : (int32_t)d);
+}
+__device__ __forceinline__ void rel_threshold(int64_t ref, int64_t committed, int64_t& out) { out = ref - committed; }
+template <typename S>
+__device__ __forceinline__ bool lex_less(S h1, S s1, S h2, S s2) {
+  return h1 != h2 ? h1 < h2 : s1 < s2;
+}
+// acceptor predicate on score deltas against thresholds relative to the committed score
+template <typename S>
+__device__ __forceinline__ bool accept_delta(int acceptor, S h, S s, S lh, S ls, S th, S ts) {
+  if (acceptor == 0) return true;
+  if (acceptor == 1) return lex_less(lh, ls, h, s);
+  return !lex_less(h, s, lh, ls) || !lex_less(h, s, th, ts);
+}
+// LIST_SUM delta of moving value v from a route with sum ss to one with sum sd (a, b pre-narrowed)
+template <int SUM_FN, typename S, typename US>
+__device__ __forceinline__ S list_sum_delta(S a, S b, S v, S ss, S sd) {
+  if (SUM_FN == SFGPU_W_EXCESS) {
+    const S e0 = (S)((US)ss - (US)b), e1 = (S)((US)sd - (US)b);
+    const S z = 0;
+    const US d = ((US)max((S)((US)e0 - (US)v), z) - (US)max(e0, z)) + ((US)max((S)((US)e1 + (US)v), z) - (US)max(e1, z));
+    return (S)(d * (US)a);
+  }
+  if (SUM_FN == SFGPU_W_SQUARE) {
+    const US s0 = (US)ss, s1 = (US)sd, uv = (US)v;
+    return (S)((US)a * (((s0 - uv) * (s0 - uv) - s0 * s0) + ((s1 + uv) * (s1 + uv) - s1 * s1)));
+  }
+  return 0;  // LINEAR: -a*v + a*v = 0; CONST: the number of routes is unchanged
+}
+
 struct ForageArgs {
   ForageDev f;
   const int64_t* ref_scores;  // [R][4] = {last_step, late} or null
@@ -524,21 +576,29 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
                                                                      int64_t* __restrict__ out_scores,
                                                                      uint8_t* __restrict__ out_doable,
                                                                      const ForageArgs fa) {
+  typedef typename FastArith<CELL>::S S;
+  typedef typename FastArith<CELL>::US US;
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   const uint32_t r = blockIdx.y;
-  // fused forager partial (FORAGE): this thread's best accepted score, multiplicity, first row
-  int64_t tb_h = 0, tb_s = 0, f_lh = 0, f_ls = 0, f_th = 0, f_ts = 0;
-  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
-  if (FORAGE && fa.ref_scores) {
-    f_lh = fa.ref_scores[r * 4 + 0];
-    f_ls = fa.ref_scores[r * 4 + 1];
-    f_th = fa.ref_scores[r * 4 + 2];
-    f_ts = fa.ref_scores[r * 4 + 3];
-  }
   stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_score_bytes, &bar);
   const int64_t* cs = (const int64_t*)(smem + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
+  // fused forager partial (FORAGE): this thread's best accepted score delta, multiplicity, first
+  // row; acceptor references become thresholds on the delta
+  S tb_h = 0, tb_s = 0, f_lh = 0, f_ls = 0, f_th = 0, f_ts = 0;
+  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
+  if (FORAGE && fa.ref_scores) {
+    rel_threshold(fa.ref_scores[r * 4 + 0], ch, f_lh);
+    rel_threshold(fa.ref_scores[r * 4 + 1], csf, f_ls);
+    rel_threshold(fa.ref_scores[r * 4 + 2], ch, f_th);
+    rel_threshold(fa.ref_scores[r * 4 + 3], csf, f_ts);
+  } else if (FORAGE) {
+    rel_threshold(0, ch, f_lh);
+    rel_threshold(0, csf, f_ls);
+    rel_threshold(0, ch, f_th);
+    rel_threshold(0, csf, f_ts);
+  }
   const uint4* rr = (const uint4*)(smem + m.off_route_rec);
   const uint4* pr = (const uint4*)(smem + m.off_pos_rec);
   const uint4* sr = (const uint4*)(smem + m.off_slot_rec);
@@ -549,10 +609,12 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
   const CELL* __restrict__ mrow = (const CELL*)m.fm_row;
   const CELL* __restrict__ mcol = (const CELL*)m.fm_col;
   const uint32_t dim = pc.n0;
-  const int64_t pc_a = has_pc ? (pc.sign < 0 ? -pc.w.a : pc.w.a) : 0;
+  const S pc_a = has_pc ? (S)(pc.sign < 0 ? -pc.w.a : pc.w.a) : 0;
   const bool pc_hard = pc.w.level == 0;
   const ConsDev& ls = m.cons[SUM_FN >= 0 ? m.fast_ls : 0];
-  const int64_t ls_a = ls.sign < 0 ? -ls.w.a : ls.w.a, ls_b = ls.w.b;
+  // narrow models: |route sum| < 2^30, so a threshold clamped to +-2^30 gives the same excesses
+  const S ls_a = (S)(ls.sign < 0 ? -ls.w.a : ls.w.a);
+  const S ls_b = sizeof(S) == 4 ? clamp_to<S>(ls.w.b, 1ll << 30) : (S)ls.w.b;
   const bool ls_hard = ls.w.level == 0;
   // contiguous chunk per CTA (keeps pull order inside a chunk for the fused forager partials)
   const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
@@ -580,7 +642,7 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     // phase 1: route records + doability
     bool ok[U];
     uint32_t pidx[U], sidx[U];
-    int64_t sums[U], sumd[U];
+    S sums[U], sumd[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t se = cur[u].x, sp = cur[u].y, de = cur[u].z, dp = cur[u].w;
@@ -590,8 +652,8 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
       pidx[u] = ok[u] ? rs.x + sp : 0;
       sidx[u] = ok[u] ? rd.x + de + dp : 0;
       if (SUM_FN >= 0) {
-        sums[u] = (int64_t)(((uint64_t)rs.w << 32) | rs.z);
-        sumd[u] = (int64_t)(((uint64_t)rd.w << 32) | rd.z);
+        sums[u] = sizeof(S) == 4 ? (S)rs.z : (S)(((uint64_t)rs.w << 32) | rs.z);
+        sumd[u] = sizeof(S) == 4 ? (S)rd.z : (S)(((uint64_t)rd.w << 32) | rd.z);
       }
     }
     // phase 2: position / slot records, then the two matrix gathers
@@ -614,39 +676,30 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     for (int u = 0; u < U; ++u) {
       const uint64_t i = base + (uint64_t)u * blockDim.x;
       if (i >= c_hi) continue;
-      int64_t dh = 0, ds = 0;
+      S dh = 0, ds = 0;
       if (has_pc) {
-        const int64_t d = pc_a * (int64_t)((int32_t)p[u].y + m0[u] + m1[u] - (int32_t)sl[u].z);
+        const S d = (S)((US)pc_a * (US)(S)((int32_t)p[u].y + m0[u] + m1[u] - (int32_t)sl[u].z));
         if (pc_hard) dh += d; else ds += d;
       }
       if (SUM_FN >= 0 && cur[u].x != cur[u].z) {
-        const int64_t v = (int32_t)p[u].z;
-        int64_t d = 0;
-        if (SUM_FN == SFGPU_W_EXCESS) {
-          const int64_t e0 = sums[u] - ls_b, e1 = sumd[u] - ls_b;
-          d = (max(e0 - v, (int64_t)0) - max(e0, (int64_t)0)) + (max(e1 + v, (int64_t)0) - max(e1, (int64_t)0));
-          d *= ls_a;
-        } else if (SUM_FN == SFGPU_W_SQUARE) {
-          const int64_t ss = sums[u], sd = sumd[u];
-          d = ls_a * (((ss - v) * (ss - v) - ss * ss) + ((sd + v) * (sd + v) - sd * sd));
-        }  // LINEAR: -a*v + a*v = 0; CONST: the number of routes is unchanged
+        const S d = list_sum_delta<SUM_FN, S, US>(ls_a, ls_b, (S)(int32_t)p[u].z, sums[u], sumd[u]);
         if (ls_hard) dh += d; else ds += d;
       }
-      longlong2 o;
-      o.x = ok[u] ? ch + dh : 0;
-      o.y = ok[u] ? csf + ds : 0;
       if (!FORAGE || out_scores) {
+        longlong2 o;
+        o.x = ok[u] ? ch + (int64_t)dh : 0;
+        o.y = ok[u] ? csf + (int64_t)ds : 0;
         __stcs((longlong2*)out_scores + i, o);
         out_doable[i] = ok[u] ? 1 : 0;
       }
-      if (FORAGE && ok[u] && accept_score(fa.f.acceptor, o.x, o.y, f_lh, f_ls, f_th, f_ts)) {
+      if (FORAGE && ok[u] && accept_delta<S>(fa.f.acceptor, dh, ds, f_lh, f_ls, f_th, f_ts)) {
         t_acc++;
-        if (tb_n == 0 || score_less(tb_h, tb_s, o.x, o.y)) {
-          tb_h = o.x;
-          tb_s = o.y;
+        if (tb_n == 0 || lex_less<S>(tb_h, tb_s, dh, ds)) {
+          tb_h = dh;
+          tb_s = ds;
           tb_n = 1;
           tb_first = (uint32_t)(i - lo);
-        } else if (tb_h == o.x && tb_s == o.y) {
+        } else if (tb_h == dh && tb_s == ds) {
           tb_n++;  // rows of one thread are visited in increasing pull order: tb_first stays the minimum
         }
       }
@@ -657,10 +710,10 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     __shared__ int64_t sh_h[8], sh_s[8];
     __shared__ uint32_t sh_n[8], sh_f[8], sh_a[8];
     for (int o = 16; o > 0; o >>= 1) {
-      const int64_t oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+      const S oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
       const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
       t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
-      if (on && (!tb_n || score_less(tb_h, tb_s, oh, os))) {
+      if (on && (!tb_n || lex_less<S>(tb_h, tb_s, oh, os))) {
         tb_h = oh; tb_s = os; tb_n = on; tb_first = of;
       } else if (on && tb_n && oh == tb_h && os == tb_s) {
         tb_n += on;
@@ -669,7 +722,8 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-      sh_h[warp] = tb_h; sh_s[warp] = tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first; sh_a[warp] = t_acc;
+      sh_h[warp] = ch + (int64_t)tb_h; sh_s[warp] = csf + (int64_t)tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first;
+      sh_a[warp] = t_acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -157,12 +157,35 @@ __device__ __forceinline__ KEY nearby_gen_source(const DevModel& m, const Nearby
   return lane < K ? L : MAXK;
 }
 
-// score of candidate (source f -> slot of `key`) with the fast-path record math; returns the
+// per-launch constants of the fast record math, narrowed once (FastArith)
+template <typename S>
+struct NearbyConsts {
+  S pc_a, ls_a, ls_b;
+  bool pc_hard, ls_hard;
+  uint32_t dim;
+};
+template <int SUM_FN, typename S>
+__device__ __forceinline__ NearbyConsts<S> nearby_consts(const DevModel& m) {
+  NearbyConsts<S> c;
+  const ConsDev& pc = m.cons[m.fast_pc];
+  c.pc_a = (S)(pc.sign < 0 ? -pc.w.a : pc.w.a);
+  c.pc_hard = pc.w.level == 0;
+  c.dim = pc.n0;
+  const ConsDev& ls = m.cons[SUM_FN >= 0 ? m.fast_ls : 0];
+  c.ls_a = (S)(ls.sign < 0 ? -ls.w.a : ls.w.a);
+  c.ls_b = sizeof(S) == 4 ? clamp_to<S>(ls.w.b, 1ll << 30) : (S)ls.w.b;
+  c.ls_hard = ls.w.level == 0;
+  return c;
+}
+
+// score delta of candidate (source f -> slot of `key`) with the fast-path record math; returns the
 // destination (e, dp) too. Identical arithmetic to score_list_change_fast_kernel.
-template <int SUM_FN, typename KEY, typename CELL>
-__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyView& v, const uint32_t scan_bits,
-                                             const KEY key, const uint32_t x, const uint32_t se, const uint4 prec,
-                                             const uint4 rsrc, int64_t& dh, int64_t& ds, uint32_t& de, uint32_t& dp) {
+template <int SUM_FN, typename KEY, typename CELL, typename S>
+__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyConsts<S>& c, const NearbyView& v,
+                                             const uint32_t scan_bits, const KEY key, const uint32_t x,
+                                             const uint32_t se, const uint4 prec, const uint4 rsrc, S& dh, S& ds,
+                                             uint32_t& de, uint32_t& dp) {
+  typedef typename FastArith<CELL>::US US;
   const uint32_t scan = (uint32_t)(key & (((KEY)1 << scan_bits) - 1));
   const uint32_t slen = rsrc.y, g_own = rsrc.x + se;
   const uint32_t g = scan <= slen ? g_own + scan : (scan - (slen + 1) < g_own ? scan - (slen + 1) : scan);
@@ -173,47 +196,35 @@ __device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyView
   dh = 0;
   ds = 0;
   {
-    const ConsDev& pc = m.cons[m.fast_pc];
-    const uint32_t dim = pc.n0;
-    const int64_t pc_a = pc.sign < 0 ? -pc.w.a : pc.w.a;
-    const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * dim;
-    const CELL* __restrict__ mcol = (const CELL*)m.fm_col + (size_t)x * dim;
+    const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * c.dim;
+    const CELL* __restrict__ mcol = (const CELL*)m.fm_col + (size_t)x * c.dim;
     // d(x, b): for a non-append slot b is the slot's reference element, whose distance is in the key
     const int32_t xb = dp < rd.y ? (int32_t)(uint32_t)(key >> scan_bits) : (int32_t)__ldg(mrow + s.y);
     const int32_t ax = (int32_t)__ldg(mcol + s.x);
-    const int64_t d = pc_a * (int64_t)((int32_t)prec.y + ax + xb - (int32_t)s.z);
-    if (pc.w.level == 0) dh += d; else ds += d;
+    const S d = (S)((US)c.pc_a * (US)(S)((int32_t)prec.y + ax + xb - (int32_t)s.z));
+    if (c.pc_hard) dh += d; else ds += d;
   }
   if (SUM_FN >= 0 && se != de) {
-    const ConsDev& ls = m.cons[m.fast_ls];
-    const int64_t ls_a = ls.sign < 0 ? -ls.w.a : ls.w.a, ls_b = ls.w.b;
-    const int64_t val = (int32_t)prec.z;
-    const int64_t ss = (int64_t)(((uint64_t)rsrc.w << 32) | rsrc.z), sd = (int64_t)(((uint64_t)rd.w << 32) | rd.z);
-    int64_t d = 0;
-    if (SUM_FN == SFGPU_W_EXCESS) {
-      const int64_t e0 = ss - ls_b, e1 = sd - ls_b;
-      d = (max(e0 - val, (int64_t)0) - max(e0, (int64_t)0)) + (max(e1 + val, (int64_t)0) - max(e1, (int64_t)0));
-      d *= ls_a;
-    } else if (SUM_FN == SFGPU_W_SQUARE) {
-      d = ls_a * (((ss - val) * (ss - val) - ss * ss) + ((sd + val) * (sd + val) - sd * sd));
-    }
-    if (ls.w.level == 0) dh += d; else ds += d;
+    const S ss = sizeof(S) == 4 ? (S)rsrc.z : (S)(((uint64_t)rsrc.w << 32) | rsrc.z);
+    const S sd = sizeof(S) == 4 ? (S)rd.z : (S)(((uint64_t)rd.w << 32) | rd.z);
+    const S d = list_sum_delta<SUM_FN, S, US>(c.ls_a, c.ls_b, (S)(int32_t)prec.z, ss, sd);
+    if (c.ls_hard) dh += d; else ds += d;
   }
 }
 
-// warp-level lexicographic max of (dh, ds) over the lanes with `acc`: returns the multiplicity
-// mask of the best; `any` = at least one accepted lane. Narrow models use two REDUX instructions.
-__device__ __forceinline__ uint32_t warp_best_mask(const DevModel& m, bool acc, int64_t dh, int64_t ds, uint32_t& accm) {
+// warp-level lexicographic max of the deltas (dh, ds) over the lanes with `acc`: returns the
+// multiplicity mask of the best; accm = accepted lanes. 32-bit deltas use two REDUX instructions.
+__device__ __forceinline__ uint32_t warp_best_mask(bool acc, int32_t dh, int32_t ds, uint32_t& accm) {
   accm = __ballot_sync(0xffffffffu, acc);
   if (!accm) return 0;
-  if (m.fast_narrow) {
-    const int32_t h32 = acc ? (int32_t)dh : INT32_MIN;
-    const int32_t bh = __reduce_max_sync(0xffffffffu, h32);
-    const bool top = acc && (int32_t)dh == bh;
-    const int32_t s32 = top ? (int32_t)ds : INT32_MIN;
-    const int32_t bs = __reduce_max_sync(0xffffffffu, s32);
-    return __ballot_sync(0xffffffffu, top && (int32_t)ds == bs);
-  }
+  const int32_t bh = __reduce_max_sync(0xffffffffu, acc ? dh : INT32_MIN);
+  const bool top = acc && dh == bh;
+  const int32_t bs = __reduce_max_sync(0xffffffffu, top ? ds : INT32_MIN);
+  return __ballot_sync(0xffffffffu, top && ds == bs);
+}
+__device__ __forceinline__ uint32_t warp_best_mask(bool acc, int64_t dh, int64_t ds, uint32_t& accm) {
+  accm = __ballot_sync(0xffffffffu, acc);
+  if (!accm) return 0;
   int64_t bh = dh, bs = ds;
   uint32_t any = acc ? 1 : 0;
   for (int o = 16; o > 0; o >>= 1) {
@@ -253,19 +264,20 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
   v.pr = (const uint4*)(smem + m.off_pos_rec);
   v.sr = (const uint4*)(smem + m.off_slot_rec);
   v.pos_of = (const uint32_t*)(smem + m.off_pos_of);
+  typedef typename FastArith<CELL>::S S;
   const int64_t* cs = (const int64_t*)(smem + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
   if (threadIdx.x == 0) s_count = nearby_count(m, v.rr, a.max_nearby);
   __syncthreads();
   const uint32_t count = s_count;
   const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;  // routed elements
-  int64_t lh = 0, ls = 0, th = 0, ts = 0;
-  if (a.ref_scores) {
-    lh = a.ref_scores[r * 4 + 0];
-    ls = a.ref_scores[r * 4 + 1];
-    th = a.ref_scores[r * 4 + 2];
-    ts = a.ref_scores[r * 4 + 3];
-  }
+  // acceptor references as thresholds on the score delta (rel_threshold)
+  S lh, ls, th, ts;
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 0] : 0, ch, lh);
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 1] : 0, csf, ls);
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 2] : 0, ch, th);
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 3] : 0, csf, ts);
+  const NearbyConsts<S> nc = nearby_consts<SUM_FN, S>(m);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
   const uint32_t c_lo = per * blockIdx.x, c_hi = min(c_lo + per, total);
@@ -290,17 +302,16 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
     const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, a.max_nearby, lane, s_buf[warp], x, se, sp,
                                                  prec, rsrc);
     const bool have = lane < count && key != KeyTraits<KEY>::maxkey();
-    int64_t dh = 0, ds = 0;
+    S dh = 0, ds = 0;
     uint32_t de = 0, dp = 0;
-    if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
-    const int64_t oh = ch + dh, os = csf + ds;
-    const bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+    if (have) nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    const bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
     uint32_t accm;
-    const uint32_t eq = warp_best_mask(m, acc, dh, ds, accm);
+    const uint32_t eq = warp_best_mask(acc, dh, ds, accm);
     if (lane == (eq ? __ffs(eq) - 1 : 0)) {
       SrcPartial p;
-      p.best_h = eq ? oh : 0;
-      p.best_s = eq ? os : 0;
+      p.best_h = eq ? ch + (int64_t)dh : 0;
+      p.best_s = eq ? csf + (int64_t)ds : 0;
       p.n_best = __popc(eq);
       p.n_accepted = __popc(accm);
       p.first_lane = eq ? __ffs(eq) - 1 : 0;
@@ -313,8 +324,8 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
       ((uint4*)a.out_rows)[q] = have ? make_uint4(se, sp, de, dp) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
       if (a.out_scores) {
         longlong2 o2;
-        o2.x = have ? oh : 0;
-        o2.y = have ? os : 0;
+        o2.x = have ? ch + (int64_t)dh : 0;
+        o2.y = have ? csf + (int64_t)ds : 0;
         ((longlong2*)a.out_scores)[q] = o2;
         a.out_doable[q] = have ? 1 : 0;
       }
@@ -348,13 +359,13 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
   const int64_t ch = cs[0], csf = cs[1];
   const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;
   const SrcPartial* P = a.partials + (size_t)r * m.elem_cap;
-  int64_t lh = 0, ls = 0, th = 0, ts = 0;
-  if (a.ref_scores) {
-    lh = a.ref_scores[r * 4 + 0];
-    ls = a.ref_scores[r * 4 + 1];
-    th = a.ref_scores[r * 4 + 2];
-    ts = a.ref_scores[r * 4 + 3];
-  }
+  typedef typename FastArith<CELL>::S S;
+  S lh, ls, th, ts;
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 0] : 0, ch, lh);
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 1] : 0, csf, ls);
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 2] : 0, ch, th);
+  rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 3] : 0, csf, ts);
+  const NearbyConsts<S> nc = nearby_consts<SUM_FN, S>(m);
   if (threadIdx.x == 0) {
     s_count = nearby_count(m, v.rr, a.max_nearby);
     s_fcut = total;       // sources [0, s_fcut) count fully; source s_fcut only up to lane s_lcut
@@ -389,11 +400,11 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
       const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, lane, s_buf, x, se, sp,
                                                    prec, rsrc);
       const bool have = lane < count && key != KeyTraits<KEY>::maxkey();
-      int64_t dh = 0, ds = 0;
+      S dh = 0, ds = 0;
       uint32_t de = 0, dp = 0;
-      if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
-      const int64_t oh = ch + dh, os = csf + ds;
-      bool acc = have && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+      if (have) nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+      const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
+      bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
       const uint32_t cut_rank = s_lcut;  // read by every lane before one lane overwrites it below
       __syncwarp();
       uint32_t mm = __ballot_sync(0xffffffffu, acc);
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
       const uint32_t cut_lane = __ffs(mm) - 1;
       acc = acc && lane <= cut_lane;
       uint32_t accm;
-      const uint32_t eq = warp_best_mask(m, acc, dh, ds, accm);
+      const uint32_t eq = warp_best_mask(acc, dh, ds, accm);
       if (lane == (eq ? __ffs(eq) - 1 : 0)) {
         s_cutp.best_h = oh;
         s_cutp.best_s = os;
@@ -521,11 +532,11 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, lane, s_buf, x, se, sp, prec,
                                                  rsrc);
     const bool have = lane < count && key != KeyTraits<KEY>::maxkey() && !(fstar == fcut && lane > s_lcut);
-    int64_t dh = 0, ds = 0;
+    S dh = 0, ds = 0;
     uint32_t de = 0, dp = 0;
-    if (have) nearby_score<SUM_FN, KEY, CELL>(m, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
-    const int64_t oh = ch + dh, os = csf + ds;
-    const bool hit = have && oh == bh && os == bs && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts);
+    if (have) nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
+    const bool hit = have && oh == bh && os == bs && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
     uint32_t mm = __ballot_sync(0xffffffffu, hit);
     for (uint32_t t = 1; t < j; ++t) mm &= mm - 1;
     const uint32_t wl = __ffs(mm) - 1;
