@@ -120,3 +120,47 @@ def test_scalar_extremes():
             assert int(idx[0]) == out[1]
         else:
             assert idx[0] == 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("scale", [1, 100, 150000])
+def test_arithmetic_width_paths_and_far_acceptor_references(scale):
+    """scale 1: uint16 cells + 32-bit deltas; 100: int32 cells + 64-bit deltas (cost >= 65536);
+    150000: costs near the 2^28 fast-path limit. Acceptor references far outside the int32 delta range
+    exercise the clamped relative thresholds."""
+    c = instances.cvrp(90, 7, seed=21)
+    c.matrix = c.matrix * scale
+    R, K = 2, 20
+    starts = [instances.perturb_routes(c, 5 + r, 30) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    base = d.calculate_score()
+    for r in range(R):
+        assert base[r].tolist() == oracles[r].committed_score().tolist()
+    gen = []
+    for r in range(R):
+        rows = oracles[r].enumerate_nearby_list_change(K)
+        so, oko = oracles[r].score_list_change(rows)
+        gen.append((rows, so, oko))
+    # materialised scoring path
+    allrows = np.concatenate([g[0] for g in gen])
+    offs = np.cumsum([0] + [len(g[0]) for g in gen]).astype(np.uint64)
+    s, ok = d.score_list_change(allrows, offs)
+    assert np.array_equal(s, np.concatenate([g[1] for g in gen])) and ok.all()
+    far = 1 << 45
+    refs = [np.array([0, -far, 0, -far]), np.array([0, far, 0, far]), np.array([-3, far, 3, -far]),
+            np.array([0, -7 * scale, 0, -19 * scale]), np.array([far, 0, -far, 0])]
+    for ref_d in refs:
+        for acceptor, okind in ((1, 0), (2, 1)):
+            ref = np.stack([np.concatenate([base[r], base[r]]) + ref_d for r in range(R)])
+            idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(acceptor, 1, 0), step_seeds=[3] * R,
+                                                           ref_scores=ref)
+            for r in range(R):
+                rows, so, oko = gen[r]
+                out = oracle_lib.replay_step(so, oko, [0, 0], ref[r][:2], ref[r][2:], 3, 2, 1, True, okind)
+                what = f"scale={scale} ref={ref_d.tolist()} acc={acceptor} r={r}"
+                if out[0]:
+                    assert int(idx[r]) == out[1], what
+                    assert best[r].tolist() == so[out[1]].tolist(), what
+                    assert win[r].tolist() == rows[out[1]].tolist(), what
+                else:
+                    assert idx[r] == 0xFFFFFFFF, what
