@@ -79,6 +79,8 @@ pub struct sfgpu_solve_params {
     pub seed_base: u64,
     pub restore_best: i32,
     pub reserved: i32,
+    pub acceptor_real: f64,
+    pub step_count_limit: u64,
 }
 
 extern "C" {

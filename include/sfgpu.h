@@ -199,11 +199,17 @@ int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candida
 /* ---- winner selection on device ------------------------------------------------------- */
 /* Per replica: replay of acceptor + forager over the scored rows in pull order
  * (phase/candidates.rs:66-282 with BestCandidate::consider, forager.rs:99-155).
- * acceptor: 0 = accept every doable candidate, 1 = HillClimbing (score > last_step_score),
- *           2 = LateAcceptance (score >= last_step_score || score >= late_score)
+ * acceptor: 0 = accept every doable candidate, 1 = HillClimbing (score > last_step_score,
+ *           acceptor/hill_climbing.rs:33-42), 2 = LateAcceptance form (score >= last_step_score ||
+ *           score >= threshold, late_acceptance.rs:89-101), 3 = GreatDeluge form (score >
+ *           last_step_score || score >= threshold, great_deluge.rs:53-68). The stateful acceptors reduce
+ *           to these per step: StepCountingHillClimbing = 0 or 1 (step_counting.rs:56-67);
+ *           DiversifiedLateAcceptance = 2 with threshold min(late score, best - |best| * tolerance)
+ *           (diversified_late_acceptance.rs:72-101). Tabu and SimulatedAnnealing need per-move metadata /
+ *           a random stream: they replay on the host over the materialised scores.
  * forager : accepted_limit 0 = BestScore (never quits early); N > 0 = AcceptedCount(N)
  * tie_mode: 0 = ScoreTieBreak::First, 1 = reservoir (random_ties)
- * ref_scores[R][2][2] = {last_step_score, late_score}; step_seeds[R].
+ * ref_scores[R][2][2] = {last_step_score, threshold (late score / water level)}; step_seeds[R].
  * out_index[R] = winning pull index inside the replica's range, or UINT32_MAX when none accepted;
  * out_best[R][2] its score; out_evaluated[R] = moves_evaluated (pulls up to the quit point). */
 typedef struct sfgpu_forage_params {
@@ -262,7 +268,10 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
 /* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
  * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.
- * acceptor: 1 HillClimbing, 2 LateAcceptance(late_size). The reference draws step seeds from
+ * acceptor: 1 HillClimbing, 2 LateAcceptance(late_size), 3 GreatDeluge(acceptor_real = rain_speed),
+ * 4 StepCountingHillClimbing(step_count_limit), 5 DiversifiedLateAcceptance(late_size, acceptor_real =
+ * tolerance) — acceptor/{hill_climbing,late_acceptance,great_deluge,step_counting,
+ * diversified_late_acceptance}.rs, state kept per replica on the device. The reference draws step seeds from
  * rand::StdRng (unpinned third-party stream); here step t of replica r uses
  * splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t), so a trajectory is reproducible and each of its
  * steps can be checked against the oracle, but it is not the reference's trajectory.
@@ -279,6 +288,8 @@ typedef struct sfgpu_solve_params {
   uint64_t seed_base;
   int32_t restore_best;
   int32_t reserved;
+  double acceptor_real;      /* GreatDeluge rain_speed / DiversifiedLateAcceptance tolerance */
+  uint64_t step_count_limit; /* StepCountingHillClimbing */
 } sfgpu_solve_params;
 int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* params, int64_t* out_best_scores,
                                        uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps);

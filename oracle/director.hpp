@@ -545,12 +545,43 @@ struct Forager {  // forager.rs:167-425, forager/improving.rs:17-227
   }
 };
 
-enum class AcceptorKind { HillClimbing, LateAcceptance, SimulatedAnnealing, AcceptAll };
+// Tabu metadata of a move (heuristic/move/metadata.rs:12-107). The reference hashes variable names and
+// Debug-formatted values with SipHash (DefaultHasher) into u64 ids; the ids are only ever compared for
+// equality, so this restatement uses the raw indices (injective) and a numeric scope id instead.
+struct TabuSignature {
+  uint64_t scope = 0;  // (descriptor_index, variable) pair
+  std::vector<uint64_t> entity_ids, value_ids;
+  std::vector<uint64_t> move_id, undo_move_id;
+};
+static constexpr uint64_t TABU_NONE_ID = UINT64_MAX;            // metadata.rs:7
+static constexpr uint64_t TABU_OP_SWAP = 0xF000000000000001ull;  // metadata.rs:150
+
+// TabuMemory (tabu_search.rs:64-101): FIFO of at most `tenure` entries; tenure 0 = dimension off.
+template <class T>
+struct TabuMemory {
+  size_t tenure = 0;
+  std::vector<T> entries;
+  bool contains(const T& e) const {
+    for (const T& x : entries)
+      if (x == e) return true;
+    return false;
+  }
+  void record(const T& e) {
+    if (!tenure) return;
+    if (entries.size() >= tenure) entries.erase(entries.begin());
+    entries.push_back(e);
+  }
+};
+
+enum class AcceptorKind {
+  HillClimbing, LateAcceptance, SimulatedAnnealing, AcceptAll,
+  GreatDeluge, StepCountingHillClimbing, DiversifiedLateAcceptance, TabuSearch
+};
 
 template <class Sc>
 struct Acceptor {
   AcceptorKind kind = AcceptorKind::HillClimbing;
-  // LateAcceptance (late_acceptance.rs:89-126)
+  // LateAcceptance (late_acceptance.rs:89-126) and DiversifiedLateAcceptance share the ring
   std::vector<Sc> history;
   size_t history_idx = 0;
   // SimulatedAnnealing (simulated_annealing.rs): the uniform stream is injected by the caller
@@ -563,9 +594,25 @@ struct Acceptor {
   std::vector<size_t> sample_count;
   bool calibrated = false;
   bool never_accept_hard_regression = false;
+  // GreatDeluge (great_deluge.rs:52-101)
+  double rain_speed = 0.001;
+  bool has_water = false;
+  Sc water_level = Sc::zero(), initial_abs_score = Sc::zero();
+  // StepCountingHillClimbing (step_counting.rs:55-104)
+  uint64_t step_count_limit = 100, steps_since_improvement = 0;
+  // DiversifiedLateAcceptance (diversified_late_acceptance.rs:71-140) and TabuSearch aspiration
+  double tolerance = 0.01;
+  bool has_best = false;
+  Sc best_score = Sc::zero();
+  // TabuSearch (tabu_search.rs:103-237); a zero tenure disables the dimension (Option::None)
+  TabuMemory<std::pair<uint64_t, uint64_t>> entity_memory, value_memory;  // (scope, id) tokens
+  TabuMemory<std::vector<uint64_t>> move_memory, reverse_move_memory;
+  bool aspiration_enabled = true;
+
+  bool requires_move_signatures() const { return kind == AcceptorKind::TabuSearch; }
 
   void phase_started(Sc initial, size_t late_size = 400) {
-    if (kind == AcceptorKind::LateAcceptance) {
+    if (kind == AcceptorKind::LateAcceptance || kind == AcceptorKind::DiversifiedLateAcceptance) {
       history.assign(late_size, initial);
       history_idx = 0;
     }
@@ -575,12 +622,67 @@ struct Acceptor {
       sample_count.assign(Sc::levels, 0);
       calibrated = false;
     }
+    if (kind == AcceptorKind::GreatDeluge) {
+      has_water = true;
+      water_level = initial;
+      initial_abs_score = initial.abs();
+    }
+    if (kind == AcceptorKind::StepCountingHillClimbing) steps_since_improvement = 0;
+    if (kind == AcceptorKind::TabuSearch) {
+      entity_memory.entries.clear();
+      value_memory.entries.clear();
+      move_memory.entries.clear();
+      reverse_move_memory.entries.clear();
+    }
+    has_best = true;
+    best_score = initial;
   }
-  bool is_accepted(Sc last, Sc mv) {
+  void phase_ended() {
+    if (kind == AcceptorKind::GreatDeluge) has_water = false;  // great_deluge.rs:87-90
+    if (kind == AcceptorKind::StepCountingHillClimbing) {      // step_counting.rs:92-95
+      has_best = false;
+      steps_since_improvement = 0;
+    }
+    if (kind == AcceptorKind::TabuSearch) {  // tabu_search.rs:196-202
+      entity_memory.entries.clear();
+      value_memory.entries.clear();
+      move_memory.entries.clear();
+      reverse_move_memory.entries.clear();
+      has_best = false;
+    }
+  }
+  bool is_tabu(const TabuSignature& sig) const {  // tabu_search.rs:150-162
+    for (uint64_t e : sig.entity_ids)
+      if (entity_memory.contains({sig.scope, e})) return true;
+    for (uint64_t v : sig.value_ids)
+      if (value_memory.contains({sig.scope, v})) return true;
+    return move_memory.contains(sig.move_id) || reverse_move_memory.contains(sig.move_id);
+  }
+  bool is_accepted(Sc last, Sc mv, const TabuSignature* sig = nullptr) {
     switch (kind) {
       case AcceptorKind::AcceptAll: return true;
       case AcceptorKind::HillClimbing: return mv > last;  // hill_climbing.rs:33-42
       case AcceptorKind::LateAcceptance: return mv >= last || mv >= history[history_idx];
+      case AcceptorKind::GreatDeluge:  // great_deluge.rs:53-68
+        if (mv > last) return true;
+        return has_water ? mv >= water_level : true;
+      case AcceptorKind::StepCountingHillClimbing:  // step_counting.rs:56-67
+        if (mv > last) return true;
+        return steps_since_improvement < step_count_limit;
+      case AcceptorKind::DiversifiedLateAcceptance: {  // diversified_late_acceptance.rs:72-101
+        if (mv >= last) return true;
+        if (mv >= history[history_idx]) return true;
+        if (has_best) {
+          Sc threshold = best_score - best_score.abs().multiply(tolerance);
+          if (mv >= threshold) return true;
+        }
+        return false;
+      }
+      case AcceptorKind::TabuSearch: {  // tabu_search.rs:170-186
+        if (!sig) throw std::logic_error("tabu search requires move signatures");
+        bool aspirational = has_best && aspiration_enabled && mv > best_score;
+        return aspirational || !is_tabu(*sig);
+      }
       case AcceptorKind::SimulatedAnnealing: {
         if (mv >= last) return true;
         int lvl = 0;
@@ -608,13 +710,35 @@ struct Acceptor {
     }
     return false;
   }
-  void step_ended(Sc step_score) {
-    if (kind == AcceptorKind::LateAcceptance) {
+  void step_ended(Sc step_score, const TabuSignature* accepted = nullptr) {
+    if (kind == AcceptorKind::LateAcceptance || kind == AcceptorKind::DiversifiedLateAcceptance) {
       history[history_idx] = step_score;
       history_idx = (history_idx + 1) % history.size();
     }
     if (kind == AcceptorKind::SimulatedAnnealing && calibrated)
       for (auto& t : level_temperature) t = std::max(t * decay, hill_climbing_temperature);
+    if (kind == AcceptorKind::GreatDeluge && has_water)  // great_deluge.rs:76-85
+      water_level = water_level + initial_abs_score.multiply(rain_speed);
+    if (kind == AcceptorKind::StepCountingHillClimbing) {  // step_counting.rs:74-90
+      if (!has_best || step_score > best_score) {
+        has_best = true;
+        best_score = step_score;
+        steps_since_improvement = 0;
+      } else {
+        steps_since_improvement += 1;
+      }
+      return;
+    }
+    if (kind == AcceptorKind::TabuSearch && accepted) {  // tabu_search.rs:214-225
+      for (uint64_t e : accepted->entity_ids) entity_memory.record({accepted->scope, e});
+      for (uint64_t v : accepted->value_ids) value_memory.record({accepted->scope, v});
+      move_memory.record(accepted->move_id);
+      reverse_move_memory.record(accepted->undo_move_id);
+    }
+    if (!has_best || step_score > best_score) {  // DLA :126-133, tabu :227-234
+      has_best = true;
+      best_score = step_score;
+    }
   }
 };
 
@@ -627,9 +751,71 @@ struct StepOutcome {
   uint64_t moves_evaluated = 0, score_calculations = 0, moves_accepted = 0;
 };
 
-template <class Sc, class GetEval>
+struct NoSignatures {
+  const TabuSignature* operator()(size_t) const { return nullptr; }
+};
+
+// tabu_signature of the scalar and list moves against the CURRENT working solution
+// (change.rs:189-220, swap.rs:228-260, list_kernel/change.rs:155-204, list_kernel/swap.rs:110-155).
+// Value ids: the reference hashes the Debug form of the value; raw index (None = NONE_ID) here.
+template <class S, class Sc>
+TabuSignature tabu_signature(const Move& m, ScoreDirector<S, Sc>& dir, uint64_t variable_id = 0) {
+  S& s = dir.working;
+  auto& ac = dir.access;
+  auto vid = [](OptVal v) { return v ? (uint64_t)*v : TABU_NONE_ID; };
+  TabuSignature sig;
+  sig.scope = ((uint64_t)m.desc << 32) | variable_id;
+  switch (m.kind) {
+    case Move::Change: {
+      const uint64_t from = vid(ac.get(s, m.desc, m.a)), to = vid(m.to);
+      sig.move_id = {(uint64_t)m.desc, variable_id, (uint64_t)m.a, from, to};
+      sig.undo_move_id = {(uint64_t)m.desc, variable_id, (uint64_t)m.a, to, from};
+      sig.entity_ids = {(uint64_t)m.a};
+      sig.value_ids = {to};
+      return sig;
+    }
+    case Move::Swap: {
+      const uint64_t lv = vid(ac.get(s, m.desc, m.a)), rv = vid(ac.get(s, m.desc, m.b));
+      const uint64_t lo = std::min<uint64_t>(m.a, m.b), hi = std::max<uint64_t>(m.a, m.b);
+      sig.move_id = {TABU_OP_SWAP, (uint64_t)m.desc, variable_id, lo, hi};
+      sig.undo_move_id = sig.move_id;
+      sig.entity_ids = {(uint64_t)m.a, (uint64_t)m.b};
+      sig.value_ids = {rv, lv};
+      return sig;
+    }
+    case Move::ListChange: {
+      const auto& src = ac.list(s, m.desc, m.a);
+      const uint64_t moved = m.b < src.size() ? (uint64_t)src[m.b] : TABU_NONE_ID;
+      const uint64_t adj = adjusted_destination(m);
+      sig.move_id = {(uint64_t)m.desc, variable_id, (uint64_t)m.a, (uint64_t)m.b, (uint64_t)m.c, adj, moved};
+      sig.undo_move_id = {(uint64_t)m.desc, variable_id, (uint64_t)m.c, adj, (uint64_t)m.a, (uint64_t)m.b, moved};
+      sig.entity_ids = {(uint64_t)m.a};
+      if (m.a != m.c) sig.entity_ids.push_back((uint64_t)m.c);
+      sig.value_ids = {moved};
+      return sig;
+    }
+    case Move::ListSwap: {
+      const auto& l1 = ac.list(s, m.desc, m.a);
+      const uint64_t v1 = m.b < l1.size() ? (uint64_t)l1[m.b] : TABU_NONE_ID;
+      const auto& l2 = ac.list(s, m.desc, m.c);
+      const uint64_t v2 = m.d < l2.size() ? (uint64_t)l2[m.d] : TABU_NONE_ID;
+      std::pair<uint64_t, uint64_t> p1{m.a, m.b}, p2{m.c, m.d};
+      if (p2 < p1) std::swap(p1, p2);
+      sig.move_id = {0xF000000000000003ull, (uint64_t)m.desc, variable_id, p1.first, p1.second, p2.first, p2.second};
+      sig.undo_move_id = sig.move_id;
+      sig.entity_ids = {(uint64_t)m.a};
+      if (m.a != m.c) sig.entity_ids.push_back((uint64_t)m.c);
+      sig.value_ids = {v2, v1};
+      return sig;
+    }
+    default: throw std::logic_error("tabu_signature: move kind not restated");
+  }
+}
+
+template <class Sc, class GetEval, class GetSig = NoSignatures>
 StepOutcome<Sc> replay_step(size_t n_candidates, GetEval eval, Sc best_score, Sc last_step_score,
-                            uint64_t step_seed, Forager<Sc>& forager, Acceptor<Sc>& acceptor) {
+                            uint64_t step_seed, Forager<Sc>& forager, Acceptor<Sc>& acceptor,
+                            GetSig signature = GetSig()) {
   StepOutcome<Sc> out;
   forager.step_started(best_score, last_step_score, step_seed);
   for (size_t i = 0; i < n_candidates; ++i) {
@@ -639,7 +825,7 @@ StepOutcome<Sc> replay_step(size_t n_candidates, GetEval eval, Sc best_score, Sc
     if (ev.kind == EvalKind::NotDoable) continue;
     out.score_calculations += 1;
     if (ev.kind != EvalKind::Scored) continue;
-    if (acceptor.is_accepted(last_step_score, ev.score)) {
+    if (acceptor.is_accepted(last_step_score, ev.score, signature(i))) {
       out.moves_accepted += 1;
       forager.add_move_index(i, ev.score);
     }

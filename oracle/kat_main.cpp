@@ -633,6 +633,204 @@ static void kat_moves_and_loop() {
   CHECK(out.has_winner && out.winner == 1);
 }
 
+// ---------------------------------------------------------------- acceptors
+// solverforge-solver/src/phase/localsearch/acceptor/{tests.rs, great_deluge/tests.rs,
+// step_counting/tests.rs, diversified_late_acceptance/tests.rs}
+static TabuSignature kat_sig(uint64_t scope, std::vector<uint64_t> ent, std::vector<uint64_t> val,
+                             std::vector<uint64_t> mv, std::vector<uint64_t> undo) {
+  TabuSignature t;
+  t.scope = scope;
+  t.entity_ids = std::move(ent);
+  t.value_ids = std::move(val);
+  t.move_id = std::move(mv);
+  t.undo_move_id = std::move(undo);
+  return t;
+}
+static Acceptor<SoftScore> kat_tabu(size_t e, size_t v, size_t m, size_t u, bool aspiration) {
+  Acceptor<SoftScore> a;
+  a.kind = AcceptorKind::TabuSearch;
+  a.entity_memory.tenure = e;
+  a.value_memory.tenure = v;
+  a.move_memory.tenure = m;
+  a.reverse_move_memory.tenure = u;
+  a.aspiration_enabled = aspiration;
+  return a;
+}
+static void kat_acceptors() {
+  auto S = [](int64_t v) { return SoftScore::of(v); };
+  {  // tests.rs:82-111 hill climbing; :113-121 late acceptance
+    Acceptor<SoftScore> hc;
+    hc.kind = AcceptorKind::HillClimbing;
+    CHECK(hc.is_accepted(S(-10), S(-5)));
+    CHECK(!hc.is_accepted(S(-5), S(-10)));
+    CHECK(!hc.is_accepted(S(-5), S(-5)));
+    Acceptor<SoftScore> la;
+    la.kind = AcceptorKind::LateAcceptance;
+    la.phase_started(S(-10), 5);
+    CHECK(la.is_accepted(S(-10), S(-5)));
+    CHECK(la.is_accepted(S(-10), S(-10)));
+    CHECK(!la.is_accepted(S(-10), S(-15)));
+  }
+  {  // great_deluge/tests.rs:22-77
+    Acceptor<SoftScore> gd;
+    gd.kind = AcceptorKind::GreatDeluge;
+    gd.rain_speed = 0.001;
+    gd.phase_started(S(-100));
+    CHECK(gd.is_accepted(S(-100), S(-50)));
+    CHECK(gd.is_accepted(S(-100), S(-100)));
+    CHECK(gd.is_accepted(S(-100), S(-90)));
+    CHECK(!gd.is_accepted(S(-100), S(-110)));
+    Acceptor<SoftScore> g2;
+    g2.kind = AcceptorKind::GreatDeluge;
+    g2.rain_speed = 0.1;
+    g2.phase_started(S(-100));
+    CHECK(g2.is_accepted(S(-100), S(-100)));
+    CHECK(!g2.is_accepted(S(-100), S(-101)));
+    g2.step_ended(S(-100));  // water -100 + round(100 * 0.1) = -90
+    CHECK(g2.is_accepted(S(-90), S(-90)));
+    CHECK(!g2.is_accepted(S(-90), S(-91)));
+    g2.step_ended(S(-90));
+    CHECK(g2.is_accepted(S(-80), S(-80)));
+    CHECK(!g2.is_accepted(S(-80), S(-81)));
+    g2.phase_ended();
+    g2.phase_started(S(-50));
+    CHECK(g2.is_accepted(S(-50), S(-50)));
+    CHECK(!g2.is_accepted(S(-50), S(-51)));
+  }
+  {  // step_counting/tests.rs:22-101
+    Acceptor<SoftScore> sc;
+    sc.kind = AcceptorKind::StepCountingHillClimbing;
+    sc.step_count_limit = 5;
+    sc.phase_started(S(-100));
+    CHECK(sc.is_accepted(S(-100), S(-50)));
+    CHECK(sc.is_accepted(S(-100), S(-110)));
+    Acceptor<SoftScore> s3;
+    s3.kind = AcceptorKind::StepCountingHillClimbing;
+    s3.step_count_limit = 3;
+    s3.phase_started(S(-100));
+    CHECK(s3.is_accepted(S(-100), S(-110)));
+    s3.step_ended(S(-110));
+    CHECK(s3.is_accepted(S(-110), S(-120)));
+    s3.step_ended(S(-120));
+    CHECK(s3.is_accepted(S(-120), S(-130)));
+    s3.step_ended(S(-130));
+    CHECK(!s3.is_accepted(S(-130), S(-140)));
+    s3.phase_started(S(-100));  // test_resets_on_improvement
+    s3.step_ended(S(-110));
+    s3.step_ended(S(-120));
+    CHECK(s3.steps_since_improvement == 2);
+    s3.step_ended(S(-50));
+    CHECK(s3.steps_since_improvement == 0);
+    s3.step_ended(S(-60));
+    s3.step_ended(S(-70));
+    CHECK(s3.is_accepted(S(-70), S(-80)));
+    Acceptor<SoftScore> s2;
+    s2.kind = AcceptorKind::StepCountingHillClimbing;
+    s2.step_count_limit = 2;
+    s2.phase_started(S(-100));
+    s2.step_ended(S(-110));
+    s2.step_ended(S(-120));
+    CHECK(!s2.is_accepted(S(-120), S(-130)));
+    CHECK(s2.is_accepted(S(-120), S(-50)));
+    s2.phase_ended();
+    s2.phase_started(S(-200));
+    CHECK(s2.steps_since_improvement == 0);
+  }
+  {  // diversified_late_acceptance/tests.rs:17-77
+    Acceptor<SoftScore> d;
+    d.kind = AcceptorKind::DiversifiedLateAcceptance;
+    d.tolerance = 0.1;
+    d.phase_started(S(-100), 5);
+    CHECK(d.is_accepted(S(-100), S(-90)));
+    d.phase_started(S(-100), 3);
+    CHECK(d.is_accepted(S(-90), S(-100)));  // equals the late score
+    d.step_ended(S(-80));
+    d.step_ended(S(-70));
+    d.step_ended(S(-60));
+    CHECK(d.is_accepted(S(-60), S(-65)));  // best -60, threshold -60 - round(6.0) = -66
+    CHECK(d.is_accepted(S(-60), S(-75)));  // history cycled: late = -80
+    Acceptor<SoftScore> d2;
+    d2.kind = AcceptorKind::DiversifiedLateAcceptance;
+    d2.tolerance = 0.05;
+    d2.phase_started(S(-100), 3);
+    d2.step_ended(S(-40));
+    d2.step_ended(S(-40));
+    d2.step_ended(S(-40));
+    CHECK(!d2.is_accepted(S(-40), S(-50)));  // threshold -42
+  }
+  {  // tests.rs:123-137 entity tabu + aspiration
+    auto a = kat_tabu(3, 0, 0, 0, true);
+    auto first = kat_sig(1, {7}, {}, {10}, {11}), second = kat_sig(1, {7}, {}, {12}, {13});
+    a.phase_started(S(-10));
+    a.step_ended(S(-9), &first);
+    CHECK(!a.is_accepted(S(-9), S(-9), &second));
+    CHECK(a.is_accepted(S(-9), S(-5), &second));
+  }
+  {  // tests.rs:139-150 value tabu
+    auto a = kat_tabu(0, 2, 0, 0, false);
+    auto first = kat_sig(1, {}, {42}, {10}, {11}), second = kat_sig(1, {}, {42}, {12}, {13});
+    a.phase_started(S(-10));
+    a.step_ended(S(-9), &first);
+    CHECK(!a.is_accepted(S(-9), S(-8), &second));
+  }
+  {  // tests.rs:152-166 exact move + undo move
+    auto a = kat_tabu(0, 0, 2, 2, false);
+    auto committed = kat_sig(1, {}, {}, {10, 20}, {30, 40});
+    auto exact = kat_sig(1, {}, {}, {10, 20}, {99}), undo = kat_sig(1, {}, {}, {30, 40}, {10, 20});
+    a.phase_started(S(-10));
+    a.step_ended(S(-9), &committed);
+    CHECK(!a.is_accepted(S(-9), S(-8), &exact));
+    CHECK(!a.is_accepted(S(-9), S(-8), &undo));
+  }
+  {  // tests.rs:168-186 undo memory matches the candidate's move identity
+    auto a = kat_tabu(0, 0, 0, 2, false);
+    auto committed = kat_sig(1, {}, {}, {10}, {20}), reverse = kat_sig(1, {}, {}, {20}, {10});
+    auto unrelated = kat_sig(1, {}, {}, {30}, {20});
+    a.phase_started(S(-10));
+    a.step_ended(S(-9), &committed);
+    CHECK(!a.is_accepted(S(-9), S(-8), &reverse));
+    CHECK(a.is_accepted(S(-9), S(-8), &unrelated));
+  }
+  {  // tests.rs:188-201 signatures required; :203-218 memories cleared at phase end
+    auto a = kat_tabu(1, 0, 0, 0, true);
+    a.phase_started(S(-10));
+    bool threw = false;
+    try {
+      a.is_accepted(S(-10), S(-9), nullptr);
+    } catch (const std::logic_error&) {
+      threw = true;
+    }
+    CHECK(threw);
+    CHECK(a.requires_move_signatures());
+    auto b = kat_tabu(1, 1, 1, 1, false);
+    auto sig = kat_sig(1, {1}, {2}, {3}, {4});
+    b.phase_started(S(-10));
+    b.step_ended(S(-9), &sig);
+    CHECK(!b.is_accepted(S(-9), S(-8), &sig));
+    b.phase_ended();
+    b.phase_started(S(-10));
+    CHECK(b.is_accepted(S(-10), S(-9), &sig));
+  }
+  {  // tests.rs:220-231 move-only policy; :258-270 scopes do not collide
+    auto a = kat_tabu(0, 0, 10, 0, true);
+    auto committed = kat_sig(1, {}, {}, {10, 20}, {30, 40}), repeated = kat_sig(1, {}, {}, {10, 20}, {99});
+    a.phase_started(S(-10));
+    a.step_ended(S(-9), &committed);
+    CHECK(!a.is_accepted(S(-9), S(-9), &repeated));
+    auto b = kat_tabu(2, 2, 0, 0, false);
+    auto first = kat_sig(1, {7}, {42}, {10}, {11}), second = kat_sig(2, {7}, {42}, {12}, {13});
+    b.phase_started(S(-10));
+    b.step_ended(S(-9), &first);
+    CHECK(b.is_accepted(S(-9), S(-8), &second));
+  }
+  {  // Score::multiply / abs (macros.rs:61-71): half away from zero on every level
+    CHECK(HardSoftScore::of(-3, 25).multiply(0.5) == HardSoftScore::of(-2, 13));
+    CHECK(HardSoftScore::of(-3, 25).abs() == HardSoftScore::of(3, 25));
+    CHECK(SoftScore::of(-100).multiply(0.001).v == 0);
+    CHECK(SoftScore::of(-15).multiply(0.1).v == -2);
+  }
+}
+
 int main() {
   kat_scores();
   kat_director();
@@ -644,6 +842,7 @@ int main() {
   kat_projected();
   kat_nearby_sort();
   kat_moves_and_loop();
+  kat_acceptors();
   if (g_fail) {
     std::printf("KAT FAILED %d of %d\n", g_fail, g_checks);
     return 1;

@@ -31,6 +31,7 @@ struct OracleModel {
   virtual size_t scalar_desc() const { return 0; }
   virtual size_t list_desc() const { return 0; }
   virtual uint64_t score_calculations() const = 0;
+  virtual TabuSignature signature(const Move& m) = 0;
 };
 
 template <class S>
@@ -46,6 +47,7 @@ struct ModelImpl : OracleModel {
     do_move(m, dir);
   }
   uint64_t score_calculations() const override { return dir.score_calculations; }
+  TabuSignature signature(const Move& m) override { return tabu_signature(m, dir); }
 };
 
 struct ConstKey {

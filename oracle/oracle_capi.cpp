@@ -234,4 +234,97 @@ int sfo_replay_step(uint64_t n, const int64_t* hard, const int64_t* soft, const 
   return 0;
 }
 
+// ---- stateful acceptors (acceptor/*.rs) for multi-step trajectories ---------------------------
+// kind: AcceptorKind order (0 HillClimbing, 1 LateAcceptance, 3 AcceptAll, 4 GreatDeluge,
+// 5 StepCountingHillClimbing, 6 DiversifiedLateAcceptance, 7 TabuSearch).
+// size = late-acceptance size / step_count_limit; real = rain_speed / tolerance;
+// tabu[4] = entity, value, move, undo-move tenures (0 = off); aspiration flag.
+void* sfo_acceptor_create(int kind, uint64_t size, double real, const uint64_t tabu[4], int aspiration) {
+  auto* a = new Acceptor<Sc>();
+  a->kind = (AcceptorKind)kind;
+  a->history.assign(size ? size : 1, Sc::zero());
+  a->step_count_limit = size;
+  a->rain_speed = real;
+  a->tolerance = real;
+  if (tabu) {
+    a->entity_memory.tenure = tabu[0];
+    a->value_memory.tenure = tabu[1];
+    a->move_memory.tenure = tabu[2];
+    a->reverse_move_memory.tenure = tabu[3];
+  }
+  a->aspiration_enabled = aspiration != 0;
+  return a;
+}
+void sfo_acceptor_destroy(void* h) { delete (Acceptor<Sc>*)h; }
+void sfo_acceptor_phase_started(void* h, const int64_t initial[2]) {
+  auto* a = (Acceptor<Sc>*)h;
+  a->phase_started(Sc::of(initial[0], initial[1]), a->history.size());
+}
+// tabu signatures of ListChangeMove rows against the handle's working solution, flattened:
+// sig[i] = {scope, n_entities, e0, e1, value, move_id[7], undo_move_id[7]} (18 u64 per row)
+static TabuSignature unpack_sig(const uint64_t* p) {
+  TabuSignature t;
+  t.scope = p[0];
+  for (uint64_t k = 0; k < p[1]; ++k) t.entity_ids.push_back(p[2 + k]);
+  t.value_ids = {p[4]};
+  t.move_id.assign(p + 5, p + 12);
+  t.undo_move_id.assign(p + 12, p + 19);
+  return t;
+}
+// One step with the stateful acceptor: replay, then acceptor.step_ended(step_score, accepted signature)
+// where step_score = winner's score, or last_step_score when nothing was picked (step.rs:122-221).
+// sigs may be null (19 u64 per candidate otherwise). out as sfo_replay_step.
+int sfo_acceptor_step(void* h, uint64_t n, const int64_t* hard, const int64_t* soft, const uint8_t* doable,
+                      const uint64_t* sigs, const int64_t best_score[2], const int64_t last_step_score[2],
+                      uint64_t step_seed, int forager_kind, uint64_t accepted_limit, int random_ties, uint64_t out[5]) {
+  auto* a = (Acceptor<Sc>*)h;
+  Forager<Sc> fg;
+  fg.kind = (ForagerKind)forager_kind;
+  fg.accepted_count_limit = accepted_limit;
+  fg.best.random_ties = random_ties != 0;
+  std::vector<TabuSignature> ts;
+  if (sigs)
+    for (uint64_t i = 0; i < n; ++i) ts.push_back(unpack_sig(sigs + 19 * i));
+  auto eval = [&](size_t i) {
+    return CandidateEvaluation<Sc>{doable[i] ? EvalKind::Scored : EvalKind::NotDoable, Sc::of(hard[i], soft[i])};
+  };
+  const Sc best = Sc::of(best_score[0], best_score[1]), last = Sc::of(last_step_score[0], last_step_score[1]);
+  StepOutcome<Sc> o;
+  try {
+    if (sigs)
+      o = replay_step<Sc>(n, eval, best, last, step_seed, fg, *a, [&](size_t i) { return &ts[i]; });
+    else
+      o = replay_step<Sc>(n, eval, best, last, step_seed, fg, *a);
+  } catch (const std::exception&) {
+    return -1;
+  }
+  a->step_ended(o.has_winner ? o.winner_score : last, (o.has_winner && sigs) ? &ts[o.winner] : nullptr);
+  out[0] = o.has_winner;
+  out[1] = o.winner;
+  out[2] = o.moves_evaluated;
+  out[3] = o.score_calculations;
+  out[4] = o.moves_accepted;
+  return 0;
+}
+// packs tabu_signature of n moves of the model behind `model` (19 u64 each, layout above).
+// move_kind: 0 ChangeMove rows {entity, to_value(-1 = None)}, 2 ListChangeMove rows {se, sp, de, dp}
+int sfo_move_signatures(void* model, int move_kind, uint64_t n, const uint32_t* rows, uint64_t* out_sigs) {
+  auto* m = static_cast<OracleModel*>(model);
+  for (uint64_t i = 0; i < n; ++i) {
+    Move mv = move_kind == 0 ? Move::change(m->scalar_desc(), rows[2 * i], opt((int32_t)rows[2 * i + 1]))
+                             : Move::list_change(m->list_desc(), rows[4 * i], rows[4 * i + 1], rows[4 * i + 2],
+                                                 rows[4 * i + 3]);
+    TabuSignature t = m->signature(mv);
+    uint64_t* p = out_sigs + 19 * i;
+    for (int k = 0; k < 19; ++k) p[k] = 0;
+    p[0] = t.scope;
+    p[1] = t.entity_ids.size();
+    for (size_t k = 0; k < t.entity_ids.size() && k < 2; ++k) p[2 + k] = t.entity_ids[k];
+    p[4] = t.value_ids.empty() ? TABU_NONE_ID : t.value_ids[0];
+    for (size_t k = 0; k < t.move_id.size() && k < 7; ++k) p[5 + k] = t.move_id[k];
+    for (size_t k = 0; k < t.undo_move_id.size() && k < 7; ++k) p[12 + k] = t.undo_move_id[k];
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -11,10 +11,22 @@
 //   Ord = hard, then soft  hard_soft.rs:130-137
 //   hard_score_delta       solverforge-solver/src/phase/hard_delta.rs:11-35
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <string>
 
 namespace sfo {
+
+// Score::multiply / Score::abs (macros.rs:61-71): per level `(x as f64 * m).round() as i64` (round half
+// away from zero, saturating cast) and `x.abs()`.
+inline int64_t mul_round(int64_t x, double m) {
+  const double r = std::round((double)x * m);
+  if (r != r) return 0;
+  if (r >= 9223372036854775807.0) return INT64_MAX;
+  if (r <= -9223372036854775808.0) return INT64_MIN;
+  return (int64_t)r;
+}
+inline int64_t abs_i64(int64_t x) { return x < 0 ? (int64_t)(0 - (uint64_t)x) : x; }
 
 struct SoftScore {
   int64_t v = 0;
@@ -32,6 +44,8 @@ struct SoftScore {
   static constexpr int levels = 1;
   static bool level_is_hard(int) { return false; }
   int64_t level(int) const { return v; }
+  SoftScore abs() const { return {abs_i64(v)}; }
+  SoftScore multiply(double m) const { return {mul_round(v, m)}; }
 };
 
 // Release-build Rust i64 arithmetic wraps; we wrap explicitly (macros.rs:24-48).
@@ -60,6 +74,8 @@ struct HardSoftScore {
   static bool level_is_hard(int l) { return l == 0; }
   int64_t level(int l) const { return l == 0 ? hard : soft; }
   std::string str() const { return std::to_string(hard) + "hard/" + std::to_string(soft) + "soft"; }
+  HardSoftScore abs() const { return {abs_i64(hard), abs_i64(soft)}; }
+  HardSoftScore multiply(double m) const { return {mul_round(hard, m), mul_round(soft, m)}; }
 };
 
 // Same layout; values pre-scaled by 100000 (hard_soft_decimal.rs:14,45-48,81-86).
@@ -84,6 +100,8 @@ struct HardSoftDecimalScore {
   static constexpr int levels = 2;
   static bool level_is_hard(int l) { return l == 0; }
   int64_t level(int l) const { return l == 0 ? hard : soft; }
+  HardSoftDecimalScore abs() const { return {abs_i64(hard), abs_i64(soft)}; }
+  HardSoftDecimalScore multiply(double m) const { return {mul_round(hard, m), mul_round(soft, m)}; }
 };
 
 // phase/hard_delta.rs:11-35 — first differing Hard-labelled level decides.

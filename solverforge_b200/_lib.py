@@ -47,7 +47,8 @@ class ConstraintDesc(C.Structure):
 class SolveParams(C.Structure):
     _fields_ = [("max_nearby", C.c_uint32), ("n_steps", C.c_uint32), ("acceptor", C.c_int32),
                 ("late_size", C.c_uint32), ("tie_mode", C.c_int32), ("accepted_limit", C.c_uint32),
-                ("seed_base", C.c_uint64), ("restore_best", C.c_int32), ("reserved", C.c_int32)]
+                ("seed_base", C.c_uint64), ("restore_best", C.c_int32), ("reserved", C.c_int32),
+                ("acceptor_real", C.c_double), ("step_count_limit", C.c_uint64)]
 
 
 class ForageParams(C.Structure):

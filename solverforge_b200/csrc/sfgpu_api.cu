@@ -1080,7 +1080,7 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
   if (!cand_offsets || !rows || !params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   if ((out_scores == nullptr) != (out_doable == nullptr))
     return fail(ctx, SFGPU_E_INVALID, "out_scores and out_doable are given together or not at all");
-  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad forage params");
   if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
   const DevModel& dm = ctx->dm;
@@ -1181,7 +1181,7 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
                 "device-side nearby neighbourhood needs the fast list program (int32 path-cost matrix as the "
                 "distance meter, every cell finite); enumerate on the host and call sfgpu_step_list_change");
   if (max_nearby == 0 || max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
-  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad forage params");
   if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
   if (out_scores && (!out_rows || !out_doable)) return fail(ctx, SFGPU_E_INVALID, "out_scores needs out_rows and out_doable");
@@ -1276,7 +1276,12 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
     if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
   }
-  if (p->acceptor < 1 || p->acceptor > 2) return fail(ctx, SFGPU_E_INVALID, "acceptor: 1 HillClimbing, 2 LateAcceptance");
+  if (p->acceptor < 1 || p->acceptor > 5)
+    return fail(ctx, SFGPU_E_INVALID,
+                "acceptor: 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing, "
+                "5 DiversifiedLateAcceptance");
+  if ((p->acceptor == 3 || p->acceptor == 5) && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1e6))
+    return fail(ctx, SFGPU_E_INVALID, "acceptor_real (rain_speed / tolerance) must be a finite value >= 0");
   if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
   CU(cudaSetDevice(ctx->device));
   const uint32_t R = dm.R;
@@ -1288,6 +1293,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   const size_t o_hist = take((size_t)R * late * 16), o_hidx = take((size_t)R * 4), o_bests = take((size_t)R * 16);
   const size_t o_eval = take((size_t)R * 8), o_acc = take((size_t)R * 8), o_idx = take((size_t)R * 4);
   const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
+  const size_t o_accst = take((size_t)R * 32);
   const size_t o_snap = take((size_t)R * dm.block_bytes);
   if (o > ctx->solve_bytes) {
     if (ctx->solve_buf) cudaFree(ctx->solve_buf);
@@ -1314,6 +1320,10 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   s.seed_base = p->seed_base;
   s.late_size = late;
   s.acceptor = p->acceptor;
+  s.acc_state = (int64_t*)(b + o_accst);
+  s.real = p->acceptor_real;
+  s.step_count_limit = p->step_count_limit;
+  const int forage_code = solve_forage_code(p->acceptor);
   NearbyArgs a{};
   ChangeStepArgs ca{};
   uint32_t c_chunks = 0;
@@ -1323,7 +1333,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     c_chunks = (dm.n_entities + per - 1) / per;
     rc = ensure_partials(ctx, (size_t)R * c_chunks * sizeof(ChunkPartial));
     if (rc) return rc;
-    ca.f = ForageDev{p->acceptor, p->tie_mode, p->accepted_limit};
+    ca.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
     ca.ents_per_cta = per;
     ca.step_seeds = s.step_seeds;
     ca.ref_scores = s.ref_scores;
@@ -1331,7 +1341,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   } else {
     rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
     if (rc) return rc;
-    a.f = ForageDev{p->acceptor, p->tie_mode, p->accepted_limit};
+    a.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
     a.max_nearby = p->max_nearby;
     a.step_seeds = s.step_seeds;
     a.ref_scores = s.ref_scores;
@@ -1414,7 +1424,7 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
   if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
   if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
-  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad forage params");
   if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
   if (out_scores && (!out_rows || !out_doable)) return fail(ctx, SFGPU_E_INVALID, "out_scores needs out_rows and out_doable");
@@ -1515,7 +1525,7 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
   if (rc) return rc;
   if (!params || !cand_offsets || !scores || !doable || !out_index || !out_best)
     return fail(ctx, SFGPU_E_INVALID, "null pointer");
-  if (params->acceptor < 0 || params->acceptor > 2 || params->tie_mode < 0 || params->tie_mode > 1)
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad forage params");
   if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
   CU(cudaSetDevice(ctx->device));

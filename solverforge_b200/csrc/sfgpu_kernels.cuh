@@ -503,11 +503,13 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   }
 }
 
-// acceptor predicate on a score (HillClimbing: move > last; LateAcceptance: >= last || >= late)
+// acceptor predicate on a score (1 HillClimbing: move > last; 2 LateAcceptance: >= last || >= late;
+// 3 GreatDeluge form: > last || >= threshold; see sfgpu_forage_params)
 __device__ __forceinline__ bool accept_score(int acceptor, int64_t h, int64_t s, int64_t lh, int64_t ls, int64_t th,
                                              int64_t ts) {
   if (acceptor == 0) return true;
   if (acceptor == 1) return score_less(lh, ls, h, s);
+  if (acceptor == 3) return score_less(lh, ls, h, s) || !score_less(h, s, th, ts);  // > last || >= threshold
   return !score_less(h, s, lh, ls) || !score_less(h, s, th, ts);
 }
 
@@ -545,6 +547,7 @@ template <typename S>
 __device__ __forceinline__ bool accept_delta(int acceptor, S h, S s, S lh, S ls, S th, S ts) {
   if (acceptor == 0) return true;
   if (acceptor == 1) return lex_less(lh, ls, h, s);
+  if (acceptor == 3) return lex_less(lh, ls, h, s) || !lex_less(h, s, th, ts);
   return !lex_less(h, s, lh, ls) || !lex_less(h, s, th, ts);
 }
 // LIST_SUM delta of moving value v from a route with sum ss to one with sum sd (a, b pre-narrowed)
@@ -1286,8 +1289,7 @@ __device__ __forceinline__ bool accepted_at(const ForageDev& f, const int64_t* s
   if (!doable[i]) return false;
   if (f.acceptor == 0) return true;
   longlong2 s = ((const longlong2*)scores)[i];
-  if (f.acceptor == 1) return score_less(lh, ls, s.x, s.y);                          // move > last
-  return !score_less(s.x, s.y, lh, ls) || !score_less(s.x, s.y, th, ts);             // >= last || >= late
+  return accept_score(f.acceptor, s.x, s.y, lh, ls, th, ts);
 }
 
 // inclusive block scan of a 32-bit count; returns this thread's inclusive prefix, total in *total

@@ -14,11 +14,13 @@
 // CPU scoring fallback (north_star). The host replay below only *orders* already-computed scores, which
 // is what the reference's acceptor/forager do.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfgpu.h"
@@ -49,6 +51,11 @@ struct HardSoftScore {
   bool operator<=(HardSoftScore o) const { return !(o < *this); }
   bool operator>=(HardSoftScore o) const { return !(*this < o); }
   int64_t level(int l) const { return l == 0 ? hard : soft; }
+  // Score::abs / Score::multiply (solverforge-core/src/score/macros.rs:61-71)
+  HardSoftScore abs() const { return {hard < 0 ? -hard : hard, soft < 0 ? -soft : soft}; }
+  HardSoftScore multiply(double m) const {
+    return {(int64_t)std::round((double)hard * m), (int64_t)std::round((double)soft * m)};
+  }
 };
 // HardSoftDecimalScore shares the layout with levels pre-scaled by 100000.
 struct HardSoftDecimalScore : HardSoftScore {
@@ -272,6 +279,14 @@ class GpuScoreDirector {
     check(sfgpu_add_scalar_variable(ctx_, coll, name.c_str(), n_values, allows_unassigned ? 1 : 0, &id));
     return id;
   }
+  // working_solution() of the scalar variable: values[R][n_entities], -1 = None
+  std::vector<std::vector<int32_t>> scalar_state(uint32_t n_entities) {
+    std::vector<int32_t> flat((size_t)R_ * n_entities);
+    check(sfgpu_get_scalar_state(ctx_, 0, flat.data()));
+    std::vector<std::vector<int32_t>> out(R_);
+    for (uint32_t r = 0; r < R_; ++r) out[r].assign(flat.begin() + (size_t)r * n_entities, flat.begin() + (size_t)(r + 1) * n_entities);
+    return out;
+  }
   uint32_t add_list_variable(uint32_t owners, uint32_t elements, const std::string& name) {
     uint32_t id;
     check(sfgpu_add_list_variable(ctx_, owners, elements, name.c_str(), &id));
@@ -358,14 +373,62 @@ inline bool reservoir_pick(uint64_t step_seed, uint64_t equal_count) {  // forag
   return splitmix64(step_seed ^ (equal_count * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull) % equal_count == 0;
 }
 
+// Tabu metadata of one candidate (heuristic/move/metadata.rs:12-107). Ids are compared for equality
+// only, so the raw indices stand in for the reference's SipHash-ed names and Debug strings.
+struct MoveTabuSignature {
+  uint64_t scope = 0;  // (descriptor_index, variable)
+  std::vector<uint64_t> entity_ids, destination_value_ids, move_id, undo_move_id;
+};
+constexpr uint64_t TABU_NONE_ID = UINT64_MAX;
+// ChangeMove::tabu_signature (change.rs:189-220); from/to = value index, -1 = None
+inline MoveTabuSignature change_signature(uint64_t descriptor, uint64_t entity, int64_t from, int64_t to) {
+  MoveTabuSignature g;
+  const uint64_t f = from < 0 ? TABU_NONE_ID : (uint64_t)from, t = to < 0 ? TABU_NONE_ID : (uint64_t)to;
+  g.scope = descriptor << 32;
+  g.move_id = {descriptor, 0, entity, f, t};
+  g.undo_move_id = {descriptor, 0, entity, t, f};
+  g.entity_ids = {entity};
+  g.destination_value_ids = {t};
+  return g;
+}
+// change_tabu_signature (list_kernel/change.rs:155-204); moved = the element at (src_e, src_p)
+inline MoveTabuSignature list_change_signature(uint64_t descriptor, uint64_t se, uint64_t sp, uint64_t de, uint64_t dp,
+                                               uint64_t moved) {
+  MoveTabuSignature g;
+  const uint64_t adj = (se == de && dp > sp) ? dp - 1 : dp;
+  g.scope = descriptor << 32;
+  g.move_id = {descriptor, 0, se, sp, de, adj, moved};
+  g.undo_move_id = {descriptor, 0, de, adj, se, sp, moved};
+  g.entity_ids = {se};
+  if (se != de) g.entity_ids.push_back(de);
+  g.destination_value_ids = {moved};
+  return g;
+}
+
+// How one step of an acceptor is expressed for the fused device steps (sfgpu_forage_params.acceptor
+// + ref_scores {last_step, threshold}); acceptors that need per-move metadata or a random stream are
+// not expressible and replay on the host over the materialised scores.
+struct DeviceAcceptance {
+  bool expressible = false;
+  uint32_t acceptor = 0;  // 0 accept all, 1 move > last, 2 move >= last || move >= threshold,
+                          // 3 move > last || move >= threshold
+  HardSoftScore threshold;
+};
+
 struct Acceptor {  // acceptor/traits.rs:13-43
   virtual ~Acceptor() = default;
+  virtual bool requires_move_signatures() const { return false; }
   virtual void phase_started(HardSoftScore) {}
-  virtual bool is_accepted(HardSoftScore last_step, HardSoftScore move) = 0;
-  virtual void step_ended(HardSoftScore) {}
+  virtual void phase_ended() {}
+  virtual bool is_accepted(HardSoftScore last_step, HardSoftScore move, const MoveTabuSignature* sig = nullptr) = 0;
+  virtual void step_ended(HardSoftScore, const MoveTabuSignature* accepted = nullptr) { (void)accepted; }
+  virtual DeviceAcceptance device_form(HardSoftScore /*last_step*/) const { return {}; }
 };
 struct HillClimbingAcceptor : Acceptor {  // hill_climbing.rs:33-42
-  bool is_accepted(HardSoftScore last, HardSoftScore mv) override { return mv > last; }
+  bool is_accepted(HardSoftScore last, HardSoftScore mv, const MoveTabuSignature* = nullptr) override {
+    return mv > last;
+  }
+  DeviceAcceptance device_form(HardSoftScore last) const override { return {true, 1, last}; }
 };
 struct LateAcceptanceAcceptor : Acceptor {  // late_acceptance.rs:89-126
   size_t size;
@@ -376,10 +439,168 @@ struct LateAcceptanceAcceptor : Acceptor {  // late_acceptance.rs:89-126
     history.assign(size, initial);
     idx = 0;
   }
-  bool is_accepted(HardSoftScore last, HardSoftScore mv) override { return mv >= last || mv >= history[idx]; }
-  void step_ended(HardSoftScore step) override {
+  bool is_accepted(HardSoftScore last, HardSoftScore mv, const MoveTabuSignature* = nullptr) override {
+    return mv >= last || mv >= history[idx];
+  }
+  void step_ended(HardSoftScore step, const MoveTabuSignature* = nullptr) override {
     history[idx] = step;
     idx = (idx + 1) % size;
+  }
+  DeviceAcceptance device_form(HardSoftScore) const override { return {true, 2, history[idx]}; }
+};
+struct GreatDelugeAcceptor : Acceptor {  // great_deluge.rs:52-101
+  double rain_speed;
+  bool has_water = false;
+  HardSoftScore water_level, initial_abs;
+  explicit GreatDelugeAcceptor(double rain = 0.001) : rain_speed(rain) {}
+  void phase_started(HardSoftScore initial) override {
+    has_water = true;
+    water_level = initial;
+    initial_abs = initial.abs();
+  }
+  void phase_ended() override { has_water = false; }
+  bool is_accepted(HardSoftScore last, HardSoftScore mv, const MoveTabuSignature* = nullptr) override {
+    return mv > last || !has_water || mv >= water_level;
+  }
+  void step_ended(HardSoftScore, const MoveTabuSignature* = nullptr) override {
+    if (has_water) water_level = water_level + initial_abs.multiply(rain_speed);
+  }
+  DeviceAcceptance device_form(HardSoftScore) const override {
+    return has_water ? DeviceAcceptance{true, 3, water_level} : DeviceAcceptance{true, 0, {}};
+  }
+};
+struct StepCountingHillClimbingAcceptor : Acceptor {  // step_counting.rs:55-104
+  uint64_t step_count_limit, steps_since_improvement = 0;
+  bool has_best = false;
+  HardSoftScore best;
+  explicit StepCountingHillClimbingAcceptor(uint64_t limit = 100) : step_count_limit(limit) {}
+  void phase_started(HardSoftScore initial) override {
+    has_best = true;
+    best = initial;
+    steps_since_improvement = 0;
+  }
+  void phase_ended() override {
+    has_best = false;
+    steps_since_improvement = 0;
+  }
+  bool is_accepted(HardSoftScore last, HardSoftScore mv, const MoveTabuSignature* = nullptr) override {
+    return mv > last || steps_since_improvement < step_count_limit;
+  }
+  void step_ended(HardSoftScore step, const MoveTabuSignature* = nullptr) override {
+    if (!has_best || step > best) {
+      has_best = true;
+      best = step;
+      steps_since_improvement = 0;
+    } else {
+      steps_since_improvement++;
+    }
+  }
+  DeviceAcceptance device_form(HardSoftScore last) const override {
+    return {true, steps_since_improvement < step_count_limit ? 0u : 1u, last};
+  }
+};
+struct DiversifiedLateAcceptanceAcceptor : Acceptor {  // diversified_late_acceptance.rs:71-140
+  size_t size;
+  double tolerance;
+  std::vector<HardSoftScore> history;
+  size_t idx = 0;
+  bool has_best = false;
+  HardSoftScore best;
+  explicit DiversifiedLateAcceptanceAcceptor(size_t n = 400, double tol = 0.01) : size(n), tolerance(tol) {}
+  void phase_started(HardSoftScore initial) override {
+    history.assign(size, initial);
+    idx = 0;
+    has_best = true;
+    best = initial;
+  }
+  HardSoftScore floor_score() const {  // the weaker of the late score and best - |best| * tolerance
+    HardSoftScore t = history[idx];
+    if (has_best) {
+      const HardSoftScore d = best - best.abs().multiply(tolerance);
+      if (d < t) t = d;
+    }
+    return t;
+  }
+  bool is_accepted(HardSoftScore last, HardSoftScore mv, const MoveTabuSignature* = nullptr) override {
+    if (mv >= last || mv >= history[idx]) return true;
+    return has_best && mv >= best - best.abs().multiply(tolerance);
+  }
+  void step_ended(HardSoftScore step, const MoveTabuSignature* = nullptr) override {
+    if (!has_best || step > best) {
+      has_best = true;
+      best = step;
+    }
+    history[idx] = step;
+    idx = (idx + 1) % size;
+  }
+  DeviceAcceptance device_form(HardSoftScore) const override { return {true, 2, floor_score()}; }
+};
+struct TabuSearchAcceptor : Acceptor {  // tabu_search.rs:103-237; tenure 0 = dimension off (None)
+  template <class T>
+  struct Memory {  // TabuMemory :64-101
+    size_t tenure = 0;
+    std::vector<T> entries;
+    bool contains(const T& e) const { return std::find(entries.begin(), entries.end(), e) != entries.end(); }
+    void record(const T& e) {
+      if (!tenure) return;
+      if (entries.size() >= tenure) entries.erase(entries.begin());
+      entries.push_back(e);
+    }
+  };
+  Memory<std::pair<uint64_t, uint64_t>> entity_memory, value_memory;
+  Memory<std::vector<uint64_t>> move_memory, reverse_move_memory;
+  bool aspiration_enabled;
+  bool has_best = false;
+  HardSoftScore best;
+  TabuSearchAcceptor(size_t entity_tabu, size_t value_tabu, size_t move_tabu, size_t undo_move_tabu,
+                     bool aspiration = true)
+      : aspiration_enabled(aspiration) {
+    if (!entity_tabu && !value_tabu && !move_tabu && !undo_move_tabu)
+      throw std::invalid_argument("tabu_search requires at least one tabu dimension");  // :35-41
+    entity_memory.tenure = entity_tabu;
+    value_memory.tenure = value_tabu;
+    move_memory.tenure = move_tabu;
+    reverse_move_memory.tenure = undo_move_tabu;
+  }
+  bool requires_move_signatures() const override { return true; }
+  void clear() {
+    entity_memory.entries.clear();
+    value_memory.entries.clear();
+    move_memory.entries.clear();
+    reverse_move_memory.entries.clear();
+  }
+  void phase_started(HardSoftScore initial) override {
+    clear();
+    has_best = true;
+    best = initial;
+  }
+  void phase_ended() override {
+    clear();
+    has_best = false;
+  }
+  bool is_tabu(const MoveTabuSignature& g) const {
+    for (uint64_t e : g.entity_ids)
+      if (entity_memory.contains({g.scope, e})) return true;
+    for (uint64_t v : g.destination_value_ids)
+      if (value_memory.contains({g.scope, v})) return true;
+    return move_memory.contains(g.move_id) || reverse_move_memory.contains(g.move_id);
+  }
+  bool is_accepted(HardSoftScore, HardSoftScore mv, const MoveTabuSignature* sig = nullptr) override {
+    if (!sig) throw std::logic_error("tabu search requires move signatures");
+    const bool aspirational = has_best && aspiration_enabled && mv > best;
+    return aspirational || !is_tabu(*sig);
+  }
+  void step_ended(HardSoftScore step, const MoveTabuSignature* accepted = nullptr) override {
+    if (accepted) {
+      for (uint64_t e : accepted->entity_ids) entity_memory.record({accepted->scope, e});
+      for (uint64_t v : accepted->destination_value_ids) value_memory.record({accepted->scope, v});
+      move_memory.record(accepted->move_id);
+      reverse_move_memory.record(accepted->undo_move_id);
+    }
+    if (!has_best || step > best) {
+      has_best = true;
+      best = step;
+    }
   }
 };
 struct SimulatedAnnealingAcceptor : Acceptor {  // simulated_annealing.rs:338-431 (uniform stream injected)
@@ -390,7 +611,7 @@ struct SimulatedAnnealingAcceptor : Acceptor {  // simulated_annealing.rs:338-43
   size_t count[2] = {0, 0};
   bool calibrated = false;
   explicit SimulatedAnnealingAcceptor(std::function<double()> u) : uniform(std::move(u)) {}
-  bool is_accepted(HardSoftScore last, HardSoftScore mv) override {
+  bool is_accepted(HardSoftScore last, HardSoftScore mv, const MoveTabuSignature* = nullptr) override {
     if (mv >= last) return true;
     int lvl = mv.hard != last.hard ? 0 : 1;
     double delta = (double)(mv.level(lvl) - last.level(lvl));
@@ -405,7 +626,7 @@ struct SimulatedAnnealingAcceptor : Acceptor {  // simulated_annealing.rs:338-43
     if (temperature[lvl] <= hill_climbing_temperature) return false;
     return uniform() < std::exp(delta / temperature[lvl]);
   }
-  void step_ended(HardSoftScore) override {
+  void step_ended(HardSoftScore, const MoveTabuSignature* = nullptr) override {
     if (calibrated)
       for (double& t : temperature) t = std::max(t * decay, hill_climbing_temperature);
   }
@@ -426,9 +647,13 @@ struct StepOutcome {
 };
 
 // Replays phase/candidates.rs:66-282 over batched scores: pull order, quit-early, acceptor, forager.
+// `signature(i)` supplies the tabu metadata of candidate i for acceptors that require it.
 inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doable, size_t n, HardSoftScore best_score,
                                HardSoftScore last_step, uint64_t step_seed, const ForagerConfig& fc,
-                               Acceptor& acceptor) {
+                               Acceptor& acceptor,
+                               const std::function<MoveTabuSignature(size_t)>& signature = nullptr) {
+  if (acceptor.requires_move_signatures() && !signature)
+    throw std::logic_error("this acceptor requires move signatures");
   StepOutcome out;
   uint64_t equal_count = 0;
   size_t accepted = 0;
@@ -465,7 +690,12 @@ inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doabl
     out.moves_evaluated++;
     if (!doable[i]) continue;
     out.score_calculations++;
-    if (!acceptor.is_accepted(last_step, scores[i])) continue;
+    if (signature) {
+      const MoveTabuSignature g = signature(i);
+      if (!acceptor.is_accepted(last_step, scores[i], &g)) continue;
+    } else if (!acceptor.is_accepted(last_step, scores[i])) {
+      continue;
+    }
     out.moves_accepted++;
     switch (fc.kind) {
       case ForagerConfig::FirstAccepted:

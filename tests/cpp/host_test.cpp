@@ -71,6 +71,105 @@ static int test_replay() {
   return 0;
 }
 
+// Multi-step trajectories: every stateful acceptor of the host mirror against the oracle's restatement
+// on the same random candidate streams (scores, doability, tabu signatures), including the device
+// form (acceptor code + threshold) that the fused GPU steps take.
+static bool device_accepts(const sf::DeviceAcceptance& d, sf::HardSoftScore last, sf::HardSoftScore mv) {
+  switch (d.acceptor) {
+    case 0: return true;
+    case 1: return mv > last;
+    case 2: return mv >= last || mv >= d.threshold;
+    default: return mv > last || mv >= d.threshold;
+  }
+}
+static int test_acceptor_trajectories() {
+  uint64_t s = 777;
+  for (int kind = 0; kind < 6; ++kind)
+    for (int trial = 0; trial < 30; ++trial) {
+      sf::HillClimbingAcceptor hc;
+      sf::LateAcceptanceAcceptor la(3 + trial % 5);
+      sf::GreatDelugeAcceptor gd(trial % 2 ? 0.05 : 0.001);
+      sf::StepCountingHillClimbingAcceptor sc(1 + trial % 4);
+      sf::DiversifiedLateAcceptanceAcceptor dla(2 + trial % 6, trial % 3 ? 0.1 : 0.01);
+      sf::TabuSearchAcceptor tabu(trial % 4, (trial / 2) % 3, 1 + trial % 3, trial % 2 ? 2 : 0, trial % 5 != 0);
+      sf::Acceptor* accs[6] = {&hc, &la, &gd, &sc, &dla, &tabu};
+      sf::Acceptor& acc = *accs[kind];
+      sfo::Acceptor<sfo::Sc> oa;
+      const sfo::AcceptorKind kinds[6] = {sfo::AcceptorKind::HillClimbing, sfo::AcceptorKind::LateAcceptance,
+                                          sfo::AcceptorKind::GreatDeluge, sfo::AcceptorKind::StepCountingHillClimbing,
+                                          sfo::AcceptorKind::DiversifiedLateAcceptance, sfo::AcceptorKind::TabuSearch};
+      oa.kind = kinds[kind];
+      oa.rain_speed = gd.rain_speed;
+      oa.step_count_limit = sc.step_count_limit;
+      oa.tolerance = dla.tolerance;
+      oa.entity_memory.tenure = tabu.entity_memory.tenure;
+      oa.value_memory.tenure = tabu.value_memory.tenure;
+      oa.move_memory.tenure = tabu.move_memory.tenure;
+      oa.reverse_move_memory.tenure = tabu.reverse_move_memory.tenure;
+      oa.aspiration_enabled = tabu.aspiration_enabled;
+      sf::HardSoftScore last{-2, -(int64_t)(40 + trial)};
+      sf::HardSoftScore best = last;
+      acc.phase_started(last);
+      oa.phase_started(sfo::Sc::of(last.hard, last.soft), kind == 1 ? la.size : dla.size);
+      for (int step = 0; step < 40; ++step) {
+        const size_t n = 1 + sfo::splitmix64(s++) % 60;
+        std::vector<sf::HardSoftScore> scores(n);
+        std::vector<uint8_t> doable(n);
+        std::vector<sf::MoveTabuSignature> sigs(n);
+        std::vector<sfo::TabuSignature> osigs(n);
+        for (size_t i = 0; i < n; ++i) {
+          scores[i] = {last.hard + (int64_t)(sfo::splitmix64(s++) % 3) - 1, last.soft + (int64_t)(sfo::splitmix64(s++) % 21) - 11};
+          doable[i] = sfo::splitmix64(s++) % 8 != 0;
+          const uint64_t e = sfo::splitmix64(s++) % 6, from = sfo::splitmix64(s++) % 4, to = sfo::splitmix64(s++) % 4;
+          sigs[i] = sf::change_signature(0, e, (int64_t)from - 1, (int64_t)to - 1);
+          osigs[i].scope = sigs[i].scope;
+          osigs[i].entity_ids = sigs[i].entity_ids;
+          osigs[i].value_ids = sigs[i].destination_value_ids;
+          osigs[i].move_id = sigs[i].move_id;
+          osigs[i].undo_move_id = sigs[i].undo_move_id;
+        }
+        const uint64_t seed = sfo::splitmix64(s++);
+        sf::ForagerConfig fc;
+        fc.kind = step % 3 == 0 ? sf::ForagerConfig::AcceptedCount : sf::ForagerConfig::BestScore;
+        fc.accepted_count_limit = 1 + step % 7;
+        sfo::Forager<sfo::Sc> of;
+        of.kind = step % 3 == 0 ? sfo::ForagerKind::AcceptedCount : sfo::ForagerKind::BestScore;
+        of.accepted_count_limit = fc.accepted_count_limit;
+        // device form agrees with is_accepted for every candidate (before the replay mutates nothing)
+        const sf::DeviceAcceptance df = acc.device_form(last);
+        CHECK(df.expressible == (kind != 5));
+        if (df.expressible)
+          for (size_t i = 0; i < n; ++i) CHECK(device_accepts(df, last, scores[i]) == acc.is_accepted(last, scores[i], &sigs[i]));
+        auto got = sf::replay_step(scores.data(), doable.data(), n, best, last, seed, fc, acc,
+                                   [&](size_t i) { return sigs[i]; });
+        auto want = sfo::replay_step<sfo::Sc>(
+            n,
+            [&](size_t i) {
+              return sfo::CandidateEvaluation<sfo::Sc>{doable[i] ? sfo::EvalKind::Scored : sfo::EvalKind::NotDoable,
+                                                       sfo::Sc::of(scores[i].hard, scores[i].soft)};
+            },
+            sfo::Sc::of(best.hard, best.soft), sfo::Sc::of(last.hard, last.soft), seed, of, oa,
+            [&](size_t i) { return &osigs[i]; });
+        CHECK(got.has_winner == want.has_winner);
+        CHECK(got.moves_accepted == want.moves_accepted);
+        CHECK(got.moves_evaluated == want.moves_evaluated);
+        if (want.has_winner) {
+          CHECK(got.winner == want.winner);
+          last = scores[got.winner];
+          if (last > best) best = last;
+          acc.step_ended(last, &sigs[got.winner]);
+          oa.step_ended(sfo::Sc::of(last.hard, last.soft), &osigs[want.winner]);
+        } else {
+          acc.step_ended(last, nullptr);
+          oa.step_ended(sfo::Sc::of(last.hard, last.soft), nullptr);
+        }
+      }
+      acc.phase_ended();
+      oa.phase_ended();
+    }
+  return 0;
+}
+
 static int test_gpu() {
   // graph colouring, 400 nodes, through the C++ ConstraintFactory
   const uint32_t n = 400, k = 5;
@@ -132,6 +231,56 @@ static int test_gpu() {
     CHECK(c == out.score && c == fr);
     CHECK(c.hard == o2.hard && c.soft == o2.soft);
   }
+  // Tabu search over GPU scores: the acceptor needs per-move signatures, so it replays on the host
+  // over the materialised batch (tabu_search.rs:170-235) — same trajectory as the oracle's tabu
+  // acceptor over the oracle's own scores and signatures.
+  {
+    sf::TabuSearchAcceptor tabu(3, 0, 4, 4, true);
+    sfo::Acceptor<sfo::Sc> ot;
+    ot.kind = sfo::AcceptorKind::TabuSearch;
+    ot.entity_memory.tenure = 3;
+    ot.move_memory.tenure = 4;
+    ot.reverse_move_memory.tenure = 4;
+    auto start = d.calculate_score()[0];
+    tabu.phase_started(start);
+    ot.phase_started(sfo::Sc::of(start.hard, start.soft));
+    sf::HardSoftScore best = start;
+    std::vector<int32_t> cur = d.scalar_state(n)[0];
+    for (int step = 0; step < 12; ++step) {
+      auto mv = oracle.enumerate_scalar({});
+      std::vector<sf::ScalarEdit> b2;
+      for (auto& m : mv) b2.push_back({(uint32_t)m.a, m.to ? (int32_t)*m.to : -1});
+      d.score_candidates(b2, {0, b2.size()}, scores, doable);
+      auto last = d.calculate_score()[0];
+      sf::ForagerConfig fc2;
+      fc2.kind = sf::ForagerConfig::AcceptedCount;
+      fc2.accepted_count_limit = 50;
+      auto got = sf::replay_step(scores.data(), doable.data(), scores.size(), best, last, 500 + step, fc2, tabu,
+                                 [&](size_t i) { return sf::change_signature(0, b2[i].entity_index, cur[b2[i].entity_index], b2[i].to_value); });
+      sfo::Forager<sfo::Sc> of;
+      of.kind = sfo::ForagerKind::AcceptedCount;
+      of.accepted_count_limit = 50;
+      std::vector<sfo::TabuSignature> osig(mv.size());
+      for (size_t i = 0; i < mv.size(); ++i) osig[i] = oracle.signature(mv[i]);
+      auto want = sfo::replay_step<sfo::Sc>(
+          mv.size(), [&](size_t i) { return oracle.evaluate(mv[i]); }, sfo::Sc::of(best.hard, best.soft),
+          sfo::Sc::of(last.hard, last.soft), 500 + step, of, ot, [&](size_t i) { return &osig[i]; });
+      CHECK(got.has_winner == want.has_winner);
+      CHECK(got.moves_accepted == want.moves_accepted);
+      if (!want.has_winner) break;
+      CHECK(got.winner == want.winner);
+      const sf::MoveTabuSignature sig = sf::change_signature(0, b2[got.winner].entity_index, cur[b2[got.winner].entity_index], b2[got.winner].to_value);
+      d.apply(std::vector<sf::ScalarEdit>{b2[got.winner]});
+      cur[b2[got.winner].entity_index] = b2[got.winner].to_value;
+      oracle.apply(mv[want.winner]);
+      auto now = d.calculate_score()[0];
+      auto onow = oracle.calculate_score();
+      CHECK(now.hard == onow.hard && now.soft == onow.soft);
+      tabu.step_ended(now, &sig);
+      ot.step_ended(onow, &osig[want.winner]);
+      if (now > best) best = now;
+    }
+  }
   // error behaviour: unknown constraint kind is rejected, never emulated
   try {
     sf::GpuScoreDirector bad(1);
@@ -147,7 +296,10 @@ static int test_gpu() {
 
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
-  if (!std::strcmp(argv[1], "replay")) test_replay();
+  if (!std::strcmp(argv[1], "replay")) {
+    test_replay();
+    test_acceptor_trajectories();
+  }
   else if (!std::strcmp(argv[1], "gpu")) test_gpu();
   else return 2;
   if (g_fail) {

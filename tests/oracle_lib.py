@@ -59,6 +59,13 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_nearby_list_change.restype = C.c_int64
         l.sfo_replay_step.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
                                       C.c_int, _P]
+        l.sfo_acceptor_create.restype = _P
+        l.sfo_acceptor_create.argtypes = [C.c_int, C.c_uint64, C.c_double, _P, C.c_int]
+        l.sfo_acceptor_destroy.argtypes = [_P]
+        l.sfo_acceptor_phase_started.argtypes = [_P, _P]
+        l.sfo_acceptor_step.argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64,
+                                        C.c_int, _P]
+        l.sfo_move_signatures.argtypes = [_P, C.c_int, C.c_uint64, _P, _P]
         _lib = l
     return _lib
 
@@ -213,6 +220,53 @@ def replay_step(scores, doable, best_score, last_step_score, late_score, step_se
     lib().sfo_replay_step(len(h), _p(h), _p(s), _p(d), _p(b), _p(l_), _p(t), step_seed, forager_kind, accepted_limit,
                           1 if random_ties else 0, acceptor_kind, _p(out))
     return tuple(int(x) for x in out)
+
+
+class OracleAcceptor:
+    """Stateful restatement of one reference acceptor (acceptor/*.rs) for multi-step trajectories.
+    kind: 0 HillClimbing, 1 LateAcceptance(size), 3 AcceptAll, 4 GreatDeluge(real = rain_speed),
+    5 StepCountingHillClimbing(size = limit), 6 DiversifiedLateAcceptance(size, real = tolerance),
+    7 TabuSearch(tabu = entity/value/move/undo tenures, aspiration)."""
+    HILL_CLIMBING, LATE_ACCEPTANCE, ACCEPT_ALL, GREAT_DELUGE, STEP_COUNTING, DIVERSIFIED_LATE, TABU = 0, 1, 3, 4, 5, 6, 7
+
+    def __init__(self, kind, size=0, real=0.0, tabu=None, aspiration=True):
+        self.l = lib()
+        t = np.asarray(tabu if tabu is not None else [0, 0, 0, 0], dtype=np.uint64)
+        self.h = self.l.sfo_acceptor_create(kind, size, float(real), _p(t), 1 if aspiration else 0)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.sfo_acceptor_destroy(self.h)
+            self.h = None
+
+    def phase_started(self, initial):
+        i = np.asarray(initial, dtype=np.int64)
+        self.l.sfo_acceptor_phase_started(self.h, _p(i))
+
+    def step(self, scores, doable, best_score, last_step_score, step_seed, forager_kind, accepted_limit, random_ties,
+             signatures=None):
+        """replay + acceptor.step_ended; returns (has_winner, winner, moves_evaluated, score_calcs, accepted)."""
+        scores = np.asarray(scores, dtype=np.int64).reshape(-1, 2)
+        h = np.ascontiguousarray(scores[:, 0])
+        s = np.ascontiguousarray(scores[:, 1])
+        d = np.ascontiguousarray(doable, dtype=np.uint8)
+        b = np.asarray(best_score, dtype=np.int64)
+        l_ = np.asarray(last_step_score, dtype=np.int64)
+        out = np.zeros(5, dtype=np.uint64)
+        sg = None if signatures is None else np.ascontiguousarray(signatures, dtype=np.uint64)
+        rc = self.l.sfo_acceptor_step(self.h, len(h), _p(h), _p(s), _p(d), None if sg is None else _p(sg), _p(b), _p(l_),
+                                      step_seed, forager_kind, accepted_limit, 1 if random_ties else 0, _p(out))
+        assert rc == 0
+        return tuple(int(x) for x in out)
+
+
+def move_signatures(oracle: "Oracle", move_kind: int, rows) -> np.ndarray:
+    """tabu signatures (19 u64 each) of ChangeMove (kind 0) / ListChangeMove (kind 2) rows."""
+    rows = _u32(rows)
+    n = len(rows)
+    out = np.zeros((n, 19), dtype=np.uint64)
+    lib().sfo_move_signatures(oracle.h, move_kind, n, _p(rows), _p(out))
+    return out
 
 
 # ---- the stronger O(1)-delta CPU baseline (oracle/fast_cpu.cpp) ---------------------------------

@@ -123,3 +123,50 @@ def test_device_resident_change_loop_equals_step_by_step():
     assert np.array_equal(best, best_h) and np.array_equal(evaluated, ev_h)
     assert np.array_equal(loop.fresh_score(), loop.calculate_score())
     assert (best[:, 0] > init[:, 0]).all()      # hard score improved (conflicts / unassigned removed)
+
+
+@pytest.mark.parametrize("kind,okind,size,real,limit", [
+    (3, 4, 0, 0.01, 0), (4, 5, 2, 0.0, 15), (5, 6, 5, 0.02, 0),
+])
+def test_scalar_device_loop_stateful_acceptors_follow_the_oracle(kind, okind, size, real, limit):
+    """sfgpu_solve_change with GreatDeluge / StepCountingHillClimbing / DiversifiedLateAcceptance against the
+    oracle's stateful acceptors driving the oracle's ChangeMoveSelector + scoring + forager."""
+    from solverforge_b200.selectors import splitmix64
+    from tests.oracle_lib import OracleAcceptor
+    g = instances.graph_coloring(150, 500, 4, seed_edges=6, seed_colors=9, unassigned_permille=100)
+    R, steps = 2, 25
+    colors = np.stack([instances.graph_coloring(150, 500, 4, seed_edges=6, seed_colors=50 + r, unassigned_permille=100).color
+                       for r in range(R)])
+    loop = models.graph_coloring_director(g, R, colors=colors)
+    seed_base = 31337
+    best, evaluated, committed = loop.solve_change(steps, kind, max(size, 1), 1, limit, seed_base, acceptor_real=real,
+                                                   step_count_limit=size)
+    final = loop.calculate_score()
+    state = loop.scalar_state()
+    for r in range(R):
+        o = Oracle.graph_coloring(g, colors[r])
+        acc = OracleAcceptor(okind, size=size, real=real)
+        init = o.committed_score()
+        acc.phase_started(init)
+        best_o, ev_o, steps_o = init.copy(), 0, 0
+        cur = colors[r].copy()
+        for t in range(steps):
+            last = o.committed_score()
+            rows = o.enumerate_change()
+            so, oko = o.score_change(rows)
+            seed = splitmix64(seed_base ^ ((r * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) ^ t)
+            out = acc.step(so, oko, best_o, last, seed, 0 if limit else 2, max(limit, 1), True)
+            ev_o += out[2]
+            if out[0]:
+                e, v = rows[out[1]]
+                o.apply_change(e, v)
+                cur[int(e)] = int(v)
+                steps_o += 1
+            now = o.committed_score()
+            if (now[0], now[1]) > (best_o[0], best_o[1]):
+                best_o = now.copy()
+        assert final[r].tolist() == o.committed_score().tolist(), f"kind={kind} r={r}"
+        assert best[r].tolist() == best_o.tolist()
+        assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o
+        assert np.array_equal(state[r], cur)
+    assert np.array_equal(loop.fresh_score(), final)

@@ -7,7 +7,7 @@ import pytest
 from solverforge_b200 import ForageParams, instances, models
 from solverforge_b200 import _lib as L
 from tests import oracle_lib
-from tests.oracle_lib import Oracle
+from tests.oracle_lib import Oracle, OracleAcceptor
 
 pytestmark = pytest.mark.gpu
 
@@ -214,3 +214,76 @@ def test_device_loop_restore_best_and_improves():
         assert (best[r][0], best[r][1]) > (init[r][0], init[r][1])
     offs, el = d.list_state()
     assert sorted(el[0][:200].tolist()) == list(range(1, 201))
+
+
+@pytest.mark.parametrize("kind,okind,size,real,limit", [
+    (3, OracleAcceptor.GREAT_DELUGE, 0, 0.002, 0),
+    (3, OracleAcceptor.GREAT_DELUGE, 0, 0.0005, 25),
+    (4, OracleAcceptor.STEP_COUNTING, 3, 0.0, 0),
+    (4, OracleAcceptor.STEP_COUNTING, 2, 0.0, 30),
+    (5, OracleAcceptor.DIVERSIFIED_LATE, 4, 0.01, 0),
+    (5, OracleAcceptor.DIVERSIFIED_LATE, 6, 0.003, 40),
+])
+def test_device_loop_stateful_acceptors_follow_the_oracle_trajectory(kind, okind, size, real, limit):
+    """GreatDeluge / StepCountingHillClimbing / DiversifiedLateAcceptance kept on the device
+    (sfgpu_solve_nearby_list_change) against the oracle's stateful restatement of
+    acceptor/{great_deluge,step_counting,diversified_late_acceptance}.rs driving the oracle's own
+    selector + scoring + forager, step by step: same final solution, best score and counters."""
+    c = instances.cvrp(70, 6, seed=19)
+    R, K, steps = 2, 8, 30
+    starts = [instances.perturb_routes(c, 40 + r, 20) for r in range(R)]
+    offs = np.stack([s[0] for s in starts])
+    elems = np.concatenate([s[1] for s in starts])
+    loop = models.cvrp_director(c, R, offsets=offs, elems=elems)
+    seed_base = 0xBEEF
+    best, evaluated, committed = loop.solve_nearby_list_change(
+        steps, K, kind, max(size, 1), 1, limit, seed_base, acceptor_real=real, step_count_limit=size)
+    final = loop.calculate_score()
+    for r in range(R):
+        o = Oracle.cvrp(c, *starts[r])
+        acc = OracleAcceptor(okind, size=size, real=real)
+        init = o.committed_score()
+        acc.phase_started(init)
+        best_o = init.copy()
+        ev_o = 0
+        steps_o = 0
+        for t in range(steps):
+            last = o.committed_score()
+            rows = o.enumerate_nearby_list_change(K)
+            so, oko = o.score_list_change(rows)
+            out = acc.step(so, oko, best_o, last, _solve_seed(seed_base, r, t), 0 if limit else 2, max(limit, 1), True)
+            ev_o += out[2]
+            if out[0]:
+                o.apply_list_change(*rows[out[1]])
+                steps_o += 1
+            now = o.committed_score()
+            if (now[0], now[1]) > (best_o[0], best_o[1]):
+                best_o = now.copy()
+        what = f"kind={kind} replica={r}"
+        assert final[r].tolist() == o.committed_score().tolist(), what
+        assert best[r].tolist() == best_o.tolist(), what
+        assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o, what
+    assert np.array_equal(loop.fresh_score(), final)
+
+
+def test_great_deluge_form_on_the_fused_step():
+    """forage acceptor 3 (score > last || score >= threshold) on sfgpu_step_nearby_list_change."""
+    c = instances.cvrp(60, 5, seed=4)
+    d = models.cvrp_director(c)
+    o = Oracle.cvrp(c)
+    K = 12
+    base = d.calculate_score()[0]
+    rows = o.enumerate_nearby_list_change(K)
+    so, oko = o.score_list_change(rows)
+    for dl, dt in ((0, -30), (0, 0), (-1, 0), (0, 40), (1, 0)):
+        last = base + [0, dl * 10]
+        water = base + [0, dt]
+        idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(3, 1, 0), step_seeds=[11],
+                                                       ref_scores=[np.concatenate([last, water])])
+        acc = OracleAcceptor(OracleAcceptor.GREAT_DELUGE, real=0.0)
+        acc.phase_started(water)   # water level := threshold, rain 0
+        out = acc.step(so, oko, base, last, 11, 2, 1, True)
+        if out[0]:
+            assert int(idx[0]) == out[1] and best[0].tolist() == so[out[1]].tolist()
+        else:
+            assert idx[0] == 0xFFFFFFFF
