@@ -63,6 +63,25 @@ __device__ __forceinline__ KEY warp_sort32(KEY k, const uint32_t lane) {
   return k;
 }
 
+// ascending sort of 32 nearly-sorted keys: odd-even transposition rounds until sorted. The batch keys
+// arrive in increasing distance (the static neighbour list), so only ties in distance are out of
+// order and one or two rounds suffice; any input is sorted correctly (at most 16 rounds).
+template <typename KEY>
+__device__ __forceinline__ KEY warp_sort32_adaptive(KEY k, const uint32_t lane) {
+  const bool odd = lane & 1;
+  const uint32_t partner = (odd ? lane + 1 : lane - 1) & 31;
+  const bool edge = lane == 0 || lane == 31;
+  while (true) {
+    const KEY nx = __shfl_down_sync(0xffffffffu, k, 1);
+    if (!__any_sync(0xffffffffu, lane < 31 && nx < k)) break;
+    KEY p = __shfl_xor_sync(0xffffffffu, k, 1);  // pairs (0,1), (2,3), ...
+    k = odd ? (k > p ? k : p) : (k < p ? k : p);
+    p = __shfl_sync(0xffffffffu, k, partner);     // pairs (1,2), (3,4), ...
+    if (!edge) k = odd ? (k < p ? k : p) : (k > p ? k : p);
+  }
+  return k;
+}
+
 // merges a sorted batch b into the kept sorted list L: the 32 smallest of the union, ascending
 template <typename KEY>
 __device__ __forceinline__ KEY warp_merge32(KEY L, KEY b, const uint32_t lane) {
@@ -102,22 +121,25 @@ __device__ __forceinline__ KEY nearby_gen_source(const DevModel& m, const Nearby
   const uint32_t* __restrict__ nb = m.nbr + (size_t)x * m.nbr_stride;
   const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * m.cons[m.fast_pc].n0;
   KEY L = MAXK;
+  uint32_t d_next = 0;  // distance of the first neighbour of the next trip (loaded by lane NB_BATCH)
   for (uint32_t start = 0; start < m.nbr_stride; start += NB_BATCH) {
     if (start > 0) {
       const KEY kth = __shfl_sync(0xffffffffu, L, K - 1);
-      if (kth != MAXK) {
-        const uint32_t d_next = (uint32_t)__ldg(mrow + __ldg(nb + start));
-        if ((KEY)d_next > (kth >> scan_bits)) break;  // strictly farther: cannot enter the top K
-      }
+      if (kth != MAXK && (KEY)d_next > (kth >> scan_bits)) break;  // strictly farther: cannot enter the top K
     }
     KEY k0 = MAXK, k1 = MAXK;
     const uint32_t idx = start + lane;
+    uint32_t y = 0, dyu = 0;
+    if (lane <= NB_BATCH && idx < m.nbr_stride) {
+      y = __ldg(nb + idx);
+      dyu = (uint32_t)__ldg(mrow + y);
+    }
+    d_next = __shfl_sync(0xffffffffu, dyu, NB_BATCH);
     if (lane < NB_BATCH && idx < m.nbr_stride) {
-      const uint32_t y = __ldg(nb + idx);
       const uint32_t where = v.pos_of[y];
       if (where != 0xFFFFFFFFu) {
         const uint32_t e = where >> 16, py = where & 0xFFFFu;
-        const KEY dy = (KEY)(uint32_t)__ldg(mrow + y);
+        const KEY dy = (KEY)dyu;
         const uint4 re = v.rr[e];
         const uint32_t g = re.x + e + py;
         const bool own = e == se;
@@ -136,17 +158,19 @@ __device__ __forceinline__ KEY nearby_gen_source(const DevModel& m, const Nearby
         }
       }
     }
-    // compaction: all k0 keys first, then the append-slot keys
+    // compaction in list order (an append-slot key right behind its element's key): the sequence
+    // stays sorted by distance, only equal distances may be out of order
     const uint32_t m0 = __ballot_sync(0xffffffffu, k0 != MAXK), m1 = __ballot_sync(0xffffffffu, k1 != MAXK);
-    const uint32_t n0 = __popc(m0), total = n0 + __popc(m1);
+    const uint32_t total = __popc(m0) + __popc(m1);
     const uint32_t lt = (1u << lane) - 1;
+    const uint32_t at = __popc(m0 & lt) + __popc(m1 & lt);
     buf[lane] = MAXK;
     buf[lane + 32] = MAXK;
     __syncwarp();
-    if (k0 != MAXK) buf[__popc(m0 & lt)] = k0;
-    if (k1 != MAXK) buf[n0 + __popc(m1 & lt)] = k1;
+    if (k0 != MAXK) buf[at] = k0;
+    if (k1 != MAXK) buf[at + (k0 != MAXK ? 1 : 0)] = k1;
     __syncwarp();
-    KEY b = warp_sort32(buf[lane], lane);
+    KEY b = warp_sort32_adaptive(buf[lane], lane);
     L = (start == 0) ? b : warp_merge32(L, b, lane);
     if (total > 32) {  // rare: more than 32 slots from one batch
       b = warp_sort32(buf[lane + 32], lane);
