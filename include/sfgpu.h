@@ -252,6 +252,20 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
                                       int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
                                       int32_t apply_winners);
 
+/* The same whole step over the nearby list-SWAP neighbourhood (NearbyListSwapMoveSelector,
+ * heuristic/selector/nearby_list_swap.rs:165-213 + list_kernel/nearby_swap.rs:99-262, canonical order): for
+ * every source position the destinations are the later positions of its own list and every position of the
+ * later entities, the max_nearby nearest by the matrix meter (stable ties); sources without destinations are
+ * skipped, so out_index (CandidateId) counts only existing candidates. Scored as ListSwapMove
+ * (heuristic/move/list_kernel/swap.rs). Pointer conventions and the materialised layout (fixed stride of
+ * max_nearby rows per source, sentinels elsewhere) as sfgpu_step_nearby_list_change; out_winner_rows[R][4] =
+ * {first_entity, first_position, second_entity, second_position}. */
+int32_t sfgpu_step_nearby_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
+                                    const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                    const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
+                                    int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index, int64_t* out_best,
+                                    uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners);
+
 /* The same whole step for scalar models: generates the full ChangeMove neighbourhood of every replica in
  * the canonical order of ChangeMoveSelector (heuristic/selector/move_selector/change.rs:66-104,246-307:
  * entities in order, per entity every value then the to-None move when it is assigned), scores it with

@@ -432,6 +432,47 @@ std::vector<Move> enumerate_nearby_list_change_moves(S& s, const Access<S>& ac, 
   return out;
 }
 
+// list_kernel/nearby_swap.rs:99-262 (NearbySwapCursor; no owner restriction, no precedence graph,
+// not fixed to the current entity): for every source (entity order, position order from the stream
+// context) the destinations are the later positions of the same list and every position of the
+// entities later in the entity ORDER, ranked by the meter with the stable bounded top-k; sources
+// without destinations are skipped.
+template <class S, class Dist>
+std::vector<Move> enumerate_nearby_list_swap_moves(S& s, const Access<S>& ac, size_t desc, size_t max_nearby,
+                                                   MoveStreamContext ctx, Dist distance) {
+  constexpr uint64_t ENTITY_SALT = 0xA1EA25A090000001ull, SOURCE_SALT = 0xA1EA25A090000002ull;
+  size_t n = ac.entity_count(s, desc);
+  std::vector<size_t> entities(n), lens(n);
+  for (size_t o = 0; o < n; ++o) {
+    size_t e = n <= 1 ? o : ctx.selection_index(o, n, ENTITY_SALT ^ (uint64_t)desc);
+    entities[o] = e;
+    lens[o] = ac.list(s, desc, e).size();
+  }
+  std::vector<Move> out;
+  std::vector<NearbyCandidate> cand;
+  for (size_t si = 0; si < n; ++si) {
+    size_t se = entities[si], slen = lens[si];
+    for (size_t po = 0; po < slen; ++po) {
+      size_t sp = ctx.selection_index(po, slen, SOURCE_SALT ^ (uint64_t)se ^ (uint64_t)desc);
+      cand.clear();
+      for (size_t dp = sp + 1; dp < slen; ++dp) {
+        double dist = distance(s, se, sp, se, dp);
+        if (std::isfinite(dist)) cand.push_back({se, dp, dist});
+      }
+      for (size_t di = si + 1; di < n; ++di) {
+        size_t de = entities[di], dlen = lens[di];
+        for (size_t dp = 0; dp < dlen; ++dp) {
+          double dist = distance(s, se, sp, de, dp);
+          if (std::isfinite(dist)) cand.push_back({de, dp, dist});
+        }
+      }
+      sort_and_limit_nearby_candidates(cand, max_nearby);
+      for (auto& c : cand) out.push_back(Move::list_swap(desc, se, sp, c.entity, c.position));
+    }
+  }
+  return out;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Foragers (forager.rs). CandidateId = pull index.
 inline bool reservoir_pick(uint64_t step_seed, uint64_t equal_count) {  // forager.rs:143-148

@@ -607,6 +607,19 @@ static void kat_moves_and_loop() {
   m.apply(Move::list_change(0, 0, 1, 1, 1));
   CHECK(m.calculate_score() == m.fresh_score());
   CHECK(m.calculate_score() == Sc::of(-3, -20));
+  {  // heuristic/selector/tests/nearby_list.rs:302-347: nearby list swap, unique pairs in stable order
+    CvrpPlan p2;
+    p2.shared = pd;
+    p2.customers = plan.customers;
+    p2.routes = {{0, {1, 2}, pd.get()}, {1, {3, 4}, pd.get()}};
+    CvrpModel m2(p2);
+    auto equal = [](const CvrpPlan&, size_t, size_t, size_t, size_t) { return 1.0; };
+    auto mv = enumerate_nearby_list_swap_moves(m2.dir.working, m2.dir.access, 0, 4, MoveStreamContext{}, equal);
+    const size_t want[6][4] = {{0, 0, 0, 1}, {0, 0, 1, 0}, {0, 0, 1, 1}, {0, 1, 1, 0}, {0, 1, 1, 1}, {1, 0, 1, 1}};
+    CHECK(mv.size() == 6);
+    for (size_t i = 0; i < 6 && i < mv.size(); ++i)
+      CHECK(mv[i].a == want[i][0] && mv[i].b == want[i][1] && mv[i].c == want[i][2] && mv[i].d == want[i][3]);
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

@@ -28,6 +28,7 @@ struct OracleModel {
   virtual void apply(const Move& m) = 0;
   virtual std::vector<Move> enumerate_scalar(MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_list(size_t max_nearby, MoveStreamContext ctx) { return {}; }
+  virtual std::vector<Move> enumerate_list_swap(size_t max_nearby, MoveStreamContext ctx) { return {}; }
   virtual size_t scalar_desc() const { return 0; }
   virtual size_t list_desc() const { return 0; }
   virtual uint64_t score_calculations() const = 0;
@@ -218,6 +219,9 @@ struct CvrpModel final : ModelImpl<CvrpPlan> {
   }
   std::vector<Move> enumerate_list(size_t max_nearby, MoveStreamContext ctx) override {
     return enumerate_nearby_list_change_moves(dir.working, dir.access, 0, max_nearby, ctx, meter);
+  }
+  std::vector<Move> enumerate_list_swap(size_t max_nearby, MoveStreamContext ctx) override {
+    return enumerate_nearby_list_swap_moves(dir.working, dir.access, 0, max_nearby, ctx, meter);
   }
 };
 

@@ -202,6 +202,19 @@ int64_t sfo_enumerate_nearby_list_change(void* h, uint32_t max_nearby, uint64_t 
   return (int64_t)moves.size();
 }
 
+int64_t sfo_enumerate_nearby_list_swap(void* h, uint32_t max_nearby, uint64_t step_index, uint64_t step_seed,
+                                       int order, uint64_t cap, uint32_t* se, uint32_t* sp, uint32_t* de,
+                                       uint32_t* dp) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_list_swap(max_nearby, make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    se[i] = (uint32_t)moves[i].a;
+    sp[i] = (uint32_t)moves[i].b;
+    de[i] = (uint32_t)moves[i].c;
+    dp[i] = (uint32_t)moves[i].d;
+  }
+  return (int64_t)moves.size();
+}
+
 // Replay of the candidate loop (phase/candidates.rs:66-282) over precomputed evaluations.
 // forager: 0 AcceptedCount(limit) 1 FirstAccepted 2 BestScore 3 FirstBestScoreImproving
 //          4 FirstLastStepScoreImproving; acceptor: 0 HillClimbing 1 LateAcceptance(late_score) 3 AcceptAll.

@@ -291,9 +291,18 @@ class GpuScoreDirector:
                                                     v(ref_ptr), v(scores_ptr), v(doable_ptr), v(index_ptr),
                                                     v(best_ptr), v(evaluated_ptr)))
 
+    def step_nearby_list_swap(self, max_nearby: int = 20, params: "ForageParams" = None, step_seeds=None,
+                              ref_scores=None, apply: bool = False, out_rows_ptr: int = 0, out_scores_ptr: int = 0,
+                              out_doable_ptr: int = 0, out_offsets_ptr: int = 0):
+        """One whole step over the nearby list-swap neighbourhood (sfgpu_step_nearby_list_swap); same
+        conventions and return values as step_nearby_list_change."""
+        return self.step_nearby_list_change(max_nearby, params, step_seeds, ref_scores, apply, out_rows_ptr,
+                                            out_scores_ptr, out_doable_ptr, out_offsets_ptr,
+                                            _fn=self.lib.sfgpu_step_nearby_list_swap)
+
     def step_nearby_list_change(self, max_nearby: int = 20, params: "ForageParams" = None, step_seeds=None,
                                 ref_scores=None, apply: bool = False, out_rows_ptr: int = 0, out_scores_ptr: int = 0,
-                                out_doable_ptr: int = 0, out_offsets_ptr: int = 0):
+                                out_doable_ptr: int = 0, out_offsets_ptr: int = 0, _fn=None):
         """One whole local-search step on device (sfgpu_step_nearby_list_change) with HOST per-replica
         arrays: returns (index[R], best[R,2], moves_evaluated[R], winner_rows[R,4])."""
         params = params or ForageParams()
@@ -305,7 +314,7 @@ class GpuScoreDirector:
         ev = np.zeros(self.R, dtype=np.uint32)
         win = np.zeros((self.R, 4), dtype=np.uint32)
         v = lambda p: C.c_void_p(p) if p else None
-        self._check(self.lib.sfgpu_step_nearby_list_change(
+        self._check((_fn or self.lib.sfgpu_step_nearby_list_change)(
             self.h, 0, max_nearby, C.byref(fp), _ptr(seeds), _ptr(ref), v(out_offsets_ptr), v(out_rows_ptr),
             v(out_scores_ptr), v(out_doable_ptr), _ptr(idx), _ptr(best), _ptr(ev), _ptr(win), 1 if apply else 0))
         return idx, best, ev, win

@@ -922,9 +922,6 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
           size_t need = (size_t)chunks * dm.R * sizeof(ChunkPartial);
           if (need > ctx->partials_bytes) {
             if (ctx->partials) cudaFree(ctx->partials);
-  if (ctx->solve_buf) cudaFree(ctx->solve_buf);
-  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
-  if (ctx->small_dev) cudaFree(ctx->small_dev);
             ctx->partials = nullptr;
             ctx->partials_bytes = 0;
             CU(cudaMalloc(&ctx->partials, need));
@@ -1124,7 +1121,7 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
 namespace {
 // generate + score + forage (two kernels) on the context's stream
 int launch_nearby_kernels(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t* d_best, uint32_t* d_eval,
-                          uint32_t* d_win) {
+                          uint32_t* d_win, int move = MOVE_CHANGE) {
   const DevModel& dm = ctx->dm;
   const uint32_t R = dm.R;
   // sources per CTA: 8 warps, >= 24 sources each when there is enough work
@@ -1137,8 +1134,13 @@ int launch_nearby_kernels(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_
   size_t smem = dm.fast_stage_bytes;
   int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
 #define NEARBYK(FN, KEY, CELL)                                                                       \
-  nearby_step_kernel<FN, KEY, CELL><<<grid, 256, smem, ctx->stream>>>(dm, a);                         \
-  nearby_finish_kernel<FN, KEY, CELL><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win)
+  if (move == MOVE_SWAP) {                                                                           \
+    nearby_step_kernel<FN, KEY, CELL, MOVE_SWAP><<<grid, 256, smem, ctx->stream>>>(dm, a);            \
+    nearby_finish_kernel<FN, KEY, CELL, MOVE_SWAP><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win); \
+  } else {                                                                                           \
+    nearby_step_kernel<FN, KEY, CELL><<<grid, 256, smem, ctx->stream>>>(dm, a);                       \
+    nearby_finish_kernel<FN, KEY, CELL><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win); \
+  }
 #define NEARBYK4(FN)                                                                                 \
   if (ctx->nb_key32) {                                                                               \
     if (dm.fm_u16) { NEARBYK(FN, uint32_t, uint16_t); } else { NEARBYK(FN, uint32_t, int32_t); }     \
@@ -1166,12 +1168,11 @@ int ensure_partials(sfgpu_ctx* ctx, size_t need) {
 
 // ------------------------------------------------------------------------------------------
 // Whole local-search step on device: nearby list-change neighbourhood generation + scoring + forager.
-int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
-                                      const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                                      const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
-                                      int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
-                                      int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                                      int32_t apply_winners) {
+namespace {
+int step_nearby_impl(sfgpu_ctx* ctx, int move, uint32_t flags, uint32_t max_nearby, const sfgpu_forage_params* params,
+                     const uint64_t* step_seeds, const int64_t* ref_scores, uint64_t* out_cand_offsets,
+                     uint32_t* out_rows, int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
+                     int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
   int rc = check_committed(ctx);
   if (rc) return rc;
   const DevModel& dm = ctx->dm;
@@ -1200,8 +1201,7 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   int64_t* d_best = out_best;
   if (!dev_io) {
     if (small > ctx->small_bytes) {
-      if (ctx->solve_buf) cudaFree(ctx->solve_buf);
-  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
       if (ctx->small_dev) cudaFree(ctx->small_dev);
       ctx->small_pin = ctx->small_dev = nullptr;
       ctx->small_bytes = 0;
@@ -1234,14 +1234,15 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
   a.out_doable = out_doable;
   a.out_offsets = out_cand_offsets;
   ev_begin(ctx);
-  rc = launch_nearby_kernels(ctx, a, d_idx, d_best, d_eval, d_win);
+  rc = launch_nearby_kernels(ctx, a, d_idx, d_best, d_eval, d_win, move);
   if (rc) return rc;
   ev_end(ctx);
   ctx->launches += 2;
   CU(cudaGetLastError());
   if (apply_winners) {
     // a replica without a winner carries the sentinel row (owner 0xFFFFFFFF): not doable, skipped
-    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, d_win, nullptr, nullptr, nullptr);
+    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, move == MOVE_SWAP ? 3 : 2, d_win, nullptr,
+                                                                       nullptr, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -1256,6 +1257,29 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
     if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
   }
   return SFGPU_OK;
+}
+}  // namespace
+
+int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
+                                      const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                      const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
+                                      int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
+                                      int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                                      int32_t apply_winners) {
+  return step_nearby_impl(ctx, MOVE_CHANGE, flags, max_nearby, params, step_seeds, ref_scores, out_cand_offsets,
+                          out_rows, out_scores, out_doable, out_index, out_best, out_evaluated, out_winner_rows,
+                          apply_winners);
+}
+
+int32_t sfgpu_step_nearby_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
+                                    const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                    const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
+                                    int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index, int64_t* out_best,
+                                    uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+  if (ctx && ctx->dm.fast_pc < 0)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "nearby list swap needs a path-cost constraint (its matrix is the distance meter)");
+  return step_nearby_impl(ctx, MOVE_SWAP, flags, max_nearby, params, step_seeds, ref_scores, out_cand_offsets, out_rows,
+                          out_scores, out_doable, out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
 }
 
 // ------------------------------------------------------------------------------------------

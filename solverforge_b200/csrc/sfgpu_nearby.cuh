@@ -263,6 +263,122 @@ __device__ __forceinline__ uint32_t warp_best_mask(bool acc, int64_t dh, int64_t
   return __ballot_sync(0xffffffffu, acc && dh == bh && ds == bs);
 }
 
+// ---- nearby list SWAP (NearbySwapCursor, list_kernel/nearby_swap.rs:99-262) -------------------
+// Destinations of source (se, sp): the later positions of its own list, then every position of the
+// later entities — exactly the flat positions g > f in scan order — ranked by d(x, element at g)
+// with the stable bounded top-k (ties keep scan order = flat position). Source f has
+// min(K, total - 1 - f) candidates; sources without destinations are skipped, so pull indices are
+// a prefix sum over sources (swap_prefix).
+#define MOVE_CHANGE 0
+#define MOVE_SWAP 1
+
+__device__ __forceinline__ uint32_t swap_count(uint32_t f, uint32_t total, uint32_t K) {
+  const uint32_t e = total - 1 - f;
+  return e < K ? e : K;
+}
+// number of candidates pulled before source f
+__device__ __forceinline__ uint32_t swap_prefix(uint32_t f, uint32_t total, uint32_t K) {
+  const uint32_t n_full = total > K ? total - K : 0;  // sources that yield K candidates
+  if (f <= n_full) return f * K;
+  // sources n_full .. f-1 yield total-1-f' each
+  const uint32_t cnt = f - n_full, first = total - 1 - n_full, last = total - f;  // first down to last
+  return n_full * K + (uint32_t)(((uint64_t)(first + last) * cnt) / 2);
+}
+
+template <typename KEY, typename CELL>
+__device__ __forceinline__ KEY nearby_swap_gen_source(const DevModel& m, const NearbyView& v, const uint32_t scan_bits,
+                                                      const uint32_t f, const uint32_t K, const uint32_t total,
+                                                      const uint32_t lane, KEY* __restrict__ buf, uint32_t& x,
+                                                      uint32_t& se, uint32_t& sp, uint4& prec, uint4& rsrc) {
+  const KEY MAXK = KeyTraits<KEY>::maxkey();
+  prec = v.pr[f];
+  x = prec.x;
+  se = prec.w;
+  rsrc = v.rr[se];
+  sp = f - rsrc.x;
+  const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * m.cons[m.fast_pc].n0;
+  const uint32_t eligible = total - 1 - f;
+  KEY L = MAXK;
+  if (eligible <= 64) {
+    // few destinations: rank them all directly (the walk below would scan most of the list)
+    for (uint32_t base = 0; base < eligible; base += 32) {
+      const uint32_t g = f + 1 + base + lane;
+      KEY k = MAXK;
+      if (base + lane < eligible) k = ((KEY)(uint32_t)__ldg(mrow + v.pr[g].x) << scan_bits) | g;
+      k = warp_sort32(k, lane);
+      L = base == 0 ? k : warp_merge32(L, k, lane);
+    }
+    return lane < K ? L : MAXK;
+  }
+  const uint32_t* __restrict__ nb = m.nbr + (size_t)x * m.nbr_stride;
+  uint32_t d_next = 0;
+  for (uint32_t start = 0; start < m.nbr_stride; start += 31) {
+    if (start > 0) {
+      const KEY kth = __shfl_sync(0xffffffffu, L, K - 1);
+      if (kth != MAXK && (KEY)d_next > (kth >> scan_bits)) break;  // strictly farther: cannot enter the top K
+    }
+    const uint32_t idx = start + lane;
+    uint32_t dyu = 0;
+    KEY k = MAXK;
+    if (idx < m.nbr_stride) {
+      const uint32_t y = __ldg(nb + idx);
+      dyu = (uint32_t)__ldg(mrow + y);
+      const uint32_t where = v.pos_of[y];
+      if (lane < 31 && where != 0xFFFFFFFFu) {
+        const uint32_t g = v.rr[where >> 16].x + (where & 0xFFFFu);
+        if (g > f) k = ((KEY)dyu << scan_bits) | g;
+      }
+    }
+    d_next = __shfl_sync(0xffffffffu, dyu, 31);
+    k = warp_sort32(k, lane);
+    L = start == 0 ? k : warp_merge32(L, k, lane);
+  }
+  return lane < K ? L : MAXK;
+}
+
+// score delta of swapping the source element x (flat f) with the element at flat position g of `key`
+// — packed-record restatement of list_swap_delta (ListSwapMove::do_move, list_kernel/swap.rs): the four
+// legs around both positions change; adjacent positions share one leg.
+template <int SUM_FN, typename KEY, typename CELL, typename S>
+__device__ __forceinline__ void nearby_swap_score(const DevModel& m, const NearbyConsts<S>& c, const NearbyView& v,
+                                                  const uint32_t scan_bits, const KEY key, const uint32_t f,
+                                                  const uint32_t x, const uint32_t se, const uint4 prec,
+                                                  const uint4 rsrc, S& dh, S& ds, uint32_t& de, uint32_t& dp) {
+  typedef typename FastArith<CELL>::US US;
+  const uint32_t g = (uint32_t)(key & (((KEY)1 << scan_bits) - 1));
+  const uint4 py = v.pr[g];
+  const uint32_t y = py.x;
+  de = py.w;
+  const uint4 rd = v.rr[de];
+  dp = g - rd.x;
+  const uint4 sx0 = v.sr[f + se], sx1 = v.sr[f + se + 1];  // legs (a, x) and (x, b)
+  const uint4 sy0 = v.sr[g + de], sy1 = v.sr[g + de + 1];  // legs (c, y) and (y, d)
+  const CELL* __restrict__ xrow = (const CELL*)m.fm_row + (size_t)x * c.dim;
+  const CELL* __restrict__ xcol = (const CELL*)m.fm_col + (size_t)x * c.dim;
+  const CELL* __restrict__ yrow = (const CELL*)m.fm_row + (size_t)y * c.dim;
+  const CELL* __restrict__ ycol = (const CELL*)m.fm_col + (size_t)y * c.dim;
+  int32_t dl;
+  if (g == f + 1 && de == se) {
+    // a x y d -> a y x d
+    dl = (int32_t)__ldg(ycol + sx0.x) + (int32_t)__ldg(yrow + x) + (int32_t)__ldg(xrow + sy1.y) - (int32_t)sx0.z -
+         (int32_t)sx1.z - (int32_t)sy1.z;
+  } else {
+    dl = (int32_t)__ldg(ycol + sx0.x) + (int32_t)__ldg(yrow + sx1.y) - (int32_t)sx0.z - (int32_t)sx1.z +
+         (int32_t)__ldg(xcol + sy0.x) + (int32_t)__ldg(xrow + sy1.y) - (int32_t)sy0.z - (int32_t)sy1.z;
+  }
+  dh = 0;
+  ds = 0;
+  const S d = (S)((US)c.pc_a * (US)(S)dl);
+  if (c.pc_hard) dh += d; else ds += d;
+  if (SUM_FN >= 0 && se != de) {
+    const S ss = sizeof(S) == 4 ? (S)rsrc.z : (S)(((uint64_t)rsrc.w << 32) | rsrc.z);
+    const S sd = sizeof(S) == 4 ? (S)rd.z : (S)(((uint64_t)rd.w << 32) | rd.z);
+    // x leaves se and y enters it: the net transfer se -> de is val(x) - val(y)
+    const S d2 = list_sum_delta<SUM_FN, S, US>(c.ls_a, c.ls_b, (S)((US)(S)(int32_t)prec.z - (US)(S)(int32_t)py.z), ss, sd);
+    if (c.ls_hard) dh += d2; else ds += d2;
+  }
+}
+
 // number of candidates every source yields: min(K, slots of non-empty routes - 2)
 __device__ __forceinline__ uint32_t nearby_count(const DevModel& m, const uint4* rr, uint32_t K) {
   uint32_t slots = 0;
@@ -275,7 +391,7 @@ __device__ __forceinline__ uint32_t nearby_count(const DevModel& m, const uint4*
 }
 
 // grid = (chunks, R), 256 threads. Warp w of chunk c handles sources c_lo + w, c_lo + w + 8, ...
-template <int SUM_FN, typename KEY, typename CELL>
+template <int SUM_FN, typename KEY, typename CELL, int MOVE = MOVE_CHANGE>
 __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant__ DevModel m, const NearbyArgs a) {
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
@@ -323,12 +439,22 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
   for (uint32_t f = c_lo + warp; f < c_hi; f += 8) {
     uint32_t x, se, sp;
     uint4 prec, rsrc;
-    const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, a.max_nearby, lane, s_buf[warp], x, se, sp,
-                                                 prec, rsrc);
-    const bool have = lane < count && key != KeyTraits<KEY>::maxkey();
+    KEY key;
+    if (MOVE == MOVE_SWAP)
+      key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, f, a.max_nearby, total, lane, s_buf[warp], x, se, sp,
+                                              prec, rsrc);
+    else
+      key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, a.max_nearby, lane, s_buf[warp], x, se, sp, prec, rsrc);
+    const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(f, total, a.max_nearby) : count;
+    const bool have = lane < cnt && key != KeyTraits<KEY>::maxkey();
     S dh = 0, ds = 0;
     uint32_t de = 0, dp = 0;
-    if (have) nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    if (have) {
+      if (MOVE == MOVE_SWAP)
+        nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, f, x, se, prec, rsrc, dh, ds, de, dp);
+      else
+        nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    }
     const bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
     uint32_t accm;
     const uint32_t eq = warp_best_mask(acc, dh, ds, accm);
@@ -359,7 +485,7 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
 
 // One CTA per replica: ordered replay over the per-source partials (AcceptedCount cut, best, tie
 // rule), regeneration of the one or two sources whose lanes matter, winner row out.
-template <int SUM_FN, typename KEY, typename CELL>
+template <int SUM_FN, typename KEY, typename CELL, int MOVE = MOVE_CHANGE>
 __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constant__ DevModel m, const NearbyArgs a,
                                                             uint32_t* __restrict__ out_index,
                                                             int64_t* __restrict__ out_best,
@@ -421,12 +547,22 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
       // regenerate the cut source; keep lanes up to the s_lcut-th accepted one
       uint32_t x, se, sp;
       uint4 prec, rsrc;
-      const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, lane, s_buf, x, se, sp,
-                                                   prec, rsrc);
-      const bool have = lane < count && key != KeyTraits<KEY>::maxkey();
+      KEY key;
+      if (MOVE == MOVE_SWAP)
+        key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, total, lane, s_buf, x, se, sp,
+                                                prec, rsrc);
+      else
+        key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, lane, s_buf, x, se, sp, prec, rsrc);
+      const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(s_fcut, total, a.max_nearby) : count;
+      const bool have = lane < cnt && key != KeyTraits<KEY>::maxkey();
       S dh = 0, ds = 0;
       uint32_t de = 0, dp = 0;
-      if (have) nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+      if (have) {
+        if (MOVE == MOVE_SWAP)
+          nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, s_fcut, x, se, prec, rsrc, dh, ds, de, dp);
+        else
+          nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+      }
       const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
       bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
       const uint32_t cut_rank = s_lcut;  // read by every lane before one lane overwrites it below
@@ -489,7 +625,10 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     s_bh = h;
     s_bs = s2;
     s_any = an;
-    s_evaluated = fcut < total ? fcut * count + s_lcut + 1 : total * count;
+    if (MOVE == MOVE_SWAP)
+      s_evaluated = fcut < total ? swap_prefix(fcut, total, a.max_nearby) + s_lcut + 1 : swap_prefix(total, total, a.max_nearby);
+    else
+      s_evaluated = fcut < total ? fcut * count + s_lcut + 1 : total * count;
   }
   __syncthreads();
   bh = s_bh;
@@ -553,19 +692,29 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     const uint32_t fstar = s_fstar, j = s_jstar;
     uint32_t x, se, sp;
     uint4 prec, rsrc;
-    const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, lane, s_buf, x, se, sp, prec,
-                                                 rsrc);
-    const bool have = lane < count && key != KeyTraits<KEY>::maxkey() && !(fstar == fcut && lane > s_lcut);
+    KEY key;
+    if (MOVE == MOVE_SWAP)
+      key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, total, lane, s_buf, x, se, sp, prec,
+                                              rsrc);
+    else
+      key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, lane, s_buf, x, se, sp, prec, rsrc);
+    const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(fstar, total, a.max_nearby) : count;
+    const bool have = lane < cnt && key != KeyTraits<KEY>::maxkey() && !(fstar == fcut && lane > s_lcut);
     S dh = 0, ds = 0;
     uint32_t de = 0, dp = 0;
-    if (have) nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    if (have) {
+      if (MOVE == MOVE_SWAP)
+        nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, fstar, x, se, prec, rsrc, dh, ds, de, dp);
+      else
+        nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+    }
     const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
     const bool hit = have && oh == bh && os == bs && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
     uint32_t mm = __ballot_sync(0xffffffffu, hit);
     for (uint32_t t = 1; t < j; ++t) mm &= mm - 1;
     const uint32_t wl = __ffs(mm) - 1;
     if (lane == wl) {
-      out_index[r] = fstar * count + wl;
+      out_index[r] = (MOVE == MOVE_SWAP ? swap_prefix(fstar, total, a.max_nearby) : fstar * count) + wl;
       out_best[r * 2] = bh;
       out_best[r * 2 + 1] = bs;
       if (out_evaluated) out_evaluated[r] = s_evaluated;

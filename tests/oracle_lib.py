@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_nearby_list_change.argtypes = [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P,
                                                        _P, _P, _P]
         l.sfo_enumerate_nearby_list_change.restype = C.c_int64
+        l.sfo_enumerate_nearby_list_swap.argtypes = l.sfo_enumerate_nearby_list_change.argtypes
+        l.sfo_enumerate_nearby_list_swap.restype = C.c_int64
         l.sfo_replay_step.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
                                       C.c_int, _P]
         l.sfo_acceptor_create.restype = _P
@@ -195,6 +197,14 @@ class Oracle:
         v = np.zeros(n, dtype=np.int32)
         self.l.sfo_enumerate_change(self.h, step_index, step_seed, order, n, _p(e), _p(v))
         return np.stack([e.astype(np.int64), v.astype(np.int64)], axis=1)
+
+    def enumerate_nearby_list_swap(self, max_nearby=20, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_nearby_list_swap(self.h, max_nearby, step_index, step_seed, order, 0, None, None,
+                                                  None, None)
+        c = [np.zeros(n, dtype=np.uint32) for _ in range(4)]
+        self.l.sfo_enumerate_nearby_list_swap(self.h, max_nearby, step_index, step_seed, order, n, _p(c[0]),
+                                              _p(c[1]), _p(c[2]), _p(c[3]))
+        return np.stack(c, axis=1)
 
     def enumerate_nearby_list_change(self, max_nearby=20, step_index=0, step_seed=0, order=0) -> np.ndarray:
         n = self.l.sfo_enumerate_nearby_list_change(self.h, max_nearby, step_index, step_seed, order, 0, None, None,

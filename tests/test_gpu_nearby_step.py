@@ -287,3 +287,98 @@ def test_great_deluge_form_on_the_fused_step():
             assert int(idx[0]) == out[1] and best[0].tolist() == so[out[1]].tolist()
         else:
             assert idx[0] == 0xFFFFFFFF
+
+
+def _swap_pull_layout(total, K):
+    """per-source candidate counts of the nearby swap cursor: min(K, total - 1 - f)."""
+    return [min(K, total - 1 - f) for f in range(total)]
+
+
+@pytest.mark.parametrize("n,routes,K,coarse", [(150, 9, 20, 1), (150, 9, 20, 30), (40, 3, 32, 1), (90, 6, 5, 7)])
+def test_nearby_list_swap_generation_and_step_match_oracle(n, routes, K, coarse):
+    """sfgpu_step_nearby_list_swap: generated ListSwapMove rows in the reference cursor order
+    (list_kernel/nearby_swap.rs), their scores, forager/acceptor replay and the committed winner."""
+    c = instances.cvrp(n, routes, seed=31)
+    c.matrix = (c.matrix // coarse) * coarse
+    R = 2
+    starts = [instances.perturb_routes(c, 90 + r, 40) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    cap = n
+    bufs = _materialise(d, R, cap, K)
+    base = d.calculate_score()
+    d.step_nearby_list_swap(K, ForageParams(0, 1, 0), step_seeds=[1, 2], out_offsets_ptr=bufs[0].data_ptr(),
+                            out_rows_ptr=bufs[1].data_ptr(), out_scores_ptr=bufs[2].data_ptr(),
+                            out_doable_ptr=bufs[3].data_ptr())
+    rows = bufs[1].cpu().numpy().view(np.uint32)
+    scores = bufs[2].cpu().numpy()
+    doable = bufs[3].cpu().numpy()
+    S = cap * K
+    gen = []
+    for r in range(R):
+        want = oracles[r].enumerate_nearby_list_swap(K)
+        blk = slice(r * S, (r + 1) * S)
+        ok = doable[blk] == 1
+        got = rows[blk][ok]
+        assert got.shape == want.shape, f"replica {r}: {got.shape} vs {want.shape}"
+        assert np.array_equal(got, want), f"replica {r}: generated swap rows differ from the reference cursor order"
+        # fixed stride of K rows per source, existing rows first
+        counts = _swap_pull_layout(n, K)
+        per_src = ok.reshape(cap, K).sum(axis=1)
+        assert per_src.tolist() == counts
+        so, oko = oracles[r].score_list_swap(want)
+        assert oko.all()
+        assert np.array_equal(scores[blk][ok], so), f"replica {r}: swap scores differ"
+        gen.append((want, so))
+    for seed in (3, 8):
+        for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+            for ties in (0, 1):
+                for limit in (0, 1, 50, 100000):
+                    ref = np.stack([np.concatenate([base[r] + [0, -15], base[r] + [0, -60]]) for r in range(R)])
+                    idx, best, ev, win = d.step_nearby_list_swap(K, ForageParams(acceptor, ties, limit),
+                                                                 step_seeds=[seed] * R, ref_scores=ref)
+                    for r in range(R):
+                        want, so = gen[r]
+                        out = oracle_lib.replay_step(so, np.ones(len(so), np.uint8), [0, 0], ref[r][:2], ref[r][2:],
+                                                     seed, 0 if limit else 2, max(limit, 1), bool(ties), okind)
+                        what = f"seed={seed} acc={acceptor} ties={ties} limit={limit} r={r}"
+                        assert int(ev[r]) == out[2], what + " moves_evaluated"
+                        if out[0]:
+                            assert int(idx[r]) == out[1], what
+                            assert best[r].tolist() == so[out[1]].tolist(), what
+                            assert win[r].tolist() == want[out[1]].tolist(), what + " winner row"
+                        else:
+                            assert idx[r] == 0xFFFFFFFF, what
+    # committing the winners on device keeps cached == fresh == oracle
+    last = d.calculate_score()
+    idx, best, ev, win = d.step_nearby_list_swap(K, ForageParams(1, 0, 0), step_seeds=[5] * R,
+                                                 ref_scores=np.concatenate([last, last], axis=1), apply=True)
+    after = d.calculate_score()
+    for r in range(R):
+        if idx[r] != 0xFFFFFFFF:
+            oracles[r].apply_list_swap(*win[r])
+        assert after[r].tolist() == oracles[r].committed_score().tolist()
+    assert np.array_equal(d.fresh_score(), after)
+
+
+def test_full_size_cvrp_1000_nearby_swap_matches_oracle():
+    """C3 size (1000 customers / 80 routes, max_nearby 20): the whole swap neighbourhood, every score, the winner."""
+    c = instances.cvrp()
+    K = 20
+    start = instances.perturb_routes(c, 78, 300)
+    d = models.cvrp_director(c, 1, offsets=start[0][None, :], elems=start[1])
+    o = Oracle.cvrp(c, *start)
+    bufs = _materialise(d, 1, 1000, K)
+    idx, best, ev, win = d.step_nearby_list_swap(K, ForageParams(0, 1, 0), step_seeds=[9],
+                                                 out_offsets_ptr=bufs[0].data_ptr(), out_rows_ptr=bufs[1].data_ptr(),
+                                                 out_scores_ptr=bufs[2].data_ptr(), out_doable_ptr=bufs[3].data_ptr())
+    want = o.enumerate_nearby_list_swap(K)
+    ok = bufs[3].cpu().numpy() == 1
+    got = bufs[1].cpu().numpy().view(np.uint32)[ok]
+    assert len(want) == sum(_swap_pull_layout(1000, K))
+    assert np.array_equal(got, want)
+    so, oko = o.score_list_swap(want)
+    assert oko.all() and np.array_equal(bufs[2].cpu().numpy()[ok], so)
+    out = oracle_lib.replay_step(so, np.ones(len(so), np.uint8), [0, 0], [0, 0], [0, 0], 9, 2, 1, True, 3)
+    assert int(idx[0]) == out[1] and int(ev[0]) == len(want)
+    assert win[0].tolist() == want[out[1]].tolist()
