@@ -148,3 +148,54 @@ def nearby_list_change_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.n
             rows[:, 3] = o_p[top]
             out.append(rows)
     return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint32)
+
+
+def nearby_list_swap_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.ndarray, max_nearby: int = 20,
+                          ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0) -> np.ndarray:
+    """rows[n][4] = (first_entity, first_position, second_entity, second_position) uint32 in the pull order of
+    NearbyListSwapMoveSelector (heuristic/selector/nearby_list_swap.rs:165-213, cursor
+    list_kernel/nearby_swap.rs:99-262): for every source (entity order and position order from the stream
+    context) the destinations are the later positions of the same list, then every position of the entities
+    later in the entity ORDER; distance(source element, destination element), infinite cells dropped; the
+    max_nearby smallest, ties in scan order; sources without destinations are skipped.
+    """
+    offsets = np.asarray(offsets, dtype=np.int64)
+    elems = np.asarray(elems, dtype=np.int64)
+    n_owners = len(offsets) - 1
+    lens = np.diff(offsets)
+    entity_salt = 0xA1EA25A090000001 ^ descriptor_index
+    if n_owners <= 1 or ctx.is_canonical():
+        entities = np.arange(n_owners)
+    else:
+        entities = np.array([ctx.selection_index(o, n_owners, entity_salt) for o in range(n_owners)])
+    out = []
+    for si in range(n_owners):
+        se = int(entities[si])
+        slen = int(lens[se])
+        if slen == 0:
+            continue
+        later = entities[si + 1:]
+        l_e = np.repeat(later, lens[later])
+        l_first = np.concatenate([[0], np.cumsum(lens[later])])[:-1]
+        l_p = np.arange(len(l_e)) - np.repeat(l_first, lens[later])
+        source_salt = 0xA1EA25A090000002 ^ se ^ descriptor_index
+        for po in range(slen):
+            sp = ctx.selection_index(po, slen, source_salt)
+            own_p = np.arange(sp + 1, slen)
+            d_e = np.concatenate([np.full(len(own_p), se, dtype=np.int64), l_e])
+            d_p = np.concatenate([own_p, l_p])
+            if len(d_e) == 0:
+                continue
+            x = elems[offsets[se] + sp]
+            cell = matrix[x, elems[offsets[d_e] + d_p]]
+            idx = np.flatnonzero((cell >= 0) & (cell != _I64_MAX))
+            if len(idx) == 0:
+                continue
+            top = idx[np.argsort(cell[idx].astype(np.float64), kind="stable")[:max_nearby]]
+            rows = np.empty((len(top), 4), dtype=np.uint32)
+            rows[:, 0] = se
+            rows[:, 1] = sp
+            rows[:, 2] = d_e[top]
+            rows[:, 3] = d_p[top]
+            out.append(rows)
+    return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint32)

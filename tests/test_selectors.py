@@ -41,3 +41,27 @@ def test_nearby_handles_empty_routes_and_unreachable_cells():
     el = np.array([x for r in routes for x in r], dtype=np.uint32)
     o = Oracle.cvrp(c, offs, el)
     assert np.array_equal(selectors.nearby_list_change_rows(offs, el, c.matrix, 6), o.enumerate_nearby_list_change(6))
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_nearby_list_swap_order_matches_reference(order):
+    c = instances.cvrp(60, 6, seed=8)
+    c.matrix = (c.matrix // 25) * 25
+    offs, el = instances.perturb_routes(c, 6, 30)
+    o = Oracle.cvrp(c, offs, el)
+    for step_index, seed in ((0, 0), (2, 55555), (31, 0x123456789ABCDEF)):
+        want = o.enumerate_nearby_list_swap(7, step_index, seed, order)
+        got = selectors.nearby_list_swap_rows(offs, el, c.matrix, 7, MoveStreamContext(step_index, seed, order))
+        assert np.array_equal(got, want), f"order={order} step={step_index}"
+
+
+def test_nearby_swap_handles_empty_routes_and_unreachable_cells():
+    c = instances.cvrp(20, 5, seed=2)
+    c.matrix = c.matrix.copy()
+    c.matrix[3, 7] = np.iinfo(np.int64).max
+    c.matrix[5, :] = -1
+    routes = [[1, 2, 3, 7, 9], [], [4, 5, 10], [], list(range(11, 21)) + [6, 8]]
+    offs = np.cumsum([0] + [len(r) for r in routes]).astype(np.uint32)
+    el = np.array([x for r in routes for x in r], dtype=np.uint32)
+    o = Oracle.cvrp(c, offs, el)
+    assert np.array_equal(selectors.nearby_list_swap_rows(offs, el, c.matrix, 6), o.enumerate_nearby_list_swap(6))
