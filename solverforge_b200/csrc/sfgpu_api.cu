@@ -85,6 +85,7 @@ struct sfgpu_ctx {
   size_t dscr_bytes = 0;
   void* partials = nullptr;  // fused forager chunk partials
   void* solve_buf = nullptr;  // device-resident loop state
+  std::vector<uint32_t> relabel_host, inverse_host;  // element id <-> internal id of the fast records
   size_t solve_bytes = 0;
   void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
   void* small_dev = nullptr;
@@ -759,34 +760,79 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     if (mt.rows != mt.cols) {
       dm.fm_row = mt.dev;  // rectangular: no transpose trick, plain int32 gathers
       dm.fm_col = nullptr;
-    } else if (dm.fm_u16) {
-      std::vector<uint16_t> a(mt.host.size()), t(mt.host.size());
-      for (uint32_t i = 0; i < mt.rows; ++i)
-        for (uint32_t j = 0; j < mt.cols; ++j) {
-          a[(size_t)i * mt.cols + j] = (uint16_t)mt.host[(size_t)i * mt.cols + j];
-          t[(size_t)j * mt.cols + i] = (uint16_t)mt.host[(size_t)i * mt.cols + j];
-        }
-      uint16_t *da = nullptr, *dt = nullptr;
-      int rc = dev_upload(ctx, a.data(), a.size(), &da);
-      if (rc) return rc;
-      dm.fm_row = da;
-      dm.fm_col = da;
-      if (!sym) {
-        rc = dev_upload(ctx, t.data(), t.size(), &dt);
-        if (rc) return rc;
-        dm.fm_col = dt;
-      }
     } else {
-      dm.fm_row = mt.dev;
-      dm.fm_col = mt.dev;
-      if (!sym) {
-        std::vector<int32_t> t(mt.host.size());
-        for (uint32_t i = 0; i < mt.rows; ++i)
-          for (uint32_t j = 0; j < mt.cols; ++j) t[(size_t)j * mt.cols + i] = (int32_t)mt.host[(size_t)i * mt.cols + j];
-        int32_t* dt = nullptr;
-        int rc = dev_upload(ctx, t.data(), t.size(), &dt);
+      // Internal relabelling for gather locality: a greedy nearest-neighbour tour from row 0 gives
+      // elements that are close in cost neighbouring internal ids, so the ~20 candidates of one source
+      // (all near it) read few 32-byte sectors of its matrix row. Only the record ids, these matrix
+      // copies and the neighbour lists live in the internal id space; rows, state and outputs do not.
+      const uint32_t n = mt.rows;
+      std::vector<uint32_t> relabel(n), inverse(n);
+      if (n <= 20000 && !getenv("SFGPU_NO_RELABEL")) {
+        std::vector<uint8_t> seen(n, 0);
+        uint32_t cur = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+          seen[cur] = 1;
+          inverse[k] = cur;
+          relabel[cur] = k;
+          const int64_t* row = mt.host.data() + (size_t)cur * n;
+          int64_t best = INT64_MAX;
+          uint32_t nxt = cur;
+          for (uint32_t y = 0; y < n; ++y)
+            if (!seen[y] && row[y] < best) {
+              best = row[y];
+              nxt = y;
+            }
+          cur = nxt;
+        }
+      } else {
+        for (uint32_t i = 0; i < n; ++i) relabel[i] = inverse[i] = i;
+      }
+      while (relabel.size() < dm.n_elem_rows) {  // element rows beyond the matrix keep their own id
+        inverse.push_back((uint32_t)relabel.size());
+        relabel.push_back((uint32_t)relabel.size());
+      }
+      ctx->relabel_host = relabel;
+      ctx->inverse_host = inverse;
+      uint32_t* drl = nullptr;
+      int rc = dev_upload(ctx, relabel.data(), relabel.size(), &drl);
+      if (rc) return rc;
+      dm.relabel = drl;
+      if (dm.fm_u16) {
+        std::vector<uint16_t> a(mt.host.size()), t(mt.host.size());
+        for (uint32_t i = 0; i < n; ++i)
+          for (uint32_t j = 0; j < n; ++j) {
+            const uint16_t c = (uint16_t)mt.host[(size_t)i * n + j];
+            a[(size_t)relabel[i] * n + relabel[j]] = c;
+            t[(size_t)relabel[j] * n + relabel[i]] = c;
+          }
+        uint16_t *da = nullptr, *dt = nullptr;
+        rc = dev_upload(ctx, a.data(), a.size(), &da);
         if (rc) return rc;
-        dm.fm_col = dt;
+        dm.fm_row = da;
+        dm.fm_col = da;
+        if (!sym) {
+          rc = dev_upload(ctx, t.data(), t.size(), &dt);
+          if (rc) return rc;
+          dm.fm_col = dt;
+        }
+      } else {
+        std::vector<int32_t> a(mt.host.size()), t(mt.host.size());
+        for (uint32_t i = 0; i < n; ++i)
+          for (uint32_t j = 0; j < n; ++j) {
+            const int32_t c = (int32_t)mt.host[(size_t)i * n + j];
+            a[(size_t)relabel[i] * n + relabel[j]] = c;
+            t[(size_t)relabel[j] * n + relabel[i]] = c;
+          }
+        int32_t *da = nullptr, *dt = nullptr;
+        rc = dev_upload(ctx, a.data(), a.size(), &da);
+        if (rc) return rc;
+        dm.fm_row = da;
+        dm.fm_col = da;
+        if (!sym) {
+          rc = dev_upload(ctx, t.data(), t.size(), &dt);
+          if (rc) return rc;
+          dm.fm_col = dt;
+        }
       }
     }
     if (!dm.fm_col) {  // rectangular matrix: keep the generic kernel
@@ -801,6 +847,9 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     dm.nbr_stride = nrow > 0 ? nrow - 1 : 0;
     std::vector<uint32_t> nbr((size_t)nrow * dm.nbr_stride);
     std::vector<uint32_t> order(dm.nbr_stride);
+    // (internal ids on both sides: row relabel[x] lists relabel[y]; equal distances may come in any
+    // order, the kernels rank them by scan index)
+    const std::vector<uint32_t>& rl = ctx->relabel_host;
     for (uint32_t x = 0; x < nrow; ++x) {
       uint32_t k = 0;
       for (uint32_t y = 0; y < nrow; ++y)
@@ -809,14 +858,17 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       std::sort(order.begin(), order.end(), [row](uint32_t l, uint32_t r) {
         return row[l] != row[r] ? row[l] < row[r] : l < r;
       });
-      std::copy(order.begin(), order.end(), nbr.begin() + (size_t)x * dm.nbr_stride);
+      uint32_t* dst = nbr.data() + (size_t)rl[x] * dm.nbr_stride;
+      for (uint32_t q = 0; q < dm.nbr_stride; ++q) dst[q] = rl[order[q]];
     }
     uint32_t* dn = nullptr;
     int rc = dev_upload(ctx, nbr.data(), nbr.size(), &dn);
     if (rc) return rc;
     dm.nbr = dn;
     int bytes = (int)dm.fast_stage_bytes;
-#define NB_ATTR(FN, KEY, CELL) CU(cudaFuncSetAttribute(nearby_step_kernel<FN, KEY, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+#define NB_ATTR(FN, KEY, CELL)                                                                                        \
+  CU(cudaFuncSetAttribute(nearby_step_kernel<FN, KEY, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+  CU(cudaFuncSetAttribute(nearby_step_kernel<FN, KEY, CELL, MOVE_SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
 #define NB_ATTR4(FN) NB_ATTR(FN, uint32_t, uint16_t); NB_ATTR(FN, uint32_t, int32_t); NB_ATTR(FN, uint64_t, uint16_t); NB_ATTR(FN, uint64_t, int32_t)
     NB_ATTR4(-1);
     NB_ATTR4(SFGPU_W_SQUARE);

@@ -54,6 +54,7 @@ struct DevModel {
   uint32_t fm_u16;           // 1: fm_row / fm_col hold uint16 cells (every cost < 65536), else int32
   const void* fm_row;        // path-cost matrix, row-major: d(x, .) is row x
   const void* fm_col;        // its transpose: d(., x) is row x (same array when the matrix is symmetric)
+  const uint32_t* relabel;   // element id -> internal id of the fast records / fm_* / nbr (locality order), or null
   uint32_t off_pos_of;       // uint32[n_elem_rows]: (owner << 16 | position) of each element, or 0xFFFFFFFF
   uint32_t nbr_stride;       // entries per row of `nbr`
   const uint32_t* nbr;       // static: for every element row, the other rows sorted by (distance, row)

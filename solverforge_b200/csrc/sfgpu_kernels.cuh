@@ -466,6 +466,7 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   const uint32_t dim = pc ? pc->n0 : 0;
   const uint32_t depot = pc ? (uint32_t)pc->p0 : 0;
   uint32_t* pos_of = m.nearby_ok ? (uint32_t*)(st + m.off_pos_of) : nullptr;
+  const uint32_t* __restrict__ rl = m.relabel;
   if (pos_of) {
     for (uint32_t i = threadIdx.x; i < m.n_elem_rows; i += blockDim.x) pos_of[i] = 0xFFFFFFFFu;
     __syncthreads();
@@ -477,8 +478,8 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
       const uint32_t a_el = p > 0 ? el[b + p - 1] : depot;
       const uint32_t b_el = p < len ? el[b + p] : depot;
       SlotRec s;
-      s.a = a_el;
-      s.b = b_el;
+      s.a = rl ? rl[a_el] : a_el;  // ids stored in records address the relabelled matrices only
+      s.b = rl ? rl[b_el] : b_el;
       s.gap = (pc && len > 0) ? mat[a_el * dim + b_el] : 0;
       s.where = (o << 16) | p;
       sr[b + o + p] = s;
@@ -486,12 +487,12 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
         const uint32_t x = b_el;
         const uint32_t nx = p + 1 < len ? el[b + p + 1] : depot;
         PosRec q;
-        q.elem = x;
+        q.elem = rl ? rl[x] : x;
         q.rem = pc ? (-mat[a_el * dim + x] - mat[x * dim + nx] + (len > 1 ? mat[a_el * dim + nx] : 0)) : 0;
         q.val = ls ? (int32_t)((const int64_t*)ls->g0)[x] : 0;
         q.owner = o;
         pr[b + p] = q;
-        if (pos_of) pos_of[x] = (o << 16) | p;
+        if (pos_of) pos_of[q.elem] = (o << 16) | p;
         sum += q.val;
       }
     }
