@@ -482,16 +482,21 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       // reduce deltas with 32-bit REDUX instead of 64-bit shuffles)
       bool narrow = true;
       double bound = 0;
+      int64_t cell_max = 0, val_abs_max = 0;
+      bool square = true;
       if (dm.fast_pc >= 0) {
         const sfgpu_constraint_desc& d = ctx->cons[dm.fast_pc].d;
         int64_t mx = 0;
         for (int64_t c : ctx->mats[d.aux0].host) mx = std::max(mx, c);
+        cell_max = mx;
+        square = ctx->mats[d.aux0].rows == ctx->mats[d.aux0].cols;
         bound += std::fabs((double)d.weight.a) * 4.0 * (double)mx;
       }
       if (dm.fast_ls >= 0) {
         const sfgpu_constraint_desc& d = ctx->cons[dm.fast_ls].d;
         double tot = 0;
         for (int64_t c : ctx->cols[d.aux0].host) tot += std::fabs((double)c);
+        for (int64_t c : ctx->cols[d.aux0].host) val_abs_max = std::max<int64_t>(val_abs_max, c < 0 ? -c : c);
         if (d.weight.fn == SFGPU_W_EXCESS) bound += std::fabs((double)d.weight.a) * 2.0 * tot;
         else if (d.weight.fn == SFGPU_W_SQUARE) bound += std::fabs((double)d.weight.a) * 4.0 * tot * tot;
       }
@@ -513,6 +518,19 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       }
       dm.fast_stage_bytes = off;
       if (!dm.nearby_ok) dm.fast_score_bytes = off;
+      // compact 8-byte record copies for the score kernel (the uint16-cell / 32-bit arithmetic path
+      // with 16-bit ids, positions and values); placed behind the staged range of the nearby kernels
+      if (narrow && dm.fast_pc >= 0 && square && cell_max < 65536 && dm.n_elem_rows < 65536 &&
+          dm.elem_cap + dm.n_owners < 65536 && val_abs_max < 32768 && !getenv("SFGPU_NO_COMPACT")) {
+        dm.off_route8 = off;
+        off += dm.n_owners * 8;
+        dm.off_pos8 = off;
+        off += dm.elem_cap * 8;
+        dm.off_slot8 = off;
+        off += (dm.elem_cap + dm.n_owners) * 8;
+        off = align_up(off, 16);
+        dm.compact_bytes = off - dm.off_route8;
+      }
     } else {
       dm.fast_pc = dm.fast_ls = -1;
     }
@@ -910,6 +928,21 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
   }
+  if (dm.fast_list && dm.compact_bytes) {
+    if (!dm.fm_u16 || 16 + dm.compact_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
+      dm.compact_bytes = 0;
+    } else {
+      const int bytes = (int)(16 + dm.compact_bytes);
+#define COMPACT_ATTR(FN)                                                                                              \
+  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 2, 4, false, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 2, 4, true, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+      COMPACT_ATTR(-1);
+      COMPACT_ATTR(SFGPU_W_CONST);
+      COMPACT_ATTR(SFGPU_W_LINEAR);
+      COMPACT_ATTR(SFGPU_W_SQUARE);
+      COMPACT_ATTR(SFGPU_W_EXCESS);
+    }
+  }
   if (dm.has_list) {
     int bytes = (int)dm.elem_cap * 4;
     if (bytes > ctx->max_smem_optin) return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the apply kernel");
@@ -985,7 +1018,11 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
         size_t fsm = dm.fast_score_bytes;
         int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
 #define FASTK(FN)                                                                                              \
-  if (forage)                                                                                                  \
+  if (dm.compact_bytes && dm.fm_u16) {                                                                         \
+    const size_t csm = 16 + dm.compact_bytes;                                                                  \
+    if (forage) score_list_change_fast_kernel<FN, 2, 4, true, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
+    else score_list_change_fast_kernel<FN, 2, 4, false, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
+  } else if (forage)                                                                                           \
     if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 4, true, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
     else score_list_change_fast_kernel<FN, 2, 3, true, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
   else                                                                                                         \

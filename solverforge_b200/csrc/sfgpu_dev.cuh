@@ -46,6 +46,10 @@ struct DevModel {
   uint32_t fast_list;       // 1 when the constraint program fits the specialised list-change kernel
   uint32_t fast_stage_bytes;  // records + pos_of (nearby kernels)
   uint32_t fast_score_bytes;  // records only (score kernels)
+  // compact 8-byte copies of the records (narrow models with 16-bit ids / positions / values): halves
+  // the shared-memory wavefronts of the score kernel and its staged bytes. 0 = not available.
+  uint32_t compact_bytes;     // Route8 + Pos8 + Slot8, contiguous from off_route8
+  uint32_t off_route8, off_pos8, off_slot8;
   uint32_t off_route_rec, off_pos_rec, off_slot_rec;
   int32_t fast_pc, fast_ls;  // constraint indices of the path-cost / list-sum constraint, or -1
   // device-side nearby neighbourhood
@@ -166,6 +170,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                : "memory");
 }
 
+// Two ranges behind one barrier: [src0, +bytes0) -> dst0 and [src1, +bytes1) -> dst1 (bytes1 <= 64 KB).
+__device__ __forceinline__ void stage_block2(char* dst0, const char* src0, uint32_t bytes0, char* dst1,
+                                             const char* src1, uint32_t bytes1, uint64_t* bar);
+
 // Stage `bytes` (multiple of 16, 16 B aligned both sides) of global memory into shared memory
 // with TMA bulk copies; every thread of the CTA must call this. `bar` is a shared mbarrier slot.
 __device__ __forceinline__ void stage_block(char* smem_dst, const char* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -180,6 +188,25 @@ __device__ __forceinline__ void stage_block(char* smem_dst, const char* gmem_src
     for (uint32_t o = 0; o < bytes; o += piece) {
       uint32_t n = bytes - o < piece ? bytes - o : piece;
       tma_bulk_g2s(smem_dst + o, gmem_src + o, n, bar);
+    }
+  }
+  mbar_wait(bar, 0);
+}
+
+__device__ __forceinline__ void stage_block2(char* dst0, const char* src0, uint32_t bytes0, char* dst1,
+                                             const char* src1, uint32_t bytes1, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes0 + bytes1);
+    tma_bulk_g2s(dst0, src0, bytes0, bar);
+    const uint32_t piece = 32768;
+    for (uint32_t o = 0; o < bytes1; o += piece) {
+      uint32_t n = bytes1 - o < piece ? bytes1 - o : piece;
+      tma_bulk_g2s(dst1 + o, src1 + o, n, bar);
     }
   }
   mbar_wait(bar, 0);

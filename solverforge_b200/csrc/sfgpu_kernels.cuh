@@ -467,6 +467,9 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   const uint32_t depot = pc ? (uint32_t)pc->p0 : 0;
   uint32_t* pos_of = m.nearby_ok ? (uint32_t*)(st + m.off_pos_of) : nullptr;
   const uint32_t* __restrict__ rl = m.relabel;
+  uint2* r8 = m.compact_bytes ? (uint2*)(st + m.off_route8) : nullptr;
+  uint2* p8 = m.compact_bytes ? (uint2*)(st + m.off_pos8) : nullptr;
+  uint2* s8 = m.compact_bytes ? (uint2*)(st + m.off_slot8) : nullptr;
   if (pos_of) {
     for (uint32_t i = threadIdx.x; i < m.n_elem_rows; i += blockDim.x) pos_of[i] = 0xFFFFFFFFu;
     __syncthreads();
@@ -483,6 +486,7 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
       s.gap = (pc && len > 0) ? mat[a_el * dim + b_el] : 0;
       s.where = (o << 16) | p;
       sr[b + o + p] = s;
+      if (s8) s8[b + o + p] = make_uint2(s.a | (s.b << 16), (uint32_t)s.gap);
       if (p < len) {
         const uint32_t x = b_el;
         const uint32_t nx = p + 1 < len ? el[b + p + 1] : depot;
@@ -492,6 +496,7 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
         q.val = ls ? (int32_t)((const int64_t*)ls->g0)[x] : 0;
         q.owner = o;
         pr[b + p] = q;
+        if (p8) p8[b + p] = make_uint2(q.elem | ((uint32_t)(uint16_t)(int16_t)q.val << 16), (uint32_t)q.rem);
         if (pos_of) pos_of[q.elem] = (o << 16) | p;
         sum += q.val;
       }
@@ -501,6 +506,7 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
     r.len = len;
     r.sum = sum;
     rr[o] = r;
+    if (r8) r8[o] = make_uint2(b | (len << 16), (uint32_t)(int32_t)sum);
   }
 }
 
@@ -573,7 +579,8 @@ struct ForageArgs {
   ChunkPartial* partials;     // [R][gridDim.x]
 };
 
-template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3, bool FORAGE = false, typename CELL = int32_t>
+template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3, bool FORAGE = false, typename CELL = int32_t,
+          bool COMPACT = false>
 __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const __grid_constant__ DevModel m,
                                                                      const uint64_t* __restrict__ cand_offsets,
                                                                      const uint32_t* __restrict__ rows,
@@ -585,8 +592,12 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   const uint32_t r = blockIdx.y;
-  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_score_bytes, &bar);
-  const int64_t* cs = (const int64_t*)(smem + m.off_score);
+  if (COMPACT)  // committed score (first 16 bytes of the block) + the 8-byte records
+    stage_block2(smem, m.state + (size_t)r * m.block_bytes + m.off_score, 16, smem + 16,
+                 m.state + (size_t)r * m.block_bytes + m.off_route8, m.compact_bytes, &bar);
+  else
+    stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_score_bytes, &bar);
+  const int64_t* cs = (const int64_t*)(smem + (COMPACT ? 0 : m.off_score));
   const int64_t ch = cs[0], csf = cs[1];
   // fused forager partial (FORAGE): this thread's best accepted score delta, multiplicity, first
   // row; acceptor references become thresholds on the delta
@@ -606,6 +617,9 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
   const uint4* rr = (const uint4*)(smem + m.off_route_rec);
   const uint4* pr = (const uint4*)(smem + m.off_pos_rec);
   const uint4* sr = (const uint4*)(smem + m.off_slot_rec);
+  const uint2* rr8 = (const uint2*)(smem + 16);
+  const uint2* pr8 = (const uint2*)(smem + 16 + (m.off_pos8 - m.off_route8));
+  const uint2* sr8 = (const uint2*)(smem + 16 + (m.off_slot8 - m.off_route8));
   const uint32_t n_owners = m.n_owners;
   // path cost: LINEAR weight => weight(old + d) - weight(old) = a * d
   const bool has_pc = m.fast_pc >= 0;
@@ -651,7 +665,15 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     for (int u = 0; u < U; ++u) {
       const uint32_t se = cur[u].x, sp = cur[u].y, de = cur[u].z, dp = cur[u].w;
       ok[u] = se < n_owners && de < n_owners;
-      const uint4 rs = rr[ok[u] ? se : 0], rd = rr[ok[u] ? de : 0];
+      uint4 rs, rd;  // {base, len, sum lo, sum hi}
+      if (COMPACT) {
+        const uint2 a8 = rr8[ok[u] ? se : 0], b8 = rr8[ok[u] ? de : 0];
+        rs = make_uint4(a8.x & 0xFFFFu, a8.x >> 16, a8.y, 0);
+        rd = make_uint4(b8.x & 0xFFFFu, b8.x >> 16, b8.y, 0);
+      } else {
+        rs = rr[ok[u] ? se : 0];
+        rd = rr[ok[u] ? de : 0];
+      }
       ok[u] = ok[u] && sp < rs.y && dp <= rd.y && !(se == de && (dp == sp || dp == sp + 1));
       pidx[u] = ok[u] ? rs.x + sp : 0;
       sidx[u] = ok[u] ? rd.x + de + dp : 0;
@@ -664,8 +686,14 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     uint4 p[U], sl[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      p[u] = pr[pidx[u]];
-      sl[u] = sr[sidx[u]];
+      if (COMPACT) {
+        const uint2 p8 = pr8[pidx[u]], s8 = sr8[sidx[u]];
+        p[u] = make_uint4(p8.x & 0xFFFFu, p8.y, (uint32_t)(int32_t)(int16_t)(p8.x >> 16), 0);  // {elem, rem, val}
+        sl[u] = make_uint4(s8.x & 0xFFFFu, s8.x >> 16, s8.y, 0);                              // {a, b, gap}
+      } else {
+        p[u] = pr[pidx[u]];
+        sl[u] = sr[sidx[u]];
+      }
     }
     int32_t m0[U], m1[U];
 #pragma unroll

@@ -122,13 +122,20 @@ def test_scalar_extremes():
             assert idx[0] == 0xFFFFFFFF
 
 
-@pytest.mark.parametrize("scale", [1, 100, 150000])
-def test_arithmetic_width_paths_and_far_acceptor_references(scale):
-    """scale 1: uint16 cells + 32-bit deltas; 100: int32 cells + 64-bit deltas (cost >= 65536);
-    150000: costs near the 2^28 fast-path limit. Acceptor references far outside the int32 delta range
-    exercise the clamped relative thresholds."""
+@pytest.mark.parametrize("scale,demand_scale,env", [
+    (1, 1, {}), (100, 1, {}), (150000, 1, {}), (1, 3000, {}), (1, 1, {"SFGPU_NO_COMPACT": "1"}),
+    (1, 1, {"SFGPU_NO_RELABEL": "1"})])
+def test_arithmetic_width_paths_and_far_acceptor_references(scale, demand_scale, env, monkeypatch):
+    """scale 1: uint16 cells + 32-bit deltas + compact 8-byte records; 100: int32 cells + 64-bit deltas
+    (cost >= 65536); 150000: costs near the 2^28 fast-path limit; demand_scale 3000: values beyond int16
+    (16-byte records with 32-bit arithmetic); env switches the compact records / the internal relabelling
+    off. Acceptor references far outside the int32 delta range exercise the clamped relative thresholds."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     c = instances.cvrp(90, 7, seed=21)
     c.matrix = c.matrix * scale
+    c.demands = (c.demands.astype(np.int64) * demand_scale).astype(np.int32)
+    c.capacity = int(c.capacity) * demand_scale
     R, K = 2, 20
     starts = [instances.perturb_routes(c, 5 + r, 30) for r in range(R)]
     d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
