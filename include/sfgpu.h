@@ -223,6 +223,17 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
                       const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
                       int64_t* out_best, uint32_t* out_evaluated);
 
+/* sfgpu_argbest with the per-candidate improvement gates of evaluate_candidate
+ * (phase/localsearch/evaluation.rs:76-111): gates[i] bit 0 = Move::requires_hard_improvement (the candidate
+ * only reaches the acceptor when hard_score_delta(last_step_score, score) is Improving), bit 1 =
+ * Move::requires_score_improvement (only when score > last_step_score). Gated-out candidates still count as
+ * evaluated. CompoundScalarMove carries the first flag (heuristic/move/compound_scalar.rs:340). gates may be
+ * NULL; it lives where scores / doable live (host, or device with SFGPU_DEVICE_IO). */
+int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                            const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
+                            const uint8_t* gates, const uint64_t* step_seeds, const int64_t* ref_scores,
+                            uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated);
+
 /* Fused step for list-change batches (DEVICE pointers, stream-asynchronous): scores every candidate and
  * replays acceptor + forager in the same pass — evaluate_candidates (phase/candidates.rs:47-285) for a
  * whole neighbourhood. out_scores / out_doable may both be NULL: then per-candidate scores are never

@@ -247,6 +247,42 @@ int sfo_replay_step(uint64_t n, const int64_t* hard, const int64_t* soft, const 
   return 0;
 }
 
+// sfo_replay_step with the improvement gates of evaluate_candidate (evaluation.rs:62-111): gates[i] bit 0 =
+// requires_hard_improvement, bit 1 = requires_score_improvement, judged against last_step_score.
+int sfo_replay_step_gated(uint64_t n, const int64_t* hard, const int64_t* soft, const uint8_t* doable,
+                          const uint8_t* gates, const int64_t best_score[2], const int64_t last_step_score[2],
+                          const int64_t late_score[2], uint64_t step_seed, int forager_kind, uint64_t accepted_limit,
+                          int random_ties, int acceptor_kind, uint64_t out[5]) {
+  Forager<Sc> fg;
+  fg.kind = (ForagerKind)forager_kind;
+  fg.accepted_count_limit = accepted_limit;
+  fg.best.random_ties = random_ties != 0;
+  Acceptor<Sc> ac;
+  ac.kind = (AcceptorKind)acceptor_kind;
+  if (ac.kind == AcceptorKind::LateAcceptance) {
+    ac.history.assign(1, Sc::of(late_score[0], late_score[1]));
+    ac.history_idx = 0;
+  }
+  const Sc last = Sc::of(last_step_score[0], last_step_score[1]);
+  auto o = replay_step<Sc>(
+      n,
+      [&](size_t i) {
+        const Sc sc = Sc::of(hard[i], soft[i]);
+        if (!doable[i]) return CandidateEvaluation<Sc>{EvalKind::NotDoable, sc};
+        if ((gates[i] & 1) && hard_score_delta(last, sc) != HardDelta::Improving)
+          return CandidateEvaluation<Sc>{EvalKind::RejectedByHardImprovement, sc};
+        if ((gates[i] & 2) && sc <= last) return CandidateEvaluation<Sc>{EvalKind::RejectedByScoreImprovement, sc};
+        return CandidateEvaluation<Sc>{EvalKind::Scored, sc};
+      },
+      Sc::of(best_score[0], best_score[1]), last, step_seed, fg, ac);
+  out[0] = o.has_winner;
+  out[1] = o.winner;
+  out[2] = o.moves_evaluated;
+  out[3] = o.score_calculations;
+  out[4] = o.moves_accepted;
+  return 0;
+}
+
 // ---- stateful acceptors (acceptor/*.rs) for multi-step trajectories ---------------------------
 // kind: AcceptorKind order (0 HillClimbing, 1 LateAcceptance, 3 AcceptAll, 4 GreatDeluge,
 // 5 StepCountingHillClimbing, 6 DiversifiedLateAcceptance, 7 TabuSearch).

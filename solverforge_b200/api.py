@@ -387,7 +387,9 @@ class GpuScoreDirector:
 
     # ---- forager / acceptor replay on device ------------------------------------------
     def argbest(self, scores, doable, cand_offsets=None, params: "ForageParams" = None, step_seeds=None,
-                ref_scores=None):
+                ref_scores=None, gates=None):
+        """Acceptor + forager replay over scored rows (sfgpu_argbest / sfgpu_argbest_gated). gates[i]: bit 0 =
+        requires_hard_improvement, bit 1 = requires_score_improvement (evaluation.rs:76-111)."""
         params = params or ForageParams()
         scores = np.ascontiguousarray(scores, dtype=np.int64).reshape(-1, 2)
         doable = np.ascontiguousarray(doable, dtype=np.uint8)
@@ -398,6 +400,11 @@ class GpuScoreDirector:
         best = np.zeros((self.R, 2), dtype=np.int64)
         ev = np.zeros(self.R, dtype=np.uint32)
         fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        if gates is not None:
+            g = np.ascontiguousarray(gates, dtype=np.uint8)
+            self._check(self.lib.sfgpu_argbest_gated(self.h, 0, C.byref(fp), _ptr(offs), _ptr(scores), _ptr(doable),
+                                                     _ptr(g), _ptr(seeds), _ptr(ref), _ptr(idx), _ptr(best), _ptr(ev)))
+            return idx, best, ev
         self._check(self.lib.sfgpu_argbest(self.h, 0, C.byref(fp), _ptr(offs), _ptr(scores), _ptr(doable),
                                            _ptr(seeds), _ptr(ref), _ptr(idx), _ptr(best), _ptr(ev)))
         return idx, best, ev

@@ -1630,20 +1630,21 @@ int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t*
 }
 
 // ------------------------------------------------------------------------------------------
-int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
-                      const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
-                      const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
-                      int64_t* out_best, uint32_t* out_evaluated) {
+int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                            const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
+                            const uint8_t* gates, const uint64_t* step_seeds, const int64_t* ref_scores,
+                            uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!params || !cand_offsets || !scores || !doable || !out_index || !out_best)
     return fail(ctx, SFGPU_E_INVALID, "null pointer");
   if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad forage params");
-  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  if ((params->acceptor != 0 || gates) && !ref_scores)
+    return fail(ctx, SFGPU_E_INVALID, "acceptor / improvement gates need ref_scores (last_step_score)");
   CU(cudaSetDevice(ctx->device));
   const uint32_t R = ctx->dm.R;
-  ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit};
+  ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit, gates};
   if (flags & SFGPU_DEVICE_IO) {
     argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, cand_offsets, scores, doable, step_seeds, ref_scores, out_index,
                                                 out_best, out_evaluated);
@@ -1655,7 +1656,8 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
   auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
   size_t o_off = 0, o_seed = a16(o_off + (R + 1) * 8), o_ref = a16(o_seed + R * 8), o_scores = a16(o_ref + R * 32);
   size_t o_doable = o_scores + n * 16;
-  size_t o_idx = (o_doable + n + 15) / 16 * 16, o_best = o_idx + (R * 4 + 15) / 16 * 16, o_eval = o_best + R * 16;
+  size_t o_gates = (o_doable + n + 15) / 16 * 16;
+  size_t o_idx = (o_gates + (gates ? n : 0) + 15) / 16 * 16, o_best = o_idx + (R * 4 + 15) / 16 * 16, o_eval = o_best + R * 16;
   size_t total = o_eval + (R * 4 + 15) / 16 * 16;
   rc = ensure_staging(ctx, total, total);
   if (rc) return rc;
@@ -1666,6 +1668,10 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
   if (ref_scores) memcpy(pin + o_ref, ref_scores, R * 32); else memset(pin + o_ref, 0, R * 32);
   memcpy(pin + o_scores, scores, n * 16);
   memcpy(pin + o_doable, doable, n);
+  if (gates) {
+    memcpy(pin + o_gates, gates, n);
+    f.gates = (const uint8_t*)(dv + o_gates);
+  }
   CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
   argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, (const uint64_t*)(dv + o_off), (const int64_t*)(dv + o_scores),
                                               (const uint8_t*)(dv + o_doable), (const uint64_t*)(dv + o_seed),
@@ -1679,6 +1685,14 @@ int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params*
   memcpy(out_best, pin + o_best, R * 16);
   if (out_evaluated) memcpy(out_evaluated, pin + o_eval, R * 4);
   return SFGPU_OK;
+}
+
+int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                      const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
+                      const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
+                      int64_t* out_best, uint32_t* out_evaluated) {
+  return sfgpu_argbest_gated(ctx, flags, params, cand_offsets, scores, doable, nullptr, step_seeds, ref_scores,
+                             out_index, out_best, out_evaluated);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -97,6 +97,9 @@ struct Score2 {
 struct ForageDev {
   int32_t acceptor, tie_mode;
   uint32_t accepted_limit;
+  // per-candidate improvement gates of evaluate_candidate (phase/localsearch/evaluation.rs:76-111), or
+  // null: bit 0 = requires_hard_improvement, bit 1 = requires_score_improvement (argbest only)
+  const uint8_t* gates;
 };
 
 // Per (replica, chunk) partial of the fused score+forage path: best accepted score of the chunk,

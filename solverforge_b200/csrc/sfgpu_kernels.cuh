@@ -1316,8 +1316,16 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
 __device__ __forceinline__ bool accepted_at(const ForageDev& f, const int64_t* scores, const uint8_t* doable,
                                             uint64_t i, int64_t lh, int64_t ls, int64_t th, int64_t ts) {
   if (!doable[i]) return false;
-  if (f.acceptor == 0) return true;
+  if (f.acceptor == 0 && !f.gates) return true;
   longlong2 s = ((const longlong2*)scores)[i];
+  if (f.gates) {
+    // a gated candidate that does not improve on last_step_score is evaluated but never reaches the
+    // acceptor (RejectedByHardImprovement / RejectedByScoreImprovement); hard_score_delta of a
+    // two-level score is Improving iff the hard level rose (phase/hard_delta.rs:19-34)
+    const uint8_t g = f.gates[i];
+    if ((g & 1) && !(s.x > lh)) return false;
+    if ((g & 2) && !score_less(lh, ls, s.x, s.y)) return false;
+  }
   return accept_score(f.acceptor, s.x, s.y, lh, ls, th, ts);
 }
 

@@ -647,11 +647,13 @@ struct StepOutcome {
 };
 
 // Replays phase/candidates.rs:66-282 over batched scores: pull order, quit-early, acceptor, forager.
-// `signature(i)` supplies the tabu metadata of candidate i for acceptors that require it.
+// `signature(i)` supplies the tabu metadata of candidate i for acceptors that require it; gates[i] bit 0 =
+// Move::requires_hard_improvement, bit 1 = Move::requires_score_improvement (may be null).
 inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doable, size_t n, HardSoftScore best_score,
                                HardSoftScore last_step, uint64_t step_seed, const ForagerConfig& fc,
                                Acceptor& acceptor,
-                               const std::function<MoveTabuSignature(size_t)>& signature = nullptr) {
+                               const std::function<MoveTabuSignature(size_t)>& signature = nullptr,
+                               const uint8_t* gates = nullptr) {
   if (acceptor.requires_move_signatures() && !signature)
     throw std::logic_error("this acceptor requires move signatures");
   StepOutcome out;
@@ -690,6 +692,10 @@ inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doabl
     out.moves_evaluated++;
     if (!doable[i]) continue;
     out.score_calculations++;
+    if (gates) {  // evaluation.rs:76-111: improvement gates run before the acceptor sees the candidate
+      if ((gates[i] & 1) && !(scores[i].hard > last_step.hard)) continue;  // requires_hard_improvement
+      if ((gates[i] & 2) && !(scores[i] > last_step)) continue;            // requires_score_improvement
+    }
     if (signature) {
       const MoveTabuSignature g = signature(i);
       if (!acceptor.is_accepted(last_step, scores[i], &g)) continue;

@@ -42,7 +42,13 @@ static int test_replay() {
           la.phase_started({-1, -5});
           sf::Acceptor& acc = ak == 0 ? (sf::Acceptor&)hc : (sf::Acceptor&)la;
           const sf::HardSoftScore best_so_far{-1, -2};
-          auto got = sf::replay_step(scores.data(), doable.data(), n, best_so_far, last, seed, fc, acc);
+          // improvement gates on some trials (evaluation.rs:76-111)
+          std::vector<uint8_t> gates(n, 0);
+          const bool gated = trial % 3 == 0;
+          if (gated)
+            for (size_t i = 0; i < n; ++i) gates[i] = (uint8_t)(sfo::splitmix64(seed + i) % 4);
+          auto got = sf::replay_step(scores.data(), doable.data(), n, best_so_far, last, seed, fc, acc, nullptr,
+                                     gated ? gates.data() : nullptr);
           sfo::Forager<sfo::Sc> of;
           of.kind = fk == 0 ? sfo::ForagerKind::AcceptedCount : fk == 1 ? sfo::ForagerKind::FirstAccepted : fk == 2 ? sfo::ForagerKind::BestScore : fk == 3 ? sfo::ForagerKind::FirstBestScoreImproving : sfo::ForagerKind::FirstLastStepScoreImproving;
           of.has_improving_limit = fc.has_improving_limit;
@@ -57,8 +63,15 @@ static int test_replay() {
           auto want = sfo::replay_step<sfo::Sc>(
               n,
               [&](size_t i) {
-                return sfo::CandidateEvaluation<sfo::Sc>{doable[i] ? sfo::EvalKind::Scored : sfo::EvalKind::NotDoable,
-                                                         sfo::Sc::of(scores[i].hard, scores[i].soft)};
+                const sfo::Sc sc = sfo::Sc::of(scores[i].hard, scores[i].soft), ol = sfo::Sc::of(last.hard, last.soft);
+                sfo::EvalKind k = doable[i] ? sfo::EvalKind::Scored : sfo::EvalKind::NotDoable;
+                if (k == sfo::EvalKind::Scored && gated) {
+                  if ((gates[i] & 1) && sfo::hard_score_delta(ol, sc) != sfo::HardDelta::Improving)
+                    k = sfo::EvalKind::RejectedByHardImprovement;
+                  else if ((gates[i] & 2) && sc <= ol)
+                    k = sfo::EvalKind::RejectedByScoreImprovement;
+                }
+                return sfo::CandidateEvaluation<sfo::Sc>{k, sc};
               },
               sfo::Sc::of(best_so_far.hard, best_so_far.soft), sfo::Sc::of(last.hard, last.soft), seed, of, oa);
           CHECK(got.has_winner == want.has_winner);

@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_nearby_list_swap.restype = C.c_int64
         l.sfo_replay_step.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
                                       C.c_int, _P]
+        l.sfo_replay_step_gated.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64,
+                                            C.c_int, C.c_int, _P]
         l.sfo_acceptor_create.restype = _P
         l.sfo_acceptor_create.argtypes = [C.c_int, C.c_uint64, C.c_double, _P, C.c_int]
         l.sfo_acceptor_destroy.argtypes = [_P]
@@ -216,7 +218,7 @@ class Oracle:
 
 
 def replay_step(scores, doable, best_score, last_step_score, late_score, step_seed, forager_kind, accepted_limit,
-                random_ties, acceptor_kind):
+                random_ties, acceptor_kind, gates=None):
     """Oracle replay of phase/candidates.rs:66-282. Returns (has_winner, winner, moves_evaluated,
     score_calculations, moves_accepted)."""
     scores = np.asarray(scores, dtype=np.int64).reshape(-1, 2)
@@ -227,6 +229,11 @@ def replay_step(scores, doable, best_score, last_step_score, late_score, step_se
     b = np.asarray(best_score, dtype=np.int64)
     l_ = np.asarray(last_step_score, dtype=np.int64)
     t = np.asarray(late_score, dtype=np.int64)
+    if gates is not None:
+        g = np.ascontiguousarray(gates, dtype=np.uint8)
+        lib().sfo_replay_step_gated(len(h), _p(h), _p(s), _p(d), _p(g), _p(b), _p(l_), _p(t), step_seed, forager_kind,
+                                    accepted_limit, 1 if random_ties else 0, acceptor_kind, _p(out))
+        return tuple(int(x) for x in out)
     lib().sfo_replay_step(len(h), _p(h), _p(s), _p(d), _p(b), _p(l_), _p(t), step_seed, forager_kind, accepted_limit,
                           1 if random_ties else 0, acceptor_kind, _p(out))
     return tuple(int(x) for x in out)

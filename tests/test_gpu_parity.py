@@ -194,6 +194,28 @@ def test_graph_coloring_swap_and_compound_match_oracle():
     so, oko = o.score_compound(eo, edits)
     _eq(ok, oko, "compound doable")
     _eq(s, so, "compound scores")
+    # improvement gates of evaluate_candidate (evaluation.rs:76-111) on the compound batch: every third move
+    # requires hard improvement, every fifth score improvement; replay on device vs the oracle loop
+    gates = np.zeros(n_c, dtype=np.uint8)
+    gates[::3] |= 1
+    gates[::5] |= 2
+    base = d.calculate_score()[0]
+    for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+        for limit in (0, 3, 40):
+            for dl in (0, -2):
+                last = base + [dl, 0]
+                late = base + [dl - 1, 0]
+                ref = [np.concatenate([last, late])]
+                idx, best, ev = d.argbest(s, ok, None, ForageParams(acceptor, 1, limit), [21], ref, gates=gates)
+                out = oracle_lib.replay_step(so, oko, [0, 0], last, late, 21, 0 if limit else 2, max(limit, 1), True,
+                                             okind, gates=gates)
+                what = f"gated acceptor={acceptor} limit={limit} dl={dl}"
+                assert int(ev[0]) == out[2], what
+                if out[0]:
+                    assert int(idx[0]) == out[1], what
+                    assert best[0].tolist() == so[out[1]].tolist(), what
+                else:
+                    assert idx[0] == 0xFFFFFFFF, what
 
 
 def test_job_shop_matches_oracle():
