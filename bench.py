@@ -281,7 +281,8 @@ def run_ours(args):
             d.argbest_device(fp, t_offsets.data_ptr(), t_scores.data_ptr(), t_doable.data_ptr(), t_seeds.data_ptr(), 0,
                              t_idx.data_ptr(), t_best.data_ptr(), t_eval.data_ptr())
         if world > 1 and (i + 1) % args.sync_every == 0:
-            # best packed score over this rank's replicas, then one 8-byte MAX all-reduce (NCCL)
+            # best packed score over this rank's replicas, then one 8-byte MAX all-reduce (NCCL):
+            # SURVEY 8(e) — the only collective of the path, every K steps
             best = (((t_best[:, 0] + (1 << 22)) << 40) | (t_best[:, 1] + (1 << 39))).max().reshape(1)
             dist.all_reduce(best, op=dist.ReduceOp.MAX)
 
@@ -469,7 +470,8 @@ def main():
     ap.add_argument("--replicas", type=int, default=1024, help="independent seeded replicas per GPU per launch")
     ap.add_argument("--distinct", type=int, default=16, help="distinct replica starts (tiled over the replicas)")
     ap.add_argument("--loop-steps", type=int, default=64, help="steps of the device-resident loop demo (0 = skip)")
-    ap.add_argument("--sync-every", type=int, default=4, help="steps between NCCL best-score syncs (N > 1)")
+    ap.add_argument("--sync-every", type=int, default=64,
+                    help="steps between NCCL best-score syncs (N > 1); SURVEY 8(d) C5: K = 64")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
