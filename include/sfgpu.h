@@ -142,6 +142,16 @@ typedef struct sfgpu_weight {
 /* for_each(E).group_by((), load_balance(var, metric column|1)).penalize(w(unfairness))
  *   stream/collector/load_balance.rs:104-240; aux0: metric column id or UINT32_MAX (metric = 1) */
 #define SFGPU_K_LOAD_BALANCE 8
+/* for_each(E).project(P).group_by(key, count()|sum(amount)).penalize(w(result)) with P::MAX_EMITS <= 8:
+ *   projected scoring rows, stream/projected_stream/source.rs:13-147 (Projection, RowCoordinate),
+ *   constraint/projected/grouped/{state.rs,terminal.rs}. An ASSIGNED entity e emits one row per entry j
+ *   of its csr row: key = var[e] * p0 + csr.col[j] (p0 = number of key offsets per value, e.g. days),
+ *   amount = aux1 column[j] (one row per csr entry) or 1 (count). Groups with no rows score nothing
+ *   (grouped/state.rs:320-332); two rows of one entity may share a group.
+ *   aux0: csr id (rows = entities); aux1: amount column id or UINT32_MAX. A projected UNI terminal
+ *   (.project(P).penalize(w(row))) lowers on the host to SFGPU_K_UNI over the per-entity sum of row weights
+ *   (constraint/projected/uni.rs:61-263). */
+#define SFGPU_K_PROJECT_GROUP 9
 
 typedef struct sfgpu_constraint_desc {
   int32_t kind;

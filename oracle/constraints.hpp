@@ -1271,4 +1271,225 @@ struct CrossComplementedGroupedConstraint final : IncrementalConstraint<S, Sc> {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Projected rows, single source: for_each(src).project(P) with P::MAX_EMITS >= 1
+//   stream/projected_stream/source.rs:13-147 (Projection / RowCoordinate / Source),
+//   source/single.rs (SingleSource: rows of entity i are (slot 0, i, emit_index)),
+//   constraint/projected/uni.rs:61-263 (row_contributions keyed by RowCoordinate, rows_by_owner),
+//   constraint/projected/grouped/{state.rs, terminal.rs} (grouped node over projected rows; the
+//   group semantics are those of grouped/state.rs: only groups with count > 0 score).
+// `project(const A&, std::vector<Out>&)` appends the emitted rows in emit order.
+template <class S, class A, class Out, class Sc, class P, class F, class W>
+struct ProjectedUniConstraint final : IncrementalConstraint<S, Sc> {
+  Source<S, A> src;
+  Impact impact;
+  P project;  // (const A&, std::vector<Out>&) -> void
+  F filter;   // (const S&, const Out&) -> bool
+  W weight;   // (const Out&) -> Sc
+  std::unordered_map<std::pair<size_t, size_t>, Sc, PairHash> row_contributions;  // (entity, emit_index)
+  std::unordered_map<size_t, std::vector<size_t>> rows_by_owner;
+  ProjectedUniConstraint(std::string n, Impact i, Source<S, A> s, P p, F f, W w, bool hard)
+      : src(s), impact(i), project(std::move(p)), filter(std::move(f)), weight(std::move(w)) {
+    this->name = std::move(n);
+    this->is_hard = hard;
+  }
+  Sc evaluate(const S& s) const override {
+    Sc t = Sc::zero();
+    std::vector<Out> rows;
+    for (auto& e : src.extract(s)) {
+      rows.clear();
+      project(e, rows);
+      for (auto& r : rows)
+        if (filter(s, r)) t = t + signed_weight(impact, weight(r));
+    }
+    return t;
+  }
+  size_t match_count(const S& s) const override {
+    size_t n = 0;
+    std::vector<Out> rows;
+    for (auto& e : src.extract(s)) {
+      rows.clear();
+      project(e, rows);
+      for (auto& r : rows) n += filter(s, r) ? 1 : 0;
+    }
+    return n;
+  }
+  Sc insert_rows(const S& s, size_t idx) {
+    auto& es = src.extract(s);
+    if (idx >= es.size()) return Sc::zero();
+    std::vector<Out> rows;
+    project(es[idx], rows);
+    Sc t = Sc::zero();
+    for (size_t j = 0; j < rows.size(); ++j) {
+      if (row_contributions.count({idx, j}) || !filter(s, rows[j])) continue;  // uni.rs:103-112
+      Sc c = signed_weight(impact, weight(rows[j]));
+      row_contributions[{idx, j}] = c;
+      rows_by_owner[idx].push_back(j);
+      t = t + c;
+    }
+    return t;
+  }
+  Sc initialize(const S& s) override {
+    reset();
+    Sc t = Sc::zero();
+    for (size_t i = 0; i < src.extract(s).size(); ++i) t = t + insert_rows(s, i);
+    return t;
+  }
+  Sc on_insert(const S& s, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    return insert_rows(s, idx);
+  }
+  Sc on_retract(const S&, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    Sc t = Sc::zero();
+    auto it = rows_by_owner.find(idx);
+    if (it == rows_by_owner.end()) return t;
+    for (size_t j : it->second) {  // uni.rs:114-120
+      auto rc = row_contributions.find({idx, j});
+      if (rc == row_contributions.end()) continue;
+      t = t - rc->second;
+      row_contributions.erase(rc);
+    }
+    rows_by_owner.erase(it);
+    return t;
+  }
+  void reset() override {
+    row_contributions.clear();
+    rows_by_owner.clear();
+  }
+};
+
+template <class S, class A, class Out, class K, class Sc, class Acc, class P, class F, class KF, class VF, class W,
+          class KH = std::hash<K>>
+struct ProjectedGroupedConstraint final : IncrementalConstraint<S, Sc> {
+  Source<S, A> src;
+  Impact impact;
+  P project;   // (const A&, std::vector<Out>&) -> void
+  F filter;    // (const S&, const Out&) -> bool
+  KF key_fn;   // (const Out&) -> K
+  VF value_fn; // (const Out&) -> Acc::Value
+  W weight;    // (const K&, const Acc::Result&) -> Sc
+  struct Group {
+    K key;
+    Acc acc;
+    size_t count = 0;
+  };
+  std::vector<Group> groups;
+  std::unordered_map<K, size_t, KH> group_ids;
+  struct RowState {
+    size_t group;
+    typename Acc::Retraction retraction;
+  };
+  std::unordered_map<std::pair<size_t, size_t>, RowState, PairHash> row_state;  // (entity, emit_index)
+  std::unordered_map<size_t, std::vector<size_t>> rows_by_owner;
+  std::vector<size_t> changed;
+  std::vector<Sc> cached;  // per group slot (grouped/scorer.rs:89-101)
+  ProjectedGroupedConstraint(std::string n, Impact i, Source<S, A> s, P p, F f, KF kf, VF vf, W w, bool hard)
+      : src(s), impact(i), project(std::move(p)), filter(std::move(f)), key_fn(std::move(kf)),
+        value_fn(std::move(vf)), weight(std::move(w)) {
+    this->name = std::move(n);
+    this->is_hard = hard;
+  }
+  Sc evaluate(const S& s) const override {
+    std::unordered_map<K, Acc, KH> g;
+    std::vector<Out> rows;
+    for (auto& e : src.extract(s)) {
+      rows.clear();
+      project(e, rows);
+      for (auto& r : rows)
+        if (filter(s, r)) g[key_fn(r)].accumulate(value_fn(r));
+    }
+    Sc t = Sc::zero();
+    for (auto& kv : g) t = t + signed_weight(impact, weight(kv.first, kv.second.result()));
+    return t;
+  }
+  size_t match_count(const S& s) const override {
+    std::unordered_set<K, KH> g;
+    std::vector<Out> rows;
+    for (auto& e : src.extract(s)) {
+      rows.clear();
+      project(e, rows);
+      for (auto& r : rows)
+        if (filter(s, r)) g.insert(key_fn(r));
+    }
+    return g.size();
+  }
+  void mark(size_t g) {
+    if (std::find(changed.begin(), changed.end(), g) == changed.end()) changed.push_back(g);
+  }
+  void insert_rows(const S& s, size_t idx) {
+    auto& es = src.extract(s);
+    if (idx >= es.size()) return;
+    std::vector<Out> rows;
+    project(es[idx], rows);
+    for (size_t j = 0; j < rows.size(); ++j) {
+      if (row_state.count({idx, j}) || !filter(s, rows[j])) continue;  // grouped/state.rs insert_row
+      K k = key_fn(rows[j]);
+      auto it = group_ids.find(k);
+      size_t g;
+      if (it == group_ids.end()) {
+        g = groups.size();
+        groups.push_back(Group{k, Acc{}, 0});
+        group_ids.emplace(k, g);
+      } else {
+        g = it->second;
+      }
+      if (groups[g].count == 0) groups[g].acc.reset();
+      auto r = groups[g].acc.accumulate(value_fn(rows[j]));
+      groups[g].count += 1;
+      row_state[{idx, j}] = RowState{g, r};
+      rows_by_owner[idx].push_back(j);
+      mark(g);
+    }
+  }
+  void retract_rows(size_t idx) {
+    auto it = rows_by_owner.find(idx);
+    if (it == rows_by_owner.end()) return;
+    for (size_t j : it->second) {
+      auto rs = row_state.find({idx, j});
+      if (rs == row_state.end()) continue;
+      Group& g = groups[rs->second.group];
+      g.acc.retract(rs->second.retraction);
+      g.count = g.count > 0 ? g.count - 1 : 0;
+      mark(rs->second.group);
+      row_state.erase(rs);
+    }
+    rows_by_owner.erase(it);
+  }
+  Sc refresh() {  // grouped/scorer.rs:89-101,145-152: new - cached for every changed group
+    Sc delta = Sc::zero();
+    for (size_t g : changed) {
+      if (cached.size() <= g) cached.resize(g + 1, Sc::zero());
+      Sc now = groups[g].count > 0 ? signed_weight(impact, weight(groups[g].key, groups[g].acc.result())) : Sc::zero();
+      delta = delta + (now - cached[g]);
+      cached[g] = now;
+    }
+    changed.clear();
+    return delta;
+  }
+  Sc initialize(const S& s) override {
+    reset();
+    for (size_t i = 0; i < src.extract(s).size(); ++i) insert_rows(s, i);
+    return refresh();
+  }
+  Sc on_insert(const S& s, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    insert_rows(s, idx);
+    return refresh();
+  }
+  Sc on_retract(const S&, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    retract_rows(idx);
+    return refresh();
+  }
+  void reset() override {
+    groups.clear();
+    group_ids.clear();
+    row_state.clear();
+    rows_by_owner.clear();
+    changed.clear();
+    cached.clear();
+  }
+};
+
 }  // namespace sfo

@@ -512,6 +512,7 @@ static void kat_cross_complemented() {
 struct PWork {
   size_t bucket;
   int64_t demand;
+  bool enabled = true;
 };
 struct PCapacity {
   size_t bucket;
@@ -550,6 +551,81 @@ static void kat_projected() {
   total = total + c.on_insert(plan, 0, 0);
   CHECK(total == SoftScore::of(-20));
   CHECK(total == c.evaluate(plan));
+}
+
+struct PEntry {
+  size_t bucket;
+  int64_t delta;
+};
+static void kat_projected_multi_emit() {
+  auto always = [](const PPlan&, const PEntry&) { return true; };
+  {  // constraint/tests/projected/self_join.rs:26-55: zero and multiple outputs (WorkTwoEntries, MAX_EMITS = 2)
+    auto two = [](const PWork& w, std::vector<PEntry>& out) {
+      if (!w.enabled) return;
+      out.push_back({w.bucket, w.demand});
+      out.push_back({w.bucket + 1, w.demand});
+    };
+    auto wt = [](const PEntry& e) { return SoftScore::of(e.delta); };
+    ProjectedUniConstraint<PPlan, PWork, PEntry, SoftScore, decltype(two), decltype(always), decltype(wt)> c(
+        "projected work", Impact::Penalty, {pp_work, ChangeSource::Desc(0)}, two, always, wt, false);
+    PPlan plan{{{0, 3, true}, {0, 100, false}}, {}};
+    CHECK(c.match_count(plan) == 2);
+    CHECK(c.evaluate(plan) == SoftScore::of(-6));
+    SoftScore total = c.initialize(plan);
+    CHECK(total == SoftScore::of(-6));
+    total = total + c.on_retract(plan, 1, 0);  // enabling the second entity emits two more rows
+    plan.work[1].enabled = true;
+    total = total + c.on_insert(plan, 1, 0);
+    CHECK(total == SoftScore::of(-206) && total == c.evaluate(plan));
+    total = total + c.on_retract(plan, 0, 1);  // foreign descriptor: ignored (collection_extract.rs:83-93)
+    total = total + c.on_insert(plan, 0, 1);
+    CHECK(total == SoftScore::of(-206));
+  }
+  auto one = [](const PWork& w, std::vector<PEntry>& out) { out.push_back({w.bucket, w.demand}); };
+  auto kf = [](const PEntry& e) { return e.bucket; };
+  auto vf = [](const PEntry& e) { return e.delta; };
+  {  // localization.rs:4-36: previous outputs are retracted before an update
+    auto gw = [](const size_t&, const int64_t& d) { return SoftScore::of(d > 0 ? d : 0); };
+    ProjectedGroupedConstraint<PPlan, PWork, PEntry, size_t, SoftScore, SumAcc, decltype(one), decltype(always),
+                               decltype(kf), decltype(vf), decltype(gw)>
+        c("demand", Impact::Penalty, {pp_work, ChangeSource::Desc(0)}, one, always, kf, vf, gw, false);
+    PPlan plan{{{0, 5, true}}, {}};
+    SoftScore total = c.initialize(plan);
+    CHECK(total == SoftScore::of(-5));
+    total = total + c.on_retract(plan, 0, 0);
+    plan.work[0].demand = 2;
+    total = total + c.on_insert(plan, 0, 0);
+    CHECK(total == SoftScore::of(-2));
+    CHECK(total == c.evaluate(plan));
+  }
+  {  // localization.rs:38-70: the grouped weight can use the key
+    auto gw = [](const size_t& b, const int64_t& d) { return SoftScore::of((int64_t)b + (d > 0 ? d : 0)); };
+    ProjectedGroupedConstraint<PPlan, PWork, PEntry, size_t, SoftScore, SumAcc, decltype(one), decltype(always),
+                               decltype(kf), decltype(vf), decltype(gw)>
+        c("key weighted demand", Impact::Penalty, {pp_work, ChangeSource::Desc(0)}, one, always, kf, vf, gw, false);
+    PPlan plan{{{2, 3, true}, {4, 1, true}}, {}};
+    CHECK(c.evaluate(plan) == SoftScore::of(-10));
+  }
+  {  // two rows of one entity in the same group (support.rs OrderedWorkEntries) with a non-linear weight:
+     // the group is re-scored once per notification, incremental == evaluate
+    auto ordered = [](const PWork& w, std::vector<PEntry>& out) {
+      out.push_back({w.bucket, w.demand});
+      out.push_back({w.bucket, w.demand + 10});
+    };
+    auto gw = [](const size_t&, const int64_t& d) { return SoftScore::of(d > 12 ? (d - 12) * (d - 12) : 0); };
+    ProjectedGroupedConstraint<PPlan, PWork, PEntry, size_t, SoftScore, SumAcc, decltype(ordered), decltype(always),
+                               decltype(kf), decltype(vf), decltype(gw)>
+        c("ordered", Impact::Penalty, {pp_work, ChangeSource::Desc(0)}, ordered, always, kf, vf, gw, false);
+    PPlan plan{{{0, 1, true}, {0, 2, true}, {1, 4, true}}, {}};
+    SoftScore total = c.initialize(plan);
+    CHECK(total == c.evaluate(plan));
+    CHECK(total == SoftScore::of(-((26 - 12) * (26 - 12) + (18 - 12) * (18 - 12))));
+    total = total + c.on_retract(plan, 1, 0);
+    plan.work[1].bucket = 1;
+    total = total + c.on_insert(plan, 1, 0);
+    CHECK(total == c.evaluate(plan));
+    CHECK(c.match_count(plan) == 2);
+  }
 }
 
 // ---------------------------------------------------------------- selectors / foragers
@@ -853,6 +929,7 @@ int main() {
   kat_grouped();
   kat_cross_complemented();
   kat_projected();
+  kat_projected_multi_emit();
   kat_nearby_sort();
   kat_moves_and_loop();
   kat_acceptors();

@@ -389,4 +389,69 @@ struct ShiftModel final : ModelImpl<ShiftSchedule> {
   }
 };
 
+// ------------------------------------------------------------------------------ roster (projected rows)
+// Authored with the reference's `.project(..)` API (stream/projected_stream/uni.rs): a shift spans one
+// or more days; when it is assigned it emits one row per spanned day, Row{nurse, day, hours}
+// (MAX_EMITS = 8). Constraints:
+//   1 for_each(shifts).filter(required && unassigned).penalize(ONE_HARD)
+//   2 .project(rows).group_by(|r| (r.nurse, r.day), sum(|r| r.hours)).penalize(hard max(0, total - limit))
+//   3 .project(rows).group_by(|r| (r.nurse, r.day), count()).penalize(soft count^2)
+//   4 .project(rows).penalize(|r| soft r.hours)       (projected uni terminal, every row scored on its own)
+struct RShift {
+  size_t id;
+  bool required;
+  std::vector<std::pair<int64_t, int64_t>> spans;  // (day, hours) rows, in emit order
+  OptVal nurse_idx;
+};
+struct RRow {
+  size_t nurse;
+  int64_t day, hours;
+};
+struct Roster {
+  std::vector<RShift> shifts;
+  size_t n_nurses = 0;
+  int64_t n_days = 0;
+};
+inline const std::vector<RShift>& rs_shifts(const Roster& s) { return s.shifts; }
+
+struct RosterModel final : ModelImpl<Roster> {
+  explicit RosterModel(Roster sol, int64_t limit) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const Roster& s, size_t, size_t e) { return s.shifts[e].nurse_idx; };
+    dir.access.set = [](Roster& s, size_t, size_t e, OptVal v) { s.shifts[e].nurse_idx = v; };
+    dir.access.entity_count = [](const Roster& s, size_t) { return s.shifts.size(); };
+    Source<Roster, RShift> shifts{rs_shifts, ChangeSource::Desc(0)};
+    auto uf = [](const Roster&, const RShift& s) { return s.required && !s.nurse_idx.has_value(); };
+    auto uw = [](const RShift&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<Roster, RShift, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned required shift", Impact::Penalty, shifts, uf, uw, true));
+    auto project = [](const RShift& s, std::vector<RRow>& out) {
+      if (!s.nurse_idx) return;
+      for (auto& sp : s.spans) out.push_back({*s.nurse_idx, sp.first, sp.second});
+    };
+    auto always = [](const Roster&, const RRow&) { return true; };
+    const int64_t n_days = dir.working.n_days;
+    auto key = [n_days](const RRow& r) { return (int64_t)r.nurse * n_days + r.day; };
+    auto hours = [](const RRow& r) { return r.hours; };
+    auto hw = [limit](const int64_t&, const int64_t& total) { return Sc::of_hard(total > limit ? total - limit : 0); };
+    dir.constraints.add(
+        std::make_unique<ProjectedGroupedConstraint<Roster, RShift, RRow, int64_t, Sc, SumAcc, decltype(project),
+                                                    decltype(always), decltype(key), decltype(hours), decltype(hw)>>(
+            "Daily hours", Impact::Penalty, shifts, project, always, key, hours, hw, true));
+    auto unit = [](const RRow&) { return (char)0; };
+    auto cw = [](const int64_t&, const size_t& n) { return Sc::of_soft((int64_t)(n * n)); };
+    dir.constraints.add(
+        std::make_unique<ProjectedGroupedConstraint<Roster, RShift, RRow, int64_t, Sc, CountAcc, decltype(project),
+                                                    decltype(always), decltype(key), decltype(unit), decltype(cw)>>(
+            "Fragmented days", Impact::Penalty, shifts, project, always, key, unit, cw, false));
+    auto rw = [](const RRow& r) { return Sc::of_soft(r.hours); };
+    dir.constraints.add(
+        std::make_unique<ProjectedUniConstraint<Roster, RShift, RRow, Sc, decltype(project), decltype(always), decltype(rw)>>(
+            "Worked hours", Impact::Penalty, shifts, project, always, rw, false));
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.n_nurses, true, ctx);
+  }
+};
+
 }  // namespace sfo

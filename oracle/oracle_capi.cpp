@@ -92,6 +92,21 @@ void* sfo_shift_create(uint32_t n_shifts, uint32_t n_nurses, const int64_t* day,
   return new ShiftModel(std::move(s), target);
 }
 
+// roster with projected rows: span rows of shift i are span_day/span_hours[span_ptr[i] .. span_ptr[i+1])
+void* sfo_roster_create(uint32_t n_shifts, uint32_t n_nurses, int64_t n_days, int64_t limit, const uint8_t* required,
+                        const uint32_t* span_ptr, const int64_t* span_day, const int64_t* span_hours,
+                        const int32_t* nurse_idx) {
+  Roster s;
+  s.n_nurses = n_nurses;
+  s.n_days = n_days;
+  for (uint32_t i = 0; i < n_shifts; ++i) {
+    RShift sh{i, required[i] != 0, {}, opt(nurse_idx[i])};
+    for (uint32_t j = span_ptr[i]; j < span_ptr[i + 1]; ++j) sh.spans.push_back({span_day[j], span_hours[j]});
+    s.shifts.push_back(std::move(sh));
+  }
+  return new RosterModel(std::move(s), limit);
+}
+
 void sfo_destroy(void* h) { delete static_cast<OracleModel*>(h); }
 
 int sfo_committed_score(void* h, int64_t out[2]) {

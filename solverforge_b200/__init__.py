@@ -7,11 +7,12 @@ the host-side mirror of the reference interface above it. There is no CPU scorin
 """
 from . import _lib
 from .api import (AdjacentEqual, ConstraintFactory, Count, EqualId, EqualKey, EqualVarToRow, ForageParams,
-                  GpuScoreDirector, HardSoftDecimalScore, HardSoftScore, ListSum, LoadBalance, PathCost, Sum,
+                  GpuScoreDirector, HardSoftDecimalScore, HardSoftScore, ListSum, LoadBalance, PathCost, Projection, Sum,
                   WeightFn, hard, soft)
 
 __all__ = [
     "AdjacentEqual", "ConstraintFactory", "Count", "EqualId", "EqualKey", "EqualVarToRow", "ForageParams",
-    "GpuScoreDirector", "HardSoftDecimalScore", "HardSoftScore", "ListSum", "LoadBalance", "PathCost", "Sum",
+    "GpuScoreDirector", "HardSoftDecimalScore", "HardSoftScore", "ListSum", "LoadBalance", "PathCost", "Projection",
+    "Sum",
     "WeightFn", "hard", "soft",
 ]

@@ -174,6 +174,8 @@ class GpuScoreDirector:
         ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
         out = C.c_uint32()
         self._check(self.lib.sfgpu_add_csr(self.h, name.encode(), len(rp) - 1, _ptr(rp), _ptr(ci), C.byref(out)))
+        self._csr_host = getattr(self, "_csr_host", {})
+        self._csr_host[out.value] = (rp.copy(), ci.copy())
         return out.value
 
     def add_matrix(self, name: str, values, cost_semantics: bool = False) -> int:
@@ -520,6 +522,16 @@ class ListSum:
 
 
 @dataclass
+class Projection:
+    """Data form of a `Projection<A>` (stream/projected_stream/source.rs:13-24): an ASSIGNED entity e emits one
+    row per entry j of csr row e — key offset csr.col[j] (< keys_per_value), amount amounts[j] (or 1). The group
+    key of a row is var[e] * keys_per_value + key offset, e.g. (nurse, day). MAX_EMITS <= 8."""
+    csr: int
+    keys_per_value: int
+    amounts: Optional[np.ndarray] = None   # int64 per csr entry
+
+
+@dataclass
 class Count:
     pass
 
@@ -588,6 +600,67 @@ class UniStream:
     def group_by(self, collector) -> "GroupedStream":
         # for_each(E).group_by(|e| e.var, collector) over assigned entities
         return GroupedStream(self.d, self.collection, collector)
+
+    def project(self, projection: "Projection") -> "ProjectedStream":
+        """for_each(E).project(P) — projected scoring rows (stream/projected_stream/uni.rs)."""
+        return ProjectedStream(self.d, self.collection, projection)
+
+
+class ProjectedStream:
+    def __init__(self, d, collection, projection: "Projection"):
+        self.d, self.collection, self.p = d, collection, projection
+
+    def _impact(self, impact, weight: "WeightFn") -> _Terminal:
+        # .project(P).penalize(|row| w(row.amount)) scores every emitted row on its own
+        # (constraint/projected/uni.rs:61-263): with a LINEAR weight (b = 0) or a CONST weight the rows of an
+        # entity sum to one per-entity weight, i.e. a uni constraint over assigned entities.
+        if weight.fn not in (L.W_CONST, L.W_LINEAR) or (weight.fn == L.W_LINEAR and weight.b != 0):
+            raise L.SfgpuError(L.E_UNSUPPORTED, "projected row weights must be CONST or LINEAR (a * amount)")
+        rp, _ = self.d._csr_host[self.p.csr]
+        nnz = int(rp[-1])
+        amt = np.ones(nnz, dtype=np.int64) if self.p.amounts is None else np.asarray(self.p.amounts, dtype=np.int64)
+        per_row = np.full(nnz, weight.a, dtype=np.int64) if weight.fn == L.W_CONST else amt
+        sums = np.add.reduceat(np.concatenate([per_row, [0]]), rp[:-1].astype(np.int64)) if nnz else np.zeros(len(rp) - 1, np.int64)
+        sums = np.where(np.diff(rp.astype(np.int64)) > 0, sums, 0)
+        col = self.d.add_column(self.collection, f"projected_row_sum_{self.p.csr}_{id(self) & 0xFFFF}", sums)
+        w = WeightFn(L.W_LINEAR, weight.level, 1 if weight.fn == L.W_CONST else weight.a, 0)
+        return _Terminal(self.d, kind=L.K_UNI, impact=impact, weight=w, collection=self.collection, aux0=col,
+                         aux1=L.NO_COLUMN, p0=1, p1=0)
+
+    def penalize(self, weight: "WeightFn") -> _Terminal:
+        return self._impact(L.PENALTY, weight)
+
+    def reward(self, weight: "WeightFn") -> _Terminal:
+        return self._impact(L.REWARD, weight)
+
+    def group_by(self, collector) -> "ProjectedGroupedStream":
+        """.group_by(|row| row.key, count() | sum(|row| row.amount))"""
+        if not isinstance(collector, (Count, Sum)):
+            raise L.SfgpuError(L.E_UNSUPPORTED, "projected group_by supports count() and sum(amount)")
+        return ProjectedGroupedStream(self.d, self.collection, self.p, collector)
+
+
+class ProjectedGroupedStream:
+    def __init__(self, d, collection, projection: "Projection", collector):
+        self.d, self.collection, self.p, self.collector = d, collection, projection, collector
+
+    def _impact(self, impact, weight: "WeightFn") -> _Terminal:
+        aux1 = L.NO_COLUMN
+        if isinstance(self.collector, Sum):
+            rp, _ = self.d._csr_host[self.p.csr]
+            nnz = int(rp[-1])
+            rows = self.d.add_collection(f"projected_rows_{self.p.csr}_{id(self) & 0xFFFF}", max(nnz, 1), -1)
+            amt = np.zeros(max(nnz, 1), dtype=np.int64)
+            amt[:nnz] = np.asarray(self.p.amounts, dtype=np.int64)
+            aux1 = self.d.add_column(rows, "amount", amt)
+        return _Terminal(self.d, kind=L.K_PROJECT_GROUP, impact=impact, weight=weight, collection=self.collection,
+                         aux0=self.p.csr, aux1=aux1, p0=self.p.keys_per_value, p1=0)
+
+    def penalize(self, weight: "WeightFn") -> _Terminal:
+        return self._impact(L.PENALTY, weight)
+
+    def reward(self, weight: "WeightFn") -> _Terminal:
+        return self._impact(L.REWARD, weight)
 
 
 class ExistsStream:

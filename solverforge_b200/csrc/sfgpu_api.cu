@@ -341,7 +341,7 @@ int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, 
   if (!ctx || !desc) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
-  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_LOAD_BALANCE)
+  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_PROJECT_GROUP)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
   if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_ABSDIFF || desc->weight.level < 0 ||
       desc->weight.level > 1)
@@ -558,7 +558,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       return SFGPU_OK;
     };
     bool scalar_kind = d.kind == SFGPU_K_UNI || d.kind == SFGPU_K_PAIR_CSR_EQUAL || d.kind == SFGPU_K_PAIR_KEY_EQUAL ||
-                       d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE;
+                       d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE || d.kind == SFGPU_K_PROJECT_GROUP;
     if (scalar_kind && !dm.has_scalar) return fail(ctx, SFGPU_E_INVALID, "constraint needs a scalar variable");
     if (!scalar_kind && !dm.has_list) return fail(ctx, SFGPU_E_INVALID, "constraint needs a list variable");
     switch (d.kind) {
@@ -659,6 +659,45 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         off = align_up(off + dm.n_values * 4, 16);
         c.off1 = off;
         off = align_up(off + dm.n_values * 8, 16);
+        break;
+      }
+      case SFGPU_K_PROJECT_GROUP: {
+        if (d.aux0 >= ctx->csrs.size()) return fail(ctx, SFGPU_E_INVALID, "PROJECT_GROUP: unknown csr");
+        const Csr& g = ctx->csrs[d.aux0];
+        if (g.n_rows != dm.n_entities) return fail(ctx, SFGPU_E_INVALID, "PROJECT_GROUP: csr row count != entity count");
+        if (d.p0 <= 0 || (uint64_t)d.p0 * dm.n_values >= (1ull << 31))
+          return fail(ctx, SFGPU_E_INVALID, "PROJECT_GROUP: p0 (key offsets per value) out of range");
+        const uint32_t nnz = g.row_ptr[g.n_rows];
+        const std::vector<int64_t>* amounts = nullptr;
+        if (d.aux1 != 0xFFFFFFFFu) {
+          if (d.aux1 >= ctx->cols.size() || ctx->cols[d.aux1].host.size() < nnz)
+            return fail(ctx, SFGPU_E_INVALID, "PROJECT_GROUP: aux1 must be a column with one row per csr entry");
+          amounts = &ctx->cols[d.aux1].host;
+        }
+        std::vector<int64_t> em((size_t)nnz * 2);
+        for (uint32_t e = 0; e < g.n_rows; ++e) {
+          if (g.row_ptr[e + 1] - g.row_ptr[e] > 8)
+            return fail(ctx, SFGPU_E_UNSUPPORTED, "PROJECT_GROUP: more than 8 projected rows per entity (MAX_EMITS)");
+          for (uint32_t j = g.row_ptr[e]; j < g.row_ptr[e + 1]; ++j) {
+            if ((int64_t)g.col[j] >= d.p0) return fail(ctx, SFGPU_E_INVALID, "PROJECT_GROUP: key offset >= p0");
+            em[(size_t)j * 2] = g.col[j];
+            em[(size_t)j * 2 + 1] = amounts ? (*amounts)[j] : 1;
+          }
+        }
+        if (em.empty()) em.assign(2, 0);
+        int64_t* dem = nullptr;
+        int rc = dev_upload(ctx, em.data(), em.size(), &dem);
+        if (rc) return rc;
+        uint32_t* drp = nullptr;
+        rc = dev_upload(ctx, g.row_ptr.data(), g.row_ptr.size(), &drp);
+        if (rc) return rc;
+        c.g0 = drp;
+        c.g1 = dem;
+        c.n0 = (uint32_t)d.p0;
+        c.off0 = off;
+        off = align_up(off + dm.n_values * c.n0 * 4, 16);
+        c.off1 = off;
+        off = align_up(off + dm.n_values * c.n0 * 8, 16);
         break;
       }
       case SFGPU_K_LOAD_BALANCE: {

@@ -173,6 +173,52 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const char*
         add_level(d, c, weight_eval(c.w, lb_unfairness(nk, sum, sumsq)) - before);
         break;
       }
+      case SFGPU_K_PROJECT_GROUP: {
+        // projected rows of ONE entity change groups together: collect the affected groups first, then
+        // re-score each once (two rows of an entity may share a group; weights need not be linear)
+        const uint32_t* rp = (const uint32_t*)c.g0;
+        const longlong2* em = (const longlong2*)c.g1;  // {key offset, amount}
+        const int32_t* gc = (const int32_t*)(st + c.off0);
+        const int64_t* gs = (const int64_t*)(st + c.off1);
+        const uint32_t stride = c.n0;
+        uint32_t keys[16];
+        int32_t dcn[16];
+        int64_t dsm[16];
+        int ng = 0;
+        for (int side = 0; side < 2; ++side) {
+          const int32_t v = side == 0 ? cur.old_v : cur.new_v;
+          if (v < 0) continue;
+          for (uint32_t j = rp[cur.e]; j < rp[cur.e + 1]; ++j) {
+            const longlong2 row = em[j];
+            const uint32_t key = (uint32_t)v * stride + (uint32_t)row.x;
+            int g = 0;
+            while (g < ng && keys[g] != key) ++g;
+            if (g == ng) {
+              keys[ng] = key;
+              dcn[ng] = 0;
+              dsm[ng] = 0;
+              ++ng;
+            }
+            dcn[g] += side == 0 ? -1 : 1;
+            dsm[g] += side == 0 ? -row.y : row.y;
+          }
+        }
+        int64_t delta = 0;
+        for (int g = 0; g < ng; ++g) {
+          int64_t cn = gc[keys[g]], sm = gs[keys[g]];
+          for (int i = 0; i < n_prev; ++i)  // edits already applied by the same compound candidate
+            for (uint32_t j = rp[prev[i].e]; j < rp[prev[i].e + 1]; ++j) {
+              const longlong2 row = em[j];
+              if (prev[i].new_v >= 0 && (uint32_t)prev[i].new_v * stride + (uint32_t)row.x == keys[g]) { cn += 1; sm += row.y; }
+              if (prev[i].old_v >= 0 && (uint32_t)prev[i].old_v * stride + (uint32_t)row.x == keys[g]) { cn -= 1; sm -= row.y; }
+            }
+          const int64_t before = cn > 0 ? weight_eval(c.w, sm) : 0;
+          const int64_t after = cn + dcn[g] > 0 ? weight_eval(c.w, sm + dsm[g]) : 0;
+          delta += after - before;
+        }
+        add_level(d, c, delta);
+        break;
+      }
       default: break;  // list-only kinds do not react to scalar edits (ChangeSource routing)
     }
   }
@@ -1013,6 +1059,30 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
           local += group_score(c, i, gc[i], (int64_t)gs[i]);
         break;
       }
+      case SFGPU_K_PROJECT_GROUP: {
+        int32_t* gc = (int32_t*)(st + c.off0);
+        unsigned long long* gs = (unsigned long long*)(st + c.off1);
+        const uint32_t* rp = (const uint32_t*)c.g0;
+        const longlong2* em = (const longlong2*)c.g1;
+        const uint32_t n_groups = m.n_values * c.n0;
+        for (uint32_t i = threadIdx.x; i < n_groups; i += blockDim.x) {
+          gc[i] = 0;
+          gs[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x)
+          if (var[e] >= 0)
+            for (uint32_t j = rp[e]; j < rp[e + 1]; ++j) {
+              const longlong2 row = em[j];
+              const uint32_t key = (uint32_t)var[e] * c.n0 + (uint32_t)row.x;
+              atomicAdd(&gc[key], 1);
+              atomicAdd(&gs[key], (unsigned long long)row.y);
+            }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_groups; i += blockDim.x)
+          if (gc[i] > 0) local += weight_eval(c.w, (int64_t)gs[i]);
+        break;
+      }
       case SFGPU_K_LOAD_BALANCE: {
         unsigned long long* loads = (unsigned long long*)(st + c.off0);
         int32_t* icnt = (int32_t*)(st + c.off1);
@@ -1138,6 +1208,16 @@ __device__ void apply_scalar_edit(const DevModel& m, char* st, EditDev cur) {
       int64_t x = c.g0 ? ((const int64_t*)c.g0)[cur.e] : 1;
       if (cur.old_v >= 0) { gc[cur.old_v] -= 1; gs[cur.old_v] -= x; }
       if (cur.new_v >= 0) { gc[cur.new_v] += 1; gs[cur.new_v] += x; }
+    } else if (c.kind == SFGPU_K_PROJECT_GROUP) {
+      int32_t* gc = (int32_t*)(st + c.off0);
+      int64_t* gs = (int64_t*)(st + c.off1);
+      const uint32_t* rp = (const uint32_t*)c.g0;
+      const longlong2* em = (const longlong2*)c.g1;
+      for (uint32_t j = rp[cur.e]; j < rp[cur.e + 1]; ++j) {
+        const longlong2 row = em[j];
+        if (cur.old_v >= 0) { gc[(uint32_t)cur.old_v * c.n0 + row.x] -= 1; gs[(uint32_t)cur.old_v * c.n0 + row.x] -= row.y; }
+        if (cur.new_v >= 0) { gc[(uint32_t)cur.new_v * c.n0 + row.x] += 1; gs[(uint32_t)cur.new_v * c.n0 + row.x] += row.y; }
+      }
     } else if (c.kind == SFGPU_K_LOAD_BALANCE) {
       int64_t* loads = (int64_t*)(st + c.off0);
       int32_t* icnt = (int32_t*)(st + c.off1);

@@ -94,6 +94,15 @@ struct ListSum { uint32_t column; };
 struct Count {};
 struct Sum { uint32_t column; };
 struct LoadBalance { uint32_t metric_column = UINT32_MAX; };
+// Data form of a `Projection<A>` (stream/projected_stream/source.rs:13-24): an ASSIGNED entity e emits one row per
+// entry j of csr row e with key offset csr.col[j] (< keys_per_value) and amount amounts[j] (empty = 1 each); the
+// group key of a row is var[e] * keys_per_value + key offset. MAX_EMITS <= 8.
+struct Projection {
+  uint32_t csr;
+  uint32_t keys_per_value;
+  std::vector<uint32_t> row_ptr;  // the csr's row pointers (host copy, for the per-row terminal)
+  std::vector<int64_t> amounts;
+};
 
 struct Terminal {
   GpuScoreDirector* d;
@@ -237,6 +246,30 @@ struct UniStream {
   GroupedStream group_by(LoadBalance lb) const { return {d, collection, lb.metric_column, true}; }
 };
 
+// for_each(E).project(P)... — projected scoring rows (stream/projected_stream/uni.rs)
+struct ProjectedGroupedStream {
+  GpuScoreDirector* d;
+  uint32_t collection;
+  Projection p;
+  bool sum;
+  Terminal impact(int imp, Weight w) const;  // lowers to SFGPU_K_PROJECT_GROUP
+  Terminal penalize(Weight w) const { return impact(SFGPU_PENALTY, w); }
+  Terminal reward(Weight w) const { return impact(SFGPU_REWARD, w); }
+};
+struct ProjectedStream {
+  GpuScoreDirector* d;
+  uint32_t collection;
+  Projection p;
+  // .penalize(|row| w(row.amount)): every row scored on its own (constraint/projected/uni.rs); CONST or
+  // LINEAR (b = 0) weights sum per entity into one uni constraint over assigned entities
+  Terminal impact(int imp, Weight w) const;
+  Terminal penalize(Weight w) const { return impact(SFGPU_PENALTY, w); }
+  Terminal reward(Weight w) const { return impact(SFGPU_REWARD, w); }
+  ProjectedGroupedStream group_by(Count) const { return {d, collection, p, false}; }
+  ProjectedGroupedStream group_by(Sum) const { return {d, collection, p, true}; }  // sums the projection's amounts
+};
+inline ProjectedStream project(const UniStream& s, Projection p) { return {s.d, s.collection, std::move(p)}; }
+
 struct ConstraintFactory {
   GpuScoreDirector* d;
   explicit ConstraintFactory(GpuScoreDirector& dir) : d(&dir) {}
@@ -352,6 +385,47 @@ class GpuScoreDirector {
   sfgpu_ctx* ctx_ = nullptr;
   uint32_t R_;
 };
+
+inline Terminal ProjectedStream::impact(int imp, Weight w) const {
+  if (w.w.fn != SFGPU_W_CONST && !(w.w.fn == SFGPU_W_LINEAR && w.w.b == 0))
+    throw GpuError(SFGPU_E_UNSUPPORTED, "projected row weights must be CONST or LINEAR (a * amount)");
+  const size_t n = p.row_ptr.size() - 1;
+  std::vector<int64_t> sums(n, 0);
+  for (size_t e = 0; e < n; ++e)
+    for (uint32_t j = p.row_ptr[e]; j < p.row_ptr[e + 1]; ++j)
+      sums[e] += w.w.fn == SFGPU_W_CONST ? w.w.a : (p.amounts.empty() ? 1 : p.amounts[j]);
+  const uint32_t col = d->add_column(collection, "projected_row_sum", sums);
+  sfgpu_constraint_desc c{};
+  c.kind = SFGPU_K_UNI;
+  c.impact = imp;
+  c.weight = w.w;
+  c.weight.fn = SFGPU_W_LINEAR;
+  c.weight.a = w.w.fn == SFGPU_W_CONST ? 1 : w.w.a;
+  c.weight.b = 0;
+  c.collection = collection;
+  c.aux0 = col;
+  c.aux1 = UINT32_MAX;
+  c.p0 = 1;  // assigned entities only: unassigned ones emit no rows
+  return {d, c};
+}
+inline Terminal ProjectedGroupedStream::impact(int imp, Weight w) const {
+  sfgpu_constraint_desc c{};
+  c.kind = SFGPU_K_PROJECT_GROUP;
+  c.impact = imp;
+  c.weight = w.w;
+  c.collection = collection;
+  c.aux0 = p.csr;
+  c.aux1 = UINT32_MAX;
+  if (sum) {
+    const uint32_t nnz = p.row_ptr.back();
+    std::vector<int64_t> amt(std::max<uint32_t>(nnz, 1), 0);
+    for (uint32_t j = 0; j < nnz; ++j) amt[j] = p.amounts.empty() ? 1 : p.amounts[j];
+    const uint32_t rows = d->add_collection("projected_rows", (uint32_t)amt.size(), -1);
+    c.aux1 = d->add_column(rows, "amount", amt);
+  }
+  c.p0 = p.keys_per_value;
+  return {d, c};
+}
 
 inline uint32_t Terminal::named(const std::string& name) {
   desc.name = name.c_str();

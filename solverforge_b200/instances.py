@@ -193,3 +193,41 @@ def shift_scheduling(n_days: int = 14, slots_per_day: int = 3, n_nurses: int = 6
     hours = (s[3 * n:4 * n] % np.uint64(4)).astype(np.int64) * 4   # 0, 4, 8, 12
     return ShiftInstance(n, n_nurses, (ids // slots_per_day).astype(np.int64), (ids % slots_per_day).astype(np.uint32),
                          required, hours, nurse)
+
+
+@dataclass
+class RosterInstance:
+    n_shifts: int
+    n_nurses: int
+    n_days: int
+    limit: int               # daily hour limit per nurse
+    required: np.ndarray     # uint8 [n_shifts]
+    span_ptr: np.ndarray     # uint32 [n_shifts + 1]: projected rows of shift i are span_*[span_ptr[i]:span_ptr[i+1]]
+    span_day: np.ndarray     # int64 [rows]
+    span_hours: np.ndarray   # int64 [rows]
+    nurse_idx: np.ndarray    # int32 [n_shifts], -1 = unassigned
+
+
+def roster(n_shifts: int = 120, n_nurses: int = 7, n_days: int = 10, seed: int = 33, limit: int = 10,
+           unassigned_permille: int = 120, max_spans: int = 3) -> RosterInstance:
+    """Shifts that span 0..max_spans days (projected rows, MAX_EMITS <= 8): a night shift contributes hours to
+    two days, some shifts emit two rows for the SAME day (split shift), a few emit none."""
+    s = splitmix64_stream(seed, 4 * n_shifts + 2 * n_shifts * max_spans)
+    nurse = (s[:n_shifts] % np.uint64(n_nurses)).astype(np.int32)
+    nurse[(s[n_shifts:2 * n_shifts] % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    required = ((s[2 * n_shifts:3 * n_shifts] % np.uint64(4)) != 0).astype(np.uint8)
+    n_spans = (s[3 * n_shifts:4 * n_shifts] % np.uint64(max_spans + 1)).astype(np.int64)
+    rest = s[4 * n_shifts:]
+    ptr = np.zeros(n_shifts + 1, dtype=np.uint32)
+    ptr[1:] = np.cumsum(n_spans)
+    days, hours = [], []
+    k = 0
+    for i in range(n_shifts):
+        start = int(rest[k] % np.uint64(n_days))
+        for j in range(int(n_spans[i])):
+            split = int(rest[k + 1] % np.uint64(5)) == 0          # same day twice
+            days.append(min(start + (0 if split else j), n_days - 1))
+            hours.append(int(rest[k + 1] % np.uint64(7)) + 2)
+            k += 2
+    return RosterInstance(n_shifts, n_nurses, n_days, limit, required, ptr, np.array(days, dtype=np.int64),
+                          np.array(hours, dtype=np.int64), nurse)

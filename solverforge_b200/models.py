@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from .api import (AdjacentEqual, ConstraintFactory, Count, EqualId, EqualKey, EqualVarToRow, GpuScoreDirector,
-                  HardSoftScore, ListSum, PathCost, hard, soft)
+                  HardSoftScore, ListSum, PathCost, Sum, hard, soft)
 from .instances import CvrpInstance, GraphColoringInstance, JobShopInstance, NQueensInstance
 
 
@@ -116,6 +116,28 @@ def shift_scheduling_director(inst, n_replicas: int = 1, nurse_idx=None, device:
     f.for_each(shifts).assigned().group_by(Count()).complement(nurses, 0).penalize(
         soft(L.W_ABSDIFF, 1, inst.target)).named("Balanced workload")
     f.for_each(shifts).assigned().group_by(LoadBalance(hours)).penalize(soft(L.W_LINEAR, 1, 0)).named("Fair hours")
+    d.set_scalar_state(inst.nurse_idx if nurse_idx is None else nurse_idx)
+    d.commit()
+    return d
+
+
+def roster_director(inst, n_replicas: int = 1, nurse_idx=None, device: int = 0, stream=None,
+                    flags: int = 0) -> GpuScoreDirector:
+    """Projected scoring rows (`.project(..)`, stream/projected_stream/): every assigned shift emits one row per
+    spanned day; grouped by (nurse, day) with sum(hours) / count(), plus a per-row terminal."""
+    from .api import Projection
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
+    d.add_collection("nurses", inst.n_nurses, -1)
+    shifts = d.add_collection("shifts", inst.n_shifts, 0)
+    d.add_scalar_variable(shifts, "nurse_idx", inst.n_nurses, allows_unassigned=True)
+    required = d.add_column(shifts, "required", inst.required)
+    spans = d.add_csr("spans", inst.span_ptr, inst.span_day)
+    rows = Projection(spans, inst.n_days, inst.span_hours)
+    f = ConstraintFactory(d)
+    f.for_each(shifts).filter(required).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned required shift")
+    f.for_each(shifts).project(rows).group_by(Sum(L.NO_COLUMN)).penalize(hard(L.W_EXCESS, 1, inst.limit)).named("Daily hours")
+    f.for_each(shifts).project(rows).group_by(Count()).penalize(soft(L.W_SQUARE, 1, 0)).named("Fragmented days")
+    f.for_each(shifts).project(rows).penalize(soft(L.W_LINEAR, 1, 0)).named("Worked hours")
     d.set_scalar_state(inst.nurse_idx if nurse_idx is None else nurse_idx)
     d.commit()
     return d

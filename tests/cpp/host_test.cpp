@@ -294,6 +294,60 @@ static int test_gpu() {
       if (now > best) best = now;
     }
   }
+  // projected scoring rows through the C++ factory (`.project(..)`): roster with shifts spanning days
+  {
+    const uint32_t n_shifts = 90, n_nurses = 5;
+    const int64_t n_days = 7, limit = 9;
+    sfo::Roster ro;
+    ro.n_nurses = n_nurses;
+    ro.n_days = n_days;
+    std::vector<uint32_t> ptr(1, 0), days;
+    std::vector<int64_t> hours, required(n_shifts);
+    std::vector<int32_t> nurse(n_shifts);
+    uint64_t q = 4242;
+    for (uint32_t i = 0; i < n_shifts; ++i) {
+      required[i] = sfo::splitmix64(q++) % 3 != 0;
+      nurse[i] = (int32_t)(sfo::splitmix64(q++) % (n_nurses + 1)) - 1;
+      sfo::RShift sh{i, required[i] != 0, {}, nurse[i] < 0 ? sfo::OptVal() : sfo::OptVal((size_t)nurse[i])};
+      const uint32_t spans = sfo::splitmix64(q++) % 4;
+      const int64_t start = sfo::splitmix64(q++) % n_days;
+      for (uint32_t j = 0; j < spans; ++j) {
+        const int64_t day = std::min<int64_t>(start + (j % 2), n_days - 1), h = 2 + sfo::splitmix64(q++) % 6;
+        sh.spans.push_back({day, h});
+        days.push_back((uint32_t)day);
+        hours.push_back(h);
+      }
+      ptr.push_back((uint32_t)days.size());
+      ro.shifts.push_back(sh);
+    }
+    sfo::RosterModel orc(ro, limit);
+    sf::GpuScoreDirector rd(1);
+    rd.add_collection("nurses", n_nurses, -1);
+    uint32_t shifts = rd.add_collection("shifts", n_shifts, 0);
+    rd.add_scalar_variable(shifts, "nurse_idx", n_nurses, true);
+    uint32_t req = rd.add_column(shifts, "required", required);
+    uint32_t spans = rd.add_csr("spans", ptr, days);
+    sf::Projection rows{spans, (uint32_t)n_days, ptr, hours};
+    sf::ConstraintFactory rf(rd);
+    rf.for_each(shifts).filtered(req).unassigned().penalize(sf::HardSoftScore::ONE_HARD()).named("Unassigned required shift");
+    sf::project(rf.for_each(shifts), rows).group_by(sf::Sum{UINT32_MAX}).penalize(sf::Weight::hard(SFGPU_W_EXCESS, 1, limit)).named("Daily hours");
+    sf::project(rf.for_each(shifts), rows).group_by(sf::Count{}).penalize(sf::Weight::soft(SFGPU_W_SQUARE, 1, 0)).named("Fragmented days");
+    sf::project(rf.for_each(shifts), rows).penalize(sf::Weight::soft(SFGPU_W_LINEAR, 1, 0)).named("Worked hours");
+    rd.set_scalar_state(nurse);
+    auto ri = rd.commit();
+    auto ros = orc.calculate_score();
+    CHECK(ri[0].hard == ros.hard && ri[0].soft == ros.soft);
+    auto rmoves = orc.enumerate_scalar({});
+    std::vector<sf::ScalarEdit> rb;
+    for (auto& m : rmoves) rb.push_back({(uint32_t)m.a, m.to ? (int32_t)*m.to : -1});
+    rd.score_candidates(rb, {0, rb.size()}, scores, doable);
+    for (size_t i = 0; i < rmoves.size(); ++i) {
+      auto ev = orc.evaluate(rmoves[i]);
+      bool ok = ev.kind != sfo::EvalKind::NotDoable;
+      CHECK(ok == (doable[i] != 0));
+      if (ok) CHECK(scores[i].hard == ev.score.hard && scores[i].soft == ev.score.soft);
+    }
+  }
   // error behaviour: unknown constraint kind is rejected, never emulated
   try {
     sf::GpuScoreDirector bad(1);

@@ -30,13 +30,15 @@ def lib() -> C.CDLL:
         if not os.path.exists(LIB):
             build()
         l = C.CDLL(LIB)
-        for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create", "sfo_shift_create"):
+        for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create", "sfo_shift_create",
+                     "sfo_roster_create"):
             getattr(l, name).restype = _P
         l.sfo_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
         l.sfo_nq_create.argtypes = [C.c_uint32, _P]
         l.sfo_cvrp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, _P, _P, _P, _P]
         l.sfo_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int]
         l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64]
+        l.sfo_roster_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]
         l.sfo_destroy.argtypes = [_P]
         l.sfo_committed_score.argtypes = [_P, _P]
         l.sfo_evaluate_all.argtypes = [_P, _P]
@@ -125,6 +127,14 @@ class Oracle:
         return Oracle(lib().sfo_shift_create(inst.n_shifts, inst.n_nurses, _p(np.ascontiguousarray(inst.day, np.int64)),
                                              _p(_u32(inst.slot)), _p(np.ascontiguousarray(inst.required, np.uint8)),
                                              _p(np.ascontiguousarray(inst.hours, np.int64)), _p(n), inst.target))
+
+    @staticmethod
+    def roster(inst, nurse_idx=None) -> "Oracle":
+        n = np.ascontiguousarray(inst.nurse_idx if nurse_idx is None else nurse_idx, dtype=np.int32)
+        return Oracle(lib().sfo_roster_create(inst.n_shifts, inst.n_nurses, inst.n_days, inst.limit,
+                                              _p(np.ascontiguousarray(inst.required, np.uint8)), _p(_u32(inst.span_ptr)),
+                                              _p(np.ascontiguousarray(inst.span_day, np.int64)),
+                                              _p(np.ascontiguousarray(inst.span_hours, np.int64)), _p(n)))
 
     # ---- scores -------------------------------------------------------------------------
     def committed_score(self) -> np.ndarray:

@@ -596,3 +596,53 @@ def test_full_size_c4_parity_slice_and_invariants():
     so, oko = o.score_change(rows[sl])
     _eq(s[sl], so, "job-shop slice")
     _eq(ok[sl], oko)
+
+
+def test_projected_rows_roster_matches_oracle():
+    """`.project(..)` multi-emit rows (stream/projected_stream/, constraint/projected/{uni.rs,grouped/}):
+    grouped sum with an EXCESS weight, grouped count with a SQUARE weight, and a per-row terminal; change,
+    swap and compound candidates, then committed moves with cached == fresh == oracle."""
+    inst = instances.roster(160, 6, 9, seed=5)
+    o = Oracle.roster(inst)
+    d = models.roster_director(inst)
+    assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+    assert d.fresh_score()[0].tolist() == o.evaluate_all().tolist()
+    rows = o.enumerate_change()
+    s, ok = d.score_change(rows)
+    so, oko = o.score_change(rows)
+    _eq(ok, oko, "projected change doable")
+    _eq(s, so, "projected change scores")
+    r = instances.splitmix64_stream(99, 3000)
+    swaps = np.stack([r[:400] % np.uint64(inst.n_shifts), r[400:800] % np.uint64(inst.n_shifts)], axis=1).astype(np.int64)
+    s, ok = d.score_swap(swaps)
+    so, oko = o.score_swap(swaps)
+    _eq(ok, oko, "projected swap doable")
+    _eq(s, so, "projected swap scores")
+    # compound candidates: several shifts moved at once, often onto the same (nurse, day) group
+    n_c = 300
+    sizes = (r[800:800 + n_c] % np.uint64(4)).astype(np.int64) + 1
+    eo = np.concatenate([[0], np.cumsum(sizes)])
+    tot = int(eo[-1])
+    rr = instances.splitmix64_stream(98, 2 * tot)
+    ent = (rr[:tot] % np.uint64(inst.n_shifts)).astype(np.int64)
+    val = (rr[tot:] % np.uint64(3)).astype(np.int64) - 1            # few nurses => shared groups
+    edits = np.stack([ent, val], axis=1)
+    s, ok = d.score_compound(eo, edits)
+    so, oko = o.score_compound(eo, edits)
+    _eq(ok, oko, "projected compound doable")
+    _eq(s, so, "projected compound scores")
+    # a short hill-climbing trajectory on device, replayed on the oracle
+    for step in range(8):
+        last = d.calculate_score()
+        idx, best, ev, win = d.step_change(ForageParams(1, 1, 0), step_seeds=[60 + step],
+                                           ref_scores=np.concatenate([last, last], axis=1), apply=True)
+        rows = o.enumerate_change()
+        so, oko = o.score_change(rows)
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 60 + step, 2, 1, True, 0)
+        if out[0]:
+            assert int(idx[0]) == out[1], f"step {step}"
+            o.apply_change(*rows[out[1]])
+        else:
+            assert idx[0] == 0xFFFFFFFF
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        assert d.fresh_score()[0].tolist() == o.committed_score().tolist()

@@ -172,3 +172,18 @@ def test_fast_cpu_baseline_matches_the_oracle():
     sf, okf = f.score(rows)
     assert np.array_equal(okf, oko) and np.array_equal(sf, so)
     assert f.bench(rows, 2, 0.2) > 0
+
+
+def test_roster_projected_rows_incremental_equals_fresh():
+    """Projected multi-emit rows in the oracle (ProjectedUni / ProjectedGrouped): cached == evaluate_all
+    along a random walk of committed change moves (FullAssert invariant, scope_core.rs:642-653)."""
+    from solverforge_b200 import instances
+    inst = instances.roster(60, 4, 6, seed=2)
+    o = Oracle.roster(inst)
+    assert o.committed_score().tolist() == o.evaluate_all().tolist()
+    r = instances.splitmix64_stream(12, 400)
+    for i in range(200):
+        e = int(r[2 * i] % np.uint64(inst.n_shifts))
+        v = int(r[2 * i + 1] % np.uint64(inst.n_nurses + 1)) - 1
+        o.apply_change(e, v)
+        assert o.committed_score().tolist() == o.evaluate_all().tolist(), f"step {i}"
