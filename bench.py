@@ -283,8 +283,22 @@ def run_ours(args):
         if world > 1 and (i + 1) % args.sync_every == 0:
             # best packed score over this rank's replicas, then one 8-byte MAX all-reduce (NCCL):
             # SURVEY 8(e) — the only collective of the path, every K steps
+            dbg = os.environ.get("BENCH_DEBUG_SYNC")
+            if dbg:
+                import time as _t
+                torch.cuda.synchronize()
+                h0 = _t.perf_counter()
             best = (((t_best[:, 0] + (1 << 22)) << 40) | (t_best[:, 1] + (1 << 39))).max().reshape(1)
+            if dbg:
+                torch.cuda.synchronize()
+                h1 = _t.perf_counter()
             dist.all_reduce(best, op=dist.ReduceOp.MAX)
+            if dbg:
+                h2 = _t.perf_counter()
+                torch.cuda.synchronize()
+                h3 = _t.perf_counter()
+                print(f"[rank {rank}] sync at step {i}: pack {1e3 * (h1 - h0):.3f} ms, all_reduce call {1e3 * (h2 - h1):.3f} ms, "
+                      f"drain {1e3 * (h3 - h2):.3f} ms", file=sys.stderr, flush=True)
 
     # cpu_baseline leg (rank 0): the oracle scores replica 0's batch on one host core; its output
     # doubles as the parity gate — an incorrect kernel is never timed.
@@ -320,6 +334,13 @@ def run_ours(args):
         torch.cuda.synchronize()
     launches0 = d.launch_count()
     if world > 1:
+        # warm the collective itself (NCCL connects its channels lazily on the first all-reduce of a shape):
+        # with a sync only every K steps no warm-up step would reach it otherwise
+        # ... and torch loads the few elementwise / reduce kernels of the key packing lazily (tens of ms on
+        # first use): run the exact sync expression untimed
+        for _ in range(3):
+            warm = (((t_best[:, 0] + (1 << 22)) << 40) | (t_best[:, 1] + (1 << 39))).max().reshape(1)
+            dist.all_reduce(warm, op=dist.ReduceOp.MAX)
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
