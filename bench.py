@@ -259,7 +259,7 @@ def run_ours(args):
     t_best = torch.empty((R, 2), dtype=torch.int64, device=dev)
     t_eval = torch.empty(R, dtype=torch.int32, device=dev)
     t_keys = torch.empty(R, dtype=torch.int64, device=dev)
-    fp = ForageParams(acceptor=0, tie_mode=1, accepted_limit=0)
+    fp = ForageParams(acceptor=0, tie_mode=int(os.environ.get("BENCH_TIE_MODE", "1")), accepted_limit=0)
 
     use_fused = name == "cvrp"
 

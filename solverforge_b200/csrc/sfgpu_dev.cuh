@@ -108,7 +108,9 @@ struct ForageDev {
 struct ChunkPartial {
   int64_t best_h, best_s;
   uint32_t n_best, n_accepted;
-  uint32_t first_idx, pad;
+  uint32_t first_idx;
+  uint32_t second_idx;  // second accepted row equal to the best (0xFFFFFFFF when n_best < 2): the common
+                        // tie of two rows never needs the ordered rescan
 };
 
 __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {

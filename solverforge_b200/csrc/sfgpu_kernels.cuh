@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
   // fused forager partial (FORAGE): this thread's best accepted score delta, multiplicity, first
   // row; acceptor references become thresholds on the delta
   S tb_h = 0, tb_s = 0, f_lh = 0, f_ls = 0, f_th = 0, f_ts = 0;
-  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
+  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, tb_second = 0xFFFFFFFFu, t_acc = 0;
   if (FORAGE && fa.ref_scores) {
     rel_threshold(fa.ref_scores[r * 4 + 0], ch, f_lh);
     rel_threshold(fa.ref_scores[r * 4 + 1], csf, f_ls);
@@ -777,8 +777,11 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
           tb_s = ds;
           tb_n = 1;
           tb_first = (uint32_t)(i - lo);
+          tb_second = 0xFFFFFFFFu;
         } else if (tb_h == dh && tb_s == ds) {
-          tb_n++;  // rows of one thread are visited in increasing pull order: tb_first stays the minimum
+          // rows of one thread are visited in increasing pull order: tb_first stays the minimum
+          if (tb_n == 1) tb_second = (uint32_t)(i - lo);
+          tb_n++;
         }
       }
     }
@@ -790,29 +793,35 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     for (int o = 16; o > 0; o >>= 1) {
       const S oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
       const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
+      const uint32_t osec = __shfl_down_sync(0xffffffffu, tb_second, o);
       t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
       if (on && (!tb_n || lex_less<S>(tb_h, tb_s, oh, os))) {
-        tb_h = oh; tb_s = os; tb_n = on; tb_first = of;
+        tb_h = oh; tb_s = os; tb_n = on; tb_first = of; tb_second = osec;
       } else if (on && tb_n && oh == tb_h && os == tb_s) {
         tb_n += on;
+        tb_second = min(max(tb_first, of), min(tb_second, osec));  // second smallest of the four indices
         tb_first = min(tb_first, of);
       }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t sh_2[8];
     if (lane == 0) {
       sh_h[warp] = ch + (int64_t)tb_h; sh_s[warp] = csf + (int64_t)tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first;
       sh_a[warp] = t_acc;
+      sh_2[warp] = tb_second;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      ChunkPartial cp{0, 0, 0, 0, 0xFFFFFFFFu, 0};
+      ChunkPartial cp{0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
       for (int w = 0; w < 8; ++w) {
         cp.n_accepted += sh_a[w];
         if (!sh_n[w]) continue;
         if (!cp.n_best || score_less(cp.best_h, cp.best_s, sh_h[w], sh_s[w])) {
           cp.best_h = sh_h[w]; cp.best_s = sh_s[w]; cp.n_best = sh_n[w]; cp.first_idx = sh_f[w];
+          cp.second_idx = sh_2[w];
         } else if (sh_h[w] == cp.best_h && sh_s[w] == cp.best_s) {
           cp.n_best += sh_n[w];
+          cp.second_idx = min(max(cp.first_idx, sh_f[w]), min(cp.second_idx, sh_2[w]));
           cp.first_idx = min(cp.first_idx, sh_f[w]);
         }
       }
@@ -892,6 +901,10 @@ __global__ void __launch_bounds__(256) forage_finish_kernel(const __grid_constan
       s_cstar = c_star;
       s_j = want - before;  // 1-based rank inside the chunk
       s_winner = any ? cp[c_star].first_idx : 0xFFFFFFFFu;
+      if (any && s_j == 2 && cp[c_star].second_idx != 0xFFFFFFFFu) {  // the chunk's second best row is recorded
+        s_winner = cp[c_star].second_idx;
+        s_j = 1;
+      }
       if (out_evaluated) out_evaluated[r] = (uint32_t)(hi - lo);
     }
   }
@@ -913,30 +926,44 @@ __global__ void __launch_bounds__(256) forage_finish_kernel(const __grid_constan
       th = fa.ref_scores[r * 4 + 2];
       ts = fa.ref_scores[r * 4 + 3];
     }
+    // every thread owns a contiguous run of rows (thread order == pull order) and first collects the
+    // hit mask of its whole run with independent loads; one block scan then locates the j-th hit.
+    // Super-blocks of 256 * 64 rows keep the mask in one 64-bit register.
     uint32_t seen = 0;
-    for (uint64_t base = c_lo; base < c_hi; base += 1024) {
-      uint32_t hits = 0;  // bit q set: row base + 4*tid + q is an accepted best row
+    for (uint64_t base = c_lo; base < c_hi; base += 256 * 64) {
+      const uint64_t b_hi = base + 256 * 64 < c_hi ? base + 256 * 64 : c_hi;
+      const uint32_t run = (uint32_t)((b_hi - base + 255) / 256);  // rows per thread, <= 64
+      const uint64_t t_lo = base + (uint64_t)threadIdx.x * run;
+      uint64_t hits = 0;  // bit q set: row t_lo + q is an accepted best row
+      if (scores) {
+        // eight independent 128-bit loads in flight per thread: the rescan is latency-, not bandwidth-bound
+        for (uint32_t q0 = 0; q0 < run; q0 += 8) {
+          longlong2 v[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint64_t i = base + (uint64_t)threadIdx.x * 4 + q;
-        if (i >= c_hi) continue;
-        int64_t h, s2;
-        bool ok;
-        if (scores) {
-          const longlong2 v = ((const longlong2*)scores)[i];
-          h = v.x;
-          s2 = v.y;
-          ok = doable[i] != 0;
-        } else {
-          Score2 d;
-          ok = list_change_delta(m, st, ((const uint4*)rows)[i], d);
-          h = cs[0] + d.hard;
-          s2 = cs[1] + d.soft;
+          for (int u = 0; u < 8; ++u) {
+            const uint64_t i = t_lo + q0 + u;
+            v[u] = (q0 + u < run && i < b_hi) ? __ldcs((const longlong2*)scores + i) : make_longlong2(bh - 1, 0);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint64_t i = t_lo + q0 + u;
+            if (v[u].x == bh && v[u].y == bs && q0 + u < run && i < b_hi && doable[i] != 0 &&
+                accept_score(fa.f.acceptor, bh, bs, lh, ls, th, ts))
+              hits |= 1ull << (q0 + u);
+          }
         }
-        if (ok && h == bh && s2 == bs && accept_score(fa.f.acceptor, h, s2, lh, ls, th, ts)) hits |= 1u << q;
+      } else {
+        for (uint32_t q = 0; q < run; ++q) {
+          const uint64_t i = t_lo + q;
+          if (i >= b_hi) break;
+          Score2 d;
+          const bool ok = list_change_delta(m, st, ((const uint4*)rows)[i], d);
+          const int64_t h = cs[0] + d.hard, s2 = cs[1] + d.soft;
+          if (ok && h == bh && s2 == bs && accept_score(fa.f.acceptor, h, s2, lh, ls, th, ts)) hits |= 1ull << q;
+        }
       }
-      const uint32_t mine = __popc(hits);
-      // inclusive scan over the 256 threads (thread order == pull order)
+      const uint32_t mine = __popcll(hits);
+      // inclusive scan over the 256 threads
       uint32_t incl = mine;
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
@@ -951,9 +978,9 @@ __global__ void __launch_bounds__(256) forage_finish_kernel(const __grid_constan
       }
       const uint32_t excl = seen + warp_base + incl - mine;
       if (mine && excl < j && j <= excl + mine) {
-        uint32_t mm = hits;
+        uint64_t mm = hits;
         for (uint32_t t = 1; t < j - excl; ++t) mm &= mm - 1;
-        s_winner = (uint32_t)(base + (uint64_t)threadIdx.x * 4 + (__ffs(mm) - 1) - lo);
+        s_winner = (uint32_t)(t_lo + (__ffsll((long long)mm) - 1) - lo);
       }
       seen += total;
       __syncthreads();
