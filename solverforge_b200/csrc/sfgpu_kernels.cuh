@@ -660,6 +660,30 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     rel_threshold(0, ch, f_th);
     rel_threshold(0, csf, f_ts);
   }
+  // one branch-free form for every acceptor code: accept(d) = (A < d) || (d >= B), lexicographic.
+  //   0 accept all: A = +inf, B = -inf      1 d > last: A = last, B = +inf
+  //   2 d >= last || d >= t: A = +inf, B = min(last, t)      3 d > last || d >= t: A = last, B = t
+  // (deltas are strictly inside the representable range, so +-inf never compare equal)
+  const S S_MAX = sizeof(S) == 4 ? (S)INT32_MAX : (S)INT64_MAX, S_MIN = sizeof(S) == 4 ? (S)INT32_MIN : (S)INT64_MIN;
+  S a_h = S_MAX, a_s = S_MAX, b_h = S_MIN, b_s = S_MIN;
+  if (FORAGE) {
+    const int acc = fa.f.acceptor;
+    if (acc == 1 || acc == 3) {
+      a_h = f_lh;
+      a_s = f_ls;
+    }
+    if (acc == 1) {
+      b_h = S_MAX;
+      b_s = S_MAX;
+    } else if (acc == 2) {
+      const bool l_lt = lex_less<S>(f_lh, f_ls, f_th, f_ts);
+      b_h = l_lt ? f_lh : f_th;
+      b_s = l_lt ? f_ls : f_ts;
+    } else if (acc == 3) {
+      b_h = f_th;
+      b_s = f_ts;
+    }
+  }
   const uint4* rr = (const uint4*)(smem + m.off_route_rec);
   const uint4* pr = (const uint4*)(smem + m.off_pos_rec);
   const uint4* sr = (const uint4*)(smem + m.off_slot_rec);
@@ -675,33 +699,41 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
   const uint32_t dim = pc.n0;
   const S pc_a = has_pc ? (S)(pc.sign < 0 ? -pc.w.a : pc.w.a) : 0;
   const bool pc_hard = pc.w.level == 0;
+  // level routing as 0/1 multipliers (one IMAD per level instead of a select + add)
+  const S pc_mh = pc_hard ? 1 : 0, pc_ms = pc_hard ? 0 : 1;
   const ConsDev& ls = m.cons[SUM_FN >= 0 ? m.fast_ls : 0];
   // narrow models: |route sum| < 2^30, so a threshold clamped to +-2^30 gives the same excesses
   const S ls_a = (S)(ls.sign < 0 ? -ls.w.a : ls.w.a);
   const S ls_b = sizeof(S) == 4 ? clamp_to<S>(ls.w.b, 1ll << 30) : (S)ls.w.b;
   const bool ls_hard = ls.w.level == 0;
-  // contiguous chunk per CTA (keeps pull order inside a chunk for the fused forager partials)
+  const S ls_mh = ls_hard ? 1 : 0, ls_ms = ls_hard ? 0 : 1;
+  // contiguous chunk per CTA (keeps pull order inside a chunk for the fused forager partials);
+  // inside the chunk every index is 32-bit (a replica's pull indices are 32-bit by contract)
   const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
   const uint64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
-  const uint64_t c_lo = lo + per * blockIdx.x;
-  const uint64_t c_hi = c_lo + per < hi ? c_lo + per : hi;
+  const uint64_t c_lo64 = lo + per * blockIdx.x < hi ? lo + per * blockIdx.x : hi;
+  const uint64_t c_hi64 = c_lo64 + per < hi ? c_lo64 + per : hi;
+  const uint32_t n_c = (uint32_t)(c_hi64 - c_lo64);
+  const uint32_t first_base = (uint32_t)(c_lo64 - lo);
   // U candidates per thread per trip with the next trip's rows prefetched into registers: the
   // DRAM latency of the streamed rows is hidden by 2*U independent 128-bit loads per thread.
-  const uint4* __restrict__ rows4 = (const uint4*)rows;
-  const uint64_t stride = (uint64_t)blockDim.x * U;
+  const uint4* __restrict__ rows4 = (const uint4*)rows + c_lo64;
+  longlong2* __restrict__ scores_c = out_scores ? (longlong2*)out_scores + c_lo64 : nullptr;
+  uint8_t* __restrict__ doable_c = out_doable ? out_doable + c_lo64 : nullptr;
+  const uint32_t stride = blockDim.x * U;
   uint4 nxt[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const uint64_t i = c_lo + threadIdx.x + (uint64_t)u * blockDim.x;
-    nxt[u] = i < c_hi ? __ldcs(rows4 + i) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+    const uint32_t i = threadIdx.x + u * blockDim.x;
+    nxt[u] = i < n_c ? __ldcs(rows4 + i) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
   }
-  for (uint64_t base = c_lo + threadIdx.x; base < c_hi; base += stride) {
+  for (uint32_t base = threadIdx.x; base < n_c; base += stride) {
     uint4 cur[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       cur[u] = nxt[u];
-      const uint64_t i = base + stride + (uint64_t)u * blockDim.x;
-      nxt[u] = i < c_hi ? __ldcs(rows4 + i) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
+      const uint32_t i = base + stride + u * blockDim.x;
+      nxt[u] = i < n_c ? __ldcs(rows4 + i) : make_uint4(0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0);
     }
     // phase 1: route records + doability
     bool ok[U];
@@ -752,35 +784,37 @@ __global__ void __launch_bounds__(256, MINB) score_list_change_fast_kernel(const
     // phase 3: deltas + stores
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint64_t i = base + (uint64_t)u * blockDim.x;
-      if (i >= c_hi) continue;
+      const uint32_t i = base + u * blockDim.x;
+      if (i >= n_c) continue;
       S dh = 0, ds = 0;
       if (has_pc) {
-        const S d = (S)((US)pc_a * (US)(S)((int32_t)p[u].y + m0[u] + m1[u] - (int32_t)sl[u].z));
-        if (pc_hard) dh += d; else ds += d;
+        const US d = (US)pc_a * (US)(S)((int32_t)p[u].y + m0[u] + m1[u] - (int32_t)sl[u].z);
+        dh = (S)(d * (US)pc_mh);
+        ds = (S)(d * (US)pc_ms);
       }
       if (SUM_FN >= 0 && cur[u].x != cur[u].z) {
-        const S d = list_sum_delta<SUM_FN, S, US>(ls_a, ls_b, (S)(int32_t)p[u].z, sums[u], sumd[u]);
-        if (ls_hard) dh += d; else ds += d;
+        const US d = (US)list_sum_delta<SUM_FN, S, US>(ls_a, ls_b, (S)(int32_t)p[u].z, sums[u], sumd[u]);
+        dh = (S)((US)dh + d * (US)ls_mh);
+        ds = (S)((US)ds + d * (US)ls_ms);
       }
       if (!FORAGE || out_scores) {
         longlong2 o;
         o.x = ok[u] ? ch + (int64_t)dh : 0;
         o.y = ok[u] ? csf + (int64_t)ds : 0;
-        __stcs((longlong2*)out_scores + i, o);
-        out_doable[i] = ok[u] ? 1 : 0;
+        __stcs(scores_c + i, o);
+        doable_c[i] = ok[u] ? 1 : 0;
       }
-      if (FORAGE && ok[u] && accept_delta<S>(fa.f.acceptor, dh, ds, f_lh, f_ls, f_th, f_ts)) {
+      if (FORAGE && ok[u] && (lex_less<S>(a_h, a_s, dh, ds) || !lex_less<S>(dh, ds, b_h, b_s))) {
         t_acc++;
         if (tb_n == 0 || lex_less<S>(tb_h, tb_s, dh, ds)) {
           tb_h = dh;
           tb_s = ds;
           tb_n = 1;
-          tb_first = (uint32_t)(i - lo);
+          tb_first = first_base + i;
           tb_second = 0xFFFFFFFFu;
         } else if (tb_h == dh && tb_s == ds) {
           // rows of one thread are visited in increasing pull order: tb_first stays the minimum
-          if (tb_n == 1) tb_second = (uint32_t)(i - lo);
+          if (tb_n == 1) tb_second = first_base + i;
           tb_n++;
         }
       }
