@@ -973,8 +973,8 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     } else {
       const int bytes = (int)(16 + dm.compact_bytes);
 #define COMPACT_ATTR(FN)                                                                                              \
-  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 2, 4, false, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
-  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 2, 4, true, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 1, 4, false, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 1, 4, true, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
       COMPACT_ATTR(-1);
       COMPACT_ATTR(SFGPU_W_CONST);
       COMPACT_ATTR(SFGPU_W_LINEAR);
@@ -1059,8 +1059,8 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
 #define FASTK(FN)                                                                                              \
   if (dm.compact_bytes && dm.fm_u16) {                                                                         \
     const size_t csm = 16 + dm.compact_bytes;                                                                  \
-    if (forage) score_list_change_fast_kernel<FN, 2, 4, true, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
-    else score_list_change_fast_kernel<FN, 2, 4, false, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
+    if (forage) score_list_change_fast_kernel<FN, 1, 4, true, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
+    else score_list_change_fast_kernel<FN, 1, 4, false, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
   } else if (forage)                                                                                           \
     if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 4, true, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
     else score_list_change_fast_kernel<FN, 2, 3, true, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
