@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -68,9 +69,44 @@ struct ScalarEdit {  // planning/scalar/candidate.rs:6-12 (descriptor + variable
   uint32_t entity_index;
   int32_t to_value;  // -1 = None
 };
+struct ScalarSwap {  // heuristic/move/swap.rs: the two entities exchange their values
+  uint32_t left_entity, right_entity;
+};
 struct ListChange {  // heuristic/move/list_kernel/change.rs:15-21
   uint32_t source_entity, source_position, destination_entity, destination_position;
 };
+struct ListSwap {  // heuristic/move/list_kernel/swap.rs:16-30
+  uint32_t first_entity, first_position, second_entity, second_position;
+};
+// acceptor + forager of one fused device step (sfgpu_forage_params) and what it returns per replica
+struct StepParams {
+  int acceptor = 0;            // 0 accept all, 1 > last, 2 >= last || >= threshold, 3 > last || >= threshold
+  bool random_ties = true;     // ScoreTieBreak: reservoir (forager.rs:99-155) or first
+  uint32_t accepted_limit = 0; // 0 = BestScore, N = AcceptedCount(N)
+};
+struct StepResult {
+  std::vector<uint32_t> index;      // winning CandidateId per replica (UINT32_MAX: none accepted)
+  std::vector<struct HardSoftScore> best;
+  std::vector<uint32_t> evaluated;  // moves_evaluated
+  std::vector<uint32_t> winner_rows;  // [R][4] list moves / [R][2] scalar edits
+};
+struct SolveParams {  // sfgpu_solve_params: device-resident loop (phase.rs:237-320)
+  uint32_t max_nearby = 20, n_steps = 0;
+  int acceptor = 2;            // 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing,
+                               // 5 DiversifiedLateAcceptance
+  uint32_t late_size = 400;
+  bool random_ties = true;
+  uint32_t accepted_limit = 0;
+  uint64_t seed_base = 0;
+  bool restore_best = false;
+  double acceptor_real = 0.0;  // rain_speed / tolerance
+  uint64_t step_count_limit = 0;
+};
+struct SolveResult {
+  std::vector<struct HardSoftScore> best;
+  std::vector<uint64_t> moves_evaluated, accepted_steps;
+};
+
 
 struct Weight {
   sfgpu_weight w;
@@ -374,6 +410,107 @@ class GpuScoreDirector {
                                   reinterpret_cast<const uint32_t*>(batch.data()),
                                   reinterpret_cast<int64_t*>(scores.data()), doable.data()));
   }
+  void score_candidates(const std::vector<ScalarSwap>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_swap(ctx_, 0, batch.size(), cand_offsets.data(), reinterpret_cast<const uint32_t*>(batch.data()),
+                           reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void score_candidates(const std::vector<ListSwap>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_list_swap(ctx_, 0, batch.size(), cand_offsets.data(),
+                                reinterpret_cast<const uint32_t*>(batch.data()),
+                                reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  // CompoundScalarMove batch: candidate i owns edits [edit_offsets[i], edit_offsets[i+1]) (compound_scalar.rs:289-319)
+  void score_compound(const std::vector<uint64_t>& edit_offsets, const std::vector<ScalarEdit>& edits,
+                      const std::vector<uint64_t>& cand_offsets, std::vector<HardSoftScore>& scores,
+                      std::vector<uint8_t>& doable) {
+    const size_t n = edit_offsets.size() - 1;
+    scores.resize(n);
+    doable.resize(n);
+    check(sfgpu_score_compound(ctx_, 0, n, cand_offsets.data(), edit_offsets.data(),
+                               reinterpret_cast<const uint32_t*>(edits.data()),
+                               reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  // acceptor + forager replay on device over scored rows (sfgpu_argbest[_gated]); ref = {last_step, threshold}
+  StepResult argbest(const std::vector<HardSoftScore>& scores, const std::vector<uint8_t>& doable,
+                     const std::vector<uint64_t>& cand_offsets, StepParams p, const std::vector<uint64_t>& step_seeds,
+                     const std::vector<HardSoftScore>& ref_pairs = {}, const uint8_t* gates = nullptr) {
+    StepResult out = make_result(0);
+    sfgpu_forage_params fp{p.acceptor, p.random_ties ? 1 : 0, p.accepted_limit, 0};
+    check(sfgpu_argbest_gated(ctx_, 0, &fp, cand_offsets.data(), reinterpret_cast<const int64_t*>(scores.data()),
+                              doable.data(), gates, step_seeds.empty() ? nullptr : step_seeds.data(),
+                              ref_pairs.empty() ? nullptr : reinterpret_cast<const int64_t*>(ref_pairs.data()),
+                              out.index.data(), reinterpret_cast<int64_t*>(out.best.data()), out.evaluated.data()));
+    return out;
+  }
+  // whole steps on device (evaluate_candidates + pick [+ apply], phase/step.rs:30-225)
+  StepResult step_change(StepParams p, const std::vector<uint64_t>& step_seeds,
+                         const std::vector<HardSoftScore>& ref_pairs = {}, bool apply_winners = false) {
+    StepResult out = make_result(2);
+    sfgpu_forage_params fp{p.acceptor, p.random_ties ? 1 : 0, p.accepted_limit, 0};
+    check(sfgpu_step_change(ctx_, 0, &fp, step_seeds.empty() ? nullptr : step_seeds.data(),
+                            ref_pairs.empty() ? nullptr : reinterpret_cast<const int64_t*>(ref_pairs.data()), nullptr,
+                            nullptr, nullptr, nullptr, out.index.data(), reinterpret_cast<int64_t*>(out.best.data()),
+                            out.evaluated.data(), out.winner_rows.data(), apply_winners ? 1 : 0));
+    return out;
+  }
+  StepResult step_nearby_list_change(uint32_t max_nearby, StepParams p, const std::vector<uint64_t>& step_seeds,
+                                     const std::vector<HardSoftScore>& ref_pairs = {}, bool apply_winners = false,
+                                     bool swap_moves = false) {
+    StepResult out = make_result(4);
+    sfgpu_forage_params fp{p.acceptor, p.random_ties ? 1 : 0, p.accepted_limit, 0};
+    auto fn = swap_moves ? sfgpu_step_nearby_list_swap : sfgpu_step_nearby_list_change;
+    check(fn(ctx_, 0, max_nearby, &fp, step_seeds.empty() ? nullptr : step_seeds.data(),
+             ref_pairs.empty() ? nullptr : reinterpret_cast<const int64_t*>(ref_pairs.data()), nullptr, nullptr, nullptr,
+             nullptr, out.index.data(), reinterpret_cast<int64_t*>(out.best.data()), out.evaluated.data(),
+             out.winner_rows.data(), apply_winners ? 1 : 0));
+    return out;
+  }
+  StepResult step_nearby_list_swap(uint32_t max_nearby, StepParams p, const std::vector<uint64_t>& step_seeds,
+                                   const std::vector<HardSoftScore>& ref_pairs = {}, bool apply_winners = false) {
+    return step_nearby_list_change(max_nearby, p, step_seeds, ref_pairs, apply_winners, true);
+  }
+  // device-resident loops (solve_local_search_with_resources for every replica)
+  SolveResult solve(const SolveParams& p, bool scalar_model) {
+    sfgpu_solve_params sp{};
+    sp.max_nearby = p.max_nearby;
+    sp.n_steps = p.n_steps;
+    sp.acceptor = p.acceptor;
+    sp.late_size = p.late_size;
+    sp.tie_mode = p.random_ties ? 1 : 0;
+    sp.accepted_limit = p.accepted_limit;
+    sp.seed_base = p.seed_base;
+    sp.restore_best = p.restore_best ? 1 : 0;
+    sp.acceptor_real = p.acceptor_real;
+    sp.step_count_limit = p.step_count_limit;
+    SolveResult out;
+    out.best.resize(R_);
+    out.moves_evaluated.resize(R_);
+    out.accepted_steps.resize(R_);
+    auto fn = scalar_model ? sfgpu_solve_change : sfgpu_solve_nearby_list_change;
+    check(fn(ctx_, &sp, reinterpret_cast<int64_t*>(out.best.data()), out.moves_evaluated.data(),
+             out.accepted_steps.data()));
+    return out;
+  }
+  // working_solution() of the list variable: per replica (offsets[n_owners + 1], elems[capacity])
+  void list_state(uint32_t n_owners, std::vector<uint32_t>& offsets, std::vector<uint32_t>& elems) {
+    uint32_t cap = 0;
+    check(sfgpu_list_capacity(ctx_, 0x80000000u, &cap));
+    offsets.assign((size_t)R_ * (n_owners + 1), 0);
+    elems.assign((size_t)R_ * cap, 0);
+    check(sfgpu_get_list_state(ctx_, 0x80000000u, offsets.data(), elems.data()));
+  }
+  void apply(const std::vector<ScalarSwap>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_swap(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
+  }
+  void apply(const std::vector<ListSwap>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_list_swap(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
+  }
   void apply(const std::vector<ScalarEdit>& one_per_replica, const uint8_t* mask = nullptr) {
     check(sfgpu_apply_change(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
   }
@@ -382,6 +519,14 @@ class GpuScoreDirector {
   }
 
  private:
+  StepResult make_result(uint32_t row_words) const {
+    StepResult out;
+    out.index.assign(R_, UINT32_MAX);
+    out.best.resize(R_);
+    out.evaluated.assign(R_, 0);
+    out.winner_rows.assign((size_t)R_ * (row_words ? row_words : 1), UINT32_MAX);
+    return out;
+  }
   sfgpu_ctx* ctx_ = nullptr;
   uint32_t R_;
 };
@@ -569,8 +714,11 @@ struct StepCountingHillClimbingAcceptor : Acceptor {  // step_counting.rs:55-104
       steps_since_improvement++;
     }
   }
-  DeviceAcceptance device_form(HardSoftScore last) const override {
-    return {true, steps_since_improvement < step_count_limit ? 0u : 1u, last};
+  DeviceAcceptance device_form(HardSoftScore) const override {
+    // "> last || anything" while under the limit, "> last" afterwards: predicate 3 with a -inf / +inf threshold
+    // (one predicate code for every replica of a batch)
+    const int64_t inf = 1ll << 62;
+    return {true, 3u, steps_since_improvement < step_count_limit ? HardSoftScore{-inf, -inf} : HardSoftScore{inf, inf}};
   }
 };
 struct DiversifiedLateAcceptanceAcceptor : Acceptor {  // diversified_late_acceptance.rs:71-140
@@ -807,5 +955,59 @@ inline StepOutcome replay_step(const HardSoftScore* scores, const uint8_t* doabl
   }
   return out;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Local-search phase over R replicas with one host-side acceptor per replica and the whole step on the
+// device: solve_local_search_with_resources / execute_step (phase/localsearch/phase.rs:237-320,
+// phase/step.rs:30-225) — phase_started, then per step: reference scores from the acceptor state ->
+// neighbourhood + scoring + forager + commit on the GPU -> acceptor.step_ended(step score) -> best score.
+// Acceptors must reduce to a device predicate per step (device_form); tabu / simulated annealing use
+// replay_step over materialised scores instead.
+class LocalSearch {
+ public:
+  enum Neighbourhood { Change, NearbyListChange, NearbyListSwap };
+  LocalSearch(GpuScoreDirector& d, const std::function<std::unique_ptr<Acceptor>()>& make_acceptor, StepParams forager)
+      : d_(d), forager_(forager) {
+    for (uint32_t r = 0; r < d.replicas(); ++r) acceptors_.push_back(make_acceptor());
+  }
+  void phase_started() {
+    best_ = d_.calculate_score();
+    for (uint32_t r = 0; r < d_.replicas(); ++r) acceptors_[r]->phase_started(best_[r]);
+  }
+  void phase_ended() {
+    for (auto& a : acceptors_) a->phase_ended();
+  }
+  // step seeds: one per replica (the reference draws them from the solver's StdRng, phase/step.rs:60-64)
+  StepResult step(Neighbourhood n, const std::vector<uint64_t>& step_seeds, uint32_t max_nearby = 20) {
+    const std::vector<HardSoftScore> last = d_.calculate_score();
+    std::vector<HardSoftScore> refs(2 * last.size());
+    StepParams p = forager_;
+    for (size_t r = 0; r < last.size(); ++r) {
+      const DeviceAcceptance f = acceptors_[r]->device_form(last[r]);
+      if (!f.expressible) throw GpuError(SFGPU_E_UNSUPPORTED, "acceptor has no per-step device form: use replay_step");
+      if (r > 0 && (int)f.acceptor != p.acceptor)
+        throw GpuError(SFGPU_E_UNSUPPORTED, "replicas of one batch must share the acceptor predicate");
+      p.acceptor = (int)f.acceptor;
+      refs[2 * r] = last[r];
+      refs[2 * r + 1] = f.threshold;
+    }
+    StepResult res = n == Change ? d_.step_change(p, step_seeds, refs, true)
+                                 : d_.step_nearby_list_change(max_nearby, p, step_seeds, refs, true, n == NearbyListSwap);
+    const std::vector<HardSoftScore> now = d_.calculate_score();
+    for (size_t r = 0; r < now.size(); ++r) {
+      acceptors_[r]->step_ended(now[r]);
+      if (now[r] > best_[r]) best_[r] = now[r];
+    }
+    return res;
+  }
+  const std::vector<HardSoftScore>& best_scores() const { return best_; }
+  Acceptor& acceptor(uint32_t r) { return *acceptors_[r]; }
+
+ private:
+  GpuScoreDirector& d_;
+  StepParams forager_;
+  std::vector<std::unique_ptr<Acceptor>> acceptors_;
+  std::vector<HardSoftScore> best_;
+};
 
 }  // namespace sf

@@ -1,6 +1,7 @@
 // Tests of the C++ host mirror (solverforge_b200/host/solverforge_gpu.hpp) against the oracle.
 //   host_test replay   CPU only: acceptor/forager replay vs the oracle's restatement
 //   host_test gpu      needs a B200: ConstraintFactory -> libsfgpu -> scores vs the oracle, bit-exact
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -347,6 +348,130 @@ static int test_gpu() {
       CHECK(ok == (doable[i] != 0));
       if (ok) CHECK(scores[i].hard == ev.score.hard && scores[i].soft == ev.score.soft);
     }
+  }
+  // Whole local-search phases through the C++ host mirror (sf::LocalSearch: host acceptor state, device
+  // steps) on a small CVRP against the oracle's selector + scoring + acceptor + forager, step by step —
+  // hill climbing, late acceptance, great deluge, step counting, diversified late acceptance; nearby
+  // list change and nearby list swap neighbourhoods.
+  {
+    const uint32_t n_cust = 60, n_routes = 5, dim = n_cust + 1;
+    auto pd = std::make_shared<sfo::ProblemData>();
+    pd->depot = 0;
+    pd->demands.assign(dim, 0);
+    std::vector<int64_t> xs(dim), ys(dim), flat((size_t)dim * dim), demand64(dim, 0);
+    uint64_t q = 9001;
+    int64_t total = 0;
+    for (uint32_t i = 0; i < dim; ++i) {
+      xs[i] = sfo::splitmix64(q++) % 300;
+      ys[i] = sfo::splitmix64(q++) % 300;
+      if (i) {
+        pd->demands[i] = 1 + (int32_t)(sfo::splitmix64(q++) % 9);
+        demand64[i] = pd->demands[i];
+        total += pd->demands[i];
+      }
+    }
+    pd->capacity = total / n_routes + 3;
+    pd->distance_matrix.assign(dim, std::vector<int64_t>(dim, 0));
+    for (uint32_t i = 0; i < dim; ++i)
+      for (uint32_t j = 0; j < dim; ++j) {
+        const double dx = (double)(xs[i] - xs[j]), dy = (double)(ys[i] - ys[j]);
+        pd->distance_matrix[i][j] = flat[(size_t)i * dim + j] = (int64_t)std::llround(std::sqrt(dx * dx + dy * dy));
+      }
+    std::vector<std::vector<size_t>> routes(n_routes);
+    for (uint32_t c = 1; c < dim; ++c) routes[sfo::splitmix64(q++) % n_routes].push_back(c);
+    std::vector<uint32_t> offs(1, 0), el;
+    for (auto& rt : routes) {
+      for (size_t c : rt) el.push_back((uint32_t)c);
+      offs.push_back((uint32_t)el.size());
+    }
+    std::vector<int64_t> ids;
+    for (uint32_t c = 1; c < dim; ++c) ids.push_back(c);
+    for (int kind = 0; kind < 5; ++kind)
+      for (int swap_moves = 0; swap_moves < 2; ++swap_moves) {
+        sfo::CvrpPlan plan;
+        plan.shared = pd;
+        for (uint32_t c = 1; c < dim; ++c) plan.customers.push_back({c});
+        for (uint32_t r = 0; r < n_routes; ++r) plan.routes.push_back({r, routes[r], pd.get()});
+        sfo::CvrpModel orc(plan);
+        sf::GpuScoreDirector cd(1);
+        uint32_t locations = cd.add_collection("locations", dim, -1);
+        uint32_t customers = cd.add_collection("customers", n_cust, -1);
+        uint32_t rts = cd.add_collection("routes", n_routes, 0);
+        cd.add_list_variable(rts, locations, "visits");
+        uint32_t cid = cd.add_column(customers, "id", ids);
+        uint32_t dem = cd.add_column(locations, "demand", demand64);
+        uint32_t mat = cd.add_matrix("distance_matrix", dim, dim, flat, true);
+        sf::ConstraintFactory cf(cd);
+        cf.for_each(customers).if_not_exists(cf.for_each(rts).flattened(), sf::EqualId{cid}).penalize(sf::HardSoftScore::ONE_HARD()).named("all_customers_assigned");
+        cf.for_each(rts).penalize(sf::Weight::hard(SFGPU_W_EXCESS, 1, pd->capacity), sf::ListSum{dem}).named("vehicle_capacity");
+        cf.for_each(rts).penalize(sf::Weight::soft(SFGPU_W_LINEAR, 1, 0), sf::PathCost{mat, 0}).named("total_distance");
+        cd.set_list_state(offs, el);
+        auto c0 = cd.commit();
+        auto o0 = orc.calculate_score();
+        CHECK(c0[0].hard == o0.hard && c0[0].soft == o0.soft);
+        auto make = [&]() -> std::unique_ptr<sf::Acceptor> {
+          switch (kind) {
+            case 0: return std::make_unique<sf::HillClimbingAcceptor>();
+            case 1: return std::make_unique<sf::LateAcceptanceAcceptor>(4);
+            case 2: return std::make_unique<sf::GreatDelugeAcceptor>(0.002);
+            case 3: return std::make_unique<sf::StepCountingHillClimbingAcceptor>(2);
+            default: return std::make_unique<sf::DiversifiedLateAcceptanceAcceptor>(3, 0.01);
+          }
+        };
+        sf::StepParams fp;
+        fp.accepted_limit = swap_moves ? 0 : 30;  // AcceptedCount(30) for relocations, BestScore for swaps
+        sf::LocalSearch ls(cd, make, fp);
+        ls.phase_started();
+        sfo::Acceptor<sfo::Sc> oa;
+        const sfo::AcceptorKind kinds[5] = {sfo::AcceptorKind::HillClimbing, sfo::AcceptorKind::LateAcceptance,
+                                            sfo::AcceptorKind::GreatDeluge, sfo::AcceptorKind::StepCountingHillClimbing,
+                                            sfo::AcceptorKind::DiversifiedLateAcceptance};
+        oa.kind = kinds[kind];
+        oa.rain_speed = 0.002;
+        oa.step_count_limit = 2;
+        oa.tolerance = 0.01;
+        oa.phase_started(o0, kind == 1 ? 4 : 3);
+        sfo::Sc obest = o0;
+        for (int step = 0; step < 14; ++step) {
+          const uint64_t seed = 7000 + step;
+          auto res = ls.step(swap_moves ? sf::LocalSearch::NearbyListSwap : sf::LocalSearch::NearbyListChange, {seed}, 8);
+          auto mv = swap_moves ? orc.enumerate_list_swap(8, {}) : orc.enumerate_list(8, {});
+          sfo::Forager<sfo::Sc> of;
+          of.kind = swap_moves ? sfo::ForagerKind::BestScore : sfo::ForagerKind::AcceptedCount;
+          of.accepted_count_limit = 30;
+          const sfo::Sc olast = orc.calculate_score();
+          auto want = sfo::replay_step<sfo::Sc>(
+              mv.size(), [&](size_t i) { return orc.evaluate(mv[i]); }, obest, olast, seed, of, oa);
+          CHECK(want.has_winner == (res.index[0] != UINT32_MAX));
+          if (want.has_winner) {
+            CHECK(res.index[0] == want.winner);
+            CHECK(res.evaluated[0] == want.moves_evaluated);
+            orc.apply(mv[want.winner]);
+          }
+          const sfo::Sc onow = orc.calculate_score();
+          oa.step_ended(onow);
+          if (onow > obest) obest = onow;
+          auto now = cd.calculate_score()[0];
+          CHECK(now.hard == onow.hard && now.soft == onow.soft);
+        }
+        CHECK(ls.best_scores()[0].hard == obest.hard && ls.best_scores()[0].soft == obest.soft);
+        auto fr = cd.fresh_score()[0], cm = cd.calculate_score()[0];
+        CHECK(fr == cm);
+        // the device-resident loop through the mirror runs and keeps cached == fresh
+        sf::SolveParams sp;
+        sp.n_steps = 10;
+        sp.max_nearby = 8;
+        sp.acceptor = kind + 1;
+        sp.late_size = 4;
+        sp.acceptor_real = kind == 2 ? 0.002 : 0.01;
+        sp.step_count_limit = 2;
+        sp.seed_base = 11;
+        if (!swap_moves) {
+          auto sr = cd.solve(sp, false);
+          CHECK(sr.best[0] >= cm);
+          CHECK(cd.fresh_score()[0] == cd.calculate_score()[0]);
+        }
+      }
   }
   // error behaviour: unknown constraint kind is rejected, never emulated
   try {

@@ -32,3 +32,5 @@ def test_host_cpp_gpu_parity():
     _build()
     out = subprocess.run([BIN, "gpu"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+    # every section ran: graph colouring + tabu, projected roster, ten CVRP local-search phases
+    assert int(out.stdout.split("HOST TEST OK")[1]) > 5000, out.stdout
