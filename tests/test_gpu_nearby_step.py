@@ -46,9 +46,11 @@ def _check_generated(t_off, t_rows, t_scores, t_doable, R, cap, K, oracles):
     return out
 
 
-@pytest.mark.parametrize("coarse", [1, 40])
-def test_generated_neighbourhood_and_step_match_oracle(coarse):
-    c = instances.cvrp(180, 11, seed=13)
+@pytest.mark.parametrize("coarse,n_routes", [(1, 11), (40, 11), (1, 70), (25, 90)])
+def test_generated_neighbourhood_and_step_match_oracle(coarse, n_routes):
+    # many short routes: most neighbours are route-last, so a batch of 28 expands to more than 32 slot keys
+    # (the overflow half of the compaction buffer) and empty routes appear after perturbation
+    c = instances.cvrp(180, n_routes, seed=13)
     c.matrix = (c.matrix // coarse) * coarse       # coarse => many equal distances => tie order matters
     R, K = 3, 20
     starts = [instances.perturb_routes(c, 70 + r, 60) for r in range(R)]
