@@ -206,6 +206,11 @@ int32_t sfgpu_score_list_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candi
 int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
                               int64_t* out_scores, uint8_t* out_doable);
 
+/* rows[n][4] = {entity, start, end, 0}: ListReverseMove reverses [start, end) of one list (2-opt segment
+ * reversal, heuristic/move/list_kernel/reverse.rs:21-58; doable iff end > start + 1 && end <= len) */
+int32_t sfgpu_score_list_reverse(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
+
 /* ---- winner selection on device ------------------------------------------------------- */
 /* Per replica: replay of acceptor + forager over the scored rows in pull order
  * (phase/candidates.rs:66-282 with BestCandidate::consider, forager.rs:99-155).
@@ -340,9 +345,10 @@ int32_t sfgpu_apply_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows,
 int32_t sfgpu_apply_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 /* apply the winner found by sfgpu_argbest straight from the batch, no host round trip:
  * row = batch_rows[cand_offsets[r] + index[r]]; replicas with index == UINT32_MAX are skipped.
- * move_kind: 0 change, 1 swap, 2 list change, 3 list swap. All pointers are device pointers. */
+ * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse. All pointers are device pointers. */
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
                             const uint32_t* batch_rows, const uint32_t* index);
 

@@ -8,6 +8,7 @@
 //   CompoundScalarMove       heuristic/move/compound_scalar.rs:245-319,397-406
 //   ListChangeMove           heuristic/move/list_kernel/change.rs:23-153
 //   ListSwapMove             heuristic/move/list_kernel/swap.rs:31-110
+//   ListReverseMove          heuristic/move/list_kernel/reverse.rs:21-58 (2-opt segment reversal)
 //   evaluate_candidate       phase/localsearch/evaluation.rs:20-115
 //   MoveStreamContext        heuristic/selector/move_selector/iter.rs:14-207
 //   ChangeMove order         heuristic/selector/move_selector/change.rs:66-104,246-307
@@ -91,7 +92,7 @@ struct ScalarEdit {  // planning/scalar/candidate.rs:6-12
 };
 
 struct Move {
-  enum Kind { Change, Swap, Compound, ListChange, ListSwap } kind = Change;
+  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse } kind = Change;
   size_t desc = 0;
   size_t a = 0, b = 0, c = 0, d = 0;  // Change: a=entity; Swap: a,b; List*: a=src_e b=src_p c=dst_e d=dst_p
   OptVal to;
@@ -107,6 +108,9 @@ struct Move {
   }
   static Move list_swap(size_t desc, size_t e1, size_t p1, size_t e2, size_t p2) {
     Move m; m.kind = ListSwap; m.desc = desc; m.a = e1; m.b = p1; m.c = e2; m.d = p2; return m;
+  }
+  static Move list_reverse(size_t desc, size_t entity, size_t start, size_t end) {  // reverses [start, end)
+    Move m; m.kind = ListReverse; m.desc = desc; m.a = entity; m.b = start; m.c = end; return m;
   }
 };
 
@@ -151,6 +155,8 @@ bool is_doable(const Move& m, ScoreDirector<S, Sc>& dir) {
       if (m.b >= l1.size() || m.d >= l2.size() || (m.a == m.c && m.b == m.d)) return false;
       return l1[m.b] != l2[m.d];
     }
+    case Move::ListReverse:  // reverse.rs:21-33
+      return m.c > m.b + 1 && m.c <= ac.list(s, m.desc, m.a).size();
   }
   return false;
 }
@@ -219,6 +225,13 @@ Undo do_move(const Move& m, ScoreDirector<S, Sc>& dir) {
       if (!intra) dir.after_variable_changed(m.desc, m.c);
       break;
     }
+    case Move::ListReverse: {  // reverse.rs:35-58
+      dir.before_variable_changed(m.desc, m.a);
+      auto& l = ac.list(s, m.desc, m.a);
+      std::reverse(l.begin() + m.b, l.begin() + m.c);
+      dir.after_variable_changed(m.desc, m.a);
+      break;
+    }
   }
   return u;
 }
@@ -263,7 +276,8 @@ void undo_move(const Move& m, ScoreDirector<S, Sc>& dir, const Undo& u) {
       if (!intra) dir.after_variable_changed(m.desc, m.a);
       break;
     }
-    case Move::ListSwap: {  // a swap is its own inverse
+    case Move::ListSwap:     // a swap is its own inverse
+    case Move::ListReverse: {  // so is a reversal
       do_move(m, dir);
       break;
     }
@@ -468,6 +482,31 @@ std::vector<Move> enumerate_nearby_list_swap_moves(S& s, const Access<S>& ac, si
       }
       sort_and_limit_nearby_candidates(cand, max_nearby);
       for (auto& c : cand) out.push_back(Move::list_swap(desc, se, sp, c.entity, c.position));
+    }
+  }
+  return out;
+}
+
+// heuristic/selector/list_reverse.rs:139-172 + list_kernel/reverse.rs:66-108 (ReverseCursor): entities in
+// stream order; per entity with len >= 2 every start (stream order) and every end in start+2..=len
+// (stream order over the end_count = len - start - 1 choices).
+template <class S>
+std::vector<Move> enumerate_list_reverse_moves(S& s, const Access<S>& ac, size_t desc, MoveStreamContext ctx) {
+  constexpr uint64_t ENTITY_SALT = 0x11572A0700000001ull, START_SALT = 0x11572A0700000002ull,
+                     END_SALT = 0x11572A0700000003ull;
+  size_t n = ac.entity_count(s, desc);
+  std::vector<Move> out;
+  for (size_t o = 0; o < n; ++o) {
+    size_t e = ctx.selection_index(o, n, ENTITY_SALT ^ (uint64_t)desc);
+    size_t len = ac.list(s, desc, e).size();
+    if (len < 2) continue;
+    for (size_t so = 0; so < len; ++so) {
+      size_t start = ctx.selection_index(so, len, START_SALT ^ (uint64_t)e ^ (uint64_t)desc);
+      size_t end_count = len > start + 1 ? len - (start + 1) : 0;
+      for (size_t eo = 0; eo < end_count; ++eo) {
+        size_t end = start + 2 + ctx.selection_index(eo, end_count, END_SALT ^ (uint64_t)e ^ (uint64_t)start);
+        out.push_back(Move::list_reverse(desc, e, start, end));
+      }
     }
   }
   return out;
@@ -847,6 +886,14 @@ TabuSignature tabu_signature(const Move& m, ScoreDirector<S, Sc>& dir, uint64_t 
       sig.entity_ids = {(uint64_t)m.a};
       if (m.a != m.c) sig.entity_ids.push_back((uint64_t)m.c);
       sig.value_ids = {v2, v1};
+      return sig;
+    }
+    case Move::ListReverse: {  // reverse.rs:60-98
+      const auto& l = ac.list(s, m.desc, m.a);
+      for (size_t p = m.b; p < m.c && p < l.size(); ++p) sig.value_ids.push_back((uint64_t)l[p]);
+      sig.move_id = {0xF000000000000004ull, (uint64_t)m.desc, variable_id, (uint64_t)m.a, (uint64_t)m.b, (uint64_t)m.c};
+      sig.undo_move_id = sig.move_id;
+      sig.entity_ids = {(uint64_t)m.a};
       return sig;
     }
     default: throw std::logic_error("tabu_signature: move kind not restated");

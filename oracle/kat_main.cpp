@@ -696,6 +696,34 @@ static void kat_moves_and_loop() {
     for (size_t i = 0; i < 6 && i < mv.size(); ++i)
       CHECK(mv[i].a == want[i][0] && mv[i].b == want[i][1] && mv[i].c == want[i][2] && mv[i].d == want[i][3]);
   }
+  {  // heuristic/move/tests/list_reverse.rs:63-160: segment reversal, doability; selector order
+     // heuristic/selector/tests/list_precedence.rs:215-223 (len 3: (0,2), (0,3), (1,3))
+    CvrpPlan p3;
+    p3.shared = pd;
+    p3.customers = plan.customers;
+    p3.routes = {{0, {1, 2, 3, 4}, pd.get()}, {1, {}, pd.get()}};
+    CvrpModel m3(p3);
+    CHECK(is_doable(Move::list_reverse(0, 0, 1, 4), m3.dir));
+    CHECK(!is_doable(Move::list_reverse(0, 0, 1, 2), m3.dir));   // single element
+    CHECK(!is_doable(Move::list_reverse(0, 0, 1, 10), m3.dir));  // out of bounds
+    const Sc before = m3.calculate_score();
+    auto evr = m3.evaluate(Move::list_reverse(0, 0, 0, 4));
+    CHECK(evr.kind == EvalKind::Scored);
+    CHECK(m3.calculate_score() == before);  // undo restores the cached score
+    m3.apply(Move::list_reverse(0, 0, 1, 4));
+    CHECK((m3.dir.working.routes[0].visits == std::vector<size_t>{1, 4, 3, 2}));
+    CHECK(m3.calculate_score() == m3.fresh_score());
+    m3.apply(Move::list_reverse(0, 0, 0, 4));
+    CHECK((m3.dir.working.routes[0].visits == std::vector<size_t>{2, 3, 4, 1}));
+    CHECK(m3.calculate_score() == m3.fresh_score());
+    CvrpPlan p4 = p3;
+    p4.routes = {{0, {1, 2, 3}, pd.get()}};
+    CvrpModel m4(p4);
+    auto rv = m4.enumerate_list_reverse({});
+    const size_t wantr[3][2] = {{0, 2}, {0, 3}, {1, 3}};
+    CHECK(rv.size() == 3);
+    for (size_t i = 0; i < 3 && i < rv.size(); ++i) CHECK(rv[i].a == 0 && rv[i].b == wantr[i][0] && rv[i].c == wantr[i][1]);
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

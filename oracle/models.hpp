@@ -29,6 +29,7 @@ struct OracleModel {
   virtual std::vector<Move> enumerate_scalar(MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_list(size_t max_nearby, MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_list_swap(size_t max_nearby, MoveStreamContext ctx) { return {}; }
+  virtual std::vector<Move> enumerate_list_reverse(MoveStreamContext ctx) { return {}; }
   virtual size_t scalar_desc() const { return 0; }
   virtual size_t list_desc() const { return 0; }
   virtual uint64_t score_calculations() const = 0;
@@ -222,6 +223,9 @@ struct CvrpModel final : ModelImpl<CvrpPlan> {
   }
   std::vector<Move> enumerate_list_swap(size_t max_nearby, MoveStreamContext ctx) override {
     return enumerate_nearby_list_swap_moves(dir.working, dir.access, 0, max_nearby, ctx, meter);
+  }
+  std::vector<Move> enumerate_list_reverse(MoveStreamContext ctx) override {
+    return enumerate_list_reverse_moves(dir.working, dir.access, 0, ctx);
   }
 };
 

@@ -158,6 +158,17 @@ int sfo_score_list_swap(void* h, uint64_t n, const uint32_t* e1, const uint32_t*
                      doable);
 }
 
+// ListReverseMove rows {entity, start, end}: reverses [start, end) (heuristic/move/list_kernel/reverse.rs)
+int sfo_score_list_reverse(void* h, uint64_t n, const uint32_t* e, const uint32_t* start, const uint32_t* end,
+                           int64_t* hard, int64_t* soft, uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->list_desc();
+  return score_batch(h, n, [&](uint64_t i) { return Move::list_reverse(d, e[i], start[i], end[i]); }, hard, soft, doable);
+}
+int sfo_apply_list_reverse(void* h, uint32_t e, uint32_t start, uint32_t end) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(Move::list_reverse(m->list_desc(), e, start, end));
+  return 0;
+}
 int sfo_apply_change(void* h, uint32_t e, int32_t v) {
   auto* m = static_cast<OracleModel*>(h);
   m->apply(Move::change(m->scalar_desc(), e, opt(v)));
@@ -213,6 +224,17 @@ int64_t sfo_enumerate_nearby_list_change(void* h, uint32_t max_nearby, uint64_t 
     sp[i] = (uint32_t)moves[i].b;
     de[i] = (uint32_t)moves[i].c;
     dp[i] = (uint32_t)moves[i].d;
+  }
+  return (int64_t)moves.size();
+}
+
+int64_t sfo_enumerate_list_reverse(void* h, uint64_t step_index, uint64_t step_seed, int order, uint64_t cap,
+                                   uint32_t* e, uint32_t* start, uint32_t* end) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_list_reverse(make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    e[i] = (uint32_t)moves[i].a;
+    start[i] = (uint32_t)moves[i].b;
+    end[i] = (uint32_t)moves[i].c;
   }
   return (int64_t)moves.size();
 }

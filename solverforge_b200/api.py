@@ -258,6 +258,13 @@ class GpuScoreDirector:
     def score_list_swap(self, rows, cand_offsets=None):
         return self._score(self.lib.sfgpu_score_list_swap, rows, 4, cand_offsets)
 
+    def score_list_reverse(self, rows, cand_offsets=None):
+        """rows[n][3 or 4] = (entity, start, end[, 0]): ListReverseMove (2-opt segment reversal)."""
+        rows = np.asarray(rows).astype(np.int64)
+        if rows.ndim == 2 and rows.shape[1] == 3:
+            rows = np.concatenate([rows, np.zeros((len(rows), 1), dtype=np.int64)], axis=1)
+        return self._score(self.lib.sfgpu_score_list_reverse, rows, 4, cand_offsets)
+
     def score_compound(self, edit_offsets, edit_rows, cand_offsets=None):
         eo = np.ascontiguousarray(edit_offsets, dtype=np.uint64)
         rows = np.ascontiguousarray(np.asarray(edit_rows).astype(np.int64).astype(np.uint32)).reshape(-1, 2)
@@ -428,6 +435,12 @@ class GpuScoreDirector:
 
     def apply_list_swap(self, rows, mask=None):
         self._apply(self.lib.sfgpu_apply_list_swap, rows, 4, mask)
+
+    def apply_list_reverse(self, rows, mask=None):
+        rows = np.asarray(rows).astype(np.int64).reshape(self.R, -1)
+        if rows.shape[1] == 3:
+            rows = np.concatenate([rows, np.zeros((self.R, 1), dtype=np.int64)], axis=1)
+        self._apply(self.lib.sfgpu_apply_list_reverse, rows, 4, mask)
 
     # ---- state read-back ------------------------------------------------------------------
     def scalar_state(self) -> np.ndarray:

@@ -458,7 +458,33 @@ __device__ __forceinline__ bool list_swap_delta(const DevModel& m, const char* s
   return true;
 }
 
-enum { LMODE_CHANGE = 0, LMODE_SWAP = 1 };
+// ListReverseMove {entity, start, end}: reverses [start, end) of one list (2-opt segment reversal,
+// heuristic/move/list_kernel/reverse.rs:21-58). Only the path cost can change: the two boundary legs are
+// replaced and every inner leg is traversed the other way (zero net effect on a symmetric matrix).
+__device__ __forceinline__ bool list_reverse_delta(const DevModel& m, const char* st, uint4 row, Score2& d) {
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  d.hard = 0;
+  d.soft = 0;
+  const uint32_t e = row.x, start = row.y, end = row.z;
+  if (e >= m.n_owners) return false;
+  const uint32_t b = off[e], len = off[e + 1] - b;
+  if (!(end > start + 1 && end <= len)) return false;  // reverse.rs:21-33
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind != SFGPU_K_LIST_PATH_COST) continue;
+    const uint32_t depot = (uint32_t)c.p0;
+    const uint32_t a = start > 0 ? el[b + start - 1] : depot, z = end < len ? el[b + end] : depot;
+    const uint32_t xs = el[b + start], xe = el[b + end - 1];
+    int64_t delta = mat_at(c, a, xe) + mat_at(c, xs, z) - mat_at(c, a, xs) - mat_at(c, xe, z);
+    for (uint32_t i = start; i + 1 < end; ++i) delta += mat_at(c, el[b + i + 1], el[b + i]) - mat_at(c, el[b + i], el[b + i + 1]);
+    const int64_t oc = ((const int64_t*)(st + c.off0))[e];
+    add_level(d, c, weight_eval(c.w, oc + delta) - weight_eval(c.w, oc));
+  }
+  return true;
+}
+
+enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2 };
 
 template <int LMODE, bool STAGED>
 __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__ DevModel m,
@@ -482,7 +508,8 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
        i += (uint64_t)gridDim.x * blockDim.x) {
     uint4 row = ((const uint4*)rows)[i];  // one 128-bit load per candidate
     Score2 d;
-    bool ok = LMODE == LMODE_CHANGE ? list_change_delta(m, st, row, d) : list_swap_delta(m, st, row, d);
+    bool ok = LMODE == LMODE_CHANGE ? list_change_delta(m, st, row, d)
+                                    : (LMODE == LMODE_SWAP ? list_swap_delta(m, st, row, d) : list_reverse_delta(m, st, row, d));
     longlong2 o;
     o.x = ok ? ch + d.hard : 0;
     o.y = ok ? csf + d.soft : 0;
@@ -1363,9 +1390,14 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) old_el[i] = el[i];
   if (threadIdx.x == 0) {
     Score2 d;
-    bool ok = kind == 2 ? list_change_delta(m, st, row, d) : list_swap_delta(m, st, row, d);
+    bool ok = kind == 2 ? list_change_delta(m, st, row, d)
+                        : (kind == 3 ? list_swap_delta(m, st, row, d) : list_reverse_delta(m, st, row, d));
     s_ok = ok ? 1 : 0;
-    if (ok) {
+    if (ok && kind == 4) {  // a reversal keeps every per-route sum
+      int64_t* cs = (int64_t*)(st + m.off_score);
+      cs[0] += d.hard;
+      cs[1] += d.soft;
+    } else if (ok) {
       // retained per-route aggregates
       const uint32_t e1 = row.x, p1 = row.y, e2 = row.z, p2 = row.w;
       const uint32_t x1 = el[off[e1] + p1];
@@ -1391,7 +1423,10 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   }
   __syncthreads();
   if (!s_ok) return;
-  if (kind == 3) {
+  if (kind == 4) {
+    const uint32_t b = off[row.x];
+    for (uint32_t i = row.y + threadIdx.x; i < row.z; i += blockDim.x) el[b + i] = old_el[b + row.y + (row.z - 1 - i)];
+  } else if (kind == 3) {
     if (threadIdx.x == 0) {
       uint32_t f1 = off[row.x] + row.y, f2 = off[row.z] + row.w;
       el[f1] = old_el[f2];
@@ -1429,8 +1464,8 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
     int64_t* rcost = (int64_t*)(st + c.off0);
     const uint32_t depot = (uint32_t)c.p0;
     if (threadIdx.x < 2) {
-      uint32_t o = threadIdx.x == 0 ? row.x : row.z;
-      if (!(threadIdx.x == 1 && row.x == row.z)) {
+      uint32_t o = threadIdx.x == 0 || kind == 4 ? row.x : row.z;
+      if (!(threadIdx.x == 1 && (row.x == row.z || kind == 4))) {
         int64_t cost = 0;
         uint32_t b = off[o], e = off[o + 1];
         if (e > b) {

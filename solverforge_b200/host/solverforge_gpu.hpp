@@ -78,6 +78,9 @@ struct ListChange {  // heuristic/move/list_kernel/change.rs:15-21
 struct ListSwap {  // heuristic/move/list_kernel/swap.rs:16-30
   uint32_t first_entity, first_position, second_entity, second_position;
 };
+struct ListReverse {  // heuristic/move/list_kernel/reverse.rs:14-19: reverses [start, end) of one list
+  uint32_t entity, start, end, reserved = 0;
+};
 // acceptor + forager of one fused device step (sfgpu_forage_params) and what it returns per replica
 struct StepParams {
   int acceptor = 0;            // 0 accept all, 1 > last, 2 >= last || >= threshold, 3 > last || >= threshold
@@ -424,6 +427,17 @@ class GpuScoreDirector {
     check(sfgpu_score_list_swap(ctx_, 0, batch.size(), cand_offsets.data(),
                                 reinterpret_cast<const uint32_t*>(batch.data()),
                                 reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void score_candidates(const std::vector<ListReverse>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_list_reverse(ctx_, 0, batch.size(), cand_offsets.data(),
+                                   reinterpret_cast<const uint32_t*>(batch.data()),
+                                   reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void apply(const std::vector<ListReverse>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_list_reverse(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
   }
   // CompoundScalarMove batch: candidate i owns edits [edit_offsets[i], edit_offsets[i+1]) (compound_scalar.rs:289-319)
   void score_compound(const std::vector<uint64_t>& edit_offsets, const std::vector<ScalarEdit>& edits,

@@ -199,3 +199,26 @@ def nearby_list_swap_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.nda
             rows[:, 3] = d_p[top]
             out.append(rows)
     return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint32)
+
+
+def list_reverse_rows(offsets: np.ndarray, ctx: MoveStreamContext = MoveStreamContext(),
+                      descriptor_index: int = 0) -> np.ndarray:
+    """rows[n][4] = (entity, start, end, 0) uint32 in the pull order of ListReverseMoveSelector
+    (heuristic/selector/list_reverse.rs:139-172, cursor list_kernel/reverse.rs:66-108): entities in stream
+    order; per entity with len >= 2 every start and every end in start+2..=len, both in stream order."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n_owners = len(offsets) - 1
+    lens = np.diff(offsets)
+    out = []
+    for o in range(n_owners):
+        e = ctx.selection_index(o, n_owners, 0x11572A0700000001 ^ descriptor_index)
+        ln = int(lens[e])
+        if ln < 2:
+            continue
+        for so in range(ln):
+            start = ctx.selection_index(so, ln, 0x11572A0700000002 ^ e ^ descriptor_index)
+            end_count = max(ln - (start + 1), 0)
+            for eo in range(end_count):
+                end = start + 2 + ctx.selection_index(eo, end_count, 0x11572A0700000003 ^ e ^ start)
+                out.append((e, start, end, 0))
+    return np.array(out, dtype=np.uint32).reshape(-1, 4)

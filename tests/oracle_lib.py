@@ -63,6 +63,10 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_nearby_list_swap.restype = C.c_int64
         l.sfo_replay_step.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
                                       C.c_int, _P]
+        l.sfo_score_list_reverse.argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P, _P]
+        l.sfo_apply_list_reverse.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint32]
+        l.sfo_enumerate_list_reverse.argtypes = [_P, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P, _P, _P]
+        l.sfo_enumerate_list_reverse.restype = C.c_int64
         l.sfo_replay_step_gated.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64,
                                             C.c_int, C.c_int, _P]
         l.sfo_acceptor_create.restype = _P
@@ -188,6 +192,22 @@ class Oracle:
 
     def score_list_swap(self, rows):
         return self._score_list(self.l.sfo_score_list_swap, rows)
+
+    def score_list_reverse(self, rows):
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 4)
+        c = [_u32(rows[:, i]) for i in range(3)]
+        h, s, d = self._out(len(rows))
+        self.l.sfo_score_list_reverse(self.h, len(rows), _p(c[0]), _p(c[1]), _p(c[2]), _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
+
+    def apply_list_reverse(self, e, start, end, *_):
+        self.l.sfo_apply_list_reverse(self.h, int(e), int(start), int(end))
+
+    def enumerate_list_reverse(self, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_list_reverse(self.h, step_index, step_seed, order, 0, None, None, None)
+        c = [np.zeros(n, dtype=np.uint32) for _ in range(3)]
+        self.l.sfo_enumerate_list_reverse(self.h, step_index, step_seed, order, n, _p(c[0]), _p(c[1]), _p(c[2]))
+        return np.stack(c + [np.zeros(n, dtype=np.uint32)], axis=1)
 
     # ---- apply --------------------------------------------------------------------------
     def apply_change(self, e, v):

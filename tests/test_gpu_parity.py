@@ -646,3 +646,45 @@ def test_projected_rows_roster_matches_oracle():
             assert idx[0] == 0xFFFFFFFF
         assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
         assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
+
+
+@pytest.mark.parametrize("asymmetric", [False, True])
+def test_list_reverse_moves_match_oracle(asymmetric):
+    """ListReverseMove (2-opt segment reversal, heuristic/move/list_kernel/reverse.rs): the whole reverse
+    neighbourhood in the selector's order, not-doable rows, forager replay and committed winners."""
+    from solverforge_b200 import selectors
+    c = instances.cvrp(70, 6, seed=12)
+    if asymmetric:   # inner legs of a reversed segment change cost when d(a,b) != d(b,a)
+        r = instances.splitmix64_stream(5, c.dim * c.dim).reshape(c.dim, c.dim)
+        c.matrix = c.matrix + (r % np.uint64(9)).astype(np.int64)
+        np.fill_diagonal(c.matrix, 0)
+    offs, el = instances.perturb_routes(c, 8, 35)
+    o = Oracle.cvrp(c, offs, el)
+    d = models.cvrp_director(c, 1, offsets=offs[None, :], elems=el)
+    rows = selectors.list_reverse_rows(offs)
+    assert np.array_equal(rows, o.enumerate_list_reverse())
+    bad = np.array([[0, 1, 2, 0], [0, 0, 999, 0], [99, 0, 2, 0], [1, 3, 1, 0]], dtype=np.uint32)
+    allrows = np.concatenate([rows, bad])
+    s, ok = d.score_list_reverse(allrows)
+    so, oko = o.score_list_reverse(allrows[:-2])          # the oracle indexes lists directly: keep entities valid
+    _eq(ok[:-2], oko, "reverse doable")
+    _eq(s[:-2], so, "reverse scores")
+    assert ok[-4:].tolist() == [0, 0, 0, 0]
+    for step in range(6):
+        rows = o.enumerate_list_reverse()
+        so, oko = o.score_list_reverse(rows)
+        sg, okg = d.score_list_reverse(rows)
+        _eq(sg, so, f"reverse scores step {step}")
+        last = d.calculate_score()
+        idx, best, ev = d.argbest(sg, okg, None, ForageParams(1, 1, 0), [70 + step], [np.concatenate([last[0], last[0]])])
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 70 + step, 2, 1, True, 0)
+        if not out[0]:
+            assert idx[0] == 0xFFFFFFFF
+            break
+        assert int(idx[0]) == out[1]
+        d.apply_list_reverse(rows[out[1]][None, :])
+        o.apply_list_reverse(*rows[out[1]])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
+        lo, le = d.list_state()
+        assert best[0].tolist() == o.committed_score().tolist()

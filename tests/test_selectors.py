@@ -65,3 +65,14 @@ def test_nearby_swap_handles_empty_routes_and_unreachable_cells():
     el = np.array([x for r in routes for x in r], dtype=np.uint32)
     o = Oracle.cvrp(c, offs, el)
     assert np.array_equal(selectors.nearby_list_swap_rows(offs, el, c.matrix, 6), o.enumerate_nearby_list_swap(6))
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_list_reverse_order_matches_reference(order):
+    c = instances.cvrp(40, 6, seed=4)
+    offs, el = instances.perturb_routes(c, 2, 25)
+    o = Oracle.cvrp(c, offs, el)
+    for step_index, seed in ((0, 0), (9, 4242), (77, 0xFEEDFACE12345)):
+        want = o.enumerate_list_reverse(step_index, seed, order)
+        got = selectors.list_reverse_rows(offs, MoveStreamContext(step_index, seed, order))
+        assert np.array_equal(got, want), f"order={order} step={step_index}"
