@@ -1674,6 +1674,34 @@ int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t*
 }
 
 // ------------------------------------------------------------------------------------------
+namespace {
+// acceptor + forager replay over materialised scores: BestScore goes through chunk partials on the whole
+// machine + the finish kernel; AcceptedCount(N) and gated batches use the one-CTA-per-replica kernel
+int launch_argbest(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, const int64_t* d_scores,
+                   const uint8_t* d_doable, const uint64_t* d_seeds, const int64_t* d_ref, uint32_t* d_idx,
+                   int64_t* d_best, uint32_t* d_eval, uint64_t n_hint) {
+  const uint32_t R = ctx->dm.R;
+  if (f.accepted_limit == 0 && !f.gates) {
+    uint32_t chunks = std::max<uint32_t>(1, (uint32_t)((uint64_t)ctx->sm_count * 4 / R));
+    const uint64_t per_rep = n_hint / std::max<uint32_t>(R, 1);
+    while (chunks > 1 && per_rep / chunks < 2048) chunks /= 2;
+    chunks = std::min<uint32_t>(chunks, 64);
+    int rc = ensure_partials(ctx, (size_t)chunks * R * sizeof(ChunkPartial));
+    if (rc) return rc;
+    ForageArgs fa{f, d_ref, (ChunkPartial*)ctx->partials};
+    argbest_partial_kernel<<<dim3(chunks, R), 256, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_ref, fa.partials);
+    forage_finish_kernel<<<R, 256, 0, ctx->stream>>>(ctx->dm, fa, chunks, d_offs, nullptr, d_scores, d_doable, d_seeds,
+                                                    d_idx, d_best, d_eval);
+    ctx->launches += 2;
+  } else {
+    argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_seeds, d_ref, d_idx, d_best, d_eval);
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+}  // namespace
+
 int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
                             const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
                             const uint8_t* gates, const uint64_t* step_seeds, const int64_t* ref_scores,
@@ -1689,13 +1717,9 @@ int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_p
   CU(cudaSetDevice(ctx->device));
   const uint32_t R = ctx->dm.R;
   ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit, gates};
-  if (flags & SFGPU_DEVICE_IO) {
-    argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, cand_offsets, scores, doable, step_seeds, ref_scores, out_index,
-                                                out_best, out_evaluated);
-    ctx->launches++;
-    CU(cudaGetLastError());
-    return SFGPU_OK;
-  }
+  if (flags & SFGPU_DEVICE_IO)  // the candidate total is not known on the host: assume a saturating batch
+    return launch_argbest(ctx, f, cand_offsets, scores, doable, step_seeds, ref_scores, out_index, out_best,
+                          out_evaluated, (uint64_t)R << 20);
   const uint64_t n = cand_offsets[R];
   auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
   size_t o_off = 0, o_seed = a16(o_off + (R + 1) * 8), o_ref = a16(o_seed + R * 8), o_scores = a16(o_ref + R * 32);
@@ -1717,12 +1741,10 @@ int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_p
     f.gates = (const uint8_t*)(dv + o_gates);
   }
   CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
-  argbest_kernel<<<R, 1024, 0, ctx->stream>>>(f, (const uint64_t*)(dv + o_off), (const int64_t*)(dv + o_scores),
-                                              (const uint8_t*)(dv + o_doable), (const uint64_t*)(dv + o_seed),
-                                              (const int64_t*)(dv + o_ref), (uint32_t*)(dv + o_idx),
-                                              (int64_t*)(dv + o_best), (uint32_t*)(dv + o_eval));
-  ctx->launches++;
-  CU(cudaGetLastError());
+  rc = launch_argbest(ctx, f, (const uint64_t*)(dv + o_off), (const int64_t*)(dv + o_scores),
+                      (const uint8_t*)(dv + o_doable), (const uint64_t*)(dv + o_seed), (const int64_t*)(dv + o_ref),
+                      (uint32_t*)(dv + o_idx), (int64_t*)(dv + o_best), (uint32_t*)(dv + o_eval), n);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, total - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   memcpy(out_index, pin + o_idx, R * 4);

@@ -1056,6 +1056,89 @@ __global__ void __launch_bounds__(256) forage_finish_kernel(const __grid_constan
   }
 }
 
+// First phase of the two-phase argbest over MATERIALISED scores (BestScore forager): grid (chunks, R);
+// every CTA reduces one contiguous chunk of a replica's rows to a ChunkPartial (best accepted score, its
+// multiplicity, first and second row, accepted count); forage_finish_kernel then replays the tie rule.
+// One CTA per replica (argbest_kernel) leaves most SMs idle when R is small and the rows are many.
+__global__ void __launch_bounds__(256) argbest_partial_kernel(ForageDev f, const uint64_t* __restrict__ cand_offsets,
+                                                              const int64_t* __restrict__ scores,
+                                                              const uint8_t* __restrict__ doable,
+                                                              const int64_t* __restrict__ ref_scores,
+                                                              ChunkPartial* __restrict__ partials) {
+  const uint32_t r = blockIdx.y;
+  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  const uint64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  const uint64_t c_lo = lo + per * blockIdx.x < hi ? lo + per * blockIdx.x : hi;
+  const uint64_t c_hi = c_lo + per < hi ? c_lo + per : hi;
+  const int64_t lh = ref_scores ? ref_scores[r * 4 + 0] : 0, ls = ref_scores ? ref_scores[r * 4 + 1] : 0;
+  const int64_t th = ref_scores ? ref_scores[r * 4 + 2] : 0, ts = ref_scores ? ref_scores[r * 4 + 3] : 0;
+  int64_t tb_h = 0, tb_s = 0;
+  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, tb_second = 0xFFFFFFFFu, t_acc = 0;
+  for (uint64_t base = c_lo + threadIdx.x; base < c_hi; base += 256 * 4) {
+    longlong2 v[4];
+    uint8_t ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t i = base + (uint64_t)u * 256;
+      v[u] = i < c_hi ? __ldcs((const longlong2*)scores + i) : make_longlong2(0, 0);
+      ok[u] = i < c_hi ? doable[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t i = base + (uint64_t)u * 256;
+      if (!ok[u] || !accept_score(f.acceptor, v[u].x, v[u].y, lh, ls, th, ts)) continue;
+      t_acc++;
+      if (tb_n == 0 || score_less(tb_h, tb_s, v[u].x, v[u].y)) {
+        tb_h = v[u].x;
+        tb_s = v[u].y;
+        tb_n = 1;
+        tb_first = (uint32_t)(i - lo);
+        tb_second = 0xFFFFFFFFu;
+      } else if (tb_h == v[u].x && tb_s == v[u].y) {
+        if (tb_n == 1) tb_second = (uint32_t)(i - lo);  // a thread's rows come in increasing pull order
+        tb_n++;
+      }
+    }
+  }
+  __shared__ int64_t sh_h[8], sh_s[8];
+  __shared__ uint32_t sh_n[8], sh_f[8], sh_2[8], sh_a[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+    const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
+    const uint32_t osec = __shfl_down_sync(0xffffffffu, tb_second, o);
+    t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
+    if (on && (!tb_n || score_less(tb_h, tb_s, oh, os))) {
+      tb_h = oh; tb_s = os; tb_n = on; tb_first = of; tb_second = osec;
+    } else if (on && tb_n && oh == tb_h && os == tb_s) {
+      tb_n += on;
+      tb_second = min(max(tb_first, of), min(tb_second, osec));
+      tb_first = min(tb_first, of);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh_h[warp] = tb_h; sh_s[warp] = tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first; sh_2[warp] = tb_second;
+    sh_a[warp] = t_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ChunkPartial cp{0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    for (int w = 0; w < 8; ++w) {
+      cp.n_accepted += sh_a[w];
+      if (!sh_n[w]) continue;
+      if (!cp.n_best || score_less(cp.best_h, cp.best_s, sh_h[w], sh_s[w])) {
+        cp.best_h = sh_h[w]; cp.best_s = sh_s[w]; cp.n_best = sh_n[w]; cp.first_idx = sh_f[w];
+        cp.second_idx = sh_2[w];
+      } else if (sh_h[w] == cp.best_h && sh_s[w] == cp.best_s) {
+        cp.n_best += sh_n[w];
+        cp.second_idx = min(max(cp.first_idx, sh_f[w]), min(cp.second_idx, sh_2[w]));
+        cp.first_idx = min(cp.first_idx, sh_f[w]);
+      }
+    }
+    partials[(size_t)r * gridDim.x + blockIdx.x] = cp;
+  }
+}
+
 // =============================================================================================
 // block reductions
 // =============================================================================================
