@@ -19,6 +19,7 @@ pub const SFGPU_W_LINEAR: i32 = 1;
 pub const SFGPU_W_SQUARE: i32 = 2;
 pub const SFGPU_W_EXCESS: i32 = 3;
 pub const SFGPU_W_ABSDIFF: i32 = 4;
+pub const SFGPU_W_PAIRS: i32 = 5;
 pub const SFGPU_PENALTY: i32 = 0;
 pub const SFGPU_REWARD: i32 = 1;
 pub const SFGPU_K_UNI: i32 = 1;

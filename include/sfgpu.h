@@ -98,6 +98,7 @@ int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, ui
 #define SFGPU_W_SQUARE 2 /* a*x*x + b */
 #define SFGPU_W_EXCESS 3 /* a*max(0, x - b) */
 #define SFGPU_W_ABSDIFF 4 /* a*|x - b| */
+#define SFGPU_W_PAIRS 5   /* a*x*(x-1)/2: unordered pairs among x rows (keyed self-join of projected rows) */
 typedef struct sfgpu_weight {
   int32_t fn;
   int32_t level; /* 0 = hard, 1 = soft */
@@ -148,7 +149,10 @@ typedef struct sfgpu_weight {
  *   of its csr row: key = var[e] * p0 + csr.col[j] (p0 = number of key offsets per value, e.g. days),
  *   amount = aux1 column[j] (one row per csr entry) or 1 (count). Groups with no rows score nothing
  *   (grouped/state.rs:320-332); two rows of one entity may share a group.
- *   aux0: csr id (rows = entities); aux1: amount column id or UINT32_MAX. A projected UNI terminal
+ *   aux0: csr id (rows = entities); aux1: amount column id or UINT32_MAX. The keyed self-join of projected
+ *   rows, .project(P).join(equal(key)).penalize(CONST) (constraint/projected/bi.rs: every unordered pair of
+ *   rows with equal keys, rows of one entity included), is this kind with count() and SFGPU_W_PAIRS.
+ *   A projected UNI terminal
  *   (.project(P).penalize(w(row))) lowers on the host to SFGPU_K_UNI over the per-entity sum of row weights
  *   (constraint/projected/uni.rs:61-263). */
 #define SFGPU_K_PROJECT_GROUP 9

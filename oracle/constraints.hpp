@@ -1492,4 +1492,122 @@ struct ProjectedGroupedConstraint final : IncrementalConstraint<S, Sc> {
   }
 };
 
+// for_each(src).project(P).join(equal(key)).filter(pair).penalize(w(left, right))
+//   constraint/projected/bi.rs:251-330,367-392: rows that pass the row filter are self-joined by key; every
+//   unordered pair of distinct rows (rows of one entity included) is oriented by RowCoordinate
+//   (entity index, then emit index) and scored when the pair filter accepts (left, right).
+// Retained state: rows by key; the notification protocol retracts / inserts all rows of one entity.
+template <class S, class A, class Out, class K, class Sc, class P, class F, class KF, class PF, class W,
+          class KH = std::hash<K>>
+struct ProjectedBiConstraint final : IncrementalConstraint<S, Sc> {
+  Source<S, A> src;
+  Impact impact;
+  P project;      // (const A&, std::vector<Out>&) -> void
+  F filter;       // (const S&, const Out&) -> bool
+  KF key_fn;      // (const Out&) -> K
+  PF pair_filter; // (const Out& left, const Out& right) -> bool
+  W weight;       // (const Out& left, const Out& right) -> Sc
+  struct Row {
+    std::pair<size_t, size_t> coord;  // (entity, emit_index)
+    Out out;
+  };
+  std::unordered_map<K, std::vector<Row>, KH> by_key;
+  std::unordered_map<size_t, std::vector<std::pair<K, size_t>>> rows_by_owner;  // (key, emit_index)
+  ProjectedBiConstraint(std::string n, Impact i, Source<S, A> s, P p, F f, KF kf, PF pf, W w, bool hard)
+      : src(s), impact(i), project(std::move(p)), filter(std::move(f)), key_fn(std::move(kf)),
+        pair_filter(std::move(pf)), weight(std::move(w)) {
+    this->name = std::move(n);
+    this->is_hard = hard;
+  }
+  Sc pair_score(const Row& x, const Row& y) const {
+    const Row& l = x.coord <= y.coord ? x : y;
+    const Row& r = x.coord <= y.coord ? y : x;
+    return pair_filter(l.out, r.out) ? signed_weight(impact, weight(l.out, r.out)) : Sc::zero();
+  }
+  std::vector<Row> all_rows(const S& s) const {
+    std::vector<Row> rows;
+    std::vector<Out> tmp;
+    auto& es = src.extract(s);
+    for (size_t i = 0; i < es.size(); ++i) {
+      tmp.clear();
+      project(es[i], tmp);
+      for (size_t j = 0; j < tmp.size(); ++j)
+        if (filter(s, tmp[j])) rows.push_back({{i, j}, tmp[j]});
+    }
+    return rows;
+  }
+  Sc evaluate(const S& s) const override {
+    auto rows = all_rows(s);
+    Sc t = Sc::zero();
+    for (size_t a = 0; a < rows.size(); ++a)
+      for (size_t b = a + 1; b < rows.size(); ++b)
+        if (key_fn(rows[a].out) == key_fn(rows[b].out)) t = t + pair_score(rows[a], rows[b]);
+    return t;
+  }
+  size_t match_count(const S& s) const override {
+    auto rows = all_rows(s);
+    size_t n = 0;
+    for (size_t a = 0; a < rows.size(); ++a)
+      for (size_t b = a + 1; b < rows.size(); ++b)
+        if (key_fn(rows[a].out) == key_fn(rows[b].out)) {
+          const Row& l = rows[a].coord <= rows[b].coord ? rows[a] : rows[b];
+          const Row& r = rows[a].coord <= rows[b].coord ? rows[b] : rows[a];
+          n += pair_filter(l.out, r.out) ? 1 : 0;
+        }
+    return n;
+  }
+  Sc insert_rows(const S& s, size_t idx) {
+    auto& es = src.extract(s);
+    if (idx >= es.size()) return Sc::zero();
+    std::vector<Out> tmp;
+    project(es[idx], tmp);
+    Sc t = Sc::zero();
+    for (size_t j = 0; j < tmp.size(); ++j) {
+      if (!filter(s, tmp[j])) continue;
+      Row row{{idx, j}, tmp[j]};
+      K k = key_fn(tmp[j]);
+      auto& bucket = by_key[k];
+      for (const Row& other : bucket) t = t + pair_score(row, other);
+      bucket.push_back(row);
+      rows_by_owner[idx].push_back({k, j});
+    }
+    return t;
+  }
+  Sc retract_rows(size_t idx) {
+    Sc t = Sc::zero();
+    auto it = rows_by_owner.find(idx);
+    if (it == rows_by_owner.end()) return t;
+    for (auto& kj : it->second) {
+      auto& bucket = by_key[kj.first];
+      size_t pos = 0;
+      for (; pos < bucket.size(); ++pos)
+        if (bucket[pos].coord == std::make_pair(idx, kj.second)) break;
+      if (pos == bucket.size()) continue;
+      Row row = bucket[pos];
+      bucket.erase(bucket.begin() + pos);
+      for (const Row& other : bucket) t = t - pair_score(row, other);
+    }
+    rows_by_owner.erase(it);
+    return t;
+  }
+  Sc initialize(const S& s) override {
+    reset();
+    Sc t = Sc::zero();
+    for (size_t i = 0; i < src.extract(s).size(); ++i) t = t + insert_rows(s, i);
+    return t;
+  }
+  Sc on_insert(const S& s, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    return insert_rows(s, idx);
+  }
+  Sc on_retract(const S&, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    return retract_rows(idx);
+  }
+  void reset() override {
+    by_key.clear();
+    rows_by_owner.clear();
+  }
+};
+
 }  // namespace sfo

@@ -606,6 +606,23 @@ static void kat_projected_multi_emit() {
     PPlan plan{{{2, 3, true}, {4, 1, true}}, {}};
     CHECK(c.evaluate(plan) == SoftScore::of(-10));
   }
+  {  // self_join.rs:109-154: projected rows self-join by key, pair filter on (left, right) in coordinate order
+    auto pf = [](const PEntry& l, const PEntry& r) { return l.delta < r.delta; };
+    auto pw = [](const PEntry&, const PEntry&) { return SoftScore::of(1); };
+    ProjectedBiConstraint<PPlan, PWork, PEntry, size_t, SoftScore, decltype(one), decltype(always), decltype(kf),
+                          decltype(pf), decltype(pw)>
+        c("projected duplicate bucket", Impact::Penalty, {pp_work, ChangeSource::Desc(0)}, one, always, kf, pf, pw, false);
+    PPlan plan{{{0, 1, true}, {0, 2, true}, {1, 3, true}}, {}};
+    SoftScore total = c.initialize(plan);
+    CHECK(c.match_count(plan) == 1);
+    CHECK(total == SoftScore::of(-1));
+    total = total + c.on_retract(plan, 2, 0);
+    plan.work[2].bucket = 0;
+    total = total + c.on_insert(plan, 2, 0);
+    CHECK(c.match_count(plan) == 3);
+    CHECK(total == SoftScore::of(-3));
+    CHECK(total == c.evaluate(plan));
+  }
   {  // two rows of one entity in the same group (support.rs OrderedWorkEntries) with a non-linear weight:
      // the group is re-scored once per notification, incremental == evaluate
     auto ordered = [](const PWork& w, std::vector<PEntry>& out) {

@@ -401,6 +401,7 @@ struct ShiftModel final : ModelImpl<ShiftSchedule> {
 //   2 .project(rows).group_by(|r| (r.nurse, r.day), sum(|r| r.hours)).penalize(hard max(0, total - limit))
 //   3 .project(rows).group_by(|r| (r.nurse, r.day), count()).penalize(soft count^2)
 //   4 .project(rows).penalize(|r| soft r.hours)       (projected uni terminal, every row scored on its own)
+//   5 .project(rows).join(equal(key)).penalize(ONE_HARD)   (projected keyed self-join)
 struct RShift {
   size_t id;
   bool required;
@@ -448,6 +449,14 @@ struct RosterModel final : ModelImpl<Roster> {
         std::make_unique<ProjectedGroupedConstraint<Roster, RShift, RRow, int64_t, Sc, CountAcc, decltype(project),
                                                     decltype(always), decltype(key), decltype(unit), decltype(cw)>>(
             "Fragmented days", Impact::Penalty, shifts, project, always, key, unit, cw, false));
+    // 5 .project(rows).join(equal(|r| (r.nurse, r.day))).penalize(ONE_HARD): every pair of rows of one nurse
+    //   on one day (constraint/projected/bi.rs), rows of the same shift included
+    auto pf = [](const RRow&, const RRow&) { return true; };
+    auto pw = [](const RRow&, const RRow&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(
+        std::make_unique<ProjectedBiConstraint<Roster, RShift, RRow, int64_t, Sc, decltype(project), decltype(always),
+                                               decltype(key), decltype(pf), decltype(pw)>>(
+            "Double booking", Impact::Penalty, shifts, project, always, key, pf, pw, true));
     auto rw = [](const RRow& r) { return Sc::of_soft(r.hours); };
     dir.constraints.add(
         std::make_unique<ProjectedUniConstraint<Roster, RShift, RRow, Sc, decltype(project), decltype(always), decltype(rw)>>(

@@ -646,11 +646,33 @@ class ProjectedStream:
     def reward(self, weight: "WeightFn") -> _Terminal:
         return self._impact(L.REWARD, weight)
 
+    def join_self(self) -> "ProjectedPairStream":
+        """.join(equal(|row| row.key)) — keyed self-join of the projected rows (constraint/projected/bi.rs): every
+        unordered pair of rows with equal keys, rows of one entity included."""
+        return ProjectedPairStream(self.d, self.collection, self.p)
+
     def group_by(self, collector) -> "ProjectedGroupedStream":
         """.group_by(|row| row.key, count() | sum(|row| row.amount))"""
         if not isinstance(collector, (Count, Sum)):
             raise L.SfgpuError(L.E_UNSUPPORTED, "projected group_by supports count() and sum(amount)")
         return ProjectedGroupedStream(self.d, self.collection, self.p, collector)
+
+
+class ProjectedPairStream:
+    def __init__(self, d, collection, projection: "Projection"):
+        self.d, self.collection, self.p = d, collection, projection
+
+    def _impact(self, impact, weight: HardSoftScore) -> _Terminal:
+        # n rows in a key group form n(n-1)/2 pairs: the grouped count with the triangular weight
+        w = _const_weight(weight)
+        return _Terminal(self.d, kind=L.K_PROJECT_GROUP, impact=impact, weight=WeightFn(L.W_PAIRS, w.level, w.a, 0),
+                         collection=self.collection, aux0=self.p.csr, aux1=L.NO_COLUMN, p0=self.p.keys_per_value, p1=0)
+
+    def penalize(self, weight: HardSoftScore) -> _Terminal:
+        return self._impact(L.PENALTY, weight)
+
+    def reward(self, weight: HardSoftScore) -> _Terminal:
+        return self._impact(L.REWARD, weight)
 
 
 class ProjectedGroupedStream:

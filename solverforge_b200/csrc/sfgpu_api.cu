@@ -343,7 +343,7 @@ int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, 
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
   if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_PROJECT_GROUP)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
-  if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_ABSDIFF || desc->weight.level < 0 ||
+  if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_PAIRS || desc->weight.level < 0 ||
       desc->weight.level > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad weight");
   bool needs_const = desc->kind == SFGPU_K_PAIR_CSR_EQUAL || desc->kind == SFGPU_K_PAIR_KEY_EQUAL ||
@@ -470,7 +470,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         if (!mt.i32 || mx >= (1 << 28) || (uint64_t)mt.rows * mt.cols >= (1ull << 31)) { fast = false; break; }
         dm.fast_pc = (int32_t)k;
       } else if (d.kind == SFGPU_K_LIST_SUM) {
-        if (dm.fast_ls >= 0 || d.aux0 >= ctx->cols.size() || d.weight.fn == SFGPU_W_ABSDIFF) { fast = false; break; }
+        if (dm.fast_ls >= 0 || d.aux0 >= ctx->cols.size() || d.weight.fn == SFGPU_W_ABSDIFF || d.weight.fn == SFGPU_W_PAIRS) { fast = false; break; }
         for (int64_t c : ctx->cols[d.aux0].host)
           if (c < -(1ll << 30) || c > (1ll << 30)) fast = false;
         dm.fast_ls = (int32_t)k;

@@ -122,6 +122,7 @@ __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
       int64_t d = x - w.b;
       return w.a * (d < 0 ? -d : d);
     }
+    case SFGPU_W_PAIRS: return w.a * (x * (x - 1) / 2);
     default: {
       int64_t d = x - w.b;
       return d > 0 ? w.a * d : 0;

@@ -304,6 +304,13 @@ struct ProjectedStream {
   Terminal impact(int imp, Weight w) const;
   Terminal penalize(Weight w) const { return impact(SFGPU_PENALTY, w); }
   Terminal reward(Weight w) const { return impact(SFGPU_REWARD, w); }
+  // .join(equal(key)).penalize(CONST): every unordered pair of rows with equal keys (constraint/projected/bi.rs)
+  Terminal penalize_pairs(HardSoftScore w) const {
+    ProjectedGroupedStream g{d, collection, p, false};
+    Weight cw = Weight::constant(w);
+    cw.w.fn = SFGPU_W_PAIRS;
+    return g.impact(SFGPU_PENALTY, cw);
+  }
   ProjectedGroupedStream group_by(Count) const { return {d, collection, p, false}; }
   ProjectedGroupedStream group_by(Sum) const { return {d, collection, p, true}; }  // sums the projection's amounts
 };

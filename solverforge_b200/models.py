@@ -137,6 +137,7 @@ def roster_director(inst, n_replicas: int = 1, nurse_idx=None, device: int = 0, 
     f.for_each(shifts).filter(required).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned required shift")
     f.for_each(shifts).project(rows).group_by(Sum(L.NO_COLUMN)).penalize(hard(L.W_EXCESS, 1, inst.limit)).named("Daily hours")
     f.for_each(shifts).project(rows).group_by(Count()).penalize(soft(L.W_SQUARE, 1, 0)).named("Fragmented days")
+    f.for_each(shifts).project(rows).join_self().penalize(HardSoftScore.ONE_HARD).named("Double booking")
     f.for_each(shifts).project(rows).penalize(soft(L.W_LINEAR, 1, 0)).named("Worked hours")
     d.set_scalar_state(inst.nurse_idx if nurse_idx is None else nurse_idx)
     d.commit()

@@ -333,6 +333,7 @@ static int test_gpu() {
     rf.for_each(shifts).filtered(req).unassigned().penalize(sf::HardSoftScore::ONE_HARD()).named("Unassigned required shift");
     sf::project(rf.for_each(shifts), rows).group_by(sf::Sum{UINT32_MAX}).penalize(sf::Weight::hard(SFGPU_W_EXCESS, 1, limit)).named("Daily hours");
     sf::project(rf.for_each(shifts), rows).group_by(sf::Count{}).penalize(sf::Weight::soft(SFGPU_W_SQUARE, 1, 0)).named("Fragmented days");
+    sf::project(rf.for_each(shifts), rows).penalize_pairs(sf::HardSoftScore::ONE_HARD()).named("Double booking");
     sf::project(rf.for_each(shifts), rows).penalize(sf::Weight::soft(SFGPU_W_LINEAR, 1, 0)).named("Worked hours");
     rd.set_scalar_state(nurse);
     auto ri = rd.commit();
