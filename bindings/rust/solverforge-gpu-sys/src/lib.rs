@@ -31,6 +31,7 @@ pub const SFGPU_K_LIST_PATH_COST: i32 = 6;
 pub const SFGPU_K_LIST_SUM: i32 = 7;
 pub const SFGPU_K_LOAD_BALANCE: i32 = 8;
 pub const SFGPU_K_PROJECT_GROUP: i32 = 9;
+pub const SFGPU_K_RUNS: i32 = 10;
 
 #[repr(C)]
 pub struct sfgpu_ctx {

@@ -157,6 +157,13 @@ typedef struct sfgpu_weight {
  *   (constraint/projected/uni.rs:61-263). */
 #define SFGPU_K_PROJECT_GROUP 9
 
+/* for_each(E).filter(assigned).group_by(var, consecutive_runs(point column)).penalize(sum over runs of
+ *   w(run.point_count)): stream/collector/runs.rs:14-229 (unique points as maximal runs of consecutive
+ *   integers; duplicates do not lengthen a run) — "Long work streaks" of examples/minimal-shift-scheduling
+ *   (schedule.rs:43-58) is EXCESS with b = 2. aux0: entity column with the point (0 <= point < p0);
+ *   p0: number of points. */
+#define SFGPU_K_RUNS 10
+
 typedef struct sfgpu_constraint_desc {
   int32_t kind;
   int32_t impact;      /* SFGPU_PENALTY / SFGPU_REWARD (constraint/incremental.rs:70-76) */

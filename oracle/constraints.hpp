@@ -21,6 +21,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <map>
 #include <cstddef>
 #include <cstdint>
 #include <memory>
@@ -743,6 +744,59 @@ struct SumAcc {  // sum.rs: Result = T (i64 here)
   void retract(Retraction v) { sum = wsub(sum, v); }
   Result result() const { return sum; }
   void reset() { sum = 0; }
+};
+// runs.rs:14-229 — consecutive_runs(index): the unique integer points of a group as maximal runs of
+// consecutive values; duplicates raise a run's item_count, not its point_count.
+struct Run {
+  int64_t start = 0, end = 0;
+  size_t point_count = 0, item_count = 0;
+};
+struct Runs {
+  std::vector<Run> runs;
+  size_t point_count = 0, item_count = 0;
+};
+struct RunsAcc {
+  using Value = int64_t;
+  using Result = Runs;
+  using Retraction = int64_t;
+  std::map<int64_t, size_t> points;  // BTreeMap: ordered
+  size_t items = 0;
+  Retraction accumulate(Value v) {
+    points[v] += 1;
+    items += 1;
+    return v;
+  }
+  void retract(Retraction v) {  // :151-161
+    auto it = points.find(v);
+    if (it == points.end()) return;
+    it->second = it->second > 0 ? it->second - 1 : 0;
+    items = items > 0 ? items - 1 : 0;
+    if (it->second == 0) points.erase(it);
+  }
+  Result result() const {  // runs_from_counts_and_item_count :179-229
+    Runs out;
+    out.point_count = points.size();
+    out.item_count = items;
+    bool open = false;
+    Run cur;
+    for (auto& kv : points) {
+      if (open && cur.end + 1 == kv.first) {
+        cur.end = kv.first;
+        cur.point_count += 1;
+        cur.item_count += kv.second;
+      } else {
+        if (open) out.runs.push_back(cur);
+        cur = Run{kv.first, kv.first, 1, kv.second};
+        open = true;
+      }
+    }
+    if (open) out.runs.push_back(cur);
+    return out;
+  }
+  void reset() {
+    points.clear();
+    items = 0;
+  }
 };
 // load_balance.rs:104-240. Result carries `unfairness` (the per-key loads map is not scored).
 struct LoadBalanceAcc {

@@ -645,6 +645,35 @@ static void kat_projected_multi_emit() {
   }
 }
 
+// stream/collector/tests/collector.rs:266-331 — consecutive_runs
+static void kat_runs_collector() {
+  RunsAcc empty;
+  CHECK(empty.result().runs.empty() && empty.result().point_count == 0 && empty.result().item_count == 0);
+  RunsAcc one;
+  for (int64_t v : {3, 1, 2}) one.accumulate(v);
+  auto r1 = one.result();
+  CHECK(r1.runs.size() == 1 && r1.runs[0].start == 1 && r1.runs[0].end == 3 && r1.runs[0].point_count == 3 &&
+        r1.runs[0].item_count == 3);
+  RunsAcc many;
+  for (int64_t v : {8, 1, 2, 4, 5, 10}) many.accumulate(v);
+  auto r2 = many.result();
+  CHECK(r2.runs.size() == 4);
+  CHECK(r2.runs[0].start == 1 && r2.runs[0].end == 2 && r2.runs[1].start == 4 && r2.runs[1].end == 5);
+  CHECK(r2.runs[2].start == 8 && r2.runs[2].end == 8 && r2.runs[3].start == 10 && r2.runs[3].end == 10);
+  RunsAcc dup;
+  for (int64_t v : {1, 1, 2, 4, 4, 4}) dup.accumulate(v);
+  auto r3 = dup.result();
+  CHECK(r3.point_count == 3 && r3.item_count == 6);
+  CHECK(r3.runs[0].point_count == 2 && r3.runs[0].item_count == 3 && r3.runs[1].point_count == 1 &&
+        r3.runs[1].item_count == 3);
+  dup.retract(1);  // one of the two items at point 1: the point stays
+  CHECK(dup.result().runs[0].point_count == 2 && dup.result().runs[0].item_count == 2);
+  dup.retract(1);  // the point goes: the run shrinks to {2}
+  CHECK(dup.result().runs[0].start == 2 && dup.result().runs[0].point_count == 1);
+  dup.retract(99);  // unknown point: ignored (:151-154)
+  CHECK(dup.result().item_count == 4);
+}
+
 // ---------------------------------------------------------------- selectors / foragers
 static void kat_nearby_sort() {
   // solverforge-solver/src/heuristic/selector/nearby_list_support.rs:51-73
@@ -975,6 +1004,7 @@ int main() {
   kat_cross_complemented();
   kat_projected();
   kat_projected_multi_emit();
+  kat_runs_collector();
   kat_nearby_sort();
   kat_moves_and_loop();
   kat_acceptors();

@@ -320,8 +320,8 @@ struct JobShopModel final : ModelImpl<JobShopPlan> {
 };
 
 // ------------------------------------------------------------------------------ shift scheduling
-// examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 — constraints 1, 2 and 4 verbatim
-// ("Long work streaks" uses the consecutive_runs collector, out of scope per SURVEY §2 row 10), plus
+// examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 — all four constraints verbatim
+// ("Long work streaks" uses the consecutive_runs collector, stream/collector/runs.rs), plus
 // one authored load_balance constraint over stream/collector/load_balance.rs (metric = `hours`).
 struct SNurse {
   size_t id;
@@ -342,7 +342,7 @@ inline const std::vector<SNurse>& ss_nurses(const ShiftSchedule& s) { return s.n
 inline const std::vector<SShift>& ss_shifts(const ShiftSchedule& s) { return s.shifts; }
 
 struct ShiftModel final : ModelImpl<ShiftSchedule> {
-  explicit ShiftModel(ShiftSchedule sol, int64_t target = 4) {
+  explicit ShiftModel(ShiftSchedule sol, int64_t target = 4, bool with_load_balance = true) {
     dir.working = std::move(sol);
     dir.access.get = [](const ShiftSchedule& s, size_t, size_t e) { return s.shifts[e].nurse_idx; };
     dir.access.set = [](ShiftSchedule& s, size_t, size_t e, OptVal v) { s.shifts[e].nurse_idx = v; };
@@ -361,6 +361,20 @@ struct ShiftModel final : ModelImpl<ShiftSchedule> {
         std::make_unique<CrossBiConstraint<ShiftSchedule, SShift, SShift, uint8_t, Sc, ConstKey, ConstKey,
                                            decltype(pf), decltype(pw)>>(
             "One shift per nurse day", Impact::Penalty, shifts, shifts, ConstKey{}, ConstKey{}, pf, pw, true));
+    // Long work streaks (schedule.rs:43-58): group_by(nurse, consecutive_runs(day))
+    //   .penalize(|_, runs| of_soft(sum over runs of max(0, point_count - 2)))
+    auto sf_ = [](const ShiftSchedule&, const SShift& s) { return s.nurse_idx.has_value(); };
+    auto sk = [](const SShift& s) { return s.nurse_idx.value_or((size_t)-1); };
+    auto sv = [](const SShift& s) { return s.day; };
+    auto sw = [](const size_t&, const Runs& runs) {
+      int64_t excess = 0;
+      for (auto& r : runs.runs) excess += r.point_count > 2 ? (int64_t)r.point_count - 2 : 0;
+      return Sc::of_soft(excess);
+    };
+    dir.constraints.add(
+        std::make_unique<GroupedConstraint<ShiftSchedule, SShift, size_t, Sc, RunsAcc, decltype(sf_), decltype(sk),
+                                           decltype(sv), decltype(sw)>>("Long work streaks", Impact::Penalty, shifts,
+                                                                        sf_, sk, sv, sw, false));
     // Balanced workload: group_by(nurse, count()).complement(nurses, id, 0).penalize(|count - target|)
     auto jka = [](const SShift& s) { return s.nurse_idx; };
     auto jkb = [](const SNurse& n) { return OptVal(n.id); };
@@ -378,6 +392,7 @@ struct ShiftModel final : ModelImpl<ShiftSchedule> {
             ShiftSchedule, SShift, SNurse, SNurse, OptVal, size_t, Sc, CountAcc, decltype(jka), decltype(jkb),
             decltype(jf), decltype(gk), decltype(vf), decltype(kt), decltype(df), decltype(gw), OptHash>>(
             "Balanced workload", Impact::Penalty, shifts, nurses, nurses, jka, jkb, jf, gk, vf, kt, df, gw, false));
+    if (!with_load_balance) return;  // the example as shipped (swap / compound candidates stay expressible)
     // authored: group_by(|_| (), load_balance(|s| nurse, |s| hours)).penalize(|_, lb| of_soft(lb.unfairness()))
     auto lf = [](const ShiftSchedule&, const SShift& s) { return s.nurse_idx.has_value(); };
     auto lk = [](const SShift&) { return (char)0; };

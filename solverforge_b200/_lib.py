@@ -19,7 +19,7 @@ CTX_LEGACY_DEFAULT_STREAM, CTX_GENERIC_KERNELS = 1, 2
 W_CONST, W_LINEAR, W_SQUARE, W_EXCESS, W_ABSDIFF, W_PAIRS = 0, 1, 2, 3, 4, 5
 PENALTY, REWARD = 0, 1
 K_UNI, K_PAIR_CSR_EQUAL, K_PAIR_KEY_EQUAL, K_EXISTS_FLAT, K_GROUP = 1, 2, 3, 4, 5
-K_LIST_PATH_COST, K_LIST_SUM, K_LOAD_BALANCE, K_PROJECT_GROUP = 6, 7, 8, 9
+K_LIST_PATH_COST, K_LIST_SUM, K_LOAD_BALANCE, K_PROJECT_GROUP, K_RUNS = 6, 7, 8, 9, 10
 NO_COLUMN = 0xFFFFFFFF
 LIST_VAR = 0x80000000
 MAX_EDITS = 8

@@ -555,6 +555,14 @@ class Sum:
 
 
 @dataclass
+class ConsecutiveRuns:
+    """consecutive_runs(|e| e.point) (stream/collector/runs.rs): the weight applies to every run's point_count
+    and the group scores their sum. point_column: entity column with 0 <= point < n_points."""
+    point_column: int
+    n_points: int
+
+
+@dataclass
 class LoadBalance:
     metric_column: int = L.NO_COLUMN
 
@@ -748,6 +756,11 @@ class GroupedStream:
 
     def _impact(self, impact, weight: WeightFn, key_offset_column: int = L.NO_COLUMN) -> _Terminal:
         c = self.collector
+        if isinstance(c, ConsecutiveRuns):
+            if self.complemented:
+                raise L.SfgpuError(L.E_UNSUPPORTED, "consecutive_runs with a complement is not expressible on device")
+            return _Terminal(self.d, kind=L.K_RUNS, impact=impact, weight=weight, collection=self.collection,
+                             aux0=c.point_column, p0=c.n_points)
         if isinstance(c, LoadBalance):
             return _Terminal(self.d, kind=L.K_LOAD_BALANCE, impact=impact, weight=weight, collection=self.collection,
                              aux0=c.metric_column)

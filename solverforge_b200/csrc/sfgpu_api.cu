@@ -341,7 +341,7 @@ int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, 
   if (!ctx || !desc) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
-  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_PROJECT_GROUP)
+  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_RUNS)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
   if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_PAIRS || desc->weight.level < 0 ||
       desc->weight.level > 1)
@@ -558,7 +558,8 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       return SFGPU_OK;
     };
     bool scalar_kind = d.kind == SFGPU_K_UNI || d.kind == SFGPU_K_PAIR_CSR_EQUAL || d.kind == SFGPU_K_PAIR_KEY_EQUAL ||
-                       d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE || d.kind == SFGPU_K_PROJECT_GROUP;
+                       d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE || d.kind == SFGPU_K_PROJECT_GROUP ||
+                       d.kind == SFGPU_K_RUNS;
     if (scalar_kind && !dm.has_scalar) return fail(ctx, SFGPU_E_INVALID, "constraint needs a scalar variable");
     if (!scalar_kind && !dm.has_list) return fail(ctx, SFGPU_E_INVALID, "constraint needs a list variable");
     switch (d.kind) {
@@ -659,6 +660,21 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         off = align_up(off + dm.n_values * 4, 16);
         c.off1 = off;
         off = align_up(off + dm.n_values * 8, 16);
+        break;
+      }
+      case SFGPU_K_RUNS: {
+        const int64_t* col = nullptr;
+        int rc = column(d.aux0, dm.n_entities, &col);
+        if (rc) return rc;
+        if (!col) return fail(ctx, SFGPU_E_INVALID, "RUNS: aux0 must be the entity column holding the point");
+        if (d.p0 <= 0 || (uint64_t)d.p0 * dm.n_values >= (1ull << 28))
+          return fail(ctx, SFGPU_E_INVALID, "RUNS: p0 (number of points) out of range");
+        for (int64_t v : ctx->cols[d.aux0].host)
+          if (v < 0 || v >= d.p0) return fail(ctx, SFGPU_E_INVALID, "RUNS: point outside [0, p0)");
+        c.g0 = col;
+        c.n0 = (uint32_t)d.p0;
+        c.off0 = off;
+        off = align_up(off + dm.n_values * c.n0 * 4, 16);
         break;
       }
       case SFGPU_K_PROJECT_GROUP: {

@@ -173,6 +173,39 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const char*
         add_level(d, c, weight_eval(c.w, lb_unfairness(nk, sum, sumsq)) - before);
         break;
       }
+      case SFGPU_K_RUNS: {
+        // cnt[v][point] items of group v at each point. Leaving a point whose count drops to zero splits
+        // the run around it (L + 1 + R -> L, R); entering an empty point merges its neighbours.
+        const int32_t* cnt = (const int32_t*)(st + c.off0);
+        const int32_t np = (int32_t)c.n0;
+        const int32_t pt = (int32_t)((const int64_t*)c.g0)[cur.e];
+        int64_t delta = 0;
+        for (int side = 0; side < 2; ++side) {
+          const int32_t v = side == 0 ? cur.old_v : cur.new_v;
+          if (v < 0) continue;
+          const int32_t* row = cnt + (size_t)v * np;
+          auto at = [&](int32_t q) {  // items at point q of group v, earlier edits of this candidate included
+            int32_t n = row[q];
+            for (int i = 0; i < n_prev; ++i) {
+              const int32_t pq = (int32_t)((const int64_t*)c.g0)[prev[i].e];
+              if (pq != q) continue;
+              if (prev[i].new_v == v) n += 1;
+              if (prev[i].old_v == v) n -= 1;
+            }
+            return n;
+          };
+          const int32_t here = at(pt);
+          if (side == 0 ? here != 1 : here != 0) continue;  // the set of points does not change
+          int64_t L = 0, R = 0;
+          for (int32_t q = pt - 1; q >= 0 && at(q) > 0; --q) ++L;
+          for (int32_t q = pt + 1; q < np && at(q) > 0; ++q) ++R;
+          const int64_t merged = weight_eval(c.w, L + 1 + R);
+          const int64_t split = (L > 0 ? weight_eval(c.w, L) : 0) + (R > 0 ? weight_eval(c.w, R) : 0);
+          delta += side == 0 ? split - merged : merged - split;
+        }
+        add_level(d, c, delta);
+        break;
+      }
       case SFGPU_K_PROJECT_GROUP: {
         // projected rows of ONE entity change groups together: collect the affected groups first, then
         // re-score each once (two rows of an entity may share a group; weights need not be linear)
@@ -1230,6 +1263,27 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
           local += group_score(c, i, gc[i], (int64_t)gs[i]);
         break;
       }
+      case SFGPU_K_RUNS: {
+        int32_t* cnt = (int32_t*)(st + c.off0);
+        const uint32_t np = c.n0;
+        for (uint32_t i = threadIdx.x; i < m.n_values * np; i += blockDim.x) cnt[i] = 0;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x)
+          if (var[e] >= 0) atomicAdd(&cnt[(size_t)var[e] * np + (uint32_t)((const int64_t*)c.g0)[e]], 1);
+        __syncthreads();
+        for (uint32_t v = threadIdx.x; v < m.n_values; v += blockDim.x) {
+          int64_t run = 0;
+          for (uint32_t q = 0; q <= np; ++q) {
+            if (q < np && cnt[(size_t)v * np + q] > 0) {
+              ++run;
+            } else {
+              if (run > 0) local += weight_eval(c.w, run);
+              run = 0;
+            }
+          }
+        }
+        break;
+      }
       case SFGPU_K_PROJECT_GROUP: {
         int32_t* gc = (int32_t*)(st + c.off0);
         unsigned long long* gs = (unsigned long long*)(st + c.off1);
@@ -1379,6 +1433,11 @@ __device__ void apply_scalar_edit(const DevModel& m, char* st, EditDev cur) {
       int64_t x = c.g0 ? ((const int64_t*)c.g0)[cur.e] : 1;
       if (cur.old_v >= 0) { gc[cur.old_v] -= 1; gs[cur.old_v] -= x; }
       if (cur.new_v >= 0) { gc[cur.new_v] += 1; gs[cur.new_v] += x; }
+    } else if (c.kind == SFGPU_K_RUNS) {
+      int32_t* cnt = (int32_t*)(st + c.off0);
+      const uint32_t pt = (uint32_t)((const int64_t*)c.g0)[cur.e];
+      if (cur.old_v >= 0) cnt[(size_t)cur.old_v * c.n0 + pt] -= 1;
+      if (cur.new_v >= 0) cnt[(size_t)cur.new_v * c.n0 + pt] += 1;
     } else if (c.kind == SFGPU_K_PROJECT_GROUP) {
       int32_t* gc = (int32_t*)(st + c.off0);
       int64_t* gs = (int64_t*)(st + c.off1);

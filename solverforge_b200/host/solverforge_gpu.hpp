@@ -133,6 +133,8 @@ struct ListSum { uint32_t column; };
 struct Count {};
 struct Sum { uint32_t column; };
 struct LoadBalance { uint32_t metric_column = UINT32_MAX; };
+// consecutive_runs(|e| e.point) (stream/collector/runs.rs): the weight applies to every run's point_count
+struct ConsecutiveRuns { uint32_t point_column; uint32_t n_points; };
 // Data form of a `Projection<A>` (stream/projected_stream/source.rs:13-24): an ASSIGNED entity e emits one row per
 // entry j of csr row e with key offset csr.col[j] (< keys_per_value) and amount amounts[j] (empty = 1 each); the
 // group key of a row is var[e] * keys_per_value + key offset. MAX_EMITS <= 8.
@@ -283,6 +285,18 @@ struct UniStream {
   GroupedStream group_by(Count) const { return {d, collection, UINT32_MAX, false}; }
   GroupedStream group_by(Sum s) const { return {d, collection, s.column, false}; }
   GroupedStream group_by(LoadBalance lb) const { return {d, collection, lb.metric_column, true}; }
+  // group_by(var, consecutive_runs(point)).penalize(sum over runs of w(point_count)) -> SFGPU_K_RUNS
+  Terminal penalize_runs(ConsecutiveRuns r, Weight w) const {
+    sfgpu_constraint_desc c{};
+    c.kind = SFGPU_K_RUNS;
+    c.impact = SFGPU_PENALTY;
+    c.weight = w.w;
+    c.collection = collection;
+    c.aux0 = r.point_column;
+    c.aux1 = UINT32_MAX;
+    c.p0 = r.n_points;
+    return {d, c};
+  }
 };
 
 // for_each(E).project(P)... — projected scoring rows (stream/projected_stream/uni.rs)

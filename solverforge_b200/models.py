@@ -98,10 +98,10 @@ def job_shop_director(inst: JobShopInstance, n_replicas: int = 1, machine_idx=No
 
 
 def shift_scheduling_director(inst, n_replicas: int = 1, nurse_idx=None, device: int = 0, stream=None,
-                              flags: int = 0) -> GpuScoreDirector:
-    """examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 (constraints 1, 2, 4) + an authored
-    load_balance constraint; "Long work streaks" (consecutive_runs collector) is out of scope."""
-    from .api import LoadBalance
+                              flags: int = 0, with_load_balance: bool = True) -> GpuScoreDirector:
+    """examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 (all four constraints, incl. "Long work
+    streaks" over the consecutive_runs collector) + an authored load_balance constraint."""
+    from .api import ConsecutiveRuns, LoadBalance
     d = GpuScoreDirector(n_replicas, device, stream, flags)
     nurses = d.add_collection("nurses", inst.n_nurses, -1)
     shifts = d.add_collection("shifts", inst.n_shifts, 0)
@@ -113,9 +113,12 @@ def shift_scheduling_director(inst, n_replicas: int = 1, nurse_idx=None, device:
     f.for_each(shifts).filter(required).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned required shift")
     f.for_each(shifts).join(f.for_each(shifts), EqualKey(day, inst.n_nurses, 1)).penalize(
         HardSoftScore.ONE_HARD).named("One shift per nurse day")
+    f.for_each(shifts).assigned().group_by(ConsecutiveRuns(day, int(np.max(inst.day)) + 1)).penalize(
+        soft(L.W_EXCESS, 1, 2)).named("Long work streaks")
     f.for_each(shifts).assigned().group_by(Count()).complement(nurses, 0).penalize(
         soft(L.W_ABSDIFF, 1, inst.target)).named("Balanced workload")
-    f.for_each(shifts).assigned().group_by(LoadBalance(hours)).penalize(soft(L.W_LINEAR, 1, 0)).named("Fair hours")
+    if with_load_balance:
+        f.for_each(shifts).assigned().group_by(LoadBalance(hours)).penalize(soft(L.W_LINEAR, 1, 0)).named("Fair hours")
     d.set_scalar_state(inst.nurse_idx if nurse_idx is None else nurse_idx)
     d.commit()
     return d

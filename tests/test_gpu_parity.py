@@ -688,3 +688,51 @@ def test_list_reverse_moves_match_oracle(asymmetric):
         assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
         lo, le = d.list_state()
         assert best[0].tolist() == o.committed_score().tolist()
+
+
+def test_consecutive_runs_collector_matches_oracle():
+    """group_by(nurse, consecutive_runs(day)) — "Long work streaks" of examples/minimal-shift-scheduling
+    (stream/collector/runs.rs): change, swap and compound candidates (several shifts of one candidate landing
+    on adjacent days of one nurse), committed trajectories with cached == fresh == oracle."""
+    for seed in (3, 8):
+        inst = instances.shift_scheduling(n_days=12, slots_per_day=3, n_nurses=4, seed=seed, unassigned_permille=250)
+        o = Oracle.shift_scheduling(inst, with_load_balance=False)
+        d = models.shift_scheduling_director(inst, with_load_balance=False)
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        rows = o.enumerate_change()
+        s, ok = d.score_change(rows)
+        so, oko = o.score_change(rows)
+        _eq(ok, oko, "runs change doable")
+        _eq(s, so, "runs change scores")
+        r = instances.splitmix64_stream(40 + seed, 4000)
+        swaps = np.stack([r[:300] % np.uint64(inst.n_shifts), r[300:600] % np.uint64(inst.n_shifts)], axis=1).astype(np.int64)
+        s, ok = d.score_swap(swaps)
+        so, oko = o.score_swap(swaps)
+        _eq(ok, oko, "runs swap doable")
+        _eq(s, so, "runs swap scores")
+        n_c = 300
+        sizes = (r[600:600 + n_c] % np.uint64(5)).astype(np.int64) + 1
+        eo = np.concatenate([[0], np.cumsum(sizes)])
+        tot = int(eo[-1])
+        rr = instances.splitmix64_stream(41 + seed, 2 * tot)
+        ent = (rr[:tot] % np.uint64(inst.n_shifts)).astype(np.int64)
+        for i in range(1, tot, 2):                       # neighbouring days in one candidate
+            ent[i] = min(int(ent[i - 1]) + 3, inst.n_shifts - 1)
+        val = (rr[tot:] % np.uint64(3)).astype(np.int64) - 1
+        edits = np.stack([ent, val], axis=1)
+        s, ok = d.score_compound(eo, edits)
+        so, oko = o.score_compound(eo, edits)
+        _eq(ok, oko, "runs compound doable")
+        _eq(s, so, "runs compound scores")
+        for step in range(10):
+            last = d.calculate_score()
+            idx, best, ev, win = d.step_change(ForageParams(2, 1, 0), step_seeds=[90 + step],
+                                               ref_scores=np.concatenate([last, last + [0, -3]], axis=1), apply=True)
+            rows = o.enumerate_change()
+            so, oko = o.score_change(rows)
+            out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0] + [0, -3], 90 + step, 2, 1, True, 1)
+            if out[0]:
+                assert int(idx[0]) == out[1], f"step {step}"
+                o.apply_change(*rows[out[1]])
+            assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+            assert d.fresh_score()[0].tolist() == o.committed_score().tolist()

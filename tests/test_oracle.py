@@ -139,6 +139,14 @@ def test_shift_scheduling_invariant_and_unfairness():
                 hard -= 1
     counts = np.bincount(m[m >= 0], minlength=inst.n_nurses)
     soft = -int(np.abs(counts - inst.target).sum())
+    # Long work streaks (schedule.rs:43-58): per nurse, runs of consecutive worked days, excess over 2 days
+    for nurse in range(inst.n_nurses):
+        days = sorted(set(int(x) for x in inst.day[m == nurse]))
+        run = 0
+        for i, day in enumerate(days):
+            run = run + 1 if i > 0 and days[i - 1] + 1 == day else 1
+            if i + 1 == len(days) or days[i + 1] != day + 1:
+                soft -= max(0, run - 2)
     loads = {}
     for i in range(inst.n_shifts):
         if m[i] >= 0 and inst.hours[i] != 0:
