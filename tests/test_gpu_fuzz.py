@@ -74,8 +74,12 @@ def test_fuzz_nearby_change_and_swap_steps(seed):
 @pytest.mark.parametrize("seed", range(max(10, FUZZ // 3)))
 def test_fuzz_scalar_models(seed):
     s = [int(x) for x in splitmix64_stream(500 + seed, 8)]
-    which = s[0] % 3
-    if which == 0:
+    which = s[0] % 4
+    if which == 3:   # the shipped shift-scheduling example (keyed pairs, complemented count, consecutive runs)
+        sh = instances.shift_scheduling(n_days=3 + s[1] % 14, slots_per_day=1 + s[2] % 4, n_nurses=2 + s[3] % 6, seed=seed,
+                                        unassigned_permille=s[4] % 400)
+        o, d = Oracle.shift_scheduling(sh, with_load_balance=False), models.shift_scheduling_director(sh, with_load_balance=False)
+    elif which == 0:
         n = 20 + s[1] % 300
         g = instances.graph_coloring(n, min(n * (1 + s[2] % 6), n * (n - 1) // 2), 2 + s[3] % 9, seed_edges=seed,
                                      seed_colors=seed + 1, unassigned_permille=s[4] % 300)
