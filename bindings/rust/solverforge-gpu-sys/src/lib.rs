@@ -137,4 +137,5 @@ extern "C" {
     pub fn sfgpu_last_kernel_ns(ctx: *mut sfgpu_ctx, out_ns: *mut u64) -> i32;
     pub fn sfgpu_kernel_times_ns(ctx: *mut sfgpu_ctx, max_n: u32, out_ns: *mut u64, out_n: *mut u32) -> i32;
     pub fn sfgpu_launch_count(ctx: *mut sfgpu_ctx, out_count: *mut u64) -> i32;
+    pub fn sfgpu_scalar_program(ctx: *mut sfgpu_ctx, out_program: *mut i32) -> i32;
 }

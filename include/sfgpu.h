@@ -390,6 +390,11 @@ int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns);
 int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, uint32_t* out_n);
 /* number of kernels this context has launched since creation */
 int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count);
+/* Which scalar scoring program the committed model runs: >= 0 = index of the monomorphised kernel
+ * (the tuple of scalar constraint kinds has a template instantiation — the counterpart of the reference's
+ * monomorphised ConstraintSet tuples, solverforge-scoring/src/api/constraint_set/incremental.rs:339-408),
+ * -1 = the constraint-table interpreter (any program). Results are identical either way. */
+int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program);
 
 #ifdef __cplusplus
 }

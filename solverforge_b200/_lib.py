@@ -110,6 +110,7 @@ SYMBOLS = {
     "sfgpu_last_kernel_ns": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "sfgpu_kernel_times_ns": (C.c_int32, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
     "sfgpu_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "sfgpu_scalar_program": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

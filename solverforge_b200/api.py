@@ -476,6 +476,12 @@ class GpuScoreDirector:
     def synchronize(self):
         self._check(self.lib.sfgpu_synchronize(self.h))
 
+    def scalar_program(self) -> int:
+        """>= 0: the monomorphised scalar scoring kernel the model runs; -1: the interpreter."""
+        out = C.c_int32()
+        self._check(self.lib.sfgpu_scalar_program(self.h, C.byref(out)))
+        return out.value
+
 
 @dataclass
 class ForageParams:

@@ -78,6 +78,8 @@ struct sfgpu_ctx {
   bool nb_key32 = false;      // nearby keys fit 32 bits
   uint32_t nb_scan_bits = 24;
   bool force_generic = false;  // SFGPU_CTX_GENERIC_KERNELS: never take a specialised fast path (testing)
+  int spec_id = -1;            // monomorphised scalar program (sfgpu_spec.cuh), -1 = interpreter
+  SpecIdx spec_idx{{-1, -1, -1, -1}};
   // staging for host-pointer calls
   void* pin = nullptr;
   size_t pin_bytes = 0;
@@ -99,6 +101,41 @@ struct sfgpu_ctx {
 };
 
 namespace {
+
+// Monomorphised scalar programs: (sorted) kinds of the scalar constraints -> kernel instantiations.
+// The tuples of the reference's scalar examples (graph colouring, n-queens, job shop) and their prefixes.
+typedef void (*SpecScoreFn)(const DevModel, const SpecIdx, const uint64_t*, const uint32_t*, int64_t*, uint8_t*);
+typedef void (*SpecStepFn)(const DevModel, const ChangeStepArgs, const SpecIdx);
+struct SpecEntry {
+  int k[4];
+  SpecScoreFn score;
+  SpecStepFn step;
+};
+#define SPEC_ENTRY(a, b, c, d) \
+  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProg<a, b, c, d>> }
+#define U_ SFGPU_K_UNI
+#define C_ SFGPU_K_PAIR_CSR_EQUAL
+#define K_ SFGPU_K_PAIR_KEY_EQUAL
+#define G_ SFGPU_K_GROUP
+#define UC SPEC_K_UNI_CONST
+const SpecEntry g_spec[] = {  // kinds ascending; UC (uni without column / mask) sorts last
+    SPEC_ENTRY(U_, 0, 0, 0),   SPEC_ENTRY(UC, 0, 0, 0),    // unassigned only
+    SPEC_ENTRY(U_, C_, 0, 0),  SPEC_ENTRY(C_, UC, 0, 0),   // graph colouring
+    SPEC_ENTRY(U_, K_, 0, 0),  SPEC_ENTRY(K_, UC, 0, 0),
+    SPEC_ENTRY(U_, G_, 0, 0),  SPEC_ENTRY(G_, UC, 0, 0),
+    SPEC_ENTRY(U_, C_, G_, 0), SPEC_ENTRY(C_, G_, UC, 0),
+    SPEC_ENTRY(U_, K_, G_, 0), SPEC_ENTRY(K_, G_, UC, 0),  // job shop
+    SPEC_ENTRY(U_, K_, K_, 0), SPEC_ENTRY(K_, K_, UC, 0),
+    SPEC_ENTRY(U_, K_, K_, K_), SPEC_ENTRY(K_, K_, K_, UC),  // n-queens
+    SPEC_ENTRY(U_, K_, G_, G_), SPEC_ENTRY(K_, G_, G_, UC),
+    SPEC_ENTRY(U_, U_, K_, G_), SPEC_ENTRY(U_, K_, G_, UC),
+};
+#undef U_
+#undef C_
+#undef K_
+#undef G_
+#undef UC
+#undef SPEC_ENTRY
 
 thread_local std::string g_noctx_err;
 
@@ -808,11 +845,44 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
   if (ctx->staged) {
     int bytes = (int)dm.stage_bytes;
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(change_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(change_step_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
+  // monomorphised scalar program: every constraint that reacts to scalar edits must be one of the
+  // specialised kinds and the sorted tuple one of the instantiated ones; otherwise the interpreter
+  ctx->spec_id = -1;
+  if (ctx->staged && dm.n_values > 0 && !ctx->force_generic && !getenv("SFGPU_NO_SPEC")) {
+    std::vector<std::pair<int, int>> sc;  // (kind, index)
+    bool ok = true;
+    for (uint32_t k = 0; k < dm.n_cons; ++k) {
+      const ConsDev& c = dm.cons[k];
+      switch (c.kind) {
+        case SFGPU_K_UNI: sc.push_back({(!c.g0 && !c.g1) ? SPEC_K_UNI_CONST : SFGPU_K_UNI, (int)k}); break;
+        case SFGPU_K_PAIR_KEY_EQUAL: case SFGPU_K_GROUP: sc.push_back({c.kind, (int)k}); break;
+        case SFGPU_K_PAIR_CSR_EQUAL:
+          if (c.off0 == 0xFFFFFFFFu) ok = false;  // no retained partner-value counts
+          sc.push_back({c.kind, (int)k});
+          break;
+        case SFGPU_K_LOAD_BALANCE: case SFGPU_K_RUNS: case SFGPU_K_PROJECT_GROUP: ok = false; break;
+        default: break;  // list-only kinds do not react to scalar edits
+      }
+    }
+    if (ok && !sc.empty() && sc.size() <= 4) {
+      std::stable_sort(sc.begin(), sc.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+      int kinds[4] = {0, 0, 0, 0};
+      for (size_t i = 0; i < sc.size(); ++i) kinds[i] = sc[i].first;
+      for (size_t t = 0; t < sizeof(g_spec) / sizeof(g_spec[0]); ++t) {
+        if (memcmp(g_spec[t].k, kinds, sizeof(kinds)) != 0) continue;
+        ctx->spec_id = (int)t;
+        for (size_t i = 0; i < 4; ++i) ctx->spec_idx.k[i] = i < sc.size() ? sc[i].second : -1;
+        CU(cudaFuncSetAttribute((const void*)g_spec[t].score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+        CU(cudaFuncSetAttribute((const void*)g_spec[t].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+        break;
+      }
+    }
   }
   if (dm.fast_list && dm.fast_stage_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
     dm.fast_list = 0;
@@ -1044,7 +1114,12 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
   else                                                                                                         \
     score_list_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable)
   switch (kind) {
-    case SK_CHANGE: LAUNCH_SCALAR(MODE_CHANGE); break;
+    case SK_CHANGE:
+      if (ctx->spec_id >= 0)
+        g_spec[ctx->spec_id].score<<<grid, threads, smem, ctx->stream>>>(dm, ctx->spec_idx, d_offs, d_rows, d_scores, d_doable);
+      else
+        LAUNCH_SCALAR(MODE_CHANGE);
+      break;
     case SK_SWAP: LAUNCH_SCALAR(MODE_SWAP); break;
     case SK_COMPOUND: LAUNCH_SCALAR(MODE_COMPOUND); break;
     case SK_LIST_CHANGE:
@@ -1527,10 +1602,12 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     solve_prep_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s);
     if (scalar) {
       dim3 grid(c_chunks, R);
-      if (ctx->staged)
-        change_step_kernel<true><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, ca);
+      if (ctx->spec_id >= 0)
+        g_spec[ctx->spec_id].step<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, ca, ctx->spec_idx);
+      else if (ctx->staged)
+        change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, ca, ctx->spec_idx);
       else
-        change_step_kernel<false><<<grid, 256, 0, ctx->stream>>>(dm, ca);
+        change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, ca, ctx->spec_idx);
       change_finish_kernel<<<R, 256, 0, ctx->stream>>>(dm, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated,
                                                       s.winner_rows);
       apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, 0, s.winner_rows, nullptr, nullptr, nullptr);
@@ -1653,10 +1730,12 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
   a.partials = (ChunkPartial*)ctx->partials;
   dim3 grid(chunks, R);
   ev_begin(ctx);
-  if (ctx->staged)
-    change_step_kernel<true><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a);
+  if (ctx->spec_id >= 0)
+    g_spec[ctx->spec_id].step<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
+  else if (ctx->staged)
+    change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
   else
-    change_step_kernel<false><<<grid, 256, 0, ctx->stream>>>(dm, a);
+    change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx);
   ev_end(ctx);
   change_finish_kernel<<<R, 256, 0, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
   ctx->launches += 2;
@@ -1955,6 +2034,13 @@ int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, 
 int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count) {
   if (!ctx || !out_count) return SFGPU_E_INVALID;
   *out_count = ctx->launches;
+  return SFGPU_OK;
+}
+
+int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program) {
+  if (!ctx || !out_program) return SFGPU_E_INVALID;
+  if (!ctx->committed) return fail(ctx, SFGPU_E_STATE, "model not committed");
+  *out_program = ctx->spec_id;
   return SFGPU_OK;
 }
 

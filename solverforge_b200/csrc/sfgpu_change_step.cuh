@@ -9,6 +9,7 @@
 // the generic scalar_edit_delta (every scalar constraint kind) and keeps a forager partial.
 #pragma once
 #include "sfgpu_kernels.cuh"
+#include "sfgpu_spec.cuh"
 
 struct ChangeStepArgs {
   ForageDev f;
@@ -31,8 +32,11 @@ __device__ __forceinline__ uint32_t block_count_assigned(const int32_t* var, uin
   return tot;
 }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant__ DevModel m, const ChangeStepArgs a) {
+// PROG = the scoring program (sfgpu_spec.cuh): InterpProg for any constraint table, SpecProg<..> for the
+// monomorphised tuples.
+template <bool STAGED, class PROG>
+__global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant__ DevModel m, const ChangeStepArgs a,
+                                                          const SpecIdx idx) {
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t scratch[33];
@@ -48,6 +52,7 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
   const int32_t* var = (const int32_t*)(st + m.off_var);
   const int64_t* cs = (const int64_t*)(st + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
+  const PROG prog(m, idx, st, gblock);
   const uint32_t k = m.n_values, n = m.n_entities;
   const bool with_none = m.allows_unassigned != 0;
   int64_t lh = 0, ls = 0, th = 0, ts = 0;
@@ -95,9 +100,9 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
     for (uint32_t v = 0; v < n_cand; ++v) {
       const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
       const bool ok = nv != old;
-      Score2 d{0, 0};
-      if (ok) scalar_edit_delta(m, st, gblock, nullptr, 0, EditDev{e, old, nv}, d);
-      const int64_t oh = ok ? ch + d.hard : 0, os = ok ? csf + d.soft : 0;
+      int64_t dh, ds;
+      prog.delta(e, old, ok ? nv : old, dh, ds);  // null edit when not doable
+      const int64_t oh = ok ? ch + dh : 0, os = ok ? csf + ds : 0;
       if (a.out_rows) {
         const size_t q = (size_t)r * stride + base + v;
         ((uint2*)a.out_rows)[q] = make_uint2(e, (uint32_t)nv);
