@@ -24,10 +24,12 @@ struct SpecRoute {
     neg = c.sign < 0;
     hard = c.w.level == 0;
   }
+  // constraints whose delta is linear in the weight fold the impact sign into the weight once
+  __device__ __forceinline__ int64_t signed_weight(int64_t w) const { return neg ? -w : w; }
+  __device__ __forceinline__ int64_t apply_sign(int64_t v) const { return neg ? -v : v; }
+  // v already carries the impact sign
   __device__ __forceinline__ void add(int64_t& dh, int64_t& ds, int64_t v) const {
-    const int64_t sv = neg ? -v : v;
-    dh += hard ? sv : 0;
-    ds += hard ? 0 : sv;
+    if (hard) dh += v; else ds += v;
   }
 };
 
@@ -64,7 +66,7 @@ struct SpecCons<SFGPU_K_UNI> : SpecRoute {  // constraint/incremental.rs:97-156
   }
   __device__ __forceinline__ int64_t delta(uint32_t e, int32_t ov, int32_t nv) const {
     const bool out = mask && mask[e] == 0;
-    return contrib(e, nv, out) - contrib(e, ov, out);
+    return apply_sign(contrib(e, nv, out) - contrib(e, ov, out));
   }
 };
 
@@ -78,8 +80,8 @@ struct SpecCons<SPEC_K_UNI_CONST> : SpecRoute {
   __device__ __forceinline__ SpecCons(const DevModel& m, int k, const char*, const char*) {
     const ConsDev& c = m.cons[k];
     filt = (int32_t)c.p0;
-    w0 = weight_eval(c.w, 0);
     route_init(c);
+    w0 = signed_weight(weight_eval(c.w, 0));
   }
   __device__ __forceinline__ int64_t delta(uint32_t, int32_t ov, int32_t nv) const {
     // pass(v): filt 0 = unassigned, 1 = assigned, 2 = always
@@ -98,8 +100,8 @@ struct SpecCons<SFGPU_K_PAIR_CSR_EQUAL> : SpecRoute {  // retained partner-value
     const ConsDev& c = m.cons[idx];
     cc = (const uint16_t*)(gblock + c.off0);
     k = m.n_values;
-    a = c.w.a;
     route_init(c);
+    a = signed_weight(c.w.a);
   }
   __device__ __forceinline__ int64_t delta(uint32_t e, int32_t ov, int32_t nv) const {
     const uint16_t* row = cc + (size_t)e * k;
@@ -112,22 +114,23 @@ template <>
 struct SpecCons<SFGPU_K_PAIR_KEY_EQUAL> : SpecRoute {  // keyed self-join, per-key counts (staged)
   const int32_t* tab;
   const int64_t* col;
-  int64_t p0, p1, p2, a;
+  uint32_t p0, p1, p2;  // key arithmetic modulo 2^32: the final index lies in [0, table length)
+  int64_t a;
   __device__ __forceinline__ SpecCons(const DevModel& m, int idx, const char* st, const char*) {
     const ConsDev& c = m.cons[idx];
     tab = (const int32_t*)(st + c.off0);
     col = (const int64_t*)c.g0;
-    p0 = c.p0;
-    p1 = c.p1;
-    p2 = c.p2;
-    a = c.w.a;
+    p0 = (uint32_t)c.p0;
+    p1 = (uint32_t)c.p1;
+    p2 = (uint32_t)c.p2;
     route_init(c);
+    a = signed_weight(c.w.a);
   }
   __device__ __forceinline__ int64_t delta(uint32_t e, int32_t ov, int32_t nv) const {
-    const int64_t base = (col ? col[e] : 0) * p0 - p2;
-    const int64_t cn = nv >= 0 ? (int64_t)tab[base + (int64_t)nv * p1] : 0;
-    const int64_t co = ov >= 0 ? (int64_t)tab[base + (int64_t)ov * p1] - 1 : 0;
-    return (cn - co) * a;
+    const uint32_t base = (col ? (uint32_t)col[e] : 0u) * p0 - p2;
+    const int32_t cn = nv >= 0 ? tab[base + (uint32_t)nv * p1] : 0;
+    const int32_t co = ov >= 0 ? tab[base + (uint32_t)ov * p1] - 1 : 0;
+    return (int64_t)(cn - co) * a;
   }
 };
 
@@ -139,7 +142,7 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
   const int64_t* key_off;
   WeightDev w;
   bool complement;
-  int64_t dflt;
+  int64_t dflt, empty0;
   __device__ __forceinline__ SpecCons(const DevModel& m, int idx, const char* st, const char*) {
     const ConsDev& c = m.cons[idx];
     gc = (const int32_t*)(st + c.off0);
@@ -149,40 +152,46 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
     w = c.w;
     complement = (c.flags & SFGPU_CF_COMPLEMENT) != 0;
     dflt = c.p1;
+    empty0 = complement ? weight_eval(c.w, c.p1) : 0;
     route_init(c);
   }
   template <int FN>
-  __device__ __forceinline__ int64_t score(int64_t wb, int64_t count, int64_t sum) const {
+  __device__ __forceinline__ int64_t wfn(int64_t wb, int64_t x) const {
     WeightDev ww;
     ww.fn = FN;
     ww.a = w.a;
     ww.b = wb;
-    if (count > 0) return weight_eval(ww, col ? sum : count);
-    return complement ? weight_eval(ww, dflt) : 0;
+    return weight_eval(ww, x);
   }
+  // score of an empty group: the complement's default result, or nothing (grouped/state.rs:349-365)
+  template <int FN>
+  __device__ __forceinline__ int64_t empty(int64_t wb) const {
+    return key_off ? (complement ? wfn<FN>(wb, dflt) : 0) : empty0;
+  }
+  // e sits in group `ov`, so that group has count >= 1 before the edit; group `nv` has count >= 1 after it
   template <int FN>
   __device__ __forceinline__ int64_t delta_fn(uint32_t e, int32_t ov, int32_t nv) const {
     const int64_t x = col ? col[e] : 1;
     int64_t v = 0;
     if (ov >= 0) {
-      const int64_t cn = gc[ov], sm = gs[ov], wb = key_off ? key_off[ov] : w.b;
-      v += score<FN>(wb, cn - 1, sm - x) - score<FN>(wb, cn, sm);
+      const int64_t cn = gc[ov], sm = col ? gs[ov] : cn, wb = key_off ? key_off[ov] : w.b;
+      v += (cn > 1 ? wfn<FN>(wb, sm - x) : empty<FN>(wb)) - wfn<FN>(wb, sm);
     }
     if (nv >= 0) {
-      const int64_t cn = gc[nv], sm = gs[nv], wb = key_off ? key_off[nv] : w.b;
-      v += score<FN>(wb, cn + 1, sm + x) - score<FN>(wb, cn, sm);
+      const int64_t cn = gc[nv], sm = col ? gs[nv] : cn, wb = key_off ? key_off[nv] : w.b;
+      v += wfn<FN>(wb, sm + x) - (cn > 0 ? wfn<FN>(wb, sm) : empty<FN>(wb));
     }
     return v;
   }
   // one (warp-uniform) dispatch on the weight function per candidate instead of one per evaluation
   __device__ __forceinline__ int64_t delta(uint32_t e, int32_t ov, int32_t nv) const {
     switch (w.fn) {
-      case SFGPU_W_CONST: return delta_fn<SFGPU_W_CONST>(e, ov, nv);
-      case SFGPU_W_LINEAR: return delta_fn<SFGPU_W_LINEAR>(e, ov, nv);
-      case SFGPU_W_SQUARE: return delta_fn<SFGPU_W_SQUARE>(e, ov, nv);
-      case SFGPU_W_ABSDIFF: return delta_fn<SFGPU_W_ABSDIFF>(e, ov, nv);
-      case SFGPU_W_PAIRS: return delta_fn<SFGPU_W_PAIRS>(e, ov, nv);
-      default: return delta_fn<SFGPU_W_EXCESS>(e, ov, nv);
+      case SFGPU_W_CONST: return apply_sign(delta_fn<SFGPU_W_CONST>(e, ov, nv));
+      case SFGPU_W_LINEAR: return apply_sign(delta_fn<SFGPU_W_LINEAR>(e, ov, nv));
+      case SFGPU_W_SQUARE: return apply_sign(delta_fn<SFGPU_W_SQUARE>(e, ov, nv));
+      case SFGPU_W_ABSDIFF: return apply_sign(delta_fn<SFGPU_W_ABSDIFF>(e, ov, nv));
+      case SFGPU_W_PAIRS: return apply_sign(delta_fn<SFGPU_W_PAIRS>(e, ov, nv));
+      default: return apply_sign(delta_fn<SFGPU_W_EXCESS>(e, ov, nv));
     }
   }
 };
