@@ -222,6 +222,16 @@ int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candida
 int32_t sfgpu_score_list_reverse(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
                                  const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
 
+/* rows[n][4] = {src_entity, start | size << 24, dst_entity, dst_position}: SublistChangeMove relocates the
+ * contiguous segment [start, start + size) (heuristic/move/list_kernel/sublist_change.rs:17-125). For an
+ * intra-list move dst_position is a position of the list AFTER the removal. Doable iff size >= 1,
+ * start + size <= len(src), dst_position <= (intra ? len - size : len(dst)) and not (intra && dst_position ==
+ * start). Positions are limited to 2^24 and segment sizes to 255 by the packing (reference default: 1..=3,
+ * solverforge-config/src/move_selector.rs:713-715). SFGPU_SEG(start, size) packs the second word. */
+#define SFGPU_SEG(start, size) (((uint32_t)(start) & 0xFFFFFFu) | ((uint32_t)(size) << 24))
+int32_t sfgpu_score_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                                   const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
+
 /* ---- winner selection on device ------------------------------------------------------- */
 /* Per replica: replay of acceptor + forager over the scored rows in pull order
  * (phase/candidates.rs:66-282 with BestCandidate::consider, forager.rs:99-155).
@@ -357,9 +367,10 @@ int32_t sfgpu_apply_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, c
 int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 /* apply the winner found by sfgpu_argbest straight from the batch, no host round trip:
  * row = batch_rows[cand_offsets[r] + index[r]]; replicas with index == UINT32_MAX are skipped.
- * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse. All pointers are device pointers. */
+ * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse, 5 sublist change. All pointers are device pointers. */
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
                             const uint32_t* batch_rows, const uint32_t* index);
 

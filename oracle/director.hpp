@@ -9,6 +9,7 @@
 //   ListChangeMove           heuristic/move/list_kernel/change.rs:23-153
 //   ListSwapMove             heuristic/move/list_kernel/swap.rs:31-110
 //   ListReverseMove          heuristic/move/list_kernel/reverse.rs:21-58 (2-opt segment reversal)
+//   SublistChangeMove        heuristic/move/list_kernel/sublist_change.rs:17-125 + segment_layout.rs:49-75
 //   evaluate_candidate       phase/localsearch/evaluation.rs:20-115
 //   MoveStreamContext        heuristic/selector/move_selector/iter.rs:14-207
 //   ChangeMove order         heuristic/selector/move_selector/change.rs:66-104,246-307
@@ -92,9 +93,10 @@ struct ScalarEdit {  // planning/scalar/candidate.rs:6-12
 };
 
 struct Move {
-  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse } kind = Change;
+  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse, SublistChange } kind = Change;
   size_t desc = 0;
   size_t a = 0, b = 0, c = 0, d = 0;  // Change: a=entity; Swap: a,b; List*: a=src_e b=src_p c=dst_e d=dst_p
+  size_t e = 0;                       // SublistChange: a=src_e [b, c)=source range d=dst_e e=dst_position
   OptVal to;
   std::vector<ScalarEdit> edits;
   bool requires_hard_improvement = false;
@@ -113,6 +115,17 @@ struct Move {
     Move m; m.kind = ListReverse; m.desc = desc; m.a = entity; m.b = start; m.c = end; return m;
   }
 };
+
+// relocates the contiguous segment [start, end) of src_e to dst_e at dst_pos; for an intra-list move dst_pos is
+// a position of the list AFTER the removal (sublist_change.rs:17-49)
+inline Move move_sublist_change(size_t desc, size_t src_e, size_t start, size_t end, size_t dst_e, size_t dst_pos) {
+  Move m; m.kind = Move::SublistChange; m.desc = desc; m.a = src_e; m.b = start; m.c = end; m.d = dst_e; m.e = dst_pos;
+  return m;
+}
+// segment_layout.rs:49-75: the move that puts the segment back
+inline Move sublist_change_inverse(const Move& m) {
+  return move_sublist_change(m.desc, m.d, m.e, m.e + (m.c - m.b), m.a, m.b);
+}
 
 struct Undo {
   OptVal v0, v1;
@@ -157,6 +170,15 @@ bool is_doable(const Move& m, ScoreDirector<S, Sc>& dir) {
     }
     case Move::ListReverse:  // reverse.rs:21-33
       return m.c > m.b + 1 && m.c <= ac.list(s, m.desc, m.a).size();
+    case Move::SublistChange: {  // sublist_change.rs:17-49
+      if (m.b >= m.c) return false;
+      size_t src_len = ac.list(s, m.desc, m.a).size();
+      if (m.c > src_len) return false;
+      size_t dst_len = ac.list(s, m.desc, m.d).size();
+      size_t max_dst = m.a == m.d ? src_len - (m.c - m.b) : dst_len;
+      if (m.e > max_dst) return false;
+      return m.a != m.d || m.e != m.b;
+    }
   }
   return false;
 }
@@ -232,6 +254,19 @@ Undo do_move(const Move& m, ScoreDirector<S, Sc>& dir) {
       dir.after_variable_changed(m.desc, m.a);
       break;
     }
+    case Move::SublistChange: {  // sublist_change.rs:87-125: source notified first, then destination
+      bool intra = m.a == m.d;
+      dir.before_variable_changed(m.desc, m.a);
+      if (!intra) dir.before_variable_changed(m.desc, m.d);
+      auto& src = ac.list(s, m.desc, m.a);
+      std::vector<size_t> seg(src.begin() + (ptrdiff_t)m.b, src.begin() + (ptrdiff_t)m.c);
+      src.erase(src.begin() + (ptrdiff_t)m.b, src.begin() + (ptrdiff_t)m.c);
+      auto& dst = ac.list(s, m.desc, m.d);
+      dst.insert(dst.begin() + (ptrdiff_t)m.e, seg.begin(), seg.end());
+      dir.after_variable_changed(m.desc, m.a);
+      if (!intra) dir.after_variable_changed(m.desc, m.d);
+      break;
+    }
   }
   return u;
 }
@@ -279,6 +314,10 @@ void undo_move(const Move& m, ScoreDirector<S, Sc>& dir, const Undo& u) {
     case Move::ListSwap:     // a swap is its own inverse
     case Move::ListReverse: {  // so is a reversal
       do_move(m, dir);
+      break;
+    }
+    case Move::SublistChange: {  // sublist_change.rs:69-85: the inverse layout applied the same way
+      do_move(sublist_change_inverse(m), dir);
       break;
     }
   }
@@ -511,6 +550,54 @@ std::vector<Move> enumerate_list_reverse_moves(S& s, const Access<S>& ac, size_t
   }
   return out;
 }
+
+// heuristic/selector/sublist_change.rs:166-205 + list_kernel/sublist_change.rs:103-268 (SublistChangeCursor, no
+// owner restriction, no precedence graph): entities in stream order; per source every segment start (stream
+// order), every valid size min..=max (stream order); intra-list destinations over the post-removal list
+// (skipping the segment's own start) before the insertions into every other entity in entity order.
+template <class S>
+std::vector<Move> enumerate_sublist_change_moves(S& s, const Access<S>& ac, size_t desc, size_t min_size,
+                                                 size_t max_size, MoveStreamContext ctx) {
+  constexpr uint64_t ENTITY_SALT = 0x5B157C4A46E00001ull, START_SALT = 0x5B157C4A46E00002ull,
+                     SIZE_SALT = 0x5B157C4A46E00003ull, INTRA_SALT = 0x5B157C4A46E00004ull,
+                     INTER_SALT = 0x5B157C4A46E00005ull;
+  size_t n = ac.entity_count(s, desc);
+  std::vector<size_t> entities(n), lens(n);
+  for (size_t o = 0; o < n; ++o) {
+    size_t e = n <= 1 ? o : ctx.selection_index(o, n, ENTITY_SALT ^ (uint64_t)desc);
+    entities[o] = e;
+    lens[o] = ac.list(s, desc, e).size();
+  }
+  std::vector<Move> out;
+  for (size_t si = 0; si < n; ++si) {
+    const size_t se = entities[si], slen = lens[si];
+    if (slen < min_size) continue;
+    for (size_t so = 0; so < slen; ++so) {
+      const size_t start = ctx.selection_index(so, slen, START_SALT ^ (uint64_t)se ^ (uint64_t)desc);
+      const size_t max_valid = std::min(max_size, slen - start);
+      const size_t size_count = max_valid >= min_size ? max_valid - min_size + 1 : 0;
+      for (size_t zo = 0; zo < size_count; ++zo) {
+        const size_t size = min_size + ctx.selection_index(zo, size_count, SIZE_SALT ^ (uint64_t)se ^ (uint64_t)start);
+        const size_t end = start + size, post = slen - size;
+        for (size_t po = 0; po <= post; ++po) {
+          const size_t dp = ctx.selection_index(po, post + 1, INTRA_SALT ^ (uint64_t)se ^ (uint64_t)start);
+          if (dp == start) continue;
+          out.push_back(move_sublist_change(desc, se, start, end, se, dp));
+        }
+        for (size_t di = 0; di < n; ++di) {
+          if (di == si) continue;
+          const size_t de = entities[di], dlen = lens[di];
+          for (size_t po = 0; po <= dlen; ++po) {
+            const size_t dp = ctx.selection_index(po, dlen + 1, INTER_SALT ^ (uint64_t)se ^ (uint64_t)de ^ (uint64_t)start);
+            out.push_back(move_sublist_change(desc, se, start, end, de, dp));
+          }
+        }
+      }
+    }
+  }
+  return out;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Foragers (forager.rs). CandidateId = pull index.
@@ -894,6 +981,20 @@ TabuSignature tabu_signature(const Move& m, ScoreDirector<S, Sc>& dir, uint64_t 
       sig.move_id = {0xF000000000000004ull, (uint64_t)m.desc, variable_id, (uint64_t)m.a, (uint64_t)m.b, (uint64_t)m.c};
       sig.undo_move_id = sig.move_id;
       sig.entity_ids = {(uint64_t)m.a};
+      return sig;
+    }
+    case Move::SublistChange: {  // sublist_change.rs:127-196
+      const auto& l = ac.list(s, m.desc, m.a);
+      std::vector<uint64_t> moved;
+      for (size_t p = m.b; p < m.c && p < l.size(); ++p) moved.push_back((uint64_t)l[p]);
+      const Move inv = sublist_change_inverse(m);
+      sig.move_id = {(uint64_t)m.desc, variable_id, (uint64_t)m.a, (uint64_t)m.b, (uint64_t)m.c, (uint64_t)m.d, (uint64_t)m.e};
+      sig.undo_move_id = {(uint64_t)m.desc, variable_id, (uint64_t)inv.a, (uint64_t)inv.b, (uint64_t)inv.c, (uint64_t)inv.d, (uint64_t)inv.e};
+      sig.move_id.insert(sig.move_id.end(), moved.begin(), moved.end());
+      sig.undo_move_id.insert(sig.undo_move_id.end(), moved.begin(), moved.end());
+      sig.entity_ids = {(uint64_t)m.a};
+      if (m.a != m.d) sig.entity_ids.push_back((uint64_t)m.d);
+      sig.value_ids = moved;
       return sig;
     }
     default: throw std::logic_error("tabu_signature: move kind not restated");

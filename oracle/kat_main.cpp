@@ -770,6 +770,79 @@ static void kat_moves_and_loop() {
     CHECK(rv.size() == 3);
     for (size_t i = 0; i < 3 && i < rv.size(); ++i) CHECK(rv[i].a == 0 && rv[i].b == wantr[i][0] && rv[i].c == wantr[i][1]);
   }
+  {  // heuristic/move/tests/sublist_change.rs:80-266 (relocation forward / backward / inter-list, doability)
+     // heuristic/selector/tests/sublist_neighborhood.rs:133-187 (canonical segment order)
+    CvrpPlan p5;
+    p5.shared = pd;
+    p5.customers = plan.customers;
+    p5.routes = {{0, {1, 2, 3, 4, 5, 6}, pd.get()}, {1, {}, pd.get()}};
+    {
+      CvrpModel m5(p5);
+      const Move fwd = move_sublist_change(0, 0, 1, 3, 0, 4);
+      CHECK(is_doable(fwd, m5.dir));
+      const Sc before = m5.calculate_score();
+      auto ev = m5.evaluate(fwd);
+      CHECK(ev.kind == EvalKind::Scored);
+      CHECK(m5.calculate_score() == before);  // undo (inverse layout) restores list and cached score
+      CHECK((m5.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4, 5, 6}));
+      m5.apply(fwd);
+      CHECK((m5.dir.working.routes[0].visits == std::vector<size_t>{1, 4, 5, 6, 2, 3}));
+      CHECK(m5.calculate_score() == m5.fresh_score() && m5.calculate_score() == ev.score);
+      m5.apply(sublist_change_inverse(fwd));
+      CHECK((m5.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4, 5, 6}));
+      m5.apply(move_sublist_change(0, 0, 3, 5, 0, 1));  // backward
+      CHECK((m5.dir.working.routes[0].visits == std::vector<size_t>{1, 4, 5, 2, 3, 6}));
+      CHECK(m5.calculate_score() == m5.fresh_score());
+    }
+    {
+      CvrpPlan p6 = p5;
+      p6.routes = {{0, {1, 2, 3, 4}, pd.get()}, {1, {5, 6}, pd.get()}};
+      CvrpModel m6(p6);
+      const Move inter = move_sublist_change(0, 0, 1, 3, 1, 1);
+      CHECK(is_doable(inter, m6.dir));
+      auto ev = m6.evaluate(inter);
+      m6.apply(inter);
+      CHECK((m6.dir.working.routes[0].visits == std::vector<size_t>{1, 4}));
+      CHECK((m6.dir.working.routes[1].visits == std::vector<size_t>{5, 2, 3, 6}));
+      CHECK(m6.calculate_score() == m6.fresh_score() && m6.calculate_score() == ev.score);
+      m6.apply(sublist_change_inverse(inter));
+      CHECK((m6.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4}));
+      CHECK((m6.dir.working.routes[1].visits == std::vector<size_t>{5, 6}));
+      // tabu: the undo id of a move is the move id of its inverse (sublist_change.rs tests :270-378)
+      auto sg = m6.signature(inter);
+      m6.apply(inter);
+      auto rs = m6.signature(sublist_change_inverse(inter));
+      CHECK(sg.move_id != sg.undo_move_id && sg.undo_move_id == rs.move_id);
+    }
+    {
+      CvrpPlan p7 = p5;
+      p7.routes = {{0, {1, 2, 3}, pd.get()}};
+      CvrpModel m7(p7);
+      CHECK(!is_doable(move_sublist_change(0, 0, 2, 2, 0, 0), m7.dir));   // empty range
+      CHECK(!is_doable(move_sublist_change(0, 0, 1, 10, 0, 0), m7.dir));  // out of bounds
+      CvrpPlan p8 = p5;
+      p8.routes = {{0, {1, 2, 3, 4, 5}, pd.get()}};
+      CvrpModel m8(p8);
+      CHECK(!is_doable(move_sublist_change(0, 0, 1, 4, 0, 1), m8.dir));   // destination == source start
+      CHECK(!is_doable(move_sublist_change(0, 0, 1, 4, 0, 3), m8.dir));   // beyond the post-removal list
+      CHECK(is_doable(move_sublist_change(0, 0, 1, 4, 0, 2), m8.dir));
+    }
+    {
+      CvrpPlan p9 = p5;
+      p9.routes = {{0, {1, 2, 3}, pd.get()}, {1, {4, 5}, pd.get()}};
+      CvrpModel m9(p9);
+      auto sv = m9.enumerate_sublist_change(2, 2, {});
+      const size_t want[12][5] = {{0, 0, 2, 0, 1}, {0, 0, 2, 1, 0}, {0, 0, 2, 1, 1}, {0, 0, 2, 1, 2},
+                                  {0, 1, 3, 0, 0}, {0, 1, 3, 1, 0}, {0, 1, 3, 1, 1}, {0, 1, 3, 1, 2},
+                                  {1, 0, 2, 0, 0}, {1, 0, 2, 0, 1}, {1, 0, 2, 0, 2}, {1, 0, 2, 0, 3}};
+      CHECK(sv.size() == 12);
+      for (size_t i = 0; i < 12 && i < sv.size(); ++i) {
+        CHECK(sv[i].a == want[i][0] && sv[i].b == want[i][1] && sv[i].c == want[i][2] && sv[i].d == want[i][3] &&
+              sv[i].e == want[i][4]);
+        CHECK(is_doable(sv[i], m9.dir));  // sublist_neighborhood.rs:190-218
+      }
+    }
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

@@ -165,6 +165,18 @@ int sfo_score_list_reverse(void* h, uint64_t n, const uint32_t* e, const uint32_
   size_t d = static_cast<OracleModel*>(h)->list_desc();
   return score_batch(h, n, [&](uint64_t i) { return Move::list_reverse(d, e[i], start[i], end[i]); }, hard, soft, doable);
 }
+// SublistChangeMove rows {src_entity, start, end, dst_entity, dst_position} (heuristic/move/list_kernel/sublist_change.rs)
+int sfo_score_sublist_change(void* h, uint64_t n, const uint32_t* se, const uint32_t* start, const uint32_t* end,
+                             const uint32_t* de, const uint32_t* dp, int64_t* hard, int64_t* soft, uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->list_desc();
+  return score_batch(h, n, [&](uint64_t i) { return move_sublist_change(d, se[i], start[i], end[i], de[i], dp[i]); },
+                     hard, soft, doable);
+}
+int sfo_apply_sublist_change(void* h, uint32_t se, uint32_t start, uint32_t end, uint32_t de, uint32_t dp) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(move_sublist_change(m->list_desc(), se, start, end, de, dp));
+  return 0;
+}
 int sfo_apply_list_reverse(void* h, uint32_t e, uint32_t start, uint32_t end) {
   auto* m = static_cast<OracleModel*>(h);
   m->apply(Move::list_reverse(m->list_desc(), e, start, end));
@@ -225,6 +237,20 @@ int64_t sfo_enumerate_nearby_list_change(void* h, uint32_t max_nearby, uint64_t 
     sp[i] = (uint32_t)moves[i].b;
     de[i] = (uint32_t)moves[i].c;
     dp[i] = (uint32_t)moves[i].d;
+  }
+  return (int64_t)moves.size();
+}
+
+int64_t sfo_enumerate_sublist_change(void* h, uint32_t min_size, uint32_t max_size, uint64_t step_index,
+                                     uint64_t step_seed, int order, uint64_t cap, uint32_t* se, uint32_t* start,
+                                     uint32_t* end, uint32_t* de, uint32_t* dp) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_sublist_change(min_size, max_size, make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    se[i] = (uint32_t)moves[i].a;
+    start[i] = (uint32_t)moves[i].b;
+    end[i] = (uint32_t)moves[i].c;
+    de[i] = (uint32_t)moves[i].d;
+    dp[i] = (uint32_t)moves[i].e;
   }
   return (int64_t)moves.size();
 }

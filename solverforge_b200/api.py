@@ -265,6 +265,20 @@ class GpuScoreDirector:
             rows = np.concatenate([rows, np.zeros((len(rows), 1), dtype=np.int64)], axis=1)
         return self._score(self.lib.sfgpu_score_list_reverse, rows, 4, cand_offsets)
 
+    @staticmethod
+    def pack_sublist_change(rows) -> np.ndarray:
+        """(src_entity, start, end, dst_entity, dst_position) -> the 4-word device row
+        {src_entity, start | size << 24, dst_entity, dst_position} (SFGPU_SEG in sfgpu.h)."""
+        rows = np.asarray(rows).astype(np.int64).reshape(-1, 5)
+        size = rows[:, 2] - rows[:, 1]
+        if len(rows) and (size.min() < 0 or size.max() > 255 or rows[:, 1].max() >= 1 << 24):
+            raise L.SfgpuError(L.E_INVALID, "sublist segment outside the packed range (size 0..255, start < 2^24)")
+        return np.stack([rows[:, 0], rows[:, 1] | (size << 24), rows[:, 3], rows[:, 4]], axis=1)
+
+    def score_sublist_change(self, rows, cand_offsets=None):
+        """rows[n][5] = (src_entity, start, end, dst_entity, dst_position): SublistChangeMove."""
+        return self._score(self.lib.sfgpu_score_sublist_change, self.pack_sublist_change(rows), 4, cand_offsets)
+
     def score_compound(self, edit_offsets, edit_rows, cand_offsets=None):
         eo = np.ascontiguousarray(edit_offsets, dtype=np.uint64)
         rows = np.ascontiguousarray(np.asarray(edit_rows).astype(np.int64).astype(np.uint32)).reshape(-1, 2)
@@ -441,6 +455,10 @@ class GpuScoreDirector:
         if rows.shape[1] == 3:
             rows = np.concatenate([rows, np.zeros((self.R, 1), dtype=np.int64)], axis=1)
         self._apply(self.lib.sfgpu_apply_list_reverse, rows, 4, mask)
+
+    def apply_sublist_change(self, rows, mask=None):
+        """rows[R][5] = (src_entity, start, end, dst_entity, dst_position), one per replica."""
+        self._apply(self.lib.sfgpu_apply_sublist_change, self.pack_sublist_change(rows), 4, mask)
 
     # ---- state read-back ------------------------------------------------------------------
     def scalar_state(self) -> np.ndarray:

@@ -517,7 +517,70 @@ __device__ __forceinline__ bool list_reverse_delta(const DevModel& m, const char
   return true;
 }
 
-enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2 };
+// SublistChangeMove {src_entity, start | size << 24, dst_entity, dst_position}: relocates the contiguous segment
+// [start, start + size) (heuristic/move/list_kernel/sublist_change.rs:17-125). For an intra-list move the
+// destination is a position of the list AFTER the removal. The segment keeps its direction, so its inner legs
+// move with it; per-route sums change by the segment's total.
+#define SFGPU_SEG_POS(w) ((w) & 0xFFFFFFu)
+#define SFGPU_SEG_SIZE(w) ((w) >> 24)
+__device__ __forceinline__ bool list_sublist_change_delta(const DevModel& m, const char* st, uint4 row, Score2& d) {
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  d.hard = 0;
+  d.soft = 0;
+  const uint32_t se = row.x, start = SFGPU_SEG_POS(row.y), size = SFGPU_SEG_SIZE(row.y), de = row.z, dp = row.w;
+  if (se >= m.n_owners || de >= m.n_owners || size == 0) return false;
+  const uint32_t sb = off[se], slen = off[se + 1] - sb;
+  const uint32_t end = start + size;
+  if (end > slen) return false;
+  const bool intra = se == de;
+  const uint32_t db = off[de], dlen = off[de + 1] - db;
+  if (dp > (intra ? slen - size : dlen)) return false;
+  if (intra && dp == start) return false;
+  const uint32_t first = el[sb + start], last = el[sb + end - 1];
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind == SFGPU_K_LIST_PATH_COST) {
+      const uint32_t depot = (uint32_t)c.p0;
+      const uint32_t prev = start > 0 ? el[sb + start - 1] : depot;
+      const uint32_t next = end < slen ? el[sb + end] : depot;
+      const int64_t* rcost = (const int64_t*)(st + c.off0);
+      // closing the gap; a route emptied by the move costs 0 (no depot->depot leg)
+      const int64_t gap = -mat_at(c, prev, first) - mat_at(c, last, next) + (slen > size ? mat_at(c, prev, next) : 0);
+      if (intra) {
+        // neighbours of the insertion point in the post-removal list
+        const uint32_t ia = dp > 0 ? dp - 1 : 0, ib = dp;
+        const uint32_t a = dp > 0 ? el[sb + (ia < start ? ia : ia + size)] : depot;
+        const uint32_t b = dp < slen - size ? el[sb + (ib < start ? ib : ib + size)] : depot;
+        const int64_t ins = mat_at(c, a, first) + mat_at(c, last, b) - mat_at(c, a, b);
+        const int64_t oc = rcost[se];
+        add_level(d, c, weight_eval(c.w, oc + gap + ins) - weight_eval(c.w, oc));
+      } else {
+        int64_t inner = 0;
+        for (uint32_t i = start; i + 1 < end; ++i) inner += mat_at(c, el[sb + i], el[sb + i + 1]);
+        const uint32_t a = dp > 0 ? el[db + dp - 1] : depot;
+        const uint32_t b = dp < dlen ? el[db + dp] : depot;
+        const int64_t ins = mat_at(c, a, first) + mat_at(c, last, b) - (dlen > 0 ? mat_at(c, a, b) : 0);
+        const int64_t os = rcost[se], od = rcost[de];
+        add_level(d, c, weight_eval(c.w, os + gap - inner) - weight_eval(c.w, os) + weight_eval(c.w, od + ins + inner) -
+                            weight_eval(c.w, od));
+      }
+    } else if (c.kind == SFGPU_K_LIST_SUM) {
+      if (!intra) {
+        const int64_t* rsum = (const int64_t*)(st + c.off0);
+        int64_t v = 0;
+        for (uint32_t i = start; i < end; ++i) v += ((const int64_t*)c.g0)[el[sb + i]];
+        const int64_t ss = rsum[se], ds = rsum[de];
+        add_level(d, c, weight_eval(c.w, ss - v) - weight_eval(c.w, ss) + weight_eval(c.w, ds + v) -
+                            weight_eval(c.w, ds));
+      }
+    }
+    // EXISTS_FLAT: a relocation keeps the multiset of flattened keys => 0.
+  }
+  return true;
+}
+
+enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2, LMODE_SUBLIST_CHANGE = 3 };
 
 template <int LMODE, bool STAGED>
 __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__ DevModel m,
@@ -541,8 +604,11 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
        i += (uint64_t)gridDim.x * blockDim.x) {
     uint4 row = ((const uint4*)rows)[i];  // one 128-bit load per candidate
     Score2 d;
-    bool ok = LMODE == LMODE_CHANGE ? list_change_delta(m, st, row, d)
-                                    : (LMODE == LMODE_SWAP ? list_swap_delta(m, st, row, d) : list_reverse_delta(m, st, row, d));
+    bool ok = LMODE == LMODE_CHANGE
+                  ? list_change_delta(m, st, row, d)
+                  : (LMODE == LMODE_SWAP ? list_swap_delta(m, st, row, d)
+                                         : (LMODE == LMODE_REVERSE ? list_reverse_delta(m, st, row, d)
+                                                                   : list_sublist_change_delta(m, st, row, d)));
     longlong2 o;
     o.x = ok ? ch + d.hard : 0;
     o.y = ok ? csf + d.soft : 0;
@@ -1509,7 +1575,7 @@ __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind
   cs[1] += d.soft;
 }
 
-// kind 2 list change, 3 list swap. Dynamic smem: elem_cap uint32 (old element copy).
+// kind 2 list change, 3 list swap, 4 list reverse, 5 sublist change. Dynamic smem: elem_cap uint32 (old element copy).
 __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__ DevModel m, int kind,
                                                          const uint32_t* __restrict__ rows,
                                                          const uint8_t* __restrict__ mask,
@@ -1533,7 +1599,8 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     Score2 d;
     bool ok = kind == 2 ? list_change_delta(m, st, row, d)
-                        : (kind == 3 ? list_swap_delta(m, st, row, d) : list_reverse_delta(m, st, row, d));
+                        : (kind == 3 ? list_swap_delta(m, st, row, d)
+                                     : (kind == 4 ? list_reverse_delta(m, st, row, d) : list_sublist_change_delta(m, st, row, d)));
     s_ok = ok ? 1 : 0;
     if (ok && kind == 4) {  // a reversal keeps every per-route sum
       int64_t* cs = (int64_t*)(st + m.off_score);
@@ -1541,14 +1608,18 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
       cs[1] += d.soft;
     } else if (ok) {
       // retained per-route aggregates
-      const uint32_t e1 = row.x, p1 = row.y, e2 = row.z, p2 = row.w;
+      const uint32_t e1 = row.x, p1 = kind == 5 ? SFGPU_SEG_POS(row.y) : row.y, e2 = row.z, p2 = row.w;
       const uint32_t x1 = el[off[e1] + p1];
       for (uint32_t k = 0; k < m.n_cons; ++k) {
         const ConsDev& c = m.cons[k];
         if (c.kind == SFGPU_K_LIST_SUM && e1 != e2) {
           int64_t* rsum = (int64_t*)(st + c.off0);
           int64_t v1 = ((const int64_t*)c.g0)[x1];
-          if (kind == 2) {
+          if (kind == 5) {
+            for (uint32_t i = 1; i < SFGPU_SEG_SIZE(row.y); ++i) v1 += ((const int64_t*)c.g0)[el[off[e1] + p1 + i]];
+            rsum[e1] -= v1;
+            rsum[e2] += v1;
+          } else if (kind == 2) {
             rsum[e1] -= v1;
             rsum[e2] += v1;
           } else {
@@ -1575,25 +1646,27 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
       el[f2] = old_el[f1];
     }
   } else {
-    const uint32_t se = row.x, sp = row.y, de = row.z, dp = row.w;
+    // relocation of n consecutive elements (n = 1: ListChange, whose destination is given in pre-removal
+    // coordinates; a sublist change gives it in post-removal coordinates already)
+    const uint32_t se = row.x, sp = kind == 5 ? SFGPU_SEG_POS(row.y) : row.y, de = row.z, dp = row.w;
+    const uint32_t n = kind == 5 ? SFGPU_SEG_SIZE(row.y) : 1;
     const uint32_t S = off[se] + sp;
-    const uint32_t adj = (se == de && dp > sp) ? dp - 1 : dp;
-    const uint32_t T = off[de] - (de > se ? 1 : 0) + adj;  // insertion index in the post-removal array
-    const uint32_t x = old_el[S];
+    const uint32_t adj = (kind != 5 && se == de && dp > sp) ? dp - 1 : dp;
+    const uint32_t T = off[de] - (de > se ? n : 0) + adj;  // insertion index in the post-removal array
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
       uint32_t v;
-      if (i == T) v = x;
+      if (i >= T && i < T + n) v = old_el[S + (i - T)];
       else {
-        uint32_t j = i > T ? i - 1 : i;      // index in post-removal array
-        v = old_el[j < S ? j : j + 1];
+        uint32_t j = i >= T + n ? i - n : i;  // index in post-removal array
+        v = old_el[j < S ? j : j + n];
       }
       el[i] = v;
     }
     __syncthreads();
     for (uint32_t o = threadIdx.x; o <= m.n_owners; o += blockDim.x) {
       uint32_t v = off[o];
-      v = v - (o > se ? 1 : 0) + (o > de ? 1 : 0);
+      v = v - (o > se ? n : 0) + (o > de ? n : 0);
       // all reads of off[] above happened before this barrier-separated write phase
       off[o] = v;
     }

@@ -81,6 +81,13 @@ struct ListSwap {  // heuristic/move/list_kernel/swap.rs:16-30
 struct ListReverse {  // heuristic/move/list_kernel/reverse.rs:14-19: reverses [start, end) of one list
   uint32_t entity, start, end, reserved = 0;
 };
+// heuristic/move/sublist_change.rs: relocates [start, start + size) of source_entity to dest_entity at
+// dest_position (a position of the post-removal list when both entities are the same)
+struct SublistChange {
+  uint32_t source_entity, packed_segment, dest_entity, dest_position;
+  SublistChange(uint32_t se, uint32_t start, uint32_t end, uint32_t de, uint32_t dp)
+      : source_entity(se), packed_segment(SFGPU_SEG(start, end - start)), dest_entity(de), dest_position(dp) {}
+};
 // acceptor + forager of one fused device step (sfgpu_forage_params) and what it returns per replica
 struct StepParams {
   int acceptor = 0;            // 0 accept all, 1 > last, 2 >= last || >= threshold, 3 > last || >= threshold
@@ -459,6 +466,17 @@ class GpuScoreDirector {
   }
   void apply(const std::vector<ListReverse>& one_per_replica, const uint8_t* mask = nullptr) {
     check(sfgpu_apply_list_reverse(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
+  }
+  void score_candidates(const std::vector<SublistChange>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_sublist_change(ctx_, 0, batch.size(), cand_offsets.data(),
+                                     reinterpret_cast<const uint32_t*>(batch.data()),
+                                     reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void apply(const std::vector<SublistChange>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_sublist_change(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
   }
   // CompoundScalarMove batch: candidate i owns edits [edit_offsets[i], edit_offsets[i+1]) (compound_scalar.rs:289-319)
   void score_compound(const std::vector<uint64_t>& edit_offsets, const std::vector<ScalarEdit>& edits,

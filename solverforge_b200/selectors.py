@@ -201,6 +201,42 @@ def nearby_list_swap_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.nda
     return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint32)
 
 
+def sublist_change_rows(offsets: np.ndarray, min_size: int = 1, max_size: int = 3,
+                        ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0) -> np.ndarray:
+    """rows[n][5] = (src_entity, start, end, dst_entity, dst_position) in the pull order of
+    SublistChangeMoveSelector (heuristic/selector/sublist_change.rs:166-205, cursor
+    list_kernel/sublist_change.rs:103-268; defaults 1..=3 from solverforge-config move_selector.rs:713-715):
+    entities in stream order; per source every start, every valid size; intra-list destinations over the
+    post-removal list (skipping the segment's own start) before the insertions into the other entities."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    ents = [ctx.selection_index(o, n, 0x5B157C4A46E00001 ^ descriptor_index) if n > 1 else o for o in range(n)]
+    out = []
+    for si, se in enumerate(ents):
+        slen = int(lens[se])
+        if slen < min_size:
+            continue
+        for so in range(slen):
+            start = ctx.selection_index(so, slen, 0x5B157C4A46E00002 ^ se ^ descriptor_index)
+            max_valid = min(max_size, slen - start)
+            size_count = max_valid - min_size + 1 if max_valid >= min_size else 0
+            for zo in range(size_count):
+                size = min_size + ctx.selection_index(zo, size_count, 0x5B157C4A46E00003 ^ se ^ start)
+                end, post = start + size, slen - size
+                for po in range(post + 1):
+                    dp = ctx.selection_index(po, post + 1, 0x5B157C4A46E00004 ^ se ^ start)
+                    if dp != start:
+                        out.append((se, start, end, se, dp))
+                for di, de in enumerate(ents):
+                    if di == si:
+                        continue
+                    dlen = int(lens[de])
+                    for po in range(dlen + 1):
+                        out.append((se, start, end, de, ctx.selection_index(po, dlen + 1, 0x5B157C4A46E00005 ^ se ^ de ^ start)))
+    return np.array(out, dtype=np.uint32).reshape(-1, 5)
+
+
 def list_reverse_rows(offsets: np.ndarray, ctx: MoveStreamContext = MoveStreamContext(),
                       descriptor_index: int = 0) -> np.ndarray:
     """rows[n][4] = (entity, start, end, 0) uint32 in the pull order of ListReverseMoveSelector

@@ -690,6 +690,79 @@ def test_list_reverse_moves_match_oracle(asymmetric):
         assert best[0].tolist() == o.committed_score().tolist()
 
 
+@pytest.mark.parametrize("asymmetric", [False, True])
+def test_sublist_change_moves_match_oracle(asymmetric):
+    """SublistChangeMove (heuristic/move/list_kernel/sublist_change.rs): the whole neighbourhood (sizes 1..=3) in
+    the selector's order, intra-list moves in post-removal coordinates, emptied / empty routes, not-doable rows,
+    forager replay and committed winners tracked against the oracle."""
+    from solverforge_b200 import selectors
+    c = instances.cvrp(60, 7, seed=14)
+    if asymmetric:
+        r = instances.splitmix64_stream(6, c.dim * c.dim).reshape(c.dim, c.dim)
+        c.matrix = c.matrix + (r % np.uint64(9)).astype(np.int64)
+        np.fill_diagonal(c.matrix, 0)
+    offs, el = instances.perturb_routes(c, 9, 40)
+    # one short route (emptied by a size-2 move) and one empty route
+    lens = np.diff(offs).tolist()
+    o = Oracle.cvrp(c, offs, el)
+    d = models.cvrp_director(c, 1, offsets=offs[None, :], elems=el)
+    rows = selectors.sublist_change_rows(offs, 1, 3)
+    assert np.array_equal(rows, o.enumerate_sublist_change(1, 3))
+    s, ok = d.score_sublist_change(rows)
+    so, oko = o.score_sublist_change(rows)
+    _eq(ok, oko, "sublist change doable")
+    _eq(s, so, "sublist change scores")
+    assert ok.all()
+    # rows the reference rejects in is_doable (sublist_change.rs:17-49); entities stay valid for the oracle
+    L0 = lens[0]
+    bad = np.array([[0, 1, 1, 1, 0], [0, 0, L0 + 1, 1, 0], [0, 0, 2, 0, 0], [0, 0, 2, 0, L0 - 1], [0, 0, 1, 1, lens[1] + 1],
+                    [0, 1, 3, 0, 1]], dtype=np.int64)
+    sb, okb = d.score_sublist_change(bad)
+    sob, okob = o.score_sublist_change(bad)
+    _eq(okb, okob, "sublist change not-doable rows")
+    assert okb.tolist() == [0, 0, 0, 0, 0, 0]
+    sx, okx = d.score_sublist_change(np.array([[99, 0, 1, 0, 0], [0, 0, 1, 99, 0]]))
+    assert okx.tolist() == [0, 0]
+    for step in range(8):
+        rows = o.enumerate_sublist_change(1, 3)
+        so, oko = o.score_sublist_change(rows)
+        sg, okg = d.score_sublist_change(rows)
+        _eq(sg, so, f"sublist change scores step {step}")
+        _eq(okg, oko, f"sublist change doable step {step}")
+        last = d.calculate_score()
+        idx, best, ev = d.argbest(sg, okg, None, ForageParams(1, 1, 0), [90 + step], [np.concatenate([last[0], last[0]])])
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 90 + step, 2, 1, True, 0)
+        if not out[0]:
+            assert idx[0] == 0xFFFFFFFF
+            break
+        assert int(idx[0]) == out[1]
+        d.apply_sublist_change(rows[out[1]][None, :])
+        o.apply_sublist_change(*rows[out[1]])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
+        assert best[0].tolist() == o.committed_score().tolist()
+    # a forced inter-route relocation that empties a route, then one into the empty route
+    lo, le = d.list_state()
+    lens = np.diff(lo[0]).tolist()
+    short = int(np.argmin([x if x > 0 else 10 ** 9 for x in lens]))
+    if lens[short] <= 3:
+        other = (short + 1) % len(lens)
+        mv = np.array([[short, 0, lens[short], other, 0]])
+        sg, okg = d.score_sublist_change(mv)
+        so, oko = o.score_sublist_change(mv)
+        _eq(sg, so, "emptying move score")
+        d.apply_sublist_change(mv)
+        o.apply_sublist_change(*mv[0])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+        back = np.array([[other, 0, 2, short, 0]])
+        sg, okg = d.score_sublist_change(back)
+        so, oko = o.score_sublist_change(back)
+        _eq(sg, so, "move into the empty route")
+        d.apply_sublist_change(back)
+        o.apply_sublist_change(*back[0])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+
+
 def test_consecutive_runs_collector_matches_oracle():
     """group_by(nurse, consecutive_runs(day)) — "Long work streaks" of examples/minimal-shift-scheduling
     (stream/collector/runs.rs): change, swap and compound candidates (several shifts of one candidate landing

@@ -76,3 +76,22 @@ def test_list_reverse_order_matches_reference(order):
         want = o.enumerate_list_reverse(step_index, seed, order)
         got = selectors.list_reverse_rows(offs, MoveStreamContext(step_index, seed, order))
         assert np.array_equal(got, want), f"order={order} step={step_index}"
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_sublist_change_order_matches_reference(order):
+    """SublistChangeMoveSelector pull order (list_kernel/sublist_change.rs:103-268) incl. routes shorter than the
+    minimum segment and empty routes."""
+    c = instances.cvrp(40, 7, seed=4)
+    offs, el = instances.perturb_routes(c, 2, 25)
+    o = Oracle.cvrp(c, offs, el)
+    for (lo, hi) in ((1, 3), (2, 2), (3, 9)):
+        for step_index, seed in ((0, 0), (9, 4242)):
+            want = o.enumerate_sublist_change(lo, hi, step_index, seed, order)
+            got = selectors.sublist_change_rows(offs, lo, hi, MoveStreamContext(step_index, seed, order))
+            assert np.array_equal(got, want), f"order={order} step={step_index} sizes={lo}..{hi}"
+    # reference KAT (selector/tests/sublist_neighborhood.rs:133-187)
+    kat = selectors.sublist_change_rows(np.array([0, 3, 5]), 2, 2)
+    assert kat.tolist() == [[0, 0, 2, 0, 1], [0, 0, 2, 1, 0], [0, 0, 2, 1, 1], [0, 0, 2, 1, 2], [0, 1, 3, 0, 0],
+                            [0, 1, 3, 1, 0], [0, 1, 3, 1, 1], [0, 1, 3, 1, 2], [1, 0, 2, 0, 0], [1, 0, 2, 0, 1],
+                            [1, 0, 2, 0, 2], [1, 0, 2, 0, 3]]
