@@ -232,6 +232,12 @@ int32_t sfgpu_score_list_reverse(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_cand
 int32_t sfgpu_score_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
                                    const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
 
+/* rows[n][4] = {first_entity, start1 | size1 << 24, second_entity, start2 | size2 << 24}: SublistSwapMove
+ * exchanges two contiguous segments, sizes may differ (heuristic/move/list_kernel/sublist_swap.rs:17-170).
+ * Doable iff both sizes >= 1, both segments inside their lists and, inside one list, the segments do not overlap. */
+int32_t sfgpu_score_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
+
 /* ---- winner selection on device ------------------------------------------------------- */
 /* Per replica: replay of acceptor + forager over the scored rows in pull order
  * (phase/candidates.rs:66-282 with BestCandidate::consider, forager.rs:99-155).
@@ -368,9 +374,10 @@ int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* 
 int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 /* apply the winner found by sfgpu_argbest straight from the batch, no host round trip:
  * row = batch_rows[cand_offsets[r] + index[r]]; replicas with index == UINT32_MAX are skipped.
- * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse, 5 sublist change. All pointers are device pointers. */
+ * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap. All pointers are device pointers. */
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
                             const uint32_t* batch_rows, const uint32_t* index);
 

@@ -10,6 +10,7 @@
 //   ListSwapMove             heuristic/move/list_kernel/swap.rs:31-110
 //   ListReverseMove          heuristic/move/list_kernel/reverse.rs:21-58 (2-opt segment reversal)
 //   SublistChangeMove        heuristic/move/list_kernel/sublist_change.rs:17-125 + segment_layout.rs:49-75
+//   SublistSwapMove          heuristic/move/list_kernel/sublist_swap.rs:17-170 + segment_layout.rs:118-165
 //   evaluate_candidate       phase/localsearch/evaluation.rs:20-115
 //   MoveStreamContext        heuristic/selector/move_selector/iter.rs:14-207
 //   ChangeMove order         heuristic/selector/move_selector/change.rs:66-104,246-307
@@ -93,10 +94,11 @@ struct ScalarEdit {  // planning/scalar/candidate.rs:6-12
 };
 
 struct Move {
-  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse, SublistChange } kind = Change;
+  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse, SublistChange, SublistSwap } kind = Change;
   size_t desc = 0;
   size_t a = 0, b = 0, c = 0, d = 0;  // Change: a=entity; Swap: a,b; List*: a=src_e b=src_p c=dst_e d=dst_p
   size_t e = 0;                       // SublistChange: a=src_e [b, c)=source range d=dst_e e=dst_position
+  size_t f = 0;                       // SublistSwap: a=first_e [b, c)  d=second_e [e, f)
   OptVal to;
   std::vector<ScalarEdit> edits;
   bool requires_hard_improvement = false;
@@ -125,6 +127,19 @@ inline Move move_sublist_change(size_t desc, size_t src_e, size_t start, size_t 
 // segment_layout.rs:49-75: the move that puts the segment back
 inline Move sublist_change_inverse(const Move& m) {
   return move_sublist_change(m.desc, m.d, m.e, m.e + (m.c - m.b), m.a, m.b);
+}
+
+// exchanges the segments [s1, e1) of first_e and [s2, e2) of second_e (sublist_swap.rs:17-42)
+inline Move move_sublist_swap(size_t desc, size_t first_e, size_t s1, size_t e1, size_t second_e, size_t s2, size_t e2) {
+  Move m; m.kind = Move::SublistSwap; m.desc = desc; m.a = first_e; m.b = s1; m.c = e1; m.d = second_e; m.e = s2; m.f = e2;
+  return m;
+}
+// segment_layout.rs:118-165: where the two segments sit after the swap
+inline Move sublist_swap_inverse(const Move& m) {
+  const size_t l1 = m.c - m.b, l2 = m.f - m.e;
+  if (m.a != m.d) return move_sublist_swap(m.desc, m.a, m.b, m.b + l2, m.d, m.e, m.e + l1);
+  if (m.b < m.e) return move_sublist_swap(m.desc, m.a, m.b, m.b + l2, m.d, m.e - l1 + l2, m.e - l1 + l2 + l1);
+  return move_sublist_swap(m.desc, m.a, m.b - l2 + l1, m.b - l2 + l1 + l2, m.d, m.e, m.e + l1);
 }
 
 struct Undo {
@@ -178,6 +193,11 @@ bool is_doable(const Move& m, ScoreDirector<S, Sc>& dir) {
       size_t max_dst = m.a == m.d ? src_len - (m.c - m.b) : dst_len;
       if (m.e > max_dst) return false;
       return m.a != m.d || m.e != m.b;
+    }
+    case Move::SublistSwap: {  // sublist_swap.rs:17-42
+      if (m.b >= m.c || m.e >= m.f) return false;
+      if (m.c > ac.list(s, m.desc, m.a).size() || m.f > ac.list(s, m.desc, m.d).size()) return false;
+      return !(m.a == m.d && m.b < m.f && m.e < m.c);
     }
   }
   return false;
@@ -267,6 +287,36 @@ Undo do_move(const Move& m, ScoreDirector<S, Sc>& dir) {
       if (!intra) dir.after_variable_changed(m.desc, m.d);
       break;
     }
+    case Move::SublistSwap: {  // sublist_swap.rs:87-170
+      bool intra = m.a == m.d;
+      dir.before_variable_changed(m.desc, m.a);
+      if (!intra) dir.before_variable_changed(m.desc, m.d);
+      if (intra) {  // later segment out first, then the earlier; later elements go to the earlier start
+        auto& l = ac.list(s, m.desc, m.a);
+        const bool first_early = m.b <= m.e;
+        const size_t es = first_early ? m.b : m.e, ee = first_early ? m.c : m.f;
+        const size_t ls = first_early ? m.e : m.b, le = first_early ? m.f : m.c;
+        std::vector<size_t> late(l.begin() + (ptrdiff_t)ls, l.begin() + (ptrdiff_t)le);
+        l.erase(l.begin() + (ptrdiff_t)ls, l.begin() + (ptrdiff_t)le);
+        std::vector<size_t> early(l.begin() + (ptrdiff_t)es, l.begin() + (ptrdiff_t)ee);
+        l.erase(l.begin() + (ptrdiff_t)es, l.begin() + (ptrdiff_t)ee);
+        l.insert(l.begin() + (ptrdiff_t)es, late.begin(), late.end());
+        const size_t new_late = ls - early.size() + late.size();
+        l.insert(l.begin() + (ptrdiff_t)new_late, early.begin(), early.end());
+      } else {
+        auto& l1 = ac.list(s, m.desc, m.a);
+        auto& l2 = ac.list(s, m.desc, m.d);
+        std::vector<size_t> s1(l1.begin() + (ptrdiff_t)m.b, l1.begin() + (ptrdiff_t)m.c);
+        l1.erase(l1.begin() + (ptrdiff_t)m.b, l1.begin() + (ptrdiff_t)m.c);
+        std::vector<size_t> s2(l2.begin() + (ptrdiff_t)m.e, l2.begin() + (ptrdiff_t)m.f);
+        l2.erase(l2.begin() + (ptrdiff_t)m.e, l2.begin() + (ptrdiff_t)m.f);
+        l1.insert(l1.begin() + (ptrdiff_t)m.b, s2.begin(), s2.end());
+        l2.insert(l2.begin() + (ptrdiff_t)m.e, s1.begin(), s1.end());
+      }
+      dir.after_variable_changed(m.desc, m.a);
+      if (!intra) dir.after_variable_changed(m.desc, m.d);
+      break;
+    }
   }
   return u;
 }
@@ -318,6 +368,10 @@ void undo_move(const Move& m, ScoreDirector<S, Sc>& dir, const Undo& u) {
     }
     case Move::SublistChange: {  // sublist_change.rs:69-85: the inverse layout applied the same way
       do_move(sublist_change_inverse(m), dir);
+      break;
+    }
+    case Move::SublistSwap: {  // sublist_swap.rs:66-85
+      do_move(sublist_swap_inverse(m), dir);
       break;
     }
   }
@@ -548,6 +602,48 @@ std::vector<Move> enumerate_list_reverse_moves(S& s, const Access<S>& ac, size_t
       }
     }
   }
+  return out;
+}
+
+// heuristic/selector/sublist_swap.rs:160-190 + list_kernel/sublist_swap.rs:28-318 (SublistSwapCursor, no owner
+// restriction, no precedence graph): first segments in entity / start / size stream order; second segments from
+// the same entity onwards (entity order); inside one list only segments starting at or after the first one's end.
+template <class S>
+std::vector<Move> enumerate_sublist_swap_moves(S& s, const Access<S>& ac, size_t desc, size_t min_size, size_t max_size,
+                                               MoveStreamContext ctx) {
+  constexpr uint64_t ENTITY_SALT = 0x5B1575A090000001ull, START_SALT = 0x5B1575A090000002ull,
+                     SIZE_SALT = 0x5B1575A090000003ull;
+  size_t n = ac.entity_count(s, desc);
+  std::vector<size_t> entities(n), lens(n);
+  for (size_t o = 0; o < n; ++o) {
+    size_t e = n <= 1 ? o : ctx.selection_index(o, n, ENTITY_SALT ^ (uint64_t)desc);
+    entities[o] = e;
+    lens[o] = ac.list(s, desc, e).size();
+  }
+  auto segments = [&](size_t idx) {  // SublistSegmentCursor
+    std::vector<std::pair<size_t, size_t>> out;
+    const size_t e = entities[idx], len = lens[idx];
+    if (len < min_size) return out;
+    for (size_t so = 0; so < len; ++so) {
+      const size_t start = ctx.selection_index(so, len, START_SALT ^ (uint64_t)e ^ (uint64_t)desc);
+      const size_t max_valid = std::min(max_size, len - start);
+      if (max_valid < min_size) continue;
+      const size_t count = max_valid - min_size + 1;
+      for (size_t zo = 0; zo < count; ++zo)
+        out.push_back({start, start + min_size + ctx.selection_index(zo, count, SIZE_SALT ^ (uint64_t)e ^ (uint64_t)start)});
+    }
+    return out;
+  };
+  std::vector<std::vector<std::pair<size_t, size_t>>> segs(n);
+  for (size_t i = 0; i < n; ++i) segs[i] = segments(i);
+  std::vector<Move> out;
+  for (size_t fi = 0; fi < n; ++fi)
+    for (auto& first : segs[fi])
+      for (size_t si = fi; si < n; ++si)
+        for (auto& second : segs[si]) {
+          if (fi == si && (second.first < first.second || (first == second))) continue;
+          out.push_back(move_sublist_swap(desc, entities[fi], first.first, first.second, entities[si], second.first, second.second));
+        }
   return out;
 }
 
@@ -995,6 +1091,25 @@ TabuSignature tabu_signature(const Move& m, ScoreDirector<S, Sc>& dir, uint64_t 
       sig.entity_ids = {(uint64_t)m.a};
       if (m.a != m.d) sig.entity_ids.push_back((uint64_t)m.d);
       sig.value_ids = moved;
+      return sig;
+    }
+    case Move::SublistSwap: {  // sublist_swap.rs:172-253
+      const auto& l1 = ac.list(s, m.desc, m.a);
+      const auto& l2 = ac.list(s, m.desc, m.d);
+      std::vector<uint64_t> v1, v2;
+      for (size_t p = m.b; p < m.c && p < l1.size(); ++p) v1.push_back((uint64_t)l1[p]);
+      for (size_t p = m.e; p < m.f && p < l2.size(); ++p) v2.push_back((uint64_t)l2[p]);
+      const Move inv = sublist_swap_inverse(m);
+      sig.move_id = {(uint64_t)m.desc, variable_id, (uint64_t)m.a, (uint64_t)m.b, (uint64_t)m.c, (uint64_t)m.d, (uint64_t)m.e, (uint64_t)m.f};
+      sig.undo_move_id = {(uint64_t)m.desc, variable_id, (uint64_t)inv.a, (uint64_t)inv.b, (uint64_t)inv.c, (uint64_t)inv.d, (uint64_t)inv.e, (uint64_t)inv.f};
+      sig.move_id.insert(sig.move_id.end(), v1.begin(), v1.end());
+      sig.move_id.insert(sig.move_id.end(), v2.begin(), v2.end());
+      sig.undo_move_id.insert(sig.undo_move_id.end(), v2.begin(), v2.end());
+      sig.undo_move_id.insert(sig.undo_move_id.end(), v1.begin(), v1.end());
+      sig.entity_ids = {(uint64_t)m.a};
+      if (m.a != m.d) sig.entity_ids.push_back((uint64_t)m.d);
+      sig.value_ids = v1;
+      sig.value_ids.insert(sig.value_ids.end(), v2.begin(), v2.end());
       return sig;
     }
     default: throw std::logic_error("tabu_signature: move kind not restated");

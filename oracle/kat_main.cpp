@@ -843,6 +843,80 @@ static void kat_moves_and_loop() {
       }
     }
   }
+  {  // heuristic/move/tests/sublist_swap.rs:80-236 (inter / intra exchange, doability), :238-350 (unequal lengths:
+     // the undo id is the move id of the inverse layout); selector/tests/sublist_neighborhood.rs:315-364
+    CvrpPlan q;
+    q.shared = pd;
+    q.customers = plan.customers;
+    q.routes = {{0, {1, 2, 3, 4}, pd.get()}, {1, {5, 6, 7}, pd.get()}};
+    {
+      CvrpModel m(q);
+      const Move sw = move_sublist_swap(0, 0, 1, 3, 1, 0, 2);
+      CHECK(is_doable(sw, m.dir));
+      const Sc before = m.calculate_score();
+      auto ev = m.evaluate(sw);
+      CHECK(ev.kind == EvalKind::Scored && m.calculate_score() == before);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4}));
+      m.apply(sw);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 5, 6, 4}));
+      CHECK((m.dir.working.routes[1].visits == std::vector<size_t>{2, 3, 7}));
+      CHECK(m.calculate_score() == m.fresh_score() && m.calculate_score() == ev.score);
+      m.apply(sublist_swap_inverse(sw));
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4}));
+      CHECK((m.dir.working.routes[1].visits == std::vector<size_t>{5, 6, 7}));
+      // unequal lengths across lists
+      const Move un = move_sublist_swap(0, 0, 1, 2, 1, 0, 3);
+      auto sg = m.signature(un);
+      auto evu = m.evaluate(un);
+      m.apply(un);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 5, 6, 7, 3, 4}));
+      CHECK((m.dir.working.routes[1].visits == std::vector<size_t>{2}));
+      CHECK(m.calculate_score() == m.fresh_score() && m.calculate_score() == evu.score);
+      auto rs = m.signature(sublist_swap_inverse(un));
+      CHECK(sg.move_id != sg.undo_move_id && sg.undo_move_id == rs.move_id);
+    }
+    {
+      CvrpPlan q2 = q;
+      q2.routes = {{0, {1, 2, 3, 4, 5, 6, 7, 8}, pd.get()}};
+      CvrpModel m(q2);
+      const Move sw = move_sublist_swap(0, 0, 1, 3, 0, 5, 7);
+      CHECK(is_doable(sw, m.dir));
+      auto ev = m.evaluate(sw);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4, 5, 6, 7, 8}));
+      m.apply(sw);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 6, 7, 4, 5, 2, 3, 8}));
+      CHECK(m.calculate_score() == m.fresh_score() && m.calculate_score() == ev.score);
+      m.apply(sublist_swap_inverse(sw));
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4, 5, 6, 7, 8}));
+      // unequal lengths inside one list, later segment given first
+      const Move un = move_sublist_swap(0, 0, 5, 8, 0, 1, 3);
+      auto sg = m.signature(un);
+      auto evu = m.evaluate(un);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4, 5, 6, 7, 8}));
+      m.apply(un);
+      CHECK((m.dir.working.routes[0].visits == std::vector<size_t>{1, 6, 7, 8, 4, 5, 2, 3}));
+      CHECK(m.calculate_score() == m.fresh_score() && m.calculate_score() == evu.score);
+      auto rs = m.signature(sublist_swap_inverse(un));
+      CHECK(sg.undo_move_id == rs.move_id);
+      CHECK(!is_doable(move_sublist_swap(0, 0, 1, 4, 0, 2, 5), m.dir));   // overlapping
+      CHECK(!is_doable(move_sublist_swap(0, 0, 1, 1, 0, 2, 3), m.dir));   // empty range
+      CHECK(!is_doable(move_sublist_swap(0, 0, 0, 2, 0, 2, 10), m.dir));  // out of bounds
+    }
+    {
+      CvrpPlan q3 = q;
+      q3.routes = {{0, {1, 2, 3, 4}, pd.get()}, {1, {5, 6, 7}, pd.get()}};
+      CvrpModel m(q3);
+      auto sv = m.enumerate_sublist_swap(2, 2, {});
+      const size_t want[7][6] = {{0, 0, 2, 0, 2, 4}, {0, 0, 2, 1, 0, 2}, {0, 0, 2, 1, 1, 3}, {0, 1, 3, 1, 0, 2},
+                                 {0, 1, 3, 1, 1, 3}, {0, 2, 4, 1, 0, 2}, {0, 2, 4, 1, 1, 3}};
+      CHECK(sv.size() == 7);
+      for (size_t i = 0; i < 7 && i < sv.size(); ++i) {
+        CHECK(sv[i].a == want[i][0] && sv[i].b == want[i][1] && sv[i].c == want[i][2] && sv[i].d == want[i][3] &&
+              sv[i].e == want[i][4] && sv[i].f == want[i][5]);
+        CHECK(is_doable(sv[i], m.dir));
+      }
+    }
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

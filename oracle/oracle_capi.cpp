@@ -177,6 +177,19 @@ int sfo_apply_sublist_change(void* h, uint32_t se, uint32_t start, uint32_t end,
   m->apply(move_sublist_change(m->list_desc(), se, start, end, de, dp));
   return 0;
 }
+// SublistSwapMove rows {first_entity, start1, end1, second_entity, start2, end2} (heuristic/move/list_kernel/sublist_swap.rs)
+int sfo_score_sublist_swap(void* h, uint64_t n, const uint32_t* e1, const uint32_t* s1, const uint32_t* t1,
+                           const uint32_t* e2, const uint32_t* s2, const uint32_t* t2, int64_t* hard, int64_t* soft,
+                           uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->list_desc();
+  return score_batch(h, n, [&](uint64_t i) { return move_sublist_swap(d, e1[i], s1[i], t1[i], e2[i], s2[i], t2[i]); },
+                     hard, soft, doable);
+}
+int sfo_apply_sublist_swap(void* h, uint32_t e1, uint32_t s1, uint32_t t1, uint32_t e2, uint32_t s2, uint32_t t2) {
+  auto* m = static_cast<OracleModel*>(h);
+  m->apply(move_sublist_swap(m->list_desc(), e1, s1, t1, e2, s2, t2));
+  return 0;
+}
 int sfo_apply_list_reverse(void* h, uint32_t e, uint32_t start, uint32_t end) {
   auto* m = static_cast<OracleModel*>(h);
   m->apply(Move::list_reverse(m->list_desc(), e, start, end));
@@ -251,6 +264,21 @@ int64_t sfo_enumerate_sublist_change(void* h, uint32_t min_size, uint32_t max_si
     end[i] = (uint32_t)moves[i].c;
     de[i] = (uint32_t)moves[i].d;
     dp[i] = (uint32_t)moves[i].e;
+  }
+  return (int64_t)moves.size();
+}
+
+int64_t sfo_enumerate_sublist_swap(void* h, uint32_t min_size, uint32_t max_size, uint64_t step_index, uint64_t step_seed,
+                                   int order, uint64_t cap, uint32_t* e1, uint32_t* s1, uint32_t* t1, uint32_t* e2,
+                                   uint32_t* s2, uint32_t* t2) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_sublist_swap(min_size, max_size, make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    e1[i] = (uint32_t)moves[i].a;
+    s1[i] = (uint32_t)moves[i].b;
+    t1[i] = (uint32_t)moves[i].c;
+    e2[i] = (uint32_t)moves[i].d;
+    s2[i] = (uint32_t)moves[i].e;
+    t2[i] = (uint32_t)moves[i].f;
   }
   return (int64_t)moves.size();
 }

@@ -84,6 +84,7 @@ SYMBOLS = {
     "sfgpu_score_list_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
     "sfgpu_score_list_reverse": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
     "sfgpu_score_sublist_change": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
+    "sfgpu_score_sublist_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
     "sfgpu_argbest": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     "sfgpu_argbest_gated": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sfgpu_step_list_change": (C.c_int32, [_P, C.c_uint64, _P, _P, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P,
@@ -102,6 +103,7 @@ SYMBOLS = {
     "sfgpu_apply_list_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_list_reverse": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_sublist_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_apply_sublist_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_winners": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
     "sfgpu_committed_scores": (C.c_int32, [_P, _P]),
     "sfgpu_evaluate_all": (C.c_int32, [_P, _P]),

@@ -279,6 +279,20 @@ class GpuScoreDirector:
         """rows[n][5] = (src_entity, start, end, dst_entity, dst_position): SublistChangeMove."""
         return self._score(self.lib.sfgpu_score_sublist_change, self.pack_sublist_change(rows), 4, cand_offsets)
 
+    @staticmethod
+    def pack_sublist_swap(rows) -> np.ndarray:
+        """(first_entity, start1, end1, second_entity, start2, end2) -> {e1, start1 | size1 << 24, e2, start2 | size2 << 24}."""
+        rows = np.asarray(rows).astype(np.int64).reshape(-1, 6)
+        n1, n2 = rows[:, 2] - rows[:, 1], rows[:, 5] - rows[:, 4]
+        if len(rows) and (min(n1.min(), n2.min()) < 0 or max(n1.max(), n2.max()) > 255 or
+                          max(rows[:, 1].max(), rows[:, 4].max()) >= 1 << 24):
+            raise L.SfgpuError(L.E_INVALID, "sublist segment outside the packed range (size 0..255, start < 2^24)")
+        return np.stack([rows[:, 0], rows[:, 1] | (n1 << 24), rows[:, 3], rows[:, 4] | (n2 << 24)], axis=1)
+
+    def score_sublist_swap(self, rows, cand_offsets=None):
+        """rows[n][6] = (first_entity, start1, end1, second_entity, start2, end2): SublistSwapMove."""
+        return self._score(self.lib.sfgpu_score_sublist_swap, self.pack_sublist_swap(rows), 4, cand_offsets)
+
     def score_compound(self, edit_offsets, edit_rows, cand_offsets=None):
         eo = np.ascontiguousarray(edit_offsets, dtype=np.uint64)
         rows = np.ascontiguousarray(np.asarray(edit_rows).astype(np.int64).astype(np.uint32)).reshape(-1, 2)
@@ -459,6 +473,10 @@ class GpuScoreDirector:
     def apply_sublist_change(self, rows, mask=None):
         """rows[R][5] = (src_entity, start, end, dst_entity, dst_position), one per replica."""
         self._apply(self.lib.sfgpu_apply_sublist_change, self.pack_sublist_change(rows), 4, mask)
+
+    def apply_sublist_swap(self, rows, mask=None):
+        """rows[R][6] = (first_entity, start1, end1, second_entity, start2, end2), one per replica."""
+        self._apply(self.lib.sfgpu_apply_sublist_swap, self.pack_sublist_swap(rows), 4, mask)
 
     # ---- state read-back ------------------------------------------------------------------
     def scalar_state(self) -> np.ndarray:

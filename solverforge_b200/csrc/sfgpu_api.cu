@@ -1089,7 +1089,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
 // ------------------------------------------------------------------------------------------
 namespace {
 
-enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP, SK_LIST_REVERSE, SK_SUBLIST_CHANGE };
+enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP, SK_LIST_REVERSE, SK_SUBLIST_CHANGE, SK_SUBLIST_SWAP };
 
 // forage != nullptr (fast list path only): the kernel also emits per-chunk forager partials into
 // forage->partials and *out_chunks receives the chunk count the finishing kernel needs.
@@ -1172,6 +1172,7 @@ int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_
     case SK_LIST_SWAP: LAUNCH_LIST(LMODE_SWAP); break;
     case SK_LIST_REVERSE: LAUNCH_LIST(LMODE_REVERSE); break;
     case SK_SUBLIST_CHANGE: LAUNCH_LIST(LMODE_SUBLIST_CHANGE); break;
+    case SK_SUBLIST_SWAP: LAUNCH_LIST(LMODE_SUBLIST_SWAP); break;
   }
   ev_end(ctx);
   ctx->launches++;
@@ -1293,6 +1294,10 @@ int32_t sfgpu_score_list_reverse(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_cand
 int32_t sfgpu_score_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
                                    const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
   return score_entry(ctx, SK_SUBLIST_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+}
+int32_t sfgpu_score_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
+  return score_entry(ctx, SK_SUBLIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1918,9 +1923,12 @@ int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t*
 int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
   return apply_entry(ctx, 5, flags, rows, mask, nullptr, nullptr);
 }
+int32_t sfgpu_apply_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+  return apply_entry(ctx, 6, flags, rows, mask, nullptr, nullptr);
+}
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
                             const uint32_t* batch_rows, const uint32_t* index) {
-  if (move_kind < 0 || move_kind > 5) return fail(ctx, SFGPU_E_INVALID, "bad move kind");
+  if (move_kind < 0 || move_kind > 6) return fail(ctx, SFGPU_E_INVALID, "bad move kind");
   if (!cand_offsets || !index) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   return apply_entry(ctx, move_kind, SFGPU_DEVICE_IO, batch_rows, nullptr, cand_offsets, index);
 }

@@ -580,7 +580,72 @@ __device__ __forceinline__ bool list_sublist_change_delta(const DevModel& m, con
   return true;
 }
 
-enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2, LMODE_SUBLIST_CHANGE = 3 };
+// SublistSwapMove {first_entity, start1 | size1 << 24, second_entity, start2 | size2 << 24}: exchanges two
+// contiguous segments, possibly of different sizes (heuristic/move/list_kernel/sublist_swap.rs:17-170). Inside
+// one list the segments must not overlap. Both segments keep their direction.
+__device__ __forceinline__ bool list_sublist_swap_delta(const DevModel& m, const char* st, uint4 row, Score2& d) {
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  d.hard = 0;
+  d.soft = 0;
+  const uint32_t e1 = row.x, s1 = SFGPU_SEG_POS(row.y), n1 = SFGPU_SEG_SIZE(row.y);
+  const uint32_t e2 = row.z, s2 = SFGPU_SEG_POS(row.w), n2 = SFGPU_SEG_SIZE(row.w);
+  if (e1 >= m.n_owners || e2 >= m.n_owners || n1 == 0 || n2 == 0) return false;
+  const uint32_t b1 = off[e1], len1 = off[e1 + 1] - b1;
+  const uint32_t b2 = off[e2], len2 = off[e2 + 1] - b2;
+  const uint32_t t1 = s1 + n1, t2 = s2 + n2;
+  if (t1 > len1 || t2 > len2) return false;
+  const bool intra = e1 == e2;
+  if (intra && s1 < t2 && s2 < t1) return false;
+  for (uint32_t k = 0; k < m.n_cons; ++k) {
+    const ConsDev& c = m.cons[k];
+    if (c.kind == SFGPU_K_LIST_PATH_COST) {
+      const uint32_t depot = (uint32_t)c.p0;
+      const int64_t* rcost = (const int64_t*)(st + c.off0);
+      if (intra) {
+        // early segment E = [es, et), late segment L = [ls, lt), gap M = [et, ls) (may be empty)
+        const bool first_early = s1 < s2;
+        const uint32_t es = first_early ? s1 : s2, et = first_early ? t1 : t2;
+        const uint32_t ls = first_early ? s2 : s1, lt = first_early ? t2 : t1;
+        const uint32_t pE = es > 0 ? el[b1 + es - 1] : depot, nL = lt < len1 ? el[b1 + lt] : depot;
+        const uint32_t fE = el[b1 + es], lE = el[b1 + et - 1], fL = el[b1 + ls], lL = el[b1 + lt - 1];
+        int64_t delta = mat_at(c, pE, fL) + mat_at(c, lE, nL) - mat_at(c, pE, fE) - mat_at(c, lL, nL);
+        if (et == ls) {
+          delta += mat_at(c, lL, fE) - mat_at(c, lE, fL);
+        } else {
+          const uint32_t m0 = el[b1 + et], mk = el[b1 + ls - 1];
+          delta += mat_at(c, lL, m0) + mat_at(c, mk, fE) - mat_at(c, lE, m0) - mat_at(c, mk, fL);
+        }
+        const int64_t oc = rcost[e1];
+        add_level(d, c, weight_eval(c.w, oc + delta) - weight_eval(c.w, oc));
+      } else {
+        const uint32_t p1 = s1 > 0 ? el[b1 + s1 - 1] : depot, x1 = t1 < len1 ? el[b1 + t1] : depot;
+        const uint32_t p2 = s2 > 0 ? el[b2 + s2 - 1] : depot, x2 = t2 < len2 ? el[b2 + t2] : depot;
+        const uint32_t f1 = el[b1 + s1], l1 = el[b1 + t1 - 1], f2 = el[b2 + s2], l2 = el[b2 + t2 - 1];
+        int64_t in1 = 0, in2 = 0;
+        for (uint32_t i = s1; i + 1 < t1; ++i) in1 += mat_at(c, el[b1 + i], el[b1 + i + 1]);
+        for (uint32_t i = s2; i + 1 < t2; ++i) in2 += mat_at(c, el[b2 + i], el[b2 + i + 1]);
+        const int64_t d1 = mat_at(c, p1, f2) + mat_at(c, l2, x1) + in2 - mat_at(c, p1, f1) - mat_at(c, l1, x1) - in1;
+        const int64_t d2 = mat_at(c, p2, f1) + mat_at(c, l1, x2) + in1 - mat_at(c, p2, f2) - mat_at(c, l2, x2) - in2;
+        const int64_t o1 = rcost[e1], o2 = rcost[e2];
+        add_level(d, c, weight_eval(c.w, o1 + d1) - weight_eval(c.w, o1) + weight_eval(c.w, o2 + d2) - weight_eval(c.w, o2));
+      }
+    } else if (c.kind == SFGPU_K_LIST_SUM) {
+      if (!intra) {
+        const int64_t* rsum = (const int64_t*)(st + c.off0);
+        int64_t v1 = 0, v2 = 0;
+        for (uint32_t i = s1; i < t1; ++i) v1 += ((const int64_t*)c.g0)[el[b1 + i]];
+        for (uint32_t i = s2; i < t2; ++i) v2 += ((const int64_t*)c.g0)[el[b2 + i]];
+        const int64_t a1 = rsum[e1], a2 = rsum[e2];
+        add_level(d, c, weight_eval(c.w, a1 - v1 + v2) - weight_eval(c.w, a1) + weight_eval(c.w, a2 - v2 + v1) -
+                            weight_eval(c.w, a2));
+      }
+    }
+  }
+  return true;
+}
+
+enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2, LMODE_SUBLIST_CHANGE = 3, LMODE_SUBLIST_SWAP = 4 };
 
 template <int LMODE, bool STAGED>
 __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__ DevModel m,
@@ -607,8 +672,10 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
     bool ok = LMODE == LMODE_CHANGE
                   ? list_change_delta(m, st, row, d)
                   : (LMODE == LMODE_SWAP ? list_swap_delta(m, st, row, d)
-                                         : (LMODE == LMODE_REVERSE ? list_reverse_delta(m, st, row, d)
-                                                                   : list_sublist_change_delta(m, st, row, d)));
+                                         : (LMODE == LMODE_REVERSE
+                                                ? list_reverse_delta(m, st, row, d)
+                                                : (LMODE == LMODE_SUBLIST_CHANGE ? list_sublist_change_delta(m, st, row, d)
+                                                                                 : list_sublist_swap_delta(m, st, row, d))));
     longlong2 o;
     o.x = ok ? ch + d.hard : 0;
     o.y = ok ? csf + d.soft : 0;
@@ -1575,7 +1642,7 @@ __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind
   cs[1] += d.soft;
 }
 
-// kind 2 list change, 3 list swap, 4 list reverse, 5 sublist change. Dynamic smem: elem_cap uint32 (old element copy).
+// kind 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap. Dynamic smem: elem_cap uint32 (old element copy).
 __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__ DevModel m, int kind,
                                                          const uint32_t* __restrict__ rows,
                                                          const uint8_t* __restrict__ mask,
@@ -1600,7 +1667,9 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
     Score2 d;
     bool ok = kind == 2 ? list_change_delta(m, st, row, d)
                         : (kind == 3 ? list_swap_delta(m, st, row, d)
-                                     : (kind == 4 ? list_reverse_delta(m, st, row, d) : list_sublist_change_delta(m, st, row, d)));
+                                     : (kind == 4 ? list_reverse_delta(m, st, row, d)
+                                                  : (kind == 5 ? list_sublist_change_delta(m, st, row, d)
+                                                               : list_sublist_swap_delta(m, st, row, d))));
     s_ok = ok ? 1 : 0;
     if (ok && kind == 4) {  // a reversal keeps every per-route sum
       int64_t* cs = (int64_t*)(st + m.off_score);
@@ -1608,7 +1677,7 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
       cs[1] += d.soft;
     } else if (ok) {
       // retained per-route aggregates
-      const uint32_t e1 = row.x, p1 = kind == 5 ? SFGPU_SEG_POS(row.y) : row.y, e2 = row.z, p2 = row.w;
+      const uint32_t e1 = row.x, p1 = kind >= 5 ? SFGPU_SEG_POS(row.y) : row.y, e2 = row.z, p2 = row.w;
       const uint32_t x1 = el[off[e1] + p1];
       for (uint32_t k = 0; k < m.n_cons; ++k) {
         const ConsDev& c = m.cons[k];
@@ -1619,6 +1688,12 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
             for (uint32_t i = 1; i < SFGPU_SEG_SIZE(row.y); ++i) v1 += ((const int64_t*)c.g0)[el[off[e1] + p1 + i]];
             rsum[e1] -= v1;
             rsum[e2] += v1;
+          } else if (kind == 6) {
+            for (uint32_t i = 1; i < SFGPU_SEG_SIZE(row.y); ++i) v1 += ((const int64_t*)c.g0)[el[off[e1] + p1 + i]];
+            int64_t v2 = 0;
+            for (uint32_t i = 0; i < SFGPU_SEG_SIZE(row.w); ++i) v2 += ((const int64_t*)c.g0)[el[off[e2] + SFGPU_SEG_POS(row.w) + i]];
+            rsum[e1] += v2 - v1;
+            rsum[e2] += v1 - v2;
           } else if (kind == 2) {
             rsum[e1] -= v1;
             rsum[e2] += v1;
@@ -1639,6 +1714,27 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   if (kind == 4) {
     const uint32_t b = off[row.x];
     for (uint32_t i = row.y + threadIdx.x; i < row.z; i += blockDim.x) el[b + i] = old_el[b + row.y + (row.z - 1 - i)];
+  } else if (kind == 6) {
+    // routes are contiguous in the flat element array, so both the intra- and the inter-list exchange are a swap
+    // of two disjoint flat segments: [.. Ea) late [Ea + ne, La) early [La + nl ..)
+    const uint32_t A = off[row.x] + SFGPU_SEG_POS(row.y), nA = SFGPU_SEG_SIZE(row.y);
+    const uint32_t B = off[row.z] + SFGPU_SEG_POS(row.w), nB = SFGPU_SEG_SIZE(row.w);
+    const bool a_early = A < B;
+    const uint32_t Ea = a_early ? A : B, ne = a_early ? nA : nB, La = a_early ? B : A, nl = a_early ? nB : nA;
+    const uint32_t oe = a_early ? row.x : row.z, ol = a_early ? row.z : row.x;  // owners of the early / late segment
+    const uint32_t mid = La - Ea - ne;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+      uint32_t v;
+      if (i < Ea || i >= La + nl) v = old_el[i];
+      else if (i < Ea + nl) v = old_el[La + (i - Ea)];
+      else if (i < Ea + nl + mid) v = old_el[Ea + ne + (i - Ea - nl)];
+      else v = old_el[Ea + (i - Ea - nl - mid)];
+      el[i] = v;
+    }
+    __syncthreads();
+    for (uint32_t o = threadIdx.x; o <= m.n_owners; o += blockDim.x)
+      if (o > oe && o <= ol) off[o] = off[o] + nl - ne;
   } else if (kind == 3) {
     if (threadIdx.x == 0) {
       uint32_t f1 = off[row.x] + row.y, f2 = off[row.z] + row.w;

@@ -88,6 +88,12 @@ struct SublistChange {
   SublistChange(uint32_t se, uint32_t start, uint32_t end, uint32_t de, uint32_t dp)
       : source_entity(se), packed_segment(SFGPU_SEG(start, end - start)), dest_entity(de), dest_position(dp) {}
 };
+// heuristic/move/sublist_swap.rs: exchanges [first_start, first_end) and [second_start, second_end)
+struct SublistSwap {
+  uint32_t first_entity, packed_first, second_entity, packed_second;
+  SublistSwap(uint32_t e1, uint32_t s1, uint32_t t1, uint32_t e2, uint32_t s2, uint32_t t2)
+      : first_entity(e1), packed_first(SFGPU_SEG(s1, t1 - s1)), second_entity(e2), packed_second(SFGPU_SEG(s2, t2 - s2)) {}
+};
 // acceptor + forager of one fused device step (sfgpu_forage_params) and what it returns per replica
 struct StepParams {
   int acceptor = 0;            // 0 accept all, 1 > last, 2 >= last || >= threshold, 3 > last || >= threshold
@@ -477,6 +483,17 @@ class GpuScoreDirector {
   }
   void apply(const std::vector<SublistChange>& one_per_replica, const uint8_t* mask = nullptr) {
     check(sfgpu_apply_sublist_change(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
+  }
+  void score_candidates(const std::vector<SublistSwap>& batch, const std::vector<uint64_t>& cand_offsets,
+                        std::vector<HardSoftScore>& scores, std::vector<uint8_t>& doable) {
+    scores.resize(batch.size());
+    doable.resize(batch.size());
+    check(sfgpu_score_sublist_swap(ctx_, 0, batch.size(), cand_offsets.data(),
+                                   reinterpret_cast<const uint32_t*>(batch.data()),
+                                   reinterpret_cast<int64_t*>(scores.data()), doable.data()));
+  }
+  void apply(const std::vector<SublistSwap>& one_per_replica, const uint8_t* mask = nullptr) {
+    check(sfgpu_apply_sublist_swap(ctx_, 0, reinterpret_cast<const uint32_t*>(one_per_replica.data()), mask));
   }
   // CompoundScalarMove batch: candidate i owns edits [edit_offsets[i], edit_offsets[i+1]) (compound_scalar.rs:289-319)
   void score_compound(const std::vector<uint64_t>& edit_offsets, const std::vector<ScalarEdit>& edits,

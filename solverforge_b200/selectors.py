@@ -237,6 +237,44 @@ def sublist_change_rows(offsets: np.ndarray, min_size: int = 1, max_size: int = 
     return np.array(out, dtype=np.uint32).reshape(-1, 5)
 
 
+def sublist_swap_rows(offsets: np.ndarray, min_size: int = 1, max_size: int = 3,
+                      ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0) -> np.ndarray:
+    """rows[n][6] = (first_entity, start1, end1, second_entity, start2, end2) in the pull order of
+    SublistSwapMoveSelector (heuristic/selector/sublist_swap.rs, cursor list_kernel/sublist_swap.rs:28-318): first
+    segments in entity / start / size stream order; second segments from the same entity onwards; inside one list
+    only segments that start at or after the end of the first one."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    ents = [ctx.selection_index(o, n, 0x5B1575A090000001 ^ descriptor_index) if n > 1 else o for o in range(n)]
+
+    def segments(e):
+        ln = int(lens[e])
+        out = []
+        if ln < min_size:
+            return out
+        for so in range(ln):
+            start = ctx.selection_index(so, ln, 0x5B1575A090000002 ^ e ^ descriptor_index)
+            max_valid = min(max_size, ln - start)
+            if max_valid < min_size:
+                continue
+            count = max_valid - min_size + 1
+            for zo in range(count):
+                out.append((start, start + min_size + ctx.selection_index(zo, count, 0x5B1575A090000003 ^ e ^ start)))
+        return out
+
+    segs = [segments(e) for e in ents]
+    out = []
+    for fi in range(n):
+        for (s1, t1) in segs[fi]:
+            for si in range(fi, n):
+                for (s2, t2) in segs[si]:
+                    if fi == si and (s2 < t1 or (s1, t1) == (s2, t2)):
+                        continue
+                    out.append((ents[fi], s1, t1, ents[si], s2, t2))
+    return np.array(out, dtype=np.uint32).reshape(-1, 6)
+
+
 def list_reverse_rows(offsets: np.ndarray, ctx: MoveStreamContext = MoveStreamContext(),
                       descriptor_index: int = 0) -> np.ndarray:
     """rows[n][4] = (entity, start, end, 0) uint32 in the pull order of ListReverseMoveSelector

@@ -72,6 +72,11 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_sublist_change.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int,
                                                    C.c_uint64, _P, _P, _P, _P, _P]
         l.sfo_enumerate_sublist_change.restype = C.c_int64
+        l.sfo_score_sublist_swap.argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P]
+        l.sfo_apply_sublist_swap.argtypes = [_P] + [C.c_uint32] * 6
+        l.sfo_enumerate_sublist_swap.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int,
+                                                 C.c_uint64, _P, _P, _P, _P, _P, _P]
+        l.sfo_enumerate_sublist_swap.restype = C.c_int64
         l.sfo_replay_step_gated.argtypes = [C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64,
                                             C.c_int, C.c_int, _P]
         l.sfo_acceptor_create.restype = _P
@@ -223,6 +228,24 @@ class Oracle:
         c = [np.zeros(n, dtype=np.uint32) for _ in range(5)]
         self.l.sfo_enumerate_sublist_change(self.h, min_size, max_size, step_index, step_seed, order, n, _p(c[0]),
                                             _p(c[1]), _p(c[2]), _p(c[3]), _p(c[4]))
+        return np.stack(c, axis=1)
+
+    def score_sublist_swap(self, rows):
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 6)
+        c = [_u32(rows[:, i]) for i in range(6)]
+        h, s, d = self._out(len(rows))
+        self.l.sfo_score_sublist_swap(self.h, len(rows), *[_p(x) for x in c], _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
+
+    def apply_sublist_swap(self, e1, s1, t1, e2, s2, t2):
+        self.l.sfo_apply_sublist_swap(self.h, int(e1), int(s1), int(t1), int(e2), int(s2), int(t2))
+
+    def enumerate_sublist_swap(self, min_size=1, max_size=3, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_sublist_swap(self.h, min_size, max_size, step_index, step_seed, order, 0, None, None,
+                                              None, None, None, None)
+        c = [np.zeros(n, dtype=np.uint32) for _ in range(6)]
+        self.l.sfo_enumerate_sublist_swap(self.h, min_size, max_size, step_index, step_seed, order, n,
+                                          *[_p(x) for x in c])
         return np.stack(c, axis=1)
 
     def apply_list_reverse(self, e, start, end, *_):

@@ -763,6 +763,76 @@ def test_sublist_change_moves_match_oracle(asymmetric):
         assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
 
 
+@pytest.mark.parametrize("asymmetric", [False, True])
+def test_sublist_swap_moves_match_oracle(asymmetric):
+    """SublistSwapMove (heuristic/move/list_kernel/sublist_swap.rs): the whole neighbourhood (sizes 1..=3, unequal
+    sizes, adjacent and distant segments inside one list, segments at route ends), rows given late-segment-first,
+    not-doable rows, forager replay and committed winners tracked against the oracle."""
+    from solverforge_b200 import selectors
+    c = instances.cvrp(44, 6, seed=15)
+    if asymmetric:
+        r = instances.splitmix64_stream(7, c.dim * c.dim).reshape(c.dim, c.dim)
+        c.matrix = c.matrix + (r % np.uint64(9)).astype(np.int64)
+        np.fill_diagonal(c.matrix, 0)
+    offs, el = instances.perturb_routes(c, 10, 30)
+    lens = np.diff(offs).tolist()
+    o = Oracle.cvrp(c, offs, el)
+    d = models.cvrp_director(c, 1, offsets=offs[None, :], elems=el)
+    rows = selectors.sublist_swap_rows(offs, 1, 3)
+    assert np.array_equal(rows, o.enumerate_sublist_swap(1, 3))
+    s, ok = d.score_sublist_swap(rows)
+    so, oko = o.score_sublist_swap(rows)
+    _eq(ok, oko, "sublist swap doable")
+    _eq(s, so, "sublist swap scores")
+    assert ok.all()
+    # the same moves with the two segments exchanged in the row (later segment first): same scores
+    flipped = rows[:, [3, 4, 5, 0, 1, 2]]
+    sf, okf = d.score_sublist_swap(flipped)
+    _eq(sf, so, "flipped sublist swap scores")
+    sof, okof = o.score_sublist_swap(flipped[:2000])
+    _eq(sof, so[:2000], "oracle agrees on flipped rows")
+    L0 = lens[0]
+    bad = np.array([[0, 1, 4, 0, 2, 5], [0, 1, 1, 0, 2, 3], [0, 0, 2, 0, 2, L0 + 1], [0, 0, 2, 1, 0, lens[1] + 1],
+                    [0, 0, 3, 0, 2, 4], [0, 2, 4, 0, 2, 4]], dtype=np.int64)
+    sb, okb = d.score_sublist_swap(bad)
+    sob, okob = o.score_sublist_swap(bad)
+    _eq(okb, okob, "sublist swap not-doable rows")
+    assert okb.tolist() == [0, 0, 0, 0, 0, 0]
+    assert d.score_sublist_swap(np.array([[99, 0, 1, 0, 0, 1], [0, 0, 1, 99, 0, 1]]))[1].tolist() == [0, 0]
+    for step in range(8):
+        rows = o.enumerate_sublist_swap(1, 3)
+        so, oko = o.score_sublist_swap(rows)
+        sg, okg = d.score_sublist_swap(rows)
+        _eq(sg, so, f"sublist swap scores step {step}")
+        last = d.calculate_score()
+        idx, best, ev = d.argbest(sg, okg, None, ForageParams(1, 1, 0), [110 + step], [np.concatenate([last[0], last[0]])])
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 110 + step, 2, 1, True, 0)
+        if not out[0]:
+            assert idx[0] == 0xFFFFFFFF
+            break
+        assert int(idx[0]) == out[1]
+        mv = rows[out[1]] if step % 2 == 0 else rows[out[1]][[3, 4, 5, 0, 1, 2]]
+        d.apply_sublist_swap(mv[None, :])
+        o.apply_sublist_swap(*mv)
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
+        assert best[0].tolist() == o.committed_score().tolist()
+    # forced unequal exchanges (not necessarily improving): inter-list 3 <-> 1 and intra-list 1 <-> 3 with a gap
+    lo, le = d.list_state()
+    lens = np.diff(lo[0]).tolist()
+    big = [i for i, x in enumerate(lens) if x >= 6]
+    for mv in ([big[0], 0, 3, big[1], lens[big[1]] - 1, lens[big[1]]], [big[0], 0, 1, big[0], 2, 5],
+               [big[1], 3, 5, big[1], 0, 3]):
+        mv = np.array(mv)
+        sg, okg = d.score_sublist_swap(mv[None, :])
+        so, oko = o.score_sublist_swap(mv[None, :])
+        _eq(sg, so, f"forced swap {mv.tolist()}")
+        assert okg[0] == 1
+        d.apply_sublist_swap(mv[None, :])
+        o.apply_sublist_swap(*mv)
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+
+
 def test_consecutive_runs_collector_matches_oracle():
     """group_by(nurse, consecutive_runs(day)) — "Long work streaks" of examples/minimal-shift-scheduling
     (stream/collector/runs.rs): change, swap and compound candidates (several shifts of one candidate landing

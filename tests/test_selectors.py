@@ -95,3 +95,20 @@ def test_sublist_change_order_matches_reference(order):
     assert kat.tolist() == [[0, 0, 2, 0, 1], [0, 0, 2, 1, 0], [0, 0, 2, 1, 1], [0, 0, 2, 1, 2], [0, 1, 3, 0, 0],
                             [0, 1, 3, 1, 0], [0, 1, 3, 1, 1], [0, 1, 3, 1, 2], [1, 0, 2, 0, 0], [1, 0, 2, 0, 1],
                             [1, 0, 2, 0, 2], [1, 0, 2, 0, 3]]
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_sublist_swap_order_matches_reference(order):
+    """SublistSwapMoveSelector pull order (list_kernel/sublist_swap.rs:28-318)."""
+    c = instances.cvrp(36, 6, seed=5)
+    offs, el = instances.perturb_routes(c, 3, 25)
+    o = Oracle.cvrp(c, offs, el)
+    for (lo, hi) in ((1, 3), (2, 2), (4, 9)):
+        for step_index, seed in ((0, 0), (9, 4242)):
+            want = o.enumerate_sublist_swap(lo, hi, step_index, seed, order)
+            got = selectors.sublist_swap_rows(offs, lo, hi, MoveStreamContext(step_index, seed, order))
+            assert np.array_equal(got, want), f"order={order} step={step_index} sizes={lo}..{hi}"
+    # reference KAT (selector/tests/sublist_neighborhood.rs:315-364)
+    kat = selectors.sublist_swap_rows(np.array([0, 4, 7]), 2, 2)
+    assert kat.tolist() == [[0, 0, 2, 0, 2, 4], [0, 0, 2, 1, 0, 2], [0, 0, 2, 1, 1, 3], [0, 1, 3, 1, 0, 2],
+                            [0, 1, 3, 1, 1, 3], [0, 2, 4, 1, 0, 2], [0, 2, 4, 1, 1, 3]]
