@@ -121,7 +121,10 @@ typedef struct sfgpu_weight {
 #define SFGPU_K_PAIR_CSR_EQUAL 2
 /* for_each(E).join(E, equal(key)).filter(l.id < r.id && var.is_some()); key(e) = column[e]*p0 + var[e]*p1
  *   keyed self-join, constraint/nary_incremental/bi.rs:78-206 (and the keyed form of predicate joins)
- *   aux0: key column id or UINT32_MAX (column = 0); weight must be CONST */
+ *   aux0: key column id or UINT32_MAX (column = 0); weight must be CONST;
+ *   aux1: join arity — UINT32_MAX / 0 / 2 = pairs; 3, 4, 5 = the keyed tri / quad / penta self-joins
+ *   `.join(equal(key)).join(equal(key))…` with index-ordered tuples a < b < c … and a constant weight per tuple
+ *   (constraint/nary_incremental/higher_arity/shared.rs:28-417): a bucket of n rows holds C(n, arity) tuples */
 #define SFGPU_K_PAIR_KEY_EQUAL 3
 /* for_each(A).if_exists|if_not_exists(for_each(owners).flattened(list), equal(a.row, element))
  *   constraint/exists.rs:126-417; p0: 0 = exists, 1 = not exists; weight must be CONST */

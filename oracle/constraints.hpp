@@ -12,6 +12,7 @@
 //   UniConstraint                           constraint/incremental.rs:97-156
 //   CrossBiConstraint                       constraint/cross_bi_incremental/{state.rs:215-460, incremental.rs:27-137}
 //   SelfJoinBiConstraint                    constraint/nary_incremental/bi.rs:78-206
+//   SelfJoinNaryConstraint (tri/quad/penta) constraint/nary_incremental/higher_arity/shared.rs:114-380
 //   ExistsConstraint                        constraint/exists.rs:126-417 (+ exists/key_state.rs:95-253)
 //   GroupedConstraint                       constraint/grouped/{state.rs:102-261, scorer.rs:46-152}
 //   collectors count / sum / load_balance   stream/collector/{count.rs, sum.rs, load_balance.rs:104-240}
@@ -30,6 +31,8 @@
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
+#include <set>
+#include <array>
 #include <utility>
 #include <vector>
 
@@ -536,6 +539,146 @@ struct SelfJoinBiConstraint final : IncrementalConstraint<S, Sc> {
   void reset() override {
     entity_to_matches.clear();
     matches.clear();
+    key_to_indices.clear();
+    index_to_key.clear();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Keyed self-join of arity N = 3 (tri), 4 (quad), 5 (penta): index-ordered tuples a < b < c .. inside a key
+// bucket.                         constraint/nary_incremental/higher_arity/{shared.rs:114-380, tri.rs, quad.rs, penta.rs}
+// A tuple is its ascending index list padded with SIZE_MAX; `filter(s, es, tuple)` and `weight(s, es, tuple)`.
+using NaryTuple = std::array<size_t, 5>;
+struct NaryTupleHash {
+  size_t operator()(const NaryTuple& t) const {
+    size_t h = 0xcbf29ce484222325ull;
+    for (size_t v : t) h = (h ^ v) * 0x100000001b3ull;
+    return h;
+  }
+};
+template <class S, class A, class K, class Sc, class KF, class F, class W, class KH = std::hash<K>>
+struct SelfJoinNaryConstraint final : IncrementalConstraint<S, Sc> {
+  Source<S, A> src;
+  Impact impact;
+  size_t arity;
+  KF key_fn;
+  F filter;
+  W weight;
+  std::unordered_set<NaryTuple, NaryTupleHash> matches;
+  std::unordered_map<size_t, std::unordered_set<NaryTuple, NaryTupleHash>> entity_to_matches;
+  std::unordered_map<K, std::set<size_t>, KH> key_to_indices;
+  std::unordered_map<size_t, K> index_to_key;
+
+  SelfJoinNaryConstraint(std::string n, Impact i, size_t ar, Source<S, A> s, KF kf, F f, W w, bool hard)
+      : src(s), impact(i), arity(ar), key_fn(std::move(kf)), filter(std::move(f)), weight(std::move(w)) {
+    this->name = std::move(n);
+    this->is_hard = hard;
+  }
+  // every ascending combination of `need` members of `pool` starting at position `from`, appended to `cur`
+  template <class V>
+  static void combos(const std::vector<size_t>& pool, size_t from, size_t need, std::vector<size_t>& cur, V&& visit) {
+    if (need == 0) {
+      visit(cur);
+      return;
+    }
+    for (size_t p = from; p + need <= pool.size(); ++p) {
+      cur.push_back(pool[p]);
+      combos(pool, p + 1, need - 1, cur, visit);
+      cur.pop_back();
+    }
+  }
+  static NaryTuple make_tuple(std::vector<size_t> v) {
+    std::sort(v.begin(), v.end());
+    NaryTuple t;
+    t.fill(SIZE_MAX);
+    for (size_t i = 0; i < v.size(); ++i) t[i] = v[i];
+    return t;
+  }
+  Sc evaluate(const S& s) const override {  // shared.rs:281-304
+    auto& es = src.extract(s);
+    std::unordered_map<K, std::vector<size_t>, KH> idx;
+    for (size_t i = 0; i < es.size(); ++i) idx[key_fn(es[i])].push_back(i);
+    Sc t = Sc::zero();
+    std::vector<size_t> cur;
+    for (auto& kv : idx)
+      combos(kv.second, 0, arity, cur, [&](const std::vector<size_t>& c) {
+        NaryTuple tp = make_tuple(c);
+        if (filter(s, es, tp)) t = t + signed_weight(impact, weight(s, es, tp));
+      });
+    return t;
+  }
+  size_t match_count(const S& s) const override { return matches.size(); }
+  Sc insert_entity(const S& s, const std::vector<A>& es, size_t idx) {  // shared.rs:170-223
+    if (idx >= es.size()) return Sc::zero();
+    K k = key_fn(es[idx]);
+    index_to_key[idx] = k;
+    auto& bucket = key_to_indices[k];
+    bucket.insert(idx);
+    std::vector<size_t> others;
+    for (size_t o : bucket)
+      if (o != idx) others.push_back(o);
+    Sc t = Sc::zero();
+    std::vector<size_t> cur{idx};
+    combos(others, 0, arity - 1, cur, [&](const std::vector<size_t>& c) {
+      NaryTuple tp = make_tuple(c);
+      if (matches.count(tp)) return;
+      if (!filter(s, es, tp)) return;
+      matches.insert(tp);
+      for (size_t i = 0; i < arity; ++i) entity_to_matches[tp[i]].insert(tp);
+      t = t + signed_weight(impact, weight(s, es, tp));
+    });
+    return t;
+  }
+  Sc retract_entity(const S& s, const std::vector<A>& es, size_t idx) {  // shared.rs:225-270
+    auto ik = index_to_key.find(idx);
+    if (ik != index_to_key.end()) {
+      auto ib = key_to_indices.find(ik->second);
+      if (ib != key_to_indices.end()) {
+        ib->second.erase(idx);
+        if (ib->second.empty()) key_to_indices.erase(ib);
+      }
+      index_to_key.erase(ik);
+    }
+    auto it = entity_to_matches.find(idx);
+    if (it == entity_to_matches.end()) return Sc::zero();
+    auto tuples = std::move(it->second);
+    entity_to_matches.erase(it);
+    Sc t = Sc::zero();
+    for (const NaryTuple& tp : tuples) {
+      matches.erase(tp);
+      bool in_range = true;
+      for (size_t i = 0; i < arity; ++i) {
+        if (tp[i] != idx) {
+          auto io = entity_to_matches.find(tp[i]);
+          if (io != entity_to_matches.end()) {
+            io->second.erase(tp);
+            if (io->second.empty()) entity_to_matches.erase(io);
+          }
+        }
+        in_range = in_range && tp[i] < es.size();
+      }
+      if (in_range) t = t + (-signed_weight(impact, weight(s, es, tp)));
+    }
+    return t;
+  }
+  Sc initialize(const S& s) override {
+    reset();
+    auto& es = src.extract(s);
+    Sc t = Sc::zero();
+    for (size_t i = 0; i < es.size(); ++i) t = t + insert_entity(s, es, i);
+    return t;
+  }
+  Sc on_insert(const S& s, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    return insert_entity(s, src.extract(s), idx);
+  }
+  Sc on_retract(const S& s, size_t idx, size_t d) override {
+    if (!src.change.assert_localizes(d, this->name)) return Sc::zero();
+    return retract_entity(s, src.extract(s), idx);
+  }
+  void reset() override {
+    matches.clear();
+    entity_to_matches.clear();
     key_to_indices.clear();
     index_to_key.clear();
   }

@@ -917,6 +917,63 @@ static void kat_moves_and_loop() {
       }
     }
   }
+  {  // constraint/tests/tri_incr.rs:22-138, quad_incr.rs, penta_incr.rs: tuples per team bucket, retract / insert
+    struct T { uint32_t team; };
+    struct Sol { std::vector<T> tasks; };
+    using SS = SoftScore;
+    auto mk = [](size_t arity) {
+      Source<Sol, T> src{+[](const Sol& s) -> const std::vector<T>& { return s.tasks; }, ChangeSource::Desc(0)};
+      auto kf = [](const T& t) { return t.team; };
+      auto ff = [](const Sol&, const std::vector<T>&, const NaryTuple&) { return true; };
+      auto wf = [](const Sol&, const std::vector<T>&, const NaryTuple&) { return SS::of(1); };
+      return SelfJoinNaryConstraint<Sol, T, uint32_t, SS, decltype(kf), decltype(ff), decltype(wf)>(
+          "Cluster", Impact::Penalty, arity, src, kf, ff, wf, false);
+    };
+    {
+      auto c = mk(3);
+      CHECK(c.evaluate(Sol{{{1}, {1}, {1}, {2}}}) == SS::of(-1));       // tri_incr.rs:22-57
+      CHECK(c.evaluate(Sol{{{1}, {1}, {1}, {1}}}) == SS::of(-4));       // :59-94, C(4,3)
+      Sol s{{{1}, {1}, {1}}};
+      CHECK(c.initialize(s) == SS::of(-1));                             // :96-138
+      CHECK(c.on_retract(s, 0, 0) == SS::of(1));
+      CHECK(c.on_insert(s, 0, 0) == SS::of(-1));
+      CHECK(c.on_insert(s, 0, 1) == SS::of(0));                         // foreign descriptor: not localised
+    }
+    {
+      auto c = mk(4);
+      CHECK(c.evaluate(Sol{{{1}, {1}, {1}, {1}, {2}}}) == SS::of(-1));
+      CHECK(c.evaluate(Sol{{{1}, {1}, {1}, {1}, {1}}}) == SS::of(-5));  // C(5,4)
+      Sol s{{{1}, {1}, {1}, {1}}};
+      CHECK(c.initialize(s) == SS::of(-1));
+      CHECK(c.on_retract(s, 2, 0) == SS::of(1));
+      CHECK(c.on_insert(s, 2, 0) == SS::of(-1));
+    }
+    {
+      auto c = mk(5);
+      CHECK(c.evaluate(Sol{{{1}, {1}, {1}, {1}, {1}, {2}}}) == SS::of(-1));
+      CHECK(c.evaluate(Sol{{{1}, {1}, {1}, {1}, {1}, {1}}}) == SS::of(-6));  // C(6,5)
+      Sol s{{{3}, {3}, {3}, {3}, {3}, {3}}};
+      CHECK(c.initialize(s) == SS::of(-6));
+      CHECK(c.on_retract(s, 5, 0) == SS::of(5));                        // the C(5,4) tuples that contain row 5
+      s.tasks[5].team = 4;
+      CHECK(c.on_insert(s, 5, 0) == SS::of(0));
+      CHECK(c.evaluate(s) == SS::of(-1));
+    }
+    // the planning model: incremental score == fresh score along a walk of ChangeMoves
+    ClusterPlan cp;
+    cp.n_teams = 3;
+    for (size_t i = 0; i < 14; ++i) cp.tasks.push_back({i, i % 5 == 4 ? OptVal{} : OptVal{i % 3}});
+    ClusterModel cm(cp, {{2, 1}, {3, 10}, {4, 100}, {5, 1000}});
+    CHECK(cm.calculate_score() == cm.fresh_score());
+    auto mvs = cm.enumerate_scalar({});
+    for (size_t i = 0; i < mvs.size(); i += 7) {
+      if (!is_doable(mvs[i], cm.dir)) continue;
+      auto ev = cm.evaluate(mvs[i]);
+      cm.apply(mvs[i]);
+      CHECK(cm.calculate_score() == ev.score && cm.calculate_score() == cm.fresh_score());
+      mvs = cm.enumerate_scalar({});
+    }
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

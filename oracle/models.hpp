@@ -96,6 +96,55 @@ struct GraphColoringModel final : ModelImpl<GraphColoring> {
   }
 };
 
+// ------------------------------------------------------------------------- task clustering (authored)
+// The shape of the reference's tri / quad / penta known-answer tests (constraint/tests/{tri,quad,penta}_incr.rs:
+// tasks keyed by team) as a planning model: Task{team_idx: Option}, "Unassigned task" (1 hard) and one keyed
+// self-join per requested arity: for_each(tasks).join(equal(team)).join(equal(team))[..] filtered to assigned
+// tasks, penalised arity_weight soft per tuple.
+struct ClusterTask {
+  size_t id;
+  OptVal team_idx;
+};
+struct ClusterPlan {
+  std::vector<ClusterTask> tasks;
+  size_t n_teams = 0;
+};
+inline const std::vector<ClusterTask>& cluster_tasks(const ClusterPlan& s) { return s.tasks; }
+
+struct ClusterModel final : ModelImpl<ClusterPlan> {
+  ClusterModel(ClusterPlan sol, const std::vector<std::pair<size_t, int64_t>>& joins /* (arity, soft weight) */) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const ClusterPlan& s, size_t, size_t e) { return s.tasks[e].team_idx; };
+    dir.access.set = [](ClusterPlan& s, size_t, size_t e, OptVal v) { s.tasks[e].team_idx = v; };
+    dir.access.entity_count = [](const ClusterPlan& s, size_t) { return s.tasks.size(); };
+    Source<ClusterPlan, ClusterTask> src{cluster_tasks, ChangeSource::Desc(0)};
+    auto uf = [](const ClusterPlan&, const ClusterTask& t) { return !t.team_idx.has_value(); };
+    auto uw = [](const ClusterTask&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<ClusterPlan, ClusterTask, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned task", Impact::Penalty, src, uf, uw, true));
+    for (auto& j : joins) {
+      auto kf = [](const ClusterTask& t) { return t.team_idx.has_value() ? (int64_t)*t.team_idx : (int64_t)-1; };
+      auto ff = [](const ClusterPlan&, const std::vector<ClusterTask>& es, const NaryTuple& t) {
+        return es[t[0]].team_idx.has_value();
+      };
+      const int64_t wt = j.second;
+      auto wf = [wt](const ClusterPlan&, const std::vector<ClusterTask>&, const NaryTuple&) { return Sc{0, wt}; };
+      if (j.first == 2) {
+        auto f2 = [](const ClusterPlan&, const ClusterTask& l, const ClusterTask&, size_t, size_t) { return l.team_idx.has_value(); };
+        auto w2 = [wt](const ClusterPlan&, const ClusterTask&, const ClusterTask&) { return Sc{0, wt}; };
+        dir.constraints.add(std::make_unique<SelfJoinBiConstraint<ClusterPlan, ClusterTask, int64_t, Sc, decltype(kf), decltype(f2), decltype(w2)>>(
+            "Cluster pairs", Impact::Penalty, src, kf, f2, w2, false));
+      } else {
+        dir.constraints.add(std::make_unique<SelfJoinNaryConstraint<ClusterPlan, ClusterTask, int64_t, Sc, decltype(kf), decltype(ff), decltype(wf)>>(
+            "Cluster arity " + std::to_string(j.first), Impact::Penalty, j.first, src, kf, ff, wf, false));
+      }
+    }
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.n_teams, true, ctx);
+  }
+};
+
 // ------------------------------------------------------------------------------------------- C1
 struct Queen {
   size_t id, column;

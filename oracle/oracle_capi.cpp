@@ -42,6 +42,16 @@ void* sfo_gc_create(uint32_t n, uint32_t k, const uint32_t* row_ptr, const uint3
   return new GraphColoringModel(std::move(g));
 }
 
+// task clustering: joins = n_joins (arity, weight) pairs
+void* sfo_cluster_create(uint32_t n, uint32_t n_teams, const int32_t* team, uint32_t n_joins, const int64_t* joins) {
+  ClusterPlan p;
+  p.n_teams = n_teams;
+  for (uint32_t i = 0; i < n; ++i) p.tasks.push_back({i, opt(team[i])});
+  std::vector<std::pair<size_t, int64_t>> js;
+  for (uint32_t j = 0; j < n_joins; ++j) js.push_back({(size_t)joins[2 * j], joins[2 * j + 1]});
+  return new ClusterModel(std::move(p), js);
+}
+
 void* sfo_nq_create(uint32_t n, const int32_t* row) {
   Board b;
   b.n_rows = n;

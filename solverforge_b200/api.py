@@ -551,6 +551,7 @@ class EqualKey:
     column: int = L.NO_COLUMN
     col_mul: int = 0
     var_mul: int = 1
+    arity: int = 2   # 3 / 4 / 5 after further .join(.., same joiner): tri / quad / penta self-join
 
 
 @dataclass
@@ -773,7 +774,7 @@ class BiStream:
                              aux0=j.csr)
         if isinstance(j, EqualKey):
             return _Terminal(self.d, kind=L.K_PAIR_KEY_EQUAL, impact=impact, weight=w, collection=self.collection,
-                             aux0=j.column, p0=j.col_mul, p1=j.var_mul)
+                             aux0=j.column, aux1=j.arity, p0=j.col_mul, p1=j.var_mul)
         raise L.SfgpuError(L.E_UNSUPPORTED, f"joiner {type(j).__name__} is not expressible on device")
 
     def penalize(self, weight) -> _Terminal:
@@ -781,6 +782,17 @@ class BiStream:
 
     def reward(self, weight) -> _Terminal:
         return self._impact(L.REWARD, weight)
+
+    def join(self, other, joiner) -> "BiStream":
+        """Third / fourth / fifth member of a keyed self-join (TriConstraintStream .. PentaConstraintStream,
+        nary_incremental/higher_arity/shared.rs): same collection, same equal(key) joiner, index-ordered tuples."""
+        j = self.joiner
+        if not isinstance(j, EqualKey) or not isinstance(joiner, EqualKey) or \
+                (joiner.column, joiner.col_mul, joiner.var_mul) != (j.column, j.col_mul, j.var_mul):
+            raise L.SfgpuError(L.E_UNSUPPORTED, "higher-arity joins need the same equal(key) joiner on every member")
+        if j.arity >= 5:
+            raise L.SfgpuError(L.E_UNSUPPORTED, "joins beyond penta are not part of the reference API")
+        return BiStream(self.d, self.collection, other, EqualKey(j.column, j.col_mul, j.var_mul, j.arity + 1))
 
     def group_by(self, collector) -> "GroupedStream":
         if not isinstance(self.joiner, EqualVarToRow):

@@ -665,6 +665,9 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
         c.p0 = d.p0;
         c.p1 = d.p1;
         if (d.p1 == 0) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EQUAL needs p1 != 0 (the variable must enter the key)");
+        // join arity: 2 (bi, the default) .. 5 (penta) — nary_incremental/higher_arity/{tri,quad,penta}.rs
+        c.pad = (d.aux1 == 0xFFFFFFFFu || d.aux1 == 0) ? 2 : d.aux1;
+        if (c.pad < 2 || c.pad > 5) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EQUAL: aux1 (join arity) must be 2..5");
         // key range over every (entity, value)
         int64_t kmin = std::numeric_limits<int64_t>::max(), kmax = std::numeric_limits<int64_t>::min();
         for (uint32_t e = 0; e < dm.n_entities; ++e) {
@@ -861,7 +864,11 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       const ConsDev& c = dm.cons[k];
       switch (c.kind) {
         case SFGPU_K_UNI: sc.push_back({(!c.g0 && !c.g1) ? SPEC_K_UNI_CONST : SFGPU_K_UNI, (int)k}); break;
-        case SFGPU_K_PAIR_KEY_EQUAL: case SFGPU_K_GROUP: sc.push_back({c.kind, (int)k}); break;
+        case SFGPU_K_PAIR_KEY_EQUAL:
+          if (c.pad != 2) ok = false;  // tri / quad / penta joins keep the interpreter
+          sc.push_back({c.kind, (int)k});
+          break;
+        case SFGPU_K_GROUP: sc.push_back({c.kind, (int)k}); break;
         case SFGPU_K_PAIR_CSR_EQUAL:
           if (c.off0 == 0xFFFFFFFFu) ok = false;  // no retained partner-value counts
           sc.push_back({c.kind, (int)k});

@@ -130,6 +130,16 @@ __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
   }
 }
 
+// C(n, k) for the keyed self-joins of arity k + 1 (tuples that gain / lose one member of a bucket of n rows);
+// exact while the result fits int64 (every prefix product of i consecutive integers is divisible by i!)
+__device__ __forceinline__ int64_t choose_small(int64_t n, int k) {
+  if (k == 1) return n;
+  if (n < k) return 0;
+  int64_t r = 1;
+  for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+  return r;
+}
+
 // adds sign * v to the constraint's level
 __device__ __forceinline__ void add_level(Score2& s, const ConsDev& c, int64_t v) {
   int64_t sv = c.sign < 0 ? -v : v;

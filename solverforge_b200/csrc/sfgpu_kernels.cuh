@@ -102,6 +102,7 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const char*
       }
       case SFGPU_K_PAIR_KEY_EQUAL: {
         const int32_t* tab = (const int32_t*)(st + c.off0);
+        const int ar = (int)c.pad;  // join arity 2..5: a bucket of n rows holds C(n, arity) tuples
         int64_t cnt = 0;
         if (cur.new_v >= 0) {
           int64_t key = pair_key(c, cur.e, cur.new_v);
@@ -110,7 +111,7 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const char*
             n += (prev[i].new_v >= 0 && pair_key(c, prev[i].e, prev[i].new_v) == key) ? 1 : 0;
             n -= (prev[i].old_v >= 0 && pair_key(c, prev[i].e, prev[i].old_v) == key) ? 1 : 0;
           }
-          cnt += n;
+          cnt += choose_small(n, ar - 1);
         }
         if (cur.old_v >= 0) {
           int64_t key = pair_key(c, cur.e, cur.old_v);
@@ -119,7 +120,7 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const char*
             n += (prev[i].new_v >= 0 && pair_key(c, prev[i].e, prev[i].new_v) == key) ? 1 : 0;
             n -= (prev[i].old_v >= 0 && pair_key(c, prev[i].e, prev[i].old_v) == key) ? 1 : 0;
           }
-          cnt -= n - 1;
+          cnt -= choose_small(n - 1, ar - 1);
         }
         add_level(d, c, cnt * c.w.a);
         break;
@@ -1374,7 +1375,7 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < c.n0; i += blockDim.x) {
           int64_t n = tab[i];
-          local += n * (n - 1) / 2 * c.w.a;
+          local += choose_small(n, (int)c.pad) * c.w.a;
         }
         break;
       }

@@ -73,6 +73,24 @@ def nqueens(n: int = 64, seed: int | None = None) -> NQueensInstance:
 
 
 @dataclass
+class ClusterInstance:
+    n: int
+    n_teams: int
+    team: np.ndarray  # int32 [n], -1 = unassigned
+    joins: tuple      # ((arity, soft weight), ...) keyed self-joins on the team, arity 2..5
+
+
+def cluster(n: int = 60, n_teams: int = 5, seed: int = 17, unassigned_permille: int = 80,
+            joins=((2, 1), (3, 10), (4, 100), (5, 1000))) -> ClusterInstance:
+    """Task clustering (the shape of the reference's tri / quad / penta known-answer tests,
+    constraint/tests/{tri,quad,penta}_incr.rs, as a planning model): tasks keyed by their team."""
+    r = splitmix64_stream(seed, 2 * n)
+    team = (r[:n] % np.uint64(n_teams)).astype(np.int32)
+    team[(r[n:] % np.uint64(1000)) < unassigned_permille] = -1
+    return ClusterInstance(n, n_teams, team, tuple(joins))
+
+
+@dataclass
 class CvrpInstance:
     dim: int              # locations incl. depot 0
     n_routes: int

@@ -53,6 +53,26 @@ def nqueens_director(inst: NQueensInstance, n_replicas: int = 1, rows=None, devi
     return d
 
 
+def cluster_director(inst, n_replicas: int = 1, team=None, device: int = 0, stream=None,
+                     flags: int = 0) -> GpuScoreDirector:
+    """Keyed tri / quad / penta self-joins (`for_each(tasks).join(equal(team)).join(equal(team))…`,
+    constraint/nary_incremental/higher_arity/shared.rs): a bucket of n rows holds C(n, arity) tuples."""
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
+    d.add_collection("teams", inst.n_teams, -1)
+    tasks = d.add_collection("tasks", inst.n, 0)
+    d.add_scalar_variable(tasks, "team_idx", inst.n_teams, allows_unassigned=True)
+    f = ConstraintFactory(d)
+    f.for_each(tasks).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned task")
+    for arity, weight in inst.joins:
+        s = f.for_each(tasks).join(f.for_each(tasks), EqualKey())
+        for _ in range(arity - 2):
+            s = s.join(f.for_each(tasks), EqualKey())
+        s.penalize(HardSoftScore(0, weight)).named(f"Cluster arity {arity}")
+    d.set_scalar_state(inst.team if team is None else team)
+    d.commit()
+    return d
+
+
 def cvrp_director(inst: CvrpInstance, n_replicas: int = 1, offsets=None, elems=None, device: int = 0,
                   stream=None, flags: int = 0) -> GpuScoreDirector:
     d = GpuScoreDirector(n_replicas, device, stream, flags)

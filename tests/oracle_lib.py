@@ -31,10 +31,11 @@ def lib() -> C.CDLL:
             build()
         l = C.CDLL(LIB)
         for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create", "sfo_shift_create",
-                     "sfo_roster_create"):
+                     "sfo_roster_create", "sfo_cluster_create"):
             getattr(l, name).restype = _P
         l.sfo_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
         l.sfo_nq_create.argtypes = [C.c_uint32, _P]
+        l.sfo_cluster_create.argtypes = [C.c_uint32, C.c_uint32, _P, C.c_uint32, _P]
         l.sfo_cvrp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, _P, _P, _P, _P]
         l.sfo_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int]
         l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64, C.c_int]
@@ -113,6 +114,12 @@ class Oracle:
     def graph_coloring(inst, colors=None) -> "Oracle":
         c = np.ascontiguousarray(inst.color if colors is None else colors, dtype=np.int32)
         return Oracle(lib().sfo_gc_create(inst.n, inst.k, _p(_u32(inst.row_ptr)), _p(_u32(inst.col)), _p(c)))
+
+    @staticmethod
+    def cluster(inst, team=None) -> "Oracle":
+        t = np.ascontiguousarray(inst.team if team is None else team, dtype=np.int32)
+        j = np.ascontiguousarray(np.array(inst.joins, dtype=np.int64).reshape(-1))
+        return Oracle(lib().sfo_cluster_create(inst.n, inst.n_teams, _p(t), len(inst.joins), _p(j)))
 
     @staticmethod
     def nqueens(inst, rows=None) -> "Oracle":

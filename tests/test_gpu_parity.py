@@ -833,6 +833,55 @@ def test_sublist_swap_moves_match_oracle(asymmetric):
         assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
 
 
+@pytest.mark.parametrize("joins", [((3, 1),), ((2, 1), (3, 10), (4, 100), (5, 1000)), ((5, 7), (4, 3))])
+def test_higher_arity_keyed_joins_match_oracle(joins):
+    """Keyed tri / quad / penta self-joins (constraint/nary_incremental/higher_arity/shared.rs): C(n, arity) tuples
+    per bucket. Reference KATs (tri_incr.rs:22-138 and the quad / penta twins) as columns, then the cluster model:
+    full ChangeMove neighbourhood, swaps, compound moves with overlays, fused device step, committed winners."""
+    for arity, teams, want in ((3, [1, 1, 1, 2], -1), (3, [1, 1, 1, 1], -4), (4, [1, 1, 1, 1, 2], -1),
+                               (4, [1, 1, 1, 1, 1], -5), (5, [1, 1, 1, 1, 1, 2], -1), (5, [1, 1, 1, 1, 1, 1], -6)):
+        k = instances.ClusterInstance(len(teams), 3, np.array(teams, dtype=np.int32), ((arity, 1),))
+        dk = models.cluster_director(k)
+        assert dk.calculate_score()[0].tolist() == [0, want] == dk.fresh_score()[0].tolist()
+        dk.apply_change(np.array([[0, -1]]))                      # retract row 0: its tuples go, one unassigned task
+        left = {3: {-1: 0, -4: -1}, 4: {-1: 0, -5: -1}, 5: {-1: 0, -6: -1}}[arity][want]
+        assert dk.calculate_score()[0].tolist() == [-1, left] == dk.fresh_score()[0].tolist()
+    c = instances.cluster(70, 4, seed=23, joins=joins)
+    o = Oracle.cluster(c)
+    d = models.cluster_director(c)
+    assert d.scalar_program() == -1 or all(a == 2 for a, _ in joins)
+    assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+    r = instances.splitmix64_stream(91, 6000)
+    for step in range(5):
+        rows = o.enumerate_change()
+        so, oko = o.score_change(rows)
+        s, ok = d.score_change(rows)
+        _eq(ok, oko, f"change doable step {step}")
+        _eq(s, so, f"change scores step {step}")
+        swaps = np.stack([r[:600] % np.uint64(c.n), r[600:1200] % np.uint64(c.n)], axis=1).astype(np.int64)
+        s2, ok2 = d.score_swap(swaps)
+        so2, oko2 = o.score_swap(swaps)
+        _eq(ok2, oko2, "swap doable")
+        _eq(s2, so2, "swap scores")
+        sizes = (r[1200:1500] % np.uint64(4)).astype(np.int64) + 1
+        eo = np.concatenate([[0], np.cumsum(sizes)])
+        tot = int(eo[-1])
+        ent = (r[1500:1500 + tot] % np.uint64(c.n // 3)).astype(np.int64)      # few entities: edits overlap
+        val = (r[3000:3000 + tot] % np.uint64(c.n_teams + 1)).astype(np.int64) - 1
+        s3, ok3 = d.score_compound(eo, np.stack([ent, val], axis=1))
+        so3, oko3 = o.score_compound(eo, np.stack([ent, val], axis=1))
+        _eq(ok3, oko3, "compound doable")
+        _eq(s3, so3, "compound scores")
+        last = d.calculate_score()
+        idx, best, ev, win = d.step_change(ForageParams(0, 1, 0), step_seeds=[300 + step],
+                                           ref_scores=np.concatenate([last, last], axis=1), apply=True)
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 300 + step, 2, 1, True, 3)
+        assert out[0] and int(idx[0]) == out[1]
+        o.apply_change(int(rows[out[1]][0]), int(rows[out[1]][1]))
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+        r = instances.splitmix64_stream(92 + step, 6000)
+
+
 def test_consecutive_runs_collector_matches_oracle():
     """group_by(nurse, consecutive_runs(day)) — "Long work streaks" of examples/minimal-shift-scheduling
     (stream/collector/runs.rs): change, swap and compound candidates (several shifts of one candidate landing
