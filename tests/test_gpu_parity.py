@@ -846,7 +846,7 @@ def test_higher_arity_keyed_joins_match_oracle(joins):
         dk.apply_change(np.array([[0, -1]]))                      # retract row 0: its tuples go, one unassigned task
         left = {3: {-1: 0, -4: -1}, 4: {-1: 0, -5: -1}, 5: {-1: 0, -6: -1}}[arity][want]
         assert dk.calculate_score()[0].tolist() == [-1, left] == dk.fresh_score()[0].tolist()
-    c = instances.cluster(70, 4, seed=23, joins=joins)
+    c = instances.cluster(44, 4, seed=23, joins=joins)   # buckets of ~10 rows: the oracle materialises every tuple
     o = Oracle.cluster(c)
     d = models.cluster_director(c)
     assert d.scalar_program() == -1 or all(a == 2 for a, _ in joins)
@@ -858,12 +858,12 @@ def test_higher_arity_keyed_joins_match_oracle(joins):
         s, ok = d.score_change(rows)
         _eq(ok, oko, f"change doable step {step}")
         _eq(s, so, f"change scores step {step}")
-        swaps = np.stack([r[:600] % np.uint64(c.n), r[600:1200] % np.uint64(c.n)], axis=1).astype(np.int64)
+        swaps = np.stack([r[:200] % np.uint64(c.n), r[600:800] % np.uint64(c.n)], axis=1).astype(np.int64)
         s2, ok2 = d.score_swap(swaps)
         so2, oko2 = o.score_swap(swaps)
         _eq(ok2, oko2, "swap doable")
         _eq(s2, so2, "swap scores")
-        sizes = (r[1200:1500] % np.uint64(4)).astype(np.int64) + 1
+        sizes = (r[1200:1350] % np.uint64(4)).astype(np.int64) + 1
         eo = np.concatenate([[0], np.cumsum(sizes)])
         tot = int(eo[-1])
         ent = (r[1500:1500 + tot] % np.uint64(c.n // 3)).astype(np.int64)      # few entities: edits overlap

@@ -79,13 +79,22 @@ def test_spec_multi_replica_full_size_c2():
     colors = np.stack([instances.graph_coloring(seed_colors=50 + r).color for r in range(R)])
     spec, gen = _pair(models.graph_coloring_director, g, R, colors=colors)
     assert spec.scalar_program() >= 0
-    rows = Oracle.graph_coloring(g, colors[0]).enumerate_change()
-    per = [Oracle.graph_coloring(g, colors[r]).enumerate_change() for r in range(R)]
+    def change_rows(color):   # canonical ChangeMoveSelector order (change.rs:66-104): k values, then to-None when assigned
+        out = []
+        for e in range(g.n):
+            out += [(e, v) for v in range(g.k)]
+            if color[e] >= 0:
+                out.append((e, -1))
+        return np.array(out, dtype=np.int64)
+
+    per = [change_rows(colors[r]) for r in range(R)]
     offs = np.concatenate([[0], np.cumsum([len(p) for p in per])]).astype(np.uint64)
     allrows = np.concatenate(per)
     s1, ok1 = spec.score_change(allrows, offs)
     s2, ok2 = gen.score_change(allrows, offs)
     assert np.array_equal(s1, s2) and np.array_equal(ok1, ok2)
-    so, oko = Oracle.graph_coloring(g, colors[1]).score_change(per[1])
-    assert np.array_equal(s1[int(offs[1]):int(offs[2])], so) and np.array_equal(ok1[int(offs[1]):int(offs[2])], oko)
-    assert len(rows) == len(per[0])
+    o1 = Oracle.graph_coloring(g, colors[1])   # one oracle only: its predicate join initialises in O(n^2)
+    assert np.array_equal(o1.enumerate_change(), per[1])
+    so, oko = o1.score_change(per[1][::7])
+    lo = int(offs[1])
+    assert np.array_equal(s1[lo:int(offs[2])][::7], so) and np.array_equal(ok1[lo:int(offs[2])][::7], oko)
