@@ -335,6 +335,19 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
                           int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
                           int32_t apply_winners);
 
+/* The same whole step over the SublistChange neighbourhood (SublistChangeMoveSelector, SelectionOrder::Original,
+ * heuristic/selector/sublist_change.rs:166-205 + list_kernel/sublist_change.rs:103-268): per source entity every
+ * segment start and size min_size..=max_size (reference defaults 1..=3), intra-list destinations first, then every
+ * position of every other entity. The neighbourhood (CVRP-1000: ~3.2 M candidates per replica) is never
+ * materialised: candidates are decoded from their pull index on device, scored, and only the winner leaves the
+ * SM. out_index = CandidateId (pull index) or UINT32_MAX; out_winner_rows[R][4] = the packed SublistChange row
+ * {src_entity, start | size << 24, dst_entity, dst_position}; apply_winners commits it. With SFGPU_DEVICE_IO
+ * every pointer is a device pointer and the call is asynchronous. */
+int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
+                                  const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                  const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
+                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners);
+
 /* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
  * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.

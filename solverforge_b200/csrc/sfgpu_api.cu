@@ -11,6 +11,7 @@
 
 #include "sfgpu_change_step.cuh"
 #include "sfgpu_solve.cuh"
+#include "sfgpu_index_step.cuh"
 
 namespace {
 
@@ -853,6 +854,9 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_REVERSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SUBLIST_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SUBLIST_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
   // monomorphised scalar program: every constraint that reacts to scalar edits must be one of the
   // specialised kinds and the sorted tuple one of the instantiated ones; otherwise the interpreter
@@ -1771,6 +1775,112 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
     memcpy(out_best, pin + o_best, (size_t)R * 16);
     if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
     if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 8);
+  }
+  return SFGPU_OK;
+}
+
+// Whole step over the SublistChange neighbourhood, enumerated on device by pull index (sfgpu_index_step.cuh).
+int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
+                                  const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                  const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
+                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  const DevModel& dm = ctx->dm;
+  if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
+  if (min_size < 1 || max_size < min_size || max_size > 255)
+    return fail(ctx, SFGPU_E_INVALID, "segment sizes must satisfy 1 <= min <= max <= 255");
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  // upper bound of the neighbourhood of one replica: every element starts (max - min + 1) segments, each
+  // with fewer than elements + entities destinations
+  const uint64_t ub = (uint64_t)dm.elem_cap * (max_size - min_size + 1) * ((uint64_t)dm.elem_cap + dm.n_owners);
+  if (ub >= 0xFFFFFFFFull || dm.elem_cap >= (1u << 24))
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
+  const size_t table_bytes = (size_t)2 * (dm.n_owners + 1) * 4;
+  const bool staged = ctx->staged && dm.stage_bytes + table_bytes + 1024 <= (size_t)ctx->max_smem_optin;
+  if (table_bytes + 1024 > (size_t)ctx->max_smem_optin)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "too many list owners for the shared-memory index tables");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R;
+  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
+  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
+  size_t o_eval = a16(o_best + (size_t)R * 16), o_win = a16(o_eval + (size_t)R * 4), small = a16(o_win + (size_t)R * 16);
+  const uint64_t* d_seeds = step_seeds;
+  const int64_t* d_ref = ref_scores;
+  uint32_t *d_idx = out_index, *d_eval = out_evaluated, *d_win = out_winner_rows;
+  int64_t* d_best = out_best;
+  if (!dev_io) {
+    if (small > ctx->small_bytes) {
+      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+      if (ctx->small_dev) cudaFree(ctx->small_dev);
+      ctx->small_pin = ctx->small_dev = nullptr;
+      ctx->small_bytes = 0;
+      CU(cudaMallocHost(&ctx->small_pin, small));
+      CU(cudaMalloc(&ctx->small_dev, small));
+      ctx->small_bytes = small;
+    }
+    char* pin = (char*)ctx->small_pin;
+    char* dv = (char*)ctx->small_dev;
+    if (step_seeds) memcpy(pin + o_seed, step_seeds, (size_t)R * 8);
+    if (ref_scores) memcpy(pin + o_ref, ref_scores, (size_t)R * 32);
+    if (step_seeds || ref_scores) CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
+    d_seeds = step_seeds ? (const uint64_t*)(dv + o_seed) : nullptr;
+    d_ref = ref_scores ? (const int64_t*)(dv + o_ref) : nullptr;
+    d_idx = (uint32_t*)(dv + o_idx);
+    d_best = (int64_t*)(dv + o_best);
+    d_eval = (uint32_t*)(dv + o_eval);
+    d_win = (uint32_t*)(dv + o_win);
+  } else if (apply_winners && !d_win) {
+    return fail(ctx, SFGPU_E_INVALID, "apply_winners needs out_winner_rows on the device path");
+  }
+  IndexStepArgs a{};
+  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
+  a.min_size = min_size;
+  a.max_size = max_size;
+  a.step_seeds = d_seeds;
+  a.ref_scores = d_ref;
+  // candidates per CTA: amortise staging + table build, but cover the machine when replicas are few
+  uint32_t per = 16384;
+  while (per > 1024 && ((ub + per - 1) / per) * R < (uint64_t)ctx->sm_count * 4) per /= 2;
+  a.per_chunk = per;
+  const uint32_t chunks = (uint32_t)std::min<uint64_t>((ub + per - 1) / per, 65535);
+  if ((uint64_t)chunks * per < ub) return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood needs more than 65535 chunks");
+  rc = ensure_partials(ctx, (size_t)R * chunks * sizeof(ChunkPartial));
+  if (rc) return rc;
+  a.partials = (ChunkPartial*)ctx->partials;
+  dim3 grid(chunks, R);
+  ev_begin(ctx);
+  if (staged) {
+    const int bytes = (int)(dm.stage_bytes + table_bytes);
+    CU(cudaFuncSetAttribute(index_step_kernel<true, SublistChangeNb>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    index_step_kernel<true, SublistChangeNb><<<grid, 256, bytes, ctx->stream>>>(dm, a);
+  } else {
+    CU(cudaFuncSetAttribute(index_step_kernel<false, SublistChangeNb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+    index_step_kernel<false, SublistChangeNb><<<grid, 256, table_bytes, ctx->stream>>>(dm, a);
+  }
+  ev_end(ctx);
+  CU(cudaFuncSetAttribute(index_finish_kernel<SublistChangeNb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+  index_finish_kernel<SublistChangeNb><<<R, 256, table_bytes, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  if (apply_winners) {
+    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 5, d_win, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  if (!dev_io) {
+    char* pin = (char*)ctx->small_pin;
+    char* dv = (char*)ctx->small_dev;
+    CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, small - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_index, pin + o_idx, (size_t)R * 4);
+    memcpy(out_best, pin + o_best, (size_t)R * 16);
+    if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
+    if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
   }
   return SFGPU_OK;
 }

@@ -1,0 +1,393 @@
+// Device-side enumeration of a list neighbourhood by PULL INDEX, fused with scoring and the forager replay.
+//
+// The sublist neighbourhoods are too large to materialise (CVRP-1000 / 80 routes, sizes 1..=3: ~3.2 M
+// SublistChange candidates per replica and step = 100 MB of rows + scores per replica), so nothing is written to
+// HBM: a thread decodes candidate `idx` of the canonical selector order straight from the staged route lengths,
+// scores it against the staged replica block and keeps a forager partial; only chunk partials and the winner
+// leave the SM. The finish kernel replays the AcceptedCount cut and the tie rule by re-decoding one chunk in order.
+//
+// SublistChangeNb: SublistChangeMoveSelector, SelectionOrder::Original
+//   (heuristic/selector/sublist_change.rs:166-205 + list_kernel/sublist_change.rs:103-268): entities in order; per
+//   source every segment start, every valid size min..=max; intra-list destinations 0..=len-size of the
+//   post-removal list except the segment's own start, then every position 0..=len of every other entity in entity
+//   order. A segment of `size` therefore owns T - size candidates, T = total elements + entities - 1.
+#pragma once
+#include "sfgpu_kernels.cuh"
+
+struct IndexStepArgs {
+  ForageDev f;
+  uint32_t per_chunk;            // candidates per CTA (multiple of blockDim.x)
+  uint32_t min_size, max_size;   // segment sizes
+  const uint64_t* step_seeds;    // [R] or null
+  const int64_t* ref_scores;     // [R][4] or null
+  ChunkPartial* partials;        // [R][gridDim.x]
+};
+
+struct SublistChangeNb {
+  const uint32_t* off;   // staged route offsets
+  uint32_t* ent_base;    // [n + 1] first pull index of every source entity
+  uint32_t* dst_pre;     // [n + 1] prefix of (len + 1): destination slots before every entity
+  uint32_t n, T, min_size, max_size, n_sizes, size_sum;
+
+  // candidates of one source route
+  __device__ __forceinline__ uint32_t per_start(uint32_t mv) const {  // sizes min..=mv of one start
+    if (mv < min_size) return 0;
+    const uint32_t c = mv - min_size + 1;
+    return c * T - (min_size + mv) * c / 2;
+  }
+  __device__ __forceinline__ uint32_t route_count(uint32_t slen) const {
+    if (slen < min_size) return 0;
+    const uint32_t nf = slen >= max_size ? slen - max_size + 1 : 0;  // starts that fit every size
+    uint32_t tot = nf * per_start(max_size);
+    for (uint32_t start = nf; start < slen; ++start) tot += per_start(slen - start);
+    return tot;
+  }
+  // tables in shared memory; all threads of the CTA must call. scratch: 2 * (n + 1) uint32
+  __device__ __forceinline__ void build(const DevModel& m, const char* st, uint32_t* scratch, uint32_t mn, uint32_t mx) {
+    off = (const uint32_t*)(st + m.off_offsets);
+    n = m.n_owners;
+    ent_base = scratch;
+    dst_pre = scratch + n + 1;
+    min_size = mn;
+    max_size = mx;
+    n_sizes = mx - mn + 1;
+    size_sum = (mn + mx) * n_sizes / 2;
+    T = off[n] + n - 1;
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const uint32_t slen = off[e + 1] - off[e];
+      ent_base[e + 1] = route_count(slen);
+      dst_pre[e + 1] = slen + 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ent_base[0] = 0;
+      dst_pre[0] = 0;
+      for (uint32_t e = 0; e < n; ++e) {
+        ent_base[e + 1] += ent_base[e];
+        dst_pre[e + 1] += dst_pre[e];
+      }
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ uint32_t total() const { return ent_base[n]; }
+  // last e with tab[e] <= v (tab non-decreasing, tab[0] = 0, v < tab[n])
+  __device__ __forceinline__ uint32_t find(const uint32_t* tab, uint32_t v) const {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (tab[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+  }
+  // candidate `idx` (< total()) as the packed device row {src_e, start | size << 24, dst_e, dst_position}
+  __device__ __forceinline__ uint4 decode(uint32_t idx) const {
+    const uint32_t e = find(ent_base, idx);
+    uint32_t r = idx - ent_base[e];
+    const uint32_t slen = off[e + 1] - off[e];
+    const uint32_t nf = slen >= max_size ? slen - max_size + 1 : 0;
+    const uint32_t k_full = n_sizes * T - size_sum;
+    uint32_t start, mv;
+    if (r < nf * k_full) {
+      start = r / k_full;
+      r -= start * k_full;
+      mv = max_size;
+    } else {
+      r -= nf * k_full;
+      start = nf;
+      for (;;) {
+        mv = slen - start;
+        const uint32_t k = per_start(mv);
+        if (r < k) break;
+        r -= k;
+        ++start;
+      }
+    }
+    uint32_t size = min_size;
+    while (size < mv && r >= T - size) {
+      r -= T - size;
+      ++size;
+    }
+    const uint32_t post = slen - size;  // intra-list destinations (own start skipped)
+    if (r < post) return make_uint4(e, start | (size << 24), e, r < start ? r : r + 1);
+    uint32_t k = r - post;                     // slot among the other entities' (len + 1) positions
+    if (k >= dst_pre[e]) k += slen + 1;        // jump over the source's own slots
+    const uint32_t de = find(dst_pre, k);
+    return make_uint4(e, start | (size << 24), de, k - dst_pre[de]);
+  }
+  __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
+    return list_sublist_change_delta(m, st, row, d);
+  }
+};
+
+// grid = (chunks, R): chunk c scores pull indices [c * per_chunk, (c + 1) * per_chunk) of its replica.
+// Dynamic shared memory: [staged block (STAGED)] [2 * (n_owners + 1) uint32].
+template <bool STAGED, class NB>
+__global__ void __launch_bounds__(256) index_step_kernel(const __grid_constant__ DevModel m, const IndexStepArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  __shared__ int64_t sh_h[8], sh_s[8];
+  __shared__ uint32_t sh_n[8], sh_f[8], sh_a[8];
+  const uint32_t r = blockIdx.y;
+  const char* gblock = m.state + (size_t)r * m.block_bytes;
+  const char* st = gblock;
+  uint32_t* tables = (uint32_t*)smem;
+  if (STAGED) {
+    stage_block(smem, gblock, m.stage_bytes, &bar);
+    st = smem;
+    tables = (uint32_t*)(smem + m.stage_bytes);
+  }
+  NB nb;
+  nb.build(m, st, tables, a.min_size, a.max_size);
+  const int64_t* cs = (const int64_t*)(st + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  int64_t lh = 0, ls = 0, th = 0, ts = 0;
+  if (a.ref_scores) {
+    lh = a.ref_scores[r * 4 + 0];
+    ls = a.ref_scores[r * 4 + 1];
+    th = a.ref_scores[r * 4 + 2];
+    ts = a.ref_scores[r * 4 + 3];
+  }
+  const uint32_t total = nb.total();
+  const uint64_t c_lo64 = (uint64_t)blockIdx.x * a.per_chunk;
+  const uint32_t c_lo = c_lo64 < total ? (uint32_t)c_lo64 : total;
+  const uint32_t c_hi = (uint64_t)c_lo + a.per_chunk < total ? c_lo + a.per_chunk : total;
+  int64_t tb_h = 0, tb_s = 0;
+  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
+  for (uint32_t idx = c_lo + threadIdx.x; idx < c_hi; idx += blockDim.x) {
+    Score2 d;
+    if (!nb.delta(m, st, nb.decode(idx), d)) continue;
+    const int64_t oh = ch + d.hard, os = csf + d.soft;
+    if (!accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) continue;
+    t_acc++;
+    if (tb_n == 0 || score_less(tb_h, tb_s, oh, os)) {
+      tb_h = oh;
+      tb_s = os;
+      tb_n = 1;
+      tb_first = idx;
+    } else if (tb_h == oh && tb_s == os) {
+      tb_n++;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+    const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
+    t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
+    if (on && (!tb_n || score_less(tb_h, tb_s, oh, os))) {
+      tb_h = oh; tb_s = os; tb_n = on; tb_first = of;
+    } else if (on && tb_n && oh == tb_h && os == tb_s) {
+      tb_n += on;
+      tb_first = min(tb_first, of);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh_h[warp] = tb_h; sh_s[warp] = tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first; sh_a[warp] = t_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ChunkPartial cp{0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    for (int w = 0; w < 8; ++w) {
+      cp.n_accepted += sh_a[w];
+      if (!sh_n[w]) continue;
+      if (!cp.n_best || score_less(cp.best_h, cp.best_s, sh_h[w], sh_s[w])) {
+        cp.best_h = sh_h[w]; cp.best_s = sh_s[w]; cp.n_best = sh_n[w]; cp.first_idx = sh_f[w];
+      } else if (sh_h[w] == cp.best_h && sh_s[w] == cp.best_s) {
+        cp.n_best += sh_n[w];
+        cp.first_idx = min(cp.first_idx, sh_f[w]);
+      }
+    }
+    a.partials[(size_t)r * gridDim.x + blockIdx.x] = cp;
+  }
+}
+
+// Ordered search over pull indices [lo, hi): the `want`-th (1-based) candidate that is accepted (mode 0) or
+// accepted and equal to (bh, bs) (mode 1). All threads participate; result in *s_out (untouched when absent).
+template <class NB>
+__device__ __forceinline__ void index_find(const DevModel& m, const char* st, const NB& nb, const ForageDev& f,
+                                           uint32_t lo, uint32_t hi, int mode, int64_t bh, int64_t bs, uint32_t want,
+                                           int64_t ch, int64_t csf, int64_t lh, int64_t ls, int64_t th, int64_t ts,
+                                           uint32_t* scratch, uint32_t* s_out) {
+  uint32_t seen = 0;
+  for (uint32_t base = lo; base < hi; base += blockDim.x) {
+    const uint32_t idx = base + threadIdx.x;
+    uint32_t hit = 0;
+    if (idx < hi) {
+      Score2 d;
+      if (nb.delta(m, st, nb.decode(idx), d)) {
+        const int64_t oh = ch + d.hard, os = csf + d.soft;
+        hit = (accept_score(f.acceptor, oh, os, lh, ls, th, ts) && (mode == 0 || (oh == bh && os == bs))) ? 1 : 0;
+      }
+    }
+    uint32_t tot;
+    const uint32_t incl = block_scan_u32(hit, scratch, &tot);
+    if (hit && seen + incl == want) *s_out = idx;
+    seen += tot;
+    __syncthreads();
+    if (seen >= want) break;
+  }
+}
+
+// One CTA per replica: AcceptedCount cut, best over chunks, tie rule, winner (forager.rs:70-155, 167-425).
+// Dynamic shared memory: 2 * (n_owners + 1) uint32.
+template <class NB>
+__global__ void __launch_bounds__(256) index_finish_kernel(const __grid_constant__ DevModel m, const IndexStepArgs a,
+                                                           uint32_t n_chunks, uint32_t* __restrict__ out_index,
+                                                           int64_t* __restrict__ out_best,
+                                                           uint32_t* __restrict__ out_evaluated,
+                                                           uint32_t* __restrict__ out_winner_rows) {
+  extern __shared__ __align__(16) uint32_t tables[];
+  __shared__ uint32_t scratch[33];
+  __shared__ uint32_t s_idx, s_cut_chunk, s_cut_rank, s_any, s_cstar, s_jstar;
+  __shared__ int64_t s_bh, s_bs;
+  __shared__ ChunkPartial s_cutp;
+  const uint32_t r = blockIdx.x;
+  const char* st = m.state + (size_t)r * m.block_bytes;
+  NB nb;
+  nb.build(m, st, tables, a.min_size, a.max_size);
+  const uint32_t total = nb.total();
+  const int64_t* cs = (const int64_t*)(st + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const ChunkPartial* P = a.partials + (size_t)r * n_chunks;
+  int64_t lh = 0, ls = 0, th = 0, ts = 0;
+  if (a.ref_scores) {
+    lh = a.ref_scores[r * 4 + 0];
+    ls = a.ref_scores[r * 4 + 1];
+    th = a.ref_scores[r * 4 + 2];
+    ts = a.ref_scores[r * 4 + 3];
+  }
+  auto chunk_lo = [&](uint32_t c) { return (uint32_t)min((uint64_t)c * a.per_chunk, (uint64_t)total); };
+  auto chunk_hi = [&](uint32_t c) { return (uint32_t)min((uint64_t)(c + 1) * a.per_chunk, (uint64_t)total); };
+  uint32_t limit_idx = 0xFFFFFFFFu;  // last pull index that counts
+  uint32_t n_eff = n_chunks;
+  if (threadIdx.x == 0) {
+    s_cut_chunk = n_chunks;
+    s_cutp = ChunkPartial{0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  }
+  __syncthreads();
+  if (a.f.accepted_limit > 0) {
+    if (threadIdx.x == 0) {
+      uint32_t seen = 0;
+      for (uint32_t c = 0; c < n_chunks; ++c) {
+        if (seen + P[c].n_accepted >= a.f.accepted_limit) {
+          s_cut_chunk = c;
+          s_cut_rank = a.f.accepted_limit - seen;
+          break;
+        }
+        seen += P[c].n_accepted;
+      }
+    }
+    __syncthreads();
+    if (s_cut_chunk < n_chunks) {
+      const uint32_t c_lo = chunk_lo(s_cut_chunk), c_hi = chunk_hi(s_cut_chunk);
+      index_find(m, st, nb, a.f, c_lo, c_hi, 0, 0, 0, s_cut_rank, ch, csf, lh, ls, th, ts, scratch, &s_idx);
+      __syncthreads();
+      limit_idx = s_idx;
+      n_eff = s_cut_chunk + 1;
+      // partial of the cut chunk truncated at the limit
+      int64_t tb_h = 0, tb_s = 0;
+      uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu;
+      for (uint32_t idx = c_lo + threadIdx.x; idx <= limit_idx && idx < c_hi; idx += blockDim.x) {
+        Score2 d;
+        if (!nb.delta(m, st, nb.decode(idx), d)) continue;
+        const int64_t oh = ch + d.hard, os = csf + d.soft;
+        if (!accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) continue;
+        if (tb_n == 0 || score_less(tb_h, tb_s, oh, os)) {
+          tb_h = oh; tb_s = os; tb_n = 1; tb_first = idx;
+        } else if (tb_h == oh && tb_s == os) {
+          tb_n++;
+        }
+      }
+      for (uint32_t t = 0; t < blockDim.x; ++t) {  // serialised merge (rare path)
+        if (threadIdx.x == t && tb_n) {
+          if (!s_cutp.n_best || score_less(s_cutp.best_h, s_cutp.best_s, tb_h, tb_s)) {
+            s_cutp.best_h = tb_h; s_cutp.best_s = tb_s; s_cutp.n_best = tb_n; s_cutp.first_idx = tb_first;
+          } else if (s_cutp.best_h == tb_h && s_cutp.best_s == tb_s) {
+            s_cutp.n_best += tb_n;
+            s_cutp.first_idx = min(s_cutp.first_idx, tb_first);
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t cut_chunk = s_cut_chunk;
+  const uint32_t evaluated = limit_idx == 0xFFFFFFFFu ? total : limit_idx + 1;
+  if (threadIdx.x == 0) {
+    int64_t bh = 0, bs = 0;
+    uint32_t any = 0;
+    for (uint32_t c = 0; c < n_eff; ++c) {
+      const ChunkPartial p = c == cut_chunk ? s_cutp : P[c];
+      if (!p.n_best) continue;
+      if (!any || score_less(bh, bs, p.best_h, p.best_s)) {
+        bh = p.best_h;
+        bs = p.best_s;
+      }
+      any = 1;
+    }
+    s_bh = bh;
+    s_bs = bs;
+    s_any = any;
+    s_jstar = 1;
+  }
+  __syncthreads();
+  const int64_t bh = s_bh, bs = s_bs;
+  if (!s_any) {
+    if (threadIdx.x == 0) {
+      out_index[r] = 0xFFFFFFFFu;
+      out_best[r * 2] = 0;
+      out_best[r * 2 + 1] = 0;
+      if (out_evaluated) out_evaluated[r] = evaluated;
+      if (out_winner_rows) ((uint4*)out_winner_rows)[r] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+    return;
+  }
+  uint32_t mtot = 0;
+  for (uint32_t c = 0; c < n_eff; ++c) {
+    const ChunkPartial p = c == cut_chunk ? s_cutp : P[c];
+    if (p.n_best && p.best_h == bh && p.best_s == bs) mtot += p.n_best;
+  }
+  if (a.f.tie_mode == 1) {  // reservoir_pick replay: the last k with splitmix64(..) % k == 0 wins (forager.rs:143-155)
+    const uint64_t seed = a.step_seeds ? a.step_seeds[r] : 0;
+    uint32_t best_k = 1;
+    for (uint32_t kk = 2 + threadIdx.x; kk <= mtot; kk += blockDim.x) {
+      const uint64_t mixed = splitmix64_dev(seed ^ ((uint64_t)kk * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);
+      if (mixed % kk == 0) best_k = kk;
+    }
+    atomicMax(&s_jstar, best_k);
+  }
+  __syncthreads();
+  const uint32_t want = s_jstar;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t before = 0;
+    for (uint32_t c = 0; c < n_eff; ++c) {
+      const ChunkPartial p = c == cut_chunk ? s_cutp : P[c];
+      const uint32_t nb_ = (p.n_best && p.best_h == bh && p.best_s == bs) ? p.n_best : 0;
+      if (before + nb_ >= want) {
+        s_cstar = c;
+        s_jstar = want - before;
+        s_idx = p.first_idx;
+        break;
+      }
+      before += nb_;
+    }
+  }
+  __syncthreads();
+  if (s_jstar > 1) {
+    const uint32_t c_lo = chunk_lo(s_cstar);
+    const uint32_t c_hi = min(chunk_hi(s_cstar), limit_idx == 0xFFFFFFFFu ? 0xFFFFFFFFu : limit_idx + 1);
+    const uint32_t j = s_jstar;
+    __syncthreads();
+    index_find(m, st, nb, a.f, c_lo, c_hi, 1, bh, bs, j, ch, csf, lh, ls, th, ts, scratch, &s_idx);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t idx = s_idx;
+    out_index[r] = idx;
+    out_best[r * 2] = bh;
+    out_best[r * 2 + 1] = bs;
+    if (out_evaluated) out_evaluated[r] = evaluated;
+    if (out_winner_rows) ((uint4*)out_winner_rows)[r] = nb.decode(idx);
+  }
+}

@@ -1,0 +1,133 @@
+"""GPU parity of the device-enumerated SublistChange step (sfgpu_step_sublist_change, sfgpu_index_step.cuh) against
+the oracle's SublistChangeMoveSelector order (list_kernel/sublist_change.rs:103-268), scores and candidate-loop
+replay: pull index of the winner, moves_evaluated, best score, the winning move and the committed state. Bit-exact."""
+import numpy as np
+import pytest
+
+from solverforge_b200 import ForageParams, instances, models
+from tests import oracle_lib
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0):
+    lo, hi = sizes
+    base = d.calculate_score()
+    ref = np.concatenate([base + [0, dl], base + [0, dl - 7]], axis=1)
+    idx, best, ev, win = d.step_sublist_change(lo, hi, ForageParams(acceptor, ties, limit), step_seeds=seeds, ref_scores=ref)
+    for r, o in enumerate(oracles):
+        rows = o.enumerate_sublist_change(lo, hi)
+        if len(rows):
+            so, oko = o.score_sublist_change(rows)
+        else:
+            so, oko = np.zeros((0, 2), np.int64), np.zeros(0, np.uint8)
+        out = oracle_lib.replay_step(so, oko, [0, 0], ref[r][:2], ref[r][2:], seeds[r], 0 if limit else 2, max(limit, 1),
+                                     bool(ties), okind)
+        what = f"replica={r} sizes={sizes} acc={acceptor} ties={ties} limit={limit} dl={dl}"
+        assert int(ev[r]) == out[2], what + " moves_evaluated"
+        if out[0]:
+            assert int(idx[r]) == out[1], what
+            assert best[r].tolist() == so[out[1]].tolist(), what
+            assert win[r].tolist() == rows[out[1]].astype(np.int64).tolist(), what
+        else:
+            assert idx[r] == 0xFFFFFFFF and win[r].tolist() == [-1] * 5, what
+
+
+@pytest.mark.parametrize("sizes", [(1, 3), (2, 2), (3, 6)])
+def test_sublist_change_step_matches_oracle(sizes):
+    c = instances.cvrp(46, 7, seed=31)
+    c.matrix = (c.matrix // 40) * 40     # coarse distances: many equal scores, the tie rule matters
+    R = 3
+    starts = [instances.perturb_routes(c, 40 + r, 30 + 10 * r) for r in range(R)]
+    offs = np.stack([s[0] for s in starts])
+    el = np.concatenate([s[1] for s in starts])
+    d = models.cvrp_director(c, R, offsets=offs, elems=el)
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    for r in range(R):
+        assert d.calculate_score()[r].tolist() == oracles[r].committed_score().tolist()
+    seeds = [5, 77, 0xDEADBEEF]
+    for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+        for ties in (0, 1):
+            for limit in (0, 1, 17, 900, 10 ** 7):
+                _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0 if acceptor != 1 else -30)
+
+
+def test_sublist_change_step_apply_chain_and_degenerate_routes():
+    """A single route, an empty route and a route shorter than the minimum segment; winners committed on device."""
+    c = instances.cvrp(30, 5, seed=33)
+    offs, el = instances.perturb_routes(c, 3, 20)
+    # move everything of route 4 into route 0 (route 4 empty) by rebuilding the lists
+    lens = np.diff(offs).tolist()
+    lists = [el[offs[i]:offs[i + 1]].tolist() for i in range(5)]
+    lists[0] += lists[4]
+    lists[4] = []
+    while len(lists[3]) > 1:              # route 3 keeps one element
+        lists[1].append(lists[3].pop())
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.uint32)
+    el = np.array([x for l in lists for x in l], dtype=np.uint32)
+    d = models.cvrp_director(c, 1, offsets=offs[None, :], elems=el)
+    o = Oracle.cvrp(c, offs, el)
+    for step in range(6):
+        last = d.calculate_score()
+        ref = np.concatenate([last, last], axis=1)
+        rows = o.enumerate_sublist_change(2, 3)
+        so, oko = o.score_sublist_change(rows)
+        idx, best, ev, win = d.step_sublist_change(2, 3, ForageParams(1, 1, 0), step_seeds=[400 + step], ref_scores=ref,
+                                                   apply=True)
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 400 + step, 2, 1, True, 0)
+        assert int(ev[0]) == out[2] == len(rows)
+        if not out[0]:
+            assert idx[0] == 0xFFFFFFFF
+            break
+        assert int(idx[0]) == out[1] and win[0].tolist() == rows[out[1]].astype(np.int64).tolist()
+        o.apply_sublist_change(*rows[out[1]])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+    # one route only: intra-list candidates only
+    one = instances.cvrp(12, 1, seed=2)
+    d1 = models.cvrp_director(one)
+    o1 = Oracle.cvrp(one)
+    _check_step(d1, [o1], (1, 3), [9], 0, 3, 1, 0)
+    _check_step(d1, [o1], (1, 3), [9], 0, 3, 1, 5)
+    # segments longer than every route: empty neighbourhood, a step without a winner
+    idx, best, ev, win = d1.step_sublist_change(20, 25, ForageParams(0, 1, 0), step_seeds=[1])
+    assert idx[0] == 0xFFFFFFFF and int(ev[0]) == 0
+
+
+def test_sublist_change_step_full_size_properties():
+    """CVRP-1000 / 80 (BASELINE C3 shape): ~3.2 M candidates per replica, never materialised. The winner's score
+    must equal the score of that move through the rows-resident call, no candidate may beat it (sampled), and
+    moves_evaluated equals the closed-form neighbourhood size."""
+    c = instances.cvrp()
+    R = 2
+    starts = [instances.perturb_routes(c, 60 + r, 200) for r in range(R)]
+    offs = np.stack([s[0] for s in starts])
+    el = np.concatenate([s[1] for s in starts])
+    d = models.cvrp_director(c, R, offsets=offs, elems=el)
+    idx, best, ev, win = d.step_sublist_change(1, 3, ForageParams(0, 1, 0), step_seeds=[3, 4])
+    for r in range(R):
+        lens = np.diff(offs[r]).astype(np.int64)
+        T = int(lens.sum()) + len(lens) - 1
+        want = sum(int(T - size) for ln in lens for s in range(ln) for size in range(1, min(3, ln - s) + 1))
+        assert int(ev[r]) == want
+    offs_c = np.arange(R + 1, dtype=np.uint64)
+    s, ok = d.score_sublist_change(win, offs_c)
+    assert ok.tolist() == [1] * R and np.array_equal(s, best)
+    # a random sample of replica 0's neighbourhood through the rows-resident call: nothing beats the winner
+    lens = np.diff(offs[0]).astype(np.int64)
+    rnd = instances.splitmix64_stream(123, 5 * 30000).reshape(-1, 5)
+    se = (rnd[:, 0] % np.uint64(len(lens))).astype(np.int64)
+    keep = lens[se] > 0
+    se, rnd = se[keep], rnd[keep]
+    start = (rnd[:, 1] % lens[se].astype(np.uint64)).astype(np.int64)
+    size = np.minimum((rnd[:, 2] % np.uint64(3)).astype(np.int64) + 1, lens[se] - start)
+    de = (rnd[:, 3] % np.uint64(len(lens))).astype(np.int64)
+    room = np.where(de == se, lens[se] - size, lens[de])
+    dp = (rnd[:, 4] % (room + 1).astype(np.uint64)).astype(np.int64)
+    rows0 = np.stack([se, start, start + size, de, dp], axis=1)
+    d0 = models.cvrp_director(c, 1, offsets=offs[0][None, :], elems=starts[0][1])
+    s0, ok0 = d0.score_sublist_change(rows0)
+    assert ok0.sum() > 20000
+    s0 = s0[ok0 == 1]
+    better = (s0[:, 0] > best[0][0]) | ((s0[:, 0] == best[0][0]) & (s0[:, 1] > best[0][1]))
+    assert not better.any()
