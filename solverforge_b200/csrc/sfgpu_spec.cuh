@@ -142,6 +142,7 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
   const int64_t* key_off;
   WeightDev w;
   bool complement;
+  bool square_uniform;  // a*x*x + b with the empty group scoring exactly w(0): the delta has a closed form
   int64_t dflt, empty0;
   __device__ __forceinline__ SpecCons(const DevModel& m, int idx, const char* st, const char*) {
     const ConsDev& c = m.cons[idx];
@@ -153,6 +154,7 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
     complement = (c.flags & SFGPU_CF_COMPLEMENT) != 0;
     dflt = c.p1;
     empty0 = complement ? weight_eval(c.w, c.p1) : 0;
+    square_uniform = c.w.fn == SFGPU_W_SQUARE && !key_off && empty0 == c.w.b;
     route_init(c);
   }
   template <int FN>
@@ -185,6 +187,21 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
   }
   // one (warp-uniform) dispatch on the weight function per candidate instead of one per evaluation
   __device__ __forceinline__ int64_t delta(uint32_t e, int32_t ov, int32_t nv) const {
+    if (square_uniform) {
+      // every group, empty or not, scores a*s*s + b (s = its count or sum, 0 when empty), so moving x from
+      // group o to group n changes the total by a*((so - x)^2 - so^2 + (sn + x)^2 - sn^2)
+      const int64_t x = col ? col[e] : 1;
+      int64_t v = 0;
+      if (ov >= 0) {
+        const int64_t so = col ? gs[ov] : (int64_t)gc[ov];
+        v += x * (x - 2 * so);
+      }
+      if (nv >= 0) {
+        const int64_t sn = col ? gs[nv] : (int64_t)gc[nv];
+        v += x * (x + 2 * sn);
+      }
+      return apply_sign(w.a * v);
+    }
     switch (w.fn) {
       case SFGPU_W_CONST: return apply_sign(delta_fn<SFGPU_W_CONST>(e, ov, nv));
       case SFGPU_W_LINEAR: return apply_sign(delta_fn<SFGPU_W_LINEAR>(e, ov, nv));
