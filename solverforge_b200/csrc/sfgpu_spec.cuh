@@ -251,10 +251,21 @@ struct SpecProg {
   }
 };
 
+// resident CTAs per SM the rows-resident kernel is compiled for: light programs are latency-bound on their table
+// gathers and gain from a fifth CTA (<= 51 registers); heavy ones keep their registers
+template <class PROG>
+struct SpecOccupancy {
+  static constexpr int min_ctas = 1;
+};
+template <>
+struct SpecOccupancy<SpecProg<SFGPU_K_PAIR_CSR_EQUAL, SPEC_K_UNI_CONST, 0, 0>> {
+  static constexpr int min_ctas = 5;
+};
+
 // Rows-resident ChangeMove scoring with a monomorphised program; same contract as
 // score_scalar_kernel<MODE_CHANGE, true> (grid = (chunks, R), staged replica block).
 template <class PROG>
-__global__ void __launch_bounds__(256) spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx,
+__global__ void __launch_bounds__(256, SpecOccupancy<PROG>::min_ctas) spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx,
                                                           const uint64_t* __restrict__ cand_offsets,
                                                           const uint32_t* __restrict__ rows,
                                                           int64_t* __restrict__ out_scores,
