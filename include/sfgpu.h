@@ -348,6 +348,15 @@ int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_s
                                   const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
                                   uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners);
 
+/* The same for the SublistSwap neighbourhood (SublistSwapMoveSelector, SelectionOrder::Original,
+ * list_kernel/sublist_swap.rs:28-318): first segments in entity / start / size order, each paired with the later
+ * non-overlapping segments of its own list and every segment of the later entities (CVRP-1000: ~4.4 M pairs per
+ * replica). out_winner_rows[R][4] = {first_entity, start1 | size1 << 24, second_entity, start2 | size2 << 24}. */
+int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
+                                const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
+                                uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners);
+
 /* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
  * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.

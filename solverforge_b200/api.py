@@ -407,6 +407,26 @@ class GpuScoreDirector:
         rows[idx == 0xFFFFFFFF] = -1
         return idx, best, ev, rows
 
+    def step_sublist_swap(self, min_size: int = 1, max_size: int = 3, params: "ForageParams" = None, step_seeds=None,
+                          ref_scores=None, apply: bool = False):
+        """One whole step over the SublistSwap neighbourhood, enumerated on device (sfgpu_step_sublist_swap). Winner
+        rows come back as (first_entity, start1, end1, second_entity, start2, end2); -1 when there is no winner."""
+        params = params or ForageParams()
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        seeds = None if step_seeds is None else np.ascontiguousarray(step_seeds, dtype=np.uint64)
+        ref = None if ref_scores is None else np.ascontiguousarray(ref_scores, dtype=np.int64).reshape(self.R, 4)
+        idx = np.zeros(self.R, dtype=np.uint32)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint32)
+        win = np.zeros((self.R, 4), dtype=np.uint32)
+        self._check(self.lib.sfgpu_step_sublist_swap(self.h, 0, min_size, max_size, C.byref(fp), _ptr(seeds), _ptr(ref),
+                                                     _ptr(idx), _ptr(best), _ptr(ev), _ptr(win), 1 if apply else 0))
+        w = win.astype(np.int64)
+        s1, n1, s2, n2 = w[:, 1] & 0xFFFFFF, w[:, 1] >> 24, w[:, 3] & 0xFFFFFF, w[:, 3] >> 24
+        rows = np.stack([w[:, 0], s1, s1 + n1, w[:, 2], s2, s2 + n2], axis=1)
+        rows[idx == 0xFFFFFFFF] = -1
+        return idx, best, ev, rows
+
     def solve_nearby_list_change(self, n_steps: int, max_nearby: int = 20, acceptor: int = 2, late_size: int = 400,
                                  tie_mode: int = 1, accepted_limit: int = 0, seed_base: int = 0,
                                  restore_best: bool = False, acceptor_real: float = 0.0,

@@ -1779,11 +1779,16 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
   return SFGPU_OK;
 }
 
-// Whole step over the SublistChange neighbourhood, enumerated on device by pull index (sfgpu_index_step.cuh).
-int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
-                                  const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                                  const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
-                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+}  // extern "C" (templates below)
+
+namespace {
+// Whole step over a neighbourhood enumerated on device by pull index (sfgpu_index_step.cuh). NB = the decoder,
+// apply_kind = the apply_list_kernel kind of its rows, ub = an upper bound of the candidates of one replica.
+template <class NB>
+int step_index_neighbourhood(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size, int apply_kind, uint64_t ub,
+                             const sfgpu_forage_params* params, const uint64_t* step_seeds, const int64_t* ref_scores,
+                             uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                             int32_t apply_winners) {
   int rc = check_committed(ctx);
   if (rc) return rc;
   const DevModel& dm = ctx->dm;
@@ -1794,15 +1799,12 @@ int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_s
   if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
     return fail(ctx, SFGPU_E_INVALID, "bad forage params");
   if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
-  // upper bound of the neighbourhood of one replica: every element starts (max - min + 1) segments, each
-  // with fewer than elements + entities destinations
-  const uint64_t ub = (uint64_t)dm.elem_cap * (max_size - min_size + 1) * ((uint64_t)dm.elem_cap + dm.n_owners);
   if (ub >= 0xFFFFFFFFull || dm.elem_cap >= (1u << 24))
     return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
-  const size_t table_bytes = (size_t)2 * (dm.n_owners + 1) * 4;
+  const size_t table_bytes = NB::table_words(dm.n_owners, dm.elem_cap) * 4;
   const bool staged = ctx->staged && dm.stage_bytes + table_bytes + 1024 <= (size_t)ctx->max_smem_optin;
   if (table_bytes + 1024 > (size_t)ctx->max_smem_optin)
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "too many list owners for the shared-memory index tables");
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the shared-memory index tables");
   CU(cudaSetDevice(ctx->device));
   const uint32_t R = dm.R;
   const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
@@ -1856,19 +1858,19 @@ int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_s
   ev_begin(ctx);
   if (staged) {
     const int bytes = (int)(dm.stage_bytes + table_bytes);
-    CU(cudaFuncSetAttribute(index_step_kernel<true, SublistChangeNb>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    index_step_kernel<true, SublistChangeNb><<<grid, 256, bytes, ctx->stream>>>(dm, a);
+    CU(cudaFuncSetAttribute(index_step_kernel<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    index_step_kernel<true, NB><<<grid, 256, bytes, ctx->stream>>>(dm, a);
   } else {
-    CU(cudaFuncSetAttribute(index_step_kernel<false, SublistChangeNb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-    index_step_kernel<false, SublistChangeNb><<<grid, 256, table_bytes, ctx->stream>>>(dm, a);
+    CU(cudaFuncSetAttribute(index_step_kernel<false, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+    index_step_kernel<false, NB><<<grid, 256, table_bytes, ctx->stream>>>(dm, a);
   }
   ev_end(ctx);
-  CU(cudaFuncSetAttribute(index_finish_kernel<SublistChangeNb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-  index_finish_kernel<SublistChangeNb><<<R, 256, table_bytes, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
+  CU(cudaFuncSetAttribute(index_finish_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+  index_finish_kernel<NB><<<R, 256, table_bytes, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
   ctx->launches += 2;
   CU(cudaGetLastError());
   if (apply_winners) {
-    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 5, d_win, nullptr, nullptr, nullptr);
+    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, apply_kind, d_win, nullptr, nullptr, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -1883,6 +1885,35 @@ int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_s
     if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
   }
   return SFGPU_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
+                                  const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                  const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
+                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+  if (!ctx) return SFGPU_E_INVALID;
+  // every element starts at most (max - min + 1) segments, each with fewer than elements + entities destinations
+  const DevModel& dm = ctx->dm;
+  const uint64_t ub = (uint64_t)dm.elem_cap * (max_size >= min_size ? max_size - min_size + 1 : 1) *
+                      ((uint64_t)dm.elem_cap + dm.n_owners);
+  return step_index_neighbourhood<SublistChangeNb>(ctx, flags, min_size, max_size, 5, ub, params, step_seeds, ref_scores,
+                                                   out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
+}
+
+int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
+                                const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                                const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
+                                uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+  if (!ctx) return SFGPU_E_INVALID;
+  // unordered pairs of segments: fewer than (segments)^2 / 2 + segments
+  const DevModel& dm = ctx->dm;
+  const uint64_t segs = (uint64_t)dm.elem_cap * (max_size >= min_size ? max_size - min_size + 1 : 1);
+  const uint64_t ub = segs * segs / 2 + segs;
+  return step_index_neighbourhood<SublistSwapNb>(ctx, flags, min_size, max_size, 6, ub, params, step_seeds, ref_scores,
+                                                 out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
 }
 
 int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,

@@ -29,6 +29,9 @@ struct SublistChangeNb {
   uint32_t* dst_pre;     // [n + 1] prefix of (len + 1): destination slots before every entity
   uint32_t n, T, min_size, max_size, n_sizes, size_sum;
 
+  static __host__ __device__ __forceinline__ size_t table_words(uint32_t n_owners, uint32_t) {
+    return (size_t)2 * (n_owners + 1);
+  }
   // candidates of one source route
   __device__ __forceinline__ uint32_t per_start(uint32_t mv) const {  // sizes min..=mv of one start
     if (mv < min_size) return 0;
@@ -119,8 +122,130 @@ struct SublistChangeNb {
   }
 };
 
+// SublistSwapNb: SublistSwapMoveSelector, SelectionOrder::Original (heuristic/selector/sublist_swap.rs +
+//   list_kernel/sublist_swap.rs:28-318): first segments in entity / start / size order; for each, the second
+//   segments are those of the same list that start at or after the first one's end, then every segment of every
+//   later entity. With G(m) = number of segments inside a list suffix of length m, a first segment (e, s, size)
+//   owns G(len - s - size) + (segments of the entities after e) candidates. Tables: pull index of the first
+//   candidate per flat element position, and the segment-count prefix per entity.
+struct SublistSwapNb {
+  const uint32_t* off;
+  uint32_t* pos_base;  // [elems + 1]
+  uint32_t* seg_pre;   // [n + 1] segments of the entities before e
+  uint32_t n, elems, min_size, max_size, n_sizes;
+
+  static __host__ __device__ __forceinline__ size_t table_words(uint32_t n_owners, uint32_t elem_cap) {
+    return (size_t)elem_cap + 1 + n_owners + 1 + 40;
+  }
+  __device__ __forceinline__ uint32_t sizes_at(uint32_t m) const {  // valid sizes with m elements left
+    const uint32_t mv = m < max_size ? m : max_size;
+    return mv >= min_size ? mv - min_size + 1 : 0;
+  }
+  __device__ __forceinline__ uint32_t G(uint32_t m) const {  // segments inside a suffix of length m
+    if (m < min_size) return 0;
+    const uint32_t mm = m < max_size ? m : max_size;
+    const uint32_t t = mm - min_size + 1;
+    return t * (t + 1) / 2 + (m > max_size ? (m - max_size) * n_sizes : 0);
+  }
+  __device__ __forceinline__ uint32_t entity_of(uint32_t p) const {  // last e with off[e] <= p and a non-empty route
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (off[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+  }
+  __device__ __forceinline__ void build(const DevModel& m, const char* st, uint32_t* scratch, uint32_t mn, uint32_t mx) {
+    off = (const uint32_t*)(st + m.off_offsets);
+    n = m.n_owners;
+    elems = off[n];
+    min_size = mn;
+    max_size = mx;
+    n_sizes = mx - mn + 1;
+    pos_base = scratch;
+    seg_pre = scratch + elems + 1;
+    uint32_t* scan = seg_pre + n + 1;  // 33 words for the block scan
+    if (threadIdx.x == 0) {
+      seg_pre[0] = 0;
+      for (uint32_t e = 0; e < n; ++e) seg_pre[e + 1] = seg_pre[e] + G(off[e + 1] - off[e]);
+    }
+    __syncthreads();
+    // candidates owned by the first segments that start at flat position p, then an exclusive prefix over p
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < elems; base += blockDim.x) {
+      const uint32_t p = base + threadIdx.x;
+      uint32_t cnt = 0;
+      if (p < elems) {
+        const uint32_t e = entity_of(p), L = off[e + 1] - off[e], s = p - off[e];
+        const uint32_t later = seg_pre[n] - seg_pre[e + 1];
+        const uint32_t ns = sizes_at(L - s);
+        for (uint32_t k = 0; k < ns; ++k) cnt += G(L - s - (min_size + k)) + later;
+      }
+      uint32_t tot;
+      const uint32_t incl = block_scan_u32(cnt, scan, &tot);
+      if (p < elems) pos_base[p] = carry + incl - cnt;
+      carry += tot;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) pos_base[elems] = carry;
+    __syncthreads();
+  }
+  __device__ __forceinline__ uint32_t total() const { return pos_base[elems]; }
+  // the r-th segment (start asc, size asc) among those of a list of length L that start at or after `from`
+  __device__ __forceinline__ uint32_t segment_at(uint32_t L, uint32_t from, uint32_t r) const {
+    const uint32_t m = L - from;
+    const uint32_t nf = m >= max_size ? m - max_size + 1 : 0;
+    uint32_t start, size;
+    if (r < nf * n_sizes) {
+      start = from + r / n_sizes;
+      size = min_size + r % n_sizes;
+    } else {
+      r -= nf * n_sizes;
+      start = from + nf;
+      for (;;) {
+        const uint32_t c = sizes_at(L - start);
+        if (r < c) break;
+        r -= c;
+        ++start;
+      }
+      size = min_size + r;
+    }
+    return start | (size << 24);
+  }
+  __device__ __forceinline__ uint4 decode(uint32_t idx) const {
+    uint32_t lo = 0, hi = elems;  // last p with pos_base[p] <= idx (pos_base[elems] = total > idx)
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (pos_base[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const uint32_t p = lo;
+    uint32_t r = idx - pos_base[p];
+    const uint32_t e = entity_of(p), L = off[e + 1] - off[e], s1 = p - off[e];
+    const uint32_t later = seg_pre[n] - seg_pre[e + 1];
+    uint32_t size1 = min_size;
+    for (;;) {
+      const uint32_t cnt = G(L - s1 - size1) + later;
+      if (r < cnt) break;
+      r -= cnt;
+      ++size1;
+    }
+    const uint32_t own = G(L - s1 - size1);
+    if (r < own) return make_uint4(e, s1 | (size1 << 24), e, segment_at(L, s1 + size1, r));
+    const uint32_t q = seg_pre[e + 1] + (r - own);  // rank among the segments of all entities
+    uint32_t a = e + 1, b = n;                     // last si with seg_pre[si] <= q
+    while (b - a > 1) {
+      const uint32_t mid = (a + b) >> 1;
+      if (seg_pre[mid] <= q) a = mid; else b = mid;
+    }
+    return make_uint4(e, s1 | (size1 << 24), a, segment_at(off[a + 1] - off[a], 0, q - seg_pre[a]));
+  }
+  __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
+    return list_sublist_swap_delta(m, st, row, d);
+  }
+};
+
 // grid = (chunks, R): chunk c scores pull indices [c * per_chunk, (c + 1) * per_chunk) of its replica.
-// Dynamic shared memory: [staged block (STAGED)] [2 * (n_owners + 1) uint32].
+// Dynamic shared memory: [staged block (STAGED)] [NB::table_words(..) uint32].
 template <bool STAGED, class NB>
 __global__ void __launch_bounds__(256) index_step_kernel(const __grid_constant__ DevModel m, const IndexStepArgs a) {
   extern __shared__ __align__(128) char smem[];
@@ -228,7 +353,7 @@ __device__ __forceinline__ void index_find(const DevModel& m, const char* st, co
 }
 
 // One CTA per replica: AcceptedCount cut, best over chunks, tie rule, winner (forager.rs:70-155, 167-425).
-// Dynamic shared memory: 2 * (n_owners + 1) uint32.
+// Dynamic shared memory: NB::table_words(..) uint32.
 template <class NB>
 __global__ void __launch_bounds__(256) index_finish_kernel(const __grid_constant__ DevModel m, const IndexStepArgs a,
                                                            uint32_t n_chunks, uint32_t* __restrict__ out_index,

@@ -11,27 +11,28 @@ from tests.oracle_lib import Oracle
 pytestmark = pytest.mark.gpu
 
 
-def _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0):
+def _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0, swap=False):
     lo, hi = sizes
     base = d.calculate_score()
     ref = np.concatenate([base + [0, dl], base + [0, dl - 7]], axis=1)
-    idx, best, ev, win = d.step_sublist_change(lo, hi, ForageParams(acceptor, ties, limit), step_seeds=seeds, ref_scores=ref)
+    step = d.step_sublist_swap if swap else d.step_sublist_change
+    idx, best, ev, win = step(lo, hi, ForageParams(acceptor, ties, limit), step_seeds=seeds, ref_scores=ref)
     for r, o in enumerate(oracles):
-        rows = o.enumerate_sublist_change(lo, hi)
+        rows = o.enumerate_sublist_swap(lo, hi) if swap else o.enumerate_sublist_change(lo, hi)
         if len(rows):
-            so, oko = o.score_sublist_change(rows)
+            so, oko = o.score_sublist_swap(rows) if swap else o.score_sublist_change(rows)
         else:
             so, oko = np.zeros((0, 2), np.int64), np.zeros(0, np.uint8)
         out = oracle_lib.replay_step(so, oko, [0, 0], ref[r][:2], ref[r][2:], seeds[r], 0 if limit else 2, max(limit, 1),
                                      bool(ties), okind)
-        what = f"replica={r} sizes={sizes} acc={acceptor} ties={ties} limit={limit} dl={dl}"
+        what = f"replica={r} swap={swap} sizes={sizes} acc={acceptor} ties={ties} limit={limit} dl={dl}"
         assert int(ev[r]) == out[2], what + " moves_evaluated"
         if out[0]:
             assert int(idx[r]) == out[1], what
             assert best[r].tolist() == so[out[1]].tolist(), what
             assert win[r].tolist() == rows[out[1]].astype(np.int64).tolist(), what
         else:
-            assert idx[r] == 0xFFFFFFFF and win[r].tolist() == [-1] * 5, what
+            assert idx[r] == 0xFFFFFFFF and win[r].tolist() == [-1] * (6 if swap else 5), what
 
 
 @pytest.mark.parametrize("sizes", [(1, 3), (2, 2), (3, 6)])
@@ -51,6 +52,82 @@ def test_sublist_change_step_matches_oracle(sizes):
         for ties in (0, 1):
             for limit in (0, 1, 17, 900, 10 ** 7):
                 _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0 if acceptor != 1 else -30)
+
+
+@pytest.mark.parametrize("sizes", [(1, 3), (2, 2), (2, 5)])
+def test_sublist_swap_step_matches_oracle(sizes):
+    """sfgpu_step_sublist_swap vs SublistSwapMoveSelector (list_kernel/sublist_swap.rs:28-318) + candidate loop."""
+    c = instances.cvrp(34, 6, seed=35)
+    c.matrix = (c.matrix // 40) * 40
+    R = 3
+    starts = [instances.perturb_routes(c, 50 + r, 20 + 15 * r) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    seeds = [6, 78, 0xFEEDF00D]
+    for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+        for ties in (0, 1):
+            for limit in (0, 1, 23, 1500, 10 ** 7):
+                _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0 if acceptor != 1 else -30, swap=True)
+
+
+def test_sublist_swap_step_apply_chain_and_degenerate_routes():
+    c = instances.cvrp(26, 5, seed=36)
+    offs, el = instances.perturb_routes(c, 4, 20)
+    lists = [el[offs[i]:offs[i + 1]].tolist() for i in range(5)]
+    lists[0] += lists[2]
+    lists[2] = []                         # an empty route in the middle
+    while len(lists[4]) > 1:              # the last route keeps one element
+        lists[1].append(lists[4].pop())
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.uint32)
+    el = np.array([x for l in lists for x in l], dtype=np.uint32)
+    d = models.cvrp_director(c, 1, offsets=offs[None, :], elems=el)
+    o = Oracle.cvrp(c, offs, el)
+    for step in range(6):
+        last = d.calculate_score()
+        ref = np.concatenate([last, last], axis=1)
+        rows = o.enumerate_sublist_swap(1, 3)
+        so, oko = o.score_sublist_swap(rows)
+        idx, best, ev, win = d.step_sublist_swap(1, 3, ForageParams(1, 1, 0), step_seeds=[500 + step], ref_scores=ref,
+                                                 apply=True)
+        out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 500 + step, 2, 1, True, 0)
+        assert int(ev[0]) == out[2] == len(rows)
+        if not out[0]:
+            assert idx[0] == 0xFFFFFFFF
+            break
+        assert int(idx[0]) == out[1] and win[0].tolist() == rows[out[1]].astype(np.int64).tolist()
+        o.apply_sublist_swap(*rows[out[1]])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+    one = instances.cvrp(12, 1, seed=2)
+    d1 = models.cvrp_director(one)
+    o1 = Oracle.cvrp(one)
+    _check_step(d1, [o1], (1, 3), [9], 0, 3, 1, 0, swap=True)
+    _check_step(d1, [o1], (2, 4), [9], 0, 3, 1, 7, swap=True)
+    idx, best, ev, win = d1.step_sublist_swap(20, 25, ForageParams(0, 1, 0), step_seeds=[1])
+    assert idx[0] == 0xFFFFFFFF and int(ev[0]) == 0
+
+
+def test_sublist_swap_step_full_size_properties():
+    """CVRP-1000 / 80: ~4.4 M segment pairs per replica, never materialised; moves_evaluated equals the closed-form
+    pair count and the winner re-scores to the reported best through the rows-resident call."""
+    c = instances.cvrp()
+    R = 2
+    starts = [instances.perturb_routes(c, 80 + r, 200) for r in range(R)]
+    offs = np.stack([s[0] for s in starts])
+    d = models.cvrp_director(c, R, offsets=offs, elems=np.concatenate([s[1] for s in starts]))
+    idx, best, ev, win = d.step_sublist_swap(1, 3, ForageParams(0, 1, 0), step_seeds=[3, 4])
+    for r in range(R):
+        lens = np.diff(offs[r]).astype(np.int64)
+        segs = [[(s, s + z) for s in range(ln) for z in range(1, min(3, ln - s) + 1)] for ln in lens]
+        nseg = np.array([len(x) for x in segs])
+        later = nseg.sum() - np.cumsum(nseg)
+        want = 0
+        for e, sg in enumerate(segs):
+            starts_e = np.array([a for a, _ in sg])
+            for (a, b) in sg:
+                want += int((starts_e >= b).sum()) + int(later[e])
+        assert int(ev[r]) == want
+    s, ok = d.score_sublist_swap(win, np.arange(R + 1, dtype=np.uint64))
+    assert ok.tolist() == [1] * R and np.array_equal(s, best)
 
 
 def test_sublist_change_step_apply_chain_and_degenerate_routes():
