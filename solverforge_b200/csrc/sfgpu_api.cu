@@ -1802,7 +1802,8 @@ int step_index_neighbourhood(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, 
   if (ub >= 0xFFFFFFFFull || dm.elem_cap >= (1u << 24))
     return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
   const size_t table_bytes = NB::table_words(dm.n_owners, dm.elem_cap) * 4;
-  const bool staged = ctx->staged && dm.stage_bytes + table_bytes + 1024 <= (size_t)ctx->max_smem_optin;
+  static const bool no_stage = getenv("SFGPU_INDEX_UNSTAGED") != nullptr;  // tuning knob
+  const bool staged = !no_stage && ctx->staged && dm.stage_bytes + table_bytes + 1024 <= (size_t)ctx->max_smem_optin;
   if (table_bytes + 1024 > (size_t)ctx->max_smem_optin)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the shared-memory index tables");
   CU(cudaSetDevice(ctx->device));
