@@ -1791,7 +1791,8 @@ int step_index_neighbourhood(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, 
                              int32_t apply_winners) {
   int rc = check_committed(ctx);
   if (rc) return rc;
-  const DevModel& dm = ctx->dm;
+  DevModel dm = ctx->dm;
+  if (ctx->force_generic) dm.fast_list = 0;  // SFGPU_CTX_GENERIC_KERNELS: cursor walks with the generic delta
   if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
   if (min_size < 1 || max_size < min_size || max_size > 255)

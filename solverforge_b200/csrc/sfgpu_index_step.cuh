@@ -120,6 +120,111 @@ struct SublistChangeNb {
   __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
     return list_sublist_change_delta(m, st, row, d);
   }
+
+  // ---- cursor: a thread walks a run of consecutive pull indices. Consecutive candidates differ only in the
+  // destination until the segment changes (~every T candidates), so the decode is incremental and, for
+  // CVRP-shaped programs (m.fast_list: at most one linear path cost and one per-route sum), everything that
+  // depends on the source segment only is computed once per segment. Same integer arithmetic as the generic
+  // delta, regrouped — the finish kernel re-scores single candidates with the generic one.
+  static constexpr bool kHasCursor = true;
+  struct Cursor {
+    uint32_t e, start, size, slen, sb;   // source segment
+    uint32_t de, dp, dlen, db;           // destination
+    uint32_t first, last;
+    int64_t gap, inner, v;               // path: closing the gap, inner legs; sum: segment total
+    int64_t os, ss, w_ss, ls_src_after;  // retained per-route aggregates of the source and their weights
+  };
+  __device__ __forceinline__ void set_dest(Cursor& c, uint32_t de, uint32_t dp) const {
+    c.de = de;
+    c.dp = dp;
+    c.db = off[de];
+    c.dlen = off[de + 1] - c.db;
+  }
+  __device__ __forceinline__ void seek(const DevModel& m, const char* st, uint32_t idx, Cursor& c) const {
+    const uint4 row = decode(idx);
+    c.e = row.x;
+    c.start = SFGPU_SEG_POS(row.y);
+    c.size = SFGPU_SEG_SIZE(row.y);
+    c.sb = off[c.e];
+    c.slen = off[c.e + 1] - c.sb;
+    set_dest(c, row.z, row.w);
+    if (!m.fast_list) return;
+    const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+    const uint32_t end = c.start + c.size;
+    c.first = el[c.sb + c.start];
+    c.last = el[c.sb + end - 1];
+    c.gap = c.inner = c.v = c.os = c.ss = c.w_ss = c.ls_src_after = 0;
+    if (m.fast_pc >= 0) {
+      const ConsDev& pc = m.cons[m.fast_pc];
+      const uint32_t depot = (uint32_t)pc.p0;
+      const uint32_t prev = c.start > 0 ? el[c.sb + c.start - 1] : depot;
+      const uint32_t next = end < c.slen ? el[c.sb + end] : depot;
+      c.gap = -mat_at(pc, prev, c.first) - mat_at(pc, c.last, next) + (c.slen > c.size ? mat_at(pc, prev, next) : 0);
+      for (uint32_t i = c.start; i + 1 < end; ++i) c.inner += mat_at(pc, el[c.sb + i], el[c.sb + i + 1]);
+      c.os = ((const int64_t*)(st + pc.off0))[c.e];
+    }
+    if (m.fast_ls >= 0) {
+      const ConsDev& ls = m.cons[m.fast_ls];
+      for (uint32_t i = c.start; i < end; ++i) c.v += ((const int64_t*)ls.g0)[el[c.sb + i]];
+      c.ss = ((const int64_t*)(st + ls.off0))[c.e];
+      c.w_ss = weight_eval(ls.w, c.ss);
+      c.ls_src_after = weight_eval(ls.w, c.ss - c.v);
+    }
+  }
+  // cursor -> candidate next_idx = current + 1
+  __device__ __forceinline__ void advance(const DevModel& m, const char* st, uint32_t next_idx, Cursor& c) const {
+    if (c.de == c.e) {  // intra-list destinations 0..=post except the segment's own start
+      uint32_t dp = c.dp + 1;
+      if (dp == c.start) ++dp;
+      if (dp <= c.slen - c.size) {
+        c.dp = dp;
+        return;
+      }
+      const uint32_t de = c.e == 0 ? 1 : 0;
+      if (de >= n) return seek(m, st, next_idx, c);
+      return set_dest(c, de, 0);
+    }
+    if (c.dp < c.dlen) {
+      ++c.dp;
+      return;
+    }
+    uint32_t de = c.de + 1;
+    if (de == c.e) ++de;
+    if (de >= n) return seek(m, st, next_idx, c);
+    set_dest(c, de, 0);
+  }
+  __device__ __forceinline__ bool eval(const DevModel& m, const char* st, const Cursor& c, Score2& d) const {
+    if (!m.fast_list)
+      return list_sublist_change_delta(m, st, make_uint4(c.e, c.start | (c.size << 24), c.de, c.dp), d);
+    d.hard = 0;
+    d.soft = 0;
+    const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+    const bool intra = c.de == c.e;
+    if (m.fast_pc >= 0) {  // linear weight (fast_list): w(x + delta) - w(x) = a * delta
+      const ConsDev& pc = m.cons[m.fast_pc];
+      const uint32_t depot = (uint32_t)pc.p0;
+      uint32_t a, b;
+      int64_t delta;
+      if (intra) {
+        const uint32_t ia = c.dp > 0 ? c.dp - 1 : 0, ib = c.dp;
+        a = c.dp > 0 ? el[c.sb + (ia < c.start ? ia : ia + c.size)] : depot;
+        b = c.dp < c.slen - c.size ? el[c.sb + (ib < c.start ? ib : ib + c.size)] : depot;
+        delta = c.gap + mat_at(pc, a, c.first) + mat_at(pc, c.last, b) - mat_at(pc, a, b);
+      } else {
+        a = c.dp > 0 ? el[c.db + c.dp - 1] : depot;
+        b = c.dp < c.dlen ? el[c.db + c.dp] : depot;
+        // source: gap - inner; destination: legs + inner; the inner legs cancel under a linear weight
+        delta = c.gap + mat_at(pc, a, c.first) + mat_at(pc, c.last, b) - (c.dlen > 0 ? mat_at(pc, a, b) : 0);
+      }
+      add_level(d, pc, pc.w.a * delta);
+    }
+    if (m.fast_ls >= 0 && !intra) {
+      const ConsDev& ls = m.cons[m.fast_ls];
+      const int64_t ds = ((const int64_t*)(st + ls.off0))[c.de];
+      add_level(d, ls, c.ls_src_after - c.w_ss + weight_eval(ls.w, ds + c.v) - weight_eval(ls.w, ds));
+    }
+    return true;
+  }
 };
 
 // SublistSwapNb: SublistSwapMoveSelector, SelectionOrder::Original (heuristic/selector/sublist_swap.rs +
@@ -242,6 +347,7 @@ struct SublistSwapNb {
   __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
     return list_sublist_swap_delta(m, st, row, d);
   }
+  static constexpr bool kHasCursor = false;
 };
 
 // grid = (chunks, R): chunk c scores pull indices [c * per_chunk, (c + 1) * per_chunk) of its replica.
@@ -278,11 +384,9 @@ __global__ void __launch_bounds__(256) index_step_kernel(const __grid_constant__
   const uint32_t c_hi = (uint64_t)c_lo + a.per_chunk < total ? c_lo + a.per_chunk : total;
   int64_t tb_h = 0, tb_s = 0;
   uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
-  for (uint32_t idx = c_lo + threadIdx.x; idx < c_hi; idx += blockDim.x) {
-    Score2 d;
-    if (!nb.delta(m, st, nb.decode(idx), d)) continue;
+  auto consider = [&](uint32_t idx, const Score2& d) {
     const int64_t oh = ch + d.hard, os = csf + d.soft;
-    if (!accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) continue;
+    if (!accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) return;
     t_acc++;
     if (tb_n == 0 || score_less(tb_h, tb_s, oh, os)) {
       tb_h = oh;
@@ -291,6 +395,27 @@ __global__ void __launch_bounds__(256) index_step_kernel(const __grid_constant__
       tb_first = idx;
     } else if (tb_h == oh && tb_s == os) {
       tb_n++;
+    }
+  };
+  if constexpr (NB::kHasCursor) {
+    // each thread walks one run of consecutive pull indices
+    const uint32_t run = a.per_chunk / blockDim.x;
+    uint32_t idx = c_lo + threadIdx.x * run;
+    const uint32_t end = idx < c_hi ? (idx + run < c_hi ? idx + run : c_hi) : idx;
+    if (idx < end) {
+      typename NB::Cursor cur;
+      nb.seek(m, st, idx, cur);
+      for (;;) {
+        Score2 d;
+        if (nb.eval(m, st, cur, d)) consider(idx, d);
+        if (++idx >= end) break;
+        nb.advance(m, st, idx, cur);
+      }
+    }
+  } else {
+    for (uint32_t idx = c_lo + threadIdx.x; idx < c_hi; idx += blockDim.x) {
+      Score2 d;
+      if (nb.delta(m, st, nb.decode(idx), d)) consider(idx, d);
     }
   }
   for (int o = 16; o > 0; o >>= 1) {

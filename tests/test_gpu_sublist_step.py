@@ -35,15 +35,19 @@ def _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0, sw
             assert idx[r] == 0xFFFFFFFF and win[r].tolist() == [-1] * (6 if swap else 5), what
 
 
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("sizes", [(1, 3), (2, 2), (3, 6)])
-def test_sublist_change_step_matches_oracle(sizes):
+def test_sublist_change_step_matches_oracle(sizes, generic):
+    """generic = SFGPU_CTX_GENERIC_KERNELS: the cursor walks with the constraint-table delta instead of the
+    CVRP-shaped one with hoisted source invariants."""
+    from solverforge_b200 import _lib as L
     c = instances.cvrp(46, 7, seed=31)
     c.matrix = (c.matrix // 40) * 40     # coarse distances: many equal scores, the tie rule matters
     R = 3
     starts = [instances.perturb_routes(c, 40 + r, 30 + 10 * r) for r in range(R)]
     offs = np.stack([s[0] for s in starts])
     el = np.concatenate([s[1] for s in starts])
-    d = models.cvrp_director(c, R, offsets=offs, elems=el)
+    d = models.cvrp_director(c, R, offsets=offs, elems=el, flags=L.CTX_GENERIC_KERNELS if generic else 0)
     oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
     for r in range(R):
         assert d.calculate_score()[r].tolist() == oracles[r].committed_score().tolist()
