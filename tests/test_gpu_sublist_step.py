@@ -54,7 +54,7 @@ def test_sublist_change_step_matches_oracle(sizes, generic):
     seeds = [5, 77, 0xDEADBEEF]
     for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
         for ties in (0, 1):
-            for limit in (0, 1, 17, 900, 10 ** 7):
+            for limit in ((0, 17) if generic else (0, 1, 17, 900, 10 ** 7)):
                 _check_step(d, oracles, sizes, seeds, acceptor, okind, ties, limit, dl=0 if acceptor != 1 else -30)
 
 
