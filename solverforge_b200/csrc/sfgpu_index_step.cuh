@@ -353,7 +353,7 @@ struct SublistSwapNb {
 // grid = (chunks, R): chunk c scores pull indices [c * per_chunk, (c + 1) * per_chunk) of its replica.
 // Dynamic shared memory: [staged block (STAGED)] [NB::table_words(..) uint32].
 template <bool STAGED, class NB>
-__global__ void __launch_bounds__(256) index_step_kernel(const __grid_constant__ DevModel m, const IndexStepArgs a) {
+__global__ void __launch_bounds__(256, 3) index_step_kernel(const __grid_constant__ DevModel m, const IndexStepArgs a) {
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   __shared__ int64_t sh_h[8], sh_s[8];
