@@ -164,7 +164,12 @@ typedef struct sfgpu_weight {
  *   w(run.point_count)): stream/collector/runs.rs:14-229 (unique points as maximal runs of consecutive
  *   integers; duplicates do not lengthen a run) — "Long work streaks" of examples/minimal-shift-scheduling
  *   (schedule.rs:43-58) is EXCESS with b = 2. aux0: entity column with the point (0 <= point < p0);
- *   p0: number of points. */
+ *   p0: number of points.
+ *   aux1 selects a view of the indexed_presence collector over the same per-group point counts
+ *   (stream/collector/indexed_presence.rs:6-147; UINT32_MAX / 0 = consecutive_runs as above):
+ *   1 = sum over complement_runs(lo..hi) of w(run.point_count); 2 = any_in(lo..hi) ? w(1) : 0;
+ *   3 = w(count()) of the distinct points; p1 = lo | hi << 32 with 0 <= lo <= hi <= p0. Groups without items
+ *   do not exist and score nothing. */
 #define SFGPU_K_RUNS 10
 
 typedef struct sfgpu_constraint_desc {

@@ -941,6 +941,70 @@ struct RunsAcc {
     items = 0;
   }
 };
+// indexed_presence.rs:6-147 — indexed_presence(index): the distinct integer points of a group with their item
+// counts; the result offers membership, counts in a range, the active runs and the complement runs of a horizon.
+struct IndexedPresence {
+  std::map<int64_t, size_t> points;
+  size_t items = 0;
+  bool contains(int64_t i) const { return points.count(i) != 0; }
+  size_t count() const { return points.size(); }
+  size_t item_count() const { return items; }
+  bool is_empty() const { return points.empty(); }
+  static Runs runs_from_counts(const std::map<int64_t, size_t>& pts) {  // runs.rs:179-229
+    Runs out;
+    out.point_count = pts.size();
+    bool open = false;
+    Run cur;
+    for (auto& kv : pts) {
+      out.item_count += kv.second;
+      if (open && cur.end + 1 == kv.first) {
+        cur.end = kv.first;
+        cur.point_count += 1;
+        cur.item_count += kv.second;
+      } else {
+        if (open) out.runs.push_back(cur);
+        cur = Run{kv.first, kv.first, 1, kv.second};
+        open = true;
+      }
+    }
+    if (open) out.runs.push_back(cur);
+    return out;
+  }
+  Runs runs() const { return runs_from_counts(points); }
+  Runs complement_runs(int64_t lo, int64_t hi) const {  // :72-91
+    std::map<int64_t, size_t> comp;
+    for (int64_t i = lo; i < hi; ++i)
+      if (!points.count(i)) comp[i] = 1;
+    return runs_from_counts(comp);
+  }
+  size_t count_in(int64_t lo, int64_t hi) const {  // :93-98
+    if (lo >= hi) return 0;
+    size_t n = 0;
+    for (auto it = points.lower_bound(lo); it != points.end() && it->first < hi; ++it) ++n;
+    return n;
+  }
+  bool any_in(int64_t lo, int64_t hi) const { return count_in(lo, hi) > 0; }
+};
+struct IndexedPresenceAcc {  // :104-147
+  using Value = int64_t;
+  using Result = IndexedPresence;
+  using Retraction = int64_t;
+  IndexedPresence presence;
+  Retraction accumulate(Value v) {
+    presence.points[v] += 1;
+    presence.items += 1;
+    return v;
+  }
+  void retract(Retraction v) {
+    auto it = presence.points.find(v);
+    if (it == presence.points.end()) return;
+    it->second = it->second > 0 ? it->second - 1 : 0;
+    presence.items = presence.items > 0 ? presence.items - 1 : 0;
+    if (it->second == 0) presence.points.erase(it);
+  }
+  Result result() const { return presence; }
+  void reset() { presence = IndexedPresence{}; }
+};
 // load_balance.rs:104-240. Result carries `unfairness` (the per-key loads map is not scored).
 struct LoadBalanceAcc {
   using Value = std::pair<int64_t, int64_t>;  // (balanced key, metric)

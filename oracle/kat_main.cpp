@@ -974,6 +974,45 @@ static void kat_moves_and_loop() {
       mvs = cm.enumerate_scalar({});
     }
   }
+  {  // stream/collector/tests/collector.rs:333-395 (indexed_presence) and the macro example
+     // solverforge-macros/tests/ui/pass/solverforge_constraints_indexed_presence.rs:57-64 (initialize_all == -2)
+    IndexedPresenceAcc acc;
+    for (int64_t v : {4, 2, 3, 7, 7}) acc.accumulate(v);
+    IndexedPresence r = acc.result();
+    CHECK(r.contains(3) && !r.contains(5) && r.count() == 4 && r.item_count() == 5);
+    CHECK(r.count_in(2, 5) == 3 && r.any_in(7, 8));
+    Runs rr = r.runs();
+    CHECK(rr.runs.size() == 2 && rr.runs[0].start == 2 && rr.runs[0].end == 4 && rr.runs[1].start == 7 &&
+          rr.runs[1].item_count == 2);
+    IndexedPresenceAcc a2;
+    for (int64_t v : {0, 2, 5}) a2.accumulate(v);
+    Runs cr = a2.result().complement_runs(0, 7);
+    CHECK(cr.runs.size() == 3 && cr.runs[0].start == 1 && cr.runs[0].end == 1 && cr.runs[1].start == 3 &&
+          cr.runs[1].end == 4 && cr.runs[2].start == 6 && cr.runs[2].end == 6);
+    IndexedPresenceAcc a3;
+    a3.accumulate(-1);
+    a3.accumulate(-1);
+    a3.accumulate(0);
+    a3.retract(-1);
+    CHECK(a3.result().contains(-1) && a3.result().item_count() == 2);
+    a3.retract(-1);
+    CHECK(!a3.result().contains(-1));
+    a3.reset();
+    CHECK(a3.result().is_empty() && a3.result().item_count() == 0);
+    // the macro example: one nurse works days 0, 1, 2 of a 5-day horizon: streak excess 1 (runs collector form)
+    // + rest excess 1 = -2; the model below holds the rest / weekend / days-worked constraints
+    ShiftSchedule ss;
+    ss.nurses = {{0}, {1}};
+    for (size_t i = 0; i < 3; ++i) ss.shifts.push_back({i, (int64_t)i, 0, false, 8, OptVal{0}});
+    ShiftModel pm(ss, 0, false, 5);
+    // unassigned 0, one-per-day 0, long streaks -1, rest streaks -1, weekend 0, days worked -6, balanced |3-0| + |0-0| = -3
+    CHECK(pm.calculate_score() == (Sc{0, -11}));
+    CHECK(pm.calculate_score() == pm.fresh_score());
+    pm.apply(Move::change(0, 1, OptVal{1}));  // nurse 1 takes day 1: nurse 0 {0, 2}, nurse 1 {1}
+    // streaks 0; rest: nurse 0 gaps {1}, {3,4} -> 1, nurse 1 gaps {0}, {2,3,4} -> 2; days worked -6; balanced 2 + 1
+    CHECK(pm.calculate_score() == (Sc{0, -12}));
+    CHECK(pm.calculate_score() == pm.fresh_score());
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

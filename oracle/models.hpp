@@ -399,7 +399,7 @@ inline const std::vector<SNurse>& ss_nurses(const ShiftSchedule& s) { return s.n
 inline const std::vector<SShift>& ss_shifts(const ShiftSchedule& s) { return s.shifts; }
 
 struct ShiftModel final : ModelImpl<ShiftSchedule> {
-  explicit ShiftModel(ShiftSchedule sol, int64_t target = 4, bool with_load_balance = true) {
+  explicit ShiftModel(ShiftSchedule sol, int64_t target = 4, bool with_load_balance = true, int64_t presence_days = 0) {
     dir.working = std::move(sol);
     dir.access.get = [](const ShiftSchedule& s, size_t, size_t e) { return s.shifts[e].nurse_idx; };
     dir.access.set = [](ShiftSchedule& s, size_t, size_t e, OptVal v) { s.shifts[e].nurse_idx = v; };
@@ -432,6 +432,32 @@ struct ShiftModel final : ModelImpl<ShiftSchedule> {
         std::make_unique<GroupedConstraint<ShiftSchedule, SShift, size_t, Sc, RunsAcc, decltype(sf_), decltype(sk),
                                            decltype(sv), decltype(sw)>>("Long work streaks", Impact::Penalty, shifts,
                                                                         sf_, sk, sv, sw, false));
+    if (presence_days > 0) {
+      // the three constraints of the reference's indexed_presence example
+      // (solverforge-macros/tests/ui/pass/solverforge_constraints_indexed_presence.rs:13-55) over a horizon of
+      // presence_days days: rest streaks (complement runs, excess over 1), weekend work (any_in(5..7)), and an
+      // authored one on the number of distinct days worked
+      const int64_t H = presence_days;
+      auto w_rest = [H](const size_t&, const IndexedPresence& p) {
+        int64_t t = 0;
+        for (auto& r : p.complement_runs(0, H).runs) t += r.point_count > 1 ? (int64_t)r.point_count - 1 : 0;
+        return Sc::of_soft(t);
+      };
+      auto w_weekend = [](const size_t&, const IndexedPresence& p) { return Sc::of_soft(p.any_in(5, 7) ? 1 : 0); };
+      auto w_days = [](const size_t&, const IndexedPresence& p) { return Sc::of_soft(2 * (int64_t)p.count()); };
+      dir.constraints.add(
+          std::make_unique<GroupedConstraint<ShiftSchedule, SShift, size_t, Sc, IndexedPresenceAcc, decltype(sf_),
+                                             decltype(sk), decltype(sv), decltype(w_rest)>>(
+              "Rest streaks", Impact::Penalty, shifts, sf_, sk, sv, w_rest, false));
+      dir.constraints.add(
+          std::make_unique<GroupedConstraint<ShiftSchedule, SShift, size_t, Sc, IndexedPresenceAcc, decltype(sf_),
+                                             decltype(sk), decltype(sv), decltype(w_weekend)>>(
+              "Weekend work", Impact::Penalty, shifts, sf_, sk, sv, w_weekend, false));
+      dir.constraints.add(
+          std::make_unique<GroupedConstraint<ShiftSchedule, SShift, size_t, Sc, IndexedPresenceAcc, decltype(sf_),
+                                             decltype(sk), decltype(sv), decltype(w_days)>>(
+              "Days worked", Impact::Penalty, shifts, sf_, sk, sv, w_days, false));
+    }
     // Balanced workload: group_by(nurse, count()).complement(nurses, id, 0).penalize(|count - target|)
     auto jka = [](const SShift& s) { return s.nurse_idx; };
     auto jkb = [](const SNurse& n) { return OptVal(n.id); };

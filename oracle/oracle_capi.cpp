@@ -95,12 +95,12 @@ void* sfo_js_create(uint32_t n_ops, uint32_t n_machines, const uint32_t* job, co
 
 void* sfo_shift_create(uint32_t n_shifts, uint32_t n_nurses, const int64_t* day, const uint32_t* slot,
                        const uint8_t* required, const int64_t* hours, const int32_t* nurse_idx, int64_t target,
-                       int with_load_balance) {
+                       int with_load_balance, int64_t presence_days) {
   ShiftSchedule s;
   for (uint32_t i = 0; i < n_nurses; ++i) s.nurses.push_back({i});
   for (uint32_t i = 0; i < n_shifts; ++i)
     s.shifts.push_back({i, day[i], slot[i], required[i] != 0, hours[i], opt(nurse_idx[i])});
-  return new ShiftModel(std::move(s), target, with_load_balance != 0);
+  return new ShiftModel(std::move(s), target, with_load_balance != 0, presence_days);
 }
 
 // roster with projected rows: span rows of shift i are span_day/span_hours[span_ptr[i] .. span_ptr[i+1])

@@ -648,6 +648,18 @@ class ConsecutiveRuns:
 
 
 @dataclass
+class IndexedPresence:
+    """indexed_presence(|e| e.point) (stream/collector/indexed_presence.rs) scored through one of its views:
+    "complement_runs" — the weight applies to every run of absent points inside [lo, hi) and the group scores their
+    sum; "any_in" — weight(1) when a point of [lo, hi) is present; "count" — weight(distinct points)."""
+    point_column: int
+    n_points: int
+    view: str = "count"
+    lo: int = 0
+    hi: int = 0
+
+
+@dataclass
 class LoadBalance:
     metric_column: int = L.NO_COLUMN
 
@@ -857,6 +869,12 @@ class GroupedStream:
                 raise L.SfgpuError(L.E_UNSUPPORTED, "consecutive_runs with a complement is not expressible on device")
             return _Terminal(self.d, kind=L.K_RUNS, impact=impact, weight=weight, collection=self.collection,
                              aux0=c.point_column, p0=c.n_points)
+        if isinstance(c, IndexedPresence):
+            if self.complemented:
+                raise L.SfgpuError(L.E_UNSUPPORTED, "indexed_presence with a complement is not expressible on device")
+            view = {"complement_runs": 1, "any_in": 2, "count": 3}[c.view]
+            return _Terminal(self.d, kind=L.K_RUNS, impact=impact, weight=weight, collection=self.collection,
+                             aux0=c.point_column, aux1=view, p0=c.n_points, p1=c.lo | (c.hi << 32))
         if isinstance(c, LoadBalance):
             return _Terminal(self.d, kind=L.K_LOAD_BALANCE, impact=impact, weight=weight, collection=self.collection,
                              aux0=c.metric_column)

@@ -714,6 +714,15 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
           if (v < 0 || v >= d.p0) return fail(ctx, SFGPU_E_INVALID, "RUNS: point outside [0, p0)");
         c.g0 = col;
         c.n0 = (uint32_t)d.p0;
+        // indexed_presence views (aux1): p1 = lo | hi << 32, a horizon / range inside [0, p0)
+        if (d.aux1 != 0xFFFFFFFFu && d.aux1 != 0) {
+          if (d.aux1 > 3) return fail(ctx, SFGPU_E_INVALID, "RUNS: aux1 (indexed_presence view) must be 0..3");
+          const int64_t lo = d.p1 & 0xFFFFFFFFll, hi = (d.p1 >> 32) & 0xFFFFFFFFll;
+          if (d.aux1 != 3 && (lo > hi || hi > d.p0)) return fail(ctx, SFGPU_E_INVALID, "RUNS: range outside [0, p0)");
+          c.p0 = d.aux1;
+          c.p1 = lo;
+          c.p2 = hi;
+        }
         c.off0 = off;
         off = align_up(off + dm.n_values * c.n0 * 4, 16);
         break;

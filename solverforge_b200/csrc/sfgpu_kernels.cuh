@@ -64,6 +64,35 @@ __device__ __forceinline__ int64_t lb_unfairness(int64_t n, int64_t sum, int64_t
   return (int64_t)round(sqrt(tmp));
 }
 
+// indexed_presence views of one group (stream/collector/indexed_presence.rs): cntf(q) = items at point q.
+// c.p0: 1 = complement_runs(lo..hi) scored run by run, 2 = any_in(lo..hi), 3 = count() of distinct points;
+// c.p1 / c.p2 = lo / hi. A group without items does not exist and scores nothing (grouped/state.rs:349-365).
+template <class F>
+__device__ __forceinline__ int64_t presence_group_score(const ConsDev& c, F cntf) {
+  const int32_t np = (int32_t)c.n0, lo = (int32_t)c.p1, hi = (int32_t)c.p2;
+  int64_t items = 0, distinct = 0, gaps = 0, gap = 0;
+  bool any = false;
+  for (int32_t q = 0; q < np; ++q) {
+    const int32_t n = cntf(q);
+    items += n;
+    distinct += n > 0 ? 1 : 0;
+    if (q >= lo && q < hi) {
+      any = any || n > 0;
+      if (n == 0) {
+        ++gap;
+      } else {
+        if (gap > 0) gaps += weight_eval(c.w, gap);
+        gap = 0;
+      }
+    }
+  }
+  if (gap > 0) gaps += weight_eval(c.w, gap);
+  if (items == 0) return 0;
+  if (c.p0 == 1) return gaps;
+  if (c.p0 == 2) return any ? weight_eval(c.w, 1) : 0;
+  return weight_eval(c.w, distinct);
+}
+
 // Delta of ONE edit (e: old -> new) against the replica state `st` overlaid with the edits
 // prev[0..n_prev) that were already applied by the same candidate.
 // `st` = the replica block as the kernel sees it (possibly the staged shared-memory prefix); `gst` = the
@@ -181,6 +210,27 @@ __device__ void scalar_edit_delta(const DevModel& m, const char* st, const char*
         const int32_t np = (int32_t)c.n0;
         const int32_t pt = (int32_t)((const int64_t*)c.g0)[cur.e];
         int64_t delta = 0;
+        if (c.p0 != 0) {  // indexed_presence views: re-score the (at most two) touched groups from their rows
+          for (int side = 0; side < 2; ++side) {
+            const int32_t v = side == 0 ? cur.old_v : cur.new_v;
+            if (v < 0) continue;
+            const int32_t* row = cnt + (size_t)v * np;
+            auto at = [&](int32_t q) {  // earlier edits of this candidate included
+              int32_t n = row[q];
+              for (int i = 0; i < n_prev; ++i) {
+                if ((int32_t)((const int64_t*)c.g0)[prev[i].e] != q) continue;
+                if (prev[i].new_v == v) n += 1;
+                if (prev[i].old_v == v) n -= 1;
+              }
+              return n;
+            };
+            const int32_t dn = side == 0 ? -1 : 1;
+            delta += presence_group_score(c, [&](int32_t q) { return at(q) + (q == pt ? dn : 0); }) -
+                     presence_group_score(c, at);
+          }
+          add_level(d, c, delta);
+          break;
+        }
         for (int side = 0; side < 2; ++side) {
           const int32_t v = side == 0 ? cur.old_v : cur.new_v;
           if (v < 0) continue;
@@ -1406,6 +1456,11 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
           if (var[e] >= 0) atomicAdd(&cnt[(size_t)var[e] * np + (uint32_t)((const int64_t*)c.g0)[e]], 1);
         __syncthreads();
         for (uint32_t v = threadIdx.x; v < m.n_values; v += blockDim.x) {
+          if (c.p0 != 0) {
+            const int32_t* row = cnt + (size_t)v * np;
+            local += presence_group_score(c, [&](int32_t q) { return row[q]; });
+            continue;
+          }
           int64_t run = 0;
           for (uint32_t q = 0; q <= np; ++q) {
             if (q < np && cnt[(size_t)v * np + q] > 0) {

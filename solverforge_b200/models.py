@@ -118,10 +118,10 @@ def job_shop_director(inst: JobShopInstance, n_replicas: int = 1, machine_idx=No
 
 
 def shift_scheduling_director(inst, n_replicas: int = 1, nurse_idx=None, device: int = 0, stream=None,
-                              flags: int = 0, with_load_balance: bool = True) -> GpuScoreDirector:
+                              flags: int = 0, with_load_balance: bool = True, presence_days: int = 0) -> GpuScoreDirector:
     """examples/minimal-shift-scheduling/src/domain/schedule.rs:21-84 (all four constraints, incl. "Long work
     streaks" over the consecutive_runs collector) + an authored load_balance constraint."""
-    from .api import ConsecutiveRuns, LoadBalance
+    from .api import ConsecutiveRuns, IndexedPresence, LoadBalance
     d = GpuScoreDirector(n_replicas, device, stream, flags)
     nurses = d.add_collection("nurses", inst.n_nurses, -1)
     shifts = d.add_collection("shifts", inst.n_shifts, 0)
@@ -135,6 +135,16 @@ def shift_scheduling_director(inst, n_replicas: int = 1, nurse_idx=None, device:
         HardSoftScore.ONE_HARD).named("One shift per nurse day")
     f.for_each(shifts).assigned().group_by(ConsecutiveRuns(day, int(np.max(inst.day)) + 1)).penalize(
         soft(L.W_EXCESS, 1, 2)).named("Long work streaks")
+    if presence_days > 0:
+        # the indexed_presence example of the reference (solverforge-macros/tests/ui/pass/
+        # solverforge_constraints_indexed_presence.rs:13-55) + an authored distinct-days constraint
+        n_points = max(int(np.max(inst.day)) + 1, presence_days, 7)   # the views' ranges must lie inside the table
+        f.for_each(shifts).assigned().group_by(IndexedPresence(day, n_points, "complement_runs", 0, presence_days)).penalize(
+            soft(L.W_EXCESS, 1, 1)).named("Rest streaks")
+        f.for_each(shifts).assigned().group_by(IndexedPresence(day, n_points, "any_in", 5, 7)).penalize(
+            soft(L.W_CONST, 1, 0)).named("Weekend work")
+        f.for_each(shifts).assigned().group_by(IndexedPresence(day, n_points, "count")).penalize(
+            soft(L.W_LINEAR, 2, 0)).named("Days worked")
     f.for_each(shifts).assigned().group_by(Count()).complement(nurses, 0).penalize(
         soft(L.W_ABSDIFF, 1, inst.target)).named("Balanced workload")
     if with_load_balance:

@@ -38,7 +38,7 @@ def lib() -> C.CDLL:
         l.sfo_cluster_create.argtypes = [C.c_uint32, C.c_uint32, _P, C.c_uint32, _P]
         l.sfo_cvrp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, _P, _P, _P, _P]
         l.sfo_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int]
-        l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64, C.c_int]
+        l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64]
         l.sfo_roster_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]
         l.sfo_destroy.argtypes = [_P]
         l.sfo_committed_score.argtypes = [_P, _P]
@@ -143,12 +143,12 @@ class Oracle:
                                           1 if with_complement else 0))
 
     @staticmethod
-    def shift_scheduling(inst, nurse_idx=None, with_load_balance=True) -> "Oracle":
+    def shift_scheduling(inst, nurse_idx=None, with_load_balance=True, presence_days=0) -> "Oracle":
         n = np.ascontiguousarray(inst.nurse_idx if nurse_idx is None else nurse_idx, dtype=np.int32)
         return Oracle(lib().sfo_shift_create(inst.n_shifts, inst.n_nurses, _p(np.ascontiguousarray(inst.day, np.int64)),
                                              _p(_u32(inst.slot)), _p(np.ascontiguousarray(inst.required, np.uint8)),
                                              _p(np.ascontiguousarray(inst.hours, np.int64)), _p(n), inst.target,
-                                             1 if with_load_balance else 0))
+                                             1 if with_load_balance else 0, presence_days))
 
     @staticmethod
     def roster(inst, nurse_idx=None) -> "Oracle":

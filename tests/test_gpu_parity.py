@@ -928,3 +928,61 @@ def test_consecutive_runs_collector_matches_oracle():
                 o.apply_change(*rows[out[1]])
             assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
             assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
+
+
+def test_indexed_presence_collector_matches_oracle():
+    """group_by(nurse, indexed_presence(day)) scored through complement_runs(0..H), any_in(5..7) and count()
+    (stream/collector/indexed_presence.rs; the reference's macro example
+    solverforge-macros/tests/ui/pass/solverforge_constraints_indexed_presence.rs): the known answer of that example
+    as columns, then change, swap and compound candidates and committed trajectories, cached == fresh == oracle.
+    Groups that lose their last item disappear (their complement runs are not scored)."""
+    kat = instances.shift_scheduling(n_days=5, slots_per_day=1, n_nurses=2, seed=1)
+    kat.n_shifts, kat.day, kat.slot = 3, kat.day[:3], kat.slot[:3]
+    kat.required, kat.hours = np.zeros(3, dtype=np.uint8), kat.hours[:3]
+    kat.nurse_idx, kat.target = np.zeros(3, dtype=np.int32), 0
+    dk = models.shift_scheduling_director(kat, with_load_balance=False, presence_days=5)
+    assert dk.calculate_score()[0].tolist() == [0, -11] == dk.fresh_score()[0].tolist()
+    dk.apply_change(np.array([[1, 1]]))
+    assert dk.calculate_score()[0].tolist() == [0, -12] == dk.fresh_score()[0].tolist()
+    for seed in (3, 8):
+        inst = instances.shift_scheduling(n_days=12, slots_per_day=3, n_nurses=4, seed=seed, unassigned_permille=250)
+        o = Oracle.shift_scheduling(inst, with_load_balance=False, presence_days=12)
+        d = models.shift_scheduling_director(inst, with_load_balance=False, presence_days=12)
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+        rows = o.enumerate_change()
+        s, ok = d.score_change(rows)
+        so, oko = o.score_change(rows)
+        _eq(ok, oko, "presence change doable")
+        _eq(s, so, "presence change scores")
+        r = instances.splitmix64_stream(40 + seed, 4000)
+        swaps = np.stack([r[:300] % np.uint64(inst.n_shifts), r[300:600] % np.uint64(inst.n_shifts)], axis=1).astype(np.int64)
+        s, ok = d.score_swap(swaps)
+        so, oko = o.score_swap(swaps)
+        _eq(ok, oko, "presence swap doable")
+        _eq(s, so, "presence swap scores")
+        n_c = 300
+        sizes = (r[600:600 + n_c] % np.uint64(5)).astype(np.int64) + 1
+        eo = np.concatenate([[0], np.cumsum(sizes)])
+        tot = int(eo[-1])
+        rr = instances.splitmix64_stream(41 + seed, 2 * tot)
+        ent = (rr[:tot] % np.uint64(inst.n_shifts)).astype(np.int64)
+        for i in range(1, tot, 2):                       # neighbouring days in one candidate
+            ent[i] = min(int(ent[i - 1]) + 3, inst.n_shifts - 1)
+        val = (rr[tot:] % np.uint64(3)).astype(np.int64) - 1
+        edits = np.stack([ent, val], axis=1)
+        s, ok = d.score_compound(eo, edits)
+        so, oko = o.score_compound(eo, edits)
+        _eq(ok, oko, "presence compound doable")
+        _eq(s, so, "presence compound scores")
+        for step in range(10):
+            last = d.calculate_score()
+            idx, best, ev, win = d.step_change(ForageParams(2, 1, 0), step_seeds=[90 + step],
+                                               ref_scores=np.concatenate([last, last + [0, -3]], axis=1), apply=True)
+            rows = o.enumerate_change()
+            so, oko = o.score_change(rows)
+            out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0] + [0, -3], 90 + step, 2, 1, True, 1)
+            if out[0]:
+                assert int(idx[0]) == out[1], f"step {step}"
+                o.apply_change(*rows[out[1]])
+            assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
+            assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
