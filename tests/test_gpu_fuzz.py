@@ -108,3 +108,45 @@ def test_fuzz_scalar_models(seed):
             assert idx[0] == 0xFFFFFFFF
         assert d.calculate_score()[0].tolist() == o.committed_score().tolist()
         assert d.fresh_score()[0].tolist() == o.committed_score().tolist()
+
+
+@pytest.mark.parametrize("seed", range(max(FUZZ // 2, 6)))
+def test_fuzz_sublist_steps(seed):
+    """Device-enumerated SublistChange / SublistSwap steps on random shapes: one to many routes, empty and
+    one-element routes, coarse distances (ties), random segment sizes, acceptors, limits and tie modes."""
+    s = [int(x) for x in splitmix64_stream(5000 + seed, 12)]
+    n = 8 + s[0] % 40
+    routes = 1 + s[1] % min(n, 9)
+    coarse = [1, 7, 40, 200][s[2] % 4]
+    lo = 1 + s[3] % 3
+    hi = lo + s[4] % 4
+    acceptor = s[5] % 3
+    limit = [0, 0, 1, 5, 60, 100000][s[6] % 6]
+    ties = s[7] % 2
+    step_seed = s[8]
+    c = instances.cvrp(n, routes, seed=seed + 11)
+    c.matrix = (c.matrix // coarse) * coarse
+    start = instances.perturb_routes(c, seed, s[9] % 60)
+    d = models.cvrp_director(c, 1, offsets=start[0][None, :], elems=start[1])
+    o = Oracle.cvrp(c, *start)
+    base = d.calculate_score()[0]
+    okind = {0: 3, 1: 0, 2: 1}[acceptor]
+    ref = np.concatenate([base + [0, -(step_seed % 50)], base + [0, -(step_seed % 170)]])
+    what = f"n={n} routes={routes} coarse={coarse} sizes={lo}..{hi} acc={acceptor} limit={limit} ties={ties}"
+    for swap in (False, True):
+        rows = o.enumerate_sublist_swap(lo, hi) if swap else o.enumerate_sublist_change(lo, hi)
+        if len(rows):
+            so, oko = (o.score_sublist_swap if swap else o.score_sublist_change)(rows)
+        else:
+            so, oko = np.zeros((0, 2), np.int64), np.zeros(0, np.uint8)
+        step = d.step_sublist_swap if swap else d.step_sublist_change
+        idx, best, ev, win = step(lo, hi, ForageParams(acceptor, ties, limit), step_seeds=[step_seed], ref_scores=[ref])
+        out = oracle_lib.replay_step(so, oko, [0, 0], ref[:2], ref[2:], step_seed, 0 if limit else 2, max(limit, 1),
+                                     bool(ties), okind)
+        assert int(ev[0]) == out[2], what + f" swap={swap} moves_evaluated"
+        if out[0]:
+            assert int(idx[0]) == out[1], what + f" swap={swap}"
+            assert best[0].tolist() == so[out[1]].tolist(), what + f" swap={swap}"
+            assert win[0].tolist() == rows[out[1]].astype(np.int64).tolist(), what + f" swap={swap}"
+        else:
+            assert idx[0] == 0xFFFFFFFF, what + f" swap={swap}"
