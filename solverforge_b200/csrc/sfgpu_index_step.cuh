@@ -347,7 +347,110 @@ struct SublistSwapNb {
   __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
     return list_sublist_swap_delta(m, st, row, d);
   }
-  static constexpr bool kHasCursor = false;
+
+  // ---- cursor (see SublistChangeNb): consecutive pull indices keep the first segment and step the second one
+  // through size, start and entity; everything that depends on the first segment only is hoisted.
+  static constexpr bool kHasCursor = true;
+  struct Cursor {
+    uint32_t e1, s1, n1, b1, L1;
+    uint32_t e2, s2, n2, b2, L2;
+    uint32_t p1, x1, f1, l1;         // first segment: element before / after, first / last element
+    int64_t c_pf, c_lx;              // legs (p1, f1) and (l1, x1)
+    int64_t v1, a1, w_a1;            // per-route sum constraint: segment total, route sum, its weight
+  };
+  __device__ __forceinline__ void set_second(Cursor& c, uint32_t e2, uint32_t s2, uint32_t n2) const {
+    c.e2 = e2;
+    c.s2 = s2;
+    c.n2 = n2;
+    c.b2 = off[e2];
+    c.L2 = off[e2 + 1] - c.b2;
+  }
+  __device__ __forceinline__ void seek(const DevModel& m, const char* st, uint32_t idx, Cursor& c) const {
+    const uint4 row = decode(idx);
+    c.e1 = row.x;
+    c.s1 = SFGPU_SEG_POS(row.y);
+    c.n1 = SFGPU_SEG_SIZE(row.y);
+    c.b1 = off[c.e1];
+    c.L1 = off[c.e1 + 1] - c.b1;
+    set_second(c, row.z, SFGPU_SEG_POS(row.w), SFGPU_SEG_SIZE(row.w));
+    if (!m.fast_list) return;
+    const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+    const uint32_t t1 = c.s1 + c.n1;
+    c.f1 = el[c.b1 + c.s1];
+    c.l1 = el[c.b1 + t1 - 1];
+    c.p1 = c.x1 = 0;
+    c.c_pf = c.c_lx = c.v1 = c.a1 = c.w_a1 = 0;
+    if (m.fast_pc >= 0) {
+      const ConsDev& pc = m.cons[m.fast_pc];
+      const uint32_t depot = (uint32_t)pc.p0;
+      c.p1 = c.s1 > 0 ? el[c.b1 + c.s1 - 1] : depot;
+      c.x1 = t1 < c.L1 ? el[c.b1 + t1] : depot;
+      c.c_pf = mat_at(pc, c.p1, c.f1);
+      c.c_lx = mat_at(pc, c.l1, c.x1);
+    }
+    if (m.fast_ls >= 0) {
+      const ConsDev& ls = m.cons[m.fast_ls];
+      for (uint32_t i = c.s1; i < t1; ++i) c.v1 += ((const int64_t*)ls.g0)[el[c.b1 + i]];
+      c.a1 = ((const int64_t*)(st + ls.off0))[c.e1];
+      c.w_a1 = weight_eval(ls.w, c.a1);
+    }
+  }
+  __device__ __forceinline__ void advance(const DevModel& m, const char* st, uint32_t next_idx, Cursor& c) const {
+    if (c.n2 < max_size && c.s2 + c.n2 + 1 <= c.L2) {  // next size at the same start
+      ++c.n2;
+      return;
+    }
+    if (c.s2 + 1 + min_size <= c.L2) {  // next start of the same list
+      ++c.s2;
+      c.n2 = min_size;
+      return;
+    }
+    uint32_t e = c.e2 + 1;  // next entity that holds a segment
+    while (e < n && off[e + 1] - off[e] < min_size) ++e;
+    if (e >= n) return seek(m, st, next_idx, c);
+    set_second(c, e, 0, min_size);
+  }
+  __device__ __forceinline__ bool eval(const DevModel& m, const char* st, const Cursor& c, Score2& d) const {
+    if (!m.fast_list)
+      return list_sublist_swap_delta(m, st, make_uint4(c.e1, c.s1 | (c.n1 << 24), c.e2, c.s2 | (c.n2 << 24)), d);
+    d.hard = 0;
+    d.soft = 0;
+    const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+    const bool intra = c.e1 == c.e2;
+    const uint32_t t1 = c.s1 + c.n1, t2 = c.s2 + c.n2;
+    if (m.fast_pc >= 0) {  // linear weight: the inner legs of both segments cancel, w(x + delta) - w(x) = a * delta
+      const ConsDev& pc = m.cons[m.fast_pc];
+      const uint32_t depot = (uint32_t)pc.p0;
+      const uint32_t f2 = el[c.b2 + c.s2], l2 = el[c.b2 + t2 - 1];
+      const uint32_t x2 = t2 < c.L2 ? el[c.b2 + t2] : depot;
+      int64_t delta;
+      if (intra) {  // the first segment is the earlier one (second.start >= first.end)
+        delta = mat_at(pc, c.p1, f2) + mat_at(pc, c.l1, x2) - c.c_pf - mat_at(pc, l2, x2);
+        if (t1 == c.s2) {
+          delta += mat_at(pc, l2, c.f1) - mat_at(pc, c.l1, f2);
+        } else {
+          const uint32_t mk = el[c.b1 + c.s2 - 1];
+          delta += mat_at(pc, l2, c.x1) + mat_at(pc, mk, c.f1) - c.c_lx - mat_at(pc, mk, f2);
+        }
+      } else {
+        const uint32_t p2 = c.s2 > 0 ? el[c.b2 + c.s2 - 1] : depot;
+        delta = mat_at(pc, c.p1, f2) + mat_at(pc, l2, c.x1) - c.c_pf - c.c_lx + mat_at(pc, p2, c.f1) +
+                mat_at(pc, c.l1, x2) - mat_at(pc, p2, f2) - mat_at(pc, l2, x2);
+      }
+      add_level(d, pc, pc.w.a * delta);
+    }
+    if (m.fast_ls >= 0 && !intra) {
+      const ConsDev& ls = m.cons[m.fast_ls];
+      // the per-position records of the fast list path carry the element's column value (staged with the block)
+      const PosRec* pr = (const PosRec*)(st + m.off_pos_rec);
+      int64_t v2 = 0;
+      for (uint32_t i = c.s2; i < t2; ++i) v2 += pr[c.b2 + i].val;
+      const int64_t a2 = ((const int64_t*)(st + ls.off0))[c.e2];
+      add_level(d, ls, weight_eval(ls.w, c.a1 - c.v1 + v2) - c.w_a1 + weight_eval(ls.w, a2 - v2 + c.v1) -
+                           weight_eval(ls.w, a2));
+    }
+    return true;
+  }
 };
 
 // grid = (chunks, R): chunk c scores pull indices [c * per_chunk, (c + 1) * per_chunk) of its replica.
