@@ -416,6 +416,33 @@ def run_ours(args):
                        "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
                        "best_score_replica0": [int(best_l[0][0]), int(best_l[0][1])]}
 
+    # informational, outside every timed region: the device-enumerated sublist neighbourhoods of the reference's
+    # default list policy (SublistChange / SublistSwap, sizes 1..=3, ~3 M / ~3.8 M candidates per replica and
+    # step, never materialised) — whole steps incl. commit through the host call, on a small replica count
+    sublist_steps = None
+    if name == "cvrp" and world == 1 and args.loop_steps > 0:
+        try:
+            Rs = min(R, 32)
+            ds = models.cvrp_director(inst, Rs, offsets=np.stack([starts[r % D][0][0] for r in range(Rs)]),
+                                      elems=np.concatenate([starts[r % D][0][1] for r in range(Rs)]), device=local)
+            sublist_steps = {"replicas": Rs, "sizes": "1..=3"}
+            for label, fn in (("sublist_change", ds.step_sublist_change), ("sublist_swap", ds.step_sublist_swap)):
+                last = ds.calculate_score()
+                ref = np.concatenate([last, last], axis=1)
+                fn(1, 3, ForageParams(1, 1, 0), step_seeds=list(range(Rs)), ref_scores=ref)   # warm-up
+                t0 = time.perf_counter()
+                tot = 0
+                for s_i in range(3):
+                    idx_s, best_s, ev_s, win_s = fn(1, 3, ForageParams(1, 1, 0), step_seeds=[7 * s_i + r for r in range(Rs)],
+                                                    ref_scores=ref, apply=True)
+                    tot += int(ev_s.astype(np.int64).sum())
+                dt = time.perf_counter() - t0
+                sublist_steps[label] = {"candidates_per_s": tot / dt, "ms_per_step": dt * 1e3 / 3,
+                                        "candidates_per_replica_step": tot // (3 * Rs)}
+            del ds
+        except Exception as exc:  # informational only: never fail the bench line
+            sublist_steps = {"error": str(exc)[:200]}
+
     t = torch.tensor([elapsed_ms, kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -449,6 +476,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "device_loop": device_loop,
+            "sublist_steps": sublist_steps,
         }
         print(json.dumps(line))
     if world > 1:
