@@ -511,6 +511,22 @@ class GpuScoreDirector {
                                     reinterpret_cast<int64_t*>(out_best.data()), out_evaluated.data(),
                                     out_winner_rows.data(), apply_winners ? 1 : 0));
   }
+  // the same over the SublistSwap neighbourhood (sfgpu_step_sublist_swap)
+  void step_sublist_swap(uint32_t min_size, uint32_t max_size, const StepParams& p, const std::vector<uint64_t>& step_seeds,
+                         const std::vector<int64_t>& ref_scores, std::vector<uint32_t>& out_index,
+                         std::vector<HardSoftScore>& out_best, std::vector<uint32_t>& out_evaluated,
+                         std::vector<uint32_t>& out_winner_rows, bool apply_winners) {
+    sfgpu_forage_params fp{p.acceptor, p.random_ties ? 1 : 0, p.accepted_limit, 0};
+    const size_t R = step_seeds.size();
+    out_index.resize(R);
+    out_best.resize(R);
+    out_evaluated.resize(R);
+    out_winner_rows.resize(R * 4);
+    check(sfgpu_step_sublist_swap(ctx_, 0, min_size, max_size, &fp, step_seeds.data(),
+                                  ref_scores.empty() ? nullptr : ref_scores.data(), out_index.data(),
+                                  reinterpret_cast<int64_t*>(out_best.data()), out_evaluated.data(),
+                                  out_winner_rows.data(), apply_winners ? 1 : 0));
+  }
   // CompoundScalarMove batch: candidate i owns edits [edit_offsets[i], edit_offsets[i+1]) (compound_scalar.rs:289-319)
   void score_compound(const std::vector<uint64_t>& edit_offsets, const std::vector<ScalarEdit>& edits,
                       const std::vector<uint64_t>& cand_offsets, std::vector<HardSoftScore>& scores,
