@@ -459,6 +459,36 @@ static int test_gpu() {
         auto fr = cd.fresh_score()[0], cm = cd.calculate_score()[0];
         CHECK(fr == cm);
         // the device-resident loop through the mirror runs and keeps cached == fresh
+        if (kind == 0 && !swap_moves) {
+          // device-enumerated SublistChange step (sfgpu_step_sublist_change) vs the oracle's selector order and
+          // do / score / undo evaluation: BestScore, first of equal scores
+          auto moves = orc.enumerate_sublist_change(1, 3, {});
+          bool any = false;
+          size_t widx = 0;
+          int64_t bh = 0, bs = 0;
+          for (size_t i = 0; i < moves.size(); ++i) {
+            auto ev = orc.evaluate(moves[i]);
+            if (ev.kind != sfo::EvalKind::Scored) continue;
+            if (!any || ev.score.hard > bh || (ev.score.hard == bh && ev.score.soft > bs)) {
+              bh = ev.score.hard;
+              bs = ev.score.soft;
+              widx = i;
+              any = true;
+            }
+          }
+          std::vector<uint32_t> s_idx, s_ev, s_win;
+          std::vector<sf::HardSoftScore> s_best;
+          sf::StepParams stp;
+          stp.acceptor = 0;
+          stp.random_ties = false;
+          stp.accepted_limit = 0;
+          cd.step_sublist_change(1, 3, stp, {1}, {}, s_idx, s_best, s_ev, s_win, false);
+          CHECK(any && s_idx[0] == widx);
+          CHECK(s_ev[0] == moves.size());
+          CHECK(s_best[0].hard == bh && s_best[0].soft == bs);
+          CHECK(s_win[0] == moves[widx].a && (s_win[1] & 0xFFFFFFu) == moves[widx].b && s_win[2] == moves[widx].d &&
+                s_win[3] == moves[widx].e);
+        }
         sf::SolveParams sp;
         sp.n_steps = 10;
         sp.max_nearby = 8;
