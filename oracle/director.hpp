@@ -469,6 +469,26 @@ std::vector<Move> enumerate_change_moves(const S& s, const Access<S>& ac, size_t
   return out;
 }
 
+// heuristic/selector/move_selector/swap.rs:64-100,196-233 (SwapMoveSelector over one entity class on both sides):
+// the left and the right entity lists are permuted independently by the stream context; every (left, right)
+// pair with left.entity_index < right.entity_index is a SwapMove, left-major.
+template <class S>
+std::vector<Move> enumerate_swap_moves(const S& s, const Access<S>& ac, size_t desc, size_t variable_index,
+                                       MoveStreamContext ctx) {
+  std::vector<Move> out;
+  const size_t n = ac.entity_count(s, desc);
+  const uint64_t salt = ((uint64_t)desc << 32) ^ (uint64_t)variable_index;
+  std::vector<size_t> left(n), right(n);
+  for (size_t o = 0; o < n; ++o) {
+    left[o] = ctx.selection_index(o, n, 0x5A09000000000001ull ^ salt);
+    right[o] = ctx.selection_index(o, n, 0x5A09000000000002ull ^ salt);
+  }
+  for (size_t lo = 0; lo < n; ++lo)
+    for (size_t ro = 0; ro < n; ++ro)
+      if (left[lo] < right[ro]) out.push_back(Move::swap(desc, left[lo], right[ro]));
+  return out;
+}
+
 // nearby_list_support.rs:3-34 — stable bounded insertion sort on the f64 distance.
 struct NearbyCandidate {
   size_t entity, position;

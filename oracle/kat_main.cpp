@@ -1013,6 +1013,17 @@ static void kat_moves_and_loop() {
     CHECK(pm.calculate_score() == (Sc{0, -12}));
     CHECK(pm.calculate_score() == pm.fresh_score());
   }
+  {  // move_selector/swap.rs:64-100: canonical SwapMove order = left-major pairs with left < right; size() = n(n-1)/2
+    GraphColoring g4;
+    g4.n_colors = 2;
+    for (size_t i = 0; i < 4; ++i) g4.nodes.push_back({i, {}, OptVal{i % 2}});
+    GraphColoringModel gm(g4);
+    auto sw = gm.enumerate_scalar_swap({});
+    const size_t want[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    CHECK(sw.size() == 6);
+    for (size_t i = 0; i < 6 && i < sw.size(); ++i) CHECK(sw[i].a == want[i][0] && sw[i].b == want[i][1]);
+    CHECK(is_doable(sw[0], gm.dir) && !is_doable(sw[1], gm.dir));  // swap.rs:140-157: equal values are not doable
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);

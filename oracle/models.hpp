@@ -27,6 +27,7 @@ struct OracleModel {
   virtual CandidateEvaluation<Sc> evaluate(const Move& m) = 0;
   virtual void apply(const Move& m) = 0;
   virtual std::vector<Move> enumerate_scalar(MoveStreamContext ctx) { return {}; }
+  virtual std::vector<Move> enumerate_scalar_swap(MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_list(size_t max_nearby, MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_list_swap(size_t max_nearby, MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_list_reverse(MoveStreamContext ctx) { return {}; }
@@ -93,6 +94,9 @@ struct GraphColoringModel final : ModelImpl<GraphColoring> {
   }
   std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
     return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.n_colors, true, ctx);
+  }
+  std::vector<Move> enumerate_scalar_swap(MoveStreamContext ctx) override {
+    return enumerate_swap_moves(dir.working, dir.access, 0, 0, ctx);
   }
 };
 

@@ -251,6 +251,15 @@ int64_t sfo_enumerate_change(void* h, uint64_t step_index, uint64_t step_seed, i
   }
   return (int64_t)moves.size();
 }
+int64_t sfo_enumerate_swap(void* h, uint64_t step_index, uint64_t step_seed, int order, uint64_t cap, uint32_t* l,
+                           uint32_t* r) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_scalar_swap(make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    l[i] = (uint32_t)moves[i].a;
+    r[i] = (uint32_t)moves[i].b;
+  }
+  return (int64_t)moves.size();
+}
 int64_t sfo_enumerate_nearby_list_change(void* h, uint32_t max_nearby, uint64_t step_index, uint64_t step_seed,
                                          int order, uint64_t cap, uint32_t* se, uint32_t* sp, uint32_t* de,
                                          uint32_t* dp) {

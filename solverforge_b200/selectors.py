@@ -86,6 +86,20 @@ def change_move_rows(values: np.ndarray, n_values: int, allows_unassigned: bool 
     return np.array(out, dtype=np.int64).reshape(-1, 2)
 
 
+def swap_move_rows(n_entities: int, ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0,
+                   variable_index: int = 0) -> np.ndarray:
+    """rows[n][2] = (left_entity, right_entity) in the pull order of SwapMoveSelector over one entity class
+    (heuristic/selector/move_selector/swap.rs:64-100,196-233): the left and the right entity lists are permuted
+    independently by the stream context; every pair with left < right is a SwapMove, left-major."""
+    salt = (descriptor_index << 32) ^ variable_index
+    n = n_entities
+    left = np.array([ctx.selection_index(o, n, 0x5A09000000000001 ^ salt) for o in range(n)], dtype=np.int64)
+    right = np.array([ctx.selection_index(o, n, 0x5A09000000000002 ^ salt) for o in range(n)], dtype=np.int64)
+    li, ri = np.meshgrid(left, right, indexing="ij")
+    keep = li < ri
+    return np.stack([li[keep], ri[keep]], axis=1).astype(np.int64)
+
+
 def nearby_list_change_rows(offsets: np.ndarray, elems: np.ndarray, matrix: np.ndarray, max_nearby: int = 20,
                             ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0) -> np.ndarray:
     """rows[n][4] = (src_entity, src_position, dst_entity, dst_position) uint32 in pull order.

@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
         l.sfo_apply_list_swap.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         l.sfo_enumerate_change.argtypes = [_P, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P, _P]
         l.sfo_enumerate_change.restype = C.c_int64
+        l.sfo_enumerate_swap.argtypes = [_P, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P, _P]
+        l.sfo_enumerate_swap.restype = C.c_int64
         l.sfo_enumerate_nearby_list_change.argtypes = [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P,
                                                        _P, _P, _P]
         l.sfo_enumerate_nearby_list_change.restype = C.c_int64
@@ -284,6 +286,13 @@ class Oracle:
         v = np.zeros(n, dtype=np.int32)
         self.l.sfo_enumerate_change(self.h, step_index, step_seed, order, n, _p(e), _p(v))
         return np.stack([e.astype(np.int64), v.astype(np.int64)], axis=1)
+
+    def enumerate_swap(self, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_swap(self.h, step_index, step_seed, order, 0, None, None)
+        a = np.zeros(n, dtype=np.uint32)
+        b = np.zeros(n, dtype=np.uint32)
+        self.l.sfo_enumerate_swap(self.h, step_index, step_seed, order, n, _p(a), _p(b))
+        return np.stack([a.astype(np.int64), b.astype(np.int64)], axis=1)
 
     def enumerate_nearby_list_swap(self, max_nearby=20, step_index=0, step_seed=0, order=0) -> np.ndarray:
         n = self.l.sfo_enumerate_nearby_list_swap(self.h, max_nearby, step_index, step_seed, order, 0, None, None,

@@ -882,6 +882,35 @@ def test_higher_arity_keyed_joins_match_oracle(joins):
         r = instances.splitmix64_stream(92 + step, 6000)
 
 
+def test_scalar_swap_neighbourhood_steps_match_oracle():
+    """The whole SwapMoveSelector neighbourhood (move_selector/swap.rs, canonical and seeded orders) generated by the
+    host selector, scored on device, winner by the device forager replay, committed; tracked against the oracle."""
+    from solverforge_b200 import selectors
+    from solverforge_b200.selectors import MoveStreamContext
+    g = instances.graph_coloring(120, 420, 4, seed_edges=12, seed_colors=13, unassigned_permille=60)
+    o = Oracle.graph_coloring(g)
+    d = models.graph_coloring_director(g)
+    for step, order in enumerate((selectors.ORIGINAL, selectors.SHUFFLED, selectors.RANDOM, selectors.ORIGINAL)):
+        ctx = MoveStreamContext(step, 900 + step, order)
+        rows = selectors.swap_move_rows(g.n, ctx)
+        assert np.array_equal(rows, o.enumerate_swap(step, 900 + step, order))
+        s, ok = d.score_swap(rows)
+        so, oko = o.score_swap(rows)
+        _eq(ok, oko, f"swap doable step {step}")
+        _eq(s, so, f"swap scores step {step}")
+        last = d.calculate_score()
+        for limit in (0, 25):
+            idx, best, ev = d.argbest(s, ok, None, ForageParams(1, 1, limit), [70 + step], [np.concatenate([last[0], last[0]])])
+            out = oracle_lib.replay_step(so, oko, [0, 0], last[0], last[0], 70 + step, 0 if limit else 2, max(limit, 1), True, 0)
+            assert int(ev[0]) == out[2]
+            assert (int(idx[0]) == out[1]) if out[0] else idx[0] == 0xFFFFFFFF
+        if not out[0]:
+            break
+        d.apply_swap(rows[out[1]][None, :])
+        o.apply_swap(*rows[out[1]])
+        assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+
+
 def test_consecutive_runs_collector_matches_oracle():
     """group_by(nurse, consecutive_runs(day)) — "Long work streaks" of examples/minimal-shift-scheduling
     (stream/collector/runs.rs): change, swap and compound candidates (several shifts of one candidate landing

@@ -112,3 +112,16 @@ def test_sublist_swap_order_matches_reference(order):
     kat = selectors.sublist_swap_rows(np.array([0, 4, 7]), 2, 2)
     assert kat.tolist() == [[0, 0, 2, 0, 2, 4], [0, 0, 2, 1, 0, 2], [0, 0, 2, 1, 1, 3], [0, 1, 3, 1, 0, 2],
                             [0, 1, 3, 1, 1, 3], [0, 2, 4, 1, 0, 2], [0, 2, 4, 1, 1, 3]]
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_scalar_swap_order_matches_reference(order):
+    """SwapMoveSelector pull order (move_selector/swap.rs:64-100,196-233)."""
+    g = instances.graph_coloring(60, 150, 4, seed_edges=2, seed_colors=3)
+    o = Oracle.graph_coloring(g)
+    for step_index, seed in ((0, 0), (9, 4242), (77, 0xFEEDFACE12345)):
+        want = o.enumerate_swap(step_index, seed, order)
+        got = selectors.swap_move_rows(g.n, MoveStreamContext(step_index, seed, order))
+        assert np.array_equal(got, want), f"order={order} step={step_index}"
+    assert selectors.swap_move_rows(4).tolist() == [[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]]
+    assert len(selectors.swap_move_rows(g.n)) == g.n * (g.n - 1) // 2
