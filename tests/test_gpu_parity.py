@@ -838,14 +838,12 @@ def test_higher_arity_keyed_joins_match_oracle(joins):
     """Keyed tri / quad / penta self-joins (constraint/nary_incremental/higher_arity/shared.rs): C(n, arity) tuples
     per bucket. Reference KATs (tri_incr.rs:22-138 and the quad / penta twins) as columns, then the cluster model:
     full ChangeMove neighbourhood, swaps, compound moves with overlays, fused device step, committed winners."""
-    for arity, teams, want in ((3, [1, 1, 1, 2], -1), (3, [1, 1, 1, 1], -4), (4, [1, 1, 1, 1, 2], -1),
-                               (4, [1, 1, 1, 1, 1], -5), (5, [1, 1, 1, 1, 1, 2], -1), (5, [1, 1, 1, 1, 1, 1], -6)):
-        k = instances.ClusterInstance(len(teams), 3, np.array(teams, dtype=np.int32), ((arity, 1),))
+    for v in GOLDEN["higher_arity_joins"]:   # committed golden vectors of the reference's tri / quad / penta tests
+        k = instances.ClusterInstance(len(v["team"]), v["n_values"], np.array(v["team"], dtype=np.int32), ((v["arity"], 1),))
         dk = models.cluster_director(k)
-        assert dk.calculate_score()[0].tolist() == [0, want] == dk.fresh_score()[0].tolist()
+        assert dk.calculate_score()[0].tolist() == [0, v["soft"]] == dk.fresh_score()[0].tolist(), v["cite"]
         dk.apply_change(np.array([[0, -1]]))                      # retract row 0: its tuples go, one unassigned task
-        left = {3: {-1: 0, -4: -1}, 4: {-1: 0, -5: -1}, 5: {-1: 0, -6: -1}}[arity][want]
-        assert dk.calculate_score()[0].tolist() == [-1, left] == dk.fresh_score()[0].tolist()
+        assert dk.calculate_score()[0].tolist() == [-1, v["retract_row0_soft"]] == dk.fresh_score()[0].tolist(), v["cite"]
     c = instances.cluster(44, 4, seed=23, joins=joins)   # buckets of ~10 rows: the oracle materialises every tuple
     o = Oracle.cluster(c)
     d = models.cluster_director(c)
@@ -969,10 +967,12 @@ def test_indexed_presence_collector_matches_oracle():
     kat.n_shifts, kat.day, kat.slot = 3, kat.day[:3], kat.slot[:3]
     kat.required, kat.hours = np.zeros(3, dtype=np.uint8), kat.hours[:3]
     kat.nurse_idx, kat.target = np.zeros(3, dtype=np.int32), 0
-    dk = models.shift_scheduling_director(kat, with_load_balance=False, presence_days=5)
-    assert dk.calculate_score()[0].tolist() == [0, -11] == dk.fresh_score()[0].tolist()
-    dk.apply_change(np.array([[1, 1]]))
-    assert dk.calculate_score()[0].tolist() == [0, -12] == dk.fresh_score()[0].tolist()
+    gv = GOLDEN["indexed_presence"][0]
+    assert kat.day.tolist() == gv["days"] and kat.nurse_idx.tolist() == gv["nurse"]
+    dk = models.shift_scheduling_director(kat, with_load_balance=False, presence_days=gv["horizon"])
+    assert dk.calculate_score()[0].tolist() == [0, gv["model_soft"]] == dk.fresh_score()[0].tolist()
+    dk.apply_change(np.array([gv["change"]]))
+    assert dk.calculate_score()[0].tolist() == [0, gv["model_soft_after"]] == dk.fresh_score()[0].tolist()
     for seed in (3, 8):
         inst = instances.shift_scheduling(n_days=12, slots_per_day=3, n_nurses=4, seed=seed, unassigned_permille=250)
         o = Oracle.shift_scheduling(inst, with_load_balance=False, presence_days=12)

@@ -125,3 +125,13 @@ def test_scalar_swap_order_matches_reference(order):
         assert np.array_equal(got, want), f"order={order} step={step_index}"
     assert selectors.swap_move_rows(4).tolist() == [[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]]
     assert len(selectors.swap_move_rows(g.n)) == g.n * (g.n - 1) // 2
+
+
+def test_sublist_selector_golden_vectors():
+    """tests/golden/reference_kats.json: the reference's canonical sublist change / swap orders."""
+    import json
+    import os
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+    for v in golden["sublist_selectors"]:
+        fn = selectors.sublist_change_rows if v["kind"] == "change" else selectors.sublist_swap_rows
+        assert fn(np.array(v["offsets"]), v["min"], v["max"]).tolist() == v["rows"], v["cite"]
