@@ -195,3 +195,44 @@ def test_roster_projected_rows_incremental_equals_fresh():
         v = int(r[2 * i + 1] % np.uint64(inst.n_nurses + 1)) - 1
         o.apply_change(e, v)
         assert o.committed_score().tolist() == o.evaluate_all().tolist(), f"step {i}"
+
+
+def test_sublist_moves_incremental_equals_fresh():
+    """SublistChange / SublistSwap / ListReverse walks: the oracle's retained score equals a fresh evaluation after
+    every applied move and do/undo evaluation leaves the committed score untouched (inverse layouts of
+    segment_layout.rs)."""
+    c = instances.cvrp(36, 5, seed=9)
+    o = Oracle.cvrp(c)
+    for step in range(6):
+        base = o.committed_score().copy()
+        for enum, score, apply in ((lambda: o.enumerate_sublist_change(1, 3), o.score_sublist_change, o.apply_sublist_change),
+                                   (lambda: o.enumerate_sublist_swap(1, 3), o.score_sublist_swap, o.apply_sublist_swap),
+                                   (lambda: o.enumerate_list_reverse()[:, :3], o.score_list_reverse, o.apply_list_reverse)):
+            sample = enum()[step::37]   # enumerated against the current state
+            s, d = score(sample if sample.shape[1] != 3 else np.concatenate([sample, np.zeros((len(sample), 1), sample.dtype)], axis=1))
+            assert d.all()
+            assert np.array_equal(o.committed_score(), base)
+            pick = int(np.lexsort((s[:, 1], s[:, 0]))[-1])
+            apply(*sample[pick])
+            assert np.array_equal(o.committed_score(), s[pick])
+            assert np.array_equal(o.committed_score(), o.evaluate_all())
+            base = o.committed_score().copy()
+
+
+def test_cluster_and_presence_models_incremental_equals_fresh():
+    """Keyed tri / quad / penta joins (higher_arity/shared.rs) and the indexed_presence views along ChangeMove walks."""
+    c = instances.cluster(26, 3, seed=5)
+    o = Oracle.cluster(c)
+    assert np.array_equal(o.committed_score(), o.evaluate_all())
+    s_inst = instances.shift_scheduling(n_days=9, slots_per_day=2, n_nurses=3, seed=6, unassigned_permille=200)
+    p = Oracle.shift_scheduling(s_inst, with_load_balance=False, presence_days=9)
+    assert np.array_equal(p.committed_score(), p.evaluate_all())
+    for o_ in (o, p):
+        for step in range(8):
+            rows = o_.enumerate_change()
+            s, d = o_.score_change(rows[step::11])
+            k = int(np.flatnonzero(d)[step % max(int(d.sum()), 1)])
+            e, v = rows[step::11][k]
+            o_.apply_change(int(e), int(v))
+            assert np.array_equal(o_.committed_score(), s[k])
+            assert np.array_equal(o_.committed_score(), o_.evaluate_all())
