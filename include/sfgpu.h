@@ -353,6 +353,14 @@ int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_s
                                   const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
                                   uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners);
 
+/* The same for the ListReverse (2-opt segment reversal) neighbourhood (ListReverseMoveSelector, SelectionOrder::Original,
+ * heuristic/selector/list_reverse.rs:139-172 + list_kernel/reverse.rs:66-108): per entity every start and every end
+ * in start + 2 ..= len. out_winner_rows[R][4] = {entity, start, end, 0}. */
+int32_t sfgpu_step_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
+                                const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
+                                int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                                int32_t apply_winners);
+
 /* The same for the SublistSwap neighbourhood (SublistSwapMoveSelector, SelectionOrder::Original,
  * list_kernel/sublist_swap.rs:28-318): first segments in entity / start / size order, each paired with the later
  * non-overlapping segments of its own list and every segment of the later entities (CVRP-1000: ~4.4 M pairs per

@@ -97,6 +97,7 @@ SYMBOLS = {
                                       C.c_int32]),
     "sfgpu_step_sublist_change": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ForageParams), _P, _P,
                                               _P, _P, _P, _P, C.c_int32]),
+    "sfgpu_step_list_reverse": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, C.c_int32]),
     "sfgpu_step_sublist_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ForageParams), _P, _P,
                                             _P, _P, _P, _P, C.c_int32]),
     "sfgpu_solve_nearby_list_change": (C.c_int32, [_P, C.POINTER(SolveParams), _P, _P, _P]),

@@ -407,6 +407,23 @@ class GpuScoreDirector:
         rows[idx == 0xFFFFFFFF] = -1
         return idx, best, ev, rows
 
+    def step_list_reverse(self, params: "ForageParams" = None, step_seeds=None, ref_scores=None, apply: bool = False):
+        """One whole step over the ListReverse (2-opt) neighbourhood, enumerated on device (sfgpu_step_list_reverse).
+        Winner rows come back as (entity, start, end); -1 when there is no winner."""
+        params = params or ForageParams()
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        seeds = None if step_seeds is None else np.ascontiguousarray(step_seeds, dtype=np.uint64)
+        ref = None if ref_scores is None else np.ascontiguousarray(ref_scores, dtype=np.int64).reshape(self.R, 4)
+        idx = np.zeros(self.R, dtype=np.uint32)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint32)
+        win = np.zeros((self.R, 4), dtype=np.uint32)
+        self._check(self.lib.sfgpu_step_list_reverse(self.h, 0, C.byref(fp), _ptr(seeds), _ptr(ref), _ptr(idx), _ptr(best),
+                                                     _ptr(ev), _ptr(win), 1 if apply else 0))
+        rows = win.astype(np.int64)[:, :3]
+        rows[idx == 0xFFFFFFFF] = -1
+        return idx, best, ev, rows
+
     def step_sublist_swap(self, min_size: int = 1, max_size: int = 3, params: "ForageParams" = None, step_seeds=None,
                           ref_scores=None, apply: bool = False):
         """One whole step over the SublistSwap neighbourhood, enumerated on device (sfgpu_step_sublist_swap). Winner

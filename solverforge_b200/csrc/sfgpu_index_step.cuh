@@ -453,6 +453,50 @@ struct SublistSwapNb {
   }
 };
 
+// ReverseNb: ListReverseMoveSelector, SelectionOrder::Original (heuristic/selector/list_reverse.rs:139-172 +
+//   list_kernel/reverse.rs:66-108): per entity with len >= 2 every start and every end in start + 2 ..= len, so a
+//   list of length L owns L (L - 1) / 2 candidates and start s owns L - 1 - s of them. Rows {entity, start, end, 0}.
+struct ReverseNb {
+  const uint32_t* off;
+  uint32_t* ent_base;  // [n + 1]
+  uint32_t n;
+  static constexpr bool kHasCursor = false;
+  static __host__ __device__ __forceinline__ size_t table_words(uint32_t n_owners, uint32_t) { return (size_t)n_owners + 1; }
+  __device__ __forceinline__ void build(const DevModel& m, const char* st, uint32_t* scratch, uint32_t, uint32_t) {
+    off = (const uint32_t*)(st + m.off_offsets);
+    n = m.n_owners;
+    ent_base = scratch;
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const uint32_t L = off[e + 1] - off[e];
+      ent_base[e + 1] = L >= 2 ? L * (L - 1) / 2 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ent_base[0] = 0;
+      for (uint32_t e = 0; e < n; ++e) ent_base[e + 1] += ent_base[e];
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ uint32_t total() const { return ent_base[n]; }
+  __device__ __forceinline__ uint4 decode(uint32_t idx) const {
+    uint32_t lo = 0, hi = n;  // last e with ent_base[e] <= idx
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (ent_base[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const uint32_t e = lo, L = off[e + 1] - off[e];
+    uint32_t r = idx - ent_base[e], s = 0;
+    while (r >= L - 1 - s) {
+      r -= L - 1 - s;
+      ++s;
+    }
+    return make_uint4(e, s, s + 2 + r, 0);
+  }
+  __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
+    return list_reverse_delta(m, st, row, d);
+  }
+};
+
 // grid = (chunks, R): chunk c scores pull indices [c * per_chunk, (c + 1) * per_chunk) of its replica.
 // Dynamic shared memory: [staged block (STAGED)] [NB::table_words(..) uint32].
 template <bool STAGED, class NB>

@@ -212,3 +212,54 @@ def test_sublist_change_step_full_size_properties():
     s0 = s0[ok0 == 1]
     better = (s0[:, 0] > best[0][0]) | ((s0[:, 0] == best[0][0]) & (s0[:, 1] > best[0][1]))
     assert not better.any()
+
+
+def test_list_reverse_step_matches_oracle():
+    """sfgpu_step_list_reverse vs ListReverseMoveSelector (list_kernel/reverse.rs:66-108) + candidate loop, symmetric
+    and asymmetric costs, empty / one-element routes, apply chain."""
+    c = instances.cvrp(40, 6, seed=37)
+    r = instances.splitmix64_stream(8, c.dim * c.dim).reshape(c.dim, c.dim)
+    c.matrix = (c.matrix // 30) * 30 + (r % np.uint64(3)).astype(np.int64)   # asymmetric, many ties
+    np.fill_diagonal(c.matrix, 0)
+    R = 3
+    starts = [instances.perturb_routes(c, 90 + q, 25 + 10 * q) for q in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    oracles = [Oracle.cvrp(c, *starts[q]) for q in range(R)]
+    seeds = [4, 99, 0xABCDEF]
+    for acceptor, okind in ((0, 3), (1, 0), (2, 1)):
+        for ties in (0, 1):
+            for limit in (0, 1, 9, 10 ** 6):
+                base = d.calculate_score()
+                dl = -20 if acceptor == 1 else 0
+                ref = np.concatenate([base + [0, dl], base + [0, dl - 7]], axis=1)
+                idx, best, ev, win = d.step_list_reverse(ForageParams(acceptor, ties, limit), step_seeds=seeds, ref_scores=ref)
+                for q, o in enumerate(oracles):
+                    rows = o.enumerate_list_reverse()
+                    so, oko = o.score_list_reverse(rows)
+                    out = oracle_lib.replay_step(so, oko, [0, 0], ref[q][:2], ref[q][2:], seeds[q], 0 if limit else 2,
+                                                 max(limit, 1), bool(ties), okind)
+                    what = f"replica={q} acc={acceptor} ties={ties} limit={limit}"
+                    assert int(ev[q]) == out[2], what
+                    if out[0]:
+                        assert int(idx[q]) == out[1] and best[q].tolist() == so[out[1]].tolist(), what
+                        assert win[q].tolist() == rows[out[1]][:3].astype(np.int64).tolist(), what
+                    else:
+                        assert idx[q] == 0xFFFFFFFF, what
+    for step in range(5):   # committed winners
+        last = d.calculate_score()
+        idx, best, ev, win = d.step_list_reverse(ForageParams(1, 1, 0), step_seeds=[600 + step] * R,
+                                                 ref_scores=np.concatenate([last, last], axis=1), apply=True)
+        for q, o in enumerate(oracles):
+            rows = o.enumerate_list_reverse()
+            so, oko = o.score_list_reverse(rows)
+            out = oracle_lib.replay_step(so, oko, [0, 0], last[q], last[q], 600 + step, 2, 1, True, 0)
+            if out[0]:
+                assert int(idx[q]) == out[1]
+                o.apply_list_reverse(*rows[out[1]])
+            else:
+                assert idx[q] == 0xFFFFFFFF
+            assert d.calculate_score()[q].tolist() == o.committed_score().tolist() == d.fresh_score()[q].tolist()
+    one = instances.cvrp(3, 3, seed=1)   # every route holds one element: empty neighbourhood
+    d1 = models.cvrp_director(one)
+    idx, best, ev, win = d1.step_list_reverse(ForageParams(0, 1, 0), step_seeds=[1])
+    assert idx[0] == 0xFFFFFFFF and int(ev[0]) == 0
