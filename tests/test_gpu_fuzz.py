@@ -150,3 +150,18 @@ def test_fuzz_sublist_steps(seed):
             assert win[0].tolist() == rows[out[1]].astype(np.int64).tolist(), what + f" swap={swap}"
         else:
             assert idx[0] == 0xFFFFFFFF, what + f" swap={swap}"
+    # the ListReverse neighbourhood of the same state
+    rows = o.enumerate_list_reverse()
+    if len(rows):
+        so, oko = o.score_list_reverse(rows)
+    else:
+        so, oko = np.zeros((0, 2), np.int64), np.zeros(0, np.uint8)
+    idx, best, ev, win = d.step_list_reverse(ForageParams(acceptor, ties, limit), step_seeds=[step_seed], ref_scores=[ref])
+    out = oracle_lib.replay_step(so, oko, [0, 0], ref[:2], ref[2:], step_seed, 0 if limit else 2, max(limit, 1), bool(ties),
+                                 okind)
+    assert int(ev[0]) == out[2], what + " reverse moves_evaluated"
+    if out[0]:
+        assert int(idx[0]) == out[1] and best[0].tolist() == so[out[1]].tolist(), what + " reverse"
+        assert win[0].tolist() == rows[out[1]][:3].astype(np.int64).tolist(), what + " reverse"
+    else:
+        assert idx[0] == 0xFFFFFFFF, what + " reverse"
