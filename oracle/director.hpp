@@ -11,6 +11,8 @@
 //   ListReverseMove          heuristic/move/list_kernel/reverse.rs:21-58 (2-opt segment reversal)
 //   SublistChangeMove        heuristic/move/list_kernel/sublist_change.rs:17-125 + segment_layout.rs:49-75
 //   SublistSwapMove          heuristic/move/list_kernel/sublist_swap.rs:17-170 + segment_layout.rs:118-165
+//   KOptMove (one list)      heuristic/move/list_kernel/k_opt.rs:11-110 + k_opt_reconnection.rs (patterns); CPU only —
+//                            groundwork for a device path, not yet scored on the GPU
 //   evaluate_candidate       phase/localsearch/evaluation.rs:20-115
 //   MoveStreamContext        heuristic/selector/move_selector/iter.rs:14-207
 //   ChangeMove order         heuristic/selector/move_selector/change.rs:66-104,246-307
@@ -94,11 +96,14 @@ struct ScalarEdit {  // planning/scalar/candidate.rs:6-12
 };
 
 struct Move {
-  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse, SublistChange, SublistSwap } kind = Change;
+  enum Kind { Change, Swap, Compound, ListChange, ListSwap, ListReverse, SublistChange, SublistSwap, KOpt } kind = Change;
   size_t desc = 0;
   size_t a = 0, b = 0, c = 0, d = 0;  // Change: a=entity; Swap: a,b; List*: a=src_e b=src_p c=dst_e d=dst_p
   size_t e = 0;                       // SublistChange: a=src_e [b, c)=source range d=dst_e e=dst_position
   size_t f = 0;                       // SublistSwap: a=first_e [b, c)  d=second_e [e, f)
+  std::vector<size_t> cuts;           // KOpt: a=entity, k cut positions; the k + 1 segments are re-ordered by
+  uint8_t seg_order[6] = {0, 0, 0, 0, 0, 0};  //   seg_order (position -> original segment) and reversed where
+  uint8_t reverse_mask = 0, seg_len = 0;      //   bit i of reverse_mask is set (k_opt_reconnection.rs)
   OptVal to;
   std::vector<ScalarEdit> edits;
   bool requires_hard_improvement = false;
@@ -142,9 +147,68 @@ inline Move sublist_swap_inverse(const Move& m) {
   return move_sublist_swap(m.desc, m.a, m.b - l2 + l1, m.b - l2 + l1 + l2, m.d, m.e, m.e + l1);
 }
 
+// k_opt_reconnection.rs:63-205
+struct KOptReconnection {
+  uint8_t order[6];
+  uint8_t reverse_mask, len;
+  size_t k() const { return (size_t)len - 1; }
+  bool should_reverse(size_t i) const { return (reverse_mask >> i) & 1; }
+  bool is_identity() const {
+    if (reverse_mask) return false;
+    for (size_t i = 0; i < len; ++i)
+      if (order[i] != i) return false;
+    return true;
+  }
+};
+// k_opt_reconnection.rs:218-262: middle segments in every order (first item first, recursively), every reversal mask
+inline std::vector<KOptReconnection> enumerate_reconnections(size_t k) {
+  std::vector<KOptReconnection> out;
+  std::vector<uint8_t> middle;
+  for (size_t i = 1; i < k; ++i) middle.push_back((uint8_t)i);
+  std::vector<std::vector<uint8_t>> perms;
+  std::function<void(std::vector<uint8_t>, std::vector<uint8_t>)> rec = [&](std::vector<uint8_t> head, std::vector<uint8_t> rest) {
+    if (rest.empty()) {
+      perms.push_back(head);
+      return;
+    }
+    for (size_t i = 0; i < rest.size(); ++i) {
+      auto h = head;
+      h.push_back(rest[i]);
+      auto r = rest;
+      r.erase(r.begin() + (ptrdiff_t)i);
+      rec(h, r);
+    }
+  };
+  rec({}, middle);
+  for (auto& perm : perms) {
+    KOptReconnection r{};
+    r.len = (uint8_t)(k + 1);
+    r.order[0] = 0;
+    for (size_t i = 0; i < perm.size(); ++i) r.order[i + 1] = perm[i];
+    r.order[k] = (uint8_t)k;
+    for (uint32_t mask = 0; mask < (1u << (k - 1)); ++mask) {
+      r.reverse_mask = (uint8_t)(mask << 1);
+      if (!r.is_identity()) out.push_back(r);
+    }
+  }
+  return out;
+}
+inline Move move_k_opt(size_t desc, size_t entity, std::vector<size_t> cuts, const KOptReconnection& r) {
+  Move m;
+  m.kind = Move::KOpt;
+  m.desc = desc;
+  m.a = entity;
+  m.cuts = std::move(cuts);
+  for (size_t i = 0; i < 6; ++i) m.seg_order[i] = r.order[i];
+  m.reverse_mask = r.reverse_mask;
+  m.seg_len = r.len;
+  return m;
+}
+
 struct Undo {
   OptVal v0, v1;
   std::vector<OptVal> many;
+  std::vector<size_t> list;  // KOpt: the whole route before the move (k_opt.rs:40-85 returns it as the undo)
 };
 
 inline size_t adjusted_destination(const Move& m) {  // list_kernel/change.rs:28-34
@@ -193,6 +257,16 @@ bool is_doable(const Move& m, ScoreDirector<S, Sc>& dir) {
       size_t max_dst = m.a == m.d ? src_len - (m.c - m.b) : dst_len;
       if (m.e > max_dst) return false;
       return m.a != m.d || m.e != m.b;
+    }
+    case Move::KOpt: {  // k_opt.rs:11-38 (all cuts on one entity)
+      const size_t k = m.cuts.size();
+      if (k < 2 || (size_t)m.seg_len != k + 1) return false;
+      const size_t len = ac.list(s, m.desc, m.a).size();
+      for (size_t c : m.cuts)
+        if (c > len) return false;
+      for (size_t i = 1; i < k; ++i)
+        if (m.cuts[i] <= m.cuts[i - 1]) return false;
+      return true;
     }
     case Move::SublistSwap: {  // sublist_swap.rs:17-42
       if (m.b >= m.c || m.e >= m.f) return false;
@@ -287,6 +361,24 @@ Undo do_move(const Move& m, ScoreDirector<S, Sc>& dir) {
       if (!intra) dir.after_variable_changed(m.desc, m.d);
       break;
     }
+    case Move::KOpt: {  // k_opt.rs:40-85: cut, re-order, reverse, rebuild the whole route
+      dir.before_variable_changed(m.desc, m.a);
+      auto& l = ac.list(s, m.desc, m.a);
+      u.list = l;
+      std::vector<size_t> bounds{0};
+      bounds.insert(bounds.end(), m.cuts.begin(), m.cuts.end());
+      bounds.push_back(l.size());
+      std::vector<size_t> out;
+      for (size_t pos = 0; pos < m.seg_len; ++pos) {
+        const size_t seg = m.seg_order[pos];
+        std::vector<size_t> part(u.list.begin() + (ptrdiff_t)bounds[seg], u.list.begin() + (ptrdiff_t)bounds[seg + 1]);
+        if ((m.reverse_mask >> seg) & 1) std::reverse(part.begin(), part.end());
+        out.insert(out.end(), part.begin(), part.end());
+      }
+      l = out;
+      dir.after_variable_changed(m.desc, m.a);
+      break;
+    }
     case Move::SublistSwap: {  // sublist_swap.rs:87-170
       bool intra = m.a == m.d;
       dir.before_variable_changed(m.desc, m.a);
@@ -372,6 +464,12 @@ void undo_move(const Move& m, ScoreDirector<S, Sc>& dir, const Undo& u) {
     }
     case Move::SublistSwap: {  // sublist_swap.rs:66-85
       do_move(sublist_swap_inverse(m), dir);
+      break;
+    }
+    case Move::KOpt: {  // k_opt.rs:87-110: the saved route goes back
+      dir.before_variable_changed(m.desc, m.a);
+      ac.list(s, m.desc, m.a) = u.list;
+      dir.after_variable_changed(m.desc, m.a);
       break;
     }
   }

@@ -1024,6 +1024,46 @@ static void kat_moves_and_loop() {
     for (size_t i = 0; i < 6 && i < sw.size(); ++i) CHECK(sw[i].a == want[i][0] && sw[i].b == want[i][1]);
     CHECK(is_doable(sw[0], gm.dir) && !is_doable(sw[1], gm.dir));  // swap.rs:140-157: equal values are not doable
   }
+  {  // heuristic/move/k_opt_reconnection_tests.rs:4-47 (pattern counts, no identity) and move/tests/k_opt.rs:86-222
+    CHECK(enumerate_reconnections(2).size() == 1 && enumerate_reconnections(2)[0].should_reverse(1));
+    auto three = enumerate_reconnections(3);
+    CHECK(three.size() == 7);
+    const uint8_t t_order[7][4] = {{0, 1, 2, 3}, {0, 1, 2, 3}, {0, 1, 2, 3}, {0, 2, 1, 3}, {0, 2, 1, 3}, {0, 2, 1, 3}, {0, 2, 1, 3}};
+    const uint8_t t_mask[7] = {0b0010, 0b0100, 0b0110, 0b0000, 0b0010, 0b0100, 0b0110};  // THREE_OPT_RECONNECTIONS
+    for (size_t i = 0; i < 7 && i < three.size(); ++i) {
+      CHECK(three[i].reverse_mask == t_mask[i] && three[i].k() == 3);
+      for (size_t j = 0; j < 4; ++j) CHECK(three[i].order[j] == t_order[i][j]);
+    }
+    CHECK(enumerate_reconnections(4).size() == 47 && enumerate_reconnections(5).size() == 383);
+    for (size_t k = 2; k <= 5; ++k)
+      for (auto& r : enumerate_reconnections(k)) CHECK(!r.is_identity());
+    CvrpPlan kp;
+    kp.shared = pd;
+    kp.customers = plan.customers;
+    kp.routes = {{0, {1, 2, 3, 4, 5, 6, 7, 8}, pd.get()}};
+    CvrpModel km(kp);
+    const Move swap_bc = move_k_opt(0, 0, {2, 4, 6}, three[3]);
+    CHECK(is_doable(swap_bc, km.dir));
+    const Sc before = km.calculate_score();
+    auto ev = km.evaluate(swap_bc);
+    CHECK(ev.kind == EvalKind::Scored && km.calculate_score() == before);
+    CHECK((km.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 3, 4, 5, 6, 7, 8}));
+    km.apply(swap_bc);
+    CHECK((km.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 5, 6, 3, 4, 7, 8}));
+    CHECK(km.calculate_score() == km.fresh_score() && km.calculate_score() == ev.score);
+    CvrpModel km2(kp);
+    km2.apply(move_k_opt(0, 0, {2, 4, 6}, three[0]));
+    CHECK((km2.dir.working.routes[0].visits == std::vector<size_t>{1, 2, 4, 3, 5, 6, 7, 8}));
+    CHECK(km2.calculate_score() == km2.fresh_score());
+    CHECK(!is_doable(move_k_opt(0, 0, {2, 4, 10}, three[0]), km2.dir));  // cut beyond the list
+    CHECK(!is_doable(move_k_opt(0, 0, {4, 2, 6}, three[0]), km2.dir));   // cuts not increasing
+    // a 2-opt pattern is the segment reversal: same score as ListReverseMove on the same window
+    CvrpModel km3(kp);
+    auto two = enumerate_reconnections(2);
+    auto e2 = km3.evaluate(move_k_opt(0, 0, {2, 6}, two[0]));
+    auto er = km3.evaluate(Move::list_reverse(0, 0, 2, 6));
+    CHECK(e2.kind == EvalKind::Scored && er.kind == EvalKind::Scored && e2.score == er.score);
+  }
   // forager.rs:99-155: first of equal scores kept unless the reservoir pick fires
   BestCandidate<Sc> bc;
   bc.reset(42);
