@@ -135,3 +135,24 @@ def test_sublist_selector_golden_vectors():
     for v in golden["sublist_selectors"]:
         fn = selectors.sublist_change_rows if v["kind"] == "change" else selectors.sublist_swap_rows
         assert fn(np.array(v["offsets"]), v["min"], v["max"]).tolist() == v["rows"], v["cite"]
+
+
+def test_segment_row_packing_round_trip():
+    """The 4-word device rows of the sublist moves ({entity, start | size << 24, ...}, SFGPU_SEG in sfgpu.h)."""
+    from solverforge_b200 import _lib as L
+    from solverforge_b200.api import GpuScoreDirector
+    rows = selectors.sublist_change_rows(np.array([0, 5, 9, 9, 12]), 1, 3)
+    packed = GpuScoreDirector.pack_sublist_change(rows)
+    assert packed.shape == (len(rows), 4)
+    assert np.array_equal(packed[:, 1] & 0xFFFFFF, rows[:, 1]) and np.array_equal(packed[:, 1] >> 24, rows[:, 2] - rows[:, 1])
+    assert np.array_equal(packed[:, [0, 2, 3]], rows[:, [0, 3, 4]].astype(np.int64))
+    sw = selectors.sublist_swap_rows(np.array([0, 5, 9, 9, 12]), 1, 3)
+    ps = GpuScoreDirector.pack_sublist_swap(sw)
+    assert np.array_equal(ps[:, 1] >> 24, sw[:, 2] - sw[:, 1]) and np.array_equal(ps[:, 3] >> 24, sw[:, 5] - sw[:, 4])
+    assert np.array_equal(ps[:, 3] & 0xFFFFFF, sw[:, 4])
+    with pytest.raises(L.SfgpuError):
+        GpuScoreDirector.pack_sublist_change(np.array([[0, 0, 300, 1, 0]]))      # size > 255
+    with pytest.raises(L.SfgpuError):
+        GpuScoreDirector.pack_sublist_change(np.array([[0, 5, 3, 1, 0]]))        # end < start
+    with pytest.raises(L.SfgpuError):
+        GpuScoreDirector.pack_sublist_swap(np.array([[0, 1 << 24, (1 << 24) + 1, 1, 0, 1]]))  # start beyond the packing
