@@ -723,6 +723,66 @@ std::vector<Move> enumerate_list_reverse_moves(S& s, const Access<S>& ac, size_t
   return out;
 }
 
+// heuristic/selector/k_opt/iterators.rs:93-176: binomial, number of cut combinations, and the combination of a given
+// rank (lexicographic over the k chosen slots; position = choice + min_seg + index * (min_seg - 1))
+inline size_t binomial(size_t n, size_t k) {
+  if (k > n) return 0;
+  if (k == 0 || k == n) return 1;
+  k = std::min(k, n - k);
+  size_t r = 1;
+  for (size_t i = 0; i < k; ++i) r = r * (n - i) / (i + 1);
+  return r;
+}
+inline size_t count_cut_combinations(size_t k, size_t len, size_t min_seg) {
+  const size_t min_len = (k + 1) * min_seg;
+  return len < min_len ? 0 : binomial(len - min_len + k, k);
+}
+inline bool cut_combination_at(size_t k, size_t len, size_t min_seg, size_t rank, std::vector<size_t>& cuts) {
+  cuts.clear();
+  if (k == 0 || min_seg == 0 || len < (k + 1) * min_seg) return false;
+  const size_t choice_count = len - (k + 1) * min_seg + k;
+  if (rank >= binomial(choice_count, k)) return false;
+  size_t start = 0;
+  for (size_t position = 0; position < k; ++position) {
+    const size_t remaining = k - position - 1, maximum = choice_count - (k - position);
+    bool found = false;
+    for (size_t cand = start; cand <= maximum; ++cand) {
+      const size_t suffix = binomial(choice_count - cand - 1, remaining);
+      if (rank < suffix) {
+        cuts.push_back(cand + min_seg + position * (min_seg - 1));
+        start = cand + 1;
+        found = true;
+        break;
+      }
+      rank -= suffix;
+    }
+    if (!found) return false;
+  }
+  return true;
+}
+// heuristic/selector/list_kernel/k_opt/full.rs:34-98 (KOptCursor): per entity the moves are
+// (cut combination rank) x (reconnection pattern), pulled through selection_index over their product; 3-opt uses
+// the static THREE_OPT_RECONNECTIONS table (selector.rs:111-115), which enumerate_reconnections(3) reproduces.
+// Entities in canonical order only (selection_index_without_replacement is not restated).
+template <class S>
+std::vector<Move> enumerate_k_opt_moves(S& s, const Access<S>& ac, size_t desc, size_t k, size_t min_seg,
+                                        MoveStreamContext ctx) {
+  const auto patterns = enumerate_reconnections(k);
+  std::vector<Move> out;
+  std::vector<size_t> cuts;
+  const size_t n = ac.entity_count(s, desc);
+  for (size_t e = 0; e < n; ++e) {
+    const size_t len = ac.list(s, desc, e).size();
+    const size_t move_count = count_cut_combinations(k, len, min_seg) * patterns.size();
+    for (size_t off = 0; off < move_count; ++off) {
+      const size_t sel = ctx.selection_index(off, move_count, 0x4B0F7E1171000002ull ^ (uint64_t)desc ^ (uint64_t)e);
+      if (!cut_combination_at(k, len, min_seg, sel / patterns.size(), cuts)) throw std::logic_error("k-opt cut rank");
+      out.push_back(move_k_opt(desc, e, cuts, patterns[sel % patterns.size()]));
+    }
+  }
+  return out;
+}
+
 // heuristic/selector/sublist_swap.rs:160-190 + list_kernel/sublist_swap.rs:28-318 (SublistSwapCursor, no owner
 // restriction, no precedence graph): first segments in entity / start / size stream order; second segments from
 // the same entity onwards (entity order); inside one list only segments starting at or after the first one's end.

@@ -1057,6 +1057,36 @@ static void kat_moves_and_loop() {
     CHECK(km2.calculate_score() == km2.fresh_score());
     CHECK(!is_doable(move_k_opt(0, 0, {2, 4, 10}, three[0]), km2.dir));  // cut beyond the list
     CHECK(!is_doable(move_k_opt(0, 0, {4, 2, 6}, three[0]), km2.dir));   // cuts not increasing
+    // heuristic/selector/k_opt/tests.rs:80-170: cut combinations and the whole 3-opt neighbourhood of one tour
+    CHECK(binomial(5, 2) == 10 && binomial(7, 3) == 35 && binomial(10, 5) == 252);
+    CHECK(count_cut_combinations(3, 8, 1) == 35 && count_cut_combinations(3, 3, 1) == 0);
+    std::vector<size_t> cc;
+    CHECK(cut_combination_at(3, 8, 1, 0, cc) && cc == (std::vector<size_t>{1, 2, 3}));
+    CHECK(cut_combination_at(3, 8, 1, 34, cc) && cc == (std::vector<size_t>{5, 6, 7}));
+    CHECK(!cut_combination_at(3, 8, 1, 35, cc));
+    {
+      // CutCombinationIterator order (iterators.rs:12-91) == rank order
+      std::vector<size_t> pos{1, 2, 3};
+      for (size_t rank = 0; rank < 35; ++rank) {
+        CHECK(cut_combination_at(3, 8, 1, rank, cc) && cc == pos);
+        for (int i = 2; i >= 0; --i) {
+          const size_t max_pos = 8 - 1 * (3 - (size_t)i);
+          if (pos[(size_t)i] < max_pos) {
+            pos[(size_t)i] += 1;
+            for (size_t j = (size_t)i + 1; j < 3; ++j) pos[j] = pos[j - 1] + 1;
+            break;
+          }
+        }
+      }
+    }
+    CvrpModel km4(kp);
+    auto kmoves = enumerate_k_opt_moves(km4.dir.working, km4.dir.access, 0, 3, 1, {});
+    CHECK(kmoves.size() == 245);  // 35 cut combinations x 7 patterns
+    for (auto& mv : kmoves) CHECK(is_doable(mv, km4.dir));
+    for (size_t i = 0; i < kmoves.size(); i += 31) {
+      auto evk = km4.evaluate(kmoves[i]);
+      CHECK(evk.kind == EvalKind::Scored && km4.calculate_score() == km4.fresh_score());
+    }
     // a 2-opt pattern is the segment reversal: same score as ListReverseMove on the same window
     CvrpModel km3(kp);
     auto two = enumerate_reconnections(2);
