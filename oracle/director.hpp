@@ -778,6 +778,7 @@ std::vector<Move> enumerate_k_opt_moves(S& s, const Access<S>& ac, size_t desc, 
       const size_t sel = ctx.selection_index(off, move_count, 0x4B0F7E1171000002ull ^ (uint64_t)desc ^ (uint64_t)e);
       if (!cut_combination_at(k, len, min_seg, sel / patterns.size(), cuts)) throw std::logic_error("k-opt cut rank");
       out.push_back(move_k_opt(desc, e, cuts, patterns[sel % patterns.size()]));
+      out.back().f = sel % patterns.size();  // pattern index inside enumerate_reconnections(k)
     }
   }
   return out;

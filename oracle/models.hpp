@@ -33,6 +33,7 @@ struct OracleModel {
   virtual std::vector<Move> enumerate_list_reverse(MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_sublist_change(size_t min_size, size_t max_size, MoveStreamContext ctx) { return {}; }
   virtual std::vector<Move> enumerate_sublist_swap(size_t min_size, size_t max_size, MoveStreamContext ctx) { return {}; }
+  virtual std::vector<Move> enumerate_k_opt(size_t k, size_t min_seg, MoveStreamContext ctx) { return {}; }
   virtual size_t scalar_desc() const { return 0; }
   virtual size_t list_desc() const { return 0; }
   virtual uint64_t score_calculations() const = 0;
@@ -287,6 +288,9 @@ struct CvrpModel final : ModelImpl<CvrpPlan> {
   }
   std::vector<Move> enumerate_sublist_swap(size_t min_size, size_t max_size, MoveStreamContext ctx) override {
     return enumerate_sublist_swap_moves(dir.working, dir.access, 0, min_size, max_size, ctx);
+  }
+  std::vector<Move> enumerate_k_opt(size_t k, size_t min_seg, MoveStreamContext ctx) override {
+    return enumerate_k_opt_moves(dir.working, dir.access, 0, k, min_seg, ctx);
   }
 };
 

@@ -302,6 +302,29 @@ int64_t sfo_enumerate_sublist_swap(void* h, uint32_t min_size, uint32_t max_size
   return (int64_t)moves.size();
 }
 
+// KOptMove rows: k + 2 words each = {entity, cut_0 .. cut_{k-1}, pattern index in enumerate_reconnections(k)}
+int64_t sfo_enumerate_k_opt(void* h, uint32_t k, uint32_t min_seg, uint64_t step_index, uint64_t step_seed, int order,
+                            uint64_t cap, uint32_t* rows) {
+  auto moves = static_cast<OracleModel*>(h)->enumerate_k_opt(k, min_seg, make_ctx(step_index, step_seed, order));
+  for (size_t i = 0; i < moves.size() && i < cap; ++i) {
+    uint32_t* r = rows + i * (k + 2);
+    r[0] = (uint32_t)moves[i].a;
+    for (uint32_t c = 0; c < k; ++c) r[1 + c] = (uint32_t)moves[i].cuts[c];
+    r[k + 1] = (uint32_t)moves[i].f;
+  }
+  return (int64_t)moves.size();
+}
+// scores k-opt rows of the layout above (do / score / undo per candidate)
+int sfo_score_k_opt(void* h, uint32_t k, uint64_t n, const uint32_t* rows, int64_t* hard, int64_t* soft, uint8_t* doable) {
+  size_t d = static_cast<OracleModel*>(h)->list_desc();
+  const auto patterns = enumerate_reconnections(k);
+  return score_batch(h, n, [&](uint64_t i) {
+    const uint32_t* r = rows + i * (k + 2);
+    std::vector<size_t> cuts(r + 1, r + 1 + k);
+    return move_k_opt(d, r[0], cuts, patterns[r[k + 1] % patterns.size()]);
+  }, hard, soft, doable);
+}
+
 int64_t sfo_enumerate_list_reverse(void* h, uint64_t step_index, uint64_t step_seed, int order, uint64_t cap,
                                    uint32_t* e, uint32_t* start, uint32_t* end) {
   auto moves = static_cast<OracleModel*>(h)->enumerate_list_reverse(make_ctx(step_index, step_seed, order));

@@ -289,6 +289,60 @@ def sublist_swap_rows(offsets: np.ndarray, min_size: int = 1, max_size: int = 3,
     return np.array(out, dtype=np.uint32).reshape(-1, 6)
 
 
+def _binomial(n: int, k: int) -> int:
+    if k > n:
+        return 0
+    k = min(k, n - k)
+    r = 1
+    for i in range(k):
+        r = r * (n - i) // (i + 1)
+    return r
+
+
+def k_opt_cut_combination_at(k: int, length: int, min_seg: int, rank: int):
+    """heuristic/selector/k_opt/iterators.rs:110-160 — the cut positions of the combination with this rank."""
+    choice_count = length - (k + 1) * min_seg + k
+    cuts, start = [], 0
+    for position in range(k):
+        remaining, maximum = k - position - 1, choice_count - (k - position)
+        for cand in range(start, maximum + 1):
+            suffix = _binomial(choice_count - cand - 1, remaining)
+            if rank < suffix:
+                cuts.append(cand + min_seg + position * (min_seg - 1))
+                start = cand + 1
+                break
+            rank -= suffix
+    return cuts
+
+
+def k_opt_pattern_count(k: int) -> int:
+    """Non-identity reconnection patterns of k-opt (k_opt_reconnection.rs:218-262): (k-1)! * 2^(k-1) - 1."""
+    f = 1
+    for i in range(2, k):
+        f *= i
+    return f * (1 << (k - 1)) - 1
+
+
+def k_opt_rows(offsets: np.ndarray, k: int = 3, min_seg: int = 1, ctx: MoveStreamContext = MoveStreamContext(),
+               descriptor_index: int = 0) -> np.ndarray:
+    """rows[n][k + 2] = (entity, cut_0 .. cut_{k-1}, pattern index) in the pull order of KOptMoveSelector
+    (heuristic/selector/list_kernel/k_opt/full.rs:34-98): per entity the (cut combination rank) x (pattern)
+    product pulled through selection_index. Entities in canonical order. Host-side groundwork: the device does not
+    score k-opt rows yet."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lens = np.diff(offsets)
+    n_pat = k_opt_pattern_count(k)
+    out = []
+    for e, ln in enumerate(lens):
+        ln = int(ln)
+        combos = _binomial(ln - (k + 1) * min_seg + k, k) if ln >= (k + 1) * min_seg else 0
+        move_count = combos * n_pat
+        for off in range(move_count):
+            sel = ctx.selection_index(off, move_count, 0x4B0F7E1171000002 ^ descriptor_index ^ e)
+            out.append([e] + k_opt_cut_combination_at(k, ln, min_seg, sel // n_pat) + [sel % n_pat])
+    return np.array(out, dtype=np.uint32).reshape(-1, k + 2)
+
+
 def list_reverse_rows(offsets: np.ndarray, ctx: MoveStreamContext = MoveStreamContext(),
                       descriptor_index: int = 0) -> np.ndarray:
     """rows[n][4] = (entity, start, end, 0) uint32 in the pull order of ListReverseMoveSelector

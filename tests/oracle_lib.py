@@ -59,6 +59,9 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_change.restype = C.c_int64
         l.sfo_enumerate_swap.argtypes = [_P, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P, _P]
         l.sfo_enumerate_swap.restype = C.c_int64
+        l.sfo_enumerate_k_opt.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P]
+        l.sfo_enumerate_k_opt.restype = C.c_int64
+        l.sfo_score_k_opt.argtypes = [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]
         l.sfo_enumerate_nearby_list_change.argtypes = [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P,
                                                        _P, _P, _P]
         l.sfo_enumerate_nearby_list_change.restype = C.c_int64
@@ -286,6 +289,18 @@ class Oracle:
         v = np.zeros(n, dtype=np.int32)
         self.l.sfo_enumerate_change(self.h, step_index, step_seed, order, n, _p(e), _p(v))
         return np.stack([e.astype(np.int64), v.astype(np.int64)], axis=1)
+
+    def enumerate_k_opt(self, k=3, min_seg=1, step_index=0, step_seed=0, order=0) -> np.ndarray:
+        n = self.l.sfo_enumerate_k_opt(self.h, k, min_seg, step_index, step_seed, order, 0, None)
+        rows = np.zeros((n, k + 2), dtype=np.uint32)
+        self.l.sfo_enumerate_k_opt(self.h, k, min_seg, step_index, step_seed, order, n, _p(rows))
+        return rows
+
+    def score_k_opt(self, rows, k=3):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1, k + 2)
+        h, s, d = self._out(len(rows))
+        self.l.sfo_score_k_opt(self.h, k, len(rows), _p(rows), _p(h), _p(s), _p(d))
+        return np.stack([h, s], axis=1), d
 
     def enumerate_swap(self, step_index=0, step_seed=0, order=0) -> np.ndarray:
         n = self.l.sfo_enumerate_swap(self.h, step_index, step_seed, order, 0, None, None)

@@ -156,3 +156,29 @@ def test_segment_row_packing_round_trip():
         GpuScoreDirector.pack_sublist_change(np.array([[0, 5, 3, 1, 0]]))        # end < start
     with pytest.raises(L.SfgpuError):
         GpuScoreDirector.pack_sublist_swap(np.array([[0, 1 << 24, (1 << 24) + 1, 1, 0, 1]]))  # start beyond the packing
+
+
+@pytest.mark.parametrize("order", [selectors.ORIGINAL, selectors.RANDOM, selectors.SHUFFLED])
+def test_k_opt_order_matches_reference(order):
+    """KOptMoveSelector pull order (list_kernel/k_opt/full.rs:34-98, cut unranking k_opt/iterators.rs:110-160); the
+    oracle scores the rows (CPU groundwork — no device path yet). Reference KAT: 245 moves for one 8-city tour."""
+    assert selectors.k_opt_pattern_count(2) == 1 and selectors.k_opt_pattern_count(3) == 7
+    assert selectors.k_opt_pattern_count(4) == 47 and selectors.k_opt_pattern_count(5) == 383
+    assert len(selectors.k_opt_rows(np.array([0, 8]), 3)) == 245
+    assert selectors.k_opt_rows(np.array([0, 8]), 3)[0].tolist() == [0, 1, 2, 3, 0]
+    c = instances.cvrp(22, 3, seed=6)
+    offs, el = instances.perturb_routes(c, 5, 12)
+    o = Oracle.cvrp(c, offs, el)
+    for k, min_seg in ((2, 1), (3, 1), (3, 2)):
+        for step_index, seed in ((0, 0), (4, 99)):
+            want = o.enumerate_k_opt(k, min_seg, step_index, seed, order)
+            got = selectors.k_opt_rows(offs, k, min_seg, MoveStreamContext(step_index, seed, order))
+            assert np.array_equal(got, want), f"k={k} min_seg={min_seg} order={order}"
+    rows = o.enumerate_k_opt(2, 1)
+    s2, d2 = o.score_k_opt(rows, 2)
+    assert d2.all()
+    # 2-opt == ListReverseMove on the same window [cut_0, cut_1)
+    rev = np.stack([rows[:, 0], rows[:, 1], rows[:, 2], np.zeros(len(rows), dtype=np.uint32)], axis=1)
+    keep = rows[:, 2] > rows[:, 1] + 1          # a one-element window is not a doable reversal
+    sr, dr = o.score_list_reverse(rev[keep])
+    assert dr.all() and np.array_equal(sr, s2[keep])
