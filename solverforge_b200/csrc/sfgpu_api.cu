@@ -1,223 +1,12 @@
-// libsfgpu — host side of the C ABI declared in include/sfgpu.h: context, model lowering,
-// HBM layout, kernel launches. No CPU scoring path exists in this file: every compute entry
-// point launches a CUDA kernel or fails with SFGPU_E_CUDA.
-#include <algorithm>
-#include <cstdio>
-#include <cmath>
-#include <cstring>
-#include <limits>
-#include <string>
-#include <vector>
+// libsfgpu — host side of the C ABI declared in include/sfgpu.h: context, model lowering, HBM layout, the
+// generic entry points (score, argbest, apply, state read-back). The kernel families live in their own
+// translation units (sfgpu_scalar.cu, sfgpu_list.cu, sfgpu_nearby.cu, sfgpu_index.cu, sfgpu_solve.cu) so the
+// build parallelises. No CPU scoring path exists anywhere in the library: every compute entry point launches
+// a CUDA kernel or fails with SFGPU_E_CUDA.
+#include "sfgpu_ctx.hpp"
+#include "sfgpu_core_kernels.cuh"
 
-#include "sfgpu_change_step.cuh"
-#include "sfgpu_solve.cuh"
-#include "sfgpu_index_step.cuh"
-
-namespace {
-
-struct Collection {
-  std::string name;
-  uint32_t n_rows;
-  int32_t descriptor;
-};
-struct Column {
-  uint32_t coll;
-  std::vector<int64_t> host;
-  int64_t* dev = nullptr;
-};
-struct Csr {
-  uint32_t n_rows;
-  std::vector<uint32_t> row_ptr, col;
-};
-struct Matrix {
-  uint32_t rows, cols;
-  std::vector<int64_t> host;
-  void* dev = nullptr;
-  bool i32 = false;
-};
-struct ScalarVar {
-  uint32_t coll, n_values;
-  int allows_unassigned;
-  std::vector<int32_t> init;  // [n] or [R][n]
-  bool per_replica = false;
-};
-struct ListVar {
-  uint32_t owner_coll, elem_coll;
-  std::vector<uint32_t> offsets, elems;
-  bool per_replica = false;
-};
-struct ConsHost {
-  sfgpu_constraint_desc d;
-  std::string name;
-};
-
-}  // namespace
-
-struct sfgpu_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  std::string err;
-  // model under construction
-  bool building = false, committed = false;
-  uint32_t R = 0;
-  std::vector<Collection> colls;
-  std::vector<Column> cols;
-  std::vector<Csr> csrs;
-  std::vector<Matrix> mats;
-  std::vector<ScalarVar> svars;
-  std::vector<ListVar> lvars;
-  std::vector<ConsHost> cons;
-  // device
-  DevModel dm{};
-  char* scratch_state = nullptr;
-  std::vector<void*> dev_allocs;
-  int max_smem_optin = 0;
-  int sm_count = 0;
-  bool staged = false;
-  bool has_load_balance = false;
-  bool nb_key32 = false;      // nearby keys fit 32 bits
-  uint32_t nb_scan_bits = 24;
-  bool force_generic = false;  // SFGPU_CTX_GENERIC_KERNELS: never take a specialised fast path (testing)
-  int spec_id = -1;            // monomorphised scalar program (sfgpu_spec.cuh), -1 = interpreter
-  SpecIdx spec_idx{{-1, -1, -1, -1}};
-  // staging for host-pointer calls
-  void* pin = nullptr;
-  size_t pin_bytes = 0;
-  void* dscr = nullptr;
-  size_t dscr_bytes = 0;
-  void* partials = nullptr;  // fused forager chunk partials
-  void* solve_buf = nullptr;  // device-resident loop state
-  std::vector<uint32_t> relabel_host, inverse_host;  // element id <-> internal id of the fast records
-  size_t solve_bytes = 0;
-  void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
-  void* small_dev = nullptr;
-  size_t small_bytes = 0;
-  size_t partials_bytes = 0;
-  // ring of CUDA event pairs around the dominant (scoring) kernel of each call
-  static constexpr uint32_t EV_RING = 512;
-  std::vector<cudaEvent_t> ev_a, ev_b;
-  uint64_t ev_count = 0;  // scoring launches recorded so far
-  uint64_t launches = 0;
-};
-
-namespace {
-
-// Monomorphised scalar programs: (sorted) kinds of the scalar constraints -> kernel instantiations.
-// The tuples of the reference's scalar examples (graph colouring, n-queens, job shop) and their prefixes.
-typedef void (*SpecScoreFn)(const DevModel, const SpecIdx, const uint64_t*, const uint32_t*, int64_t*, uint8_t*);
-typedef void (*SpecStepFn)(const DevModel, const ChangeStepArgs, const SpecIdx);
-struct SpecEntry {
-  int k[4];
-  SpecScoreFn score;
-  SpecStepFn step;
-};
-#define SPEC_ENTRY(a, b, c, d) \
-  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProg<a, b, c, d>> }
-#define U_ SFGPU_K_UNI
-#define C_ SFGPU_K_PAIR_CSR_EQUAL
-#define K_ SFGPU_K_PAIR_KEY_EQUAL
-#define G_ SFGPU_K_GROUP
-#define UC SPEC_K_UNI_CONST
-const SpecEntry g_spec[] = {  // kinds ascending; UC (uni without column / mask) sorts last
-    SPEC_ENTRY(U_, 0, 0, 0),   SPEC_ENTRY(UC, 0, 0, 0),    // unassigned only
-    SPEC_ENTRY(U_, C_, 0, 0),  SPEC_ENTRY(C_, UC, 0, 0),   // graph colouring
-    SPEC_ENTRY(U_, K_, 0, 0),  SPEC_ENTRY(K_, UC, 0, 0),
-    SPEC_ENTRY(U_, G_, 0, 0),  SPEC_ENTRY(G_, UC, 0, 0),
-    SPEC_ENTRY(U_, C_, G_, 0), SPEC_ENTRY(C_, G_, UC, 0),
-    SPEC_ENTRY(U_, K_, G_, 0), SPEC_ENTRY(K_, G_, UC, 0),  // job shop
-    SPEC_ENTRY(U_, K_, K_, 0), SPEC_ENTRY(K_, K_, UC, 0),
-    SPEC_ENTRY(U_, K_, K_, K_), SPEC_ENTRY(K_, K_, K_, UC),  // n-queens
-    SPEC_ENTRY(U_, K_, G_, G_), SPEC_ENTRY(K_, G_, G_, UC),
-    SPEC_ENTRY(U_, U_, K_, G_), SPEC_ENTRY(U_, K_, G_, UC),
-};
-#undef U_
-#undef C_
-#undef K_
-#undef G_
-#undef UC
-#undef SPEC_ENTRY
-
-thread_local std::string g_noctx_err;
-
-int fail(sfgpu_ctx* c, int code, const std::string& msg) {
-  if (c) c->err = msg; else g_noctx_err = msg;
-  return code;
-}
-#define CU(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess)                                                                         \
-      return fail(ctx, e_ == cudaErrorMemoryAllocation ? SFGPU_E_OOM : SFGPU_E_CUDA,               \
-                  std::string(#call) + ": " + cudaGetErrorString(e_));                             \
-  } while (0)
-
-template <class T>
-int dev_upload(sfgpu_ctx* ctx, const T* host, size_t n, T** out) {
-  void* p = nullptr;
-  CU(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
-  ctx->dev_allocs.push_back(p);
-  if (n) CU(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  *out = (T*)p;
-  return SFGPU_OK;
-}
-
-uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
-
-int ensure_staging(sfgpu_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
-  if (pin_bytes > ctx->pin_bytes) {
-    if (ctx->pin) cudaFreeHost(ctx->pin);
-    ctx->pin = nullptr;
-    ctx->pin_bytes = 0;
-    CU(cudaMallocHost(&ctx->pin, pin_bytes));
-    ctx->pin_bytes = pin_bytes;
-  }
-  if (dev_bytes > ctx->dscr_bytes) {
-    if (ctx->dscr) cudaFree(ctx->dscr);
-    ctx->dscr = nullptr;
-    ctx->dscr_bytes = 0;
-    CU(cudaMalloc(&ctx->dscr, dev_bytes));
-    ctx->dscr_bytes = dev_bytes;
-  }
-  return SFGPU_OK;
-}
-
-void ev_begin(sfgpu_ctx* ctx) {
-  if (ctx->ev_a.empty()) {
-    ctx->ev_a.resize(sfgpu_ctx::EV_RING);
-    ctx->ev_b.resize(sfgpu_ctx::EV_RING);
-    for (uint32_t i = 0; i < sfgpu_ctx::EV_RING; ++i) {
-      cudaEventCreate(&ctx->ev_a[i]);
-      cudaEventCreate(&ctx->ev_b[i]);
-    }
-  }
-  cudaEventRecord(ctx->ev_a[ctx->ev_count % sfgpu_ctx::EV_RING], ctx->stream);
-}
-void ev_end(sfgpu_ctx* ctx) {
-  cudaEventRecord(ctx->ev_b[ctx->ev_count % sfgpu_ctx::EV_RING], ctx->stream);
-  ctx->ev_count++;
-}
-
-int check_committed(sfgpu_ctx* ctx) {
-  if (!ctx) return SFGPU_E_INVALID;
-  if (!ctx->committed) return fail(ctx, SFGPU_E_STATE, "model not committed");
-  return SFGPU_OK;
-}
-
-// chunks per replica so that the grid covers the machine a few times over (measured on C2: more, smaller
-// CTAs beat fewer fat ones for the generic kernels even though each stages the replica block again)
-uint32_t chunks_for(const sfgpu_ctx* ctx, uint64_t n_total, uint32_t R, uint32_t threads) {
-  uint64_t per_replica = (n_total + R - 1) / std::max<uint32_t>(R, 1);
-  uint64_t max_chunks = std::max<uint64_t>(1, (per_replica + threads - 1) / threads);
-  uint64_t target_ctas = (uint64_t)ctx->sm_count * 8;
-  uint64_t want = std::max<uint64_t>(1, (target_ctas + R - 1) / R);
-  uint64_t amort = std::max<uint64_t>(1, per_replica / (threads * 4ull));
-  uint64_t chunks = std::min(max_chunks, std::max(want, std::min<uint64_t>(amort, want * 4)));
-  return (uint32_t)std::min<uint64_t>(chunks, 65535);
-}
-
-}  // namespace
+using namespace sfgpu_host;
 
 extern "C" {
 
@@ -853,56 +642,10 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     CU(cudaMemcpyAsync(dm.state, img.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
-  // shared-memory staging of the replica block (TMA bulk copy) when it fits
   ctx->staged = dm.stage_bytes + 1024 <= (uint32_t)ctx->max_smem_optin;
-  if (ctx->staged) {
-    int bytes = (int)dm.stage_bytes;
-    CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(change_step_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_REVERSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SUBLIST_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SUBLIST_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  }
-  // monomorphised scalar program: every constraint that reacts to scalar edits must be one of the
-  // specialised kinds and the sorted tuple one of the instantiated ones; otherwise the interpreter
-  ctx->spec_id = -1;
-  if (ctx->staged && dm.n_values > 0 && !ctx->force_generic && !getenv("SFGPU_NO_SPEC")) {
-    std::vector<std::pair<int, int>> sc;  // (kind, index)
-    bool ok = true;
-    for (uint32_t k = 0; k < dm.n_cons; ++k) {
-      const ConsDev& c = dm.cons[k];
-      switch (c.kind) {
-        case SFGPU_K_UNI: sc.push_back({(!c.g0 && !c.g1) ? SPEC_K_UNI_CONST : SFGPU_K_UNI, (int)k}); break;
-        case SFGPU_K_PAIR_KEY_EQUAL:
-          if (c.pad != 2) ok = false;  // tri / quad / penta joins keep the interpreter
-          sc.push_back({c.kind, (int)k});
-          break;
-        case SFGPU_K_GROUP: sc.push_back({c.kind, (int)k}); break;
-        case SFGPU_K_PAIR_CSR_EQUAL:
-          if (c.off0 == 0xFFFFFFFFu) ok = false;  // no retained partner-value counts
-          sc.push_back({c.kind, (int)k});
-          break;
-        case SFGPU_K_LOAD_BALANCE: case SFGPU_K_RUNS: case SFGPU_K_PROJECT_GROUP: ok = false; break;
-        default: break;  // list-only kinds do not react to scalar edits
-      }
-    }
-    if (ok && !sc.empty() && sc.size() <= 4) {
-      std::stable_sort(sc.begin(), sc.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
-      int kinds[4] = {0, 0, 0, 0};
-      for (size_t i = 0; i < sc.size(); ++i) kinds[i] = sc[i].first;
-      for (size_t t = 0; t < sizeof(g_spec) / sizeof(g_spec[0]); ++t) {
-        if (memcmp(g_spec[t].k, kinds, sizeof(kinds)) != 0) continue;
-        ctx->spec_id = (int)t;
-        for (size_t i = 0; i < 4; ++i) ctx->spec_idx.k[i] = i < sc.size() ? sc[i].second : -1;
-        CU(cudaFuncSetAttribute((const void*)g_spec[t].score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
-        CU(cudaFuncSetAttribute((const void*)g_spec[t].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
-        break;
-      }
-    }
+  {
+    int rc = sfgpu_configure_scalar(ctx);  // monomorphised program choice + shared-memory opt-in
+    if (rc) return rc;
   }
   if (dm.fast_list && dm.fast_stage_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
     dm.fast_list = 0;
@@ -1028,14 +771,6 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
     int rc = dev_upload(ctx, nbr.data(), nbr.size(), &dn);
     if (rc) return rc;
     dm.nbr = dn;
-    int bytes = (int)dm.fast_stage_bytes;
-#define NB_ATTR(FN, KEY, CELL)                                                                                        \
-  CU(cudaFuncSetAttribute(nearby_step_kernel<FN, KEY, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
-  CU(cudaFuncSetAttribute(nearby_step_kernel<FN, KEY, CELL, MOVE_SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
-#define NB_ATTR4(FN) NB_ATTR(FN, uint32_t, uint16_t); NB_ATTR(FN, uint32_t, int32_t); NB_ATTR(FN, uint64_t, uint16_t); NB_ATTR(FN, uint64_t, int32_t)
-    NB_ATTR4(-1);
-    NB_ATTR4(SFGPU_W_SQUARE);
-    NB_ATTR4(SFGPU_W_EXCESS);
     // key layout: distance bits above scan-index bits; 32-bit keys when both fit in 31 bits
     {
       const Matrix& mt2 = ctx->mats[ctx->cons[dm.fast_pc].d.aux0];
@@ -1048,44 +783,14 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
       ctx->nb_scan_bits = ctx->nb_key32 ? sbits : 24;
     }
   }
-  if (dm.fast_list) {
-    {
-      int bytes = (int)dm.fast_stage_bytes;
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<-1, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_CONST, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_LINEAR, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_SQUARE, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 4, false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 3, true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute(score_list_change_fast_kernel<SFGPU_W_EXCESS, 2, 4, true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    }
-  }
-  if (dm.fast_list && dm.compact_bytes) {
-    if (!dm.fm_u16 || 16 + dm.compact_bytes + 1024 > (uint32_t)ctx->max_smem_optin) {
-      dm.compact_bytes = 0;
-    } else {
-      const int bytes = (int)(16 + dm.compact_bytes);
-#define COMPACT_ATTR(FN)                                                                                              \
-  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 1, 4, false, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
-  CU(cudaFuncSetAttribute(score_list_change_fast_kernel<FN, 1, 4, true, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
-      COMPACT_ATTR(-1);
-      COMPACT_ATTR(SFGPU_W_CONST);
-      COMPACT_ATTR(SFGPU_W_LINEAR);
-      COMPACT_ATTR(SFGPU_W_SQUARE);
-      COMPACT_ATTR(SFGPU_W_EXCESS);
+  if (dm.fast_list && dm.compact_bytes && (!dm.fm_u16 || 16 + dm.compact_bytes + 1024 > (uint32_t)ctx->max_smem_optin))
+    dm.compact_bytes = 0;
+  {
+    int rc = sfgpu_configure_list(ctx);
+    if (rc) return rc;
+    if (dm.nearby_ok) {
+      rc = sfgpu_configure_nearby(ctx);
+      if (rc) return rc;
     }
   }
   if (dm.has_list) {
@@ -1104,100 +809,24 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
   return SFGPU_OK;
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------
 // scoring
 // ------------------------------------------------------------------------------------------
+int sfgpu_launch_score_scalar(sfgpu_ctx* ctx, int kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
+                              const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable);
+int sfgpu_launch_score_list(sfgpu_ctx* ctx, int kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
+                            int64_t* d_scores, uint8_t* d_doable, ForageArgs* forage, uint32_t* out_chunks);
+
 namespace {
 
 enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP, SK_LIST_REVERSE, SK_SUBLIST_CHANGE, SK_SUBLIST_SWAP };
 
-// forage != nullptr (fast list path only): the kernel also emits per-chunk forager partials into
-// forage->partials and *out_chunks receives the chunk count the finishing kernel needs.
 int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
-                 const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable, ForageArgs* forage = nullptr,
-                 uint32_t* out_chunks = nullptr) {
-  const DevModel& dm = ctx->dm;
-  const uint32_t threads = 256;
-  dim3 grid(chunks_for(ctx, n_total, dm.R, threads), dm.R);
-  size_t smem = ctx->staged ? dm.stage_bytes : 0;
-  ev_begin(ctx);
-#define LAUNCH_SCALAR(MODE)                                                                                    \
-  if (ctx->staged)                                                                                             \
-    score_scalar_kernel<MODE, true><<<grid, threads, smem, ctx->stream>>>(dm, d_offs, d_rows, d_edit_offs,    \
-                                                                          d_scores, d_doable);                 \
-  else                                                                                                         \
-    score_scalar_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(dm, d_offs, d_rows, d_edit_offs,      \
-                                                                        d_scores, d_doable)
-#define LAUNCH_LIST(MODE)                                                                                      \
-  if (ctx->staged)                                                                                             \
-    score_list_kernel<MODE, true><<<grid, threads, smem, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable); \
-  else                                                                                                         \
-    score_list_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable)
-  switch (kind) {
-    case SK_CHANGE:
-      if (ctx->spec_id >= 0)
-        g_spec[ctx->spec_id].score<<<grid, threads, smem, ctx->stream>>>(dm, ctx->spec_idx, d_offs, d_rows, d_scores, d_doable);
-      else
-        LAUNCH_SCALAR(MODE_CHANGE);
-      break;
-    case SK_SWAP: LAUNCH_SCALAR(MODE_SWAP); break;
-    case SK_COMPOUND: LAUNCH_SCALAR(MODE_COMPOUND); break;
-    case SK_LIST_CHANGE:
-      if (dm.fast_list && !ctx->force_generic) {
-        // contiguous chunk per CTA; fewer, fatter CTAs amortise the 16 B/record staging
-        uint64_t per_replica = (n_total + dm.R - 1) / dm.R;
-        // ~10k candidates per CTA: the 35 KB record staging is paid once per CTA (measured: 2 chunks of
-        // 10 000 beat 4 x 5 000 by 7 %); with few replicas split further until the machine is covered
-        uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 10239) / 10240, 64));
-        while ((uint64_t)chunks * dm.R < (uint64_t)ctx->sm_count * 6 && (uint64_t)chunks * 512 < per_replica) chunks *= 2;
-        static const int chunk_override = getenv("SFGPU_FAST_CHUNKS") ? atoi(getenv("SFGPU_FAST_CHUNKS")) : 0;  // tuning knob
-        if (chunk_override > 0) chunks = (uint32_t)chunk_override;
-        dim3 fgrid(chunks, dm.R);
-        if (forage) {
-          size_t need = (size_t)chunks * dm.R * sizeof(ChunkPartial);
-          if (need > ctx->partials_bytes) {
-            if (ctx->partials) cudaFree(ctx->partials);
-            ctx->partials = nullptr;
-            ctx->partials_bytes = 0;
-            CU(cudaMalloc(&ctx->partials, need));
-            ctx->partials_bytes = need;
-          }
-          forage->partials = (ChunkPartial*)ctx->partials;
-          if (out_chunks) *out_chunks = chunks;
-        }
-        size_t fsm = dm.fast_score_bytes;
-        int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
-#define FASTK(FN)                                                                                              \
-  if (dm.compact_bytes && dm.fm_u16) {                                                                         \
-    const size_t csm = 16 + dm.compact_bytes;                                                                  \
-    if (forage) score_list_change_fast_kernel<FN, 1, 4, true, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
-    else score_list_change_fast_kernel<FN, 1, 4, false, uint16_t, true><<<fgrid, threads, csm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
-  } else if (forage)                                                                                           \
-    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 4, true, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
-    else score_list_change_fast_kernel<FN, 2, 3, true, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, *forage); \
-  else                                                                                                         \
-    if (dm.fm_u16) score_list_change_fast_kernel<FN, 2, 4, false, uint16_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{}); \
-    else score_list_change_fast_kernel<FN, 2, 3, false, int32_t><<<fgrid, threads, fsm, ctx->stream>>>(dm, d_offs, d_rows, d_scores, d_doable, ForageArgs{})
-        switch (fn) {
-          case -1: FASTK(-1); break;
-          case SFGPU_W_CONST: FASTK(SFGPU_W_CONST); break;
-          case SFGPU_W_LINEAR: FASTK(SFGPU_W_LINEAR); break;
-          case SFGPU_W_SQUARE: FASTK(SFGPU_W_SQUARE); break;
-          default: FASTK(SFGPU_W_EXCESS); break;
-        }
-      } else {
-        LAUNCH_LIST(LMODE_CHANGE);
-      }
-      break;
-    case SK_LIST_SWAP: LAUNCH_LIST(LMODE_SWAP); break;
-    case SK_LIST_REVERSE: LAUNCH_LIST(LMODE_REVERSE); break;
-    case SK_SUBLIST_CHANGE: LAUNCH_LIST(LMODE_SUBLIST_CHANGE); break;
-    case SK_SUBLIST_SWAP: LAUNCH_LIST(LMODE_SUBLIST_SWAP); break;
-  }
-  ev_end(ctx);
-  ctx->launches++;
-  CU(cudaGetLastError());
-  return SFGPU_OK;
+                 const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable) {
+  if (kind <= SK_COMPOUND) return sfgpu_launch_score_scalar(ctx, (int)kind, n_total, d_offs, d_rows, d_edit_offs, d_scores, d_doable);
+  return sfgpu_launch_score_list(ctx, (int)kind, n_total, d_offs, d_rows, d_scores, d_doable, nullptr, nullptr);
 }
 
 bool is_pinned(const void* p) {
@@ -1286,6 +915,8 @@ int score_entry(sfgpu_ctx* ctx, ScoreKind kind, uint32_t flags, uint64_t n_candi
 
 }  // namespace
 
+extern "C" {
+
 int32_t sfgpu_score_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
                            int64_t* out_scores, uint8_t* out_doable) {
   return score_entry(ctx, SK_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
@@ -1318,634 +949,6 @@ int32_t sfgpu_score_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_ca
 int32_t sfgpu_score_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
                                  const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
   return score_entry(ctx, SK_SUBLIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused step: score every candidate and replay acceptor + forager in one call. Device pointers only.
-int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint64_t* cand_offsets,
-                               const uint32_t* rows, const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                               const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
-                               uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) {
-  int rc = check_committed(ctx);
-  if (rc) return rc;
-  if (!cand_offsets || !rows || !params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
-  if ((out_scores == nullptr) != (out_doable == nullptr))
-    return fail(ctx, SFGPU_E_INVALID, "out_scores and out_doable are given together or not at all");
-  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
-    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
-  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
-  const DevModel& dm = ctx->dm;
-  if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
-  CU(cudaSetDevice(ctx->device));
-  const bool fused = dm.fast_list && !ctx->force_generic && params->accepted_limit == 0;
-  if (fused) {
-    ForageArgs fa{};
-    fa.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
-    fa.ref_scores = ref_scores;
-    uint32_t chunks = 0;
-    rc = launch_score(ctx, SK_LIST_CHANGE, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable, &fa,
-                      &chunks);
-    if (rc) return rc;
-    forage_finish_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, fa, chunks, cand_offsets, rows, out_scores, out_doable,
-                                                       step_seeds, out_index, out_best, out_evaluated);
-    ctx->launches++;
-    CU(cudaGetLastError());
-    return SFGPU_OK;
-  }
-  // unfused: materialise scores (caller's buffers or internal scratch), then the ordered replay kernel
-  int64_t* d_scores = out_scores;
-  uint8_t* d_doable = out_doable;
-  if (!d_scores) {
-    size_t need = n_candidates * 16 + (n_candidates + 15) / 16 * 16;
-    rc = ensure_staging(ctx, 64, need);
-    if (rc) return rc;
-    d_scores = (int64_t*)ctx->dscr;
-    d_doable = (uint8_t*)ctx->dscr + n_candidates * 16;
-  }
-  rc = launch_score(ctx, SK_LIST_CHANGE, n_candidates, cand_offsets, rows, nullptr, d_scores, d_doable);
-  if (rc) return rc;
-  ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit};
-  argbest_kernel<<<dm.R, 1024, 0, ctx->stream>>>(f, cand_offsets, d_scores, d_doable, step_seeds, ref_scores, out_index,
-                                                 out_best, out_evaluated);
-  ctx->launches++;
-  CU(cudaGetLastError());
-  return SFGPU_OK;
-}
-
-namespace {
-// generate + score + forage (two kernels) on the context's stream
-int launch_nearby_kernels(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t* d_best, uint32_t* d_eval,
-                          uint32_t* d_win, int move = MOVE_CHANGE) {
-  const DevModel& dm = ctx->dm;
-  const uint32_t R = dm.R;
-  // sources per CTA: 8 warps, >= 24 sources each when there is enough work
-  // few fat CTAs when there are many replicas (amortises the record staging); with few replicas
-  // spread the sources over the machine: down to one source per warp
-  uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((dm.elem_cap + 255) / 256, 64));
-  const uint32_t max_chunks = std::max<uint32_t>(1, (dm.elem_cap + 7) / 8);
-  while ((uint64_t)chunks * R < (uint64_t)ctx->sm_count * 2 && chunks * 2 <= max_chunks) chunks *= 2;
-  dim3 grid(chunks, R);
-  size_t smem = dm.fast_stage_bytes;
-  int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
-#define NEARBYK(FN, KEY, CELL)                                                                       \
-  if (move == MOVE_SWAP) {                                                                           \
-    nearby_step_kernel<FN, KEY, CELL, MOVE_SWAP><<<grid, 256, smem, ctx->stream>>>(dm, a);            \
-    nearby_finish_kernel<FN, KEY, CELL, MOVE_SWAP><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win); \
-  } else {                                                                                           \
-    nearby_step_kernel<FN, KEY, CELL><<<grid, 256, smem, ctx->stream>>>(dm, a);                       \
-    nearby_finish_kernel<FN, KEY, CELL><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win); \
-  }
-#define NEARBYK4(FN)                                                                                 \
-  if (ctx->nb_key32) {                                                                               \
-    if (dm.fm_u16) { NEARBYK(FN, uint32_t, uint16_t); } else { NEARBYK(FN, uint32_t, int32_t); }     \
-  } else {                                                                                           \
-    if (dm.fm_u16) { NEARBYK(FN, uint64_t, uint16_t); } else { NEARBYK(FN, uint64_t, int32_t); }     \
-  }
-  a.scan_bits = ctx->nb_scan_bits;
-  if (fn == SFGPU_W_EXCESS) { NEARBYK4(SFGPU_W_EXCESS) }
-  else if (fn == SFGPU_W_SQUARE) { NEARBYK4(SFGPU_W_SQUARE) }
-  else { NEARBYK4(-1) }  // no LIST_SUM, or a LINEAR / CONST weight whose relocation delta is 0
-  return SFGPU_OK;
-}
-
-int ensure_partials(sfgpu_ctx* ctx, size_t need) {
-  if (need > ctx->partials_bytes) {
-    if (ctx->partials) cudaFree(ctx->partials);
-    ctx->partials = nullptr;
-    ctx->partials_bytes = 0;
-    CU(cudaMalloc(&ctx->partials, need));
-    ctx->partials_bytes = need;
-  }
-  return SFGPU_OK;
-}
-}  // namespace
-
-// ------------------------------------------------------------------------------------------
-// Whole local-search step on device: nearby list-change neighbourhood generation + scoring + forager.
-namespace {
-int step_nearby_impl(sfgpu_ctx* ctx, int move, uint32_t flags, uint32_t max_nearby, const sfgpu_forage_params* params,
-                     const uint64_t* step_seeds, const int64_t* ref_scores, uint64_t* out_cand_offsets,
-                     uint32_t* out_rows, int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
-                     int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
-  int rc = check_committed(ctx);
-  if (rc) return rc;
-  const DevModel& dm = ctx->dm;
-  if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
-  if (!dm.nearby_ok || ctx->force_generic)
-    return fail(ctx, SFGPU_E_UNSUPPORTED,
-                "device-side nearby neighbourhood needs the fast list program (int32 path-cost matrix as the "
-                "distance meter, every cell finite); enumerate on the host and call sfgpu_step_list_change");
-  if (max_nearby == 0 || max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
-  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
-    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
-  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
-  if (out_scores && (!out_rows || !out_doable)) return fail(ctx, SFGPU_E_INVALID, "out_scores needs out_rows and out_doable");
-  CU(cudaSetDevice(ctx->device));
-  const uint32_t R = dm.R;
-  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
-  rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
-  if (rc) return rc;
-  // small per-replica arrays: host pointers are staged through pinned memory
-  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
-  size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
-  size_t o_eval = a16(o_best + (size_t)R * 16), o_win = a16(o_eval + (size_t)R * 4), small = a16(o_win + (size_t)R * 16);
-  const uint64_t* d_seeds = step_seeds;
-  const int64_t* d_ref = ref_scores;
-  uint32_t *d_idx = out_index, *d_eval = out_evaluated, *d_win = out_winner_rows;
-  int64_t* d_best = out_best;
-  if (!dev_io) {
-    if (small > ctx->small_bytes) {
-      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
-      if (ctx->small_dev) cudaFree(ctx->small_dev);
-      ctx->small_pin = ctx->small_dev = nullptr;
-      ctx->small_bytes = 0;
-      CU(cudaMallocHost(&ctx->small_pin, small));
-      CU(cudaMalloc(&ctx->small_dev, small));
-      ctx->small_bytes = small;
-    }
-    char* pin = (char*)ctx->small_pin;
-    char* dv = (char*)ctx->small_dev;
-    if (step_seeds) memcpy(pin + o_seed, step_seeds, (size_t)R * 8);
-    if (ref_scores) memcpy(pin + o_ref, ref_scores, (size_t)R * 32);
-    if (step_seeds || ref_scores) CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
-    d_seeds = step_seeds ? (const uint64_t*)(dv + o_seed) : nullptr;
-    d_ref = ref_scores ? (const int64_t*)(dv + o_ref) : nullptr;
-    d_idx = (uint32_t*)(dv + o_idx);
-    d_best = (int64_t*)(dv + o_best);
-    d_eval = (uint32_t*)(dv + o_eval);
-    d_win = (uint32_t*)(dv + o_win);
-  } else if (apply_winners && !d_win) {
-    return fail(ctx, SFGPU_E_INVALID, "apply_winners needs out_winner_rows on the device path");
-  }
-  NearbyArgs a{};
-  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
-  a.max_nearby = max_nearby;
-  a.step_seeds = d_seeds;
-  a.ref_scores = d_ref;
-  a.partials = (SrcPartial*)ctx->partials;
-  a.out_rows = out_rows;
-  a.out_scores = out_scores;
-  a.out_doable = out_doable;
-  a.out_offsets = out_cand_offsets;
-  ev_begin(ctx);
-  rc = launch_nearby_kernels(ctx, a, d_idx, d_best, d_eval, d_win, move);
-  if (rc) return rc;
-  ev_end(ctx);
-  ctx->launches += 2;
-  CU(cudaGetLastError());
-  if (apply_winners) {
-    // a replica without a winner carries the sentinel row (owner 0xFFFFFFFF): not doable, skipped
-    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, move == MOVE_SWAP ? 3 : 2, d_win, nullptr,
-                                                                       nullptr, nullptr);
-    ctx->launches++;
-    CU(cudaGetLastError());
-  }
-  if (!dev_io) {
-    char* pin = (char*)ctx->small_pin;
-    char* dv = (char*)ctx->small_dev;
-    CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, small - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    memcpy(out_index, pin + o_idx, (size_t)R * 4);
-    memcpy(out_best, pin + o_best, (size_t)R * 16);
-    if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
-    if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
-  }
-  return SFGPU_OK;
-}
-}  // namespace
-
-int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
-                                      const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                                      const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
-                                      int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
-                                      int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                                      int32_t apply_winners) {
-  return step_nearby_impl(ctx, MOVE_CHANGE, flags, max_nearby, params, step_seeds, ref_scores, out_cand_offsets,
-                          out_rows, out_scores, out_doable, out_index, out_best, out_evaluated, out_winner_rows,
-                          apply_winners);
-}
-
-int32_t sfgpu_step_nearby_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
-                                    const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                                    const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
-                                    int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index, int64_t* out_best,
-                                    uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
-  if (ctx && ctx->dm.fast_pc < 0)
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "nearby list swap needs a path-cost constraint (its matrix is the distance meter)");
-  return step_nearby_impl(ctx, MOVE_SWAP, flags, max_nearby, params, step_seeds, ref_scores, out_cand_offsets, out_rows,
-                          out_scores, out_doable, out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
-}
-
-// ------------------------------------------------------------------------------------------
-// Device-resident local-search loop (sfgpu_solve.cuh).
-namespace {
-int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t* out_best_scores,
-               uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
-  int rc = check_committed(ctx);
-  if (rc) return rc;
-  if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
-  const DevModel& dm = ctx->dm;
-  if (scalar) {
-    if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
-    if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
-      return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
-  } else {
-    if (!dm.nearby_ok || ctx->force_generic)
-      return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
-    if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
-  }
-  if (p->acceptor < 1 || p->acceptor > 5)
-    return fail(ctx, SFGPU_E_INVALID,
-                "acceptor: 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing, "
-                "5 DiversifiedLateAcceptance");
-  if ((p->acceptor == 3 || p->acceptor == 5) && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1e6))
-    return fail(ctx, SFGPU_E_INVALID, "acceptor_real (rain_speed / tolerance) must be a finite value >= 0");
-  if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
-  CU(cudaSetDevice(ctx->device));
-  const uint32_t R = dm.R;
-  const uint32_t late = std::max<uint32_t>(p->late_size, 1);
-  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t at = o; o = a16(o + bytes); return at; };
-  const size_t o_cnt = take(8), o_seed = take((size_t)R * 8), o_ref = take((size_t)R * 32);
-  const size_t o_hist = take((size_t)R * late * 16), o_hidx = take((size_t)R * 4), o_bests = take((size_t)R * 16);
-  const size_t o_eval = take((size_t)R * 8), o_acc = take((size_t)R * 8), o_idx = take((size_t)R * 4);
-  const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
-  const size_t o_accst = take((size_t)R * 32);
-  const size_t o_snap = take((size_t)R * dm.block_bytes);
-  if (o > ctx->solve_bytes) {
-    if (ctx->solve_buf) cudaFree(ctx->solve_buf);
-    ctx->solve_buf = nullptr;
-    ctx->solve_bytes = 0;
-    CU(cudaMalloc(&ctx->solve_buf, o));
-    ctx->solve_bytes = o;
-  }
-  char* b = (char*)ctx->solve_buf;
-  SolveState s{};
-  s.step_counter = (uint64_t*)(b + o_cnt);
-  s.step_seeds = (uint64_t*)(b + o_seed);
-  s.ref_scores = (int64_t*)(b + o_ref);
-  s.history = (int64_t*)(b + o_hist);
-  s.hist_idx = (uint32_t*)(b + o_hidx);
-  s.best_scores = (int64_t*)(b + o_bests);
-  s.evaluated = (uint64_t*)(b + o_eval);
-  s.accepted_steps = (uint64_t*)(b + o_acc);
-  s.out_index = (uint32_t*)(b + o_idx);
-  s.out_best = (int64_t*)(b + o_ob);
-  s.out_evaluated = (uint32_t*)(b + o_oe);
-  s.winner_rows = (uint32_t*)(b + o_win);
-  s.best_state = b + o_snap;
-  s.seed_base = p->seed_base;
-  s.late_size = late;
-  s.acceptor = p->acceptor;
-  s.acc_state = (int64_t*)(b + o_accst);
-  s.real = p->acceptor_real;
-  s.step_count_limit = p->step_count_limit;
-  const int forage_code = solve_forage_code(p->acceptor);
-  NearbyArgs a{};
-  ChangeStepArgs ca{};
-  uint32_t c_chunks = 0;
-  if (scalar) {
-    uint32_t per = 2048;
-    while (per > 256 && (uint64_t)((dm.n_entities + per - 1) / per) * R < (uint64_t)ctx->sm_count * 4) per /= 2;
-    c_chunks = (dm.n_entities + per - 1) / per;
-    rc = ensure_partials(ctx, (size_t)R * c_chunks * sizeof(ChunkPartial));
-    if (rc) return rc;
-    ca.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
-    ca.ents_per_cta = per;
-    ca.step_seeds = s.step_seeds;
-    ca.ref_scores = s.ref_scores;
-    ca.partials = (ChunkPartial*)ctx->partials;
-  } else {
-    rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
-    if (rc) return rc;
-    a.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
-    a.max_nearby = p->max_nearby;
-    a.step_seeds = s.step_seeds;
-    a.ref_scores = s.ref_scores;
-    a.partials = (SrcPartial*)ctx->partials;
-  }
-  solve_init_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
-  ctx->launches++;
-  CU(cudaGetLastError());
-  auto one_step = [&]() -> int {
-    solve_prep_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s);
-    if (scalar) {
-      dim3 grid(c_chunks, R);
-      if (ctx->spec_id >= 0)
-        g_spec[ctx->spec_id].step<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, ca, ctx->spec_idx);
-      else if (ctx->staged)
-        change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, ca, ctx->spec_idx);
-      else
-        change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, ca, ctx->spec_idx);
-      change_finish_kernel<<<R, 256, 0, ctx->stream>>>(dm, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated,
-                                                      s.winner_rows);
-      apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, 0, s.winner_rows, nullptr, nullptr, nullptr);
-    } else {
-      int rc2 = launch_nearby_kernels(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
-      if (rc2) return rc2;
-      apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, s.winner_rows, nullptr, nullptr, nullptr);
-    }
-    solve_post_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
-    return SFGPU_OK;
-  };
-  // steps are captured once into a CUDA graph of `per_graph` steps and replayed
-  const uint32_t per_graph = std::min<uint32_t>(p->n_steps, 16);
-  uint32_t done = 0;
-  if (per_graph >= 2) {
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int rc2 = SFGPU_OK;
-    for (uint32_t i = 0; i < per_graph && rc2 == SFGPU_OK; ++i) rc2 = one_step();
-    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-    if (rc2 != SFGPU_OK || ce != cudaSuccess) {
-      if (graph) cudaGraphDestroy(graph);
-      return fail(ctx, SFGPU_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-    }
-    CU(cudaGraphInstantiate(&exec, graph, 0));
-    for (; done + per_graph <= p->n_steps; done += per_graph) {
-      CU(cudaGraphLaunch(exec, ctx->stream));
-      ctx->launches += 5ull * per_graph;
-    }
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-  }
-  for (; done < p->n_steps; ++done) {
-    rc = one_step();
-    if (rc) return rc;
-    ctx->launches += 5;
-  }
-  if (p->restore_best) {
-    solve_restore_best_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
-    ctx->launches++;
-  }
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (out_best_scores) CU(cudaMemcpy(out_best_scores, s.best_scores, (size_t)R * 16, cudaMemcpyDeviceToHost));
-  if (out_moves_evaluated) CU(cudaMemcpy(out_moves_evaluated, s.evaluated, (size_t)R * 8, cudaMemcpyDeviceToHost));
-  if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
-  return SFGPU_OK;
-}
-
-}  // namespace
-
-// ------------------------------------------------------------------------------------------
-// Whole step for scalar models: ChangeMove neighbourhood generation + scoring + forager on device.
-int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
-                          const uint64_t* step_seeds, const int64_t* ref_scores, uint64_t* out_cand_offsets,
-                          uint32_t* out_rows, int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
-                          int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                          int32_t apply_winners) {
-  int rc = check_committed(ctx);
-  if (rc) return rc;
-  const DevModel& dm = ctx->dm;
-  if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
-  if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
-  if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
-  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
-    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
-  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
-  if (out_scores && (!out_rows || !out_doable)) return fail(ctx, SFGPU_E_INVALID, "out_scores needs out_rows and out_doable");
-  CU(cudaSetDevice(ctx->device));
-  const uint32_t R = dm.R;
-  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
-  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
-  size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
-  size_t o_eval = a16(o_best + (size_t)R * 16), o_win = a16(o_eval + (size_t)R * 4), small = a16(o_win + (size_t)R * 8);
-  const uint64_t* d_seeds = step_seeds;
-  const int64_t* d_ref = ref_scores;
-  uint32_t *d_idx = out_index, *d_eval = out_evaluated, *d_win = out_winner_rows;
-  int64_t* d_best = out_best;
-  if (!dev_io) {
-    if (small > ctx->small_bytes) {
-      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
-      if (ctx->small_dev) cudaFree(ctx->small_dev);
-      ctx->small_pin = ctx->small_dev = nullptr;
-      ctx->small_bytes = 0;
-      CU(cudaMallocHost(&ctx->small_pin, small));
-      CU(cudaMalloc(&ctx->small_dev, small));
-      ctx->small_bytes = small;
-    }
-    char* pin = (char*)ctx->small_pin;
-    char* dv = (char*)ctx->small_dev;
-    if (step_seeds) memcpy(pin + o_seed, step_seeds, (size_t)R * 8);
-    if (ref_scores) memcpy(pin + o_ref, ref_scores, (size_t)R * 32);
-    if (step_seeds || ref_scores) CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
-    d_seeds = step_seeds ? (const uint64_t*)(dv + o_seed) : nullptr;
-    d_ref = ref_scores ? (const int64_t*)(dv + o_ref) : nullptr;
-    d_idx = (uint32_t*)(dv + o_idx);
-    d_best = (int64_t*)(dv + o_best);
-    d_eval = (uint32_t*)(dv + o_eval);
-    d_win = (uint32_t*)(dv + o_win);
-  } else if (apply_winners && !d_win) {
-    return fail(ctx, SFGPU_E_INVALID, "apply_winners needs out_winner_rows on the device path");
-  }
-  ChangeStepArgs a{};
-  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
-  a.step_seeds = d_seeds;
-  a.ref_scores = d_ref;
-  a.out_rows = out_rows;
-  a.out_scores = out_scores;
-  a.out_doable = out_doable;
-  a.out_offsets = out_cand_offsets;
-  // entities per CTA: amortise the state staging, but cover the machine when replicas are few
-  uint32_t per = 2048;
-  while (per > 256 && (uint64_t)((dm.n_entities + per - 1) / per) * R < (uint64_t)ctx->sm_count * 4) per /= 2;
-  a.ents_per_cta = per;
-  const uint32_t chunks = (dm.n_entities + per - 1) / per;
-  rc = ensure_partials(ctx, (size_t)R * chunks * sizeof(ChunkPartial));
-  if (rc) return rc;
-  a.partials = (ChunkPartial*)ctx->partials;
-  dim3 grid(chunks, R);
-  ev_begin(ctx);
-  if (ctx->spec_id >= 0)
-    g_spec[ctx->spec_id].step<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
-  else if (ctx->staged)
-    change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
-  else
-    change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx);
-  ev_end(ctx);
-  change_finish_kernel<<<R, 256, 0, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
-  ctx->launches += 2;
-  CU(cudaGetLastError());
-  if (apply_winners) {
-    apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, 0, d_win, nullptr, nullptr, nullptr);
-    ctx->launches++;
-    CU(cudaGetLastError());
-  }
-  if (!dev_io) {
-    char* pin = (char*)ctx->small_pin;
-    char* dv = (char*)ctx->small_dev;
-    CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, small - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    memcpy(out_index, pin + o_idx, (size_t)R * 4);
-    memcpy(out_best, pin + o_best, (size_t)R * 16);
-    if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
-    if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 8);
-  }
-  return SFGPU_OK;
-}
-
-}  // extern "C" (templates below)
-
-namespace {
-// Whole step over a neighbourhood enumerated on device by pull index (sfgpu_index_step.cuh). NB = the decoder,
-// apply_kind = the apply_list_kernel kind of its rows, ub = an upper bound of the candidates of one replica.
-template <class NB>
-int step_index_neighbourhood(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size, int apply_kind, uint64_t ub,
-                             const sfgpu_forage_params* params, const uint64_t* step_seeds, const int64_t* ref_scores,
-                             uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                             int32_t apply_winners) {
-  int rc = check_committed(ctx);
-  if (rc) return rc;
-  DevModel dm = ctx->dm;
-  if (ctx->force_generic) dm.fast_list = 0;  // SFGPU_CTX_GENERIC_KERNELS: cursor walks with the generic delta
-  if (!params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
-  if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
-  if (min_size < 1 || max_size < min_size || max_size > 255)
-    return fail(ctx, SFGPU_E_INVALID, "segment sizes must satisfy 1 <= min <= max <= 255");
-  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
-    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
-  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
-  if (ub >= 0xFFFFFFFFull || dm.elem_cap >= (1u << 24))
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
-  const size_t table_bytes = NB::table_words(dm.n_owners, dm.elem_cap) * 4;
-  static const bool no_stage = getenv("SFGPU_INDEX_UNSTAGED") != nullptr;  // tuning knob
-  const bool staged = !no_stage && ctx->staged && dm.stage_bytes + table_bytes + 1024 <= (size_t)ctx->max_smem_optin;
-  if (table_bytes + 1024 > (size_t)ctx->max_smem_optin)
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the shared-memory index tables");
-  CU(cudaSetDevice(ctx->device));
-  const uint32_t R = dm.R;
-  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
-  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
-  size_t o_seed = 0, o_ref = a16((size_t)R * 8), o_idx = a16(o_ref + (size_t)R * 32), o_best = a16(o_idx + (size_t)R * 4);
-  size_t o_eval = a16(o_best + (size_t)R * 16), o_win = a16(o_eval + (size_t)R * 4), small = a16(o_win + (size_t)R * 16);
-  const uint64_t* d_seeds = step_seeds;
-  const int64_t* d_ref = ref_scores;
-  uint32_t *d_idx = out_index, *d_eval = out_evaluated, *d_win = out_winner_rows;
-  int64_t* d_best = out_best;
-  if (!dev_io) {
-    if (small > ctx->small_bytes) {
-      if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
-      if (ctx->small_dev) cudaFree(ctx->small_dev);
-      ctx->small_pin = ctx->small_dev = nullptr;
-      ctx->small_bytes = 0;
-      CU(cudaMallocHost(&ctx->small_pin, small));
-      CU(cudaMalloc(&ctx->small_dev, small));
-      ctx->small_bytes = small;
-    }
-    char* pin = (char*)ctx->small_pin;
-    char* dv = (char*)ctx->small_dev;
-    if (step_seeds) memcpy(pin + o_seed, step_seeds, (size_t)R * 8);
-    if (ref_scores) memcpy(pin + o_ref, ref_scores, (size_t)R * 32);
-    if (step_seeds || ref_scores) CU(cudaMemcpyAsync(dv, pin, o_idx, cudaMemcpyHostToDevice, ctx->stream));
-    d_seeds = step_seeds ? (const uint64_t*)(dv + o_seed) : nullptr;
-    d_ref = ref_scores ? (const int64_t*)(dv + o_ref) : nullptr;
-    d_idx = (uint32_t*)(dv + o_idx);
-    d_best = (int64_t*)(dv + o_best);
-    d_eval = (uint32_t*)(dv + o_eval);
-    d_win = (uint32_t*)(dv + o_win);
-  } else if (apply_winners && !d_win) {
-    return fail(ctx, SFGPU_E_INVALID, "apply_winners needs out_winner_rows on the device path");
-  }
-  IndexStepArgs a{};
-  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
-  a.min_size = min_size;
-  a.max_size = max_size;
-  a.step_seeds = d_seeds;
-  a.ref_scores = d_ref;
-  // candidates per CTA: amortise staging + table build, but cover the machine when replicas are few
-  uint32_t per = 16384;
-  while (per > 1024 && ((ub + per - 1) / per) * R < (uint64_t)ctx->sm_count * 4) per /= 2;
-  a.per_chunk = per;
-  const uint32_t chunks = (uint32_t)std::min<uint64_t>((ub + per - 1) / per, 65535);
-  if ((uint64_t)chunks * per < ub) return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood needs more than 65535 chunks");
-  rc = ensure_partials(ctx, (size_t)R * chunks * sizeof(ChunkPartial));
-  if (rc) return rc;
-  a.partials = (ChunkPartial*)ctx->partials;
-  dim3 grid(chunks, R);
-  ev_begin(ctx);
-  if (staged) {
-    const int bytes = (int)(dm.stage_bytes + table_bytes);
-    CU(cudaFuncSetAttribute(index_step_kernel<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    index_step_kernel<true, NB><<<grid, 256, bytes, ctx->stream>>>(dm, a);
-  } else {
-    CU(cudaFuncSetAttribute(index_step_kernel<false, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-    index_step_kernel<false, NB><<<grid, 256, table_bytes, ctx->stream>>>(dm, a);
-  }
-  ev_end(ctx);
-  CU(cudaFuncSetAttribute(index_finish_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-  index_finish_kernel<NB><<<R, 256, table_bytes, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
-  ctx->launches += 2;
-  CU(cudaGetLastError());
-  if (apply_winners) {
-    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, apply_kind, d_win, nullptr, nullptr, nullptr);
-    ctx->launches++;
-    CU(cudaGetLastError());
-  }
-  if (!dev_io) {
-    char* pin = (char*)ctx->small_pin;
-    char* dv = (char*)ctx->small_dev;
-    CU(cudaMemcpyAsync(pin + o_idx, dv + o_idx, small - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    memcpy(out_index, pin + o_idx, (size_t)R * 4);
-    memcpy(out_best, pin + o_best, (size_t)R * 16);
-    if (out_evaluated) memcpy(out_evaluated, pin + o_eval, (size_t)R * 4);
-    if (out_winner_rows) memcpy(out_winner_rows, pin + o_win, (size_t)R * 16);
-  }
-  return SFGPU_OK;
-}
-}  // namespace
-
-extern "C" {
-
-int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
-                                  const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                                  const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
-                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
-  if (!ctx) return SFGPU_E_INVALID;
-  // every element starts at most (max - min + 1) segments, each with fewer than elements + entities destinations
-  const DevModel& dm = ctx->dm;
-  const uint64_t ub = (uint64_t)dm.elem_cap * (max_size >= min_size ? max_size - min_size + 1 : 1) *
-                      ((uint64_t)dm.elem_cap + dm.n_owners);
-  return step_index_neighbourhood<SublistChangeNb>(ctx, flags, min_size, max_size, 5, ub, params, step_seeds, ref_scores,
-                                                   out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
-}
-
-int32_t sfgpu_step_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
-                                const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
-                                int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                                int32_t apply_winners) {
-  if (!ctx) return SFGPU_E_INVALID;
-  const DevModel& dm = ctx->dm;
-  const uint64_t ub = (uint64_t)dm.elem_cap * dm.elem_cap / 2 + 1;  // one list holding every element
-  return step_index_neighbourhood<ReverseNb>(ctx, flags, 1, 1, 4, ub, params, step_seeds, ref_scores, out_index, out_best,
-                                             out_evaluated, out_winner_rows, apply_winners);
-}
-
-int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
-                                const sfgpu_forage_params* params, const uint64_t* step_seeds,
-                                const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
-                                uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
-  if (!ctx) return SFGPU_E_INVALID;
-  // unordered pairs of segments: fewer than (segments)^2 / 2 + segments
-  const DevModel& dm = ctx->dm;
-  const uint64_t segs = (uint64_t)dm.elem_cap * (max_size >= min_size ? max_size - min_size + 1 : 1);
-  const uint64_t ub = segs * segs / 2 + segs;
-  return step_index_neighbourhood<SublistSwapNb>(ctx, flags, min_size, max_size, 6, ub, params, step_seeds, ref_scores,
-                                                 out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
-}
-
-int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
-                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
-  return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps);
-}
-
-int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
-                           uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
-  return solve_impl(ctx, p, true, out_best_scores, out_moves_evaluated, out_accepted_steps);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2231,3 +1234,38 @@ int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program) {
 }
 
 }  // extern "C"
+
+// ---- launch wrappers for the other translation units -------------------------------------------------------
+int sfgpu_launch_apply_list(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, const uint8_t* d_mask,
+                            const uint64_t* d_offsets, const uint32_t* d_index) {
+  const DevModel& dm = ctx->dm;
+  apply_list_kernel<<<dm.R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+int sfgpu_launch_apply_scalar(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, const uint8_t* d_mask,
+                              const uint64_t* d_offsets, const uint32_t* d_index) {
+  const DevModel& dm = ctx->dm;
+  apply_scalar_kernel<<<dm.R, 32, 0, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+int sfgpu_launch_forage_finish(sfgpu_ctx* ctx, const ForageArgs& fa, uint32_t chunks, const uint64_t* d_offs,
+                               const uint32_t* d_rows, const int64_t* d_scores, const uint8_t* d_doable,
+                               const uint64_t* d_seeds, uint32_t* d_idx, int64_t* d_best, uint32_t* d_eval) {
+  forage_finish_kernel<<<ctx->dm.R, 256, 0, ctx->stream>>>(ctx->dm, fa, chunks, d_offs, d_rows, d_scores, d_doable, d_seeds,
+                                                          d_idx, d_best, d_eval);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+int sfgpu_launch_argbest_ordered(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, const int64_t* d_scores,
+                                 const uint8_t* d_doable, const uint64_t* d_seeds, const int64_t* d_ref, uint32_t* d_idx,
+                                 int64_t* d_best, uint32_t* d_eval) {
+  argbest_kernel<<<ctx->dm.R, 1024, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_seeds, d_ref, d_idx, d_best, d_eval);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}

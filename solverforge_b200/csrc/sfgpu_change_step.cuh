@@ -11,17 +11,6 @@
 #include "sfgpu_kernels.cuh"
 #include "sfgpu_spec.cuh"
 
-struct ChangeStepArgs {
-  ForageDev f;
-  uint32_t ents_per_cta;         // multiple of blockDim.x
-  const uint64_t* step_seeds;    // [R] or null
-  const int64_t* ref_scores;     // [R][4] or null
-  ChunkPartial* partials;        // [R][gridDim.x]; first_idx holds e * (k + 1) + v
-  uint32_t* out_rows;            // [R][n_entities * (k + 1)][2] or null (materialised batch, padded)
-  int64_t* out_scores;
-  uint8_t* out_doable;
-  uint64_t* out_offsets;         // [R + 1] or null
-};
 
 // number of currently assigned entities in [0, end) — block-wide, all threads must call
 __device__ __forceinline__ uint32_t block_count_assigned(const int32_t* var, uint32_t end, uint32_t* scratch) {

@@ -89,6 +89,11 @@ struct SrcPartial {
   uint32_t first_lane, pad;
 };
 
+// indices into DevModel::cons of the (sorted) scalar constraints of a monomorphised program, -1 = none
+struct SpecIdx {
+  int32_t k[4];
+};
+
 struct Score2 {
   int64_t hard, soft;
 };
@@ -111,6 +116,43 @@ struct ChunkPartial {
   uint32_t first_idx;
   uint32_t second_idx;  // second accepted row equal to the best (0xFFFFFFFF when n_best < 2): the common
                         // tie of two rows never needs the ordered rescan
+};
+
+// ---- argument blocks of the whole-step kernels (defined here so host-only translation units can fill them) ----
+#define MOVE_CHANGE 0
+#define MOVE_SWAP 1
+struct NearbyArgs {
+  ForageDev f;
+  uint32_t max_nearby;           // <= 32
+  uint32_t scan_bits;            // low bits of a key that hold the scan index
+  const uint64_t* step_seeds;    // [R] or null
+  const int64_t* ref_scores;     // [R][4] or null
+  SrcPartial* partials;          // [R][elem_cap]
+  uint32_t* out_rows;            // [R][elem_cap * max_nearby][4] or null
+  int64_t* out_scores;           // [R][elem_cap * max_nearby][2] or null
+  uint8_t* out_doable;           // or null
+  uint64_t* out_offsets;         // [R+1] or null: candidate offsets of the materialised batch
+};
+
+struct ChangeStepArgs {
+  ForageDev f;
+  uint32_t ents_per_cta;         // multiple of blockDim.x
+  const uint64_t* step_seeds;    // [R] or null
+  const int64_t* ref_scores;     // [R][4] or null
+  ChunkPartial* partials;        // [R][gridDim.x]; first_idx holds e * (k + 1) + v
+  uint32_t* out_rows;            // [R][n_entities * (k + 1)][2] or null (materialised batch, padded)
+  int64_t* out_scores;
+  uint8_t* out_doable;
+  uint64_t* out_offsets;         // [R + 1] or null
+};
+
+struct IndexStepArgs {
+  ForageDev f;
+  uint32_t per_chunk;            // candidates per CTA (multiple of blockDim.x)
+  uint32_t min_size, max_size;   // segment sizes
+  const uint64_t* step_seeds;    // [R] or null
+  const int64_t* ref_scores;     // [R][4] or null
+  ChunkPartial* partials;        // [R][gridDim.x]
 };
 
 __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {

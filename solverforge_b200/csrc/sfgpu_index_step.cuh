@@ -14,14 +14,6 @@
 #pragma once
 #include "sfgpu_kernels.cuh"
 
-struct IndexStepArgs {
-  ForageDev f;
-  uint32_t per_chunk;            // candidates per CTA (multiple of blockDim.x)
-  uint32_t min_size, max_size;   // segment sizes
-  const uint64_t* step_seeds;    // [R] or null
-  const int64_t* ref_scores;     // [R][4] or null
-  ChunkPartial* partials;        // [R][gridDim.x]
-};
 
 struct SublistChangeNb {
   const uint32_t* off;   // staged route offsets

@@ -23,18 +23,6 @@
 
 #define NB_BATCH 28  // neighbours expanded per trip: 28 + their append slots rarely exceed 32 keys
 
-struct NearbyArgs {
-  ForageDev f;
-  uint32_t max_nearby;           // <= 32
-  uint32_t scan_bits;            // low bits of a key that hold the scan index
-  const uint64_t* step_seeds;    // [R] or null
-  const int64_t* ref_scores;     // [R][4] or null
-  SrcPartial* partials;          // [R][elem_cap]
-  uint32_t* out_rows;            // [R][elem_cap * max_nearby][4] or null
-  int64_t* out_scores;           // [R][elem_cap * max_nearby][2] or null
-  uint8_t* out_doable;           // or null
-  uint64_t* out_offsets;         // [R+1] or null: candidate offsets of the materialised batch
-};
 
 template <typename KEY>
 struct KeyTraits;
@@ -269,8 +257,6 @@ __device__ __forceinline__ uint32_t warp_best_mask(bool acc, int64_t dh, int64_t
 // with the stable bounded top-k (ties keep scan order = flat position). Source f has
 // min(K, total - 1 - f) candidates; sources without destinations are skipped, so pull indices are
 // a prefix sum over sources (swap_prefix).
-#define MOVE_CHANGE 0
-#define MOVE_SWAP 1
 
 __device__ __forceinline__ uint32_t swap_count(uint32_t f, uint32_t total, uint32_t K) {
   const uint32_t e = total - 1 - f;

@@ -1,0 +1,165 @@
+// Device-resident local-search loop of libsfgpu (sfgpu_solve.cuh): whole steps without a host round trip.
+#include "sfgpu_ctx.hpp"
+#include "sfgpu_solve.cuh"
+
+using namespace sfgpu_host;
+
+namespace {
+int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t* out_best_scores,
+               uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
+  const DevModel& dm = ctx->dm;
+  if (scalar) {
+    if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
+    if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
+      return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
+  } else {
+    if (!dm.nearby_ok || ctx->force_generic)
+      return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
+    if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+  }
+  if (p->acceptor < 1 || p->acceptor > 5)
+    return fail(ctx, SFGPU_E_INVALID,
+                "acceptor: 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing, "
+                "5 DiversifiedLateAcceptance");
+  if ((p->acceptor == 3 || p->acceptor == 5) && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1e6))
+    return fail(ctx, SFGPU_E_INVALID, "acceptor_real (rain_speed / tolerance) must be a finite value >= 0");
+  if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R;
+  const uint32_t late = std::max<uint32_t>(p->late_size, 1);
+  auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = a16(o + bytes); return at; };
+  const size_t o_cnt = take(8), o_seed = take((size_t)R * 8), o_ref = take((size_t)R * 32);
+  const size_t o_hist = take((size_t)R * late * 16), o_hidx = take((size_t)R * 4), o_bests = take((size_t)R * 16);
+  const size_t o_eval = take((size_t)R * 8), o_acc = take((size_t)R * 8), o_idx = take((size_t)R * 4);
+  const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
+  const size_t o_accst = take((size_t)R * 32);
+  const size_t o_snap = take((size_t)R * dm.block_bytes);
+  if (o > ctx->solve_bytes) {
+    if (ctx->solve_buf) cudaFree(ctx->solve_buf);
+    ctx->solve_buf = nullptr;
+    ctx->solve_bytes = 0;
+    CU(cudaMalloc(&ctx->solve_buf, o));
+    ctx->solve_bytes = o;
+  }
+  char* b = (char*)ctx->solve_buf;
+  SolveState s{};
+  s.step_counter = (uint64_t*)(b + o_cnt);
+  s.step_seeds = (uint64_t*)(b + o_seed);
+  s.ref_scores = (int64_t*)(b + o_ref);
+  s.history = (int64_t*)(b + o_hist);
+  s.hist_idx = (uint32_t*)(b + o_hidx);
+  s.best_scores = (int64_t*)(b + o_bests);
+  s.evaluated = (uint64_t*)(b + o_eval);
+  s.accepted_steps = (uint64_t*)(b + o_acc);
+  s.out_index = (uint32_t*)(b + o_idx);
+  s.out_best = (int64_t*)(b + o_ob);
+  s.out_evaluated = (uint32_t*)(b + o_oe);
+  s.winner_rows = (uint32_t*)(b + o_win);
+  s.best_state = b + o_snap;
+  s.seed_base = p->seed_base;
+  s.late_size = late;
+  s.acceptor = p->acceptor;
+  s.acc_state = (int64_t*)(b + o_accst);
+  s.real = p->acceptor_real;
+  s.step_count_limit = p->step_count_limit;
+  const int forage_code = solve_forage_code(p->acceptor);
+  NearbyArgs a{};
+  ChangeStepArgs ca{};
+  uint32_t c_chunks = 0;
+  if (scalar) {
+    uint32_t per = 0;
+    sfgpu_change_step_chunks(ctx, &per, &c_chunks);
+    rc = ensure_partials(ctx, (size_t)R * c_chunks * sizeof(ChunkPartial));
+    if (rc) return rc;
+    ca.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
+    ca.ents_per_cta = per;
+    ca.step_seeds = s.step_seeds;
+    ca.ref_scores = s.ref_scores;
+    ca.partials = (ChunkPartial*)ctx->partials;
+  } else {
+    rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
+    if (rc) return rc;
+    a.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
+    a.max_nearby = p->max_nearby;
+    a.step_seeds = s.step_seeds;
+    a.ref_scores = s.ref_scores;
+    a.partials = (SrcPartial*)ctx->partials;
+  }
+  solve_init_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  auto one_step = [&]() -> int {
+    solve_prep_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s);
+    int rc2;
+    if (scalar) {
+      rc2 = sfgpu_launch_change_step(ctx, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
+      if (rc2) return rc2;
+      rc2 = sfgpu_launch_apply_scalar(ctx, 0, s.winner_rows, nullptr, nullptr, nullptr);
+    } else {
+      rc2 = sfgpu_launch_nearby(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows, MOVE_CHANGE);
+      if (rc2) return rc2;
+      rc2 = sfgpu_launch_apply_list(ctx, 2, s.winner_rows, nullptr, nullptr, nullptr);
+    }
+    if (rc2) return rc2;
+    solve_post_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
+    return SFGPU_OK;
+  };
+  // steps are captured once into a CUDA graph of `per_graph` steps and replayed
+  const uint32_t per_graph = std::min<uint32_t>(p->n_steps, 16);
+  uint32_t done = 0;
+  if (per_graph >= 2) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc2 = SFGPU_OK;
+    for (uint32_t i = 0; i < per_graph && rc2 == SFGPU_OK; ++i) rc2 = one_step();
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc2 != SFGPU_OK || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return fail(ctx, SFGPU_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    }
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    for (; done + per_graph <= p->n_steps; done += per_graph) {
+      CU(cudaGraphLaunch(exec, ctx->stream));
+      ctx->launches += 5ull * per_graph;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+  }
+  for (; done < p->n_steps; ++done) {
+    rc = one_step();
+    if (rc) return rc;
+    ctx->launches += 5;
+  }
+  if (p->restore_best) {
+    solve_restore_best_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (out_best_scores) CU(cudaMemcpy(out_best_scores, s.best_scores, (size_t)R * 16, cudaMemcpyDeviceToHost));
+  if (out_moves_evaluated) CU(cudaMemcpy(out_moves_evaluated, s.evaluated, (size_t)R * 8, cudaMemcpyDeviceToHost));
+  if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
+  return SFGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
+                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+  return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps);
+}
+
+int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
+                           uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+  return solve_impl(ctx, p, true, out_best_scores, out_moves_evaluated, out_accepted_steps);
+}
+
+}  // extern "C"

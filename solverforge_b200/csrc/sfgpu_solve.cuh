@@ -10,7 +10,7 @@
 // The reference draws step seeds from rand::StdRng (third party, unpinned — SURVEY §0.1-6); here
 // step t of replica r uses splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t), stated in the API.
 #pragma once
-#include "sfgpu_nearby.cuh"
+#include "sfgpu_dev.cuh"
 
 struct SolveState {
   uint64_t* step_counter;   // [1] steps executed so far

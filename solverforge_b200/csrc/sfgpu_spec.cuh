@@ -213,10 +213,6 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
   }
 };
 
-struct SpecIdx {
-  int32_t k[4];  // indices into DevModel::cons of the (sorted) scalar constraints, -1 = none
-};
-
 // The scoring program of a model as the kernels see it: delta(e, old, new) of one ChangeMove-shaped edit.
 // InterpProg walks the constraint table (any program); SpecProg is the monomorphised tuple.
 struct InterpProg {
