@@ -143,6 +143,11 @@ extern "C" {
     pub fn sfgpu_get_list_state(ctx: *mut sfgpu_ctx, variable: u32, out_offsets: *mut u32, out_elems: *mut u32) -> i32;
     pub fn sfgpu_list_capacity(ctx: *mut sfgpu_ctx, variable: u32, out_capacity: *mut u32) -> i32;
     pub fn sfgpu_pack_best_keys(ctx: *mut sfgpu_ctx, out_keys_device: *mut i64) -> i32;
+    pub fn sfgpu_comm_unique_id(out_id128: *mut u8) -> i32;
+    pub fn sfgpu_comm_init_rank(n_ranks: i32, id128: *const u8, rank: i32, device: i32, out_comm: *mut *mut c_void) -> i32;
+    pub fn sfgpu_comm_destroy(comm: *mut c_void) -> i32;
+    pub fn sfgpu_sync_best(ctx: *mut sfgpu_ctx, nccl_comm: *mut c_void, flags: u32, scores_device: *const i64,
+                           out_best: *mut i64, out_owner_rank: *mut i32, out_owner_replica: *mut u32) -> i32;
     pub fn sfgpu_last_kernel_ns(ctx: *mut sfgpu_ctx, out_ns: *mut u64) -> i32;
     pub fn sfgpu_kernel_times_ns(ctx: *mut sfgpu_ctx, max_n: u32, out_ns: *mut u64, out_n: *mut u32) -> i32;
     pub fn sfgpu_launch_count(ctx: *mut sfgpu_ctx, out_count: *mut u64) -> i32;

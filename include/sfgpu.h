@@ -432,9 +432,24 @@ int32_t sfgpu_list_capacity(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_cap
 /* ---- replicas across GPUs -------------------------------------------------------------- */
 /* Order-preserving packed key of each replica's committed score for a MAX all-reduce:
  * key = ((hard + 2^22) << 40) | (soft + 2^39), valid for hard in [-2^22, 2^22), soft in [-2^39, 2^39)
- * (out-of-range levels saturate). out_keys is a DEVICE pointer to R int64 (e.g. a torch tensor the
+ * (out-of-range levels saturate — sfgpu_sync_best below is exact for every score). out_keys is a DEVICE pointer to R int64 (e.g. a torch tensor the
  * caller then passes to torch.distributed.all_reduce(MAX) / ncclAllReduce). */
 int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys);
+
+/* Best-score sync for hosts without torch (SURVEY §8b `sfgpu_sync_best`, §8e): NCCL resolved at run time
+ * (dlopen of libnccl.so.2; without it these calls fail with SFGPU_E_NCCL, everything else works).
+ * One communicator per process / GPU: rank 0 creates the 128-byte id and ships it to the other ranks by any
+ * host channel (the reference's SolverManager jobs share a process; across processes: MPI, a file, a socket). */
+int32_t sfgpu_comm_unique_id(uint8_t* out_id128);
+int32_t sfgpu_comm_init_rank(int32_t n_ranks, const uint8_t* id128, int32_t rank, int32_t device, void** out_comm);
+int32_t sfgpu_comm_destroy(void* comm);
+/* All ranks learn the best score over every replica of every rank, its owner rank (lowest rank on ties) and the
+ * replica index inside the owner. scores: DEVICE pointer (flags & SFGPU_DEVICE_IO) to R (hard, soft) pairs —
+ * e.g. the best-so-far scores of a solve loop — or NULL for the committed scores. One device reduction over the
+ * replicas, one ncclAllGather of 24 B per rank on the context's stream, a local lexicographic max: exact over
+ * the whole int64 range (no packed key). nccl_comm NULL = single rank (no collective). Synchronises the stream. */
+int32_t sfgpu_sync_best(sfgpu_ctx* ctx, void* nccl_comm, uint32_t flags, const int64_t* scores, int64_t* out_best,
+                        int32_t* out_owner_rank, uint32_t* out_owner_replica);
 
 /* ---- timing ----------------------------------------------------------------------------- */
 /* device time of the most recent scoring kernel launch of this context (CUDA events recorded on

@@ -116,6 +116,10 @@ SYMBOLS = {
     "sfgpu_get_list_state": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_list_capacity": (C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "sfgpu_pack_best_keys": (C.c_int32, [_P, _P]),
+    "sfgpu_comm_unique_id": (C.c_int32, [_P]),
+    "sfgpu_comm_init_rank": (C.c_int32, [C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "sfgpu_comm_destroy": (C.c_int32, [_P]),
+    "sfgpu_sync_best": (C.c_int32, [_P, _P, C.c_uint32, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
     "sfgpu_last_kernel_ns": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "sfgpu_kernel_times_ns": (C.c_int32, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
     "sfgpu_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),

@@ -44,7 +44,7 @@ int32_t sfgpu_ctx_create(int32_t device, uint64_t flags, void* cuda_stream, sfgp
   return SFGPU_OK;
 }
 
-int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
+int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) try {
   if (!ctx) return SFGPU_E_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -55,39 +55,41 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) {
   if (ctx->solve_buf) cudaFree(ctx->solve_buf);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
+  if (ctx->sync_dev) cudaFree(ctx->sync_dev);
+  if (ctx->sync_pin) cudaFreeHost(ctx->sync_pin);
   for (auto e : ctx->ev_a) cudaEventDestroy(e);
   for (auto e : ctx->ev_b) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_synchronize(sfgpu_ctx* ctx) {
+int32_t sfgpu_synchronize(sfgpu_ctx* ctx) try {
   if (!ctx) return SFGPU_E_INVALID;
   CU(cudaStreamSynchronize(ctx->stream));
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_model_begin(sfgpu_ctx* ctx, uint32_t n_replicas) {
+int32_t sfgpu_model_begin(sfgpu_ctx* ctx, uint32_t n_replicas) try {
   if (!ctx) return SFGPU_E_INVALID;
   if (ctx->committed || ctx->building) return fail(ctx, SFGPU_E_STATE, "model already begun");
   if (n_replicas == 0 || n_replicas > 65535) return fail(ctx, SFGPU_E_INVALID, "n_replicas must be in [1, 65535]");
   ctx->building = true;
   ctx->R = n_replicas;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_add_collection(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, int32_t descriptor_index,
-                             uint32_t* out_collection) {
+                             uint32_t* out_collection) try {
   if (!ctx || !out_collection) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   ctx->colls.push_back({name ? name : "", n_rows, descriptor_index});
   *out_collection = (uint32_t)ctx->colls.size() - 1;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_add_column_i64(sfgpu_ctx* ctx, uint32_t collection, const char* name, const int64_t* values,
-                             uint32_t* out_column) {
+                             uint32_t* out_column) try {
   (void)name;
   if (!ctx || !values || !out_column) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
@@ -98,10 +100,10 @@ int32_t sfgpu_add_column_i64(sfgpu_ctx* ctx, uint32_t collection, const char* na
   ctx->cols.push_back(std::move(c));
   *out_column = (uint32_t)ctx->cols.size() - 1;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_add_scalar_variable(sfgpu_ctx* ctx, uint32_t collection, const char* name, uint32_t n_values,
-                                  int32_t allows_unassigned, uint32_t* out_variable) {
+                                  int32_t allows_unassigned, uint32_t* out_variable) try {
   (void)name;
   if (!ctx || !out_variable) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
@@ -111,10 +113,10 @@ int32_t sfgpu_add_scalar_variable(sfgpu_ctx* ctx, uint32_t collection, const cha
   ctx->svars.push_back({collection, n_values, allows_unassigned, {}, false});
   *out_variable = 0;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_add_list_variable(sfgpu_ctx* ctx, uint32_t owner_collection, uint32_t element_collection,
-                                const char* name, uint32_t* out_variable) {
+                                const char* name, uint32_t* out_variable) try {
   (void)name;
   if (!ctx || !out_variable) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
@@ -124,10 +126,10 @@ int32_t sfgpu_add_list_variable(sfgpu_ctx* ctx, uint32_t owner_collection, uint3
   ctx->lvars.push_back({owner_collection, element_collection, {}, {}, false});
   *out_variable = 0x80000000u;  // list variables live in their own id space
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_add_csr(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, const uint32_t* row_ptr,
-                      const uint32_t* col_idx, uint32_t* out_csr) {
+                      const uint32_t* col_idx, uint32_t* out_csr) try {
   (void)name;
   if (!ctx || !row_ptr || !out_csr) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
@@ -142,10 +144,10 @@ int32_t sfgpu_add_csr(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, const u
   ctx->csrs.push_back(std::move(c));
   *out_csr = (uint32_t)ctx->csrs.size() - 1;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, uint32_t cols,
-                             const int64_t* values, int32_t cost_semantics, uint32_t* out_matrix) {
+                             const int64_t* values, int32_t cost_semantics, uint32_t* out_matrix) try {
   (void)name;
   if (!ctx || !values || !out_matrix) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
@@ -162,9 +164,9 @@ int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, ui
   ctx->mats.push_back(std::move(m));
   *out_matrix = (uint32_t)ctx->mats.size() - 1;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, uint32_t* out_constraint) {
+int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, uint32_t* out_constraint) try {
   if (!ctx || !desc) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
@@ -184,9 +186,9 @@ int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, 
   ctx->cons.push_back(std::move(c));
   if (out_constraint) *out_constraint = (uint32_t)ctx->cons.size() - 1;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_set_scalar_state(sfgpu_ctx* ctx, uint32_t variable, const int32_t* values, int32_t per_replica) {
+int32_t sfgpu_set_scalar_state(sfgpu_ctx* ctx, uint32_t variable, const int32_t* values, int32_t per_replica) try {
   if (!ctx || !values) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "state is uploaded before sfgpu_model_commit");
   if (variable != 0 || ctx->svars.empty()) return fail(ctx, SFGPU_E_INVALID, "unknown scalar variable");
@@ -200,10 +202,10 @@ int32_t sfgpu_set_scalar_state(sfgpu_ctx* ctx, uint32_t variable, const int32_t*
     if (x < 0) x = SFGPU_NONE;
   v.per_replica = per_replica != 0;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_set_list_state(sfgpu_ctx* ctx, uint32_t variable, const uint32_t* offsets, const uint32_t* elems,
-                             int32_t per_replica) {
+                             int32_t per_replica) try {
   if (!ctx || !offsets) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "state is uploaded before sfgpu_model_commit");
   if (variable != 0x80000000u || ctx->lvars.empty()) return fail(ctx, SFGPU_E_INVALID, "unknown list variable");
@@ -223,11 +225,27 @@ int32_t sfgpu_set_list_state(sfgpu_ctx* ctx, uint32_t variable, const uint32_t* 
   v.elems.assign(elems, elems + total);
   for (uint32_t e : v.elems)
     if (e >= ne) return fail(ctx, SFGPU_E_INVALID, "list element out of range");
+  {
+    // an element sits in at most one list of a replica (a list variable partitions its elements): duplicates
+    // would silently corrupt the per-element inverse index and the flattened exists counts
+    std::vector<uint8_t> seen(ne);
+    size_t at = 0;
+    for (uint32_t c = 0; c < copies; ++c) {
+      std::fill(seen.begin(), seen.end(), 0);
+      const uint32_t cnt = offsets[(size_t)c * (no + 1) + no];
+      for (uint32_t i = 0; i < cnt; ++i) {
+        const uint32_t e = v.elems[at + i];
+        if (seen[e]) return fail(ctx, SFGPU_E_INVALID, "list element appears twice in one replica");
+        seen[e] = 1;
+      }
+      at += cnt;
+    }
+  }
   v.per_replica = per_replica != 0;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
+int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
   if (!ctx) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   CU(cudaSetDevice(ctx->device));
@@ -807,7 +825,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) {
   ctx->committed = true;
   if (out_scores) return sfgpu_committed_scores(ctx, out_scores);
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"
 
@@ -918,38 +936,38 @@ int score_entry(sfgpu_ctx* ctx, ScoreKind kind, uint32_t flags, uint64_t n_candi
 extern "C" {
 
 int32_t sfgpu_score_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
-                           int64_t* out_scores, uint8_t* out_doable) {
+                           int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
-                         int64_t* out_scores, uint8_t* out_doable) {
+                         int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_compound(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
                              const uint64_t* edit_offsets, const uint32_t* edit_rows, int64_t* out_scores,
-                             uint8_t* out_doable) {
+                             uint8_t* out_doable) try {
   return score_entry(ctx, SK_COMPOUND, flags, n_candidates, cand_offsets, edit_rows, edit_offsets, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_list_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
-                                const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
+                                const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_LIST_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
-                              int64_t* out_scores, uint8_t* out_doable) {
+                              int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_LIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_list_reverse(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
-                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
+                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_LIST_REVERSE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
-                                   const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
+                                   const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_SUBLIST_CHANGE, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_score_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
-                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) {
+                                 const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_SUBLIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
-}
+} SFGPU_API_CATCH(ctx)
 
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -983,7 +1001,7 @@ int launch_argbest(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, c
 int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
                             const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
                             const uint8_t* gates, const uint64_t* step_seeds, const int64_t* ref_scores,
-                            uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) {
+                            uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!params || !cand_offsets || !scores || !doable || !out_index || !out_best)
@@ -1029,15 +1047,15 @@ int32_t sfgpu_argbest_gated(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_p
   memcpy(out_best, pin + o_best, R * 16);
   if (out_evaluated) memcpy(out_evaluated, pin + o_eval, R * 4);
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_argbest(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
                       const uint64_t* cand_offsets, const int64_t* scores, const uint8_t* doable,
                       const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
-                      int64_t* out_best, uint32_t* out_evaluated) {
+                      int64_t* out_best, uint32_t* out_evaluated) try {
   return sfgpu_argbest_gated(ctx, flags, params, cand_offsets, scores, doable, nullptr, step_seeds, ref_scores,
                              out_index, out_best, out_evaluated);
-}
+} SFGPU_API_CATCH(ctx)
 
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -1078,33 +1096,33 @@ int apply_entry(sfgpu_ctx* ctx, int kind, uint32_t flags, const uint32_t* rows, 
 }
 }  // namespace
 
-int32_t sfgpu_apply_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+int32_t sfgpu_apply_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 0, flags, rows, mask, nullptr, nullptr);
-}
-int32_t sfgpu_apply_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 1, flags, rows, mask, nullptr, nullptr);
-}
-int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_list_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 2, flags, rows, mask, nullptr, nullptr);
-}
-int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 3, flags, rows, mask, nullptr, nullptr);
-}
-int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 4, flags, rows, mask, nullptr, nullptr);
-}
-int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 5, flags, rows, mask, nullptr, nullptr);
-}
-int32_t sfgpu_apply_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) {
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 6, flags, rows, mask, nullptr, nullptr);
-}
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
-                            const uint32_t* batch_rows, const uint32_t* index) {
+                            const uint32_t* batch_rows, const uint32_t* index) try {
   if (move_kind < 0 || move_kind > 6) return fail(ctx, SFGPU_E_INVALID, "bad move kind");
   if (!cand_offsets || !index) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   return apply_entry(ctx, move_kind, SFGPU_DEVICE_IO, batch_rows, nullptr, cand_offsets, index);
-}
+} SFGPU_API_CATCH(ctx)
 
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -1131,15 +1149,15 @@ int read_scores(sfgpu_ctx* ctx, const char* state, int64_t* out) {
 }
 }  // namespace
 
-int32_t sfgpu_committed_scores(sfgpu_ctx* ctx, int64_t* out_scores) {
+int32_t sfgpu_committed_scores(sfgpu_ctx* ctx, int64_t* out_scores) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!out_scores) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   CU(cudaSetDevice(ctx->device));
   return read_scores(ctx, ctx->dm.state, out_scores);
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_evaluate_all(sfgpu_ctx* ctx, int64_t* out_scores) {
+int32_t sfgpu_evaluate_all(sfgpu_ctx* ctx, int64_t* out_scores) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!out_scores) return fail(ctx, SFGPU_E_INVALID, "null pointer");
@@ -1151,9 +1169,9 @@ int32_t sfgpu_evaluate_all(sfgpu_ctx* ctx, int64_t* out_scores) {
   ctx->launches++;
   CU(cudaGetLastError());
   return read_scores(ctx, ctx->scratch_state, out_scores);
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_get_scalar_state(sfgpu_ctx* ctx, uint32_t variable, int32_t* out_values) {
+int32_t sfgpu_get_scalar_state(sfgpu_ctx* ctx, uint32_t variable, int32_t* out_values) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   const DevModel& dm = ctx->dm;
@@ -1163,17 +1181,17 @@ int32_t sfgpu_get_scalar_state(sfgpu_ctx* ctx, uint32_t variable, int32_t* out_v
   CU(cudaMemcpy2D(out_values, (size_t)dm.n_entities * 4, dm.state + dm.off_var, dm.block_bytes,
                   (size_t)dm.n_entities * 4, dm.R, cudaMemcpyDeviceToHost));
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_list_capacity(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_capacity) {
+int32_t sfgpu_list_capacity(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_capacity) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (variable != 0x80000000u || !ctx->dm.has_list || !out_capacity) return fail(ctx, SFGPU_E_INVALID, "unknown list variable");
   *out_capacity = ctx->dm.elem_cap;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_get_list_state(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_offsets, uint32_t* out_elems) {
+int32_t sfgpu_get_list_state(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_offsets, uint32_t* out_elems) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   const DevModel& dm = ctx->dm;
@@ -1186,9 +1204,9 @@ int32_t sfgpu_get_list_state(sfgpu_ctx* ctx, uint32_t variable, uint32_t* out_of
   CU(cudaMemcpy2D(out_elems, (size_t)dm.elem_cap * 4, dm.state + dm.off_elems, dm.block_bytes,
                   (size_t)dm.elem_cap * 4, dm.R, cudaMemcpyDeviceToHost));
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys) {
+int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!out_keys) return fail(ctx, SFGPU_E_INVALID, "null pointer");
@@ -1197,14 +1215,14 @@ int32_t sfgpu_pack_best_keys(sfgpu_ctx* ctx, int64_t* out_keys) {
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns) {
+int32_t sfgpu_last_kernel_ns(sfgpu_ctx* ctx, uint64_t* out_ns) try {
   uint32_t n = 0;
   return sfgpu_kernel_times_ns(ctx, 1, out_ns, &n);
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, uint32_t* out_n) {
+int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, uint32_t* out_n) try {
   if (!ctx || !out_ns || !out_n) return SFGPU_E_INVALID;
   if (ctx->ev_count == 0) return fail(ctx, SFGPU_E_STATE, "no scoring kernel launched yet");
   const uint64_t avail = std::min<uint64_t>(ctx->ev_count, sfgpu_ctx::EV_RING);
@@ -1218,20 +1236,20 @@ int32_t sfgpu_kernel_times_ns(sfgpu_ctx* ctx, uint32_t max_n, uint64_t* out_ns, 
   }
   *out_n = n;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count) {
+int32_t sfgpu_launch_count(sfgpu_ctx* ctx, uint64_t* out_count) try {
   if (!ctx || !out_count) return SFGPU_E_INVALID;
   *out_count = ctx->launches;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
-int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program) {
+int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program) try {
   if (!ctx || !out_program) return SFGPU_E_INVALID;
   if (!ctx->committed) return fail(ctx, SFGPU_E_STATE, "model not committed");
   *out_program = ctx->spec_id;
   return SFGPU_OK;
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"
 

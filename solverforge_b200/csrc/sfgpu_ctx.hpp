@@ -95,6 +95,9 @@ struct sfgpu_ctx {
   void* small_dev = nullptr;
   size_t small_bytes = 0;
   size_t partials_bytes = 0;
+  void* sync_dev = nullptr;  // best-score sync: {hard, soft, replica} of this rank + the gathered records
+  void* sync_pin = nullptr;
+  size_t sync_bytes = 0;
   // ring of CUDA event pairs around the dominant (scoring) kernel of each call
   static constexpr uint32_t EV_RING = 512;
   std::vector<cudaEvent_t> ev_a, ev_b;
@@ -117,6 +120,27 @@ inline int fail(sfgpu_ctx* c, int code, const std::string& msg) {
       return fail(ctx, e_ == cudaErrorMemoryAllocation ? SFGPU_E_OOM : SFGPU_E_CUDA,               \
                   std::string(#call) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
+
+// Nothing unwinds across the C boundary: every extern "C" entry point is a function-try-block
+// that ends with this handler. Building the message may itself run out of memory: then only the code is returned.
+#define SFGPU_API_CATCH(CTX)                                                                        \
+  catch (const std::bad_alloc&) {                                                                   \
+    try {                                                                                           \
+      return sfgpu_host::fail(CTX, SFGPU_E_OOM, "out of host memory");                              \
+    } catch (...) {                                                                                 \
+      return SFGPU_E_OOM;                                                                           \
+    }                                                                                               \
+  }                                                                                                 \
+  catch (const std::exception& e_) {                                                                \
+    try {                                                                                           \
+      return sfgpu_host::fail(CTX, SFGPU_E_INVALID, std::string("internal error: ") + e_.what());   \
+    } catch (...) {                                                                                 \
+      return SFGPU_E_INVALID;                                                                       \
+    }                                                                                               \
+  }                                                                                                 \
+  catch (...) {                                                                                     \
+    return SFGPU_E_INVALID;                                                                         \
+  }
 
 template <class T>
 int dev_upload(sfgpu_ctx* ctx, const T* host, size_t n, T** out) {

@@ -83,7 +83,7 @@ extern "C" {
 int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
                                   const sfgpu_forage_params* params, const uint64_t* step_seeds,
                                   const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
-                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+                                  uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) try {
   if (!ctx) return SFGPU_E_INVALID;
   // every element starts at most (max - min + 1) segments, each with fewer than elements + entities destinations
   const DevModel& dm = ctx->dm;
@@ -91,23 +91,23 @@ int32_t sfgpu_step_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_s
                       ((uint64_t)dm.elem_cap + dm.n_owners);
   return step_index_neighbourhood<SublistChangeNb>(ctx, flags, min_size, max_size, 5, ub, params, step_seeds, ref_scores,
                                                    out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_step_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_params* params,
                                 const uint64_t* step_seeds, const int64_t* ref_scores, uint32_t* out_index,
                                 int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                                int32_t apply_winners) {
+                                int32_t apply_winners) try {
   if (!ctx) return SFGPU_E_INVALID;
   const DevModel& dm = ctx->dm;
   const uint64_t ub = (uint64_t)dm.elem_cap * dm.elem_cap / 2 + 1;  // one list holding every element
   return step_index_neighbourhood<ReverseNb>(ctx, flags, 1, 1, 4, ub, params, step_seeds, ref_scores, out_index, out_best,
                                              out_evaluated, out_winner_rows, apply_winners);
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_size, uint32_t max_size,
                                 const sfgpu_forage_params* params, const uint64_t* step_seeds,
                                 const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
-                                uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+                                uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) try {
   if (!ctx) return SFGPU_E_INVALID;
   // unordered pairs of segments: fewer than (segments)^2 / 2 + segments
   const DevModel& dm = ctx->dm;
@@ -115,6 +115,6 @@ int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_siz
   const uint64_t ub = segs * segs / 2 + segs;
   return step_index_neighbourhood<SublistSwapNb>(ctx, flags, min_size, max_size, 6, ub, params, step_seeds, ref_scores,
                                                  out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"

@@ -477,12 +477,16 @@ struct ReverseNb {
       if (ent_base[mid] <= idx) lo = mid; else hi = mid;
     }
     const uint32_t e = lo, L = off[e + 1] - off[e];
-    uint32_t r = idx - ent_base[e], s = 0;
-    while (r >= L - 1 - s) {
-      r -= L - 1 - s;
-      ++s;
-    }
-    return make_uint4(e, s, s + 2 + r, 0);
+    // start s owns L - 1 - s candidates, so B(s) = s (2L - 1 - s) / 2 precede it: invert the triangular number
+    // in closed form (double sqrt, exact for L < 2^24) and fix the estimate up by one step either way
+    const uint32_t r = idx - ent_base[e];
+    const double t = 2.0 * (double)L - 1.0;
+    uint32_t s = (uint32_t)((t - sqrt(t * t - 8.0 * (double)r)) * 0.5);
+    if (s > L - 2) s = L - 2;
+    auto before = [&](uint32_t q) { return (uint32_t)(((uint64_t)q * (2ull * L - 1 - q)) / 2); };
+    while (s > 0 && before(s) > r) --s;
+    while (s + 1 <= L - 2 && before(s + 1) <= r) ++s;
+    return make_uint4(e, s, s + 2 + (r - before(s)), 0);
   }
   __device__ __forceinline__ bool delta(const DevModel& m, const char* st, uint4 row, Score2& d) const {
     return list_reverse_delta(m, st, row, d);

@@ -142,7 +142,7 @@ extern "C" {
 int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint64_t* cand_offsets,
                                const uint32_t* rows, const sfgpu_forage_params* params, const uint64_t* step_seeds,
                                const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
-                               uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) {
+                               uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!cand_offsets || !rows || !params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
@@ -180,6 +180,6 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
   ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit};
   return sfgpu_launch_argbest_ordered(ctx, f, cand_offsets, d_scores, d_doable, step_seeds, ref_scores, out_index, out_best,
                                       out_evaluated);
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"

@@ -114,21 +114,21 @@ int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t m
                                       const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
                                       int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
                                       int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                                      int32_t apply_winners) {
+                                      int32_t apply_winners) try {
   return step_nearby_impl(ctx, MOVE_CHANGE, flags, max_nearby, params, step_seeds, ref_scores, out_cand_offsets,
                           out_rows, out_scores, out_doable, out_index, out_best, out_evaluated, out_winner_rows,
                           apply_winners);
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_step_nearby_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
                                     const sfgpu_forage_params* params, const uint64_t* step_seeds,
                                     const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,
                                     int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index, int64_t* out_best,
-                                    uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) {
+                                    uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners) try {
   if (ctx && ctx->dm.fast_pc < 0)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "nearby list swap needs a path-cost constraint (its matrix is the distance meter)");
   return step_nearby_impl(ctx, MOVE_SWAP, flags, max_nearby, params, step_seeds, ref_scores, out_cand_offsets, out_rows,
                           out_scores, out_doable, out_index, out_best, out_evaluated, out_winner_rows, apply_winners);
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"

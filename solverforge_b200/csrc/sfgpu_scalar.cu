@@ -161,7 +161,7 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
                           const uint64_t* step_seeds, const int64_t* ref_scores, uint64_t* out_cand_offsets,
                           uint32_t* out_rows, int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index,
                           int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
-                          int32_t apply_winners) {
+                          int32_t apply_winners) try {
   int rc = check_committed(ctx);
   if (rc) return rc;
   const DevModel& dm = ctx->dm;
@@ -204,6 +204,6 @@ int32_t sfgpu_step_change(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_forage_par
     if (rc) return rc;
   }
   return small_io_end(ctx, io, out_index, out_best, out_evaluated, out_winner_rows);
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"

@@ -153,13 +153,13 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
 extern "C" {
 
 int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
-                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+                                       uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) try {
   return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps);
-}
+} SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
-                           uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+                           uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) try {
   return solve_impl(ctx, p, true, out_best_scores, out_moves_evaluated, out_accepted_steps);
-}
+} SFGPU_API_CATCH(ctx)
 
 }  // extern "C"
