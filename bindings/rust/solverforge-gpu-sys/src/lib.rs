@@ -119,6 +119,7 @@ extern "C" {
     pub fn sfgpu_argbest(ctx: *mut sfgpu_ctx, flags: u32, params: *const sfgpu_forage_params, cand_offsets: *const u64, scores: *const i64, doable: *const u8, step_seeds: *const u64, ref_scores: *const i64, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32) -> i32;
     pub fn sfgpu_argbest_gated(ctx: *mut sfgpu_ctx, flags: u32, params: *const sfgpu_forage_params, cand_offsets: *const u64, scores: *const i64, doable: *const u8, gates: *const u8, step_seeds: *const u64, ref_scores: *const i64, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32) -> i32;
     pub fn sfgpu_step_list_change(ctx: *mut sfgpu_ctx, n: u64, cand_offsets: *const u64, rows: *const u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_scores: *mut i64, out_doable: *mut u8, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32) -> i32;
+    pub fn sfgpu_step_change_rows(ctx: *mut sfgpu_ctx, n: u64, cand_offsets: *const u64, rows: *const u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_scores: *mut i64, out_doable: *mut u8, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32) -> i32;
     pub fn sfgpu_step_nearby_list_change(ctx: *mut sfgpu_ctx, flags: u32, max_nearby: u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_cand_offsets: *mut u64, out_rows: *mut u32, out_scores: *mut i64, out_doable: *mut u8, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32, out_winner_rows: *mut u32, apply_winners: i32) -> i32;
     pub fn sfgpu_step_nearby_list_swap(ctx: *mut sfgpu_ctx, flags: u32, max_nearby: u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_cand_offsets: *mut u64, out_rows: *mut u32, out_scores: *mut i64, out_doable: *mut u8, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32, out_winner_rows: *mut u32, apply_winners: i32) -> i32;
     pub fn sfgpu_step_sublist_change(ctx: *mut sfgpu_ctx, flags: u32, min_size: u32, max_size: u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32, out_winner_rows: *mut u32, apply_winners: i32) -> i32;

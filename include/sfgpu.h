@@ -293,6 +293,15 @@ int32_t sfgpu_step_list_change(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
                                const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
                                uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated);
 
+/* The same fused step over resident ChangeMove rows {entity, to_value} of a scalar model (DEVICE pointers,
+ * stream-asynchronous): models whose scalar constraint tuple has a monomorphised program (sfgpu_scalar_program
+ * >= 0) score and reduce in one pass — the scores are never re-read; others, and AcceptedCount(N), materialise
+ * the scores and run the ordered replay. out_scores / out_doable may both be NULL. Same outputs as sfgpu_argbest. */
+int32_t sfgpu_step_change_rows(sfgpu_ctx* ctx, uint64_t n_candidates, const uint64_t* cand_offsets,
+                               const uint32_t* rows, const sfgpu_forage_params* params, const uint64_t* step_seeds,
+                               const int64_t* ref_scores, int64_t* out_scores, uint8_t* out_doable,
+                               uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated);
+
 /* Whole local-search step on device: generates the nearby list-change neighbourhood of every replica
  * (NearbyListChangeMoveSelector, heuristic/selector/list_kernel/nearby_change.rs:102-232 with the matrix
  * distance meter crates/solverforge-cvrp/src/meters.rs:10-28; canonical SelectionOrder::Original), scores

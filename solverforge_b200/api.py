@@ -328,6 +328,17 @@ class GpuScoreDirector:
                                                     v(ref_ptr), v(scores_ptr), v(doable_ptr), v(index_ptr),
                                                     v(best_ptr), v(evaluated_ptr)))
 
+    def step_change_rows_device(self, n: int, offsets_ptr: int, rows_ptr: int, params: "ForageParams", seeds_ptr: int,
+                                ref_ptr: int, scores_ptr: int, doable_ptr: int, index_ptr: int, best_ptr: int,
+                                evaluated_ptr: int):
+        """Fused score + acceptor/forager replay over resident ChangeMove rows (sfgpu_step_change_rows);
+        scores_ptr/doable_ptr may be 0."""
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        v = lambda p: C.c_void_p(p) if p else None
+        self._check(self.lib.sfgpu_step_change_rows(self.h, n, v(offsets_ptr), v(rows_ptr), C.byref(fp), v(seeds_ptr),
+                                                    v(ref_ptr), v(scores_ptr), v(doable_ptr), v(index_ptr),
+                                                    v(best_ptr), v(evaluated_ptr)))
+
     def step_nearby_list_swap(self, max_nearby: int = 20, params: "ForageParams" = None, step_seeds=None,
                               ref_scores=None, apply: bool = False, out_rows_ptr: int = 0, out_scores_ptr: int = 0,
                               out_doable_ptr: int = 0, out_offsets_ptr: int = 0):
@@ -480,6 +491,17 @@ class GpuScoreDirector:
 
     def pack_best_keys_device(self, keys_ptr: int):
         self._check(self.lib.sfgpu_pack_best_keys(self.h, C.c_void_p(keys_ptr)))
+
+    def sync_best(self, comm=None, scores_ptr: int = 0):
+        """Best (hard, soft) over every replica of every rank of `comm` (an ncclComm_t created with
+        sfgpu_comm_init_rank; None = this context only), its owner rank and replica (sfgpu_sync_best).
+        scores_ptr: device pointer to R (hard, soft) pairs, 0 = the committed scores."""
+        best = np.zeros(2, dtype=np.int64)
+        owner, rep = C.c_int32(), C.c_uint32()
+        self._check(self.lib.sfgpu_sync_best(self.h, comm, L.DEVICE_IO if scores_ptr else 0,
+                                             C.c_void_p(scores_ptr) if scores_ptr else None, _ptr(best),
+                                             C.byref(owner), C.byref(rep)))
+        return (int(best[0]), int(best[1])), owner.value, rep.value
 
     # ---- forager / acceptor replay on device ------------------------------------------
     def argbest(self, scores, doable, cand_offsets=None, params: "ForageParams" = None, step_seeds=None,

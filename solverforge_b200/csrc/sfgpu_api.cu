@@ -256,6 +256,14 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
   for (auto& c : ctx->cols) {
     int rc = dev_upload(ctx, c.host.data(), c.host.size(), &c.dev);
     if (rc) return rc;
+    bool fits = true;
+    for (int64_t v : c.host)
+      if (v <= -(1ll << 30) || v >= (1ll << 30)) fits = false;
+    if (fits) {
+      std::vector<int32_t> narrow(c.host.begin(), c.host.end());
+      rc = dev_upload(ctx, narrow.data(), narrow.size(), &c.dev32);
+      if (rc) return rc;
+    }
   }
   for (auto& m : ctx->mats) {
     bool fits = true;
@@ -470,6 +478,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
         int rc = column(d.aux0, dm.n_entities, &col);
         if (rc) return rc;
         c.g0 = col;
+        c.g2 = col ? ctx->cols[d.aux0].dev32 : nullptr;
         c.p0 = d.p0;
         c.p1 = d.p1;
         if (d.p1 == 0) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EQUAL needs p1 != 0 (the variable must enter the key)");
@@ -497,6 +506,7 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
         int rc = column(d.aux0, dm.n_entities, &col);
         if (rc) return rc;
         c.g0 = col;
+        c.g2 = col ? ctx->cols[d.aux0].dev32 : nullptr;
         if (d.p0 == 1) c.flags |= SFGPU_CF_COMPLEMENT;
         c.p1 = d.p1;
         if (d.aux1 != 0xFFFFFFFFu) {  // per-value weight offset column (key-dependent weight)
@@ -833,7 +843,8 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
 // scoring
 // ------------------------------------------------------------------------------------------
 int sfgpu_launch_score_scalar(sfgpu_ctx* ctx, int kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
-                              const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable);
+                              const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable, ForageArgs* forage,
+                              uint32_t* out_chunks);
 int sfgpu_launch_score_list(sfgpu_ctx* ctx, int kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
                             int64_t* d_scores, uint8_t* d_doable, ForageArgs* forage, uint32_t* out_chunks);
 
@@ -843,7 +854,7 @@ enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP, 
 
 int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
                  const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable) {
-  if (kind <= SK_COMPOUND) return sfgpu_launch_score_scalar(ctx, (int)kind, n_total, d_offs, d_rows, d_edit_offs, d_scores, d_doable);
+  if (kind <= SK_COMPOUND) return sfgpu_launch_score_scalar(ctx, (int)kind, n_total, d_offs, d_rows, d_edit_offs, d_scores, d_doable, nullptr, nullptr);
   return sfgpu_launch_score_list(ctx, (int)kind, n_total, d_offs, d_rows, d_scores, d_doable, nullptr, nullptr);
 }
 
@@ -984,7 +995,7 @@ int launch_argbest(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, c
     chunks = std::min<uint32_t>(chunks, 64);
     int rc = ensure_partials(ctx, (size_t)chunks * R * sizeof(ChunkPartial));
     if (rc) return rc;
-    ForageArgs fa{f, d_ref, (ChunkPartial*)ctx->partials};
+    ForageArgs fa{f, d_ref, (ChunkPartial*)ctx->partials, 0};
     argbest_partial_kernel<<<dim3(chunks, R), 256, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_ref, fa.partials);
     forage_finish_kernel<<<R, 256, 0, ctx->stream>>>(ctx->dm, fa, chunks, d_offs, nullptr, d_scores, d_doable, d_seeds,
                                                     d_idx, d_best, d_eval);

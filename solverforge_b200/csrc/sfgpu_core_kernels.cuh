@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) forage_finish_kernel(const __grid_constan
           const uint64_t i = t_lo + q;
           if (i >= b_hi) break;
           Score2 d;
-          const bool ok = list_change_delta(m, st, ((const uint4*)rows)[i], d);
+          const bool ok = fa.row_kind == 1 ? score_change_row(m, st, st, ((const uint2*)rows)[i], d)
+                                           : list_change_delta(m, st, ((const uint4*)rows)[i], d);
           const int64_t h = cs[0] + d.hard, s2 = cs[1] + d.soft;
           if (ok && h == bh && s2 == bs && accept_score(fa.f.acceptor, h, s2, lh, ls, th, ts)) hits |= 1ull << q;
         }

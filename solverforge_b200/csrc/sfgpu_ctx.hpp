@@ -25,6 +25,7 @@ struct Column {
   uint32_t coll;
   std::vector<int64_t> host;
   int64_t* dev = nullptr;
+  int32_t* dev32 = nullptr;  // narrowed copy (uploaded when every value fits int32 with two bits of headroom)
 };
 struct Csr {
   uint32_t n_rows;
@@ -81,6 +82,7 @@ struct sfgpu_ctx {
   uint32_t nb_scan_bits = 24;
   bool force_generic = false;  // SFGPU_CTX_GENERIC_KERNELS: never take a specialised fast path (testing)
   int spec_id = -1;            // monomorphised scalar program (sfgpu_spec.cuh), -1 = interpreter
+  bool spec_narrow = false;    // the program runs its deltas in int32 (every delta provably fits, commit-time bound)
   SpecIdx spec_idx{{-1, -1, -1, -1}};
   // staging for host-pointer calls
   void* pin = nullptr;

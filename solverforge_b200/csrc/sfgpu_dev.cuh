@@ -23,6 +23,7 @@ struct ConsDev {
   uint32_t n0;                // table length / stride
   const void* g0;             // shared static arrays (CSR row_ptr, column, matrix ...)
   const void* g1;
+  const void* g2;             // int32 copy of the int64 column g0 when every value fits (narrow programs), or null
   int64_t p0, p1, p2;
   uint32_t flags;
   uint32_t pad;

@@ -867,6 +867,8 @@ struct ForageArgs {
   ForageDev f;
   const int64_t* ref_scores;  // [R][4] = {last_step, late} or null
   ChunkPartial* partials;     // [R][gridDim.x]
+  int32_t row_kind;           // rows the finish kernel re-derives when scores were not materialised:
+                              // 0 = ListChange {se, sp, de, dp}, 1 = ScalarEdit {entity, to_value}
 };
 
 template <int SUM_FN /* -1: no LIST_SUM constraint */, int U = 2, int MINB = 3, bool FORAGE = false, typename CELL = int32_t,

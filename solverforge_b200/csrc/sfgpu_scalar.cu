@@ -9,38 +9,104 @@ namespace {
 
 // Monomorphised scalar programs: (sorted) kinds of the scalar constraints -> kernel instantiations.
 // The tuples of the reference's scalar examples (graph colouring, n-queens, job shop) and their prefixes.
-typedef void (*SpecScoreFn)(const DevModel, const SpecIdx, const uint64_t*, const uint32_t*, int64_t*, uint8_t*);
+// Every tuple has the wide (int64) kernels; tuples made only of kinds with an int32 form also carry the narrow ones.
+typedef void (*SpecScoreFn)(const DevModel, const SpecIdx, const uint64_t*, const uint32_t*, int64_t*, uint8_t*, const ForageArgs);
 typedef void (*SpecStepFn)(const DevModel, const ChangeStepArgs, const SpecIdx);
 struct SpecEntry {
   int k[4];
-  SpecScoreFn score;
+  SpecScoreFn score, fused;      // rows-resident: scores only / scores + forager partials
+  SpecScoreFn score_n, fused_n;  // int32 forms, or null
   SpecStepFn step;
 };
-#define SPEC_ENTRY(a, b, c, d) \
-  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProg<a, b, c, d>> }
+#define SPEC_WIDE(a, b, c, d) \
+  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, nullptr, nullptr, \
+    change_step_kernel<true, SpecProg<a, b, c, d>> }
+#define SPEC_BOTH(a, b, c, d) \
+  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, \
+    spec_change_kernel<SpecProgN<a, b, c, d>, false>, spec_change_kernel<SpecProgN<a, b, c, d>, true>, \
+    change_step_kernel<true, SpecProg<a, b, c, d>> }
 #define U_ SFGPU_K_UNI
 #define C_ SFGPU_K_PAIR_CSR_EQUAL
 #define K_ SFGPU_K_PAIR_KEY_EQUAL
 #define G_ SFGPU_K_GROUP
 #define UC SPEC_K_UNI_CONST
 const SpecEntry g_spec[] = {  // kinds ascending; UC (uni without column / mask) sorts last
-    SPEC_ENTRY(U_, 0, 0, 0),   SPEC_ENTRY(UC, 0, 0, 0),    // unassigned only
-    SPEC_ENTRY(U_, C_, 0, 0),  SPEC_ENTRY(C_, UC, 0, 0),   // graph colouring
-    SPEC_ENTRY(U_, K_, 0, 0),  SPEC_ENTRY(K_, UC, 0, 0),
-    SPEC_ENTRY(U_, G_, 0, 0),  SPEC_ENTRY(G_, UC, 0, 0),
-    SPEC_ENTRY(U_, C_, G_, 0), SPEC_ENTRY(C_, G_, UC, 0),
-    SPEC_ENTRY(U_, K_, G_, 0), SPEC_ENTRY(K_, G_, UC, 0),  // job shop
-    SPEC_ENTRY(U_, K_, K_, 0), SPEC_ENTRY(K_, K_, UC, 0),
-    SPEC_ENTRY(U_, K_, K_, K_), SPEC_ENTRY(K_, K_, K_, UC),  // n-queens
-    SPEC_ENTRY(U_, K_, G_, G_), SPEC_ENTRY(K_, G_, G_, UC),
-    SPEC_ENTRY(U_, U_, K_, G_), SPEC_ENTRY(U_, K_, G_, UC),
+    SPEC_WIDE(U_, 0, 0, 0),   SPEC_BOTH(UC, 0, 0, 0),    // unassigned only
+    SPEC_WIDE(U_, C_, 0, 0),  SPEC_BOTH(C_, UC, 0, 0),   // graph colouring
+    SPEC_WIDE(U_, K_, 0, 0),  SPEC_BOTH(K_, UC, 0, 0),
+    SPEC_WIDE(U_, G_, 0, 0),  SPEC_BOTH(G_, UC, 0, 0),
+    SPEC_WIDE(U_, C_, G_, 0), SPEC_BOTH(C_, G_, UC, 0),
+    SPEC_WIDE(U_, K_, G_, 0), SPEC_BOTH(K_, G_, UC, 0),  // job shop
+    SPEC_WIDE(U_, K_, K_, 0), SPEC_BOTH(K_, K_, UC, 0),
+    SPEC_WIDE(U_, K_, K_, K_), SPEC_BOTH(K_, K_, K_, UC),  // n-queens
+    SPEC_WIDE(U_, K_, G_, G_), SPEC_BOTH(K_, G_, G_, UC),
+    SPEC_WIDE(U_, U_, K_, G_), SPEC_WIDE(U_, K_, G_, UC),
 };
 #undef U_
 #undef C_
 #undef K_
 #undef G_
 #undef UC
-#undef SPEC_ENTRY
+#undef SPEC_WIDE
+#undef SPEC_BOTH
+
+// Upper bound of |delta| of one ChangeMove over the scalar constraints of a monomorphised program, or a negative
+// value when some quantity the int32 structs compare or store may not fit (then the program stays wide).
+// Sums / products wrap in uint32 and are exact whenever the true result fits, so only the FINAL deltas, the
+// stored operands (weights, offsets, column values, table cells) and the operands of comparisons need a bound.
+double scalar_narrow_bound(const sfgpu_ctx* ctx) {
+  const DevModel& dm = ctx->dm;
+  const double LIM = 1073741824.0;  // 2^30
+  double total = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int k = ctx->spec_idx.k[i];
+    if (k < 0) continue;
+    const ConsDev& c = dm.cons[k];
+    const sfgpu_constraint_desc& d = ctx->cons[k].d;
+    const double a = std::fabs((double)c.w.a), b = std::fabs((double)c.w.b);
+    if (a >= LIM || b >= LIM) return -1;
+    switch (c.kind) {
+      case SFGPU_K_UNI:
+        if (c.g0 || c.g1) return -1;  // only the column-free form has an int32 struct
+        total += a + b + a * b;  // |weight(0)| for every weight function
+        break;
+      case SFGPU_K_PAIR_CSR_EQUAL: total += a * (double)dm.n_entities; break;
+      case SFGPU_K_PAIR_KEY_EQUAL:
+        if (c.g0 && !c.g2) return -1;  // key column does not fit int32
+        if (std::fabs((double)c.p0) >= LIM || std::fabs((double)c.p1) >= LIM || std::fabs((double)c.p2) >= LIM) return -1;
+        total += a * (double)dm.n_entities;
+        break;
+      case SFGPU_K_GROUP: {
+        if (c.g1) return -1;                      // per-key weight offsets keep the wide struct
+        if (c.g0 && !c.g2) return -1;
+        if (c.w.fn == SFGPU_W_PAIRS) return -1;   // x (x - 1) / 2 is not a ring expression
+        double X = (double)dm.n_entities + 1, xmax = 1;  // largest |group aggregate| after an edit, largest |x|
+        if (c.g0) {
+          X = 0;
+          xmax = 0;
+          for (int64_t v : ctx->cols[d.aux0].host) {
+            X += std::fabs((double)v);
+            xmax = std::max(xmax, std::fabs((double)v));
+          }
+          X += xmax;
+        }
+        X = std::max(X, std::fabs((double)c.p1));  // the complement's default result
+        if (X + b >= LIM) return -1;               // compared quantity x - b
+        double w;
+        switch (c.w.fn) {
+          case SFGPU_W_CONST: w = a; break;
+          case SFGPU_W_LINEAR: w = a * X + b; break;
+          case SFGPU_W_SQUARE: w = a * X * X + b; break;
+          default: w = a * (X + b); break;  // EXCESS, ABSDIFF
+        }
+        total += 4 * w + 4 * a * xmax * (xmax + 2 * X);  // generic form / closed square form
+        break;
+      }
+      default: return -1;
+    }
+  }
+  return total;
+}
 
 }  // namespace
 
@@ -85,7 +151,17 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
         ctx->spec_id = (int)t;
         for (size_t i = 0; i < 4; ++i) ctx->spec_idx.k[i] = i < sc.size() ? sc[i].second : -1;
         CU(cudaFuncSetAttribute((const void*)g_spec[t].score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+        CU(cudaFuncSetAttribute((const void*)g_spec[t].fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
         CU(cudaFuncSetAttribute((const void*)g_spec[t].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+        ctx->spec_narrow = false;
+        if (g_spec[t].score_n && !getenv("SFGPU_NO_NARROW")) {
+          const double bound = scalar_narrow_bound(ctx);
+          if (bound >= 0 && bound < 1073741824.0) {
+            ctx->spec_narrow = true;
+            CU(cudaFuncSetAttribute((const void*)g_spec[t].score_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+            CU(cudaFuncSetAttribute((const void*)g_spec[t].fused_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+          }
+        }
         break;
       }
     }
@@ -104,13 +180,46 @@ void sfgpu_change_step_chunks(const sfgpu_ctx* ctx, uint32_t* out_per, uint32_t*
 }
 
 
-// kind: 0 change, 1 swap, 2 compound (ScoreKind of sfgpu_api.cu)
+// chunks per replica of the rows-resident monomorphised kernel: contiguous chunks, fat enough to amortise the
+// staging of the replica block, enough of them to cover the machine when replicas are few
+static uint32_t spec_chunks(const sfgpu_ctx* ctx, uint64_t n_total) {
+  const DevModel& dm = ctx->dm;
+  const uint64_t per_replica = (n_total + dm.R - 1) / dm.R;
+  static const int override_chunks = getenv("SFGPU_SPEC_CHUNKS") ? atoi(getenv("SFGPU_SPEC_CHUNKS")) : 0;  // tuning knob
+  if (override_chunks > 0) return (uint32_t)override_chunks;
+  uint32_t chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((per_replica + 8191) / 8192, 64));
+  while ((uint64_t)chunks * dm.R < (uint64_t)ctx->sm_count * 6 && (uint64_t)chunks * 1024 < per_replica) chunks *= 2;
+  return chunks;
+}
+
+// kind: 0 change, 1 swap, 2 compound (ScoreKind of sfgpu_api.cu). forage != nullptr (monomorphised ChangeMove
+// programs only): the kernel also emits per-chunk forager partials and *out_chunks receives the chunk count.
 int sfgpu_launch_score_scalar(sfgpu_ctx* ctx, int kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
-                              const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable) {
+                              const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable, ForageArgs* forage,
+                              uint32_t* out_chunks) {
   const DevModel& dm = ctx->dm;
   const uint32_t threads = 256;
   dim3 grid(chunks_for(ctx, n_total, dm.R, threads), dm.R);
   size_t smem = ctx->staged ? dm.stage_bytes : 0;
+  if (forage && !(kind == 0 && ctx->spec_id >= 0)) return fail(ctx, SFGPU_E_STATE, "fused forager needs a monomorphised ChangeMove program");
+  if (kind == 0 && ctx->spec_id >= 0) {
+    const uint32_t chunks = spec_chunks(ctx, n_total);
+    const SpecEntry& se = g_spec[ctx->spec_id];
+    dim3 sgrid(chunks, dm.R);
+    if (forage) {
+      int rc = ensure_partials(ctx, (size_t)chunks * dm.R * sizeof(ChunkPartial));
+      if (rc) return rc;
+      forage->partials = (ChunkPartial*)ctx->partials;
+      if (out_chunks) *out_chunks = chunks;
+    }
+    ev_begin(ctx);
+    const SpecScoreFn fn = forage ? (ctx->spec_narrow ? se.fused_n : se.fused) : (ctx->spec_narrow ? se.score_n : se.score);
+    fn<<<sgrid, threads, smem, ctx->stream>>>(dm, ctx->spec_idx, d_offs, d_rows, d_scores, d_doable, forage ? *forage : ForageArgs{});
+    ev_end(ctx);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SFGPU_OK;
+  }
   ev_begin(ctx);
 #define LAUNCH_SCALAR(MODE)                                                                                    \
   if (ctx->staged)                                                                                             \
@@ -120,12 +229,7 @@ int sfgpu_launch_score_scalar(sfgpu_ctx* ctx, int kind, uint64_t n_total, const 
     score_scalar_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(dm, d_offs, d_rows, d_edit_offs,      \
                                                                         d_scores, d_doable)
   switch (kind) {
-    case 0:
-      if (ctx->spec_id >= 0)
-        g_spec[ctx->spec_id].score<<<grid, threads, smem, ctx->stream>>>(dm, ctx->spec_idx, d_offs, d_rows, d_scores, d_doable);
-      else
-        LAUNCH_SCALAR(MODE_CHANGE);
-      break;
+    case 0: LAUNCH_SCALAR(MODE_CHANGE); break;
     case 1: LAUNCH_SCALAR(MODE_SWAP); break;
     default: LAUNCH_SCALAR(MODE_COMPOUND); break;
   }
@@ -153,7 +257,61 @@ int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t c
   return SFGPU_OK;
 }
 
+int sfgpu_launch_forage_finish(sfgpu_ctx* ctx, const ForageArgs& fa, uint32_t chunks, const uint64_t* d_offs,
+                               const uint32_t* d_rows, const int64_t* d_scores, const uint8_t* d_doable,
+                               const uint64_t* d_seeds, uint32_t* d_idx, int64_t* d_best, uint32_t* d_eval);
+int sfgpu_launch_argbest_ordered(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, const int64_t* d_scores,
+                                 const uint8_t* d_doable, const uint64_t* d_seeds, const int64_t* d_ref, uint32_t* d_idx,
+                                 int64_t* d_best, uint32_t* d_eval);
+
 extern "C" {
+
+// ------------------------------------------------------------------------------------------
+// Fused step over resident ChangeMove rows: score every candidate and replay acceptor + forager in one pass
+// (the scalar counterpart of sfgpu_step_list_change). Device pointers only.
+int32_t sfgpu_step_change_rows(sfgpu_ctx* ctx, uint64_t n_candidates, const uint64_t* cand_offsets, const uint32_t* rows,
+                               const sfgpu_forage_params* params, const uint64_t* step_seeds, const int64_t* ref_scores,
+                               int64_t* out_scores, uint8_t* out_doable, uint32_t* out_index, int64_t* out_best,
+                               uint32_t* out_evaluated) try {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!cand_offsets || !rows || !params || !out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if ((out_scores == nullptr) != (out_doable == nullptr))
+    return fail(ctx, SFGPU_E_INVALID, "out_scores and out_doable are given together or not at all");
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  if (params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  const DevModel& dm = ctx->dm;
+  if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
+  CU(cudaSetDevice(ctx->device));
+  if (n_candidates == 0) return fail(ctx, SFGPU_E_INVALID, "empty batch");
+  if (ctx->spec_id >= 0 && params->accepted_limit == 0) {
+    ForageArgs fa{};
+    fa.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit};
+    fa.ref_scores = ref_scores;
+    fa.row_kind = 1;
+    uint32_t chunks = 0;
+    rc = sfgpu_launch_score_scalar(ctx, 0, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable, &fa, &chunks);
+    if (rc) return rc;
+    return sfgpu_launch_forage_finish(ctx, fa, chunks, cand_offsets, rows, out_scores, out_doable, step_seeds, out_index,
+                                      out_best, out_evaluated);
+  }
+  // interpreter programs / AcceptedCount(N): materialise the scores, then the ordered replay kernel
+  int64_t* d_scores = out_scores;
+  uint8_t* d_doable = out_doable;
+  if (!d_scores) {
+    const size_t need = n_candidates * 16 + (n_candidates + 15) / 16 * 16;
+    rc = ensure_staging(ctx, 64, need);
+    if (rc) return rc;
+    d_scores = (int64_t*)ctx->dscr;
+    d_doable = (uint8_t*)ctx->dscr + n_candidates * 16;
+  }
+  rc = sfgpu_launch_score_scalar(ctx, 0, n_candidates, cand_offsets, rows, nullptr, d_scores, d_doable, nullptr, nullptr);
+  if (rc) return rc;
+  ForageDev f{params->acceptor, params->tie_mode, params->accepted_limit};
+  return sfgpu_launch_argbest_ordered(ctx, f, cand_offsets, d_scores, d_doable, step_seeds, ref_scores, out_index, out_best,
+                                      out_evaluated);
+} SFGPU_API_CATCH(ctx)
 
 // ------------------------------------------------------------------------------------------
 // Whole step for scalar models: ChangeMove neighbourhood generation + scoring + forager on device.

@@ -213,9 +213,159 @@ struct SpecCons<SFGPU_K_GROUP> : SpecRoute {  // grouped count / sum, optional c
   }
 };
 
+// ---- narrow (int32) forms of the kinds that have one --------------------------------------------------------
+// Selected at commit when every delta of a ChangeMove provably fits int32 with headroom (sfgpu_scalar.cu,
+// scalar_narrow_bound): table cells, column values (ConsDev::g2), weights and every compared quantity are then
+// below 2^30 in magnitude, sums / products go through uint32 (two's-complement ring, exact whenever the result
+// fits) and the 64-bit committed score is only added for the store. Same closed forms as the wide structs.
+template <int KIND>
+struct SpecConsN;
+
+struct SpecRouteN {
+  bool hard;
+  __device__ __forceinline__ void add(int32_t& dh, int32_t& ds, int32_t v) const {
+    if (hard) dh += v; else ds += v;
+  }
+};
+
+template <>
+struct SpecConsN<0> {
+  __device__ __forceinline__ SpecConsN(const DevModel&, int, const char*, const char*) {}
+  __device__ __forceinline__ int32_t delta(uint32_t, int32_t, int32_t) const { return 0; }
+  __device__ __forceinline__ void add(int32_t&, int32_t&, int32_t) const {}
+};
+
+template <>
+struct SpecConsN<SPEC_K_UNI_CONST> : SpecRouteN {
+  int32_t filt, w0;
+  __device__ __forceinline__ SpecConsN(const DevModel& m, int k, const char*, const char*) {
+    const ConsDev& c = m.cons[k];
+    filt = (int32_t)c.p0;
+    hard = c.w.level == 0;
+    const int64_t w = weight_eval(c.w, 0);
+    w0 = (int32_t)(c.sign < 0 ? -w : w);
+  }
+  __device__ __forceinline__ int32_t delta(uint32_t, int32_t ov, int32_t nv) const {
+    const int32_t pn = filt == 2 ? 1 : ((nv < 0) == (filt == 0) ? 1 : 0);
+    const int32_t po = filt == 2 ? 1 : ((ov < 0) == (filt == 0) ? 1 : 0);
+    return (pn - po) * w0;
+  }
+};
+
+template <>
+struct SpecConsN<SFGPU_K_PAIR_CSR_EQUAL> : SpecRouteN {
+  const uint16_t* cc;
+  uint32_t k;
+  int32_t a;
+  __device__ __forceinline__ SpecConsN(const DevModel& m, int idx, const char*, const char* gblock) {
+    const ConsDev& c = m.cons[idx];
+    cc = (const uint16_t*)(gblock + c.off0);
+    k = m.n_values;
+    hard = c.w.level == 0;
+    a = (int32_t)(c.sign < 0 ? -c.w.a : c.w.a);
+  }
+  __device__ __forceinline__ int32_t delta(uint32_t e, int32_t ov, int32_t nv) const {
+    const uint16_t* row = cc + (size_t)e * k;
+    const int32_t cn = nv >= 0 ? (int32_t)row[nv] : 0, co = ov >= 0 ? (int32_t)row[ov] : 0;
+    return (cn - co) * a;
+  }
+};
+
+template <>
+struct SpecConsN<SFGPU_K_PAIR_KEY_EQUAL> : SpecRouteN {
+  const int32_t* tab;
+  const int32_t* col;
+  uint32_t p0, p1, p2;
+  int32_t a;
+  __device__ __forceinline__ SpecConsN(const DevModel& m, int idx, const char* st, const char*) {
+    const ConsDev& c = m.cons[idx];
+    tab = (const int32_t*)(st + c.off0);
+    col = (const int32_t*)c.g2;
+    p0 = (uint32_t)c.p0;
+    p1 = (uint32_t)c.p1;
+    p2 = (uint32_t)c.p2;
+    hard = c.w.level == 0;
+    a = (int32_t)(c.sign < 0 ? -c.w.a : c.w.a);
+  }
+  __device__ __forceinline__ int32_t delta(uint32_t e, int32_t ov, int32_t nv) const {
+    const uint32_t base = (col ? (uint32_t)__ldg(col + e) : 0u) * p0 - p2;
+    const int32_t cn = nv >= 0 ? tab[base + (uint32_t)nv * p1] : 0;
+    const int32_t co = ov >= 0 ? tab[base + (uint32_t)ov * p1] - 1 : 0;
+    return (cn - co) * a;
+  }
+};
+
+template <>
+struct SpecConsN<SFGPU_K_GROUP> : SpecRouteN {  // count() / sum(col), optional complement; no per-key offsets
+  const int32_t* gc;
+  const int32_t* gs_lo;  // low words of the int64 sums (they fit: narrow bound)
+  const int32_t* col;
+  int32_t fn, a, b, dflt, empty0;
+  bool neg, complement, counting, square_uniform;
+  __device__ __forceinline__ int32_t w32(int32_t x) const {
+    const uint32_t ua = (uint32_t)a, ux = (uint32_t)x;
+    switch (fn) {
+      case SFGPU_W_CONST: return a;
+      case SFGPU_W_LINEAR: return (int32_t)(ua * ux + (uint32_t)b);
+      case SFGPU_W_SQUARE: return (int32_t)(ua * ux * ux + (uint32_t)b);
+      case SFGPU_W_ABSDIFF: {
+        const int32_t d = x - b;
+        return (int32_t)(ua * (uint32_t)(d < 0 ? -d : d));
+      }
+      default: {
+        const int32_t d = x - b;
+        return d > 0 ? (int32_t)(ua * (uint32_t)d) : 0;
+      }
+    }
+  }
+  __device__ __forceinline__ SpecConsN(const DevModel& m, int idx, const char* st, const char*) {
+    const ConsDev& c = m.cons[idx];
+    gc = (const int32_t*)(st + c.off0);
+    gs_lo = (const int32_t*)(st + c.off1);
+    counting = c.g0 == nullptr;
+    col = (const int32_t*)c.g2;
+    fn = c.w.fn;
+    a = (int32_t)c.w.a;
+    b = (int32_t)c.w.b;
+    complement = (c.flags & SFGPU_CF_COMPLEMENT) != 0;
+    dflt = (int32_t)c.p1;
+    empty0 = complement ? w32(dflt) : 0;
+    square_uniform = c.w.fn == SFGPU_W_SQUARE && empty0 == b;
+    neg = c.sign < 0;
+    hard = c.w.level == 0;
+  }
+  __device__ __forceinline__ int32_t delta(uint32_t e, int32_t ov, int32_t nv) const {
+    const int32_t x = counting ? 1 : __ldg(col + e);
+    int32_t v = 0;
+    if (square_uniform) {
+      if (ov >= 0) {
+        const int32_t so = counting ? gc[ov] : gs_lo[2 * ov];
+        v += (int32_t)((uint32_t)x * (uint32_t)(x - 2 * so));
+      }
+      if (nv >= 0) {
+        const int32_t sn = counting ? gc[nv] : gs_lo[2 * nv];
+        v += (int32_t)((uint32_t)x * (uint32_t)(x + 2 * sn));
+      }
+      v = (int32_t)((uint32_t)a * (uint32_t)v);
+    } else {
+      if (ov >= 0) {
+        const int32_t cn = gc[ov], sm = counting ? cn : gs_lo[2 * ov];
+        v += (cn > 1 ? w32(sm - x) : empty0) - w32(sm);
+      }
+      if (nv >= 0) {
+        const int32_t cn = gc[nv], sm = counting ? cn : gs_lo[2 * nv];
+        v += w32(sm + x) - (cn > 0 ? w32(sm) : empty0);
+      }
+    }
+    return neg ? -v : v;
+  }
+};
+
 // The scoring program of a model as the kernels see it: delta(e, old, new) of one ChangeMove-shaped edit.
-// InterpProg walks the constraint table (any program); SpecProg is the monomorphised tuple.
+// InterpProg walks the constraint table (any program); SpecProg is the monomorphised tuple; SpecProgN its
+// int32 form. S = the type score deltas are computed (and forager partials compared) in.
 struct InterpProg {
+  typedef int64_t S;
   const DevModel& m;
   const char* st;
   const char* gst;
@@ -231,6 +381,7 @@ struct InterpProg {
 
 template <int K0, int K1, int K2, int K3>
 struct SpecProg {
+  typedef int64_t S;
   const SpecCons<K0> c0;
   const SpecCons<K1> c1;
   const SpecCons<K2> c2;
@@ -247,8 +398,27 @@ struct SpecProg {
   }
 };
 
+template <int K0, int K1, int K2, int K3>
+struct SpecProgN {
+  typedef int32_t S;
+  const SpecConsN<K0> c0;
+  const SpecConsN<K1> c1;
+  const SpecConsN<K2> c2;
+  const SpecConsN<K3> c3;
+  __device__ __forceinline__ SpecProgN(const DevModel& m, const SpecIdx& idx, const char* st, const char* gst)
+      : c0(m, idx.k[0], st, gst), c1(m, idx.k[1], st, gst), c2(m, idx.k[2], st, gst), c3(m, idx.k[3], st, gst) {}
+  __device__ __forceinline__ void delta(uint32_t e, int32_t ov, int32_t nv, int32_t& dh, int32_t& ds) const {
+    dh = 0;
+    ds = 0;
+    c0.add(dh, ds, c0.delta(e, ov, nv));
+    c1.add(dh, ds, c1.delta(e, ov, nv));
+    c2.add(dh, ds, c2.delta(e, ov, nv));
+    c3.add(dh, ds, c3.delta(e, ov, nv));
+  }
+};
+
 // resident CTAs per SM the rows-resident kernel is compiled for: light programs are latency-bound on their table
-// gathers and gain from a fifth CTA (<= 51 registers); heavy ones keep their registers
+// gathers and gain from more CTAs; heavy ones keep their registers
 template <class PROG>
 struct SpecOccupancy {
   static constexpr int min_ctas = 1;
@@ -257,15 +427,22 @@ template <>
 struct SpecOccupancy<SpecProg<SFGPU_K_PAIR_CSR_EQUAL, SPEC_K_UNI_CONST, 0, 0>> {
   static constexpr int min_ctas = 5;
 };
+template <int K0, int K1, int K2, int K3>
+struct SpecOccupancy<SpecProgN<K0, K1, K2, K3>> {
+  static constexpr int min_ctas = 4;
+};
 
-// Rows-resident ChangeMove scoring with a monomorphised program; same contract as
-// score_scalar_kernel<MODE_CHANGE, true> (grid = (chunks, R), staged replica block).
-template <class PROG>
-__global__ void __launch_bounds__(256, SpecOccupancy<PROG>::min_ctas) spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx,
-                                                          const uint64_t* __restrict__ cand_offsets,
-                                                          const uint32_t* __restrict__ rows,
-                                                          int64_t* __restrict__ out_scores,
-                                                          uint8_t* __restrict__ out_doable) {
+// Rows-resident ChangeMove scoring with a monomorphised program: grid = (chunks, R), every CTA stages its replica
+// block (TMA bulk copy) and scores ONE CONTIGUOUS chunk of the replica's rows (pull order inside a chunk), U rows per
+// thread per trip with the loads issued first. FORAGE: the kernel also keeps the forager partial of its chunk
+// (best accepted score, multiplicity, first and second row — ChunkPartial, same contract as
+// score_list_change_fast_kernel) so the step never re-reads the scores; out_scores / out_doable may then be null.
+template <class PROG, bool FORAGE>
+__global__ void __launch_bounds__(256, SpecOccupancy<PROG>::min_ctas)
+spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const uint64_t* __restrict__ cand_offsets,
+                   const uint32_t* __restrict__ rows, int64_t* __restrict__ out_scores, uint8_t* __restrict__ out_doable,
+                   const ForageArgs fa) {
+  typedef typename PROG::S S;
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   const uint32_t r = blockIdx.y;
@@ -278,15 +455,51 @@ __global__ void __launch_bounds__(256, SpecOccupancy<PROG>::min_ctas) spec_chang
   const PROG prog(m, idx, st, gblock);
   const uint32_t n_entities = m.n_entities;
   const int32_t n_values = (int32_t)m.n_values;
+  // acceptor as one branch-free form on deltas: accept(d) = (A < d) || (d >= B) (see score_list_change_fast_kernel)
+  const S S_MAX = sizeof(S) == 4 ? (S)INT32_MAX : (S)INT64_MAX, S_MIN = sizeof(S) == 4 ? (S)INT32_MIN : (S)INT64_MIN;
+  S a_h = S_MAX, a_s = S_MAX, b_h = S_MIN, b_s = S_MIN;
+  S tb_h = 0, tb_s = 0;
+  uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, tb_second = 0xFFFFFFFFu, t_acc = 0;
+  if (FORAGE) {
+    S f_lh, f_ls, f_th, f_ts;
+    rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 0] : 0, ch, f_lh);
+    rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 1] : 0, csf, f_ls);
+    rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 2] : 0, ch, f_th);
+    rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 3] : 0, csf, f_ts);
+    const int acc = fa.f.acceptor;
+    if (acc == 1 || acc == 3) {
+      a_h = f_lh;
+      a_s = f_ls;
+    }
+    if (acc == 1) {
+      b_h = S_MAX;
+      b_s = S_MAX;
+    } else if (acc == 2) {
+      const bool l_lt = lex_less<S>(f_lh, f_ls, f_th, f_ts);
+      b_h = l_lt ? f_lh : f_th;
+      b_s = l_lt ? f_ls : f_ts;
+    } else if (acc == 3) {
+      b_h = f_th;
+      b_s = f_ts;
+    }
+  }
   const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  const uint64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  const uint64_t c_lo64 = lo + per * blockIdx.x < hi ? lo + per * blockIdx.x : hi;
+  const uint64_t c_hi64 = c_lo64 + per < hi ? c_lo64 + per : hi;
+  const uint32_t n_c = (uint32_t)(c_hi64 - c_lo64);
+  const uint32_t first_base = (uint32_t)(c_lo64 - lo);
+  const uint2* __restrict__ rows2 = (const uint2*)rows + c_lo64;
+  longlong2* __restrict__ scores_c = out_scores ? (longlong2*)out_scores + c_lo64 : nullptr;
+  uint8_t* __restrict__ doable_c = out_doable ? out_doable + c_lo64 : nullptr;
   constexpr int U = 4;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t base = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < hi; base += stride * U) {
+  const uint32_t stride = blockDim.x * U;
+  for (uint32_t base = threadIdx.x; base < n_c; base += stride) {
     uint2 row[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint64_t i = base + u * stride;
-      row[u] = i < hi ? __ldcs((const uint2*)rows + i) : make_uint2(0xFFFFFFFFu, 0);
+      const uint32_t i = base + u * blockDim.x;
+      row[u] = i < n_c ? __ldcs(rows2 + i) : make_uint2(0xFFFFFFFFu, 0);
     }
     uint32_t e[U];
     int32_t nv[U], ov[U];
@@ -301,18 +514,73 @@ __global__ void __launch_bounds__(256, SpecOccupancy<PROG>::min_ctas) spec_chang
       ok[u] = ok[u] && ov[u] != nv[u];
       if (!ok[u]) nv[u] = ov[u];  // null edit: every table index stays in range
     }
-    int64_t dh[U], ds[U];
+    S dh[U], ds[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) prog.delta(e[u], ov[u], nv[u], dh[u], ds[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint64_t i = base + u * stride;
-      if (i >= hi) break;
-      longlong2 o;
-      o.x = ok[u] ? ch + dh[u] : 0;
-      o.y = ok[u] ? csf + ds[u] : 0;
-      __stcs((longlong2*)out_scores + i, o);
-      out_doable[i] = ok[u] ? 1 : 0;
+      const uint32_t i = base + u * blockDim.x;
+      if (i >= n_c) break;
+      if (!FORAGE || out_scores) {
+        longlong2 o;
+        o.x = ok[u] ? ch + (int64_t)dh[u] : 0;
+        o.y = ok[u] ? csf + (int64_t)ds[u] : 0;
+        __stcs(scores_c + i, o);
+        doable_c[i] = ok[u] ? 1 : 0;
+      }
+      if (FORAGE && ok[u] && (lex_less<S>(a_h, a_s, dh[u], ds[u]) || !lex_less<S>(dh[u], ds[u], b_h, b_s))) {
+        t_acc++;
+        if (tb_n == 0 || lex_less<S>(tb_h, tb_s, dh[u], ds[u])) {
+          tb_h = dh[u];
+          tb_s = ds[u];
+          tb_n = 1;
+          tb_first = first_base + i;
+          tb_second = 0xFFFFFFFFu;
+        } else if (tb_h == dh[u] && tb_s == ds[u]) {
+          if (tb_n == 1) tb_second = first_base + i;  // a thread's rows come in increasing pull order
+          tb_n++;
+        }
+      }
+    }
+  }
+  if (FORAGE) {
+    __shared__ int64_t sh_h[8], sh_s[8];
+    __shared__ uint32_t sh_n[8], sh_f[8], sh_a[8], sh_2[8];
+    for (int o = 16; o > 0; o >>= 1) {
+      const S oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+      const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
+      const uint32_t osec = __shfl_down_sync(0xffffffffu, tb_second, o);
+      t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
+      if (on && (!tb_n || lex_less<S>(tb_h, tb_s, oh, os))) {
+        tb_h = oh; tb_s = os; tb_n = on; tb_first = of; tb_second = osec;
+      } else if (on && tb_n && oh == tb_h && os == tb_s) {
+        tb_n += on;
+        tb_second = min(max(tb_first, of), min(tb_second, osec));  // second smallest of the four indices
+        tb_first = min(tb_first, of);
+      }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+      sh_h[warp] = ch + (int64_t)tb_h; sh_s[warp] = csf + (int64_t)tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first;
+      sh_a[warp] = t_acc;
+      sh_2[warp] = tb_second;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ChunkPartial cp{0, 0, 0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      for (int w = 0; w < 8; ++w) {
+        cp.n_accepted += sh_a[w];
+        if (!sh_n[w]) continue;
+        if (!cp.n_best || score_less(cp.best_h, cp.best_s, sh_h[w], sh_s[w])) {
+          cp.best_h = sh_h[w]; cp.best_s = sh_s[w]; cp.n_best = sh_n[w]; cp.first_idx = sh_f[w];
+          cp.second_idx = sh_2[w];
+        } else if (sh_h[w] == cp.best_h && sh_s[w] == cp.best_s) {
+          cp.n_best += sh_n[w];
+          cp.second_idx = min(max(cp.first_idx, sh_f[w]), min(cp.second_idx, sh_2[w]));
+          cp.first_idx = min(cp.first_idx, sh_f[w]);
+        }
+      }
+      fa.partials[(size_t)r * gridDim.x + blockIdx.x] = cp;
     }
   }
 }

@@ -57,6 +57,14 @@ def graph_coloring(n: int = 10_000, m: int = 50_000, k: int = 8, seed_edges: int
     return GraphColoringInstance(n, k, row_ptr, dst.astype(np.uint32), color)
 
 
+def graph_coloring_colors(inst: GraphColoringInstance, seed: int, unassigned_permille: int = 10) -> np.ndarray:
+    """Another seeded colouring of the same graph (replica-specific start)."""
+    cs = splitmix64_stream(seed, 2 * inst.n)
+    color = (cs[:inst.n] % np.uint64(inst.k)).astype(np.int32)
+    color[(cs[inst.n:] % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    return color
+
+
 @dataclass
 class NQueensInstance:
     n: int
@@ -171,6 +179,16 @@ def job_shop(n_jobs: int = 200, n_steps: int = 20, n_machines: int = 20, seed: i
     elems = np.concatenate(seqs).astype(np.uint32) if n else np.zeros(0, np.uint32)
     return JobShopInstance(n, n_machines, (ids // n_steps).astype(np.uint32), (ids % n_steps).astype(np.uint32), mach,
                            offsets, elems)
+
+
+def job_shop_machines(inst: JobShopInstance, seed: int, unassigned_permille: int = 0) -> np.ndarray:
+    """Another seeded machine assignment of the same operations (replica-specific start; the machine sequences
+    of the list variable stay those of the base instance)."""
+    s = splitmix64_stream(seed, 2 * inst.n_ops)
+    mach = (s[:inst.n_ops] % np.uint64(inst.n_machines)).astype(np.int32)
+    if unassigned_permille:
+        mach[(s[inst.n_ops:] % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    return mach
 
 
 def change_neighbourhood(values: np.ndarray, n_values: int, allows_unassigned: bool = True) -> np.ndarray:

@@ -412,6 +412,16 @@ def fast_lib() -> C.CDLL:
         l.sfo_fast_cvrp_score.argtypes = [_P, C.c_uint64, _P, _P, _P]
         l.sfo_fast_cvrp_bench.restype = C.c_double
         l.sfo_fast_cvrp_bench.argtypes = [_P, C.c_uint64, _P, C.c_uint32, C.c_double]
+        l.sfo_fast_cvrp_set_routes.argtypes = [_P, _P, _P, _P]
+        l.sfo_fast_cvrp_committed.argtypes = [_P, _P]
+        l.sfo_fast_gc_create.restype = _P
+        l.sfo_fast_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P]
+        l.sfo_fast_gc_destroy.argtypes = [_P]
+        l.sfo_fast_gc_score.argtypes = [_P, _P, C.c_uint64, _P, _P, _P, _P]
+        l.sfo_fast_js_create.restype = _P
+        l.sfo_fast_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, C.c_int64, C.c_int]
+        l.sfo_fast_js_destroy.argtypes = [_P]
+        l.sfo_fast_js_score.argtypes = [_P, _P, C.c_uint64, _P, _P, _P, _P]
         _fast = l
     return _fast
 
@@ -424,6 +434,7 @@ class FastCvrp:
         o = _u32(inst.offsets if offsets is None else offsets)
         e = _u32(inst.elems if elems is None else elems)
         dm = np.ascontiguousarray(inst.demands, dtype=np.int32)
+        self._dm = dm
         mx = np.ascontiguousarray(inst.matrix, dtype=np.int64)
         self.h = self.l.sfo_fast_cvrp_create(inst.dim, inst.n_routes, inst.capacity, inst.depot, _p(dm), _p(mx), _p(o),
                                              _p(e))
@@ -442,6 +453,66 @@ class FastCvrp:
         self.l.sfo_fast_cvrp_score(self.h, len(rows), _p(rows), _p(sc), _p(ok))
         return sc, ok
 
+    def set_routes(self, offsets, elems):
+        """Rebinds the scorer to another route state (keeps the converted matrix)."""
+        o, e = _u32(offsets), _u32(elems)
+        self.l.sfo_fast_cvrp_set_routes(self.h, _p(o), _p(e), _p(self._dm))
+
+    def committed_score(self) -> np.ndarray:
+        out = np.zeros(2, dtype=np.int64)
+        self.l.sfo_fast_cvrp_committed(self.h, _p(out))
+        return out
+
     def bench(self, rows, n_threads: int, seconds: float) -> float:
         rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1, 4)
         return float(self.l.sfo_fast_cvrp_bench(self.h, len(rows), _p(rows), n_threads, seconds))
+
+
+class FastGraphColoring:
+    """O(degree) CPU checker for graph-colouring ChangeMove batches (oracle/fast_cpu.cpp); checked against the
+    oracle on small instances."""
+
+    def __init__(self, inst):
+        self.l = fast_lib()
+        self.n = inst.n
+        rp, ci = _u32(inst.row_ptr), _u32(inst.col)
+        self.h = self.l.sfo_fast_gc_create(inst.n, inst.k, _p(rp), _p(ci))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.sfo_fast_gc_destroy(self.h)
+            self.h = None
+
+    def score_change(self, colors, rows):
+        """Returns (scores[n,2], doable[n], committed[2]) for rows[n][2] = (entity, to_value)."""
+        col = np.ascontiguousarray(colors, dtype=np.int32)
+        r = np.ascontiguousarray(np.asarray(rows).astype(np.int64).astype(np.int32)).reshape(-1, 2)
+        sc = np.zeros((len(r), 2), dtype=np.int64)
+        ok = np.zeros(len(r), dtype=np.uint8)
+        com = np.zeros(2, dtype=np.int64)
+        self.l.sfo_fast_gc_score(self.h, _p(col), len(r), _p(r), _p(sc), _p(ok), _p(com))
+        return sc, ok, com
+
+
+class FastJobShop:
+    """O(1) CPU checker for job-shop ChangeMove batches (oracle/fast_cpu.cpp)."""
+
+    def __init__(self, inst, with_complement=True):
+        self.l = fast_lib()
+        job = _u32(inst.job)
+        unscheduled = int(inst.n_ops - len(np.unique(inst.seq_elems)))
+        self.h = self.l.sfo_fast_js_create(inst.n_ops, inst.n_machines, _p(job), unscheduled, 1 if with_complement else 0)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.sfo_fast_js_destroy(self.h)
+            self.h = None
+
+    def score_change(self, machine_idx, rows):
+        mi = np.ascontiguousarray(machine_idx, dtype=np.int32)
+        r = np.ascontiguousarray(np.asarray(rows).astype(np.int64).astype(np.int32)).reshape(-1, 2)
+        sc = np.zeros((len(r), 2), dtype=np.int64)
+        ok = np.zeros(len(r), dtype=np.uint8)
+        com = np.zeros(2, dtype=np.int64)
+        self.l.sfo_fast_js_score(self.h, _p(mi), len(r), _p(r), _p(sc), _p(ok), _p(com))
+        return sc, ok, com

@@ -171,3 +171,24 @@ def test_arithmetic_width_paths_and_far_acceptor_references(scale, demand_scale,
                     assert win[r].tolist() == rows[out[1]].tolist(), what
                 else:
                     assert idx[r] == 0xFFFFFFFF, what
+
+
+def test_sync_best_single_rank_is_the_lexicographic_max_over_replicas():
+    """sfgpu_sync_best without a communicator: device reduction over the replicas' committed scores (or a given
+    score array), first replica on ties — the N = 1 leg of the best-score sync (the NCCL leg runs in bench.py)."""
+    import torch
+    c = instances.cvrp(60, 5, seed=3)
+    R = 7
+    starts = [instances.perturb_routes(c, 40 + r, 20 + 5 * r) for r in range(R)]
+    d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    sc = d.calculate_score()
+    want = max(range(R), key=lambda r: (sc[r][0], sc[r][1], -r))
+    best, owner, rep = d.sync_best()
+    assert best == (int(sc[want][0]), int(sc[want][1])) and owner == 0 and rep == want
+    # an explicit device score array, far outside the packed key's range, with a tie (first replica wins)
+    arr = np.array([[-(1 << 40), 3], [5, -(1 << 45)], [5, -(1 << 45)], [4, 1 << 50], [5, -(1 << 45) - 1], [0, 0], [-1, 9]],
+                   dtype=np.int64)
+    t = torch.from_numpy(arr).cuda()
+    torch.cuda.synchronize()
+    best, owner, rep = d.sync_best(scores_ptr=t.data_ptr())
+    assert best == (5, -(1 << 45)) and rep == 1

@@ -529,33 +529,48 @@ def test_argbest_replays_forager_and_acceptor_rules():
 
 
 # ------------------------------------------------------------------ full BASELINE sizes
-def test_full_size_c2_properties_and_sampled_parity():
+def test_full_size_c2_every_row_of_every_replica():
+    """C2 at BASELINE size, no slices: every candidate of six differently coloured replicas against the O(degree)
+    CPU checker (oracle/fast_cpu.cpp, itself pinned to the oracle in tests/test_oracle.py), a brute-force
+    recompute of sampled candidates and the reference-faithful oracle on a window."""
+    from tests.oracle_lib import FastGraphColoring
     g = instances.graph_coloring()            # 10 000 / 50 000 / k=8
-    d = models.graph_coloring_director(g)
-    rows = instances.change_neighbourhood(g.color, g.k)
-    s, ok = d.score_change(rows)
-    assert len(rows) == 10_000 * 8 + int((g.color >= 0).sum())
-    assert int((ok == 0).sum()) == int((g.color >= 0).sum())     # exactly the move-to-current-value rows
-    base = d.calculate_score()[0]
-    _eq(base, d.fresh_score()[0], "committed == fresh")
-    # brute-force full recompute of sampled candidates (independent of both engines)
+    R = 6
+    colors = np.stack([g.color] + [instances.graph_coloring_colors(g, 43 + r) for r in range(1, R)])
+    d = models.graph_coloring_director(g, R, colors=colors)
+    per = [instances.change_neighbourhood(colors[r], g.k) for r in range(R)]
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in per])]).astype(np.uint64)
+    rows = np.concatenate(per)
+    s, ok = d.score_change(rows, offs)
+    assert len(per[0]) == 10_000 * 8 + int((g.color >= 0).sum())
+    f = FastGraphColoring(g)
+    base = d.calculate_score()
+    _eq(base, d.fresh_score(), "committed == fresh")
+    for r in range(R):
+        sl = slice(int(offs[r]), int(offs[r + 1]))
+        sf, okf, com = f.score_change(colors[r], per[r])
+        _eq(ok[sl], okf, f"doable replica {r}")
+        _eq(s[sl], sf, f"scores replica {r}")
+        _eq(base[r], com, f"committed replica {r}")
+        assert int((ok[sl] == 0).sum()) == int((colors[r] >= 0).sum())     # exactly the move-to-current-value rows
+    # brute-force full recompute of sampled candidates (independent of every engine)
     def full(color):
         un = int((color < 0).sum())
         src = np.repeat(np.arange(g.n), np.diff(g.row_ptr.astype(np.int64)))
         dst = g.col.astype(np.int64)
         m = (src < dst) & (color[src] >= 0) & (color[src] == color[dst])
         return -(un + int(m.sum()))
-    assert base[0] == full(g.color)
-    for i in instances.splitmix64_stream(9, 60) % np.uint64(len(rows)):
-        e, v = rows[int(i)]
+    assert base[0][0] == full(g.color)
+    for i in instances.splitmix64_stream(9, 60) % np.uint64(len(per[0])):
+        e, v = per[0][int(i)]
         if ok[int(i)]:
             c2 = g.color.copy()
             c2[e] = v
             assert s[int(i)][0] == full(c2)
-    # oracle parity on a slice (the reference-faithful engine does O(n) work per candidate)
+    # the reference-faithful engine (O(n) work per candidate) on a window
     o = Oracle.graph_coloring(g)
     sl = slice(40_000, 40_600)
-    so, oko = o.score_change(rows[sl])
+    so, oko = o.score_change(per[0][sl])
     _eq(s[sl], so, "oracle slice")
     _eq(ok[sl], oko)
 
@@ -583,17 +598,31 @@ def test_full_size_c3_parity_and_round_trip():
     _eq(el1, el0)
 
 
-def test_full_size_c4_parity_slice_and_invariants():
+def test_full_size_c4_every_row_of_every_replica():
+    """C4 at BASELINE size, no slices: all 84 000 candidates of six replicas with different machine assignments
+    (a few operations unassigned) against the O(1) CPU checker, plus the oracle on a window."""
+    from tests.oracle_lib import FastJobShop
     j = instances.job_shop()                  # 200 x 20 / 20 machines
-    d = models.job_shop_director(j)
-    rows = instances.change_neighbourhood(j.machine_idx, j.n_machines)
-    assert len(rows) == 84_000
-    s, ok = d.score_change(rows)
-    _eq(d.calculate_score()[0], d.fresh_score()[0])
+    R = 6
+    mach = np.stack([j.machine_idx] + [instances.job_shop_machines(j, 11 + r, unassigned_permille=5 * r) for r in range(1, R)])
+    d = models.job_shop_director(j, R, machine_idx=mach)
+    per = [instances.change_neighbourhood(mach[r], j.n_machines) for r in range(R)]
+    assert len(per[0]) == 84_000
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in per])]).astype(np.uint64)
+    s, ok = d.score_change(np.concatenate(per), offs)
+    base = d.calculate_score()
+    _eq(base, d.fresh_score())
+    f = FastJobShop(j)
+    for r in range(R):
+        sl = slice(int(offs[r]), int(offs[r + 1]))
+        sf, okf, com = f.score_change(mach[r], per[r])
+        _eq(ok[sl], okf, f"doable replica {r}")
+        _eq(s[sl], sf, f"scores replica {r}")
+        _eq(base[r], com, f"committed replica {r}")
     o = Oracle.job_shop(j)
-    _eq(d.calculate_score()[0], o.committed_score())
+    _eq(base[0], o.committed_score())
     sl = slice(21_000, 21_400)
-    so, oko = o.score_change(rows[sl])
+    so, oko = o.score_change(per[0][sl])
     _eq(s[sl], so, "job-shop slice")
     _eq(ok[sl], oko)
 

@@ -98,3 +98,83 @@ def test_spec_multi_replica_full_size_c2():
     so, oko = o1.score_change(per[1][::7])
     lo = int(offs[1])
     assert np.array_equal(s1[lo:int(offs[2])][::7], so) and np.array_equal(ok1[lo:int(offs[2])][::7], oko)
+
+
+def _rows_step(d, rows, offs, params, seeds, ref, materialise):
+    """sfgpu_step_change_rows through torch device buffers; returns (index, best, evaluated[, scores, doable])."""
+    import torch
+    R, n = d.R, len(rows)
+    t_rows = torch.from_numpy(np.ascontiguousarray(rows.astype(np.int64).astype(np.uint32)).view(np.int32)).cuda()
+    t_offs = torch.from_numpy(np.asarray(offs, dtype=np.uint64).view(np.int64)).cuda()
+    t_seeds = torch.tensor(seeds, dtype=torch.int64).cuda()
+    t_ref = torch.from_numpy(np.ascontiguousarray(ref, dtype=np.int64)).cuda()
+    t_idx = torch.zeros(R, dtype=torch.int32).cuda()
+    t_best = torch.zeros((R, 2), dtype=torch.int64).cuda()
+    t_ev = torch.zeros(R, dtype=torch.int32).cuda()
+    t_sc = torch.zeros((n, 2), dtype=torch.int64).cuda()
+    t_ok = torch.zeros(n, dtype=torch.uint8).cuda()
+    torch.cuda.synchronize()
+    d.step_change_rows_device(n, t_offs.data_ptr(), t_rows.data_ptr(), params, t_seeds.data_ptr(), t_ref.data_ptr(),
+                              t_sc.data_ptr() if materialise else 0, t_ok.data_ptr() if materialise else 0,
+                              t_idx.data_ptr(), t_best.data_ptr(), t_ev.data_ptr())
+    d.synchronize()
+    out = [t_idx.cpu().numpy().view(np.uint32), t_best.cpu().numpy(), t_ev.cpu().numpy().view(np.uint32)]
+    if materialise:
+        out += [t_sc.cpu().numpy(), t_ok.cpu().numpy()]
+    return out
+
+
+@pytest.mark.parametrize("model", ["graph_coloring", "job_shop", "job_shop_plain", "nqueens", "shift"])
+def test_fused_rows_step_equals_score_plus_argbest(model, monkeypatch):
+    """sfgpu_step_change_rows (monomorphised kernel with fused forager partials, int32 or int64 deltas) picks the
+    same winner as scoring + the ordered argbest replay for every acceptor / tie mode / limit, with and without
+    materialised scores, on several replicas with ragged batches; the int32 programs equal the int64 ones."""
+    R = 3
+    if model == "graph_coloring":
+        inst = instances.graph_coloring(700, 3000, 5, seed_edges=3, seed_colors=4, unassigned_permille=60)
+        states = np.stack([instances.graph_coloring_colors(inst, 4 + r, 60) for r in range(R)])
+        make = lambda **kw: models.graph_coloring_director(inst, R, colors=states, **kw)
+        k = inst.k
+    elif model.startswith("job_shop"):
+        inst = instances.job_shop(50, 8, 7, seed=6, unassigned_permille=40)
+        states = np.stack([instances.job_shop_machines(inst, 6 + r, 40) for r in range(R)])
+        make = lambda **kw: models.job_shop_director(inst, R, machine_idx=states, with_complement=model == "job_shop", **kw)
+        k = inst.n_machines
+    elif model == "nqueens":
+        inst = instances.nqueens(30, seed=2)
+        states = np.stack([instances.nqueens(30, seed=2 + r).row for r in range(R)])
+        make = lambda **kw: models.nqueens_director(inst, R, rows=states, **kw)
+        k = inst.n
+    else:
+        inst = instances.shift_scheduling(seed=9)
+        states = np.stack([instances.shift_scheduling(seed=9 + r).nurse_idx for r in range(R)])
+        make = lambda **kw: models.shift_scheduling_director(inst, R, nurse_idx=states, **kw)
+        k = inst.n_nurses
+    d = make()
+    monkeypatch.setenv("SFGPU_NO_NARROW", "1")
+    wide = make()
+    monkeypatch.delenv("SFGPU_NO_NARROW")
+    per = [instances.change_neighbourhood(states[r], k) for r in range(R)]
+    per[1] = per[1][: len(per[1]) // 3]                      # ragged: a short batch
+    per[2] = np.concatenate([per[2], per[2][:50], [[0, k + 5], [10 ** 6, 0]]])   # duplicates (ties) + not-doable rows
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in per])]).astype(np.uint64)
+    rows = np.concatenate(per)
+    s_ref, ok_ref = wide.score_change(rows, offs)
+    s_n, ok_n = d.score_change(rows, offs)
+    assert np.array_equal(s_n, s_ref) and np.array_equal(ok_n, ok_ref)
+    base = d.calculate_score()
+    late = base - np.array([[1, 3], [0, 40], [2, 0]])
+    ref = np.concatenate([base, late], axis=1)
+    seeds = [5, 77, 123456789]
+    for acceptor in (0, 1, 2, 3):
+        for tie in (0, 1):
+            for limit in (0, 5):
+                p = ForageParams(acceptor, tie, limit)
+                want = d.argbest(s_ref, ok_ref, offs, p, seeds, ref)
+                for dd in (d, wide):
+                    for mat in (True, False):
+                        got = _rows_step(dd, rows, offs, p, seeds, ref, mat)
+                        assert np.array_equal(got[0], want[0]), (model, acceptor, tie, limit, mat)
+                        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+                        if mat:
+                            assert np.array_equal(got[3], s_ref) and np.array_equal(got[4], ok_ref)

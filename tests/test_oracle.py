@@ -182,6 +182,44 @@ def test_fast_cpu_baseline_matches_the_oracle():
     assert f.bench(rows, 2, 0.2) > 0
 
 
+def test_fast_scalar_checkers_match_the_oracle():
+    """The O(1) / O(degree) CPU checkers of the scalar configs (oracle/fast_cpu.cpp) are only trusted because they
+    reproduce the reference-faithful oracle on every candidate of small instances, unassigned and not-doable
+    rows included."""
+    from tests.oracle_lib import FastGraphColoring, FastJobShop
+    for seed in (1, 2, 3):
+        g = instances.graph_coloring(300, 1200, 5, seed_edges=seed, seed_colors=seed + 10, unassigned_permille=60)
+        o = Oracle.graph_coloring(g)
+        rows = np.concatenate([instances.change_neighbourhood(g.color, g.k), [[5, int(g.color[5])], [7, -1]]])
+        so, oko = o.score_change(rows)
+        f = FastGraphColoring(g)
+        sf, okf, com = f.score_change(g.color, rows)
+        assert np.array_equal(okf, oko) and np.array_equal(sf, so)
+        assert np.array_equal(com, o.committed_score())
+        for with_c in (True, False):
+            j = instances.job_shop(30, 6, 5, seed=seed, unassigned_permille=80)
+            oj = Oracle.job_shop(j, with_complement=with_c)
+            jr = np.concatenate([instances.change_neighbourhood(j.machine_idx, j.n_machines), [[3, int(j.machine_idx[3])], [4, -1]]])
+            so, oko = oj.score_change(jr)
+            fj = FastJobShop(j, with_c)
+            sf, okf, com = fj.score_change(j.machine_idx, jr)
+            assert np.array_equal(okf, oko) and np.array_equal(sf, so)
+            assert np.array_equal(com, oj.committed_score())
+    # FastCvrp rebinding keeps the converted matrix and follows the new routes
+    from tests.oracle_lib import FastCvrp
+    c = instances.cvrp(120, 7, seed=5)
+    f = FastCvrp(c)
+    for seed in (11, 12):
+        offs, el = instances.perturb_routes(c, seed, 50)
+        o = Oracle.cvrp(c, offs, el)
+        f.set_routes(offs, el)
+        rows = o.enumerate_nearby_list_change(12)
+        so, oko = o.score_list_change(rows)
+        sf, okf = f.score(rows)
+        assert np.array_equal(okf, oko) and np.array_equal(sf, so)
+        assert np.array_equal(f.committed_score(), o.committed_score())
+
+
 def test_roster_projected_rows_incremental_equals_fresh():
     """Projected multi-emit rows in the oracle (ProjectedUni / ProjectedGrouped): cached == evaluate_all
     along a random walk of committed change moves (FullAssert invariant, scope_core.rs:642-653)."""

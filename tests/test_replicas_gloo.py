@@ -33,6 +33,10 @@ def _worker(rank, world, port, out):
     # a tie is owned by the lowest rank
     tie = torch.tensor([replicas.pack_score_key(0, -5)], dtype=torch.int64)
     out[rank + 10] = replicas.sync_best(tie)[1]
+    # the exact (hard, soft) sync: scores far outside the packed key's range still order correctly
+    big = {0: [[-(1 << 30), 5], [-(1 << 30), 9]], 1: [[-(1 << 30) - 1, 1 << 50], [-(1 << 31), 0]]}[rank]
+    out[rank + 20] = replicas.sync_best_scores(torch.tensor(big, dtype=torch.int64))
+    out[rank + 30] = replicas.sync_best_scores(torch.tensor([[3, -7]], dtype=torch.int64))   # tie -> lowest rank
     dist.destroy_process_group()
 
 
@@ -46,3 +50,6 @@ def test_sync_best_world_size_2():
         mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
         assert out[0] == ((0, -250), 1) and out[1] == ((0, -250), 1)
         assert out[10] == 0 and out[11] == 0
+        assert out[20] == (-(1 << 30), 9, 0) and out[21] == (-(1 << 30), 9, 0)
+        assert out[30] == (3, -7, 0) and out[31] == (3, -7, 0)
+        assert replicas.key_saturates(-(1 << 30), 0) and not replicas.key_saturates(-89, -511236)
