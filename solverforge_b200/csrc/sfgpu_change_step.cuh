@@ -42,14 +42,25 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
   const int64_t* cs = (const int64_t*)(st + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
   const PROG prog(m, idx, st, gblock);
+  typedef typename PROG::S S;
+  typedef DeltaKey<S> Key;
   const uint32_t k = m.n_values, n = m.n_entities;
   const bool with_none = m.allows_unassigned != 0;
-  int64_t lh = 0, ls = 0, th = 0, ts = 0;
-  if (a.ref_scores) {
-    lh = a.ref_scores[r * 4 + 0];
-    ls = a.ref_scores[r * 4 + 1];
-    th = a.ref_scores[r * 4 + 2];
-    ts = a.ref_scores[r * 4 + 3];
+  // acceptor on score deltas: accept(d) = (A < d) || (d >= B), thresholds relative to the committed score
+  // (see spec_change_kernel; the int32 programs compare one packed 64-bit key)
+  Key kA = Key::highest(), kB = Key::lowest(), tb = Key::lowest();
+  {
+    S f_lh, f_ls, f_th, f_ts;
+    rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 0] : 0, ch, f_lh);
+    rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 1] : 0, csf, f_ls);
+    rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 2] : 0, ch, f_th);
+    rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 3] : 0, csf, f_ts);
+    const Key kl = Key::make(f_lh, f_ls), kt = Key::make(f_th, f_ts);
+    const int acc = a.f.acceptor;
+    if (acc == 1 || acc == 3) kA = kl;
+    if (acc == 1) kB = Key::highest();
+    else if (acc == 2) kB = kl.less(kt) ? kl : kt;
+    else if (acc == 3) kB = kt;
   }
   const uint32_t c_lo = blockIdx.x * a.ents_per_cta, c_hi = min(c_lo + a.ents_per_cta, n);
   const size_t stride = (size_t)n * (k + 1);  // padded rows per replica in the materialised batch
@@ -70,7 +81,6 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
       }
     }
   }
-  int64_t tb_h = 0, tb_s = 0;
   uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, t_acc = 0;
   for (uint32_t g = c_lo; g < c_hi; g += blockDim.x) {
     const uint32_t e = g + threadIdx.x;
@@ -89,25 +99,24 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
     for (uint32_t v = 0; v < n_cand; ++v) {
       const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
       const bool ok = nv != old;
-      int64_t dh, ds;
+      S dh, ds;
       prog.delta(e, old, ok ? nv : old, dh, ds);  // null edit when not doable
-      const int64_t oh = ok ? ch + dh : 0, os = ok ? csf + ds : 0;
       if (a.out_rows) {
         const size_t q = (size_t)r * stride + base + v;
         ((uint2*)a.out_rows)[q] = make_uint2(e, (uint32_t)nv);
         if (a.out_scores) {
-          ((longlong2*)a.out_scores)[q] = make_longlong2(oh, os);
+          ((longlong2*)a.out_scores)[q] = make_longlong2(ok ? ch + (int64_t)dh : 0, ok ? csf + (int64_t)ds : 0);
           a.out_doable[q] = ok ? 1 : 0;
         }
       }
-      if (ok && accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) {
+      const Key kk = Key::make(dh, ds);
+      if (ok && (kA.less(kk) || !kk.less(kB))) {
         t_acc++;
-        if (tb_n == 0 || score_less(tb_h, tb_s, oh, os)) {
-          tb_h = oh;
-          tb_s = os;
+        if (tb_n == 0 || tb.less(kk)) {
+          tb = kk;
           tb_n = 1;
           tb_first = e * (k + 1) + v;
-        } else if (tb_h == oh && tb_s == os) {
+        } else if (tb.equal(kk)) {
           tb_n++;
         }
       }
@@ -115,16 +124,17 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
   }
   // block merge of the forager partial (better score wins; equal adds multiplicity, keeps earliest)
   for (int o = 16; o > 0; o >>= 1) {
-    const int64_t oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+    const Key ok_ = tb.shfl_down(o);
     const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
     t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
-    if (on && (!tb_n || score_less(tb_h, tb_s, oh, os))) {
-      tb_h = oh; tb_s = os; tb_n = on; tb_first = of;
-    } else if (on && tb_n && oh == tb_h && os == tb_s) {
+    if (on && (!tb_n || tb.less(ok_))) {
+      tb = ok_; tb_n = on; tb_first = of;
+    } else if (on && tb_n && tb.equal(ok_)) {
       tb_n += on;
       tb_first = min(tb_first, of);
     }
   }
+  const int64_t tb_h = tb_n ? ch + tb.hard() : 0, tb_s = tb_n ? csf + tb.soft() : 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
     sh_h[warp] = tb_h; sh_s[warp] = tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first; sh_a[warp] = t_acc;

@@ -16,15 +16,15 @@ struct SpecEntry {
   int k[4];
   SpecScoreFn score, fused;      // rows-resident: scores only / scores + forager partials
   SpecScoreFn score_n, fused_n;  // int32 forms, or null
-  SpecStepFn step;
+  SpecStepFn step, step_n;
 };
 #define SPEC_WIDE(a, b, c, d) \
   { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, nullptr, nullptr, \
-    change_step_kernel<true, SpecProg<a, b, c, d>> }
+    change_step_kernel<true, SpecProg<a, b, c, d>>, nullptr }
 #define SPEC_BOTH(a, b, c, d) \
   { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, \
     spec_change_kernel<SpecProgN<a, b, c, d>, false>, spec_change_kernel<SpecProgN<a, b, c, d>, true>, \
-    change_step_kernel<true, SpecProg<a, b, c, d>> }
+    change_step_kernel<true, SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProgN<a, b, c, d>> }
 #define U_ SFGPU_K_UNI
 #define C_ SFGPU_K_PAIR_CSR_EQUAL
 #define K_ SFGPU_K_PAIR_KEY_EQUAL
@@ -160,6 +160,7 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
             ctx->spec_narrow = true;
             CU(cudaFuncSetAttribute((const void*)g_spec[t].score_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
             CU(cudaFuncSetAttribute((const void*)g_spec[t].fused_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+            CU(cudaFuncSetAttribute((const void*)g_spec[t].step_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
           }
         }
         break;
@@ -246,7 +247,7 @@ int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t c
   const DevModel& dm = ctx->dm;
   dim3 grid(chunks, dm.R);
   if (ctx->spec_id >= 0)
-    g_spec[ctx->spec_id].step<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
+    (ctx->spec_narrow ? g_spec[ctx->spec_id].step_n : g_spec[ctx->spec_id].step)<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
   else if (ctx->staged)
     change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
   else

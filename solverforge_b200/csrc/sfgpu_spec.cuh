@@ -417,6 +417,9 @@ struct SpecProgN {
   }
 };
 
+#ifndef SFGPU_SPECN_CTAS
+#define SFGPU_SPECN_CTAS 4
+#endif
 // resident CTAs per SM the rows-resident kernel is compiled for: light programs are latency-bound on their table
 // gathers and gain from more CTAs; heavy ones keep their registers
 template <class PROG>
@@ -429,24 +432,76 @@ struct SpecOccupancy<SpecProg<SFGPU_K_PAIR_CSR_EQUAL, SPEC_K_UNI_CONST, 0, 0>> {
 };
 template <int K0, int K1, int K2, int K3>
 struct SpecOccupancy<SpecProgN<K0, K1, K2, K3>> {
-  static constexpr int min_ctas = 4;
+  static constexpr int min_ctas = SFGPU_SPECN_CTAS;
+};
+
+// Score deltas as the forager compares them. Wide programs keep the (hard, soft) int64 pair; int32 programs pack
+// the pair into ONE int64 key k = hard * 2^32 + soft (a true 64-bit sum): |soft| < 2^31, so numeric order and
+// equality of keys are exactly the lexicographic order and equality of the pairs, and the acceptor test and the
+// running best cost one 64-bit compare each. Thresholds clamped to int32 (rel_threshold) pack the same way.
+template <typename S>
+struct DeltaKey;
+template <>
+struct DeltaKey<int64_t> {
+  int64_t h, s;
+  __device__ __forceinline__ static DeltaKey make(int64_t dh, int64_t ds) { return DeltaKey{dh, ds}; }
+  __device__ __forceinline__ static DeltaKey lowest() { return DeltaKey{INT64_MIN, INT64_MIN}; }
+  __device__ __forceinline__ static DeltaKey highest() { return DeltaKey{INT64_MAX, INT64_MAX}; }
+  __device__ __forceinline__ bool less(const DeltaKey& o) const { return h != o.h ? h < o.h : s < o.s; }
+  __device__ __forceinline__ bool equal(const DeltaKey& o) const { return h == o.h && s == o.s; }
+  __device__ __forceinline__ int64_t hard() const { return h; }
+  __device__ __forceinline__ int64_t soft() const { return s; }
+  __device__ __forceinline__ DeltaKey shfl_down(int o) const {
+    return DeltaKey{__shfl_down_sync(0xffffffffu, h, o), __shfl_down_sync(0xffffffffu, s, o)};
+  }
+};
+template <>
+struct DeltaKey<int32_t> {
+  int64_t k;
+  __device__ __forceinline__ static DeltaKey make(int32_t dh, int32_t ds) {
+    return DeltaKey{(int64_t)(((uint64_t)(uint32_t)dh << 32) + (uint64_t)(int64_t)ds)};
+  }
+  __device__ __forceinline__ static DeltaKey lowest() { return DeltaKey{INT64_MIN}; }
+  __device__ __forceinline__ static DeltaKey highest() { return DeltaKey{INT64_MAX}; }
+  __device__ __forceinline__ bool less(const DeltaKey& o) const { return k < o.k; }
+  __device__ __forceinline__ bool equal(const DeltaKey& o) const { return k == o.k; }
+  __device__ __forceinline__ int64_t soft() const { return (int64_t)(int32_t)(uint32_t)k; }
+  __device__ __forceinline__ int64_t hard() const { return (k - soft()) >> 32; }
+  __device__ __forceinline__ DeltaKey shfl_down(int o) const { return DeltaKey{__shfl_down_sync(0xffffffffu, k, o)}; }
 };
 
 // Rows-resident ChangeMove scoring with a monomorphised program: grid = (chunks, R), every CTA stages its replica
 // block (TMA bulk copy) and scores ONE CONTIGUOUS chunk of the replica's rows (pull order inside a chunk), U rows per
-// thread per trip with the loads issued first. FORAGE: the kernel also keeps the forager partial of its chunk
-// (best accepted score, multiplicity, first and second row — ChunkPartial, same contract as
-// score_list_change_fast_kernel) so the step never re-reads the scores; out_scores / out_doable may then be null.
+// thread per trip, the next trip's rows prefetched into registers while the current ones are scored. FORAGE: the
+// kernel also keeps the forager partial of its chunk (best accepted score, multiplicity, first and second row —
+// ChunkPartial, same contract as score_list_change_fast_kernel) so the step never re-reads the scores; out_scores /
+// out_doable may then be null.
 template <class PROG, bool FORAGE>
 __global__ void __launch_bounds__(256, SpecOccupancy<PROG>::min_ctas)
 spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const uint64_t* __restrict__ cand_offsets,
                    const uint32_t* __restrict__ rows, int64_t* __restrict__ out_scores, uint8_t* __restrict__ out_doable,
                    const ForageArgs fa) {
   typedef typename PROG::S S;
+  typedef DeltaKey<S> Key;
   extern __shared__ __align__(128) char smem[];
   __shared__ uint64_t bar;
   const uint32_t r = blockIdx.y;
   const char* gblock = m.state + (size_t)r * m.block_bytes;
+  // the first rows of the chunk are requested before the replica block is staged: both latencies overlap
+  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
+  const uint64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  const uint64_t c_lo64 = lo + per * blockIdx.x < hi ? lo + per * blockIdx.x : hi;
+  const uint64_t c_hi64 = c_lo64 + per < hi ? c_lo64 + per : hi;
+  const uint32_t n_c = (uint32_t)(c_hi64 - c_lo64);
+  const uint32_t first_base = (uint32_t)(c_lo64 - lo);
+  const uint2* __restrict__ rows2 = (const uint2*)rows + c_lo64;
+  constexpr int U = 4;
+  uint2 nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t i = threadIdx.x + u * 256;
+    nxt[u] = i < n_c ? __ldcs(rows2 + i) : make_uint2(0xFFFFFFFFu, 0);
+  }
   stage_block(smem, gblock, m.stage_bytes, &bar);
   const char* st = smem;
   const int32_t* var = (const int32_t*)(st + m.off_var);
@@ -456,9 +511,7 @@ spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const 
   const uint32_t n_entities = m.n_entities;
   const int32_t n_values = (int32_t)m.n_values;
   // acceptor as one branch-free form on deltas: accept(d) = (A < d) || (d >= B) (see score_list_change_fast_kernel)
-  const S S_MAX = sizeof(S) == 4 ? (S)INT32_MAX : (S)INT64_MAX, S_MIN = sizeof(S) == 4 ? (S)INT32_MIN : (S)INT64_MIN;
-  S a_h = S_MAX, a_s = S_MAX, b_h = S_MIN, b_s = S_MIN;
-  S tb_h = 0, tb_s = 0;
+  Key kA = Key::highest(), kB = Key::lowest(), tb = Key::lowest();
   uint32_t tb_n = 0, tb_first = 0xFFFFFFFFu, tb_second = 0xFFFFFFFFu, t_acc = 0;
   if (FORAGE) {
     S f_lh, f_ls, f_th, f_ts;
@@ -466,40 +519,24 @@ spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const 
     rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 1] : 0, csf, f_ls);
     rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 2] : 0, ch, f_th);
     rel_threshold(fa.ref_scores ? fa.ref_scores[r * 4 + 3] : 0, csf, f_ts);
+    const Key kl = Key::make(f_lh, f_ls), kt = Key::make(f_th, f_ts);
     const int acc = fa.f.acceptor;
-    if (acc == 1 || acc == 3) {
-      a_h = f_lh;
-      a_s = f_ls;
-    }
-    if (acc == 1) {
-      b_h = S_MAX;
-      b_s = S_MAX;
-    } else if (acc == 2) {
-      const bool l_lt = lex_less<S>(f_lh, f_ls, f_th, f_ts);
-      b_h = l_lt ? f_lh : f_th;
-      b_s = l_lt ? f_ls : f_ts;
-    } else if (acc == 3) {
-      b_h = f_th;
-      b_s = f_ts;
-    }
+    if (acc == 1 || acc == 3) kA = kl;
+    if (acc == 1) kB = Key::highest();
+    else if (acc == 2) kB = kl.less(kt) ? kl : kt;
+    else if (acc == 3) kB = kt;
   }
-  const uint64_t lo = cand_offsets[r], hi = cand_offsets[r + 1];
-  const uint64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
-  const uint64_t c_lo64 = lo + per * blockIdx.x < hi ? lo + per * blockIdx.x : hi;
-  const uint64_t c_hi64 = c_lo64 + per < hi ? c_lo64 + per : hi;
-  const uint32_t n_c = (uint32_t)(c_hi64 - c_lo64);
-  const uint32_t first_base = (uint32_t)(c_lo64 - lo);
-  const uint2* __restrict__ rows2 = (const uint2*)rows + c_lo64;
   longlong2* __restrict__ scores_c = out_scores ? (longlong2*)out_scores + c_lo64 : nullptr;
   uint8_t* __restrict__ doable_c = out_doable ? out_doable + c_lo64 : nullptr;
-  constexpr int U = 4;
-  const uint32_t stride = blockDim.x * U;
+  const bool store = !FORAGE || out_scores != nullptr;
+  const uint32_t stride = 256 * U;
   for (uint32_t base = threadIdx.x; base < n_c; base += stride) {
     uint2 row[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t i = base + u * blockDim.x;
-      row[u] = i < n_c ? __ldcs(rows2 + i) : make_uint2(0xFFFFFFFFu, 0);
+      row[u] = nxt[u];
+      const uint32_t i = base + stride + u * 256;
+      nxt[u] = i < n_c ? __ldcs(rows2 + i) : make_uint2(0xFFFFFFFFu, 0);
     }
     uint32_t e[U];
     int32_t nv[U], ov[U];
@@ -519,26 +556,28 @@ spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const 
     for (int u = 0; u < U; ++u) prog.delta(e[u], ov[u], nv[u], dh[u], ds[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t i = base + u * blockDim.x;
+      const uint32_t i = base + u * 256;
       if (i >= n_c) break;
-      if (!FORAGE || out_scores) {
+      if (store) {
         longlong2 o;
         o.x = ok[u] ? ch + (int64_t)dh[u] : 0;
         o.y = ok[u] ? csf + (int64_t)ds[u] : 0;
         __stcs(scores_c + i, o);
         doable_c[i] = ok[u] ? 1 : 0;
       }
-      if (FORAGE && ok[u] && (lex_less<S>(a_h, a_s, dh[u], ds[u]) || !lex_less<S>(dh[u], ds[u], b_h, b_s))) {
-        t_acc++;
-        if (tb_n == 0 || lex_less<S>(tb_h, tb_s, dh[u], ds[u])) {
-          tb_h = dh[u];
-          tb_s = ds[u];
-          tb_n = 1;
-          tb_first = first_base + i;
-          tb_second = 0xFFFFFFFFu;
-        } else if (tb_h == dh[u] && tb_s == ds[u]) {
-          if (tb_n == 1) tb_second = first_base + i;  // a thread's rows come in increasing pull order
-          tb_n++;
+      if (FORAGE) {
+        const Key k = Key::make(dh[u], ds[u]);
+        if (ok[u] && (kA.less(k) || !k.less(kB))) {
+          t_acc++;
+          if (tb_n == 0 || tb.less(k)) {
+            tb = k;
+            tb_n = 1;
+            tb_first = first_base + i;
+            tb_second = 0xFFFFFFFFu;
+          } else if (tb.equal(k)) {
+            if (tb_n == 1) tb_second = first_base + i;  // a thread's rows come in increasing pull order
+            tb_n++;
+          }
         }
       }
     }
@@ -547,13 +586,13 @@ spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const 
     __shared__ int64_t sh_h[8], sh_s[8];
     __shared__ uint32_t sh_n[8], sh_f[8], sh_a[8], sh_2[8];
     for (int o = 16; o > 0; o >>= 1) {
-      const S oh = __shfl_down_sync(0xffffffffu, tb_h, o), os = __shfl_down_sync(0xffffffffu, tb_s, o);
+      const Key ok_ = tb.shfl_down(o);
       const uint32_t on = __shfl_down_sync(0xffffffffu, tb_n, o), of = __shfl_down_sync(0xffffffffu, tb_first, o);
       const uint32_t osec = __shfl_down_sync(0xffffffffu, tb_second, o);
       t_acc += __shfl_down_sync(0xffffffffu, t_acc, o);
-      if (on && (!tb_n || lex_less<S>(tb_h, tb_s, oh, os))) {
-        tb_h = oh; tb_s = os; tb_n = on; tb_first = of; tb_second = osec;
-      } else if (on && tb_n && oh == tb_h && os == tb_s) {
+      if (on && (!tb_n || tb.less(ok_))) {
+        tb = ok_; tb_n = on; tb_first = of; tb_second = osec;
+      } else if (on && tb_n && tb.equal(ok_)) {
         tb_n += on;
         tb_second = min(max(tb_first, of), min(tb_second, osec));  // second smallest of the four indices
         tb_first = min(tb_first, of);
@@ -561,7 +600,7 @@ spec_change_kernel(const __grid_constant__ DevModel m, const SpecIdx idx, const 
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-      sh_h[warp] = ch + (int64_t)tb_h; sh_s[warp] = csf + (int64_t)tb_s; sh_n[warp] = tb_n; sh_f[warp] = tb_first;
+      sh_h[warp] = tb_n ? ch + tb.hard() : 0; sh_s[warp] = tb_n ? csf + tb.soft() : 0; sh_n[warp] = tb_n; sh_f[warp] = tb_first;
       sh_a[warp] = t_acc;
       sh_2[warp] = tb_second;
     }
