@@ -379,6 +379,66 @@ int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_siz
                                 const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best,
                                 uint32_t* out_evaluated, uint32_t* out_winner_rows, int32_t apply_winners);
 
+/* ---- union of neighbourhoods in seeded pull order (the reference's default list local search) -------------
+ * One step over a VecUnionSelector of list move families (heuristic/selector/decorator/vec_union.rs:204-366)
+ * exactly as the reference pulls it: every leaf walks its cursor in SelectionOrder `selection_order`
+ * (MoveStreamContext::selection_index, move_selector/iter.rs:109-125 — Random is with replacement, Shuffled a
+ * strided permutation), the children are interleaved by `union_order` (the default list policy,
+ * runtime/compiler/default_local_search/policy/list.rs:24-33, is Random leaves + StratifiedRandom), and the
+ * acceptor + forager replay stops where the reference stops. Only a prefix of the union stream is generated:
+ * each child emits its first `window` candidates, the step is complete when the forager quit inside that
+ * window (AcceptedCount) or every cursor ended; otherwise the window grows by x8 up to `max_window` per child.
+ * A step still incomplete at max_window picks the best of what it saw and sets bit 0 of out_flags[r]
+ * (BestScore over a multi-million sublist neighbourhood is not what this call is for — use the per-family
+ * whole-neighbourhood steps above).
+ *   families : canonical cursors restated per family — NearbyListChange / NearbyListSwap (p0 = max_nearby <= 32),
+ *              SublistChange / SublistSwap (p0 = min_size, p1 = max_size), ListReverse.
+ *   step_indices[R] (may be NULL = 0) and step_seeds[R] are the MoveStreamContext of each replica's step.
+ *   out_index = CandidateId of the union cursor (pull index, vec_union.rs:447-455) or UINT32_MAX;
+ *   out_winner_rows[R][8] = {family, child, row[4], child-local pull index, 0}.
+ * Pointer conventions as sfgpu_step_nearby_list_change (HOST arrays unless SFGPU_DEVICE_IO). Needs the fast
+ * list program when a nearby family is present. */
+#define SFGPU_FAM_NEARBY_LIST_CHANGE 0
+#define SFGPU_FAM_NEARBY_LIST_SWAP 1
+#define SFGPU_FAM_SUBLIST_CHANGE 2
+#define SFGPU_FAM_SUBLIST_SWAP 3
+#define SFGPU_FAM_LIST_REVERSE 4
+#define SFGPU_ORDER_ORIGINAL 0
+#define SFGPU_ORDER_RANDOM 1
+#define SFGPU_ORDER_SHUFFLED 2
+#define SFGPU_UNION_SEQUENTIAL 0
+#define SFGPU_UNION_ROUND_ROBIN 1
+#define SFGPU_UNION_ROTATING_ROUND_ROBIN 2
+#define SFGPU_UNION_RANDOM 3
+#define SFGPU_UNION_STRATIFIED_RANDOM 4
+#define SFGPU_UNION_MAX_CHILDREN 8
+typedef struct sfgpu_union_child {
+  int32_t family;
+  uint32_t p0, p1;
+  uint32_t reserved;
+  uint64_t weight; /* UnionWeighting::Equal = 1 */
+} sfgpu_union_child;
+typedef struct sfgpu_union_desc {
+  uint32_t n_children;
+  int32_t union_order;     /* SFGPU_UNION_* */
+  int32_t selection_order; /* SFGPU_ORDER_* of every leaf */
+  uint32_t window;         /* first window per child (0 = 64) */
+  uint32_t max_window;     /* largest window per child (0 = 4096) */
+  uint32_t reserved;
+  sfgpu_union_child children[SFGPU_UNION_MAX_CHILDREN];
+} sfgpu_union_desc;
+int32_t sfgpu_step_union(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_union_desc* desc,
+                         const sfgpu_forage_params* params, const uint64_t* step_seeds, const uint64_t* step_indices,
+                         const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated,
+                         uint32_t* out_winner_rows, uint32_t* out_flags, int32_t apply_winners);
+/* The device-resident loop (below) over this union step: step t of replica r uses step_index = t and
+ * step_seed = splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t); three window passes per step (window,
+ * x8, max_window). out_window_overflows (may be NULL) counts the steps per replica that hit max_window. */
+struct sfgpu_solve_params;
+int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const struct sfgpu_solve_params* params,
+                          int64_t* out_best_scores, uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps,
+                          uint64_t* out_window_overflows);
+
 /* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
  * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.

@@ -875,6 +875,129 @@ std::vector<Move> enumerate_sublist_change_moves(S& s, const Access<S>& ac, size
 
 
 // ---------------------------------------------------------------------------------------------
+// Union of selector families: heuristic/selector/decorator/vec_union.rs:190-366 (UnionScheduler). Children are
+// finite streams here (sizes[c] candidates each); the result is the union's pull order as (child, child-local
+// index) pairs — CandidateId of the union cursor = position in this list (vec_union.rs:447-455).
+enum class UnionOrder { Sequential, RoundRobin, RotatingRoundRobin, Random, StratifiedRandom };
+
+struct UnionScheduler {
+  size_t current_cursor = 0, live = 0, cursor_offset = 0, cursor_stride = 1, count = 0;
+  UnionOrder order;
+  std::vector<bool> exhausted;
+  MoveStreamContext ctx;
+  uint64_t random_draw = 0, total_live_weight = 0;
+  std::vector<uint64_t> weights;
+  std::vector<__int128> weighted_current;
+
+  UnionScheduler(size_t cursor_count, UnionOrder o, MoveStreamContext c, std::vector<uint64_t> w)
+      : count(cursor_count), order(o), ctx(c), weights(std::move(w)) {
+    if (weights.size() != count) throw std::logic_error("union weight count must match child count");
+    for (size_t i = 0; i < count; ++i) {
+      exhausted.push_back(weights[i] == 0);
+      if (weights[i] != 0) ++live;
+      total_live_weight += weights[i];
+    }
+    if (order == UnionOrder::RotatingRoundRobin || order == UnionOrder::StratifiedRandom)
+      cursor_offset = ctx.random_index(count, 0xA11CE5E1EC700001ull);
+    if (order == UnionOrder::StratifiedRandom) cursor_stride = ctx.random_stride(count, 0xA11CE5E1EC700002ull);
+    current_cursor = order == UnionOrder::StratifiedRandom ? 0 : cursor_offset;
+    weighted_current.assign(count, 0);
+  }
+
+  // next_child(c) -> true when child c yields another candidate
+  template <class F>
+  bool next(F next_child, size_t& out_child) {
+    switch (order) {
+      case UnionOrder::Sequential:
+        while (current_cursor < count) {
+          if (next_child(current_cursor)) {
+            out_child = current_cursor;
+            return true;
+          }
+          ++current_cursor;
+        }
+        return false;
+      case UnionOrder::RoundRobin:
+      case UnionOrder::RotatingRoundRobin:
+        while (live > 0) {
+          const size_t c = current_cursor % count;
+          current_cursor = (current_cursor + 1) % count;
+          if (exhausted[c]) continue;
+          if (next_child(c)) {
+            out_child = c;
+            return true;
+          }
+          exhausted[c] = true;
+          --live;
+        }
+        return false;
+      case UnionOrder::Random:
+        while (live > 0) {
+          const uint64_t draw = ctx.mixed_seed(0xA11CE5E1EC701000ull + random_draw) % total_live_weight;
+          ++random_draw;
+          uint64_t cumulative = 0;
+          size_t c = count;
+          for (size_t i = 0; i < count; ++i) {
+            if (exhausted[i]) continue;
+            cumulative += weights[i];
+            if (draw < cumulative) {
+              c = i;
+              break;
+            }
+          }
+          if (c == count) throw std::logic_error("random union live weights must select one child");
+          if (next_child(c)) {
+            out_child = c;
+            return true;
+          }
+          exhausted[c] = true;
+          --live;
+          total_live_weight -= weights[c];
+        }
+        return false;
+      case UnionOrder::StratifiedRandom:
+        while (live > 0) {
+          size_t sel = count;
+          __int128 sel_w = 0;
+          for (size_t position = 0; position < count; ++position) {
+            const size_t c = (cursor_offset + position * cursor_stride) % count;
+            if (exhausted[c]) continue;
+            weighted_current[c] += (__int128)weights[c];
+            if (sel == count || weighted_current[c] > sel_w) {
+              sel = c;
+              sel_w = weighted_current[c];
+            }
+          }
+          weighted_current[sel] -= (__int128)total_live_weight;
+          if (next_child(sel)) {
+            out_child = sel;
+            return true;
+          }
+          exhausted[sel] = true;
+          --live;
+          total_live_weight -= weights[sel];
+        }
+        return false;
+    }
+    return false;
+  }
+};
+
+inline std::vector<std::pair<size_t, size_t>> union_pull_order(const std::vector<size_t>& sizes, UnionOrder order,
+                                                               MoveStreamContext ctx, std::vector<uint64_t> weights,
+                                                               size_t limit = SIZE_MAX) {
+  UnionScheduler sched(sizes.size(), order, ctx, std::move(weights));
+  std::vector<size_t> at(sizes.size(), 0);
+  std::vector<std::pair<size_t, size_t>> out;
+  size_t c = 0;
+  while (out.size() < limit && sched.next([&](size_t k) { return at[k] < sizes[k]; }, c)) {
+    out.push_back({c, at[c]});
+    ++at[c];
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Foragers (forager.rs). CandidateId = pull index.
 inline bool reservoir_pick(uint64_t step_seed, uint64_t equal_count) {  // forager.rs:143-148
   uint64_t mixed = splitmix64(step_seed ^ (equal_count * 0x9E3779B97F4A7C15ull) ^ 0xF04A63E239B74D11ull);

@@ -5,6 +5,7 @@
 // Exit code 0 and a final "KAT OK n" line mean every vector matched.
 #include <cstdio>
 #include <cstdlib>
+#include <set>
 
 #include "models.hpp"
 
@@ -1318,6 +1319,53 @@ static void kat_acceptors() {
   }
 }
 
+// ---------------------------------------------------------------- union scheduler
+static void kat_union() {
+  // heuristic/selector/decorator/vec_union/tests.rs:204-297: children hold the listed values
+  auto drain = [](std::vector<std::vector<int>> kids, UnionOrder order, MoveStreamContext ctx) {
+    std::vector<size_t> sizes;
+    for (auto& k : kids) sizes.push_back(k.size());
+    std::vector<int> out;
+    for (auto& pr : union_pull_order(sizes, order, ctx, std::vector<uint64_t>(kids.size(), 1))) out.push_back(kids[pr.first][pr.second]);
+    return out;
+  };
+  CHECK((drain({{1, 2, 3}, {10, 11}}, UnionOrder::Sequential, MoveStreamContext{}) == std::vector<int>{1, 2, 3, 10, 11}));
+  CHECK((drain({{1, 2, 3}, {}, {10}, {20, 21}}, UnionOrder::RoundRobin, MoveStreamContext{}) ==
+         std::vector<int>{1, 10, 20, 2, 21, 3}));
+  {
+    MoveStreamContext ctx;
+    ctx.step_index = 0;
+    ctx.step_seed = 2;
+    const size_t offset = ctx.random_index(3, 0xA11CE5E1EC700001ull);  // start_offset of a seeded context
+    std::vector<std::vector<int>> expected = {{1, 10, 20, 2, 11, 21}, {10, 20, 1, 11, 21, 2}, {20, 1, 10, 21, 2, 11}};
+    ctx.order = SelectionOrder::Random;
+    CHECK(drain({{1, 2}, {10, 11}, {20, 21}}, UnionOrder::RotatingRoundRobin, ctx) == expected[offset]);
+  }
+  {
+    MoveStreamContext ctx;
+    ctx.step_index = 3;
+    ctx.step_seed = 42;
+    auto v = drain({{1, 2}, {10, 11}, {20, 21}}, UnionOrder::StratifiedRandom, ctx);
+    CHECK(v.size() == 6);
+    // smooth weighted round-robin with equal weights: every child once per round, in one strided order
+    CHECK((std::set<int>{v[0], v[1], v[2]} == std::set<int>{1, 10, 20}));
+    CHECK((std::set<int>{v[3], v[4], v[5]} == std::set<int>{2, 11, 21}));
+    CHECK(v[3] / 10 == v[0] / 10 && v[4] / 10 == v[1] / 10 && v[5] / 10 == v[2] / 10);
+  }
+  {  // uneven children: an exhausted child drops out, the others keep their relative order
+    MoveStreamContext ctx;
+    ctx.step_seed = 7;
+    auto v = drain({{1}, {10, 11, 12}, {20, 21}}, UnionOrder::StratifiedRandom, ctx);
+    CHECK(v.size() == 6);
+    std::vector<int> c1;
+    for (int x : v)
+      if (x >= 10 && x < 20) c1.push_back(x);
+    CHECK((c1 == std::vector<int>{10, 11, 12}));
+    auto w = drain({{1}, {10, 11, 12}, {20, 21}}, UnionOrder::Random, ctx);
+    CHECK(w.size() == 6);
+  }
+}
+
 int main() {
   kat_scores();
   kat_director();
@@ -1332,6 +1380,7 @@ int main() {
   kat_nearby_sort();
   kat_moves_and_loop();
   kat_acceptors();
+  kat_union();
   if (g_fail) {
     std::printf("KAT FAILED %d of %d\n", g_fail, g_checks);
     return 1;

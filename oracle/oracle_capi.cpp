@@ -241,6 +241,27 @@ static MoveStreamContext make_ctx(uint64_t step_index, uint64_t step_seed, int o
   return c;
 }
 
+// union pull order (vec_union.rs UnionScheduler) over children of the given sizes: writes (child, child-local
+// index) pairs; returns the number of pulls (<= cap). union_order: 0 Sequential, 1 RoundRobin,
+// 2 RotatingRoundRobin, 3 Random, 4 StratifiedRandom.
+int64_t sfo_union_pull_order(uint32_t n_children, const uint64_t* sizes, const uint64_t* weights, int union_order,
+                             uint64_t step_index, uint64_t step_seed, int order, uint64_t cap, uint32_t* out_child,
+                             uint64_t* out_local) {
+  std::vector<size_t> sz(sizes, sizes + n_children);
+  std::vector<uint64_t> w(weights, weights + n_children);
+  const UnionOrder uo = union_order == 1   ? UnionOrder::RoundRobin
+                        : union_order == 2 ? UnionOrder::RotatingRoundRobin
+                        : union_order == 3 ? UnionOrder::Random
+                        : union_order == 4 ? UnionOrder::StratifiedRandom
+                                           : UnionOrder::Sequential;
+  auto pulls = union_pull_order(sz, uo, make_ctx(step_index, step_seed, order), w, (size_t)cap);
+  for (size_t i = 0; i < pulls.size(); ++i) {
+    out_child[i] = (uint32_t)pulls[i].first;
+    out_local[i] = (uint64_t)pulls[i].second;
+  }
+  return (int64_t)pulls.size();
+}
+
 // Returns the number of candidates (may exceed cap; only the first cap are written).
 int64_t sfo_enumerate_change(void* h, uint64_t step_index, uint64_t step_seed, int order, uint64_t cap, uint32_t* e,
                              int32_t* v) {

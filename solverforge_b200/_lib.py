@@ -51,6 +51,22 @@ class SolveParams(C.Structure):
                 ("acceptor_real", C.c_double), ("step_count_limit", C.c_uint64)]
 
 
+class UnionChild(C.Structure):
+    _fields_ = [("family", C.c_int32), ("p0", C.c_uint32), ("p1", C.c_uint32), ("reserved", C.c_uint32),
+                ("weight", C.c_uint64)]
+
+
+class UnionDesc(C.Structure):
+    _fields_ = [("n_children", C.c_uint32), ("union_order", C.c_int32), ("selection_order", C.c_int32),
+                ("window", C.c_uint32), ("max_window", C.c_uint32), ("reserved", C.c_uint32),
+                ("children", UnionChild * 8)]
+
+
+FAM_NEARBY_LIST_CHANGE, FAM_NEARBY_LIST_SWAP, FAM_SUBLIST_CHANGE, FAM_SUBLIST_SWAP, FAM_LIST_REVERSE = 0, 1, 2, 3, 4
+ORDER_ORIGINAL, ORDER_RANDOM, ORDER_SHUFFLED = 0, 1, 2
+UNION_SEQUENTIAL, UNION_ROUND_ROBIN, UNION_ROTATING_ROUND_ROBIN, UNION_RANDOM, UNION_STRATIFIED_RANDOM = 0, 1, 2, 3, 4
+
+
 class ForageParams(C.Structure):
     _fields_ = [("acceptor", C.c_int32), ("tie_mode", C.c_int32), ("accepted_limit", C.c_uint32),
                 ("reserved", C.c_uint32)]
@@ -102,6 +118,9 @@ SYMBOLS = {
     "sfgpu_step_list_reverse": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, C.c_int32]),
     "sfgpu_step_sublist_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ForageParams), _P, _P,
                                             _P, _P, _P, _P, C.c_int32]),
+    "sfgpu_step_union": (C.c_int32, [_P, C.c_uint32, C.POINTER(UnionDesc), C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P,
+                                     _P, _P, C.c_int32]),
+    "sfgpu_solve_union": (C.c_int32, [_P, C.POINTER(UnionDesc), C.POINTER(SolveParams), _P, _P, _P, _P]),
     "sfgpu_solve_nearby_list_change": (C.c_int32, [_P, C.POINTER(SolveParams), _P, _P, _P]),
     "sfgpu_solve_change": (C.c_int32, [_P, C.POINTER(SolveParams), _P, _P, _P]),
     "sfgpu_apply_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),

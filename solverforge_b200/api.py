@@ -455,6 +455,67 @@ class GpuScoreDirector:
         rows[idx == 0xFFFFFFFF] = -1
         return idx, best, ev, rows
 
+    @staticmethod
+    def union_desc(children, union_order: int = L.UNION_STRATIFIED_RANDOM, selection_order: int = L.ORDER_RANDOM,
+                   window: int = 0, max_window: int = 0) -> "L.UnionDesc":
+        """children: [(family, p0, p1[, weight])] — see sfgpu_union_desc. The reference's default list policy is
+        `default_list_union()`."""
+        d = L.UnionDesc()
+        d.n_children = len(children)
+        d.union_order = union_order
+        d.selection_order = selection_order
+        d.window = window
+        d.max_window = max_window
+        for i, ch in enumerate(children):
+            d.children[i].family = ch[0]
+            d.children[i].p0 = ch[1] if len(ch) > 1 else 0
+            d.children[i].p1 = ch[2] if len(ch) > 2 else 0
+            d.children[i].weight = ch[3] if len(ch) > 3 else 1
+        return d
+
+    @staticmethod
+    def default_list_union(max_nearby: int = 20, window: int = 0, max_window: int = 0) -> "L.UnionDesc":
+        """The device-enumerable rows of the reference's default list policy table
+        (runtime/compiler/default_local_search/policy/list.rs:24-33): NearbyChange, NearbySwap, SublistChange,
+        SublistSwap, Reverse; seeded Random leaves interleaved by StratifiedRandom."""
+        return GpuScoreDirector.union_desc(
+            [(L.FAM_NEARBY_LIST_CHANGE, max_nearby), (L.FAM_NEARBY_LIST_SWAP, max_nearby), (L.FAM_SUBLIST_CHANGE, 1, 3),
+             (L.FAM_SUBLIST_SWAP, 1, 3), (L.FAM_LIST_REVERSE,)], L.UNION_STRATIFIED_RANDOM, L.ORDER_RANDOM, window,
+            max_window)
+
+    def step_union(self, desc: "L.UnionDesc", params: "ForageParams" = None, step_seeds=None, step_indices=None,
+                   ref_scores=None, apply: bool = False):
+        """One step over a union of list neighbourhoods in the reference's seeded pull order (sfgpu_step_union).
+        Returns (index[R], best[R,2], moves_evaluated[R], winner_rows[R,8], flags[R]); winner row =
+        {family, child, packed row[4], child-local pull index, 0}."""
+        params = params or ForageParams()
+        fp = L.ForageParams(params.acceptor, params.tie_mode, params.accepted_limit, 0)
+        seeds = None if step_seeds is None else np.ascontiguousarray(step_seeds, dtype=np.uint64)
+        steps = None if step_indices is None else np.ascontiguousarray(step_indices, dtype=np.uint64)
+        ref = None if ref_scores is None else np.ascontiguousarray(ref_scores, dtype=np.int64).reshape(self.R, 4)
+        idx = np.zeros(self.R, dtype=np.uint32)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint32)
+        win = np.zeros((self.R, 8), dtype=np.uint32)
+        flags = np.zeros(self.R, dtype=np.uint32)
+        self._check(self.lib.sfgpu_step_union(self.h, 0, C.byref(desc), C.byref(fp), _ptr(seeds), _ptr(steps), _ptr(ref),
+                                              _ptr(idx), _ptr(best), _ptr(ev), _ptr(win), _ptr(flags), 1 if apply else 0))
+        return idx, best, ev, win, flags
+
+    def solve_union(self, desc: "L.UnionDesc", n_steps: int, acceptor: int = 2, late_size: int = 400, tie_mode: int = 1,
+                    accepted_limit: int = 256, seed_base: int = 0, restore_best: bool = False,
+                    acceptor_real: float = 0.0, step_count_limit: int = 0):
+        """Device-resident loop over the union step (sfgpu_solve_union): returns (best_scores[R,2],
+        moves_evaluated[R], committed_steps[R], window_overflows[R])."""
+        p = L.SolveParams(0, n_steps, acceptor, late_size, tie_mode, accepted_limit, seed_base,
+                          1 if restore_best else 0, 0, acceptor_real, step_count_limit)
+        best = np.zeros((self.R, 2), dtype=np.int64)
+        ev = np.zeros(self.R, dtype=np.uint64)
+        acc = np.zeros(self.R, dtype=np.uint64)
+        ovf = np.zeros(self.R, dtype=np.uint64)
+        self._check(self.lib.sfgpu_solve_union(self.h, C.byref(desc), C.byref(p), _ptr(best), _ptr(ev), _ptr(acc), _ptr(ovf)))
+        return best, ev, acc, ovf
+
     def solve_nearby_list_change(self, n_steps: int, max_nearby: int = 20, acceptor: int = 2, late_size: int = 400,
                                  tie_mode: int = 1, accepted_limit: int = 0, seed_base: int = 0,
                                  restore_best: bool = False, acceptor_real: float = 0.0,

@@ -53,6 +53,7 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) try {
   if (ctx->dscr) cudaFree(ctx->dscr);
   if (ctx->partials) cudaFree(ctx->partials);
   if (ctx->solve_buf) cudaFree(ctx->solve_buf);
+  if (ctx->union_buf) cudaFree(ctx->union_buf);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->sync_dev) cudaFree(ctx->sync_dev);
@@ -1269,6 +1270,23 @@ int sfgpu_launch_apply_list(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, co
                             const uint64_t* d_offsets, const uint32_t* d_index) {
   const DevModel& dm = ctx->dm;
   apply_list_kernel<<<dm.R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+int sfgpu_launch_apply_list_kinds(sfgpu_ctx* ctx, const uint32_t* d_rows, const int32_t* d_kinds) {
+  const DevModel& dm = ctx->dm;
+  apply_list_kernel<<<dm.R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+int sfgpu_launch_argbest_counts(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, const uint32_t* d_counts,
+                                const uint32_t* d_skip, const int64_t* d_scores, const uint8_t* d_doable,
+                                const uint64_t* d_seeds, const int64_t* d_ref, uint32_t* d_idx, int64_t* d_best,
+                                uint32_t* d_eval) {
+  argbest_kernel<<<ctx->dm.R, 1024, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_seeds, d_ref, d_idx, d_best, d_eval,
+                                                      d_counts, d_skip);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;

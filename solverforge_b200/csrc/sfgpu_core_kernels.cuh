@@ -579,11 +579,16 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
                                                          const uint32_t* __restrict__ rows,
                                                          const uint8_t* __restrict__ mask,
                                                          const uint64_t* __restrict__ cand_offsets,
-                                                         const uint32_t* __restrict__ index) {
+                                                         const uint32_t* __restrict__ index,
+                                                         const int32_t* __restrict__ kinds = nullptr) {
   extern __shared__ __align__(16) uint32_t old_el[];
   __shared__ int s_ok;
   const uint32_t r = blockIdx.x;
   if (mask && !mask[r]) return;
+  if (kinds) {  // one move kind per replica (union of neighbourhoods); < 0 = no winner
+    kind = kinds[r];
+    if (kind < 0) return;
+  }
   uint64_t ri = r;
   if (index) {
     if (index[r] == 0xFFFFFFFFu) return;
@@ -755,13 +760,17 @@ __global__ void __launch_bounds__(1024) argbest_kernel(ForageDev f, const uint64
                                                        const int64_t* __restrict__ ref_scores,
                                                        uint32_t* __restrict__ out_index,
                                                        int64_t* __restrict__ out_best,
-                                                       uint32_t* __restrict__ out_evaluated) {
+                                                       uint32_t* __restrict__ out_evaluated,
+                                                       const uint32_t* __restrict__ counts = nullptr,
+                                                       const uint32_t* __restrict__ skip = nullptr) {
   __shared__ uint32_t scratch[33];
   __shared__ int64_t s_h[32], s_s[32];
   __shared__ uint64_t s_end;
   __shared__ uint32_t s_pick;
   const uint32_t r = blockIdx.x;
-  const uint64_t lo = cand_offsets[r], hi0 = cand_offsets[r + 1];
+  if (skip && skip[r]) return;
+  // counts: replica r owns rows [cand_offsets[r], cand_offsets[r] + counts[r]) of a fixed-stride batch
+  const uint64_t lo = cand_offsets[r], hi0 = counts ? lo + counts[r] : cand_offsets[r + 1];
   const int64_t lh = ref_scores ? ref_scores[r * 4 + 0] : 0, ls = ref_scores ? ref_scores[r * 4 + 1] : 0;
   const int64_t th = ref_scores ? ref_scores[r * 4 + 2] : 0, ts = ref_scores ? ref_scores[r * 4 + 3] : 0;
   const uint64_t seed = step_seeds ? step_seeds[r] : 0;

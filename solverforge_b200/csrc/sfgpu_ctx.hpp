@@ -55,6 +55,16 @@ struct ConsHost {
 
 }  // namespace sfgpu_host
 
+// buffers and arguments of the union step (sfgpu_union.cu), sized for the largest window
+struct UnionPlan {
+  UnionArgs a{};
+  uint32_t* pending = nullptr;     // [1] replicas that need a larger window
+  uint32_t* apply_rows = nullptr;  // [R][4] winner rows
+  int32_t* apply_kinds = nullptr;  // [R] apply_list_kernel kind of each winner, -1 = none
+  uint32_t w0 = 64, wmax = 4096;
+  bool configured = false;
+};
+
 struct sfgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -91,6 +101,9 @@ struct sfgpu_ctx {
   size_t dscr_bytes = 0;
   void* partials = nullptr;  // fused forager chunk partials
   void* solve_buf = nullptr;  // device-resident loop state
+  void* union_buf = nullptr;  // union step buffers
+  size_t union_bytes = 0;
+  UnionPlan union_plan;
   std::vector<uint32_t> relabel_host, inverse_host;  // element id <-> internal id of the fast records
   size_t solve_bytes = 0;
   void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
@@ -302,6 +315,18 @@ int sfgpu_launch_apply_list(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, co
                             const uint64_t* d_offsets, const uint32_t* d_index);
 int sfgpu_launch_apply_scalar(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, const uint8_t* d_mask,
                               const uint64_t* d_offsets, const uint32_t* d_index);
+struct ForageDev;
+int sfgpu_launch_apply_list_kinds(sfgpu_ctx* ctx, const uint32_t* d_rows, const int32_t* d_kinds);
+int sfgpu_launch_argbest_counts(sfgpu_ctx* ctx, const ForageDev& f, const uint64_t* d_offs, const uint32_t* d_counts,
+                                const uint32_t* d_skip, const int64_t* d_scores, const uint8_t* d_doable,
+                                const uint64_t* d_seeds, const int64_t* d_ref, uint32_t* d_idx, int64_t* d_best,
+                                uint32_t* d_eval);
+// sfgpu_union.cu
+inline size_t rank_tables_words_host(uint32_t n_owners) { return 5 * (size_t)n_owners + 2; }
+int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgpu_forage_params* params, UnionPlan& plan);
+int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan);
+int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bool last_pass, uint32_t* d_idx, int64_t* d_best,
+                            uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc);
 // sfgpu_scalar.cu
 int sfgpu_configure_scalar(sfgpu_ctx* ctx);
 void sfgpu_change_step_chunks(const sfgpu_ctx* ctx, uint32_t* out_per, uint32_t* out_chunks);

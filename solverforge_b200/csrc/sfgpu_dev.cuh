@@ -156,6 +156,43 @@ struct IndexStepArgs {
   ChunkPartial* partials;        // [R][gridDim.x]
 };
 
+// ---- union of neighbourhoods (sfgpu_union.cuh) ----
+#define UNION_MAX_CHILDREN 8
+#define UNION_NONE 0xFFFFFFFFu
+
+struct UnionChildDev {
+  int32_t family;   // SFGPU_FAM_*
+  uint32_t p0, p1;  // max_nearby | min_size, max_size
+  uint32_t pad;
+  uint64_t weight;
+};
+
+struct UnionArgs {
+  ForageDev f;
+  uint32_t n_children;
+  int32_t union_order;      // SFGPU_UNION_*
+  int32_t order;            // SFGPU_ORDER_* of every leaf (VecUnionSelector::child_context)
+  uint32_t desc;            // descriptor index of the list owner collection (salts)
+  uint32_t window;          // rows a child may emit in this pass
+  uint32_t t_cap;           // union pulls per replica in this pass (n_children * window)
+  uint32_t scan_bits;       // low key bits holding the scan index (nearby families)
+  UnionChildDev child[UNION_MAX_CHILDREN];
+  const uint64_t* step_seeds;    // [R]
+  const uint64_t* step_indices;  // [R] or null (0), or step_counter (one value for all replicas) with step_index_shared
+  int32_t step_index_shared;
+  const int64_t* ref_scores;     // [R][4] or null
+  uint32_t* rows;                // [R][n_children][window][4]
+  uint32_t* n_emit;              // [R][n_children]
+  uint32_t* ended;               // [R][n_children] 1 = the child's cursor ended inside the window
+  uint32_t* sched;               // [R][t_cap] child << 28 | child-local index
+  uint32_t* n_sched;             // [R]
+  uint32_t* stream_end;          // [R] 1 = the union stream ended inside the window
+  int64_t* scores;               // [R][t_cap][2]
+  uint8_t* doable;               // [R][t_cap]
+  uint64_t* offsets;             // [R + 1] = r * t_cap
+  uint32_t* done;                // [R] step already complete (earlier pass): skip
+};
+
 __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
   switch (w.fn) {
     case SFGPU_W_CONST: return w.a;

@@ -6,7 +6,8 @@ using namespace sfgpu_host;
 
 namespace {
 int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t* out_best_scores,
-               uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) {
+               uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps, const sfgpu_union_desc* udesc = nullptr,
+               uint64_t* out_window_overflows = nullptr) {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
@@ -15,7 +16,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
     if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)
       return fail(ctx, SFGPU_E_UNSUPPORTED, "neighbourhood too large for 32-bit pull indices");
-  } else {
+  } else if (!udesc) {
     if (!dm.nearby_ok || ctx->force_generic)
       return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
     if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
@@ -38,6 +39,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   const size_t o_eval = take((size_t)R * 8), o_acc = take((size_t)R * 8), o_idx = take((size_t)R * 4);
   const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
   const size_t o_accst = take((size_t)R * 32);
+  const size_t o_ovf = take((size_t)R * 8);
   const size_t o_snap = take((size_t)R * dm.block_bytes);
   if (o > ctx->solve_bytes) {
     if (ctx->solve_buf) cudaFree(ctx->solve_buf);
@@ -68,6 +70,18 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   s.real = p->acceptor_real;
   s.step_count_limit = p->step_count_limit;
   const int forage_code = solve_forage_code(p->acceptor);
+  uint64_t* d_overflows = (uint64_t*)(b + o_ovf);
+  CU(cudaMemsetAsync(d_overflows, 0, (size_t)R * 8, ctx->stream));
+  UnionPlan& plan = ctx->union_plan;
+  if (udesc) {
+    sfgpu_forage_params fp{forage_code, p->tie_mode, p->accepted_limit, 0};
+    rc = sfgpu_union_prepare(ctx, udesc, &fp, plan);
+    if (rc) return rc;
+    plan.a.step_seeds = s.step_seeds;
+    plan.a.step_indices = s.step_counter;
+    plan.a.step_index_shared = 1;
+    plan.a.ref_scores = s.ref_scores;
+  }
   NearbyArgs a{};
   ChangeStepArgs ca{};
   uint32_t c_chunks = 0;
@@ -81,7 +95,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     ca.step_seeds = s.step_seeds;
     ca.ref_scores = s.ref_scores;
     ca.partials = (ChunkPartial*)ctx->partials;
-  } else {
+  } else if (!udesc) {
     rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
     if (rc) return rc;
     a.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
@@ -100,6 +114,20 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       rc2 = sfgpu_launch_change_step(ctx, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
       if (rc2) return rc2;
       rc2 = sfgpu_launch_apply_scalar(ctx, 0, s.winner_rows, nullptr, nullptr, nullptr);
+    } else if (udesc) {
+      // three window passes (window, x8, max_window); complete replicas skip the later ones
+      rc2 = sfgpu_union_begin_step(ctx, plan);
+      if (rc2) return rc2;
+      const uint32_t w1 = (uint32_t)std::min<uint64_t>((uint64_t)plan.w0 * 8, plan.wmax);
+      const uint32_t ws[3] = {plan.w0, w1, plan.wmax};
+      for (int k = 0; k < 3; ++k) {
+        const bool last = k == 2 || ws[k] >= plan.wmax;
+        rc2 = sfgpu_union_launch_pass(ctx, plan, ws[k], last, s.out_index, s.out_best, s.out_evaluated, nullptr, nullptr,
+                                      d_overflows);
+        if (rc2) return rc2;
+        if (last) break;
+      }
+      rc2 = sfgpu_launch_apply_list_kinds(ctx, plan.apply_rows, plan.apply_kinds);
     } else {
       rc2 = sfgpu_launch_nearby(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows, MOVE_CHANGE);
       if (rc2) return rc2;
@@ -145,6 +173,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   if (out_best_scores) CU(cudaMemcpy(out_best_scores, s.best_scores, (size_t)R * 16, cudaMemcpyDeviceToHost));
   if (out_moves_evaluated) CU(cudaMemcpy(out_moves_evaluated, s.evaluated, (size_t)R * 8, cudaMemcpyDeviceToHost));
   if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
+  if (out_window_overflows) CU(cudaMemcpy(out_window_overflows, d_overflows, (size_t)R * 8, cudaMemcpyDeviceToHost));
   return SFGPU_OK;
 }
 
@@ -160,6 +189,12 @@ int32_t sfgpu_solve_nearby_list_change(sfgpu_ctx* ctx, const sfgpu_solve_params*
 int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t* out_best_scores,
                            uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps) try {
   return solve_impl(ctx, p, true, out_best_scores, out_moves_evaluated, out_accepted_steps);
+} SFGPU_API_CATCH(ctx)
+
+int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgpu_solve_params* p, int64_t* out_best_scores,
+                          uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps, uint64_t* out_window_overflows) try {
+  if (!desc) return fail(ctx, SFGPU_E_INVALID, "null union description");
+  return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps, desc, out_window_overflows);
 } SFGPU_API_CATCH(ctx)
 
 }  // extern "C"

@@ -1,0 +1,234 @@
+// Union of list neighbourhoods in seeded pull order (sfgpu_union.cuh): host side of sfgpu_step_union and the
+// per-step launcher the device-resident loop (sfgpu_solve.cu) captures.
+#include "sfgpu_ctx.hpp"
+#include "sfgpu_union.cuh"
+
+using namespace sfgpu_host;
+
+namespace {
+bool is_nearby(int family) { return family == SFGPU_FAM_NEARBY_LIST_CHANGE || family == SFGPU_FAM_NEARBY_LIST_SWAP; }
+}  // namespace
+
+int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgpu_forage_params* params, UnionPlan& plan) {
+  const DevModel& dm = ctx->dm;
+  if (!desc || !params) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
+  if (desc->n_children == 0 || desc->n_children > SFGPU_UNION_MAX_CHILDREN)
+    return fail(ctx, SFGPU_E_INVALID, "union needs 1..8 children");
+  if (desc->union_order < 0 || desc->union_order > SFGPU_UNION_STRATIFIED_RANDOM)
+    return fail(ctx, SFGPU_E_INVALID, "bad union_order");
+  if (desc->selection_order < 0 || desc->selection_order > SFGPU_ORDER_SHUFFLED)
+    return fail(ctx, SFGPU_E_INVALID, "bad selection_order");
+  if (params->acceptor < 0 || params->acceptor > 3 || params->tie_mode < 0 || params->tie_mode > 1)
+    return fail(ctx, SFGPU_E_INVALID, "bad forage params");
+  bool any_nearby = false;
+  for (uint32_t c = 0; c < desc->n_children; ++c) {
+    const sfgpu_union_child& ch = desc->children[c];
+    if (ch.family < 0 || ch.family > SFGPU_FAM_LIST_REVERSE) return fail(ctx, SFGPU_E_INVALID, "unknown move family");
+    if (is_nearby(ch.family)) {
+      any_nearby = true;
+      if (ch.p0 == 0 || ch.p0 > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+    } else if (ch.family != SFGPU_FAM_LIST_REVERSE) {
+      if (ch.p0 == 0 || ch.p1 < ch.p0 || ch.p1 > 255) return fail(ctx, SFGPU_E_INVALID, "sublist sizes: 1 <= min <= max <= 255");
+    }
+    if (desc->union_order != SFGPU_UNION_RANDOM && desc->union_order != SFGPU_UNION_STRATIFIED_RANDOM && ch.weight != 1)
+      return fail(ctx, SFGPU_E_INVALID, "union weights require random or stratified_random selection order");
+    if (ch.weight > (1ull << 40)) return fail(ctx, SFGPU_E_INVALID, "union weight too large");
+  }
+  if (any_nearby && (!dm.nearby_ok || ctx->force_generic || dm.fast_pc < 0))
+    return fail(ctx, SFGPU_E_UNSUPPORTED,
+                "nearby families need the fast list program (int32 path-cost matrix as the distance meter, every cell finite)");
+  if (any_nearby && rank_tables_words_host(dm.n_owners) * 4 + 8192 > (size_t)ctx->max_smem_optin)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "too many list owners for the shared-memory rank tables");
+  const uint32_t w0 = desc->window ? desc->window : 64;
+  const uint32_t wmax = std::max(w0, desc->max_window ? desc->max_window : 4096u);
+  if (wmax >= (1u << 28)) return fail(ctx, SFGPU_E_INVALID, "max_window must be below 2^28");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t R = dm.R, C = desc->n_children;
+  const size_t T = (size_t)C * wmax;
+  auto a256 = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = a256(o + bytes); return at; };
+  const size_t o_rows = take((size_t)R * T * 16), o_sched = take((size_t)R * T * 4), o_scores = take((size_t)R * T * 16);
+  const size_t o_doable = take((size_t)R * T), o_emit = take((size_t)R * C * 4), o_ended = take((size_t)R * C * 4);
+  const size_t o_nsched = take((size_t)R * 4), o_send = take((size_t)R * 4), o_offs = take((size_t)(R + 1) * 8);
+  const size_t o_done = take((size_t)R * 4), o_pend = take(16), o_arows = take((size_t)R * 16), o_akind = take((size_t)R * 4);
+  if (o > ctx->union_bytes) {
+    if (ctx->union_buf) cudaFree(ctx->union_buf);
+    ctx->union_buf = nullptr;
+    ctx->union_bytes = 0;
+    CU(cudaMalloc(&ctx->union_buf, o));
+    ctx->union_bytes = o;
+  }
+  char* b = (char*)ctx->union_buf;
+  UnionArgs& a = plan.a;
+  a = UnionArgs{};
+  a.f = ForageDev{params->acceptor, params->tie_mode, params->accepted_limit, nullptr};
+  a.n_children = C;
+  a.union_order = desc->union_order;
+  a.order = desc->selection_order;
+  a.desc = (uint32_t)std::max(0, ctx->colls[ctx->lvars[0].owner_coll].descriptor);
+  a.scan_bits = 32;
+  for (uint32_t c = 0; c < C; ++c) a.child[c] = UnionChildDev{desc->children[c].family, desc->children[c].p0, desc->children[c].p1, 0, desc->children[c].weight};
+  a.rows = (uint32_t*)(b + o_rows);
+  a.sched = (uint32_t*)(b + o_sched);
+  a.scores = (int64_t*)(b + o_scores);
+  a.doable = (uint8_t*)(b + o_doable);
+  a.n_emit = (uint32_t*)(b + o_emit);
+  a.ended = (uint32_t*)(b + o_ended);
+  a.n_sched = (uint32_t*)(b + o_nsched);
+  a.stream_end = (uint32_t*)(b + o_send);
+  a.offsets = (uint64_t*)(b + o_offs);
+  a.done = (uint32_t*)(b + o_done);
+  plan.pending = (uint32_t*)(b + o_pend);
+  plan.apply_rows = (uint32_t*)(b + o_arows);
+  plan.apply_kinds = (int32_t*)(b + o_akind);
+  plan.w0 = w0;
+  plan.wmax = wmax;
+  if (!plan.configured) {
+    const int tb = (int)(rank_tables_words_host(dm.n_owners) * 4);
+#define UW_ATTR(CELL, MOVE) \
+  CU(cudaFuncSetAttribute(union_walk_nearby_kernel<uint64_t, CELL, MOVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb))
+    UW_ATTR(uint16_t, MOVE_CHANGE);
+    UW_ATTR(uint16_t, MOVE_SWAP);
+    UW_ATTR(int32_t, MOVE_CHANGE);
+    UW_ATTR(int32_t, MOVE_SWAP);
+    if (ctx->staged) CU(cudaFuncSetAttribute(union_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+    plan.configured = true;
+  }
+  return SFGPU_OK;
+}
+
+int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan) {
+  const uint32_t R = ctx->dm.R;
+  union_reset_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>(plan.a.done, plan.pending, R);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
+// one window pass: walk every child, schedule, score, replay, pick
+int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bool last_pass, uint32_t* d_idx, int64_t* d_best,
+                            uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc) {
+  const DevModel& dm = ctx->dm;
+  const uint32_t R = dm.R;
+  UnionArgs a = plan.a;
+  a.window = window;
+  a.t_cap = a.n_children * window;
+  for (uint32_t c = 0; c < a.n_children; ++c) {
+    const int fam = a.child[c].family;
+    if (is_nearby(fam)) {
+      const size_t tb = rank_tables_words_host(dm.n_owners) * 4;
+      if (fam == SFGPU_FAM_NEARBY_LIST_CHANGE) {
+        if (dm.fm_u16) union_walk_nearby_kernel<uint64_t, uint16_t, MOVE_CHANGE><<<R, 256, tb, ctx->stream>>>(dm, a, c);
+        else union_walk_nearby_kernel<uint64_t, int32_t, MOVE_CHANGE><<<R, 256, tb, ctx->stream>>>(dm, a, c);
+      } else {
+        if (dm.fm_u16) union_walk_nearby_kernel<uint64_t, uint16_t, MOVE_SWAP><<<R, 256, tb, ctx->stream>>>(dm, a, c);
+        else union_walk_nearby_kernel<uint64_t, int32_t, MOVE_SWAP><<<R, 256, tb, ctx->stream>>>(dm, a, c);
+      }
+    } else {
+      union_walk_index_kernel<<<R, 32, 0, ctx->stream>>>(dm, a, c);
+    }
+  }
+  union_schedule_kernel<<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R);
+  const uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((a.t_cap + 255) / 256, 64));
+  if (ctx->staged) union_score_kernel<true><<<dim3(chunks, R), 256, dm.stage_bytes, ctx->stream>>>(dm, a);
+  else union_score_kernel<false><<<dim3(chunks, R), 256, 0, ctx->stream>>>(dm, a);
+  ctx->launches += a.n_children + 2;
+  CU(cudaGetLastError());
+  int rc = sfgpu_launch_argbest_counts(ctx, a.f, a.offsets, a.n_sched, a.done, a.scores, a.doable, a.step_seeds, a.ref_scores,
+                                       d_idx, d_best, d_eval);
+  if (rc) return rc;
+  union_pick_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(a, R, last_pass ? 1u : 0u, d_idx, d_eval, d_win8, plan.apply_rows,
+                                                              plan.apply_kinds, d_flags, plan.pending, d_overflow_acc);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
+extern "C" {
+
+int32_t sfgpu_step_union(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_union_desc* desc, const sfgpu_forage_params* params,
+                         const uint64_t* step_seeds, const uint64_t* step_indices, const int64_t* ref_scores,
+                         uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated, uint32_t* out_winner_rows,
+                         uint32_t* out_flags, int32_t apply_winners) try {
+  int rc = check_committed(ctx);
+  if (rc) return rc;
+  if (!out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
+  if (params && params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
+  UnionPlan& plan = ctx->union_plan;
+  rc = sfgpu_union_prepare(ctx, desc, params, plan);
+  if (rc) return rc;
+  const uint32_t R = ctx->dm.R;
+  const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
+  SmallIo io;
+  rc = small_io_begin(ctx, io, dev_io, 32, step_seeds, ref_scores, out_index, out_best, out_evaluated, out_winner_rows);
+  if (rc) return rc;
+  // step indices and flags ride in a second small staging area
+  uint64_t* d_steps = nullptr;
+  uint32_t* d_flags = nullptr;
+  if (dev_io) {
+    d_steps = const_cast<uint64_t*>(step_indices);
+    d_flags = out_flags;
+    if (!io.d_eval) return fail(ctx, SFGPU_E_INVALID, "the device path needs out_evaluated");
+  } else {
+    rc = ensure_staging(ctx, (size_t)R * 16, (size_t)R * 16);
+    if (rc) return rc;
+    if (step_indices) {
+      memcpy(ctx->pin, step_indices, (size_t)R * 8);
+      CU(cudaMemcpyAsync(ctx->dscr, ctx->pin, (size_t)R * 8, cudaMemcpyHostToDevice, ctx->stream));
+      d_steps = (uint64_t*)ctx->dscr;
+    }
+    d_flags = (uint32_t*)((char*)ctx->dscr + (size_t)R * 8);
+  }
+  plan.a.step_seeds = io.d_seeds;
+  plan.a.step_indices = d_steps;
+  plan.a.step_index_shared = 0;
+  plan.a.ref_scores = io.d_ref;
+  rc = sfgpu_union_begin_step(ctx, plan);
+  if (rc) return rc;
+  ev_begin(ctx);
+  for (uint32_t window = plan.w0;;) {
+    const bool last = window >= plan.wmax;
+    rc = sfgpu_union_launch_pass(ctx, plan, window, last, io.d_idx, io.d_best, io.d_eval, io.d_win, d_flags, nullptr);
+    if (rc) return rc;
+    if (last) break;
+    uint32_t pending = 0;
+    CU(cudaMemcpyAsync(&pending, plan.pending, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (pending == 0) break;
+    CU(cudaMemsetAsync(plan.pending, 0, 4, ctx->stream));
+    window = (uint32_t)std::min<uint64_t>((uint64_t)window * 8, plan.wmax);
+  }
+  ev_end(ctx);
+  if (apply_winners) {
+    rc = sfgpu_launch_apply_list_kinds(ctx, plan.apply_rows, plan.apply_kinds);
+    if (rc) return rc;
+  }
+  if (!dev_io && out_flags) {
+    CU(cudaMemcpyAsync((char*)ctx->pin + (size_t)R * 8, d_flags, (size_t)R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = small_io_end(ctx, io, out_index, out_best, out_evaluated, out_winner_rows);
+    if (rc) return rc;
+    memcpy(out_flags, (char*)ctx->pin + (size_t)R * 8, (size_t)R * 4);
+    return SFGPU_OK;
+  }
+  return small_io_end(ctx, io, out_index, out_best, out_evaluated, out_winner_rows);
+} SFGPU_API_CATCH(ctx)
+
+}  // extern "C"
+
+// test hook (not part of the ABI): the rows child `child` of replica `replica` emitted in the last pass
+extern "C" int32_t sfgpu_debug_union_rows(sfgpu_ctx* ctx, uint32_t replica, uint32_t child, uint32_t window, uint32_t* out_rows,
+                                          uint32_t cap, uint32_t* out_n, uint32_t* out_ended) {
+  const UnionPlan& plan = ctx->union_plan;
+  const UnionArgs& a = plan.a;
+  uint32_t n = 0, ended = 0;
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpy(&n, a.n_emit + (size_t)replica * a.n_children + child, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&ended, a.ended + (size_t)replica * a.n_children + child, 4, cudaMemcpyDeviceToHost);
+  *out_n = n;
+  *out_ended = ended;
+  const uint32_t k = n < cap ? n : cap;
+  cudaMemcpy(out_rows, a.rows + ((size_t)replica * a.n_children + child) * window * 4, (size_t)k * 16, cudaMemcpyDeviceToHost);
+  return SFGPU_OK;
+}

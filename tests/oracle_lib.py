@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         l.sfo_acceptor_step.argtypes = [_P, C.c_uint64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_uint64,
                                         C.c_int, _P]
         l.sfo_move_signatures.argtypes = [_P, C.c_int, C.c_uint64, _P, _P]
+        l.sfo_union_pull_order.argtypes = [C.c_uint32, _P, _P, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P, _P]
+        l.sfo_union_pull_order.restype = C.c_int64
         _lib = l
     return _lib
 
@@ -346,6 +348,66 @@ def replay_step(scores, doable, best_score, last_step_score, late_score, step_se
     lib().sfo_replay_step(len(h), _p(h), _p(s), _p(d), _p(b), _p(l_), _p(t), step_seed, forager_kind, accepted_limit,
                           1 if random_ties else 0, acceptor_kind, _p(out))
     return tuple(int(x) for x in out)
+
+
+def union_pull_order(sizes, union_order, step_index=0, step_seed=0, order=0, weights=None, limit=None):
+    """UnionScheduler of the reference (vec_union.rs:190-366) over children of the given sizes: (child[], local[])."""
+    sz = np.ascontiguousarray(sizes, dtype=np.uint64)
+    w = np.ones(len(sz), dtype=np.uint64) if weights is None else np.ascontiguousarray(weights, dtype=np.uint64)
+    cap = int(sz.sum()) if limit is None else int(limit)
+    child = np.zeros(max(cap, 1), dtype=np.uint32)
+    local = np.zeros(max(cap, 1), dtype=np.uint64)
+    n = lib().sfo_union_pull_order(len(sz), _p(sz), _p(w), union_order, step_index, step_seed, order, cap, _p(child),
+                                   _p(local))
+    return child[:n], local[:n].astype(np.int64)
+
+
+# families of sfgpu_union_child: (enumerate, score, pack to the device row format)
+def union_children(o: "Oracle", children, step_index, step_seed, order):
+    """Per child: (rows as the oracle enumerates them, packed device rows[n,4], scores[n,2], doable[n])."""
+    out = []
+    for ch in children:
+        fam = ch[0]
+        if fam == 0:
+            rows = o.enumerate_nearby_list_change(ch[1], step_index, step_seed, order)
+            sc, ok = o.score_list_change(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            packed = rows.astype(np.int64)
+        elif fam == 1:
+            rows = o.enumerate_nearby_list_swap(ch[1], step_index, step_seed, order)
+            sc, ok = o.score_list_swap(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            packed = rows.astype(np.int64)
+        elif fam == 2:
+            rows = o.enumerate_sublist_change(ch[1], ch[2], step_index, step_seed, order)
+            sc, ok = o.score_sublist_change(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            r = rows.astype(np.int64).reshape(-1, 5)
+            packed = np.stack([r[:, 0], r[:, 1] | ((r[:, 2] - r[:, 1]) << 24), r[:, 3], r[:, 4]], axis=1)
+        elif fam == 3:
+            rows = o.enumerate_sublist_swap(ch[1], ch[2], step_index, step_seed, order)
+            sc, ok = o.score_sublist_swap(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            r = rows.astype(np.int64).reshape(-1, 6)
+            packed = np.stack([r[:, 0], r[:, 1] | ((r[:, 2] - r[:, 1]) << 24), r[:, 3], r[:, 4] | ((r[:, 5] - r[:, 4]) << 24)],
+                              axis=1)
+        else:
+            rows = o.enumerate_list_reverse(step_index, step_seed, order)
+            sc, ok = o.score_list_reverse(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            packed = rows.astype(np.int64).reshape(-1, 4)
+        out.append((rows, packed.reshape(-1, 4), np.asarray(sc).reshape(-1, 2), np.asarray(ok)))
+    return out
+
+
+def union_step(o: "Oracle", children, union_order, order, step_index, step_seed, last, late, forager_kind, accepted_limit,
+               random_ties, acceptor_kind, weights=None):
+    """One reference step over the union cursor: returns (replay outcome, child[], local[], per-child data)."""
+    kids = union_children(o, children, step_index, step_seed, order)
+    child, local = union_pull_order([len(k[1]) for k in kids], union_order, step_index, step_seed, order, weights)
+    sc = np.zeros((len(child), 2), dtype=np.int64)
+    ok = np.zeros(len(child), dtype=np.uint8)
+    for c, k in enumerate(kids):
+        sel = child == c
+        sc[sel] = k[2][local[sel]]
+        ok[sel] = k[3][local[sel]]
+    out = replay_step(sc, ok, [0, 0], last, late, step_seed, forager_kind, accepted_limit, random_ties, acceptor_kind)
+    return out, child, local, kids, sc
 
 
 class OracleAcceptor:
