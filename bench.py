@@ -620,6 +620,42 @@ def run_ours(args):
                        "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
                        "best_score_replica0": [int(best_l[0][0]), int(best_l[0][1])]}
 
+    # the reference's DEFAULT list local search on device (sfgpu_solve_union): seeded Random leaves, StratifiedRandom
+    # union of nearby change / nearby swap / sublist change / sublist swap / reverse, LateAcceptance(400) +
+    # AcceptedCount(256); only a window of the union stream is generated and scored per step
+    default_search = None
+    if name == "cvrp" and args.loop_steps > 0:
+        try:
+            desc = d.default_list_union()
+            d.solve_union(desc, 16, 2, 400, 1, 256, seed_base=500)     # warm-up: buffers, graph capture
+            d.synchronize()
+            t0 = time.perf_counter()
+            best_u, ev_u, acc_u, ovf_u = d.solve_union(desc, args.loop_steps, 2, 400, 1, 256, seed_base=1000)
+            dt = time.perf_counter() - t0
+            pulls = float(d.last_pulls_scored.sum())
+            default_search = {"steps": args.loop_steps, "replicas": R, "ms_per_step": dt * 1e3 / args.loop_steps,
+                              "moves_evaluated_per_s": float(ev_u.sum()) / dt, "pulls_scored_per_s": pulls / dt,
+                              "scored_over_evaluated": pulls / max(float(ev_u.sum()), 1.0),
+                              "committed_steps": int(acc_u.sum()), "window_overflows": int(ovf_u.sum()),
+                              "selector": "union[NearbyListChange(20), NearbyListSwap(20), SublistChange(1..=3), "
+                                          "SublistSwap(1..=3), ListReverse], Random leaves, StratifiedRandom",
+                              "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
+                              "windows_per_child": "adaptive per replica (first 64), x4, then 4096"}
+            # the canonical nearby list-change loop again, windowed: same winners as device_loop above (one child,
+            # SelectionOrder::Original), but only the prefix of the cursor the forager consumes is generated
+            one = d.union_desc([(0, 20)], 0, 0)
+            d.solve_union(one, 16, 2, 400, 1, 256, seed_base=500)
+            d.synchronize()
+            t0 = time.perf_counter()
+            best_w, ev_w, acc_w, ovf_w = d.solve_union(one, args.loop_steps, 2, 400, 1, 256, seed_base=1000)
+            dt = time.perf_counter() - t0
+            default_search["nearby_change_windowed"] = {
+                "ms_per_step": dt * 1e3 / args.loop_steps, "moves_evaluated_per_s": float(ev_w.sum()) / dt,
+                "scored_over_evaluated": float(d.last_pulls_scored.sum()) / max(float(ev_w.sum()), 1.0),
+                "window_overflows": int(ovf_w.sum())}
+        except Exception as exc:  # informational only
+            default_search = {"error": str(exc)[:200]}
+
     # informational, outside every timed region: the device-enumerated sublist neighbourhoods of the reference's
     # default list policy (SublistChange / SublistSwap, sizes 1..=3, ~3 M / ~3.8 M candidates per replica and
     # step, never materialised) — whole steps incl. commit through the host call, on a small replica count
@@ -673,6 +709,7 @@ def run_ours(args):
             if k in main:
                 line[k] = main[k]
         line["device_loop"] = device_loop
+        line["default_search"] = default_search
         line["sublist_steps"] = sublist_steps
         line["extra"] = extra
         print(json.dumps(line))

@@ -149,7 +149,7 @@ extern "C" {
     pub fn sfgpu_step_sublist_swap(ctx: *mut sfgpu_ctx, flags: u32, min_size: u32, max_size: u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32, out_winner_rows: *mut u32, apply_winners: i32) -> i32;
     pub fn sfgpu_step_change(ctx: *mut sfgpu_ctx, flags: u32, params: *const sfgpu_forage_params, step_seeds: *const u64, ref_scores: *const i64, out_cand_offsets: *mut u64, out_rows: *mut u32, out_scores: *mut i64, out_doable: *mut u8, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32, out_winner_rows: *mut u32, apply_winners: i32) -> i32;
     pub fn sfgpu_step_union(ctx: *mut sfgpu_ctx, flags: u32, desc: *const sfgpu_union_desc, params: *const sfgpu_forage_params, step_seeds: *const u64, step_indices: *const u64, ref_scores: *const i64, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32, out_winner_rows: *mut u32, out_flags: *mut u32, apply_winners: i32) -> i32;
-    pub fn sfgpu_solve_union(ctx: *mut sfgpu_ctx, desc: *const sfgpu_union_desc, params: *const sfgpu_solve_params, out_best_scores: *mut i64, out_moves_evaluated: *mut u64, out_accepted_steps: *mut u64, out_window_overflows: *mut u64) -> i32;
+    pub fn sfgpu_solve_union(ctx: *mut sfgpu_ctx, desc: *const sfgpu_union_desc, params: *const sfgpu_solve_params, out_best_scores: *mut i64, out_moves_evaluated: *mut u64, out_accepted_steps: *mut u64, out_window_overflows: *mut u64, out_pulls_scored: *mut u64) -> i32;
     pub fn sfgpu_solve_nearby_list_change(ctx: *mut sfgpu_ctx, params: *const sfgpu_solve_params, out_best_scores: *mut i64, out_moves_evaluated: *mut u64, out_accepted_steps: *mut u64) -> i32;
     pub fn sfgpu_solve_change(ctx: *mut sfgpu_ctx, params: *const sfgpu_solve_params, out_best_scores: *mut i64, out_moves_evaluated: *mut u64, out_accepted_steps: *mut u64) -> i32;
 

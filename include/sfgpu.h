@@ -432,12 +432,15 @@ int32_t sfgpu_step_union(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_union_desc*
                          const int64_t* ref_scores, uint32_t* out_index, int64_t* out_best, uint32_t* out_evaluated,
                          uint32_t* out_winner_rows, uint32_t* out_flags, int32_t apply_winners);
 /* The device-resident loop (below) over this union step: step t of replica r uses step_index = t and
- * step_seed = splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t); three window passes per step (window,
- * x8, max_window). out_window_overflows (may be NULL) counts the steps per replica that hit max_window. */
+ * step_seed = splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t); three window passes per step: the
+ * replica's adaptive window (what its previous step needed per child plus half, starting at `window`), four
+ * times that, then max_window — each only for the replicas whose forager had not quit in the pass before. out_window_overflows (may be NULL) counts the steps per replica that hit max_window;
+ * out_pulls_scored (may be NULL) the union pulls scored per replica over all passes (speculation included —
+ * compare with out_moves_evaluated, the pulls the reference's loop would have evaluated). */
 struct sfgpu_solve_params;
 int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const struct sfgpu_solve_params* params,
                           int64_t* out_best_scores, uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps,
-                          uint64_t* out_window_overflows);
+                          uint64_t* out_window_overflows, uint64_t* out_pulls_scored);
 
 /* Device-resident local-search loop: n_steps whole steps (seed, neighbourhood, scoring, acceptor, forager,
  * commit, acceptor.step_ended, best-solution tracking) without a host round trip, captured in a CUDA

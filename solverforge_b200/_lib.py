@@ -120,7 +120,7 @@ SYMBOLS = {
                                             _P, _P, _P, _P, C.c_int32]),
     "sfgpu_step_union": (C.c_int32, [_P, C.c_uint32, C.POINTER(UnionDesc), C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P,
                                      _P, _P, C.c_int32]),
-    "sfgpu_solve_union": (C.c_int32, [_P, C.POINTER(UnionDesc), C.POINTER(SolveParams), _P, _P, _P, _P]),
+    "sfgpu_solve_union": (C.c_int32, [_P, C.POINTER(UnionDesc), C.POINTER(SolveParams), _P, _P, _P, _P, _P]),
     "sfgpu_solve_nearby_list_change": (C.c_int32, [_P, C.POINTER(SolveParams), _P, _P, _P]),
     "sfgpu_solve_change": (C.c_int32, [_P, C.POINTER(SolveParams), _P, _P, _P]),
     "sfgpu_apply_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),

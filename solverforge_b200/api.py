@@ -506,14 +506,18 @@ class GpuScoreDirector:
                     accepted_limit: int = 256, seed_base: int = 0, restore_best: bool = False,
                     acceptor_real: float = 0.0, step_count_limit: int = 0):
         """Device-resident loop over the union step (sfgpu_solve_union): returns (best_scores[R,2],
-        moves_evaluated[R], committed_steps[R], window_overflows[R])."""
+        moves_evaluated[R], committed_steps[R], window_overflows[R]); self.last_pulls_scored[R] = union pulls scored
+        over all window passes (speculation included)."""
         p = L.SolveParams(0, n_steps, acceptor, late_size, tie_mode, accepted_limit, seed_base,
                           1 if restore_best else 0, 0, acceptor_real, step_count_limit)
         best = np.zeros((self.R, 2), dtype=np.int64)
         ev = np.zeros(self.R, dtype=np.uint64)
         acc = np.zeros(self.R, dtype=np.uint64)
         ovf = np.zeros(self.R, dtype=np.uint64)
-        self._check(self.lib.sfgpu_solve_union(self.h, C.byref(desc), C.byref(p), _ptr(best), _ptr(ev), _ptr(acc), _ptr(ovf)))
+        pulls = np.zeros(self.R, dtype=np.uint64)
+        self._check(self.lib.sfgpu_solve_union(self.h, C.byref(desc), C.byref(p), _ptr(best), _ptr(ev), _ptr(acc), _ptr(ovf),
+                                               _ptr(pulls)))
+        self.last_pulls_scored = pulls
         return best, ev, acc, ovf
 
     def solve_nearby_list_change(self, n_steps: int, max_nearby: int = 20, acceptor: int = 2, late_size: int = 400,

@@ -61,6 +61,7 @@ struct UnionPlan {
   uint32_t* pending = nullptr;     // [1] replicas that need a larger window
   uint32_t* apply_rows = nullptr;  // [R][4] winner rows
   int32_t* apply_kinds = nullptr;  // [R] apply_list_kernel kind of each winner, -1 = none
+  uint32_t* win_state = nullptr;   // [R] adaptive first window of each replica (resident loop)
   uint32_t w0 = 64, wmax = 4096;
   bool configured = false;
 };
@@ -326,7 +327,9 @@ inline size_t rank_tables_words_host(uint32_t n_owners) { return 5 * (size_t)n_o
 int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgpu_forage_params* params, UnionPlan& plan);
 int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan);
 int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bool last_pass, uint32_t* d_idx, int64_t* d_best,
-                            uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc);
+                            uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc, bool adaptive,
+                            uint32_t win_shift = 0);
+int sfgpu_union_reset_windows(sfgpu_ctx* ctx, UnionPlan& plan);
 // sfgpu_scalar.cu
 int sfgpu_configure_scalar(sfgpu_ctx* ctx);
 void sfgpu_change_step_chunks(const sfgpu_ctx* ctx, uint32_t* out_per, uint32_t* out_chunks);

@@ -191,6 +191,10 @@ struct UnionArgs {
   uint8_t* doable;               // [R][t_cap]
   uint64_t* offsets;             // [R + 1] = r * t_cap
   uint32_t* done;                // [R] step already complete (earlier pass): skip
+  const uint32_t* win_r;         // [R] rows a child of replica r may emit in this pass (<= window), or null = window
+  uint32_t* next_win;            // [R] or null: adaptive window of the replica's next step (resident loop)
+  uint32_t win_max;              // largest adaptive window
+  uint32_t win_shift;            // this pass offers win_r[r] << win_shift rows per child
 };
 
 __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {

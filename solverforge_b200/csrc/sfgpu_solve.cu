@@ -7,7 +7,7 @@ using namespace sfgpu_host;
 namespace {
 int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t* out_best_scores,
                uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps, const sfgpu_union_desc* udesc = nullptr,
-               uint64_t* out_window_overflows = nullptr) {
+               uint64_t* out_window_overflows = nullptr, uint64_t* out_pulls_scored = nullptr) {
   int rc = check_committed(ctx);
   if (rc) return rc;
   if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
@@ -39,7 +39,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   const size_t o_eval = take((size_t)R * 8), o_acc = take((size_t)R * 8), o_idx = take((size_t)R * 4);
   const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
   const size_t o_accst = take((size_t)R * 32);
-  const size_t o_ovf = take((size_t)R * 8);
+  const size_t o_ovf = take((size_t)R * 16);
   const size_t o_snap = take((size_t)R * dm.block_bytes);
   if (o > ctx->solve_bytes) {
     if (ctx->solve_buf) cudaFree(ctx->solve_buf);
@@ -71,7 +71,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   s.step_count_limit = p->step_count_limit;
   const int forage_code = solve_forage_code(p->acceptor);
   uint64_t* d_overflows = (uint64_t*)(b + o_ovf);
-  CU(cudaMemsetAsync(d_overflows, 0, (size_t)R * 8, ctx->stream));
+  CU(cudaMemsetAsync(d_overflows, 0, (size_t)R * 16, ctx->stream));  // [R] overflows, [R] pulls scored
   UnionPlan& plan = ctx->union_plan;
   if (udesc) {
     sfgpu_forage_params fp{forage_code, p->tie_mode, p->accepted_limit, 0};
@@ -81,6 +81,8 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     plan.a.step_indices = s.step_counter;
     plan.a.step_index_shared = 1;
     plan.a.ref_scores = s.ref_scores;
+    rc = sfgpu_union_reset_windows(ctx, plan);
+    if (rc) return rc;
   }
   NearbyArgs a{};
   ChangeStepArgs ca{};
@@ -115,17 +117,14 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       if (rc2) return rc2;
       rc2 = sfgpu_launch_apply_scalar(ctx, 0, s.winner_rows, nullptr, nullptr, nullptr);
     } else if (udesc) {
-      // three window passes (window, x8, max_window); complete replicas skip the later ones
+      // three window passes: the replica's adaptive window (what its previous step needed plus half), four times
+      // that, then max_window — each only for the replicas whose forager had not quit in the pass before
       rc2 = sfgpu_union_begin_step(ctx, plan);
       if (rc2) return rc2;
-      const uint32_t w1 = (uint32_t)std::min<uint64_t>((uint64_t)plan.w0 * 8, plan.wmax);
-      const uint32_t ws[3] = {plan.w0, w1, plan.wmax};
       for (int k = 0; k < 3; ++k) {
-        const bool last = k == 2 || ws[k] >= plan.wmax;
-        rc2 = sfgpu_union_launch_pass(ctx, plan, ws[k], last, s.out_index, s.out_best, s.out_evaluated, nullptr, nullptr,
-                                      d_overflows);
+        rc2 = sfgpu_union_launch_pass(ctx, plan, plan.wmax, k == 2, s.out_index, s.out_best, s.out_evaluated, nullptr, nullptr,
+                                      d_overflows, true, k == 1 ? 2 : 0);
         if (rc2) return rc2;
-        if (last) break;
       }
       rc2 = sfgpu_launch_apply_list_kinds(ctx, plan.apply_rows, plan.apply_kinds);
     } else {
@@ -174,6 +173,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   if (out_moves_evaluated) CU(cudaMemcpy(out_moves_evaluated, s.evaluated, (size_t)R * 8, cudaMemcpyDeviceToHost));
   if (out_accepted_steps) CU(cudaMemcpy(out_accepted_steps, s.accepted_steps, (size_t)R * 8, cudaMemcpyDeviceToHost));
   if (out_window_overflows) CU(cudaMemcpy(out_window_overflows, d_overflows, (size_t)R * 8, cudaMemcpyDeviceToHost));
+  if (out_pulls_scored) CU(cudaMemcpy(out_pulls_scored, d_overflows + R, (size_t)R * 8, cudaMemcpyDeviceToHost));
   return SFGPU_OK;
 }
 
@@ -192,9 +192,11 @@ int32_t sfgpu_solve_change(sfgpu_ctx* ctx, const sfgpu_solve_params* p, int64_t*
 } SFGPU_API_CATCH(ctx)
 
 int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgpu_solve_params* p, int64_t* out_best_scores,
-                          uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps, uint64_t* out_window_overflows) try {
+                          uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps, uint64_t* out_window_overflows,
+                          uint64_t* out_pulls_scored) try {
   if (!desc) return fail(ctx, SFGPU_E_INVALID, "null union description");
-  return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps, desc, out_window_overflows);
+  return solve_impl(ctx, p, false, out_best_scores, out_moves_evaluated, out_accepted_steps, desc, out_window_overflows,
+                    out_pulls_scored);
 } SFGPU_API_CATCH(ctx)
 
 }  // extern "C"

@@ -53,6 +53,7 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   const size_t o_doable = take((size_t)R * T), o_emit = take((size_t)R * C * 4), o_ended = take((size_t)R * C * 4);
   const size_t o_nsched = take((size_t)R * 4), o_send = take((size_t)R * 4), o_offs = take((size_t)(R + 1) * 8);
   const size_t o_done = take((size_t)R * 4), o_pend = take(16), o_arows = take((size_t)R * 16), o_akind = take((size_t)R * 4);
+  const size_t o_win = take((size_t)R * 4);
   if (o > ctx->union_bytes) {
     if (ctx->union_buf) cudaFree(ctx->union_buf);
     ctx->union_buf = nullptr;
@@ -83,6 +84,8 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   plan.pending = (uint32_t*)(b + o_pend);
   plan.apply_rows = (uint32_t*)(b + o_arows);
   plan.apply_kinds = (int32_t*)(b + o_akind);
+  plan.win_state = (uint32_t*)(b + o_win);
+  a.win_max = wmax;
   plan.w0 = w0;
   plan.wmax = wmax;
   if (!plan.configured) {
@@ -99,6 +102,15 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   return SFGPU_OK;
 }
 
+// resident loop: every replica starts with the first window
+int sfgpu_union_reset_windows(sfgpu_ctx* ctx, UnionPlan& plan) {
+  const uint32_t R = ctx->dm.R;
+  union_fill_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>(plan.win_state, plan.w0, R);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
 int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan) {
   const uint32_t R = ctx->dm.R;
   union_reset_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>(plan.a.done, plan.pending, R);
@@ -109,11 +121,15 @@ int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan) {
 
 // one window pass: walk every child, schedule, score, replay, pick
 int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bool last_pass, uint32_t* d_idx, int64_t* d_best,
-                            uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc) {
+                            uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc, bool adaptive,
+                            uint32_t win_shift) {
   const DevModel& dm = ctx->dm;
   const uint32_t R = dm.R;
   UnionArgs a = plan.a;
   a.window = window;
+  a.win_r = adaptive && !last_pass ? plan.win_state : nullptr;  // the last pass always offers the whole window
+  a.next_win = adaptive ? plan.win_state : nullptr;
+  a.win_shift = win_shift;
   a.t_cap = a.n_children * window;
   for (uint32_t c = 0; c < a.n_children; ++c) {
     const int fam = a.child[c].family;
@@ -130,8 +146,18 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
       union_walk_index_kernel<<<R, 32, 0, ctx->stream>>>(dm, a, c);
     }
   }
-  union_schedule_kernel<<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R);
-  const uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((a.t_cap + 255) / 256, 64));
+  switch (a.union_order) {
+    case SFGPU_UNION_SEQUENTIAL: union_schedule_kernel<SFGPU_UNION_SEQUENTIAL><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R); break;
+    case SFGPU_UNION_ROUND_ROBIN: union_schedule_kernel<SFGPU_UNION_ROUND_ROBIN><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R); break;
+    case SFGPU_UNION_ROTATING_ROUND_ROBIN:
+      union_schedule_kernel<SFGPU_UNION_ROTATING_ROUND_ROBIN><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R);
+      break;
+    case SFGPU_UNION_RANDOM: union_schedule_kernel<SFGPU_UNION_RANDOM><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R); break;
+    default: union_schedule_kernel<SFGPU_UNION_STRATIFIED_RANDOM><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R); break;
+  }
+  // grid-stride over the scheduled pulls: a few CTAs per replica, more when replicas are few
+  const uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((a.t_cap + 255) / 256,
+                                                                   std::max<uint32_t>(4, (uint32_t)ctx->sm_count * 4 / std::max(R, 1u))));
   if (ctx->staged) union_score_kernel<true><<<dim3(chunks, R), 256, dm.stage_bytes, ctx->stream>>>(dm, a);
   else union_score_kernel<false><<<dim3(chunks, R), 256, 0, ctx->stream>>>(dm, a);
   ctx->launches += a.n_children + 2;
@@ -190,7 +216,7 @@ int32_t sfgpu_step_union(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_union_desc*
   ev_begin(ctx);
   for (uint32_t window = plan.w0;;) {
     const bool last = window >= plan.wmax;
-    rc = sfgpu_union_launch_pass(ctx, plan, window, last, io.d_idx, io.d_best, io.d_eval, io.d_win, d_flags, nullptr);
+    rc = sfgpu_union_launch_pass(ctx, plan, window, last, io.d_idx, io.d_best, io.d_eval, io.d_win, d_flags, nullptr, false, 0);
     if (rc) return rc;
     if (last) break;
     uint32_t pending = 0;

@@ -57,6 +57,13 @@ __device__ __forceinline__ StreamCtx stream_ctx(const UnionArgs& a, uint32_t r) 
   return c;
 }
 
+// rows a child of replica r may emit in this pass
+__device__ __forceinline__ uint32_t union_cap(const UnionArgs& a, uint32_t r) {
+  if (!a.win_r) return a.window;
+  const uint64_t w = (uint64_t)a.win_r[r] << a.win_shift;
+  return w < a.window ? (uint32_t)w : a.window;
+}
+
 // selection_index(offset, len, salt) for one (len, salt): the Shuffled start / stride are computed once
 struct SelMap {
   const StreamCtx* c;
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_const
   const StreamCtx cx = stream_ctx(a, r);
   RowSink out;
   out.rows = (uint4*)a.rows + ((size_t)r * a.n_children + child) * a.window;
-  out.cap = a.window;
+  out.cap = union_cap(a, r);
   out.n = 0;
   out.more = false;
   const UnionChildDev& c = a.child[child];
@@ -489,13 +496,13 @@ __global__ void __launch_bounds__(256) union_walk_nearby_kernel(const __grid_con
   v.sr = (const uint4*)(st + m.off_slot_rec);
   v.pos_of = (const uint32_t*)(st + m.off_pos_of);
   const StreamCtx cx = stream_ctx(a, r);
-  const uint32_t n = m.n_owners, K = a.child[child].p0, M = a.window;
+  const uint32_t n = m.n_owners, K = a.child[child].p0, M = union_cap(a, r);
   RankTables t;
   build_rank_tables(t, u_smem, cx, (MOVE == MOVE_SWAP ? 0xA1EA25A090000001ull : 0xA1EA2B17C4A40001ull) ^ (uint64_t)a.desc,
                     v.rr, n, &s_max_occ);
   const uint64_t source_salt = (MOVE == MOVE_SWAP ? 0xA1EA25A090000002ull : 0xA1EA2B17C4A40002ull) ^ (uint64_t)a.desc;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint4* rows = (uint4*)a.rows + ((size_t)r * a.n_children + child) * M;
+  uint4* rows = (uint4*)a.rows + ((size_t)r * a.n_children + child) * a.window;
   const uint32_t n_src = t.pos_first[n];
   const KEY mask = ((KEY)1 << a.scan_bits) - 1;
   if (MOVE == MOVE_CHANGE) {
@@ -584,114 +591,128 @@ __global__ void __launch_bounds__(256) union_walk_nearby_kernel(const __grid_con
 
 // ---- the scheduler (vec_union.rs:190-366) replayed over the emitted counts -------------------------------------
 // one thread per replica. A pull from a child whose WINDOW is used up (cursor not ended) stops the schedule before
-// the scheduler state changes: the next pass resumes from scratch with a larger window.
-__global__ void union_schedule_kernel(const UnionArgs a, const uint32_t R) {
+// the scheduler state changes: the next pass resumes from scratch with a larger window. Every per-child array is
+// indexed by compile-time constants after unrolling (the dynamic child of a pull is found with predicated sweeps),
+// so the whole scheduler state lives in registers; StratifiedRandom keeps its arrays in the strided child order
+// (position p holds child cid[p]) because that is the order its ties are broken in.
+#define UNION_FOR(p) _Pragma("unroll") for (int p = 0; p < UNION_MAX_CHILDREN; ++p)
+template <int UORDER>
+__global__ void __launch_bounds__(64) union_schedule_kernel(const UnionArgs a, const uint32_t R) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   if (r == 0) a.offsets[R] = (uint64_t)R * a.t_cap;
   a.offsets[r] = (uint64_t)r * a.t_cap;
   if (a.done && a.done[r]) return;
-  const uint32_t C = a.n_children;
-  StreamCtx cx = stream_ctx(a, r);
-  uint32_t at[UNION_MAX_CHILDREN], n_emit[UNION_MAX_CHILDREN];
-  bool ended[UNION_MAX_CHILDREN], exhausted[UNION_MAX_CHILDREN];
-  int64_t weighted[UNION_MAX_CHILDREN];
-  uint64_t weight[UNION_MAX_CHILDREN];
-  uint32_t live = 0;
-  uint64_t total_live_weight = 0;
-  for (uint32_t c = 0; c < C; ++c) {
-    at[c] = 0;
-    n_emit[c] = a.n_emit[(size_t)r * C + c];
-    ended[c] = a.ended[(size_t)r * C + c] != 0;
-    weight[c] = a.child[c].weight;
-    exhausted[c] = weight[c] == 0;
-    weighted[c] = 0;
-    if (!exhausted[c]) ++live;
-    total_live_weight += weight[c];
-  }
+  const int C = (int)a.n_children;
+  const StreamCtx cx = stream_ctx(a, r);
   uint32_t offset = 0, stride = 1;
-  if (a.union_order == SFGPU_UNION_ROTATING_ROUND_ROBIN || a.union_order == SFGPU_UNION_STRATIFIED_RANDOM)
+  if (UORDER == SFGPU_UNION_ROTATING_ROUND_ROBIN || UORDER == SFGPU_UNION_STRATIFIED_RANDOM)
     offset = cx.random_index(C, 0xA11CE5E1EC700001ull);
-  if (a.union_order == SFGPU_UNION_STRATIFIED_RANDOM) stride = cx.random_stride(C, 0xA11CE5E1EC700002ull);
-  uint32_t current = a.union_order == SFGPU_UNION_STRATIFIED_RANDOM ? 0 : offset;
+  if (UORDER == SFGPU_UNION_STRATIFIED_RANDOM) stride = cx.random_stride(C, 0xA11CE5E1EC700002ull);
+  uint32_t at[UNION_MAX_CHILDREN], ne[UNION_MAX_CHILDREN], cid[UNION_MAX_CHILDREN];
+  bool ended[UNION_MAX_CHILDREN], exhausted[UNION_MAX_CHILDREN];
+  int64_t weighted[UNION_MAX_CHILDREN], weight[UNION_MAX_CHILDREN];
+  int live = 0;
+  int64_t total_live_weight = 0;
+  UNION_FOR(p) {
+    at[p] = 0;
+    weighted[p] = 0;
+    const bool in = p < C;
+    const uint32_t c = !in ? 0u : (UORDER == SFGPU_UNION_STRATIFIED_RANDOM ? (offset + (uint32_t)p * stride) % (uint32_t)C : (uint32_t)p);
+    cid[p] = c;
+    ne[p] = in ? a.n_emit[(size_t)r * C + c] : 0u;
+    ended[p] = in ? a.ended[(size_t)r * C + c] != 0 : true;
+    weight[p] = in ? (int64_t)a.child[c].weight : 0;
+    exhausted[p] = weight[p] == 0;
+    if (!exhausted[p]) ++live;
+    total_live_weight += weight[p];
+  }
+  int current = UORDER == SFGPU_UNION_STRATIFIED_RANDOM ? 0 : (int)offset;
   uint64_t random_draw = 0;
   uint32_t* sched = a.sched + (size_t)r * a.t_cap;
   uint32_t t = 0;
   bool window_out = false;
-  // has_next(c): 1 yes, 0 cursor ended, -1 window used up
-  auto probe = [&](uint32_t c) -> int { return at[c] < n_emit[c] ? 1 : (ended[c] ? 0 : -1); };
   while (t < a.t_cap && !window_out) {
-    uint32_t pick = UNION_NONE;
-    if (a.union_order == SFGPU_UNION_SEQUENTIAL) {
-      while (current < C) {
-        const int p = probe(current);
-        if (p == 1) { pick = current; break; }
-        if (p < 0) { window_out = true; break; }
-        ++current;
-      }
-      if (pick == UNION_NONE) break;
-    } else if (a.union_order == SFGPU_UNION_ROUND_ROBIN || a.union_order == SFGPU_UNION_ROTATING_ROUND_ROBIN) {
-      while (live > 0) {
-        const uint32_t c = current % C;
-        if (exhausted[c]) { current = (current + 1) % C; continue; }
-        const int p = probe(c);
-        if (p < 0) { window_out = true; break; }
-        current = (current + 1) % C;
-        if (p == 1) { pick = c; break; }
-        exhausted[c] = true;
-        --live;
-      }
-      if (pick == UNION_NONE) break;
-    } else if (a.union_order == SFGPU_UNION_RANDOM) {
-      while (live > 0) {
-        const uint64_t draw = cx.mixed(0xA11CE5E1EC701000ull + random_draw) % total_live_weight;
+    int pick = -1;
+    // one scheduler decision: `sel` = the position asked for its next candidate
+    while (pick < 0 && !window_out) {
+      int sel = -1;
+      if (UORDER == SFGPU_UNION_SEQUENTIAL) {
+        if (current >= C) break;
+        sel = current;
+      } else if (UORDER == SFGPU_UNION_ROUND_ROBIN || UORDER == SFGPU_UNION_ROTATING_ROUND_ROBIN) {
+        if (live == 0) break;
+        bool ex = false;
+        UNION_FOR(p) if (p == current) ex = exhausted[p];
+        if (ex) {
+          current = (current + 1) % C;
+          continue;
+        }
+        sel = current;
+      } else if (UORDER == SFGPU_UNION_RANDOM) {
+        if (live == 0) break;
+        const uint64_t draw = cx.mixed(0xA11CE5E1EC701000ull + random_draw) % (uint64_t)total_live_weight;
         uint64_t cumulative = 0;
-        uint32_t c = 0;
-        for (uint32_t i = 0; i < C; ++i) {
-          if (exhausted[i]) continue;
-          cumulative += weight[i];
-          if (draw < cumulative) { c = i; break; }
+        UNION_FOR(p) {
+          if (!exhausted[p]) {
+            cumulative += (uint64_t)weight[p];
+            if (sel < 0 && draw < cumulative) sel = p;
+          }
         }
-        const int p = probe(c);
-        if (p < 0) { window_out = true; break; }
-        ++random_draw;
-        if (p == 1) { pick = c; break; }
-        exhausted[c] = true;
-        --live;
-        total_live_weight -= weight[c];
-      }
-      if (pick == UNION_NONE) break;
-    } else {  // StratifiedRandom: smooth weighted round-robin over the strided child order
-      while (live > 0) {
-        uint32_t sel = UNION_NONE;
+      } else {
+        if (live == 0) break;
         int64_t sel_w = 0;
-        for (uint32_t position = 0; position < C; ++position) {
-          const uint32_t c = (offset + position * stride) % C;
-          if (exhausted[c]) continue;
-          const int64_t w = weighted[c] + (int64_t)weight[c];
-          if (sel == UNION_NONE || w > sel_w) { sel = c; sel_w = w; }
+        UNION_FOR(p) {
+          if (!exhausted[p]) {
+            const int64_t w = weighted[p] + weight[p];
+            if (sel < 0 || w > sel_w) {
+              sel = p;
+              sel_w = w;
+            }
+          }
         }
-        const int p = probe(sel);
-        if (p < 0) { window_out = true; break; }
-        for (uint32_t c = 0; c < C; ++c)
-          if (!exhausted[c]) weighted[c] += (int64_t)weight[c];
-        weighted[sel] -= (int64_t)total_live_weight;
-        if (p == 1) { pick = sel; break; }
-        exhausted[sel] = true;
-        --live;
-        total_live_weight -= weight[sel];
       }
-      if (pick == UNION_NONE) break;
+      bool has = false, end = false;
+      UNION_FOR(p) if (p == sel) {
+        has = at[p] < ne[p];
+        end = ended[p];
+      }
+      if (!has && !end) {  // the window (not the cursor) ran out: stop before any state changes
+        window_out = true;
+        break;
+      }
+      if (UORDER == SFGPU_UNION_ROUND_ROBIN || UORDER == SFGPU_UNION_ROTATING_ROUND_ROBIN) current = (current + 1) % C;
+      if (UORDER == SFGPU_UNION_RANDOM) ++random_draw;
+      if (UORDER == SFGPU_UNION_STRATIFIED_RANDOM) {
+        UNION_FOR(p) {
+          if (!exhausted[p]) weighted[p] += weight[p];
+          if (p == sel) weighted[p] -= total_live_weight;
+        }
+      }
+      if (has) {
+        pick = sel;
+      } else if (UORDER == SFGPU_UNION_SEQUENTIAL) {
+        ++current;
+      } else {
+        UNION_FOR(p) if (p == sel) {
+          exhausted[p] = true;
+          total_live_weight -= weight[p];
+        }
+        --live;
+      }
     }
-    sched[t++] = (pick << 28) | at[pick];
-    ++at[pick];
+    if (pick < 0) break;
+    uint32_t word = 0;
+    UNION_FOR(p) if (p == pick) {
+      word = (cid[p] << 28) | at[p];
+      ++at[p];
+    }
+    sched[t++] = word;
   }
   a.n_sched[r] = t;
-  // the stream ended iff the loop stopped with no child able to deliver and no window cut
+  // the stream ended iff no window cut happened and no child can deliver any more
   bool any_left = window_out;
-  if (!any_left)
-    for (uint32_t c = 0; c < C; ++c)
-      if (weight[c] != 0 && (at[c] < n_emit[c] || !ended[c])) any_left = true;
+  UNION_FOR(p) if (p < C && weight[p] != 0 && (at[p] < ne[p] || !ended[p])) any_left = true;
   a.stream_end[r] = any_left ? 0 : 1;
 }
 
@@ -744,11 +765,12 @@ __global__ void union_pick_kernel(const UnionArgs a, const uint32_t R, const uin
                                   const uint32_t* out_evaluated, uint32_t* out_winner_rows /* [R][8] or null */,
                                   uint32_t* apply_rows /* [R][4] */, int32_t* apply_kinds /* [R] */,
                                   uint32_t* out_flags /* [R] or null */, uint32_t* pending /* [1] */,
-                                  uint64_t* overflow_acc /* [R] or null */) {
+                                  uint64_t* overflow_acc /* [2][R] or null: overflows, pulls scored */) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   if (a.done[r]) return;
   const uint32_t T = a.n_sched[r];
+  if (overflow_acc) overflow_acc[R + r] += T;
   const bool quit = a.f.accepted_limit > 0 && out_evaluated[r] < T;
   const bool complete = a.stream_end[r] != 0 || quit;
   if (!complete && !last_pass) {
@@ -756,6 +778,11 @@ __global__ void union_pick_kernel(const UnionArgs a, const uint32_t R, const uin
     return;
   }
   a.done[r] = 1;
+  if (a.next_win) {
+    // next step's first window: what this step needed per child plus half, at least 16
+    const uint32_t per = (out_evaluated[r] + a.n_children - 1) / a.n_children;
+    a.next_win[r] = min(a.win_max, max(16u, per + per / 2 + 8));
+  }
   if (out_flags) out_flags[r] = complete ? 0u : 1u;  // bit 0: the window limit cut the step short
   if (overflow_acc && !complete) overflow_acc[r] += 1;
   const uint32_t idx = out_index[r];
@@ -786,4 +813,9 @@ __global__ void union_reset_kernel(uint32_t* done, uint32_t* pending, uint32_t R
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) done[r] = 0;
   if (r == 0) *pending = 0;
+}
+
+__global__ void union_fill_kernel(uint32_t* dst, uint32_t value, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = value;
 }
