@@ -447,8 +447,15 @@ int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const st
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.
  * acceptor: 1 HillClimbing, 2 LateAcceptance(late_size), 3 GreatDeluge(acceptor_real = rain_speed),
  * 4 StepCountingHillClimbing(step_count_limit), 5 DiversifiedLateAcceptance(late_size, acceptor_real =
- * tolerance) — acceptor/{hill_climbing,late_acceptance,great_deluge,step_counting,
- * diversified_late_acceptance}.rs, state kept per replica on the device. The reference draws step seeds from
+ * tolerance), 6 SimulatedAnnealing (sfgpu_solve_change / sfgpu_solve_union; acceptor_real = decay rate, 0 = the
+ * default 0.999985; late_size = calibration sample size, 0 = 128; step_count_limit bit 0 =
+ * HardRegressionPolicy::NeverAcceptHardRegression) — acceptor/{hill_climbing,late_acceptance,great_deluge,
+ * step_counting,diversified_late_acceptance,simulated_annealing}.rs, state kept per replica on the device.
+ * SimulatedAnnealing replays is_accepted in pull order over the step's scores (calibration from the first
+ * worsening candidates the phase evaluates, Boltzmann test on the first differing level, geometric decay once
+ * calibrated). The reference draws its uniforms from rand::SmallRng (third party, unpinned); here draw j of a
+ * step is (splitmix64(step_seed ^ 0x5A17EA11EA1DF00D ^ j * 0x9E3779B97F4A7C15) >> 11) * 2^-53, consumed exactly
+ * where the reference draws (worsening candidates whose level temperature exceeds 1e-9). The reference draws step seeds from
  * rand::StdRng (unpinned third-party stream); here step t of replica r uses
  * splitmix64(seed_base ^ r * 0x9E3779B97F4A7C15 ^ t), so a trajectory is reproducible and each of its
  * steps can be checked against the oracle, but it is not the reference's trajectory.

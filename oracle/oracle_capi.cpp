@@ -457,6 +457,11 @@ void* sfo_acceptor_create(int kind, uint64_t size, double real, const uint64_t t
     a->reverse_move_memory.tenure = tabu[3];
   }
   a->aspiration_enabled = aspiration != 0;
+  if (a->kind == AcceptorKind::SimulatedAnnealing) {  // size = calibration samples, real = decay rate (0 = defaults)
+    if (size) a->calibration_samples = size;
+    if (real > 0.0) a->decay = real;
+    a->never_accept_hard_regression = aspiration == 2;
+  }
   return a;
 }
 void sfo_acceptor_destroy(void* h) { delete (Acceptor<Sc>*)h; }
@@ -493,6 +498,15 @@ int sfo_acceptor_step(void* h, uint64_t n, const int64_t* hard, const int64_t* s
     return CandidateEvaluation<Sc>{doable[i] ? EvalKind::Scored : EvalKind::NotDoable, Sc::of(hard[i], soft[i])};
   };
   const Sc best = Sc::of(best_score[0], best_score[1]), last = Sc::of(last_step_score[0], last_step_score[1]);
+  // SimulatedAnnealing: the uniform stream is injected (the reference's SmallRng is third party and unpinned):
+  // draw j of a step = (splitmix64(step_seed ^ 0x5A17EA11EA1DF00D ^ j * 0x9E3779B97F4A7C15) >> 11) * 2^-53, the
+  // stream include/sfgpu.h states for the device loop.
+  uint64_t draw = 0;
+  a->uniform = [&draw, step_seed]() {
+    const uint64_t x = splitmix64(step_seed ^ 0x5A17EA11EA1DF00Dull ^ (draw * 0x9E3779B97F4A7C15ull));
+    ++draw;
+    return (double)(x >> 11) * 0x1.0p-53;
+  };
   StepOutcome<Sc> o;
   try {
     if (sigs)

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
   if (a.out_rows && blockIdx.x == 0) {
     // padding of the materialised batch: rows beyond this replica's neighbourhood are not doable
     const uint32_t total_assigned = with_none ? block_count_assigned(var, n, scratch) : 0;
+    if (a.out_counts && threadIdx.x == 0) a.out_counts[r] = n * k + total_assigned;
     for (size_t q = (size_t)n * k + total_assigned + threadIdx.x; q < stride; q += blockDim.x) {
       ((uint2*)a.out_rows)[(size_t)r * stride + q] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
       if (a.out_scores) {

@@ -14,6 +14,7 @@
 
 #include "sfgpu_dev.cuh"
 
+
 namespace sfgpu_host {
 
 struct Collection {
@@ -64,6 +65,11 @@ struct UnionPlan {
   uint32_t* win_state = nullptr;   // [R] adaptive first window of each replica (resident loop)
   uint32_t w0 = 64, wmax = 4096;
   bool configured = false;
+  // SimulatedAnnealing in the resident loop (sfgpu_solve.cuh): sa_accept_kernel runs between scoring and the replay
+  bool sa = false;
+  SaState* sa_cur = nullptr;
+  SaState* sa_nxt = nullptr;
+  SaParams sa_params{};
 };
 
 struct sfgpu_ctx {
@@ -330,6 +336,10 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
                             uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc, bool adaptive,
                             uint32_t win_shift = 0);
 int sfgpu_union_reset_windows(sfgpu_ctx* ctx, UnionPlan& plan);
+// sfgpu_solve.cu
+int sfgpu_launch_sa_accept(sfgpu_ctx* ctx, const uint64_t* d_offs, const uint32_t* d_counts, const uint32_t* d_skip,
+                           const int64_t* d_scores, uint8_t* d_doable, const int64_t* d_ref, const uint64_t* d_seeds,
+                           const SaState* cur, SaState* nxt, const SaParams& p, uint32_t accepted_limit);
 // sfgpu_scalar.cu
 int sfgpu_configure_scalar(sfgpu_ctx* ctx);
 void sfgpu_change_step_chunks(const sfgpu_ctx* ctx, uint32_t* out_per, uint32_t* out_chunks);

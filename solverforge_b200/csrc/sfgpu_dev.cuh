@@ -145,6 +145,7 @@ struct ChangeStepArgs {
   int64_t* out_scores;
   uint8_t* out_doable;
   uint64_t* out_offsets;         // [R + 1] or null
+  uint32_t* out_counts;          // [R] or null: rows of the replica's neighbourhood (the rest of its stride is padding)
 };
 
 struct IndexStepArgs {
@@ -154,6 +155,21 @@ struct IndexStepArgs {
   const uint64_t* step_seeds;    // [R] or null
   const int64_t* ref_scores;     // [R][4] or null
   ChunkPartial* partials;        // [R][gridDim.x]
+};
+
+// SimulatedAnnealing (acceptor/simulated_annealing.rs): per-level temperatures, calibrated from the first
+// `sample_size` worsening candidates the phase evaluates (CalibrationState, :57-88), Boltzmann acceptance on the first
+// differing level (:338-375), geometric decay per step once calibrated (:416-431).
+struct SaParams {
+  double decay, hc_temp, fallback, neg_log_target;  // -ln(target acceptance), computed on the host
+  uint32_t sample_size;
+  int32_t never_hard;  // HardRegressionPolicy::NeverAcceptHardRegression
+};
+struct SaState {
+  double temp[2];
+  int64_t sum[2];
+  uint32_t cnt[2];
+  uint32_t calibrated, pad;
 };
 
 // ---- union of neighbourhoods (sfgpu_union.cuh) ----

@@ -4,6 +4,16 @@
 
 using namespace sfgpu_host;
 
+int sfgpu_launch_sa_accept(sfgpu_ctx* ctx, const uint64_t* d_offs, const uint32_t* d_counts, const uint32_t* d_skip,
+                           const int64_t* d_scores, uint8_t* d_doable, const int64_t* d_ref, const uint64_t* d_seeds,
+                           const SaState* cur, SaState* nxt, const SaParams& p, uint32_t accepted_limit) {
+  sa_accept_kernel<<<ctx->dm.R, 1024, 0, ctx->stream>>>(d_offs, d_counts, d_skip, d_scores, d_doable, d_ref, d_seeds, cur, nxt, p,
+                                                        accepted_limit);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
 namespace {
 int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t* out_best_scores,
                uint64_t* out_moves_evaluated, uint64_t* out_accepted_steps, const sfgpu_union_desc* udesc = nullptr,
@@ -21,10 +31,15 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
     if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
   }
-  if (p->acceptor < 1 || p->acceptor > 5)
+  if (p->acceptor < 1 || p->acceptor > 6)
     return fail(ctx, SFGPU_E_INVALID,
                 "acceptor: 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing, "
-                "5 DiversifiedLateAcceptance");
+                "5 DiversifiedLateAcceptance, 6 SimulatedAnnealing");
+  const bool sa = p->acceptor == 6;
+  if (sa && !scalar && !udesc)
+    return fail(ctx, SFGPU_E_UNSUPPORTED, "SimulatedAnnealing runs in sfgpu_solve_change and sfgpu_solve_union");
+  if (sa && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1.0))
+    return fail(ctx, SFGPU_E_INVALID, "simulated_annealing decay_rate must be finite and in (0, 1] (0 = default)");
   if ((p->acceptor == 3 || p->acceptor == 5) && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1e6))
     return fail(ctx, SFGPU_E_INVALID, "acceptor_real (rain_speed / tolerance) must be a finite value >= 0");
   if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
@@ -40,6 +55,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   const size_t o_ob = take((size_t)R * 16), o_oe = take((size_t)R * 4), o_win = take((size_t)R * 16);
   const size_t o_accst = take((size_t)R * 32);
   const size_t o_ovf = take((size_t)R * 16);
+  const size_t o_sa = take((size_t)R * sizeof(SaState) * 2), o_cnts = take((size_t)R * 4);
   const size_t o_snap = take((size_t)R * dm.block_bytes);
   if (o > ctx->solve_bytes) {
     if (ctx->solve_buf) cudaFree(ctx->solve_buf);
@@ -69,6 +85,18 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   s.acc_state = (int64_t*)(b + o_accst);
   s.real = p->acceptor_real;
   s.step_count_limit = p->step_count_limit;
+  s.sa_cur = (SaState*)(b + o_sa);
+  s.sa_nxt = s.sa_cur + R;
+  if (sa) {  // simulated_annealing.rs:11-15 defaults; late_size = calibration sample size, step_count_limit bit 0 =
+             // HardRegressionPolicy::NeverAcceptHardRegression
+    s.sa.decay = p->acceptor_real > 0.0 ? p->acceptor_real : 0.999985;
+    s.sa.hc_temp = 1.0e-9;
+    s.sa.fallback = 1.0;
+    s.sa.neg_log_target = -std::log(0.80);
+    s.sa.sample_size = p->late_size ? p->late_size : 128;
+    s.sa.never_hard = (int32_t)(p->step_count_limit & 1);
+  }
+  uint32_t* d_counts = (uint32_t*)(b + o_cnts);
   const int forage_code = solve_forage_code(p->acceptor);
   uint64_t* d_overflows = (uint64_t*)(b + o_ovf);
   CU(cudaMemsetAsync(d_overflows, 0, (size_t)R * 16, ctx->stream));  // [R] overflows, [R] pulls scored
@@ -81,6 +109,10 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     plan.a.step_indices = s.step_counter;
     plan.a.step_index_shared = 1;
     plan.a.ref_scores = s.ref_scores;
+    plan.sa = sa;
+    plan.sa_cur = s.sa_cur;
+    plan.sa_nxt = s.sa_nxt;
+    plan.sa_params = s.sa;
     rc = sfgpu_union_reset_windows(ctx, plan);
     if (rc) return rc;
   }
@@ -97,6 +129,18 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     ca.step_seeds = s.step_seeds;
     ca.ref_scores = s.ref_scores;
     ca.partials = (ChunkPartial*)ctx->partials;
+    if (sa) {  // the acceptor replays over the materialised, pull-ordered scores
+      const size_t stride = (size_t)dm.n_entities * (dm.n_values + 1);
+      const size_t need = (size_t)R * stride * (8 + 16 + 1) + (size_t)(R + 1) * 8 + 64;
+      rc = ensure_staging(ctx, 64, need);
+      if (rc) return rc;
+      char* q = (char*)ctx->dscr;
+      ca.out_scores = (int64_t*)q;
+      ca.out_rows = (uint32_t*)(q + (size_t)R * stride * 16);
+      ca.out_offsets = (uint64_t*)(q + (size_t)R * stride * 24);
+      ca.out_doable = (uint8_t*)(q + (size_t)R * stride * 24 + (size_t)(R + 1) * 8);
+      ca.out_counts = d_counts;
+    }
   } else if (!udesc) {
     rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
     if (rc) return rc;
@@ -115,7 +159,18 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     if (scalar) {
       rc2 = sfgpu_launch_change_step(ctx, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
       if (rc2) return rc2;
-      rc2 = sfgpu_launch_apply_scalar(ctx, 0, s.winner_rows, nullptr, nullptr, nullptr);
+      if (sa) {  // the fused partials of the step kernel are ignored: SA decides in pull order
+        rc2 = sfgpu_launch_sa_accept(ctx, ca.out_offsets, d_counts, nullptr, ca.out_scores, ca.out_doable, s.ref_scores,
+                                     s.step_seeds, s.sa_cur, s.sa_nxt, s.sa, p->accepted_limit);
+        if (rc2) return rc2;
+        rc2 = sfgpu_launch_argbest_counts(ctx, ForageDev{0, p->tie_mode, p->accepted_limit, nullptr}, ca.out_offsets, d_counts,
+                                          nullptr, ca.out_scores, ca.out_doable, s.step_seeds, s.ref_scores, s.out_index,
+                                          s.out_best, s.out_evaluated);
+        if (rc2) return rc2;
+        rc2 = sfgpu_launch_apply_scalar(ctx, 0, ca.out_rows, nullptr, ca.out_offsets, s.out_index);
+      } else {
+        rc2 = sfgpu_launch_apply_scalar(ctx, 0, s.winner_rows, nullptr, nullptr, nullptr);
+      }
     } else if (udesc) {
       // three window passes: the replica's adaptive window (what its previous step needed plus half), four times
       // that, then max_window — each only for the replicas whose forager had not quit in the pass before

@@ -32,6 +32,9 @@ struct SolveState {
   int32_t acceptor;         // sfgpu_solve_params.acceptor (1..5)
   double real;              // rain_speed / tolerance
   uint64_t step_count_limit;
+  SaState* sa_cur;          // [R] state at the start of the step
+  SaState* sa_nxt;          // [R] state after the step's evaluated candidates (committed by solve_post_kernel)
+  SaParams sa;
 };
 
 // forage acceptor code (sfgpu_forage_params) that one step of the solve-level acceptor reduces to
@@ -41,6 +44,7 @@ __host__ __device__ inline int solve_forage_code(int acceptor) {
     case 2: return 2;
     case 3: return 3;  // GreatDeluge: > last || >= water
     case 4: return 3;  // StepCounting: > last || >= (-inf | +inf)
+    case 6: return 0;  // SimulatedAnnealing: sa_accept_kernel leaves the accepted candidates as the doable ones
     default: return 2; // DiversifiedLateAcceptance: >= last || >= min(late, best - |best| * tol)
   }
 }
@@ -69,6 +73,11 @@ __global__ void solve_init_kernel(const __grid_constant__ DevModel m, SolveState
       s.acc_state[r * 4 + 3] = mul_round_dev(abs64_dev(cs[1]), s.real);
     } else {
       s.acc_state[r * 4 + 0] = 0;  // step_counting.rs:69-72: steps_since_improvement
+    }
+    if (s.acceptor == 6) {
+      SaState z{};
+      s.sa_cur[r] = z;
+      s.sa_nxt[r] = z;
     }
     s.best_scores[r * 2] = cs[0];
     s.best_scores[r * 2 + 1] = cs[1];
@@ -125,6 +134,14 @@ __global__ void __launch_bounds__(256) solve_post_kernel(const __grid_constant__
       s.acc_state[r * 4 + 1] += s.acc_state[r * 4 + 3];
     } else if (s.acceptor == 4) {  // step_counting.rs:74-90 (its best score == the phase's best score)
       s.acc_state[r * 4 + 0] = improved ? 0 : s.acc_state[r * 4 + 0] + 1;
+    } else if (s.acceptor == 6) {  // simulated_annealing.rs:416-431: no decay while calibrating
+      SaState z = s.sa_nxt[r];
+      if (z.calibrated)
+        for (int l = 0; l < 2; ++l) {
+          z.temp[l] = __dmul_rn(z.temp[l], s.sa.decay);
+          if (z.temp[l] < s.sa.hc_temp) z.temp[l] = s.sa.hc_temp;
+        }
+      s.sa_cur[r] = z;
     }
     if (improved) {
       s.best_scores[r * 2] = cs[0];
@@ -144,4 +161,161 @@ __global__ void solve_restore_best_kernel(const __grid_constant__ DevModel m, So
   char* st = m.state + (size_t)r * m.block_bytes;
   for (uint32_t i = threadIdx.x; i < m.block_bytes / 16; i += blockDim.x)
     ((uint4*)st)[i] = ((const uint4*)(s.best_state + (size_t)r * m.block_bytes))[i];
+}
+
+
+// inclusive block scan of a 32-bit count (same contract as block_scan_u32 of sfgpu_kernels.cuh)
+__device__ __forceinline__ uint32_t solve_scan_u32(uint32_t v, uint32_t* scratch /* >= 33 */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[warp] = x;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (warp == 0) {
+    uint32_t w = lane < nw ? scratch[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    scratch[lane] = w;
+  }
+  __syncthreads();
+  const uint32_t base = warp > 0 ? scratch[warp - 1] : 0;
+  *total = scratch[nw - 1];
+  __syncthreads();
+  return x + base;
+}
+
+// uniform stream of the SimulatedAnnealing acceptor. The reference draws from rand::SmallRng (third party, unpinned);
+// here draw j of a step is a pure function of the step seed, stated in the API, and only worsening candidates whose
+// level temperature is above the hill-climbing temperature consume a draw — exactly where the reference draws.
+__device__ __forceinline__ double sa_uniform(uint64_t step_seed, uint32_t j) {
+  const uint64_t x = splitmix64_dev(step_seed ^ 0x5A17EA11EA1DF00Dull ^ ((uint64_t)j * 0x9E3779B97F4A7C15ull));
+  return (double)(x >> 11) * 0x1.0p-53;
+}
+
+// One CTA per replica over its materialised, pull-ordered scores: replays SimulatedAnnealingAcceptor::is_accepted in
+// pull order up to the AcceptedCount cut and leaves doable[i] = accepted (argbest_kernel then runs with acceptor 0).
+// counts: rows of replica r (fixed-stride batch) or null (cand_offsets[r + 1]); skip[r] != 0: nothing to do.
+__global__ void __launch_bounds__(1024) sa_accept_kernel(const uint64_t* __restrict__ cand_offsets,
+                                                         const uint32_t* __restrict__ counts,
+                                                         const uint32_t* __restrict__ skip,
+                                                         const int64_t* __restrict__ scores, uint8_t* __restrict__ doable,
+                                                         const int64_t* __restrict__ ref_scores,
+                                                         const uint64_t* __restrict__ step_seeds, const SaState* cur,
+                                                         SaState* nxt, const SaParams p, const uint32_t accepted_limit) {
+  __shared__ uint32_t scratch[33];
+  __shared__ SaState z;
+  __shared__ uint32_t s_cut, s_cal;
+  __shared__ unsigned long long s_sum[2];
+  __shared__ uint32_t s_cnt[2];
+  const uint32_t r = blockIdx.x;
+  if (skip && skip[r]) return;
+  const uint64_t lo = cand_offsets[r], hi = counts ? lo + counts[r] : cand_offsets[r + 1];
+  const int64_t lh = ref_scores[r * 4 + 0], ls = ref_scores[r * 4 + 1];
+  const uint64_t seed = step_seeds ? step_seeds[r] : 0;
+  if (threadIdx.x == 0) z = cur[r];
+  __syncthreads();
+  uint32_t accepted_before = 0, draws_before = 0;
+  for (uint64_t base = lo; base < hi; base += blockDim.x) {
+    const uint64_t i = base + threadIdx.x;
+    const bool in = i < hi;
+    bool good = false, worse = false;
+    int lvl = 0;
+    int64_t delta = 0;
+    if (in && doable[i]) {
+      const longlong2 sc = ((const longlong2*)scores)[i];
+      if (!score_less(sc.x, sc.y, lh, ls)) good = true;  // move_score >= last_step_score
+      else {
+        lvl = sc.x != lh ? 0 : 1;
+        delta = lvl == 0 ? sc.x - lh : sc.y - ls;  // < 0
+        worse = !(p.never_hard && lvl == 0);       // a barred hard regression is rejected before it is sampled
+      }
+    }
+    uint32_t from = 0;  // positions of this chunk below `from` are settled (calibrating mode decided them)
+    bool acc = good;
+    if (!z.calibrated) {
+      uint32_t g_tot, w_tot;
+      const uint32_t g_incl = solve_scan_u32(good ? 1u : 0u, scratch, &g_tot);
+      const uint32_t w_incl = solve_scan_u32(worse ? 1u : 0u, scratch, &w_tot);
+      if (threadIdx.x == 0) {
+        s_cut = 0xFFFFFFFFu;
+        s_cal = 0xFFFFFFFFu;
+        s_sum[0] = s_sum[1] = 0;
+        s_cnt[0] = s_cnt[1] = 0;
+      }
+      __syncthreads();
+      const uint32_t seen = z.cnt[0] + z.cnt[1];
+      if (accepted_limit && good && accepted_before + g_incl == accepted_limit) s_cut = threadIdx.x;
+      if (worse && seen + w_incl == p.sample_size) s_cal = threadIdx.x;
+      __syncthreads();
+      const uint32_t cut = s_cut, cal = s_cal;
+      const uint32_t last = cut < cal ? cut : cal;  // samples are recorded up to here (inclusive)
+      if (worse && threadIdx.x <= last) {
+        atomicAdd(&s_sum[lvl], (unsigned long long)(-delta));
+        atomicAdd(&s_cnt[lvl], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int l = 0; l < 2; ++l) {
+          z.sum[l] += (int64_t)s_sum[l];
+          z.cnt[l] += s_cnt[l];
+        }
+        if (cal < cut) {  // CalibrationState::temperatures
+          const double denom = p.neg_log_target;
+          for (int l = 0; l < 2; ++l) {
+            double t = p.fallback;
+            if (z.cnt[l]) {
+              t = ((double)z.sum[l] / (double)z.cnt[l]) / denom;
+              if (t < p.fallback) t = p.fallback;
+            }
+            z.temp[l] = t;
+          }
+          z.calibrated = 1;
+        }
+      }
+      __syncthreads();
+      if (cut < cal) {  // the forager quits inside the calibrating part
+        if (in && threadIdx.x <= cut) doable[i] = acc ? 1 : 0;
+        break;
+      }
+      if (cal == 0xFFFFFFFFu) {  // still calibrating after this chunk: worsening candidates are rejected
+        if (in) doable[i] = acc ? 1 : 0;
+        accepted_before += g_tot;
+        continue;
+      }
+      // calibration completed at `cal`: that candidate and the later ones of the chunk go through the Boltzmann test
+      if (in && threadIdx.x < cal) doable[i] = acc ? 1 : 0;
+      uint32_t gb_tot;
+      solve_scan_u32((good && threadIdx.x < cal) ? 1u : 0u, scratch, &gb_tot);
+      accepted_before += gb_tot;
+      from = cal;
+    }
+    // calibrated: worsening candidates above the hill-climbing temperature draw in pull order
+    const bool active = threadIdx.x >= from;
+    const double T = z.temp[lvl];
+    const bool draws = active && worse && T > p.hc_temp;
+    uint32_t d_tot;
+    const uint32_t d_incl = solve_scan_u32(draws ? 1u : 0u, scratch, &d_tot);
+    if (draws) acc = sa_uniform(seed, draws_before + d_incl - 1) < exp((double)delta / T);
+    uint32_t a_tot;
+    const uint32_t a_incl = solve_scan_u32((active && acc) ? 1u : 0u, scratch, &a_tot);
+    if (threadIdx.x == 0) s_cut = 0xFFFFFFFFu;
+    __syncthreads();
+    if (accepted_limit && active && acc && accepted_before + a_incl == accepted_limit) s_cut = threadIdx.x;
+    __syncthreads();
+    const uint32_t cut = s_cut;
+    if (in && active && threadIdx.x <= cut) doable[i] = acc ? 1 : 0;
+    if (cut != 0xFFFFFFFFu) break;
+    accepted_before += a_tot;
+    draws_before += d_tot;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) nxt[r] = z;
 }

@@ -162,6 +162,11 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
   else union_score_kernel<false><<<dim3(chunks, R), 256, 0, ctx->stream>>>(dm, a);
   ctx->launches += a.n_children + 2;
   CU(cudaGetLastError());
+  if (plan.sa) {
+    int rc0 = sfgpu_launch_sa_accept(ctx, a.offsets, a.n_sched, a.done, a.scores, a.doable, a.ref_scores, a.step_seeds, plan.sa_cur,
+                                     plan.sa_nxt, plan.sa_params, a.f.accepted_limit);
+    if (rc0) return rc0;
+  }
   int rc = sfgpu_launch_argbest_counts(ctx, a.f, a.offsets, a.n_sched, a.done, a.scores, a.doable, a.step_seeds, a.ref_scores,
                                        d_idx, d_best, d_eval);
   if (rc) return rc;
@@ -183,6 +188,7 @@ int32_t sfgpu_step_union(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_union_desc*
   if (!out_index || !out_best) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   if (params && params->acceptor != 0 && !ref_scores) return fail(ctx, SFGPU_E_INVALID, "acceptor needs ref_scores");
   UnionPlan& plan = ctx->union_plan;
+  plan.sa = false;
   rc = sfgpu_union_prepare(ctx, desc, params, plan);
   if (rc) return rc;
   const uint32_t R = ctx->dm.R;

@@ -416,11 +416,12 @@ class OracleAcceptor:
     5 StepCountingHillClimbing(size = limit), 6 DiversifiedLateAcceptance(size, real = tolerance),
     7 TabuSearch(tabu = entity/value/move/undo tenures, aspiration)."""
     HILL_CLIMBING, LATE_ACCEPTANCE, ACCEPT_ALL, GREAT_DELUGE, STEP_COUNTING, DIVERSIFIED_LATE, TABU = 0, 1, 3, 4, 5, 6, 7
+    SIMULATED_ANNEALING = 2   # size = calibration samples, real = decay rate; aspiration=2: never accept hard regression
 
     def __init__(self, kind, size=0, real=0.0, tabu=None, aspiration=True):
         self.l = lib()
         t = np.asarray(tabu if tabu is not None else [0, 0, 0, 0], dtype=np.uint64)
-        self.h = self.l.sfo_acceptor_create(kind, size, float(real), _p(t), 1 if aspiration else 0)
+        self.h = self.l.sfo_acceptor_create(kind, size, float(real), _p(t), int(aspiration))
 
     def __del__(self):
         if getattr(self, "h", None):

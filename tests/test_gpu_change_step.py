@@ -170,3 +170,51 @@ def test_scalar_device_loop_stateful_acceptors_follow_the_oracle(kind, okind, si
         assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o
         assert np.array_equal(state[r], cur)
     assert np.array_equal(loop.fresh_score(), final)
+
+
+@pytest.mark.parametrize("limit,samples,decay,never_hard", [(0, 16, 0.9, False), (40, 128, 0.0, False), (7, 24, 0.95, True),
+                                                            (1, 8, 0.9, False)])
+def test_scalar_device_loop_simulated_annealing_follows_the_oracle(limit, samples, decay, never_hard):
+    """sfgpu_solve_change with SimulatedAnnealing (acceptor 6) against the oracle's SimulatedAnnealingAcceptor
+    (acceptor/simulated_annealing.rs:338-431: calibration over the evaluated worsening candidates, Boltzmann test,
+    decay) fed the same stated uniform stream: same trajectory, best score, moves_evaluated, committed steps."""
+    from solverforge_b200.selectors import splitmix64
+    from tests.oracle_lib import OracleAcceptor
+    g = instances.graph_coloring(150, 500, 4, seed_edges=6, seed_colors=9, unassigned_permille=100)
+    R, steps = 2, 30
+    colors = np.stack([instances.graph_coloring(150, 500, 4, seed_edges=6, seed_colors=50 + r, unassigned_permille=100).color
+                       for r in range(R)])
+    loop = models.graph_coloring_director(g, R, colors=colors)
+    seed_base = 777
+    best, evaluated, committed = loop.solve_change(steps, 6, samples, 1, limit, seed_base, acceptor_real=decay,
+                                                   step_count_limit=1 if never_hard else 0)
+    final = loop.calculate_score()
+    state = loop.scalar_state()
+    for r in range(R):
+        o = Oracle.graph_coloring(g, colors[r])
+        acc = OracleAcceptor(OracleAcceptor.SIMULATED_ANNEALING, size=samples, real=decay, aspiration=2 if never_hard else 1)
+        init = o.committed_score()
+        acc.phase_started(init)
+        best_o, ev_o, steps_o = init.copy(), 0, 0
+        cur = colors[r].copy()
+        for t in range(steps):
+            last = o.committed_score()
+            rows = o.enumerate_change()
+            so, oko = o.score_change(rows)
+            seed = splitmix64(seed_base ^ ((r * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) ^ t)
+            out = acc.step(so, oko, best_o, last, seed, 0 if limit else 2, max(limit, 1), True)
+            ev_o += out[2]
+            if out[0]:
+                e, v = rows[out[1]]
+                o.apply_change(e, v)
+                cur[int(e)] = int(v)
+                steps_o += 1
+            now = o.committed_score()
+            if (now[0], now[1]) > (best_o[0], best_o[1]):
+                best_o = now.copy()
+        what = f"limit={limit} samples={samples} r={r}"
+        assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o, what
+        assert final[r].tolist() == o.committed_score().tolist(), what
+        assert best[r].tolist() == best_o.tolist(), what
+        assert np.array_equal(state[r], cur), what
+    assert np.array_equal(loop.fresh_score(), final)

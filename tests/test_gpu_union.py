@@ -201,3 +201,47 @@ def test_solve_union_default_policy_trajectory_cvrp100_200_steps():
     assert int(ev[0]) == evaluated and int(acc[0]) == committed
     assert best[0].tolist() == best_o.tolist()
     assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+
+
+def test_solve_union_simulated_annealing_follows_the_oracle():
+    """SimulatedAnnealing inside the union loop (windows re-run from the state at the start of the step)."""
+    from solverforge_b200.selectors import splitmix64
+    from tests.oracle_lib import OracleAcceptor
+    c = instances.cvrp(40, 5, seed=12)
+    start = instances.perturb_routes(c, 3, 30)
+    d = models.cvrp_director(c, 1, offsets=start[0][None, :], elems=start[1])
+    o = Oracle.cvrp(c, *start)
+    desc = GpuScoreDirector.default_list_union(window=8)
+    n_steps, limit, seed_base, samples = 40, 12, 99, 20
+    best, ev, acc, ovf = d.solve_union(desc, n_steps, acceptor=6, late_size=samples, tie_mode=1, accepted_limit=limit,
+                                       seed_base=seed_base, acceptor_real=0.9)
+    apply_fn = {0: "apply_list_change", 1: "apply_list_swap", 2: "apply_sublist_change", 3: "apply_sublist_swap",
+                4: "apply_list_reverse"}
+    sa = OracleAcceptor(OracleAcceptor.SIMULATED_ANNEALING, size=samples, real=0.9)
+    init = o.committed_score().copy()
+    sa.phase_started(init)
+    best_o, evaluated, committed = init.copy(), 0, 0
+    for t in range(n_steps):
+        last = o.committed_score().copy()
+        seed = splitmix64(seed_base ^ 0 ^ t)
+        kids = oracle_lib.union_children(o, DEFAULT, t, seed, L.ORDER_RANDOM)
+        child, local = oracle_lib.union_pull_order([len(k[1]) for k in kids], L.UNION_STRATIFIED_RANDOM, t, seed, L.ORDER_RANDOM)
+        sc = np.zeros((len(child), 2), dtype=np.int64)
+        ok = np.zeros(len(child), dtype=np.uint8)
+        for ci, k in enumerate(kids):
+            sel = child == ci
+            sc[sel] = k[2][local[sel]]
+            ok[sel] = k[3][local[sel]]
+        out = sa.step(sc, ok, best_o, last, seed, 0, limit, True)
+        evaluated += out[2]
+        if out[0]:
+            ci, j = int(child[out[1]]), int(local[out[1]])
+            getattr(o, apply_fn[DEFAULT[ci][0]])(*[int(x) for x in kids[ci][0][j]])
+            committed += 1
+        now = o.committed_score().copy()
+        if tuple(now) > tuple(best_o):
+            best_o = now
+    assert ovf.tolist() == [0]
+    assert int(ev[0]) == evaluated and int(acc[0]) == committed
+    assert best[0].tolist() == best_o.tolist()
+    assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
