@@ -63,6 +63,14 @@ pub struct sfgpu_constraint_desc {
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
+pub struct sfgpu_expr_op {
+    pub op: i32,
+    pub arg: u32,
+    pub imm: i64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
 pub struct sfgpu_union_child {
     pub family: i32,
     pub p0: u32,
@@ -122,6 +130,7 @@ extern "C" {
     pub fn sfgpu_add_list_variable(ctx: *mut sfgpu_ctx, owner_collection: u32, element_collection: u32, name: *const c_char, out: *mut u32) -> i32;
     pub fn sfgpu_add_csr(ctx: *mut sfgpu_ctx, name: *const c_char, n_rows: u32, row_ptr: *const u32, col_idx: *const u32, out: *mut u32) -> i32;
     pub fn sfgpu_add_matrix_i64(ctx: *mut sfgpu_ctx, name: *const c_char, rows: u32, cols: u32, values: *const i64, cost_semantics: i32, out: *mut u32) -> i32;
+    pub fn sfgpu_add_expr(ctx: *mut sfgpu_ctx, ops: *const sfgpu_expr_op, n_ops: u32, out_expr: *mut u32) -> i32;
     pub fn sfgpu_add_constraint(ctx: *mut sfgpu_ctx, desc: *const sfgpu_constraint_desc, out: *mut u32) -> i32;
     pub fn sfgpu_set_scalar_state(ctx: *mut sfgpu_ctx, variable: u32, values: *const i32, per_replica: i32) -> i32;
     pub fn sfgpu_set_list_state(ctx: *mut sfgpu_ctx, variable: u32, offsets: *const u32, elems: *const u32, per_replica: i32) -> i32;

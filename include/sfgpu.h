@@ -83,7 +83,8 @@ int32_t sfgpu_add_scalar_variable(sfgpu_ctx* ctx, uint32_t collection, const cha
  * (#[planning_list_variable], crates/solverforge-cvrp/src/solution.rs:11-16) */
 int32_t sfgpu_add_list_variable(sfgpu_ctx* ctx, uint32_t owner_collection, uint32_t element_collection,
                                 const char* name, uint32_t* out_variable);
-/* CSR adjacency over one collection (Node::neighbors) */
+/* CSR over one collection: adjacency (Node::neighbors; PAIR_CSR_EQUAL needs column indices < n_rows) or any
+ * per-row list of int values (Employee::unavailable_days) for SFGPU_X_CSR_CONTAINS / JOIN_EXPR buckets */
 int32_t sfgpu_add_csr(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, const uint32_t* row_ptr,
                       const uint32_t* col_idx, uint32_t* out_csr);
 /* dense int64 matrix. cost_semantics 1 applies ProblemData::distance_cost at upload: a cell v is
@@ -171,6 +172,53 @@ typedef struct sfgpu_weight {
  *   3 = w(count()) of the distinct points; p1 = lo | hi << 32 with 0 <= lo <= hi <= p0. Groups without items
  *   do not exist and score nothing. */
 #define SFGPU_K_RUNS 10
+/* for_each(A).join(for_each(B), equal(a.var, b.key)).filter(pair filter).penalize(pair weight) — the general
+ * cross-collection join of the reference (constraint/cross_bi_incremental/state.rs:260-460, stream/join_target.rs:
+ * 57-110, stream/filter/adapters.rs:63-93) for the planning-model form: the A side is the entity collection, its join
+ * key is the scalar planning variable (None joins nothing) and the B side is a fact collection. Pair filter and
+ * pair weight are column expressions (sfgpu_add_expr) over (a, b, index of a, index of b) — closures cannot run
+ * on a GPU. No retained state: a ChangeMove of a re-evaluates the pairs of its old and its new key.
+ *   collection = A; p1 = B collection;
+ *   p0 = -1: b.key is the row index of B (a.var references a B row), else a CSR id mapping every key value to the
+ *        B rows that carry it (several B rows per key);
+ *   aux0 = pair filter expression id or UINT32_MAX (every joined pair matches);
+ *   aux1 = pair weight expression id or UINT32_MAX: the pair scores weight(x) with x = the expression's value
+ *        (x = 0 without one), e.g. {SFGPU_W_LINEAR, level, 1, 0} scores x itself, SFGPU_W_CONST a constant. */
+#define SFGPU_K_JOIN_EXPR 11
+
+/* Column expressions: a postfix program over an int64 stack (depth <= 8); booleans are 0 / 1. */
+#define SFGPU_X_CONST 1        /* push imm */
+#define SFGPU_X_A_COL 2        /* push column[arg][a] (a column of collection A) */
+#define SFGPU_X_B_COL 3        /* push column[arg][b] (a column of collection B) */
+#define SFGPU_X_A_IDX 4        /* push index of a */
+#define SFGPU_X_B_IDX 5        /* push index of b */
+#define SFGPU_X_VALUE 6        /* push the join key (value of a's planning variable) */
+#define SFGPU_X_ADD 10
+#define SFGPU_X_SUB 11
+#define SFGPU_X_MUL 12
+#define SFGPU_X_NEG 13
+#define SFGPU_X_ABS 14
+#define SFGPU_X_MIN 15
+#define SFGPU_X_MAX 16
+#define SFGPU_X_MOD 17         /* Euclidean-free: x % y with the sign of x, 0 when y == 0 */
+#define SFGPU_X_EQ 20
+#define SFGPU_X_NE 21
+#define SFGPU_X_LT 22
+#define SFGPU_X_LE 23
+#define SFGPU_X_GT 24
+#define SFGPU_X_GE 25
+#define SFGPU_X_AND 30
+#define SFGPU_X_OR 31
+#define SFGPU_X_NOT 32
+#define SFGPU_X_CSR_CONTAINS 40 /* pops x, then row: pushes csr[arg].row(row).contains(x) (e.g. unavailable_days) */
+#define SFGPU_X_SELECT 41       /* pops else, then, cond: pushes cond ? then : else */
+typedef struct sfgpu_expr_op {
+  int32_t op;
+  uint32_t arg;
+  int64_t imm;
+} sfgpu_expr_op;
+/* registers a program (validated: stack discipline, one result); ids are per context */
+int32_t sfgpu_add_expr(sfgpu_ctx* ctx, const sfgpu_expr_op* ops, uint32_t n_ops, uint32_t* out_expr);
 
 typedef struct sfgpu_constraint_desc {
   int32_t kind;

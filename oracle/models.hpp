@@ -573,4 +573,89 @@ struct RosterModel final : ModelImpl<Roster> {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// The fixture of the reference's cross-bi known-answer tests (constraint/tests/cross_bi_incr.rs:17-165:
+// Shift{employee_id: Option, day} x Employee{id, unavailable_days}) as a planning model, with the reference's own
+// constraints and authored pair-weight / index-aware / multi-row-per-key variants of the same CrossBiConstraint:
+//   1 "Unassigned shift"      for_each(shifts).filter(employee.is_none()).penalize(1 hard)
+//   2 "Unavailable employee"  join(employees, equal_bi(shift.employee, Some(employee.id)))
+//                             .filter(employee.unavailable_days.contains(shift.day)).penalize(1 hard)  [:63-88]
+//   3 "Skill gap"             same join, filter shift.required > employee.skill,
+//                             penalize((required - skill) * shift.hours soft) — a pair weight reading both sides
+//   4 "Indexed pairs"         same join, filter (shift_idx + 2 * employee_idx) % 3 == 0, penalize(shift.day soft)
+//                             — the index-aware filter of :308-341
+//   5 "Contract window"       join(contracts, equal_bi(shift.employee, Some(contract.employee))) — several
+//                             contract rows per employee —, filter day outside [from, to], penalize(contract.fee soft)
+struct AvShift {
+  size_t id;
+  int64_t day, required, hours;
+  OptVal employee;
+};
+struct AvEmployee {
+  size_t id;
+  int64_t skill;
+  std::vector<int64_t> unavailable_days;
+};
+struct AvContract {
+  size_t employee;
+  int64_t from, to, fee;
+};
+struct AvSchedule {
+  std::vector<AvShift> shifts;
+  std::vector<AvEmployee> employees;
+  std::vector<AvContract> contracts;
+};
+inline const std::vector<AvShift>& av_shifts(const AvSchedule& s) { return s.shifts; }
+inline const std::vector<AvEmployee>& av_employees(const AvSchedule& s) { return s.employees; }
+inline const std::vector<AvContract>& av_contracts(const AvSchedule& s) { return s.contracts; }
+
+struct AvailabilityModel final : ModelImpl<AvSchedule> {
+  explicit AvailabilityModel(AvSchedule sol) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const AvSchedule& s, size_t, size_t e) { return s.shifts[e].employee; };
+    dir.access.set = [](AvSchedule& s, size_t, size_t e, OptVal v) { s.shifts[e].employee = v; };
+    dir.access.entity_count = [](const AvSchedule& s, size_t) { return s.shifts.size(); };
+    Source<AvSchedule, AvShift> shifts{av_shifts, ChangeSource::Desc(0)};
+    Source<AvSchedule, AvEmployee> employees{av_employees, ChangeSource::Stat()};
+    Source<AvSchedule, AvContract> contracts{av_contracts, ChangeSource::Stat()};
+    auto uf = [](const AvSchedule&, const AvShift& s) { return !s.employee.has_value(); };
+    auto uw = [](const AvShift&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<AvSchedule, AvShift, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned shift", Impact::Penalty, shifts, uf, uw, true));
+    auto ka = [](const AvShift& s) { return s.employee.has_value() ? (int64_t)*s.employee : (int64_t)-1; };
+    auto kb = [](const AvEmployee& e) { return (int64_t)e.id; };
+    auto f2 = [](const AvSchedule&, const AvShift& s, const AvEmployee& e, size_t, size_t) {
+      return s.employee.has_value() && std::find(e.unavailable_days.begin(), e.unavailable_days.end(), s.day) != e.unavailable_days.end();
+    };
+    auto w2 = [](const AvSchedule&, const AvShift&, const AvEmployee&, size_t, size_t) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<CrossBiConstraint<AvSchedule, AvShift, AvEmployee, int64_t, Sc, decltype(ka),
+                                                           decltype(kb), decltype(f2), decltype(w2)>>(
+        "Unavailable employee", Impact::Penalty, shifts, employees, ka, kb, f2, w2, true));
+    auto f3 = [](const AvSchedule&, const AvShift& s, const AvEmployee& e, size_t, size_t) { return s.required > e.skill; };
+    auto w3 = [](const AvSchedule&, const AvShift& s, const AvEmployee& e, size_t, size_t) {
+      return Sc::of_soft((s.required - e.skill) * s.hours);
+    };
+    dir.constraints.add(std::make_unique<CrossBiConstraint<AvSchedule, AvShift, AvEmployee, int64_t, Sc, decltype(ka),
+                                                           decltype(kb), decltype(f3), decltype(w3)>>(
+        "Skill gap", Impact::Penalty, shifts, employees, ka, kb, f3, w3, false));
+    auto f4 = [](const AvSchedule&, const AvShift&, const AvEmployee&, size_t ia, size_t ib) { return (ia + 2 * ib) % 3 == 0; };
+    auto w4 = [](const AvSchedule&, const AvShift& s, const AvEmployee&, size_t, size_t) { return Sc::of_soft(s.day); };
+    dir.constraints.add(std::make_unique<CrossBiConstraint<AvSchedule, AvShift, AvEmployee, int64_t, Sc, decltype(ka),
+                                                           decltype(kb), decltype(f4), decltype(w4)>>(
+        "Indexed pairs", Impact::Penalty, shifts, employees, ka, kb, f4, w4, false));
+    auto kc = [](const AvContract& c) { return (int64_t)c.employee; };
+    auto f5 = [](const AvSchedule&, const AvShift& s, const AvContract& c, size_t, size_t) { return s.day < c.from || s.day > c.to; };
+    auto w5 = [](const AvSchedule&, const AvShift&, const AvContract& c, size_t, size_t) { return Sc::of_soft(c.fee); };
+    dir.constraints.add(std::make_unique<CrossBiConstraint<AvSchedule, AvShift, AvContract, int64_t, Sc, decltype(ka),
+                                                           decltype(kc), decltype(f5), decltype(w5)>>(
+        "Contract window", Impact::Penalty, shifts, contracts, ka, kc, f5, w5, false));
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.employees.size(), true, ctx);
+  }
+  std::vector<Move> enumerate_scalar_swap(MoveStreamContext ctx) override {
+    return enumerate_swap_moves(dir.working, dir.access, 0, 0, ctx);
+  }
+};
+
 }  // namespace sfo

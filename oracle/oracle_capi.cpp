@@ -118,6 +118,22 @@ void* sfo_roster_create(uint32_t n_shifts, uint32_t n_nurses, int64_t n_days, in
   return new RosterModel(std::move(s), limit);
 }
 
+// unavailable: CSR over employees (row_ptr[n_emp + 1], days); contracts: [n][4] = {employee, from, to, fee}
+void* sfo_availability_create(uint32_t n_shifts, uint32_t n_emp, const int64_t* day, const int64_t* required,
+                              const int64_t* hours, const int32_t* employee, const int64_t* skill, const uint32_t* un_ptr,
+                              const int64_t* un_days, uint32_t n_contracts, const int64_t* contracts) {
+  AvSchedule s;
+  for (uint32_t i = 0; i < n_shifts; ++i) s.shifts.push_back({i, day[i], required[i], hours[i], opt(employee[i])});
+  for (uint32_t e = 0; e < n_emp; ++e) {
+    AvEmployee emp{e, skill[e], {}};
+    for (uint32_t j = un_ptr[e]; j < un_ptr[e + 1]; ++j) emp.unavailable_days.push_back(un_days[j]);
+    s.employees.push_back(std::move(emp));
+  }
+  for (uint32_t k = 0; k < n_contracts; ++k)
+    s.contracts.push_back({(size_t)contracts[4 * k], contracts[4 * k + 1], contracts[4 * k + 2], contracts[4 * k + 3]});
+  return new AvailabilityModel(std::move(s));
+}
+
 void sfo_destroy(void* h) { delete static_cast<OracleModel*>(h); }
 
 int sfo_committed_score(void* h, int64_t out[2]) {

@@ -20,6 +20,11 @@ W_CONST, W_LINEAR, W_SQUARE, W_EXCESS, W_ABSDIFF, W_PAIRS = 0, 1, 2, 3, 4, 5
 PENALTY, REWARD = 0, 1
 K_UNI, K_PAIR_CSR_EQUAL, K_PAIR_KEY_EQUAL, K_EXISTS_FLAT, K_GROUP = 1, 2, 3, 4, 5
 K_LIST_PATH_COST, K_LIST_SUM, K_LOAD_BALANCE, K_PROJECT_GROUP, K_RUNS = 6, 7, 8, 9, 10
+K_JOIN_EXPR = 11
+X_CONST, X_A_COL, X_B_COL, X_A_IDX, X_B_IDX, X_VALUE = 1, 2, 3, 4, 5, 6
+X_ADD, X_SUB, X_MUL, X_NEG, X_ABS, X_MIN, X_MAX, X_MOD = 10, 11, 12, 13, 14, 15, 16, 17
+X_EQ, X_NE, X_LT, X_LE, X_GT, X_GE = 20, 21, 22, 23, 24, 25
+X_AND, X_OR, X_NOT, X_CSR_CONTAINS, X_SELECT = 30, 31, 32, 40, 41
 NO_COLUMN = 0xFFFFFFFF
 LIST_VAR = 0x80000000
 MAX_EDITS = 8
@@ -49,6 +54,10 @@ class SolveParams(C.Structure):
                 ("late_size", C.c_uint32), ("tie_mode", C.c_int32), ("accepted_limit", C.c_uint32),
                 ("seed_base", C.c_uint64), ("restore_best", C.c_int32), ("reserved", C.c_int32),
                 ("acceptor_real", C.c_double), ("step_count_limit", C.c_uint64)]
+
+
+class ExprOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("arg", C.c_uint32), ("imm", C.c_int64)]
 
 
 class UnionChild(C.Structure):
@@ -89,6 +98,7 @@ SYMBOLS = {
     "sfgpu_add_csr": (C.c_int32, [_P, C.c_char_p, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "sfgpu_add_matrix_i64": (C.c_int32, [_P, C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_int32,
                                          C.POINTER(C.c_uint32)]),
+    "sfgpu_add_expr": (C.c_int32, [_P, C.POINTER(ExprOp), C.c_uint32, C.POINTER(C.c_uint32)]),
     "sfgpu_add_constraint": (C.c_int32, [_P, C.POINTER(ConstraintDesc), C.POINTER(C.c_uint32)]),
     "sfgpu_set_scalar_state": (C.c_int32, [_P, C.c_uint32, _P, C.c_int32]),
     "sfgpu_set_list_state": (C.c_int32, [_P, C.c_uint32, _P, _P, C.c_int32]),

@@ -151,6 +151,8 @@ class GpuScoreDirector:
             raise L.SfgpuError(L.E_INVALID, "column length != collection rows")
         out = C.c_uint32()
         self._check(self.lib.sfgpu_add_column_i64(self.h, collection, name.encode(), _ptr(v), C.byref(out)))
+        self._col_host = getattr(self, "_col_host", {})
+        self._col_host[out.value] = v.copy()
         return out.value
 
     def add_scalar_variable(self, collection: int, name: str, n_values: int, allows_unassigned: bool = True) -> int:
@@ -183,6 +185,13 @@ class GpuScoreDirector:
         out = C.c_uint32()
         self._check(self.lib.sfgpu_add_matrix_i64(self.h, name.encode(), m.shape[0], m.shape[1], _ptr(m),
                                                   1 if cost_semantics else 0, C.byref(out)))
+        return out.value
+
+    def add_expr(self, expr: "Expr") -> int:
+        """Registers a column expression (sfgpu_add_expr) and returns its id."""
+        ops = (L.ExprOp * len(expr.ops))(*[L.ExprOp(o, a, i) for o, a, i in expr.ops])
+        out = C.c_uint32()
+        self._check(self.lib.sfgpu_add_expr(self.h, ops, len(expr.ops), C.byref(out)))
         return out.value
 
     def add_constraint(self, kind: int, impact: int, weight: WeightFn, collection: int = 0, variable: int = 0,
@@ -700,6 +709,80 @@ class EqualKey:
     arity: int = 2   # 3 / 4 / 5 after further .join(.., same joiner): tri / quad / penta self-join
 
 
+class Expr:
+    """Column expression over a joined pair (a, b): the data form of the reference's pair filter / pair weight
+    closures (stream/filter/adapters.rs:63-93). Built with the static constructors and Python operators; lowers to
+    the postfix program of sfgpu_add_expr."""
+
+    def __init__(self, ops):
+        self.ops = list(ops)
+
+    @staticmethod
+    def const(v: int) -> "Expr":
+        return Expr([(L.X_CONST, 0, int(v))])
+
+    @staticmethod
+    def a(column: int) -> "Expr":
+        return Expr([(L.X_A_COL, column, 0)])
+
+    @staticmethod
+    def b(column: int) -> "Expr":
+        return Expr([(L.X_B_COL, column, 0)])
+
+    @staticmethod
+    def a_index() -> "Expr":
+        return Expr([(L.X_A_IDX, 0, 0)])
+
+    @staticmethod
+    def b_index() -> "Expr":
+        return Expr([(L.X_B_IDX, 0, 0)])
+
+    @staticmethod
+    def value() -> "Expr":
+        return Expr([(L.X_VALUE, 0, 0)])
+
+    @staticmethod
+    def _lift(x) -> "Expr":
+        return x if isinstance(x, Expr) else Expr.const(x)
+
+    def _bin(self, other, op) -> "Expr":
+        return Expr(self.ops + Expr._lift(other).ops + [(op, 0, 0)])
+
+    def __add__(self, o): return self._bin(o, L.X_ADD)
+    def __sub__(self, o): return self._bin(o, L.X_SUB)
+    def __mul__(self, o): return self._bin(o, L.X_MUL)
+    def __mod__(self, o): return self._bin(o, L.X_MOD)
+    def __neg__(self): return Expr(self.ops + [(L.X_NEG, 0, 0)])
+    def __abs__(self): return Expr(self.ops + [(L.X_ABS, 0, 0)])
+    def eq(self, o): return self._bin(o, L.X_EQ)
+    def ne(self, o): return self._bin(o, L.X_NE)
+    def __lt__(self, o): return self._bin(o, L.X_LT)
+    def __le__(self, o): return self._bin(o, L.X_LE)
+    def __gt__(self, o): return self._bin(o, L.X_GT)
+    def __ge__(self, o): return self._bin(o, L.X_GE)
+    def __and__(self, o): return self._bin(o, L.X_AND)
+    def __or__(self, o): return self._bin(o, L.X_OR)
+    def __invert__(self): return Expr(self.ops + [(L.X_NOT, 0, 0)])
+    def min(self, o): return self._bin(o, L.X_MIN)
+    def max(self, o): return self._bin(o, L.X_MAX)
+
+    @staticmethod
+    def csr_contains(csr: int, row, x) -> "Expr":
+        """csr.row(row).contains(x), e.g. employee.unavailable_days.contains(shift.day)"""
+        return Expr(Expr._lift(row).ops + Expr._lift(x).ops + [(L.X_CSR_CONTAINS, csr, 0)])
+
+    @staticmethod
+    def select(cond, then, other) -> "Expr":
+        return Expr(Expr._lift(cond).ops + Expr._lift(then).ops + Expr._lift(other).ops + [(L.X_SELECT, 0, 0)])
+
+
+@dataclass
+class EqualVarToKey:
+    """equal_bi(|a| a.var, |b| Some(b.key)) where several B rows may share a key: bucket_csr row k lists the B rows
+    whose key is k (cross_bi_incremental/state.rs: b rows indexed by key)."""
+    bucket_csr: int
+
+
 @dataclass
 class EqualVarToRow:
     """equal_bi(|e| e.var, |v| Some(v.row)) — joins an entity with the value row it is assigned to."""
@@ -813,10 +896,14 @@ class UniStream:
     def join(self, other, joiner) -> "BiStream":
         return BiStream(self.d, self.collection, other, joiner)
 
-    def if_exists(self, flattened_owners: "UniStream", joiner: EqualId) -> "ExistsStream":
+    def if_exists(self, other: "UniStream", joiner) -> "ExistsStream":
+        if isinstance(joiner, (EqualVarToRow, EqualVarToKey)):
+            return DirectExistsStream(self.d, self.collection, other, joiner, 0)
         return ExistsStream(self.d, self.collection, joiner, 0)
 
-    def if_not_exists(self, flattened_owners: "UniStream", joiner: EqualId) -> "ExistsStream":
+    def if_not_exists(self, other: "UniStream", joiner) -> "ExistsStream":
+        if isinstance(joiner, (EqualVarToRow, EqualVarToKey)):
+            return DirectExistsStream(self.d, self.collection, other, joiner, 1)
         return ExistsStream(self.d, self.collection, joiner, 1)
 
     def group_by(self, collector) -> "GroupedStream":
@@ -920,13 +1007,70 @@ class ExistsStream:
                          collection=self.collection, variable=L.LIST_VAR, aux0=self.joiner.column, p0=self.mode)
 
 
-class BiStream:
-    def __init__(self, d, collection, other, joiner):
-        self.d, self.collection, self.other, self.joiner = d, collection, other, joiner
+class DirectExistsStream:
+    """for_each(A).if_[not_]exists(for_each(B).filter(fb), equal_bi(|a| a.var, |b| Some(b.key))) — the direct
+    (non-flattened) exists of the reference (constraint/exists.rs:167-272) with the planning variable as the A key and
+    a fact collection on the B side. B never changes during a solve, so the per-key count of filter-passing B rows is
+    a constant table: the constraint lowers on the host to a uni constraint over the per-value indicator
+    [b_count(key) > 0] (exists) / [b_count(key) == 0] (not exists) — exists.rs:148-159."""
+
+    def __init__(self, d, collection, other: "UniStream", joiner, mode: int):
+        self.d, self.collection, self.other, self.joiner, self.mode = d, collection, other, joiner, mode
 
     def _impact(self, impact, weight: HardSoftScore) -> _Terminal:
+        d = self.d
+        n_b = d.coll_rows[self.other.collection]
+        passing = np.ones(n_b, dtype=np.int64) if self.other.mask == L.NO_COLUMN else \
+            (d._col_host[self.other.mask] != 0).astype(np.int64)
+        if isinstance(self.joiner, EqualVarToKey):
+            rp, ci = d._csr_host[self.joiner.bucket_csr]
+            count = np.array([int(passing[ci[rp[k]:rp[k + 1]]].sum()) for k in range(len(rp) - 1)], dtype=np.int64)
+            values_coll = None
+        else:
+            count = passing
+            values_coll = self.other.collection
+        indicator = (count > 0).astype(np.int64) if self.mode == 0 else (count == 0).astype(np.int64)
+        if values_coll is None:
+            values_coll = d.add_collection(f"exists_keys_{len(d.coll_rows)}", len(indicator), -1)
+        col = d.add_column(values_coll, "exists_indicator", indicator)
         w = _const_weight(weight)
+        return _Terminal(d, kind=L.K_UNI, impact=impact, weight=WeightFn(L.W_LINEAR, w.level, w.a, 0),
+                         collection=self.collection, aux0=col, p0=1, p1=1)
+
+    def penalize(self, weight: HardSoftScore) -> _Terminal:
+        return self._impact(L.PENALTY, weight)
+
+    def reward(self, weight: HardSoftScore) -> _Terminal:
+        return self._impact(L.REWARD, weight)
+
+
+class BiStream:
+    def __init__(self, d, collection, other, joiner, pair_filter: Optional["Expr"] = None):
+        self.d, self.collection, self.other, self.joiner = d, collection, other, joiner
+        self.pair_filter = pair_filter
+
+    def filter(self, expr: "Expr") -> "BiStream":
+        """Pair filter |a, b, index of a, index of b| as a column expression (general cross-collection joins:
+        the entity's variable on the A side, a fact collection on the B side)."""
+        if not isinstance(self.joiner, (EqualVarToRow, EqualVarToKey)):
+            raise L.SfgpuError(L.E_UNSUPPORTED, "pair filters need the var -> row / var -> key joiner")
+        f = expr if self.pair_filter is None else (self.pair_filter & expr)
+        return BiStream(self.d, self.collection, self.other, self.joiner, f)
+
+    def _impact_expr(self, impact, weight, x: Optional["Expr"]) -> _Terminal:
+        """weight: HardSoftScore (constant per pair) or WeightFn of the pair expression x."""
         j = self.joiner
+        w = weight if isinstance(weight, WeightFn) else _const_weight(weight)
+        fid = L.NO_COLUMN if self.pair_filter is None else self.d.add_expr(self.pair_filter)
+        xid = L.NO_COLUMN if x is None else self.d.add_expr(x)
+        return _Terminal(self.d, kind=L.K_JOIN_EXPR, impact=impact, weight=w, collection=self.collection, aux0=fid, aux1=xid,
+                         p0=j.bucket_csr if isinstance(j, EqualVarToKey) else -1, p1=self.other.collection)
+
+    def _impact(self, impact, weight, x: Optional["Expr"] = None) -> _Terminal:
+        j = self.joiner
+        if isinstance(j, (EqualVarToRow, EqualVarToKey)):
+            return self._impact_expr(impact, weight, x)
+        w = _const_weight(weight)
         if isinstance(j, AdjacentEqual):
             return _Terminal(self.d, kind=L.K_PAIR_CSR_EQUAL, impact=impact, weight=w, collection=self.collection,
                              aux0=j.csr)
@@ -935,11 +1079,11 @@ class BiStream:
                              aux0=j.column, aux1=j.arity, p0=j.col_mul, p1=j.var_mul)
         raise L.SfgpuError(L.E_UNSUPPORTED, f"joiner {type(j).__name__} is not expressible on device")
 
-    def penalize(self, weight) -> _Terminal:
-        return self._impact(L.PENALTY, weight)
+    def penalize(self, weight, x: Optional["Expr"] = None) -> _Terminal:
+        return self._impact(L.PENALTY, weight, x)
 
-    def reward(self, weight) -> _Terminal:
-        return self._impact(L.REWARD, weight)
+    def reward(self, weight, x: Optional["Expr"] = None) -> _Terminal:
+        return self._impact(L.REWARD, weight, x)
 
     def join(self, other, joiner) -> "BiStream":
         """Third / fourth / fifth member of a keyed self-join (TriConstraintStream .. PentaConstraintStream,

@@ -140,8 +140,6 @@ int32_t sfgpu_add_csr(sfgpu_ctx* ctx, const char* name, uint32_t n_rows, const u
   uint32_t nnz = row_ptr[n_rows];
   if (nnz && !col_idx) return SFGPU_E_INVALID;
   c.col.assign(col_idx, col_idx + nnz);
-  for (uint32_t v : c.col)
-    if (v >= n_rows) return fail(ctx, SFGPU_E_INVALID, "csr column index out of range");
   ctx->csrs.push_back(std::move(c));
   *out_csr = (uint32_t)ctx->csrs.size() - 1;
   return SFGPU_OK;
@@ -167,11 +165,46 @@ int32_t sfgpu_add_matrix_i64(sfgpu_ctx* ctx, const char* name, uint32_t rows, ui
   return SFGPU_OK;
 } SFGPU_API_CATCH(ctx)
 
+int32_t sfgpu_add_expr(sfgpu_ctx* ctx, const sfgpu_expr_op* ops, uint32_t n_ops, uint32_t* out_expr) try {
+  if (!ctx || !ops || !out_expr) return SFGPU_E_INVALID;
+  if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
+  if (n_ops == 0 || n_ops > 4096) return fail(ctx, SFGPU_E_INVALID, "expression length must be in [1, 4096]");
+  int depth = 0;
+  for (uint32_t i = 0; i < n_ops; ++i) {
+    int pops = 0, pushes = 1;
+    switch (ops[i].op) {
+      case SFGPU_X_CONST: case SFGPU_X_A_IDX: case SFGPU_X_B_IDX: case SFGPU_X_VALUE: break;
+      case SFGPU_X_A_COL: case SFGPU_X_B_COL:
+        if (ops[i].arg >= ctx->cols.size()) return fail(ctx, SFGPU_E_INVALID, "expression reads an unknown column");
+        break;
+      case SFGPU_X_NEG: case SFGPU_X_ABS: case SFGPU_X_NOT: pops = 1; break;
+      case SFGPU_X_ADD: case SFGPU_X_SUB: case SFGPU_X_MUL: case SFGPU_X_MIN: case SFGPU_X_MAX: case SFGPU_X_MOD:
+      case SFGPU_X_EQ: case SFGPU_X_NE: case SFGPU_X_LT: case SFGPU_X_LE: case SFGPU_X_GT: case SFGPU_X_GE:
+      case SFGPU_X_AND: case SFGPU_X_OR: pops = 2; break;
+      case SFGPU_X_CSR_CONTAINS:
+        if (ops[i].arg >= ctx->csrs.size()) return fail(ctx, SFGPU_E_INVALID, "expression reads an unknown csr");
+        pops = 2;
+        break;
+      case SFGPU_X_SELECT: pops = 3; break;
+      default: return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown expression op (not expressible on device)");
+    }
+    if (depth < pops) return fail(ctx, SFGPU_E_INVALID, "expression stack underflow");
+    depth += pushes - pops;
+    if (depth > 8) return fail(ctx, SFGPU_E_UNSUPPORTED, "expression stack deeper than 8");
+  }
+  if (depth != 1) return fail(ctx, SFGPU_E_INVALID, "an expression leaves exactly one value");
+  ExprHost e;
+  e.ops.assign(ops, ops + n_ops);
+  ctx->exprs.push_back(std::move(e));
+  *out_expr = (uint32_t)ctx->exprs.size() - 1;
+  return SFGPU_OK;
+} SFGPU_API_CATCH(ctx)
+
 int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, uint32_t* out_constraint) try {
   if (!ctx || !desc) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
-  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_RUNS)
+  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_JOIN_EXPR)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
   if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_PAIRS || desc->weight.level < 0 ||
       desc->weight.level > 1)
@@ -245,6 +278,34 @@ int32_t sfgpu_set_list_state(sfgpu_ctx* ctx, uint32_t variable, const uint32_t* 
   v.per_replica = per_replica != 0;
   return SFGPU_OK;
 } SFGPU_API_CATCH(ctx)
+
+// device tables of the column expressions: pointers of every column and every CSR, uploaded once per model
+static int expr_tables(sfgpu_ctx* ctx) {
+  if (ctx->expr_cols_dev) return SFGPU_OK;
+  std::vector<const int64_t*> cols;
+  for (auto& c : ctx->cols) cols.push_back(c.dev);
+  if (cols.empty()) cols.push_back(nullptr);
+  std::vector<const uint32_t*> csrs;
+  for (auto& g : ctx->csrs) {
+    uint32_t *rp = nullptr, *ci = nullptr;
+    int rc = dev_upload(ctx, g.row_ptr.data(), g.row_ptr.size(), &rp);
+    if (rc) return rc;
+    rc = dev_upload(ctx, g.col.data(), g.col.size(), &ci);
+    if (rc) return rc;
+    csrs.push_back(rp);
+    csrs.push_back(ci);
+  }
+  if (csrs.empty()) csrs.push_back(nullptr);
+  const int64_t** dc = nullptr;
+  const uint32_t** dg = nullptr;
+  int rc = dev_upload(ctx, cols.data(), cols.size(), &dc);
+  if (rc) return rc;
+  rc = dev_upload(ctx, csrs.data(), csrs.size(), &dg);
+  if (rc) return rc;
+  ctx->expr_cols_dev = dc;
+  ctx->expr_csrs_dev = dg;
+  return SFGPU_OK;
+}
 
 int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
   if (!ctx) return SFGPU_E_INVALID;
@@ -413,10 +474,53 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
     };
     bool scalar_kind = d.kind == SFGPU_K_UNI || d.kind == SFGPU_K_PAIR_CSR_EQUAL || d.kind == SFGPU_K_PAIR_KEY_EQUAL ||
                        d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE || d.kind == SFGPU_K_PROJECT_GROUP ||
-                       d.kind == SFGPU_K_RUNS;
+                       d.kind == SFGPU_K_RUNS || d.kind == SFGPU_K_JOIN_EXPR;
     if (scalar_kind && !dm.has_scalar) return fail(ctx, SFGPU_E_INVALID, "constraint needs a scalar variable");
     if (!scalar_kind && !dm.has_list) return fail(ctx, SFGPU_E_INVALID, "constraint needs a list variable");
     switch (d.kind) {
+      case SFGPU_K_JOIN_EXPR: {
+        int rc = expr_tables(ctx);
+        if (rc) return rc;
+        if (d.collection != ctx->svars[0].coll) return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: the A side is the entity collection");
+        if (d.p1 < 0 || (size_t)d.p1 >= ctx->colls.size()) return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: unknown B collection");
+        const uint32_t a_coll = d.collection, b_coll = (uint32_t)d.p1, b_rows = ctx->colls[b_coll].n_rows;
+        if (d.p0 >= 0) {
+          if ((size_t)d.p0 >= ctx->csrs.size()) return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: unknown bucket csr");
+          const Csr& g = ctx->csrs[d.p0];
+          if (g.n_rows < dm.n_values) return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: the bucket csr needs a row per key value");
+          for (uint32_t v : g.col)
+            if (v >= b_rows) return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: bucket csr lists a B row out of range");
+        } else if (b_rows < dm.n_values) {
+          return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: the variable's values must be rows of B");
+        }
+        std::vector<sfgpu_expr_op> prog;
+        uint32_t lens[2] = {0, 0};
+        const uint32_t ids[2] = {d.aux0, d.aux1};
+        for (int w = 0; w < 2; ++w) {
+          if (ids[w] == 0xFFFFFFFFu) continue;
+          if (ids[w] >= ctx->exprs.size()) return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: unknown expression");
+          for (sfgpu_expr_op o : ctx->exprs[ids[w]].ops) {
+            if (o.op == SFGPU_X_A_COL && ctx->cols[o.arg].coll != a_coll)
+              return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: A_COL reads a column of another collection");
+            if (o.op == SFGPU_X_B_COL && ctx->cols[o.arg].coll != b_coll)
+              return fail(ctx, SFGPU_E_INVALID, "JOIN_EXPR: B_COL reads a column of another collection");
+            if (o.op == SFGPU_X_CSR_CONTAINS) o.imm = ctx->csrs[o.arg].n_rows;
+            prog.push_back(o);
+          }
+          lens[w] = (uint32_t)ctx->exprs[ids[w]].ops.size();
+        }
+        if (lens[0] > 0xFFFF || lens[1] > 0xFFFF) return fail(ctx, SFGPU_E_UNSUPPORTED, "expression too long");
+        sfgpu_expr_op* dprog = nullptr;
+        if (prog.empty()) prog.push_back(sfgpu_expr_op{SFGPU_X_CONST, 0, 0});
+        rc = dev_upload(ctx, prog.data(), prog.size(), &dprog);
+        if (rc) return rc;
+        c.g0 = dprog;
+        c.g1 = ctx->expr_cols_dev;
+        c.g2 = ctx->expr_csrs_dev;
+        c.n0 = lens[0] | (lens[1] << 16);
+        c.p0 = d.p0;
+        break;
+      }
       case SFGPU_K_UNI: {
         c.p0 = d.p0;
         const int64_t* col = nullptr;
@@ -439,6 +543,8 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
         if (d.aux0 >= ctx->csrs.size()) return fail(ctx, SFGPU_E_INVALID, "unknown csr");
         const Csr& g = ctx->csrs[d.aux0];
         if (g.n_rows != dm.n_entities) return fail(ctx, SFGPU_E_INVALID, "csr row count != entity count");
+        for (uint32_t v : g.col)
+          if (v >= g.n_rows) return fail(ctx, SFGPU_E_INVALID, "csr column index out of range");
         // partner lists: b is a partner of e iff the ordered pair (min,max) passes
         // `left.id < right.id && left.neighbors.contains(right.id)` (row index == id).
         std::vector<std::vector<uint32_t>> partners(g.n_rows);

@@ -272,6 +272,9 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
       case SFGPU_K_UNI:
         for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) local += uni_contrib(c, e, var[e]);
         break;
+      case SFGPU_K_JOIN_EXPR:
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) local += join_expr_contrib(c, e, var[e]);
+        break;
       case SFGPU_K_PAIR_CSR_EQUAL: {
         const uint32_t* rp = (const uint32_t*)c.g0;
         const uint32_t* ci = (const uint32_t*)c.g1;

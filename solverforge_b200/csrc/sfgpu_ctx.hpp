@@ -49,6 +49,9 @@ struct ListVar {
   std::vector<uint32_t> offsets, elems;
   bool per_replica = false;
 };
+struct ExprHost {
+  std::vector<sfgpu_expr_op> ops;
+};
 struct ConsHost {
   sfgpu_constraint_desc d;
   std::string name;
@@ -87,6 +90,9 @@ struct sfgpu_ctx {
   std::vector<sfgpu_host::ScalarVar> svars;
   std::vector<sfgpu_host::ListVar> lvars;
   std::vector<sfgpu_host::ConsHost> cons;
+  std::vector<sfgpu_host::ExprHost> exprs;
+  const void* expr_cols_dev = nullptr;  // column / CSR pointer tables of the column expressions
+  const void* expr_csrs_dev = nullptr;
   // device
   DevModel dm{};
   char* scratch_state = nullptr;

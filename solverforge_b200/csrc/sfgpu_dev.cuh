@@ -32,6 +32,12 @@ struct ConsDev {
 #define SFGPU_CF_COMPLEMENT 2u
 #define SFGPU_CF_COL_BY_VALUE 4u
 
+// column expressions of SFGPU_K_JOIN_EXPR (sfgpu_expr_op), evaluated per joined pair
+struct ExprTables {
+  const int64_t* const* cols;   // device pointer of every column, by column id
+  const uint32_t* const* csrs;  // {row_ptr, col} device pointers of every CSR, by 2 * csr id
+};
+
 struct DevModel {
   char* state;  // [R][block_bytes]
   uint32_t block_bytes;
@@ -228,6 +234,91 @@ __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
       return d > 0 ? w.a * d : 0;
     }
   }
+}
+
+// postfix evaluation of a column expression for the pair (a, b) joined on key value v
+__device__ __forceinline__ int64_t expr_eval(const sfgpu_expr_op* __restrict__ ops, uint32_t n, const ExprTables& t,
+                                             uint32_t a, uint32_t b, int64_t v) {
+  int64_t s[8];
+  int sp = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const sfgpu_expr_op o = ops[i];
+    switch (o.op) {
+      case SFGPU_X_CONST: s[sp++] = o.imm; break;
+      case SFGPU_X_A_COL: s[sp++] = t.cols[o.arg][a]; break;
+      case SFGPU_X_B_COL: s[sp++] = t.cols[o.arg][b]; break;
+      case SFGPU_X_A_IDX: s[sp++] = (int64_t)a; break;
+      case SFGPU_X_B_IDX: s[sp++] = (int64_t)b; break;
+      case SFGPU_X_VALUE: s[sp++] = v; break;
+      case SFGPU_X_NEG: s[sp - 1] = -s[sp - 1]; break;
+      case SFGPU_X_ABS: s[sp - 1] = s[sp - 1] < 0 ? -s[sp - 1] : s[sp - 1]; break;
+      case SFGPU_X_NOT: s[sp - 1] = s[sp - 1] == 0 ? 1 : 0; break;
+      case SFGPU_X_SELECT: {
+        const int64_t e = s[sp - 1], th = s[sp - 2], c = s[sp - 3];
+        sp -= 2;
+        s[sp - 1] = c != 0 ? th : e;
+        break;
+      }
+      case SFGPU_X_CSR_CONTAINS: {
+        const int64_t x = s[sp - 1], row = s[sp - 2];
+        --sp;
+        const uint32_t* rp = t.csrs[2 * o.arg];
+        const uint32_t* ci = t.csrs[2 * o.arg + 1];
+        int64_t hit = 0;
+        if (row >= 0 && row < o.imm)  // imm = row count of the CSR (set at commit)
+          for (uint32_t j = rp[row]; j < rp[row + 1]; ++j) hit |= (int64_t)ci[j] == x ? 1 : 0;
+        s[sp - 1] = hit;
+        break;
+      }
+      default: {
+        const int64_t y = s[sp - 1], x = s[sp - 2];
+        --sp;
+        int64_t r = 0;
+        switch (o.op) {
+          case SFGPU_X_ADD: r = x + y; break;
+          case SFGPU_X_SUB: r = x - y; break;
+          case SFGPU_X_MUL: r = x * y; break;
+          case SFGPU_X_MIN: r = x < y ? x : y; break;
+          case SFGPU_X_MAX: r = x > y ? x : y; break;
+          case SFGPU_X_MOD: r = y == 0 ? 0 : x % y; break;
+          case SFGPU_X_EQ: r = x == y; break;
+          case SFGPU_X_NE: r = x != y; break;
+          case SFGPU_X_LT: r = x < y; break;
+          case SFGPU_X_LE: r = x <= y; break;
+          case SFGPU_X_GT: r = x > y; break;
+          case SFGPU_X_GE: r = x >= y; break;
+          case SFGPU_X_AND: r = (x != 0) && (y != 0); break;
+          case SFGPU_X_OR: r = (x != 0) || (y != 0); break;
+        }
+        s[sp - 1] = r;
+      }
+    }
+  }
+  return s[0];
+}
+
+// SFGPU_K_JOIN_EXPR: sum over the B rows joined to key v of [filter(a, b)] * weight(x(a, b))
+// (CrossBiConstraint::evaluate restricted to one A row, cross_bi_incremental/state.rs:260-460)
+__device__ __forceinline__ int64_t join_expr_contrib(const ConsDev& c, uint32_t a, int32_t v) {
+  if (v < 0) return 0;  // key None joins nothing
+  const sfgpu_expr_op* ops = (const sfgpu_expr_op*)c.g0;
+  const ExprTables t{(const int64_t* const*)c.g1, (const uint32_t* const*)c.g2};
+  const uint32_t nf = c.n0 & 0xFFFFu, nw = c.n0 >> 16;
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)v + 1;
+  const uint32_t* bucket = nullptr;
+  if (c.p0 >= 0) {
+    const uint32_t* rp = t.csrs[2 * c.p0];
+    bucket = t.csrs[2 * c.p0 + 1];
+    lo = rp[v];
+    hi = rp[v + 1];
+  }
+  int64_t total = 0;
+  for (uint32_t j = lo; j < hi; ++j) {
+    const uint32_t b = bucket ? bucket[j] : j;
+    if (nf && expr_eval(ops, nf, t, a, b, v) == 0) continue;
+    total += weight_eval(c.w, nw ? expr_eval(ops + nf, nw, t, a, b, v) : 0);
+  }
+  return total;
 }
 
 // C(n, k) for the keyed self-joins of arity k + 1 (tuples that gain / lose one member of a bucket of n rows);

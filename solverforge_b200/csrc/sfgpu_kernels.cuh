@@ -108,6 +108,10 @@ static __device__ void scalar_edit_delta(const DevModel& m, const char* st, cons
         add_level(d, c, uni_contrib(c, cur.e, cur.new_v) - uni_contrib(c, cur.e, cur.old_v));
         break;
       }
+      case SFGPU_K_JOIN_EXPR: {  // pairs of one A row depend on that row only: no overlay needed
+        add_level(d, c, join_expr_contrib(c, cur.e, cur.new_v) - join_expr_contrib(c, cur.e, cur.old_v));
+        break;
+      }
       case SFGPU_K_PAIR_CSR_EQUAL: {
         // g0 = partner row_ptr, g1 = partner ids (symmetrised, deduplicated at commit)
         const uint32_t* rp = (const uint32_t*)c.g0;

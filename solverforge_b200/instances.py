@@ -267,3 +267,52 @@ def roster(n_shifts: int = 120, n_nurses: int = 7, n_days: int = 10, seed: int =
             k += 2
     return RosterInstance(n_shifts, n_nurses, n_days, limit, required, ptr, np.array(days, dtype=np.int64),
                           np.array(hours, dtype=np.int64), nurse)
+
+
+@dataclass
+class AvailabilityInstance:
+    """Shift x Employee (the fixture shape of the reference's cross-bi tests, constraint/tests/cross_bi_incr.rs:17-165)
+    plus skills / hours / contracts for the authored pair-weight and multi-row-per-key joins."""
+    n_shifts: int
+    n_employees: int
+    day: np.ndarray          # int64 per shift
+    required: np.ndarray     # int64 per shift: required skill
+    hours: np.ndarray        # int64 per shift
+    employee: np.ndarray     # int32 per shift, -1 = unassigned (the planning variable)
+    skill: np.ndarray        # int64 per employee
+    un_ptr: np.ndarray       # uint32 CSR over employees: unavailable days
+    un_days: np.ndarray      # uint32
+    contracts: np.ndarray    # int64 [n_contracts, 4] = employee, from, to, fee
+
+
+def availability(n_shifts: int = 60, n_employees: int = 7, n_days: int = 14, seed: int = 51,
+                 unassigned_permille: int = 120) -> AvailabilityInstance:
+    s = splitmix64_stream(seed, 6 * n_shifts + 4 * n_employees * 4 + 8)
+    at = 0
+
+    def take(n):
+        nonlocal at
+        out = s[at:at + n]
+        at += n
+        return out
+    day = (take(n_shifts) % np.uint64(n_days)).astype(np.int64)
+    required = (take(n_shifts) % np.uint64(5)).astype(np.int64)
+    hours = (take(n_shifts) % np.uint64(3)).astype(np.int64) * 4 + 4
+    employee = (take(n_shifts) % np.uint64(n_employees)).astype(np.int32)
+    employee[(take(n_shifts) % np.uint64(1000)) < np.uint64(unassigned_permille)] = -1
+    skill = (take(n_employees) % np.uint64(5)).astype(np.int64)
+    un_lists = []
+    pick = take(n_employees * 4)
+    for e in range(n_employees):
+        k = int(pick[4 * e] % np.uint64(4))       # 0..3 unavailable days
+        un_lists.append(sorted({int(pick[4 * e + 1 + j] % np.uint64(n_days)) for j in range(k)}))
+    un_ptr = np.concatenate([[0], np.cumsum([len(x) for x in un_lists])]).astype(np.uint32)
+    un_days = np.array([d for x in un_lists for d in x], dtype=np.uint32)
+    cs = take(n_employees * 4)
+    contracts = []
+    for e in range(n_employees):
+        for j in range(int(cs[4 * e] % np.uint64(3))):   # 0..2 contract rows per employee
+            lo = int(cs[4 * e + 1 + j] % np.uint64(n_days))
+            contracts.append([e, lo, min(n_days - 1, lo + 4), 3 + 2 * j])
+    contracts = np.array(contracts, dtype=np.int64).reshape(-1, 4)
+    return AvailabilityInstance(n_shifts, n_employees, day, required, hours, employee, skill, un_ptr, un_days, contracts)

@@ -175,3 +175,49 @@ def roster_director(inst, n_replicas: int = 1, nurse_idx=None, device: int = 0, 
     d.set_scalar_state(inst.nurse_idx if nurse_idx is None else nurse_idx)
     d.commit()
     return d
+
+
+def availability_director(inst, n_replicas: int = 1, employee=None, device: int = 0, stream=None,
+                          flags: int = 0) -> GpuScoreDirector:
+    """General cross-collection joins with pair filters and pair weights (SFGPU_K_JOIN_EXPR): the Shift x Employee
+    fixture of the reference's cross-bi tests (constraint/tests/cross_bi_incr.rs:63-88 "Unavailable employee",
+    :308-341 index-aware filter) plus authored pair-weight and multi-row-per-key joins — the same five constraints
+    as the oracle's AvailabilityModel."""
+    from .api import EqualVarToKey, Expr
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
+    employees = d.add_collection("employees", inst.n_employees, -1)
+    contracts = d.add_collection("contracts", max(len(inst.contracts), 1), -1)
+    shifts = d.add_collection("shifts", inst.n_shifts, 0)
+    d.add_scalar_variable(shifts, "employee", inst.n_employees, allows_unassigned=True)
+    day = d.add_column(shifts, "day", inst.day)
+    required = d.add_column(shifts, "required", inst.required)
+    hours = d.add_column(shifts, "hours", inst.hours)
+    skill = d.add_column(employees, "skill", inst.skill)
+    unavailable = d.add_csr("unavailable_days", inst.un_ptr, inst.un_days)
+    n_c = len(inst.contracts)
+    pad = np.zeros(max(n_c, 1), dtype=np.int64)
+    c_from, c_to, c_fee = pad.copy(), pad.copy(), pad.copy()
+    if n_c:
+        c_from[:], c_to[:], c_fee[:] = inst.contracts[:, 1], inst.contracts[:, 2], inst.contracts[:, 3]
+    c_from = d.add_column(contracts, "from", c_from)
+    c_to = d.add_column(contracts, "to", c_to)
+    c_fee = d.add_column(contracts, "fee", c_fee)
+    # bucket CSR: employee id -> its contract rows
+    order = np.argsort(inst.contracts[:, 0], kind="stable") if n_c else np.zeros(0, dtype=np.int64)
+    counts = np.bincount(inst.contracts[:, 0], minlength=inst.n_employees) if n_c else np.zeros(inst.n_employees, dtype=np.int64)
+    by_employee = d.add_csr("contracts_by_employee", np.concatenate([[0], np.cumsum(counts)]), order)
+    f = ConstraintFactory(d)
+    f.for_each(shifts).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned shift")
+    joined = f.for_each(shifts).join(f.for_each(employees), EqualVarToRow())
+    joined.filter(Expr.csr_contains(unavailable, Expr.b_index(), Expr.a(day))).penalize(HardSoftScore.ONE_HARD) \
+        .named("Unavailable employee")
+    joined.filter(Expr.a(required) > Expr.b(skill)) \
+        .penalize(soft(L.W_LINEAR, 1, 0), (Expr.a(required) - Expr.b(skill)) * Expr.a(hours)).named("Skill gap")
+    joined.filter(((Expr.a_index() + Expr.b_index() * 2) % 3).eq(0)).penalize(soft(L.W_LINEAR, 1, 0), Expr.a(day)) \
+        .named("Indexed pairs")
+    f.for_each(shifts).join(f.for_each(contracts), EqualVarToKey(by_employee)) \
+        .filter((Expr.a(day) < Expr.b(c_from)) | (Expr.a(day) > Expr.b(c_to))) \
+        .penalize(soft(L.W_LINEAR, 1, 0), Expr.b(c_fee)).named("Contract window")
+    d.set_scalar_state(inst.employee if employee is None else employee)
+    d.commit()
+    return d

@@ -31,7 +31,7 @@ def lib() -> C.CDLL:
             build()
         l = C.CDLL(LIB)
         for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create", "sfo_shift_create",
-                     "sfo_roster_create", "sfo_cluster_create"):
+                     "sfo_roster_create", "sfo_cluster_create", "sfo_availability_create"):
             getattr(l, name).restype = _P
         l.sfo_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
         l.sfo_nq_create.argtypes = [C.c_uint32, _P]
@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         l.sfo_js_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int]
         l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64]
         l.sfo_roster_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]
+        l.sfo_availability_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P]
         l.sfo_destroy.argtypes = [_P]
         l.sfo_committed_score.argtypes = [_P, _P]
         l.sfo_evaluate_all.argtypes = [_P, _P]
@@ -127,6 +128,17 @@ class Oracle:
         t = np.ascontiguousarray(inst.team if team is None else team, dtype=np.int32)
         j = np.ascontiguousarray(np.array(inst.joins, dtype=np.int64).reshape(-1))
         return Oracle(lib().sfo_cluster_create(inst.n, inst.n_teams, _p(t), len(inst.joins), _p(j)))
+
+    @staticmethod
+    def availability(inst, employee=None) -> "Oracle":
+        e = np.ascontiguousarray(inst.employee if employee is None else employee, dtype=np.int32)
+        day, req, hrs = (np.ascontiguousarray(x, dtype=np.int64) for x in (inst.day, inst.required, inst.hours))
+        skill = np.ascontiguousarray(inst.skill, dtype=np.int64)
+        ptr = np.ascontiguousarray(inst.un_ptr, dtype=np.uint32)
+        days = np.ascontiguousarray(inst.un_days, dtype=np.int64)
+        con = np.ascontiguousarray(inst.contracts, dtype=np.int64).reshape(-1)
+        return Oracle(lib().sfo_availability_create(inst.n_shifts, inst.n_employees, _p(day), _p(req), _p(hrs), _p(e), _p(skill),
+                                                    _p(ptr), _p(days), len(inst.contracts), _p(con)))
 
     @staticmethod
     def nqueens(inst, rows=None) -> "Oracle":
