@@ -145,6 +145,8 @@ extern "C" {
     /// rows[n][4] = {src_entity, start | size << 24, dst_entity, dst_position} (SublistChangeMove)
     pub fn sfgpu_score_sublist_change(ctx: *mut sfgpu_ctx, flags: u32, n: u64, cand_offsets: *const u64, rows: *const u32, out_scores: *mut i64, out_doable: *mut u8) -> i32;
     /// rows[n][4] = {first_entity, start1 | size1 << 24, second_entity, start2 | size2 << 24} (SublistSwapMove)
+    pub fn sfgpu_score_k_opt(ctx: *mut sfgpu_ctx, flags: u32, n_candidates: u64, cand_offsets: *const u64, rows: *const u32, out_scores: *mut i64, out_doable: *mut u8) -> i32;
+    pub fn sfgpu_apply_k_opt(ctx: *mut sfgpu_ctx, flags: u32, rows: *const u32, mask: *const u8) -> i32;
     pub fn sfgpu_score_sublist_swap(ctx: *mut sfgpu_ctx, flags: u32, n: u64, cand_offsets: *const u64, rows: *const u32, out_scores: *mut i64, out_doable: *mut u8) -> i32;
 
     pub fn sfgpu_argbest(ctx: *mut sfgpu_ctx, flags: u32, params: *const sfgpu_forage_params, cand_offsets: *const u64, scores: *const i64, doable: *const u8, step_seeds: *const u64, ref_scores: *const i64, out_index: *mut u32, out_best: *mut i64, out_evaluated: *mut u32) -> i32;

@@ -295,6 +295,16 @@ int32_t sfgpu_score_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_cand
                                  const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
 
 /* ---- winner selection on device ------------------------------------------------------- */
+/* KOptMove on one list (heuristic/move/k_opt.rs:11-110): cuts c_0 < .. < c_{k-1} (2 <= k <= 5) split the list into
+ * k + 1 segments; reconnection pattern p re-orders the middle segments and reverses some of them — p indexes
+ * enumerate_reconnections(k) (k_opt_reconnection.rs:218-262: every order of the middle segments, lexicographic,
+ * times every reversal mask, the identity dropped; 1 / 7 / 47 / 383 patterns for k = 2..5, the 3-opt table of
+ * k_opt/selector.rs:111-115 included). rows[n][4] = {entity | k << 28, c0 | c1 << 16, c2 | c3 << 16,
+ * c4 | p << 16} (positions < 65536). */
+#define SFGPU_KOPT_ROW0(entity, k) (((uint32_t)(entity) & 0x0FFFFFFFu) | ((uint32_t)(k) << 28))
+int32_t sfgpu_score_k_opt(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                          const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable);
+
 /* Per replica: replay of acceptor + forager over the scored rows in pull order
  * (phase/candidates.rs:66-282 with BestCandidate::consider, forager.rs:99-155).
  * acceptor: 0 = accept every doable candidate, 1 = HillClimbing (score > last_step_score,
@@ -440,7 +450,8 @@ int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_siz
  * (BestScore over a multi-million sublist neighbourhood is not what this call is for — use the per-family
  * whole-neighbourhood steps above).
  *   families : canonical cursors restated per family — NearbyListChange / NearbyListSwap (p0 = max_nearby <= 32),
- *              SublistChange / SublistSwap (p0 = min_size, p1 = max_size), ListReverse.
+ *              SublistChange / SublistSwap (p0 = min_size, p1 = max_size), ListReverse, KOpt (p0 = k, p1 =
+ *              min_segment_len; winner row = the packed k-opt row of sfgpu_score_k_opt).
  *   step_indices[R] (may be NULL = 0) and step_seeds[R] are the MoveStreamContext of each replica's step.
  *   out_index = CandidateId of the union cursor (pull index, vec_union.rs:447-455) or UINT32_MAX;
  *   out_winner_rows[R][8] = {family, child, row[4], child-local pull index, 0}.
@@ -451,6 +462,7 @@ int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_siz
 #define SFGPU_FAM_SUBLIST_CHANGE 2
 #define SFGPU_FAM_SUBLIST_SWAP 3
 #define SFGPU_FAM_LIST_REVERSE 4
+#define SFGPU_FAM_K_OPT 5 /* KOptMoveSelector, p0 = k (2..5), p1 = min_segment_len; list_kernel/k_opt/full.rs:34-98 */
 #define SFGPU_ORDER_ORIGINAL 0
 #define SFGPU_ORDER_RANDOM 1
 #define SFGPU_ORDER_SHUFFLED 2
@@ -540,9 +552,10 @@ int32_t sfgpu_apply_list_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* ro
 int32_t sfgpu_apply_list_reverse(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 int32_t sfgpu_apply_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
+int32_t sfgpu_apply_k_opt(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask);
 /* apply the winner found by sfgpu_argbest straight from the batch, no host round trip:
  * row = batch_rows[cand_offsets[r] + index[r]]; replicas with index == UINT32_MAX are skipped.
- * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap. All pointers are device pointers. */
+ * move_kind: 0 change, 1 swap, 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap, 7 k-opt. All pointers are device pointers. */
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
                             const uint32_t* batch_rows, const uint32_t* index);
 

@@ -544,6 +544,13 @@ struct MoveStreamContext {  // iter.rs:14-184
       default: return offset;
     }
   }
+  // iter.rs:130-147: an outer source dimension is walked once — Random and Shuffled share the strided permutation
+  size_t selection_index_without_replacement(size_t offset, size_t len, uint64_t salt) const {
+    if (is_canonical()) return offset;
+    size_t start = random_index(len, salt);
+    size_t stride = random_stride(len, salt ^ 0xA24BAED4963EE407ull);
+    return (start + offset * stride) % len;
+  }
 };
 
 // move_selector/change.rs:66-104,246-307 — values in order, then the to-None move when
@@ -763,7 +770,7 @@ inline bool cut_combination_at(size_t k, size_t len, size_t min_seg, size_t rank
 // heuristic/selector/list_kernel/k_opt/full.rs:34-98 (KOptCursor): per entity the moves are
 // (cut combination rank) x (reconnection pattern), pulled through selection_index over their product; 3-opt uses
 // the static THREE_OPT_RECONNECTIONS table (selector.rs:111-115), which enumerate_reconnections(3) reproduces.
-// Entities in canonical order only (selection_index_without_replacement is not restated).
+// Entities in the without-replacement stream order (full.rs:48-51, salt 0x4B0F7E1171000001 ^ descriptor).
 template <class S>
 std::vector<Move> enumerate_k_opt_moves(S& s, const Access<S>& ac, size_t desc, size_t k, size_t min_seg,
                                         MoveStreamContext ctx) {
@@ -771,7 +778,8 @@ std::vector<Move> enumerate_k_opt_moves(S& s, const Access<S>& ac, size_t desc, 
   std::vector<Move> out;
   std::vector<size_t> cuts;
   const size_t n = ac.entity_count(s, desc);
-  for (size_t e = 0; e < n; ++e) {
+  for (size_t eo = 0; eo < n; ++eo) {
+    const size_t e = ctx.selection_index_without_replacement(eo, n, 0x4B0F7E1171000001ull ^ (uint64_t)desc);
     const size_t len = ac.list(s, desc, e).size();
     const size_t move_count = count_cut_combinations(k, len, min_seg) * patterns.size();
     for (size_t off = 0; off < move_count; ++off) {

@@ -362,6 +362,14 @@ int sfo_score_k_opt(void* h, uint32_t k, uint64_t n, const uint32_t* rows, int64
   }, hard, soft, doable);
 }
 
+int sfo_apply_k_opt(void* h, uint32_t k, const uint32_t* row) {
+  auto* m = static_cast<OracleModel*>(h);
+  const auto patterns = enumerate_reconnections(k);
+  std::vector<size_t> cuts(row + 1, row + 1 + k);
+  m->apply(move_k_opt(m->list_desc(), row[0], cuts, patterns[row[k + 1] % patterns.size()]));
+  return 0;
+}
+
 int64_t sfo_enumerate_list_reverse(void* h, uint64_t step_index, uint64_t step_seed, int order, uint64_t cap,
                                    uint32_t* e, uint32_t* start, uint32_t* end) {
   auto moves = static_cast<OracleModel*>(h)->enumerate_list_reverse(make_ctx(step_index, step_seed, order));

@@ -72,6 +72,7 @@ class UnionDesc(C.Structure):
 
 
 FAM_NEARBY_LIST_CHANGE, FAM_NEARBY_LIST_SWAP, FAM_SUBLIST_CHANGE, FAM_SUBLIST_SWAP, FAM_LIST_REVERSE = 0, 1, 2, 3, 4
+FAM_K_OPT = 5
 ORDER_ORIGINAL, ORDER_RANDOM, ORDER_SHUFFLED = 0, 1, 2
 UNION_SEQUENTIAL, UNION_ROUND_ROBIN, UNION_ROTATING_ROUND_ROBIN, UNION_RANDOM, UNION_STRATIFIED_RANDOM = 0, 1, 2, 3, 4
 
@@ -111,6 +112,7 @@ SYMBOLS = {
     "sfgpu_score_list_reverse": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
     "sfgpu_score_sublist_change": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
     "sfgpu_score_sublist_swap": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
+    "sfgpu_score_k_opt": (C.c_int32, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]),
     "sfgpu_argbest": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     "sfgpu_argbest_gated": (C.c_int32, [_P, C.c_uint32, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sfgpu_step_list_change": (C.c_int32, [_P, C.c_uint64, _P, _P, C.POINTER(ForageParams), _P, _P, _P, _P, _P, _P,
@@ -140,6 +142,7 @@ SYMBOLS = {
     "sfgpu_apply_list_reverse": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_sublist_change": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_sublist_swap": (C.c_int32, [_P, C.c_uint32, _P, _P]),
+    "sfgpu_apply_k_opt": (C.c_int32, [_P, C.c_uint32, _P, _P]),
     "sfgpu_apply_winners": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
     "sfgpu_committed_scores": (C.c_int32, [_P, _P]),
     "sfgpu_evaluate_all": (C.c_int32, [_P, _P]),

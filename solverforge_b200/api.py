@@ -302,6 +302,23 @@ class GpuScoreDirector:
         """rows[n][6] = (first_entity, start1, end1, second_entity, start2, end2): SublistSwapMove."""
         return self._score(self.lib.sfgpu_score_sublist_swap, self.pack_sublist_swap(rows), 4, cand_offsets)
 
+    @staticmethod
+    def pack_k_opt(rows, k: int) -> np.ndarray:
+        """(entity, cut_0 .. cut_{k-1}, pattern) rows -> the packed device rows of sfgpu_score_k_opt."""
+        r = np.asarray(rows).astype(np.int64).reshape(-1, k + 2)
+        c = np.zeros((len(r), 5), dtype=np.int64)
+        c[:, :k] = r[:, 1:1 + k]
+        out = np.stack([r[:, 0] | (k << 28), c[:, 0] | (c[:, 1] << 16), c[:, 2] | (c[:, 3] << 16), c[:, 4] | (r[:, k + 1] << 16)],
+                       axis=1)
+        return np.ascontiguousarray(out.astype(np.uint32))
+
+    def score_k_opt(self, rows, k: int = 3, cand_offsets=None):
+        """rows[n][k + 2] = (entity, cuts.., pattern index) — KOptMove on one list (sfgpu_score_k_opt)."""
+        return self._score(self.lib.sfgpu_score_k_opt, self.pack_k_opt(rows, k), 4, cand_offsets)
+
+    def apply_k_opt(self, rows, k: int = 3, mask=None):
+        return self._apply(self.lib.sfgpu_apply_k_opt, self.pack_k_opt(rows, k), 4, mask)
+
     def score_compound(self, edit_offsets, edit_rows, cand_offsets=None):
         eo = np.ascontiguousarray(edit_offsets, dtype=np.uint64)
         rows = np.ascontiguousarray(np.asarray(edit_rows).astype(np.int64).astype(np.uint32)).reshape(-1, 2)

@@ -957,7 +957,8 @@ int sfgpu_launch_score_list(sfgpu_ctx* ctx, int kind, uint64_t n_total, const ui
 
 namespace {
 
-enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP, SK_LIST_REVERSE, SK_SUBLIST_CHANGE, SK_SUBLIST_SWAP };
+enum ScoreKind { SK_CHANGE, SK_SWAP, SK_COMPOUND, SK_LIST_CHANGE, SK_LIST_SWAP, SK_LIST_REVERSE, SK_SUBLIST_CHANGE, SK_SUBLIST_SWAP,
+                 SK_K_OPT };
 
 int launch_score(sfgpu_ctx* ctx, ScoreKind kind, uint64_t n_total, const uint64_t* d_offs, const uint32_t* d_rows,
                  const uint64_t* d_edit_offs, int64_t* d_scores, uint8_t* d_doable) {
@@ -1085,6 +1086,10 @@ int32_t sfgpu_score_sublist_change(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_ca
 int32_t sfgpu_score_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
                                  const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) try {
   return score_entry(ctx, SK_SUBLIST_SWAP, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
+} SFGPU_API_CATCH(ctx)
+int32_t sfgpu_score_k_opt(sfgpu_ctx* ctx, uint32_t flags, uint64_t n_candidates, const uint64_t* cand_offsets,
+                          const uint32_t* rows, int64_t* out_scores, uint8_t* out_doable) try {
+  return score_entry(ctx, SK_K_OPT, flags, n_candidates, cand_offsets, rows, nullptr, out_scores, out_doable);
 } SFGPU_API_CATCH(ctx)
 
 // ------------------------------------------------------------------------------------------
@@ -1235,9 +1240,12 @@ int32_t sfgpu_apply_sublist_change(sfgpu_ctx* ctx, uint32_t flags, const uint32_
 int32_t sfgpu_apply_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
   return apply_entry(ctx, 6, flags, rows, mask, nullptr, nullptr);
 } SFGPU_API_CATCH(ctx)
+int32_t sfgpu_apply_k_opt(sfgpu_ctx* ctx, uint32_t flags, const uint32_t* rows, const uint8_t* mask) try {
+  return apply_entry(ctx, 7, flags, rows, mask, nullptr, nullptr);
+} SFGPU_API_CATCH(ctx)
 int32_t sfgpu_apply_winners(sfgpu_ctx* ctx, int32_t move_kind, const uint64_t* cand_offsets,
                             const uint32_t* batch_rows, const uint32_t* index) try {
-  if (move_kind < 0 || move_kind > 6) return fail(ctx, SFGPU_E_INVALID, "bad move kind");
+  if (move_kind < 0 || move_kind > 7) return fail(ctx, SFGPU_E_INVALID, "bad move kind");
   if (!cand_offsets || !index) return fail(ctx, SFGPU_E_INVALID, "null pointer");
   return apply_entry(ctx, move_kind, SFGPU_DEVICE_IO, batch_rows, nullptr, cand_offsets, index);
 } SFGPU_API_CATCH(ctx)

@@ -577,7 +577,7 @@ __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind
   cs[1] += d.soft;
 }
 
-// kind 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap. Dynamic smem: elem_cap uint32 (old element copy).
+// kind 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap, 7 k-opt. Dynamic smem: elem_cap uint32 (old element copy).
 __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__ DevModel m, int kind,
                                                          const uint32_t* __restrict__ rows,
                                                          const uint8_t* __restrict__ mask,
@@ -609,9 +609,10 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
                         : (kind == 3 ? list_swap_delta(m, st, row, d)
                                      : (kind == 4 ? list_reverse_delta(m, st, row, d)
                                                   : (kind == 5 ? list_sublist_change_delta(m, st, row, d)
-                                                               : list_sublist_swap_delta(m, st, row, d))));
+                                                               : (kind == 6 ? list_sublist_swap_delta(m, st, row, d)
+                                                                            : list_k_opt_delta(m, st, row, d)))));
     s_ok = ok ? 1 : 0;
-    if (ok && kind == 4) {  // a reversal keeps every per-route sum
+    if (ok && (kind == 4 || kind == 7)) {  // a reversal / k-opt keeps every per-route sum
       int64_t* cs = (int64_t*)(st + m.off_score);
       cs[0] += d.hard;
       cs[1] += d.soft;
@@ -654,6 +655,23 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   if (kind == 4) {
     const uint32_t b = off[row.x];
     for (uint32_t i = row.y + threadIdx.x; i < row.z; i += blockDim.x) el[b + i] = old_el[b + row.y + (row.z - 1 - i)];
+  } else if (kind == 7) {
+    // k-opt: the route is rebuilt from its segments in the new order (k_opt.rs:40-85)
+    KOptDecoded q;
+    k_opt_decode(m, off, row, q);
+    const uint32_t b = off[q.e], len = q.bounds[q.k + 1];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+      uint32_t at = 0;
+      for (uint32_t pos = 0; pos <= q.k; ++pos) {
+        const uint32_t sg = q.order[pos], n = q.bounds[sg + 1] - q.bounds[sg];
+        if (i < at + n) {
+          const uint32_t j = i - at;
+          el[b + i] = old_el[b + (((q.rev >> sg) & 1) ? q.bounds[sg + 1] - 1 - j : q.bounds[sg] + j)];
+          break;
+        }
+        at += n;
+      }
+    }
   } else if (kind == 6) {
     // routes are contiguous in the flat element array, so both the intra- and the inter-list exchange are a swap
     // of two disjoint flat segments: [.. Ea) late [Ea + ne, La) early [La + nl ..)
@@ -715,8 +733,8 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
     int64_t* rcost = (int64_t*)(st + c.off0);
     const uint32_t depot = (uint32_t)c.p0;
     if (threadIdx.x < 2) {
-      uint32_t o = threadIdx.x == 0 || kind == 4 ? row.x : row.z;
-      if (!(threadIdx.x == 1 && (row.x == row.z || kind == 4))) {
+      uint32_t o = threadIdx.x == 0 || kind == 4 || kind == 7 ? (kind == 7 ? (row.x & 0x0FFFFFFFu) : row.x) : row.z;
+      if (!(threadIdx.x == 1 && (row.x == row.z || kind == 4 || kind == 7))) {
         int64_t cost = 0;
         uint32_t b = off[o], e = off[o + 1];
         if (e > b) {

@@ -700,7 +700,88 @@ __device__ __forceinline__ bool list_sublist_swap_delta(const DevModel& m, const
   return true;
 }
 
-enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2, LMODE_SUBLIST_CHANGE = 3, LMODE_SUBLIST_SWAP = 4 };
+// KOptMove on one list (heuristic/move/k_opt.rs:11-110): cuts c_0 < .. < c_{k-1} split the list into k + 1 segments;
+// the reconnection pattern re-orders the middle segments and reverses some of them (k_opt_reconnection.rs:63-262, the
+// pattern index counts enumerate_reconnections(k) — every order of the middle segments, every reversal mask, the
+// identity dropped). Row {entity | k << 28, c0 | c1 << 16, c2 | c3 << 16, c4 | pattern << 16}. Only the path cost can
+// change: the junction legs and, on an asymmetric matrix, the inner legs of the reversed segments.
+#define SFGPU_KOPT_MAX 5
+struct KOptDecoded {
+  uint32_t e, k, bounds[SFGPU_KOPT_MAX + 2], order[SFGPU_KOPT_MAX + 1], rev;  // rev: bit s = segment s reversed
+};
+__device__ __forceinline__ bool k_opt_decode(const DevModel& m, const uint32_t* off, uint4 row, KOptDecoded& q) {
+  q.e = row.x & 0x0FFFFFFFu;
+  q.k = row.x >> 28;
+  if (q.e >= m.n_owners || q.k < 2 || q.k > SFGPU_KOPT_MAX) return false;
+  const uint32_t len = off[q.e + 1] - off[q.e];
+  const uint32_t c[5] = {row.y & 0xFFFFu, row.y >> 16, row.z & 0xFFFFu, row.z >> 16, row.w & 0xFFFFu};
+  q.bounds[0] = 0;
+  for (uint32_t i = 0; i < q.k; ++i) {
+    if (c[i] > len || (i > 0 && c[i] <= c[i - 1])) return false;  // k_opt.rs:11-38
+    q.bounds[i + 1] = c[i];
+  }
+  q.bounds[q.k + 1] = len;
+  // pattern -> (permutation of the middle segments 1..k-1 in lexicographic order, reversal mask)
+  const uint32_t raw = (row.w >> 16) + 1;  // raw index 0 is the identity, which the reference drops
+  const uint32_t mid = q.k - 1;
+  uint32_t perm = raw >> mid;
+  q.rev = (raw & ((1u << mid) - 1)) << 1;
+  uint32_t fact = 1;
+  for (uint32_t i = 2; i <= mid; ++i) fact *= i;
+  if (perm >= fact) return false;
+  uint32_t avail[SFGPU_KOPT_MAX];
+  for (uint32_t i = 0; i < mid; ++i) avail[i] = i + 1;
+  q.order[0] = 0;
+  for (uint32_t i = 0; i < mid; ++i) {
+    fact /= (mid - i);
+    const uint32_t pick = perm / fact;
+    perm %= fact;
+    q.order[i + 1] = avail[pick];
+    for (uint32_t j = pick; j + 1 < mid - i; ++j) avail[j] = avail[j + 1];
+  }
+  q.order[q.k] = q.k;
+  return true;
+}
+__device__ __forceinline__ bool list_k_opt_delta(const DevModel& m, const char* st, uint4 row, Score2& d) {
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  d.hard = 0;
+  d.soft = 0;
+  KOptDecoded q;
+  if (!k_opt_decode(m, off, row, q)) return false;
+  const uint32_t b = off[q.e];
+  for (uint32_t kk = 0; kk < m.n_cons; ++kk) {
+    const ConsDev& c = m.cons[kk];
+    if (c.kind != SFGPU_K_LIST_PATH_COST) continue;
+    const uint32_t depot = (uint32_t)c.p0;
+    int64_t delta = 0;
+    uint32_t new_tail = depot, old_tail = depot;
+    bool any = false;
+    for (uint32_t pos = 0; pos <= q.k; ++pos) {
+      // the old route visits segment `pos`, the new one segment order[pos]
+      const uint32_t so = pos, sn = q.order[pos];
+      if (q.bounds[so + 1] > q.bounds[so]) {
+        delta -= mat_at(c, old_tail, el[b + q.bounds[so]]);
+        old_tail = el[b + q.bounds[so + 1] - 1];
+        any = true;
+      }
+      if (q.bounds[sn + 1] > q.bounds[sn]) {
+        const bool rv = (q.rev >> sn) & 1;
+        const uint32_t lo = b + q.bounds[sn], hi = b + q.bounds[sn + 1] - 1;
+        delta += mat_at(c, new_tail, rv ? el[hi] : el[lo]);
+        new_tail = rv ? el[lo] : el[hi];
+        if (rv)
+          for (uint32_t i = lo; i < hi; ++i) delta += mat_at(c, el[i + 1], el[i]) - mat_at(c, el[i], el[i + 1]);
+      }
+    }
+    if (any) delta += mat_at(c, new_tail, depot) - mat_at(c, old_tail, depot);
+    const int64_t oc = ((const int64_t*)(st + c.off0))[q.e];
+    add_level(d, c, weight_eval(c.w, oc + delta) - weight_eval(c.w, oc));
+  }
+  return true;
+}
+
+enum { LMODE_CHANGE = 0, LMODE_SWAP = 1, LMODE_REVERSE = 2, LMODE_SUBLIST_CHANGE = 3, LMODE_SUBLIST_SWAP = 4, LMODE_K_OPT = 5 };
 
 template <int LMODE, bool STAGED>
 __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__ DevModel m,
@@ -729,8 +810,10 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
                   : (LMODE == LMODE_SWAP ? list_swap_delta(m, st, row, d)
                                          : (LMODE == LMODE_REVERSE
                                                 ? list_reverse_delta(m, st, row, d)
-                                                : (LMODE == LMODE_SUBLIST_CHANGE ? list_sublist_change_delta(m, st, row, d)
-                                                                                 : list_sublist_swap_delta(m, st, row, d))));
+                                                : (LMODE == LMODE_SUBLIST_CHANGE
+                                                       ? list_sublist_change_delta(m, st, row, d)
+                                                       : (LMODE == LMODE_SUBLIST_SWAP ? list_sublist_swap_delta(m, st, row, d)
+                                                                                      : list_k_opt_delta(m, st, row, d)))));
     longlong2 o;
     o.x = ok ? ch + d.hard : 0;
     o.y = ok ? csf + d.soft : 0;

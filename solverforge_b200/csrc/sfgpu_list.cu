@@ -21,6 +21,7 @@ int sfgpu_configure_list(sfgpu_ctx* ctx) {
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_REVERSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SUBLIST_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_list_kernel<LMODE_SUBLIST_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(score_list_kernel<LMODE_K_OPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
   if (dm.fast_list) {
     {
@@ -127,6 +128,7 @@ int sfgpu_launch_score_list(sfgpu_ctx* ctx, int kind, uint64_t n_total, const ui
     case 4: LAUNCH_LIST(LMODE_SWAP); break;
     case 5: LAUNCH_LIST(LMODE_REVERSE); break;
     case 6: LAUNCH_LIST(LMODE_SUBLIST_CHANGE); break;
+    case 8: LAUNCH_LIST(LMODE_K_OPT); break;
     default: LAUNCH_LIST(LMODE_SUBLIST_SWAP); break;
   }
   ev_end(ctx);

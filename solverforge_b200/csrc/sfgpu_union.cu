@@ -24,10 +24,13 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   bool any_nearby = false;
   for (uint32_t c = 0; c < desc->n_children; ++c) {
     const sfgpu_union_child& ch = desc->children[c];
-    if (ch.family < 0 || ch.family > SFGPU_FAM_LIST_REVERSE) return fail(ctx, SFGPU_E_INVALID, "unknown move family");
+    if (ch.family < 0 || ch.family > SFGPU_FAM_K_OPT) return fail(ctx, SFGPU_E_INVALID, "unknown move family");
     if (is_nearby(ch.family)) {
       any_nearby = true;
       if (ch.p0 == 0 || ch.p0 > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+    } else if (ch.family == SFGPU_FAM_K_OPT) {
+      if (ch.p0 < 2 || ch.p0 > 5 || ch.p1 == 0) return fail(ctx, SFGPU_E_INVALID, "k-opt: 2 <= k <= 5, min_segment_len >= 1");
+      if (dm.elem_cap >= 65536) return fail(ctx, SFGPU_E_UNSUPPORTED, "k-opt rows hold 16-bit cut positions");
     } else if (ch.family != SFGPU_FAM_LIST_REVERSE) {
       if (ch.p0 == 0 || ch.p1 < ch.p0 || ch.p1 > 255) return fail(ctx, SFGPU_E_INVALID, "sublist sizes: 1 <= min <= max <= 255");
     }

@@ -197,6 +197,59 @@ __device__ inline void walk_sublist_swap(const StreamCtx& cx, uint32_t desc, con
   }
 }
 
+// KOptCursor: heuristic/selector/list_kernel/k_opt/full.rs:34-98 — entities in the without-replacement stream order
+// (iter.rs:130-147: Random and Shuffled both walk start + offset * stride), per entity the (cut combination rank) x
+// (reconnection pattern) product pulled through selection_index; cut_combination_at: k_opt/iterators.rs:118-176.
+__device__ __forceinline__ uint64_t binomial_dev(uint32_t n, uint32_t k) {
+  if (k > n) return 0;
+  if (k > n - k) k = n - k;
+  uint64_t r = 1;
+  for (uint32_t i = 0; i < k; ++i) r = r * (n - i) / (i + 1);
+  return r;
+}
+__device__ inline void walk_k_opt(const StreamCtx& cx, uint32_t desc, const uint32_t* off, uint32_t n, uint32_t k,
+                                  uint32_t min_seg, RowSink& out) {
+  uint32_t n_pat = 1;  // (k-1)! * 2^(k-1) - 1 reconnection patterns
+  for (uint32_t i = 2; i < k; ++i) n_pat *= i;
+  n_pat = (n_pat << (k - 1)) - 1;
+  uint32_t start = 0, stride = 1;
+  if (cx.order != SFGPU_ORDER_ORIGINAL) {
+    const uint64_t salt = 0x4B0F7E1171000001ull ^ (uint64_t)desc;
+    start = cx.random_index(n, salt);
+    stride = cx.random_stride(n, salt ^ 0xA24BAED4963EE407ull);
+  }
+  for (uint32_t o = 0; o < n; ++o) {
+    const uint32_t e = cx.order == SFGPU_ORDER_ORIGINAL ? o : (uint32_t)(((uint64_t)start + (uint64_t)o * stride) % n);
+    const uint32_t len = off[e + 1] - off[e];
+    if (len < (k + 1) * min_seg) continue;
+    const uint32_t choice_count = len - (k + 1) * min_seg + k;
+    const uint64_t combos = binomial_dev(choice_count, k);
+    const uint64_t move_count = combos * n_pat;
+    if (move_count == 0 || move_count > 0xFFFFFFFFull) continue;
+    const SelMap mm(cx, (uint32_t)move_count, 0x4B0F7E1171000002ull ^ (uint64_t)desc ^ (uint64_t)e);
+    for (uint32_t mo = 0; mo < (uint32_t)move_count; ++mo) {
+      const uint32_t sel = mm.at(mo);
+      uint64_t rank = sel / n_pat;
+      const uint32_t pattern = sel % n_pat;
+      uint32_t cuts[5] = {0, 0, 0, 0, 0};
+      uint32_t first = 0;
+      for (uint32_t position = 0; position < k; ++position) {
+        const uint32_t remaining = k - position - 1, maximum = choice_count - (k - position);
+        for (uint32_t cand = first; cand <= maximum; ++cand) {
+          const uint64_t suffix = binomial_dev(choice_count - cand - 1, remaining);
+          if (rank < suffix) {
+            cuts[position] = cand + min_seg + position * (min_seg - 1);
+            first = cand + 1;
+            break;
+          }
+          rank -= suffix;
+        }
+      }
+      if (!out.push(e | (k << 28), cuts[0] | (cuts[1] << 16), cuts[2] | (cuts[3] << 16), cuts[4] | (pattern << 16))) return;
+    }
+  }
+}
+
 // grid = R, 32 threads; lane 0 walks (the cursors are sequential state machines; replicas run side by side)
 __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_constant__ DevModel m, const UnionArgs a,
                                                               const uint32_t child) {
@@ -212,6 +265,7 @@ __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_const
   out.more = false;
   const UnionChildDev& c = a.child[child];
   if (c.family == SFGPU_FAM_LIST_REVERSE) walk_reverse(cx, a.desc, off, m.n_owners, out);
+  else if (c.family == SFGPU_FAM_K_OPT) walk_k_opt(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
   else if (c.family == SFGPU_FAM_SUBLIST_CHANGE) walk_sublist_change(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
   else walk_sublist_swap(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
   a.n_emit[(size_t)r * a.n_children + child] = out.n;
@@ -723,6 +777,7 @@ __device__ __forceinline__ bool union_delta(const DevModel& m, const char* st, i
     case SFGPU_FAM_NEARBY_LIST_SWAP: return list_swap_delta(m, st, row, d);
     case SFGPU_FAM_LIST_REVERSE: return list_reverse_delta(m, st, row, d);
     case SFGPU_FAM_SUBLIST_CHANGE: return list_sublist_change_delta(m, st, row, d);
+    case SFGPU_FAM_K_OPT: return list_k_opt_delta(m, st, row, d);
     default: return list_sublist_swap_delta(m, st, row, d);
   }
 }
@@ -799,6 +854,7 @@ __global__ void union_pick_kernel(const UnionArgs a, const uint32_t R, const uin
            : family == SFGPU_FAM_NEARBY_LIST_SWAP ? 3
            : family == SFGPU_FAM_LIST_REVERSE     ? 4
            : family == SFGPU_FAM_SUBLIST_CHANGE   ? 5
+           : family == SFGPU_FAM_K_OPT            ? 7
                                                   : 6;
   }
   ((uint4*)apply_rows)[r] = row;

@@ -65,6 +65,14 @@ class MoveStreamContext:
             return (start + offset * stride) % length
         return offset
 
+    def selection_index_without_replacement(self, offset: int, length: int, salt: int) -> int:
+        """iter.rs:130-147: outer source dimensions are walked once — Random and Shuffled share the strided order."""
+        if self.is_canonical():
+            return offset
+        start = self.random_index(length, salt)
+        stride = self.random_stride(length, salt ^ 0xA24BAED4963EE407)
+        return (start + offset * stride) % length
+
 
 def change_move_rows(values: np.ndarray, n_values: int, allows_unassigned: bool = True,
                      ctx: MoveStreamContext = MoveStreamContext(), descriptor_index: int = 0,
@@ -327,14 +335,16 @@ def k_opt_rows(offsets: np.ndarray, k: int = 3, min_seg: int = 1, ctx: MoveStrea
                descriptor_index: int = 0) -> np.ndarray:
     """rows[n][k + 2] = (entity, cut_0 .. cut_{k-1}, pattern index) in the pull order of KOptMoveSelector
     (heuristic/selector/list_kernel/k_opt/full.rs:34-98): per entity the (cut combination rank) x (pattern)
-    product pulled through selection_index. Entities in canonical order. Host-side groundwork: the device does not
-    score k-opt rows yet."""
+    product pulled through selection_index; entities in the without-replacement stream order (full.rs:48-51).
+    The device walks the same cursor (SFGPU_FAM_K_OPT) and scores these rows (sfgpu_score_k_opt)."""
     offsets = np.asarray(offsets, dtype=np.int64)
     lens = np.diff(offsets)
     n_pat = k_opt_pattern_count(k)
     out = []
-    for e, ln in enumerate(lens):
-        ln = int(ln)
+    n_owners = len(lens)
+    for eo in range(n_owners):
+        e = ctx.selection_index_without_replacement(eo, n_owners, 0x4B0F7E1171000001 ^ descriptor_index)
+        ln = int(lens[e])
         combos = _binomial(ln - (k + 1) * min_seg + k, k) if ln >= (k + 1) * min_seg else 0
         move_count = combos * n_pat
         for off in range(move_count):

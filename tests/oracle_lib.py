@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         l.sfo_enumerate_k_opt.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P]
         l.sfo_enumerate_k_opt.restype = C.c_int64
         l.sfo_score_k_opt.argtypes = [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P]
+        l.sfo_apply_k_opt.argtypes = [_P, C.c_uint32, _P]
         l.sfo_enumerate_nearby_list_change.argtypes = [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, _P,
                                                        _P, _P, _P]
         l.sfo_enumerate_nearby_list_change.restype = C.c_int64
@@ -316,6 +317,10 @@ class Oracle:
         self.l.sfo_score_k_opt(self.h, k, len(rows), _p(rows), _p(h), _p(s), _p(d))
         return np.stack([h, s], axis=1), d
 
+    def apply_k_opt(self, row, k=3):
+        r = np.ascontiguousarray(row, dtype=np.uint32)
+        self.l.sfo_apply_k_opt(self.h, k, _p(r))
+
     def enumerate_swap(self, step_index=0, step_seed=0, order=0) -> np.ndarray:
         n = self.l.sfo_enumerate_swap(self.h, step_index, step_seed, order, 0, None, None)
         a = np.zeros(n, dtype=np.uint32)
@@ -399,6 +404,15 @@ def union_children(o: "Oracle", children, step_index, step_seed, order):
             r = rows.astype(np.int64).reshape(-1, 6)
             packed = np.stack([r[:, 0], r[:, 1] | ((r[:, 2] - r[:, 1]) << 24), r[:, 3], r[:, 4] | ((r[:, 5] - r[:, 4]) << 24)],
                               axis=1)
+        elif fam == 5:
+            k = ch[1]
+            rows = o.enumerate_k_opt(k, ch[2], step_index, step_seed, order)
+            sc, ok = o.score_k_opt(rows, k) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            r = rows.astype(np.int64).reshape(-1, k + 2)
+            c5 = np.zeros((len(r), 5), dtype=np.int64)
+            c5[:, :k] = r[:, 1:1 + k]
+            packed = np.stack([r[:, 0] | (k << 28), c5[:, 0] | (c5[:, 1] << 16), c5[:, 2] | (c5[:, 3] << 16),
+                               c5[:, 4] | (r[:, k + 1] << 16)], axis=1)
         else:
             rows = o.enumerate_list_reverse(step_index, step_seed, order)
             sc, ok = o.score_list_reverse(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
