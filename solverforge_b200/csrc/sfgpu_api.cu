@@ -54,6 +54,8 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) try {
   if (ctx->partials) cudaFree(ctx->partials);
   if (ctx->solve_buf) cudaFree(ctx->solve_buf);
   if (ctx->union_buf) cudaFree(ctx->union_buf);
+  for (auto s_ : ctx->aux_streams) cudaStreamDestroy(s_);
+  for (auto e_ : ctx->aux_events) cudaEventDestroy(e_);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->sync_dev) cudaFree(ctx->sync_dev);
@@ -929,12 +931,16 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
     }
   }
   if (dm.has_list) {
-    int bytes = (int)dm.elem_cap * 4;
+    if (((size_t)dm.n_owners + 1) * 4 > 48 * 1024) {
+      if (((size_t)dm.n_owners + 1) * 4 > (size_t)ctx->max_smem_optin) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many list owners");
+      CU(cudaFuncSetAttribute(init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)dm.n_owners + 1) * 4)));
+    }
+    int bytes = (int)apply_smem_bytes(dm);
     if (bytes > ctx->max_smem_optin) return fail(ctx, SFGPU_E_UNSUPPORTED, "list variable too large for the apply kernel");
     CU(cudaFuncSetAttribute(apply_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
   // initialize_all
-  init_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, dm.state);
+  init_kernel<<<dm.R, 256, ((size_t)dm.n_owners + 1) * 4, ctx->stream>>>(dm, dm.state);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1211,7 +1217,7 @@ int apply_entry(sfgpu_ctx* ctx, int kind, uint32_t flags, const uint32_t* rows, 
   if (scalar)
     apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
   else
-    apply_list_kernel<<<R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+    apply_list_kernel<<<R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
   ctx->launches++;
   CU(cudaGetLastError());
   if (!(flags & SFGPU_DEVICE_IO)) CU(cudaStreamSynchronize(ctx->stream));
@@ -1291,7 +1297,7 @@ int32_t sfgpu_evaluate_all(sfgpu_ctx* ctx, int64_t* out_scores) try {
   const DevModel& dm = ctx->dm;
   CU(cudaMemcpyAsync(ctx->scratch_state, dm.state, (size_t)dm.block_bytes * dm.R, cudaMemcpyDeviceToDevice,
                      ctx->stream));
-  init_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, ctx->scratch_state);
+  init_kernel<<<dm.R, 256, ((size_t)dm.n_owners + 1) * 4, ctx->stream>>>(dm, ctx->scratch_state);
   ctx->launches++;
   CU(cudaGetLastError());
   return read_scores(ctx, ctx->scratch_state, out_scores);
@@ -1383,14 +1389,14 @@ int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program) try {
 int sfgpu_launch_apply_list(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, const uint8_t* d_mask,
                             const uint64_t* d_offsets, const uint32_t* d_index) {
   const DevModel& dm = ctx->dm;
-  apply_list_kernel<<<dm.R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  apply_list_kernel<<<dm.R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;
 }
 int sfgpu_launch_apply_list_kinds(sfgpu_ctx* ctx, const uint32_t* d_rows, const int32_t* d_kinds) {
   const DevModel& dm = ctx->dm;
-  apply_list_kernel<<<dm.R, 256, (size_t)dm.elem_cap * 4, ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
+  apply_list_kernel<<<dm.R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) argbest_partial_kernel(ForageDev f, const
 // sfgpu_evaluate_all).  Reference: IncrementalConstraint::evaluate of every constraint kind.
 // =============================================================================================
 __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevModel m, char* __restrict__ state) {
+  extern __shared__ __align__(16) uint32_t init_smem[];  // n_owners + 1 words (build_fast_records)
   __shared__ int64_t scratch[32];
   const uint32_t r = blockIdx.x;
   char* st = state + (size_t)r * m.block_bytes;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
   }
   if (m.fast_list) {
     __syncthreads();
-    build_fast_records(m, st);
+    build_fast_records(m, st, init_smem);
   }
 }
 
@@ -751,7 +752,7 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   }
   if (m.fast_list) {
     __syncthreads();
-    build_fast_records(m, st);
+    build_fast_records(m, st, old_el);  // the element copy is dead by now (dynamic smem >= n_owners + 1 words)
   }
 }
 

@@ -117,6 +117,8 @@ struct sfgpu_ctx {
   void* union_buf = nullptr;  // union step buffers
   size_t union_bytes = 0;
   UnionPlan union_plan;
+  std::vector<cudaStream_t> aux_streams;  // the children of a union walk side by side (fork / join by events)
+  std::vector<cudaEvent_t> aux_events;    // [0] fork, [1 + i] join of aux stream i
   std::vector<uint32_t> relabel_host, inverse_host;  // element id <-> internal id of the fast records
   size_t solve_bytes = 0;
   void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
@@ -182,6 +184,8 @@ int dev_upload(sfgpu_ctx* ctx, const T* host, size_t n, T** out) {
 }
 
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+// dynamic shared memory of apply_list_kernel: the element copy, reused as the owner table of build_fast_records
+inline size_t apply_smem_bytes(const DevModel& dm) { return (size_t)std::max(dm.elem_cap, dm.n_owners + 1) * 4; }
 
 inline int ensure_staging(sfgpu_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
   if (pin_bytes > ctx->pin_bytes) {

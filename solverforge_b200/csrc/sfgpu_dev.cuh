@@ -209,7 +209,9 @@ struct UnionArgs {
   uint32_t* sched;               // [R][t_cap] child << 28 | child-local index
   uint32_t* n_sched;             // [R]
   uint32_t* stream_end;          // [R] 1 = the union stream ended inside the window
-  int64_t* scores;               // [R][t_cap][2]
+  int64_t* scores;               // [R][t_cap][2] in union pull order (gathered from child_scores)
+  int64_t* child_scores;         // [R][n_children][window][2] by child-local index
+  uint8_t* child_doable;         // [R][n_children][window]
   uint8_t* doable;               // [R][t_cap]
   uint64_t* offsets;             // [R + 1] = r * t_cap
   uint32_t* done;                // [R] step already complete (earlier pass): skip

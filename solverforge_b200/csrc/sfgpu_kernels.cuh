@@ -830,8 +830,9 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
 // are rebuilt whenever a move is committed, and one candidate costs four 128-bit LDS, two matrix
 // gathers, one 128-bit LDG and one 128-bit STG.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) {
-  // block-parallel over owners; reads offsets/elems, writes the three record arrays
+// block-parallel over insertion slots (one thread per slot g = base + owner + position, so the record stores are
+// coalesced and every thread waits for one round of gathers); s_off = shared scratch of n_owners + 1 words
+__device__ __forceinline__ void build_fast_records(const DevModel& m, char* st, uint32_t* s_off) {
   const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
   const uint32_t* el = (const uint32_t*)(st + m.off_elems);
   RouteRec* rr = (RouteRec*)(st + m.off_route_rec);
@@ -847,43 +848,51 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st) 
   uint2* r8 = m.compact_bytes ? (uint2*)(st + m.off_route8) : nullptr;
   uint2* p8 = m.compact_bytes ? (uint2*)(st + m.off_pos8) : nullptr;
   uint2* s8 = m.compact_bytes ? (uint2*)(st + m.off_slot8) : nullptr;
-  if (pos_of) {
+  const uint32_t n_owners = m.n_owners;
+  for (uint32_t o = threadIdx.x; o <= n_owners; o += blockDim.x) s_off[o] = off[o];
+  if (pos_of)
     for (uint32_t i = threadIdx.x; i < m.n_elem_rows; i += blockDim.x) pos_of[i] = 0xFFFFFFFFu;
-    __syncthreads();
-  }
-  for (uint32_t o = threadIdx.x; o < m.n_owners; o += blockDim.x) {
-    const uint32_t b = off[o], len = off[o + 1] - b;
-    int64_t sum = 0;
-    for (uint32_t p = 0; p <= len; ++p) {
-      const uint32_t a_el = p > 0 ? el[b + p - 1] : depot;
-      const uint32_t b_el = p < len ? el[b + p] : depot;
-      SlotRec s;
-      s.a = rl ? rl[a_el] : a_el;  // ids stored in records address the relabelled matrices only
-      s.b = rl ? rl[b_el] : b_el;
-      s.gap = (pc && len > 0) ? mat[a_el * dim + b_el] : 0;
-      s.where = (o << 16) | p;
-      sr[b + o + p] = s;
-      if (s8) s8[b + o + p] = make_uint2(s.a | (s.b << 16), (uint32_t)s.gap);
-      if (p < len) {
-        const uint32_t x = b_el;
-        const uint32_t nx = p + 1 < len ? el[b + p + 1] : depot;
-        PosRec q;
-        q.elem = rl ? rl[x] : x;
-        q.rem = pc ? (-mat[a_el * dim + x] - mat[x * dim + nx] + (len > 1 ? mat[a_el * dim + nx] : 0)) : 0;
-        q.val = ls ? (int32_t)((const int64_t*)ls->g0)[x] : 0;
-        q.owner = o;
-        pr[b + p] = q;
-        if (p8) p8[b + p] = make_uint2(q.elem | ((uint32_t)(uint16_t)(int16_t)q.val << 16), (uint32_t)q.rem);
-        if (pos_of) pos_of[q.elem] = (o << 16) | p;
-        sum += q.val;
-      }
+  __syncthreads();
+  const uint32_t n_slots = s_off[n_owners] + n_owners;
+  for (uint32_t g = threadIdx.x; g < n_slots; g += blockDim.x) {
+    uint32_t lo = 0, hi = n_owners;  // owner of slot g: the largest o with s_off[o] + o <= g
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_off[mid] + mid <= g) lo = mid; else hi = mid;
     }
+    const uint32_t o = lo, b = s_off[o], len = s_off[o + 1] - b, p = g - b - o;
+    const uint32_t a_el = p > 0 ? el[b + p - 1] : depot;
+    const uint32_t b_el = p < len ? el[b + p] : depot;
+    SlotRec sl;
+    sl.a = rl ? rl[a_el] : a_el;  // ids stored in records address the relabelled matrices only
+    sl.b = rl ? rl[b_el] : b_el;
+    sl.gap = (pc && len > 0) ? mat[a_el * dim + b_el] : 0;
+    sl.where = (o << 16) | p;
+    sr[g] = sl;
+    if (s8) s8[g] = make_uint2(sl.a | (sl.b << 16), (uint32_t)sl.gap);
+    if (p < len) {
+      const uint32_t x = b_el;
+      const uint32_t nx = p + 1 < len ? el[b + p + 1] : depot;
+      PosRec q;
+      q.elem = rl ? rl[x] : x;
+      q.rem = pc ? (-mat[a_el * dim + x] - mat[x * dim + nx] + (len > 1 ? mat[a_el * dim + nx] : 0)) : 0;
+      q.val = ls ? (int32_t)((const int64_t*)ls->g0)[x] : 0;
+      q.owner = o;
+      pr[b + p] = q;
+      if (p8) p8[b + p] = make_uint2(q.elem | ((uint32_t)(uint16_t)(int16_t)q.val << 16), (uint32_t)q.rem);
+      if (pos_of) pos_of[q.elem] = (o << 16) | p;
+    }
+  }
+  // per-route records; the per-route sum is the retained LIST_SUM aggregate the caller has just brought up to date
+  const int64_t* rsum = ls ? (const int64_t*)(st + ls->off0) : nullptr;
+  for (uint32_t o = threadIdx.x; o < n_owners; o += blockDim.x) {
+    const uint32_t b = s_off[o], len = s_off[o + 1] - b;
     RouteRec r;
     r.base = b;
     r.len = len;
-    r.sum = sum;
+    r.sum = rsum ? rsum[o] : 0;
     rr[o] = r;
-    if (r8) r8[o] = make_uint2(b | (len << 16), (uint32_t)(int32_t)sum);
+    if (r8) r8[o] = make_uint2(b | (len << 16), (uint32_t)(int32_t)r.sum);
   }
 }
 

@@ -53,6 +53,7 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = a256(o + bytes); return at; };
   const size_t o_rows = take((size_t)R * T * 16), o_sched = take((size_t)R * T * 4), o_scores = take((size_t)R * T * 16);
+  const size_t o_cscores = take((size_t)R * T * 16), o_cdoable = take((size_t)R * T);
   const size_t o_doable = take((size_t)R * T), o_emit = take((size_t)R * C * 4), o_ended = take((size_t)R * C * 4);
   const size_t o_nsched = take((size_t)R * 4), o_send = take((size_t)R * 4), o_offs = take((size_t)(R + 1) * 8);
   const size_t o_done = take((size_t)R * 4), o_pend = take(16), o_arows = take((size_t)R * 16), o_akind = take((size_t)R * 4);
@@ -78,6 +79,8 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   a.sched = (uint32_t*)(b + o_sched);
   a.scores = (int64_t*)(b + o_scores);
   a.doable = (uint8_t*)(b + o_doable);
+  a.child_scores = (int64_t*)(b + o_cscores);
+  a.child_doable = (uint8_t*)(b + o_cdoable);
   a.n_emit = (uint32_t*)(b + o_emit);
   a.ended = (uint32_t*)(b + o_ended);
   a.n_sched = (uint32_t*)(b + o_nsched);
@@ -91,6 +94,16 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   a.win_max = wmax;
   plan.w0 = w0;
   plan.wmax = wmax;
+  while (ctx->aux_streams.size() + 1 < C) {
+    cudaStream_t aux = nullptr;
+    CU(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    ctx->aux_streams.push_back(aux);
+  }
+  while (ctx->aux_events.size() < C) {
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->aux_events.push_back(ev);
+  }
   if (!plan.configured) {
     const int tb = (int)(rank_tables_words_host(dm.n_owners) * 4);
 #define UW_ATTR(CELL, MOVE) \
@@ -99,7 +112,6 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
     UW_ATTR(uint16_t, MOVE_SWAP);
     UW_ATTR(int32_t, MOVE_CHANGE);
     UW_ATTR(int32_t, MOVE_SWAP);
-    if (ctx->staged) CU(cudaFuncSetAttribute(union_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
     plan.configured = true;
   }
   return SFGPU_OK;
@@ -134,19 +146,40 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
   a.next_win = adaptive ? plan.win_state : nullptr;
   a.win_shift = win_shift;
   a.t_cap = a.n_children * window;
+  // every child walks and scores on its own stream (child 0 on the context's): the cursors are independent and each
+  // is a latency-bound kernel of one small CTA per replica
+  const uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((window + 127) / 128,
+                                                                   std::max<uint32_t>(2, (uint32_t)ctx->sm_count * 8 / std::max(R, 1u))));
+  const bool fork = a.n_children > 1;
+  if (fork) CU(cudaEventRecord(ctx->aux_events[0], ctx->stream));
   for (uint32_t c = 0; c < a.n_children; ++c) {
+    cudaStream_t cs = c == 0 ? ctx->stream : ctx->aux_streams[c - 1];
+    if (c > 0) CU(cudaStreamWaitEvent(cs, ctx->aux_events[0], 0));
     const int fam = a.child[c].family;
     if (is_nearby(fam)) {
       const size_t tb = rank_tables_words_host(dm.n_owners) * 4;
       if (fam == SFGPU_FAM_NEARBY_LIST_CHANGE) {
-        if (dm.fm_u16) union_walk_nearby_kernel<uint64_t, uint16_t, MOVE_CHANGE><<<R, 256, tb, ctx->stream>>>(dm, a, c);
-        else union_walk_nearby_kernel<uint64_t, int32_t, MOVE_CHANGE><<<R, 256, tb, ctx->stream>>>(dm, a, c);
+        if (dm.fm_u16) union_walk_nearby_kernel<uint64_t, uint16_t, MOVE_CHANGE><<<R, 256, tb, cs>>>(dm, a, c);
+        else union_walk_nearby_kernel<uint64_t, int32_t, MOVE_CHANGE><<<R, 256, tb, cs>>>(dm, a, c);
       } else {
-        if (dm.fm_u16) union_walk_nearby_kernel<uint64_t, uint16_t, MOVE_SWAP><<<R, 256, tb, ctx->stream>>>(dm, a, c);
-        else union_walk_nearby_kernel<uint64_t, int32_t, MOVE_SWAP><<<R, 256, tb, ctx->stream>>>(dm, a, c);
+        if (dm.fm_u16) union_walk_nearby_kernel<uint64_t, uint16_t, MOVE_SWAP><<<R, 256, tb, cs>>>(dm, a, c);
+        else union_walk_nearby_kernel<uint64_t, int32_t, MOVE_SWAP><<<R, 256, tb, cs>>>(dm, a, c);
       }
     } else {
-      union_walk_index_kernel<<<R, 32, 0, ctx->stream>>>(dm, a, c);
+      union_walk_index_kernel<<<R, 32, 0, cs>>>(dm, a, c);
+    }
+    const dim3 g(chunks, R);
+    switch (fam) {
+      case SFGPU_FAM_NEARBY_LIST_CHANGE: union_score_child_kernel<SFGPU_FAM_NEARBY_LIST_CHANGE><<<g, 128, 0, cs>>>(dm, a, c); break;
+      case SFGPU_FAM_NEARBY_LIST_SWAP: union_score_child_kernel<SFGPU_FAM_NEARBY_LIST_SWAP><<<g, 128, 0, cs>>>(dm, a, c); break;
+      case SFGPU_FAM_SUBLIST_CHANGE: union_score_child_kernel<SFGPU_FAM_SUBLIST_CHANGE><<<g, 128, 0, cs>>>(dm, a, c); break;
+      case SFGPU_FAM_SUBLIST_SWAP: union_score_child_kernel<SFGPU_FAM_SUBLIST_SWAP><<<g, 128, 0, cs>>>(dm, a, c); break;
+      case SFGPU_FAM_LIST_REVERSE: union_score_child_kernel<SFGPU_FAM_LIST_REVERSE><<<g, 128, 0, cs>>>(dm, a, c); break;
+      default: union_score_child_kernel<SFGPU_FAM_K_OPT><<<g, 128, 0, cs>>>(dm, a, c); break;
+    }
+    if (c > 0) {
+      CU(cudaEventRecord(ctx->aux_events[c], cs));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_events[c], 0));
     }
   }
   switch (a.union_order) {
@@ -158,12 +191,11 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
     case SFGPU_UNION_RANDOM: union_schedule_kernel<SFGPU_UNION_RANDOM><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R); break;
     default: union_schedule_kernel<SFGPU_UNION_STRATIFIED_RANDOM><<<(R + 63) / 64, 64, 0, ctx->stream>>>(a, R); break;
   }
-  // grid-stride over the scheduled pulls: a few CTAs per replica, more when replicas are few
-  const uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((a.t_cap + 255) / 256,
-                                                                   std::max<uint32_t>(4, (uint32_t)ctx->sm_count * 4 / std::max(R, 1u))));
-  if (ctx->staged) union_score_kernel<true><<<dim3(chunks, R), 256, dm.stage_bytes, ctx->stream>>>(dm, a);
-  else union_score_kernel<false><<<dim3(chunks, R), 256, 0, ctx->stream>>>(dm, a);
-  ctx->launches += a.n_children + 2;
+  {
+    const uint32_t gchunks = std::max<uint32_t>(1, std::min<uint32_t>((a.t_cap + 255) / 256, std::max<uint32_t>(2, (uint32_t)ctx->sm_count * 4 / std::max(R, 1u))));
+    union_gather_kernel<<<dim3(gchunks, R), 256, 0, ctx->stream>>>(a);
+  }
+  ctx->launches += 2 * a.n_children + 2;
   CU(cudaGetLastError());
   if (plan.sa) {
     int rc0 = sfgpu_launch_sa_accept(ctx, a.offsets, a.n_sched, a.done, a.scores, a.doable, a.ref_scores, a.step_seeds, plan.sa_cur,

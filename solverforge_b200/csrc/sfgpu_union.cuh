@@ -686,6 +686,30 @@ __global__ void __launch_bounds__(64) union_schedule_kernel(const UnionArgs a, c
   uint32_t* sched = a.sched + (size_t)r * a.t_cap;
   uint32_t t = 0;
   bool window_out = false;
+  // Fast path. With equal weights RoundRobin, RotatingRoundRobin and StratifiedRandom (smooth weighted round-robin
+  // from an all-zero state) pull the live children cyclically — positions `current`, current + 1, .. — and are back in
+  // their initial state after every full cycle. So as many full cycles as the shortest child allows are written in
+  // one go; the per-pull replay below continues from there (exhaustion, window end, unequal weights, other orders).
+  if (UORDER == SFGPU_UNION_ROUND_ROBIN || UORDER == SFGPU_UNION_ROTATING_ROUND_ROBIN || UORDER == SFGPU_UNION_STRATIFIED_RANDOM) {
+    bool equal = live == C;
+    uint32_t cycles = 0xFFFFFFFFu;
+    UNION_FOR(p) if (p < C) {
+      equal = equal && weight[p] == 1;
+      cycles = min(cycles, ne[p]);
+    }
+    if (equal && cycles > 0 && cycles != 0xFFFFFFFFu) {
+      uint32_t word[UNION_MAX_CHILDREN];  // child of the q-th pull of a cycle
+      UNION_FOR(q) {
+        word[q] = 0;
+        UNION_FOR(p) if (p == (current + q) % C) word[q] = cid[p] << 28;
+      }
+      for (uint32_t i = 0; i < cycles; ++i) {
+        UNION_FOR(q) if (q < C) sched[t + q] = word[q] | i;
+        t += (uint32_t)C;
+      }
+      UNION_FOR(p) if (p < C) at[p] = cycles;
+    }
+  }
   while (t < a.t_cap && !window_out) {
     int pick = -1;
     // one scheduler decision: `sel` = the position asked for its next candidate
@@ -782,36 +806,44 @@ __device__ __forceinline__ bool union_delta(const DevModel& m, const char* st, i
   }
 }
 
-// grid = (chunks, R), 256 threads
-template <bool STAGED>
-__global__ void __launch_bounds__(256) union_score_kernel(const __grid_constant__ DevModel m, const UnionArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  __shared__ uint64_t bar;
+// Every emitted row of one child scored by child-local index (grid = (chunks, R), 128 threads; one kernel per move
+// family, so a warp runs one delta function). The replica block is read in place: a window holds a few dozen rows per
+// child, far too few to amortise staging the block.
+template <int FAMILY>
+__global__ void __launch_bounds__(128) union_score_child_kernel(const __grid_constant__ DevModel m, const UnionArgs a,
+                                                                const uint32_t child) {
   const uint32_t r = blockIdx.y;
   if (a.done && a.done[r]) return;
-  const uint32_t T = a.n_sched[r];
-  if ((uint64_t)blockIdx.x * blockDim.x >= T) return;
-  const char* gblock = m.state + (size_t)r * m.block_bytes;
-  const char* st = gblock;
-  if (STAGED) {
-    stage_block(smem, gblock, m.stage_bytes, &bar);
-    st = smem;
-  }
+  const uint32_t n = a.n_emit[(size_t)r * a.n_children + child];
+  if (blockIdx.x * blockDim.x >= n) return;
+  const char* st = m.state + (size_t)r * m.block_bytes;
   const int64_t* cs = (const int64_t*)(st + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
-  const uint32_t* sched = a.sched + (size_t)r * a.t_cap;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-    const uint32_t s = sched[t];
-    const uint32_t c = s >> 28, j = s & 0x0FFFFFFFu;
-    const uint4 row = ((const uint4*)a.rows)[((size_t)r * a.n_children + c) * a.window + j];
+  const size_t base = ((size_t)r * a.n_children + child) * a.window;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint4 row = ((const uint4*)a.rows)[base + j];
     Score2 d;
-    const bool ok = union_delta(m, st, a.child[c].family, row, d);
+    const bool ok = union_delta(m, st, FAMILY, row, d);
     longlong2 o;
     o.x = ok ? ch + d.hard : 0;
     o.y = ok ? csf + d.soft : 0;
+    ((longlong2*)a.child_scores)[base + j] = o;
+    a.child_doable[base + j] = ok ? 1 : 0;
+  }
+}
+
+// scores into union pull order: pull t of replica r = (child, child-local index) of the schedule
+__global__ void __launch_bounds__(256) union_gather_kernel(const UnionArgs a) {
+  const uint32_t r = blockIdx.y;
+  if (a.done && a.done[r]) return;
+  const uint32_t T = a.n_sched[r];
+  const uint32_t* sched = a.sched + (size_t)r * a.t_cap;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const uint32_t s = sched[t];
+    const size_t src = ((size_t)r * a.n_children + (s >> 28)) * a.window + (s & 0x0FFFFFFFu);
     const size_t q = (size_t)r * a.t_cap + t;
-    ((longlong2*)a.scores)[q] = o;
-    a.doable[q] = ok ? 1 : 0;
+    ((longlong2*)a.scores)[q] = ((const longlong2*)a.child_scores)[src];
+    a.doable[q] = a.child_doable[src];
   }
 }
 
