@@ -73,3 +73,15 @@ def test_rust_sys_crate_declares_every_symbol():
     src = open(os.path.join(ROOT, "bindings", "rust", "solverforge-gpu-sys", "src", "lib.rs")).read()
     declared = set(re.findall(r"pub fn (sfgpu_[a-z0-9_]+)\(", src))
     assert declared == set(_declared_symbols())
+
+
+def test_rust_host_crate_calls_only_declared_symbols():
+    """bindings/rust/solverforge-gpu (the `Director` + batch seam; not compilable here): every sys::sfgpu_* it calls
+    is declared by the header and by the -sys crate."""
+    src = open(os.path.join(ROOT, "bindings", "rust", "solverforge-gpu", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(sfgpu_[a-z0-9_]+)\(", src))
+    assert len(used) >= 30
+    assert used <= set(_declared_symbols())
+    sys_src = open(os.path.join(ROOT, "bindings", "rust", "solverforge-gpu-sys", "src", "lib.rs")).read()
+    for ty in set(re.findall(r"sys::(sfgpu_[a-z0-9_]+)\b(?!\()", src)):
+        assert f"pub struct {ty}" in sys_src, ty
