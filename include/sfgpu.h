@@ -455,6 +455,9 @@ int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_siz
  *   step_indices[R] (may be NULL = 0) and step_seeds[R] are the MoveStreamContext of each replica's step.
  *   out_index = CandidateId of the union cursor (pull index, vec_union.rs:447-455) or UINT32_MAX;
  *   out_winner_rows[R][8] = {family, child, row[4], child-local pull index, 0}.
+ *   Scalar models take the Change / Swap families — the reference's default for plain scalar models is
+ *   union[ChangeMoveSelector(Random), SwapMoveSelector(Random)], StratifiedRandom, SimulatedAnnealing +
+ *   AcceptedCount(1) (runtime/compiler/default_local_search/policy.rs:48-81, policy/scalar.rs:64-108).
  * Pointer conventions as sfgpu_step_nearby_list_change (HOST arrays unless SFGPU_DEVICE_IO). Needs the fast
  * list program when a nearby family is present. */
 #define SFGPU_FAM_NEARBY_LIST_CHANGE 0
@@ -462,6 +465,8 @@ int32_t sfgpu_step_sublist_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t min_siz
 #define SFGPU_FAM_SUBLIST_CHANGE 2
 #define SFGPU_FAM_SUBLIST_SWAP 3
 #define SFGPU_FAM_LIST_REVERSE 4
+#define SFGPU_FAM_CHANGE 6 /* ChangeMoveSelector of a scalar model (move_selector/change.rs:246-307); rows {entity, to_value} */
+#define SFGPU_FAM_SWAP 7   /* SwapMoveSelector (move_selector/swap.rs:196-233); rows {left, right} */
 #define SFGPU_FAM_K_OPT 5 /* KOptMoveSelector, p0 = k (2..5), p1 = min_segment_len; list_kernel/k_opt/full.rs:34-98 */
 #define SFGPU_ORDER_ORIGINAL 0
 #define SFGPU_ORDER_RANDOM 1

@@ -72,7 +72,7 @@ class UnionDesc(C.Structure):
 
 
 FAM_NEARBY_LIST_CHANGE, FAM_NEARBY_LIST_SWAP, FAM_SUBLIST_CHANGE, FAM_SUBLIST_SWAP, FAM_LIST_REVERSE = 0, 1, 2, 3, 4
-FAM_K_OPT = 5
+FAM_K_OPT, FAM_CHANGE, FAM_SWAP = 5, 6, 7
 ORDER_ORIGINAL, ORDER_RANDOM, ORDER_SHUFFLED = 0, 1, 2
 UNION_SEQUENTIAL, UNION_ROUND_ROBIN, UNION_ROTATING_ROUND_ROBIN, UNION_RANDOM, UNION_STRATIFIED_RANDOM = 0, 1, 2, 3, 4
 

@@ -509,6 +509,13 @@ class GpuScoreDirector:
              (L.FAM_SUBLIST_SWAP, 1, 3), (L.FAM_LIST_REVERSE,)], L.UNION_STRATIFIED_RANDOM, L.ORDER_RANDOM, window,
             max_window)
 
+    @staticmethod
+    def default_scalar_union(window: int = 0, max_window: int = 0) -> "L.UnionDesc":
+        """The reference's default selectors of a plain scalar model (policy/scalar.rs:64-108): ChangeMoveSelector +
+        SwapMoveSelector, seeded Random leaves, StratifiedRandom union."""
+        return GpuScoreDirector.union_desc([(L.FAM_CHANGE,), (L.FAM_SWAP,)], L.UNION_STRATIFIED_RANDOM, L.ORDER_RANDOM, window,
+                                           max_window)
+
     def step_union(self, desc: "L.UnionDesc", params: "ForageParams" = None, step_seeds=None, step_indices=None,
                    ref_scores=None, apply: bool = False):
         """One step over a union of list neighbourhoods in the reference's seeded pull order (sfgpu_step_union).

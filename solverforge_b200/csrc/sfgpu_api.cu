@@ -1396,7 +1396,11 @@ int sfgpu_launch_apply_list(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, co
 }
 int sfgpu_launch_apply_list_kinds(sfgpu_ctx* ctx, const uint32_t* d_rows, const int32_t* d_kinds) {
   const DevModel& dm = ctx->dm;
-  apply_list_kernel<<<dm.R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
+  if (dm.has_scalar) {
+    apply_scalar_kernel<<<dm.R, 32, 0, ctx->stream>>>(dm, 0, d_rows, nullptr, nullptr, nullptr, d_kinds);
+    ctx->launches++;
+  }
+  if (dm.has_list) apply_list_kernel<<<dm.R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;

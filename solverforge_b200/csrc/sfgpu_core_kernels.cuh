@@ -549,7 +549,7 @@ static __device__ void apply_scalar_edit(const DevModel& m, char* st, EditDev cu
 // rows: one per replica (mask / index select). kind 0 change, 1 swap.
 __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind, const uint32_t* __restrict__ rows,
                                     const uint8_t* __restrict__ mask, const uint64_t* __restrict__ cand_offsets,
-                                    const uint32_t* __restrict__ index) {
+                                    const uint32_t* __restrict__ index, const int32_t* __restrict__ kinds = nullptr) {
   const uint32_t r = blockIdx.x;
   if (threadIdx.x != 0) return;
   if (mask && !mask[r]) return;
@@ -557,6 +557,12 @@ __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind
   if (index) {
     if (index[r] == 0xFFFFFFFFu) return;
     ri = cand_offsets[r] + index[r];
+  }
+  if (kinds) {  // union of neighbourhoods: one move kind per replica, rows of 4 words; list kinds go to apply_list_kernel
+    kind = kinds[r];
+    if (kind < 0 || kind > 1) return;
+    rows += (size_t)r * 4;
+    ri = 0;
   }
   char* st = m.state + (size_t)r * m.block_bytes;
   int64_t* cs = (int64_t*)(st + m.off_score);
@@ -589,9 +595,9 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
   __shared__ int s_ok;
   const uint32_t r = blockIdx.x;
   if (mask && !mask[r]) return;
-  if (kinds) {  // one move kind per replica (union of neighbourhoods); < 0 = no winner
+  if (kinds) {  // one move kind per replica (union of neighbourhoods); < 0 = no winner, 0 / 1 = scalar moves
     kind = kinds[r];
-    if (kind < 0) return;
+    if (kind < 2) return;
   }
   uint64_t ri = r;
   if (index) {

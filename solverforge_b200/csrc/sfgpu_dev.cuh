@@ -195,6 +195,7 @@ struct UnionArgs {
   int32_t union_order;      // SFGPU_UNION_*
   int32_t order;            // SFGPU_ORDER_* of every leaf (VecUnionSelector::child_context)
   uint32_t desc;            // descriptor index of the list owner collection (salts)
+  uint32_t sdesc;           // descriptor index of the scalar variable's entity collection
   uint32_t window;          // rows a child may emit in this pass
   uint32_t t_cap;           // union pulls per replica in this pass (n_children * window)
   uint32_t scan_bits;       // low key bits holding the scan index (nearby families)

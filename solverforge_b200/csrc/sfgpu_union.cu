@@ -7,12 +7,12 @@ using namespace sfgpu_host;
 
 namespace {
 bool is_nearby(int family) { return family == SFGPU_FAM_NEARBY_LIST_CHANGE || family == SFGPU_FAM_NEARBY_LIST_SWAP; }
+bool is_scalar_family(int family) { return family == SFGPU_FAM_CHANGE || family == SFGPU_FAM_SWAP; }
 }  // namespace
 
 int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgpu_forage_params* params, UnionPlan& plan) {
   const DevModel& dm = ctx->dm;
   if (!desc || !params) return fail(ctx, SFGPU_E_INVALID, "null pointer");
-  if (!dm.has_list) return fail(ctx, SFGPU_E_STATE, "model has no list variable");
   if (desc->n_children == 0 || desc->n_children > SFGPU_UNION_MAX_CHILDREN)
     return fail(ctx, SFGPU_E_INVALID, "union needs 1..8 children");
   if (desc->union_order < 0 || desc->union_order > SFGPU_UNION_STRATIFIED_RANDOM)
@@ -24,10 +24,16 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   bool any_nearby = false;
   for (uint32_t c = 0; c < desc->n_children; ++c) {
     const sfgpu_union_child& ch = desc->children[c];
-    if (ch.family < 0 || ch.family > SFGPU_FAM_K_OPT) return fail(ctx, SFGPU_E_INVALID, "unknown move family");
+    if (ch.family < 0 || ch.family > SFGPU_FAM_SWAP) return fail(ctx, SFGPU_E_INVALID, "unknown move family");
+    if (is_scalar_family(ch.family) ? !dm.has_scalar : !dm.has_list)
+      return fail(ctx, SFGPU_E_STATE, "the model has no variable of the kind this move family edits");
+    if (ch.family == SFGPU_FAM_SWAP && ctx->has_load_balance)
+      return fail(ctx, SFGPU_E_UNSUPPORTED, "swap moves over a load_balance constraint");
     if (is_nearby(ch.family)) {
       any_nearby = true;
       if (ch.p0 == 0 || ch.p0 > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
+    } else if (is_scalar_family(ch.family)) {
+      // no parameters
     } else if (ch.family == SFGPU_FAM_K_OPT) {
       if (ch.p0 < 2 || ch.p0 > 5 || ch.p1 == 0) return fail(ctx, SFGPU_E_INVALID, "k-opt: 2 <= k <= 5, min_segment_len >= 1");
       if (dm.elem_cap >= 65536) return fail(ctx, SFGPU_E_UNSUPPORTED, "k-opt rows hold 16-bit cut positions");
@@ -72,7 +78,8 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   a.n_children = C;
   a.union_order = desc->union_order;
   a.order = desc->selection_order;
-  a.desc = (uint32_t)std::max(0, ctx->colls[ctx->lvars[0].owner_coll].descriptor);
+  a.desc = ctx->lvars.empty() ? 0u : (uint32_t)std::max(0, ctx->colls[ctx->lvars[0].owner_coll].descriptor);
+  a.sdesc = ctx->svars.empty() ? 0u : (uint32_t)std::max(0, ctx->colls[ctx->svars[0].coll].descriptor);
   a.scan_bits = 32;
   for (uint32_t c = 0; c < C; ++c) a.child[c] = UnionChildDev{desc->children[c].family, desc->children[c].p0, desc->children[c].p1, 0, desc->children[c].weight};
   a.rows = (uint32_t*)(b + o_rows);
@@ -175,6 +182,8 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
       case SFGPU_FAM_SUBLIST_CHANGE: union_score_child_kernel<SFGPU_FAM_SUBLIST_CHANGE><<<g, 128, 0, cs>>>(dm, a, c); break;
       case SFGPU_FAM_SUBLIST_SWAP: union_score_child_kernel<SFGPU_FAM_SUBLIST_SWAP><<<g, 128, 0, cs>>>(dm, a, c); break;
       case SFGPU_FAM_LIST_REVERSE: union_score_child_kernel<SFGPU_FAM_LIST_REVERSE><<<g, 128, 0, cs>>>(dm, a, c); break;
+      case SFGPU_FAM_CHANGE: union_score_child_kernel<SFGPU_FAM_CHANGE><<<g, 128, 0, cs>>>(dm, a, c); break;
+      case SFGPU_FAM_SWAP: union_score_child_kernel<SFGPU_FAM_SWAP><<<g, 128, 0, cs>>>(dm, a, c); break;
       default: union_score_child_kernel<SFGPU_FAM_K_OPT><<<g, 128, 0, cs>>>(dm, a, c); break;
     }
     if (c > 0) {

@@ -250,6 +250,37 @@ __device__ inline void walk_k_opt(const StreamCtx& cx, uint32_t desc, const uint
   }
 }
 
+// ChangeMoveSelector cursor (heuristic/selector/move_selector/change.rs:246-307): entities in stream order, per entity
+// its values in stream order (canonical contexts keep the value order), then the to-None move when the entity is
+// assigned. Rows {entity, to_value (0xFFFFFFFF = None), 0, 0}.
+__device__ inline void walk_change(const StreamCtx& cx, uint32_t desc, const int32_t* var, uint32_t n, uint32_t k,
+                                   bool with_none, RowSink& out) {
+  const uint64_t base = ((uint64_t)desc << 32);  // ^ variable_index (0)
+  const SelMap em(cx, n, 0xC4A46E0000000001ull ^ base);
+  for (uint32_t eo = 0; eo < n; ++eo) {
+    const uint32_t e = em.at(eo);
+    const SelMap vm(cx, k, 0xC4A46E0000000000ull ^ (uint64_t)e ^ base);
+    for (uint32_t vo = 0; vo < k; ++vo)
+      if (!out.push(e, vm.at(vo), 0, 0)) return;
+    if (with_none && var[e] >= 0)
+      if (!out.push(e, 0xFFFFFFFFu, 0, 0)) return;
+  }
+}
+
+// SwapMoveSelector cursor over one entity class (move_selector/swap.rs:196-233): the left and the right entity lists
+// are permuted independently; every (left, right) with left < right is a SwapMove, left-major. Rows {left, right, 0, 0}.
+__device__ inline void walk_swap(const StreamCtx& cx, uint32_t desc, uint32_t n, RowSink& out) {
+  const uint64_t base = ((uint64_t)desc << 32);
+  const SelMap lm(cx, n, 0x5A09000000000001ull ^ base), rm(cx, n, 0x5A09000000000002ull ^ base);
+  for (uint32_t lo = 0; lo < n; ++lo) {
+    const uint32_t l = lm.at(lo);
+    for (uint32_t ro = 0; ro < n; ++ro) {
+      const uint32_t r = rm.at(ro);
+      if (l < r && !out.push(l, r, 0, 0)) return;
+    }
+  }
+}
+
 // grid = R, 32 threads; lane 0 walks (the cursors are sequential state machines; replicas run side by side)
 __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_constant__ DevModel m, const UnionArgs a,
                                                               const uint32_t child) {
@@ -264,7 +295,10 @@ __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_const
   out.n = 0;
   out.more = false;
   const UnionChildDev& c = a.child[child];
-  if (c.family == SFGPU_FAM_LIST_REVERSE) walk_reverse(cx, a.desc, off, m.n_owners, out);
+  if (c.family == SFGPU_FAM_CHANGE)
+    walk_change(cx, a.sdesc, (const int32_t*)(st + m.off_var), m.n_entities, m.n_values, m.allows_unassigned != 0, out);
+  else if (c.family == SFGPU_FAM_SWAP) walk_swap(cx, a.sdesc, m.n_entities, out);
+  else if (c.family == SFGPU_FAM_LIST_REVERSE) walk_reverse(cx, a.desc, off, m.n_owners, out);
   else if (c.family == SFGPU_FAM_K_OPT) walk_k_opt(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
   else if (c.family == SFGPU_FAM_SUBLIST_CHANGE) walk_sublist_change(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
   else walk_sublist_swap(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
@@ -802,6 +836,11 @@ __device__ __forceinline__ bool union_delta(const DevModel& m, const char* st, i
     case SFGPU_FAM_LIST_REVERSE: return list_reverse_delta(m, st, row, d);
     case SFGPU_FAM_SUBLIST_CHANGE: return list_sublist_change_delta(m, st, row, d);
     case SFGPU_FAM_K_OPT: return list_k_opt_delta(m, st, row, d);
+    case SFGPU_FAM_CHANGE: return score_change_row(m, st, st, make_uint2(row.x, row.y), d);
+    case SFGPU_FAM_SWAP: {
+      const uint2 r2 = make_uint2(row.x, row.y);
+      return score_scalar_candidate<MODE_SWAP>(m, st, st, (const uint32_t*)&r2, nullptr, 0, d);
+    }
     default: return list_sublist_swap_delta(m, st, row, d);
   }
 }
@@ -882,7 +921,9 @@ __global__ void union_pick_kernel(const UnionArgs a, const uint32_t R, const uin
     j = s & 0x0FFFFFFFu;
     row = ((const uint4*)a.rows)[((size_t)r * a.n_children + c) * a.window + j];
     family = (uint32_t)a.child[c].family;
-    kind = family == SFGPU_FAM_NEARBY_LIST_CHANGE ? 2
+    kind = family == SFGPU_FAM_CHANGE ? 0
+           : family == SFGPU_FAM_SWAP   ? 1
+           : family == SFGPU_FAM_NEARBY_LIST_CHANGE ? 2
            : family == SFGPU_FAM_NEARBY_LIST_SWAP ? 3
            : family == SFGPU_FAM_LIST_REVERSE     ? 4
            : family == SFGPU_FAM_SUBLIST_CHANGE   ? 5

@@ -404,6 +404,16 @@ def union_children(o: "Oracle", children, step_index, step_seed, order):
             r = rows.astype(np.int64).reshape(-1, 6)
             packed = np.stack([r[:, 0], r[:, 1] | ((r[:, 2] - r[:, 1]) << 24), r[:, 3], r[:, 4] | ((r[:, 5] - r[:, 4]) << 24)],
                               axis=1)
+        elif fam == 6:
+            rows = o.enumerate_change(step_index, step_seed, order)
+            sc, ok = o.score_change(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            r = rows.astype(np.int64).reshape(-1, 2)
+            packed = np.stack([r[:, 0], r[:, 1] & 0xFFFFFFFF, np.zeros(len(r), np.int64), np.zeros(len(r), np.int64)], axis=1)
+        elif fam == 7:
+            rows = o.enumerate_swap(step_index, step_seed, order)
+            sc, ok = o.score_swap(rows) if len(rows) else (np.zeros((0, 2), np.int64), np.zeros(0, np.uint8))
+            r = rows.astype(np.int64).reshape(-1, 2)
+            packed = np.stack([r[:, 0], r[:, 1], np.zeros(len(r), np.int64), np.zeros(len(r), np.int64)], axis=1)
         elif fam == 5:
             k = ch[1]
             rows = o.enumerate_k_opt(k, ch[2], step_index, step_seed, order)

@@ -245,3 +245,78 @@ def test_solve_union_simulated_annealing_follows_the_oracle():
     assert int(ev[0]) == evaluated and int(acc[0]) == committed
     assert best[0].tolist() == best_o.tolist()
     assert d.calculate_score()[0].tolist() == o.committed_score().tolist() == d.fresh_score()[0].tolist()
+
+
+SCALAR = [(L.FAM_CHANGE,), (L.FAM_SWAP,)]
+
+
+def _gc(R=3, n=120, m=400, k=4):
+    g = instances.graph_coloring(n, m, k, seed_edges=6, seed_colors=9, unassigned_permille=100)
+    colors = np.stack([instances.graph_coloring(n, m, k, seed_edges=6, seed_colors=50 + r, unassigned_permille=100).color
+                       for r in range(R)])
+    return g, colors, models.graph_coloring_director(g, R, colors=colors), [Oracle.graph_coloring(g, colors[r]) for r in range(R)]
+
+
+@pytest.mark.parametrize("order", [L.ORDER_ORIGINAL, L.ORDER_RANDOM, L.ORDER_SHUFFLED])
+def test_scalar_change_and_swap_cursors_in_every_selection_order(order):
+    """The Change / Swap families of a scalar model (move_selector/change.rs:246-307, swap.rs:196-233) walked on device."""
+    g, colors, d, oracles = _gc()
+    seeds, steps = [5, 77, 0xDEADBEEF], [0, 3, 900]
+    for child in ([SCALAR[0]], [SCALAR[1]], SCALAR):
+        for union_order in (L.UNION_SEQUENTIAL, L.UNION_STRATIFIED_RANDOM):
+            for acceptor, okind, dl in ((0, 3, 0), (1, 0, -2), (2, 1, 0)):
+                for ties, limit in ((0, 1), (1, 25), (1, 600)):
+                    _check(d, oracles, child, union_order, order, seeds, steps, acceptor, okind, ties, limit, dl, max_window=1 << 14)
+
+
+def test_default_scalar_search_on_device_follows_the_oracle():
+    """The reference's default for a plain scalar model — union[Change, Swap] with Random leaves, StratifiedRandom,
+    SimulatedAnnealing, AcceptedCount(1) (default_local_search/policy.rs:48-81) — as a device-resident loop."""
+    from solverforge_b200.selectors import splitmix64
+    from tests.oracle_lib import OracleAcceptor
+    g, colors, d, oracles = _gc(R=2)
+    desc = GpuScoreDirector.default_scalar_union(window=4)
+    n_steps, seed_base, samples = 120, 31, 16
+    best, ev, acc, ovf = d.solve_union(desc, n_steps, acceptor=6, late_size=samples, tie_mode=1, accepted_limit=1,
+                                       seed_base=seed_base, acceptor_real=0.97)
+    final, state = d.calculate_score(), d.scalar_state()
+    for r, o in enumerate(oracles):
+        sa = OracleAcceptor(OracleAcceptor.SIMULATED_ANNEALING, size=samples, real=0.97)
+        init = o.committed_score().copy()
+        sa.phase_started(init)
+        best_o, evaluated, committed = init.copy(), 0, 0
+        cur = colors[r].copy()
+        for t in range(n_steps):
+            last = o.committed_score().copy()
+            seed = splitmix64(seed_base ^ ((r * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) ^ t)
+            kids = oracle_lib.union_children(o, SCALAR, t, seed, L.ORDER_RANDOM)
+            child, local = oracle_lib.union_pull_order([len(k[1]) for k in kids], L.UNION_STRATIFIED_RANDOM, t, seed, L.ORDER_RANDOM,
+                                                       limit=4000)
+            sc = np.zeros((len(child), 2), dtype=np.int64)
+            ok = np.zeros(len(child), dtype=np.uint8)
+            for ci, k in enumerate(kids):
+                sel = child == ci
+                sc[sel] = k[2][local[sel]]
+                ok[sel] = k[3][local[sel]]
+            out = sa.step(sc, ok, best_o, last, seed, 0, 1, True)
+            assert out[2] < 4000            # the forager quit inside the enumerated prefix
+            evaluated += out[2]
+            if out[0]:
+                ci, j = int(child[out[1]]), int(local[out[1]])
+                a, b = [int(x) for x in kids[ci][0][j]]
+                if ci == 0:
+                    o.apply_change(a, b)
+                    cur[a] = b
+                else:
+                    o.apply_swap(a, b)
+                    cur[a], cur[b] = cur[b], cur[a]
+                committed += 1
+            now = o.committed_score().copy()
+            if tuple(now) > tuple(best_o):
+                best_o = now
+        assert int(ovf[r]) == 0
+        assert int(ev[r]) == evaluated and int(acc[r]) == committed, f"r={r}"
+        assert best[r].tolist() == best_o.tolist()
+        assert final[r].tolist() == o.committed_score().tolist()
+        assert np.array_equal(state[r], cur)
+    assert np.array_equal(d.fresh_score(), final)
