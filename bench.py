@@ -591,6 +591,28 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
         res["cpu_baseline_o1_delta"] = cpu_o1
     if clocks:
         res["clocks"] = clocks
+    if name == "graph_coloring" and not primary and args.loop_steps > 0:
+        # the reference's DEFAULT search of a plain scalar model on device (sfgpu_solve_union): union[ChangeMoveSelector,
+        # SwapMoveSelector] with seeded Random leaves, StratifiedRandom, SimulatedAnnealing + AcceptedCount(1)
+        # (default_local_search/policy.rs:48-81) — a step ends at its first accepted pull, so this is steps/s, not
+        # candidates/s: informational, outside every timed region
+        try:
+            desc = d.default_scalar_union(window=8)
+            loop_steps = max(args.loop_steps, 256)
+            d.solve_union(desc, 16, 6, 0, 1, 1, seed_base=500)
+            d.synchronize()
+            t0 = time.perf_counter()
+            best_u, ev_u, acc_u, ovf_u = d.solve_union(desc, loop_steps, 6, 0, 1, 1, seed_base=1000)
+            dt = time.perf_counter() - t0
+            res["default_search"] = {
+                "steps": loop_steps, "replicas": R, "ms_per_step": dt * 1e3 / loop_steps, "solver_steps_per_s": R * loop_steps / dt,
+                "moves_evaluated_per_s": float(ev_u.sum()) / dt, "committed_steps": int(acc_u.sum()),
+                "scored_over_evaluated": float(d.last_pulls_scored.sum()) / max(float(ev_u.sum()), 1.0),
+                "window_overflows": int(ovf_u.sum()),
+                "selector": "union[ChangeMoveSelector, SwapMoveSelector], Random leaves, StratifiedRandom",
+                "acceptor": "SimulatedAnnealing(calibrated, decay 0.999985)", "forager": "AcceptedCount(1)"}
+        except Exception as exc:  # informational only
+            res["default_search"] = {"error": str(exc)[:200]}
     if primary:
         res["_director"], res["_inst"], res["_states"] = d, inst, states
     else:
