@@ -599,6 +599,71 @@ class GpuScoreDirector {
              out.accepted_steps.data()));
     return out;
   }
+  // ---- union of neighbourhoods in the reference's seeded pull order (sfgpu_step_union / sfgpu_solve_union):
+  // VecUnionSelector over move families (decorator/vec_union.rs:204-366), leaves in SelectionOrder `selection_order`
+  static sfgpu_union_desc union_desc(const std::vector<sfgpu_union_child>& children, int union_order = SFGPU_UNION_STRATIFIED_RANDOM,
+                                     int selection_order = SFGPU_ORDER_RANDOM, uint32_t window = 0, uint32_t max_window = 0) {
+    sfgpu_union_desc d{};
+    d.n_children = (uint32_t)children.size();
+    d.union_order = union_order;
+    d.selection_order = selection_order;
+    d.window = window;
+    d.max_window = max_window;
+    for (size_t i = 0; i < children.size() && i < SFGPU_UNION_MAX_CHILDREN; ++i) d.children[i] = children[i];
+    return d;
+  }
+  // the device-enumerable rows of the default list policy table (default_local_search/policy/list.rs:24-33)
+  static sfgpu_union_desc default_list_union(uint32_t max_nearby = 20) {
+    return union_desc({{SFGPU_FAM_NEARBY_LIST_CHANGE, max_nearby, 0, 0, 1}, {SFGPU_FAM_NEARBY_LIST_SWAP, max_nearby, 0, 0, 1},
+                       {SFGPU_FAM_SUBLIST_CHANGE, 1, 3, 0, 1}, {SFGPU_FAM_SUBLIST_SWAP, 1, 3, 0, 1}, {SFGPU_FAM_LIST_REVERSE, 0, 0, 0, 1}});
+  }
+  // the default selectors of a plain scalar model (default_local_search/policy/scalar.rs:64-108)
+  static sfgpu_union_desc default_scalar_union() {
+    return union_desc({{SFGPU_FAM_CHANGE, 0, 0, 0, 1}, {SFGPU_FAM_SWAP, 0, 0, 0, 1}});
+  }
+  // one step; winner_rows[R][8] = {family, child, row[4], child-local pull index, 0}; flags bit 0 = window overflow
+  StepResult step_union(const sfgpu_union_desc& desc, StepParams p, const std::vector<uint64_t>& step_seeds,
+                        const std::vector<uint64_t>& step_indices, const std::vector<HardSoftScore>& ref_pairs = {},
+                        bool apply_winners = false, std::vector<uint32_t>* flags = nullptr) {
+    sfgpu_forage_params fp{p.acceptor, p.random_ties ? 1 : 0, p.accepted_limit, 0};
+    StepResult out = make_result(8);
+    std::vector<uint32_t> fl(R_, 0);
+    check(sfgpu_step_union(ctx_, 0, &desc, &fp, step_seeds.empty() ? nullptr : step_seeds.data(),
+                           step_indices.empty() ? nullptr : step_indices.data(),
+                           ref_pairs.empty() ? nullptr : reinterpret_cast<const int64_t*>(ref_pairs.data()), out.index.data(),
+                           reinterpret_cast<int64_t*>(out.best.data()), out.evaluated.data(), out.winner_rows.data(), fl.data(),
+                           apply_winners ? 1 : 0));
+    if (flags) *flags = fl;
+    return out;
+  }
+  // the device-resident loop over the union step (acceptor 6 = SimulatedAnnealing)
+  SolveResult solve_union(const sfgpu_union_desc& desc, const SolveParams& p, std::vector<uint64_t>* window_overflows = nullptr) {
+    sfgpu_solve_params sp{};
+    sp.n_steps = p.n_steps;
+    sp.acceptor = p.acceptor;
+    sp.late_size = p.late_size;
+    sp.tie_mode = p.random_ties ? 1 : 0;
+    sp.accepted_limit = p.accepted_limit;
+    sp.seed_base = p.seed_base;
+    sp.restore_best = p.restore_best ? 1 : 0;
+    sp.acceptor_real = p.acceptor_real;
+    sp.step_count_limit = p.step_count_limit;
+    SolveResult out;
+    out.best.resize(R_);
+    out.moves_evaluated.resize(R_);
+    out.accepted_steps.resize(R_);
+    std::vector<uint64_t> ovf(R_, 0);
+    check(sfgpu_solve_union(ctx_, &desc, &sp, reinterpret_cast<int64_t*>(out.best.data()), out.moves_evaluated.data(),
+                            out.accepted_steps.data(), ovf.data(), nullptr));
+    if (window_overflows) *window_overflows = ovf;
+    return out;
+  }
+  // pair filter / pair weight of SFGPU_K_JOIN_EXPR as a postfix column expression
+  uint32_t add_expr(const std::vector<sfgpu_expr_op>& ops) {
+    uint32_t out = 0;
+    check(sfgpu_add_expr(ctx_, ops.data(), (uint32_t)ops.size(), &out));
+    return out;
+  }
   // working_solution() of the list variable: per replica (offsets[n_owners + 1], elems[capacity])
   void list_state(uint32_t n_owners, std::vector<uint32_t>& offsets, std::vector<uint32_t>& elems) {
     uint32_t cap = 0;

@@ -489,6 +489,41 @@ static int test_gpu() {
           CHECK(s_win[0] == moves[widx].a && (s_win[1] & 0xFFFFFFu) == moves[widx].b && s_win[2] == moves[widx].d &&
                 s_win[3] == moves[widx].e);
         }
+        if (kind == 1 && !swap_moves) {
+          // the union step through the mirror: three families in seeded Random order under StratifiedRandom, against
+          // the oracle's cursors + UnionScheduler + candidate loop (LateAcceptance form, AcceptedCount(12))
+          sfo::MoveStreamContext sctx;
+          sctx.step_index = 3;
+          sctx.step_seed = 4242;
+          sctx.order = sfo::SelectionOrder::Random;
+          std::vector<std::vector<sfo::Move>> kids = {orc.enumerate_list(8, sctx), orc.enumerate_list_reverse(sctx),
+                                                      orc.enumerate_sublist_change(1, 2, sctx)};
+          auto pulls = sfo::union_pull_order({kids[0].size(), kids[1].size(), kids[2].size()}, sfo::UnionOrder::StratifiedRandom,
+                                             sctx, {1, 1, 1});
+          const sfo::Sc olast = orc.calculate_score();
+          sfo::Forager<sfo::Sc> of;
+          of.kind = sfo::ForagerKind::AcceptedCount;
+          of.accepted_count_limit = 12;
+          sfo::Acceptor<sfo::Sc> la;
+          la.kind = sfo::AcceptorKind::LateAcceptance;
+          la.phase_started(olast, 1);
+          auto want = sfo::replay_step<sfo::Sc>(
+              pulls.size(), [&](size_t i) { return orc.evaluate(kids[pulls[i].first][pulls[i].second]); }, olast, olast, 4242, of, la);
+          auto ud = sf::GpuScoreDirector::union_desc({{SFGPU_FAM_NEARBY_LIST_CHANGE, 8, 0, 0, 1}, {SFGPU_FAM_LIST_REVERSE, 0, 0, 0, 1},
+                                                      {SFGPU_FAM_SUBLIST_CHANGE, 1, 2, 0, 1}});
+          sf::StepParams up;
+          up.acceptor = 2;
+          up.random_ties = true;
+          up.accepted_limit = 12;
+          std::vector<uint32_t> uflags;
+          sf::HardSoftScore last_c{olast.hard, olast.soft};
+          auto ures = cd.step_union(ud, up, {4242}, {3}, {last_c, last_c}, false, &uflags);
+          CHECK(uflags[0] == 0);
+          CHECK(want.has_winner && ures.index[0] == want.winner);
+          CHECK(ures.evaluated[0] == want.moves_evaluated);
+          CHECK(ures.best[0].hard == want.winner_score.hard && ures.best[0].soft == want.winner_score.soft);
+          CHECK(ures.winner_rows[1] == pulls[want.winner].first && ures.winner_rows[6] == pulls[want.winner].second);
+        }
         sf::SolveParams sp;
         sp.n_steps = 10;
         sp.max_nearby = 8;
@@ -500,6 +535,12 @@ static int test_gpu() {
         if (!swap_moves) {
           auto sr = cd.solve(sp, false);
           CHECK(sr.best[0] >= cm);
+          CHECK(cd.fresh_score()[0] == cd.calculate_score()[0]);
+          // and the default list search (union, seeded Random leaves, StratifiedRandom) as a resident loop
+          sp.accepted_limit = 16;
+          std::vector<uint64_t> ovf;
+          auto su = cd.solve_union(sf::GpuScoreDirector::default_list_union(8), sp, &ovf);
+          CHECK(ovf[0] == 0 && su.best[0] >= sr.best[0]);
           CHECK(cd.fresh_score()[0] == cd.calculate_score()[0]);
         }
       }
