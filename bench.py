@@ -439,16 +439,18 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
 
     # ---- best-score sync (N > 1): the only collective of the path, every K steps, inside the timed region
     K_sync = max(1, min(args.sync_every, steps))
-    best_h = np.zeros(2, dtype=np.int64)
-    owner, owner_rep = C.c_int32(), C.c_uint32()
+    # the result of a sync stays on the device (SFGPU_SYNC_ASYNC): the stream is not drained, the next steps queue
+    # right behind the collective; it is read back (and checked against the host-synchronous call) after the timed region
+    t_sync = torch.zeros(4, dtype=torch.int64, device=dev)   # {hard, soft, owner rank (i32), owner replica (u32)}
 
     def sync():
         if D.comm is not None:   # the C ABI a non-torch host uses: device reduce + one ncclAllGather of 24 B / rank
-            rc = lib.sfgpu_sync_best(d.h, D.comm, L.DEVICE_IO, C.c_void_p(t_best.data_ptr()),
-                                     best_h.ctypes.data_as(C.c_void_p), C.byref(owner), C.byref(owner_rep))
+            rc = lib.sfgpu_sync_best(d.h, D.comm, L.DEVICE_IO | L.SYNC_ASYNC, C.c_void_p(t_best.data_ptr()),
+                                     C.c_void_p(t_sync.data_ptr()), C.cast(C.c_void_p(t_sync.data_ptr() + 16), C.POINTER(C.c_int32)),
+                                     C.cast(C.c_void_p(t_sync.data_ptr() + 24), C.POINTER(C.c_uint32)))
             if rc != 0:
                 raise SystemExit("sfgpu_sync_best: " + lib.sfgpu_last_error(d.h).decode())
-            return int(best_h[0]), int(best_h[1]), owner.value
+            return None
         from solverforge_b200 import replicas
         return replicas.sync_best_scores(t_best, group=None)
 
@@ -495,6 +497,15 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
     kernel_ms = float(np.mean(kt)) / 1e6 if len(kt) else call_ms
     launches = d.launch_count() - launches0
     clocks = sampler.stop() if (rank == 0 and primary) else None
+    if world > 1 and primary and D.comm is not None and sev:
+        # the device-side result of the last in-region sync == the host-synchronous form of the same call
+        best_h = np.zeros(2, dtype=np.int64)
+        owner, owner_rep = C.c_int32(), C.c_uint32()
+        rc = lib.sfgpu_sync_best(d.h, D.comm, L.DEVICE_IO, C.c_void_p(t_best.data_ptr()), best_h.ctypes.data_as(C.c_void_p),
+                                 C.byref(owner), C.byref(owner_rep))
+        got = t_sync.cpu().numpy()
+        if rc != 0 or [int(got[0]), int(got[1])] != best_h.tolist() or int(got[2]) & 0xFFFFFFFF != owner.value:
+            raise SystemExit("bench.py: asynchronous best-score sync disagrees with the synchronous call")
 
     # ---- e2e: the same metric through the reference-facing call with HOST buffers, copies inside the timed
     # region. The whole step runs on device (sfgpu_step_nearby_list_change / sfgpu_step_change generate the
@@ -572,7 +583,7 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
                    "l2": f"inputs larger than L2 ({n * (ROW_BYTES[name] + OUT_BYTES) / 1e6:.0f} MB per step)" if n * 33 > 126e6
                          else f"{n * (ROW_BYTES[name] + OUT_BYTES) / 1e6:.1f} MB per step (L2-resident: single-solver latency case)",
                    "sync_every": K_sync if world > 1 else None,
-                   "sync_api": ("sfgpu_sync_best (C ABI, own ncclComm: device reduce + ncclAllGather)" if D.comm is not None
+                   "sync_api": ("sfgpu_sync_best (C ABI, own ncclComm: device reduce + ncclAllGather of 24 B / rank, result left on the device)" if D.comm is not None
                                 else "replicas.sync_best_scores (torch.distributed all_gather)") if world > 1 else None,
                    "parity_gate": f"every candidate of all {R} replicas bit-identical to the O(1) CPU checker; "
                                   f"replicas 0..{n_oracle - 1} bit-identical to the oracle (rows and scores) before timing"},

@@ -51,6 +51,7 @@ extern "C" {
 
 /* call flags */
 #define SFGPU_DEVICE_IO 1u /* data pointers are device pointers; call is stream-asynchronous */
+#define SFGPU_SYNC_ASYNC 2u /* sfgpu_sync_best: outputs are DEVICE pointers too and the stream is not synchronised */
 
 typedef struct sfgpu_ctx sfgpu_ctx;
 
@@ -592,7 +593,10 @@ int32_t sfgpu_comm_destroy(void* comm);
  * replica index inside the owner. scores: DEVICE pointer (flags & SFGPU_DEVICE_IO) to R (hard, soft) pairs —
  * e.g. the best-so-far scores of a solve loop — or NULL for the committed scores. One device reduction over the
  * replicas, one ncclAllGather of 24 B per rank on the context's stream, a local lexicographic max: exact over
- * the whole int64 range (no packed key). nccl_comm NULL = single rank (no collective). Synchronises the stream. */
+ * the whole int64 range (no packed key). nccl_comm NULL = single rank (no collective). Synchronises the stream —
+ * unless flags & SFGPU_SYNC_ASYNC: then out_best[2] / out_owner_rank / out_owner_replica are DEVICE pointers, the
+ * reduction over the gathered records runs on the device too and the call returns without draining the stream (a
+ * solver loop keeps queueing steps behind the collective). */
 int32_t sfgpu_sync_best(sfgpu_ctx* ctx, void* nccl_comm, uint32_t flags, const int64_t* scores, int64_t* out_best,
                         int32_t* out_owner_rank, uint32_t* out_owner_replica);
 

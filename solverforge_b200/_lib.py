@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsfgpu.so")
 OK = 0
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_NCCL, E_OOM, E_STATE = -1, -2, -3, -4, -5, -6
 DEVICE_IO = 1
+SYNC_ASYNC = 2
 CTX_LEGACY_DEFAULT_STREAM, CTX_GENERIC_KERNELS = 1, 2
 
 W_CONST, W_LINEAR, W_SQUARE, W_EXCESS, W_ABSDIFF, W_PAIRS = 0, 1, 2, 3, 4, 5

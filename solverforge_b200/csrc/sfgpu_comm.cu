@@ -113,6 +113,19 @@ __global__ void __launch_bounds__(256) rank_best_kernel(const __grid_constant__ 
   }
 }
 
+// lexicographic max over the gathered {hard, soft, replica} records (lowest rank on ties), results left on the device
+__global__ void gathered_best_kernel(const int64_t* __restrict__ recv, int n_ranks, int64_t* out_best, int32_t* out_rank,
+                                     uint32_t* out_replica) {
+  if (threadIdx.x != 0) return;
+  int best = 0;
+  for (int g = 1; g < n_ranks; ++g)
+    if (recv[g * 3] != recv[best * 3] ? recv[g * 3] > recv[best * 3] : recv[g * 3 + 1] > recv[best * 3 + 1]) best = g;
+  out_best[0] = recv[best * 3];
+  out_best[1] = recv[best * 3 + 1];
+  if (out_rank) *out_rank = best;
+  if (out_replica) *out_replica = (uint32_t)recv[best * 3 + 2];
+}
+
 }  // namespace
 
 extern "C" {
@@ -191,6 +204,13 @@ int32_t sfgpu_sync_best(sfgpu_ctx* ctx, void* nccl_comm, uint32_t flags, const i
     if (rc) return nccl_fail(ctx, "ncclAllGather", rc);
   } else {
     CU(cudaMemcpyAsync(recv, send, 24, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (flags & SFGPU_SYNC_ASYNC) {
+    // outputs stay on the device and the stream is not drained: the next step's kernels queue right behind
+    gathered_best_kernel<<<1, 32, 0, ctx->stream>>>(recv, n_ranks, out_best, out_owner_rank, out_owner_replica);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SFGPU_OK;
   }
   int64_t* host = (int64_t*)ctx->sync_pin;
   CU(cudaMemcpyAsync(host, recv, (size_t)n_ranks * 24, cudaMemcpyDeviceToHost, ctx->stream));
