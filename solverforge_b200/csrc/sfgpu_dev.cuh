@@ -7,7 +7,7 @@
 
 #include "../../include/sfgpu.h"
 
-#define SFGPU_MAX_CONS 16
+#define SFGPU_MAX_CONS 32  // constraint tuple size of the reference (api/constraint_set/incremental.rs:339-408: tuples up to 32)
 #define SFGPU_NONE (-1)
 
 struct WeightDev {

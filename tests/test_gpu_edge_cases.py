@@ -192,3 +192,46 @@ def test_sync_best_single_rank_is_the_lexicographic_max_over_replicas():
     torch.cuda.synchronize()
     best, owner, rep = d.sync_best(scores_ptr=t.data_ptr())
     assert best == (5, -(1 << 45)) and rep == 1
+
+
+def test_thirty_two_constraints_like_the_reference_tuple_limit():
+    """The reference's ConstraintSet tuples go up to 32 members (api/constraint_set/incremental.rs:339-408); so does a
+    device model. 31 uni constraints with distinct weights + one grouped constraint; the 33rd is rejected loudly."""
+    from solverforge_b200 import ConstraintFactory, Count, EqualVarToRow, GpuScoreDirector, HardSoftScore, soft
+    from solverforge_b200 import _lib as L
+    n, k = 40, 5
+    rng = np.random.default_rng(3)
+    d = GpuScoreDirector(2)
+    vals = d.add_collection("values", k, -1)
+    ents = d.add_collection("entities", n, 0)
+    d.add_scalar_variable(ents, "v", k)
+    cols = [rng.integers(0, 9, size=n) for _ in range(31)]
+    f = ConstraintFactory(d)
+    for i, c in enumerate(cols):
+        f.for_each(ents).assigned().penalize(soft(L.W_LINEAR, i + 1, 0), x=d.add_column(ents, f"c{i}", c)).named(f"uni {i}")
+    f.for_each(ents).join(f.for_each(vals), EqualVarToRow()).group_by(Count()).penalize(soft(L.W_SQUARE, 1, 0)).named("load")
+    with pytest.raises(L.SfgpuError):
+        f.for_each(ents).unassigned().penalize(HardSoftScore.ONE_HARD).named("one too many")
+    start = rng.integers(-1, k, size=(2, n)).astype(np.int32)
+    d.set_scalar_state(start)
+    got = d.commit()
+
+    def score(v):
+        s = 0
+        for i, c in enumerate(cols):
+            s -= (i + 1) * int(c[v >= 0].sum())
+        s -= int((np.bincount(v[v >= 0], minlength=k) ** 2).sum())
+        return s
+    for r in range(2):
+        assert got[r].tolist() == [0, score(start[r])]
+    rows = np.array([[e, v] for e in range(n) for v in range(-1, k)], dtype=np.int64)
+    sc, ok = d.score_change(np.concatenate([rows, rows]), np.array([0, len(rows), 2 * len(rows)], dtype=np.uint64))
+    for r in range(2):
+        for i, (e, v) in enumerate(rows):
+            j = r * len(rows) + i
+            if start[r][e] == v:
+                assert ok[j] == 0
+                continue
+            after = start[r].copy()
+            after[e] = v
+            assert ok[j] == 1 and sc[j].tolist() == [0, score(after)]
