@@ -186,6 +186,20 @@ typedef struct sfgpu_weight {
  *   aux1 = pair weight expression id or UINT32_MAX: the pair scores weight(x) with x = the expression's value
  *        (x = 0 without one), e.g. {SFGPU_W_LINEAR, level, 1, 0} scores x itself, SFGPU_W_CONST a constant. */
 #define SFGPU_K_JOIN_EXPR 11
+/* Keyed self-join of entity rows with a pair filter and a pair weight, undirected or directed — the reference's
+ * `for_each(E).join(equal(key)).filter(|l, r| ..).penalize(|l, r| ..)` (constraint/nary_incremental/bi.rs:78-206 with an
+ * arbitrary filter / weight) and its projected forms `.project(P).join(equal(key))..` (constraint/projected/bi.rs) and
+ * `.project(P).join(equal_bi(left_key, right_key))..` (constraint/projected/directed_bi.rs) for single-emit projections:
+ * every ASSIGNED entity is one row; its key(s) are column expressions of the row (SFGPU_X_A_COL, SFGPU_X_A_VAL,
+ * SFGPU_X_A_IDX, constants, arithmetic); a key outside [0, p1) means "no key" (Option::None).
+ *   undirected (right key expression UINT32_MAX): every pair of rows with equal keys once, left = the lower entity
+ *     index (projected/bi.rs:116-152, bi.rs:107-126);
+ *   directed: every ordered pair (l, r), l != r, with left_key(l) == right_key(r) (directed_bi_incremental.rs:26-45).
+ * Retained per replica: the rows of every key as intrusive doubly linked lists (the reference's rows_by_key maps).
+ *   p0 = left key expression | (uint64) right key expression << 32; p1 = number of keys (dense);
+ *   aux0 = pair filter expression or UINT32_MAX; aux1 = pair weight expression or UINT32_MAX (x = 0); in both,
+ *   A_* reads the left row, B_* the right row. */
+#define SFGPU_K_PAIR_KEY_EXPR 12
 
 /* Column expressions: a postfix program over an int64 stack (depth <= 8); booleans are 0 / 1. */
 #define SFGPU_X_CONST 1        /* push imm */
@@ -194,6 +208,8 @@ typedef struct sfgpu_weight {
 #define SFGPU_X_A_IDX 4        /* push index of a */
 #define SFGPU_X_B_IDX 5        /* push index of b */
 #define SFGPU_X_VALUE 6        /* push the join key (value of a's planning variable) */
+#define SFGPU_X_A_VAL 7        /* push the planning value of row a (the left row of a self-join) */
+#define SFGPU_X_B_VAL 8        /* push the planning value of row b (the right row of a self-join; -1 for a fact row) */
 #define SFGPU_X_ADD 10
 #define SFGPU_X_SUB 11
 #define SFGPU_X_MUL 12

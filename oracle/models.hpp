@@ -658,4 +658,66 @@ struct AvailabilityModel final : ModelImpl<AvSchedule> {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// The fixture of the reference's projected self-join tests (constraint/tests/projected/self_join.rs: Work{bucket,
+// demand}) as a planning model — the bucket is the planning variable — with the reference's own constraints:
+//   1 "Unassigned work"             1 hard
+//   2 "projected duplicate bucket"  .project(entry).join(equal(bucket)).filter(left.delta < right.delta).penalize(1)   [:108-154]
+//   3 "priority spread"             the same keyed self-join with a pair weight |left.prio - right.prio| (authored)
+//   4 "projected parent child"      .project(row).join(equal_bi(left.group, right.parent)).penalize(left.group * 10 +
+//                                   right.group), group = bucket, parent = (demand >= 0).then(demand)               [:156-290]
+struct PwWork {
+  size_t id;
+  int64_t demand, prio;
+  OptVal bucket;
+};
+struct PwPlan {
+  std::vector<PwWork> work;
+  size_t n_buckets = 0;
+};
+inline const std::vector<PwWork>& pw_work(const PwPlan& s) { return s.work; }
+
+struct PairsModel final : ModelImpl<PwPlan> {
+  explicit PairsModel(PwPlan sol) {
+    dir.working = std::move(sol);
+    dir.access.get = [](const PwPlan& s, size_t, size_t e) { return s.work[e].bucket; };
+    dir.access.set = [](PwPlan& s, size_t, size_t e, OptVal v) { s.work[e].bucket = v; };
+    dir.access.entity_count = [](const PwPlan& s, size_t) { return s.work.size(); };
+    Source<PwPlan, PwWork> src{pw_work, ChangeSource::Desc(0)};
+    auto uf = [](const PwPlan&, const PwWork& w) { return !w.bucket.has_value(); };
+    auto uw = [](const PwWork&) { return Sc::ONE_HARD(); };
+    dir.constraints.add(std::make_unique<UniConstraint<PwPlan, PwWork, Sc, decltype(uf), decltype(uw)>>(
+        "Unassigned work", Impact::Penalty, src, uf, uw, true));
+    auto kf = [](const PwWork& w) { return w.bucket.has_value() ? (int64_t)*w.bucket : (int64_t)-1; };
+    auto f2 = [](const PwPlan&, const PwWork& l, const PwWork& r, size_t, size_t) {
+      return l.bucket.has_value() && l.demand < r.demand;
+    };
+    auto w2 = [](const PwPlan&, const PwWork&, const PwWork&) { return Sc::of_soft(1); };
+    dir.constraints.add(std::make_unique<SelfJoinBiConstraint<PwPlan, PwWork, int64_t, Sc, decltype(kf), decltype(f2), decltype(w2)>>(
+        "projected duplicate bucket", Impact::Penalty, src, kf, f2, w2, false));
+    auto f3 = [](const PwPlan&, const PwWork& l, const PwWork&, size_t, size_t) { return l.bucket.has_value(); };
+    auto w3 = [](const PwPlan&, const PwWork& l, const PwWork& r) { return Sc::of_soft(std::llabs(l.prio - r.prio)); };
+    dir.constraints.add(std::make_unique<SelfJoinBiConstraint<PwPlan, PwWork, int64_t, Sc, decltype(kf), decltype(f3), decltype(w3)>>(
+        "priority spread", Impact::Penalty, src, kf, f3, w3, false));
+    // directed: left key = group, right key = parent; rows exist for assigned work only; a row never pairs with itself
+    auto kl = [](const PwWork& w) { return w.bucket.has_value() ? (int64_t)*w.bucket : (int64_t)-1; };
+    auto kr = [](const PwWork& w) { return (w.bucket.has_value() && w.demand >= 0) ? w.demand : (int64_t)-2; };
+    auto f4 = [](const PwPlan&, const PwWork& l, const PwWork& r, size_t il, size_t ir) {
+      return il != ir && l.bucket.has_value() && r.bucket.has_value();
+    };
+    auto w4 = [](const PwPlan&, const PwWork& l, const PwWork& r, size_t, size_t) {
+      return Sc::of_soft((int64_t)(*l.bucket * 10 + *r.bucket));
+    };
+    dir.constraints.add(std::make_unique<CrossBiConstraint<PwPlan, PwWork, PwWork, int64_t, Sc, decltype(kl), decltype(kr),
+                                                           decltype(f4), decltype(w4)>>(
+        "projected parent child", Impact::Penalty, src, src, kl, kr, f4, w4, false));
+  }
+  std::vector<Move> enumerate_scalar(MoveStreamContext ctx) override {
+    return enumerate_change_moves(dir.working, dir.access, 0, 0, dir.working.n_buckets, true, ctx);
+  }
+  std::vector<Move> enumerate_scalar_swap(MoveStreamContext ctx) override {
+    return enumerate_swap_moves(dir.working, dir.access, 0, 0, ctx);
+  }
+};
+
 }  // namespace sfo

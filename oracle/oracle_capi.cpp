@@ -134,6 +134,13 @@ void* sfo_availability_create(uint32_t n_shifts, uint32_t n_emp, const int64_t* 
   return new AvailabilityModel(std::move(s));
 }
 
+void* sfo_pairs_create(uint32_t n, uint32_t n_buckets, const int64_t* demand, const int64_t* prio, const int32_t* bucket) {
+  PwPlan p;
+  p.n_buckets = n_buckets;
+  for (uint32_t i = 0; i < n; ++i) p.work.push_back({i, demand[i], prio[i], opt(bucket[i])});
+  return new PairsModel(std::move(p));
+}
+
 void sfo_destroy(void* h) { delete static_cast<OracleModel*>(h); }
 
 int sfo_committed_score(void* h, int64_t out[2]) {

@@ -6,12 +6,12 @@ libsfgpu.so (hand-written sm_100a CUDA behind the C ABI in include/sfgpu.h); thi
 the host-side mirror of the reference interface above it. There is no CPU scoring fallback.
 """
 from . import _lib
-from .api import (AdjacentEqual, ConsecutiveRuns, ConstraintFactory, Count, EqualId, EqualKey, EqualVarToKey, EqualVarToRow, Expr,
+from .api import (AdjacentEqual, ConsecutiveRuns, ConstraintFactory, Count, EqualId, EqualKey, EqualKeyExpr, EqualVarToKey, EqualVarToRow, Expr,
                   ForageParams, GpuScoreDirector, HardSoftDecimalScore, HardSoftScore, ListSum, LoadBalance, PathCost, Projection, Sum,
                   WeightFn, hard, soft)
 
 __all__ = [
-    "AdjacentEqual", "ConsecutiveRuns", "ConstraintFactory", "Count", "EqualId", "EqualKey", "EqualVarToKey", "EqualVarToRow", "Expr", "ForageParams",
+    "AdjacentEqual", "ConsecutiveRuns", "ConstraintFactory", "Count", "EqualId", "EqualKey", "EqualKeyExpr", "EqualVarToKey", "EqualVarToRow", "Expr", "ForageParams",
     "GpuScoreDirector", "HardSoftDecimalScore", "HardSoftScore", "ListSum", "LoadBalance", "PathCost", "Projection",
     "Sum",
     "WeightFn", "hard", "soft",

@@ -21,8 +21,8 @@ W_CONST, W_LINEAR, W_SQUARE, W_EXCESS, W_ABSDIFF, W_PAIRS = 0, 1, 2, 3, 4, 5
 PENALTY, REWARD = 0, 1
 K_UNI, K_PAIR_CSR_EQUAL, K_PAIR_KEY_EQUAL, K_EXISTS_FLAT, K_GROUP = 1, 2, 3, 4, 5
 K_LIST_PATH_COST, K_LIST_SUM, K_LOAD_BALANCE, K_PROJECT_GROUP, K_RUNS = 6, 7, 8, 9, 10
-K_JOIN_EXPR = 11
-X_CONST, X_A_COL, X_B_COL, X_A_IDX, X_B_IDX, X_VALUE = 1, 2, 3, 4, 5, 6
+K_JOIN_EXPR, K_PAIR_KEY_EXPR = 11, 12
+X_CONST, X_A_COL, X_B_COL, X_A_IDX, X_B_IDX, X_VALUE, X_A_VAL, X_B_VAL = 1, 2, 3, 4, 5, 6, 7, 8
 X_ADD, X_SUB, X_MUL, X_NEG, X_ABS, X_MIN, X_MAX, X_MOD = 10, 11, 12, 13, 14, 15, 16, 17
 X_EQ, X_NE, X_LT, X_LE, X_GT, X_GE = 20, 21, 22, 23, 24, 25
 X_AND, X_OR, X_NOT, X_CSR_CONTAINS, X_SELECT = 30, 31, 32, 40, 41

@@ -94,6 +94,11 @@ def soft(fn: int = L.W_LINEAR, a: int = 1, b: int = 0) -> WeightFn:
     return WeightFn(fn, 1, a, b)
 
 
+def _i64(v: int) -> int:
+    """two's-complement view of an unsigned 64-bit value (ctypes int64 fields)"""
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -766,6 +771,15 @@ class Expr:
         return Expr([(L.X_VALUE, 0, 0)])
 
     @staticmethod
+    def a_value() -> "Expr":
+        """planning value of row a (the left row of a self-join)"""
+        return Expr([(L.X_A_VAL, 0, 0)])
+
+    @staticmethod
+    def b_value() -> "Expr":
+        return Expr([(L.X_B_VAL, 0, 0)])
+
+    @staticmethod
     def _lift(x) -> "Expr":
         return x if isinstance(x, Expr) else Expr.const(x)
 
@@ -798,6 +812,17 @@ class Expr:
     @staticmethod
     def select(cond, then, other) -> "Expr":
         return Expr(Expr._lift(cond).ops + Expr._lift(then).ops + Expr._lift(other).ops + [(L.X_SELECT, 0, 0)])
+
+
+@dataclass
+class EqualKeyExpr:
+    """Self-join of the entity rows on key expressions of one row (Expr over a(..) / a_value() / a_index()):
+    equal(key) when right_key is None (every pair once, left = lower index; nary_incremental/bi.rs, projected/bi.rs),
+    equal_bi(left_key, right_key) otherwise (ordered pairs, projected/directed_bi.rs). A key outside [0, n_keys) is
+    None."""
+    left_key: "Expr"
+    n_keys: int
+    right_key: Optional["Expr"] = None
 
 
 @dataclass
@@ -1076,8 +1101,8 @@ class BiStream:
     def filter(self, expr: "Expr") -> "BiStream":
         """Pair filter |a, b, index of a, index of b| as a column expression (general cross-collection joins:
         the entity's variable on the A side, a fact collection on the B side)."""
-        if not isinstance(self.joiner, (EqualVarToRow, EqualVarToKey)):
-            raise L.SfgpuError(L.E_UNSUPPORTED, "pair filters need the var -> row / var -> key joiner")
+        if not isinstance(self.joiner, (EqualVarToRow, EqualVarToKey, EqualKeyExpr)):
+            raise L.SfgpuError(L.E_UNSUPPORTED, "pair filters need the var -> row / var -> key / key-expression joiner")
         f = expr if self.pair_filter is None else (self.pair_filter & expr)
         return BiStream(self.d, self.collection, self.other, self.joiner, f)
 
@@ -1087,12 +1112,17 @@ class BiStream:
         w = weight if isinstance(weight, WeightFn) else _const_weight(weight)
         fid = L.NO_COLUMN if self.pair_filter is None else self.d.add_expr(self.pair_filter)
         xid = L.NO_COLUMN if x is None else self.d.add_expr(x)
+        if isinstance(j, EqualKeyExpr):
+            kl = self.d.add_expr(j.left_key)
+            kr = L.NO_COLUMN if j.right_key is None else self.d.add_expr(j.right_key)
+            return _Terminal(self.d, kind=L.K_PAIR_KEY_EXPR, impact=impact, weight=w, collection=self.collection, aux0=fid,
+                             aux1=xid, p0=_i64(kl | (kr << 32)), p1=j.n_keys)
         return _Terminal(self.d, kind=L.K_JOIN_EXPR, impact=impact, weight=w, collection=self.collection, aux0=fid, aux1=xid,
                          p0=j.bucket_csr if isinstance(j, EqualVarToKey) else -1, p1=self.other.collection)
 
     def _impact(self, impact, weight, x: Optional["Expr"] = None) -> _Terminal:
         j = self.joiner
-        if isinstance(j, (EqualVarToRow, EqualVarToKey)):
+        if isinstance(j, (EqualVarToRow, EqualVarToKey, EqualKeyExpr)):
             return self._impact_expr(impact, weight, x)
         w = _const_weight(weight)
         if isinstance(j, AdjacentEqual):

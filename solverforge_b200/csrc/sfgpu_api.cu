@@ -175,7 +175,7 @@ int32_t sfgpu_add_expr(sfgpu_ctx* ctx, const sfgpu_expr_op* ops, uint32_t n_ops,
   for (uint32_t i = 0; i < n_ops; ++i) {
     int pops = 0, pushes = 1;
     switch (ops[i].op) {
-      case SFGPU_X_CONST: case SFGPU_X_A_IDX: case SFGPU_X_B_IDX: case SFGPU_X_VALUE: break;
+      case SFGPU_X_CONST: case SFGPU_X_A_IDX: case SFGPU_X_B_IDX: case SFGPU_X_VALUE: case SFGPU_X_A_VAL: case SFGPU_X_B_VAL: break;
       case SFGPU_X_A_COL: case SFGPU_X_B_COL:
         if (ops[i].arg >= ctx->cols.size()) return fail(ctx, SFGPU_E_INVALID, "expression reads an unknown column");
         break;
@@ -206,7 +206,7 @@ int32_t sfgpu_add_constraint(sfgpu_ctx* ctx, const sfgpu_constraint_desc* desc, 
   if (!ctx || !desc) return SFGPU_E_INVALID;
   if (!ctx->building) return fail(ctx, SFGPU_E_STATE, "sfgpu_model_begin first");
   if (ctx->cons.size() >= SFGPU_MAX_CONS) return fail(ctx, SFGPU_E_UNSUPPORTED, "too many constraints");
-  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_JOIN_EXPR)
+  if (desc->kind < SFGPU_K_UNI || desc->kind > SFGPU_K_PAIR_KEY_EXPR)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "unknown constraint kind (not expressible on device)");
   if (desc->weight.fn < SFGPU_W_CONST || desc->weight.fn > SFGPU_W_PAIRS || desc->weight.level < 0 ||
       desc->weight.level > 1)
@@ -476,10 +476,45 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
     };
     bool scalar_kind = d.kind == SFGPU_K_UNI || d.kind == SFGPU_K_PAIR_CSR_EQUAL || d.kind == SFGPU_K_PAIR_KEY_EQUAL ||
                        d.kind == SFGPU_K_GROUP || d.kind == SFGPU_K_LOAD_BALANCE || d.kind == SFGPU_K_PROJECT_GROUP ||
-                       d.kind == SFGPU_K_RUNS || d.kind == SFGPU_K_JOIN_EXPR;
+                       d.kind == SFGPU_K_RUNS || d.kind == SFGPU_K_JOIN_EXPR || d.kind == SFGPU_K_PAIR_KEY_EXPR;
     if (scalar_kind && !dm.has_scalar) return fail(ctx, SFGPU_E_INVALID, "constraint needs a scalar variable");
     if (!scalar_kind && !dm.has_list) return fail(ctx, SFGPU_E_INVALID, "constraint needs a list variable");
     switch (d.kind) {
+      case SFGPU_K_PAIR_KEY_EXPR: {
+        int rc = expr_tables(ctx);
+        if (rc) return rc;
+        if (d.collection != ctx->svars[0].coll) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EXPR joins the entity collection with itself");
+        if (d.p1 <= 0 || d.p1 > (1 << 24)) return fail(ctx, SFGPU_E_UNSUPPORTED, "PAIR_KEY_EXPR: p1 (number of keys) must be in [1, 2^24]");
+        const uint32_t ids[4] = {(uint32_t)((uint64_t)d.p0 & 0xFFFFFFFFu), (uint32_t)((uint64_t)d.p0 >> 32), d.aux0, d.aux1};
+        if (ids[0] == 0xFFFFFFFFu) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EXPR needs a left key expression");
+        std::vector<sfgpu_expr_op> prog;
+        uint32_t lens[4] = {0, 0, 0, 0};
+        for (int w = 0; w < 4; ++w) {
+          if (ids[w] == 0xFFFFFFFFu) continue;
+          if (ids[w] >= ctx->exprs.size()) return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EXPR: unknown expression");
+          for (sfgpu_expr_op o : ctx->exprs[ids[w]].ops) {
+            if ((o.op == SFGPU_X_A_COL || o.op == SFGPU_X_B_COL) && ctx->cols[o.arg].coll != d.collection)
+              return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EXPR: expressions read columns of the entity collection");
+            if (w < 2 && (o.op == SFGPU_X_B_COL || o.op == SFGPU_X_B_IDX || o.op == SFGPU_X_B_VAL))
+              return fail(ctx, SFGPU_E_INVALID, "PAIR_KEY_EXPR: a key expression reads one row (A_* operands only)");
+            if (o.op == SFGPU_X_CSR_CONTAINS) o.imm = ctx->csrs[o.arg].n_rows;
+            prog.push_back(o);
+          }
+          lens[w] = (uint32_t)ctx->exprs[ids[w]].ops.size();
+          if (lens[w] > 0xFFFF) return fail(ctx, SFGPU_E_UNSUPPORTED, "expression too long");
+        }
+        sfgpu_expr_op* dprog = nullptr;
+        rc = dev_upload(ctx, prog.data(), prog.size(), &dprog);
+        if (rc) return rc;
+        c.g0 = dprog;
+        c.g1 = ctx->expr_cols_dev;
+        c.g2 = ctx->expr_csrs_dev;
+        c.pad = lens[0] | (lens[1] << 16);
+        c.n0 = lens[2] | (lens[3] << 16);
+        c.p1 = d.p1;
+        unstaged_bytes[k] = align_up((uint32_t)(2 * d.p1 + 4 * (int64_t)dm.n_entities) * 4, 16);
+        break;
+      }
       case SFGPU_K_JOIN_EXPR: {
         int rc = expr_tables(ctx);
         if (rc) return rc;

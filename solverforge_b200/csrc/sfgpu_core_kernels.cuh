@@ -276,6 +276,39 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
       case SFGPU_K_JOIN_EXPR:
         for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) local += join_expr_contrib(c, e, var[e]);
         break;
+      case SFGPU_K_PAIR_KEY_EXPR: {
+        const ExprTables t{(const int64_t* const*)c.g1, (const uint32_t* const*)c.g2};
+        const PairKeyLists L = pke_lists(c, st, m.n_entities);
+        const bool directed = pke_directed(c);
+        const uint32_t nk = (uint32_t)c.p1;
+        for (uint32_t i = threadIdx.x; i < nk; i += blockDim.x) L.headL[i] = L.headR[i] = -1;
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) L.nxtL[e] = L.prvL[e] = L.nxtR[e] = L.prvR[e] = -1;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) {  // lock-free push; list order does not matter
+          const int64_t kl = pke_key(c, t, 0, e, var[e]);
+          if (kl >= 0) L.nxtL[e] = atomicExch(&L.headL[kl], (int32_t)e);
+          const int64_t kr = directed ? pke_key(c, t, 1, e, var[e]) : -1;
+          if (kr >= 0) L.nxtR[e] = atomicExch(&L.headR[kr], (int32_t)e);
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) {
+          if (L.nxtL[e] >= 0) L.prvL[L.nxtL[e]] = (int32_t)e;
+          if (L.nxtR[e] >= 0) L.prvR[L.nxtR[e]] = (int32_t)e;
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < m.n_entities; e += blockDim.x) {
+          const int64_t kl = pke_key(c, t, 0, e, var[e]);
+          if (kl < 0) continue;
+          if (directed) {
+            for (int32_t x = L.headR[kl]; x >= 0; x = L.nxtR[x])
+              if ((uint32_t)x != e) local += pke_pair(c, t, e, var[e], (uint32_t)x, var[x]);
+          } else {
+            for (int32_t x = L.headL[kl]; x >= 0; x = L.nxtL[x])
+              if ((uint32_t)x > e) local += pke_pair(c, t, e, var[e], (uint32_t)x, var[x]);
+          }
+        }
+        break;
+      }
       case SFGPU_K_PAIR_CSR_EQUAL: {
         const uint32_t* rp = (const uint32_t*)c.g0;
         const uint32_t* ci = (const uint32_t*)c.g1;
@@ -491,6 +524,28 @@ static __device__ void apply_scalar_edit(const DevModel& m, char* st, EditDev cu
         uint16_t* row = cc + (size_t)ci[j] * m.n_values;
         if (cur.old_v >= 0) row[cur.old_v] -= 1;
         if (cur.new_v >= 0) row[cur.new_v] += 1;
+      }
+    } else if (c.kind == SFGPU_K_PAIR_KEY_EXPR) {
+      const ExprTables t{(const int64_t* const*)c.g1, (const uint32_t* const*)c.g2};
+      const PairKeyLists L = pke_lists(c, st, m.n_entities);
+      for (int side = 0; side < (pke_directed(c) ? 2 : 1); ++side) {
+        int32_t* head = side ? L.headR : L.headL;
+        int32_t* nxt = side ? L.nxtR : L.nxtL;
+        int32_t* prv = side ? L.prvR : L.prvL;
+        const int64_t ko = pke_key(c, t, side, cur.e, cur.old_v), kn = pke_key(c, t, side, cur.e, cur.new_v);
+        if (ko >= 0) {  // unlink
+          const int32_t p = prv[cur.e], n = nxt[cur.e];
+          if (p >= 0) nxt[p] = n; else head[ko] = n;
+          if (n >= 0) prv[n] = p;
+          nxt[cur.e] = prv[cur.e] = -1;
+        }
+        if (kn >= 0) {  // link at the head
+          const int32_t n = head[kn];
+          nxt[cur.e] = n;
+          prv[cur.e] = -1;
+          if (n >= 0) prv[n] = (int32_t)cur.e;
+          head[kn] = (int32_t)cur.e;
+        }
       }
     } else if (c.kind == SFGPU_K_PAIR_KEY_EQUAL) {
       int32_t* tab = (int32_t*)(st + c.off0);

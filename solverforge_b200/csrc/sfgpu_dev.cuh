@@ -241,7 +241,7 @@ __device__ __forceinline__ int64_t weight_eval(const WeightDev& w, int64_t x) {
 
 // postfix evaluation of a column expression for the pair (a, b) joined on key value v
 __device__ __forceinline__ int64_t expr_eval(const sfgpu_expr_op* __restrict__ ops, uint32_t n, const ExprTables& t,
-                                             uint32_t a, uint32_t b, int64_t v) {
+                                             uint32_t a, uint32_t b, int64_t v, int64_t va = -1, int64_t vb = -1) {
   int64_t s[8];
   int sp = 0;
   for (uint32_t i = 0; i < n; ++i) {
@@ -253,6 +253,8 @@ __device__ __forceinline__ int64_t expr_eval(const sfgpu_expr_op* __restrict__ o
       case SFGPU_X_A_IDX: s[sp++] = (int64_t)a; break;
       case SFGPU_X_B_IDX: s[sp++] = (int64_t)b; break;
       case SFGPU_X_VALUE: s[sp++] = v; break;
+      case SFGPU_X_A_VAL: s[sp++] = va; break;
+      case SFGPU_X_B_VAL: s[sp++] = vb; break;
       case SFGPU_X_NEG: s[sp - 1] = -s[sp - 1]; break;
       case SFGPU_X_ABS: s[sp - 1] = s[sp - 1] < 0 ? -s[sp - 1] : s[sp - 1]; break;
       case SFGPU_X_NOT: s[sp - 1] = s[sp - 1] == 0 ? 1 : 0; break;
@@ -318,10 +320,45 @@ __device__ __forceinline__ int64_t join_expr_contrib(const ConsDev& c, uint32_t 
   int64_t total = 0;
   for (uint32_t j = lo; j < hi; ++j) {
     const uint32_t b = bucket ? bucket[j] : j;
-    if (nf && expr_eval(ops, nf, t, a, b, v) == 0) continue;
-    total += weight_eval(c.w, nw ? expr_eval(ops + nf, nw, t, a, b, v) : 0);
+    if (nf && expr_eval(ops, nf, t, a, b, v, v, -1) == 0) continue;
+    total += weight_eval(c.w, nw ? expr_eval(ops + nf, nw, t, a, b, v, v, -1) : 0);
   }
   return total;
+}
+
+// ---- SFGPU_K_PAIR_KEY_EXPR: keyed self-join of entity rows with pair filter / weight expressions ----------------
+// program layout: [left key][right key][pair filter][pair weight]; lengths: pad = lkl | lkr << 16, n0 = lf | lw << 16.
+// retained section (int32): headL[n_keys] nxtL[n] prvL[n] headR[n_keys] nxtR[n] prvR[n]
+struct PairKeyLists {
+  int32_t *headL, *nxtL, *prvL, *headR, *nxtR, *prvR;
+};
+__device__ __forceinline__ PairKeyLists pke_lists(const ConsDev& c, char* block, uint32_t n_entities) {
+  int32_t* base = (int32_t*)(block + c.off0);
+  const uint32_t nk = (uint32_t)c.p1;
+  PairKeyLists l;
+  l.headL = base;
+  l.nxtL = l.headL + nk;
+  l.prvL = l.nxtL + n_entities;
+  l.headR = l.prvL + n_entities;
+  l.nxtR = l.headR + nk;
+  l.prvR = l.nxtR + n_entities;
+  return l;
+}
+__device__ __forceinline__ bool pke_directed(const ConsDev& c) { return (c.pad >> 16) != 0; }
+// key of row (e, v): which = 0 left key, 1 right key; -1 = no key
+__device__ __forceinline__ int64_t pke_key(const ConsDev& c, const ExprTables& t, int which, uint32_t e, int32_t v) {
+  if (v < 0) return -1;
+  const sfgpu_expr_op* ops = (const sfgpu_expr_op*)c.g0;
+  const uint32_t lkl = c.pad & 0xFFFFu, lkr = c.pad >> 16;
+  const int64_t k = which ? expr_eval(ops + lkl, lkr, t, e, e, v, v, v) : expr_eval(ops, lkl, t, e, e, v, v, v);
+  return (k < 0 || k >= c.p1) ? -1 : k;
+}
+// score of the joined pair (left row l with value vl, right row r with value vr), 0 when the filter rejects it
+__device__ __forceinline__ int64_t pke_pair(const ConsDev& c, const ExprTables& t, uint32_t l, int32_t vl, uint32_t r, int32_t vr) {
+  const sfgpu_expr_op* ops = (const sfgpu_expr_op*)c.g0 + (c.pad & 0xFFFFu) + (c.pad >> 16);
+  const uint32_t lf = c.n0 & 0xFFFFu, lw = c.n0 >> 16;
+  if (lf && expr_eval(ops, lf, t, l, r, vl, vl, vr) == 0) return 0;
+  return weight_eval(c.w, lw ? expr_eval(ops + lf, lw, t, l, r, vl, vl, vr) : 0);
 }
 
 // C(n, k) for the keyed self-joins of arity k + 1 (tuples that gain / lose one member of a bucket of n rows);

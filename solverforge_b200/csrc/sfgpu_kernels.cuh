@@ -93,6 +93,58 @@ __device__ __forceinline__ int64_t presence_group_score(const ConsDev& c, F cntf
   return weight_eval(c.w, distinct);
 }
 
+// SFGPU_K_PAIR_KEY_EXPR: every joined pair that involves row (e, v), against the committed lists overlaid with the
+// edits prev[0..n_prev) of the same candidate (rows of edited entities are taken from the overlay, not from the lists)
+static __device__ int64_t pke_contrib(const DevModel& m, const ConsDev& c, const char* gst, const int32_t* var, const EditDev* prev,
+                                      int n_prev, uint32_t e, int32_t v) {
+  if (v < 0) return 0;
+  const ExprTables t{(const int64_t* const*)c.g1, (const uint32_t* const*)c.g2};
+  const PairKeyLists L = pke_lists(c, const_cast<char*>(gst), m.n_entities);
+  const bool directed = pke_directed(c);
+  auto edited = [&](uint32_t x) {
+    for (int i = 0; i < n_prev; ++i)
+      if (prev[i].e == x) return true;
+    return false;
+  };
+  auto last_edit = [&](int i) {  // the overlay row of an entity is its LAST edit
+    for (int j = i + 1; j < n_prev; ++j)
+      if (prev[j].e == prev[i].e) return false;
+    return true;
+  };
+  int64_t total = 0;
+  if (!directed) {
+    const int64_t k = pke_key(c, t, 0, e, v);
+    if (k < 0) return 0;
+    for (int32_t x = L.headL[k]; x >= 0; x = L.nxtL[x]) {
+      const uint32_t mth = (uint32_t)x;
+      if (mth == e || edited(mth)) continue;
+      total += mth < e ? pke_pair(c, t, mth, var[mth], e, v) : pke_pair(c, t, e, v, mth, var[mth]);
+    }
+    for (int i = 0; i < n_prev; ++i) {
+      const uint32_t pe = prev[i].e;
+      if (pe == e || !last_edit(i) || pke_key(c, t, 0, pe, prev[i].new_v) != k) continue;
+      total += pe < e ? pke_pair(c, t, pe, prev[i].new_v, e, v) : pke_pair(c, t, e, v, pe, prev[i].new_v);
+    }
+    return total;
+  }
+  const int64_t kl = pke_key(c, t, 0, e, v), kr = pke_key(c, t, 1, e, v);
+  if (kl >= 0) {  // e as the left row: right rows whose right key equals e's left key
+    for (int32_t x = L.headR[kl]; x >= 0; x = L.nxtR[x])
+      if ((uint32_t)x != e && !edited((uint32_t)x)) total += pke_pair(c, t, e, v, (uint32_t)x, var[x]);
+    for (int i = 0; i < n_prev; ++i)
+      if (prev[i].e != e && last_edit(i) && pke_key(c, t, 1, prev[i].e, prev[i].new_v) == kl)
+        total += pke_pair(c, t, e, v, prev[i].e, prev[i].new_v);
+  }
+  if (kr >= 0) {  // e as the right row
+    for (int32_t x = L.headL[kr]; x >= 0; x = L.nxtL[x])
+      if ((uint32_t)x != e && !edited((uint32_t)x)) total += pke_pair(c, t, (uint32_t)x, var[x], e, v);
+    for (int i = 0; i < n_prev; ++i)
+      if (prev[i].e != e && last_edit(i) && pke_key(c, t, 0, prev[i].e, prev[i].new_v) == kr)
+        total += pke_pair(c, t, prev[i].e, prev[i].new_v, e, v);
+  }
+  return total;
+}
+
 // Delta of ONE edit (e: old -> new) against the replica state `st` overlaid with the edits
 // prev[0..n_prev) that were already applied by the same candidate.
 // `st` = the replica block as the kernel sees it (possibly the staged shared-memory prefix); `gst` = the
@@ -106,6 +158,11 @@ static __device__ void scalar_edit_delta(const DevModel& m, const char* st, cons
     switch (c.kind) {
       case SFGPU_K_UNI: {
         add_level(d, c, uni_contrib(c, cur.e, cur.new_v) - uni_contrib(c, cur.e, cur.old_v));
+        break;
+      }
+      case SFGPU_K_PAIR_KEY_EXPR: {
+        add_level(d, c, pke_contrib(m, c, gst, var, prev, n_prev, cur.e, cur.new_v) -
+                            pke_contrib(m, c, gst, var, prev, n_prev, cur.e, cur.old_v));
         break;
       }
       case SFGPU_K_JOIN_EXPR: {  // pairs of one A row depend on that row only: no overlay needed

@@ -138,7 +138,8 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
           if (c.off0 == 0xFFFFFFFFu) ok = false;  // no retained partner-value counts
           sc.push_back({c.kind, (int)k});
           break;
-        case SFGPU_K_LOAD_BALANCE: case SFGPU_K_RUNS: case SFGPU_K_PROJECT_GROUP: case SFGPU_K_JOIN_EXPR: ok = false; break;
+        case SFGPU_K_LOAD_BALANCE: case SFGPU_K_RUNS: case SFGPU_K_PROJECT_GROUP: case SFGPU_K_JOIN_EXPR:
+        case SFGPU_K_PAIR_KEY_EXPR: ok = false; break;
         default: break;  // list-only kinds do not react to scalar edits
       }
     }

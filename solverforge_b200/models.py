@@ -221,3 +221,32 @@ def availability_director(inst, n_replicas: int = 1, employee=None, device: int 
     d.set_scalar_state(inst.employee if employee is None else employee)
     d.commit()
     return d
+
+
+def pairs_director(demand, prio, bucket, n_buckets: int, n_replicas: int = 1, device: int = 0, stream=None,
+                   flags: int = 0) -> GpuScoreDirector:
+    """Keyed self-joins of entity rows with pair filters / pair weights, undirected and directed
+    (SFGPU_K_PAIR_KEY_EXPR): the Work{bucket, demand} fixture of the reference's projected self-join tests
+    (constraint/tests/projected/self_join.rs:108-290) with the bucket as the planning variable — the four constraints
+    of the oracle's PairsModel."""
+    from .api import EqualKeyExpr, Expr
+    bucket = np.asarray(bucket)
+    n = bucket.shape[-1]
+    d = GpuScoreDirector(n_replicas, device, stream, flags)
+    d.add_collection("buckets", n_buckets, -1)
+    work = d.add_collection("work", n, 0)
+    d.add_scalar_variable(work, "bucket", n_buckets, allows_unassigned=True)
+    dem = d.add_column(work, "demand", demand)
+    pri = d.add_column(work, "prio", prio)
+    f = ConstraintFactory(d)
+    f.for_each(work).unassigned().penalize(HardSoftScore.ONE_HARD).named("Unassigned work")
+    same_bucket = EqualKeyExpr(Expr.a_value(), n_buckets)
+    f.for_each(work).join(f.for_each(work), same_bucket).filter(Expr.a(dem) < Expr.b(dem)) \
+        .penalize(HardSoftScore(0, 1)).named("projected duplicate bucket")
+    f.for_each(work).join(f.for_each(work), same_bucket).penalize(soft(L.W_LINEAR, 1, 0), abs(Expr.a(pri) - Expr.b(pri))) \
+        .named("priority spread")
+    f.for_each(work).join(f.for_each(work), EqualKeyExpr(Expr.a_value(), n_buckets, right_key=Expr.a(dem))) \
+        .penalize(soft(L.W_LINEAR, 1, 0), Expr.a_value() * 10 + Expr.b_value()).named("projected parent child")
+    d.set_scalar_state(bucket)
+    d.commit()
+    return d

@@ -31,7 +31,7 @@ def lib() -> C.CDLL:
             build()
         l = C.CDLL(LIB)
         for name in ("sfo_gc_create", "sfo_nq_create", "sfo_cvrp_create", "sfo_js_create", "sfo_shift_create",
-                     "sfo_roster_create", "sfo_cluster_create", "sfo_availability_create"):
+                     "sfo_roster_create", "sfo_cluster_create", "sfo_availability_create", "sfo_pairs_create"):
             getattr(l, name).restype = _P
         l.sfo_gc_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
         l.sfo_nq_create.argtypes = [C.c_uint32, _P]
@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
         l.sfo_shift_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64]
         l.sfo_roster_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]
         l.sfo_availability_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P]
+        l.sfo_pairs_create.argtypes = [C.c_uint32, C.c_uint32, _P, _P, _P]
         l.sfo_destroy.argtypes = [_P]
         l.sfo_committed_score.argtypes = [_P, _P]
         l.sfo_evaluate_all.argtypes = [_P, _P]
@@ -140,6 +141,12 @@ class Oracle:
         con = np.ascontiguousarray(inst.contracts, dtype=np.int64).reshape(-1)
         return Oracle(lib().sfo_availability_create(inst.n_shifts, inst.n_employees, _p(day), _p(req), _p(hrs), _p(e), _p(skill),
                                                     _p(ptr), _p(days), len(inst.contracts), _p(con)))
+
+    @staticmethod
+    def pairs(demand, prio, bucket, n_buckets) -> "Oracle":
+        d, p = np.ascontiguousarray(demand, dtype=np.int64), np.ascontiguousarray(prio, dtype=np.int64)
+        b = np.ascontiguousarray(bucket, dtype=np.int32)
+        return Oracle(lib().sfo_pairs_create(len(b), n_buckets, _p(d), _p(p), _p(b)))
 
     @staticmethod
     def nqueens(inst, rows=None) -> "Oracle":

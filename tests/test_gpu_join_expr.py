@@ -146,3 +146,94 @@ def test_expression_errors_are_loud():
         d.add_expr(Expr([(L.X_A_COL, 99, 0)]))                    # unknown column
     with pytest.raises(L.SfgpuError):
         d.add_expr(Expr([(99, 0, 0)]))                            # unknown op
+
+
+def _pairs_kat_director(k, directed):
+    from solverforge_b200 import EqualKeyExpr
+    d = GpuScoreDirector(1)
+    d.add_collection("buckets", k["n_buckets"], -1)
+    work = d.add_collection("work", len(k["bucket"]), 0)
+    d.add_scalar_variable(work, "bucket", k["n_buckets"])
+    return d, work
+
+
+def test_reference_kats_projected_self_join_with_pair_filter_and_directed_join():
+    """constraint/tests/projected/self_join.rs:108-290 as SFGPU_K_PAIR_KEY_EXPR."""
+    from solverforge_b200 import EqualKeyExpr
+    k = GOLDEN["projected_self_join_pairs"][0]
+    d, work = _pairs_kat_director(k, False)
+    dem = d.add_column(work, "demand", k["demand"])
+    f = ConstraintFactory(d)
+    f.for_each(work).join(f.for_each(work), EqualKeyExpr(Expr.a_value(), k["n_buckets"])).filter(Expr.a(dem) < Expr.b(dem)) \
+        .penalize(HardSoftScore(0, 1)).named("projected duplicate bucket")
+    d.set_scalar_state(k["bucket"])
+    assert d.commit()[0].tolist() == [0, k["soft"]]
+    sc, ok = d.score_change(np.array([k["change"]]))
+    assert ok[0] == 1 and sc[0].tolist() == [0, k["soft_after"]]
+    d.apply_change(np.array([k["change"]]))
+    assert d.calculate_score()[0].tolist() == d.fresh_score()[0].tolist() == [0, k["soft_after"]]
+    for k in GOLDEN["projected_self_join_pairs"][1:]:
+        for demand, want in ((k["demand"], k["directed_soft"]),) + (((k["demand_after"], k["directed_soft_after"]),)
+                                                                    if "demand_after" in k else ()):
+            d, work = _pairs_kat_director(k, True)
+            dem = d.add_column(work, "demand", demand)
+            f = ConstraintFactory(d)
+            f.for_each(work).join(f.for_each(work), EqualKeyExpr(Expr.a_value(), k["n_buckets"], right_key=Expr.a(dem))) \
+                .penalize(soft(L.W_LINEAR, 1, 0), Expr.a_value() * 10 + Expr.b_value()).named("projected parent child")
+            d.set_scalar_state(k["bucket"])
+            assert d.commit()[0].tolist() == [0, want], k["cite"]
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_pair_key_expression_joins_match_the_oracle_on_every_move_kind(seed):
+    rng = np.random.default_rng(seed)
+    n, kb, R = 70, 6, 3
+    demand = rng.integers(-1, kb, size=n)
+    prio = rng.integers(0, 9, size=n)
+    starts = rng.integers(-1, kb, size=(R, n)).astype(np.int32)
+    d = models.pairs_director(demand, prio, starts, kb, R)
+    oracles = [Oracle.pairs(demand, prio, starts[r], kb) for r in range(R)]
+    for r, o in enumerate(oracles):
+        assert d.calculate_score()[r].tolist() == o.committed_score().tolist() == d.fresh_score()[r].tolist()
+    rows = [o.enumerate_change() for o in oracles]
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in rows])]).astype(np.uint64)
+    sc, ok = d.score_change(np.concatenate(rows), offs)
+    for r, o in enumerate(oracles):
+        so, oko = o.score_change(rows[r])
+        assert np.array_equal(ok[offs[r]:offs[r + 1]], oko) and np.array_equal(sc[offs[r]:offs[r + 1]], so)
+    swaps = oracles[0].enumerate_swap()[:800]
+    sc, ok = d.score_swap(np.concatenate([swaps] * R), np.arange(R + 1, dtype=np.uint64) * len(swaps))
+    for r in range(R):
+        so, oko = oracles[r].score_swap(swaps)
+        sl = slice(r * len(swaps), (r + 1) * len(swaps))
+        assert np.array_equal(ok[sl], oko) and np.array_equal(sc[sl], so)
+    n_c = 200
+    sizes = rng.integers(1, 6, size=n_c)
+    eo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    er = np.stack([rng.integers(0, n, size=eo[-1]), rng.integers(-1, kb, size=eo[-1])], axis=1)
+    d1 = models.pairs_director(demand, prio, starts[0][None, :], kb, 1)
+    sc, ok = d1.score_compound(eo, er)
+    so, oko = oracles[0].score_compound(eo, er)
+    assert np.array_equal(ok, oko) and np.array_equal(sc[ok == 1], so[oko == 1])
+    # the default scalar search (Change + Swap union, seeded Random) commits through the list maintenance
+    desc = GpuScoreDirector.default_scalar_union(window=16)
+    for step in range(15):
+        last = d.calculate_score()
+        ref = np.concatenate([last, last], axis=1)
+        seeds = [500 + step, 600 + step, 700 + step]
+        idx, best, ev, win, flags = d.step_union(desc, ForageParams(1, 1, 40), step_seeds=seeds, step_indices=[step] * R,
+                                                 ref_scores=ref, apply=True)
+        for r, o in enumerate(oracles):
+            out, child, local, data, scs = oracle_lib.union_step(o, [(L.FAM_CHANGE,), (L.FAM_SWAP,)], L.UNION_STRATIFIED_RANDOM,
+                                                                 L.ORDER_RANDOM, step, seeds[r], last[r], last[r], 0, 40, True, 0)
+            assert int(ev[r]) == out[2] and flags[r] == 0
+            if out[0]:
+                assert int(idx[r]) == out[1]
+                ci, j = int(child[out[1]]), int(local[out[1]])
+                a, b = [int(x) for x in data[ci][0][j]]
+                (o.apply_change if ci == 0 else o.apply_swap)(a, b)
+            else:
+                assert idx[r] == 0xFFFFFFFF
+        now = d.calculate_score()
+        for r, o in enumerate(oracles):
+            assert now[r].tolist() == o.committed_score().tolist() == d.fresh_score()[r].tolist()
