@@ -74,7 +74,8 @@ def cluster_director(inst, n_replicas: int = 1, team=None, device: int = 0, stre
 
 
 def cvrp_director(inst: CvrpInstance, n_replicas: int = 1, offsets=None, elems=None, device: int = 0,
-                  stream=None, flags: int = 0) -> GpuScoreDirector:
+                  stream=None, flags: int = 0, distance_weight: int = 1, capacity_weight: int = 1) -> GpuScoreDirector:
+    """distance_weight / capacity_weight scale the two authored weights (tests of the arithmetic-width switch)."""
     d = GpuScoreDirector(n_replicas, device, stream, flags)
     locations = d.add_collection("locations", inst.dim, -1)       # matrix rows: depot + customers
     customers = d.add_collection("customers", inst.dim - 1, -1)   # problem facts, id = 1..n
@@ -86,8 +87,8 @@ def cvrp_director(inst: CvrpInstance, n_replicas: int = 1, offsets=None, elems=N
     f = ConstraintFactory(d)
     f.for_each(customers).if_not_exists(f.for_each(routes).flattened(), EqualId(cust_id)).penalize(
         HardSoftScore.ONE_HARD).named("all_customers_assigned")
-    f.for_each(routes).penalize(hard(L.W_EXCESS, 1, inst.capacity), ListSum(demand)).named("vehicle_capacity")
-    f.for_each(routes).penalize(soft(L.W_LINEAR, 1, 0), PathCost(dist, inst.depot)).named("total_distance")
+    f.for_each(routes).penalize(hard(L.W_EXCESS, capacity_weight, inst.capacity), ListSum(demand)).named("vehicle_capacity")
+    f.for_each(routes).penalize(soft(L.W_LINEAR, distance_weight, 0), PathCost(dist, inst.depot)).named("total_distance")
     d.set_list_state(inst.offsets if offsets is None else offsets, inst.elems if elems is None else elems)
     d.commit()
     return d

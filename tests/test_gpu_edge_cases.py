@@ -235,3 +235,42 @@ def test_thirty_two_constraints_like_the_reference_tuple_limit():
             after = start[r].copy()
             after[e] = v
             assert ok[j] == 1 and sc[j].tolist() == [0, score(after)]
+
+
+def test_int32_delta_bound_switches_exactly_at_the_edge():
+    """The fast list kernels run their deltas in int32 when a commit-time bound proves every delta fits
+    (|w_dist| * 4 * max cell + |w_cap| * 2 * sum |demand| < 2^31 - 1). Weights just below, at and above that edge —
+    where a wrapped 32-bit product would be off by 2^32 — all score like the oracle (weights are linear per level)."""
+    c = instances.cvrp(80, 6, seed=23)
+    R, K = 2, 20
+    starts = [instances.perturb_routes(c, 9 + r, 60) for r in range(R)]
+    oracles = [Oracle.cvrp(c, *starts[r]) for r in range(R)]
+    gen = []
+    for r in range(R):
+        rows = oracles[r].enumerate_nearby_list_change(K)
+        so, oko = oracles[r].score_list_change(rows)
+        gen.append((rows, so, oko))
+    mx = int(c.matrix.max())
+    tot = int(np.abs(c.demands.astype(np.int64)).sum())
+    for w_cap in (1, 100000):
+        edge = (2 ** 31 - 1 - w_cap * 2 * tot) // (4 * mx)      # largest distance weight with bound < 2^31 - 1 (or one above)
+        for w_dist in (edge - 1, edge, edge + 1, edge + 2, 3 * edge, 1000 * edge):
+            d = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]),
+                                     distance_weight=w_dist, capacity_weight=w_cap)
+            base = d.calculate_score()
+            for r in range(R):
+                oc = oracles[r].committed_score()
+                assert base[r].tolist() == [int(oc[0]) * w_cap, int(oc[1]) * w_dist]
+            allrows = np.concatenate([g[0] for g in gen])
+            offs = np.cumsum([0] + [len(g[0]) for g in gen]).astype(np.uint64)
+            s, ok = d.score_list_change(allrows, offs)
+            want = np.concatenate([g[1] for g in gen]) * np.array([w_cap, w_dist], dtype=np.int64)
+            assert ok.all() and np.array_equal(s, want), f"w_dist={w_dist} w_cap={w_cap}"
+            # the fused device-generated step (REDUX / 64-bit shuffle reductions) picks the oracle's winner
+            idx, best, ev, win = d.step_nearby_list_change(K, ForageParams(0, 0, 0), step_seeds=[1] * R)
+            for r in range(R):
+                rows, so, oko = gen[r]
+                sw = so * np.array([w_cap, w_dist], dtype=np.int64)
+                out = oracle_lib.replay_step(sw, oko, [0, 0], [0, 0], [0, 0], 1, 2, 1, False, 3)
+                assert out[0] and int(idx[r]) == out[1] and best[r].tolist() == sw[out[1]].tolist(), f"w_dist={w_dist}"
+            del d
