@@ -23,6 +23,18 @@
 #pragma once
 #include "sfgpu_nearby.cuh"
 
+// x % len for a 64-bit hash and a 32-bit length. Lengths below 2^16 (entity counts, route lengths, value ranges) take
+// three 32-bit remainders instead of the software 64-bit division: x = hi * 2^32 + lo, so
+// x mod len = ((hi mod len) * (2^32 mod len) + lo mod len) mod len with every product below 2^32.
+__device__ __forceinline__ uint32_t mod_u64(uint64_t x, uint32_t len) {
+  if (len < 65536u) {
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    const uint32_t c = (uint32_t)(0x100000000ull % len);
+    return ((hi % len) * c + lo % len) % len;
+  }
+  return (uint32_t)(x % (uint64_t)len);
+}
+
 // MoveStreamContext (move_selector/iter.rs:14-207)
 struct StreamCtx {
   uint64_t step_index, step_seed;
@@ -31,11 +43,11 @@ struct StreamCtx {
     return splitmix64_dev(step_seed ^ (step_index * 0x9E3779B97F4A7C15ull) ^ salt);
   }
   __device__ __forceinline__ uint32_t random_index(uint32_t len, uint64_t salt) const {
-    return len <= 1 ? 0u : (uint32_t)(mixed(salt) % (uint64_t)len);
+    return len <= 1 ? 0u : mod_u64(mixed(salt), len);
   }
   __device__ __forceinline__ uint32_t random_stride(uint32_t len, uint64_t salt) const {
     if (len <= 1) return 1;
-    uint32_t stride = (uint32_t)(mixed(salt) % (uint64_t)(len - 1)) + 1;
+    uint32_t stride = mod_u64(mixed(salt), len - 1) + 1;
     while (true) {
       uint32_t a = stride, b = len;
       while (b) {
@@ -79,7 +91,7 @@ struct SelMap {
   }
   __device__ __forceinline__ uint32_t at(uint32_t offset) const {
     if (c->order == SFGPU_ORDER_RANDOM) return c->random_index(len, salt ^ ((uint64_t)offset * 0xD1B54A32D192ED03ull));
-    if (c->order == SFGPU_ORDER_SHUFFLED) return (uint32_t)(((uint64_t)start + (uint64_t)offset * stride) % len);
+    if (c->order == SFGPU_ORDER_SHUFFLED) return mod_u64((uint64_t)start + (uint64_t)offset * stride, len);
     return offset;
   }
 };
@@ -269,14 +281,31 @@ __device__ inline void walk_change(const StreamCtx& cx, uint32_t desc, const int
 
 // SwapMoveSelector cursor over one entity class (move_selector/swap.rs:196-233): the left and the right entity lists
 // are permuted independently; every (left, right) with left < right is a SwapMove, left-major. Rows {left, right, 0, 0}.
-__device__ inline void walk_swap(const StreamCtx& cx, uint32_t desc, uint32_t n, RowSink& out) {
+// The right-hand scan is spread over the warp: most (left, right) pairs of a high left entity fail left < right, so
+// the scan is a rejection loop — 32 pairs per trip, matches compacted in pull order.
+__device__ inline void walk_swap_warp(const StreamCtx& cx, uint32_t desc, uint32_t n, uint4* rows, uint32_t cap, uint32_t& n_out,
+                                      bool& more) {
+  const uint32_t lane = threadIdx.x & 31;
   const uint64_t base = ((uint64_t)desc << 32);
   const SelMap lm(cx, n, 0x5A09000000000001ull ^ base), rm(cx, n, 0x5A09000000000002ull ^ base);
+  n_out = 0;
+  more = false;
   for (uint32_t lo = 0; lo < n; ++lo) {
     const uint32_t l = lm.at(lo);
-    for (uint32_t ro = 0; ro < n; ++ro) {
-      const uint32_t r = rm.at(ro);
-      if (l < r && !out.push(l, r, 0, 0)) return;
+    for (uint32_t rb = 0; rb < n; rb += 32) {
+      const uint32_t ro = rb + lane;
+      const uint32_t r = ro < n ? rm.at(ro) : 0;
+      const bool hit = ro < n && l < r;
+      const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+      if (!hits) continue;
+      const uint32_t at = n_out + __popc(hits & ((1u << lane) - 1));
+      if (hit && at < cap) rows[at] = make_uint4(l, r, 0, 0);
+      n_out += __popc(hits);
+      if (n_out > cap) {
+        n_out = cap;
+        more = true;
+        return;
+      }
     }
   }
 }
@@ -285,10 +314,22 @@ __device__ inline void walk_swap(const StreamCtx& cx, uint32_t desc, uint32_t n,
 __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_constant__ DevModel m, const UnionArgs a,
                                                               const uint32_t child) {
   const uint32_t r = blockIdx.x;
-  if (threadIdx.x != 0 || (a.done && a.done[r])) return;
+  if (a.done && a.done[r]) return;
   const char* st = m.state + (size_t)r * m.block_bytes;
   const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
   const StreamCtx cx = stream_ctx(a, r);
+  if (a.child[child].family == SFGPU_FAM_SWAP) {  // the whole warp scans
+    uint32_t n_out;
+    bool more;
+    walk_swap_warp(cx, a.sdesc, m.n_entities, (uint4*)a.rows + ((size_t)r * a.n_children + child) * a.window, union_cap(a, r),
+                   n_out, more);
+    if (threadIdx.x == 0) {
+      a.n_emit[(size_t)r * a.n_children + child] = n_out;
+      a.ended[(size_t)r * a.n_children + child] = more ? 0 : 1;
+    }
+    return;
+  }
+  if (threadIdx.x != 0) return;
   RowSink out;
   out.rows = (uint4*)a.rows + ((size_t)r * a.n_children + child) * a.window;
   out.cap = union_cap(a, r);
@@ -297,7 +338,6 @@ __global__ void __launch_bounds__(32) union_walk_index_kernel(const __grid_const
   const UnionChildDev& c = a.child[child];
   if (c.family == SFGPU_FAM_CHANGE)
     walk_change(cx, a.sdesc, (const int32_t*)(st + m.off_var), m.n_entities, m.n_values, m.allows_unassigned != 0, out);
-  else if (c.family == SFGPU_FAM_SWAP) walk_swap(cx, a.sdesc, m.n_entities, out);
   else if (c.family == SFGPU_FAM_LIST_REVERSE) walk_reverse(cx, a.desc, off, m.n_owners, out);
   else if (c.family == SFGPU_FAM_K_OPT) walk_k_opt(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
   else if (c.family == SFGPU_FAM_SUBLIST_CHANGE) walk_sublist_change(cx, a.desc, off, m.n_owners, c.p0, c.p1, out);
