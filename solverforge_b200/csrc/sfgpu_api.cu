@@ -1444,8 +1444,11 @@ int sfgpu_launch_argbest_counts(sfgpu_ctx* ctx, const ForageDev& f, const uint64
                                 const uint32_t* d_skip, const int64_t* d_scores, const uint8_t* d_doable,
                                 const uint64_t* d_seeds, const int64_t* d_ref, uint32_t* d_idx, int64_t* d_best,
                                 uint32_t* d_eval) {
-  argbest_kernel<<<ctx->dm.R, 1024, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_seeds, d_ref, d_idx, d_best, d_eval,
-                                                      d_counts, d_skip);
+  // a window holds a few hundred pulls: a small CTA spends less time in the block scans' barriers
+  const uint32_t stride = ctx->dm.R > 1 ? (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ctx->argbest_stride_hint) : 0;
+  const int threads = (stride && stride <= 2048) ? 256 : 1024;
+  argbest_kernel<<<ctx->dm.R, threads, 0, ctx->stream>>>(f, d_offs, d_scores, d_doable, d_seeds, d_ref, d_idx, d_best, d_eval,
+                                                         d_counts, d_skip);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;

@@ -640,7 +640,7 @@ __global__ void apply_scalar_kernel(const __grid_constant__ DevModel m, int kind
 }
 
 // kind 2 list change, 3 list swap, 4 list reverse, 5 sublist change, 6 sublist swap, 7 k-opt. Dynamic smem: elem_cap uint32 (old element copy).
-__global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__ DevModel m, int kind,
+__global__ void __launch_bounds__(256, 4) apply_list_kernel(const __grid_constant__ DevModel m, int kind,
                                                          const uint32_t* __restrict__ rows,
                                                          const uint8_t* __restrict__ mask,
                                                          const uint64_t* __restrict__ cand_offsets,
@@ -788,26 +788,23 @@ __global__ void __launch_bounds__(256) apply_list_kernel(const __grid_constant__
     }
   }
   __syncthreads();
-  // per-route path costs are recomputed for the (at most two) touched routes
+  // per-route path costs are recomputed for the (at most two) touched routes: one warp per route, one leg per lane
   for (uint32_t k = 0; k < m.n_cons; ++k) {
     const ConsDev& c = m.cons[k];
     if (c.kind != SFGPU_K_LIST_PATH_COST) continue;
     int64_t* rcost = (int64_t*)(st + c.off0);
     const uint32_t depot = (uint32_t)c.p0;
-    if (threadIdx.x < 2) {
-      uint32_t o = threadIdx.x == 0 || kind == 4 || kind == 7 ? (kind == 7 ? (row.x & 0x0FFFFFFFu) : row.x) : row.z;
-      if (!(threadIdx.x == 1 && (row.x == row.z || kind == 4 || kind == 7))) {
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < 2) {
+      const bool one_route = kind == 4 || kind == 7;
+      const uint32_t o = w == 0 || one_route ? (kind == 7 ? (row.x & 0x0FFFFFFFu) : row.x) : row.z;
+      if (!(w == 1 && (row.x == row.z || one_route))) {
+        const uint32_t b = off[o], e = off[o + 1];
         int64_t cost = 0;
-        uint32_t b = off[o], e = off[o + 1];
-        if (e > b) {
-          uint32_t prev = depot;
-          for (uint32_t i = b; i < e; ++i) {
-            cost += mat_at(c, prev, el[i]);
-            prev = el[i];
-          }
-          cost += mat_at(c, prev, depot);
-        }
-        rcost[o] = cost;
+        if (e > b)  // legs: depot -> el[b], el[i] -> el[i + 1], el[e - 1] -> depot
+          for (uint32_t i = b + lane; i <= e; i += 32) cost += mat_at(c, i > b ? el[i - 1] : depot, i < e ? el[i] : depot);
+        for (int s = 16; s > 0; s >>= 1) cost += __shfl_down_sync(0xffffffffu, cost, s);
+        if (lane == 0) rcost[o] = cost;
       }
     }
   }

@@ -117,6 +117,7 @@ struct sfgpu_ctx {
   void* union_buf = nullptr;  // union step buffers
   size_t union_bytes = 0;
   UnionPlan union_plan;
+  uint64_t argbest_stride_hint = 0;  // rows per replica of the fixed-stride batch the next counted replay runs over
   std::vector<cudaStream_t> aux_streams;  // the children of a union walk side by side (fork / join by events)
   std::vector<cudaEvent_t> aux_events;    // [0] fork, [1 + i] join of aux stream i
   std::vector<uint32_t> relabel_host, inverse_host;  // element id <-> internal id of the fast records

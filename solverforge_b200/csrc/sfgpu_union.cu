@@ -211,6 +211,7 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
                                      plan.sa_nxt, plan.sa_params, a.f.accepted_limit);
     if (rc0) return rc0;
   }
+  ctx->argbest_stride_hint = (adaptive && !last_pass) ? (uint64_t)a.n_children * plan.w0 * 4 : a.t_cap;
   int rc = sfgpu_launch_argbest_counts(ctx, a.f, a.offsets, a.n_sched, a.done, a.scores, a.doable, a.step_seeds, a.ref_scores,
                                        d_idx, d_best, d_eval);
   if (rc) return rc;

@@ -29,7 +29,7 @@
 __device__ __forceinline__ uint32_t mod_u64(uint64_t x, uint32_t len) {
   if (len < 65536u) {
     const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
-    const uint32_t c = (uint32_t)(0x100000000ull % len);
+    const uint32_t c = (0u - len) % len;  // 2^32 mod len in 32-bit arithmetic
     return ((hi % len) * c + lo % len) % len;
   }
   return (uint32_t)(x % (uint64_t)len);
@@ -360,7 +360,8 @@ struct RankTables {
 };
 __device__ __forceinline__ uint32_t rank_tables_words(uint32_t n) { return 5 * n + 2; }
 
-// all threads of the block; ends with a barrier
+// all threads of the block; ends with a barrier. Global loads (the route lengths) are issued by all threads at once;
+// the serial part (prefix sums, rank lists) touches shared memory only.
 __device__ inline void build_rank_tables(RankTables& t, uint32_t* smem_words, const StreamCtx& cx, uint64_t entity_salt,
                                          const uint4* rr, uint32_t n, uint32_t* s_max_occ) {
   t.n = n;
@@ -371,31 +372,40 @@ __device__ inline void build_rank_tables(RankTables& t, uint32_t* smem_words, co
   t.occ_next = t.occ_head + n;
   const SelMap em(cx, n, entity_salt);
   for (uint32_t o = threadIdx.x; o < n; o += blockDim.x) {
-    t.ent[o] = n <= 1 ? o : em.at(o);
+    const uint32_t e = n <= 1 ? o : em.at(o);
+    t.ent[o] = e;
+    t.occ_next[o] = rr[e].y;  // route length of rank o, parked here until the prefix pass
     t.occ_head[o] = UNION_NONE;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t slots = 0, pos = 0;
     for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t len = t.occ_next[i];
       t.slot_first[i] = slots;
       t.pos_first[i] = pos;
-      const uint32_t len = rr[t.ent[i]].y;
       slots += len + 1;
       pos += len;
     }
     t.slot_first[n] = slots;
     t.pos_first[n] = pos;
     uint32_t mo = 1;
-    for (uint32_t i = n; i-- > 0;) {  // reverse, so every list is in increasing rank order
-      const uint32_t e = t.ent[i];
-      t.occ_next[i] = t.occ_head[e];
-      t.occ_head[e] = i;
-    }
-    for (uint32_t e = 0; e < n; ++e) {
-      uint32_t k = 0;
-      for (uint32_t i = t.occ_head[e]; i != UNION_NONE; i = t.occ_next[i]) ++k;
-      mo = max(mo, k);
+    if (cx.order == SFGPU_ORDER_RANDOM) {  // with replacement: an entity may hold several ranks
+      for (uint32_t i = n; i-- > 0;) {     // reverse, so every list is in increasing rank order
+        const uint32_t e = t.ent[i];
+        t.occ_next[i] = t.occ_head[e];
+        t.occ_head[e] = i;
+      }
+      for (uint32_t e = 0; e < n; ++e) {
+        uint32_t k = 0;
+        for (uint32_t i = t.occ_head[e]; i != UNION_NONE; i = t.occ_next[i]) ++k;
+        mo = max(mo, k);
+      }
+    } else {  // a permutation: exactly one rank per entity
+      for (uint32_t i = 0; i < n; ++i) {
+        t.occ_head[t.ent[i]] = i;
+        t.occ_next[i] = UNION_NONE;
+      }
     }
     *s_max_occ = mo;
   }
