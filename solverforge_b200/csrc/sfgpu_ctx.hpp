@@ -345,7 +345,9 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
 int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan);
 int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bool last_pass, uint32_t* d_idx, int64_t* d_best,
                             uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc, bool adaptive,
-                            uint32_t win_shift = 0);
+                            uint32_t win_shift = 0, uint32_t stream_set = 0);
+int sfgpu_union_conditional_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t pass_index, uint32_t window, bool last_pass, uint32_t* d_idx,
+                                 int64_t* d_best, uint32_t* d_eval, uint64_t* d_overflow_acc, uint32_t win_shift, bool* used);
 int sfgpu_union_reset_windows(sfgpu_ctx* ctx, UnionPlan& plan);
 // sfgpu_solve.cu
 int sfgpu_launch_sa_accept(sfgpu_ctx* ctx, const uint64_t* d_offs, const uint32_t* d_counts, const uint32_t* d_skip,

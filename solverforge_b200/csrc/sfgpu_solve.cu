@@ -177,8 +177,15 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       rc2 = sfgpu_union_begin_step(ctx, plan);
       if (rc2) return rc2;
       for (int k = 0; k < 3; ++k) {
-        rc2 = sfgpu_union_launch_pass(ctx, plan, plan.wmax, k == 2, s.out_index, s.out_best, s.out_evaluated, nullptr, nullptr,
-                                      d_overflows, true, k == 1 ? 2 : 0);
+        bool used = false;
+        if (k > 0) {  // inside a captured step graph the later passes are IF nodes: skipped when nothing is pending
+          rc2 = sfgpu_union_conditional_pass(ctx, plan, (uint32_t)k, plan.wmax, k == 2, s.out_index, s.out_best, s.out_evaluated,
+                                             d_overflows, k == 1 ? 2 : 0, &used);
+          if (rc2) return rc2;
+        }
+        if (!used)
+          rc2 = sfgpu_union_launch_pass(ctx, plan, plan.wmax, k == 2, s.out_index, s.out_best, s.out_evaluated, nullptr, nullptr,
+                                        d_overflows, true, k == 1 ? 2 : 0, (uint32_t)k);
         if (rc2) return rc2;
       }
       rc2 = sfgpu_launch_apply_list_kinds(ctx, plan.apply_rows, plan.apply_kinds);

@@ -101,12 +101,12 @@ int sfgpu_union_prepare(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const sfgp
   a.win_max = wmax;
   plan.w0 = w0;
   plan.wmax = wmax;
-  while (ctx->aux_streams.size() + 1 < C) {
+  while (ctx->aux_streams.size() < 3 * (size_t)(C - 1) + 2) {  // three disjoint sets (one per window pass) + 2 body streams
     cudaStream_t aux = nullptr;
     CU(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
     ctx->aux_streams.push_back(aux);
   }
-  while (ctx->aux_events.size() < C) {
+  while (ctx->aux_events.size() < 3 * (size_t)C) {
     cudaEvent_t ev = nullptr;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     ctx->aux_events.push_back(ev);
@@ -144,7 +144,7 @@ int sfgpu_union_begin_step(sfgpu_ctx* ctx, UnionPlan& plan) {
 // one window pass: walk every child, schedule, score, replay, pick
 int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bool last_pass, uint32_t* d_idx, int64_t* d_best,
                             uint32_t* d_eval, uint32_t* d_win8, uint32_t* d_flags, uint64_t* d_overflow_acc, bool adaptive,
-                            uint32_t win_shift) {
+                            uint32_t win_shift, uint32_t stream_set) {
   const DevModel& dm = ctx->dm;
   const uint32_t R = dm.R;
   UnionArgs a = plan.a;
@@ -158,10 +158,13 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
   const uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((window + 127) / 128,
                                                                    std::max<uint32_t>(2, (uint32_t)ctx->sm_count * 8 / std::max(R, 1u))));
   const bool fork = a.n_children > 1;
-  if (fork) CU(cudaEventRecord(ctx->aux_events[0], ctx->stream));
+  // side streams and events of this pass (disjoint per pass: a conditional pass is captured into its own body graph)
+  cudaStream_t* side = ctx->aux_streams.data() + (size_t)stream_set * (a.n_children - 1);
+  cudaEvent_t* evs = ctx->aux_events.data() + (size_t)stream_set * a.n_children;
+  if (fork) CU(cudaEventRecord(evs[0], ctx->stream));
   for (uint32_t c = 0; c < a.n_children; ++c) {
-    cudaStream_t cs = c == 0 ? ctx->stream : ctx->aux_streams[c - 1];
-    if (c > 0) CU(cudaStreamWaitEvent(cs, ctx->aux_events[0], 0));
+    cudaStream_t cs = c == 0 ? ctx->stream : side[c - 1];
+    if (c > 0) CU(cudaStreamWaitEvent(cs, evs[0], 0));
     const int fam = a.child[c].family;
     if (is_nearby(fam)) {
       const size_t tb = rank_tables_words_host(dm.n_owners) * 4;
@@ -187,8 +190,8 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
       default: union_score_child_kernel<SFGPU_FAM_K_OPT><<<g, 128, 0, cs>>>(dm, a, c); break;
     }
     if (c > 0) {
-      CU(cudaEventRecord(ctx->aux_events[c], cs));
-      CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_events[c], 0));
+      CU(cudaEventRecord(evs[c], cs));
+      CU(cudaStreamWaitEvent(ctx->stream, evs[c], 0));
     }
   }
   switch (a.union_order) {
@@ -219,6 +222,51 @@ int sfgpu_union_launch_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t window, bo
                                                               plan.apply_kinds, d_flags, plan.pending, d_overflow_acc);
   ctx->launches++;
   CU(cudaGetLastError());
+  return SFGPU_OK;
+}
+
+// A later window pass inside a captured step graph: an IF node whose body holds the pass, taken only when the pass
+// before left replicas pending (cudaGraphConditionalHandle set on the device by union_cond_kernel). The body is
+// captured from a dedicated stream into the node's body graph. Returns SFGPU_OK with *used = false when the stream is
+// not capturing (the caller then launches the pass unconditionally).
+int sfgpu_union_conditional_pass(sfgpu_ctx* ctx, UnionPlan& plan, uint32_t pass_index, uint32_t window, bool last_pass, uint32_t* d_idx,
+                                 int64_t* d_best, uint32_t* d_eval, uint64_t* d_overflow_acc, uint32_t win_shift, bool* used) {
+  *used = false;
+  static const bool disabled = getenv("SFGPU_NO_COND") != nullptr;  // tuning / debugging knob
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (disabled || cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusActive) return SFGPU_OK;
+  cudaGraph_t graph = nullptr;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t n_deps = 0;
+  CU(cudaStreamGetCaptureInfo(ctx->stream, &st, nullptr, &graph, &deps, &n_deps));
+  cudaGraphConditionalHandle handle;
+  CU(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+  union_cond_kernel<<<1, 1, 0, ctx->stream>>>(handle, plan.pending);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamGetCaptureInfo(ctx->stream, &st, nullptr, &graph, &deps, &n_deps));
+  cudaGraphNodeParams np{};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeIf;
+  np.conditional.size = 1;
+  cudaGraphNode_t node = nullptr;
+  CU(cudaGraphAddNode(&node, graph, deps, n_deps, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  CU(cudaStreamUpdateCaptureDependencies(ctx->stream, &node, 1, cudaStreamSetCaptureDependencies));
+  // the body: zero the pending counter, then the pass — captured from a body stream into the node's graph
+  cudaStream_t outer = ctx->stream;
+  cudaStream_t bs = ctx->aux_streams[ctx->aux_streams.size() - 1 - (pass_index & 1)];
+  CU(cudaStreamBeginCaptureToGraph(bs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  ctx->stream = bs;
+  union_fill_kernel<<<1, 1, 0, bs>>>(plan.pending, 0u, 1u);
+  int rc = sfgpu_union_launch_pass(ctx, plan, window, last_pass, d_idx, d_best, d_eval, nullptr, nullptr, d_overflow_acc, true, win_shift,
+                                   pass_index);
+  ctx->stream = outer;
+  cudaError_t ce = cudaStreamEndCapture(bs, nullptr);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(ctx, SFGPU_E_CUDA, std::string("conditional pass capture: ") + cudaGetErrorString(ce));
+  *used = true;
   return SFGPU_OK;
 }
 
@@ -267,7 +315,7 @@ int32_t sfgpu_step_union(sfgpu_ctx* ctx, uint32_t flags, const sfgpu_union_desc*
   ev_begin(ctx);
   for (uint32_t window = plan.w0;;) {
     const bool last = window >= plan.wmax;
-    rc = sfgpu_union_launch_pass(ctx, plan, window, last, io.d_idx, io.d_best, io.d_eval, io.d_win, d_flags, nullptr, false, 0);
+    rc = sfgpu_union_launch_pass(ctx, plan, window, last, io.d_idx, io.d_best, io.d_eval, io.d_win, d_flags, nullptr, false, 0, 0);
     if (rc) return rc;
     if (last) break;
     uint32_t pending = 0;

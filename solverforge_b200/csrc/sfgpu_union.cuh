@@ -998,3 +998,8 @@ __global__ void union_fill_kernel(uint32_t* dst, uint32_t value, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = value;
 }
+
+// sets the condition of a later window pass (an IF node of the step graph): taken when replicas are still pending
+__global__ void union_cond_kernel(cudaGraphConditionalHandle handle, const uint32_t* pending) {
+  cudaGraphSetConditional(handle, *pending ? 1u : 0u);
+}
