@@ -644,12 +644,14 @@ def run_ours(args):
     # AcceptedCount(256), default_local_search/policy.rs:18-82) — whole steps incl. commit, no host round trip
     device_loop = None
     if name == "cvrp" and args.loop_steps > 0:
+        d.solve_nearby_list_change(16, 20, 2, 400, 1, 256, seed_base=500)   # warm-up: buffers, graph capture
         d.synchronize()
         t0 = time.perf_counter()
         best_l, ev_l, acc_l = d.solve_nearby_list_change(args.loop_steps, 20, 2, 400, 1, 256, seed_base=1000)
         dt = time.perf_counter() - t0
         device_loop = {"steps": args.loop_steps, "replicas": R, "ms_per_step": dt * 1e3 / args.loop_steps,
                        "moves_evaluated_per_s": float(ev_l.sum()) / dt, "committed_steps": int(acc_l.sum()),
+                       "selector": "NearbyListChange(20), SelectionOrder::Original, whole neighbourhood generated and scored per step",
                        "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
                        "best_score_replica0": [int(best_l[0][0]), int(best_l[0][1])]}
 
@@ -674,18 +676,6 @@ def run_ours(args):
                                           "SublistSwap(1..=3), ListReverse], Random leaves, StratifiedRandom",
                               "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
                               "windows_per_child": "adaptive per replica (first 64), x4, then 4096"}
-            # the canonical nearby list-change loop again, windowed: same winners as device_loop above (one child,
-            # SelectionOrder::Original), but only the prefix of the cursor the forager consumes is generated
-            one = d.union_desc([(0, 20)], 0, 0)
-            d.solve_union(one, 16, 2, 400, 1, 256, seed_base=500)
-            d.synchronize()
-            t0 = time.perf_counter()
-            best_w, ev_w, acc_w, ovf_w = d.solve_union(one, args.loop_steps, 2, 400, 1, 256, seed_base=1000)
-            dt = time.perf_counter() - t0
-            default_search["nearby_change_windowed"] = {
-                "ms_per_step": dt * 1e3 / args.loop_steps, "moves_evaluated_per_s": float(ev_w.sum()) / dt,
-                "scored_over_evaluated": float(d.last_pulls_scored.sum()) / max(float(ev_w.sum()), 1.0),
-                "window_overflows": int(ovf_w.sum())}
         except Exception as exc:  # informational only
             default_search = {"error": str(exc)[:200]}
 
@@ -758,7 +748,7 @@ def main():
     ap.add_argument("--workload", default="cvrp", choices=["cvrp", "graph_coloring", "job_shop"])
     ap.add_argument("--replicas", type=int, default=0,
                     help="independent seeded replicas per GPU per launch (0 = SURVEY §8d: 1024 / 192 / 200)")
-    ap.add_argument("--loop-steps", type=int, default=64, help="steps of the device-resident loop demo (0 = skip)")
+    ap.add_argument("--loop-steps", type=int, default=512, help="steps of the device-resident loop demo (0 = skip)")
     ap.add_argument("--sync-every", type=int, default=64,
                     help="steps between best-score syncs (N > 1); SURVEY 8(d) C5: K = 64 (clamped to --steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="length of the cpu_baseline sample")

@@ -553,7 +553,8 @@ typedef struct sfgpu_solve_params {
   uint32_t accepted_limit;
   uint64_t seed_base;
   int32_t restore_best;
-  int32_t reserved;
+  int32_t reserved;          /* bit 0 (sfgpu_solve_nearby_list_change, AcceptedCount): windowed speculation — only the prefix of
+                                the cursor the forager consumes is generated (one-child union, same winners) */
   double acceptor_real;      /* GreatDeluge rain_speed / DiversifiedLateAcceptance tolerance */
   uint64_t step_count_limit; /* StepCountingHillClimbing */
 } sfgpu_solve_params;

@@ -561,14 +561,14 @@ class GpuScoreDirector:
     def solve_nearby_list_change(self, n_steps: int, max_nearby: int = 20, acceptor: int = 2, late_size: int = 400,
                                  tie_mode: int = 1, accepted_limit: int = 0, seed_base: int = 0,
                                  restore_best: bool = False, acceptor_real: float = 0.0,
-                                 step_count_limit: int = 0):
+                                 step_count_limit: int = 0, windowed: bool = False):
         """Device-resident local-search loop (sfgpu_solve_nearby_list_change): returns
         (best_scores[R,2], moves_evaluated[R], committed_steps[R]). acceptor: 1 HillClimbing,
         2 LateAcceptance(late_size), 3 GreatDeluge(acceptor_real = rain_speed),
         4 StepCountingHillClimbing(step_count_limit), 5 DiversifiedLateAcceptance(late_size,
         acceptor_real = tolerance)."""
         p = L.SolveParams(max_nearby, n_steps, acceptor, late_size, tie_mode, accepted_limit, seed_base,
-                          1 if restore_best else 0, 0, acceptor_real, step_count_limit)
+                          1 if restore_best else 0, 1 if windowed else 0, acceptor_real, step_count_limit)
         best = np.zeros((self.R, 2), dtype=np.int64)
         ev = np.zeros(self.R, dtype=np.uint64)
         acc = np.zeros(self.R, dtype=np.uint64)

@@ -22,6 +22,23 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   if (rc) return rc;
   if (!p) return fail(ctx, SFGPU_E_INVALID, "null params");
   const DevModel& dm = ctx->dm;
+  // AcceptedCount(N) consumes a prefix of the cursor: with params->reserved bit 0 the canonical nearby loop runs as a
+  // one-child union in SelectionOrder::Original, which generates and scores only the window the forager reaches — same
+  // pulls, same winners, same moves_evaluated (tests/test_gpu_union.py). It wins while the forager quits within a few
+  // hundred pulls; a replica that needs most of its neighbourhood is faster in the whole-neighbourhood step (many CTAs
+  // per replica), which stays the default.
+  sfgpu_union_desc windowed{};
+  if (!scalar && !udesc && (p->reserved & 1) && p->accepted_limit > 0 && p->max_nearby >= 1 && p->max_nearby <= 32 &&
+      dm.nearby_ok && !ctx->force_generic) {
+    windowed.n_children = 1;
+    windowed.union_order = SFGPU_UNION_SEQUENTIAL;
+    windowed.selection_order = SFGPU_ORDER_ORIGINAL;
+    windowed.children[0].family = SFGPU_FAM_NEARBY_LIST_CHANGE;
+    windowed.children[0].p0 = p->max_nearby;
+    windowed.children[0].weight = 1;
+    windowed.max_window = std::max<uint32_t>(4096u, dm.elem_cap * p->max_nearby);  // the whole neighbourhood fits
+    udesc = &windowed;
+  }
   if (scalar) {
     if (!dm.has_scalar) return fail(ctx, SFGPU_E_STATE, "model has no scalar variable");
     if ((uint64_t)dm.n_entities * (dm.n_values + 1) >= 0xFFFFFFFFull)

@@ -320,3 +320,19 @@ def test_default_scalar_search_on_device_follows_the_oracle():
         assert final[r].tolist() == o.committed_score().tolist()
         assert np.array_equal(state[r], cur)
     assert np.array_equal(d.fresh_score(), final)
+
+
+def test_windowed_nearby_loop_equals_the_whole_neighbourhood_loop():
+    """sfgpu_solve_nearby_list_change with the windowed flag runs as a one-child union in SelectionOrder::Original
+    (windowed speculation): same trajectory as the whole-neighbourhood loop."""
+    c = instances.cvrp(120, 9, seed=44)
+    R = 4
+    starts = [instances.perturb_routes(c, 60 + r, 40) for r in range(R)]
+    offs, el = np.stack([s[0] for s in starts]), np.concatenate([s[1] for s in starts])
+    out = {}
+    for mode in ("windowed", "whole"):
+        d = models.cvrp_director(c, R, offsets=offs, elems=el)
+        best, ev, acc = d.solve_nearby_list_change(80, 20, 2, 7, 1, 48, seed_base=321, windowed=mode == "windowed")
+        out[mode] = (best.tolist(), ev.tolist(), acc.tolist(), d.calculate_score().tolist(), d.list_state()[1].tolist())
+        assert np.array_equal(d.fresh_score(), d.calculate_score())
+    assert out["windowed"] == out["whole"]
