@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-source-line executed-instruction histogram from an ncu report captured with --import-source on.
-usage: ncu_lines.py report.ncu-rep [top_n]"""
+usage: ncu_lines.py report.ncu-rep [top_n] [samples]   (third argument "samples": order by stall samples)"""
 import collections
 import csv
 import subprocess
@@ -40,5 +40,6 @@ for r in csv.reader(out.splitlines()):
 tot = sum(agg.values())
 stot = sum(smp.values()) or 1
 print("warp instructions executed:", tot)
-for k, v in agg.most_common(top):
-    print(f"{v / tot * 100:5.1f}% inst {smp[k] / stot * 100:5.1f}% samples  {k[0]}:{k[1]}  {src[k].strip()[:110]}")
+by = smp if (len(sys.argv) > 3 and sys.argv[3] == "samples") else agg
+for k, _ in by.most_common(top):
+    print(f"{agg[k] / tot * 100:5.1f}% inst {smp[k] / stot * 100:5.1f}% samples  {k[0]}:{k[1]}  {src[k].strip()[:110]}")

@@ -52,10 +52,14 @@ int32_t sfgpu_ctx_destroy(sfgpu_ctx* ctx) try {
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->dscr) cudaFree(ctx->dscr);
   if (ctx->partials) cudaFree(ctx->partials);
+  if (ctx->nbc_buf) cudaFree(ctx->nbc_buf);
   if (ctx->solve_buf) cudaFree(ctx->solve_buf);
   if (ctx->union_buf) cudaFree(ctx->union_buf);
   for (auto s_ : ctx->aux_streams) cudaStreamDestroy(s_);
   for (auto e_ : ctx->aux_events) cudaEventDestroy(e_);
+  if (ctx->io_stream) cudaStreamDestroy(ctx->io_stream);
+  if (ctx->io_ready) cudaEventDestroy(ctx->io_ready);
+  if (ctx->io_done) cudaEventDestroy(ctx->io_done);
   if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->sync_dev) cudaFree(ctx->sync_dev);
@@ -963,6 +967,12 @@ int32_t sfgpu_model_commit(sfgpu_ctx* ctx, int64_t* out_scores) try {
     if (dm.nearby_ok) {
       rc = sfgpu_configure_nearby(ctx);
       if (rc) return rc;
+      // retained nearby neighbourhood: the per-replica protocol words exist from commit on (every state writer
+      // checks them); the cache itself is allocated by the first cached step
+      CU(cudaMalloc((void**)&dm.nbc_tag, (size_t)dm.R * NBC_WORDS * 4));
+      ctx->dev_allocs.push_back(dm.nbc_tag);
+      CU(cudaMemsetAsync(dm.nbc_tag, 0, (size_t)dm.R * NBC_WORDS * 4, ctx->stream));
+      ctx->nbc_off = getenv("SFGPU_NO_NBCACHE") != nullptr;
     }
   }
   if (dm.has_list) {

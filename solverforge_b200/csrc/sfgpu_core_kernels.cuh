@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(256) init_kernel(const __grid_constant__ DevMo
   __shared__ int64_t scratch[32];
   const uint32_t r = blockIdx.x;
   char* st = state + (size_t)r * m.block_bytes;
+  if (state == m.state && threadIdx.x == 0) nbc_invalidate(m.nbc_tag, r);
   const int32_t* var = (const int32_t*)(st + m.off_var);
   const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
   const uint32_t* el = (const uint32_t*)(st + m.off_elems);
@@ -648,6 +649,7 @@ __global__ void __launch_bounds__(256, 4) apply_list_kernel(const __grid_constan
                                                          const int32_t* __restrict__ kinds = nullptr) {
   extern __shared__ __align__(16) uint32_t old_el[];
   __shared__ int s_ok;
+  __shared__ uint32_t s_hot[3];  // retained nearby neighbourhood: the moved element and the old last elements of both routes
   const uint32_t r = blockIdx.x;
   if (mask && !mask[r]) return;
   if (kinds) {  // one move kind per replica (union of neighbourhoods); < 0 = no winner, 0 / 1 = scalar moves
@@ -674,6 +676,11 @@ __global__ void __launch_bounds__(256, 4) apply_list_kernel(const __grid_constan
                                                                : (kind == 6 ? list_sublist_swap_delta(m, st, row, d)
                                                                             : list_k_opt_delta(m, st, row, d)))));
     s_ok = ok ? 1 : 0;
+    if (ok && kind == 2 && m.nbc_tag) {
+      s_hot[0] = el[off[row.x] + row.y];
+      s_hot[1] = off[row.x + 1] > off[row.x] ? el[off[row.x + 1] - 1] : 0xFFFFFFFFu;
+      s_hot[2] = off[row.z + 1] > off[row.z] ? el[off[row.z + 1] - 1] : 0xFFFFFFFFu;
+    }
     if (ok && (kind == 4 || kind == 7)) {  // a reversal / k-opt keeps every per-route sum
       int64_t* cs = (int64_t*)(st + m.off_score);
       cs[0] += d.hard;
@@ -806,6 +813,28 @@ __global__ void __launch_bounds__(256, 4) apply_list_kernel(const __grid_constan
         for (int s = 16; s > 0; s >>= 1) cost += __shfl_down_sync(0xffffffffu, cost, s);
         if (lane == 0) rcost[o] = cost;
       }
+    }
+  }
+  if (m.nbc_tag && threadIdx.x == 0) {
+    // retained nearby neighbourhood (sfgpu_nearby.cuh): one ListChange commit right after a cached step is recorded —
+    // the two routes, the moved element and every element whose append slot appeared or vanished; anything else
+    // (another move kind, a second commit without a step in between) invalidates the cache
+    uint32_t* tag = m.nbc_tag + (size_t)r * NBC_WORDS;
+    if (kind == 2 && tag[NBC_STATE] == 1) {
+      const uint32_t* __restrict__ rl = m.relabel;
+      tag[NBC_A] = row.x;
+      tag[NBC_B] = row.z;
+      tag[NBC_HOT] = rl ? rl[s_hot[0]] : s_hot[0];
+      for (uint32_t w = 0; w < 2; ++w) {
+        const uint32_t o = w == 0 ? row.x : row.z;
+        const uint32_t was = s_hot[1 + w], is = off[o + 1] > off[o] ? el[off[o + 1] - 1] : 0xFFFFFFFFu;
+        const bool same = was == is;
+        tag[NBC_HOT + 1 + 2 * w] = (same || was == 0xFFFFFFFFu) ? 0xFFFFFFFFu : (rl ? rl[was] : was);
+        tag[NBC_HOT + 2 + 2 * w] = (same || is == 0xFFFFFFFFu) ? 0xFFFFFFFFu : (rl ? rl[is] : is);
+      }
+      tag[NBC_STATE] = 2;
+    } else {
+      tag[NBC_STATE] = 0;
     }
   }
   if (m.fast_list) {

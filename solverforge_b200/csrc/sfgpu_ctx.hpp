@@ -113,6 +113,9 @@ struct sfgpu_ctx {
   void* dscr = nullptr;
   size_t dscr_bytes = 0;
   void* partials = nullptr;  // fused forager chunk partials
+  void* nbc_buf = nullptr;   // retained nearby neighbourhood (nearby_step_cached_kernel): deltas, reference elements, meta
+  uint32_t nbc_K = 0;        // max_nearby the buffers are sized for
+  bool nbc_off = false;      // SFGPU_NO_NBCACHE=1: every step regenerates its whole neighbourhood
   void* solve_buf = nullptr;  // device-resident loop state
   void* union_buf = nullptr;  // union step buffers
   size_t union_bytes = 0;
@@ -122,6 +125,8 @@ struct sfgpu_ctx {
   std::vector<cudaEvent_t> aux_events;    // [0] fork, [1 + i] join of aux stream i
   std::vector<uint32_t> relabel_host, inverse_host;  // element id <-> internal id of the fast records
   size_t solve_bytes = 0;
+  cudaStream_t io_stream = nullptr;  // early result read-back of a whole-step call, side by side with its commit kernel
+  cudaEvent_t io_ready = nullptr, io_done = nullptr;
   void* small_pin = nullptr;  // per-replica seeds / winners of the host-pointer step call
   void* small_dev = nullptr;
   size_t small_bytes = 0;
@@ -260,6 +265,7 @@ struct SmallIo {
   uint32_t* d_idx = nullptr;
   int64_t* d_best = nullptr;
   uint32_t* d_eval = nullptr;
+  bool early = false;  // results already on their way back (small_io_results_ready)
   uint32_t* d_win = nullptr;
   size_t o_idx = 0, o_best = 0, o_eval = 0, o_win = 0, total = 0;
   uint32_t win_bytes = 16;
@@ -307,14 +313,37 @@ inline int small_io_begin(sfgpu_ctx* ctx, SmallIo& io, bool dev_io, uint32_t win
   io.d_win = (uint32_t*)(dv + io.o_win);
   return SFGPU_OK;
 }
+// The winners are final once the finish kernel has run: called between it and the commit kernel, this reads them back on
+// a side stream so the copy and the host's wake-up overlap the commit. small_io_end then waits for the copy only; the
+// commit stays ordered on the context's stream, ahead of whatever the next call enqueues.
+inline int small_io_results_ready(sfgpu_ctx* ctx, SmallIo& io) {
+  if (io.dev_io) return SFGPU_OK;
+  if (!ctx->io_stream) {
+    CU(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->io_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->io_done, cudaEventDisableTiming));
+  }
+  char* pin = (char*)ctx->small_pin;
+  char* dv = (char*)ctx->small_dev;
+  CU(cudaEventRecord(ctx->io_ready, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->io_stream, ctx->io_ready, 0));
+  CU(cudaMemcpyAsync(pin + io.o_idx, dv + io.o_idx, io.total - io.o_idx, cudaMemcpyDeviceToHost, ctx->io_stream));
+  CU(cudaEventRecord(ctx->io_done, ctx->io_stream));
+  io.early = true;
+  return SFGPU_OK;
+}
 inline int small_io_end(sfgpu_ctx* ctx, const SmallIo& io, uint32_t* out_index, int64_t* out_best,
                         uint32_t* out_evaluated, uint32_t* out_winner_rows) {
   if (io.dev_io) return SFGPU_OK;
   const uint32_t R = ctx->dm.R;
   char* pin = (char*)ctx->small_pin;
   char* dv = (char*)ctx->small_dev;
-  CU(cudaMemcpyAsync(pin + io.o_idx, dv + io.o_idx, io.total - io.o_idx, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (io.early) {
+    CU(cudaEventSynchronize(ctx->io_done));
+  } else {
+    CU(cudaMemcpyAsync(pin + io.o_idx, dv + io.o_idx, io.total - io.o_idx, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   memcpy(out_index, pin + io.o_idx, (size_t)R * 4);
   memcpy(out_best, pin + io.o_best, (size_t)R * 16);
   if (out_evaluated) memcpy(out_evaluated, pin + io.o_eval, (size_t)R * 4);
@@ -362,5 +391,6 @@ int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t c
 int sfgpu_configure_list(sfgpu_ctx* ctx);
 // sfgpu_nearby.cu
 int sfgpu_configure_nearby(sfgpu_ctx* ctx);
+int sfgpu_nearby_prepare_cache(sfgpu_ctx* ctx, uint32_t K);
 int sfgpu_launch_nearby(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t* d_best, uint32_t* d_eval, uint32_t* d_win,
                         int move);

@@ -69,6 +69,9 @@ struct DevModel {
   uint32_t off_pos_of;       // uint32[n_elem_rows]: (owner << 16 | position) of each element, or 0xFFFFFFFF
   uint32_t nbr_stride;       // entries per row of `nbr`
   const uint32_t* nbr;       // static: for every element row, the other rows sorted by (distance, row)
+  // retained nearby neighbourhood (sfgpu_nearby.cuh, NBC_*): 16 words per replica — what the committed moves since the
+  // last cached step touched; every kernel that writes a replica block keeps it honest. Null = no retained cache.
+  uint32_t* nbc_tag;
   ConsDev cons[SFGPU_MAX_CONS];
 };
 
@@ -139,7 +142,29 @@ struct NearbyArgs {
   int64_t* out_scores;           // [R][elem_cap * max_nearby][2] or null
   uint8_t* out_doable;           // or null
   uint64_t* out_offsets;         // [R+1] or null: candidate offsets of the materialised batch
+  // retained neighbourhood (nearby_step_cached_kernel): per (replica, source element) the score deltas of its
+  // max_nearby candidates, the reference element of each candidate slot and {k-th distance, route bloom}
+  uint32_t cache;                // 1: the cached kernel ran / runs for this step
+  int2* c_delta;                 // [R][n_elem_rows][max_nearby] (dh, ds); dh == INT32_MIN: no candidate on this lane
+  uint32_t* c_ident;             // [R][n_elem_rows][max_nearby] reference element | append << 15 | route << 16
+  uint4* c_meta;                 // [R][n_elem_rows][2] {k-th distance, 7 words of 8-bit route codes (4 lanes per word)}
 };
+
+// nbc_tag words of one replica
+#define NBC_WORDS 16
+#define NBC_STATE 0   // 0: cache invalid; 1: cache == committed state; 2: one ListChange move committed since
+#define NBC_K 1       // max_nearby the cache was built with
+#define NBC_COUNT 2   // candidates per source it was built with
+#define NBC_A 3       // routes the committed move touched
+#define NBC_B 4
+#define NBC_HOT 5     // 5 words: the moved element and the elements whose append slot appeared / vanished (or NONE)
+#define NBC_N_HOT 5
+#define NBC_STATS 10  // 3 words: sources served from kept deltas / re-scored / regenerated since commit
+
+// every kernel that rewrites a replica block outside the ListChange commit protocol calls this
+__device__ __forceinline__ void nbc_invalidate(uint32_t* nbc_tag, uint32_t r) {
+  if (nbc_tag) nbc_tag[(size_t)r * NBC_WORDS + NBC_STATE] = 0;
+}
 
 struct ChangeStepArgs {
   ForageDev f;

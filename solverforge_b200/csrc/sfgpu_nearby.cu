@@ -14,6 +14,30 @@ int sfgpu_configure_nearby(sfgpu_ctx* ctx) {
     NB_ATTR4(-1);
     NB_ATTR4(SFGPU_W_SQUARE);
     NB_ATTR4(SFGPU_W_EXCESS);
+#define NBC_ATTR(FN)                                                                                                    \
+  CU(cudaFuncSetAttribute(nearby_step_cached_kernel<FN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));      \
+  CU(cudaFuncSetAttribute(nearby_step_cached_kernel<FN, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+  NBC_ATTR(-1);
+  NBC_ATTR(SFGPU_W_SQUARE);
+  NBC_ATTR(SFGPU_W_EXCESS);
+  return SFGPU_OK;
+}
+
+// Retained neighbourhood buffers (NearbyArgs::c_*): sized for max_nearby K, allocated outside any stream capture by the
+// callers of sfgpu_launch_nearby; a reallocation invalidates every replica's cache.
+int sfgpu_nearby_prepare_cache(sfgpu_ctx* ctx, uint32_t K) {
+  const DevModel& dm = ctx->dm;
+  if (!dm.nbc_tag || ctx->nbc_off || !ctx->nb_key32 || !dm.fm_u16 || dm.n_elem_rows > 32768 || K <= ctx->nbc_K) return SFGPU_OK;
+  const size_t n_src = (size_t)dm.R * dm.n_elem_rows;
+  if (ctx->nbc_buf) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->nbc_buf);
+  }
+  ctx->nbc_buf = nullptr;
+  ctx->nbc_K = 0;
+  CU(cudaMalloc(&ctx->nbc_buf, n_src * (2 * sizeof(uint4) + (size_t)K * (sizeof(int2) + 4))));
+  ctx->nbc_K = K;
+  CU(cudaMemsetAsync(dm.nbc_tag, 0, (size_t)dm.R * NBC_WORDS * 4, ctx->stream));
   return SFGPU_OK;
 }
 
@@ -46,6 +70,25 @@ int sfgpu_launch_nearby(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t*
     if (dm.fm_u16) { NEARBYK(FN, uint64_t, uint16_t); } else { NEARBYK(FN, uint64_t, int32_t); }     \
   }
   a.scan_bits = ctx->nb_scan_bits;
+  a.cache = 0;
+  // retained neighbourhood: ListChange on the narrow uint16 / 32-bit-key program, nothing materialised
+  if (move == MOVE_CHANGE && ctx->nb_key32 && dm.fm_u16 && !a.out_rows && ctx->nbc_buf && a.max_nearby <= ctx->nbc_K) {
+    const size_t n_src = (size_t)R * dm.n_elem_rows;  // laid out for the allocated K; the kernels stride by the K of the call
+    a.c_meta = (uint4*)ctx->nbc_buf;
+    a.c_delta = (int2*)((char*)ctx->nbc_buf + n_src * 2 * sizeof(uint4));
+    a.c_ident = (uint32_t*)((char*)ctx->nbc_buf + n_src * (2 * sizeof(uint4) + (size_t)ctx->nbc_K * sizeof(int2)));
+    a.cache = 1;
+    // the reference's default max_nearby (20) with full lists folds its kept deltas fully unrolled; whether a replica's
+    // lists are full (count == K) is only known on the device, so the kernel falls back per replica
+#define NEARBYC(FN)                                                                                    \
+  if (a.max_nearby == 20) nearby_step_cached_kernel<FN, 20><<<grid, 256, smem, ctx->stream>>>(dm, a);  \
+  else nearby_step_cached_kernel<FN, 0><<<grid, 256, smem, ctx->stream>>>(dm, a);                      \
+  nearby_finish_kernel<FN, uint32_t, uint16_t><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win);
+    if (fn == SFGPU_W_EXCESS) { NEARBYC(SFGPU_W_EXCESS) }
+    else if (fn == SFGPU_W_SQUARE) { NEARBYC(SFGPU_W_SQUARE) }
+    else { NEARBYC(-1) }
+    return SFGPU_OK;
+  }
   if (fn == SFGPU_W_EXCESS) { NEARBYK4(SFGPU_W_EXCESS) }
   else if (fn == SFGPU_W_SQUARE) { NEARBYK4(SFGPU_W_SQUARE) }
   else { NEARBYK4(-1) }  // no LIST_SUM, or a LINEAR / CONST weight whose relocation delta is 0
@@ -77,6 +120,10 @@ int step_nearby_impl(sfgpu_ctx* ctx, int move, uint32_t flags, uint32_t max_near
   const bool dev_io = (flags & SFGPU_DEVICE_IO) != 0;
   rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
   if (rc) return rc;
+  if (move == MOVE_CHANGE && !out_rows) {
+    rc = sfgpu_nearby_prepare_cache(ctx, max_nearby);
+    if (rc) return rc;
+  }
   SmallIo io;
   rc = small_io_begin(ctx, io, dev_io, 16, step_seeds, ref_scores, out_index, out_best, out_evaluated, out_winner_rows);
   if (rc) return rc;
@@ -99,6 +146,8 @@ int step_nearby_impl(sfgpu_ctx* ctx, int move, uint32_t flags, uint32_t max_near
   ctx->launches += 2;
   CU(cudaGetLastError());
   if (apply_winners) {
+    rc = small_io_results_ready(ctx, io);  // the read-back overlaps the commit
+    if (rc) return rc;
     // a replica without a winner carries the sentinel row (owner 0xFFFFFFFF): not doable, skipped
     rc = sfgpu_launch_apply_list(ctx, move == MOVE_SWAP ? 3 : 2, io.d_win, nullptr, nullptr, nullptr);
     if (rc) return rc;
@@ -132,3 +181,11 @@ int32_t sfgpu_step_nearby_list_swap(sfgpu_ctx* ctx, uint32_t flags, uint32_t max
 } SFGPU_API_CATCH(ctx)
 
 }  // extern "C"
+
+// test hook (not part of the ABI): the retained-neighbourhood protocol words of every replica, [R][16]
+extern "C" int32_t sfgpu_debug_nearby_cache_tags(sfgpu_ctx* ctx, uint32_t* out_words) {
+  if (!ctx || !ctx->dm.nbc_tag) return SFGPU_E_UNSUPPORTED;
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpy(out_words, ctx->dm.nbc_tag, (size_t)ctx->dm.R * NBC_WORDS * 4, cudaMemcpyDeviceToHost);
+  return SFGPU_OK;
+}

@@ -190,28 +190,27 @@ __device__ __forceinline__ NearbyConsts<S> nearby_consts(const DevModel& m) {
   return c;
 }
 
-// score delta of candidate (source f -> slot of `key`) with the fast-path record math; returns the
-// destination (e, dp) too. Identical arithmetic to score_list_change_fast_kernel.
-template <int SUM_FN, typename KEY, typename CELL, typename S>
-__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyConsts<S>& c, const NearbyView& v,
-                                             const uint32_t scan_bits, const KEY key, const uint32_t x,
-                                             const uint32_t se, const uint4 prec, const uint4 rsrc, S& dh, S& ds,
-                                             uint32_t& de, uint32_t& dp) {
+// score delta of candidate (source x -> insertion slot g) with the fast-path record math; returns the destination
+// (e, dp) and the slot's reference element (| append << 31) too. d_ref = d(x, reference element). Identical
+// arithmetic to score_list_change_fast_kernel.
+template <int SUM_FN, typename CELL, typename S>
+__device__ __forceinline__ void nearby_score_slot(const DevModel& m, const NearbyConsts<S>& c, const NearbyView& v,
+                                                  const uint32_t g, const uint32_t d_ref, const uint32_t x,
+                                                  const uint32_t se, const uint4 prec, const uint4 rsrc, S& dh, S& ds,
+                                                  uint32_t& de, uint32_t& dp, uint32_t& ident) {
   typedef typename FastArith<CELL>::US US;
-  const uint32_t scan = (uint32_t)(key & (((KEY)1 << scan_bits) - 1));
-  const uint32_t slen = rsrc.y, g_own = rsrc.x + se;
-  const uint32_t g = scan <= slen ? g_own + scan : (scan - (slen + 1) < g_own ? scan - (slen + 1) : scan);
   const uint4 s = v.sr[g];
   de = s.w >> 16;
   dp = s.w & 0xFFFFu;
   const uint4 rd = v.rr[de];
   dh = 0;
   ds = 0;
+  ident = dp < rd.y ? s.y : (s.x | 0x80000000u);
   {
     const CELL* __restrict__ mrow = (const CELL*)m.fm_row + (size_t)x * c.dim;
     const CELL* __restrict__ mcol = (const CELL*)m.fm_col + (size_t)x * c.dim;
-    // d(x, b): for a non-append slot b is the slot's reference element, whose distance is in the key
-    const int32_t xb = dp < rd.y ? (int32_t)(uint32_t)(key >> scan_bits) : (int32_t)__ldg(mrow + s.y);
+    // d(x, b): for a non-append slot b is the slot's reference element, whose distance the caller holds
+    const int32_t xb = dp < rd.y ? (int32_t)d_ref : (int32_t)__ldg(mrow + s.y);
     const int32_t ax = (int32_t)__ldg(mcol + s.x);
     const S d = (S)((US)c.pc_a * (US)(S)((int32_t)prec.y + ax + xb - (int32_t)s.z));
     if (c.pc_hard) dh += d; else ds += d;
@@ -222,6 +221,22 @@ __device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyCons
     const S d = list_sum_delta<SUM_FN, S, US>(c.ls_a, c.ls_b, (S)(int32_t)prec.z, ss, sd);
     if (c.ls_hard) dh += d; else ds += d;
   }
+}
+
+// flat slot index of the scan index held in the low bits of a key (inverse of the scan order of nearby_gen_source)
+__device__ __forceinline__ uint32_t nearby_slot_of_scan(const uint32_t scan, const uint32_t se, const uint4 rsrc) {
+  const uint32_t slen = rsrc.y, g_own = rsrc.x + se;
+  return scan <= slen ? g_own + scan : (scan - (slen + 1) < g_own ? scan - (slen + 1) : scan);
+}
+
+template <int SUM_FN, typename KEY, typename CELL, typename S>
+__device__ __forceinline__ void nearby_score(const DevModel& m, const NearbyConsts<S>& c, const NearbyView& v,
+                                             const uint32_t scan_bits, const KEY key, const uint32_t x,
+                                             const uint32_t se, const uint4 prec, const uint4 rsrc, S& dh, S& ds,
+                                             uint32_t& de, uint32_t& dp) {
+  uint32_t ident;
+  const uint32_t g = nearby_slot_of_scan((uint32_t)(key & (((KEY)1 << scan_bits) - 1)), se, rsrc);
+  nearby_score_slot<SUM_FN, CELL, S>(m, c, v, g, (uint32_t)(key >> scan_bits), x, se, prec, rsrc, dh, ds, de, dp, ident);
 }
 
 // warp-level lexicographic max of the deltas (dh, ds) over the lanes with `acc`: returns the
@@ -376,6 +391,18 @@ __device__ __forceinline__ uint32_t nearby_count(const DevModel& m, const uint4*
   return valid < K ? valid : K;
 }
 
+// nearby_count by one warp (every lane returns it)
+__device__ __forceinline__ uint32_t nearby_count_warp(const DevModel& m, const uint4* rr, uint32_t K, uint32_t lane) {
+  uint32_t slots = 0;
+  for (uint32_t o = lane; o < m.n_owners; o += 32) {
+    const uint32_t len = rr[o].y;
+    slots += len ? len + 1 : 0;
+  }
+  slots = __reduce_add_sync(0xffffffffu, slots);
+  const uint32_t valid = slots >= 2 ? slots - 2 : 0;
+  return valid < K ? valid : K;
+}
+
 // grid = (chunks, R), 256 threads. Warp w of chunk c handles sources c_lo + w, c_lo + w + 8, ...
 template <int SUM_FN, typename KEY, typename CELL, int MOVE = MOVE_CHANGE>
 __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant__ DevModel m, const NearbyArgs a) {
@@ -469,6 +496,269 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
   }
 }
 
+// ---- retained neighbourhood (incremental step) ------------------------------------------------------------------
+// A committed ListChange move x: (A, p) -> (B, q) leaves most of the neighbourhood as it was. Per (replica, source
+// element) the kernel below keeps the score deltas of the source's candidates, the reference element of every
+// candidate slot and the k-th kept distance, and after a commit redoes only what the move can have changed:
+//   tier 3 (generate + score, as nearby_step_kernel): sources in route A or B (own legs, own exclusions), and sources
+//           within their k-th distance of a "hot" element — the moved element (its slot changes route, so its place
+//           among equal distances changes) or an element whose append slot appeared / vanished (old / new last
+//           element of A and B). Nothing else can enter, leave or reorder a kept list: the slot set is one slot per
+//           routed element plus one append slot per non-empty route, distances are static, and the scan order of two
+//           slots of unmoved elements never changes (routes keep their index, positions shift together).
+//   tier 2 (score only, from the kept reference elements through pos_of): sources with a candidate into A or B
+//           (8-bit route code per lane) — positions, legs around the edit and the route loads changed, the slot set
+//           did not; only those lanes are re-scored.
+//   tier 1 (kept deltas): everything else. The acceptor thresholds move every step, so acceptance, the best and its
+//           multiplicity are always recomputed from the deltas.
+// Keys are not kept: the finish kernel regenerates the one or two sources whose lanes matter. The protocol lives in
+// nbc_tag (sfgpu_dev.cuh): nearby_finish_kernel marks the cache current, apply_list_kernel records the one committed
+// move, every other writer of a replica block (init, restore, other move kinds) invalidates.
+// Work is laid out for throughput, not one warp per source: (A) one THREAD per source classifies it from its meta
+// word; tier 2 scans the kept reference elements (each carries its route), re-scores the few that sit in route A or B
+// through pos_of and stores their deltas; tiers 1 and 2 then fold the kept deltas into the source's partial on the
+// spot (batched independent loads, no cross-lane traffic). Tier-3 sources go to a shared-memory work list and (B) one
+// warp per such source generates and scores as nearby_step_kernel does.
+
+// kept reference element of a candidate slot: element | append << 15 | route << 16 (n_elem_rows <= 32768)
+__device__ __forceinline__ uint32_t nbc_ident(uint32_t ident31, uint32_t route) {
+  return (ident31 & 0x7FFFu) | ((ident31 >> 31) << 15) | (route << 16);
+}
+
+// the partial of one source from its kept deltas, sequentially in lane order (== warp_best_mask over the lanes);
+// branch-free so the 32 sources of a warp stay converged, NBC_FOLD_BATCH loads in flight at a time
+#define NBC_FOLD_BATCH 10
+struct NbcFold {
+  int32_t bh = INT32_MIN, bs = INT32_MIN;  // below every delta (deltas are strictly inside the int32 range)
+  uint32_t n_best = 0, n_acc = 0, first = 0;
+  __device__ __forceinline__ void add(const int32_t dx, const int32_t dy, const uint32_t j, const bool valid, const int acceptor,
+                                      const int32_t lh, const int32_t ls, const int32_t th, const int32_t ts) {
+    const bool in = valid && dx != INT32_MIN && accept_delta<int32_t>(acceptor, dx, dy, lh, ls, th, ts);
+    const bool better = in && lex_less(bh, bs, dx, dy);
+    const bool equal = in && dx == bh && dy == bs;
+    n_acc += in ? 1u : 0u;
+    n_best = better ? 1u : n_best + (equal ? 1u : 0u);
+    first = better ? j : first;
+    bh = better ? dx : bh;
+    bs = better ? dy : bs;
+  }
+  __device__ __forceinline__ void store(const int64_t ch, const int64_t csf, SrcPartial* out) const {
+    SrcPartial p;
+    p.best_h = n_best ? ch + (int64_t)bh : 0;
+    p.best_s = n_best ? csf + (int64_t)bs : 0;
+    p.n_best = n_best;
+    p.n_accepted = n_acc;
+    p.first_lane = first;
+    p.pad = 0;
+    *out = p;
+  }
+};
+// KC > 0: the row holds exactly KC candidates (count == K == KC, KC % 4 == 0): 128-bit loads, fully unrolled
+template <int KC>
+__device__ __forceinline__ void nbc_fold_source(const int2* cd, const uint32_t count, const int acceptor, const int32_t lh,
+                                                const int32_t ls, const int32_t th, const int32_t ts, const int64_t ch,
+                                                const int64_t csf, SrcPartial* out) {
+  NbcFold fo;
+  if (KC > 0) {
+    const int4* __restrict__ c4 = (const int4*)cd;
+#pragma unroll
+    for (int j0 = 0; j0 < KC / 2; j0 += 5) {
+      int4 d[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) d[u] = c4[j0 + u < KC / 2 ? j0 + u : KC / 2 - 1];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        if (j0 + u < KC / 2) {
+          fo.add(d[u].x, d[u].y, 2 * (j0 + u), true, acceptor, lh, ls, th, ts);
+          fo.add(d[u].z, d[u].w, 2 * (j0 + u) + 1, true, acceptor, lh, ls, th, ts);
+        }
+      }
+    }
+  } else {
+    for (uint32_t j0 = 0; j0 < count; j0 += NBC_FOLD_BATCH) {
+      int2 d[NBC_FOLD_BATCH];
+#pragma unroll
+      for (uint32_t u = 0; u < NBC_FOLD_BATCH; ++u) d[u] = cd[min(j0 + u, count - 1)];
+#pragma unroll
+      for (uint32_t u = 0; u < NBC_FOLD_BATCH; ++u) fo.add(d[u].x, d[u].y, j0 + u, j0 + u < count, acceptor, lh, ls, th, ts);
+    }
+  }
+  fo.store(ch, csf, out);
+}
+
+// lanes (bit j = candidate j) whose 8-bit route code equals code_a or code_b; codes = 7 words, 4 lanes each; lanes
+// 28..31 have no code and always count as hits
+__device__ __forceinline__ uint32_t nbc_route_hits(const uint32_t* codes, const uint32_t code_a, const uint32_t code_b,
+                                                   const uint32_t count) {
+  const uint32_t va = code_a * 0x01010101u, vb = code_b * 0x01010101u;
+  uint32_t hits = count > 28 ? 0xF0000000u : 0u;
+#pragma unroll
+  for (uint32_t w = 0; w < 7; ++w) {
+    const uint32_t eq = __vcmpeq4(codes[w], va) | __vcmpeq4(codes[w], vb);  // 0xFF per equal byte
+    hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * w);
+  }
+  return hits & (count >= 32 ? 0xFFFFFFFFu : (1u << count) - 1);
+}
+
+template <int SUM_FN, int KC>
+__global__ void __launch_bounds__(256, 4) nearby_step_cached_kernel(const __grid_constant__ DevModel m, const NearbyArgs a) {
+  typedef uint32_t KEY;
+  typedef uint16_t CELL;
+  typedef int32_t S;
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_n2, s_n3;
+  __shared__ uint16_t s_list3[256];  // offsets (f - tile base) of the tile's tier-3 sources
+  __shared__ KEY s_buf[8][64];
+  const uint32_t r = blockIdx.y;
+  // protocol words and acceptor references: in flight while the records are staged
+  const uint32_t* __restrict__ tag = m.nbc_tag + (size_t)r * NBC_WORDS;
+  const uint4 tag0 = *(const uint4*)tag, tag1 = *(const uint4*)(tag + 4), tag2 = *(const uint4*)(tag + 8);
+  int64_t refs[4] = {0, 0, 0, 0};
+  if (a.ref_scores) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) refs[q] = a.ref_scores[r * 4 + q];
+  }
+  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
+  NearbyView v;
+  v.rr = (const uint4*)(smem + m.off_route_rec);
+  v.pr = (const uint4*)(smem + m.off_pos_rec);
+  v.sr = (const uint4*)(smem + m.off_slot_rec);
+  v.pos_of = (const uint32_t*)(smem + m.off_pos_of);
+  const int64_t* cs = (const int64_t*)(smem + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t count = nearby_count_warp(m, v.rr, a.max_nearby, lane), K = a.max_nearby;
+  const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;
+  S lh, ls, th, ts;
+  rel_threshold(refs[0], ch, lh);
+  rel_threshold(refs[1], csf, ls);
+  rel_threshold(refs[2], ch, th);
+  rel_threshold(refs[3], csf, ts);
+  const NearbyConsts<S> nc = nearby_consts<SUM_FN, S>(m);
+  const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+  const uint32_t c_lo = per * blockIdx.x, c_hi = min(c_lo + per, total);
+  const uint32_t t_state = tag0.x;                                 // NBC_STATE, NBC_K, NBC_COUNT, NBC_A
+  const bool valid = t_state != 0 && tag0.y == K && tag0.z == count;
+  const bool moved = valid && t_state == 2;
+  const uint32_t tA = tag0.w, tB = tag1.x;                         // NBC_B, then the five hot elements
+  const uint32_t hot[NBC_N_HOT] = {moved ? tag1.y : 0xFFFFFFFFu, moved ? tag1.z : 0xFFFFFFFFu, moved ? tag1.w : 0xFFFFFFFFu,
+                                   moved ? tag2.x : 0xFFFFFFFFu, moved ? tag2.y : 0xFFFFFFFFu};
+  const size_t src0 = (size_t)r * m.n_elem_rows;
+  SrcPartial* __restrict__ P = a.partials + (size_t)r * m.elem_cap;
+  const CELL* __restrict__ fm_row = (const CELL*)m.fm_row;
+  for (uint32_t base = c_lo; base < c_hi; base += 256) {
+    if (threadIdx.x == 0) {
+      s_n2 = 0;
+      s_n3 = 0;
+    }
+    __syncthreads();
+    // ---- (A) classify; tier 2 re-scores its candidates into routes A / B; tiers 1 and 2 fold their kept deltas ------
+    {
+      const uint32_t f = base + threadIdx.x;
+      if (f < c_hi) {
+        const uint4 prec = v.pr[f];
+        const uint32_t x = prec.x, se = prec.w;
+        int tier = 3;
+        uint32_t hits = 0;  // lanes whose slot sits in route A or B
+        if (valid) {
+          tier = 1;
+          if (moved) {
+            const uint4 m0 = a.c_meta[(src0 + x) * 2], m1 = a.c_meta[(src0 + x) * 2 + 1];
+            const CELL* __restrict__ mrow = fm_row + (size_t)x * nc.dim;
+            bool near = false;
+#pragma unroll
+            for (int h = 0; h < NBC_N_HOT; ++h)
+              near |= hot[h] != 0xFFFFFFFFu && (uint32_t)__ldg(mrow + hot[h]) <= m0.x;
+            const uint32_t codes[7] = {m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            hits = nbc_route_hits(codes, tA & 255u, tB & 255u, count);
+            if (se == tA || se == tB || near) tier = 3;
+            else if (hits) tier = 2;
+          }
+        }
+        int2* cd = a.c_delta + (src0 + x) * K;
+        if (tier == 2) {
+          const uint32_t* __restrict__ ci = a.c_ident + (src0 + x) * K;
+          const uint4 rsrc = v.rr[se];
+          const CELL* __restrict__ mrow = fm_row + (size_t)x * nc.dim;
+          while (hits) {
+            const uint32_t j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const uint32_t id = ci[j];
+            if (id == 0xFFFFFFFFu) continue;
+            const uint32_t y = id & 0x7FFFu;
+            const uint32_t where = v.pos_of[y];
+            const uint32_t e = where >> 16, py = where & 0xFFFFu;
+            S dh, ds;
+            uint32_t de, dp, ident;
+            nearby_score_slot<SUM_FN, CELL, S>(m, nc, v, v.rr[e].x + e + py + ((id >> 15) & 1), (uint32_t)__ldg(mrow + y), x,
+                                               se, prec, rsrc, dh, ds, de, dp, ident);
+            cd[j] = make_int2(dh, ds);
+          }
+          atomicAdd(&s_n2, 1u);
+        }
+        if (tier != 3) nbc_fold_source<KC>(cd, count, a.f.acceptor, lh, ls, th, ts, ch, csf, P + f);
+        else s_list3[atomicAdd(&s_n3, 1u)] = (uint16_t)threadIdx.x;
+      }
+    }
+    __syncthreads();
+    const uint32_t n2 = s_n2, n3 = s_n3;
+    if (threadIdx.x == 0) {  // running totals of the three tiers (test hook / profiles)
+      uint32_t* tg = m.nbc_tag + (size_t)r * NBC_WORDS;
+      atomicAdd(tg + NBC_STATS, min(c_hi - base, 256u) - n2 - n3);
+      atomicAdd(tg + NBC_STATS + 1, n2);
+      atomicAdd(tg + NBC_STATS + 2, n3);
+    }
+    // ---- (B) generate + score, one warp per source ----------------------------------------------------------------
+    for (uint32_t i = warp; i < n3; i += 8) {
+      const uint32_t f = base + s_list3[i];
+      uint32_t x, se, sp;
+      uint4 prec, rsrc;
+      const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, K, lane, s_buf[warp], x, se, sp, prec, rsrc);
+      const bool have = lane < count && key != 0xFFFFFFFFu;
+      S dh = INT32_MIN, ds = 0;
+      uint32_t de = 0, dp = 0, ident = 0xFFFFFFFFu;
+      if (have) {
+        nearby_score_slot<SUM_FN, CELL, S>(m, nc, v, nearby_slot_of_scan(key & ((1u << a.scan_bits) - 1), se, rsrc),
+                                           key >> a.scan_bits, x, se, prec, rsrc, dh, ds, de, dp, ident);
+        ident = nbc_ident(ident, de);
+      }
+      if (lane < K) {
+        a.c_delta[(src0 + x) * K + lane] = make_int2(dh, ds);
+        a.c_ident[(src0 + x) * K + lane] = ident;
+      }
+      // meta: k-th kept distance + the 8-bit route code of every lane (4 lanes per word)
+      uint32_t cw = have ? (de & 255u) << (8 * (lane & 3)) : 0u;
+      cw |= __shfl_xor_sync(0xffffffffu, cw, 1);
+      cw |= __shfl_xor_sync(0xffffffffu, cw, 2);
+      uint32_t codes[7];
+#pragma unroll
+      for (uint32_t w = 0; w < 7; ++w) codes[w] = __shfl_sync(0xffffffffu, cw, 4 * w);
+      const uint32_t kth = __shfl_sync(0xffffffffu, key, K - 1);
+      if (lane == 0) {
+        // a list that is not full (count < K, or fewer slots than K) holds every slot: any change matters
+        a.c_meta[(src0 + x) * 2] = make_uint4((count < K || kth == 0xFFFFFFFFu) ? 0xFFFFFFFFu : kth >> a.scan_bits, codes[0],
+                                              codes[1], codes[2]);
+        a.c_meta[(src0 + x) * 2 + 1] = make_uint4(codes[3], codes[4], codes[5], codes[6]);
+      }
+      const bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
+      uint32_t accm;
+      const uint32_t eq = warp_best_mask(acc, dh, ds, accm);
+      if (lane == (eq ? __ffs(eq) - 1 : 0)) {
+        SrcPartial p;
+        p.best_h = eq ? ch + (int64_t)dh : 0;
+        p.best_s = eq ? csf + (int64_t)ds : 0;
+        p.n_best = __popc(eq);
+        p.n_accepted = __popc(accm);
+        p.first_lane = eq ? __ffs(eq) - 1 : 0;
+        p.pad = 0;
+        P[f] = p;
+      }
+    }
+    if (base + 256 < c_hi) __syncthreads();  // the next tile reuses the work list
+  }
+}
+
 // One CTA per replica: ordered replay over the per-source partials (AcceptedCount cut, best, tie
 // rule), regeneration of the one or two sources whose lanes matter, winner row out.
 template <int SUM_FN, typename KEY, typename CELL, int MOVE = MOVE_CHANGE>
@@ -511,6 +801,12 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
   }
   __syncthreads();
   const uint32_t count = s_count;
+  if (a.cache && threadIdx.x == 0) {  // the cached step kernel of this launch pair brought the retained deltas up to date
+    uint32_t* tag = m.nbc_tag + (size_t)r * NBC_WORDS;
+    tag[NBC_K] = a.max_nearby;
+    tag[NBC_COUNT] = count;
+    tag[NBC_STATE] = 1;
+  }
   // ---- AcceptedCount(N): the step ends right after the N-th accepted pull -------------------
   if (a.f.accepted_limit > 0) {
     uint32_t seen = 0;

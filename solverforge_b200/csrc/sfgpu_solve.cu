@@ -161,6 +161,8 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   } else if (!udesc) {
     rc = ensure_partials(ctx, (size_t)R * dm.elem_cap * sizeof(SrcPartial));
     if (rc) return rc;
+    rc = sfgpu_nearby_prepare_cache(ctx, p->max_nearby);  // retained neighbourhood: allocated before the capture
+    if (rc) return rc;
     a.f = ForageDev{forage_code, p->tie_mode, p->accepted_limit};
     a.max_nearby = p->max_nearby;
     a.step_seeds = s.step_seeds;

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(256) solve_post_kernel(const __grid_constant__
 __global__ void solve_restore_best_kernel(const __grid_constant__ DevModel m, SolveState s) {
   const uint32_t r = blockIdx.x;
   char* st = m.state + (size_t)r * m.block_bytes;
+  if (threadIdx.x == 0) nbc_invalidate(m.nbc_tag, r);
   for (uint32_t i = threadIdx.x; i < m.block_bytes / 16; i += blockDim.x)
     ((uint4*)st)[i] = ((const uint4*)(s.best_state + (size_t)r * m.block_bytes))[i];
 }
