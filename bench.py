@@ -507,33 +507,6 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
         if rc != 0 or [int(got[0]), int(got[1])] != best_h.tolist() or int(got[2]) & 0xFFFFFFFF != owner.value:
             raise SystemExit("bench.py: asynchronous best-score sync disagrees with the synchronous call")
 
-    # ---- e2e: the same metric through the reference-facing call with HOST buffers, copies inside the timed
-    # region. The whole step runs on device (sfgpu_step_nearby_list_change / sfgpu_step_change generate the
-    # neighbourhood, score it, replay the forager): the per-replica step seeds go in (pinned H2D) and the winners
-    # come back (D2H).
-    seeds_host = np.array(seeds, dtype=np.uint64)
-    if name == "cvrp":
-        e2e_api = "sfgpu_step_nearby_list_change (device-side neighbourhood + score + forager; host seeds in, winners out)"
-        h2d, d2h = R * 8, R * (4 + 16 + 4 + 16)
-        e2e_step = lambda: d.step_nearby_list_change(20, fp, step_seeds=seeds_host)
-    else:
-        e2e_api = "sfgpu_step_change (device-side ChangeMove neighbourhood + score + forager; host seeds in, winners out)"
-        h2d, d2h = R * 8, R * (4 + 16 + 4 + 8)
-        e2e_step = lambda: d.step_change(fp, step_seeds=seeds_host)
-    idx_e2e, best_e2e, ev_e2e, _ = e2e_step()
-    # same winners as the rows-resident path (replica starts, seeds and forager are identical)
-    if not (np.array_equal(idx_e2e, t_idx.cpu().numpy().view(np.uint32)) and
-            np.array_equal(best_e2e, t_best.cpu().numpy()) and int(ev_e2e.sum()) == n):
-        raise SystemExit("bench.py: device-generated step disagrees with the rows-resident step")
-    e2e_steps = max(5, min(steps, 50))
-    torch.cuda.synchronize()
-    D.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-
     # ---- e2e_host_rows: the call a stock reference cursor would feed — candidate rows in pinned HOST memory in,
     # every score + doable flag back to pinned host memory (sfgpu_score_*; PCIe-bound)
     e2e_host_rows = None
@@ -565,6 +538,72 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
                                 " (pinned host rows in, scores + doable out)"}
         del rows_pin, sc_pin, ok_pin
 
+    # ---- e2e: the same metric through the reference-facing call with HOST buffers, copies inside the timed
+    # region. The whole step runs on device (sfgpu_step_nearby_list_change / sfgpu_step_change generate the
+    # neighbourhood, score it, replay the forager): the per-replica step seeds go in (pinned H2D) and the winners
+    # come back (D2H). For the list workload every step also COMMITS its winner on device (apply_winners = 1), as a
+    # solver step does, so the planning state of every replica changes between timed steps and the retained
+    # neighbourhood has real work to do: sources the committed move touched are regenerated or
+    # re-scored, the rest keep their score deltas. The same loop with the cache off (every step regenerates all
+    # 20 000 candidates per replica) is reported next to it.
+    seeds_host = np.array(seeds, dtype=np.uint64)
+    e2e_extra = {}
+    if name == "cvrp":
+        e2e_api = ("sfgpu_step_nearby_list_change, apply_winners = 1 (device-side neighbourhood + score + forager + commit; "
+                   "host seeds in, winners out)")
+        h2d, d2h = R * 8, R * (4 + 16 + 4 + 16)
+        e2e_step = lambda dd=None, s_off=0: (dd or d).step_nearby_list_change(20, fp, step_seeds=seeds_host + np.uint64(s_off), apply=True)
+        first = d.step_nearby_list_change(20, fp, step_seeds=seeds_host)      # not committed: compared below
+    else:
+        e2e_api = "sfgpu_step_change (device-side ChangeMove neighbourhood + score + forager; host seeds in, winners out)"
+        h2d, d2h = R * 8, R * (4 + 16 + 4 + 8)
+        e2e_step = lambda dd=None, s_off=0: d.step_change(fp, step_seeds=seeds_host)
+        first = e2e_step()
+    idx_e2e, best_e2e, ev_e2e, _ = first
+    # same winners as the rows-resident path (replica starts, seeds and forager are identical)
+    if not (np.array_equal(idx_e2e, t_idx.cpu().numpy().view(np.uint32)) and
+            np.array_equal(best_e2e, t_best.cpu().numpy()) and int(ev_e2e.sum()) == n):
+        raise SystemExit("bench.py: device-generated step disagrees with the rows-resident step")
+    e2e_steps = max(5, min(steps, 50))
+    d_full = None
+    if name == "cvrp":
+        # the regenerating twin: same starts, cache off (read at commit time); it must commit the same winners
+        os.environ["SFGPU_NO_NBCACHE"] = "1"
+        try:
+            d_full = models.cvrp_director(inst, R, offsets=offs, elems=elems, device=D.local, stream=stream.cuda_stream)
+        finally:
+            os.environ.pop("SFGPU_NO_NBCACHE", None)
+        for w in range(3):   # warm-up: the first cached step builds the retained rows
+            g, f_ = e2e_step(d, 7000 + w), e2e_step(d_full, 7000 + w)
+            if not all(np.array_equal(x, y) for x, y in zip(g, f_)):
+                raise SystemExit("bench.py: retained-neighbourhood step disagrees with the fully regenerated step")
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(d, i)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if d_full is not None:
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            last_full = e2e_step(d_full, i)
+        torch.cuda.synchronize()
+        full_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        if not np.array_equal(d.calculate_score(), d_full.calculate_score()):
+            raise SystemExit("bench.py: retained-neighbourhood trajectory left the fully regenerated one")
+        tags = np.zeros((R, 16), dtype=np.uint32)
+        lib.sfgpu_debug_nearby_cache_tags.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sfgpu_debug_nearby_cache_tags(d.h, tags.ctypes.data_as(C.c_void_p))
+        tiers = tags[:, 10:13].astype(np.float64).sum(axis=0)
+        e2e_extra = {"committed_every_step": True,
+                     "retained_neighbourhood": {"sources_kept": tiers[0] / tiers.sum(), "sources_rescored": tiers[1] / tiers.sum(),
+                                                "sources_regenerated": tiers[2] / tiers.sum(),
+                                                "note": "fractions since commit, incl. the first step that regenerates everything"},
+                     "full_regeneration": {"ms_per_step": full_ms, "value": n * world / (full_ms / 1e3),
+                                           "note": "same committed loop, SFGPU_NO_NBCACHE=1: identical winners and final scores"}}
+        d_full.close()
+
     elapsed_ms, kernel_ms, e2e_ms, sync_max = D.max_([elapsed_ms, kernel_ms, e2e_ms, sync_ms or 0.0])
     total_cands = n * world
     peak, peak_src = measured_peak_gbs()
@@ -591,8 +630,8 @@ def run_workload(D: Dist, name: str, R: int, steps: int, warmup: int, args, prim
                      "traffic": measured_traffic(name, R), "peak_source": peak_src, "kernel": kernel_name,
                      "kernel_ms": kernel_ms, "call_ms": call_ms, "algorithmic_bytes_per_launch": alg_bytes},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample},
-        "e2e": {"value": total_cands / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "api": e2e_api},
+        "e2e": dict({"value": total_cands / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "ms_per_step": e2e_ms, "api": e2e_api}, **e2e_extra),
         "e2e_host_rows": e2e_host_rows,
         "gpu_launches": int(launches),
     }
@@ -644,6 +683,10 @@ def run_ours(args):
     # AcceptedCount(256), default_local_search/policy.rs:18-82) — whole steps incl. commit, no host round trip
     device_loop = None
     if name == "cvrp" and args.loop_steps > 0:
+        # the committed e2e loop above moved every replica: the loops below start from the replicas' own starts again
+        d.close()
+        d = models.cvrp_director(inst, R, offsets=np.stack([s[0] for s in states]), elems=np.concatenate([s[1] for s in states]),
+                                 device=D.local)
         d.solve_nearby_list_change(16, 20, 2, 400, 1, 256, seed_base=500)   # warm-up: buffers, graph capture
         d.synchronize()
         t0 = time.perf_counter()
@@ -651,7 +694,7 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         device_loop = {"steps": args.loop_steps, "replicas": R, "ms_per_step": dt * 1e3 / args.loop_steps,
                        "moves_evaluated_per_s": float(ev_l.sum()) / dt, "committed_steps": int(acc_l.sum()),
-                       "selector": "NearbyListChange(20), SelectionOrder::Original, whole neighbourhood generated and scored per step",
+                       "selector": "NearbyListChange(20), SelectionOrder::Original, whole neighbourhood scored per step (retained between steps: only sources the committed move touched are regenerated)",
                        "acceptor": "LateAcceptance(400)", "forager": "AcceptedCount(256)",
                        "best_score_replica0": [int(best_l[0][0]), int(best_l[0][1])]}
 

@@ -1262,7 +1262,7 @@ int apply_entry(sfgpu_ctx* ctx, int kind, uint32_t flags, const uint32_t* rows, 
   if (scalar)
     apply_scalar_kernel<<<R, 32, 0, ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
   else
-    apply_list_kernel<<<R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+    apply_list_kernel<<<R, apply_threads(ctx), apply_smem_bytes(dm), ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
   ctx->launches++;
   CU(cudaGetLastError());
   if (!(flags & SFGPU_DEVICE_IO)) CU(cudaStreamSynchronize(ctx->stream));
@@ -1434,7 +1434,7 @@ int32_t sfgpu_scalar_program(sfgpu_ctx* ctx, int32_t* out_program) try {
 int sfgpu_launch_apply_list(sfgpu_ctx* ctx, int kind, const uint32_t* d_rows, const uint8_t* d_mask,
                             const uint64_t* d_offsets, const uint32_t* d_index) {
   const DevModel& dm = ctx->dm;
-  apply_list_kernel<<<dm.R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
+  apply_list_kernel<<<dm.R, apply_threads(ctx), apply_smem_bytes(dm), ctx->stream>>>(dm, kind, d_rows, d_mask, d_offsets, d_index);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;
@@ -1445,7 +1445,7 @@ int sfgpu_launch_apply_list_kinds(sfgpu_ctx* ctx, const uint32_t* d_rows, const 
     apply_scalar_kernel<<<dm.R, 32, 0, ctx->stream>>>(dm, 0, d_rows, nullptr, nullptr, nullptr, d_kinds);
     ctx->launches++;
   }
-  if (dm.has_list) apply_list_kernel<<<dm.R, 256, apply_smem_bytes(dm), ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
+  if (dm.has_list) apply_list_kernel<<<dm.R, apply_threads(ctx), apply_smem_bytes(dm), ctx->stream>>>(dm, 2, d_rows, nullptr, nullptr, nullptr, d_kinds);
   ctx->launches++;
   CU(cudaGetLastError());
   return SFGPU_OK;

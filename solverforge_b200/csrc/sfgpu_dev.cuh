@@ -147,6 +147,7 @@ struct NearbyArgs {
   uint32_t cache;                // 1: the cached kernel ran / runs for this step
   int2* c_delta;                 // [R][n_elem_rows][max_nearby] (dh, ds); dh == INT32_MIN: no candidate on this lane
   uint32_t* c_ident;             // [R][n_elem_rows][max_nearby] reference element | append << 15 | route << 16
+  uint32_t* c_work;              // [R][elem_cap + 1] {n, flat positions of the sources to regenerate this step}
   uint4* c_meta;                 // [R][n_elem_rows][2] {k-th distance, 7 words of 8-bit route codes (4 lanes per word)}
 };
 

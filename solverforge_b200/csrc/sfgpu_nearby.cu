@@ -20,6 +20,9 @@ int sfgpu_configure_nearby(sfgpu_ctx* ctx) {
   NBC_ATTR(-1);
   NBC_ATTR(SFGPU_W_SQUARE);
   NBC_ATTR(SFGPU_W_EXCESS);
+  CU(cudaFuncSetAttribute(nearby_regen_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CU(cudaFuncSetAttribute(nearby_regen_kernel<SFGPU_W_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CU(cudaFuncSetAttribute(nearby_regen_kernel<SFGPU_W_EXCESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return SFGPU_OK;
 }
 
@@ -35,7 +38,9 @@ int sfgpu_nearby_prepare_cache(sfgpu_ctx* ctx, uint32_t K) {
   }
   ctx->nbc_buf = nullptr;
   ctx->nbc_K = 0;
-  CU(cudaMalloc(&ctx->nbc_buf, n_src * (2 * sizeof(uint4) + (size_t)K * (sizeof(int2) + 4))));
+  const size_t work_bytes = (size_t)dm.R * (dm.elem_cap + 1) * 4;
+  CU(cudaMalloc(&ctx->nbc_buf, n_src * (2 * sizeof(uint4) + (size_t)K * (sizeof(int2) + 4)) + work_bytes));
+  CU(cudaMemsetAsync((char*)ctx->nbc_buf + n_src * (2 * sizeof(uint4) + (size_t)K * (sizeof(int2) + 4)), 0, work_bytes, ctx->stream));
   ctx->nbc_K = K;
   CU(cudaMemsetAsync(dm.nbc_tag, 0, (size_t)dm.R * NBC_WORDS * 4, ctx->stream));
   return SFGPU_OK;
@@ -77,12 +82,14 @@ int sfgpu_launch_nearby(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t*
     a.c_meta = (uint4*)ctx->nbc_buf;
     a.c_delta = (int2*)((char*)ctx->nbc_buf + n_src * 2 * sizeof(uint4));
     a.c_ident = (uint32_t*)((char*)ctx->nbc_buf + n_src * (2 * sizeof(uint4) + (size_t)ctx->nbc_K * sizeof(int2)));
+    a.c_work = (uint32_t*)((char*)ctx->nbc_buf + n_src * (2 * sizeof(uint4) + (size_t)ctx->nbc_K * (sizeof(int2) + 4)));
     a.cache = 1;
     // the reference's default max_nearby (20) with full lists folds its kept deltas fully unrolled; whether a replica's
     // lists are full (count == K) is only known on the device, so the kernel falls back per replica
 #define NEARBYC(FN)                                                                                    \
   if (a.max_nearby == 20) nearby_step_cached_kernel<FN, 20><<<grid, 256, smem, ctx->stream>>>(dm, a);  \
   else nearby_step_cached_kernel<FN, 0><<<grid, 256, smem, ctx->stream>>>(dm, a);                      \
+  nearby_regen_kernel<FN><<<grid, 256, smem, ctx->stream>>>(dm, a);                                  \
   nearby_finish_kernel<FN, uint32_t, uint16_t><<<R, 256, 0, ctx->stream>>>(dm, a, d_idx, d_best, d_eval, d_win);
     if (fn == SFGPU_W_EXCESS) { NEARBYC(SFGPU_W_EXCESS) }
     else if (fn == SFGPU_W_SQUARE) { NEARBYC(SFGPU_W_SQUARE) }
@@ -143,7 +150,7 @@ int step_nearby_impl(sfgpu_ctx* ctx, int move, uint32_t flags, uint32_t max_near
   rc = sfgpu_launch_nearby(ctx, a, io.d_idx, io.d_best, io.d_eval, io.d_win, move);
   if (rc) return rc;
   ev_end(ctx);
-  ctx->launches += 2;
+  ctx->launches += a.cache ? 3 : 2;
   CU(cudaGetLastError());
   if (apply_winners) {
     rc = small_io_results_ready(ctx, io);  // the read-back overlaps the commit

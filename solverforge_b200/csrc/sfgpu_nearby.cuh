@@ -609,7 +609,6 @@ __global__ void __launch_bounds__(256, 4) nearby_step_cached_kernel(const __grid
   __shared__ uint64_t bar;
   __shared__ uint32_t s_n2, s_n3;
   __shared__ uint16_t s_list3[256];  // offsets (f - tile base) of the tile's tier-3 sources
-  __shared__ KEY s_buf[8][64];
   const uint32_t r = blockIdx.y;
   // protocol words and acceptor references: in flight while the records are staged
   const uint32_t* __restrict__ tag = m.nbc_tag + (size_t)r * NBC_WORDS;
@@ -627,7 +626,7 @@ __global__ void __launch_bounds__(256, 4) nearby_step_cached_kernel(const __grid
   v.pos_of = (const uint32_t*)(smem + m.off_pos_of);
   const int64_t* cs = (const int64_t*)(smem + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t count = nearby_count_warp(m, v.rr, a.max_nearby, lane), K = a.max_nearby;
   const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;
   S lh, ls, th, ts;
@@ -698,7 +697,7 @@ __global__ void __launch_bounds__(256, 4) nearby_step_cached_kernel(const __grid
           atomicAdd(&s_n2, 1u);
         }
         if (tier != 3) nbc_fold_source<KC>(cd, count, a.f.acceptor, lh, ls, th, ts, ch, csf, P + f);
-        else s_list3[atomicAdd(&s_n3, 1u)] = (uint16_t)threadIdx.x;
+        else s_list3[atomicAdd(&s_n3, 1u)] = (uint16_t)threadIdx.x;  // appended to the replica's work list below
       }
     }
     __syncthreads();
@@ -709,54 +708,128 @@ __global__ void __launch_bounds__(256, 4) nearby_step_cached_kernel(const __grid
       atomicAdd(tg + NBC_STATS + 1, n2);
       atomicAdd(tg + NBC_STATS + 2, n3);
     }
-    // ---- (B) generate + score, one warp per source ----------------------------------------------------------------
-    for (uint32_t i = warp; i < n3; i += 8) {
-      const uint32_t f = base + s_list3[i];
-      uint32_t x, se, sp;
-      uint4 prec, rsrc;
-      const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, K, lane, s_buf[warp], x, se, sp, prec, rsrc);
-      const bool have = lane < count && key != 0xFFFFFFFFu;
-      S dh = INT32_MIN, ds = 0;
-      uint32_t de = 0, dp = 0, ident = 0xFFFFFFFFu;
-      if (have) {
-        nearby_score_slot<SUM_FN, CELL, S>(m, nc, v, nearby_slot_of_scan(key & ((1u << a.scan_bits) - 1), se, rsrc),
-                                           key >> a.scan_bits, x, se, prec, rsrc, dh, ds, de, dp, ident);
-        ident = nbc_ident(ident, de);
-      }
-      if (lane < K) {
-        a.c_delta[(src0 + x) * K + lane] = make_int2(dh, ds);
-        a.c_ident[(src0 + x) * K + lane] = ident;
-      }
-      // meta: k-th kept distance + the 8-bit route code of every lane (4 lanes per word)
-      uint32_t cw = have ? (de & 255u) << (8 * (lane & 3)) : 0u;
-      cw |= __shfl_xor_sync(0xffffffffu, cw, 1);
-      cw |= __shfl_xor_sync(0xffffffffu, cw, 2);
-      uint32_t codes[7];
-#pragma unroll
-      for (uint32_t w = 0; w < 7; ++w) codes[w] = __shfl_sync(0xffffffffu, cw, 4 * w);
-      const uint32_t kth = __shfl_sync(0xffffffffu, key, K - 1);
-      if (lane == 0) {
-        // a list that is not full (count < K, or fewer slots than K) holds every slot: any change matters
-        a.c_meta[(src0 + x) * 2] = make_uint4((count < K || kth == 0xFFFFFFFFu) ? 0xFFFFFFFFu : kth >> a.scan_bits, codes[0],
-                                              codes[1], codes[2]);
-        a.c_meta[(src0 + x) * 2 + 1] = make_uint4(codes[3], codes[4], codes[5], codes[6]);
-      }
-      const bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
-      uint32_t accm;
-      const uint32_t eq = warp_best_mask(acc, dh, ds, accm);
-      if (lane == (eq ? __ffs(eq) - 1 : 0)) {
-        SrcPartial p;
-        p.best_h = eq ? ch + (int64_t)dh : 0;
-        p.best_s = eq ? csf + (int64_t)ds : 0;
-        p.n_best = __popc(eq);
-        p.n_accepted = __popc(accm);
-        p.first_lane = eq ? __ffs(eq) - 1 : 0;
-        p.pad = 0;
-        P[f] = p;
-      }
+    // tier-3 sources of this tile -> the replica's work list (nearby_regen_kernel)
+    if (n3) {
+      __shared__ uint32_t s_at;
+      if (threadIdx.x == 0) s_at = atomicAdd(a.c_work + (size_t)r * (m.elem_cap + 1), n3);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n3; i += 256) a.c_work[(size_t)r * (m.elem_cap + 1) + 1 + s_at + i] = base + s_list3[i];
     }
     if (base + 256 < c_hi) __syncthreads();  // the next tile reuses the work list
   }
+}
+
+// (B) the tier-3 sources of every replica, generated and scored one warp per source as nearby_step_kernel does; the
+// work list of replica r is c_work[r] = {n, flat source positions...}. grid = (G, R): the warps of the G CTAs of a
+// replica stride over its list; CTAs without work leave before staging anything.
+template <int SUM_FN>
+__global__ void __launch_bounds__(256) nearby_regen_kernel(const __grid_constant__ DevModel m, const NearbyArgs a) {
+  typedef uint32_t KEY;
+  typedef uint16_t CELL;
+  typedef int32_t S;
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
+  __shared__ KEY s_buf[8][64];
+  const uint32_t r = blockIdx.y;
+  const uint32_t* __restrict__ work = a.c_work + (size_t)r * (m.elem_cap + 1);
+  const uint32_t n3 = work[0];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // three or more sources per warp before another CTA (and its 38 KB of staging) joins in
+  const uint32_t active = min(max((n3 + 23) / 24, 1u), gridDim.x);
+  if (n3 == 0 || blockIdx.x >= active) return;
+  int64_t refs[4] = {0, 0, 0, 0};
+  if (a.ref_scores) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) refs[q] = a.ref_scores[r * 4 + q];
+  }
+  stage_block(smem, m.state + (size_t)r * m.block_bytes, m.fast_stage_bytes, &bar);
+  NearbyView v;
+  v.rr = (const uint4*)(smem + m.off_route_rec);
+  v.pr = (const uint4*)(smem + m.off_pos_rec);
+  v.sr = (const uint4*)(smem + m.off_slot_rec);
+  v.pos_of = (const uint32_t*)(smem + m.off_pos_of);
+  const int64_t* cs = (const int64_t*)(smem + m.off_score);
+  const int64_t ch = cs[0], csf = cs[1];
+  const uint32_t count = nearby_count_warp(m, v.rr, a.max_nearby, lane), K = a.max_nearby;
+  S lh, ls, th, ts;
+  rel_threshold(refs[0], ch, lh);
+  rel_threshold(refs[1], csf, ls);
+  rel_threshold(refs[2], ch, th);
+  rel_threshold(refs[3], csf, ts);
+  const NearbyConsts<S> nc = nearby_consts<SUM_FN, S>(m);
+  const size_t src0 = (size_t)r * m.n_elem_rows;
+  SrcPartial* __restrict__ P = a.partials + (size_t)r * m.elem_cap;
+  for (uint32_t i = blockIdx.x * 8 + warp; i < n3; i += active * 8) {
+    const uint32_t f = work[1 + i];
+    uint32_t x, se, sp;
+    uint4 prec, rsrc;
+    const KEY key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, f, K, lane, s_buf[warp], x, se, sp, prec, rsrc);
+    const bool have = lane < count && key != 0xFFFFFFFFu;
+    S dh = INT32_MIN, ds = 0;
+    uint32_t de = 0, dp = 0, ident = 0xFFFFFFFFu;
+    if (have) {
+      nearby_score_slot<SUM_FN, CELL, S>(m, nc, v, nearby_slot_of_scan(key & ((1u << a.scan_bits) - 1), se, rsrc),
+                                         key >> a.scan_bits, x, se, prec, rsrc, dh, ds, de, dp, ident);
+      ident = nbc_ident(ident, de);
+    }
+    if (lane < K) {
+      a.c_delta[(src0 + x) * K + lane] = make_int2(dh, ds);
+      a.c_ident[(src0 + x) * K + lane] = ident;
+    }
+    // meta: k-th kept distance + the 8-bit route code of every lane (4 lanes per word)
+    uint32_t cw = have ? (de & 255u) << (8 * (lane & 3)) : 0u;
+    cw |= __shfl_xor_sync(0xffffffffu, cw, 1);
+    cw |= __shfl_xor_sync(0xffffffffu, cw, 2);
+    uint32_t codes[7];
+#pragma unroll
+    for (uint32_t w = 0; w < 7; ++w) codes[w] = __shfl_sync(0xffffffffu, cw, 4 * w);
+    const uint32_t kth = __shfl_sync(0xffffffffu, key, K - 1);
+    if (lane == 0) {
+      // a list that is not full (count < K, or fewer slots than K) holds every slot: any change matters
+      a.c_meta[(src0 + x) * 2] = make_uint4((count < K || kth == 0xFFFFFFFFu) ? 0xFFFFFFFFu : kth >> a.scan_bits, codes[0],
+                                            codes[1], codes[2]);
+      a.c_meta[(src0 + x) * 2 + 1] = make_uint4(codes[3], codes[4], codes[5], codes[6]);
+    }
+    const bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
+    uint32_t accm;
+    const uint32_t eq = warp_best_mask(acc, dh, ds, accm);
+    if (lane == (eq ? __ffs(eq) - 1 : 0)) {
+      SrcPartial p;
+      p.best_h = eq ? ch + (int64_t)dh : 0;
+      p.best_s = eq ? csf + (int64_t)ds : 0;
+      p.n_best = __popc(eq);
+      p.n_accepted = __popc(accm);
+      p.first_lane = eq ? __ffs(eq) - 1 : 0;
+      p.pad = 0;
+      P[f] = p;
+    }
+  }
+}
+
+// the lanes of source f from the retained rows of the cached step (instead of regenerating the source): delta, and for
+// the winner its destination through the kept reference element. Only valid right behind nearby_step_cached_kernel.
+template <typename S>
+__device__ __forceinline__ bool nbc_source_lane(const DevModel& m, const NearbyArgs& a, const NearbyView& v, const uint32_t r,
+                                                const uint32_t f, const uint32_t lane, const uint32_t count, uint32_t& se,
+                                                uint32_t& sp, S& dh, S& ds, uint32_t& id) {
+  const uint4 prec = v.pr[f];
+  se = prec.w;
+  sp = f - v.rr[se].x;
+  dh = 0;
+  ds = 0;
+  id = 0xFFFFFFFFu;
+  if (lane >= a.max_nearby) return false;
+  const size_t at = ((size_t)r * m.n_elem_rows + prec.x) * a.max_nearby + lane;
+  const int2 d = a.c_delta[at];
+  id = a.c_ident[at];
+  dh = (S)d.x;
+  ds = (S)d.y;
+  return lane < count && d.x != INT32_MIN;
+}
+__device__ __forceinline__ void nbc_destination(const NearbyView& v, const uint32_t id, uint32_t& de, uint32_t& dp) {
+  const uint32_t where = v.pos_of[id & 0x7FFFu];
+  de = where >> 16;
+  dp = (where & 0xFFFFu) + ((id >> 15) & 1u);
 }
 
 // One CTA per replica: ordered replay over the per-source partials (AcceptedCount cut, best, tie
@@ -806,6 +879,7 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     tag[NBC_K] = a.max_nearby;
     tag[NBC_COUNT] = count;
     tag[NBC_STATE] = 1;
+    a.c_work[(size_t)r * (m.elem_cap + 1)] = 0;  // the regeneration work list of the next step starts empty
   }
   // ---- AcceptedCount(N): the step ends right after the N-th accepted pull -------------------
   if (a.f.accepted_limit > 0) {
@@ -829,21 +903,27 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
       // regenerate the cut source; keep lanes up to the s_lcut-th accepted one
       uint32_t x, se, sp;
       uint4 prec, rsrc;
-      KEY key;
-      if (MOVE == MOVE_SWAP)
-        key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, total, lane, s_buf, x, se, sp,
-                                                prec, rsrc);
-      else
-        key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, lane, s_buf, x, se, sp, prec, rsrc);
-      const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(s_fcut, total, a.max_nearby) : count;
-      const bool have = lane < cnt && key != KeyTraits<KEY>::maxkey();
       S dh = 0, ds = 0;
       uint32_t de = 0, dp = 0;
-      if (have) {
+      bool have;
+      if (a.cache) {  // the cached step kernel holds this source's deltas
+        uint32_t id;
+        have = nbc_source_lane<S>(m, a, v, r, s_fcut, lane, count, se, sp, dh, ds, id);
+      } else {
+        KEY key;
         if (MOVE == MOVE_SWAP)
-          nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, s_fcut, x, se, prec, rsrc, dh, ds, de, dp);
+          key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, total, lane, s_buf, x, se, sp,
+                                                  prec, rsrc);
         else
-          nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+          key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, s_fcut, a.max_nearby, lane, s_buf, x, se, sp, prec, rsrc);
+        const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(s_fcut, total, a.max_nearby) : count;
+        have = lane < cnt && key != KeyTraits<KEY>::maxkey();
+        if (have) {
+          if (MOVE == MOVE_SWAP)
+            nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, s_fcut, x, se, prec, rsrc, dh, ds, de, dp);
+          else
+            nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+        }
       }
       const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
       bool acc = have && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
@@ -974,21 +1054,26 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     const uint32_t fstar = s_fstar, j = s_jstar;
     uint32_t x, se, sp;
     uint4 prec, rsrc;
-    KEY key;
-    if (MOVE == MOVE_SWAP)
-      key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, total, lane, s_buf, x, se, sp, prec,
-                                              rsrc);
-    else
-      key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, lane, s_buf, x, se, sp, prec, rsrc);
-    const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(fstar, total, a.max_nearby) : count;
-    const bool have = lane < cnt && key != KeyTraits<KEY>::maxkey() && !(fstar == fcut && lane > s_lcut);
     S dh = 0, ds = 0;
-    uint32_t de = 0, dp = 0;
-    if (have) {
+    uint32_t de = 0, dp = 0, id = 0xFFFFFFFFu;
+    bool have;
+    if (a.cache) {
+      have = nbc_source_lane<S>(m, a, v, r, fstar, lane, count, se, sp, dh, ds, id) && !(fstar == fcut && lane > s_lcut);
+    } else {
+      KEY key;
       if (MOVE == MOVE_SWAP)
-        nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, fstar, x, se, prec, rsrc, dh, ds, de, dp);
+        key = nearby_swap_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, total, lane, s_buf, x, se, sp, prec,
+                                                rsrc);
       else
-        nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+        key = nearby_gen_source<KEY, CELL>(m, v, a.scan_bits, fstar, a.max_nearby, lane, s_buf, x, se, sp, prec, rsrc);
+      const uint32_t cnt = MOVE == MOVE_SWAP ? swap_count(fstar, total, a.max_nearby) : count;
+      have = lane < cnt && key != KeyTraits<KEY>::maxkey() && !(fstar == fcut && lane > s_lcut);
+      if (have) {
+        if (MOVE == MOVE_SWAP)
+          nearby_swap_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, fstar, x, se, prec, rsrc, dh, ds, de, dp);
+        else
+          nearby_score<SUM_FN, KEY, CELL, S>(m, nc, v, a.scan_bits, key, x, se, prec, rsrc, dh, ds, de, dp);
+      }
     }
     const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
     const bool hit = have && oh == bh && os == bs && accept_delta<S>(a.f.acceptor, dh, ds, lh, ls, th, ts);
@@ -996,6 +1081,7 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
     for (uint32_t t = 1; t < j; ++t) mm &= mm - 1;
     const uint32_t wl = __ffs(mm) - 1;
     if (lane == wl) {
+      if (a.cache) nbc_destination(v, id, de, dp);
       out_index[r] = (MOVE == MOVE_SWAP ? swap_prefix(fstar, total, a.max_nearby) : fstar * count) + wl;
       out_best[r * 2] = bh;
       out_best[r * 2 + 1] = bs;

@@ -234,7 +234,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     CU(cudaGraphInstantiate(&exec, graph, 0));
     for (; done + per_graph <= p->n_steps; done += per_graph) {
       CU(cudaGraphLaunch(exec, ctx->stream));
-      ctx->launches += 5ull * per_graph;
+      ctx->launches += (5ull + (a.cache ? 1 : 0)) * per_graph;
     }
     cudaGraphExecDestroy(exec);
     cudaGraphDestroy(graph);
@@ -242,7 +242,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   for (; done < p->n_steps; ++done) {
     rc = one_step();
     if (rc) return rc;
-    ctx->launches += 5;
+    ctx->launches += 5 + (a.cache ? 1 : 0);
   }
   if (p->restore_best) {
     solve_restore_best_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
