@@ -839,7 +839,12 @@ __global__ void __launch_bounds__(256, 4) apply_list_kernel(const __grid_constan
   }
   if (m.fast_list) {
     __syncthreads();
-    build_fast_records(m, st, old_el);  // the element copy is dead by now (dynamic smem >= n_owners + 1 words)
+    // the element copy is dead by now (its first max(elem_cap, n_owners + 1) words become the offsets scratch); the new
+    // element array is staged behind it
+    uint32_t* s_el = old_el + max(m.elem_cap, m.n_owners + 1);
+    const uint32_t n_now = off[m.n_owners];
+    for (uint32_t i = threadIdx.x; i < n_now; i += blockDim.x) s_el[i] = el[i];
+    build_fast_records(m, st, old_el, s_el);  // its first barrier orders the staging above
   }
 }
 

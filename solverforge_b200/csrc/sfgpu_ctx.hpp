@@ -191,7 +191,9 @@ int dev_upload(sfgpu_ctx* ctx, const T* host, size_t n, T** out) {
 
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 // dynamic shared memory of apply_list_kernel: the element copy, reused as the owner table of build_fast_records
-inline size_t apply_smem_bytes(const DevModel& dm) { return (size_t)std::max(dm.elem_cap, dm.n_owners + 1) * 4; }
+inline size_t apply_smem_bytes(const DevModel& dm) {  // old element copy / offsets scratch + the new element array
+  return ((size_t)std::max(dm.elem_cap, dm.n_owners + 1) + dm.elem_cap) * 4;
+}
 // apply_list_kernel is one CTA per replica and a chain of short barrier-separated phases: with more replicas than the
 // machine holds 256-thread CTAs (4 per SM at 64 registers) half-size CTAs keep every replica resident in one wave
 inline unsigned apply_threads(const sfgpu_ctx* ctx) { return ctx->dm.R > 4u * (unsigned)ctx->sm_count ? 128u : 256u; }

@@ -889,9 +889,12 @@ __global__ void __launch_bounds__(256) score_list_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // block-parallel over insertion slots (one thread per slot g = base + owner + position, so the record stores are
 // coalesced and every thread waits for one round of gathers); s_off = shared scratch of n_owners + 1 words
-__device__ __forceinline__ void build_fast_records(const DevModel& m, char* st, uint32_t* s_off) {
+// s_el (optional) = a shared-memory copy of the element array: every slot reads three neighbouring elements before its
+// matrix gathers, and the copy takes that dependent global round trip out of each slot's chain
+__device__ __forceinline__ void build_fast_records(const DevModel& m, char* st, uint32_t* s_off,
+                                                   const uint32_t* s_el = nullptr) {
   const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
-  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  const uint32_t* el = s_el ? s_el : (const uint32_t*)(st + m.off_elems);
   RouteRec* rr = (RouteRec*)(st + m.off_route_rec);
   PosRec* pr = (PosRec*)(st + m.off_pos_rec);
   SlotRec* sr = (SlotRec*)(st + m.off_slot_rec);
@@ -911,6 +914,7 @@ __device__ __forceinline__ void build_fast_records(const DevModel& m, char* st, 
     for (uint32_t i = threadIdx.x; i < m.n_elem_rows; i += blockDim.x) pos_of[i] = 0xFFFFFFFFu;
   __syncthreads();
   const uint32_t n_slots = s_off[n_owners] + n_owners;
+#pragma unroll 2
   for (uint32_t g = threadIdx.x; g < n_slots; g += blockDim.x) {
     uint32_t lo = 0, hi = n_owners;  // owner of slot g: the largest o with s_off[o] + o <= g
     while (hi - lo > 1) {
