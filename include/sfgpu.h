@@ -389,7 +389,15 @@ int32_t sfgpu_step_change_rows(sfgpu_ctx* ctx, uint64_t n_candidates, const uint
  *   owns rows f*max_nearby .. +max_nearby in pull order; rows that do not exist are not-doable sentinels.
  *   out_index is the reference pull index (CandidateId): source_position * candidates_per_source + rank.
  *   out_winner_rows[R][4] = the winning ListChangeMove of each replica (sentinel 0xFFFFFFFF when none).
- * Requires the fast list program (SFGPU_E_UNSUPPORTED otherwise) and max_nearby <= 32. */
+ * Requires the fast list program (SFGPU_E_UNSUPPORTED otherwise) and max_nearby <= 32.
+ * Retained neighbourhood: when nothing is materialised (out_rows NULL) the library keeps every source's score
+ * deltas between calls; after a winner committed through apply_winners (or sfgpu_apply_list_change /
+ * sfgpu_apply_winners of one ListChange move) the next call regenerates only the sources that move can have changed
+ * and re-scores the candidates into the two touched routes — results are bit-identical to a full regeneration;
+ * any other writer of the planning state invalidates the kept deltas (environment SFGPU_NO_NBCACHE=1, read at
+ * commit, turns it off).
+ * With host pointers and apply_winners the call returns once the winners have reached the host; the commit kernel is
+ * still ordered on the context's stream ahead of any later call (sfgpu_synchronize waits for it). */
 int32_t sfgpu_step_nearby_list_change(sfgpu_ctx* ctx, uint32_t flags, uint32_t max_nearby,
                                       const sfgpu_forage_params* params, const uint64_t* step_seeds,
                                       const int64_t* ref_scores, uint64_t* out_cand_offsets, uint32_t* out_rows,

@@ -57,6 +57,7 @@ int sfgpu_launch_nearby(sfgpu_ctx* ctx, NearbyArgs& a, uint32_t* d_idx, int64_t*
   uint32_t chunks = std::max<uint32_t>(1, std::min<uint32_t>((dm.elem_cap + 255) / 256, 64));
   const uint32_t max_chunks = std::max<uint32_t>(1, (dm.elem_cap + 7) / 8);
   while ((uint64_t)chunks * R < (uint64_t)ctx->sm_count * 2 && chunks * 2 <= max_chunks) chunks *= 2;
+  if (const char* cv = getenv("SFGPU_NB_CHUNKS")) chunks = std::max(1, atoi(cv));  // tuning experiments
   dim3 grid(chunks, R);
   size_t smem = dm.fast_stage_bytes;
   int fn = dm.fast_ls >= 0 ? dm.cons[dm.fast_ls].w.fn : -1;
