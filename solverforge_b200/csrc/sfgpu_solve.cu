@@ -48,10 +48,20 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       return fail(ctx, SFGPU_E_UNSUPPORTED, "device-resident loop needs the fast list program (see sfgpu_step_nearby_list_change)");
     if (p->max_nearby == 0 || p->max_nearby > 32) return fail(ctx, SFGPU_E_UNSUPPORTED, "max_nearby must be in [1, 32]");
   }
-  if (p->acceptor < 1 || p->acceptor > 6)
+  if (p->acceptor < 1 || p->acceptor > 7)
     return fail(ctx, SFGPU_E_INVALID,
                 "acceptor: 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing, "
-                "5 DiversifiedLateAcceptance, 6 SimulatedAnnealing");
+                "5 DiversifiedLateAcceptance, 6 SimulatedAnnealing, 7 TabuSearch");
+  const bool tabu = p->acceptor == 7;
+  uint32_t tabu_tenure[4] = {0, 0, 0, 0};
+  if (tabu) {
+    if (!scalar) return fail(ctx, SFGPU_E_UNSUPPORTED, "TabuSearch runs in sfgpu_solve_change");
+    for (int q = 0; q < 4; ++q) tabu_tenure[q] = (p->late_size >> (8 * q)) & 0xFFu;
+    if (!(tabu_tenure[0] | tabu_tenure[1] | tabu_tenure[2] | tabu_tenure[3]))
+      return fail(ctx, SFGPU_E_INVALID, "tabu_search requires at least one tabu dimension");  // tabu_search.rs:35-41
+    for (int q = 0; q < 4; ++q)
+      if (tabu_tenure[q] > TABU_CAP) return fail(ctx, SFGPU_E_UNSUPPORTED, "tabu tenure above 64");
+  }
   const bool sa = p->acceptor == 6;
   if (sa && !scalar && !udesc)
     return fail(ctx, SFGPU_E_UNSUPPORTED, "SimulatedAnnealing runs in sfgpu_solve_change and sfgpu_solve_union");
@@ -62,7 +72,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   if (p->tie_mode < 0 || p->tie_mode > 1) return fail(ctx, SFGPU_E_INVALID, "bad tie_mode");
   CU(cudaSetDevice(ctx->device));
   const uint32_t R = dm.R;
-  const uint32_t late = std::max<uint32_t>(p->late_size, 1);
+  const uint32_t late = tabu ? 1u : std::max<uint32_t>(p->late_size, 1);
   auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = a16(o + bytes); return at; };
@@ -73,6 +83,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   const size_t o_accst = take((size_t)R * 32);
   const size_t o_ovf = take((size_t)R * 16);
   const size_t o_sa = take((size_t)R * sizeof(SaState) * 2), o_cnts = take((size_t)R * 4);
+  const size_t o_tabu = take(tabu ? (size_t)R * sizeof(TabuState) : 16);
   const size_t o_snap = take((size_t)R * dm.block_bytes);
   if (o > ctx->solve_bytes) {
     if (ctx->solve_buf) cudaFree(ctx->solve_buf);
@@ -104,6 +115,9 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   s.step_count_limit = p->step_count_limit;
   s.sa_cur = (SaState*)(b + o_sa);
   s.sa_nxt = s.sa_cur + R;
+  s.tabu = (TabuState*)(b + o_tabu);
+  for (int q = 0; q < 4; ++q) s.tabu_tenure[q] = tabu_tenure[q];
+  s.tabu_aspiration = (uint32_t)(p->step_count_limit & 1);
   if (sa) {  // simulated_annealing.rs:11-15 defaults; late_size = calibration sample size, step_count_limit bit 0 =
              // HardRegressionPolicy::NeverAcceptHardRegression
     s.sa.decay = p->acceptor_real > 0.0 ? p->acceptor_real : 0.999985;
@@ -146,7 +160,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     ca.step_seeds = s.step_seeds;
     ca.ref_scores = s.ref_scores;
     ca.partials = (ChunkPartial*)ctx->partials;
-    if (sa) {  // the acceptor replays over the materialised, pull-ordered scores
+    if (sa || tabu) {  // the acceptor replays over the materialised, pull-ordered scores
       const size_t stride = (size_t)dm.n_entities * (dm.n_values + 1);
       const size_t need = (size_t)R * stride * (8 + 16 + 1) + (size_t)(R + 1) * 8 + 64;
       rc = ensure_staging(ctx, 64, need);
@@ -178,14 +192,19 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     if (scalar) {
       rc2 = sfgpu_launch_change_step(ctx, ca, c_chunks, s.out_index, s.out_best, s.out_evaluated, s.winner_rows);
       if (rc2) return rc2;
-      if (sa) {  // the fused partials of the step kernel are ignored: SA decides in pull order
-        rc2 = sfgpu_launch_sa_accept(ctx, ca.out_offsets, d_counts, nullptr, ca.out_scores, ca.out_doable, s.ref_scores,
-                                     s.step_seeds, s.sa_cur, s.sa_nxt, s.sa, p->accepted_limit);
-        if (rc2) return rc2;
+      if (sa || tabu) {  // the fused partials of the step kernel are ignored: the acceptor decides over the batch
+        if (sa) {
+          rc2 = sfgpu_launch_sa_accept(ctx, ca.out_offsets, d_counts, nullptr, ca.out_scores, ca.out_doable, s.ref_scores,
+                                       s.step_seeds, s.sa_cur, s.sa_nxt, s.sa, p->accepted_limit);
+          if (rc2) return rc2;
+        } else {
+          tabu_accept_kernel<<<R, 256, 0, ctx->stream>>>(dm, s, ca.out_offsets, d_counts, ca.out_rows, ca.out_scores, ca.out_doable);
+        }
         rc2 = sfgpu_launch_argbest_counts(ctx, ForageDev{0, p->tie_mode, p->accepted_limit, nullptr}, ca.out_offsets, d_counts,
                                           nullptr, ca.out_scores, ca.out_doable, s.step_seeds, s.ref_scores, s.out_index,
                                           s.out_best, s.out_evaluated);
         if (rc2) return rc2;
+        if (tabu) tabu_record_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s, ca.out_offsets, ca.out_rows);
         rc2 = sfgpu_launch_apply_scalar(ctx, 0, ca.out_rows, nullptr, ca.out_offsets, s.out_index);
       } else {
         rc2 = sfgpu_launch_apply_scalar(ctx, 0, s.winner_rows, nullptr, nullptr, nullptr);

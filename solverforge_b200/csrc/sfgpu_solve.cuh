@@ -35,6 +35,20 @@ struct SolveState {
   SaState* sa_cur;          // [R] state at the start of the step
   SaState* sa_nxt;          // [R] state after the step's evaluated candidates (committed by solve_post_kernel)
   SaParams sa;
+  struct TabuState* tabu;   // [R] TabuSearch memories (acceptor 7)
+  uint32_t tabu_tenure[4];  // entity, value, move, undo-move tenures (0 = dimension off)
+  uint32_t tabu_aspiration;
+};
+
+// TabuSearchAcceptor memories of one replica (tabu_search.rs:64-101: FIFO of at most `tenure` entries; membership does
+// not depend on the order, so each memory is a ring: slot = (head + k) % tenure). Entries of the scalar ChangeMove
+// (heuristic/move/change.rs:189-220): entity id, destination value id (0xFFFFFFFF = None), move id (entity, from, to),
+// undo move id (entity, to, from); the scope (descriptor, variable) is the same for every move of the loop.
+#define TABU_CAP 64
+struct TabuState {
+  uint32_t n[4], head[4];
+  uint32_t ent[TABU_CAP], val[TABU_CAP];
+  uint32_t mov[TABU_CAP][3], und[TABU_CAP][3];
 };
 
 // forage acceptor code (sfgpu_forage_params) that one step of the solve-level acceptor reduces to
@@ -45,6 +59,7 @@ __host__ __device__ inline int solve_forage_code(int acceptor) {
     case 3: return 3;  // GreatDeluge: > last || >= water
     case 4: return 3;  // StepCounting: > last || >= (-inf | +inf)
     case 6: return 0;  // SimulatedAnnealing: sa_accept_kernel leaves the accepted candidates as the doable ones
+    case 7: return 0;  // TabuSearch: tabu_accept_kernel does the same
     default: return 2; // DiversifiedLateAcceptance: >= last || >= min(late, best - |best| * tol)
   }
 }
@@ -79,6 +94,8 @@ __global__ void solve_init_kernel(const __grid_constant__ DevModel m, SolveState
       s.sa_cur[r] = z;
       s.sa_nxt[r] = z;
     }
+    if (s.acceptor == 7)  // tabu_search.rs:188-194 phase_started: memories cleared, best = initial
+      for (int q = 0; q < 4; ++q) s.tabu[r].n[q] = s.tabu[r].head[q] = 0;
     s.best_scores[r * 2] = cs[0];
     s.best_scores[r * 2 + 1] = cs[1];
     s.evaluated[r] = 0;
@@ -319,4 +336,77 @@ __global__ void __launch_bounds__(1024) sa_accept_kernel(const uint64_t* __restr
   }
   __syncthreads();
   if (threadIdx.x == 0) nxt[r] = z;
+}
+
+
+// ---- TabuSearch (acceptor/tabu_search.rs:103-237) over the materialised ChangeMove batch of a scalar step ---------
+// is_accepted = aspirational (aspiration enabled and move score > best score) or not tabu; tabu = the move's entity is
+// in the entity memory, or its destination value in the value memory, or its move id in the move memory or in the
+// undo-move memory (:150-186). One CTA per replica; leaves doable[i] = accepted (argbest then runs with acceptor 0).
+__global__ void __launch_bounds__(256) tabu_accept_kernel(const __grid_constant__ DevModel m, SolveState s,
+                                                          const uint64_t* __restrict__ cand_offsets,
+                                                          const uint32_t* __restrict__ counts,
+                                                          const uint32_t* __restrict__ rows,
+                                                          const int64_t* __restrict__ scores, uint8_t* __restrict__ doable) {
+  __shared__ TabuState z;
+  const uint32_t r = blockIdx.x;
+  for (uint32_t i = threadIdx.x; i < sizeof(TabuState) / 4; i += blockDim.x) ((uint32_t*)&z)[i] = ((const uint32_t*)(s.tabu + r))[i];
+  __syncthreads();
+  const int32_t* var = (const int32_t*)(m.state + (size_t)r * m.block_bytes + m.off_var);
+  const int64_t bh = s.best_scores[r * 2], bs = s.best_scores[r * 2 + 1];
+  const uint64_t lo = cand_offsets[r], hi = lo + counts[r];
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (!doable[i]) continue;
+    const uint2 row = ((const uint2*)rows)[i];
+    const uint32_t e = row.x, to = (int32_t)row.y < 0 ? 0xFFFFFFFFu : row.y;
+    const int32_t fv = var[e];
+    const uint32_t from = fv < 0 ? 0xFFFFFFFFu : (uint32_t)fv;
+    bool tabu = false;
+    for (uint32_t k = 0; k < z.n[0]; ++k) tabu |= z.ent[k] == e;
+    for (uint32_t k = 0; k < z.n[1]; ++k) tabu |= z.val[k] == to;
+    for (uint32_t k = 0; k < z.n[2]; ++k) tabu |= z.mov[k][0] == e && z.mov[k][1] == from && z.mov[k][2] == to;
+    for (uint32_t k = 0; k < z.n[3]; ++k) tabu |= z.und[k][0] == e && z.und[k][1] == from && z.und[k][2] == to;
+    if (tabu) {
+      const longlong2 sc = ((const longlong2*)scores)[i];
+      const bool aspirational = s.tabu_aspiration && score_less(bh, bs, sc.x, sc.y);
+      if (!aspirational) doable[i] = 0;
+    }
+  }
+}
+
+// step_ended (:204-236): the accepted move's entity, destination value, move id and undo move id enter the memories
+// (before the commit kernel: `from` is still the committed value). One thread per replica.
+__global__ void tabu_record_kernel(const __grid_constant__ DevModel m, SolveState s, const uint64_t* __restrict__ cand_offsets,
+                                   const uint32_t* __restrict__ rows) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m.R) return;
+  const uint32_t idx = s.out_index[r];
+  if (idx == 0xFFFFFFFFu) return;
+  const uint2 row = ((const uint2*)rows)[cand_offsets[r] + idx];
+  const int32_t* var = (const int32_t*)(m.state + (size_t)r * m.block_bytes + m.off_var);
+  const uint32_t e = row.x, to = (int32_t)row.y < 0 ? 0xFFFFFFFFu : row.y;
+  const int32_t fv = var[e];
+  const uint32_t from = fv < 0 ? 0xFFFFFFFFu : (uint32_t)fv;
+  TabuState& z = s.tabu[r];
+  auto slot = [&](int q) -> uint32_t {  // FIFO: the oldest entry leaves when the memory is full
+    const uint32_t t = s.tabu_tenure[q];
+    if (z.n[q] < t) return z.n[q]++;
+    const uint32_t at = z.head[q];
+    z.head[q] = (at + 1) % t;
+    return at;
+  };
+  if (s.tabu_tenure[0]) z.ent[slot(0)] = e;
+  if (s.tabu_tenure[1]) z.val[slot(1)] = to;
+  if (s.tabu_tenure[2]) {
+    const uint32_t k = slot(2);
+    z.mov[k][0] = e;
+    z.mov[k][1] = from;
+    z.mov[k][2] = to;
+  }
+  if (s.tabu_tenure[3]) {
+    const uint32_t k = slot(3);
+    z.und[k][0] = e;
+    z.und[k][1] = to;
+    z.und[k][2] = from;
+  }
 }

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from solverforge_b200 import ForageParams, instances, models
+from solverforge_b200 import _lib as L
 from tests import oracle_lib
 from tests.oracle_lib import Oracle
 
@@ -170,6 +171,59 @@ def test_scalar_device_loop_stateful_acceptors_follow_the_oracle(kind, okind, si
         assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o
         assert np.array_equal(state[r], cur)
     assert np.array_equal(loop.fresh_score(), final)
+
+
+@pytest.mark.parametrize("tenures,aspiration,limit", [((5, 0, 0, 0), True, 0), ((0, 3, 0, 0), True, 12), ((0, 0, 7, 0), False, 0),
+                                                      ((0, 0, 0, 4), True, 0), ((6, 2, 9, 3), True, 25), ((64, 0, 0, 1), False, 1)])
+def test_scalar_device_loop_tabu_search_follows_the_oracle(tenures, aspiration, limit):
+    """sfgpu_solve_change with TabuSearch (acceptor 7) against the oracle's TabuSearchAcceptor (tabu_search.rs:103-237)
+    fed the ChangeMove signatures of the oracle's own selector: entity / value / move / undo-move memories, FIFO
+    tenure, aspiration — same trajectory, best score, moves_evaluated, committed steps."""
+    from solverforge_b200.selectors import splitmix64
+    from tests.oracle_lib import OracleAcceptor, move_signatures
+    g = instances.graph_coloring(120, 400, 4, seed_edges=16, seed_colors=19, unassigned_permille=100)
+    R, steps = 2, 40
+    colors = np.stack([instances.graph_coloring(120, 400, 4, seed_edges=16, seed_colors=70 + r, unassigned_permille=100).color
+                       for r in range(R)])
+    loop = models.graph_coloring_director(g, R, colors=colors)
+    seed_base = 4242
+    packed = tenures[0] | (tenures[1] << 8) | (tenures[2] << 16) | (tenures[3] << 24)
+    best, evaluated, committed = loop.solve_change(steps, 7, packed, 1, limit, seed_base, step_count_limit=1 if aspiration else 0)
+    final = loop.calculate_score()
+    state = loop.scalar_state()
+    for r in range(R):
+        o = Oracle.graph_coloring(g, colors[r])
+        acc = OracleAcceptor(OracleAcceptor.TABU, tabu=list(tenures), aspiration=aspiration)
+        init = o.committed_score()
+        acc.phase_started(init)
+        best_o, ev_o, steps_o = init.copy(), 0, 0
+        cur = colors[r].copy()
+        for t in range(steps):
+            last = o.committed_score()
+            rows = o.enumerate_change()
+            so, oko = o.score_change(rows)
+            sigs = move_signatures(o, 0, rows)
+            seed = splitmix64(seed_base ^ ((r * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) ^ t)
+            out = acc.step(so, oko, best_o, last, seed, 0 if limit else 2, max(limit, 1), True, signatures=sigs)
+            ev_o += out[2]
+            if out[0]:
+                e, v = rows[out[1]]
+                o.apply_change(e, v)
+                cur[int(e)] = int(v)
+                steps_o += 1
+            now = o.committed_score()
+            if (now[0], now[1]) > (best_o[0], best_o[1]):
+                best_o = now.copy()
+        what = f"tenures={tenures} aspiration={aspiration} limit={limit} r={r}"
+        assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o, what
+        assert final[r].tolist() == o.committed_score().tolist(), what
+        assert best[r].tolist() == best_o.tolist(), what
+        assert np.array_equal(state[r], cur), what
+    assert np.array_equal(loop.fresh_score(), final)
+    with pytest.raises(L.SfgpuError):
+        loop.solve_change(2, 7, 0, 1, 0, 1)           # no tabu dimension
+    with pytest.raises(L.SfgpuError):
+        loop.solve_change(2, 7, 65, 1, 0, 1)          # tenure above the device memory
 
 
 @pytest.mark.parametrize("limit,samples,decay,never_hard", [(0, 16, 0.9, False), (40, 128, 0.0, False), (7, 24, 0.95, True),
