@@ -97,28 +97,41 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
     }
     if (!live) continue;
     const uint32_t n_cand = k + ((with_none && old >= 0) ? 1 : 0);
-    for (uint32_t v = 0; v < n_cand; ++v) {
-      const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
-      const bool ok = nv != old;
-      S dh, ds;
-      prog.delta(e, old, ok ? nv : old, dh, ds);  // null edit when not doable
-      if (a.out_rows) {
-        const size_t q = (size_t)r * stride + base + v;
-        ((uint2*)a.out_rows)[q] = make_uint2(e, (uint32_t)nv);
-        if (a.out_scores) {
-          ((longlong2*)a.out_scores)[q] = make_longlong2(ok ? ch + (int64_t)dh : 0, ok ? csf + (int64_t)ds : 0);
-          a.out_doable[q] = ok ? 1 : 0;
-        }
+    // four candidates of the entity at a time: their table gathers are independent, so they overlap
+    constexpr uint32_t U = 4;
+    for (uint32_t v0 = 0; v0 < n_cand; v0 += U) {
+      S dh[U], ds[U];
+      int32_t nv[U];
+      bool ok[U];
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u) {
+        const uint32_t v = v0 + u;
+        nv[u] = v < k ? (int32_t)v : SFGPU_NONE;
+        ok[u] = v < n_cand && nv[u] != old;
+        prog.delta(e, old, ok[u] ? nv[u] : old, dh[u], ds[u]);  // null edit when not doable
       }
-      const Key kk = Key::make(dh, ds);
-      if (ok && (kA.less(kk) || !kk.less(kB))) {
-        t_acc++;
-        if (tb_n == 0 || tb.less(kk)) {
-          tb = kk;
-          tb_n = 1;
-          tb_first = e * (k + 1) + v;
-        } else if (tb.equal(kk)) {
-          tb_n++;
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u) {
+        const uint32_t v = v0 + u;
+        if (v >= n_cand) break;
+        if (a.out_rows) {
+          const size_t q = (size_t)r * stride + base + v;
+          ((uint2*)a.out_rows)[q] = make_uint2(e, (uint32_t)nv[u]);
+          if (a.out_scores) {
+            ((longlong2*)a.out_scores)[q] = make_longlong2(ok[u] ? ch + (int64_t)dh[u] : 0, ok[u] ? csf + (int64_t)ds[u] : 0);
+            a.out_doable[q] = ok[u] ? 1 : 0;
+          }
+        }
+        const Key kk = Key::make(dh[u], ds[u]);
+        if (ok[u] && (kA.less(kk) || !kk.less(kB))) {
+          t_acc++;
+          if (tb_n == 0 || tb.less(kk)) {
+            tb = kk;
+            tb_n = 1;
+            tb_first = e * (k + 1) + v;
+          } else if (tb.equal(kk)) {
+            tb_n++;
+          }
         }
       }
     }
@@ -160,7 +173,8 @@ __global__ void __launch_bounds__(256) change_step_kernel(const __grid_constant_
 // Ordered search inside one chunk of entities [c_lo, c_hi): the `want`-th candidate (1-based, pull
 // order) satisfying pred(accepted, score). Returns e*(k+1)+v via s_out. All 256 threads participate.
 // mode 0: accepted candidates (AcceptedCount cut); mode 1: accepted candidates equal to (bh, bs).
-__device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, const ForageDev& f, uint32_t c_lo,
+template <class PROG>
+__device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, const PROG& prog, const ForageDev& f, uint32_t c_lo,
                                            uint32_t c_hi, uint32_t limit_code, int mode, int64_t bh, int64_t bs,
                                            uint32_t want, int64_t lh, int64_t ls, int64_t th, int64_t ts,
                                            uint32_t* scratch, uint32_t* s_out) {
@@ -180,9 +194,9 @@ __device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, co
       if (e * (k + 1) + v > limit_code) break;  // beyond the AcceptedCount cut
       const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
       if (nv == old) continue;
-      Score2 d{0, 0};
-      scalar_edit_delta(m, st, st, nullptr, 0, EditDev{e, old, nv}, d);
-      const int64_t oh = ch + d.hard, os = csf + d.soft;
+      typename PROG::S dh, ds;
+      prog.delta(e, old, nv, dh, ds);
+      const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
       if (accept_score(f.acceptor, oh, os, lh, ls, th, ts) && (mode == 0 || (oh == bh && os == bs))) mine++;
     }
     uint32_t tot;
@@ -195,9 +209,9 @@ __device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, co
         if (e * (k + 1) + v > limit_code) break;
         const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
         if (nv == old) continue;
-        Score2 d{0, 0};
-        scalar_edit_delta(m, st, st, nullptr, 0, EditDev{e, old, nv}, d);
-        const int64_t oh = ch + d.hard, os = csf + d.soft;
+        typename PROG::S dh, ds;
+        prog.delta(e, old, nv, dh, ds);
+        const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
         if (accept_score(f.acceptor, oh, os, lh, ls, th, ts) && (mode == 0 || (oh == bh && os == bs))) {
           if (++hit == want - excl) {
             *s_out = e * (k + 1) + v;
@@ -212,18 +226,30 @@ __device__ __forceinline__ void chunk_find(const DevModel& m, const char* st, co
   }
 }
 
-// One CTA per replica: combine chunk partials, AcceptedCount cut, tie rule, winner.
+// One CTA per replica: combine chunk partials, AcceptedCount cut, tie rule, winner. The ordered searches inside a chunk
+// (AcceptedCount cut, j-th of several equal bests) re-score that chunk with the same program the step kernel ran
+// (PROG, replica block staged): with the interpreter on the unstaged block they cost 3-4 x the whole step kernel.
+template <bool STAGED, class PROG>
 __global__ void __launch_bounds__(256) change_finish_kernel(const __grid_constant__ DevModel m, const ChangeStepArgs a,
-                                                            uint32_t n_chunks, uint32_t* __restrict__ out_index,
+                                                            const SpecIdx idx, uint32_t n_chunks,
+                                                            uint32_t* __restrict__ out_index,
                                                             int64_t* __restrict__ out_best,
                                                             uint32_t* __restrict__ out_evaluated,
                                                             uint32_t* __restrict__ out_winner_rows) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ uint64_t bar;
   __shared__ uint32_t scratch[33];
   __shared__ uint32_t s_code, s_cut_chunk, s_cut_rank, s_any, s_cstar, s_jstar;
   __shared__ int64_t s_bh, s_bs;
   __shared__ ChunkPartial s_cutp;
   const uint32_t r = blockIdx.x;
-  const char* st = m.state + (size_t)r * m.block_bytes;
+  const char* gblock = m.state + (size_t)r * m.block_bytes;
+  const char* st = gblock;
+  if (STAGED) {
+    stage_block(smem, gblock, m.stage_bytes, &bar);
+    st = smem;
+  }
+  const PROG prog(m, idx, st, gblock);
   const int32_t* var = (const int32_t*)(st + m.off_var);
   const uint32_t k = m.n_values, n = m.n_entities;
   const ChunkPartial* P = a.partials + (size_t)r * n_chunks;
@@ -256,7 +282,7 @@ __global__ void __launch_bounds__(256) change_finish_kernel(const __grid_constan
     __syncthreads();
     if (s_cut_chunk < n_chunks) {
       const uint32_t c_lo = s_cut_chunk * a.ents_per_cta, c_hi = min(c_lo + a.ents_per_cta, n);
-      chunk_find(m, st, a.f, c_lo, c_hi, 0xFFFFFFFFu, 0, 0, 0, s_cut_rank, lh, ls, th, ts, scratch, &s_code);
+      chunk_find(m, st, prog, a.f, c_lo, c_hi, 0xFFFFFFFFu, 0, 0, 0, s_cut_rank, lh, ls, th, ts, scratch, &s_code);
       __syncthreads();
       limit_code = s_code;
       n_eff = s_cut_chunk + 1;
@@ -274,9 +300,9 @@ __global__ void __launch_bounds__(256) change_finish_kernel(const __grid_constan
             if (e * (k + 1) + v > limit_code) break;
             const int32_t nv = v < k ? (int32_t)v : SFGPU_NONE;
             if (nv == old) continue;
-            Score2 d{0, 0};
-            scalar_edit_delta(m, st, st, nullptr, 0, EditDev{e, old, nv}, d);
-            const int64_t oh = ch + d.hard, os = csf + d.soft;
+            typename PROG::S dh, ds;
+            prog.delta(e, old, nv, dh, ds);
+            const int64_t oh = ch + (int64_t)dh, os = csf + (int64_t)ds;
             if (!accept_score(a.f.acceptor, oh, os, lh, ls, th, ts)) continue;
             if (tb_n == 0 || score_less(tb_h, tb_s, oh, os)) {
               tb_h = oh; tb_s = os; tb_n = 1; tb_first = e * (k + 1) + v;
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(256) change_finish_kernel(const __grid_constan
     const uint32_t c_lo = s_cstar * a.ents_per_cta, c_hi = min(c_lo + a.ents_per_cta, n);
     const uint32_t j = s_jstar;
     __syncthreads();
-    chunk_find(m, st, a.f, c_lo, c_hi, limit_code, 1, bh, bs, j, lh, ls, th, ts, scratch, &s_code);
+    chunk_find(m, st, prog, a.f, c_lo, c_hi, limit_code, 1, bh, bs, j, lh, ls, th, ts, scratch, &s_code);
     __syncthreads();
   }
   const uint32_t code = s_code;

@@ -12,19 +12,22 @@ namespace {
 // Every tuple has the wide (int64) kernels; tuples made only of kinds with an int32 form also carry the narrow ones.
 typedef void (*SpecScoreFn)(const DevModel, const SpecIdx, const uint64_t*, const uint32_t*, int64_t*, uint8_t*, const ForageArgs);
 typedef void (*SpecStepFn)(const DevModel, const ChangeStepArgs, const SpecIdx);
+typedef void (*SpecFinishFn)(const DevModel, const ChangeStepArgs, const SpecIdx, uint32_t, uint32_t*, int64_t*, uint32_t*, uint32_t*);
 struct SpecEntry {
   int k[4];
   SpecScoreFn score, fused;      // rows-resident: scores only / scores + forager partials
   SpecScoreFn score_n, fused_n;  // int32 forms, or null
   SpecStepFn step, step_n;
+  SpecFinishFn finish, finish_n;
 };
 #define SPEC_WIDE(a, b, c, d) \
   { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, nullptr, nullptr, \
-    change_step_kernel<true, SpecProg<a, b, c, d>>, nullptr }
+    change_step_kernel<true, SpecProg<a, b, c, d>>, nullptr, change_finish_kernel<true, SpecProg<a, b, c, d>>, nullptr }
 #define SPEC_BOTH(a, b, c, d) \
   { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, \
     spec_change_kernel<SpecProgN<a, b, c, d>, false>, spec_change_kernel<SpecProgN<a, b, c, d>, true>, \
-    change_step_kernel<true, SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProgN<a, b, c, d>> }
+    change_step_kernel<true, SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProgN<a, b, c, d>>,              \
+    change_finish_kernel<true, SpecProg<a, b, c, d>>, change_finish_kernel<true, SpecProgN<a, b, c, d>> }
 #define U_ SFGPU_K_UNI
 #define C_ SFGPU_K_PAIR_CSR_EQUAL
 #define K_ SFGPU_K_PAIR_KEY_EQUAL
@@ -116,6 +119,7 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
     int bytes = (int)dm.stage_bytes;
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(change_step_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU(cudaFuncSetAttribute(change_finish_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
@@ -154,6 +158,7 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
         CU(cudaFuncSetAttribute((const void*)g_spec[t].score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
         CU(cudaFuncSetAttribute((const void*)g_spec[t].fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
         CU(cudaFuncSetAttribute((const void*)g_spec[t].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+        CU(cudaFuncSetAttribute((const void*)g_spec[t].finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
         ctx->spec_narrow = false;
         if (g_spec[t].score_n && !getenv("SFGPU_NO_NARROW")) {
           const double bound = scalar_narrow_bound(ctx);
@@ -162,6 +167,7 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
             CU(cudaFuncSetAttribute((const void*)g_spec[t].score_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
             CU(cudaFuncSetAttribute((const void*)g_spec[t].fused_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
             CU(cudaFuncSetAttribute((const void*)g_spec[t].step_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
+            CU(cudaFuncSetAttribute((const void*)g_spec[t].finish_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
           }
         }
         break;
@@ -253,7 +259,13 @@ int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t c
     change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
   else
     change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx);
-  change_finish_kernel<<<dm.R, 256, 0, ctx->stream>>>(dm, a, chunks, d_idx, d_best, d_eval, d_win);
+  if (ctx->spec_id >= 0)
+    (ctx->spec_narrow ? g_spec[ctx->spec_id].finish_n : g_spec[ctx->spec_id].finish)<<<dm.R, 256, dm.stage_bytes, ctx->stream>>>(
+        dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
+  else if (ctx->staged)
+    change_finish_kernel<true, InterpProg><<<dm.R, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
+  else
+    change_finish_kernel<false, InterpProg><<<dm.R, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
   ctx->launches += 2;
   CU(cudaGetLastError());
   return SFGPU_OK;
