@@ -167,3 +167,60 @@ def test_device_loop_with_the_retained_neighbourhood(monkeypatch):
         want = d_f.step_nearby_list_change(20, ForageParams(0, 1, 0), step_seeds=list(range(R)), apply=True)
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
+
+
+def test_retained_neighbourhood_fuzz(monkeypatch):
+    """Random shapes (customers, routes, max_nearby, distance granularity, acceptor, AcceptedCount): every committed
+    step of the cached context equals the regenerating one."""
+    rng = np.random.default_rng(20261017)
+    for case in range(12):
+        n = int(rng.integers(12, 260))
+        routes = int(rng.integers(1, max(2, n // 3)))
+        K = int(rng.integers(1, 33))
+        coarse = int(rng.choice([1, 1, 7, 60]))
+        acceptor = int(rng.choice([0, 1, 2]))
+        limit = int(rng.choice([0, 0, 3, 200]))
+        c = instances.cvrp(n, routes, seed=100 + case)
+        c.matrix = (c.matrix // coarse) * coarse
+        R = 3
+        starts = [instances.perturb_routes(c, 900 + 7 * case + r, n // 2) for r in range(R)]
+        d_c = _director(c, starts, monkeypatch, True)
+        d_f = _director(c, starts, monkeypatch, False)
+        fp = ForageParams(acceptor, int(rng.integers(0, 2)), limit)
+        for step in range(30):
+            last = d_c.calculate_score()
+            ref = _ref(last, acceptor, step)
+            seeds = [31 * step + r for r in range(R)]
+            got = d_c.step_nearby_list_change(K, fp, step_seeds=seeds, ref_scores=ref, apply=True)
+            want = d_f.step_nearby_list_change(K, fp, step_seeds=seeds, ref_scores=ref, apply=True)
+            for g, w, what in zip(got, want, ("index", "best", "moves_evaluated", "winner rows")):
+                assert np.array_equal(g, w), f"case {case} (n={n} routes={routes} K={K} coarse={coarse} acc={acceptor} " \
+                                             f"limit={limit}) step {step}: {what}"
+        assert np.array_equal(d_c.fresh_score(), d_f.calculate_score())
+        d_c.close()
+        d_f.close()
+
+
+def test_retained_neighbourhood_full_size(monkeypatch):
+    """CVRP-1000 / 80 routes (the bench workload), 8 replicas, 60 committed steps under accept-all and under
+    LateAcceptance-like references with AcceptedCount(256)."""
+    c = instances.cvrp()
+    R, K = 8, 20
+    starts = [instances.perturb_routes(c, 5000 + r, 64) for r in range(R)]
+    for acceptor, limit in ((0, 0), (2, 256)):
+        d_c = _director(c, starts, monkeypatch, True)
+        d_f = _director(c, starts, monkeypatch, False)
+        fp = ForageParams(acceptor, 1, limit)
+        for step in range(60):
+            last = d_c.calculate_score()
+            ref = _ref(last, acceptor, step)
+            seeds = [step * 1000 + r for r in range(R)]
+            got = d_c.step_nearby_list_change(K, fp, step_seeds=seeds, ref_scores=ref, apply=True)
+            want = d_f.step_nearby_list_change(K, fp, step_seeds=seeds, ref_scores=ref, apply=True)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), f"acceptor {acceptor} step {step}"
+        t = _tags(d_c)[:, 10:13].astype(np.float64).sum(axis=0)
+        assert t[2] / t.sum() < 0.15, "most sources keep or re-score their deltas at full size"
+        assert np.array_equal(d_c.fresh_score(), d_f.calculate_score())
+        d_c.close()
+        d_f.close()
