@@ -1,7 +1,8 @@
 // Scalar-move kernels of libsfgpu: ChangeMove / SwapMove / CompoundScalarMove batches (interpreter and
 // monomorphised programs) and the whole ChangeMove step generated on device.
 #include "sfgpu_ctx.hpp"
-#include "sfgpu_change_step.cuh"
+#include "sfgpu_spec.cuh"
+#include "sfgpu_spec_list.h"
 
 using namespace sfgpu_host;
 
@@ -11,45 +12,17 @@ namespace {
 // The tuples of the reference's scalar examples (graph colouring, n-queens, job shop) and their prefixes.
 // Every tuple has the wide (int64) kernels; tuples made only of kinds with an int32 form also carry the narrow ones.
 typedef void (*SpecScoreFn)(const DevModel, const SpecIdx, const uint64_t*, const uint32_t*, int64_t*, uint8_t*, const ForageArgs);
-typedef void (*SpecStepFn)(const DevModel, const ChangeStepArgs, const SpecIdx);
-typedef void (*SpecFinishFn)(const DevModel, const ChangeStepArgs, const SpecIdx, uint32_t, uint32_t*, int64_t*, uint32_t*, uint32_t*);
 struct SpecEntry {
   int k[4];
   SpecScoreFn score, fused;      // rows-resident: scores only / scores + forager partials
   SpecScoreFn score_n, fused_n;  // int32 forms, or null
-  SpecStepFn step, step_n;
-  SpecFinishFn finish, finish_n;
 };
 #define SPEC_WIDE(a, b, c, d) \
-  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, nullptr, nullptr, \
-    change_step_kernel<true, SpecProg<a, b, c, d>>, nullptr, change_finish_kernel<true, SpecProg<a, b, c, d>>, nullptr }
+  { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, nullptr, nullptr }
 #define SPEC_BOTH(a, b, c, d) \
   { {a, b, c, d}, spec_change_kernel<SpecProg<a, b, c, d>, false>, spec_change_kernel<SpecProg<a, b, c, d>, true>, \
-    spec_change_kernel<SpecProgN<a, b, c, d>, false>, spec_change_kernel<SpecProgN<a, b, c, d>, true>, \
-    change_step_kernel<true, SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProgN<a, b, c, d>>,              \
-    change_finish_kernel<true, SpecProg<a, b, c, d>>, change_finish_kernel<true, SpecProgN<a, b, c, d>> }
-#define U_ SFGPU_K_UNI
-#define C_ SFGPU_K_PAIR_CSR_EQUAL
-#define K_ SFGPU_K_PAIR_KEY_EQUAL
-#define G_ SFGPU_K_GROUP
-#define UC SPEC_K_UNI_CONST
-const SpecEntry g_spec[] = {  // kinds ascending; UC (uni without column / mask) sorts last
-    SPEC_WIDE(U_, 0, 0, 0),   SPEC_BOTH(UC, 0, 0, 0),    // unassigned only
-    SPEC_WIDE(U_, C_, 0, 0),  SPEC_BOTH(C_, UC, 0, 0),   // graph colouring
-    SPEC_WIDE(U_, K_, 0, 0),  SPEC_BOTH(K_, UC, 0, 0),
-    SPEC_WIDE(U_, G_, 0, 0),  SPEC_BOTH(G_, UC, 0, 0),
-    SPEC_WIDE(U_, C_, G_, 0), SPEC_BOTH(C_, G_, UC, 0),
-    SPEC_WIDE(U_, K_, G_, 0), SPEC_BOTH(K_, G_, UC, 0),  // job shop
-    SPEC_WIDE(U_, K_, K_, 0), SPEC_BOTH(K_, K_, UC, 0),
-    SPEC_WIDE(U_, K_, K_, K_), SPEC_BOTH(K_, K_, K_, UC),  // n-queens
-    SPEC_WIDE(U_, K_, G_, G_), SPEC_BOTH(K_, G_, G_, UC),
-    SPEC_WIDE(U_, U_, K_, G_), SPEC_WIDE(U_, K_, G_, UC),
-};
-#undef U_
-#undef C_
-#undef K_
-#undef G_
-#undef UC
+    spec_change_kernel<SpecProgN<a, b, c, d>, false>, spec_change_kernel<SpecProgN<a, b, c, d>, true> }
+const SpecEntry g_spec[] = {SFGPU_SPEC_TUPLES(SPEC_WIDE, SPEC_BOTH)};
 #undef SPEC_WIDE
 #undef SPEC_BOTH
 
@@ -118,8 +91,6 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
   if (ctx->staged) {
     int bytes = (int)dm.stage_bytes;
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_CHANGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(change_step_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(change_finish_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_SWAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU(cudaFuncSetAttribute(score_scalar_kernel<MODE_COMPOUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
@@ -157,8 +128,6 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
         for (size_t i = 0; i < 4; ++i) ctx->spec_idx.k[i] = i < sc.size() ? sc[i].second : -1;
         CU(cudaFuncSetAttribute((const void*)g_spec[t].score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
         CU(cudaFuncSetAttribute((const void*)g_spec[t].fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
-        CU(cudaFuncSetAttribute((const void*)g_spec[t].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
-        CU(cudaFuncSetAttribute((const void*)g_spec[t].finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
         ctx->spec_narrow = false;
         if (g_spec[t].score_n && !getenv("SFGPU_NO_NARROW")) {
           const double bound = scalar_narrow_bound(ctx);
@@ -166,15 +135,13 @@ int sfgpu_configure_scalar(sfgpu_ctx* ctx) {
             ctx->spec_narrow = true;
             CU(cudaFuncSetAttribute((const void*)g_spec[t].score_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
             CU(cudaFuncSetAttribute((const void*)g_spec[t].fused_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
-            CU(cudaFuncSetAttribute((const void*)g_spec[t].step_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
-            CU(cudaFuncSetAttribute((const void*)g_spec[t].finish_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm.stage_bytes));
           }
         }
         break;
       }
     }
   }
-  return SFGPU_OK;
+  return sfgpu_configure_scalar_step(ctx);  // the generated step + finish kernels live in sfgpu_scalar_step.cu
 }
 
 // entities per CTA of the generated ChangeMove step: amortise the state staging, but cover the machine when
@@ -243,30 +210,6 @@ int sfgpu_launch_score_scalar(sfgpu_ctx* ctx, int kind, uint64_t n_total, const 
   }
   ev_end(ctx);
   ctx->launches++;
-  CU(cudaGetLastError());
-  return SFGPU_OK;
-}
-
-// generate + score + forage (two kernels) on the context's stream; the dominant kernel is bracketed by the
-// event ring when `timed`
-int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t chunks, uint32_t* d_idx, int64_t* d_best,
-                             uint32_t* d_eval, uint32_t* d_win) {
-  const DevModel& dm = ctx->dm;
-  dim3 grid(chunks, dm.R);
-  if (ctx->spec_id >= 0)
-    (ctx->spec_narrow ? g_spec[ctx->spec_id].step_n : g_spec[ctx->spec_id].step)<<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
-  else if (ctx->staged)
-    change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
-  else
-    change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx);
-  if (ctx->spec_id >= 0)
-    (ctx->spec_narrow ? g_spec[ctx->spec_id].finish_n : g_spec[ctx->spec_id].finish)<<<dm.R, 256, dm.stage_bytes, ctx->stream>>>(
-        dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
-  else if (ctx->staged)
-    change_finish_kernel<true, InterpProg><<<dm.R, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
-  else
-    change_finish_kernel<false, InterpProg><<<dm.R, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
-  ctx->launches += 2;
   CU(cudaGetLastError());
   return SFGPU_OK;
 }
