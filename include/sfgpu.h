@@ -539,10 +539,11 @@ int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const st
  * 4 StepCountingHillClimbing(step_count_limit), 5 DiversifiedLateAcceptance(late_size, acceptor_real =
  * tolerance), 6 SimulatedAnnealing (sfgpu_solve_change / sfgpu_solve_union; acceptor_real = decay rate, 0 = the
  * default 0.999985; late_size = calibration sample size, 0 = 128; step_count_limit bit 0 =
- * HardRegressionPolicy::NeverAcceptHardRegression), 7 TabuSearch (sfgpu_solve_change; late_size packs the four
+ * HardRegressionPolicy::NeverAcceptHardRegression), 7 TabuSearch (sfgpu_solve_change and sfgpu_solve_nearby_list_change; late_size packs the four
  * tenures as bytes: entity | value << 8 | move << 16 | undo_move << 24, each <= 64, 0 = dimension off, at least one
  * set; step_count_limit bit 0 = aspiration enabled: a tabu move whose score beats the best score is accepted;
- * tabu_search.rs:103-237 with the ChangeMove signature of heuristic/move/change.rs:189-220) —
+ * tabu_search.rs:103-237 with the ChangeMove / ListChangeMove signatures of heuristic/move/change.rs:189-220 and
+ * list_kernel/change.rs:155-204) —
  * acceptor/{hill_climbing,late_acceptance,great_deluge,step_counting,diversified_late_acceptance,simulated_annealing,
  * tabu_search}.rs, state kept per replica on the device.
  * SimulatedAnnealing replays is_accepted in pull order over the step's scores (calibration from the first

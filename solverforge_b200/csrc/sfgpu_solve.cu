@@ -55,7 +55,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   const bool tabu = p->acceptor == 7;
   uint32_t tabu_tenure[4] = {0, 0, 0, 0};
   if (tabu) {
-    if (!scalar) return fail(ctx, SFGPU_E_UNSUPPORTED, "TabuSearch runs in sfgpu_solve_change");
+    if (udesc) return fail(ctx, SFGPU_E_UNSUPPORTED, "TabuSearch runs in sfgpu_solve_change and sfgpu_solve_nearby_list_change");
     for (int q = 0; q < 4; ++q) tabu_tenure[q] = (p->late_size >> (8 * q)) & 0xFFu;
     if (!(tabu_tenure[0] | tabu_tenure[1] | tabu_tenure[2] | tabu_tenure[3]))
       return fail(ctx, SFGPU_E_INVALID, "tabu_search requires at least one tabu dimension");  // tabu_search.rs:35-41
@@ -149,6 +149,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   }
   NearbyArgs a{};
   ChangeStepArgs ca{};
+  uint32_t* d_nper = nullptr;  // list TabuSearch: candidates per source of every replica
   uint32_t c_chunks = 0;
   if (scalar) {
     uint32_t per = 0;
@@ -182,6 +183,18 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     a.step_seeds = s.step_seeds;
     a.ref_scores = s.ref_scores;
     a.partials = (SrcPartial*)ctx->partials;
+    if (tabu) {  // TabuSearch decides over the materialised batch (rows, scores, doable), like the scalar loop
+      const size_t stride = (size_t)dm.elem_cap * p->max_nearby;
+      const size_t need = (size_t)R * stride * (16 + 16 + 1) + (size_t)(R + 1) * 8 + (size_t)R * 4 + 64;
+      rc = ensure_staging(ctx, 64, need);
+      if (rc) return rc;
+      char* q = (char*)ctx->dscr;
+      a.out_scores = (int64_t*)q;
+      a.out_rows = (uint32_t*)(q + (size_t)R * stride * 16);
+      a.out_offsets = (uint64_t*)(q + (size_t)R * stride * 32);
+      d_nper = (uint32_t*)(q + (size_t)R * stride * 32 + (size_t)(R + 1) * 8);
+      a.out_doable = (uint8_t*)(q + (size_t)R * stride * 32 + (size_t)(R + 1) * 8 + (size_t)R * 4);
+    }
   }
   solve_init_kernel<<<R, 256, 0, ctx->stream>>>(dm, s);
   ctx->launches++;
@@ -230,6 +243,16 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     } else {
       rc2 = sfgpu_launch_nearby(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows, MOVE_CHANGE);
       if (rc2) return rc2;
+      if (tabu) {  // the fused forager's pick is replaced: tabu filter, ordered replay, record, commit by row index
+        tabu_accept_list_kernel<<<R, 256, 0, ctx->stream>>>(dm, s, p->max_nearby, d_counts, d_nper, a.out_rows, a.out_scores,
+                                                            a.out_doable);
+        rc2 = sfgpu_launch_argbest_counts(ctx, ForageDev{0, p->tie_mode, p->accepted_limit, nullptr}, a.out_offsets, d_counts,
+                                          nullptr, a.out_scores, a.out_doable, s.step_seeds, s.ref_scores, s.out_index,
+                                          s.out_best, s.out_evaluated);
+        if (rc2) return rc2;
+        tabu_record_list_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(dm, s, p->max_nearby, d_nper, a.out_rows);
+        rc2 = sfgpu_launch_apply_list(ctx, 2, a.out_rows, nullptr, a.out_offsets, s.out_index);
+      } else
       rc2 = sfgpu_launch_apply_list(ctx, 2, s.winner_rows, nullptr, nullptr, nullptr);
     }
     if (rc2) return rc2;

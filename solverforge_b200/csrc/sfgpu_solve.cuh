@@ -43,12 +43,14 @@ struct SolveState {
 // TabuSearchAcceptor memories of one replica (tabu_search.rs:64-101: FIFO of at most `tenure` entries; membership does
 // not depend on the order, so each memory is a ring: slot = (head + k) % tenure). Entries of the scalar ChangeMove
 // (heuristic/move/change.rs:189-220): entity id, destination value id (0xFFFFFFFF = None), move id (entity, from, to),
-// undo move id (entity, to, from); the scope (descriptor, variable) is the same for every move of the loop.
+// undo move id (entity, to, from); the scope (descriptor, variable) is the same for every move of the loop. Entries of
+// ListChangeMove (list_kernel/change.rs:155-204): source and destination entity, moved element, move id (source entity,
+// source position, destination entity, adjusted destination position, element), undo id (the same with both ends swapped).
 #define TABU_CAP 64
 struct TabuState {
   uint32_t n[4], head[4];
   uint32_t ent[TABU_CAP], val[TABU_CAP];
-  uint32_t mov[TABU_CAP][3], und[TABU_CAP][3];
+  uint32_t mov[TABU_CAP][5], und[TABU_CAP][5];  // scalar moves use the first three words
 };
 
 // forage acceptor code (sfgpu_forage_params) that one step of the solve-level acceptor reduces to
@@ -408,5 +410,100 @@ __global__ void tabu_record_kernel(const __grid_constant__ DevModel m, SolveStat
     z.und[k][0] = e;
     z.und[k][1] = to;
     z.und[k][2] = from;
+  }
+}
+
+
+// ---- TabuSearch over the materialised nearby ListChange batch of a list step ----------------------------------------
+// rows {se, sp, de, dp}: fixed stride of max_nearby rows per source position, sentinel rows (not doable) where a source
+// has fewer candidates. A candidate is tabu when its source or destination entity is in the entity memory, the moved
+// element in the value memory, or its move id in the move / undo-move memory. Also leaves counts[r] = rows of the routed
+// sources (the ordered replay runs over those) and n_per[r] = candidates per source (for moves_evaluated).
+__global__ void __launch_bounds__(256) tabu_accept_list_kernel(const __grid_constant__ DevModel m, SolveState s,
+                                                               const uint32_t max_nearby, uint32_t* __restrict__ counts,
+                                                               uint32_t* __restrict__ n_per,
+                                                               const uint32_t* __restrict__ rows,
+                                                               const int64_t* __restrict__ scores,
+                                                               uint8_t* __restrict__ doable) {
+  __shared__ TabuState z;
+  const uint32_t r = blockIdx.x;
+  for (uint32_t i = threadIdx.x; i < sizeof(TabuState) / 4; i += blockDim.x) ((uint32_t*)&z)[i] = ((const uint32_t*)(s.tabu + r))[i];
+  __syncthreads();
+  const char* st = m.state + (size_t)r * m.block_bytes;
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  const uint32_t total = off[m.n_owners];
+  const size_t lo = (size_t)r * m.elem_cap * max_nearby, hi = lo + (size_t)total * max_nearby;
+  if (threadIdx.x == 0) {
+    uint32_t slots = 0;  // candidates per source: min(max_nearby, slots of non-empty routes - 2)
+    for (uint32_t o = 0; o < m.n_owners; ++o) slots += off[o + 1] > off[o] ? off[o + 1] - off[o] + 1 : 0;
+    const uint32_t valid = slots >= 2 ? slots - 2 : 0;
+    n_per[r] = valid < max_nearby ? valid : max_nearby;
+    counts[r] = total * max_nearby;
+  }
+  const int64_t bh = s.best_scores[r * 2], bs = s.best_scores[r * 2 + 1];
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (!doable[i]) continue;
+    const uint4 row = ((const uint4*)rows)[i];
+    const uint32_t se = row.x, sp = row.y, de = row.z, dp = row.w;
+    const uint32_t moved = el[off[se] + sp];
+    const uint32_t adj = (se == de && dp > sp) ? dp - 1 : dp;
+    bool tabu = false;
+    for (uint32_t k = 0; k < z.n[0]; ++k) tabu |= z.ent[k] == se || z.ent[k] == de;
+    for (uint32_t k = 0; k < z.n[1]; ++k) tabu |= z.val[k] == moved;
+    for (uint32_t k = 0; k < z.n[2]; ++k)
+      tabu |= z.mov[k][0] == se && z.mov[k][1] == sp && z.mov[k][2] == de && z.mov[k][3] == adj && z.mov[k][4] == moved;
+    for (uint32_t k = 0; k < z.n[3]; ++k)
+      tabu |= z.und[k][0] == se && z.und[k][1] == sp && z.und[k][2] == de && z.und[k][3] == adj && z.und[k][4] == moved;
+    if (tabu) {
+      const longlong2 sc = ((const longlong2*)scores)[i];
+      if (!(s.tabu_aspiration && score_less(bh, bs, sc.x, sc.y))) doable[i] = 0;
+    }
+  }
+}
+
+// step_ended for the list loop + moves_evaluated in reference pulls (the replay counted padded rows). One thread per replica.
+__global__ void tabu_record_list_kernel(const __grid_constant__ DevModel m, SolveState s, const uint32_t max_nearby,
+                                        const uint32_t* __restrict__ n_per, const uint32_t* __restrict__ rows) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m.R) return;
+  {  // padded position q = f * max_nearby + l  ->  pull f * n_per + min(l, n_per - 1)
+    const uint32_t e_pad = s.out_evaluated[r], per = n_per[r];
+    if (e_pad && per) {
+      const uint32_t f = (e_pad - 1) / max_nearby, l = (e_pad - 1) % max_nearby;
+      s.out_evaluated[r] = f * per + (l < per ? l : per - 1) + 1;
+    } else {
+      s.out_evaluated[r] = 0;
+    }
+  }
+  const uint32_t idx = s.out_index[r];
+  if (idx == 0xFFFFFFFFu) return;
+  const uint4 row = ((const uint4*)rows)[(size_t)r * m.elem_cap * max_nearby + idx];
+  const char* st = m.state + (size_t)r * m.block_bytes;
+  const uint32_t* off = (const uint32_t*)(st + m.off_offsets);
+  const uint32_t* el = (const uint32_t*)(st + m.off_elems);
+  const uint32_t se = row.x, sp = row.y, de = row.z, dp = row.w;
+  const uint32_t moved = el[off[se] + sp];
+  const uint32_t adj = (se == de && dp > sp) ? dp - 1 : dp;
+  TabuState& z = s.tabu[r];
+  auto slot = [&](int q) -> uint32_t {
+    const uint32_t t = s.tabu_tenure[q];
+    if (z.n[q] < t) return z.n[q]++;
+    const uint32_t at = z.head[q];
+    z.head[q] = (at + 1) % t;
+    return at;
+  };
+  if (s.tabu_tenure[0]) {  // every entity id of the signature is recorded in turn
+    z.ent[slot(0)] = se;
+    if (de != se) z.ent[slot(0)] = de;
+  }
+  if (s.tabu_tenure[1]) z.val[slot(1)] = moved;
+  if (s.tabu_tenure[2]) {
+    const uint32_t k = slot(2);
+    z.mov[k][0] = se; z.mov[k][1] = sp; z.mov[k][2] = de; z.mov[k][3] = adj; z.mov[k][4] = moved;
+  }
+  if (s.tabu_tenure[3]) {
+    const uint32_t k = slot(3);
+    z.und[k][0] = de; z.und[k][1] = adj; z.und[k][2] = se; z.und[k][3] = sp; z.und[k][4] = moved;
   }
 }

@@ -268,6 +268,51 @@ def test_device_loop_stateful_acceptors_follow_the_oracle_trajectory(kind, okind
     assert np.array_equal(loop.fresh_score(), final)
 
 
+@pytest.mark.parametrize("tenures,aspiration,limit,n,routes,K", [
+    ((3, 0, 0, 0), True, 0, 70, 6, 8), ((0, 6, 0, 0), True, 20, 70, 6, 8), ((0, 0, 9, 0), False, 0, 70, 6, 8),
+    ((0, 0, 0, 5), True, 0, 70, 6, 8), ((2, 4, 6, 3), True, 30, 90, 9, 12), ((1, 0, 0, 2), True, 0, 12, 2, 20),
+])
+def test_device_loop_tabu_search_follows_the_oracle_trajectory(tenures, aspiration, limit, n, routes, K):
+    """sfgpu_solve_nearby_list_change with TabuSearch (acceptor 7) against the oracle's TabuSearchAcceptor fed the
+    ListChangeMove signatures (source / destination entity, moved element, move id with the adjusted destination, undo
+    id) of the oracle's own selector. The last case has fewer candidates per source than max_nearby (padded rows)."""
+    from tests.oracle_lib import move_signatures
+    c = instances.cvrp(n, routes, seed=23)
+    R, steps = 2, 35
+    starts = [instances.perturb_routes(c, 60 + r, n // 3) for r in range(R)]
+    loop = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    seed_base = 0xFACE
+    packed = tenures[0] | (tenures[1] << 8) | (tenures[2] << 16) | (tenures[3] << 24)
+    best, evaluated, committed = loop.solve_nearby_list_change(steps, K, 7, packed, 1, limit, seed_base,
+                                                               step_count_limit=1 if aspiration else 0)
+    final = loop.calculate_score()
+    for r in range(R):
+        o = Oracle.cvrp(c, *starts[r])
+        acc = OracleAcceptor(OracleAcceptor.TABU, tabu=list(tenures), aspiration=aspiration)
+        init = o.committed_score()
+        acc.phase_started(init)
+        best_o, ev_o, steps_o = init.copy(), 0, 0
+        for t in range(steps):
+            last = o.committed_score()
+            rows = o.enumerate_nearby_list_change(K)
+            so, oko = o.score_list_change(rows)
+            sigs = move_signatures(o, 2, rows)
+            out = acc.step(so, oko, best_o, last, _solve_seed(seed_base, r, t), 0 if limit else 2, max(limit, 1), True,
+                           signatures=sigs)
+            ev_o += out[2]
+            if out[0]:
+                o.apply_list_change(*rows[out[1]])
+                steps_o += 1
+            now = o.committed_score()
+            if (now[0], now[1]) > (best_o[0], best_o[1]):
+                best_o = now.copy()
+        what = f"tenures={tenures} aspiration={aspiration} limit={limit} replica={r}"
+        assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o, what
+        assert final[r].tolist() == o.committed_score().tolist(), what
+        assert best[r].tolist() == best_o.tolist(), what
+    assert np.array_equal(loop.fresh_score(), final)
+
+
 def test_great_deluge_form_on_the_fused_step():
     """forage acceptor 3 (score > last || score >= threshold) on sfgpu_step_nearby_list_change."""
     c = instances.cvrp(60, 5, seed=4)
