@@ -537,7 +537,7 @@ int32_t sfgpu_solve_union(sfgpu_ctx* ctx, const sfgpu_union_desc* desc, const st
  * graph — solve_local_search_with_resources (phase/localsearch/phase.rs:237-320) for every replica.
  * acceptor: 1 HillClimbing, 2 LateAcceptance(late_size), 3 GreatDeluge(acceptor_real = rain_speed),
  * 4 StepCountingHillClimbing(step_count_limit), 5 DiversifiedLateAcceptance(late_size, acceptor_real =
- * tolerance), 6 SimulatedAnnealing (sfgpu_solve_change / sfgpu_solve_union; acceptor_real = decay rate, 0 = the
+ * tolerance), 6 SimulatedAnnealing (every loop; acceptor_real = decay rate, 0 = the
  * default 0.999985; late_size = calibration sample size, 0 = 128; step_count_limit bit 0 =
  * HardRegressionPolicy::NeverAcceptHardRegression), 7 TabuSearch (sfgpu_solve_change and sfgpu_solve_nearby_list_change; late_size packs the four
  * tenures as bytes: entity | value << 8 | move << 16 | undo_move << 24, each <= 64, 0 = dimension off, at least one

@@ -63,8 +63,6 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
       if (tabu_tenure[q] > TABU_CAP) return fail(ctx, SFGPU_E_UNSUPPORTED, "tabu tenure above 64");
   }
   const bool sa = p->acceptor == 6;
-  if (sa && !scalar && !udesc)
-    return fail(ctx, SFGPU_E_UNSUPPORTED, "SimulatedAnnealing runs in sfgpu_solve_change and sfgpu_solve_union");
   if (sa && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1.0))
     return fail(ctx, SFGPU_E_INVALID, "simulated_annealing decay_rate must be finite and in (0, 1] (0 = default)");
   if ((p->acceptor == 3 || p->acceptor == 5) && !(p->acceptor_real >= 0.0 && p->acceptor_real <= 1e6))
@@ -183,7 +181,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     a.step_seeds = s.step_seeds;
     a.ref_scores = s.ref_scores;
     a.partials = (SrcPartial*)ctx->partials;
-    if (tabu) {  // TabuSearch decides over the materialised batch (rows, scores, doable), like the scalar loop
+    if (tabu || sa) {  // TabuSearch / SimulatedAnnealing decide over the materialised batch (rows, scores, doable), like the scalar loop
       const size_t stride = (size_t)dm.elem_cap * p->max_nearby;
       const size_t need = (size_t)R * stride * (16 + 16 + 1) + (size_t)(R + 1) * 8 + (size_t)R * 4 + 64;
       rc = ensure_staging(ctx, 64, need);
@@ -243,9 +241,14 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
     } else {
       rc2 = sfgpu_launch_nearby(ctx, a, s.out_index, s.out_best, s.out_evaluated, s.winner_rows, MOVE_CHANGE);
       if (rc2) return rc2;
-      if (tabu) {  // the fused forager's pick is replaced: tabu filter, ordered replay, record, commit by row index
+      if (tabu || sa) {  // the fused forager's pick is replaced: acceptor over the batch, ordered replay, record, commit by row index
         tabu_accept_list_kernel<<<R, 256, 0, ctx->stream>>>(dm, s, p->max_nearby, d_counts, d_nper, a.out_rows, a.out_scores,
                                                             a.out_doable);
+        if (sa) {
+          rc2 = sfgpu_launch_sa_accept(ctx, a.out_offsets, d_counts, nullptr, a.out_scores, a.out_doable, s.ref_scores,
+                                       s.step_seeds, s.sa_cur, s.sa_nxt, s.sa, p->accepted_limit);
+          if (rc2) return rc2;
+        }
         rc2 = sfgpu_launch_argbest_counts(ctx, ForageDev{0, p->tie_mode, p->accepted_limit, nullptr}, a.out_offsets, d_counts,
                                           nullptr, a.out_scores, a.out_doable, s.step_seeds, s.ref_scores, s.out_index,
                                           s.out_best, s.out_evaluated);

@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(256) tabu_accept_list_kernel(const __grid_cons
     n_per[r] = valid < max_nearby ? valid : max_nearby;
     counts[r] = total * max_nearby;
   }
+  if (s.acceptor != 7) return;  // SimulatedAnnealing only needs the counts: sa_accept_kernel decides
   const int64_t bh = s.best_scores[r * 2], bs = s.best_scores[r * 2 + 1];
   for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     if (!doable[i]) continue;
@@ -477,7 +478,7 @@ __global__ void tabu_record_list_kernel(const __grid_constant__ DevModel m, Solv
     }
   }
   const uint32_t idx = s.out_index[r];
-  if (idx == 0xFFFFFFFFu) return;
+  if (idx == 0xFFFFFFFFu || s.acceptor != 7) return;
   const uint4 row = ((const uint4*)rows)[(size_t)r * m.elem_cap * max_nearby + idx];
   const char* st = m.state + (size_t)r * m.block_bytes;
   const uint32_t* off = (const uint32_t*)(st + m.off_offsets);

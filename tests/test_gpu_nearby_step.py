@@ -313,6 +313,44 @@ def test_device_loop_tabu_search_follows_the_oracle_trajectory(tenures, aspirati
     assert np.array_equal(loop.fresh_score(), final)
 
 
+@pytest.mark.parametrize("limit,samples,decay,never_hard,n,routes,K", [(0, 16, 0.9, False, 70, 6, 8), (30, 64, 0.0, False, 90, 9, 12),
+                                                                       (5, 24, 0.95, True, 70, 6, 8), (1, 8, 0.9, False, 12, 2, 20)])
+def test_device_loop_simulated_annealing_follows_the_oracle_trajectory(limit, samples, decay, never_hard, n, routes, K):
+    """sfgpu_solve_nearby_list_change with SimulatedAnnealing (acceptor 6) against the oracle's SimulatedAnnealingAcceptor
+    fed the same stated uniform stream over the oracle's nearby ListChange cursor."""
+    c = instances.cvrp(n, routes, seed=29)
+    R, steps = 2, 35
+    starts = [instances.perturb_routes(c, 80 + r, n // 3) for r in range(R)]
+    loop = models.cvrp_director(c, R, offsets=np.stack([s[0] for s in starts]), elems=np.concatenate([s[1] for s in starts]))
+    seed_base = 0xABCD
+    best, evaluated, committed = loop.solve_nearby_list_change(steps, K, 6, samples, 1, limit, seed_base, acceptor_real=decay,
+                                                               step_count_limit=1 if never_hard else 0)
+    final = loop.calculate_score()
+    for r in range(R):
+        o = Oracle.cvrp(c, *starts[r])
+        acc = OracleAcceptor(OracleAcceptor.SIMULATED_ANNEALING, size=samples, real=decay, aspiration=2 if never_hard else 1)
+        init = o.committed_score()
+        acc.phase_started(init)
+        best_o, ev_o, steps_o = init.copy(), 0, 0
+        for t in range(steps):
+            last = o.committed_score()
+            rows = o.enumerate_nearby_list_change(K)
+            so, oko = o.score_list_change(rows)
+            out = acc.step(so, oko, best_o, last, _solve_seed(seed_base, r, t), 0 if limit else 2, max(limit, 1), True)
+            ev_o += out[2]
+            if out[0]:
+                o.apply_list_change(*rows[out[1]])
+                steps_o += 1
+            now = o.committed_score()
+            if (now[0], now[1]) > (best_o[0], best_o[1]):
+                best_o = now.copy()
+        what = f"limit={limit} samples={samples} replica={r}"
+        assert int(evaluated[r]) == ev_o and int(committed[r]) == steps_o, what
+        assert final[r].tolist() == o.committed_score().tolist(), what
+        assert best[r].tolist() == best_o.tolist(), what
+    assert np.array_equal(loop.fresh_score(), final)
+
+
 def test_great_deluge_form_on_the_fused_step():
     """forage acceptor 3 (score > last || score >= threshold) on sfgpu_step_nearby_list_change."""
     c = instances.cvrp(60, 5, seed=4)
