@@ -100,6 +100,11 @@ pub struct sfgpu_forage_params {
     pub reserved: u32,
 }
 
+/// `acceptor`: 1 HillClimbing, 2 LateAcceptance(`late_size`), 3 GreatDeluge(`acceptor_real` = rain speed),
+/// 4 StepCountingHillClimbing(`step_count_limit`), 5 DiversifiedLateAcceptance(`late_size`, `acceptor_real` = tolerance),
+/// 6 SimulatedAnnealing(`late_size` = calibration samples, `acceptor_real` = decay), 7 TabuSearch(`late_size` =
+/// entity | value << 8 | move << 16 | undo_move << 24 tenures, `step_count_limit` bit 0 = aspiration).
+/// `reserved` bit 0: windowed speculation for `sfgpu_solve_nearby_list_change` with AcceptedCount.
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct sfgpu_solve_params {

@@ -109,8 +109,14 @@ struct StepResult {
 struct SolveParams {  // sfgpu_solve_params: device-resident loop (phase.rs:237-320)
   uint32_t max_nearby = 20, n_steps = 0;
   int acceptor = 2;            // 1 HillClimbing, 2 LateAcceptance, 3 GreatDeluge, 4 StepCountingHillClimbing,
-                               // 5 DiversifiedLateAcceptance
+                               // 5 DiversifiedLateAcceptance, 6 SimulatedAnnealing (late_size = calibration samples,
+                               // acceptor_real = decay), 7 TabuSearch (late_size = tabu_tenures(..), step_count_limit
+                               // bit 0 = aspiration)
   uint32_t late_size = 400;
+  // TabuSearchAcceptor::new(entity_tabu, value_tabu, move_tabu, undo_move_tabu) packed for acceptor 7 (each <= 64)
+  static uint32_t tabu_tenures(uint32_t entity, uint32_t value, uint32_t move, uint32_t undo_move) {
+    return entity | (value << 8) | (move << 16) | (undo_move << 24);
+  }
   bool random_ties = true;
   uint32_t accepted_limit = 0;
   uint64_t seed_base = 0;
