@@ -420,7 +420,10 @@ __global__ void __launch_bounds__(256) nearby_step_kernel(const __grid_constant_
   typedef typename FastArith<CELL>::S S;
   const int64_t* cs = (const int64_t*)(smem + m.off_score);
   const int64_t ch = cs[0], csf = cs[1];
-  if (threadIdx.x == 0) s_count = nearby_count(m, v.rr, a.max_nearby);
+  if (threadIdx.x < 32) {
+    const uint32_t c = nearby_count_warp(m, v.rr, a.max_nearby, threadIdx.x);
+    if (threadIdx.x == 0) s_count = c;
+  }
   __syncthreads();
   const uint32_t count = s_count;
   const uint32_t total = v.rr[m.n_owners - 1].x + v.rr[m.n_owners - 1].y;  // routed elements
@@ -865,8 +868,11 @@ __global__ void __launch_bounds__(256) nearby_finish_kernel(const __grid_constan
   rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 2] : 0, ch, th);
   rel_threshold(a.ref_scores ? a.ref_scores[r * 4 + 3] : 0, csf, ts);
   const NearbyConsts<S> nc = nearby_consts<SUM_FN, S>(m);
+  if (warp == 0) {  // the route lengths sit in global memory here: one load per lane instead of a serial walk
+    const uint32_t c = nearby_count_warp(m, v.rr, a.max_nearby, lane);
+    if (lane == 0) s_count = c;
+  }
   if (threadIdx.x == 0) {
-    s_count = nearby_count(m, v.rr, a.max_nearby);
     s_fcut = total;       // sources [0, s_fcut) count fully; source s_fcut only up to lane s_lcut
     s_lcut = 0;
     s_cutp.n_best = 0;
