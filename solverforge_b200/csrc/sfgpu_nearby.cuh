@@ -380,18 +380,8 @@ __device__ __forceinline__ void nearby_swap_score(const DevModel& m, const Nearb
   }
 }
 
-// number of candidates every source yields: min(K, slots of non-empty routes - 2)
-__device__ __forceinline__ uint32_t nearby_count(const DevModel& m, const uint4* rr, uint32_t K) {
-  uint32_t slots = 0;
-  for (uint32_t o = 0; o < m.n_owners; ++o) {
-    const uint32_t len = rr[o].y;
-    slots += len ? len + 1 : 0;
-  }
-  const uint32_t valid = slots >= 2 ? slots - 2 : 0;
-  return valid < K ? valid : K;
-}
-
-// nearby_count by one warp (every lane returns it)
+// number of candidates every source yields: min(K, slots of non-empty routes - 2), computed by one warp (every lane
+// returns it)
 __device__ __forceinline__ uint32_t nearby_count_warp(const DevModel& m, const uint4* rr, uint32_t K, uint32_t lane) {
   uint32_t slots = 0;
   for (uint32_t o = lane; o < m.n_owners; o += 32) {
