@@ -303,6 +303,7 @@ inline int small_io_begin(sfgpu_ctx* ctx, SmallIo& io, bool dev_io, uint32_t win
     ctx->small_bytes = 0;
     CU(cudaMallocHost(&ctx->small_pin, io.total));
     CU(cudaMalloc(&ctx->small_dev, io.total));
+    CU(cudaMemsetAsync(ctx->small_dev, 0, io.total, ctx->stream));  // the alignment gaps between the arrays travel in the read-back
     ctx->small_bytes = io.total;
   }
   char* pin = (char*)ctx->small_pin;
