@@ -211,6 +211,7 @@ inline int ensure_staging(sfgpu_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
     ctx->dscr = nullptr;
     ctx->dscr_bytes = 0;
     CU(cudaMalloc(&ctx->dscr, dev_bytes));
+    CU(cudaMemsetAsync(ctx->dscr, 0, dev_bytes, ctx->stream));  // alignment gaps between its arrays travel in read-backs
     ctx->dscr_bytes = dev_bytes;
   }
   return SFGPU_OK;

@@ -114,6 +114,7 @@ int solve_impl(sfgpu_ctx* ctx, const sfgpu_solve_params* p, bool scalar, int64_t
   s.sa_cur = (SaState*)(b + o_sa);
   s.sa_nxt = s.sa_cur + R;
   s.tabu = (TabuState*)(b + o_tabu);
+  if (tabu) CU(cudaMemsetAsync(s.tabu, 0, (size_t)R * sizeof(TabuState), ctx->stream));  // the kernels stage whole memories
   for (int q = 0; q < 4; ++q) s.tabu_tenure[q] = tabu_tenure[q];
   s.tabu_aspiration = (uint32_t)(p->step_count_limit & 1);
   if (sa) {  // simulated_annealing.rs:11-15 defaults; late_size = calibration sample size, step_count_limit bit 0 =
