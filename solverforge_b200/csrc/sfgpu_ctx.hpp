@@ -393,6 +393,9 @@ int sfgpu_launch_sa_accept(sfgpu_ctx* ctx, const uint64_t* d_offs, const uint32_
 int sfgpu_configure_scalar(sfgpu_ctx* ctx);
 void sfgpu_change_step_chunks(const sfgpu_ctx* ctx, uint32_t* out_per, uint32_t* out_chunks);
 int sfgpu_configure_scalar_step(sfgpu_ctx* ctx);  // sfgpu_scalar_step.cu
+int sfgpu_configure_scalar_finish(sfgpu_ctx* ctx);  // sfgpu_scalar_finish.cu
+int sfgpu_launch_change_finish(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t chunks, uint32_t* d_idx, int64_t* d_best,
+                               uint32_t* d_eval, uint32_t* d_win);
 int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t chunks, uint32_t* d_idx, int64_t* d_best,
                              uint32_t* d_eval, uint32_t* d_win);
 // sfgpu_list.cu

@@ -1,5 +1,5 @@
-// Generated ChangeMove step of scalar models (sfgpu_change_step.cuh): change_step_kernel / change_finish_kernel over
-// every monomorphised program — a translation unit of its own so it compiles side by side with sfgpu_scalar.cu.
+// Generated ChangeMove step of scalar models (sfgpu_change_step.cuh): change_step_kernel over every monomorphised
+// program — a translation unit of its own so it compiles side by side with sfgpu_scalar.cu and sfgpu_scalar_finish.cu.
 #include "sfgpu_ctx.hpp"
 #include "sfgpu_change_step.cuh"
 #include "sfgpu_spec_list.h"
@@ -8,16 +8,11 @@ using namespace sfgpu_host;
 
 namespace {
 typedef void (*SpecStepFn)(const DevModel, const ChangeStepArgs, const SpecIdx);
-typedef void (*SpecFinishFn)(const DevModel, const ChangeStepArgs, const SpecIdx, uint32_t, uint32_t*, int64_t*, uint32_t*, uint32_t*);
 struct StepEntry {
-  SpecStepFn step, step_n;        // int64 / int32 program (or null)
-  SpecFinishFn finish, finish_n;
+  SpecStepFn step, step_n;  // int64 / int32 program (or null)
 };
-#define STEP_WIDE(a, b, c, d) \
-  { change_step_kernel<true, SpecProg<a, b, c, d>>, nullptr, change_finish_kernel<true, SpecProg<a, b, c, d>>, nullptr }
-#define STEP_BOTH(a, b, c, d)                                                                              \
-  { change_step_kernel<true, SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProgN<a, b, c, d>>,        \
-    change_finish_kernel<true, SpecProg<a, b, c, d>>, change_finish_kernel<true, SpecProgN<a, b, c, d>> }
+#define STEP_WIDE(a, b, c, d) { change_step_kernel<true, SpecProg<a, b, c, d>>, nullptr }
+#define STEP_BOTH(a, b, c, d) { change_step_kernel<true, SpecProg<a, b, c, d>>, change_step_kernel<true, SpecProgN<a, b, c, d>> }
 const StepEntry g_step[] = {SFGPU_SPEC_TUPLES(STEP_WIDE, STEP_BOTH)};  // same order as g_spec of sfgpu_scalar.cu
 #undef STEP_WIDE
 #undef STEP_BOTH
@@ -27,20 +22,13 @@ const StepEntry g_step[] = {SFGPU_SPEC_TUPLES(STEP_WIDE, STEP_BOTH)};  // same o
 int sfgpu_configure_scalar_step(sfgpu_ctx* ctx) {
   const DevModel& dm = ctx->dm;
   const int bytes = (int)dm.stage_bytes;
-  if (ctx->staged) {
-    CU(cudaFuncSetAttribute(change_step_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute(change_finish_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  }
+  if (ctx->staged) CU(cudaFuncSetAttribute(change_step_kernel<true, InterpProg>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   if (ctx->spec_id >= 0) {
     const StepEntry& e = g_step[ctx->spec_id];
     CU(cudaFuncSetAttribute((const void*)e.step, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CU(cudaFuncSetAttribute((const void*)e.finish, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    if (ctx->spec_narrow) {
-      CU(cudaFuncSetAttribute((const void*)e.step_n, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      CU(cudaFuncSetAttribute((const void*)e.finish_n, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    }
+    if (ctx->spec_narrow) CU(cudaFuncSetAttribute((const void*)e.step_n, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
-  return SFGPU_OK;
+  return sfgpu_configure_scalar_finish(ctx);
 }
 
 // generate + score + forage (two kernels) on the context's stream; the dominant kernel is bracketed by the
@@ -55,15 +43,7 @@ int sfgpu_launch_change_step(sfgpu_ctx* ctx, const ChangeStepArgs& a, uint32_t c
     change_step_kernel<true, InterpProg><<<grid, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx);
   else
     change_step_kernel<false, InterpProg><<<grid, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx);
-  if (ctx->spec_id >= 0)
-    (ctx->spec_narrow ? g_step[ctx->spec_id].finish_n : g_step[ctx->spec_id].finish)<<<dm.R, 256, dm.stage_bytes, ctx->stream>>>(
-        dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
-  else if (ctx->staged)
-    change_finish_kernel<true, InterpProg><<<dm.R, 256, dm.stage_bytes, ctx->stream>>>(dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
-  else
-    change_finish_kernel<false, InterpProg><<<dm.R, 256, 0, ctx->stream>>>(dm, a, ctx->spec_idx, chunks, d_idx, d_best, d_eval, d_win);
-  ctx->launches += 2;
+  ctx->launches += 1;
   CU(cudaGetLastError());
-  return SFGPU_OK;
+  return sfgpu_launch_change_finish(ctx, a, chunks, d_idx, d_best, d_eval, d_win);
 }
-
